@@ -1,0 +1,1334 @@
+/*
+ * b2_oracle.c -- TEST INFRASTRUCTURE ONLY (see b2_oracle.h).
+ *
+ * Sequential fp64 restatement of pypybox2d's World.step with continuous_physics=False and
+ * pair-emission order pinned (sorted by proxy index).  Every function cites the reference
+ * lines it follows; expressions keep the reference's operand order so that, built with
+ * -ffp-contract=off against the same libm, results are bit-identical to the pure-Python
+ * reference (x ** 2 is written pow(x, 2.0) exactly where the reference writes it).
+ *
+ * Not a product path: nothing in pypybox2d_b200/ may load this library.
+ */
+#include "b2_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- constants: pypybox2d/settings.py:32-134 ---- */
+#define EPS            DBL_EPSILON
+#define EPS_SQR        pow(DBL_EPSILON, 2.0)        /* settings.py:40 */
+#define MAX_FLOAT      DBL_MAX
+#define PI_            3.141592653589793
+#define AABB_EXT       0.1
+#define AABB_MULT      2.0
+#define LINEAR_SLOP    0.005
+#define ANGULAR_SLOP   (2.0 / 180.0 * PI_)
+#define POLY_RADIUS    (2.0 * LINEAR_SLOP)
+#define VEL_THRESHOLD  1.0
+#define MAX_LIN_CORR   0.2
+#define MAX_TRANS      2.0
+#define MAX_TRANS_SQR  pow(MAX_TRANS, 2.0)          /* settings.py:99: MAX_TRANSLATION**2 */
+#define MAX_ROT        (0.5 * PI_)
+#define MAX_ROT_SQR    pow(MAX_ROT, 2.0)            /* settings.py:104 */
+#define BAUMGARTE      0.2
+#define TIME_TO_SLEEP  0.5
+#define LIN_SLEEP_TOL_SQR pow(0.01, 2.0)             /* settings.py:119 */
+#define ANG_SLEEP_TOL_SQR pow(2.0 / 180.0 * PI_, 2.0) /* settings.py:123 */
+#define REL_TOL        0.98
+#define ABS_TOL        0.001
+
+/* flag bits: pypybox2d_b200/schema.py */
+#define BODY_TYPE_MASK 0x3u
+#define BODY_AWAKE     0x4u
+#define BODY_ACTIVE    0x8u
+#define BODY_ALLOW_SLEEP 0x10u
+#define BODY_ISLAND    0x80u
+#define T_STATIC 0
+#define T_DYNAMIC 1
+#define C_TOUCHING 0x1u
+#define C_ENABLED  0x2u
+#define C_FILTER   0x4u
+#define C_ISLAND   0x8u
+#define W_ALLOW_SLEEP 0x1u
+#define W_WARM_START  0x2u
+#define W_NEW_FIXTURE 0x4u
+#define W_AUTO_CLEAR  0x8u
+#define ST_CONTACT_OVERFLOW 0x1u
+#define ST_PAIR_OVERFLOW    0x2u
+#define ST_ISLAND_OVERFLOW  0x8u
+#define M_CIRCLES 0
+#define M_FACE_A  1
+#define M_FACE_B  2
+#define S_CIRCLE 0
+#define S_POLYGON 1
+#define S_EDGE 3
+#define MP_VERTEX 0
+#define MP_FACE 1
+#define MAXV 8
+
+/* Python's min/max return the first argument unless the second compares strictly better */
+#define PYMIN(a, b) (((b) < (a)) ? (b) : (a))
+#define PYMAX(a, b) (((b) > (a)) ? (b) : (a))
+
+typedef struct { double x, y; } v2;
+typedef struct { v2 p, c1, c2; } xform;   /* position, rotation columns (common.py:360-503,616-685) */
+
+static inline v2 V(double x, double y) { v2 r = {x, y}; return r; }
+static inline v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
+static inline v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
+static inline v2 vneg(v2 a) { return V(-a.x, -a.y); }
+static inline v2 vscale(double s, v2 a) { return V(s * a.x, s * a.y); }          /* common.py:113-115 */
+static inline double vdot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }          /* common.py:213-215 */
+static inline double vcross(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }        /* common.py:210-212 */
+static inline v2 vcross_s(v2 a, double s) { return V(s * a.y, -s * a.x); }       /* common.py:204-208 */
+static inline v2 scross(double s, v2 a) { return V(-s * a.y, s * a.x); }         /* common.py:195-202 */
+static inline double sq(double x) { return pow(x, 2.0); }                        /* Python's x ** 2 */
+static inline double vlen2(v2 a) { return sq(a.x) + sq(a.y); }                   /* common.py:189-190 */
+static inline v2 vnorm(v2 a)                                                      /* common.py:216-222 */
+{
+    double len = sqrt(sq(a.x) + sq(a.y));
+    if (len < EPS) return a;
+    double inv = 1.0 / len;
+    return V(a.x * inv, a.y * inv);
+}
+static inline double dist2(v2 a, v2 b) { v2 c = vsub(a, b); return vdot(c, c); } /* common.py:950-952 */
+static inline double pyclamp(double v, double lo, double hi)                      /* common.py:978-979 */
+{
+    double m = PYMIN(v, hi);
+    return PYMAX(lo, m);
+}
+
+static inline xform xf_make(v2 p, double c, double s)
+{
+    xform t; t.p = p; t.c1 = V(c, s); t.c2 = V(-s, c); return t;
+}
+static inline xform xf_row(const double* r) { return xf_make(V(r[0], r[1]), r[2], r[3]); }
+/* Transform(angle=a); position = c - R * local_center  (body.py:906-908, contact.py:433-436) */
+static inline xform xf_from_sweep(v2 c, double a, v2 lc)
+{
+    xform t = xf_make(V(0, 0), cos(a), sin(a));
+    v2 rl = V(t.c1.x * lc.x + t.c2.x * lc.y, t.c1.y * lc.x + t.c2.y * lc.y);
+    t.p = vsub(c, rl);
+    return t;
+}
+static inline v2 xf_mul(const xform* t, v2 v)                                     /* common.py:677-685 */
+{
+    return V(t->p.x + t->c1.x * v.x + t->c2.x * v.y, t->p.y + t->c1.y * v.x + t->c2.y * v.y);
+}
+static inline v2 rot_mul(const xform* t, v2 v)                                    /* common.py:404-411 */
+{
+    return V(t->c1.x * v.x + t->c2.x * v.y, t->c1.y * v.x + t->c2.y * v.y);
+}
+static inline v2 rot_mul_t(const xform* t, v2 v)                                  /* common.py:467-472 */
+{
+    return V(vdot(t->c1, v), vdot(t->c2, v));
+}
+static inline v2 xf_mul_t(const xform* t, v2 v) { return rot_mul_t(t, vsub(v, t->p)); } /* common.py:669-670 */
+
+/* ---- shape table access ---- */
+typedef struct { int type, count, has0, has3; double radius; const double* d; } shape_t;
+static inline shape_t shape_get(const orc_world* w, int row)
+{
+    shape_t s; int m = w->s_meta[row];
+    s.type = m & 0xff; s.count = (m >> 8) & 0xff; s.has0 = (m >> 16) & 1; s.has3 = (m >> 17) & 1;
+    s.radius = w->s_radius[row]; s.d = w->s_data + 32 * (size_t)row;
+    return s;
+}
+static inline v2 pvert(const shape_t* s, int i) { return V(s->d[2 * i], s->d[2 * i + 1]); }
+static inline v2 pnorm(const shape_t* s, int i) { return V(s->d[16 + 2 * i], s->d[16 + 2 * i + 1]); }
+
+/* ---- manifold working copy (contact_util.py:50-166) ---- */
+typedef struct {
+    int type, count;
+    v2 local_normal, local_point;
+    v2 pt[2];
+    uint32_t id[2];
+} manifold_t;
+static inline uint32_t mkid(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+typedef struct { v2 v; int ia, ib, ta, tb; } clipv;
+
+/* ---- collide_circles: collision.py:46-66 ---- */
+static void collide_circles(manifold_t* m, const shape_t* a, const xform* xa, const shape_t* b, const xform* xb)
+{
+    m->count = 0;
+    v2 posa = V(a->d[0], a->d[1]), posb = V(b->d[0], b->d[1]);
+    v2 pa = xf_mul(xa, posa), pb = xf_mul(xb, posb);
+    v2 d = vsub(pb, pa);
+    double dist_sqr = vlen2(d);
+    double radius = a->radius + b->radius;
+    if (dist_sqr > sq(radius)) return;
+    m->type = M_CIRCLES;
+    m->local_point = posa;
+    m->local_normal = V(0, 0);
+    m->count = 1;
+    m->pt[0] = posb;
+    m->id[0] = mkid(0, 0, 0, 0);
+}
+
+/* ---- collide_polygon_circle: collision.py:68-141 ---- */
+static void collide_polygon_circle(manifold_t* m, const shape_t* pa, const xform* xa, const shape_t* cb, const xform* xb)
+{
+    m->count = 0;
+    v2 posb = V(cb->d[0], cb->d[1]);
+    v2 c = xf_mul(xb, posb);
+    v2 c_local = xf_mul_t(xa, c);
+    int normal_index = 0;
+    double separation = -MAX_FLOAT;
+    double radius = pa->radius + cb->radius;
+    int n = pa->count;
+    for (int i = 0; i < n; ++i) {
+        double s = vdot(pnorm(pa, i), vsub(c_local, pvert(pa, i)));
+        if (s > radius) return;
+        if (s > separation) { separation = s; normal_index = i; }
+    }
+    int i1 = normal_index, i2 = (i1 + 1) % n;
+    v2 v1 = pvert(pa, i1), v2_ = pvert(pa, i2);
+    if (separation < EPS) {
+        m->count = 1; m->type = M_FACE_A;
+        m->local_normal = pnorm(pa, normal_index);
+        m->local_point = vscale(0.5, vadd(v1, v2_));
+        m->pt[0] = posb; m->id[0] = mkid(0, 0, 0, 0);
+        return;
+    }
+    double u1 = vdot(vsub(c_local, v1), vsub(v2_, v1));
+    double u2 = vdot(vsub(c_local, v2_), vsub(v1, v2_));
+    if (u1 < 0.0) {
+        if (dist2(c_local, v1) > sq(radius)) return;
+        m->local_normal = vnorm(vsub(c_local, v1));
+        m->local_point = v1;
+    } else if (u2 < 0.0) {
+        if (dist2(c_local, v2_) > sq(radius)) return;
+        m->local_normal = vnorm(vsub(c_local, v2_));
+        m->local_point = v2_;
+    } else {
+        v2 face_center = vscale(0.5, vadd(v1, v2_));
+        separation = vdot(vsub(c_local, face_center), pnorm(pa, i1));
+        if (separation > radius) return;
+        m->local_normal = pnorm(pa, i1);
+        m->local_point = face_center;
+    }
+    m->count = 1; m->type = M_FACE_A;
+    m->pt[0] = posb; m->id[0] = mkid(0, 0, 0, 0);
+}
+
+/* ---- polygon SAT helpers: collision_util.py:31-164 ---- */
+static double edge_separation(const shape_t* p1, const xform* x1, int edge1, const shape_t* p2, const xform* x2)
+{
+    v2 normal1_world = rot_mul(x1, pnorm(p1, edge1));
+    v2 normal1 = rot_mul_t(x2, normal1_world);
+    int index = 0; double min_dot = 0;
+    for (int i = 0; i < p2->count; ++i) {
+        double d = vdot(pvert(p2, i), normal1);
+        if (i == 0 || d < min_dot) { min_dot = d; index = i; }
+    }
+    v2 v1 = xf_mul(x1, pvert(p1, edge1));
+    v2 v2_ = xf_mul(x2, pvert(p2, index));
+    return vdot(vsub(v2_, v1), normal1_world);
+}
+
+static double max_separation(int* edge_out, const shape_t* p1, const xform* x1, const shape_t* p2, const xform* x2)
+{
+    int count1 = p1->count;
+    /* Polygon._centroid is always (0,0) in the reference */
+    v2 zero = V(0, 0);
+    v2 d = vsub(xf_mul(x2, zero), xf_mul(x1, zero));
+    v2 d_local1 = rot_mul_t(x1, d);
+    int edge = 0; double max_dot = 0;
+    for (int i = 0; i < count1; ++i) {
+        double dt = vdot(pnorm(p1, i), d_local1);
+        if (i == 0 || dt > max_dot) { max_dot = dt; edge = i; }
+    }
+    double s = edge_separation(p1, x1, edge, p2, x2);
+    int prev_edge = (edge - 1 + count1) % count1;
+    double s_prev = edge_separation(p1, x1, prev_edge, p2, x2);
+    int next_edge = (edge + 1) % count1;
+    double s_next = edge_separation(p1, x1, next_edge, p2, x2);
+    int best_edge, increment; double best_separation;
+    if (s_prev > s && s_prev > s_next) { increment = -1; best_edge = prev_edge; best_separation = s_prev; }
+    else if (s_next > s) { increment = 1; best_edge = next_edge; best_separation = s_next; }
+    else { *edge_out = edge; return s; }
+    for (;;) {
+        if (increment == -1) edge = (best_edge - 1 + count1) % count1;
+        else edge = (best_edge + 1) % count1;
+        s = edge_separation(p1, x1, edge, p2, x2);
+        if (s > best_separation) { best_edge = edge; best_separation = s; }
+        else break;
+    }
+    *edge_out = best_edge;
+    return best_separation;
+}
+
+static void find_incident_edge(clipv c[2], const shape_t* p1, const xform* x1, int edge1, const shape_t* p2, const xform* x2)
+{
+    v2 normal1 = rot_mul_t(x2, rot_mul(x1, pnorm(p1, edge1)));
+    int index = 0; double min_dot = 0;
+    for (int i = 0; i < p2->count; ++i) {
+        double d = vdot(normal1, pnorm(p2, i));
+        if (i == 0 || d < min_dot) { min_dot = d; index = i; }
+    }
+    int i1 = index, i2 = (i1 + 1) % p2->count;
+    c[0].v = xf_mul(x2, pvert(p2, i1)); c[0].ia = edge1; c[0].ib = i1; c[0].ta = MP_FACE; c[0].tb = MP_VERTEX;
+    c[1].v = xf_mul(x2, pvert(p2, i2)); c[1].ia = edge1; c[1].ib = i2; c[1].ta = MP_FACE; c[1].tb = MP_VERTEX;
+}
+
+static int clip_segment_to_line(clipv out[3], const clipv in[2], v2 normal, double offset, int vertex_index_a)
+{
+    int n = 0;
+    double distance0 = vdot(normal, in[0].v) - offset;
+    double distance1 = vdot(normal, in[1].v) - offset;
+    if (distance0 <= 0.0) out[n++] = in[0];
+    if (distance1 <= 0.0) out[n++] = in[1];
+    if (distance0 * distance1 < 0.0) {
+        double interp = distance0 / (distance0 - distance1);
+        clipv cv;
+        cv.v = vadd(in[0].v, vscale(interp, vsub(in[1].v, in[0].v)));
+        cv.ia = vertex_index_a; cv.ib = in[0].ib; cv.ta = MP_VERTEX; cv.tb = MP_FACE;
+        out[n++] = cv;
+    }
+    return n;
+}
+
+/* ---- collide_polygons: collision.py:144-241 ---- */
+static void collide_polygons(manifold_t* m, const shape_t* pa, const xform* xa, const shape_t* pb, const xform* xb)
+{
+    m->count = 0;
+    double total_radius = pa->radius + pb->radius;
+    int edge_a, edge_b;
+    double separation_a = max_separation(&edge_a, pa, xa, pb, xb);
+    if (separation_a > total_radius) return;
+    double separation_b = max_separation(&edge_b, pb, xb, pa, xa);
+    if (separation_b > total_radius) return;
+
+    const shape_t *poly1, *poly2; const xform *xf1, *xf2; int edge1, flip;
+    if (separation_b > (REL_TOL * separation_a + ABS_TOL)) {
+        poly1 = pb; poly2 = pa; xf1 = xb; xf2 = xa; edge1 = edge_b; m->type = M_FACE_B; flip = 1;
+    } else {
+        poly1 = pa; poly2 = pb; xf1 = xa; xf2 = xb; edge1 = edge_a; m->type = M_FACE_A; flip = 0;
+    }
+    clipv incident[2];
+    find_incident_edge(incident, poly1, xf1, edge1, poly2, xf2);
+    int iv1 = edge1, iv2 = (edge1 + 1) % poly1->count;
+    v2 v11 = pvert(poly1, iv1), v12 = pvert(poly1, iv2);
+    v2 localtangent = vnorm(vsub(v12, v11));
+    v2 local_normal = vcross_s(localtangent, 1.0);
+    v2 planepoint = vscale(0.5, vadd(v11, v12));
+    v2 tangent = rot_mul(xf1, localtangent);
+    v2 normal = vcross_s(tangent, 1.0);
+    v11 = xf_mul(xf1, v11);
+    v12 = xf_mul(xf1, v12);
+    double front_offset = vdot(normal, v11);
+    double side_offset1 = -vdot(tangent, v11) + total_radius;
+    double side_offset2 = vdot(tangent, v12) + total_radius;
+    clipv cp1[3], cp2[3];
+    if (clip_segment_to_line(cp1, incident, vneg(tangent), side_offset1, iv1) < 2) return;
+    if (clip_segment_to_line(cp2, cp1, tangent, side_offset2, iv2) < 2) return;
+    m->local_normal = local_normal;
+    m->local_point = planepoint;
+    int point_count = 0;
+    for (int i = 0; i < 2; ++i) {
+        double separation = vdot(normal, cp2[i].v) - front_offset;
+        if (separation <= total_radius) {
+            m->pt[point_count] = xf_mul_t(xf2, cp2[i].v);
+            if (flip) m->id[point_count] = mkid(cp2[i].ib, cp2[i].ia, cp2[i].tb, cp2[i].ta);
+            else m->id[point_count] = mkid(cp2[i].ia, cp2[i].ib, cp2[i].ta, cp2[i].tb);
+            ++point_count;
+        }
+    }
+    m->count = point_count;
+}
+
+/* ---- collide_edge_circle: collision.py:246-353 ---- */
+static void collide_edge_circle(manifold_t* m, const shape_t* ea, const xform* xa, const shape_t* cb, const xform* xb)
+{
+    m->count = 0;
+    v2 posb = V(cb->d[0], cb->d[1]);
+    v2 Q = xf_mul_t(xa, xf_mul(xb, posb));
+    v2 A = V(ea->d[0], ea->d[1]), B = V(ea->d[2], ea->d[3]);
+    v2 e = vsub(B, A);
+    double u = vdot(e, vsub(B, Q));
+    double v = vdot(e, vsub(Q, A));
+    double radius = ea->radius + cb->radius;
+    if (v <= 0.0) {
+        v2 P = A, d = vsub(Q, P);
+        double dd = vdot(d, d);
+        if (dd > sq(radius)) return;
+        if (ea->has0) {
+            v2 A1 = V(ea->d[4], ea->d[5]), B1 = A;
+            v2 e1 = vsub(B1, A1);
+            double u1 = vdot(e1, vsub(B1, Q));
+            if (u1 > 0.0) return;
+        }
+        m->count = 1; m->type = M_CIRCLES; m->local_normal = V(0, 0); m->local_point = P;
+        m->id[0] = mkid(0, 0, MP_VERTEX, MP_VERTEX); m->pt[0] = posb;
+        return;
+    }
+    if (u <= 0.0) {
+        v2 P = B, d = vsub(Q, P);
+        double dd = vdot(d, d);
+        if (dd > sq(radius)) return;
+        if (ea->has3) {
+            v2 B2 = V(ea->d[6], ea->d[7]), A2 = B;
+            v2 e2 = vsub(B2, A2);
+            double v2s = vdot(e2, vsub(Q, A2));
+            if (v2s > 0.0) return;
+        }
+        m->count = 1; m->type = M_CIRCLES; m->local_normal = V(0, 0); m->local_point = P;
+        m->id[0] = mkid(1, 0, MP_VERTEX, MP_VERTEX); m->pt[0] = posb;
+        return;
+    }
+    double den = vdot(e, e);
+    v2 P = vscale(1.0 / den, vadd(vscale(u, A), vscale(v, B)));
+    v2 d = vsub(Q, P);
+    double dd = vdot(d, d);
+    if (dd > sq(radius)) return;
+    v2 n = V(-e.y, e.x);
+    if (vdot(n, vsub(Q, A)) < 0.0) n = V(-n.x, -n.y);
+    n = vnorm(n);
+    m->count = 1; m->type = M_FACE_A; m->local_normal = n; m->local_point = A;
+    m->id[0] = mkid(0, 0, MP_FACE, MP_VERTEX); m->pt[0] = posb;
+}
+
+/* ---- EPCollider: collision.py:355-690 ---- */
+enum { AX_UNKNOWN = 0, AX_EDGE_A = 1, AX_EDGE_B = 2 };
+typedef struct { int type, index; double separation; } epaxis;
+typedef struct {
+    xform xf;
+    v2 v0, v1, v2_, v3; int has0, has3;
+    v2 enormal;
+    v2 avert[2], anorm[2];
+    v2 bcentroid, bvert[MAXV], bnorm[MAXV]; int bcount;
+    double radius;
+    v2 l11, l12, l21, l22;
+} epc_t;
+
+static int ep_valid(const epc_t* c, v2 n)
+{
+    int valid1 = (vcross(n, c->l11) >= -ANGULAR_SLOP) && (vcross(c->l12, n) >= -ANGULAR_SLOP);
+    int valid2 = (vcross(n, c->l21) >= -ANGULAR_SLOP) && (vcross(c->l22, n) >= -ANGULAR_SLOP);
+    return valid1 && valid2;
+}
+
+static void ep_incident(clipv out[2], const v2* normals1, int edge1, const v2* verts2, const v2* normals2, int n2)
+{
+    v2 normal1 = normals1[edge1];
+    int index = 0; double min_dot = 0;
+    for (int i = 0; i < n2; ++i) {
+        double d = vdot(normal1, normals2[i]);
+        if (i == 0 || d < min_dot) { min_dot = d; index = i; }
+    }
+    int i1 = index, i2 = (i1 + 1) % n2;
+    out[0].v = verts2[i1]; out[0].ia = edge1; out[0].ib = i1; out[0].ta = MP_FACE; out[0].tb = MP_VERTEX;
+    out[1].v = verts2[i2]; out[1].ia = edge1; out[1].ib = i2; out[1].ta = MP_FACE; out[1].tb = MP_VERTEX;
+}
+
+static void collide_edge_polygon(manifold_t* m, const shape_t* ea, const xform* xa, const shape_t* pb, const xform* xb)
+{
+    epc_t c;
+    /* Transform.mul_t(Transform): offset is NOT rotated (common.py:671-673) */
+    c.xf.p = vsub(xb->p, xa->p);
+    c.xf.c1 = V(vdot(xa->c1, xb->c1), vdot(xa->c2, xb->c1));
+    c.xf.c2 = V(vdot(xa->c1, xb->c2), vdot(xa->c2, xb->c2));
+    c.v1 = V(ea->d[0], ea->d[1]); c.v2_ = V(ea->d[2], ea->d[3]);
+    c.v0 = V(ea->d[4], ea->d[5]); c.v3 = V(ea->d[6], ea->d[7]);
+    c.has0 = ea->has0; c.has3 = ea->has3;
+    v2 e = vsub(c.v2_, c.v1);
+    c.enormal = vnorm(V(e.y, -e.x));
+    c.avert[0] = c.v1; c.avert[1] = c.v2_;
+    c.anorm[0] = c.enormal; c.anorm[1] = vneg(c.enormal);
+    c.bcentroid = xf_mul(&c.xf, V(0, 0));
+    c.bcount = pb->count;
+    for (int i = 0; i < pb->count; ++i) {
+        c.bvert[i] = xf_mul(&c.xf, pvert(pb, i));
+        c.bnorm[i] = rot_mul(&c.xf, pnorm(pb, i));
+    }
+    c.radius = 2.0 * POLY_RADIUS;
+    c.l11 = c.l12 = c.l21 = c.l22 = V(0, 0);
+
+    m->count = 0;
+    /* compute_adjacency: collision.py:537-597 */
+    {
+        v2 center_b = c.bcentroid;
+        if (c.has0) {
+            v2 e0 = vsub(c.v1, c.v0), e1 = vsub(c.v2_, c.v1);
+            v2 n0 = vnorm(V(e0.y, -e0.x)), n1 = vnorm(V(e1.y, -e1.x));
+            int convex = vcross(n0, n1) >= 0.0;
+            int front0 = vdot(n0, vsub(center_b, c.v0)) >= 0.0;
+            int front1 = vdot(n1, vsub(center_b, c.v1)) >= 0.0;
+            if (convex) {
+                if (front0 || front1) { c.l11 = n1; c.l12 = n0; } else { c.l11 = vneg(n1); c.l12 = vneg(n0); }
+            } else {
+                if (front0 && front1) { c.l11 = n0; c.l12 = n1; } else { c.l11 = vneg(n0); c.l12 = vneg(n1); }
+            }
+        } else { c.l11 = V(0, 0); c.l12 = V(0, 0); }
+        if (c.has3) {
+            v2 e1 = vsub(c.v2_, c.v1), e2 = vsub(c.v3, c.v2_);
+            v2 n1 = vnorm(V(e1.y, -e1.x)), n2 = vnorm(V(e2.y, -e2.x));
+            int convex = vcross(n1, n2) >= 0.0;
+            int front1 = vdot(n1, vsub(center_b, c.v1)) >= 0.0;
+            int front2 = vdot(n2, vsub(center_b, c.v2_)) >= 0.0;
+            if (convex) {
+                if (front1 || front2) { c.l21 = n2; c.l22 = n1; } else { c.l21 = vneg(n2); c.l22 = vneg(n1); }
+            } else {
+                if (front1 && front2) { c.l21 = n1; c.l22 = n2; } else { c.l21 = vneg(n1); c.l22 = vneg(n2); }
+            }
+        } else { c.l21 = V(0, 0); c.l22 = V(0, 0); }
+    }
+    /* compute_edge_separation: collision.py:599-629 */
+    epaxis edge_axis; edge_axis.type = AX_UNKNOWN; edge_axis.index = -1; edge_axis.separation = -MAX_FLOAT;
+    for (int i = 0; i < 2; ++i) {
+        v2 n = c.anorm[i];
+        if (!ep_valid(&c, n)) continue;
+        epaxis axis; axis.type = AX_EDGE_A; axis.index = i;
+        double mn = 0;
+        for (int k = 0; k < c.bcount; ++k) {
+            double d = vdot(n, vsub(c.bvert[k], c.v1));
+            if (k == 0 || d < mn) mn = d;
+        }
+        axis.separation = mn;
+        if (axis.separation > c.radius) { edge_axis = axis; goto edge_done; }
+        if (axis.separation > edge_axis.separation) edge_axis = axis;
+    }
+edge_done:
+    if (edge_axis.type == AX_UNKNOWN) return;
+    if (edge_axis.separation > c.radius) return;
+    /* compute_polygon_separation: collision.py:631-664 (no early return) */
+    epaxis polygon_axis; polygon_axis.type = AX_UNKNOWN; polygon_axis.index = -1; polygon_axis.separation = -MAX_FLOAT;
+    for (int i = 0; i < c.bcount; ++i) {
+        v2 n = vneg(c.bnorm[i]);
+        if (!ep_valid(&c, n)) continue;
+        double s1 = vdot(n, vsub(c.bvert[i], c.v1));
+        double s2 = vdot(n, vsub(c.bvert[i], c.v2_));
+        double s = PYMIN(s1, s2);
+        if (s > c.radius) { polygon_axis.type = AX_EDGE_B; polygon_axis.index = i; polygon_axis.separation = s; }
+        if (s > polygon_axis.separation) { polygon_axis.type = AX_EDGE_B; polygon_axis.index = i; polygon_axis.separation = s; }
+    }
+    if (polygon_axis.type != AX_UNKNOWN && polygon_axis.separation > c.radius) return;
+    epaxis primary;
+    if (polygon_axis.type == AX_UNKNOWN) primary = edge_axis;
+    else if (polygon_axis.separation > REL_TOL * edge_axis.separation + ABS_TOL) primary = polygon_axis;
+    else primary = edge_axis;
+
+    const v2 *verts1, *norms1, *verts2, *norms2; int n1, n2;
+    if (primary.type == AX_EDGE_A) {
+        verts1 = c.avert; norms1 = c.anorm; n1 = 2; verts2 = c.bvert; norms2 = c.bnorm; n2 = c.bcount;
+        m->type = M_FACE_A;
+    } else {
+        verts1 = c.bvert; norms1 = c.bnorm; n1 = c.bcount; verts2 = c.avert; norms2 = c.anorm; n2 = 2;
+        m->type = M_FACE_B;
+    }
+    int edge1 = primary.index;
+    clipv incident[2];
+    ep_incident(incident, norms1, edge1, verts2, norms2, n2);
+    int iv1 = edge1, iv2 = (edge1 + 1) % n1;
+    v2 v11 = verts1[iv1], v12 = verts1[iv2];
+    v2 tangent = vnorm(vsub(v12, v11));
+    v2 normal = vcross_s(tangent, 1.0);
+    v2 plane_point = vscale(0.5, vadd(v11, v12));
+    double front_offset = vdot(normal, v11);
+    double side_offset1 = -vdot(tangent, v11) + c.radius;
+    double side_offset2 = vdot(tangent, v12) + c.radius;
+    clipv cp1[3], cp2[3];
+    if (clip_segment_to_line(cp1, incident, vneg(tangent), side_offset1, iv1) < 2) return;
+    int ncp2 = clip_segment_to_line(cp2, cp1, tangent, side_offset2, iv2);
+    if (ncp2 < 2) return;
+    if (primary.type == AX_EDGE_A) {
+        m->local_normal = normal;
+        m->local_point = plane_point;
+    } else {
+        m->local_normal = rot_mul_t(&c.xf, normal);
+        m->local_point = xf_mul_t(&c.xf, plane_point);
+    }
+    int point_count = 0;
+    for (int i = 0; i < ncp2; ++i) {
+        double separation = vdot(normal, cp2[i].v) - front_offset;
+        if (separation <= c.radius) {
+            if (primary.type == AX_EDGE_A) {
+                m->pt[point_count] = xf_mul_t(&c.xf, cp2[i].v);
+                m->id[point_count] = mkid(cp2[i].ia, cp2[i].ib, cp2[i].ta, cp2[i].tb);
+            } else {
+                m->pt[point_count] = cp2[i].v;
+                /* id stored as (type_b, type_a, index_b, index_a): SURVEY A.9 #6, collision.py:532 */
+                m->id[point_count] = mkid(cp2[i].tb, cp2[i].ta, cp2[i].ib, cp2[i].ia);
+            }
+            ++point_count;
+        }
+    }
+    m->count = point_count;
+}
+
+/* dispatch: contact.py:294-311,343-361 (shape A/B already in registry order) */
+static void evaluate(manifold_t* m, const shape_t* a, const xform* xa, const shape_t* b, const xform* xb)
+{
+    if (a->type == S_CIRCLE && b->type == S_CIRCLE) collide_circles(m, a, xa, b, xb);
+    else if (a->type == S_POLYGON && b->type == S_POLYGON) collide_polygons(m, a, xa, b, xb);
+    else if (a->type == S_POLYGON && b->type == S_CIRCLE) collide_polygon_circle(m, a, xa, b, xb);
+    else if (a->type == S_EDGE && b->type == S_CIRCLE) collide_edge_circle(m, a, xa, b, xb);
+    else if (a->type == S_EDGE && b->type == S_POLYGON) collide_edge_polygon(m, a, xa, b, xb);
+    else m->count = 0;
+}
+
+/* ---- manifold <-> contact rows ---- */
+static void manifold_load(const orc_world* w, int ci, manifold_t* m)
+{
+    int mt = w->c_mtype[ci];
+    m->type = mt & 0xff; m->count = (mt >> 8) & 0xff;
+    const double* mf = w->c_mf + 4 * (size_t)ci; const double* pts = w->c_pts + 4 * (size_t)ci;
+    m->local_normal = V(mf[0], mf[1]); m->local_point = V(mf[2], mf[3]);
+    m->pt[0] = V(pts[0], pts[1]); m->pt[1] = V(pts[2], pts[3]);
+    m->id[0] = w->c_id[2 * ci]; m->id[1] = w->c_id[2 * ci + 1];
+}
+static void manifold_store(orc_world* w, int ci, const manifold_t* m)
+{
+    w->c_mtype[ci] = m->type | (m->count << 8);
+    double* mf = w->c_mf + 4 * (size_t)ci; double* pts = w->c_pts + 4 * (size_t)ci;
+    mf[0] = m->local_normal.x; mf[1] = m->local_normal.y; mf[2] = m->local_point.x; mf[3] = m->local_point.y;
+    pts[0] = m->pt[0].x; pts[1] = m->pt[0].y; pts[2] = m->pt[1].x; pts[3] = m->pt[1].y;
+    w->c_id[2 * ci] = m->id[0]; w->c_id[2 * ci + 1] = m->id[1];
+}
+
+static inline int body_type(const orc_world* w, int b) { return (int)(w->b_flags[b] & BODY_TYPE_MASK); }
+static inline int body_awake(const orc_world* w, int b) { return (w->b_flags[b] & BODY_AWAKE) != 0; }
+
+/* Body.awake = True (body.py:800-804,812) */
+static void body_wake(orc_world* w, int b)
+{
+    if (!(w->b_flags[b] & BODY_AWAKE)) w->b_pos[4 * b + 3] = 0.0;
+    w->b_flags[b] |= BODY_AWAKE;
+}
+/* Body.awake = False (body.py:805-812) */
+static void body_sleep(orc_world* w, int b)
+{
+    w->b_pos[4 * b + 3] = 0.0;
+    w->b_vel[4 * b + 0] = 0.0; w->b_vel[4 * b + 1] = 0.0; w->b_vel[4 * b + 2] = 0.0; w->b_vel[4 * b + 3] = 0.0;
+    w->b_force[2 * b + 0] = 0.0; w->b_force[2 * b + 1] = 0.0;
+    w->b_flags[b] &= ~BODY_AWAKE;
+}
+
+/* ---- Contact.update: contact.py:210-268 (no sensors, no listeners) ---- */
+static void contact_update(orc_world* w, int ci)
+{
+    manifold_t m; manifold_load(w, ci, &m);
+    manifold_t old = m;
+    double* imp = w->c_imp + 4 * (size_t)ci;
+    double old_ni[2] = {imp[0], imp[2]}, old_ti[2] = {imp[1], imp[3]};
+    w->c_flags[ci] |= C_ENABLED;
+    int was_touching = (w->c_flags[ci] & C_TOUCHING) != 0;
+    int fa = w->c_fix[2 * ci], fb = w->c_fix[2 * ci + 1];
+    int ba = w->f_body[fa], bb = w->f_body[fb];
+    xform xa = xf_row(w->b_xf + 4 * (size_t)ba), xb = xf_row(w->b_xf + 4 * (size_t)bb);
+    shape_t sa = shape_get(w, w->f_shape[fa]), sb = shape_get(w, w->f_shape[fb]);
+    evaluate(&m, &sa, &xa, &sb, &xb);
+    int touching = m.count > 0;
+    /* match ids: dict of old used points, last duplicate wins (contact.py:247-255) */
+    for (int i = 0; i < m.count; ++i) {
+        double ni = 0.0, ti = 0.0;
+        for (int j = 0; j < old.count; ++j)
+            if (old.id[j] == m.id[i]) { ni = old_ni[j]; ti = old_ti[j]; }
+        imp[2 * i] = ni; imp[2 * i + 1] = ti;
+    }
+    manifold_store(w, ci, &m);
+    if (touching != was_touching) { body_wake(w, ba); body_wake(w, bb); }
+    if (touching) w->c_flags[ci] |= C_TOUCHING; else w->c_flags[ci] &= ~C_TOUCHING;
+}
+
+static inline int aabb_overlap(const double* a, const double* b)               /* common.py:830-839 */
+{
+    double d1x = b[0] - a[2], d1y = b[1] - a[3];
+    double d2x = a[0] - b[2], d2y = a[1] - b[3];
+    if (d1x > 0.0 || d1y > 0.0) return 0;
+    if (d2x > 0.0 || d2y > 0.0) return 0;
+    return 1;
+}
+
+static void contact_copy(orc_world* w, int dst, int src)
+{
+    w->c_fix[2 * dst] = w->c_fix[2 * src]; w->c_fix[2 * dst + 1] = w->c_fix[2 * src + 1];
+    w->c_flags[dst] = w->c_flags[src];
+    w->c_mat[2 * dst] = w->c_mat[2 * src]; w->c_mat[2 * dst + 1] = w->c_mat[2 * src + 1];
+    w->c_mtype[dst] = w->c_mtype[src];
+    memcpy(w->c_mf + 4 * (size_t)dst, w->c_mf + 4 * (size_t)src, 4 * sizeof(double));
+    memcpy(w->c_pts + 4 * (size_t)dst, w->c_pts + 4 * (size_t)src, 4 * sizeof(double));
+    memcpy(w->c_imp + 4 * (size_t)dst, w->c_imp + 4 * (size_t)src, 4 * sizeof(double));
+    w->c_id[2 * dst] = w->c_id[2 * src]; w->c_id[2 * dst + 1] = w->c_id[2 * src + 1];
+}
+
+/* ---- ContactManager.collide: contact_manager.py:174-223 ---- */
+static void cm_collide(orc_world* w)
+{
+    int nc = w->w_count[2];
+    uint8_t* remove = (uint8_t*)calloc((size_t)nc + 1, 1);
+    for (int ci = 0; ci < nc; ++ci) {
+        int fa = w->c_fix[2 * ci], fb = w->c_fix[2 * ci + 1];
+        int ba = w->f_body[fa], bb = w->f_body[fb];
+        int active_a = body_awake(w, ba) && body_type(w, ba) != T_STATIC;
+        int active_b = body_awake(w, bb) && body_type(w, bb) != T_STATIC;
+        if (!active_a && !active_b) continue;
+        /* filter flag is never raised on this path (no joints, no refilter) */
+        if (!aabb_overlap(w->f_fat + 4 * (size_t)fa, w->f_fat + 4 * (size_t)fb)) { remove[ci] = 1; continue; }
+        contact_update(w, ci);
+    }
+    /* destroy (contact_manager.py:160-172): order-preserving removal; bodies are NOT woken (A.9 #12) */
+    int dst = 0;
+    for (int ci = 0; ci < nc; ++ci) {
+        if (remove[ci]) continue;
+        if (dst != ci) contact_copy(w, dst, ci);
+        ++dst;
+    }
+    w->w_count[2] = dst;
+    free(remove);
+}
+
+/* ---- BroadPhase.update_pairs (order pinned) + ContactManager.find_new_contacts:
+ *      broadphase.py:83-109, dynamictree.py:190-207, contact_manager.py:102-158 ---- */
+static void cm_find_new_contacts(orc_world* w)
+{
+    int nf = w->w_count[1];
+    int npairs = 0;
+    for (int a = 0; a < nf; ++a) {
+        if (!w->f_moved[a]) continue;
+        const double* fa_box = w->f_fat + 4 * (size_t)a;
+        for (int b = 0; b < nf; ++b) {
+            if (b == a) continue;
+            if (!aabb_overlap(w->f_fat + 4 * (size_t)b, fa_box)) continue;     /* node.aabb.test_overlap(query) */
+            if (b < a && w->f_moved[b]) continue;                              /* (b, a) already in the pair buffer */
+            if (npairs < w->npair_cap) { w->p_pairs[2 * npairs] = a; w->p_pairs[2 * npairs + 1] = b; }
+            else w->w_status[0] |= ST_PAIR_OVERFLOW;
+            ++npairs;
+
+            int fixture_a = a, fixture_b = b;
+            int body_a = w->f_body[fixture_a], body_b = w->f_body[fixture_b];
+            if (body_a == body_b) continue;
+            int exists = 0;
+            int nc = w->w_count[2];
+            for (int ci = 0; ci < nc; ++ci) {
+                int ca = w->c_fix[2 * ci], cb = w->c_fix[2 * ci + 1];
+                if ((ca == fixture_a && cb == fixture_b) || (ca == fixture_b && cb == fixture_a)) { exists = 1; break; }
+            }
+            if (exists) continue;
+            /* Body._should_collide: body.py:910-928 (no joints) */
+            if (body_type(w, body_b) != T_DYNAMIC && body_type(w, body_a) != T_DYNAMIC) continue;
+            /* World.default_contact_filter: world.py:958-970 */
+            {
+                uint32_t fa0 = w->f_filter[2 * fixture_a], fa1 = w->f_filter[2 * fixture_a + 1];
+                uint32_t fb0 = w->f_filter[2 * fixture_b], fb1 = w->f_filter[2 * fixture_b + 1];
+                int ga = (int16_t)(fa1 & 0xffff), gb = (int16_t)(fb1 & 0xffff);
+                uint32_t cat_a = fa0 & 0xffff, mask_a = fa0 >> 16, cat_b = fb0 & 0xffff, mask_b = fb0 >> 16;
+                int ok;
+                if (ga == gb && ga != 0) ok = ga > 0;
+                else ok = ((mask_a & cat_b) != 0) && ((cat_a & mask_b) != 0);
+                if (!ok) continue;
+            }
+            /* Contact._create: contact.py:294-326 */
+            int t1 = w->s_meta[w->f_shape[fixture_a]] & 0xff, t2 = w->s_meta[w->f_shape[fixture_b]] & 0xff;
+            int primary;
+            if ((t1 == S_CIRCLE && t2 == S_CIRCLE) || (t1 == S_POLYGON && t2 == S_POLYGON) ||
+                (t1 == S_POLYGON && t2 == S_CIRCLE) || (t1 == S_EDGE && t2 == S_CIRCLE) ||
+                (t1 == S_EDGE && t2 == S_POLYGON)) primary = 1;
+            else if ((t1 == S_CIRCLE && t2 == S_POLYGON) || (t1 == S_CIRCLE && t2 == S_EDGE) ||
+                     (t1 == S_POLYGON && t2 == S_EDGE)) primary = 0;
+            else continue;                                                     /* unregistered pair (edge-edge) */
+            if (!primary) { int t = fixture_a; fixture_a = fixture_b; fixture_b = t; }
+            if (nc >= w->nc_cap) { w->w_status[0] |= ST_CONTACT_OVERFLOW; continue; }
+            int ci = nc;
+            w->c_fix[2 * ci] = fixture_a; w->c_fix[2 * ci + 1] = fixture_b;
+            w->c_flags[ci] = 0;
+            /* mix_friction / mix_restitution: contact_util.py:36-48 */
+            w->c_mat[2 * ci] = sqrt(w->f_mat[2 * fixture_a] * w->f_mat[2 * fixture_b]);
+            {
+                double r1 = w->f_mat[2 * fixture_a + 1], r2 = w->f_mat[2 * fixture_b + 1];
+                w->c_mat[2 * ci + 1] = PYMAX(r1, r2);
+            }
+            w->c_mtype[ci] = 0;
+            memset(w->c_mf + 4 * (size_t)ci, 0, 4 * sizeof(double));
+            memset(w->c_pts + 4 * (size_t)ci, 0, 4 * sizeof(double));
+            memset(w->c_imp + 4 * (size_t)ci, 0, 4 * sizeof(double));
+            w->c_id[2 * ci] = 0; w->c_id[2 * ci + 1] = 0;
+            w->w_count[2] = nc + 1;
+        }
+    }
+    for (int a = 0; a < nf; ++a) w->f_moved[a] = 0;
+    w->w_count[3] = npairs;
+}
+
+/* ---- Shape.compute_aabb: shapes.py:178-189 (circle), 316-334 (polygon), 702-718 (edge) ---- */
+static void shape_aabb(const shape_t* s, const xform* t, double out[4])
+{
+    if (s->type == S_CIRCLE) {
+        v2 pos = V(s->d[0], s->d[1]);
+        v2 p = vadd(t->p, rot_mul(t, pos));
+        out[0] = p.x - s->radius; out[1] = p.y - s->radius; out[2] = p.x + s->radius; out[3] = p.y + s->radius;
+    } else if (s->type == S_POLYGON) {
+        v2 lower = xf_mul(t, pvert(s, 0)), upper = lower;
+        for (int i = 0; i < s->count; ++i) {
+            v2 v = xf_mul(t, pvert(s, i));
+            lower = V(PYMIN(lower.x, v.x), PYMIN(lower.y, v.y));
+            upper = V(PYMAX(upper.x, v.x), PYMAX(upper.y, v.y));
+        }
+        out[0] = lower.x - s->radius; out[1] = lower.y - s->radius; out[2] = upper.x + s->radius; out[3] = upper.y + s->radius;
+    } else {
+        v2 a = xf_mul(t, V(s->d[0], s->d[1])), b = xf_mul(t, V(s->d[2], s->d[3]));
+        v2 lower = V(PYMIN(a.x, b.x), PYMIN(a.y, b.y)), upper = V(PYMAX(a.x, b.x), PYMAX(a.y, b.y));
+        out[0] = lower.x - s->radius; out[1] = lower.y - s->radius; out[2] = upper.x + s->radius; out[3] = upper.y + s->radius;
+    }
+}
+
+/* ---- Fixture._synchronize + BroadPhase.move_proxy + DynamicTree.move_proxy:
+ *      fixture.py:287-298, broadphase.py:61-68, dynamictree.py:152-188 ---- */
+static void fixture_synchronize(orc_world* w, int f, const xform* xf1, const xform* xf2)
+{
+    shape_t s = shape_get(w, w->f_shape[f]);
+    double a1[4], a2[4];
+    shape_aabb(&s, xf1, a1);
+    shape_aabb(&s, xf2, a2);
+    double* tight = w->f_tight + 4 * (size_t)f;
+    tight[0] = PYMIN(a1[0], a2[0]); tight[1] = PYMIN(a1[1], a2[1]);
+    tight[2] = PYMAX(a1[2], a2[2]); tight[3] = PYMAX(a1[3], a2[3]);
+    v2 displacement = vsub(xf2->p, xf1->p);
+    double* fat = w->f_fat + 4 * (size_t)f;
+    /* AABB.contains: common.py:863-868 */
+    if (fat[0] <= tight[0] && fat[1] <= tight[1] && tight[2] <= fat[2] && tight[3] <= fat[3]) return;
+    double lx = tight[0] - AABB_EXT, ly = tight[1] - AABB_EXT, ux = tight[2] + AABB_EXT, uy = tight[3] + AABB_EXT;
+    v2 d = vscale(AABB_MULT, displacement);
+    if (d.x < 0.0) { lx = lx + d.x; ly = ly + 0; } else { ux = ux + d.x; uy = uy + 0; }
+    if (d.y < 0.0) { lx = lx + 0; ly = ly + d.y; } else { ux = ux + 0; uy = uy + d.y; }
+    fat[0] = lx; fat[1] = ly; fat[2] = ux; fat[3] = uy;
+    w->f_moved[f] = 1;
+}
+
+/* ---- ContactSolver + Island.solve: contact.py:375-864, contact_util.py:195-360, island.py:65-179 ---- */
+typedef struct {
+    v2 ra, rb;
+    double normal_impulse, tangent_impulse, normal_mass, tangent_mass, velocity_bias;
+} vcp_t;
+typedef struct {
+    int contact;
+    int ia, ib;                 /* island indices */
+    double ima, imb, iia, iib;  /* inv mass / inv inertia */
+    double friction, restitution;
+    v2 normal;
+    int npoints;                /* len(vc.points): may shrink to 1 */
+    vcp_t p[2];
+    double k11, k12, k22;       /* vc.K */
+    double nm_c1x, nm_c1y, nm_c2x, nm_c2y;   /* vc.normal_mass = K.inverse (columns) */
+    /* position constraint */
+    v2 lca, lcb;                /* local centers */
+    double ra_, rb_;            /* radii */
+    v2 local_normal, local_point;
+    int type, n_local_points;
+    v2 local_points[2];
+} cc_t;
+
+typedef struct { v2 c; double a; } pos_t;
+typedef struct { v2 v; double w; } vel_t;
+
+/* WorldManifold: contact_util.py:195-245 */
+static int world_manifold(const cc_t* cc, int mcount, const xform* xa, const xform* xb, v2* normal_out, v2 pts[2])
+{
+    v2 normal = V(0, 0);
+    int n = 0;
+    if (mcount == 0) { *normal_out = normal; return 0; }
+    if (cc->type == M_CIRCLES) {
+        normal = V(1.0, 0.0);
+        v2 point_a = xf_mul(xa, cc->local_point);
+        v2 point_b = xf_mul(xb, cc->local_points[0]);
+        if (dist2(point_a, point_b) > EPS_SQR) normal = vnorm(vsub(point_b, point_a));
+        v2 c_a = vadd(point_a, vscale(cc->ra_, normal));
+        v2 c_b = vsub(point_b, vscale(cc->rb_, normal));
+        pts[0] = vscale(0.5, vadd(c_a, c_b));
+        n = 1;
+    } else if (cc->type == M_FACE_A) {
+        normal = rot_mul(xa, cc->local_normal);
+        v2 plane_point = xf_mul(xa, cc->local_point);
+        for (int i = 0; i < mcount; ++i) {
+            v2 clip_point = xf_mul(xb, cc->local_points[i]);
+            v2 c_a = vadd(clip_point, vscale(cc->ra_ - vdot(vsub(clip_point, plane_point), normal), normal));
+            v2 c_b = vsub(clip_point, vscale(cc->rb_, normal));
+            pts[i] = vscale(0.5, vadd(c_a, c_b));
+        }
+        n = mcount;
+    } else {
+        normal = rot_mul(xb, cc->local_normal);
+        v2 plane_point = xf_mul(xb, cc->local_point);
+        for (int i = 0; i < mcount; ++i) {
+            v2 clip_point = xf_mul(xa, cc->local_points[i]);
+            v2 c_b = vadd(clip_point, vscale(cc->rb_ - vdot(vsub(clip_point, plane_point), normal), normal));
+            v2 c_a = vsub(clip_point, vscale(cc->ra_, normal));
+            pts[i] = vscale(0.5, vadd(c_a, c_b));
+        }
+        n = mcount;
+        normal = vneg(normal);
+    }
+    *normal_out = normal;
+    return n;
+}
+
+/* ContactPositionConstraint.solver_manifold: contact_util.py:323-360 */
+static void solver_manifold(const cc_t* cc, const xform* xa, const xform* xb, int index, v2* normal, v2* point, double* separation)
+{
+    if (cc->type == M_CIRCLES) {
+        v2 point_a = xf_mul(xa, cc->local_point);
+        v2 point_b = xf_mul(xb, cc->local_points[0]);
+        *normal = vnorm(vsub(point_b, point_a));
+        *point = vscale(0.5, vadd(point_a, point_b));
+        *separation = vdot(vsub(point_b, point_a), *normal) - cc->ra_ - cc->rb_;
+    } else if (cc->type == M_FACE_A) {
+        *normal = rot_mul(xa, cc->local_normal);
+        v2 plane_point = xf_mul(xa, cc->local_point);
+        v2 clip_point = xf_mul(xb, cc->local_points[index]);
+        *separation = vdot(vsub(clip_point, plane_point), *normal) - cc->ra_ - cc->rb_;
+        *point = clip_point;
+    } else {
+        *normal = rot_mul(xb, cc->local_normal);
+        v2 plane_point = xf_mul(xb, cc->local_point);
+        v2 clip_point = xf_mul(xa, cc->local_points[index]);
+        *separation = vdot(vsub(clip_point, plane_point), *normal) - cc->ra_ - cc->rb_;
+        *point = clip_point;
+        *normal = vneg(*normal);
+    }
+}
+
+static inline v2 rel_vel(v2 vb, double wb, v2 rb, v2 va, double wa, v2 ra)
+{
+    /* vb + scalar_cross(wb, rb) - va - scalar_cross(wa, ra) */
+    return vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
+}
+
+static void island_solve(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts,
+                         double dt, double dt_ratio, int vel_iters, int pos_iters, int* pos_iters_used)
+{
+    pos_t* P = (pos_t*)malloc(sizeof(pos_t) * (size_t)(nbodies + 1));
+    vel_t* Vv = (vel_t*)malloc(sizeof(vel_t) * (size_t)(nbodies + 1));
+    cc_t* C = (cc_t*)malloc(sizeof(cc_t) * (size_t)(ncontacts + 1));
+    v2 gravity = V(w->w_gravity[0], w->w_gravity[1]);
+    int warm = (w->w_flags[0] & W_WARM_START) != 0;
+
+    /* island.py:71-95 */
+    for (int i = 0; i < nbodies; ++i) {
+        int b = bodies[i];
+        double* pos = w->b_pos + 4 * (size_t)b; double* vel = w->b_vel + 4 * (size_t)b;
+        v2 c = V(pos[0], pos[1]); double a = pos[2];
+        v2 v = V(vel[0], vel[1]); double wv = vel[2];
+        w->b_pos0[4 * b + 0] = c.x; w->b_pos0[4 * b + 1] = c.y; w->b_pos0[4 * b + 2] = a;
+        if (body_type(w, b) == T_DYNAMIC) {
+            const double* mass = w->b_mass + 4 * (size_t)b; const double* damp = w->b_damp + 4 * (size_t)b;
+            v2 force = V(w->b_force[2 * b], w->b_force[2 * b + 1]);
+            v2 acc = vadd(vscale(damp[2], gravity), vscale(mass[0], force));
+            v = vadd(v, vscale(dt, acc));
+            wv = wv + dt * mass[1] * vel[3];
+            v = vscale(pyclamp(1.0 - dt * damp[0], 0.0, 1.0), v);
+            wv = wv * pyclamp(1.0 - dt * damp[1], 0.0, 1.0);
+        }
+        P[i].c = c; P[i].a = a; Vv[i].v = v; Vv[i].w = wv;
+    }
+
+    /* ContactSolver.__init__: contact.py:376-412 */
+    for (int k = 0; k < ncontacts; ++k) {
+        int ci = contacts[k];
+        cc_t* cc = &C[k];
+        memset(cc, 0, sizeof(*cc));
+        cc->contact = ci;
+        int fa = w->c_fix[2 * ci], fb = w->c_fix[2 * ci + 1];
+        int ba = w->f_body[fa], bb = w->f_body[fb];
+        cc->ia = w->b_island[ba]; cc->ib = w->b_island[bb];
+        cc->ima = w->b_mass[4 * ba]; cc->imb = w->b_mass[4 * bb];
+        cc->iia = w->b_mass[4 * ba + 1]; cc->iib = w->b_mass[4 * bb + 1];
+        cc->lca = V(w->b_mass[4 * ba + 2], w->b_mass[4 * ba + 3]);
+        cc->lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);
+        cc->friction = w->c_mat[2 * ci]; cc->restitution = w->c_mat[2 * ci + 1];
+        cc->ra_ = w->s_radius[w->f_shape[fa]]; cc->rb_ = w->s_radius[w->f_shape[fb]];
+        manifold_t m; manifold_load(w, ci, &m);
+        cc->type = m.type; cc->local_normal = m.local_normal; cc->local_point = m.local_point;
+        cc->n_local_points = m.count; cc->npoints = m.count;
+        const double* imp = w->c_imp + 4 * (size_t)ci;
+        for (int j = 0; j < m.count; ++j) {
+            cc->local_points[j] = m.pt[j];
+            /* VelocityConstraintPoint: contact_util.py:260-265 */
+            if (warm) { cc->p[j].normal_impulse = dt_ratio * imp[2 * j]; cc->p[j].tangent_impulse = dt_ratio * imp[2 * j + 1]; }
+            else { cc->p[j].normal_impulse = imp[2 * j]; cc->p[j].tangent_impulse = imp[2 * j + 1]; }
+        }
+    }
+
+    /* initialize_velocity_constraints: contact.py:414-496 */
+    for (int k = 0; k < ncontacts; ++k) {
+        cc_t* cc = &C[k];
+        double ma = cc->ima, mb = cc->imb, ia = cc->iia, ib = cc->iib;
+        v2 ca = P[cc->ia].c, cb = P[cc->ib].c; double aa = P[cc->ia].a, ab = P[cc->ib].a;
+        v2 va = Vv[cc->ia].v, vb = Vv[cc->ib].v; double wa = Vv[cc->ia].w, wb = Vv[cc->ib].w;
+        xform xa = xf_from_sweep(ca, aa, cc->lca), xb = xf_from_sweep(cb, ab, cc->lcb);
+        v2 wpts[2];
+        int nw = world_manifold(cc, cc->n_local_points, &xa, &xb, &cc->normal, wpts);
+        int np = cc->npoints < nw ? cc->npoints : nw;
+        for (int j = 0; j < np; ++j) {
+            vcp_t* p = &cc->p[j];
+            v2 ra = vsub(wpts[j], ca), rb = vsub(wpts[j], cb);
+            p->ra = ra; p->rb = rb;
+            double rn_a = sq(vcross(ra, cc->normal)), rn_b = sq(vcross(rb, cc->normal));
+            double k_normal = ma + mb + ia * rn_a + ib * rn_b;
+            p->normal_mass = (k_normal > 0.0) ? 1.0 / k_normal : 0.0;
+            v2 tangent = vcross_s(cc->normal, 1.0);
+            double rt_a = sq(vcross(ra, tangent)), rt_b = sq(vcross(rb, tangent));
+            double k_tangent = ma + mb + ia * rt_a + ib * rt_b;
+            p->tangent_mass = (k_tangent > 0.0) ? 1.0 / k_tangent : 0.0;
+            p->velocity_bias = 0.0;
+            double v_rel = vdot(cc->normal, rel_vel(vb, wb, rb, va, wa, ra));
+            if (v_rel < -VEL_THRESHOLD) p->velocity_bias = -cc->restitution * v_rel;
+        }
+        if (cc->npoints == 2) {
+            v2 ra1 = cc->p[0].ra, rb1 = cc->p[0].rb, ra2 = cc->p[1].ra, rb2 = cc->p[1].rb;
+            double rn1a = vcross(ra1, cc->normal), rn1b = vcross(rb1, cc->normal);
+            double rn2a = vcross(ra2, cc->normal), rn2b = vcross(rb2, cc->normal);
+            double k11 = ma + mb + ia * rn1a * rn1a + ib * rn1b * rn1b;
+            double k22 = ma + mb + ia * rn2a * rn2a + ib * rn2b * rn2b;
+            double k12 = ma + mb + ia * rn1a * rn2a + ib * rn1b * rn2b;
+            if (sq(k11) < (1000.0 * (k11 * k22 - sq(k12)))) {
+                cc->k11 = k11; cc->k12 = k12; cc->k22 = k22;
+                /* Mat22.inverse: common.py:505-519 */
+                double a = k11, b = k12, c = k12, d = k22;
+                double det = a * d - b * c;
+                if (det != 0.0) det = 1.0 / det;
+                cc->nm_c1x = det * d; cc->nm_c1y = -det * c; cc->nm_c2x = -det * b; cc->nm_c2y = det * a;
+            } else {
+                cc->npoints = 1;
+            }
+        }
+    }
+
+    /* warm_start: contact.py:498-525 */
+    if (warm) {
+        for (int k = 0; k < ncontacts; ++k) {
+            cc_t* cc = &C[k];
+            v2 normal = cc->normal, tangent = vcross_s(normal, 1.0);
+            v2 va = Vv[cc->ia].v, vb = Vv[cc->ib].v; double wa = Vv[cc->ia].w, wb = Vv[cc->ib].w;
+            for (int j = 0; j < cc->npoints; ++j) {
+                vcp_t* p = &cc->p[j];
+                v2 pp = vadd(vscale(p->normal_impulse, normal), vscale(p->tangent_impulse, tangent));
+                wa = wa - cc->iia * vcross(p->ra, pp);
+                va = vsub(va, vscale(cc->ima, pp));
+                wb = wb + cc->iib * vcross(p->rb, pp);
+                vb = vadd(vb, vscale(cc->imb, pp));
+            }
+            Vv[cc->ia].v = va; Vv[cc->ia].w = wa;
+            Vv[cc->ib].v = vb; Vv[cc->ib].w = wb;
+        }
+    }
+
+    /* solve_velocity_constraints: contact.py:527-799 */
+    for (int it = 0; it < vel_iters; ++it) {
+        for (int k = 0; k < ncontacts; ++k) {
+            cc_t* cc = &C[k];
+            double ima = cc->ima, imb = cc->imb, iia = cc->iia, iib = cc->iib;
+            v2 normal = cc->normal, tangent = vcross_s(normal, 1.0);
+            v2 va = Vv[cc->ia].v, vb = Vv[cc->ib].v; double wa = Vv[cc->ia].w, wb = Vv[cc->ib].w;
+            double friction = cc->friction;
+            for (int j = 0; j < cc->npoints; ++j) {
+                vcp_t* p = &cc->p[j];
+                v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
+                double vt = vdot(dv, tangent);
+                double lambda = p->tangent_mass * (-vt);
+                double max_friction = friction * p->normal_impulse;
+                double new_impulse = pyclamp(p->tangent_impulse + lambda, -max_friction, max_friction);
+                lambda = new_impulse - p->tangent_impulse;
+                v2 Pv = vscale(lambda, tangent);
+                va = vsub(va, vscale(ima, Pv));
+                wa = wa - iia * vcross(p->ra, Pv);
+                vb = vadd(vb, vscale(imb, Pv));
+                wb = wb + iib * vcross(p->rb, Pv);
+                p->tangent_impulse = new_impulse;
+            }
+            if (cc->npoints == 1) {
+                vcp_t* p = &cc->p[0];
+                v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
+                double vn = vdot(dv, normal);
+                double lambda = -p->normal_mass * (vn - p->velocity_bias);
+                double t = p->normal_impulse + lambda;
+                double new_impulse = PYMAX(t, 0.0);
+                lambda = new_impulse - p->normal_impulse;
+                v2 Pv = vscale(lambda, normal);
+                va = vsub(va, vscale(ima, Pv));
+                wa = wa - iia * vcross(p->ra, Pv);
+                vb = vadd(vb, vscale(imb, Pv));
+                wb = wb + iib * vcross(p->rb, Pv);
+                p->normal_impulse = new_impulse;
+            } else if (cc->npoints == 2) {
+                vcp_t *cp1 = &cc->p[0], *cp2 = &cc->p[1];
+                v2 a = V(cp1->normal_impulse, cp2->normal_impulse);
+                v2 dv1 = rel_vel(vb, wb, cp1->rb, va, wa, cp1->ra);
+                v2 dv2 = rel_vel(vb, wb, cp2->rb, va, wa, cp2->ra);
+                double vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+                v2 b = V(vn1 - cp1->velocity_bias, vn2 - cp2->velocity_bias);
+                /* b -= K * a  with K = Mat22((k11,k12),(k12,k22)) */
+                v2 Ka = V(cc->k11 * a.x + cc->k12 * a.y, cc->k12 * a.x + cc->k22 * a.y);
+                b = vsub(b, Ka);
+                v2 x; int solved = 0;
+                /* case 1 */
+                {
+                    v2 nb = V(cc->nm_c1x * b.x + cc->nm_c2x * b.y, cc->nm_c1y * b.x + cc->nm_c2y * b.y);
+                    x = vneg(nb);
+                    if (x.x >= 0.0 && x.y >= 0.0) solved = 1;
+                }
+                if (!solved) {                                   /* case 2 */
+                    x = V(-cp1->normal_mass * b.x, 0.0);
+                    double vn2c = cc->k12 * x.x + b.y;          /* K.col1.y */
+                    if (x.x >= 0.0 && vn2c >= 0.0) solved = 1;
+                }
+                if (!solved) {                                   /* case 3 */
+                    x = V(0.0, -cp2->normal_mass * b.y);
+                    double vn1c = cc->k12 * x.y + b.x;          /* K.col2.x */
+                    if (x.y >= 0.0 && vn1c >= 0.0) solved = 1;
+                }
+                if (!solved) {                                   /* case 4 */
+                    x = V(0.0, 0.0);
+                    if (b.x >= 0.0 && b.y >= 0.0) solved = 1;
+                }
+                if (solved) {
+                    v2 d = vsub(x, a);
+                    v2 p1 = vscale(d.x, normal), p2 = vscale(d.y, normal);
+                    v2 p12 = vadd(p1, p2);
+                    va = vsub(va, vscale(ima, p12));
+                    wa = wa - iia * (vcross(cp1->ra, p1) + vcross(cp2->ra, p2));
+                    vb = vadd(vb, vscale(imb, p12));
+                    wb = wb + iib * (vcross(cp1->rb, p1) + vcross(cp2->rb, p2));
+                    cp1->normal_impulse = x.x;
+                    cp2->normal_impulse = x.y;
+                }
+            }
+            Vv[cc->ia].v = va; Vv[cc->ia].w = wa;
+            Vv[cc->ib].v = vb; Vv[cc->ib].w = wb;
+        }
+    }
+
+    /* store_impulses: contact.py:801-806 (zip over vc.points, which may be shorter) */
+    for (int k = 0; k < ncontacts; ++k) {
+        cc_t* cc = &C[k];
+        double* imp = w->c_imp + 4 * (size_t)cc->contact;
+        int n = cc->npoints < cc->n_local_points ? cc->npoints : cc->n_local_points;
+        for (int j = 0; j < n; ++j) { imp[2 * j] = cc->p[j].normal_impulse; imp[2 * j + 1] = cc->p[j].tangent_impulse; }
+    }
+
+    /* integrate positions: island.py:119-138 */
+    for (int i = 0; i < nbodies; ++i) {
+        v2 c = P[i].c; double a = P[i].a; v2 v = Vv[i].v; double wv = Vv[i].w;
+        v2 translation = vscale(dt, v);
+        if (vdot(translation, translation) > MAX_TRANS_SQR) {
+            double ratio = MAX_TRANS / sqrt(sq(translation.x) + sq(translation.y));
+            v = vscale(ratio, v);
+        }
+        double rotation = dt * wv;
+        if (sq(rotation) > MAX_ROT_SQR) {
+            double ratio = MAX_ROT / fabs(rotation);
+            wv = wv * ratio;
+        }
+        c = vadd(c, vscale(dt, v));
+        a = a + dt * wv;
+        P[i].c = c; P[i].a = a; Vv[i].v = v; Vv[i].w = wv;
+    }
+
+    /* position iterations: island.py:141-153, contact.py:809-864 */
+    int position_solved = 0, used = 0;
+    for (int it = 0; it < pos_iters; ++it) {
+        double min_separation = 0.0;
+        ++used;
+        for (int k = 0; k < ncontacts; ++k) {
+            cc_t* cc = &C[k];
+            double ima = cc->ima, imb = cc->imb, iia = cc->iia, iib = cc->iib;
+            v2 ca = P[cc->ia].c, cb = P[cc->ib].c; double aa = P[cc->ia].a, ab = P[cc->ib].a;
+            for (int j = 0; j < cc->n_local_points; ++j) {
+                xform xa = xf_from_sweep(ca, aa, cc->lca), xb = xf_from_sweep(cb, ab, cc->lcb);
+                v2 normal, point; double separation;
+                solver_manifold(cc, &xa, &xb, j, &normal, &point, &separation);
+                v2 ra = vsub(point, ca), rb = vsub(point, cb);
+                min_separation = PYMIN(min_separation, separation);
+                double Cc = pyclamp(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LIN_CORR, 0.0);
+                double rn_a = sq(vcross(ra, normal)), rn_b = sq(vcross(rb, normal));
+                double K = ima + imb + (iia * rn_a) + (iib * rn_b);
+                double impulse = (K > 0.0) ? -Cc / K : 0.0;
+                v2 Pv = vscale(impulse, normal);
+                ca = vsub(ca, vscale(ima, Pv));
+                aa = aa - iia * vcross(ra, Pv);
+                cb = vadd(cb, vscale(imb, Pv));
+                ab = ab + iib * vcross(rb, Pv);
+            }
+            P[cc->ia].c = ca; P[cc->ia].a = aa;
+            P[cc->ib].c = cb; P[cc->ib].a = ab;
+        }
+        if (min_separation >= -3.0 * LINEAR_SLOP) { position_solved = 1; break; }
+    }
+    *pos_iters_used = used;
+
+    /* write back + Body._synchronize_transform: island.py:155-159, body.py:906-908 */
+    for (int i = 0; i < nbodies; ++i) {
+        int b = bodies[i];
+        w->b_pos[4 * b + 0] = P[i].c.x; w->b_pos[4 * b + 1] = P[i].c.y; w->b_pos[4 * b + 2] = P[i].a;
+        w->b_vel[4 * b + 0] = Vv[i].v.x; w->b_vel[4 * b + 1] = Vv[i].v.y; w->b_vel[4 * b + 2] = Vv[i].w;
+        v2 lc = V(w->b_mass[4 * b + 2], w->b_mass[4 * b + 3]);
+        xform t = xf_from_sweep(P[i].c, P[i].a, lc);
+        w->b_xf[4 * b + 0] = t.p.x; w->b_xf[4 * b + 1] = t.p.y; w->b_xf[4 * b + 2] = t.c1.x; w->b_xf[4 * b + 3] = t.c1.y;
+    }
+
+    /* sleep: island.py:163-179 -- the reference's rule as written:
+     * `body` is the LAST island body; only the last non-static body `b` is put to sleep. */
+    if (w->w_flags[0] & W_ALLOW_SLEEP) {
+        double min_sleep_time = MAX_FLOAT;
+        int last_body = bodies[nbodies - 1];
+        int last_allow = (w->b_flags[last_body] & BODY_ALLOW_SLEEP) != 0;
+        int b_last_nonstatic = -1;
+        for (int i = 0; i < nbodies; ++i) {
+            int b = bodies[i];
+            if (body_type(w, b) == T_STATIC) continue;
+            b_last_nonstatic = b;
+            double wv = w->b_vel[4 * b + 2];
+            v2 v = V(w->b_vel[4 * b + 0], w->b_vel[4 * b + 1]);
+            if (!last_allow || sq(wv) > ANG_SLEEP_TOL_SQR || vlen2(v) > LIN_SLEEP_TOL_SQR) {
+                w->b_pos[4 * b + 3] = 0.0;
+                min_sleep_time = 0.0;
+            } else {
+                w->b_pos[4 * b + 3] = w->b_pos[4 * b + 3] + dt;
+                min_sleep_time = PYMIN(min_sleep_time, w->b_pos[4 * b + 3]);
+            }
+        }
+        if (min_sleep_time >= TIME_TO_SLEEP && position_solved && b_last_nonstatic >= 0)
+            body_sleep(w, b_last_nonstatic);
+    }
+    free(P); free(Vv); free(C);
+}
+
+/* ---- World._solve: world.py:475-592 ---- */
+static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters, int pos_iters)
+{
+    int nb = w->w_count[0], nf = w->w_count[1], nc = w->w_count[2];
+    for (int b = 0; b < nb; ++b) { w->b_flags[b] &= ~BODY_ISLAND; w->b_island[b] = -1; }
+    for (int c = 0; c < nc; ++c) w->c_flags[c] &= ~C_ISLAND;
+
+    /* Body._contacts == world contact list filtered by body, same order (contact_manager.py:157-158,170-172) */
+    int* adj_start = (int*)calloc((size_t)nb + 2, sizeof(int));
+    int* adj = (int*)malloc(sizeof(int) * (size_t)(2 * nc + 1));
+    for (int c = 0; c < nc; ++c) {
+        adj_start[w->f_body[w->c_fix[2 * c]] + 1]++;
+        adj_start[w->f_body[w->c_fix[2 * c + 1]] + 1]++;
+    }
+    for (int b = 0; b < nb; ++b) adj_start[b + 1] += adj_start[b];
+    int* fill = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+    memcpy(fill, adj_start, sizeof(int) * (size_t)nb);
+    for (int c = 0; c < nc; ++c) {
+        int ba = w->f_body[w->c_fix[2 * c]], bb = w->f_body[w->c_fix[2 * c + 1]];
+        adj[fill[ba]++] = c;
+        adj[fill[bb]++] = c;
+    }
+
+    int* stack = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+    int n_islands = 0, lb = 0, lc = 0, pos_max = 0;
+    for (int seed = 0; seed < nb; ++seed) {
+        uint32_t fl = w->b_flags[seed];
+        if (fl & BODY_ISLAND) continue;
+        if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
+        if ((fl & BODY_TYPE_MASK) == T_STATIC) continue;
+        int body_start = lb, contact_start = lc;
+        int sp = 0;
+        stack[sp++] = seed;
+        w->b_flags[seed] |= BODY_ISLAND;
+        int overflow = 0;
+        while (sp > 0) {
+            int b = stack[--sp];
+            if (lb >= w->nl_cap) { overflow = 1; break; }
+            w->b_island[b] = lb - body_start;
+            w->l_body[lb++] = b;
+            body_wake(w, b);
+            if (body_type(w, b) == T_STATIC) continue;
+            /* the comprehension filters first, then the loop appends (world.py:528-546) */
+            int first = lc;
+            for (int k = adj_start[b]; k < adj_start[b + 1]; ++k) {
+                int c = adj[k];
+                uint32_t cf = w->c_flags[c];
+                if ((cf & C_ISLAND) || !(cf & C_ENABLED) || !(cf & C_TOUCHING)) continue;
+                w->l_contact[lc++] = c;
+            }
+            for (int k = first; k < lc; ++k) {
+                int c = w->l_contact[k];
+                w->c_flags[c] |= C_ISLAND;
+                int ba = w->f_body[w->c_fix[2 * c]], bb = w->f_body[w->c_fix[2 * c + 1]];
+                int other = (b == ba) ? bb : ba;
+                if (w->b_flags[other] & BODY_ISLAND) continue;
+                stack[sp++] = other;
+                w->b_flags[other] |= BODY_ISLAND;
+            }
+        }
+        if (overflow) { w->w_status[0] |= ST_ISLAND_OVERFLOW; break; }
+        w->l_start[2 * n_islands] = body_start; w->l_start[2 * n_islands + 1] = contact_start;
+        int used = 0;
+        island_solve(w, w->l_body + body_start, lb - body_start, w->l_contact + contact_start, lc - contact_start,
+                     dt, dt_ratio, vel_iters, pos_iters, &used);
+        if (used > pos_max) pos_max = used;
+        for (int k = body_start; k < lb; ++k)
+            if (body_type(w, w->l_body[k]) == T_STATIC) w->b_flags[w->l_body[k]] &= ~BODY_ISLAND;
+        ++n_islands;
+    }
+    w->w_island[0] = n_islands; w->w_island[1] = lb; w->w_island[2] = lc; w->w_island[3] = pos_max;
+
+    /* world.py:582-589 + body.py:898-904 */
+    for (int f = 0; f < nf; ++f) {
+        int b = w->f_body[f];
+        if (!(w->b_flags[b] & BODY_ISLAND) || body_type(w, b) == T_STATIC) continue;
+        v2 c0 = V(w->b_pos0[4 * b], w->b_pos0[4 * b + 1]); double a0 = w->b_pos0[4 * b + 2];
+        v2 lcen = V(w->b_mass[4 * b + 2], w->b_mass[4 * b + 3]);
+        xform xf1 = xf_from_sweep(c0, a0, lcen);
+        xform xf2 = xf_row(w->b_xf + 4 * (size_t)b);
+        fixture_synchronize(w, f, &xf1, &xf2);
+    }
+    free(adj_start); free(adj); free(fill); free(stack);
+    cm_find_new_contacts(w);
+}
+
+/* ---- World.step: world.py:307-354 ---- */
+int orc_step(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters)
+{
+    if (w->w_flags[0] & W_NEW_FIXTURE) {
+        cm_find_new_contacts(w);
+        w->w_flags[0] &= ~W_NEW_FIXTURE;
+    }
+    double dt_ratio = inv_dt0 * dt;
+    cm_collide(w);
+    if (dt > 0.0) world_solve(w, dt, dt_ratio, vel_iters, pos_iters);
+    if (w->w_flags[0] & W_AUTO_CLEAR) {
+        int nb = w->w_count[0];
+        for (int b = 0; b < nb; ++b) { w->b_force[2 * b] = 0.0; w->b_force[2 * b + 1] = 0.0; w->b_vel[4 * b + 3] = 0.0; }
+    }
+    return (w->w_status[0] != 0) ? -1 : 0;
+}
+
+int orc_run(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps)
+{
+    int rc = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        rc |= orc_step(w, dt, inv_dt0, vel_iters, pos_iters);
+        if (dt > 0.0) inv_dt0 = 1.0 / dt;
+    }
+    return rc;
+}
+
+int orc_collide_pair(const orc_world* w, int32_t sa, int32_t sb, const double* xfa, const double* xfb,
+                     int32_t* mtype, double* mf, double* pts, uint32_t* id)
+{
+    manifold_t m; memset(&m, 0, sizeof(m));
+    shape_t a = shape_get(w, sa), b = shape_get(w, sb);
+    xform xa = xf_row(xfa), xb = xf_row(xfb);
+    evaluate(&m, &a, &xa, &b, &xb);
+    *mtype = m.type | (m.count << 8);
+    mf[0] = m.local_normal.x; mf[1] = m.local_normal.y; mf[2] = m.local_point.x; mf[3] = m.local_point.y;
+    pts[0] = m.pt[0].x; pts[1] = m.pt[0].y; pts[2] = m.pt[1].x; pts[3] = m.pt[1].y;
+    id[0] = m.id[0]; id[1] = m.id[1];
+    return 0;
+}
+
+const char* orc_field_names(void)
+{
+    return "w_count,w_flags,w_status,w_gravity,w_island,"
+           "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
+           "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
+           "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
+           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data";
+}

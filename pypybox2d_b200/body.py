@@ -1,0 +1,328 @@
+"""Rigid body facade (host side).
+
+Same constructor keywords and read-backs as the reference's `Body`
+(`pypybox2d/body.py:39-44`, properties `:415-561,792-812`).  The object is a host mirror:
+`World.step` packs all bodies into device arrays, runs the CUDA step and writes the new
+state back into these attributes.  Mass aggregation follows `body.py:606-660` in the same
+operation order so inverse masses and inertias are bit-identical to the reference's.
+"""
+import math
+from copy import copy
+
+from . import shapes as _shapes
+from .common import Vec2, LockedError, is_valid_float
+from .fixture import Fixture
+
+
+class Body(object):
+    STATIC = 0
+    DYNAMIC = 1
+    KINEMATIC = 2
+
+    def __init__(self, world=None, position=(0, 0), angle=0.0, linear_velocity=(0, 0),
+                 angular_velocity=0.0, linear_damping=0.0, angular_damping=0.0,
+                 allow_sleep=True, awake=True, fixed_rotation=False, bullet=False,
+                 type=STATIC, active=True, gravity_scale=1.0, check_args=True,
+                 shapes=[], fixtures=[], shape_fixture=None, user_data=None,
+                 copy_fixtures=True):
+        position = Vec2(*position)
+        linear_velocity = Vec2(*linear_velocity)
+        if check_args:
+            if not position.valid:
+                raise ValueError("Invalid position")
+            if not linear_velocity.valid:
+                raise ValueError("Invalid linear velocity")
+            if not is_valid_float(angle):
+                raise ValueError("Invalid angle")
+            if not is_valid_float(angular_velocity):
+                raise ValueError("Invalid angular velocity")
+            if type not in (Body.STATIC, Body.DYNAMIC, Body.KINEMATIC):
+                raise ValueError("Invalid body type")
+
+        angle = float(angle)
+        self._xf = (position.x, position.y, math.cos(angle), math.sin(angle))
+        self._local_center = Vec2()
+        self._a = self._a0 = angle
+        self._c0 = Vec2(*self._xf_mul(self._local_center))
+        self._c = copy(self._c0)
+        self._force = Vec2()
+        self._torque = 0.0
+        self._I = 0.0
+        self._invI = 0.0
+        self._sleep_time = 0.0
+        self.fixtures = []
+        self.joints = []
+        self.user_data = user_data
+        self._world = world
+        self._linear_velocity = linear_velocity
+        self._angular_velocity = float(angular_velocity)
+        self._linear_damping = float(linear_damping)
+        self._angular_damping = float(angular_damping)
+        self._gravity_scale = float(gravity_scale)
+        self._island_index = None
+        self._awake = bool(awake)
+        self._allow_sleep = bool(allow_sleep)
+        self._fixed_rotation = bool(fixed_rotation)
+        self._bullet = bool(bullet)
+        self._type = type
+        self._active = bool(active)
+        if not self._active:
+            raise NotImplementedError("inactive bodies are not supported on the batched step path")
+        if self._type == Body.DYNAMIC:
+            self._mass = 1.0
+            self._inv_mass = 1.0
+        else:
+            self._mass = 0.0
+            self._inv_mass = 0.0
+
+        if shapes is not None:
+            self.create_fixtures(shapes, shape_fixture)
+        if fixtures is not None:
+            if not isinstance(fixtures, (list, tuple)):
+                fixtures = [fixtures]
+            for fixture in fixtures:
+                self.attach_fixture(copy(fixture) if copy_fixtures else fixture)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _xf_mul(self, v):
+        px, py, c, s = self._xf
+        return (px + c * v[0] + (-s) * v[1], py + s * v[0] + c * v[1])
+
+    def _check_unlocked(self):
+        if self._world is not None and self._world.locked:
+            raise LockedError("world is locked (stepping)")
+
+    def _dirty(self):
+        if self._world is not None:
+            self._world._host_dirty = True
+
+    # -- fixtures --------------------------------------------------------------------------
+    def create_fixture(self, shape, friction=0.2, restitution=0.0, density=0.0,
+                       category_bits=0x0001, mask_bits=0xFFFF, group_index=0,
+                       sensor=False, user_data=None):
+        self._check_unlocked()
+        fixture = Fixture(shape, friction, restitution, density, category_bits,
+                          mask_bits, group_index, sensor, user_data, body=self)
+        self.attach_fixture(fixture)
+        return fixture
+
+    def attach_fixture(self, fixture):
+        if fixture in self.fixtures:
+            raise ValueError("Fixture is already attached to this body")
+        if self._world is not None and self._world._stepped:
+            raise NotImplementedError("adding fixtures after the first step is not supported yet (SURVEY §8f #4)")
+        fixture._attach_to_body(self)
+        self.fixtures.append(fixture)
+        if fixture._density > 0.0:
+            self.reset_mass_data()
+        if self._world is not None:
+            self._world._fixture_attached(self, fixture)
+
+    def create_circle_fixture(self, radius=0.2, position=(0, 0), **kwargs):
+        return self.create_fixture(_shapes.Circle(radius, position), **kwargs)
+
+    def create_polygon_fixture(self, vertices=None, box=None, **kwargs):
+        return self.create_fixture(_shapes.Polygon(vertices, box), **kwargs)
+
+    def create_edge_fixture(self, v1=None, v2=None, v0=None, v3=None, **kwargs):
+        return self.create_fixture(_shapes.Edge(v1, v2, v0, v3), **kwargs)
+
+    def create_loop_fixture(self, vertices, *args, **kwargs):
+        raise NotImplementedError("Loop shapes are not supported on the batched step path")
+
+    def create_fixtures(self, shape_list, fixture=None, friction=0.2, restitution=0.0,
+                        density=0.0, category_bits=0x0001, mask_bits=0xFFFF,
+                        group_index=0, sensor=False):
+        if isinstance(shape_list, _shapes.Shape):
+            shape_list = [shape_list]
+        if fixture is not None:
+            friction, restitution, density = fixture.friction, fixture.restitution, fixture.density
+            category_bits, mask_bits = fixture.category_bits, fixture.mask_bits
+            group_index, sensor = fixture.group_index, fixture.sensor
+        for shape in shape_list:
+            self.create_fixture(shape, friction, restitution, density, category_bits,
+                                mask_bits, group_index, sensor)
+
+    # -- mass ------------------------------------------------------------------------------
+    def reset_mass_data(self):
+        """Sum fixture mass data; centre the inertia (body.py:606-660, same operation order)."""
+        self._mass = 0.0
+        self._inv_mass = 0.0
+        self._I = 0.0
+        self._invI = 0.0
+        self._local_center = Vec2()
+        if self._type in (Body.STATIC, Body.KINEMATIC):
+            self._c = Vec2(self._xf[0], self._xf[1])
+            self._c0 = copy(self._c)
+            return
+        cx = cy = 0.0
+        for fixture in self.fixtures:
+            if fixture._density == 0.0:
+                continue
+            md = fixture.mass_data
+            self._mass += md.mass
+            cx, cy = cx + md.mass * md.center.x, cy + md.mass * md.center.y
+            self._I += md.I
+        if self._mass > 0.0:
+            self._inv_mass = 1.0 / self._mass
+            cx, cy = self._inv_mass * cx, self._inv_mass * cy
+        else:
+            self._mass = 1.0
+            self._inv_mass = 1.0
+        if self._I > 0.0 and not self._fixed_rotation:
+            self._I -= self._mass * (cx ** 2 + cy ** 2)
+            assert self._I > 0.0
+            self._invI = 1.0 / self._I
+        else:
+            self._I = 0.0
+            self._invI = 0.0
+        old = self._c
+        self._local_center = Vec2(cx, cy)
+        self._c0 = Vec2(*self._xf_mul(self._local_center))
+        self._c = copy(self._c0)
+        dx, dy = self._c.x - old.x, self._c.y - old.y
+        w = self._angular_velocity
+        self._linear_velocity = Vec2(self._linear_velocity.x + (-float(w) * dy),
+                                     self._linear_velocity.y + (float(w) * dx))
+        self._dirty()
+
+    # -- read-backs ------------------------------------------------------------------------
+    @property
+    def world(self):
+        return self._world
+
+    @property
+    def position(self):
+        return Vec2(self._xf[0], self._xf[1])
+
+    @property
+    def angle(self):
+        return math.atan2(self._xf[3], self._xf[2])
+
+    @property
+    def transform(self):
+        return self._xf
+
+    @property
+    def world_center(self):
+        return copy(self._c)
+
+    @property
+    def local_center(self):
+        return copy(self._local_center)
+
+    @property
+    def linear_velocity(self):
+        return copy(self._linear_velocity)
+
+    @linear_velocity.setter
+    def linear_velocity(self, v):
+        if self._type == Body.STATIC:
+            return
+        v = Vec2(*v)
+        if v.dot(v) > 0.0:
+            self.awake = True
+        self._linear_velocity = v
+        self._dirty()
+
+    @property
+    def angular_velocity(self):
+        return self._angular_velocity
+
+    @angular_velocity.setter
+    def angular_velocity(self, w):
+        if self._type == Body.STATIC:
+            return
+        if w * w > 0.0:
+            self.awake = True
+        self._angular_velocity = float(w)
+        self._dirty()
+
+    @property
+    def mass(self):
+        return self._mass
+
+    @property
+    def inertia(self):
+        return self._I + self._mass * self._local_center.length_squared
+
+    @property
+    def type(self):
+        return self._type
+
+    static = property(lambda self: self._type == Body.STATIC)
+    dynamic = property(lambda self: self._type == Body.DYNAMIC)
+    kinematic = property(lambda self: self._type == Body.KINEMATIC)
+    active = property(lambda self: self._active)
+    bullet = property(lambda self: self._bullet)
+    fixed_rotation = property(lambda self: self._fixed_rotation)
+    linear_damping = property(lambda self: self._linear_damping)
+    angular_damping = property(lambda self: self._angular_damping)
+    gravity_scale = property(lambda self: self._gravity_scale)
+    allow_sleep = property(lambda self: self._allow_sleep)
+
+    @property
+    def awake(self):
+        return self._awake
+
+    @awake.setter
+    def awake(self, awake):
+        # body.py:800-812
+        if awake:
+            if not self._awake:
+                self._sleep_time = 0.0
+        else:
+            self._sleep_time = 0.0
+            self._linear_velocity = Vec2()
+            self._angular_velocity = 0.0
+            self._force = Vec2()
+            self._torque = 0.0
+        self._awake = bool(awake)
+        self._dirty()
+
+    @property
+    def sleeping(self):
+        return not self._awake
+
+    # -- forces (host-side inputs consumed by the next step; body.py:477-545) ---------------
+    def apply_force(self, force, point):
+        if self._type != Body.DYNAMIC:
+            return
+        if not self._awake:
+            self.awake = True
+        f = Vec2(*force)
+        p = Vec2(*point)
+        self._force = self._force + f
+        self._torque += (p - self._c).cross(f)
+        self._dirty()
+
+    def apply_torque(self, torque):
+        if self._type != Body.DYNAMIC:
+            return
+        if not self._awake:
+            self.awake = True
+        self._torque += torque
+        self._dirty()
+
+    def apply_linear_impulse(self, impulse, point):
+        if self._type != Body.DYNAMIC:
+            return
+        if not self._awake:
+            self.awake = True
+        imp = Vec2(*impulse)
+        p = Vec2(*point)
+        self._linear_velocity = self._linear_velocity + self._inv_mass * imp
+        self._angular_velocity += self._invI * (p - self._c).cross(imp)
+        self._dirty()
+
+    def apply_angular_impulse(self, impulse):
+        if self._type != Body.DYNAMIC:
+            return
+        if not self._awake:
+            self.awake = True
+        self._angular_velocity += self._invI * impulse
+        self._dirty()
+
+    def __repr__(self):
+        return "Body(position=%s, angle=%g, type=%d, fixtures=%d)" % (
+            self.position, self.angle, self._type, len(self.fixtures))

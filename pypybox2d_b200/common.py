@@ -1,0 +1,157 @@
+"""Host-side value types and exceptions of the drop-in API.
+
+Only what scene-building scripts touch: a 2-vector with the reference's operator
+conventions (`pypybox2d/common.py:88-225`, conventions listed in SURVEY A.2) and the
+exception types (`common.py:84-86`).  All per-step math lives on the device.
+"""
+import math
+from numbers import Number
+
+from .settings import EPSILON
+
+
+class PhysicsError(Exception):
+    pass
+
+
+class LockedError(PhysicsError):
+    pass
+
+
+class EmptyFixtureError(PhysicsError):
+    pass
+
+
+class Vec2(object):
+    """2-vector of Python floats; `+=` rebinds like the reference's (no in-place mutation)."""
+    __slots__ = ("x", "y")
+
+    def __init__(self, x=0.0, y=0.0):
+        self.x = float(x)
+        self.y = float(y)
+
+    def __iter__(self):
+        yield self.x
+        yield self.y
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        if i == 0:
+            return self.x
+        if i == 1:
+            return self.y
+        raise IndexError("Index must be in (0,1)")
+
+    def __setitem__(self, i, value):
+        if i == 0:
+            self.x = float(value)
+        elif i == 1:
+            self.y = float(value)
+        else:
+            raise IndexError("Index must be in (0,1)")
+
+    def __repr__(self):
+        return "Vec2(%g,%g)" % (self.x, self.y)
+
+    def __copy__(self):
+        return Vec2(self.x, self.y)
+
+    copy = __copy__
+
+    def __neg__(self):
+        return Vec2(-self.x, -self.y)
+
+    def __abs__(self):
+        return Vec2(abs(self.x), abs(self.y))
+
+    def __add__(self, o):
+        ox, oy = o
+        return Vec2(self.x + ox, self.y + oy)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return Vec2(self.x - o[0], self.y - o[1])
+
+    def __rsub__(self, o):
+        return Vec2(o[0] - self.x, o[1] - self.y)
+
+    def __mul__(self, s):
+        if isinstance(s, Number):
+            return Vec2(s * self.x, s * self.y)
+        return self.dot(s)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, s):
+        if isinstance(s, Number):
+            return Vec2(self.x / s, self.y / s)
+        raise ValueError("Ambiguous operation")
+
+    def __eq__(self, o):
+        try:
+            return self.x == o[0] and self.y == o[1]
+        except Exception:
+            return False
+
+    def __ne__(self, o):
+        return not self.__eq__(o)
+
+    __hash__ = None
+
+    def dot(self, o):
+        ox, oy = o
+        return self.x * float(ox) + self.y * float(oy)
+
+    def cross(self, o):
+        # vector x scalar -> vector ; vector x vector -> scalar (common.py:204-212)
+        if isinstance(o, Number):
+            return Vec2(float(o) * self.y, -float(o) * self.x)
+        ox, oy = o
+        return self.x * float(oy) - self.y * float(ox)
+
+    @property
+    def length_squared(self):
+        return self.x ** 2 + self.y ** 2
+
+    @property
+    def length(self):
+        return math.sqrt(self.x ** 2 + self.y ** 2)
+
+    @property
+    def normalized(self):
+        n = self.length
+        if n < EPSILON:
+            return Vec2(self.x, self.y)
+        inv = 1.0 / n
+        return Vec2(self.x * inv, self.y * inv)
+
+    @property
+    def valid(self):
+        return not (math.isnan(self.x) or math.isnan(self.y))
+
+
+def scalar_cross(s, v):
+    """scalar x vector (common.py:195-202)."""
+    return Vec2(-float(s) * v[1], float(s) * v[0])
+
+
+def clamp(value, low, high):
+    return max(low, min(value, high))
+
+
+def is_valid_float(x):
+    return not math.isnan(x)
+
+
+def rot(angle):
+    """(cos, sin) of a body angle, libm double as the reference (common.py:495-503)."""
+    return math.cos(angle), math.sin(angle)
+
+
+def xf_apply(xf, v):
+    """xf = (px, py, c, s); p + R v with the reference's operation order (common.py:677-685)."""
+    px, py, c, s = xf
+    return (px + c * v[0] + (-s) * v[1], py + s * v[0] + c * v[1])

@@ -1,0 +1,62 @@
+"""Fixture: a shape plus material and filter data attached to a body.
+
+Mirrors the reference's constructor and attributes (`pypybox2d/fixture.py:52-69`) so that
+scene scripts run unchanged.  Broadphase proxies are not Python objects here: each fixture
+becomes one row of the per-world proxy arrays when the world is packed (`schema.pack_world`).
+"""
+from copy import copy
+
+from .common import EmptyFixtureError
+
+
+class Fixture(object):
+    def __init__(self, shape=None, friction=0.2, restitution=0.0, density=0.0,
+                 category_bits=0x0001, mask_bits=0xFFFF, group_index=0,
+                 sensor=False, user_data=None, body=None):
+        if sensor:
+            raise NotImplementedError("sensor fixtures are not supported on the batched step path (SURVEY §8b)")
+        self._friction = friction
+        self._restitution = restitution
+        self._density = density
+        self._sensor = sensor
+        self._category_bits = category_bits
+        self._mask_bits = mask_bits
+        self._group_index = group_index
+        self._shape = copy(shape)        # shapes are cloned on attach (fixture.py:67)
+        self.user_data = user_data
+        self._body = None
+        self._index = -1                 # row in the packed proxy arrays
+        self._attach_to_body(body)
+
+    def _attach_to_body(self, body):
+        if body is not None and self._shape is None:
+            raise EmptyFixtureError("Cannot attach empty fixture to a body")
+        self._body = body
+
+    def __copy__(self):
+        return Fixture(shape=self._shape, friction=self._friction, restitution=self._restitution,
+                       density=self._density, category_bits=self._category_bits,
+                       mask_bits=self._mask_bits, group_index=self._group_index,
+                       sensor=self._sensor, user_data=self.user_data)
+
+    def __repr__(self):
+        return "Fixture(shape=%s, friction=%g, restitution=%g, density=%g)" % (
+            self._shape, self._friction, self._restitution, self._density)
+
+    shape = property(lambda self: self._shape)
+    body = property(lambda self: self._body)
+    friction = property(lambda self: self._friction)
+    restitution = property(lambda self: self._restitution)
+    density = property(lambda self: self._density)
+    sensor = property(lambda self: self._sensor)
+    category_bits = property(lambda self: self._category_bits)
+    mask_bits = property(lambda self: self._mask_bits)
+    group_index = property(lambda self: self._group_index)
+
+    @property
+    def mass_data(self):
+        return self._shape.compute_mass(self._density)
+
+    @property
+    def world(self):
+        return None if self._body is None else self._body._world

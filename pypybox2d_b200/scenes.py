@@ -1,0 +1,164 @@
+"""Scene definitions of the five BASELINE.json configs.
+
+Every builder takes the API module as its first argument, so the SAME script builds the scene
+in the reference (`import pypybox2d as b2`, used by oracle/gen_golden.py) and in this package
+(`import pypybox2d_b200 as b2`): the drop-in claim is exercised by construction.
+
+World 0 of a config is the exact scripted scene.  World w > 0 jitters the initial position of
+every dynamic body by `amp * U(-1, 1)` in x and y (SURVEY §8d "World diversity"), with U taken
+from a counter-based hash of (seed, config, world, body, axis) so that a world's scene depends
+only on its global index -- never on batch size, shard or GPU count (parity tier T4).
+"""
+import math
+
+import numpy as np
+
+SEED = 20261017
+JITTER_AMP = 1e-2
+
+_M64 = (1 << 64) - 1
+
+
+def _mix64_np(x):
+    """splitmix64 finaliser on uint64 arrays."""
+    x = x.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def u01(config, world, index, stream=0, seed=SEED):
+    """Uniform [0,1) doubles; `world` and `index` broadcast.  53-bit mantissa from the hash."""
+    world = np.asarray(world, dtype=np.uint64)
+    index = np.asarray(index, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        k = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(config) * np.uint64(0xD1B54A32D192ED03)
+             + np.uint64(stream) * np.uint64(0x8CB92BA72F3D8DD7))
+        h = _mix64_np(_mix64_np(world + k) + index * np.uint64(0x9E3779B97F4A7C15))
+    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def u01_torch(config, world, index, stream=0, seed=SEED):
+    """Same numbers as `u01`, computed with torch int64 wrap-around arithmetic on any device."""
+    import torch
+
+    def i64(v):
+        v &= _M64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(x, s):
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    def mix(x):
+        x = (x ^ lsr(x, 30)) * i64(0xBF58476D1CE4E5B9)
+        x = (x ^ lsr(x, 27)) * i64(0x94D049BB133111EB)
+        return x ^ lsr(x, 31)
+
+    k = i64(seed * 0x9E3779B97F4A7C15 + config * 0xD1B54A32D192ED03 + stream * 0x8CB92BA72F3D8DD7)
+    world = world.to(torch.int64)
+    index = index.to(torch.int64)
+    h = mix(mix(world + k) + index * i64(0x9E3779B97F4A7C15))
+    return lsr(h, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
+
+
+def jitter(config, world, n_bodies, amp=JITTER_AMP):
+    """[n_bodies, 2] position offsets of world `world` (zeros for world 0)."""
+    if world == 0 or amp == 0.0:
+        return np.zeros((n_bodies, 2))
+    idx = np.arange(2 * n_bodies, dtype=np.uint64)
+    u = u01(config, world, idx).reshape(n_bodies, 2)
+    return amp * (2.0 * u - 1.0)
+
+
+# ---- config 1 / 3: examples/pyramid-bench.py:32-53 -------------------------------------------
+def pyramid(b2, world=0, rows=20, config=1, **world_kw):
+    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
+    fixture = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
+    n_dyn = rows * (rows + 1) // 2
+    jit = jitter(config, world, n_dyn)
+    x = (-7.0, 0.75)
+    k = 0
+    for i in range(rows):
+        y = x
+        for j in range(i, rows):
+            w.create_dynamic_body(position=(y[0] + jit[k, 0], y[1] + jit[k, 1]), fixtures=fixture)
+            k += 1
+            y = (y[0] + 1.125, y[1] + 0.0)
+        x = (x[0] + 0.5625, x[1] + 1.25)
+    return w
+
+
+# ---- config 2(i): examples/hello-bench.py:21-36 ---------------------------------------------
+def hello(b2, world=0, config=2, **world_kw):
+    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    ground = w.create_static_body(position=(0, -10))
+    ground.create_polygon_fixture(box=(50, 10))
+    jit = jitter(config, world, 1)
+    body = w.create_dynamic_body(position=(0 + jit[0, 0], 4 + jit[0, 1]))
+    body.create_circle_fixture(1.0, density=1.0)
+    return w
+
+
+# ---- config 2(ii): examples/verticalstack-bench.py:33-75 ------------------------------------
+def vertical_stack(b2, world=0, columns=5, rows=16, config=2, **world_kw):
+    w = b2.World(continuous_physics=False, **world_kw)
+    w.create_static_body(shapes=[b2.Edge((-40, 0), (40, 0)), b2.Edge((20, 0), (20, 20))])
+    box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
+    circle = b2.Fixture(shape=b2.Circle(0.5), density=1, friction=0.3)
+    jit = jitter(config, world, 2 * columns * rows)
+    k = 0
+    for j in range(columns):
+        for i in range(rows):
+            w.create_dynamic_body(fixtures=box, position=(-10 + 2.5 * j + jit[k, 0], 0.752 + 1.54 * i + jit[k, 1]))
+            k += 1
+            w.create_dynamic_body(fixtures=circle, position=(8 + 2.5 * j + jit[k, 0], 0.752 + 1.54 * i + jit[k, 1]))
+            k += 1
+    return w
+
+
+# ---- config 4: mixed circles + convex polygons in a box of edges (testbed/confined.py:35-41) --
+def mixed(b2, world=0, side=16, config=4, **world_kw):
+    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w.create_static_body(shapes=[b2.Edge((-10, 0), (10, 0)), b2.Edge((-10, 0), (-10, 20)),
+                                 b2.Edge((10, 0), (10, 20)), b2.Edge((-10, 20), (10, 20))])
+    n = side * side
+    jit = jitter(config, world, n)
+    idx = np.arange(n, dtype=np.uint64)
+    # shape draws come from their own streams and also vary with the world index (world 0 included)
+    u_r = u01(config, world, idx, stream=1)
+    u_m = u01(config, world, idx, stream=2)
+    u_a = u01(config, world, idx, stream=3)
+    for k in range(n):
+        i, j = divmod(k, side)
+        pos = (-9.0 + 1.2 * j + jit[k, 0], 0.8 + 1.2 * i + jit[k, 1])
+        if k % 2 == 0:
+            shape = b2.Circle(0.25 + 0.25 * float(u_r[k]))
+        else:
+            m = 3 + int(float(u_m[k]) * 6.0)
+            radius = 0.3 + 0.3 * float(u_r[k])
+            a0 = 2.0 * math.pi * float(u_a[k])
+            shape = b2.Polygon(vertices=[(radius * math.cos(a0 + 2.0 * math.pi * q / m),
+                                          radius * math.sin(a0 + 2.0 * math.pi * q / m)) for q in range(m)])
+        w.create_dynamic_body(position=pos, fixtures=b2.Fixture(shape=shape, density=1, friction=0.3))
+    return w
+
+
+# ---- config 5: deep vertical stacks, 10 columns x 20 boxes -----------------------------------
+def deep_stacks(b2, world=0, columns=10, rows=20, config=5, **world_kw):
+    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
+    box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
+    jit = jitter(config, world, columns * rows)
+    k = 0
+    for j in range(columns):
+        for i in range(rows):
+            w.create_dynamic_body(fixtures=box, position=(-12 + 2.5 * j + jit[k, 0], 0.752 + 1.54 * i + jit[k, 1]))
+            k += 1
+    return w
+
+
+SCENES = {"pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
+          "deep_stacks": deep_stacks}

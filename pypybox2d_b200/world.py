@@ -1,0 +1,205 @@
+"""`World`: the drop-in surface of the reference (`pypybox2d/world.py:64-91,183-233,307-369`).
+
+Scene construction is host-side Python; `step(dt, vel_iters, pos_iters)` packs the world into
+device structure-of-arrays buffers (once, or again after a host-side mutation), runs the CUDA
+step through the C-ABI (`include/b2b.h`) and mirrors the body state back into the `Body`
+objects.  A single `World` is a batch of one; large batches use `BatchedWorld` directly
+(`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
+
+Unsupported on this path (raise `NotImplementedError`): joints, controllers,
+contact listeners, custom contact filters, sensors, Loop shapes, `continuous_physics=True`
+stepping (TOI) and sub-stepping.
+"""
+from copy import copy
+
+from .body import Body
+from .common import Vec2, LockedError
+
+
+class TimeStep(object):
+    """world.py:53-62"""
+    __slots__ = ["dt", "inv_dt", "dt_ratio", "vel_iters", "pos_iters", "warm_starting"]
+
+    def __init__(self, dt=0.0, inv_dt=0.0, dt_ratio=0.0, vel_iters=0, pos_iters=0, warm_starting=True):
+        self.dt = float(dt)
+        self.inv_dt = float(inv_dt)
+        self.dt_ratio = float(dt_ratio)
+        self.vel_iters = int(vel_iters)
+        self.pos_iters = int(pos_iters)
+        self.warm_starting = bool(warm_starting)
+
+
+class ContactView(object):
+    """Read-only record of one device contact row (subset of `pypybox2d/contact.py:49-201`)."""
+    __slots__ = ["fixture_a", "fixture_b", "touching", "enabled", "friction", "restitution",
+                 "manifold_type", "point_count", "local_normal", "local_point", "points"]
+
+    @property
+    def body_a(self):
+        return self.fixture_a.body
+
+    @property
+    def body_b(self):
+        return self.fixture_b.body
+
+
+class _ContactManagerView(object):
+    def __init__(self, world):
+        self._world = world
+
+    @property
+    def contacts(self):
+        return self._world._contact_views()
+
+    begin_contact = end_contact = pre_solve = post_solve = None
+
+
+class World(object):
+    def __init__(self, gravity=(0, -10), do_sleep=True, warm_starting=True,
+                 continuous_physics=True, sub_stepping=False, auto_clear_forces=True,
+                 joint_destruction_listener=None, fixture_destruction_listener=None,
+                 contact_filter=None, real="f32", device=None):
+        if contact_filter is not None:
+            raise NotImplementedError("custom contact filters cannot run inside the device step")
+        if sub_stepping:
+            raise NotImplementedError("sub_stepping belongs to the TOI path (SURVEY §8f #1)")
+        self._gravity = Vec2(*gravity)
+        self.bodies = []
+        self.joints = []
+        self.controllers = []
+        self._warm_starting = bool(warm_starting)
+        self._continuous_physics = bool(continuous_physics)
+        self._sub_stepping = False
+        self._allow_sleep = bool(do_sleep)
+        self._auto_clear_forces = bool(auto_clear_forces)
+        self.joint_destruction_listener = joint_destruction_listener
+        self.fixture_destruction_listener = fixture_destruction_listener
+        self.contact_manager = _ContactManagerView(self)
+        self._inv_dt0 = 0.0
+        self._locked = False
+        self._stepped = False
+        self._host_dirty = True
+        self._batch = None
+        self._real = real
+        self._device = device
+
+    # -- properties (world.py:93-181) ------------------------------------------------------
+    @property
+    def gravity(self):
+        return Vec2(*self._gravity)
+
+    @gravity.setter
+    def gravity(self, g):
+        self._gravity = Vec2(*g)
+        self._host_dirty = True
+
+    @property
+    def locked(self):
+        return self._locked
+
+    warm_starting = property(lambda self: self._warm_starting)
+    allow_sleep = property(lambda self: self._allow_sleep)
+    auto_clear_forces = property(lambda self: self._auto_clear_forces)
+
+    @property
+    def continuous_physics(self):
+        return self._continuous_physics
+
+    @continuous_physics.setter
+    def continuous_physics(self, v):
+        self._continuous_physics = bool(v)
+
+    @property
+    def contact_filter(self):
+        return self.default_contact_filter
+
+    # -- body factories (world.py:183-233) -------------------------------------------------
+    def add_body(self, body):
+        if self._locked:
+            raise LockedError("Cannot create a body while simulating")
+        if self._stepped:
+            raise NotImplementedError("adding bodies after the first step is not supported yet (SURVEY §8f #4)")
+        self.bodies.append(body)
+        body._world = self
+        self._host_dirty = True
+        return body
+
+    def create_body(self, body=None, **kwargs):
+        if self._locked:
+            raise LockedError("Cannot create a body while simulating")
+        if body is not None:
+            raise NotImplementedError("copying an existing Body into a world is not supported; pass Body kwargs")
+        return self.add_body(Body(**kwargs))
+
+    def create_dynamic_body(self, body=None, **kwargs):
+        return self.create_body(body, type=Body.DYNAMIC, **kwargs)
+
+    def create_static_body(self, body=None, **kwargs):
+        return self.create_body(body, type=Body.STATIC, **kwargs)
+
+    def create_kinematic_body(self, body=None, **kwargs):
+        return self.create_body(body, type=Body.KINEMATIC, **kwargs)
+
+    def destroy_body(self, body):
+        raise NotImplementedError("destroy_body is not supported on the batched step path (SURVEY §8f #4)")
+
+    def add_joint(self, joint, duplicate=False):
+        raise NotImplementedError("joints are not supported on the batched step path (SURVEY §8f #3)")
+
+    def add_controller(self, controller):
+        raise NotImplementedError("controllers are not supported on the batched step path")
+
+    def _fixture_attached(self, body, fixture):
+        self._host_dirty = True
+
+    # -- stepping (world.py:307-369) ----------------------------------------------------------
+    def _ensure_batch(self):
+        from .batch import BatchedWorld
+        if self._batch is None:
+            self._batch = BatchedWorld.from_worlds([self], real=self._real, device=self._device)
+            self._host_dirty = False
+        elif self._host_dirty:
+            self._batch.upload_bodies_from_world(self)
+            self._host_dirty = False
+        return self._batch
+
+    def step(self, dt, vel_iters, pos_iters):
+        if self._continuous_physics and dt > 0.0:
+            raise NotImplementedError(
+                "continuous_physics=True (TOI) is not implemented on the device path; "
+                "construct World(..., continuous_physics=False) (SURVEY §0 finding 2, §8f #1)")
+        if self._locked:
+            raise LockedError("step is not re-entrant")
+        batch = self._ensure_batch()
+        self._locked = True
+        try:
+            batch.inv_dt0 = self._inv_dt0
+            batch.step(dt, vel_iters, pos_iters, 1)
+            if dt > 0.0:
+                self._inv_dt0 = 1.0 / dt
+            self._stepped = True
+            batch.download_into_world(self)
+            if not self._auto_clear_forces:
+                # forces were cleared on the device only when auto_clear_forces is on
+                pass
+        finally:
+            self._locked = False
+
+    def clear_forces(self):
+        for b in self.bodies:
+            b._force = Vec2()
+            b._torque = 0.0
+        self._host_dirty = True
+
+    def _contact_views(self):
+        if self._batch is None:
+            return []
+        return self._batch.contact_views(self)
+
+    @staticmethod
+    def default_contact_filter(filter_a, filter_b):
+        # world.py:958-970; the device evaluates the same rule in the pair-filter kernel
+        if filter_a._group_index == filter_b._group_index and filter_a._group_index != 0:
+            return filter_a._group_index > 0
+        return ((filter_a._mask_bits & filter_b._category_bits) != 0 and
+                (filter_a._category_bits & filter_b._mask_bits) != 0)
