@@ -1,0 +1,123 @@
+/*
+ * b2b.h -- C-ABI of the B200-native batched rigid-body step (libb2b.so).
+ *
+ * The reference (pypybox2d r331) has NO native boundary for this path: World.step is a chain of
+ * Python method calls (pypybox2d/world.py:307-354).  The drop-in surface is therefore the Python
+ * class API (pypybox2d_b200.World/Body/Fixture) and this header is the boundary underneath it --
+ * what a maintainer of the reference would bind with ctypes to replace the body of World.step
+ * (binding stub: INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * b2b_error on failure, with a message available from b2b_last_error().  All device arrays are
+ * owned by the caller (torch tensors in the Python host layer); the library borrows them between
+ * b2b_bind and b2b_destroy and never allocates inside b2b_step.  One context is bound to one CUDA
+ * device and is not thread-safe; calls are asynchronous on the caller's stream unless stated.
+ *
+ * Array layout: world-major structure-of-arrays, `[n_worlds][cap][k]`; the field list, element
+ * types and flag bits are documented once in pypybox2d_b200/schema.py (FIELDS) and DESIGN.md.
+ * `real` is float (real_bytes = 4) or double (real_bytes = 8) per context.
+ */
+#ifndef B2B_H
+#define B2B_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2b_error {
+    B2B_OK = 0,
+    B2B_ERR_ARG = -1,        /* bad argument / capacity */
+    B2B_ERR_CUDA = -2,       /* CUDA runtime error (message in b2b_last_error) */
+    B2B_ERR_UNBOUND = -3,    /* b2b_step before b2b_bind */
+    B2B_ERR_OVERFLOW = -4    /* a world overflowed a capacity (see b2b_status) */
+} b2b_error;
+
+typedef struct b2b_caps {
+    int32_t n_worlds;        /* worlds in this context (this GPU's shard) */
+    int32_t nb;              /* bodies per world (capacity) */
+    int32_t nf;              /* fixtures == broadphase proxies per world */
+    int32_t nc;              /* contacts per world */
+    int32_t npair;           /* pairs one BroadPhase.update_pairs may emit per world */
+    int32_t nl;              /* island body-list slots per world (>= nb + static re-visits) */
+    int32_t n_shapes;        /* rows of the shared shape table */
+    int32_t real_bytes;      /* 4: fp32 kernels, 8: fp64 kernels (parity build, no FMA contraction) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t threads;         /* threads per CTA (0: default) */
+    int32_t ctas_per_sm;     /* resident CTAs per SM the persistent grid is sized for (0: from occupancy) */
+    int32_t reserved;
+} b2b_caps;
+
+/* Device pointers, one per schema field, same names and order as pypybox2d_b200/schema.py FIELDS.
+ * Replaces the attribute storage of Body (body.py:65-103), Sweep (common.py:870-889), Fixture /
+ * FixtureProxy (fixture.py:31-69), Manifold (contact_util.py:50-166), Contact (contact.py:57-81). */
+typedef struct b2b_buffers {
+    void *w_count, *w_flags, *w_status, *w_gravity, *w_island;
+    void *b_xf, *b_pos, *b_vel, *b_pos0, *b_force, *b_mass, *b_damp, *b_flags, *b_island;
+    void *f_body, *f_shape, *f_mat, *f_filter, *f_fat, *f_tight, *f_moved;
+    void *c_fix, *c_flags, *c_mat, *c_mtype, *c_mf, *c_pts, *c_imp, *c_id;
+    void *p_pairs, *l_body, *l_contact, *l_start;
+    void *s_meta, *s_radius, *s_data;
+} b2b_buffers;
+
+typedef struct b2b_ctx b2b_ctx;
+
+/* Create / destroy a context.  Allocates only the per-CTA scratch (b2b_scratch_bytes). */
+int b2b_create(const b2b_caps* caps, b2b_ctx** out);
+void b2b_destroy(b2b_ctx* ctx);
+
+/* Bytes of device scratch a context with these capacities allocates (0 on bad caps). */
+size_t b2b_scratch_bytes(const b2b_caps* caps);
+
+/* Borrow the caller's device arrays. */
+int b2b_bind(b2b_ctx* ctx, const b2b_buffers* buffers);
+
+/* Fixture._create_proxies + DynamicTree.create_proxy for every fixture of every world
+ * (fixture.py:250-261, dynamictree.py:115-134): tight AABB from the body transform, fat AABB =
+ * tight +- AABB_EXTENSION, proxy put in the move buffer, world flagged `_new_fixture`. */
+int b2b_init_proxies(b2b_ctx* ctx, void* stream);
+
+/* World.step(dt, vel_iters, pos_iters), n_steps times, for every world of the batch
+ * (world.py:307-354 with continuous_physics=False): find_new_contacts if new fixtures,
+ * ContactManager.collide (contact_manager.py:174-223), World._solve (world.py:475-592: island DFS,
+ * Island.solve island.py:65-179, ContactSolver contact.py:375-864, fixture synchronisation,
+ * find_new_contacts contact_manager.py:102-158), clear forces.
+ * inv_dt0 is World._inv_dt0 before the first of the n_steps (0 for a fresh world); the first step
+ * uses dt_ratio = inv_dt0 * dt, later ones (1/dt) * dt, both evaluated in double as world.py:323-328.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int b2b_step(b2b_ctx* ctx, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps,
+             uint32_t flags, void* stream);
+
+/* Same step driven from HOST buffers (the end-to-end call an environment loop makes):
+ * copies h_force_torque [n_worlds][nb][3] (fx, fy, torque; may be NULL) host->device, steps, copies
+ * body state [n_worlds][nb][6] (c.x, c.y, a, v.x, v.y, w) device->host into h_state_out (may be NULL),
+ * then synchronises the stream.  Host buffers should be pinned for full PCIe bandwidth. */
+int b2b_step_host(b2b_ctx* ctx, const void* h_force_torque, void* h_state_out, double dt, double inv_dt0,
+                  int vel_iters, int pos_iters, int n_steps, uint32_t flags, void* stream);
+
+/* Test hook (T1): run only the narrowphase dispatch (collision.py collide_*) on n explicit pairs.
+ * d_shape_a/b: int32 shape rows; d_xf_a/b: real[n][4] (x, y, cos, sin); outputs as c_mtype/c_mf/c_pts/c_id. */
+int b2b_collide_pairs(b2b_ctx* ctx, int n, const void* d_shape_a, const void* d_shape_b, const void* d_xf_a,
+                      const void* d_xf_b, void* d_mtype, void* d_mf, void* d_pts, void* d_id, void* stream);
+
+/* OR of every world's status word (STATUS_* bits in schema.py); synchronises the stream. */
+int b2b_status(b2b_ctx* ctx, uint32_t* host_out, void* stream);
+
+/* Per-world state checksum and energy for the optional end-of-run gather:
+ * d_out real64[n_worlds][4] = {fnv1a64 of packed body state (as double bits), kinetic+potential
+ * energy, n_contacts, n_awake}.  masses are passed as inverse mass/inertia already in b_mass. */
+int b2b_checksum(b2b_ctx* ctx, void* d_out, void* stream);
+
+/* Launch geometry actually used and kernel launches issued so far (for bench.py's gpu_launches). */
+int b2b_info(b2b_ctx* ctx, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches);
+
+const char* b2b_last_error(void);
+const char* b2b_field_names(void);   /* comma-separated b2b_buffers member names */
+const char* b2b_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2B_H */

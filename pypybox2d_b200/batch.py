@@ -1,3 +1,310 @@
-"""placeholder, replaced below"""
+"""`BatchedWorld`: a batch of independent worlds resident on one GPU.
+
+Host-side mirror of the reference's `World` for the step path only: it owns the device
+structure-of-arrays buffers (torch tensors, `schema.FIELDS`), hands their pointers to libb2b.so
+(`include/b2b.h`) and launches `World.step` for every world of the batch at once.  No per-body
+Python runs on the step path; no CPU implementation of the step exists here -- without the CUDA
+library or a GPU every stepping call raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import schema
+from . import _lib
+
+_TORCH_DTYPES = None
+
+
+def _torch():
+    import torch
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                         np.dtype(np.int32): torch.int32, np.dtype(np.uint32): torch.int32,
+                         np.dtype(np.uint8): torch.uint8}
+    return torch
+
+
+def world_caps(worlds, contacts_per_body=4, slack=64):
+    nb = max(len(w.bodies) for w in worlds)
+    nf = max(sum(len(b.fixtures) for b in w.bodies) for w in worlds)
+    return schema.Caps(nb, nf, contacts_per_body * nb + slack)
+
+
 class BatchedWorld(object):
-    pass
+    def __init__(self, arrays, caps, real="f32", device=None, threads=0, ctas_per_sm=0):
+        """`arrays`: host numpy dict laid out as `schema.alloc` (any real dtype; cast to `real`)."""
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.B2BError("no CUDA device: the batched step has no CPU fallback")
+        self.real = real
+        self.caps = caps
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.n_worlds = int(arrays["w_flags"].shape[0])
+        self.n_shapes = int(arrays["s_meta"].shape[0])
+        self.inv_dt0 = 0.0
+        self.t = {}
+        for name, scope, tail, kind in schema.FIELDS:
+            want = schema.np_dtype(kind, real)
+            host = np.ascontiguousarray(arrays[name]).astype(want, copy=False)
+            self.t[name] = self._to_device(host)
+        self._ctx = ctypes.c_void_p()
+        c = _lib.Caps()
+        c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = self.n_worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
+        c.n_shapes = self.n_shapes
+        c.real_bytes = 8 if real == "f64" else 4
+        c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c.threads, c.ctas_per_sm = threads, ctas_per_sm
+        self._caps_struct = c
+        L = _lib.lib()
+        _lib.check(L.b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
+        self._bind()
+
+    # -- construction -----------------------------------------------------------------------
+    @classmethod
+    def from_worlds(cls, worlds, real="f32", caps=None, device=None, **kw):
+        caps = caps or world_caps(worlds)
+        table = schema.ShapeTable()
+        for w in worlds:
+            for b in w.bodies:
+                for f in b.fixtures:
+                    table.add(f._shape)
+        A = schema.alloc(caps, len(worlds), max(len(table), 1), "f64")
+        for i, w in enumerate(worlds):
+            schema.pack_world(w, A, i, table)
+        A["s_meta"], A["s_radius"], A["s_data"] = table.arrays("f64")
+        return cls(A, caps, real=real, device=device, **kw)
+
+    @classmethod
+    def replicate(cls, world, n, jitter=0.0, config=0, world_offset=0, real="f32", caps=None, device=None, **kw):
+        """`n` copies of `world`; copy k is world index `world_offset + k` of the global batch.  World index 0
+        is the scene as scripted; every other index moves each dynamic body by jitter*U(-1,1) in x and y, with
+        U from `scenes.u01_torch(config, world index, 2*body + axis)` -- so a world's scene depends only on its
+        global index.  The expansion and the jitter run on the device; proxies are (re)built there too
+        (`b2b_init_proxies`)."""
+        torch = _torch()
+        from . import scenes
+        caps = caps or world_caps([world])
+        table = schema.ShapeTable()
+        A1 = schema.alloc(caps, 1, 1, "f64")
+        for b in world.bodies:
+            for f in b.fixtures:
+                table.add(f._shape)
+        A1 = schema.alloc(caps, 1, max(len(table), 1), "f64")
+        schema.pack_world(world, A1, 0, table)
+        A1["s_meta"], A1["s_radius"], A1["s_data"] = table.arrays("f64")
+        self = cls.__new__(cls)
+        if not torch.cuda.is_available():
+            raise _lib.B2BError("no CUDA device: the batched step has no CPU fallback")
+        self.real, self.caps = real, caps
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.n_worlds, self.n_shapes, self.inv_dt0 = int(n), int(A1["s_meta"].shape[0]), 0.0
+        self.t = {}
+        for name, scope, tail, kind in schema.FIELDS:
+            host = np.ascontiguousarray(A1[name])
+            if scope == "S":
+                self.t[name] = self._to_device(host.astype(schema.np_dtype(kind, real), copy=False))
+                continue
+            one = self._to_device(host)                      # fp64 / ints, one world
+            full = one.expand((n,) + tuple(one.shape[1:]))
+            if name in ("b_xf", "b_pos") and jitter != 0.0:
+                full = full.clone()                           # jittered in fp64 below, cast after
+                self.t[name] = full
+            else:
+                want = _TORCH_DTYPES[np.dtype(schema.np_dtype(kind, real))]
+                self.t[name] = full.to(want).contiguous() if full.dtype != want else full.contiguous()
+        if jitter != 0.0:
+            nb = caps.nb
+            widx = torch.arange(world_offset, world_offset + n, device=self.device, dtype=torch.int64).view(n, 1, 1)
+            k = torch.arange(2 * nb, device=self.device, dtype=torch.int64).view(1, nb, 2)
+            u = scenes.u01_torch(config, widx, k)
+            d = jitter * (2.0 * u - 1.0)
+            dyn = ((self.t["b_flags"] & schema.BODY_TYPE_MASK) == 1).unsqueeze(-1)
+            d = torch.where(dyn & (widx != 0), d, torch.zeros_like(d))
+            xf, pos, mass = self.t["b_xf"], self.t["b_pos"], self.t["b_mass"].to(torch.float64)
+            xf[..., 0:2] += d
+            # sweep.c = xf * local_center in the reference's operand order (body.py:95)
+            lcx, lcy = mass[..., 2], mass[..., 3]
+            pos[..., 0] = xf[..., 0] + xf[..., 2] * lcx + (-xf[..., 3]) * lcy
+            pos[..., 1] = xf[..., 1] + xf[..., 3] * lcx + xf[..., 2] * lcy
+            want = torch.float64 if real == "f64" else torch.float32
+            self.t["b_xf"] = xf.to(want).contiguous()
+            self.t["b_pos"] = pos.to(want).contiguous()
+            self.t["b_pos0"] = self.t["b_pos"].clone()
+            self.t["b_pos0"][..., 3] = 0
+        self._ctx = ctypes.c_void_p()
+        c = _lib.Caps()
+        c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = self.n_worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
+        c.n_shapes = self.n_shapes
+        c.real_bytes = 8 if real == "f64" else 4
+        c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c.threads, c.ctas_per_sm = kw.get("threads", 0), kw.get("ctas_per_sm", 0)
+        self._caps_struct = c
+        _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
+        self._bind()
+        if jitter != 0.0:
+            self.init_proxies()
+        return self
+
+    def _to_device(self, host):
+        torch = _torch()
+        if host.dtype == np.uint32:
+            host = host.view(np.int32)
+        return torch.from_numpy(np.ascontiguousarray(host)).to(self.device)
+
+    def _bind(self):
+        b = _lib.Buffers()
+        for name in schema.FIELD_NAMES:
+            t = self.t[name]
+            assert t.is_contiguous(), name
+            setattr(b, name, t.data_ptr())
+        self._buffers = b
+        _lib.check(_lib.lib().b2b_bind(self._ctx, ctypes.byref(b)), "b2b_bind")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                _lib.lib().b2b_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # -- stepping ---------------------------------------------------------------------------
+    def _stream(self):
+        torch = _torch()
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def init_proxies(self):
+        _lib.check(_lib.lib().b2b_init_proxies(self._ctx, self._stream()), "b2b_init_proxies")
+
+    def step(self, dt, vel_iters, pos_iters, n_steps=1):
+        """World.step for every world, `n_steps` times (asynchronous on the current stream)."""
+        _lib.check(_lib.lib().b2b_step(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters),
+                                       int(n_steps), 0, self._stream()), "b2b_step")
+        if dt > 0.0 and n_steps > 0:
+            self.inv_dt0 = 1.0 / dt
+
+    def step_host(self, h_force_torque, h_state_out, dt, vel_iters, pos_iters, n_steps=1):
+        """The end-to-end call: pinned host forces in, pinned host body state out, synchronous."""
+        fin = ctypes.c_void_p(h_force_torque.data_ptr()) if h_force_torque is not None else None
+        fout = ctypes.c_void_p(h_state_out.data_ptr()) if h_state_out is not None else None
+        _lib.check(_lib.lib().b2b_step_host(self._ctx, fin, fout, float(dt), float(self.inv_dt0), int(vel_iters),
+                                            int(pos_iters), int(n_steps), 0, self._stream()), "b2b_step_host")
+        if dt > 0.0 and n_steps > 0:
+            self.inv_dt0 = 1.0 / dt
+
+    def status(self, raise_on_overflow=True):
+        out = ctypes.c_uint32(0)
+        rc = _lib.lib().b2b_status(self._ctx, ctypes.byref(out), self._stream())
+        _lib.check(rc, "b2b_status", allow_overflow=not raise_on_overflow)
+        return int(out.value)
+
+    def checksum(self):
+        """[n_worlds, 4] float64 tensor: state hash bits, energy, n_contacts, n_awake (device)."""
+        torch = _torch()
+        out = torch.empty((self.n_worlds, 4), dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().b2b_checksum(self._ctx, ctypes.c_void_p(out.data_ptr()), self._stream()), "b2b_checksum")
+        return out
+
+    def info(self):
+        g, t, s, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        _lib.check(_lib.lib().b2b_info(self._ctx, ctypes.byref(g), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n)),
+                   "b2b_info")
+        return {"grid": g.value, "threads": t.value, "smem_bytes": s.value, "launches": n.value}
+
+    def collide_pairs(self, shape_a, shape_b, xf_a, xf_b):
+        """Test hook: narrowphase on explicit pairs -> (mtype, mf, pts, id) numpy arrays."""
+        torch = _torch()
+        rd = torch.float64 if self.real == "f64" else torch.float32
+        n = len(shape_a)
+        sa = torch.as_tensor(np.asarray(shape_a, np.int32), device=self.device)
+        sb = torch.as_tensor(np.asarray(shape_b, np.int32), device=self.device)
+        xa = torch.as_tensor(np.asarray(xf_a, np.float64), device=self.device).to(rd).contiguous()
+        xb = torch.as_tensor(np.asarray(xf_b, np.float64), device=self.device).to(rd).contiguous()
+        mtype = torch.zeros(n, dtype=torch.int32, device=self.device)
+        mf = torch.zeros((n, 4), dtype=rd, device=self.device)
+        pts = torch.zeros((n, 4), dtype=rd, device=self.device)
+        ids = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().b2b_collide_pairs(self._ctx, n, p(sa), p(sb), p(xa), p(xb), p(mtype), p(mf), p(pts), p(ids),
+                                                self._stream()), "b2b_collide_pairs")
+        torch.cuda.synchronize(self.device)
+        return mtype.cpu().numpy(), mf.cpu().numpy(), pts.cpu().numpy(), ids.cpu().numpy().view(np.uint32)
+
+    # -- transfers --------------------------------------------------------------------------
+    def download(self, names=None, worlds=None):
+        """Host numpy copies (uint32 fields restored) of the named fields, optionally for a slice of worlds."""
+        _torch().cuda.synchronize(self.device)
+        out = {}
+        for name, scope, tail, kind in schema.FIELDS:
+            if names is not None and name not in names:
+                continue
+            t = self.t[name]
+            if worlds is not None and scope != "S":
+                t = t[worlds]
+            a = t.cpu().numpy()
+            if kind == "u32":
+                a = a.view(np.uint32)
+            out[name] = a
+        return out
+
+    def upload(self, arrays, worlds=None):
+        """Overwrite device fields from host arrays (teacher forcing / settled starts)."""
+        torch = _torch()
+        for name, a in arrays.items():
+            kind = {f[0]: f[3] for f in schema.FIELDS}[name]
+            scope = {f[0]: f[1] for f in schema.FIELDS}[name]
+            host = np.ascontiguousarray(a).astype(schema.np_dtype(kind, self.real), copy=False)
+            if host.dtype == np.uint32:
+                host = host.view(np.int32)
+            src = torch.from_numpy(host).to(self.device)
+            if worlds is not None and scope != "S":
+                self.t[name][worlds].copy_(src)
+            else:
+                self.t[name].copy_(src)
+
+    # -- single-world facade support ----------------------------------------------------------
+    def upload_bodies_from_world(self, world, w=0):
+        A = schema.alloc(self.caps, 1, 1, "f64")
+        table = schema.ShapeTable()
+        schema.pack_world(world, A, 0, table)
+        names = ["b_xf", "b_pos", "b_vel", "b_force", "b_flags", "w_gravity"]
+        self.upload({k: A[k] for k in names}, worlds=slice(w, w + 1))
+
+    def download_into_world(self, world, w=0):
+        from .common import Vec2
+        D = self.download(["b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island"], worlds=slice(w, w + 1))
+        for i, b in enumerate(world.bodies):
+            xf = D["b_xf"][0, i]
+            b._xf = (float(xf[0]), float(xf[1]), float(xf[2]), float(xf[3]))
+            p, v, p0 = D["b_pos"][0, i], D["b_vel"][0, i], D["b_pos0"][0, i]
+            b._c = Vec2(p[0], p[1]); b._a = float(p[2]); b._sleep_time = float(p[3])
+            b._c0 = Vec2(p0[0], p0[1]); b._a0 = float(p0[2])
+            b._linear_velocity = Vec2(v[0], v[1]); b._angular_velocity = float(v[2]); b._torque = float(v[3])
+            b._force = Vec2(*D["b_force"][0, i])
+            b._awake = bool(int(D["b_flags"][0, i]) & schema.BODY_AWAKE)
+            isl = int(D["b_island"][0, i])
+            b._island_index = isl if isl >= 0 else b._island_index
+
+    def contact_views(self, world, w=0):
+        from .world import ContactView
+        from .common import Vec2
+        D = self.download(["w_count", "c_fix", "c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp"],
+                          worlds=slice(w, w + 1))
+        fixtures = [f for b in world.bodies for f in b.fixtures]
+        out = []
+        for k in range(int(D["w_count"][0, 2])):
+            c = ContactView()
+            c.fixture_a, c.fixture_b = fixtures[int(D["c_fix"][0, k, 0])], fixtures[int(D["c_fix"][0, k, 1])]
+            fl = int(D["c_flags"][0, k])
+            c.touching, c.enabled = bool(fl & schema.CONTACT_TOUCHING), bool(fl & schema.CONTACT_ENABLED)
+            c.friction, c.restitution = float(D["c_mat"][0, k, 0]), float(D["c_mat"][0, k, 1])
+            mt = int(D["c_mtype"][0, k])
+            c.manifold_type, c.point_count = mt & 0xff, (mt >> 8) & 0xff
+            mf, pts, imp = D["c_mf"][0, k], D["c_pts"][0, k], D["c_imp"][0, k]
+            c.local_normal, c.local_point = Vec2(mf[0], mf[1]), Vec2(mf[2], mf[3])
+            c.points = [(Vec2(pts[2 * j], pts[2 * j + 1]), float(imp[2 * j]), float(imp[2 * j + 1]))
+                        for j in range(c.point_count)]
+            out.append(c)
+        return out

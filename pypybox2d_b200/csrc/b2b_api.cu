@@ -1,0 +1,241 @@
+// b2b_api.cu -- the C-ABI of libb2b.so (include/b2b.h): context, buffer binding, launches.
+// No physics here; the kernels live in b2b_f32.cu / b2b_f64.cu.  No CPU fallback exists: every entry point
+// that computes anything launches a CUDA kernel or fails with B2B_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/b2b.h"
+#include "b2b_launch.h"
+
+using namespace b2b;
+
+struct b2b_ctx {
+    b2b_caps caps;
+    caps_t c;
+    bool f64;
+    int n_sm;
+    launch_plan plan;
+    unsigned char* scratch;
+    uint32_t* d_status;
+    void* stage_in;       // [n_worlds][nb][3] reals
+    void* stage_out;      // [n_worlds][nb][6] reals
+    const void* fields[B2B_NFIELDS];
+    bool bound;
+    long long launches;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr, what)                                              \
+    do {                                                                  \
+        cudaError_t e_ = (expr);                                          \
+        if (e_ != cudaSuccess) return fail(B2B_ERR_CUDA, what, e_);       \
+    } while (0)
+
+static bool caps_ok(const b2b_caps* k)
+{
+    return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
+           (k->real_bytes == 4 || k->real_bytes == 8) && k->threads >= 0 && k->threads <= 256 && (k->threads % 32) == 0;
+}
+
+static caps_t to_caps(const b2b_caps* k)
+{
+    caps_t c;
+    c.n_worlds = k->n_worlds; c.nb = k->nb; c.nf = k->nf; c.nc = k->nc; c.npair = k->npair; c.nl = k->nl; c.n_shapes = k->n_shapes;
+    return c;
+}
+
+extern "C" const char* b2b_last_error(void) { return g_err.c_str(); }
+extern "C" const char* b2b_version(void) { return "b2b 0.1 (sm_100a)"; }
+extern "C" const char* b2b_field_names(void)
+{
+    return "w_count,w_flags,w_status,w_gravity,w_island,"
+           "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
+           "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
+           "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
+           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data";
+}
+
+extern "C" size_t b2b_scratch_bytes(const b2b_caps* caps)
+{
+    if (!caps_ok(caps)) return 0;
+    return scratch_plan(to_caps(caps), caps->real_bytes).total;
+}
+
+extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
+{
+    if (!out) return fail(B2B_ERR_ARG, "b2b_create: out is NULL");
+    *out = nullptr;
+    if (!caps_ok(caps)) return fail(B2B_ERR_ARG, "b2b_create: bad capacities");
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev), "cudaGetDeviceCount (is a CUDA device visible?)");
+    if (caps->device < 0 || caps->device >= n_dev) return fail(B2B_ERR_ARG, "b2b_create: no such device");
+    CUDA_TRY(cudaSetDevice(caps->device), "cudaSetDevice");
+    b2b_ctx* x = new b2b_ctx();
+    memset(x, 0, sizeof(*x));
+    x->caps = *caps;
+    x->c = to_caps(caps);
+    x->f64 = caps->real_bytes == 8;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, caps->device);
+    if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaGetDeviceProperties", e); }
+    x->n_sm = prop.multiProcessorCount;
+    const int threads = caps->threads > 0 ? caps->threads : 64;
+    int rc = x->f64 ? plan_f64(x->c, threads, caps->ctas_per_sm, x->n_sm, &x->plan)
+                    : plan_f32(x->c, threads, caps->ctas_per_sm, x->n_sm, &x->plan);
+    if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
+    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total * (size_t)x->plan.grid);
+    if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
+    e = cudaMalloc((void**)&x->d_status, sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(status)", e); }
+    *out = x;
+    return B2B_OK;
+}
+
+extern "C" void b2b_destroy(b2b_ctx* x)
+{
+    if (!x) return;
+    cudaSetDevice(x->caps.device);
+    if (x->scratch) cudaFree(x->scratch);
+    if (x->d_status) cudaFree(x->d_status);
+    if (x->stage_in) cudaFree(x->stage_in);
+    if (x->stage_out) cudaFree(x->stage_out);
+    delete x;
+}
+
+extern "C" int b2b_bind(b2b_ctx* x, const b2b_buffers* buffers)
+{
+    if (!x || !buffers) return fail(B2B_ERR_ARG, "b2b_bind: NULL argument");
+    static_assert(sizeof(b2b_buffers) == sizeof(void*) * B2B_NFIELDS, "b2b_buffers layout");
+    memcpy(x->fields, buffers, sizeof(b2b_buffers));
+    for (int i = 0; i < B2B_NFIELDS; ++i)
+        if (!x->fields[i]) return fail(B2B_ERR_ARG, "b2b_bind: a buffer pointer is NULL");
+    x->bound = true;
+    return B2B_OK;
+}
+
+static int check_launch(b2b_ctx* x, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2B_ERR_CUDA, what, e);
+    ++x->launches;
+    return B2B_OK;
+}
+
+extern "C" int b2b_init_proxies(b2b_ctx* x, void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_init_proxies: no buffers bound");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_init_proxies_f64(x->fields, x->c, (cudaStream_t)stream);
+    else launch_init_proxies_f32(x->fields, x->c, (cudaStream_t)stream);
+    return check_launch(x, "init_proxies kernel");
+}
+
+static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags)
+{
+    step_params sp;
+    sp.dt = dt;
+    sp.dt_ratio_first = inv_dt0 * dt;                              // world.py:328
+    sp.dt_ratio_rest = (dt > 0.0) ? (1.0 / dt) * dt : 0.0;         // _inv_dt0 = inv_dt after the first step (world.py:348-349)
+    sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = flags;
+    return sp;
+}
+
+extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags,
+                        void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_step: no buffers bound");
+    if (vel_iters < 0 || pos_iters < 0 || n_steps < 0 || !(dt >= 0.0)) return fail(B2B_ERR_ARG, "b2b_step: bad argument");
+    if (n_steps == 0) return B2B_OK;
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, n_steps, flags);
+    if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->scratch, sp, (cudaStream_t)stream);
+    else launch_step_f32(x->fields, x->c, x->plan, x->scratch, sp, (cudaStream_t)stream);
+    return check_launch(x, "step kernel");
+}
+
+extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_state_out, double dt, double inv_dt0,
+                             int vel_iters, int pos_iters, int n_steps, uint32_t flags, void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_step_host: no buffers bound");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rb = (size_t)x->caps.real_bytes, n = (size_t)x->c.n_worlds * x->c.nb;
+    if (h_force_torque) {
+        if (!x->stage_in) CUDA_TRY(cudaMalloc(&x->stage_in, n * 3 * rb), "cudaMalloc(stage_in)");
+        CUDA_TRY(cudaMemcpyAsync(x->stage_in, h_force_torque, n * 3 * rb, cudaMemcpyHostToDevice, st), "H2D forces");
+        if (x->f64) launch_scatter_forces_f64(x->fields, x->c, x->stage_in, st);
+        else launch_scatter_forces_f32(x->fields, x->c, x->stage_in, st);
+        int rc = check_launch(x, "scatter_forces kernel");
+        if (rc) return rc;
+    }
+    int rc = b2b_step(x, dt, inv_dt0, vel_iters, pos_iters, n_steps, flags, stream);
+    if (rc) return rc;
+    if (h_state_out) {
+        if (!x->stage_out) CUDA_TRY(cudaMalloc(&x->stage_out, n * 6 * rb), "cudaMalloc(stage_out)");
+        if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, st);
+        else launch_gather_state_f32(x->fields, x->c, x->stage_out, st);
+        rc = check_launch(x, "gather_state kernel");
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_state_out, x->stage_out, n * 6 * rb, cudaMemcpyDeviceToHost, st), "D2H state");
+    }
+    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return B2B_OK;
+}
+
+extern "C" int b2b_collide_pairs(b2b_ctx* x, int n, const void* d_shape_a, const void* d_shape_b, const void* d_xf_a,
+                                 const void* d_xf_b, void* d_mtype, void* d_mf, void* d_pts, void* d_id, void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_collide_pairs: no buffers bound");
+    if (n <= 0) return B2B_OK;
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_collide_pairs_f64(x->fields, n, d_shape_a, d_shape_b, d_xf_a, d_xf_b, d_mtype, d_mf, d_pts, d_id, (cudaStream_t)stream);
+    else launch_collide_pairs_f32(x->fields, n, d_shape_a, d_shape_b, d_xf_a, d_xf_b, d_mtype, d_mf, d_pts, d_id, (cudaStream_t)stream);
+    return check_launch(x, "collide_pairs kernel");
+}
+
+extern "C" int b2b_status(b2b_ctx* x, uint32_t* host_out, void* stream)
+{
+    if (!x || !x->bound || !host_out) return fail(B2B_ERR_UNBOUND, "b2b_status: no buffers bound");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(x->d_status, 0, sizeof(uint32_t), st), "memset status");
+    if (x->f64) launch_status_f64(x->fields, x->c, x->d_status, st);
+    else launch_status_f32(x->fields, x->c, x->d_status, st);
+    int rc = check_launch(x, "status kernel");
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(host_out, x->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H status");
+    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return (*host_out) ? fail(B2B_ERR_OVERFLOW, "a world overflowed a capacity (contacts / pairs / island list)") : B2B_OK;
+}
+
+extern "C" int b2b_checksum(b2b_ctx* x, void* d_out, void* stream)
+{
+    if (!x || !x->bound || !d_out) return fail(B2B_ERR_UNBOUND, "b2b_checksum: no buffers bound");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_checksum_f64(x->fields, x->c, (double*)d_out, (cudaStream_t)stream);
+    else launch_checksum_f32(x->fields, x->c, (double*)d_out, (cudaStream_t)stream);
+    return check_launch(x, "checksum kernel");
+}
+
+extern "C" int b2b_info(b2b_ctx* x, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches)
+{
+    if (!x) return fail(B2B_ERR_ARG, "b2b_info: NULL context");
+    if (grid) *grid = x->plan.grid;
+    if (threads) *threads = x->plan.threads;
+    if (smem_bytes) *smem_bytes = (int32_t)x->plan.smem;
+    if (launches) *launches = x->launches;
+    return B2B_OK;
+}

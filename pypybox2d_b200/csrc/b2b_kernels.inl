@@ -1,0 +1,209 @@
+// b2b_kernels.inl -- __global__ entry points and their launchers for ONE scalar type.
+// Included by b2b_f32.cu (B2B_REAL=float, FMA contraction on) and b2b_f64.cu (B2B_REAL=double,
+// compiled with -fmad=false so the parity build rounds like the reference's unfused Python floats).
+// B2B_SUFFIX names the exported launchers (launch_step_f32, ...).
+#include <cuda_runtime.h>
+#include "b2b_step.cuh"
+#include "b2b_launch.h"
+
+namespace b2b {
+
+typedef B2B_REAL real_t;
+
+// K1..K6 fused: one CTA steps one world through all phases, n_steps times, then takes the next world
+// (persistent grid, worlds strided over CTAs).  State lives in the caller's SoA arrays; the per-CTA scratch
+// slab is reused for every world the CTA owns, so it stays L1/L2 resident.
+__global__ void __launch_bounds__(256) B2B_CAT(step_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, scratch_layout L,
+                                                                          unsigned char* scratch, step_params sp)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ world_step<real_t> ws;
+    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
+    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
+        if (threadIdx.x == 0) ws.bind(B, c, w, my_scratch, L, smem);
+        __syncthreads();
+        ws.run(sp);
+        __syncthreads();
+    }
+}
+
+// Fixture._create_proxies + DynamicTree.create_proxy (fixture.py:250-261, dynamictree.py:115-134)
+__global__ void __launch_bounds__(256) B2B_CAT(init_proxies_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c)
+{
+    const long long total = (long long)c.n_worlds * c.nf;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i / c.nf), f = (int)(i % c.nf);
+        const int nf = B.w_count[4 * (size_t)w + 1];
+        if (f == 0) B.w_flags[w] |= WORLD_NEW_FIXTURE;
+        if (f >= nf) continue;
+        const size_t of = (size_t)w * c.nf + f;
+        const int b = B.f_body[of];
+        const xform<real_t> xf = xf_load<real_t>(B.b_xf + 4 * ((size_t)w * c.nb + b));
+        const shape_view<real_t> s = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, B.f_shape[of]);
+        real_t a[4];
+        shape_aabb(s, xf, a);
+        real_t* tight = B.f_tight + 4 * of; real_t* fat = B.f_fat + 4 * of;
+        const real_t ext = K<real_t>::aabb_extension;
+        tight[0] = a[0]; tight[1] = a[1]; tight[2] = a[2]; tight[3] = a[3];
+        fat[0] = a[0] - ext; fat[1] = a[1] - ext; fat[2] = a[2] + ext; fat[3] = a[3] + ext;
+        B.f_moved[of] = 1;
+    }
+}
+
+// narrowphase test hook: one thread per explicit pair, fresh manifold
+__global__ void __launch_bounds__(256) B2B_CAT(collide_pairs_kernel_, B2B_SUFFIX)(
+    batch_ptrs<real_t> B, int n, const int32_t* sa, const int32_t* sb, const real_t* xfa, const real_t* xfb,
+    int32_t* mtype, real_t* mf, real_t* pts, uint32_t* id)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        manifold<real_t> m;
+        m.type = 0; m.count = 0;
+        m.local_normal = m.local_point = m.pt[0] = m.pt[1] = mk<real_t>(real_t(0), real_t(0));
+        m.id[0] = m.id[1] = 0u;
+        const shape_view<real_t> a = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, sa[i]);
+        const shape_view<real_t> b = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, sb[i]);
+        collide_shapes(m, a, xf_load<real_t>(xfa + 4 * (size_t)i), b, xf_load<real_t>(xfb + 4 * (size_t)i));
+        mtype[i] = m.type | (m.count << 8);
+        mf[4 * (size_t)i] = m.local_normal.x; mf[4 * (size_t)i + 1] = m.local_normal.y;
+        mf[4 * (size_t)i + 2] = m.local_point.x; mf[4 * (size_t)i + 3] = m.local_point.y;
+        pts[4 * (size_t)i] = m.pt[0].x; pts[4 * (size_t)i + 1] = m.pt[0].y;
+        pts[4 * (size_t)i + 2] = m.pt[1].x; pts[4 * (size_t)i + 3] = m.pt[1].y;
+        id[2 * (size_t)i] = m.id[0]; id[2 * (size_t)i + 1] = m.id[1];
+    }
+}
+
+// host-driven step: scatter staged (fx, fy, torque) into b_force / b_vel[3]
+__global__ void __launch_bounds__(256) B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, const real_t* stage)
+{
+    const long long total = (long long)c.n_worlds * c.nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        B.b_force[2 * i] = stage[3 * i]; B.b_force[2 * i + 1] = stage[3 * i + 1];
+        B.b_vel[4 * i + 3] = stage[3 * i + 2];
+    }
+}
+
+// host-driven step: gather (c.x, c.y, a, v.x, v.y, w) for the device->host copy
+__global__ void __launch_bounds__(256) B2B_CAT(gather_state_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, real_t* stage)
+{
+    const long long total = (long long)c.n_worlds * c.nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        stage[6 * i] = B.b_pos[4 * i]; stage[6 * i + 1] = B.b_pos[4 * i + 1]; stage[6 * i + 2] = B.b_pos[4 * i + 2];
+        stage[6 * i + 3] = B.b_vel[4 * i]; stage[6 * i + 4] = B.b_vel[4 * i + 1]; stage[6 * i + 5] = B.b_vel[4 * i + 2];
+    }
+}
+
+// per-world checksum / energy / counts for the optional end-of-run gather
+__global__ void __launch_bounds__(256) B2B_CAT(checksum_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, double* out)
+{
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < c.n_worlds; w += gridDim.x * blockDim.x) {
+        const int nb = B.w_count[4 * (size_t)w];
+        const double gx = (double)B.w_gravity[2 * (size_t)w], gy = (double)B.w_gravity[2 * (size_t)w + 1];
+        unsigned long long h = 1469598103934665603ull;
+        double energy = 0.0;
+        int awake = 0;
+        for (int b = 0; b < nb; ++b) {
+            const size_t o = (size_t)w * c.nb + b;
+            const real_t* p = B.b_pos + 4 * o; const real_t* v = B.b_vel + 4 * o; const real_t* m = B.b_mass + 4 * o;
+            const double vals[6] = {(double)p[0], (double)p[1], (double)p[2], (double)v[0], (double)v[1], (double)v[2]};
+            for (int k = 0; k < 6; ++k) {
+                unsigned long long bits = (unsigned long long)__double_as_longlong(vals[k]);
+                for (int q = 0; q < 8; ++q) { h ^= (bits >> (8 * q)) & 0xffull; h *= 1099511628211ull; }
+            }
+            const double mass = (m[0] > real_t(0)) ? 1.0 / (double)m[0] : 0.0;
+            const double inertia = (m[1] > real_t(0)) ? 1.0 / (double)m[1] : 0.0;
+            energy += 0.5 * mass * (vals[3] * vals[3] + vals[4] * vals[4]) + 0.5 * inertia * vals[5] * vals[5]
+                      - mass * (gx * vals[0] + gy * vals[1]);
+            awake += (B.b_flags[o] & BODY_AWAKE) ? 1 : 0;
+        }
+        out[4 * (size_t)w] = __longlong_as_double((long long)h);
+        out[4 * (size_t)w + 1] = energy;
+        out[4 * (size_t)w + 2] = (double)B.w_count[4 * (size_t)w + 2];
+        out[4 * (size_t)w + 3] = (double)awake;
+    }
+}
+
+__global__ void B2B_CAT(status_kernel_, B2B_SUFFIX)(const uint32_t* w_status, int n, uint32_t* out)
+{
+    uint32_t acc = 0;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) acc |= w_status[w];
+    if (acc) atomicOr(out, acc);
+}
+
+// ---- launchers (plain C++ so b2b_api.cpp stays free of templates) ----
+static inline batch_ptrs<real_t> as_ptrs(const void* const* fields)
+{
+    batch_ptrs<real_t> B;
+    static_assert(sizeof(B) == sizeof(void*) * B2B_NFIELDS, "batch_ptrs must mirror b2b_buffers");
+    memcpy(&B, fields, sizeof(B));
+    return B;
+}
+
+int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int threads, int ctas_per_sm, int n_sm, launch_plan* out)
+{
+    out->threads = threads;
+    out->smem = smem_plan(c, (int)sizeof(real_t));
+    out->layout = scratch_plan(c, (int)sizeof(real_t));
+    cudaError_t e = cudaFuncSetAttribute(B2B_CAT(step_kernel_, B2B_SUFFIX), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, B2B_CAT(step_kernel_, B2B_SUFFIX), threads, out->smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
+    out->ctas_per_sm = per_sm;
+    long long g = (long long)per_sm * n_sm;
+    if (g > c.n_worlds) g = c.n_worlds;
+    if (g < 1) g = 1;
+    out->grid = (int)g;
+    return 0;
+}
+
+void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, unsigned char* scratch,
+                                       const step_params& sp, cudaStream_t st)
+{
+    B2B_CAT(step_kernel_, B2B_SUFFIX)<<<p.grid, p.threads, p.smem, st>>>(as_ptrs(fields), c, p.layout, scratch, sp);
+}
+
+void B2B_CAT(launch_init_proxies_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, cudaStream_t st)
+{
+    long long total = (long long)c.n_worlds * c.nf;
+    int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (grid < 1) grid = 1;
+    B2B_CAT(init_proxies_kernel_, B2B_SUFFIX)<<<grid, 256, 0, st>>>(as_ptrs(fields), c);
+}
+
+void B2B_CAT(launch_collide_pairs_, B2B_SUFFIX)(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,
+                                                const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st)
+{
+    int grid = (n + 127) / 128;
+    if (grid < 1) grid = 1;
+    B2B_CAT(collide_pairs_kernel_, B2B_SUFFIX)<<<grid, 128, 0, st>>>(as_ptrs(fields), n, (const int32_t*)sa, (const int32_t*)sb,
+                                                                      (const real_t*)xfa, (const real_t*)xfb, (int32_t*)mtype,
+                                                                      (real_t*)mf, (real_t*)pts, (uint32_t*)id);
+}
+
+void B2B_CAT(launch_scatter_forces_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const void* stage, cudaStream_t st)
+{
+    B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)<<<148 * 8, 256, 0, st>>>(as_ptrs(fields), c, (const real_t*)stage);
+}
+
+void B2B_CAT(launch_gather_state_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, void* stage, cudaStream_t st)
+{
+    B2B_CAT(gather_state_kernel_, B2B_SUFFIX)<<<148 * 8, 256, 0, st>>>(as_ptrs(fields), c, (real_t*)stage);
+}
+
+void B2B_CAT(launch_checksum_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, double* out, cudaStream_t st)
+{
+    int grid = (c.n_worlds + 127) / 128;
+    B2B_CAT(checksum_kernel_, B2B_SUFFIX)<<<grid, 128, 0, st>>>(as_ptrs(fields), c, out);
+}
+
+void B2B_CAT(launch_status_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, uint32_t* out, cudaStream_t st)
+{
+    batch_ptrs<real_t> B = as_ptrs(fields);
+    int grid = (c.n_worlds + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    B2B_CAT(status_kernel_, B2B_SUFFIX)<<<grid, 256, 0, st>>>(B.w_status, c.n_worlds, out);
+}
+
+}  // namespace b2b

@@ -1,0 +1,34 @@
+// b2b_launch.h -- declarations shared by the per-precision kernel units and b2b_api.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+#include "b2b_step.cuh"
+
+#define B2B_NFIELDS 36
+#define B2B_CAT_(a, b) a##b
+#define B2B_CAT(a, b) B2B_CAT_(a, b)
+
+namespace b2b {
+
+struct launch_plan {
+    int grid, threads, ctas_per_sm;
+    size_t smem;
+    scratch_layout layout;
+};
+
+#define B2B_DECLARE(S)                                                                                                        \
+    int plan_##S(const caps_t& c, int threads, int ctas_per_sm, int n_sm, launch_plan* out);                                  \
+    void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, unsigned char* scratch,            \
+                         const step_params& sp, cudaStream_t st);                                                             \
+    void launch_init_proxies_##S(const void* const* fields, const caps_t& c, cudaStream_t st);                                \
+    void launch_collide_pairs_##S(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,          \
+                                  const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st);             \
+    void launch_scatter_forces_##S(const void* const* fields, const caps_t& c, const void* stage, cudaStream_t st);           \
+    void launch_gather_state_##S(const void* const* fields, const caps_t& c, void* stage, cudaStream_t st);                   \
+    void launch_checksum_##S(const void* const* fields, const caps_t& c, double* out, cudaStream_t st);                       \
+    void launch_status_##S(const void* const* fields, const caps_t& c, uint32_t* out, cudaStream_t st);
+
+B2B_DECLARE(f32)
+B2B_DECLARE(f64)
+
+}  // namespace b2b

@@ -1,0 +1,1069 @@
+// b2b_step.cuh -- one World.step for one world, written as a CTA "block program".
+//
+// One CTA owns one world at a time (persistent grid, worlds strided over CTAs).  The step is a
+// sequence of phases separated by CTA barriers; inside a phase, work items (contacts, bodies,
+// proxies, pairs) are strided over the CTA's threads, and islands are strided over its warps with
+// the island's constraints strided over the warp's lanes level by level (see solve_islands).
+//
+// Reference call tree being replaced:
+//   World.step                      pypybox2d/world.py:307-354
+//   ContactManager.collide          contact_manager.py:174-223   -> phase_collide        (K1)
+//   Contact.update                  contact.py:210-268           -> contact_update
+//   World._solve (island DFS)       world.py:475-580             -> phase_islands        (K2)
+//   Island.solve / ContactSolver    island.py:65-179, contact.py:375-864 -> solve_islands (K3)
+//   Body._synchronize_fixtures ...  body.py:898-904, fixture.py:287-298, dynamictree.py:152-188 -> phase_sync (K4)
+//   BroadPhase.update_pairs         broadphase.py:83-109         -> phase_pairs          (K5)
+//   ContactManager.find_new_contacts contact_manager.py:102-158  -> phase_pairs          (K6)
+//
+// The parallel-loop macros have a sequential expansion when compiled without CUDA so that
+// tests/hostcheck can run this exact source under g++ for debugging; that build is test-only.
+#pragma once
+#include "b2b_collide.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define B2B_TID ((int)threadIdx.x)
+#define B2B_NT ((int)blockDim.x)
+#define B2B_PFOR(i, n) for (int i = (int)threadIdx.x; i < (n); i += (int)blockDim.x)
+#define B2B_SYNC() __syncthreads()
+#define B2B_IS_T0 (threadIdx.x == 0)
+#define B2B_WARP ((int)(threadIdx.x >> 5))
+#define B2B_NWARPS ((int)(blockDim.x >> 5))
+#define B2B_LANE ((int)(threadIdx.x & 31))
+#define B2B_NLANES 32
+#define B2B_WSYNC() __syncwarp()
+#define B2B_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define B2B_TID 0
+#define B2B_NT 1
+#define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
+#define B2B_SYNC() ((void)0)
+#define B2B_IS_T0 true
+#define B2B_WARP 0
+#define B2B_NWARPS 1
+#define B2B_LANE 0
+#define B2B_NLANES 1
+#define B2B_WSYNC() ((void)0)
+namespace b2b {
+template <class T> inline T host_atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T host_atomic_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T host_atomic_or(T* p, T v) { T o = *p; *p = o | v; return o; }
+}
+#define B2B_ATOMIC_MIN(p, v) b2b::host_atomic_min((p), (v))
+#define B2B_ATOMIC_ADD(p, v) b2b::host_atomic_add((p), (v))
+#define B2B_ATOMIC_OR(p, v) b2b::host_atomic_or((p), (v))
+#endif
+
+namespace b2b {
+
+struct caps_t {
+    int n_worlds, nb, nf, nc, npair, nl, n_shapes;
+};
+
+// Pointers to the batch arrays (world-major).  Field order == schema.FIELDS == b2b_buffers.
+template <class real> struct batch_ptrs {
+    int32_t* w_count; uint32_t* w_flags; uint32_t* w_status; real* w_gravity; int32_t* w_island;
+    real *b_xf, *b_pos, *b_vel, *b_pos0, *b_force, *b_mass, *b_damp; uint32_t* b_flags; int32_t* b_island;
+    int32_t *f_body, *f_shape; real* f_mat; uint32_t* f_filter; real *f_fat, *f_tight; uint8_t* f_moved;
+    int32_t* c_fix; uint32_t* c_flags; real* c_mat; int32_t* c_mtype; real *c_mf, *c_pts, *c_imp; uint32_t* c_id;
+    int32_t *p_pairs, *l_body, *l_contact, *l_start;
+    int32_t* s_meta; real* s_radius; real* s_data;
+};
+
+// number of real-valued SoA rows per constraint slot (see cc_* accessors below)
+enum { CC_REALS = 40 };
+
+// Per-CTA scratch in global memory (stays L1/L2 resident: it is reused for every world this CTA steps).
+struct scratch_layout {
+    // element counts, filled by scratch_plan()
+    size_t off_wake, off_scan, off_adj_start, off_adj_fill, off_adj, off_stack, off_lev, off_lstart, off_sched,
+        off_last, off_isl_nlev, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, total;
+};
+
+B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
+{
+    scratch_layout L;
+    size_t o = 0;
+    const size_t nmax = (size_t)((c.nc > c.nf ? c.nc : c.nf) > c.npair ? (c.nc > c.nf ? c.nc : c.nf) : c.npair) + 2;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+    L.off_wake = take(sizeof(int32_t) * (size_t)c.nb);
+    L.off_scan = take(sizeof(int32_t) * nmax);
+    L.off_adj_start = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_adj_fill = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_adj = take(sizeof(int32_t) * (2 * (size_t)c.nc + 2));
+    L.off_stack = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_lev = take(sizeof(int32_t) * ((size_t)c.nc + 2));
+    L.off_lstart = take(sizeof(int32_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4));
+    L.off_sched = take(sizeof(int32_t) * ((size_t)c.nc + 2));
+    L.off_last = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_isl_nlev = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
+    L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
+    // staging copy of the contact rows for order-preserving compaction: 2+1+1+2 words + 14 reals
+    L.off_tmp_contact = take((sizeof(int32_t) * 6 + (size_t)real_bytes * 14) * ((size_t)c.nc + 2));
+    L.off_pair_keep = take(sizeof(int32_t) * ((size_t)c.npair + 2));
+    L.total = align_up(o, 256);
+    return L;
+}
+
+// shared memory per CTA: body state of the world being solved (indexed by body id)
+B2B_HD size_t smem_plan(const caps_t& c, int real_bytes)
+{
+    return (size_t)real_bytes * 10 * (size_t)c.nb + sizeof(uint32_t) * (size_t)c.nb + 64 * (size_t)real_bytes + 64;
+}
+
+struct step_params {
+    double dt, dt_ratio_first, dt_ratio_rest;
+    int vel_iters, pos_iters, n_steps;
+    uint32_t flags;
+};
+
+// ================================================================================================
+template <class real> struct world_step {
+    typedef vec2<real> V2;
+    typedef xform<real> XF;
+
+    caps_t cap;
+    // this world's rows
+    int32_t* w_count; uint32_t* w_flags; uint32_t* w_status; real* w_gravity; int32_t* w_island;
+    real *b_xf, *b_pos, *b_vel, *b_pos0, *b_force; const real *b_mass, *b_damp; uint32_t* b_flags; int32_t* b_island;
+    const int32_t *f_body, *f_shape; const real* f_mat; const uint32_t* f_filter; real *f_fat, *f_tight; uint8_t* f_moved;
+    int32_t* c_fix; uint32_t* c_flags; real* c_mat; int32_t* c_mtype; real *c_mf, *c_pts, *c_imp; uint32_t* c_id;
+    int32_t *p_pairs, *l_body, *l_contact, *l_start;
+    const int32_t* s_meta; const real* s_radius; const real* s_data;
+    // scratch (global, per CTA)
+    int32_t *wake_at, *scan, *adj_start, *adj_fill, *adj, *stack, *lev, *lstart, *sched, *last, *isl_nlev, *cc_int;
+    real* cc_real;
+    int32_t* tmp_ci; real* tmp_cr;
+    int32_t* pair_keep;
+    // shared memory
+    real *s_vx, *s_vy, *s_w, *s_cx, *s_cy, *s_a, *s_im, *s_ii, *s_lcx, *s_lcy;
+    uint32_t* s_flags;
+    real* s_red;        // [64] reduction slots
+    int32_t* s_ctl;     // [16] control words
+
+    B2B_D void bind(const batch_ptrs<real>& B, const caps_t& c, int w, unsigned char* scratch, const scratch_layout& L,
+                    unsigned char* smem)
+    {
+        cap = c;
+        const size_t W = (size_t)w;
+        w_count = B.w_count + 4 * W; w_flags = B.w_flags + W; w_status = B.w_status + W;
+        w_gravity = B.w_gravity + 2 * W; w_island = B.w_island + 4 * W;
+        const size_t ob = W * c.nb, of = W * c.nf, oc = W * c.nc;
+        b_xf = B.b_xf + 4 * ob; b_pos = B.b_pos + 4 * ob; b_vel = B.b_vel + 4 * ob; b_pos0 = B.b_pos0 + 4 * ob;
+        b_force = B.b_force + 2 * ob; b_mass = B.b_mass + 4 * ob; b_damp = B.b_damp + 4 * ob;
+        b_flags = B.b_flags + ob; b_island = B.b_island + ob;
+        f_body = B.f_body + of; f_shape = B.f_shape + of; f_mat = B.f_mat + 2 * of; f_filter = B.f_filter + 2 * of;
+        f_fat = B.f_fat + 4 * of; f_tight = B.f_tight + 4 * of; f_moved = B.f_moved + of;
+        c_fix = B.c_fix + 2 * oc; c_flags = B.c_flags + oc; c_mat = B.c_mat + 2 * oc; c_mtype = B.c_mtype + oc;
+        c_mf = B.c_mf + 4 * oc; c_pts = B.c_pts + 4 * oc; c_imp = B.c_imp + 4 * oc; c_id = B.c_id + 2 * oc;
+        p_pairs = B.p_pairs + 2 * W * c.npair; l_body = B.l_body + W * c.nl; l_contact = B.l_contact + oc;
+        l_start = B.l_start + 2 * ob;
+        s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
+        wake_at = (int32_t*)(scratch + L.off_wake); scan = (int32_t*)(scratch + L.off_scan);
+        adj_start = (int32_t*)(scratch + L.off_adj_start); adj_fill = (int32_t*)(scratch + L.off_adj_fill);
+        adj = (int32_t*)(scratch + L.off_adj); stack = (int32_t*)(scratch + L.off_stack);
+        lev = (int32_t*)(scratch + L.off_lev); lstart = (int32_t*)(scratch + L.off_lstart);
+        sched = (int32_t*)(scratch + L.off_sched); last = (int32_t*)(scratch + L.off_last);
+        isl_nlev = (int32_t*)(scratch + L.off_isl_nlev); cc_int = (int32_t*)(scratch + L.off_cc_int);
+        cc_real = (real*)(scratch + L.off_cc_real);
+        tmp_cr = (real*)(scratch + L.off_tmp_contact);
+        tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)c.nc + 2));
+        pair_keep = (int32_t*)(scratch + L.off_pair_keep);
+        real* sr = (real*)smem;
+        s_vx = sr; s_vy = sr + c.nb; s_w = sr + 2 * c.nb; s_cx = sr + 3 * c.nb; s_cy = sr + 4 * c.nb; s_a = sr + 5 * c.nb;
+        s_im = sr + 6 * c.nb; s_ii = sr + 7 * c.nb; s_lcx = sr + 8 * c.nb; s_lcy = sr + 9 * c.nb;
+        s_red = sr + 10 * c.nb;
+        s_flags = (uint32_t*)(s_red + 64);
+        s_ctl = (int32_t*)(s_flags + c.nb);
+    }
+
+    B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
+    B2B_D int body_type(int b) const { return (int)(b_flags[b] & BODY_TYPE_MASK); }
+
+    // Exclusive prefix sum over scan[0..n) in place; returns the total in s_ctl[slot] (valid after the call).
+    // v1: one thread; the arrays are a few hundred entries and the call sites are off the critical path.
+    B2B_D void exclusive_scan(int32_t* a, int n, int slot)
+    {
+        B2B_SYNC();
+        if (B2B_IS_T0) {
+            int run = 0;
+            for (int i = 0; i < n; ++i) { int v = a[i]; a[i] = run; run += v; }
+            s_ctl[slot] = run;
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K1
+    // Contact.update (contact.py:210-268): evaluate, carry impulses of matching ids, touching flag.
+    // Returns true when the touching state changed (both bodies must be woken).
+    B2B_D bool contact_update(int ci)
+    {
+        manifold<real> m, old;
+        {
+            const int mt = c_mtype[ci];
+            m.type = mt & 0xff; m.count = (mt >> 8) & 0xff;
+            const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci;
+            m.local_normal = mk<real>(mf[0], mf[1]); m.local_point = mk<real>(mf[2], mf[3]);
+            m.pt[0] = mk<real>(pts[0], pts[1]); m.pt[1] = mk<real>(pts[2], pts[3]);
+            m.id[0] = c_id[2 * ci]; m.id[1] = c_id[2 * ci + 1];
+        }
+        old = m;
+        real* imp = c_imp + 4 * (size_t)ci;
+        const real old_ni0 = imp[0], old_ti0 = imp[1], old_ni1 = imp[2], old_ti1 = imp[3];
+        const uint32_t fl = c_flags[ci];
+        const bool was_touching = (fl & CONTACT_TOUCHING) != 0;
+        const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
+        const int ba = f_body[fa], bb = f_body[fb];
+        const XF xa = xf_load<real>(b_xf + 4 * (size_t)ba), xb = xf_load<real>(b_xf + 4 * (size_t)bb);
+        const shape_view<real> sa = shape_of_fixture(fa), sb = shape_of_fixture(fb);
+        collide_shapes(m, sa, xa, sb, xb);
+        const bool touching = m.count > 0;
+        for (int i = 0; i < m.count; ++i) {
+            real ni = real(0), ti = real(0);
+            if (old.count > 0 && old.id[0] == m.id[i]) { ni = old_ni0; ti = old_ti0; }
+            if (old.count > 1 && old.id[1] == m.id[i]) { ni = old_ni1; ti = old_ti1; }   // last duplicate wins
+            imp[2 * i] = ni; imp[2 * i + 1] = ti;
+        }
+        c_mtype[ci] = m.type | (m.count << 8);
+        {
+            real* mf = c_mf + 4 * (size_t)ci; real* pts = c_pts + 4 * (size_t)ci;
+            mf[0] = m.local_normal.x; mf[1] = m.local_normal.y; mf[2] = m.local_point.x; mf[3] = m.local_point.y;
+            pts[0] = m.pt[0].x; pts[1] = m.pt[0].y; pts[2] = m.pt[1].x; pts[3] = m.pt[1].y;
+            c_id[2 * ci] = m.id[0]; c_id[2 * ci + 1] = m.id[1];
+        }
+        c_flags[ci] = ((fl | CONTACT_ENABLED) & ~CONTACT_TOUCHING) | (touching ? CONTACT_TOUCHING : 0u);
+        return touching != was_touching;
+    }
+
+    // ContactManager.collide (contact_manager.py:174-223).  The reference walks the contact list in
+    // order and a touching change wakes both bodies, which can activate LATER contacts of the same
+    // step.  wake_at[b] = index of the first contact that wakes body b (-1: awake on entry) makes the
+    // parallel evaluation order-exact: contact c sees body b awake iff wake_at[b] < c.  Iterate to the
+    // fixed point (one extra round only when a sleeping body is woken).
+    B2B_D void phase_collide()
+    {
+        const int nb = w_count[0], nc = w_count[2];
+        const int NEVER = 0x7fffffff;
+        B2B_PFOR(b, nb) wake_at[b] = (b_flags[b] & BODY_AWAKE) ? -1 : NEVER;
+        B2B_PFOR(c, nc) scan[c] = 0;           // 0: pending, 1: keep (processed), 2: destroy
+        if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+        B2B_SYNC();
+        for (;;) {
+            B2B_PFOR(c, nc) {
+                if (scan[c] != 0) continue;
+                const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
+                const int ba = f_body[fa], bb = f_body[fb];
+                const bool act_a = (wake_at[ba] < c) && body_type(ba) != BODY_STATIC;
+                const bool act_b = (wake_at[bb] < c) && body_type(bb) != BODY_STATIC;
+                if (!act_a && !act_b) continue;
+                if (!aabb_overlap<real>(f_fat + 4 * (size_t)fa, f_fat + 4 * (size_t)fb)) {
+                    scan[c] = 2;
+                    s_ctl[1] = 1;              // something to destroy (benign same-value race)
+                    continue;
+                }
+                scan[c] = 1;
+                if (contact_update(c)) {
+                    if (B2B_ATOMIC_MIN(&wake_at[ba], c) == NEVER) s_ctl[0] = 1;
+                    if (B2B_ATOMIC_MIN(&wake_at[bb], c) == NEVER) s_ctl[0] = 1;
+                }
+            }
+            B2B_SYNC();
+            const int again = s_ctl[0];
+            B2B_SYNC();
+            if (!again) break;
+            if (B2B_IS_T0) s_ctl[0] = 0;
+            B2B_SYNC();
+        }
+        // Body.awake = True for bodies woken by a touching change (body.py:800-804)
+        B2B_PFOR(b, nb) {
+            if (!(b_flags[b] & BODY_AWAKE) && wake_at[b] != NEVER) {
+                b_flags[b] |= BODY_AWAKE;
+                b_pos[4 * (size_t)b + 3] = real(0);
+            }
+        }
+        // ContactManager.destroy (contact_manager.py:160-172): order-preserving removal, nobody is woken (A.9 #12)
+        if (s_ctl[1]) {
+            B2B_PFOR(c, nc) scan[c] = (scan[c] == 2) ? 0 : 1;
+            exclusive_scan(scan, nc, 2);
+            const int kept = s_ctl[2];
+            B2B_PFOR(c, nc) {
+                const bool keep = (c + 1 < nc) ? (scan[c + 1] != scan[c]) : (kept != scan[c]);
+                if (!keep) continue;
+                const int d = scan[c];
+                real* tr = tmp_cr + 14 * (size_t)d; int32_t* ti = tmp_ci + 6 * (size_t)d;
+                ti[0] = c_fix[2 * c]; ti[1] = c_fix[2 * c + 1]; ti[2] = (int32_t)c_flags[c]; ti[3] = c_mtype[c];
+                ti[4] = (int32_t)c_id[2 * c]; ti[5] = (int32_t)c_id[2 * c + 1];
+                tr[0] = c_mat[2 * c]; tr[1] = c_mat[2 * c + 1];
+                for (int k = 0; k < 4; ++k) { tr[2 + k] = c_mf[4 * (size_t)c + k]; tr[6 + k] = c_pts[4 * (size_t)c + k]; tr[10 + k] = c_imp[4 * (size_t)c + k]; }
+            }
+            B2B_SYNC();
+            B2B_PFOR(d, kept) {
+                const real* tr = tmp_cr + 14 * (size_t)d; const int32_t* ti = tmp_ci + 6 * (size_t)d;
+                c_fix[2 * d] = ti[0]; c_fix[2 * d + 1] = ti[1]; c_flags[d] = (uint32_t)ti[2]; c_mtype[d] = ti[3];
+                c_id[2 * d] = (uint32_t)ti[4]; c_id[2 * d + 1] = (uint32_t)ti[5];
+                c_mat[2 * d] = tr[0]; c_mat[2 * d + 1] = tr[1];
+                for (int k = 0; k < 4; ++k) { c_mf[4 * (size_t)d + k] = tr[2 + k]; c_pts[4 * (size_t)d + k] = tr[6 + k]; c_imp[4 * (size_t)d + k] = tr[10 + k]; }
+            }
+            if (B2B_IS_T0) w_count[2] = kept;
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K2
+    // Body._contacts of every non-static body as CSR rows in contact-creation order
+    // (contact_manager.py:157-158 appends, :170-172 removes in place).  Static bodies never expand in the
+    // island DFS (world.py:524-525), so their rows are not built.
+    B2B_D void build_adjacency()
+    {
+        const int nb = w_count[0], nc = w_count[2];
+        B2B_PFOR(b, nb + 1) adj_start[b] = 0;
+        B2B_SYNC();
+        B2B_PFOR(c, nc) {
+            const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+            if (body_type(ba) != BODY_STATIC) B2B_ATOMIC_ADD(&adj_start[ba], 1);
+            if (body_type(bb) != BODY_STATIC) B2B_ATOMIC_ADD(&adj_start[bb], 1);
+        }
+        exclusive_scan(adj_start, nb + 1, 3);
+        B2B_PFOR(b, nb) adj_fill[b] = adj_start[b];
+        B2B_SYNC();
+        B2B_PFOR(c, nc) {
+            const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+            if (body_type(ba) != BODY_STATIC) adj[B2B_ATOMIC_ADD(&adj_fill[ba], 1)] = c;
+            if (body_type(bb) != BODY_STATIC) adj[B2B_ATOMIC_ADD(&adj_fill[bb], 1)] = c;
+        }
+        B2B_SYNC();
+        // restore creation order inside each row (rows are short: <= contacts per body)
+        B2B_PFOR(b, nb) {
+            const int s = adj_start[b], e = adj_start[b + 1];
+            for (int i = s + 1; i < e; ++i) {
+                const int v = adj[i];
+                int j = i - 1;
+                while (j >= s && adj[j] > v) { adj[j + 1] = adj[j]; --j; }
+                adj[j + 1] = v;
+            }
+        }
+        B2B_SYNC();
+    }
+
+    B2B_D void wake_body(int b)
+    {
+        const uint32_t f = b_flags[b];
+        if (!(f & BODY_AWAKE)) { b_pos[4 * (size_t)b + 3] = real(0); b_flags[b] = f | BODY_AWAKE; }
+    }
+
+    // World._solve island construction (world.py:484-580): seeds in body order, LIFO DFS over
+    // Body._contacts in creation order, statics join but do not propagate.  Strictly sequential per
+    // world; the lists it emits (l_body / l_contact / l_start) are graded integer outputs.
+    B2B_D void phase_islands()
+    {
+        const int nb = w_count[0], nc = w_count[2];
+        B2B_PFOR(b, nb) { b_flags[b] &= ~BODY_ISLAND; b_island[b] = -1; }
+        B2B_PFOR(c, nc) c_flags[c] &= ~CONTACT_ISLAND;
+        B2B_SYNC();
+        if (B2B_IS_T0) {
+            int n_islands = 0, lb = 0, lc = 0;
+            bool overflow = false;
+            for (int seed = 0; seed < nb && !overflow; ++seed) {
+                const uint32_t fl = b_flags[seed];
+                if (fl & BODY_ISLAND) continue;
+                if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
+                if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                const int body_start = lb, contact_start = lc;
+                int sp = 0;
+                stack[sp++] = seed;
+                b_flags[seed] = fl | BODY_ISLAND;
+                while (sp > 0) {
+                    const int b = stack[--sp];
+                    if (lb >= cap.nl) { overflow = true; break; }
+                    b_island[b] = lb - body_start;
+                    l_body[lb++] = b;
+                    wake_body(b);
+                    if (body_type(b) == BODY_STATIC) continue;
+                    const int first = lc;
+                    for (int k = adj_start[b]; k < adj_start[b + 1]; ++k) {
+                        const int c = adj[k];
+                        const uint32_t cf = c_flags[c];
+                        if ((cf & CONTACT_ISLAND) || !(cf & CONTACT_ENABLED) || !(cf & CONTACT_TOUCHING)) continue;
+                        l_contact[lc++] = c;
+                    }
+                    for (int k = first; k < lc; ++k) {
+                        const int c = l_contact[k];
+                        c_flags[c] |= CONTACT_ISLAND;
+                        const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                        const int other = (b == ba) ? bb : ba;
+                        if (b_flags[other] & BODY_ISLAND) continue;
+                        stack[sp++] = other;
+                        b_flags[other] |= BODY_ISLAND;
+                    }
+                }
+                if (overflow) break;
+                l_start[2 * n_islands] = body_start; l_start[2 * n_islands + 1] = contact_start;
+                // statics may join other islands (world.py:577-580)
+                for (int k = body_start; k < lb; ++k)
+                    if (body_type(l_body[k]) == BODY_STATIC) b_flags[l_body[k]] &= ~BODY_ISLAND;
+                ++n_islands;
+            }
+            if (overflow) w_status[0] |= STATUS_ISLAND_OVERFLOW;
+            w_island[0] = n_islands; w_island[1] = lb; w_island[2] = lc; w_island[3] = 0;
+            s_ctl[4] = n_islands; s_ctl[5] = lb; s_ctl[6] = lc;
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K3
+    // constraint slot accessors: SoA rows of length cap.nc, slot = position in the level schedule
+    enum {
+        R_NX = 0, R_NY, R_FRICTION,
+        R_RAX0, R_RAY0, R_RBX0, R_RBY0, R_NMASS0, R_TMASS0, R_BIAS0, R_NI0, R_TI0,
+        R_RAX1, R_RAY1, R_RBX1, R_RBY1, R_NMASS1, R_TMASS1, R_BIAS1, R_NI1, R_TI1,
+        R_K11, R_K12, R_K22, R_NM11, R_NM12, R_NM22,
+        R_LNX, R_LNY, R_LPX, R_LPY, R_P0X, R_P0Y, R_P1X, R_P1Y, R_RADA, R_RADB,
+        R_COUNT
+    };
+    enum { I_BODY_A = 0, I_BODY_B, I_INFO, I_CONTACT };   // info = type | n_pos << 8 | n_vel << 16
+    B2B_D real& R(int f, int slot) { return cc_real[(size_t)f * cap.nc + slot]; }
+    B2B_D int32_t& I(int f, int slot) { return cc_int[(size_t)f * cap.nc + slot]; }
+
+    B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
+    {
+        return vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+    }
+
+    // ContactSolver.__init__ + initialize_velocity_constraints for one slot
+    // (contact.py:376-496, contact_util.py:195-245 WorldManifold, :253-277 VelocityConstraintPoint)
+    B2B_D void constraint_init(int slot, int ci, real dt_ratio, bool warm)
+    {
+        const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
+        const int ba = f_body[fa], bb = f_body[fb];
+        const int mt = c_mtype[ci];
+        const int type = mt & 0xff, count = (mt >> 8) & 0xff;
+        const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci; const real* imp = c_imp + 4 * (size_t)ci;
+        const V2 local_normal = mk<real>(mf[0], mf[1]), local_point = mk<real>(mf[2], mf[3]);
+        V2 lp[2]; lp[0] = mk<real>(pts[0], pts[1]); lp[1] = mk<real>(pts[2], pts[3]);
+        const real rad_a = s_radius[f_shape[fa]], rad_b = s_radius[f_shape[fb]];
+        const real friction = c_mat[2 * ci], restitution = c_mat[2 * ci + 1];
+        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
+        const V2 ca = mk<real>(s_cx[ba], s_cy[ba]), cb = mk<real>(s_cx[bb], s_cy[bb]);
+        const V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
+        const real wa = s_w[ba], wb = s_w[bb];
+        const XF xa = xf_from_sweep<real>(ca, s_a[ba], mk<real>(s_lcx[ba], s_lcy[ba]));
+        const XF xb = xf_from_sweep<real>(cb, s_a[bb], mk<real>(s_lcx[bb], s_lcy[bb]));
+
+        // world manifold
+        V2 normal, wp[2];
+        if (type == MANIFOLD_CIRCLES) {
+            normal = mk<real>(real(1), real(0));
+            const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, lp[0]);
+            const V2 d = pa - pb;
+            if (dot(d, d) > K<real>::epsilon_sqr) normal = normalize(pb - pa);
+            const V2 c_a = pa + rad_a * normal, c_b = pb - rad_b * normal;
+            wp[0] = real(0.5) * (c_a + c_b);
+            wp[1] = wp[0];
+        } else if (type == MANIFOLD_FACE_A) {
+            normal = rot_mul(xa, local_normal);
+            const V2 plane = xf_mul(xa, local_point);
+            for (int j = 0; j < 2; ++j) {
+                const V2 clip = xf_mul(xb, lp[j]);
+                const V2 c_a = clip + (rad_a - dot(clip - plane, normal)) * normal;
+                const V2 c_b = clip - rad_b * normal;
+                wp[j] = real(0.5) * (c_a + c_b);
+            }
+        } else {
+            normal = rot_mul(xb, local_normal);
+            const V2 plane = xf_mul(xb, local_point);
+            for (int j = 0; j < 2; ++j) {
+                const V2 clip = xf_mul(xa, lp[j]);
+                const V2 c_b = clip + (rad_b - dot(clip - plane, normal)) * normal;
+                const V2 c_a = clip - rad_a * normal;
+                wp[j] = real(0.5) * (c_a + c_b);
+            }
+            normal = -normal;
+        }
+        const V2 tangent = right_perp(normal);
+        int n_vel = count;
+        V2 ra[2], rb[2];
+        for (int j = 0; j < 2; ++j) {
+            const int o = j * 9;
+            if (j >= count) {
+                for (int k = 0; k < 9; ++k) R(R_RAX0 + o + k, slot) = real(0);
+                ra[j] = rb[j] = mk<real>(real(0), real(0));
+                continue;
+            }
+            ra[j] = wp[j] - ca; rb[j] = wp[j] - cb;
+            const real rn_a = cross(ra[j], normal), rn_b = cross(rb[j], normal);
+            const real k_normal = ma + mb + ia * (rn_a * rn_a) + ib * (rn_b * rn_b);
+            const real rt_a = cross(ra[j], tangent), rt_b = cross(rb[j], tangent);
+            const real k_tangent = ma + mb + ia * (rt_a * rt_a) + ib * (rt_b * rt_b);
+            real bias = real(0);
+            const real v_rel = dot(normal, rel_velocity(vb, wb, rb[j], va, wa, ra[j]));
+            if (v_rel < -K<real>::velocity_threshold) bias = -restitution * v_rel;
+            R(R_RAX0 + o, slot) = ra[j].x; R(R_RAY0 + o, slot) = ra[j].y;
+            R(R_RBX0 + o, slot) = rb[j].x; R(R_RBY0 + o, slot) = rb[j].y;
+            R(R_NMASS0 + o, slot) = (k_normal > real(0)) ? real(1) / k_normal : real(0);
+            R(R_TMASS0 + o, slot) = (k_tangent > real(0)) ? real(1) / k_tangent : real(0);
+            R(R_BIAS0 + o, slot) = bias;
+            R(R_NI0 + o, slot) = warm ? dt_ratio * imp[2 * j] : imp[2 * j];
+            R(R_TI0 + o, slot) = warm ? dt_ratio * imp[2 * j + 1] : imp[2 * j + 1];
+        }
+        real k11 = real(0), k12 = real(0), k22 = real(0), nm11 = real(0), nm12 = real(0), nm22 = real(0);
+        if (count == 2) {
+            const real rn1a = cross(ra[0], normal), rn1b = cross(rb[0], normal);
+            const real rn2a = cross(ra[1], normal), rn2b = cross(rb[1], normal);
+            k11 = ma + mb + ia * rn1a * rn1a + ib * rn1b * rn1b;
+            k22 = ma + mb + ia * rn2a * rn2a + ib * rn2b * rn2b;
+            k12 = ma + mb + ia * rn1a * rn2a + ib * rn1b * rn2b;
+            if (k11 * k11 < K<real>::max_condition_number * (k11 * k22 - k12 * k12)) {
+                real det = k11 * k22 - k12 * k12;            // Mat22.inverse (common.py:505-519)
+                if (det != real(0)) det = real(1) / det;
+                nm11 = det * k22; nm12 = -det * k12; nm22 = det * k11;
+            } else {
+                n_vel = 1;                                   // redundant point dropped from the velocity rows only
+            }
+        }
+        R(R_NX, slot) = normal.x; R(R_NY, slot) = normal.y; R(R_FRICTION, slot) = friction;
+        R(R_K11, slot) = k11; R(R_K12, slot) = k12; R(R_K22, slot) = k22;
+        R(R_NM11, slot) = nm11; R(R_NM12, slot) = nm12; R(R_NM22, slot) = nm22;
+        R(R_LNX, slot) = local_normal.x; R(R_LNY, slot) = local_normal.y;
+        R(R_LPX, slot) = local_point.x; R(R_LPY, slot) = local_point.y;
+        R(R_P0X, slot) = lp[0].x; R(R_P0Y, slot) = lp[0].y; R(R_P1X, slot) = lp[1].x; R(R_P1Y, slot) = lp[1].y;
+        R(R_RADA, slot) = rad_a; R(R_RADB, slot) = rad_b;
+        I(I_BODY_A, slot) = ba; I(I_BODY_B, slot) = bb;
+        I(I_INFO, slot) = type | (count << 8) | (n_vel << 16);
+        I(I_CONTACT, slot) = ci;
+    }
+
+    B2B_D void store_vel(int b, V2 v, real w)
+    {
+        if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) { s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w; }
+    }
+    B2B_D void store_pos(int b, V2 c, real a)
+    {
+        if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) { s_cx[b] = c.x; s_cy[b] = c.y; s_a[b] = a; }
+    }
+
+    // ContactSolver.warm_start for one slot (contact.py:498-525)
+    B2B_D void constraint_warm_start(int slot)
+    {
+        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
+        const int n_vel = (I(I_INFO, slot) >> 16) & 0xff;
+        const V2 normal = mk<real>(R(R_NX, slot), R(R_NY, slot)), tangent = right_perp(normal);
+        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
+        V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
+        real wa = s_w[ba], wb = s_w[bb];
+        for (int j = 0; j < n_vel; ++j) {
+            const int o = j * 9;
+            const V2 ra = mk<real>(R(R_RAX0 + o, slot), R(R_RAY0 + o, slot)), rb = mk<real>(R(R_RBX0 + o, slot), R(R_RBY0 + o, slot));
+            const V2 p = R(R_NI0 + o, slot) * normal + R(R_TI0 + o, slot) * tangent;
+            wa = wa - ia * cross(ra, p);
+            va = va - ma * p;
+            wb = wb + ib * cross(rb, p);
+            vb = vb + mb * p;
+        }
+        store_vel(ba, va, wa);
+        store_vel(bb, vb, wb);
+    }
+
+    // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
+    B2B_D void constraint_solve_velocity(int slot)
+    {
+        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
+        const int n_vel = (I(I_INFO, slot) >> 16) & 0xff;
+        const V2 normal = mk<real>(R(R_NX, slot), R(R_NY, slot)), tangent = right_perp(normal);
+        const real friction = R(R_FRICTION, slot);
+        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
+        V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
+        real wa = s_w[ba], wb = s_w[bb];
+        V2 ra[2], rb[2];
+        for (int j = 0; j < 2; ++j) {
+            const int o = j * 9;
+            ra[j] = mk<real>(R(R_RAX0 + o, slot), R(R_RAY0 + o, slot));
+            rb[j] = mk<real>(R(R_RBX0 + o, slot), R(R_RBY0 + o, slot));
+        }
+        // friction rows first, point by point
+        for (int j = 0; j < n_vel; ++j) {
+            const int o = j * 9;
+            const V2 dv = rel_velocity(vb, wb, rb[j], va, wa, ra[j]);
+            const real vt = dot(dv, tangent);
+            real lambda = R(R_TMASS0 + o, slot) * (-vt);
+            const real max_friction = friction * R(R_NI0 + o, slot);
+            const real old_imp = R(R_TI0 + o, slot);
+            const real new_imp = clamp_r(old_imp + lambda, -max_friction, max_friction);
+            lambda = new_imp - old_imp;
+            const V2 P = lambda * tangent;
+            va = va - ma * P; wa = wa - ia * cross(ra[j], P);
+            vb = vb + mb * P; wb = wb + ib * cross(rb[j], P);
+            R(R_TI0 + o, slot) = new_imp;
+        }
+        if (n_vel == 1) {
+            const V2 dv = rel_velocity(vb, wb, rb[0], va, wa, ra[0]);
+            const real vn = dot(dv, normal);
+            real lambda = -R(R_NMASS0, slot) * (vn - R(R_BIAS0, slot));
+            const real old_imp = R(R_NI0, slot);
+            const real new_imp = pymax(old_imp + lambda, real(0));
+            lambda = new_imp - old_imp;
+            const V2 P = lambda * normal;
+            va = va - ma * P; wa = wa - ia * cross(ra[0], P);
+            vb = vb + mb * P; wb = wb + ib * cross(rb[0], P);
+            R(R_NI0, slot) = new_imp;
+        } else if (n_vel == 2) {
+            // 2x2 LCP by total enumeration; first feasible case wins (contact.py:598-796)
+            const V2 a = mk<real>(R(R_NI0, slot), R(R_NI1, slot));
+            const V2 dv1 = rel_velocity(vb, wb, rb[0], va, wa, ra[0]);
+            const V2 dv2 = rel_velocity(vb, wb, rb[1], va, wa, ra[1]);
+            const real vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+            const real k11 = R(R_K11, slot), k12 = R(R_K12, slot), k22 = R(R_K22, slot);
+            V2 b = mk<real>(vn1 - R(R_BIAS0, slot), vn2 - R(R_BIAS1, slot));
+            b = b - mk<real>(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
+            const real nm11 = R(R_NM11, slot), nm12 = R(R_NM12, slot), nm22 = R(R_NM22, slot);
+            V2 x = -mk<real>(nm11 * b.x + nm12 * b.y, nm12 * b.x + nm22 * b.y);
+            bool solved = (x.x >= real(0) && x.y >= real(0));
+            if (!solved) {
+                x = mk<real>(-R(R_NMASS0, slot) * b.x, real(0));
+                solved = (x.x >= real(0)) && (k12 * x.x + b.y >= real(0));
+            }
+            if (!solved) {
+                x = mk<real>(real(0), -R(R_NMASS1, slot) * b.y);
+                solved = (x.y >= real(0)) && (k12 * x.y + b.x >= real(0));
+            }
+            if (!solved) {
+                x = mk<real>(real(0), real(0));
+                solved = (b.x >= real(0)) && (b.y >= real(0));
+            }
+            if (solved) {
+                const V2 d = x - a;
+                const V2 p1 = d.x * normal, p2 = d.y * normal;
+                const V2 p12 = p1 + p2;
+                va = va - ma * p12; wa = wa - ia * (cross(ra[0], p1) + cross(ra[1], p2));
+                vb = vb + mb * p12; wb = wb + ib * (cross(rb[0], p1) + cross(rb[1], p2));
+                R(R_NI0, slot) = x.x; R(R_NI1, slot) = x.y;
+            }
+        }
+        store_vel(ba, va, wa);
+        store_vel(bb, vb, wb);
+    }
+
+    // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
+    // returns the smallest separation seen.
+    B2B_D real constraint_solve_position(int slot)
+    {
+        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
+        const int info = I(I_INFO, slot);
+        const int type = info & 0xff, n_pos = (info >> 8) & 0xff;
+        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
+        const V2 lca = mk<real>(s_lcx[ba], s_lcy[ba]), lcb = mk<real>(s_lcx[bb], s_lcy[bb]);
+        const V2 local_normal = mk<real>(R(R_LNX, slot), R(R_LNY, slot)), local_point = mk<real>(R(R_LPX, slot), R(R_LPY, slot));
+        const real rad_a = R(R_RADA, slot), rad_b = R(R_RADB, slot);
+        V2 ca = mk<real>(s_cx[ba], s_cy[ba]), cb = mk<real>(s_cx[bb], s_cy[bb]);
+        real aa = s_a[ba], ab = s_a[bb];
+        real min_sep = real(0);
+        for (int j = 0; j < n_pos; ++j) {
+            const XF xa = xf_from_sweep<real>(ca, aa, lca), xb = xf_from_sweep<real>(cb, ab, lcb);
+            const V2 lpj = (j == 0) ? mk<real>(R(R_P0X, slot), R(R_P0Y, slot)) : mk<real>(R(R_P1X, slot), R(R_P1Y, slot));
+            V2 normal, point;
+            real separation;
+            if (type == MANIFOLD_CIRCLES) {
+                const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, mk<real>(R(R_P0X, slot), R(R_P0Y, slot)));
+                normal = normalize(pb - pa);
+                point = real(0.5) * (pa + pb);
+                separation = dot(pb - pa, normal) - rad_a - rad_b;
+            } else if (type == MANIFOLD_FACE_A) {
+                normal = rot_mul(xa, local_normal);
+                const V2 plane = xf_mul(xa, local_point);
+                const V2 clip = xf_mul(xb, lpj);
+                separation = dot(clip - plane, normal) - rad_a - rad_b;
+                point = clip;
+            } else {
+                normal = rot_mul(xb, local_normal);
+                const V2 plane = xf_mul(xb, local_point);
+                const V2 clip = xf_mul(xa, lpj);
+                separation = dot(clip - plane, normal) - rad_a - rad_b;
+                point = clip;
+                normal = -normal;
+            }
+            const V2 ra = point - ca, rb = point - cb;
+            min_sep = pymin(min_sep, separation);
+            const real C = clamp_r(K<real>::baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
+            const real rn_a = cross(ra, normal), rn_b = cross(rb, normal);
+            const real Keff = ma + mb + (ia * (rn_a * rn_a)) + (ib * (rn_b * rn_b));
+            const real impulse = (Keff > real(0)) ? -C / Keff : real(0);
+            const V2 P = impulse * normal;
+            ca = ca - ma * P; aa = aa - ia * cross(ra, P);
+            cb = cb + mb * P; ab = ab + ib * cross(rb, P);
+        }
+        store_pos(ba, ca, aa);
+        store_pos(bb, cb, ab);
+        return min_sep;
+    }
+
+    // Dependency levels of an island's contact list: level(k) = 1 + max level of an earlier contact that
+    // shares a non-static body.  Contacts of one level touch disjoint non-static bodies, so solving a level's
+    // contacts concurrently gives bit-identical results to the reference's sequential Gauss-Seidel sweep,
+    // and every body still sees its contacts in list order.  A stable counting sort by level gives `sched`;
+    // constraint rows are then laid out in schedule order so a level's rows are contiguous (coalesced).
+    B2B_D void solve_islands(const step_params& sp, real dt, real dt_ratio)
+    {
+        const int nb = w_count[0];
+        const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
+        const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
+        const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
+        // stage every body of the world (islands also read their static members)
+        B2B_PFOR(b, nb) {
+            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
+            s_cx[b] = p[0]; s_cy[b] = p[1]; s_a[b] = p[2];
+            s_vx[b] = v[0]; s_vy[b] = v[1]; s_w[b] = v[2];
+            s_im[b] = m[0]; s_ii[b] = m[1]; s_lcx[b] = m[2]; s_lcy[b] = m[3];
+            s_flags[b] = b_flags[b];
+            last[b] = 0;
+        }
+        B2B_SYNC();
+        const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
+        for (int isl = B2B_WARP; isl < n_islands; isl += B2B_NWARPS) {
+            const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
+            const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
+            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            const int ncon = c1 - c0;
+            // -- integrate velocities (island.py:71-95); statics are left untouched
+            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+                const int b = l_body[i];
+                const uint32_t fl = s_flags[b];
+                if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                real* p0 = b_pos0 + 4 * (size_t)b;
+                p0[0] = s_cx[b]; p0[1] = s_cy[b]; p0[2] = s_a[b];
+                if ((fl & BODY_TYPE_MASK) == BODY_DYNAMIC) {
+                    const real* damp = b_damp + 4 * (size_t)b;
+                    const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
+                    const real torque = b_vel[4 * (size_t)b + 3];
+                    V2 v = mk<real>(s_vx[b], s_vy[b]);
+                    real w = s_w[b];
+                    v = v + dt * (damp[2] * gravity + s_im[b] * force);
+                    w = w + dt * s_ii[b] * torque;
+                    v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
+                    w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
+                    s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w;
+                }
+            }
+            int nlev = 0;
+            int32_t* ls = lstart + c0 + 3 * isl;          // level l (1-based) occupies slots [ls[l], ls[l+1]) + c0
+            if (ncon > 0) {
+                // -- level schedule (lane 0), then constraint rows in schedule order
+                if (B2B_LANE == 0) {
+                    for (int k = 0; k < ncon + 3; ++k) ls[k] = 0;
+                    for (int k = c0; k < c1; ++k) {
+                        const int c = l_contact[k];
+                        const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                        const bool dyn_a = (s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC;
+                        const bool dyn_b = (s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC;
+                        int l = 0;
+                        if (dyn_a) l = last[ba];
+                        if (dyn_b && last[bb] > l) l = last[bb];
+                        ++l;
+                        if (dyn_a) last[ba] = l;
+                        if (dyn_b) last[bb] = l;
+                        lev[k] = l;
+                        ++ls[l + 1];                          // count of level l parked one slot up
+                        if (l > nlev) nlev = l;
+                    }
+                    // ls[l + 1] = count(l)  ->  ls[l] = start(l) for l = 1..nlev+1  (ls[nlev + 1] = ncon)
+                    int run = 0;
+                    for (int l = 1; l <= nlev; ++l) { const int cnt = ls[l + 1]; ls[l] = run; run += cnt; }
+                    ls[nlev + 1] = run;
+                    // stable placement; ls[l] is advanced while filling and restored afterwards
+                    for (int k = c0; k < c1; ++k) { const int l = lev[k]; sched[c0 + ls[l]] = k; ++ls[l]; }
+                    for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
+                    ls[1] = 0;
+                    isl_nlev[isl] = nlev;
+                }
+                B2B_WSYNC();
+                nlev = isl_nlev[isl];
+                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[sched[s]], dt_ratio, warm);
+                B2B_WSYNC();
+                if (warm) {
+                    for (int l = 1; l <= nlev; ++l) {
+                        for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_warm_start(s);
+                        B2B_WSYNC();
+                    }
+                }
+                for (int it = 0; it < sp.vel_iters; ++it) {
+                    for (int l = 1; l <= nlev; ++l) {
+                        for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_solve_velocity(s);
+                        B2B_WSYNC();
+                    }
+                }
+                // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
+                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
+                    const int ci = I(I_CONTACT, s);
+                    const int n_vel = (I(I_INFO, s) >> 16) & 0xff;
+                    real* imp = c_imp + 4 * (size_t)ci;
+                    if (n_vel > 0) { imp[0] = R(R_NI0, s); imp[1] = R(R_TI0, s); }
+                    if (n_vel > 1) { imp[2] = R(R_NI1, s); imp[3] = R(R_TI1, s); }
+                }
+            }
+            B2B_WSYNC();
+            // -- integrate positions (island.py:119-138)
+            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+                const int b = l_body[i];
+                if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                V2 v = mk<real>(s_vx[b], s_vy[b]);
+                real w = s_w[b];
+                const V2 translation = dt * v;
+                if (dot(translation, translation) > K<real>::max_translation_sqr) {
+                    const real ratio = K<real>::max_translation / sqrt_r(translation.x * translation.x + translation.y * translation.y);
+                    v = ratio * v;
+                }
+                const real rotation = dt * w;
+                if (rotation * rotation > K<real>::max_rotation_sqr) {
+                    const real ratio = K<real>::max_rotation / abs_r(rotation);
+                    w = w * ratio;
+                }
+                s_cx[b] = s_cx[b] + dt * v.x; s_cy[b] = s_cy[b] + dt * v.y; s_a[b] = s_a[b] + dt * w;
+                s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w;
+            }
+            B2B_WSYNC();
+            // -- position iterations with early exit (island.py:141-153)
+            bool position_solved = false;
+            int used = 0;
+            for (int it = 0; it < sp.pos_iters; ++it) {
+                real my_min = real(0);
+                ++used;
+                for (int l = 1; l <= nlev; ++l) {
+                    for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES)
+                        my_min = pymin(my_min, constraint_solve_position(s));
+                    B2B_WSYNC();
+                }
+                real all_min = my_min;
+#if defined(__CUDA_ARCH__)
+                for (int o = 16; o > 0; o >>= 1) {
+                    const real other = __shfl_xor_sync(0xffffffffu, all_min, o);
+                    all_min = (other < all_min) ? other : all_min;
+                }
+#endif
+                if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
+            }
+            // -- write back + Body._synchronize_transform (island.py:155-159, body.py:906-908)
+            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+                const int b = l_body[i];
+                if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                real* p = b_pos + 4 * (size_t)b; real* v = b_vel + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
+                p[0] = s_cx[b]; p[1] = s_cy[b]; p[2] = s_a[b];
+                v[0] = s_vx[b]; v[1] = s_vy[b]; v[2] = s_w[b];
+                const XF t = xf_from_sweep<real>(mk<real>(s_cx[b], s_cy[b]), s_a[b], mk<real>(s_lcx[b], s_lcy[b]));
+                x[0] = t.p.x; x[1] = t.p.y; x[2] = t.c1.x; x[3] = t.c1.y;
+            }
+            B2B_WSYNC();
+            // -- sleep bookkeeping exactly as written in the reference (island.py:163-179):
+            //    the allow-sleep test reads the LAST island body; only the last non-static body is put to sleep.
+            if (B2B_LANE == 0) {
+                if (allow_sleep) {
+                    real min_sleep = K<real>::max_float;
+                    const bool last_allow = (s_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+                    int victim = -1;
+                    for (int i = b0; i < b1; ++i) {
+                        const int b = l_body[i];
+                        if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                        victim = b;
+                        const real w = s_w[b], vx = s_vx[b], vy = s_vy[b];
+                        real* st = b_pos + 4 * (size_t)b + 3;
+                        if (!last_allow || w * w > K<real>::angular_sleep_tol_sqr || vx * vx + vy * vy > K<real>::linear_sleep_tol_sqr) {
+                            *st = real(0);
+                            min_sleep = real(0);
+                        } else {
+                            const real t = *st + dt;
+                            *st = t;
+                            min_sleep = pymin(min_sleep, t);
+                        }
+                    }
+                    if (min_sleep >= K<real>::time_to_sleep && position_solved && victim >= 0) {
+                        // Body.awake = False (body.py:805-812)
+                        b_pos[4 * (size_t)victim + 3] = real(0);
+                        real* v = b_vel + 4 * (size_t)victim;
+                        v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
+                        b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
+                        b_flags[victim] &= ~BODY_AWAKE;
+                    }
+                }
+                // max position iterations used by any island of this world (diagnostic, w_island[3])
+#if defined(__CUDA_ARCH__)
+                atomicMax(&w_island[3], used);
+#else
+                if (used > w_island[3]) w_island[3] = used;
+#endif
+            }
+            B2B_WSYNC();
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K4
+    // Body._synchronize_fixtures -> Fixture._synchronize -> BroadPhase.move_proxy -> DynamicTree.move_proxy
+    // (body.py:898-904, fixture.py:287-298, broadphase.py:61-68, dynamictree.py:152-188)
+    B2B_D void phase_sync()
+    {
+        const int nf = w_count[1];
+        B2B_PFOR(f, nf) {
+            const int b = f_body[f];
+            const uint32_t fl = b_flags[b];
+            if (!(fl & BODY_ISLAND) || (fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
+            const real* p0 = b_pos0 + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
+            const XF xf1 = xf_from_sweep<real>(mk<real>(p0[0], p0[1]), p0[2], mk<real>(m[2], m[3]));
+            const XF xf2 = xf_load<real>(b_xf + 4 * (size_t)b);
+            const shape_view<real> s = shape_of_fixture(f);
+            real a1[4], a2[4];
+            shape_aabb(s, xf1, a1);
+            shape_aabb(s, xf2, a2);
+            real* tight = f_tight + 4 * (size_t)f; real* fat = f_fat + 4 * (size_t)f;
+            const real tlx = pymin(a1[0], a2[0]), tly = pymin(a1[1], a2[1]);
+            const real tux = pymax(a1[2], a2[2]), tuy = pymax(a1[3], a2[3]);
+            tight[0] = tlx; tight[1] = tly; tight[2] = tux; tight[3] = tuy;
+            if (fat[0] <= tlx && fat[1] <= tly && tux <= fat[2] && tuy <= fat[3]) continue;   // AABB.contains
+            const real ext = K<real>::aabb_extension;
+            real lx = tlx - ext, ly = tly - ext, ux = tux + ext, uy = tuy + ext;
+            const V2 d = K<real>::aabb_multiplier * (xf2.p - xf1.p);
+            if (d.x < real(0)) lx = lx + d.x; else ux = ux + d.x;
+            if (d.y < real(0)) ly = ly + d.y; else uy = uy + d.y;
+            fat[0] = lx; fat[1] = ly; fat[2] = ux; fat[3] = uy;
+            f_moved[f] = 1;
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K5 + K6
+    // Pair (a, b) is emitted by mover a for every other proxy b whose fat AABB overlaps, except when b is
+    // itself an earlier mover (then (b, a) is already in the pair buffer): broadphase.py:83-109 with the
+    // emission order pinned to (a, b) ascending (SURVEY §0 finding 1).
+    B2B_D bool pair_candidate(int a, int b) const
+    {
+        if (b == a) return false;
+        if (!aabb_overlap<real>(f_fat + 4 * (size_t)b, f_fat + 4 * (size_t)a)) return false;
+        if (b < a && f_moved[b]) return false;
+        return true;
+    }
+
+    // should a new contact be created for pair (fa, fb)?  contact_manager.py:102-158
+    B2B_D bool pair_accept(int fa, int fb, bool have_adjacency)
+    {
+        const int ba = f_body[fa], bb = f_body[fb];
+        if (ba == bb) return false;
+        const int nc = w_count[2];
+        const int ta = body_type(ba), tb = body_type(bb);
+        if (tb != BODY_DYNAMIC && ta != BODY_DYNAMIC) return false;              // Body._should_collide
+        bool exists = false;
+        if (have_adjacency) {
+            const int bs = (tb != BODY_STATIC) ? bb : ba;                          // a row that was built
+            for (int k = adj_start[bs]; k < adj_start[bs + 1] && !exists; ++k) {
+                const int c = adj[k];
+                const int ca = c_fix[2 * c], cb = c_fix[2 * c + 1];
+                exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
+            }
+        } else {
+            for (int c = 0; c < nc && !exists; ++c) {
+                const int ca = c_fix[2 * c], cb = c_fix[2 * c + 1];
+                exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
+            }
+        }
+        if (exists) return false;
+        // World.default_contact_filter (world.py:958-970)
+        const uint32_t fa0 = f_filter[2 * fa], fa1 = f_filter[2 * fa + 1], fb0 = f_filter[2 * fb], fb1 = f_filter[2 * fb + 1];
+        const int ga = (int)(int16_t)(fa1 & 0xffff), gb = (int)(int16_t)(fb1 & 0xffff);
+        if (ga == gb && ga != 0) { if (!(ga > 0)) return false; }
+        else if (!(((fa0 >> 16) & (fb0 & 0xffff)) != 0 && ((fa0 & 0xffff) & (fb0 >> 16)) != 0)) return false;
+        // Contact registry (contact.py:294-311): polygon-polygon, circle-circle, polygon/edge-circle, edge-polygon
+        const int t1 = s_meta[f_shape[fa]] & 0xff, t2 = s_meta[f_shape[fb]] & 0xff;
+        if (t1 == SHAPE_EDGE && t2 == SHAPE_EDGE) return false;
+        if (t1 == SHAPE_LOOP || t2 == SHAPE_LOOP) return false;
+        return true;
+    }
+
+    B2B_D void phase_pairs(bool have_adjacency)
+    {
+        const int nf = w_count[1];
+        // pass 1: per-mover candidate counts
+        B2B_PFOR(a, nf) {
+            int n = 0;
+            if (f_moved[a])
+                for (int b = 0; b < nf; ++b) n += pair_candidate(a, b) ? 1 : 0;
+            scan[a] = n;
+        }
+        exclusive_scan(scan, nf, 8);
+        const int npairs = s_ctl[8];
+        // pass 2: emit in (a, b) order
+        B2B_PFOR(a, nf) {
+            if (!f_moved[a]) continue;
+            int o = scan[a];
+            for (int b = 0; b < nf; ++b) {
+                if (!pair_candidate(a, b)) continue;
+                if (o < cap.npair) { p_pairs[2 * o] = a; p_pairs[2 * o + 1] = b; }
+                ++o;
+            }
+        }
+        B2B_SYNC();
+        const int nuse = (npairs < cap.npair) ? npairs : cap.npair;
+        // pass 3: filter, then append the survivors in pair order
+        B2B_PFOR(k, nuse) pair_keep[k] = pair_accept(p_pairs[2 * k], p_pairs[2 * k + 1], have_adjacency) ? 1 : 0;
+        exclusive_scan(pair_keep, nuse, 9);
+        const int n_new = s_ctl[9];
+        const int nc0 = w_count[2];
+        B2B_PFOR(k, nuse) {
+            const bool keep = (k + 1 < nuse) ? (pair_keep[k + 1] != pair_keep[k]) : (n_new != pair_keep[k]);
+            if (!keep) continue;
+            const int ci = nc0 + pair_keep[k];
+            if (ci >= cap.nc) continue;
+            int fa = p_pairs[2 * k], fb = p_pairs[2 * k + 1];
+            const int t1 = s_meta[f_shape[fa]] & 0xff, t2 = s_meta[f_shape[fb]] & 0xff;
+            // registry order: (circle, polygon), (circle, edge), (polygon, edge) are stored swapped (contact.py:321-324)
+            const bool swap = (t1 == SHAPE_CIRCLE && (t2 == SHAPE_POLYGON || t2 == SHAPE_EDGE)) || (t1 == SHAPE_POLYGON && t2 == SHAPE_EDGE);
+            if (swap) { const int t = fa; fa = fb; fb = t; }
+            c_fix[2 * ci] = fa; c_fix[2 * ci + 1] = fb;
+            c_flags[ci] = 0u;
+            c_mat[2 * ci] = sqrt_r(f_mat[2 * fa] * f_mat[2 * fb]);                 // mix_friction
+            c_mat[2 * ci + 1] = pymax(f_mat[2 * fa + 1], f_mat[2 * fb + 1]);       // mix_restitution
+            c_mtype[ci] = 0;
+            for (int q = 0; q < 4; ++q) { c_mf[4 * (size_t)ci + q] = real(0); c_pts[4 * (size_t)ci + q] = real(0); c_imp[4 * (size_t)ci + q] = real(0); }
+            c_id[2 * ci] = 0u; c_id[2 * ci + 1] = 0u;
+        }
+        B2B_PFOR(a, nf) f_moved[a] = 0;
+        B2B_SYNC();
+        if (B2B_IS_T0) {
+            uint32_t st = 0;
+            int nc1 = nc0 + n_new;
+            if (npairs > cap.npair) st |= STATUS_PAIR_OVERFLOW;
+            if (nc1 > cap.nc) { st |= STATUS_CONTACT_OVERFLOW; nc1 = cap.nc; }
+            if (st) w_status[0] |= st;
+            w_count[2] = nc1;
+            w_count[3] = npairs;
+        }
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ World.step
+    B2B_D void run(const step_params& sp)
+    {
+        const real dt = (real)sp.dt;
+        for (int step = 0; step < sp.n_steps; ++step) {
+            const real dt_ratio = (real)(step == 0 ? sp.dt_ratio_first : sp.dt_ratio_rest);
+            if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
+                phase_pairs(false);
+                if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
+                B2B_SYNC();
+            }
+            phase_collide();                                         // world.py:338
+            if (sp.dt > 0.0) {                                       // world.py:341-342
+                build_adjacency();
+                phase_islands();
+                solve_islands(sp, dt, dt_ratio);
+                phase_sync();
+                phase_pairs(true);
+            }
+            if (w_flags[0] & WORLD_AUTO_CLEAR) {                     // world.py:351-352
+                const int nb = w_count[0];
+                B2B_PFOR(b, nb) { b_force[2 * (size_t)b] = real(0); b_force[2 * (size_t)b + 1] = real(0); b_vel[4 * (size_t)b + 3] = real(0); }
+            }
+            B2B_SYNC();
+        }
+    }
+};
+
+}  // namespace b2b

@@ -1,0 +1,45 @@
+// hostcheck.cpp -- TEST-ONLY host instantiation of the device step source.
+//
+// Compiles pypybox2d_b200/csrc/b2b_step.cuh with g++ (the parallel-loop macros expand to
+// sequential loops) so that the exact kernel source can be debugged against the oracle in the
+// CPU-only build container.  It is built by tests/test_hostcheck.py into tests/hostcheck/ and is
+// never part of libb2b.so, never imported by the package, never timed.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b2b.h"
+#include "../../pypybox2d_b200/csrc/b2b_step.cuh"
+
+using namespace b2b;
+
+template <class real>
+static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double inv_dt0, int vel_iters, int pos_iters,
+               int n_steps)
+{
+    caps_t c;
+    c.n_worlds = caps->n_worlds; c.nb = caps->nb; c.nf = caps->nf; c.nc = caps->nc; c.npair = caps->npair;
+    c.nl = caps->nl; c.n_shapes = caps->n_shapes;
+    batch_ptrs<real> B;
+    static_assert(sizeof(B) == sizeof(*buf), "b2b_buffers and batch_ptrs must have the same members");
+    std::memcpy(&B, buf, sizeof(B));
+    scratch_layout L = scratch_plan(c, (int)sizeof(real));
+    std::vector<unsigned char> scratch(L.total + 256), smem(smem_plan(c, (int)sizeof(real)) + 256);
+    step_params sp;
+    sp.dt = dt; sp.dt_ratio_first = inv_dt0 * dt; sp.dt_ratio_rest = (dt > 0.0 ? (1.0 / dt) * dt : 0.0);
+    sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = 0;
+    for (int w = 0; w < c.n_worlds; ++w) {
+        world_step<real> ws;
+        ws.bind(B, c, w, scratch.data(), L, smem.data());
+        ws.run(sp);
+    }
+    return 0;
+}
+
+extern "C" int hc_step(const b2b_caps* caps, const b2b_buffers* buf, double dt, double inv_dt0, int vel_iters,
+                       int pos_iters, int n_steps)
+{
+    if (caps->real_bytes == 8) return run<double>(caps, buf, dt, inv_dt0, vel_iters, pos_iters, n_steps);
+    if (caps->real_bytes == 4) return run<float>(caps, buf, dt, inv_dt0, vel_iters, pos_iters, n_steps);
+    return -1;
+}
