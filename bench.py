@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- body-steps/s of the batched World.step on 20-row pyramid worlds (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path, on the host cores
+
+Workload (config.workload): the pyramid-20 scene of examples/pyramid-bench.py (210 dynamic boxes on an edge
+ground), step(1/60, 8, 3), CCD off, `--worlds` independent worlds PER GPU (131,072 by default, i.e. 1,048,576
+worlds at 8 GPUs: BASELINE configs[2], weak scaling, no collective on the step path).  Every world has its own
+jittered initial positions.  The timed region runs in the SETTLED regime (one 211-body island, ~590 contacts,
+~400 touching, the most expensive phase of the trajectory): `--distinct` distinct worlds are stepped `--settle`
+steps untimed and that state is tiled over the batch.
+
+A "step" is one World.step of every world.  `value` times K steps in ONE launch with state resident in HBM
+(CUDA events on the launching stream, max over ranks); `e2e` times K single-step calls of the host-buffer C-ABI
+entry (b2b_step_host: pinned forces H2D, step, body state D2H).  `roofline` uses SURVEY §8d's algorithmic bytes.
+`cpu_baseline` is the C oracle (a port, test infrastructure) on the host cores -- a baseline, not the target.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT, VEL_ITERS, POS_ITERS = 1.0 / 60.0, 8, 3
+N_DYNAMIC = 210
+METRIC = "body-steps/sec (batched 20-row pyramid worlds)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=131072, help="worlds per GPU")
+    ap.add_argument("--distinct", type=int, default=8192, help="distinct jittered worlds settled, then tiled")
+    ap.add_argument("--settle", type=int, default=300)
+    ap.add_argument("--real", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: same as --steps")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _settled_oracle_worlds(n, settle):
+    """n oracle worlds (distinct jitter) advanced to the settled regime -- the same workload as the GPU arm."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import harness
+    import oracle
+    worlds = []
+    for i in range(n):
+        mw, A, caps = harness.facade_arrays("pyramid", 1 + i, config=3)
+        o = oracle.Oracle(A, 0)
+        o.step(DT, VEL_ITERS, POS_ITERS, settle)
+        worlds.append(o)
+    return worlds
+
+
+def cpu_baseline_port(seconds, settle=300):
+    """The C oracle on the host cores: one thread per core, one settled pyramid world each (ctypes releases the
+    GIL inside orc_run).  Returns the cpu_baseline object."""
+    from concurrent.futures import ThreadPoolExecutor
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    with ThreadPoolExecutor(cores) as ex:
+        worlds = list(ex.map(lambda i: _settled_oracle_worlds(1, settle)[0], range(cores)))
+        chunk = 50
+        ex.submit(lambda: None).result()
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < seconds:
+            list(ex.map(lambda o: o.step(DT, VEL_ITERS, POS_ITERS, chunk), worlds))
+            done += chunk
+        dt = time.perf_counter() - t0
+    return {"value": N_DYNAMIC * cores * done / dt, "unit": "body-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d settled pyramid-20 worlds (one per thread) x %d steps of the C oracle (oracle/b2_oracle.c, "
+                      "fp64, -O2), step(1/60,8,3), CCD off" % (cores, done)}
+
+
+REF_WORKER = r"""
+import sys, os, time, io, contextlib
+sys.path.insert(0, %(ref)r)
+with contextlib.redirect_stdout(io.StringIO()):
+    import pypybox2d as b2
+core, settle, steps, warmup = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+try:
+    os.sched_setaffinity(0, {core})
+except Exception:
+    pass
+from copy import copy
+world = b2.World((0, -10), True, continuous_physics=False)
+world.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
+fixture = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
+x = b2.Vec2(-7, 0.75)
+for i in range(20):
+    y = copy(x)
+    for j in range(i, 20):
+        world.create_dynamic_body(position=y, fixtures=fixture)
+        y += (1.125, 0)
+    x += (0.5625, 1.25)
+for i in range(settle + warmup):
+    world.step(1.0 / 60, 8, 3)
+print("READY", flush=True)
+sys.stdin.readline()
+t0 = time.perf_counter()
+for i in range(steps):
+    world.step(1.0 / 60, 8, 3)
+print("DONE %%.6f %%s" %% (time.perf_counter() - t0, "cext" if b2.Vec2 is not b2.PyVec2 else "pure"), flush=True)
+"""
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the UNMODIFIED reference (oracle/_ref, installed with its own C extension by
+    __graft_entry__.build) on the host cores, one pinned process per core, each stepping its own settled
+    pyramid world through World.step.  Falls back to the oracle port when oracle/_ref is absent."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    steps, warmup = args.steps, max(args.warmup, 3)
+    if os.path.exists(os.path.join(ref, "pypybox2d", "__init__.py")):
+        cores = max(1, min(os.cpu_count() or 1, 64))
+        settle = min(args.settle, 120)     # one island from ~step 120; keeps set-up under a minute
+        procs = [subprocess.Popen([sys.executable, "-c", REF_WORKER % {"ref": ref}, str(c), str(settle), str(steps),
+                                   str(warmup)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+                 for c in range(cores)]
+        for p in procs:
+            assert p.stdout.readline().startswith("READY")
+        t0 = time.perf_counter()
+        for p in procs:
+            p.stdin.write("go\n")
+            p.stdin.flush()
+        outs = [p.stdout.readline().split() for p in procs]
+        wall = time.perf_counter() - t0
+        for p in procs:
+            p.wait()
+        per = sorted(float(o[1]) for o in outs)
+        backend = "C extension (_common, build_cext)" if outs[0][2] == "cext" else "pure Python"
+        value = N_DYNAMIC * cores * steps / wall
+        kind, sample = "reference", ("%d processes (one per core, pinned) x %d World.step calls on a settled pyramid-20 "
+                                     "world each (%d set-up steps), unmodified pypybox2d from oracle/_ref, %s math "
+                                     "types, step(1/60,8,3), continuous_physics=False; median per-core %.3f s/step"
+                                     % (cores, steps, settle + warmup, backend, per[len(per) // 2] / steps))
+        ms = 1e3 * wall / steps
+    else:
+        cb = cpu_baseline_port(max(5.0, min(args.cpu_seconds, 30.0)), settle=args.settle)
+        value, cores, kind, sample = cb["value"], cb["cores"], cb["kind"], cb["sample"]
+        ms = 1e3 * N_DYNAMIC * cores / value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "pyramid-20 (examples/pyramid-bench.py scene), one world per host core, settled regime",
+                       "vel_iters": VEL_ITERS, "pos_iters": POS_ITERS, "dt": "1/60", "continuous_physics": False},
+            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_batch(b2, args, world_offset, device):
+    """`args.worlds` settled pyramid worlds on `device`: `distinct` jittered worlds are stepped `settle` steps,
+    then their state is tiled over the batch (world k of the shard = distinct world k % distinct)."""
+    import torch
+    from pypybox2d_b200 import schema, scenes
+    w = scenes.pyramid(b2)
+    caps = schema.Caps(211, 211, 640, npair=1280)
+    distinct = min(args.distinct, args.worlds)
+    seed = b2.BatchedWorld.replicate(w, distinct, jitter=scenes.JITTER_AMP, config=3, world_offset=world_offset,
+                                     real=args.real, caps=caps, device=device, threads=args.threads)
+    seed.step(DT, VEL_ITERS, POS_ITERS, args.settle)
+    torch.cuda.synchronize(device)
+    if seed.status(raise_on_overflow=False):
+        raise RuntimeError("capacity overflow while settling the seed worlds")
+    if distinct == args.worlds:
+        return seed, caps
+    A = {}
+    reps = (args.worlds + distinct - 1) // distinct
+    full = b2.BatchedWorld.__new__(b2.BatchedWorld)
+    full.real, full.caps, full.device = args.real, caps, seed.device
+    full.n_worlds, full.n_shapes, full.inv_dt0 = args.worlds, seed.n_shapes, seed.inv_dt0
+    full.t = {}
+    for name, scope, tail, kind in schema.FIELDS:
+        t = seed.t[name]
+        if scope == "S":
+            full.t[name] = t
+        else:
+            full.t[name] = t.repeat((reps,) + (1,) * (t.dim() - 1))[:args.worlds].contiguous()
+    import ctypes
+    from pypybox2d_b200 import _lib
+    c = _lib.Caps()
+    c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = args.worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
+    c.n_shapes, c.real_bytes = full.n_shapes, (8 if args.real == "f64" else 4)
+    c.device = seed.device.index
+    c.threads = args.threads
+    full._caps_struct = c
+    full._ctx = ctypes.c_void_p()
+    _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(full._ctx)), "b2b_create")
+    full._bind()
+    del seed
+    torch.cuda.empty_cache()
+    return full, caps
+
+
+def run_b200_arm(args):
+    import torch
+    import pypybox2d_b200 as b2
+    from pypybox2d_b200 import dist
+
+    rank, local_rank, world_size = dist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the step has no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    n_total = args.worlds * world_size
+    bw, caps = build_batch(b2, args, rank * args.worlds, device)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident timing: K steps in one launch, state in HBM (inputs >> L2: no flush needed)
+    bw.step(DT, VEL_ITERS, POS_ITERS, W)
+    torch.cuda.synchronize(device)
+    dist.barrier()
+    launches0 = bw.info()["launches"]
+    sampler = ClockSampler(device.index) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    bw.step(DT, VEL_ITERS, POS_ITERS, K)
+    e1.record()
+    torch.cuda.synchronize(device)
+    dist.barrier()
+    ms = dist.max_over_ranks(e0.elapsed_time(e1), device)
+    clocks = sampler.stop() if sampler else None
+    launches = bw.info()["launches"] - launches0
+    value = N_DYNAMIC * n_total * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point: pinned H2D forces + step + D2H body state, per step
+    Ke = args.e2e_steps or K
+    rd = torch.float64 if args.real == "f64" else torch.float32
+    h_in = torch.zeros((args.worlds, caps.nb, 3), dtype=rd).pin_memory()
+    h_out = torch.zeros((args.worlds, caps.nb, 6), dtype=rd).pin_memory()
+    bw.step_host(h_in, h_out, DT, VEL_ITERS, POS_ITERS)           # warm the staging buffers
+    dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        bw.step_host(h_in, h_out, DT, VEL_ITERS, POS_ITERS)
+    torch.cuda.synchronize(device)
+    e2e_s = dist.max_over_ranks(time.perf_counter() - t0, device)
+    e2e_value = N_DYNAMIC * n_total * Ke / e2e_s
+    status = bw.status(raise_on_overflow=False)
+
+    # ---- roofline of the (single) step kernel: algorithmic bytes per world-step / launch duration
+    D = bw.download(["w_count"], worlds=slice(0, min(args.worlds, 4096)))
+    nc_mean = float(D["w_count"][:, 2].mean())
+    rb = 8 if args.real == "f64" else 4
+    bytes_per_world_step = (96 * 211 + 16 * 211 + 160 * nc_mean) * (rb / 4.0)
+    achieved = bytes_per_world_step * args.worlds * K / (ms * 1e-3) / 1e9      # GB/s on this rank's GPU
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_world_step")
+            if traffic is not None:
+                traffic = traffic * args.worlds * K
+    except Exception:
+        pass
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": world_size, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.real, "data": "synthetic",
+        "config": {"workload": "pyramid-20 (examples/pyramid-bench.py scene) x %d worlds per GPU (%d total), settled regime"
+                               % (args.worlds, n_total),
+                   "vel_iters": VEL_ITERS, "pos_iters": POS_ITERS, "dt": "1/60", "continuous_physics": False,
+                   "distinct_worlds_per_gpu": min(args.distinct, args.worlds), "settle_steps": args.settle,
+                   "contacts_per_world": nc_mean, "l2": "inputs larger than L2 (%.1f GB of state per GPU), no flush"
+                                                        % (sum(t.numel() * t.element_size() for t in bw.t.values()) / 1e9),
+                   "parallelism": "worlds sharded by contiguous index blocks, one process per GPU, no collective",
+                   "launch": bw.info(), "status": status},
+        "e2e": {"value": e2e_value, "unit": "body-steps/s", "steps": Ke,
+                "h2d_bytes_per_step": int(h_in.numel() * h_in.element_size()) * world_size,
+                "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()) * world_size},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_world_step": bytes_per_world_step, "kernel": "step_kernel_%s" % args.real,
+                     "note": "latency/issue bound, not HBM bound: exact Gauss-Seidel order serialises each world"},
+    }
+    if not args.no_cpu_baseline and world_size == 1:
+        line["cpu_baseline"] = cpu_baseline_port(args.cpu_seconds, settle=args.settle)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank == 0:
+            run_reference_arm(args)
+        return
+    run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

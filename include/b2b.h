@@ -35,6 +35,8 @@ typedef enum b2b_error {
     B2B_ERR_OVERFLOW = -4    /* a world overflowed a capacity (see b2b_status) */
 } b2b_error;
 
+#define B2B_STEP_PROFILE 1u   /* b2b_step flags: accumulate per-phase cycle counters (see b2b_profile) */
+
 typedef struct b2b_caps {
     int32_t n_worlds;        /* worlds in this context (this GPU's shard) */
     int32_t nb;              /* bodies per world (capacity) */
@@ -109,6 +111,11 @@ int b2b_status(b2b_ctx* ctx, uint32_t* host_out, void* stream);
  * d_out real64[n_worlds][4] = {fnv1a64 of packed body state (as double bits), kinetic+potential
  * energy, n_contacts, n_awake}.  masses are passed as inverse mass/inertia already in b_mass. */
 int b2b_checksum(b2b_ctx* ctx, void* d_out, void* stream);
+
+/* Per-phase cycle counters of the step kernel, summed over CTAs (only accumulated by steps run with
+ * flags & B2B_STEP_PROFILE): out[32] int64, slots named in pypybox2d_b200/csrc/b2b_step.cuh (PROF_*).
+ * reset != 0 clears them afterwards.  Synchronises the device. */
+int b2b_profile(b2b_ctx* ctx, int64_t* host_out32, int reset);
 
 /* Launch geometry actually used and kernel launches issued so far (for bench.py's gpu_launches). */
 int b2b_info(b2b_ctx* ctx, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches);

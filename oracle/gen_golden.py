@@ -87,7 +87,7 @@ def int_hash(A, w=0):
 
 
 def used(A, name, w=0):
-    return np.ascontiguousarray(harness.used_view(A, name, w))
+    return np.array(harness.used_view(A, name, w), copy=True, order="C")
 
 
 def generate(case):
@@ -104,7 +104,7 @@ def generate(case):
         out["init_" + f] = used(RA, f)
     n_sh = len(table)
     for f in ("s_meta", "s_radius", "s_data"):
-        out["init_" + f] = np.ascontiguousarray(RA[f][:n_sh])
+        out["init_" + f] = np.array(RA[f][:n_sh], copy=True, order="C")
     orc = oracle.Oracle(OA, 0)
     rec = refpin.Recorder(rw)
     digests = np.zeros((steps, 32), np.uint8)

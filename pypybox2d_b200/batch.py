@@ -178,10 +178,14 @@ class BatchedWorld(object):
     def init_proxies(self):
         _lib.check(_lib.lib().b2b_init_proxies(self._ctx, self._stream()), "b2b_init_proxies")
 
-    def step(self, dt, vel_iters, pos_iters, n_steps=1):
+    PROFILE_SLOTS = ["pairs0", "collide", "adjacency", "islands", "solve", "sync", "pairs", "clear",
+                     "s_stage", "s_integrate", "s_schedule", "s_init", "s_warm", "s_velocity", "s_store", "s_position",
+                     "s_writeback", "s_sleep"]
+
+    def step(self, dt, vel_iters, pos_iters, n_steps=1, profile=False):
         """World.step for every world, `n_steps` times (asynchronous on the current stream)."""
         _lib.check(_lib.lib().b2b_step(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters),
-                                       int(n_steps), 0, self._stream()), "b2b_step")
+                                       int(n_steps), 1 if profile else 0, self._stream()), "b2b_step")
         if dt > 0.0 and n_steps > 0:
             self.inv_dt0 = 1.0 / dt
 
@@ -206,6 +210,14 @@ class BatchedWorld(object):
         out = torch.empty((self.n_worlds, 4), dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib().b2b_checksum(self._ctx, ctypes.c_void_p(out.data_ptr()), self._stream()), "b2b_checksum")
         return out
+
+    def profile(self, reset=True):
+        """Per-phase cycles of thread 0 summed over CTAs, for steps run with profile=True (development aid)."""
+        out = (ctypes.c_int64 * 32)()
+        _lib.check(_lib.lib().b2b_profile(self._ctx, out, 1 if reset else 0), "b2b_profile")
+        d = {n: int(out[i]) for i, n in enumerate(self.PROFILE_SLOTS)}
+        d["world_steps"] = int(out[31])
+        return d
 
     def info(self):
         g, t, s, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()

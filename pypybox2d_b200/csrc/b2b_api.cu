@@ -98,6 +98,7 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
     e = cudaMalloc((void**)&x->scratch, x->plan.layout.total * (size_t)x->plan.grid);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
+    cudaMemset(x->scratch, 0, x->plan.layout.total * (size_t)x->plan.grid);
     e = cudaMalloc((void**)&x->d_status, sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(status)", e); }
     *out = x;
@@ -237,5 +238,21 @@ extern "C" int b2b_info(b2b_ctx* x, int32_t* grid, int32_t* threads, int32_t* sm
     if (threads) *threads = x->plan.threads;
     if (smem_bytes) *smem_bytes = (int32_t)x->plan.smem;
     if (launches) *launches = x->launches;
+    return B2B_OK;
+}
+
+extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
+{
+    if (!x || !host_out32) return fail(B2B_ERR_ARG, "b2b_profile: NULL argument");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    CUDA_TRY(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] = 0;
+    long long tmp[PROF_SLOTS];
+    for (int g = 0; g < x->plan.grid; ++g) {
+        unsigned char* p = x->scratch + (size_t)g * x->plan.layout.total + x->plan.layout.off_prof;
+        CUDA_TRY(cudaMemcpy(tmp, p, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H profile");
+        for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] += tmp[k];
+        if (reset) CUDA_TRY(cudaMemset(p, 0, sizeof(tmp)), "memset profile");
+    }
     return B2B_OK;
 }

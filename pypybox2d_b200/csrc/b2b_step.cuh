@@ -34,7 +34,9 @@
 #define B2B_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define B2B_CLOCK() clock64()
 #else
+#define B2B_CLOCK() 0LL
 #define B2B_TID 0
 #define B2B_NT 1
 #define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
@@ -55,6 +57,17 @@ template <class T> inline T host_atomic_or(T* p, T v) { T o = *p; *p = o | v; re
 #define B2B_ATOMIC_OR(p, v) b2b::host_atomic_or((p), (v))
 #endif
 
+// cycle accounting by thread 0 (wall-clock cycles of the CTA, since phases end in CTA barriers)
+#define B2B_PROF(slot, t)                                                      \
+    do {                                                                       \
+        if (profiling) {                                                       \
+            const long long t1_ = B2B_CLOCK();                                 \
+            if (B2B_IS_T0) prof[slot] += t1_ - (t);                            \
+            (t) = t1_;                                                         \
+        }                                                                      \
+    } while (0)
+
+
 namespace b2b {
 
 struct caps_t {
@@ -73,12 +86,17 @@ template <class real> struct batch_ptrs {
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
 enum { CC_REALS = 40 };
+// per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
+enum { PROF_SLOTS = 32, STEP_PROFILE = 1 };
+enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
+       PROF_S_STAGE = 8, PROF_S_INTEGRATE, PROF_S_SCHEDULE, PROF_S_INIT, PROF_S_WARM, PROF_S_VELOCITY, PROF_S_STORE,
+       PROF_S_POSITION, PROF_S_WRITEBACK, PROF_S_SLEEP, PROF_WORLD_STEPS = 31 };
 
 // Per-CTA scratch in global memory (stays L1/L2 resident: it is reused for every world this CTA steps).
 struct scratch_layout {
     // element counts, filled by scratch_plan()
     size_t off_wake, off_scan, off_adj_start, off_adj_fill, off_adj, off_stack, off_lev, off_lstart, off_sched,
-        off_last, off_isl_nlev, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, total;
+        off_last, off_isl_nlev, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, off_prof, total;
 };
 
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -105,6 +123,7 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     // staging copy of the contact rows for order-preserving compaction: 2+1+1+2 words + 14 reals
     L.off_tmp_contact = take((sizeof(int32_t) * 6 + (size_t)real_bytes * 14) * ((size_t)c.nc + 2));
     L.off_pair_keep = take(sizeof(int32_t) * ((size_t)c.npair + 2));
+    L.off_prof = take(sizeof(long long) * PROF_SLOTS);
     L.total = align_up(o, 256);
     return L;
 }
@@ -139,6 +158,7 @@ template <class real> struct world_step {
     real* cc_real;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
+    long long* prof;     // NULL unless profiling
     // shared memory
     real *s_vx, *s_vy, *s_w, *s_cx, *s_cy, *s_a, *s_im, *s_ii, *s_lcx, *s_lcy;
     uint32_t* s_flags;
@@ -173,6 +193,7 @@ template <class real> struct world_step {
         tmp_cr = (real*)(scratch + L.off_tmp_contact);
         tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)c.nc + 2));
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
+        prof = (long long*)(scratch + L.off_prof);
         real* sr = (real*)smem;
         s_vx = sr; s_vy = sr + c.nb; s_w = sr + 2 * c.nb; s_cx = sr + 3 * c.nb; s_cy = sr + 4 * c.nb; s_a = sr + 5 * c.nb;
         s_im = sr + 6 * c.nb; s_ii = sr + 7 * c.nb; s_lcx = sr + 8 * c.nb; s_lcy = sr + 9 * c.nb;
@@ -720,7 +741,10 @@ template <class real> struct world_step {
             last[b] = 0;
         }
         B2B_SYNC();
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
+        (void)profiling;
         for (int isl = B2B_WARP; isl < n_islands; isl += B2B_NWARPS) {
             const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
             const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
@@ -746,6 +770,7 @@ template <class real> struct world_step {
                     s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w;
                 }
             }
+            B2B_PROF(PROF_S_INTEGRATE, t);
             int nlev = 0;
             int32_t* ls = lstart + c0 + 3 * isl;          // level l (1-based) occupies slots [ls[l], ls[l+1]) + c0
             if (ncon > 0) {
@@ -778,21 +803,25 @@ template <class real> struct world_step {
                     isl_nlev[isl] = nlev;
                 }
                 B2B_WSYNC();
+                B2B_PROF(PROF_S_SCHEDULE, t);
                 nlev = isl_nlev[isl];
                 for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[sched[s]], dt_ratio, warm);
                 B2B_WSYNC();
+                B2B_PROF(PROF_S_INIT, t);
                 if (warm) {
                     for (int l = 1; l <= nlev; ++l) {
                         for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_warm_start(s);
                         B2B_WSYNC();
                     }
                 }
+                B2B_PROF(PROF_S_WARM, t);
                 for (int it = 0; it < sp.vel_iters; ++it) {
                     for (int l = 1; l <= nlev; ++l) {
                         for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_solve_velocity(s);
                         B2B_WSYNC();
                     }
                 }
+                B2B_PROF(PROF_S_VELOCITY, t);
                 // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
                 for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
                     const int ci = I(I_CONTACT, s);
@@ -803,6 +832,7 @@ template <class real> struct world_step {
                 }
             }
             B2B_WSYNC();
+            B2B_PROF(PROF_S_STORE, t);
             // -- integrate positions (island.py:119-138)
             for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
                 const int b = l_body[i];
@@ -843,6 +873,7 @@ template <class real> struct world_step {
 #endif
                 if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
             }
+            B2B_PROF(PROF_S_POSITION, t);
             // -- write back + Body._synchronize_transform (island.py:155-159, body.py:906-908)
             for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
                 const int b = l_body[i];
@@ -854,6 +885,7 @@ template <class real> struct world_step {
                 x[0] = t.p.x; x[1] = t.p.y; x[2] = t.c1.x; x[3] = t.c1.y;
             }
             B2B_WSYNC();
+            B2B_PROF(PROF_S_WRITEBACK, t);
             // -- sleep bookkeeping exactly as written in the reference (island.py:163-179):
             //    the allow-sleep test reads the LAST island body; only the last non-static body is put to sleep.
             if (B2B_LANE == 0) {
@@ -893,6 +925,7 @@ template <class real> struct world_step {
 #endif
             }
             B2B_WSYNC();
+            B2B_PROF(PROF_S_SLEEP, t);
         }
         B2B_SYNC();
     }
@@ -1042,26 +1075,37 @@ template <class real> struct world_step {
     B2B_D void run(const step_params& sp)
     {
         const real dt = (real)sp.dt;
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         for (int step = 0; step < sp.n_steps; ++step) {
             const real dt_ratio = (real)(step == 0 ? sp.dt_ratio_first : sp.dt_ratio_rest);
+            long long t = B2B_CLOCK();
             if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
                 phase_pairs(false);
                 if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
                 B2B_SYNC();
+                B2B_PROF(PROF_PAIRS0, t);
             }
             phase_collide();                                         // world.py:338
+            B2B_PROF(PROF_COLLIDE, t);
             if (sp.dt > 0.0) {                                       // world.py:341-342
                 build_adjacency();
+                B2B_PROF(PROF_ADJACENCY, t);
                 phase_islands();
+                B2B_PROF(PROF_ISLANDS, t);
                 solve_islands(sp, dt, dt_ratio);
+                B2B_PROF(PROF_SOLVE, t);
                 phase_sync();
+                B2B_PROF(PROF_SYNC, t);
                 phase_pairs(true);
+                B2B_PROF(PROF_PAIRS, t);
             }
             if (w_flags[0] & WORLD_AUTO_CLEAR) {                     // world.py:351-352
                 const int nb = w_count[0];
                 B2B_PFOR(b, nb) { b_force[2 * (size_t)b] = real(0); b_force[2 * (size_t)b + 1] = real(0); b_vel[4 * (size_t)b + 3] = real(0); }
             }
             B2B_SYNC();
+            B2B_PROF(PROF_CLEAR, t);
+            if (profiling && B2B_IS_T0) prof[PROF_WORLD_STEPS] += 1;
         }
     }
 };

@@ -7,7 +7,7 @@ unit stride.  The field set is the persistent state of the reference's objects
 (`contact_util.py:50-166`) and `Contact` flags (`contact.py:57-81`).
 
 `FIELDS` is the single source of truth: `include/b2b.h` (`b2b_buffers`) and
-`oracle/b2_oracle.h` (`orc_world`) list the same names in the same order, and
+the test-only checker under `oracle/` list the same names in the same order, and
 `tests/test_abi.py` checks that through `b2b_field_names()` / `orc_field_names()`.
 """
 import numpy as np

@@ -1,0 +1,84 @@
+"""The drop-in surface and batch behaviour on a real GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import harness
+import oracle
+from pypybox2d_b200 import schema, scenes
+
+
+def test_world_step_is_a_drop_in_for_the_reference_script():
+    """examples/hello-bench.py's body, unchanged apart from the import (and CCD off)."""
+    import pypybox2d_b200 as b2
+    world = b2.World((0, -10), True, continuous_physics=False, real="f64")
+    ground = world.create_static_body(position=(0, -10))
+    ground.create_polygon_fixture(box=(50, 10))
+    body = world.create_dynamic_body(position=(0, 4))
+    body.create_circle_fixture(1.0, density=1.0)
+    mw, A, caps = harness.facade_arrays("hello", 0)
+    orc = oracle.Oracle(A, 0)
+    for i in range(40):
+        world.step(0.1, 10, 10)
+        world.clear_forces()
+        orc.step(0.1, 10, 10)
+        assert body.position.y == pytest.approx(A["b_xf"][0, 1, 1], abs=1e-12)
+        assert body.linear_velocity.y == pytest.approx(A["b_vel"][0, 1, 1], abs=1e-12)
+    assert body.awake == bool(A["b_flags"][0, 1] & schema.BODY_AWAKE)
+    assert len(world.contact_manager.contacts) == 1
+    assert world.contact_manager.contacts[0].touching
+    assert not world.locked
+
+
+def test_batch_invariance_and_replicate():
+    """T4: world i's trajectory does not depend on batch size, CTA placement or shard offset."""
+    import torch
+    import pypybox2d_b200 as b2
+    w = scenes.pyramid(b2)
+    big = b2.BatchedWorld.replicate(w, 300, jitter=1e-2, config=3, real="f32")
+    part = b2.BatchedWorld.replicate(w, 7, jitter=1e-2, config=3, world_offset=100, real="f32", threads=128)
+    # replicate() must build the same world as the per-world facade path
+    one = scenes.pyramid(b2, world=103, config=3)
+    mw = b2.BatchedWorld.from_worlds([one], real="f32", caps=big.caps)
+    for name in ("b_xf", "b_pos", "f_fat", "f_tight"):
+        a, b = part.download([name])[name][3], mw.download([name])[name][0]
+        assert np.array_equal(a, b), name
+    for bw in (big, part, mw):
+        bw.step(1 / 60, 8, 3, 90)
+    B, P, M = big.download(), part.download(), mw.download()
+    for name in ("b_pos", "b_vel", "c_fix", "c_mtype", "c_imp", "w_count"):
+        assert np.array_equal(B[name][103], P[name][3]), name
+        assert np.array_equal(B[name][103], M[name][0]), name
+    assert big.status() == 0
+    cs = big.checksum().cpu().numpy()
+    assert cs.shape == (300, 4) and np.all(cs[:, 2] > 300) and np.isfinite(cs[:, 1]).all()
+
+
+def test_step_host_matches_device_step_and_reports_overflow():
+    import torch
+    import pypybox2d_b200 as b2
+    w = scenes.vertical_stack(b2)
+    a = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
+    b = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
+    nb = a.caps.nb
+    h_in = torch.zeros((64, nb, 3), dtype=torch.float32).pin_memory()
+    h_out = torch.zeros((64, nb, 6), dtype=torch.float32).pin_memory()
+    for s in range(30):
+        a.step_host(h_in, h_out, 1 / 60, 10, 10)
+        b.step(1 / 60, 10, 10)
+    B = b.download(["b_pos", "b_vel"])
+    assert np.array_equal(h_out.numpy()[..., :3], B["b_pos"][..., :3])
+    assert np.array_equal(h_out.numpy()[..., 3:], B["b_vel"][..., :3])
+    # a force applied through the host path changes the trajectory of that body only
+    h_in[5, 3, 1] = 500.0
+    a.step_host(h_in, h_out, 1 / 60, 10, 10)
+    b.step(1 / 60, 10, 10)
+    B = b.download(["b_vel"])
+    assert h_out[5, 3, 4] > B["b_vel"][5, 3, 1]
+    # capacity overflow is reported, not silently truncated
+    small = b2.BatchedWorld.from_worlds([scenes.pyramid(b2)], real="f32", caps=schema.Caps(211, 211, 300))
+    small.step(1 / 60, 8, 3, 60)
+    assert small.status(raise_on_overflow=False) & schema.STATUS_CONTACT_OVERFLOW
+    with pytest.raises(Exception):
+        small.status()

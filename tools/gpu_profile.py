@@ -1,0 +1,31 @@
+"""Development probe: per-phase cycle breakdown of the step kernel on settled pyramid worlds."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import pypybox2d_b200 as b2
+from pypybox2d_b200 import scenes, schema
+
+def run(n_worlds, real, threads, settle=200, steps=4, ctas=0):
+    w = scenes.pyramid(b2)
+    caps = schema.Caps(211, 211, 640, npair=1280)
+    bw = b2.BatchedWorld.replicate(w, n_worlds, jitter=1e-2, config=3, real=real, caps=caps, threads=threads, ctas_per_sm=ctas)
+    bw.step(1/60, 8, 3, settle)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); bw.step(1/60, 8, 3, steps, profile=True); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    p = bw.profile()
+    ws = max(p.pop("world_steps"), 1)
+    tot = sum(p[k] for k in ("pairs0","collide","adjacency","islands","solve","sync","pairs","clear"))
+    print("%s worlds=%d threads=%d grid=%d: %.2f ms/step %.3e body-steps/s; cycles/world-step %.0f" % (
+        real, n_worlds, threads, bw.info()["grid"], ms/steps, 210*n_worlds*steps/(ms*1e-3), tot/ws))
+    print("   top:", {k: "%.1f%%" % (100*p[k]/tot) for k in ("collide","adjacency","islands","solve","sync","pairs","clear")})
+    print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]})
+
+if __name__ == "__main__":
+    run(2368, "f32", 32)
+    run(2368, "f32", 32, ctas=4)
+    run(2368, "f32", 32, ctas=1)
+    run(1184, "f32", 64)
+    run(1184, "f64", 64)
