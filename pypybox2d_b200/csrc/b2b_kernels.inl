@@ -17,11 +17,12 @@ __global__ void __launch_bounds__(256) B2B_CAT(step_kernel_, B2B_SUFFIX)(batch_p
                                                                           unsigned char* scratch, step_params sp)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ world_step<real_t> ws;
     unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
     for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
-        if (threadIdx.x == 0) ws.bind(B, c, w, my_scratch, L, smem);
-        __syncthreads();
+        // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
+        // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
+        world_step<real_t> ws;
+        ws.bind(B, c, w, my_scratch, L, smem);
         ws.run(sp);
         __syncthreads();
     }

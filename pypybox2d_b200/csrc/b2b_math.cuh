@@ -29,6 +29,7 @@ namespace b2b {
 enum : uint32_t {
     BODY_TYPE_MASK = 0x3u, BODY_AWAKE = 0x4u, BODY_ACTIVE = 0x8u, BODY_ALLOW_SLEEP = 0x10u,
     BODY_FIXED_ROT = 0x20u, BODY_BULLET = 0x40u, BODY_ISLAND = 0x80u,
+    BODY_WOKEN = 0x100u,   // transient, shared-memory copy only: woken by the island walk this step
     CONTACT_TOUCHING = 0x1u, CONTACT_ENABLED = 0x2u, CONTACT_FILTER = 0x4u, CONTACT_ISLAND = 0x8u,
     WORLD_ALLOW_SLEEP = 0x1u, WORLD_WARM_STARTING = 0x2u, WORLD_NEW_FIXTURE = 0x4u, WORLD_AUTO_CLEAR = 0x8u,
     STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u

@@ -85,7 +85,7 @@ template <class real> struct batch_ptrs {
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
-enum { CC_REALS = 40 };
+enum { CC_QUADS = 11, CC_REALS = 4 * CC_QUADS };
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1 };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
@@ -94,9 +94,7 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 
 // Per-CTA scratch in global memory (stays L1/L2 resident: it is reused for every world this CTA steps).
 struct scratch_layout {
-    // element counts, filled by scratch_plan()
-    size_t off_wake, off_scan, off_adj_start, off_adj_fill, off_adj, off_stack, off_lev, off_lstart, off_sched,
-        off_last, off_isl_nlev, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, off_prof, total;
+    size_t off_wake, off_scan, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, off_prof, total;
 };
 
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -106,18 +104,9 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     scratch_layout L;
     size_t o = 0;
     const size_t nmax = (size_t)((c.nc > c.nf ? c.nc : c.nf) > c.npair ? (c.nc > c.nf ? c.nc : c.nf) : c.npair) + 2;
-    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 32); return at; };
     L.off_wake = take(sizeof(int32_t) * (size_t)c.nb);
-    L.off_scan = take(sizeof(int32_t) * nmax);
-    L.off_adj_start = take(sizeof(int32_t) * ((size_t)c.nb + 2));
-    L.off_adj_fill = take(sizeof(int32_t) * ((size_t)c.nb + 2));
-    L.off_adj = take(sizeof(int32_t) * (2 * (size_t)c.nc + 2));
-    L.off_stack = take(sizeof(int32_t) * ((size_t)c.nb + 2));
-    L.off_lev = take(sizeof(int32_t) * ((size_t)c.nc + 2));
-    L.off_lstart = take(sizeof(int32_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4));
-    L.off_sched = take(sizeof(int32_t) * ((size_t)c.nc + 2));
-    L.off_last = take(sizeof(int32_t) * ((size_t)c.nb + 2));
-    L.off_isl_nlev = take(sizeof(int32_t) * ((size_t)c.nb + 2));
+    L.off_scan = take(sizeof(int32_t) * (nmax > (size_t)c.nb + 2 ? nmax : (size_t)c.nb + 2));
     L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
     L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
     // staging copy of the contact rows for order-preserving compaction: 2+1+1+2 words + 14 reals
@@ -128,11 +117,32 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     return L;
 }
 
-// shared memory per CTA: body state of the world being solved (indexed by body id)
-B2B_HD size_t smem_plan(const caps_t& c, int real_bytes)
+// Shared memory per CTA: the world's bodies (indexed by body id), the contact graph the island walk and the
+// level scheduler traverse, and the per-island level tables.
+struct smem_layout {
+    size_t off_real, off_flags, off_ctl, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_sched, off_ls, off_nlev,
+        off_cflag, total;
+};
+B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
 {
-    return (size_t)real_bytes * 10 * (size_t)c.nb + sizeof(uint32_t) * (size_t)c.nb + 64 * (size_t)real_bytes + 64;
+    smem_layout S;
+    size_t o = 0;
+    S.off_real = o; o = align_up(o + (size_t)real_bytes * (10 * (size_t)c.nb + 64), 16);
+    S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 16);
+    S.off_ctl = o; o = align_up(o + sizeof(int32_t) * 16, 16);
+    S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 16);
+    S.off_adj = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 16);
+    S.off_adj_start = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);
+    S.off_stack = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);      // DFS stack, then `last level` per body
+    S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 16);
+    S.off_sched = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 16);
+    S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 16);
+    S.off_nlev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);
+    S.off_cflag = o; o = align_up(o + (size_t)c.nc, 16);
+    S.total = o;
+    return S;
 }
+B2B_HD size_t smem_plan(const caps_t& c, int real_bytes) { return smem_plan_layout(c, real_bytes).total; }
 
 struct step_params {
     double dt, dt_ratio_first, dt_ratio_rest;
@@ -154,7 +164,7 @@ template <class real> struct world_step {
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     const int32_t* s_meta; const real* s_radius; const real* s_data;
     // scratch (global, per CTA)
-    int32_t *wake_at, *scan, *adj_start, *adj_fill, *adj, *stack, *lev, *lstart, *sched, *last, *isl_nlev, *cc_int;
+    int32_t *wake_at, *scan, *cc_int;
     real* cc_real;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
@@ -164,6 +174,8 @@ template <class real> struct world_step {
     uint32_t* s_flags;
     real* s_red;        // [64] reduction slots
     int32_t* s_ctl;     // [16] control words
+    uint16_t *s_cbody, *s_adj, *s_adj_start, *s_stack, *s_last, *s_lev, *s_sched, *s_ls, *s_nlev;
+    uint8_t* s_cflag;
 
     B2B_D void bind(const batch_ptrs<real>& B, const caps_t& c, int w, unsigned char* scratch, const scratch_layout& L,
                     unsigned char* smem)
@@ -184,22 +196,23 @@ template <class real> struct world_step {
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
         wake_at = (int32_t*)(scratch + L.off_wake); scan = (int32_t*)(scratch + L.off_scan);
-        adj_start = (int32_t*)(scratch + L.off_adj_start); adj_fill = (int32_t*)(scratch + L.off_adj_fill);
-        adj = (int32_t*)(scratch + L.off_adj); stack = (int32_t*)(scratch + L.off_stack);
-        lev = (int32_t*)(scratch + L.off_lev); lstart = (int32_t*)(scratch + L.off_lstart);
-        sched = (int32_t*)(scratch + L.off_sched); last = (int32_t*)(scratch + L.off_last);
-        isl_nlev = (int32_t*)(scratch + L.off_isl_nlev); cc_int = (int32_t*)(scratch + L.off_cc_int);
+        cc_int = (int32_t*)(scratch + L.off_cc_int);
         cc_real = (real*)(scratch + L.off_cc_real);
         tmp_cr = (real*)(scratch + L.off_tmp_contact);
         tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)c.nc + 2));
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
-        real* sr = (real*)smem;
+        const smem_layout S = smem_plan_layout(c, (int)sizeof(real));
+        real* sr = (real*)(smem + S.off_real);
         s_vx = sr; s_vy = sr + c.nb; s_w = sr + 2 * c.nb; s_cx = sr + 3 * c.nb; s_cy = sr + 4 * c.nb; s_a = sr + 5 * c.nb;
         s_im = sr + 6 * c.nb; s_ii = sr + 7 * c.nb; s_lcx = sr + 8 * c.nb; s_lcy = sr + 9 * c.nb;
         s_red = sr + 10 * c.nb;
-        s_flags = (uint32_t*)(s_red + 64);
-        s_ctl = (int32_t*)(s_flags + c.nb);
+        s_flags = (uint32_t*)(smem + S.off_flags);
+        s_ctl = (int32_t*)(smem + S.off_ctl);
+        s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
+        s_adj_start = (uint16_t*)(smem + S.off_adj_start); s_stack = (uint16_t*)(smem + S.off_stack); s_last = s_stack;
+        s_lev = (uint16_t*)(smem + S.off_lev); s_sched = (uint16_t*)(smem + S.off_sched); s_ls = (uint16_t*)(smem + S.off_ls);
+        s_nlev = (uint16_t*)(smem + S.off_nlev); s_cflag = (uint8_t*)(smem + S.off_cflag);
     }
 
     B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
@@ -335,97 +348,111 @@ template <class real> struct world_step {
     }
 
     // ------------------------------------------------------------------------------------ K2
+    // Stage the world's bodies in shared memory: the island builder and the solver both index them by body id.
+    B2B_D void stage_bodies()
+    {
+        const int nb = w_count[0];
+        B2B_PFOR(b, nb) {
+            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
+            s_cx[b] = p[0]; s_cy[b] = p[1]; s_a[b] = p[2];
+            s_vx[b] = v[0]; s_vy[b] = v[1]; s_w[b] = v[2];
+            s_im[b] = m[0]; s_ii[b] = m[1]; s_lcx[b] = m[2]; s_lcy[b] = m[3];
+            s_flags[b] = b_flags[b] & ~BODY_ISLAND;
+            b_island[b] = -1;
+        }
+        B2B_SYNC();
+    }
+
     // Body._contacts of every non-static body as CSR rows in contact-creation order
-    // (contact_manager.py:157-158 appends, :170-172 removes in place).  Static bodies never expand in the
-    // island DFS (world.py:524-525), so their rows are not built.
+    // (contact_manager.py:157-158 appends, :170-172 removes in place), built in shared memory together with
+    // each contact's body pair and island-eligibility bit.  Static bodies never expand in the island DFS
+    // (world.py:524-525), so their rows are not built.
     B2B_D void build_adjacency()
     {
         const int nb = w_count[0], nc = w_count[2];
-        B2B_PFOR(b, nb + 1) adj_start[b] = 0;
+        B2B_PFOR(b, nb + 1) scan[b] = 0;
         B2B_SYNC();
         B2B_PFOR(c, nc) {
             const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
-            if (body_type(ba) != BODY_STATIC) B2B_ATOMIC_ADD(&adj_start[ba], 1);
-            if (body_type(bb) != BODY_STATIC) B2B_ATOMIC_ADD(&adj_start[bb], 1);
+            s_cbody[2 * c] = (uint16_t)ba; s_cbody[2 * c + 1] = (uint16_t)bb;
+            const uint32_t cf = c_flags[c];
+            s_cflag[c] = (uint8_t)(((cf & CONTACT_ENABLED) && (cf & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
+            if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[ba], 1);
+            if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[bb], 1);
         }
-        exclusive_scan(adj_start, nb + 1, 3);
-        B2B_PFOR(b, nb) adj_fill[b] = adj_start[b];
+        exclusive_scan(scan, nb + 1, 3);
+        B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)scan[b]; }
         B2B_SYNC();
         B2B_PFOR(c, nc) {
-            const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
-            if (body_type(ba) != BODY_STATIC) adj[B2B_ATOMIC_ADD(&adj_fill[ba], 1)] = c;
-            if (body_type(bb) != BODY_STATIC) adj[B2B_ATOMIC_ADD(&adj_fill[bb], 1)] = c;
+            const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
+            if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&scan[ba], 1)] = (uint16_t)c;
+            if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&scan[bb], 1)] = (uint16_t)c;
         }
         B2B_SYNC();
         // restore creation order inside each row (rows are short: <= contacts per body)
         B2B_PFOR(b, nb) {
-            const int s = adj_start[b], e = adj_start[b + 1];
+            const int s = s_adj_start[b], e = s_adj_start[b + 1];
             for (int i = s + 1; i < e; ++i) {
-                const int v = adj[i];
+                const uint16_t v = s_adj[i];
                 int j = i - 1;
-                while (j >= s && adj[j] > v) { adj[j + 1] = adj[j]; --j; }
-                adj[j + 1] = v;
+                while (j >= s && s_adj[j] > v) { s_adj[j + 1] = s_adj[j]; --j; }
+                s_adj[j + 1] = v;
             }
         }
         B2B_SYNC();
     }
 
-    B2B_D void wake_body(int b)
-    {
-        const uint32_t f = b_flags[b];
-        if (!(f & BODY_AWAKE)) { b_pos[4 * (size_t)b + 3] = real(0); b_flags[b] = f | BODY_AWAKE; }
-    }
-
     // World._solve island construction (world.py:484-580): seeds in body order, LIFO DFS over
     // Body._contacts in creation order, statics join but do not propagate.  Strictly sequential per
-    // world; the lists it emits (l_body / l_contact / l_start) are graded integer outputs.
+    // world; the lists it emits (l_body / l_contact / l_start) are graded integer outputs.  All the state the
+    // walk touches is in shared memory; flags and sleep timers are written back afterwards.
     B2B_D void phase_islands()
     {
         const int nb = w_count[0], nc = w_count[2];
-        B2B_PFOR(b, nb) { b_flags[b] &= ~BODY_ISLAND; b_island[b] = -1; }
-        B2B_PFOR(c, nc) c_flags[c] &= ~CONTACT_ISLAND;
-        B2B_SYNC();
         if (B2B_IS_T0) {
             int n_islands = 0, lb = 0, lc = 0;
             bool overflow = false;
             for (int seed = 0; seed < nb && !overflow; ++seed) {
-                const uint32_t fl = b_flags[seed];
+                const uint32_t fl = s_flags[seed];
                 if (fl & BODY_ISLAND) continue;
                 if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
                 if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
                 const int body_start = lb, contact_start = lc;
                 int sp = 0;
-                stack[sp++] = seed;
-                b_flags[seed] = fl | BODY_ISLAND;
+                s_stack[sp++] = (uint16_t)seed;
+                s_flags[seed] = fl | BODY_ISLAND;
                 while (sp > 0) {
-                    const int b = stack[--sp];
+                    const int b = s_stack[--sp];
                     if (lb >= cap.nl) { overflow = true; break; }
                     b_island[b] = lb - body_start;
                     l_body[lb++] = b;
-                    wake_body(b);
-                    if (body_type(b) == BODY_STATIC) continue;
+                    // Body.awake = True (body.py:800-804): a sleeping body that is reached restarts its sleep timer
+                    uint32_t bf = s_flags[b];
+                    if (!(bf & BODY_AWAKE)) { bf |= BODY_AWAKE | BODY_WOKEN; s_flags[b] = bf; }
+                    if ((bf & BODY_TYPE_MASK) == BODY_STATIC) continue;
                     const int first = lc;
-                    for (int k = adj_start[b]; k < adj_start[b + 1]; ++k) {
-                        const int c = adj[k];
-                        const uint32_t cf = c_flags[c];
-                        if ((cf & CONTACT_ISLAND) || !(cf & CONTACT_ENABLED) || !(cf & CONTACT_TOUCHING)) continue;
+                    for (int k = s_adj_start[b]; k < s_adj_start[b + 1]; ++k) {
+                        const int c = s_adj[k];
+                        if (s_cflag[c] != 1) continue;                 // already in an island, disabled or not touching
                         l_contact[lc++] = c;
                     }
                     for (int k = first; k < lc; ++k) {
                         const int c = l_contact[k];
-                        c_flags[c] |= CONTACT_ISLAND;
-                        const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                        s_cflag[c] = 3;                                // island flag
+                        const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
                         const int other = (b == ba) ? bb : ba;
-                        if (b_flags[other] & BODY_ISLAND) continue;
-                        stack[sp++] = other;
-                        b_flags[other] |= BODY_ISLAND;
+                        if (s_flags[other] & BODY_ISLAND) continue;
+                        s_stack[sp++] = (uint16_t)other;
+                        s_flags[other] |= BODY_ISLAND;
                     }
                 }
                 if (overflow) break;
                 l_start[2 * n_islands] = body_start; l_start[2 * n_islands + 1] = contact_start;
                 // statics may join other islands (world.py:577-580)
-                for (int k = body_start; k < lb; ++k)
-                    if (body_type(l_body[k]) == BODY_STATIC) b_flags[l_body[k]] &= ~BODY_ISLAND;
+                for (int k = body_start; k < lb; ++k) {
+                    const int b = l_body[k];
+                    if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) s_flags[b] &= ~BODY_ISLAND;
+                }
                 ++n_islands;
             }
             if (overflow) w_status[0] |= STATUS_ISLAND_OVERFLOW;
@@ -433,21 +460,34 @@ template <class real> struct world_step {
             s_ctl[4] = n_islands; s_ctl[5] = lb; s_ctl[6] = lc;
         }
         B2B_SYNC();
+        B2B_PFOR(b, nb) {
+            uint32_t f = s_flags[b];
+            if (f & BODY_WOKEN) { b_pos[4 * (size_t)b + 3] = real(0); f &= ~BODY_WOKEN; s_flags[b] = f; }
+            b_flags[b] = f;
+            s_last[b] = 0;                                 // the DFS stack's storage becomes the scheduler's `last level`
+        }
+        B2B_PFOR(c, nc) {
+            const uint32_t cf = c_flags[c];
+            c_flags[c] = (s_cflag[c] == 3) ? (cf | CONTACT_ISLAND) : (cf & ~CONTACT_ISLAND);
+        }
+        B2B_SYNC();
     }
 
     // ------------------------------------------------------------------------------------ K3
-    // constraint slot accessors: SoA rows of length cap.nc, slot = position in the level schedule
-    enum {
-        R_NX = 0, R_NY, R_FRICTION,
-        R_RAX0, R_RAY0, R_RBX0, R_RBY0, R_NMASS0, R_TMASS0, R_BIAS0, R_NI0, R_TI0,
-        R_RAX1, R_RAY1, R_RBX1, R_RBY1, R_NMASS1, R_TMASS1, R_BIAS1, R_NI1, R_TI1,
-        R_K11, R_K12, R_K22, R_NM11, R_NM12, R_NM22,
-        R_LNX, R_LNY, R_LPX, R_LPY, R_P0X, R_P0Y, R_P1X, R_P1Y, R_RADA, R_RADB,
-        R_COUNT
-    };
-    enum { I_BODY_A = 0, I_BODY_B, I_INFO, I_CONTACT };   // info = type | n_pos << 8 | n_vel << 16
-    B2B_D real& R(int f, int slot) { return cc_real[(size_t)f * cap.nc + slot]; }
-    B2B_D int32_t& I(int f, int slot) { return cc_int[(size_t)f * cap.nc + slot]; }
+    // One constraint = CC_QUADS 4-vectors of reals, array-of-structures in schedule order, so the lane that
+    // solves it fetches it with a handful of 128-bit loads; its integers are one 4-word record alongside
+    // (body_a, body_b, n_vel | type << 8 | n_pos << 16, contact).
+    //   q0  normal.x normal.y friction -               q1  rA0.x rA0.y rB0.x rB0.y
+    //   q2  nmass0   tmass0   bias0    -               q3  rA1.x rA1.y rB1.x rB1.y
+    //   q4  nmass1   tmass1   bias1    -               q5  k11 k12 k22 nm11
+    //   q6  nm12     nm22     -        -               q7  ni0 ti0 ni1 ti1            (q7 is the only read-write quad)
+    //   q8  ln.x ln.y lp.x lp.y                        q9  p0.x p0.y p1.x p1.y
+    //   q10 radius_a radius_b -        -
+    struct alignas(4 * sizeof(real)) quad { real x, y, z, w; };
+    B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
+    struct alignas(16) iquad { int32_t body_a, body_b, info, contact; };
+    B2B_D quad* rec(int slot) { return reinterpret_cast<quad*>(cc_real) + (size_t)CC_QUADS * slot; }
+    B2B_D iquad* irec(int slot) { return reinterpret_cast<iquad*>(cc_int) + slot; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
     {
@@ -459,7 +499,7 @@ template <class real> struct world_step {
     B2B_D void constraint_init(int slot, int ci, real dt_ratio, bool warm)
     {
         const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
-        const int ba = f_body[fa], bb = f_body[fb];
+        const int ba = s_cbody[2 * ci], bb = s_cbody[2 * ci + 1];
         const int mt = c_mtype[ci];
         const int type = mt & 0xff, count = (mt >> 8) & 0xff;
         const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci; const real* imp = c_imp + 4 * (size_t)ci;
@@ -507,28 +547,22 @@ template <class real> struct world_step {
         const V2 tangent = right_perp(normal);
         int n_vel = count;
         V2 ra[2], rb[2];
+        real nmass[2], tmass[2], bias[2], ni[2], ti[2];
         for (int j = 0; j < 2; ++j) {
-            const int o = j * 9;
-            if (j >= count) {
-                for (int k = 0; k < 9; ++k) R(R_RAX0 + o + k, slot) = real(0);
-                ra[j] = rb[j] = mk<real>(real(0), real(0));
-                continue;
-            }
+            ra[j] = rb[j] = mk<real>(real(0), real(0));
+            nmass[j] = tmass[j] = bias[j] = ni[j] = ti[j] = real(0);
+            if (j >= count) continue;
             ra[j] = wp[j] - ca; rb[j] = wp[j] - cb;
             const real rn_a = cross(ra[j], normal), rn_b = cross(rb[j], normal);
             const real k_normal = ma + mb + ia * (rn_a * rn_a) + ib * (rn_b * rn_b);
             const real rt_a = cross(ra[j], tangent), rt_b = cross(rb[j], tangent);
             const real k_tangent = ma + mb + ia * (rt_a * rt_a) + ib * (rt_b * rt_b);
-            real bias = real(0);
             const real v_rel = dot(normal, rel_velocity(vb, wb, rb[j], va, wa, ra[j]));
-            if (v_rel < -K<real>::velocity_threshold) bias = -restitution * v_rel;
-            R(R_RAX0 + o, slot) = ra[j].x; R(R_RAY0 + o, slot) = ra[j].y;
-            R(R_RBX0 + o, slot) = rb[j].x; R(R_RBY0 + o, slot) = rb[j].y;
-            R(R_NMASS0 + o, slot) = (k_normal > real(0)) ? real(1) / k_normal : real(0);
-            R(R_TMASS0 + o, slot) = (k_tangent > real(0)) ? real(1) / k_tangent : real(0);
-            R(R_BIAS0 + o, slot) = bias;
-            R(R_NI0 + o, slot) = warm ? dt_ratio * imp[2 * j] : imp[2 * j];
-            R(R_TI0 + o, slot) = warm ? dt_ratio * imp[2 * j + 1] : imp[2 * j + 1];
+            if (v_rel < -K<real>::velocity_threshold) bias[j] = -restitution * v_rel;
+            nmass[j] = (k_normal > real(0)) ? real(1) / k_normal : real(0);
+            tmass[j] = (k_tangent > real(0)) ? real(1) / k_tangent : real(0);
+            ni[j] = warm ? dt_ratio * imp[2 * j] : imp[2 * j];
+            ti[j] = warm ? dt_ratio * imp[2 * j + 1] : imp[2 * j + 1];
         }
         real k11 = real(0), k12 = real(0), k22 = real(0), nm11 = real(0), nm12 = real(0), nm22 = real(0);
         if (count == 2) {
@@ -545,16 +579,20 @@ template <class real> struct world_step {
                 n_vel = 1;                                   // redundant point dropped from the velocity rows only
             }
         }
-        R(R_NX, slot) = normal.x; R(R_NY, slot) = normal.y; R(R_FRICTION, slot) = friction;
-        R(R_K11, slot) = k11; R(R_K12, slot) = k12; R(R_K22, slot) = k22;
-        R(R_NM11, slot) = nm11; R(R_NM12, slot) = nm12; R(R_NM22, slot) = nm22;
-        R(R_LNX, slot) = local_normal.x; R(R_LNY, slot) = local_normal.y;
-        R(R_LPX, slot) = local_point.x; R(R_LPY, slot) = local_point.y;
-        R(R_P0X, slot) = lp[0].x; R(R_P0Y, slot) = lp[0].y; R(R_P1X, slot) = lp[1].x; R(R_P1Y, slot) = lp[1].y;
-        R(R_RADA, slot) = rad_a; R(R_RADB, slot) = rad_b;
-        I(I_BODY_A, slot) = ba; I(I_BODY_B, slot) = bb;
-        I(I_INFO, slot) = type | (count << 8) | (n_vel << 16);
-        I(I_CONTACT, slot) = ci;
+        quad* q = rec(slot);
+        iquad iq; iq.body_a = ba; iq.body_b = bb; iq.info = n_vel | (type << 8) | (count << 16); iq.contact = ci;
+        *irec(slot) = iq;
+        q[0] = mkq(normal.x, normal.y, friction, real(0));
+        q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
+        q[2] = mkq(nmass[0], tmass[0], bias[0], real(0));
+        q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
+        q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
+        q[5] = mkq(k11, k12, k22, nm11);
+        q[6] = mkq(nm12, nm22, real(0), real(0));
+        q[7] = mkq(ni[0], ti[0], ni[1], ti[1]);
+        q[8] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
+        q[9] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
+        q[10] = mkq(rad_a, rad_b, real(0), real(0));
     }
 
     B2B_D void store_vel(int b, V2 v, real w)
@@ -569,16 +607,18 @@ template <class real> struct world_step {
     // ContactSolver.warm_start for one slot (contact.py:498-525)
     B2B_D void constraint_warm_start(int slot)
     {
-        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
-        const int n_vel = (I(I_INFO, slot) >> 16) & 0xff;
-        const V2 normal = mk<real>(R(R_NX, slot), R(R_NY, slot)), tangent = right_perp(normal);
+        const quad* q = rec(slot);
+        const iquad iq = *irec(slot);
+        const quad q0 = q[0], q1 = q[1], q3 = q[3], q7 = q[7];
+        const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
+        const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
         V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
         real wa = s_w[ba], wb = s_w[bb];
         for (int j = 0; j < n_vel; ++j) {
-            const int o = j * 9;
-            const V2 ra = mk<real>(R(R_RAX0 + o, slot), R(R_RAY0 + o, slot)), rb = mk<real>(R(R_RBX0 + o, slot), R(R_RBY0 + o, slot));
-            const V2 p = R(R_NI0 + o, slot) * normal + R(R_TI0 + o, slot) * tangent;
+            const quad r = (j == 0) ? q1 : q3;
+            const V2 ra = mk<real>(r.x, r.y), rb = mk<real>(r.z, r.w);
+            const V2 p = ((j == 0) ? q7.x : q7.z) * normal + ((j == 0) ? q7.y : q7.w) * tangent;
             wa = wa - ia * cross(ra, p);
             va = va - ma * p;
             wb = wb + ib * cross(rb, p);
@@ -591,63 +631,70 @@ template <class real> struct world_step {
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
     B2B_D void constraint_solve_velocity(int slot)
     {
-        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
-        const int n_vel = (I(I_INFO, slot) >> 16) & 0xff;
-        const V2 normal = mk<real>(R(R_NX, slot), R(R_NY, slot)), tangent = right_perp(normal);
-        const real friction = R(R_FRICTION, slot);
+        quad* q = rec(slot);
+        const iquad iq = *irec(slot);
+        const quad q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6];
+        quad q7 = q[7];
+        const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
+        const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
+        const real friction = q0.z;
         const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
         V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
         real wa = s_w[ba], wb = s_w[bb];
-        V2 ra[2], rb[2];
-        for (int j = 0; j < 2; ++j) {
-            const int o = j * 9;
-            ra[j] = mk<real>(R(R_RAX0 + o, slot), R(R_RAY0 + o, slot));
-            rb[j] = mk<real>(R(R_RBX0 + o, slot), R(R_RBY0 + o, slot));
-        }
+        const V2 ra0 = mk<real>(q1.x, q1.y), rb0 = mk<real>(q1.z, q1.w), ra1 = mk<real>(q3.x, q3.y), rb1 = mk<real>(q3.z, q3.w);
         // friction rows first, point by point
-        for (int j = 0; j < n_vel; ++j) {
-            const int o = j * 9;
-            const V2 dv = rel_velocity(vb, wb, rb[j], va, wa, ra[j]);
+        {
+            const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vt = dot(dv, tangent);
-            real lambda = R(R_TMASS0 + o, slot) * (-vt);
-            const real max_friction = friction * R(R_NI0 + o, slot);
-            const real old_imp = R(R_TI0 + o, slot);
-            const real new_imp = clamp_r(old_imp + lambda, -max_friction, max_friction);
-            lambda = new_imp - old_imp;
+            real lambda = q2.y * (-vt);
+            const real max_friction = friction * q7.x;
+            const real new_imp = clamp_r(q7.y + lambda, -max_friction, max_friction);
+            lambda = new_imp - q7.y;
             const V2 P = lambda * tangent;
-            va = va - ma * P; wa = wa - ia * cross(ra[j], P);
-            vb = vb + mb * P; wb = wb + ib * cross(rb[j], P);
-            R(R_TI0 + o, slot) = new_imp;
+            va = va - ma * P; wa = wa - ia * cross(ra0, P);
+            vb = vb + mb * P; wb = wb + ib * cross(rb0, P);
+            q7.y = new_imp;
+        }
+        if (n_vel == 2) {
+            const V2 dv = rel_velocity(vb, wb, rb1, va, wa, ra1);
+            const real vt = dot(dv, tangent);
+            real lambda = q4.y * (-vt);
+            const real max_friction = friction * q7.z;
+            const real new_imp = clamp_r(q7.w + lambda, -max_friction, max_friction);
+            lambda = new_imp - q7.w;
+            const V2 P = lambda * tangent;
+            va = va - ma * P; wa = wa - ia * cross(ra1, P);
+            vb = vb + mb * P; wb = wb + ib * cross(rb1, P);
+            q7.w = new_imp;
         }
         if (n_vel == 1) {
-            const V2 dv = rel_velocity(vb, wb, rb[0], va, wa, ra[0]);
+            const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vn = dot(dv, normal);
-            real lambda = -R(R_NMASS0, slot) * (vn - R(R_BIAS0, slot));
-            const real old_imp = R(R_NI0, slot);
-            const real new_imp = pymax(old_imp + lambda, real(0));
-            lambda = new_imp - old_imp;
+            real lambda = -q2.x * (vn - q2.z);
+            const real new_imp = pymax(q7.x + lambda, real(0));
+            lambda = new_imp - q7.x;
             const V2 P = lambda * normal;
-            va = va - ma * P; wa = wa - ia * cross(ra[0], P);
-            vb = vb + mb * P; wb = wb + ib * cross(rb[0], P);
-            R(R_NI0, slot) = new_imp;
-        } else if (n_vel == 2) {
+            va = va - ma * P; wa = wa - ia * cross(ra0, P);
+            vb = vb + mb * P; wb = wb + ib * cross(rb0, P);
+            q7.x = new_imp;
+        } else {
             // 2x2 LCP by total enumeration; first feasible case wins (contact.py:598-796)
-            const V2 a = mk<real>(R(R_NI0, slot), R(R_NI1, slot));
-            const V2 dv1 = rel_velocity(vb, wb, rb[0], va, wa, ra[0]);
-            const V2 dv2 = rel_velocity(vb, wb, rb[1], va, wa, ra[1]);
+            const V2 a = mk<real>(q7.x, q7.z);
+            const V2 dv1 = rel_velocity(vb, wb, rb0, va, wa, ra0);
+            const V2 dv2 = rel_velocity(vb, wb, rb1, va, wa, ra1);
             const real vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-            const real k11 = R(R_K11, slot), k12 = R(R_K12, slot), k22 = R(R_K22, slot);
-            V2 b = mk<real>(vn1 - R(R_BIAS0, slot), vn2 - R(R_BIAS1, slot));
+            const real k11 = q5.x, k12 = q5.y, k22 = q5.z;
+            V2 b = mk<real>(vn1 - q2.z, vn2 - q4.z);
             b = b - mk<real>(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
-            const real nm11 = R(R_NM11, slot), nm12 = R(R_NM12, slot), nm22 = R(R_NM22, slot);
+            const real nm11 = q5.w, nm12 = q6.x, nm22 = q6.y;
             V2 x = -mk<real>(nm11 * b.x + nm12 * b.y, nm12 * b.x + nm22 * b.y);
             bool solved = (x.x >= real(0) && x.y >= real(0));
             if (!solved) {
-                x = mk<real>(-R(R_NMASS0, slot) * b.x, real(0));
+                x = mk<real>(-q2.x * b.x, real(0));
                 solved = (x.x >= real(0)) && (k12 * x.x + b.y >= real(0));
             }
             if (!solved) {
-                x = mk<real>(real(0), -R(R_NMASS1, slot) * b.y);
+                x = mk<real>(real(0), -q4.x * b.y);
                 solved = (x.y >= real(0)) && (k12 * x.y + b.x >= real(0));
             }
             if (!solved) {
@@ -658,11 +705,12 @@ template <class real> struct world_step {
                 const V2 d = x - a;
                 const V2 p1 = d.x * normal, p2 = d.y * normal;
                 const V2 p12 = p1 + p2;
-                va = va - ma * p12; wa = wa - ia * (cross(ra[0], p1) + cross(ra[1], p2));
-                vb = vb + mb * p12; wb = wb + ib * (cross(rb[0], p1) + cross(rb[1], p2));
-                R(R_NI0, slot) = x.x; R(R_NI1, slot) = x.y;
+                va = va - ma * p12; wa = wa - ia * (cross(ra0, p1) + cross(ra1, p2));
+                vb = vb + mb * p12; wb = wb + ib * (cross(rb0, p1) + cross(rb1, p2));
+                q7.x = x.x; q7.z = x.y;
             }
         }
+        q[7] = q7;
         store_vel(ba, va, wa);
         store_vel(bb, vb, wb);
     }
@@ -671,23 +719,25 @@ template <class real> struct world_step {
     // returns the smallest separation seen.
     B2B_D real constraint_solve_position(int slot)
     {
-        const int ba = I(I_BODY_A, slot), bb = I(I_BODY_B, slot);
-        const int info = I(I_INFO, slot);
-        const int type = info & 0xff, n_pos = (info >> 8) & 0xff;
+        const quad* q = rec(slot);
+        const iquad iq = *irec(slot);
+        const quad q8 = q[8], q9 = q[9], q10 = q[10];
+        const int ba = iq.body_a, bb = iq.body_b;
+        const int type = (iq.info >> 8) & 0xff, n_pos = (iq.info >> 16) & 0xff;
         const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
         const V2 lca = mk<real>(s_lcx[ba], s_lcy[ba]), lcb = mk<real>(s_lcx[bb], s_lcy[bb]);
-        const V2 local_normal = mk<real>(R(R_LNX, slot), R(R_LNY, slot)), local_point = mk<real>(R(R_LPX, slot), R(R_LPY, slot));
-        const real rad_a = R(R_RADA, slot), rad_b = R(R_RADB, slot);
+        const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
+        const real rad_a = q10.x, rad_b = q10.y;
         V2 ca = mk<real>(s_cx[ba], s_cy[ba]), cb = mk<real>(s_cx[bb], s_cy[bb]);
         real aa = s_a[ba], ab = s_a[bb];
         real min_sep = real(0);
         for (int j = 0; j < n_pos; ++j) {
             const XF xa = xf_from_sweep<real>(ca, aa, lca), xb = xf_from_sweep<real>(cb, ab, lcb);
-            const V2 lpj = (j == 0) ? mk<real>(R(R_P0X, slot), R(R_P0Y, slot)) : mk<real>(R(R_P1X, slot), R(R_P1Y, slot));
+            const V2 lpj = (j == 0) ? mk<real>(q9.x, q9.y) : mk<real>(q9.z, q9.w);
             V2 normal, point;
             real separation;
             if (type == MANIFOLD_CIRCLES) {
-                const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, mk<real>(R(R_P0X, slot), R(R_P0Y, slot)));
+                const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, mk<real>(q9.x, q9.y));
                 normal = normalize(pb - pa);
                 point = real(0.5) * (pa + pb);
                 separation = dot(pb - pa, normal) - rad_a - rad_b;
@@ -724,23 +774,12 @@ template <class real> struct world_step {
     // shares a non-static body.  Contacts of one level touch disjoint non-static bodies, so solving a level's
     // contacts concurrently gives bit-identical results to the reference's sequential Gauss-Seidel sweep,
     // and every body still sees its contacts in list order.  A stable counting sort by level gives `sched`;
-    // constraint rows are then laid out in schedule order so a level's rows are contiguous (coalesced).
+    // constraint records are then laid out in schedule order so a level's records are contiguous.
     B2B_D void solve_islands(const step_params& sp, real dt, real dt_ratio)
     {
-        const int nb = w_count[0];
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
-        // stage every body of the world (islands also read their static members)
-        B2B_PFOR(b, nb) {
-            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
-            s_cx[b] = p[0]; s_cy[b] = p[1]; s_a[b] = p[2];
-            s_vx[b] = v[0]; s_vy[b] = v[1]; s_w[b] = v[2];
-            s_im[b] = m[0]; s_ii[b] = m[1]; s_lcx[b] = m[2]; s_lcy[b] = m[3];
-            s_flags[b] = b_flags[b];
-            last[b] = 0;
-        }
-        B2B_SYNC();
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
@@ -772,40 +811,40 @@ template <class real> struct world_step {
             }
             B2B_PROF(PROF_S_INTEGRATE, t);
             int nlev = 0;
-            int32_t* ls = lstart + c0 + 3 * isl;          // level l (1-based) occupies slots [ls[l], ls[l+1]) + c0
+            uint16_t* ls = s_ls + c0 + 3 * isl;          // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
             if (ncon > 0) {
-                // -- level schedule (lane 0), then constraint rows in schedule order
+                // -- level schedule (lane 0), then constraint records in schedule order
                 if (B2B_LANE == 0) {
                     for (int k = 0; k < ncon + 3; ++k) ls[k] = 0;
                     for (int k = c0; k < c1; ++k) {
                         const int c = l_contact[k];
-                        const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                        const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
                         const bool dyn_a = (s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC;
                         const bool dyn_b = (s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC;
                         int l = 0;
-                        if (dyn_a) l = last[ba];
-                        if (dyn_b && last[bb] > l) l = last[bb];
+                        if (dyn_a) l = s_last[ba];
+                        if (dyn_b && s_last[bb] > l) l = s_last[bb];
                         ++l;
-                        if (dyn_a) last[ba] = l;
-                        if (dyn_b) last[bb] = l;
-                        lev[k] = l;
+                        if (dyn_a) s_last[ba] = (uint16_t)l;
+                        if (dyn_b) s_last[bb] = (uint16_t)l;
+                        s_lev[k] = (uint16_t)l;
                         ++ls[l + 1];                          // count of level l parked one slot up
                         if (l > nlev) nlev = l;
                     }
                     // ls[l + 1] = count(l)  ->  ls[l] = start(l) for l = 1..nlev+1  (ls[nlev + 1] = ncon)
                     int run = 0;
-                    for (int l = 1; l <= nlev; ++l) { const int cnt = ls[l + 1]; ls[l] = run; run += cnt; }
-                    ls[nlev + 1] = run;
+                    for (int l = 1; l <= nlev; ++l) { const int cnt = ls[l + 1]; ls[l] = (uint16_t)run; run += cnt; }
+                    ls[nlev + 1] = (uint16_t)run;
                     // stable placement; ls[l] is advanced while filling and restored afterwards
-                    for (int k = c0; k < c1; ++k) { const int l = lev[k]; sched[c0 + ls[l]] = k; ++ls[l]; }
+                    for (int k = c0; k < c1; ++k) { const int l = s_lev[k]; s_sched[c0 + ls[l]] = (uint16_t)k; ++ls[l]; }
                     for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
                     ls[1] = 0;
-                    isl_nlev[isl] = nlev;
+                    s_nlev[isl] = (uint16_t)nlev;
                 }
                 B2B_WSYNC();
                 B2B_PROF(PROF_S_SCHEDULE, t);
-                nlev = isl_nlev[isl];
-                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[sched[s]], dt_ratio, warm);
+                nlev = s_nlev[isl];
+                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[s_sched[s]], dt_ratio, warm);
                 B2B_WSYNC();
                 B2B_PROF(PROF_S_INIT, t);
                 if (warm) {
@@ -824,11 +863,13 @@ template <class real> struct world_step {
                 B2B_PROF(PROF_S_VELOCITY, t);
                 // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
                 for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
-                    const int ci = I(I_CONTACT, s);
-                    const int n_vel = (I(I_INFO, s) >> 16) & 0xff;
+                    const quad* q = rec(s);
+                    const quad q7 = q[7];
+                    const iquad iq = *irec(s);
+                    const int ci = iq.contact, n_vel = iq.info & 0xff;
                     real* imp = c_imp + 4 * (size_t)ci;
-                    if (n_vel > 0) { imp[0] = R(R_NI0, s); imp[1] = R(R_TI0, s); }
-                    if (n_vel > 1) { imp[2] = R(R_NI1, s); imp[3] = R(R_TI1, s); }
+                    if (n_vel > 0) { imp[0] = q7.x; imp[1] = q7.y; }
+                    if (n_vel > 1) { imp[2] = q7.z; imp[3] = q7.w; }
                 }
             }
             B2B_WSYNC();
@@ -881,8 +922,8 @@ template <class real> struct world_step {
                 real* p = b_pos + 4 * (size_t)b; real* v = b_vel + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
                 p[0] = s_cx[b]; p[1] = s_cy[b]; p[2] = s_a[b];
                 v[0] = s_vx[b]; v[1] = s_vy[b]; v[2] = s_w[b];
-                const XF t = xf_from_sweep<real>(mk<real>(s_cx[b], s_cy[b]), s_a[b], mk<real>(s_lcx[b], s_lcy[b]));
-                x[0] = t.p.x; x[1] = t.p.y; x[2] = t.c1.x; x[3] = t.c1.y;
+                const XF tf = xf_from_sweep<real>(mk<real>(s_cx[b], s_cy[b]), s_a[b], mk<real>(s_lcx[b], s_lcy[b]));
+                x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
             }
             B2B_WSYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);
@@ -903,9 +944,9 @@ template <class real> struct world_step {
                             *st = real(0);
                             min_sleep = real(0);
                         } else {
-                            const real t = *st + dt;
-                            *st = t;
-                            min_sleep = pymin(min_sleep, t);
+                            const real ts = *st + dt;
+                            *st = ts;
+                            min_sleep = pymin(min_sleep, ts);
                         }
                     }
                     if (min_sleep >= K<real>::time_to_sleep && position_solved && victim >= 0) {
@@ -986,8 +1027,8 @@ template <class real> struct world_step {
         bool exists = false;
         if (have_adjacency) {
             const int bs = (tb != BODY_STATIC) ? bb : ba;                          // a row that was built
-            for (int k = adj_start[bs]; k < adj_start[bs + 1] && !exists; ++k) {
-                const int c = adj[k];
+            for (int k = s_adj_start[bs]; k < s_adj_start[bs + 1] && !exists; ++k) {
+                const int c = s_adj[k];
                 const int ca = c_fix[2 * c], cb = c_fix[2 * c + 1];
                 exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
             }
@@ -1088,6 +1129,7 @@ template <class real> struct world_step {
             phase_collide();                                         // world.py:338
             B2B_PROF(PROF_COLLIDE, t);
             if (sp.dt > 0.0) {                                       // world.py:341-342
+                stage_bodies();
                 build_adjacency();
                 B2B_PROF(PROF_ADJACENCY, t);
                 phase_islands();

@@ -18,14 +18,14 @@ def run(n_worlds, real, threads, settle=200, steps=4, ctas=0):
     p = bw.profile()
     ws = max(p.pop("world_steps"), 1)
     tot = sum(p[k] for k in ("pairs0","collide","adjacency","islands","solve","sync","pairs","clear"))
-    print("%s worlds=%d threads=%d grid=%d: %.2f ms/step %.3e body-steps/s; cycles/world-step %.0f" % (
-        real, n_worlds, threads, bw.info()["grid"], ms/steps, 210*n_worlds*steps/(ms*1e-3), tot/ws))
+    info = bw.info()
+    print("%s worlds=%d threads=%d grid=%d smem=%d: %.2f ms/step %.3e body-steps/s; cycles/world-step %.0f status=%d" % (
+        real, n_worlds, threads, info["grid"], info["smem_bytes"], ms/steps, 210*n_worlds*steps/(ms*1e-3), tot/ws, bw.status(False)))
     print("   top:", {k: "%.1f%%" % (100*p[k]/tot) for k in ("collide","adjacency","islands","solve","sync","pairs","clear")})
-    print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]})
+    print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]}, flush=True)
 
 if __name__ == "__main__":
-    run(2368, "f32", 32)
-    run(2368, "f32", 32, ctas=4)
-    run(2368, "f32", 32, ctas=1)
-    run(1184, "f32", 64)
-    run(1184, "f64", 64)
+    run(148, "f32", 32, ctas=1)
+    run(8192, "f32", 32)
+    run(8192, "f32", 64)
+    run(4096, "f64", 32)
