@@ -19,6 +19,7 @@ struct b2b_ctx {
     int n_sm;
     launch_plan plan;
     unsigned char* scratch;
+    uint16_t* plan_rows;
     uint32_t* d_status;
     void* stage_in;       // [n_worlds][nb][3] reals
     void* stage_out;      // [n_worlds][nb][6] reals
@@ -47,7 +48,8 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 static bool caps_ok(const b2b_caps* k)
 {
     return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
-           (k->real_bytes == 4 || k->real_bytes == 8) && k->threads >= 0 && k->threads <= 256 && (k->threads % 32) == 0;
+           (k->real_bytes == 4 || k->real_bytes == 8) && k->threads >= 0 && k->threads <= 128 && (k->threads % 32) == 0 &&
+           k->reserved >= 0 && k->reserved <= 128 && (k->reserved % 32) == 0 && k->nb < 65535 && k->nc < 65535;
 }
 
 static caps_t to_caps(const b2b_caps* k)
@@ -92,13 +94,17 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     cudaError_t e = cudaGetDeviceProperties(&prop, caps->device);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaGetDeviceProperties", e); }
     x->n_sm = prop.multiProcessorCount;
-    const int threads = caps->threads > 0 ? caps->threads : 64;
-    int rc = x->f64 ? plan_f64(x->c, threads, caps->ctas_per_sm, x->n_sm, &x->plan)
-                    : plan_f32(x->c, threads, caps->ctas_per_sm, x->n_sm, &x->plan);
+    const int threads = 32;   // the solve kernel is one warp per CTA (launch bounds); caps->threads is ignored
+    const int threads_aux = caps->reserved > 0 ? caps->reserved : 64;
+    int rc = x->f64 ? plan_f64(x->c, threads, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
+                    : plan_f32(x->c, threads, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
     if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
-    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total * (size_t)x->plan.grid);
+    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total * (size_t)x->plan.max_grid);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
-    cudaMemset(x->scratch, 0, x->plan.layout.total * (size_t)x->plan.grid);
+    cudaMemset(x->scratch, 0, x->plan.layout.total * (size_t)x->plan.max_grid);
+    e = cudaMalloc((void**)&x->plan_rows, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
+    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(plan rows)", e); }
+    cudaMemset(x->plan_rows, 0, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
     e = cudaMalloc((void**)&x->d_status, sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(status)", e); }
     *out = x;
@@ -110,6 +116,7 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     if (!x) return;
     cudaSetDevice(x->caps.device);
     if (x->scratch) cudaFree(x->scratch);
+    if (x->plan_rows) cudaFree(x->plan_rows);
     if (x->d_status) cudaFree(x->d_status);
     if (x->stage_in) cudaFree(x->stage_in);
     if (x->stage_out) cudaFree(x->stage_out);
@@ -161,10 +168,15 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     if (vel_iters < 0 || pos_iters < 0 || n_steps < 0 || !(dt >= 0.0)) return fail(B2B_ERR_ARG, "b2b_step: bad argument");
     if (n_steps == 0) return B2B_OK;
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
-    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, n_steps, flags);
-    if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->scratch, sp, (cudaStream_t)stream);
-    else launch_step_f32(x->fields, x->c, x->plan, x->scratch, sp, (cudaStream_t)stream);
-    return check_launch(x, "step kernel");
+    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, flags);
+    for (int s = 0; s < n_steps; ++s) {
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, sp, s == 0, (cudaStream_t)stream);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, sp, s == 0, (cudaStream_t)stream);
+        int rc = check_launch(x, "step kernels");
+        if (rc) return rc;
+        x->launches += (dt > 0.0) ? 2 : 1;       // check_launch counted one of the three
+    }
+    return B2B_OK;
 }
 
 extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_state_out, double dt, double inv_dt0,
@@ -234,9 +246,9 @@ extern "C" int b2b_checksum(b2b_ctx* x, void* d_out, void* stream)
 extern "C" int b2b_info(b2b_ctx* x, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches)
 {
     if (!x) return fail(B2B_ERR_ARG, "b2b_info: NULL context");
-    if (grid) *grid = x->plan.grid;
-    if (threads) *threads = x->plan.threads;
-    if (smem_bytes) *smem_bytes = (int32_t)x->plan.smem;
+    if (grid) *grid = x->plan.k_solve.grid;
+    if (threads) *threads = x->plan.k_solve.threads;
+    if (smem_bytes) *smem_bytes = (int32_t)x->plan.k_solve.smem;
     if (launches) *launches = x->launches;
     return B2B_OK;
 }
@@ -248,7 +260,7 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
     CUDA_TRY(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] = 0;
     long long tmp[PROF_SLOTS];
-    for (int g = 0; g < x->plan.grid; ++g) {
+    for (int g = 0; g < x->plan.max_grid; ++g) {
         unsigned char* p = x->scratch + (size_t)g * x->plan.layout.total + x->plan.layout.off_prof;
         CUDA_TRY(cudaMemcpy(tmp, p, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H profile");
         for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] += tmp[k];

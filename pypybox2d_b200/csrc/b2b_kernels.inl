@@ -10,20 +10,62 @@ namespace b2b {
 
 typedef B2B_REAL real_t;
 
-// K1..K6 fused: one CTA steps one world through all phases, n_steps times, then takes the next world
-// (persistent grid, worlds strided over CTAs).  State lives in the caller's SoA arrays; the per-CTA scratch
-// slab is reused for every world the CTA owns, so it stays L1/L2 resident.
-__global__ void __launch_bounds__(256) B2B_CAT(step_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, scratch_layout L,
-                                                                          unsigned char* scratch, step_params sp)
+// resident solve CTAs (one warp each) per SM the register allocation is sized for
+#ifndef B2B_SOLVE_MIN_CTAS
+#define B2B_SOLVE_MIN_CTAS 24
+#endif
+
+// The step is three kernels per World.step, each a persistent grid with worlds strided over CTAs:
+//   plan_kernel       narrowphase (K1), contact graph + island walk (K2), level schedule      -- CTA per world
+//   solve_kernel      Island.solve for every island (K3): the hot kernel, lean in registers and
+//                     shared memory so that many worlds are resident per SM                     -- warp per island
+//   broadphase_kernel proxy synchronisation (K4), pair finding (K5), contact creation (K6)      -- CTA per world
+// State lives in the caller's SoA arrays; per-world plan rows carry the island schedule between kernels; the
+// per-CTA scratch slab is reused for every world a CTA owns, so it stays L1/L2 resident.
+__global__ void __launch_bounds__(128) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                          scratch_layout L, unsigned char* scratch, step_params sp)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(32) unsigned char smem[];
     unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
     for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
         // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
         // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
         world_step<real_t> ws;
-        ws.bind(B, c, w, my_scratch, L, smem);
-        ws.run(sp);
+        ws.bind_rows(B, c, w, plan, P);
+        ws.bind_scratch(my_scratch, L);
+        ws.bind_smem(smem, 1);
+        ws.run_plan(sp);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                           scratch_layout L, unsigned char* scratch, step_params sp,
+                                                                           int first_step)
+{
+    extern __shared__ __align__(32) unsigned char smem[];
+    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
+    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
+        world_step<real_t> ws;
+        ws.bind_rows(B, c, w, plan, P);
+        ws.bind_scratch(my_scratch, L);
+        ws.bind_smem(smem, 2);
+        ws.run_solve(sp, first_step != 0);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                                scratch_layout L, unsigned char* scratch, step_params sp)
+{
+    extern __shared__ __align__(32) unsigned char smem[];
+    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
+    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
+        world_step<real_t> ws;
+        ws.bind_rows(B, c, w, plan, P);
+        ws.bind_scratch(my_scratch, L);
+        ws.bind_smem(smem, 3);
+        ws.run_broadphase(sp);
         __syncthreads();
     }
 }
@@ -139,15 +181,15 @@ static inline batch_ptrs<real_t> as_ptrs(const void* const* fields)
     return B;
 }
 
-int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int threads, int ctas_per_sm, int n_sm, launch_plan* out)
+template <class Kern>
+static int plan_one(Kern kern, const caps_t& c, int threads, size_t smem, int ctas_per_sm, int n_sm, kernel_plan* out)
 {
     out->threads = threads;
-    out->smem = smem_plan(c, (int)sizeof(real_t));
-    out->layout = scratch_plan(c, (int)sizeof(real_t));
-    cudaError_t e = cudaFuncSetAttribute(B2B_CAT(step_kernel_, B2B_SUFFIX), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem);
+    out->smem = smem;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, B2B_CAT(step_kernel_, B2B_SUFFIX), threads, out->smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
     if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
@@ -159,10 +201,32 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int threads, int ctas_per_sm, in
     return 0;
 }
 
-void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, unsigned char* scratch,
-                                       const step_params& sp, cudaStream_t st)
+int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int threads_solve, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out)
 {
-    B2B_CAT(step_kernel_, B2B_SUFFIX)<<<p.grid, p.threads, p.smem, st>>>(as_ptrs(fields), c, p.layout, scratch, sp);
+    const smem_layout S = smem_plan_layout(c, (int)sizeof(real_t));
+    out->layout = scratch_plan(c, (int)sizeof(real_t));
+    out->plan = plan_plan(c);
+    int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), c, threads_aux, S.total_plan, 0, n_sm, &out->k_plan);
+    if (rc) return rc;
+    rc = plan_one(B2B_CAT(solve_kernel_, B2B_SUFFIX), c, threads_solve, S.total_solve, ctas_per_sm, n_sm, &out->k_solve);
+    if (rc) return rc;
+    rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), c, threads_aux, S.total_broad, 0, n_sm, &out->k_broad);
+    if (rc) return rc;
+    out->max_grid = out->k_plan.grid;
+    if (out->k_solve.grid > out->max_grid) out->max_grid = out->k_solve.grid;
+    if (out->k_broad.grid > out->max_grid) out->max_grid = out->k_broad.grid;
+    return 0;
+}
+
+// one World.step = plan + solve + broadphase
+void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
+                                       unsigned char* scratch, const step_params& sp, int first_step, cudaStream_t st)
+{
+    const batch_ptrs<real_t> B = as_ptrs(fields);
+    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, p.k_plan.threads, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp);
+    if (sp.dt > 0.0)
+        B2B_CAT(solve_kernel_, B2B_SUFFIX)<<<p.k_solve.grid, p.k_solve.threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp, first_step);
+    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, p.k_broad.threads, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp);
 }
 
 void B2B_CAT(launch_init_proxies_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, cudaStream_t st)

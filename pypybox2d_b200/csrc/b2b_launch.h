@@ -10,16 +10,21 @@
 
 namespace b2b {
 
-struct launch_plan {
+struct kernel_plan {
     int grid, threads, ctas_per_sm;
     size_t smem;
+};
+struct launch_plan {
+    kernel_plan k_plan, k_solve, k_broad;
+    int max_grid;
     scratch_layout layout;
+    plan_layout plan;
 };
 
 #define B2B_DECLARE(S)                                                                                                        \
-    int plan_##S(const caps_t& c, int threads, int ctas_per_sm, int n_sm, launch_plan* out);                                  \
-    void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, unsigned char* scratch,            \
-                         const step_params& sp, cudaStream_t st);                                                             \
+    int plan_##S(const caps_t& c, int threads_solve, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out);           \
+    void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,                    \
+                         unsigned char* scratch, const step_params& sp, int first_step, cudaStream_t st);                     \
     void launch_init_proxies_##S(const void* const* fields, const caps_t& c, cudaStream_t st);                                \
     void launch_collide_pairs_##S(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,          \
                                   const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st);             \

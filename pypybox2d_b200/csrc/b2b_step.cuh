@@ -35,8 +35,10 @@
 #define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2B_CLOCK() clock64()
+#define B2B_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
 #define B2B_CLOCK() 0LL
+#define B2B_PREFETCH(p) ((void)0)
 #define B2B_TID 0
 #define B2B_NT 1
 #define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
@@ -85,30 +87,49 @@ template <class real> struct batch_ptrs {
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
-enum { CC_QUADS = 11, CC_REALS = 4 * CC_QUADS };
+enum { CC_QUADS = 12, CC_REALS = 4 * CC_QUADS };
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1 };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
        PROF_S_STAGE = 8, PROF_S_INTEGRATE, PROF_S_SCHEDULE, PROF_S_INIT, PROF_S_WARM, PROF_S_VELOCITY, PROF_S_STORE,
        PROF_S_POSITION, PROF_S_WRITEBACK, PROF_S_SLEEP, PROF_WORLD_STEPS = 31 };
 
-// Per-CTA scratch in global memory (stays L1/L2 resident: it is reused for every world this CTA steps).
-struct scratch_layout {
-    size_t off_wake, off_scan, off_cc_int, off_cc_real, off_tmp_contact, off_pair_keep, off_prof, total;
+// ---- memory plan --------------------------------------------------------------------------------
+// (1) caller-owned batch arrays (b2b_buffers);  (2) context-owned per-WORLD plan arrays written by the plan
+// kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
+// it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
+struct plan_layout {          // per world, in uint16_t elements
+    size_t off_cbody, off_sched, off_ls, off_nlev, off_adj, off_adj_start, stride;
 };
-
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+B2B_HD plan_layout plan_plan(const caps_t& c)
+{
+    plan_layout P;
+    size_t o = 0;
+    P.off_cbody = o; o = align_up(o + 2 * (size_t)c.nc, 8);
+    P.off_sched = o; o = align_up(o + (size_t)c.nc + 2, 8);
+    P.off_ls = o; o = align_up(o + (size_t)c.nc + 3 * (size_t)c.nb + 4, 8);
+    P.off_nlev = o; o = align_up(o + (size_t)c.nb + 2, 8);
+    P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
+    P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
+    P.stride = o;
+    return P;
+}
 
+struct scratch_layout {       // per CTA, bytes
+    size_t off_wake, off_scan, off_cc_int, off_cc_real, off_cc_imp, off_tmp_contact, off_pair_keep, off_prof, total;
+};
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
 {
     scratch_layout L;
     size_t o = 0;
     const size_t nmax = (size_t)((c.nc > c.nf ? c.nc : c.nf) > c.npair ? (c.nc > c.nf ? c.nc : c.nf) : c.npair) + 2;
-    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 32); return at; };
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 128); return at; };
     L.off_wake = take(sizeof(int32_t) * (size_t)c.nb);
     L.off_scan = take(sizeof(int32_t) * (nmax > (size_t)c.nb + 2 ? nmax : (size_t)c.nb + 2));
     L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
     L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
+    L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
     // staging copy of the contact rows for order-preserving compaction: 2+1+1+2 words + 14 reals
     L.off_tmp_contact = take((sizeof(int32_t) * 6 + (size_t)real_bytes * 14) * ((size_t)c.nc + 2));
     L.off_pair_keep = take(sizeof(int32_t) * ((size_t)c.npair + 2));
@@ -117,32 +138,36 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     return L;
 }
 
-// Shared memory per CTA: the world's bodies (indexed by body id), the contact graph the island walk and the
-// level scheduler traverse, and the per-island level tables.
+// shared memory: plan kernel (contact graph + island walk), solve kernel (bodies + level table), broadphase kernel
 struct smem_layout {
-    size_t off_real, off_flags, off_ctl, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_sched, off_ls, off_nlev,
-        off_cflag, total;
+    size_t off_vel, off_pos, off_flags, off_ctl, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag,
+        total_plan, total_solve, total_broad, total_all;
 };
 B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
 {
     smem_layout S;
+    // ---- common part [ctl | flags | ls], then the solve kernel's [vel quads | pos quads]
     size_t o = 0;
-    S.off_real = o; o = align_up(o + (size_t)real_bytes * (10 * (size_t)c.nb + 64), 16);
-    S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 16);
-    S.off_ctl = o; o = align_up(o + sizeof(int32_t) * 16, 16);
-    S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 16);
-    S.off_adj = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 16);
-    S.off_adj_start = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);
-    S.off_stack = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);      // DFS stack, then `last level` per body
-    S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 16);
-    S.off_sched = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 16);
-    S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 16);
-    S.off_nlev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 16);
-    S.off_cflag = o; o = align_up(o + (size_t)c.nc, 16);
-    S.total = o;
+    S.off_ctl = o; o = align_up(o + sizeof(int32_t) * 16, 32);
+    S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 32);
+    S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 32);
+    const size_t common = o;
+    S.off_vel = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
+    S.off_pos = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
+    S.total_solve = o;
+    // ---- plan kernel: [ctl | flags | cbody | adj | adj_start | stack/last | lev | cflag] (host check: laid out after the solve part)
+    const size_t plan_base = o;
+    S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 32);
+    S.off_adj = o; o = align_up(o + sizeof(uint16_t) * (2 * (size_t)c.nc + 2), 32);
+    S.off_adj_start = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
+    S.off_stack = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
+    S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 32);
+    S.off_cflag = o; o = align_up(o + (size_t)c.nc, 32);
+    S.total_all = o;
+    S.total_plan = common + (o - plan_base);
+    S.total_broad = common;
     return S;
 }
-B2B_HD size_t smem_plan(const caps_t& c, int real_bytes) { return smem_plan_layout(c, real_bytes).total; }
 
 struct step_params {
     double dt, dt_ratio_first, dt_ratio_rest;
@@ -154,31 +179,33 @@ struct step_params {
 template <class real> struct world_step {
     typedef vec2<real> V2;
     typedef xform<real> XF;
+    struct alignas(4 * sizeof(real)) quad { real x, y, z, w; };
+    struct alignas(16) iquad { int32_t body_a, body_b, info, contact; };
 
     caps_t cap;
-    // this world's rows
+    // this world's rows of the batch arrays
     int32_t* w_count; uint32_t* w_flags; uint32_t* w_status; real* w_gravity; int32_t* w_island;
     real *b_xf, *b_pos, *b_vel, *b_pos0, *b_force; const real *b_mass, *b_damp; uint32_t* b_flags; int32_t* b_island;
     const int32_t *f_body, *f_shape; const real* f_mat; const uint32_t* f_filter; real *f_fat, *f_tight; uint8_t* f_moved;
     int32_t* c_fix; uint32_t* c_flags; real* c_mat; int32_t* c_mtype; real *c_mf, *c_pts, *c_imp; uint32_t* c_id;
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     const int32_t* s_meta; const real* s_radius; const real* s_data;
+    // this world's rows of the plan arrays (global)
+    uint16_t *g_cbody, *g_sched, *g_ls, *g_nlev, *g_adj, *g_adj_start;
     // scratch (global, per CTA)
     int32_t *wake_at, *scan, *cc_int;
-    real* cc_real;
+    real *cc_real, *cc_imp;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
-    long long* prof;     // NULL unless profiling
+    long long* prof;
     // shared memory
-    real *s_vx, *s_vy, *s_w, *s_cx, *s_cy, *s_a, *s_im, *s_ii, *s_lcx, *s_lcy;
+    quad *s_vel, *s_pos;     // (v.x, v.y, w, -), (c.x, c.y, a, -) per body
     uint32_t* s_flags;
-    real* s_red;        // [64] reduction slots
-    int32_t* s_ctl;     // [16] control words
-    uint16_t *s_cbody, *s_adj, *s_adj_start, *s_stack, *s_last, *s_lev, *s_sched, *s_ls, *s_nlev;
+    int32_t* s_ctl;          // [16] control words
+    uint16_t *s_ls, *s_cbody, *s_adj, *s_adj_start, *s_stack, *s_last, *s_lev;
     uint8_t* s_cflag;
 
-    B2B_D void bind(const batch_ptrs<real>& B, const caps_t& c, int w, unsigned char* scratch, const scratch_layout& L,
-                    unsigned char* smem)
+    B2B_D void bind_rows(const batch_ptrs<real>& B, const caps_t& c, int w, uint16_t* plan, const plan_layout& P)
     {
         cap = c;
         const size_t W = (size_t)w;
@@ -195,24 +222,33 @@ template <class real> struct world_step {
         p_pairs = B.p_pairs + 2 * W * c.npair; l_body = B.l_body + W * c.nl; l_contact = B.l_contact + oc;
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
+        uint16_t* pw = plan + W * P.stride;
+        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_ls = pw + P.off_ls; g_nlev = pw + P.off_nlev;
+        g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
+    }
+    B2B_D void bind_scratch(unsigned char* scratch, const scratch_layout& L)
+    {
         wake_at = (int32_t*)(scratch + L.off_wake); scan = (int32_t*)(scratch + L.off_scan);
         cc_int = (int32_t*)(scratch + L.off_cc_int);
         cc_real = (real*)(scratch + L.off_cc_real);
+        cc_imp = (real*)(scratch + L.off_cc_imp);
         tmp_cr = (real*)(scratch + L.off_tmp_contact);
-        tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)c.nc + 2));
+        tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)cap.nc + 2));
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
-        const smem_layout S = smem_plan_layout(c, (int)sizeof(real));
-        real* sr = (real*)(smem + S.off_real);
-        s_vx = sr; s_vy = sr + c.nb; s_w = sr + 2 * c.nb; s_cx = sr + 3 * c.nb; s_cy = sr + 4 * c.nb; s_a = sr + 5 * c.nb;
-        s_im = sr + 6 * c.nb; s_ii = sr + 7 * c.nb; s_lcx = sr + 8 * c.nb; s_lcy = sr + 9 * c.nb;
-        s_red = sr + 10 * c.nb;
-        s_flags = (uint32_t*)(smem + S.off_flags);
+    }
+    // which = 0: every array (host check), 1: plan kernel, 2: solve kernel, 3: broadphase kernel
+    B2B_D void bind_smem(unsigned char* smem, int which)
+    {
+        const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
         s_ctl = (int32_t*)(smem + S.off_ctl);
-        s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
-        s_adj_start = (uint16_t*)(smem + S.off_adj_start); s_stack = (uint16_t*)(smem + S.off_stack); s_last = s_stack;
-        s_lev = (uint16_t*)(smem + S.off_lev); s_sched = (uint16_t*)(smem + S.off_sched); s_ls = (uint16_t*)(smem + S.off_ls);
-        s_nlev = (uint16_t*)(smem + S.off_nlev); s_cflag = (uint8_t*)(smem + S.off_cflag);
+        s_flags = (uint32_t*)(smem + S.off_flags);
+        s_vel = (quad*)(smem + S.off_vel); s_pos = (quad*)(smem + S.off_pos); s_ls = (uint16_t*)(smem + S.off_ls);
+        const size_t shift = (which == 1) ? (S.total_solve - S.off_vel) : 0;    // plan kernel: no solve arrays
+        s_cbody = (uint16_t*)(smem + S.off_cbody - shift); s_adj = (uint16_t*)(smem + S.off_adj - shift);
+        s_adj_start = (uint16_t*)(smem + S.off_adj_start - shift); s_stack = (uint16_t*)(smem + S.off_stack - shift);
+        s_last = s_stack;
+        s_lev = (uint16_t*)(smem + S.off_lev - shift); s_cflag = (uint8_t*)(smem + S.off_cflag - shift);
     }
 
     B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
@@ -347,26 +383,19 @@ template <class real> struct world_step {
         B2B_SYNC();
     }
 
-    // ------------------------------------------------------------------------------------ K2
-    // Stage the world's bodies in shared memory: the island builder and the solver both index them by body id.
-    B2B_D void stage_bodies()
+    // ------------------------------------------------------------------------------------ K2 (plan kernel)
+    B2B_D void stage_flags()
     {
         const int nb = w_count[0];
-        B2B_PFOR(b, nb) {
-            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
-            s_cx[b] = p[0]; s_cy[b] = p[1]; s_a[b] = p[2];
-            s_vx[b] = v[0]; s_vy[b] = v[1]; s_w[b] = v[2];
-            s_im[b] = m[0]; s_ii[b] = m[1]; s_lcx[b] = m[2]; s_lcy[b] = m[3];
-            s_flags[b] = b_flags[b] & ~BODY_ISLAND;
-            b_island[b] = -1;
-        }
+        B2B_PFOR(b, nb) { s_flags[b] = b_flags[b] & ~BODY_ISLAND; b_island[b] = -1; }
         B2B_SYNC();
     }
 
     // Body._contacts of every non-static body as CSR rows in contact-creation order
     // (contact_manager.py:157-158 appends, :170-172 removes in place), built in shared memory together with
-    // each contact's body pair and island-eligibility bit.  Static bodies never expand in the island DFS
-    // (world.py:524-525), so their rows are not built.
+    // each contact's body pair and island-eligibility bit; a copy goes to the world's plan rows for the
+    // solve and broadphase kernels.  Static bodies never expand in the island DFS (world.py:524-525), so
+    // their rows are not built.
     B2B_D void build_adjacency()
     {
         const int nb = w_count[0], nc = w_count[2];
@@ -375,13 +404,14 @@ template <class real> struct world_step {
         B2B_PFOR(c, nc) {
             const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
             s_cbody[2 * c] = (uint16_t)ba; s_cbody[2 * c + 1] = (uint16_t)bb;
+            g_cbody[2 * c] = (uint16_t)ba; g_cbody[2 * c + 1] = (uint16_t)bb;
             const uint32_t cf = c_flags[c];
             s_cflag[c] = (uint8_t)(((cf & CONTACT_ENABLED) && (cf & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
             if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[ba], 1);
             if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[bb], 1);
         }
         exclusive_scan(scan, nb + 1, 3);
-        B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)scan[b]; }
+        B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)scan[b]; g_adj_start[b] = (uint16_t)scan[b]; }
         B2B_SYNC();
         B2B_PFOR(c, nc) {
             const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
@@ -398,6 +428,7 @@ template <class real> struct world_step {
                 while (j >= s && s_adj[j] > v) { s_adj[j + 1] = s_adj[j]; --j; }
                 s_adj[j + 1] = v;
             }
+            for (int i = s; i < e; ++i) g_adj[i] = s_adj[i];
         }
         B2B_SYNC();
     }
@@ -473,25 +504,105 @@ template <class real> struct world_step {
         B2B_SYNC();
     }
 
-    // ------------------------------------------------------------------------------------ K3
-    // One constraint = CC_QUADS 4-vectors of reals, array-of-structures in schedule order, so the lane that
-    // solves it fetches it with a handful of 128-bit loads; its integers are one 4-word record alongside
-    // (body_a, body_b, n_vel | type << 8 | n_pos << 16, contact).
-    //   q0  normal.x normal.y friction -               q1  rA0.x rA0.y rB0.x rB0.y
-    //   q2  nmass0   tmass0   bias0    -               q3  rA1.x rA1.y rB1.x rB1.y
-    //   q4  nmass1   tmass1   bias1    -               q5  k11 k12 k22 nm11
-    //   q6  nm12     nm22     -        -               q7  ni0 ti0 ni1 ti1            (q7 is the only read-write quad)
-    //   q8  ln.x ln.y lp.x lp.y                        q9  p0.x p0.y p1.x p1.y
-    //   q10 radius_a radius_b -        -
-    struct alignas(4 * sizeof(real)) quad { real x, y, z, w; };
+    // Dependency levels of every island's contact list: level(k) = 1 + max level of an earlier contact that
+    // shares a non-static body.  Contacts of one level touch disjoint non-static bodies, so solving a level's
+    // contacts concurrently gives bit-identical results to the reference's sequential Gauss-Seidel sweep,
+    // and every body still sees its contacts in list order.  A stable counting sort by level gives `sched`
+    // (slot -> position in l_contact) and the per-island level table `ls`; both go to the world's plan rows.
+    // Islands are independent, so each one is scheduled by its own thread.
+    B2B_D void phase_schedule()
+    {
+        const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
+        (void)n_lb;
+        B2B_PFOR(isl, n_islands) {
+            const int c0 = l_start[2 * isl + 1];
+            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            const int ncon = c1 - c0;
+            uint16_t* ls = s_ls + c0 + 3 * isl;           // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
+            int nlev = 0;
+            if (ncon > 0) {
+                for (int k = 0; k < ncon + 3; ++k) ls[k] = 0;
+                for (int k = c0; k < c1; ++k) {
+                    const int c = l_contact[k];
+                    const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
+                    const bool dyn_a = (s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC;
+                    const bool dyn_b = (s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC;
+                    int l = 0;
+                    if (dyn_a) l = s_last[ba];
+                    if (dyn_b && s_last[bb] > l) l = s_last[bb];
+                    ++l;
+                    if (dyn_a) s_last[ba] = (uint16_t)l;
+                    if (dyn_b) s_last[bb] = (uint16_t)l;
+                    s_lev[k] = (uint16_t)l;
+                    ++ls[l + 1];                          // count of level l parked one slot up
+                    if (l > nlev) nlev = l;
+                }
+                // ls[l + 1] = count(l)  ->  ls[l] = start(l) for l = 1..nlev+1  (ls[nlev + 1] = ncon)
+                int run = 0;
+                for (int l = 1; l <= nlev; ++l) { const int cnt = ls[l + 1]; ls[l] = (uint16_t)run; run += cnt; }
+                ls[nlev + 1] = (uint16_t)run;
+                // stable placement; ls[l] is advanced while filling and restored afterwards
+                for (int k = c0; k < c1; ++k) { const int l = s_lev[k]; g_sched[c0 + ls[l]] = (uint16_t)k; ++ls[l]; }
+                for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
+                ls[1] = 0;
+            }
+            g_nlev[isl] = (uint16_t)nlev;
+        }
+        B2B_SYNC();
+        B2B_PFOR(k, n_lc + 3 * n_islands + 3) g_ls[k] = s_ls[k];
+        B2B_SYNC();
+    }
+
+    // ------------------------------------------------------------------------------------ K3 (solve kernel)
+    // One constraint = CC_QUADS read-only 4-vectors of reals (array-of-structures, schedule order, so the lane
+    // that solves it fetches it with a handful of 128-bit loads), one 4-word integer record
+    // (body_a, body_b, n_vel | type << 8 | n_pos << 16, contact) and one read-write quad of accumulated impulses
+    // kept in its own array so that updating it never dirties the read-only lines.
+    //   q0  normal.x normal.y friction -          q1  rA0.x rA0.y rB0.x rB0.y
+    //   q2  nmass0   tmass0   bias0    -          q3  rA1.x rA1.y rB1.x rB1.y
+    //   q4  nmass1   tmass1   bias1    -          q5  k11 k12 k22 nm11
+    //   q6  nm12     nm22     -        -          q7  inv_mass_a inv_I_a inv_mass_b inv_I_b
+    //   q8  ln.x ln.y lp.x lp.y                   q9  p0.x p0.y p1.x p1.y
+    //   q10 radius_a radius_b -  -                q11 lc_a.x lc_a.y lc_b.x lc_b.y
+    //   imp ni0 ti0 ni1 ti1
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
-    struct alignas(16) iquad { int32_t body_a, body_b, info, contact; };
     B2B_D quad* rec(int slot) { return reinterpret_cast<quad*>(cc_real) + (size_t)CC_QUADS * slot; }
+    B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
     B2B_D iquad* irec(int slot) { return reinterpret_cast<iquad*>(cc_int) + slot; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
     {
         return vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+    }
+    // Records are consumed in slot order, so the lane solving slot s asks for slot s + PREFETCH_AHEAD (a few levels
+    // ahead, wrapping to the start of the island for the next sweep) while it computes.
+    enum { PREFETCH_AHEAD = 8 };
+    B2B_D void prefetch_slot(int s, int c0, int c1, int first_quad)
+    {
+        int t = s + PREFETCH_AHEAD;
+        if (t >= c1) t = c0 + (t - c1);
+        if (t < c1) {
+            const char* r = reinterpret_cast<const char*>(rec(t)) + first_quad * sizeof(quad);
+            B2B_PREFETCH(r);
+            B2B_PREFETCH(r + 128);
+            B2B_PREFETCH(irec(t));
+            B2B_PREFETCH(imp_rec(t));
+        }
+    }
+
+    B2B_D void stage_bodies()
+    {
+        const int nb = w_count[0];
+        B2B_PFOR(b, nb) {
+            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b;
+            s_pos[b] = mkq(p[0], p[1], p[2], real(0));
+            s_vel[b] = mkq(v[0], v[1], v[2], real(0));
+            s_flags[b] = b_flags[b];
+        }
+        const int n_islands = w_island[0], n_lc = w_island[2];
+        B2B_PFOR(k, n_lc + 3 * n_islands + 3) s_ls[k] = g_ls[k];
+        if (B2B_IS_T0) { s_ctl[4] = n_islands; s_ctl[5] = w_island[1]; s_ctl[6] = n_lc; }
+        B2B_SYNC();
     }
 
     // ContactSolver.__init__ + initialize_velocity_constraints for one slot
@@ -499,7 +610,7 @@ template <class real> struct world_step {
     B2B_D void constraint_init(int slot, int ci, real dt_ratio, bool warm)
     {
         const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
-        const int ba = s_cbody[2 * ci], bb = s_cbody[2 * ci + 1];
+        const int ba = g_cbody[2 * ci], bb = g_cbody[2 * ci + 1];
         const int mt = c_mtype[ci];
         const int type = mt & 0xff, count = (mt >> 8) & 0xff;
         const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci; const real* imp = c_imp + 4 * (size_t)ci;
@@ -507,12 +618,15 @@ template <class real> struct world_step {
         V2 lp[2]; lp[0] = mk<real>(pts[0], pts[1]); lp[1] = mk<real>(pts[2], pts[3]);
         const real rad_a = s_radius[f_shape[fa]], rad_b = s_radius[f_shape[fb]];
         const real friction = c_mat[2 * ci], restitution = c_mat[2 * ci + 1];
-        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
-        const V2 ca = mk<real>(s_cx[ba], s_cy[ba]), cb = mk<real>(s_cx[bb], s_cy[bb]);
-        const V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
-        const real wa = s_w[ba], wb = s_w[bb];
-        const XF xa = xf_from_sweep<real>(ca, s_a[ba], mk<real>(s_lcx[ba], s_lcy[ba]));
-        const XF xb = xf_from_sweep<real>(cb, s_a[bb], mk<real>(s_lcx[bb], s_lcy[bb]));
+        const real* mass_a = b_mass + 4 * (size_t)ba; const real* mass_b = b_mass + 4 * (size_t)bb;
+        const real ma = mass_a[0], mb = mass_b[0], ia = mass_a[1], ib = mass_b[1];
+        const V2 lca = mk<real>(mass_a[2], mass_a[3]), lcb = mk<real>(mass_b[2], mass_b[3]);
+        const quad pa_ = s_pos[ba], pb_ = s_pos[bb], va_ = s_vel[ba], vb_ = s_vel[bb];
+        const V2 ca = mk<real>(pa_.x, pa_.y), cb = mk<real>(pb_.x, pb_.y);
+        const V2 va = mk<real>(va_.x, va_.y), vb = mk<real>(vb_.x, vb_.y);
+        const real wa = va_.z, wb = vb_.z;
+        const XF xa = xf_from_sweep<real>(ca, pa_.z, lca);
+        const XF xb = xf_from_sweep<real>(cb, pb_.z, lcb);
 
         // world manifold
         V2 normal, wp[2];
@@ -579,9 +693,13 @@ template <class real> struct world_step {
                 n_vel = 1;                                   // redundant point dropped from the velocity rows only
             }
         }
-        quad* q = rec(slot);
-        iquad iq; iq.body_a = ba; iq.body_b = bb; iq.info = n_vel | (type << 8) | (count << 16); iq.contact = ci;
+        // statics are never written back: their flag rides in the sign-free upper bits of `info`
+        const int stat_a = ((s_flags[ba] & BODY_TYPE_MASK) == BODY_STATIC) ? 1 : 0;
+        const int stat_b = ((s_flags[bb] & BODY_TYPE_MASK) == BODY_STATIC) ? 1 : 0;
+        iquad iq; iq.body_a = ba; iq.body_b = bb;
+        iq.info = n_vel | (type << 8) | (count << 16) | (stat_a << 24) | (stat_b << 25); iq.contact = ci;
         *irec(slot) = iq;
+        quad* q = rec(slot);
         q[0] = mkq(normal.x, normal.y, friction, real(0));
         q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
         q[2] = mkq(nmass[0], tmass[0], bias[0], real(0));
@@ -589,19 +707,12 @@ template <class real> struct world_step {
         q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
         q[5] = mkq(k11, k12, k22, nm11);
         q[6] = mkq(nm12, nm22, real(0), real(0));
-        q[7] = mkq(ni[0], ti[0], ni[1], ti[1]);
+        q[7] = mkq(ma, ia, mb, ib);
         q[8] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
         q[9] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
         q[10] = mkq(rad_a, rad_b, real(0), real(0));
-    }
-
-    B2B_D void store_vel(int b, V2 v, real w)
-    {
-        if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) { s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w; }
-    }
-    B2B_D void store_pos(int b, V2 c, real a)
-    {
-        if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) { s_cx[b] = c.x; s_cy[b] = c.y; s_a[b] = a; }
+        q[11] = mkq(lca.x, lca.y, lcb.x, lcb.y);
+        *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
     }
 
     // ContactSolver.warm_start for one slot (contact.py:498-525)
@@ -609,77 +720,79 @@ template <class real> struct world_step {
     {
         const quad* q = rec(slot);
         const iquad iq = *irec(slot);
-        const quad q0 = q[0], q1 = q[1], q3 = q[3], q7 = q[7];
+        const quad q0 = q[0], q1 = q[1], q3 = q[3], q7 = q[7], qi = *imp_rec(slot);
         const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
-        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
-        V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
-        real wa = s_w[ba], wb = s_w[bb];
+        const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
+        quad sa = s_vel[ba], sb = s_vel[bb];
+        V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
+        real wa = sa.z, wb = sb.z;
         for (int j = 0; j < n_vel; ++j) {
             const quad r = (j == 0) ? q1 : q3;
             const V2 ra = mk<real>(r.x, r.y), rb = mk<real>(r.z, r.w);
-            const V2 p = ((j == 0) ? q7.x : q7.z) * normal + ((j == 0) ? q7.y : q7.w) * tangent;
+            const V2 p = ((j == 0) ? qi.x : qi.z) * normal + ((j == 0) ? qi.y : qi.w) * tangent;
             wa = wa - ia * cross(ra, p);
             va = va - ma * p;
             wb = wb + ib * cross(rb, p);
             vb = vb + mb * p;
         }
-        store_vel(ba, va, wa);
-        store_vel(bb, vb, wb);
+        if (!(iq.info & (1 << 24))) s_vel[ba] = mkq(va.x, va.y, wa, real(0));
+        if (!(iq.info & (1 << 25))) s_vel[bb] = mkq(vb.x, vb.y, wb, real(0));
     }
 
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
     B2B_D void constraint_solve_velocity(int slot)
     {
-        quad* q = rec(slot);
+        const quad* q = rec(slot);
         const iquad iq = *irec(slot);
-        const quad q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6];
-        quad q7 = q[7];
+        const quad q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+        quad qi = *imp_rec(slot);
         const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real friction = q0.z;
-        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
-        V2 va = mk<real>(s_vx[ba], s_vy[ba]), vb = mk<real>(s_vx[bb], s_vy[bb]);
-        real wa = s_w[ba], wb = s_w[bb];
+        const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
+        const quad sa = s_vel[ba], sb = s_vel[bb];
+        V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
+        real wa = sa.z, wb = sb.z;
         const V2 ra0 = mk<real>(q1.x, q1.y), rb0 = mk<real>(q1.z, q1.w), ra1 = mk<real>(q3.x, q3.y), rb1 = mk<real>(q3.z, q3.w);
         // friction rows first, point by point
         {
             const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vt = dot(dv, tangent);
             real lambda = q2.y * (-vt);
-            const real max_friction = friction * q7.x;
-            const real new_imp = clamp_r(q7.y + lambda, -max_friction, max_friction);
-            lambda = new_imp - q7.y;
+            const real max_friction = friction * qi.x;
+            const real new_imp = clamp_r(qi.y + lambda, -max_friction, max_friction);
+            lambda = new_imp - qi.y;
             const V2 P = lambda * tangent;
             va = va - ma * P; wa = wa - ia * cross(ra0, P);
             vb = vb + mb * P; wb = wb + ib * cross(rb0, P);
-            q7.y = new_imp;
+            qi.y = new_imp;
         }
         if (n_vel == 2) {
             const V2 dv = rel_velocity(vb, wb, rb1, va, wa, ra1);
             const real vt = dot(dv, tangent);
             real lambda = q4.y * (-vt);
-            const real max_friction = friction * q7.z;
-            const real new_imp = clamp_r(q7.w + lambda, -max_friction, max_friction);
-            lambda = new_imp - q7.w;
+            const real max_friction = friction * qi.z;
+            const real new_imp = clamp_r(qi.w + lambda, -max_friction, max_friction);
+            lambda = new_imp - qi.w;
             const V2 P = lambda * tangent;
             va = va - ma * P; wa = wa - ia * cross(ra1, P);
             vb = vb + mb * P; wb = wb + ib * cross(rb1, P);
-            q7.w = new_imp;
+            qi.w = new_imp;
         }
         if (n_vel == 1) {
             const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vn = dot(dv, normal);
             real lambda = -q2.x * (vn - q2.z);
-            const real new_imp = pymax(q7.x + lambda, real(0));
-            lambda = new_imp - q7.x;
+            const real new_imp = pymax(qi.x + lambda, real(0));
+            lambda = new_imp - qi.x;
             const V2 P = lambda * normal;
             va = va - ma * P; wa = wa - ia * cross(ra0, P);
             vb = vb + mb * P; wb = wb + ib * cross(rb0, P);
-            q7.x = new_imp;
+            qi.x = new_imp;
         } else {
             // 2x2 LCP by total enumeration; first feasible case wins (contact.py:598-796)
-            const V2 a = mk<real>(q7.x, q7.z);
+            const V2 a = mk<real>(qi.x, qi.z);
             const V2 dv1 = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const V2 dv2 = rel_velocity(vb, wb, rb1, va, wa, ra1);
             const real vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
@@ -707,12 +820,12 @@ template <class real> struct world_step {
                 const V2 p12 = p1 + p2;
                 va = va - ma * p12; wa = wa - ia * (cross(ra0, p1) + cross(ra1, p2));
                 vb = vb + mb * p12; wb = wb + ib * (cross(rb0, p1) + cross(rb1, p2));
-                q7.x = x.x; q7.z = x.y;
+                qi.x = x.x; qi.z = x.y;
             }
         }
-        q[7] = q7;
-        store_vel(ba, va, wa);
-        store_vel(bb, vb, wb);
+        *imp_rec(slot) = qi;
+        if (!(iq.info & (1 << 24))) s_vel[ba] = mkq(va.x, va.y, wa, real(0));
+        if (!(iq.info & (1 << 25))) s_vel[bb] = mkq(vb.x, vb.y, wb, real(0));
     }
 
     // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
@@ -721,15 +834,16 @@ template <class real> struct world_step {
     {
         const quad* q = rec(slot);
         const iquad iq = *irec(slot);
-        const quad q8 = q[8], q9 = q[9], q10 = q[10];
+        const quad q7 = q[7], q8 = q[8], q9 = q[9], q10 = q[10], q11 = q[11];
         const int ba = iq.body_a, bb = iq.body_b;
         const int type = (iq.info >> 8) & 0xff, n_pos = (iq.info >> 16) & 0xff;
-        const real ma = s_im[ba], mb = s_im[bb], ia = s_ii[ba], ib = s_ii[bb];
-        const V2 lca = mk<real>(s_lcx[ba], s_lcy[ba]), lcb = mk<real>(s_lcx[bb], s_lcy[bb]);
+        const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
+        const V2 lca = mk<real>(q11.x, q11.y), lcb = mk<real>(q11.z, q11.w);
         const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
         const real rad_a = q10.x, rad_b = q10.y;
-        V2 ca = mk<real>(s_cx[ba], s_cy[ba]), cb = mk<real>(s_cx[bb], s_cy[bb]);
-        real aa = s_a[ba], ab = s_a[bb];
+        const quad sa = s_pos[ba], sb = s_pos[bb];
+        V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
+        real aa = sa.z, ab = sb.z;
         real min_sep = real(0);
         for (int j = 0; j < n_pos; ++j) {
             const XF xa = xf_from_sweep<real>(ca, aa, lca), xb = xf_from_sweep<real>(cb, ab, lcb);
@@ -765,16 +879,97 @@ template <class real> struct world_step {
             ca = ca - ma * P; aa = aa - ia * cross(ra, P);
             cb = cb + mb * P; ab = ab + ib * cross(rb, P);
         }
-        store_pos(ba, ca, aa);
-        store_pos(bb, cb, ab);
+        if (!(iq.info & (1 << 24))) s_pos[ba] = mkq(ca.x, ca.y, aa, real(0));
+        if (!(iq.info & (1 << 25))) s_pos[bb] = mkq(cb.x, cb.y, ab, real(0));
         return min_sep;
     }
 
-    // Dependency levels of an island's contact list: level(k) = 1 + max level of an earlier contact that
-    // shares a non-static body.  Contacts of one level touch disjoint non-static bodies, so solving a level's
-    // contacts concurrently gives bit-identical results to the reference's sequential Gauss-Seidel sweep,
-    // and every body still sees its contacts in list order.  A stable counting sort by level gives `sched`;
-    // constraint records are then laid out in schedule order so a level's records are contiguous.
+    // island.py:71-95 for one non-static body: save the sweep start, integrate gravity/forces, damp
+    B2B_D void integrate_velocity(int b, real dt, V2 gravity)
+    {
+        const uint32_t fl = s_flags[b];
+        const quad p = s_pos[b];
+        real* p0 = b_pos0 + 4 * (size_t)b;
+        p0[0] = p.x; p0[1] = p.y; p0[2] = p.z;
+        if ((fl & BODY_TYPE_MASK) == BODY_DYNAMIC) {
+            const real* damp = b_damp + 4 * (size_t)b; const real* mass = b_mass + 4 * (size_t)b;
+            const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
+            const real torque = b_vel[4 * (size_t)b + 3];
+            const quad sv = s_vel[b];
+            V2 v = mk<real>(sv.x, sv.y);
+            real w = sv.z;
+            v = v + dt * (damp[2] * gravity + mass[0] * force);
+            w = w + dt * mass[1] * torque;
+            v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
+            w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
+            s_vel[b] = mkq(v.x, v.y, w, real(0));
+        }
+    }
+    // island.py:119-138 for one non-static body: clamp the step, advance the sweep
+    B2B_D void integrate_position(int b, real dt)
+    {
+        const quad sv = s_vel[b], spv = s_pos[b];
+        V2 v = mk<real>(sv.x, sv.y);
+        real w = sv.z;
+        const V2 translation = dt * v;
+        if (dot(translation, translation) > K<real>::max_translation_sqr) {
+            const real ratio = K<real>::max_translation / sqrt_r(translation.x * translation.x + translation.y * translation.y);
+            v = ratio * v;
+        }
+        const real rotation = dt * w;
+        if (rotation * rotation > K<real>::max_rotation_sqr) {
+            const real ratio = K<real>::max_rotation / abs_r(rotation);
+            w = w * ratio;
+        }
+        s_pos[b] = mkq(spv.x + dt * v.x, spv.y + dt * v.y, spv.z + dt * w, real(0));
+        s_vel[b] = mkq(v.x, v.y, w, real(0));
+    }
+    // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body
+    B2B_D void write_back(int b)
+    {
+        const quad sp = s_pos[b], sv = s_vel[b];
+        real* p = b_pos + 4 * (size_t)b; real* v = b_vel + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
+        p[0] = sp.x; p[1] = sp.y; p[2] = sp.z;
+        v[0] = sv.x; v[1] = sv.y; v[2] = sv.z;
+        const real* mass = b_mass + 4 * (size_t)b;
+        const XF tf = xf_from_sweep<real>(mk<real>(sp.x, sp.y), sp.z, mk<real>(mass[2], mass[3]));
+        x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
+    }
+    // Sleep bookkeeping exactly as written in the reference (island.py:163-179): the allow-sleep
+    // test reads the LAST island body; only the last non-static body is put to sleep.
+    B2B_D void island_sleep(int b0, int b1, real dt, bool position_solved)
+    {
+        real min_sleep = K<real>::max_float;
+        const bool last_allow = (s_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+        int victim = -1;
+        for (int i = b0; i < b1; ++i) {
+            const int b = l_body[i];
+            if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+            victim = b;
+            const quad sv = s_vel[b];
+            real* st = b_pos + 4 * (size_t)b + 3;
+            if (!last_allow || sv.z * sv.z > K<real>::angular_sleep_tol_sqr || sv.x * sv.x + sv.y * sv.y > K<real>::linear_sleep_tol_sqr) {
+                *st = real(0);
+                min_sleep = real(0);
+            } else {
+                const real ts = *st + dt;
+                *st = ts;
+                min_sleep = pymin(min_sleep, ts);
+            }
+        }
+        if (min_sleep >= K<real>::time_to_sleep && position_solved && victim >= 0) {
+            // Body.awake = False (body.py:805-812)
+            b_pos[4 * (size_t)victim + 3] = real(0);
+            real* v = b_vel + 4 * (size_t)victim;
+            v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
+            b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
+            b_flags[victim] &= ~BODY_AWAKE;
+        }
+    }
+
+    // Island.solve for every island of the world (island.py:65-179).  Islands without contacts (free bodies)
+    // are whole-island-per-lane; islands with contacts are one warp each, their constraints strided over the
+    // lanes level by level (see phase_schedule).
     B2B_D void solve_islands(const step_params& sp, real dt, real dt_ratio)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
@@ -784,125 +979,83 @@ template <class real> struct world_step {
         long long t = B2B_CLOCK();
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
         (void)profiling;
+        int max_used = 0;
+        // ---- contact-free islands: one lane per island
+        B2B_PFOR(isl, n_islands) {
+            const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
+            const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
+            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            if (c1 != c0) continue;
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_velocity(b, dt, gravity); }
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt); }
+            // an empty constraint list is "solved" by its first position iteration (contact.py:811,864)
+            if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) write_back(b); }
+            if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
+        }
+        B2B_PROF(PROF_S_INTEGRATE, t);
+        // ---- islands with contacts: one warp per island
         for (int isl = B2B_WARP; isl < n_islands; isl += B2B_NWARPS) {
             const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
             const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
             const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
-            const int ncon = c1 - c0;
-            // -- integrate velocities (island.py:71-95); statics are left untouched
+            if (c1 == c0) continue;
             for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
                 const int b = l_body[i];
-                const uint32_t fl = s_flags[b];
-                if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                real* p0 = b_pos0 + 4 * (size_t)b;
-                p0[0] = s_cx[b]; p0[1] = s_cy[b]; p0[2] = s_a[b];
-                if ((fl & BODY_TYPE_MASK) == BODY_DYNAMIC) {
-                    const real* damp = b_damp + 4 * (size_t)b;
-                    const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
-                    const real torque = b_vel[4 * (size_t)b + 3];
-                    V2 v = mk<real>(s_vx[b], s_vy[b]);
-                    real w = s_w[b];
-                    v = v + dt * (damp[2] * gravity + s_im[b] * force);
-                    w = w + dt * s_ii[b] * torque;
-                    v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
-                    w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
-                    s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w;
+                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_velocity(b, dt, gravity);
+            }
+            B2B_WSYNC();
+            const uint16_t* ls = s_ls + c0 + 3 * isl;     // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
+            const int nlev = g_nlev[isl];
+            for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[g_sched[s]], dt_ratio, warm);
+            B2B_WSYNC();
+            B2B_PROF(PROF_S_INIT, t);
+            if (warm) {
+                int begin = c0;
+                for (int l = 1; l <= nlev; ++l) {
+                    const int end = c0 + ls[l + 1];
+                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 0); constraint_warm_start(s); }
+                    begin = end;
+                    B2B_WSYNC();
                 }
             }
-            B2B_PROF(PROF_S_INTEGRATE, t);
-            int nlev = 0;
-            uint16_t* ls = s_ls + c0 + 3 * isl;          // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
-            if (ncon > 0) {
-                // -- level schedule (lane 0), then constraint records in schedule order
-                if (B2B_LANE == 0) {
-                    for (int k = 0; k < ncon + 3; ++k) ls[k] = 0;
-                    for (int k = c0; k < c1; ++k) {
-                        const int c = l_contact[k];
-                        const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
-                        const bool dyn_a = (s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC;
-                        const bool dyn_b = (s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC;
-                        int l = 0;
-                        if (dyn_a) l = s_last[ba];
-                        if (dyn_b && s_last[bb] > l) l = s_last[bb];
-                        ++l;
-                        if (dyn_a) s_last[ba] = (uint16_t)l;
-                        if (dyn_b) s_last[bb] = (uint16_t)l;
-                        s_lev[k] = (uint16_t)l;
-                        ++ls[l + 1];                          // count of level l parked one slot up
-                        if (l > nlev) nlev = l;
-                    }
-                    // ls[l + 1] = count(l)  ->  ls[l] = start(l) for l = 1..nlev+1  (ls[nlev + 1] = ncon)
-                    int run = 0;
-                    for (int l = 1; l <= nlev; ++l) { const int cnt = ls[l + 1]; ls[l] = (uint16_t)run; run += cnt; }
-                    ls[nlev + 1] = (uint16_t)run;
-                    // stable placement; ls[l] is advanced while filling and restored afterwards
-                    for (int k = c0; k < c1; ++k) { const int l = s_lev[k]; s_sched[c0 + ls[l]] = (uint16_t)k; ++ls[l]; }
-                    for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
-                    ls[1] = 0;
-                    s_nlev[isl] = (uint16_t)nlev;
+            B2B_PROF(PROF_S_WARM, t);
+            for (int it = 0; it < sp.vel_iters; ++it) {
+                int begin = c0;
+                for (int l = 1; l <= nlev; ++l) {
+                    const int end = c0 + ls[l + 1];
+                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 0); constraint_solve_velocity(s); }
+                    begin = end;
+                    B2B_WSYNC();
                 }
-                B2B_WSYNC();
-                B2B_PROF(PROF_S_SCHEDULE, t);
-                nlev = s_nlev[isl];
-                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[s_sched[s]], dt_ratio, warm);
-                B2B_WSYNC();
-                B2B_PROF(PROF_S_INIT, t);
-                if (warm) {
-                    for (int l = 1; l <= nlev; ++l) {
-                        for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_warm_start(s);
-                        B2B_WSYNC();
-                    }
-                }
-                B2B_PROF(PROF_S_WARM, t);
-                for (int it = 0; it < sp.vel_iters; ++it) {
-                    for (int l = 1; l <= nlev; ++l) {
-                        for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES) constraint_solve_velocity(s);
-                        B2B_WSYNC();
-                    }
-                }
-                B2B_PROF(PROF_S_VELOCITY, t);
-                // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
-                for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
-                    const quad* q = rec(s);
-                    const quad q7 = q[7];
-                    const iquad iq = *irec(s);
-                    const int ci = iq.contact, n_vel = iq.info & 0xff;
-                    real* imp = c_imp + 4 * (size_t)ci;
-                    if (n_vel > 0) { imp[0] = q7.x; imp[1] = q7.y; }
-                    if (n_vel > 1) { imp[2] = q7.z; imp[3] = q7.w; }
-                }
+            }
+            B2B_PROF(PROF_S_VELOCITY, t);
+            // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
+            for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
+                const quad qi = *imp_rec(s);
+                const iquad iq = *irec(s);
+                const int ci = iq.contact, n_vel = iq.info & 0xff;
+                real* imp = c_imp + 4 * (size_t)ci;
+                if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+                if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
+            }
+            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+                const int b = l_body[i];
+                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt);
             }
             B2B_WSYNC();
             B2B_PROF(PROF_S_STORE, t);
-            // -- integrate positions (island.py:119-138)
-            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
-                const int b = l_body[i];
-                if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                V2 v = mk<real>(s_vx[b], s_vy[b]);
-                real w = s_w[b];
-                const V2 translation = dt * v;
-                if (dot(translation, translation) > K<real>::max_translation_sqr) {
-                    const real ratio = K<real>::max_translation / sqrt_r(translation.x * translation.x + translation.y * translation.y);
-                    v = ratio * v;
-                }
-                const real rotation = dt * w;
-                if (rotation * rotation > K<real>::max_rotation_sqr) {
-                    const real ratio = K<real>::max_rotation / abs_r(rotation);
-                    w = w * ratio;
-                }
-                s_cx[b] = s_cx[b] + dt * v.x; s_cy[b] = s_cy[b] + dt * v.y; s_a[b] = s_a[b] + dt * w;
-                s_vx[b] = v.x; s_vy[b] = v.y; s_w[b] = w;
-            }
-            B2B_WSYNC();
             // -- position iterations with early exit (island.py:141-153)
             bool position_solved = false;
             int used = 0;
             for (int it = 0; it < sp.pos_iters; ++it) {
                 real my_min = real(0);
                 ++used;
+                int begin = c0;
                 for (int l = 1; l <= nlev; ++l) {
-                    for (int s = c0 + ls[l] + B2B_LANE; s < c0 + ls[l + 1]; s += B2B_NLANES)
-                        my_min = pymin(my_min, constraint_solve_position(s));
+                    const int end = c0 + ls[l + 1];
+                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 7); my_min = pymin(my_min, constraint_solve_position(s)); }
+                    begin = end;
                     B2B_WSYNC();
                 }
                 real all_min = my_min;
@@ -914,60 +1067,24 @@ template <class real> struct world_step {
 #endif
                 if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
             }
+            if (used > max_used) max_used = used;
             B2B_PROF(PROF_S_POSITION, t);
-            // -- write back + Body._synchronize_transform (island.py:155-159, body.py:906-908)
             for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
                 const int b = l_body[i];
-                if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                real* p = b_pos + 4 * (size_t)b; real* v = b_vel + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
-                p[0] = s_cx[b]; p[1] = s_cy[b]; p[2] = s_a[b];
-                v[0] = s_vx[b]; v[1] = s_vy[b]; v[2] = s_w[b];
-                const XF tf = xf_from_sweep<real>(mk<real>(s_cx[b], s_cy[b]), s_a[b], mk<real>(s_lcx[b], s_lcy[b]));
-                x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
+                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) write_back(b);
             }
             B2B_WSYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);
-            // -- sleep bookkeeping exactly as written in the reference (island.py:163-179):
-            //    the allow-sleep test reads the LAST island body; only the last non-static body is put to sleep.
-            if (B2B_LANE == 0) {
-                if (allow_sleep) {
-                    real min_sleep = K<real>::max_float;
-                    const bool last_allow = (s_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
-                    int victim = -1;
-                    for (int i = b0; i < b1; ++i) {
-                        const int b = l_body[i];
-                        if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                        victim = b;
-                        const real w = s_w[b], vx = s_vx[b], vy = s_vy[b];
-                        real* st = b_pos + 4 * (size_t)b + 3;
-                        if (!last_allow || w * w > K<real>::angular_sleep_tol_sqr || vx * vx + vy * vy > K<real>::linear_sleep_tol_sqr) {
-                            *st = real(0);
-                            min_sleep = real(0);
-                        } else {
-                            const real ts = *st + dt;
-                            *st = ts;
-                            min_sleep = pymin(min_sleep, ts);
-                        }
-                    }
-                    if (min_sleep >= K<real>::time_to_sleep && position_solved && victim >= 0) {
-                        // Body.awake = False (body.py:805-812)
-                        b_pos[4 * (size_t)victim + 3] = real(0);
-                        real* v = b_vel + 4 * (size_t)victim;
-                        v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
-                        b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
-                        b_flags[victim] &= ~BODY_AWAKE;
-                    }
-                }
-                // max position iterations used by any island of this world (diagnostic, w_island[3])
-#if defined(__CUDA_ARCH__)
-                atomicMax(&w_island[3], used);
-#else
-                if (used > w_island[3]) w_island[3] = used;
-#endif
-            }
+            if (B2B_LANE == 0 && allow_sleep) island_sleep(b0, b1, dt, position_solved);
             B2B_WSYNC();
             B2B_PROF(PROF_S_SLEEP, t);
         }
+        // max position iterations used by any island of this world (diagnostic, w_island[3])
+#if defined(__CUDA_ARCH__)
+        if (max_used > 0) atomicMax(&w_island[3], max_used);
+#else
+        if (max_used > w_island[3]) w_island[3] = max_used;
+#endif
         B2B_SYNC();
     }
 
@@ -1027,8 +1144,8 @@ template <class real> struct world_step {
         bool exists = false;
         if (have_adjacency) {
             const int bs = (tb != BODY_STATIC) ? bb : ba;                          // a row that was built
-            for (int k = s_adj_start[bs]; k < s_adj_start[bs + 1] && !exists; ++k) {
-                const int c = s_adj[k];
+            for (int k = g_adj_start[bs]; k < g_adj_start[bs + 1] && !exists; ++k) {
+                const int c = g_adj[k];
                 const int ca = c_fix[2 * c], cb = c_fix[2 * c + 1];
                 exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
             }
@@ -1113,41 +1230,67 @@ template <class real> struct world_step {
     }
 
     // ------------------------------------------------------------------------------------ World.step
+    // ------------------------------------------------------------------------------------ World.step
+    // plan kernel: (find_new_contacts if new fixtures) + collide + island construction + level schedule
+    B2B_D void run_plan(const step_params& sp)
+    {
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
+        if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
+            phase_pairs(false);
+            if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
+            B2B_SYNC();
+            B2B_PROF(PROF_PAIRS0, t);
+        }
+        phase_collide();                                         // world.py:338
+        B2B_PROF(PROF_COLLIDE, t);
+        if (sp.dt > 0.0) {                                       // world.py:341-342, 475-580
+            stage_flags();
+            build_adjacency();
+            B2B_PROF(PROF_ADJACENCY, t);
+            phase_islands();
+            B2B_PROF(PROF_ISLANDS, t);
+            phase_schedule();
+            B2B_PROF(PROF_S_SCHEDULE, t);
+        }
+    }
+    // solve kernel: Island.solve for every island (island.py:65-179)
+    B2B_D void run_solve(const step_params& sp, bool first_step)
+    {
+        if (!(sp.dt > 0.0)) return;
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
+        stage_bodies();
+        B2B_PROF(PROF_S_STAGE, t);
+        solve_islands(sp, (real)sp.dt, (real)(first_step ? sp.dt_ratio_first : sp.dt_ratio_rest));
+        B2B_PROF(PROF_SOLVE, t);
+    }
+    // broadphase kernel: proxy synchronisation + find_new_contacts (world.py:582-592) + clear_forces (:351-352)
+    B2B_D void run_broadphase(const step_params& sp)
+    {
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
+        if (sp.dt > 0.0) {
+            phase_sync();
+            B2B_PROF(PROF_SYNC, t);
+            phase_pairs(true);
+            B2B_PROF(PROF_PAIRS, t);
+        }
+        if (w_flags[0] & WORLD_AUTO_CLEAR) {
+            const int nb = w_count[0];
+            B2B_PFOR(b, nb) { b_force[2 * (size_t)b] = real(0); b_force[2 * (size_t)b + 1] = real(0); b_vel[4 * (size_t)b + 3] = real(0); }
+        }
+        B2B_SYNC();
+        B2B_PROF(PROF_CLEAR, t);
+        if (profiling && B2B_IS_T0) prof[PROF_WORLD_STEPS] += 1;
+    }
+    // the three kernels back to back (host check and single-world debugging)
     B2B_D void run(const step_params& sp)
     {
-        const real dt = (real)sp.dt;
-        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         for (int step = 0; step < sp.n_steps; ++step) {
-            const real dt_ratio = (real)(step == 0 ? sp.dt_ratio_first : sp.dt_ratio_rest);
-            long long t = B2B_CLOCK();
-            if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
-                phase_pairs(false);
-                if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
-                B2B_SYNC();
-                B2B_PROF(PROF_PAIRS0, t);
-            }
-            phase_collide();                                         // world.py:338
-            B2B_PROF(PROF_COLLIDE, t);
-            if (sp.dt > 0.0) {                                       // world.py:341-342
-                stage_bodies();
-                build_adjacency();
-                B2B_PROF(PROF_ADJACENCY, t);
-                phase_islands();
-                B2B_PROF(PROF_ISLANDS, t);
-                solve_islands(sp, dt, dt_ratio);
-                B2B_PROF(PROF_SOLVE, t);
-                phase_sync();
-                B2B_PROF(PROF_SYNC, t);
-                phase_pairs(true);
-                B2B_PROF(PROF_PAIRS, t);
-            }
-            if (w_flags[0] & WORLD_AUTO_CLEAR) {                     // world.py:351-352
-                const int nb = w_count[0];
-                B2B_PFOR(b, nb) { b_force[2 * (size_t)b] = real(0); b_force[2 * (size_t)b + 1] = real(0); b_vel[4 * (size_t)b + 3] = real(0); }
-            }
-            B2B_SYNC();
-            B2B_PROF(PROF_CLEAR, t);
-            if (profiling && B2B_IS_T0) prof[PROF_WORLD_STEPS] += 1;
+            run_plan(sp);
+            run_solve(sp, step == 0);
+            run_broadphase(sp);
         }
     }
 };

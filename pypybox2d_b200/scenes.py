@@ -64,7 +64,8 @@ def u01_torch(config, world, index, stream=0, seed=SEED):
 
 
 def jitter(config, world, n_bodies, amp=JITTER_AMP):
-    """[n_bodies, 2] position offsets of world `world` (zeros for world 0)."""
+    """[n_bodies, 2] position offsets of world `world` (zeros for world 0), indexed by the body's position in
+    `world.bodies` (hash index 2 * body + axis) -- the same numbers `BatchedWorld.replicate` draws on the device."""
     if world == 0 or amp == 0.0:
         return np.zeros((n_bodies, 2))
     idx = np.arange(2 * n_bodies, dtype=np.uint64)
@@ -78,7 +79,7 @@ def pyramid(b2, world=0, rows=20, config=1, **world_kw):
     w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
     fixture = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
     n_dyn = rows * (rows + 1) // 2
-    jit = jitter(config, world, n_dyn)
+    jit = jitter(config, world, n_dyn + 1)[1:]      # body 0 is the ground
     x = (-7.0, 0.75)
     k = 0
     for i in range(rows):
@@ -96,7 +97,7 @@ def hello(b2, world=0, config=2, **world_kw):
     w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
     ground = w.create_static_body(position=(0, -10))
     ground.create_polygon_fixture(box=(50, 10))
-    jit = jitter(config, world, 1)
+    jit = jitter(config, world, 2)[1:]
     body = w.create_dynamic_body(position=(0 + jit[0, 0], 4 + jit[0, 1]))
     body.create_circle_fixture(1.0, density=1.0)
     return w
@@ -108,7 +109,7 @@ def vertical_stack(b2, world=0, columns=5, rows=16, config=2, **world_kw):
     w.create_static_body(shapes=[b2.Edge((-40, 0), (40, 0)), b2.Edge((20, 0), (20, 20))])
     box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
     circle = b2.Fixture(shape=b2.Circle(0.5), density=1, friction=0.3)
-    jit = jitter(config, world, 2 * columns * rows)
+    jit = jitter(config, world, 2 * columns * rows + 1)[1:]
     k = 0
     for j in range(columns):
         for i in range(rows):
@@ -125,7 +126,7 @@ def mixed(b2, world=0, side=16, config=4, **world_kw):
     w.create_static_body(shapes=[b2.Edge((-10, 0), (10, 0)), b2.Edge((-10, 0), (-10, 20)),
                                  b2.Edge((10, 0), (10, 20)), b2.Edge((-10, 20), (10, 20))])
     n = side * side
-    jit = jitter(config, world, n)
+    jit = jitter(config, world, n + 1)[1:]
     idx = np.arange(n, dtype=np.uint64)
     # shape draws come from their own streams and also vary with the world index (world 0 included)
     u_r = u01(config, world, idx, stream=1)
@@ -151,7 +152,7 @@ def deep_stacks(b2, world=0, columns=10, rows=20, config=5, **world_kw):
     w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
     w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
     box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
-    jit = jitter(config, world, columns * rows)
+    jit = jitter(config, world, columns * rows + 1)[1:]
     k = 0
     for j in range(columns):
         for i in range(rows):
