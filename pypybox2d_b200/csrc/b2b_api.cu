@@ -18,7 +18,8 @@ struct b2b_ctx {
     bool f64;
     int n_sm;
     launch_plan plan;
-    unsigned char* scratch;
+    unsigned char* scratch;        // plan / broadphase kernels: one slab per CTA
+    unsigned char* scratch_solve;  // solve kernel: one slab per team
     uint16_t* plan_rows;
     uint32_t* d_status;
     void* stage_in;       // [n_worlds][nb][3] reals
@@ -48,7 +49,7 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 static bool caps_ok(const b2b_caps* k)
 {
     return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
-           (k->real_bytes == 4 || k->real_bytes == 8) && k->threads >= 0 && k->threads <= 128 && (k->threads % 32) == 0 &&
+           (k->real_bytes == 4 || k->real_bytes == 8) && (k->threads == 0 || k->threads == 4 || k->threads == 8 || k->threads == 16 || k->threads == 32) &&
            k->reserved >= 0 && k->reserved <= 128 && (k->reserved % 32) == 0 && k->nb < 65535 && k->nc < 65535;
 }
 
@@ -73,7 +74,8 @@ extern "C" const char* b2b_field_names(void)
 extern "C" size_t b2b_scratch_bytes(const b2b_caps* caps)
 {
     if (!caps_ok(caps)) return 0;
-    return scratch_plan(to_caps(caps), caps->real_bytes).total;
+    const scratch_layout L = scratch_plan(to_caps(caps), caps->real_bytes);
+    return L.total_aux + L.total_solve;      // per resident CTA / team; the context allocates one of each per slot
 }
 
 extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
@@ -94,14 +96,19 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     cudaError_t e = cudaGetDeviceProperties(&prop, caps->device);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaGetDeviceProperties", e); }
     x->n_sm = prop.multiProcessorCount;
-    const int threads = 32;   // the solve kernel is one warp per CTA (launch bounds); caps->threads is ignored
+    // caps->threads: lanes of a warp per world in the solve kernel (8, 16 or 32); caps->reserved: threads per CTA
+    // of the plan / broadphase kernels
+    const int lanes = caps->threads > 0 ? caps->threads : 8;
     const int threads_aux = caps->reserved > 0 ? caps->reserved : 64;
-    int rc = x->f64 ? plan_f64(x->c, threads, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
-                    : plan_f32(x->c, threads, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
+    int rc = x->f64 ? plan_f64(x->c, lanes, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
+                    : plan_f32(x->c, lanes, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
     if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
-    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total * (size_t)x->plan.max_grid);
+    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
-    cudaMemset(x->scratch, 0, x->plan.layout.total * (size_t)x->plan.max_grid);
+    cudaMemset(x->scratch, 0, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
+    e = cudaMalloc((void**)&x->scratch_solve, x->plan.layout.total_solve * (size_t)x->plan.solve_slabs);
+    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(solve scratch)", e); }
+    cudaMemset(x->scratch_solve, 0, x->plan.layout.total_solve * (size_t)x->plan.solve_slabs);
     e = cudaMalloc((void**)&x->plan_rows, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(plan rows)", e); }
     cudaMemset(x->plan_rows, 0, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
@@ -116,6 +123,7 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     if (!x) return;
     cudaSetDevice(x->caps.device);
     if (x->scratch) cudaFree(x->scratch);
+    if (x->scratch_solve) cudaFree(x->scratch_solve);
     if (x->plan_rows) cudaFree(x->plan_rows);
     if (x->d_status) cudaFree(x->d_status);
     if (x->stage_in) cudaFree(x->stage_in);
@@ -170,8 +178,8 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
     const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, flags);
     for (int s = 0; s < n_steps; ++s) {
-        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, sp, s == 0, (cudaStream_t)stream);
-        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, sp, s == 0, (cudaStream_t)stream);
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
         x->launches += (dt > 0.0) ? 2 : 1;       // check_launch counted one of the three
@@ -260,11 +268,17 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
     CUDA_TRY(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] = 0;
     long long tmp[PROF_SLOTS];
-    for (int g = 0; g < x->plan.max_grid; ++g) {
-        unsigned char* p = x->scratch + (size_t)g * x->plan.layout.total + x->plan.layout.off_prof;
-        CUDA_TRY(cudaMemcpy(tmp, p, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H profile");
-        for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] += tmp[k];
-        if (reset) CUDA_TRY(cudaMemset(p, 0, sizeof(tmp)), "memset profile");
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass ? x->plan.solve_slabs : x->plan.aux_slabs;
+        const size_t stride = pass ? x->plan.layout.total_solve : x->plan.layout.total_aux;
+        const size_t off = pass ? x->plan.layout.off_sprof : x->plan.layout.off_prof;
+        unsigned char* base = pass ? x->scratch_solve : x->scratch;
+        for (int g = 0; g < n; ++g) {
+            unsigned char* p = base + (size_t)g * stride + off;
+            CUDA_TRY(cudaMemcpy(tmp, p, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H profile");
+            for (int k = 0; k < PROF_SLOTS; ++k) host_out32[k] += tmp[k];
+            if (reset) CUDA_TRY(cudaMemset(p, 0, sizeof(tmp)), "memset profile");
+        }
     }
     return B2B_OK;
 }

@@ -12,7 +12,7 @@ typedef B2B_REAL real_t;
 
 // resident solve CTAs (one warp each) per SM the register allocation is sized for
 #ifndef B2B_SOLVE_MIN_CTAS
-#define B2B_SOLVE_MIN_CTAS 24
+#define B2B_SOLVE_MIN_CTAS 20
 #endif
 
 // The step is three kernels per World.step, each a persistent grid with worlds strided over CTAs:
@@ -26,32 +26,38 @@ __global__ void __launch_bounds__(128) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_p
                                                                           scratch_layout L, unsigned char* scratch, step_params sp)
 {
     extern __shared__ __align__(32) unsigned char smem[];
-    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
+    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total_aux;
     for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
         // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
         // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
         world_step<real_t> ws;
+        ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch(my_scratch, L);
-        ws.bind_smem(smem, 1);
+        ws.bind_scratch_aux(my_scratch, L);
+        ws.bind_smem_aux(smem);
         ws.run_plan(sp);
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
-                                                                           scratch_layout L, unsigned char* scratch, step_params sp,
-                                                                           int first_step)
+// One warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its own world, so the
+// (mostly one- or two-lane-wide) dependency levels of several worlds share each issued instruction.
+__global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_, B2B_SUFFIX)(
+    batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* scratch, step_params sp,
+    int first_step, int lanes, size_t team_smem)
 {
     extern __shared__ __align__(32) unsigned char smem[];
-    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
-    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
-        world_step<real_t> ws;
+    world_step<real_t> ws;
+    const int team = ws.bind_team_lanes(lanes);
+    const int teams_per_cta = 32 / lanes;
+    const int slot = blockIdx.x * teams_per_cta + team;
+    unsigned char* my_scratch = scratch + (size_t)slot * L.total_solve;
+    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch(my_scratch, L);
-        ws.bind_smem(smem, 2);
+        ws.bind_scratch_solve(my_scratch, L);
+        ws.bind_smem_solve(smem + (size_t)team * team_smem);
         ws.run_solve(sp, first_step != 0);
-        __syncthreads();
+        __syncwarp(ws.t_mask);
     }
 }
 
@@ -59,12 +65,13 @@ __global__ void __launch_bounds__(128) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(b
                                                                                 scratch_layout L, unsigned char* scratch, step_params sp)
 {
     extern __shared__ __align__(32) unsigned char smem[];
-    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total;
+    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total_aux;
     for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
         world_step<real_t> ws;
+        ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch(my_scratch, L);
-        ws.bind_smem(smem, 3);
+        ws.bind_scratch_aux(my_scratch, L);
+        ws.bind_smem_aux(smem);
         ws.run_broadphase(sp);
         __syncthreads();
     }
@@ -182,7 +189,7 @@ static inline batch_ptrs<real_t> as_ptrs(const void* const* fields)
 }
 
 template <class Kern>
-static int plan_one(Kern kern, const caps_t& c, int threads, size_t smem, int ctas_per_sm, int n_sm, kernel_plan* out)
+static int plan_one(Kern kern, long long n_items, int threads, size_t smem, int ctas_per_sm, int n_sm, kernel_plan* out)
 {
     out->threads = threads;
     out->smem = smem;
@@ -195,38 +202,43 @@ static int plan_one(Kern kern, const caps_t& c, int threads, size_t smem, int ct
     if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
     out->ctas_per_sm = per_sm;
     long long g = (long long)per_sm * n_sm;
-    if (g > c.n_worlds) g = c.n_worlds;
+    if (g > n_items) g = n_items;
     if (g < 1) g = 1;
     out->grid = (int)g;
     return 0;
 }
 
-int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int threads_solve, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out)
+int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out)
 {
     const smem_layout S = smem_plan_layout(c, (int)sizeof(real_t));
     out->layout = scratch_plan(c, (int)sizeof(real_t));
     out->plan = plan_plan(c);
-    int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), c, threads_aux, S.total_plan, 0, n_sm, &out->k_plan);
+    out->lanes = lanes;
+    out->team_smem = S.total_solve;
+    const int teams = 32 / lanes;
+    int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), c.n_worlds, threads_aux, S.total_plan, 0, n_sm, &out->k_plan);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(solve_kernel_, B2B_SUFFIX), c, threads_solve, S.total_solve, ctas_per_sm, n_sm, &out->k_solve);
+    rc = plan_one(B2B_CAT(solve_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
+                  ctas_per_sm, n_sm, &out->k_solve);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), c, threads_aux, S.total_broad, 0, n_sm, &out->k_broad);
+    rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), c.n_worlds, threads_aux, S.total_broad, 0, n_sm, &out->k_broad);
     if (rc) return rc;
-    out->max_grid = out->k_plan.grid;
-    if (out->k_solve.grid > out->max_grid) out->max_grid = out->k_solve.grid;
-    if (out->k_broad.grid > out->max_grid) out->max_grid = out->k_broad.grid;
+    out->aux_slabs = out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid;
+    out->solve_slabs = out->k_solve.grid * teams;
     return 0;
 }
 
 // one World.step = plan + solve + broadphase
 void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
-                                       unsigned char* scratch, const step_params& sp, int first_step, cudaStream_t st)
+                                       unsigned char* scratch_aux, unsigned char* scratch_solve, const step_params& sp,
+                                       int first_step, cudaStream_t st)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
-    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, p.k_plan.threads, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp);
+    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, p.k_plan.threads, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp);
     if (sp.dt > 0.0)
-        B2B_CAT(solve_kernel_, B2B_SUFFIX)<<<p.k_solve.grid, p.k_solve.threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp, first_step);
-    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, p.k_broad.threads, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch, sp);
+        B2B_CAT(solve_kernel_, B2B_SUFFIX)<<<p.k_solve.grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp,
+                                                                                        first_step, p.lanes, p.team_smem);
+    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, p.k_broad.threads, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp);
 }
 
 void B2B_CAT(launch_init_proxies_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, cudaStream_t st)

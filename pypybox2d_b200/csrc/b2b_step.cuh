@@ -20,35 +20,28 @@
 #pragma once
 #include "b2b_collide.cuh"
 
+// A world is stepped by a TEAM of threads: the whole CTA in the plan and broadphase kernels, a group of
+// `t_n` lanes of one warp in the solve kernel (several worlds per warp).  Work items are strided over the team
+// and phases end in a team barrier.  Without CUDA the team is one sequential thread (tests/hostcheck).
 #if defined(__CUDA_ARCH__)
-#define B2B_TID ((int)threadIdx.x)
-#define B2B_NT ((int)blockDim.x)
-#define B2B_PFOR(i, n) for (int i = (int)threadIdx.x; i < (n); i += (int)blockDim.x)
-#define B2B_SYNC() __syncthreads()
-#define B2B_IS_T0 (threadIdx.x == 0)
-#define B2B_WARP ((int)(threadIdx.x >> 5))
-#define B2B_NWARPS ((int)(blockDim.x >> 5))
-#define B2B_LANE ((int)(threadIdx.x & 31))
-#define B2B_NLANES 32
-#define B2B_WSYNC() __syncwarp()
+#define B2B_PFOR(i, n) for (int i = t_id; i < (n); i += t_n)
+#define B2B_SYNC()                               \
+    do {                                         \
+        if (t_cta) __syncthreads();              \
+        else __syncwarp(t_mask);                 \
+    } while (0)
+#define B2B_IS_T0 (t_id == 0)
 #define B2B_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2B_CLOCK() clock64()
-#define B2B_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define B2B_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
-#define B2B_CLOCK() 0LL
-#define B2B_PREFETCH(p) ((void)0)
-#define B2B_TID 0
-#define B2B_NT 1
 #define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
 #define B2B_SYNC() ((void)0)
 #define B2B_IS_T0 true
-#define B2B_WARP 0
-#define B2B_NWARPS 1
-#define B2B_LANE 0
-#define B2B_NLANES 1
-#define B2B_WSYNC() ((void)0)
+#define B2B_CLOCK() 0LL
+#define B2B_PREFETCH(p) ((void)0)
 namespace b2b {
 template <class T> inline T host_atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T host_atomic_add(T* p, T v) { T o = *p; *p = o + v; return o; }
@@ -99,25 +92,26 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 // kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
 // it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
 struct plan_layout {          // per world, in uint16_t elements
-    size_t off_cbody, off_sched, off_ls, off_nlev, off_adj, off_adj_start, stride;
+    size_t off_cbody, off_sched, off_lmask, off_adj, off_adj_start, stride;
 };
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+B2B_HD int lmask_words(const caps_t& c) { return (c.nc + 31) / 32 + 2; }
 B2B_HD plan_layout plan_plan(const caps_t& c)
 {
     plan_layout P;
     size_t o = 0;
     P.off_cbody = o; o = align_up(o + 2 * (size_t)c.nc, 8);
     P.off_sched = o; o = align_up(o + (size_t)c.nc + 2, 8);
-    P.off_ls = o; o = align_up(o + (size_t)c.nc + 3 * (size_t)c.nb + 4, 8);
-    P.off_nlev = o; o = align_up(o + (size_t)c.nb + 2, 8);
+    P.off_lmask = o; o = align_up(o + 2 * (size_t)lmask_words(c), 8);       // uint32 words, counted in uint16 units
     P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
     P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
     P.stride = o;
     return P;
 }
 
-struct scratch_layout {       // per CTA, bytes
-    size_t off_wake, off_scan, off_cc_int, off_cc_real, off_cc_imp, off_tmp_contact, off_pair_keep, off_prof, total;
+struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `solve` slabs per solve team
+    size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
+    size_t off_cc_int, off_cc_real, off_cc_imp, off_sprof, total_solve;
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
 {
@@ -127,45 +121,47 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 128); return at; };
     L.off_wake = take(sizeof(int32_t) * (size_t)c.nb);
     L.off_scan = take(sizeof(int32_t) * (nmax > (size_t)c.nb + 2 ? nmax : (size_t)c.nb + 2));
-    L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
-    L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
-    L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
     // staging copy of the contact rows for order-preserving compaction: 2+1+1+2 words + 14 reals
     L.off_tmp_contact = take((sizeof(int32_t) * 6 + (size_t)real_bytes * 14) * ((size_t)c.nc + 2));
     L.off_pair_keep = take(sizeof(int32_t) * ((size_t)c.npair + 2));
     L.off_prof = take(sizeof(long long) * PROF_SLOTS);
-    L.total = align_up(o, 256);
+    L.total_aux = align_up(o, 256);
+    o = 0;
+    L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
+    L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
+    L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
+    L.off_sprof = take(sizeof(long long) * PROF_SLOTS);
+    L.total_solve = align_up(o, 256);
     return L;
 }
 
-// shared memory: plan kernel (contact graph + island walk), solve kernel (bodies + level table), broadphase kernel
+// shared memory.  plan kernel (per CTA): [ctl | flags | ls | cbody | adj | adj_start | stack/last | lev | cflag];
+// solve kernel (per team): [state quads | level mask | flags8]; broadphase kernel (per CTA): [ctl].
 struct smem_layout {
-    size_t off_vel, off_pos, off_flags, off_ctl, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag,
-        total_plan, total_solve, total_broad, total_all;
+    size_t off_ctl, off_flags, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag, total_plan;
+    size_t off_state, off_lmask, off_flags8, total_solve;     // relative to the team's base
+    size_t total_broad;
 };
 B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
 {
     smem_layout S;
-    // ---- common part [ctl | flags | ls], then the solve kernel's [vel quads | pos quads]
     size_t o = 0;
     S.off_ctl = o; o = align_up(o + sizeof(int32_t) * 16, 32);
+    S.total_broad = o;
     S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 32);
     S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 32);
-    const size_t common = o;
-    S.off_vel = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
-    S.off_pos = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
-    S.total_solve = o;
-    // ---- plan kernel: [ctl | flags | cbody | adj | adj_start | stack/last | lev | cflag] (host check: laid out after the solve part)
-    const size_t plan_base = o;
     S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 32);
     S.off_adj = o; o = align_up(o + sizeof(uint16_t) * (2 * (size_t)c.nc + 2), 32);
     S.off_adj_start = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
     S.off_stack = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
     S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 32);
     S.off_cflag = o; o = align_up(o + (size_t)c.nc, 32);
-    S.total_all = o;
-    S.total_plan = common + (o - plan_base);
-    S.total_broad = common;
+    S.total_plan = o;
+    o = 0;
+    S.off_state = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
+    S.off_lmask = o; o = align_up(o + sizeof(uint32_t) * (size_t)lmask_words(c), 32);
+    S.off_flags8 = o; o = align_up(o + (size_t)c.nb, 32);
+    S.total_solve = o;
     return S;
 }
 
@@ -191,19 +187,50 @@ template <class real> struct world_step {
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     const int32_t* s_meta; const real* s_radius; const real* s_data;
     // this world's rows of the plan arrays (global)
-    uint16_t *g_cbody, *g_sched, *g_ls, *g_nlev, *g_adj, *g_adj_start;
-    // scratch (global, per CTA)
+    uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
+    uint32_t* g_lmask;       // bit s set: slot s is the last constraint of its dependency level
+    // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan, *cc_int;
     real *cc_real, *cc_imp;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
     // shared memory
-    quad *s_vel, *s_pos;     // (v.x, v.y, w, -), (c.x, c.y, a, -) per body
-    uint32_t* s_flags;
+    quad* s_state;           // solve kernel: (v.x, v.y, w, -) during the velocity phase, then (c.x, c.y, a, -)
+    uint32_t* s_lmask;
+    uint8_t* s_flags8;       // solve kernel: body type | allow_sleep
+    uint32_t* s_flags;       // plan kernel: body flags
     int32_t* s_ctl;          // [16] control words
     uint16_t *s_ls, *s_cbody, *s_adj, *s_adj_start, *s_stack, *s_last, *s_lev;
     uint8_t* s_cflag;
+    // the team of threads stepping this world
+    int t_id, t_n;
+    unsigned t_mask;
+    bool t_cta;
+
+    B2B_D void bind_team_cta()
+    {
+#if defined(__CUDA_ARCH__)
+        t_id = (int)threadIdx.x; t_n = (int)blockDim.x; t_mask = 0xffffffffu; t_cta = true;
+#else
+        t_id = 0; t_n = 1; t_mask = 1u; t_cta = true;
+#endif
+    }
+    // `lanes` consecutive lanes of the warp (a power of two); returns the team's index inside the CTA
+    B2B_D int bind_team_lanes(int lanes)
+    {
+#if defined(__CUDA_ARCH__)
+        const int lane = (int)(threadIdx.x & 31);
+        t_n = lanes; t_id = lane % lanes; t_cta = false;
+        const int team = lane / lanes;
+        t_mask = (lanes == 32) ? 0xffffffffu : (((1u << lanes) - 1u) << (team * lanes));
+        return (int)(threadIdx.x >> 5) * (32 / lanes) + team;
+#else
+        (void)lanes;
+        t_id = 0; t_n = 1; t_mask = 1u; t_cta = false;
+        return 0;
+#endif
+    }
 
     B2B_D void bind_rows(const batch_ptrs<real>& B, const caps_t& c, int w, uint16_t* plan, const plan_layout& P)
     {
@@ -223,32 +250,41 @@ template <class real> struct world_step {
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
         uint16_t* pw = plan + W * P.stride;
-        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_ls = pw + P.off_ls; g_nlev = pw + P.off_nlev;
+        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lmask = reinterpret_cast<uint32_t*>(pw + P.off_lmask);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
     }
-    B2B_D void bind_scratch(unsigned char* scratch, const scratch_layout& L)
+    B2B_D void bind_scratch_aux(unsigned char* scratch, const scratch_layout& L)
     {
         wake_at = (int32_t*)(scratch + L.off_wake); scan = (int32_t*)(scratch + L.off_scan);
-        cc_int = (int32_t*)(scratch + L.off_cc_int);
-        cc_real = (real*)(scratch + L.off_cc_real);
-        cc_imp = (real*)(scratch + L.off_cc_imp);
         tmp_cr = (real*)(scratch + L.off_tmp_contact);
         tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)cap.nc + 2));
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
     }
-    // which = 0: every array (host check), 1: plan kernel, 2: solve kernel, 3: broadphase kernel
-    B2B_D void bind_smem(unsigned char* smem, int which)
+    B2B_D void bind_scratch_solve(unsigned char* scratch, const scratch_layout& L)
+    {
+        cc_int = (int32_t*)(scratch + L.off_cc_int);
+        cc_real = (real*)(scratch + L.off_cc_real);
+        cc_imp = (real*)(scratch + L.off_cc_imp);
+        prof = (long long*)(scratch + L.off_sprof);
+    }
+    B2B_D void bind_smem_aux(unsigned char* smem)
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
         s_ctl = (int32_t*)(smem + S.off_ctl);
         s_flags = (uint32_t*)(smem + S.off_flags);
-        s_vel = (quad*)(smem + S.off_vel); s_pos = (quad*)(smem + S.off_pos); s_ls = (uint16_t*)(smem + S.off_ls);
-        const size_t shift = (which == 1) ? (S.total_solve - S.off_vel) : 0;    // plan kernel: no solve arrays
-        s_cbody = (uint16_t*)(smem + S.off_cbody - shift); s_adj = (uint16_t*)(smem + S.off_adj - shift);
-        s_adj_start = (uint16_t*)(smem + S.off_adj_start - shift); s_stack = (uint16_t*)(smem + S.off_stack - shift);
+        s_ls = (uint16_t*)(smem + S.off_ls);
+        s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
+        s_adj_start = (uint16_t*)(smem + S.off_adj_start); s_stack = (uint16_t*)(smem + S.off_stack);
         s_last = s_stack;
-        s_lev = (uint16_t*)(smem + S.off_lev - shift); s_cflag = (uint8_t*)(smem + S.off_cflag - shift);
+        s_lev = (uint16_t*)(smem + S.off_lev); s_cflag = (uint8_t*)(smem + S.off_cflag);
+    }
+    B2B_D void bind_smem_solve(unsigned char* team_smem)
+    {
+        const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
+        s_state = (quad*)(team_smem + S.off_state);
+        s_lmask = (uint32_t*)(team_smem + S.off_lmask);
+        s_flags8 = (uint8_t*)(team_smem + S.off_flags8);
     }
 
     B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
@@ -514,6 +550,8 @@ template <class real> struct world_step {
     {
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
         (void)n_lb;
+        B2B_PFOR(k, lmask_words(cap)) scan[k] = 0;
+        B2B_SYNC();
         B2B_PFOR(isl, n_islands) {
             const int c0 = l_start[2 * isl + 1];
             const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
@@ -546,18 +584,23 @@ template <class real> struct world_step {
                 for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
                 ls[1] = 0;
             }
-            g_nlev[isl] = (uint16_t)nlev;
+            // last slot of every level -> one bit in the world's level mask
+            for (int l = 1; l <= nlev; ++l) {
+                const int last_slot = c0 + ls[l + 1] - 1;
+                B2B_ATOMIC_OR(&scan[last_slot >> 5], (int32_t)(1u << (last_slot & 31)));
+            }
         }
         B2B_SYNC();
-        B2B_PFOR(k, n_lc + 3 * n_islands + 3) g_ls[k] = s_ls[k];
+        B2B_PFOR(k, lmask_words(cap)) g_lmask[k] = (uint32_t)scan[k];
         B2B_SYNC();
     }
 
     // ------------------------------------------------------------------------------------ K3 (solve kernel)
     // One constraint = CC_QUADS read-only 4-vectors of reals (array-of-structures, schedule order, so the lane
     // that solves it fetches it with a handful of 128-bit loads), one 4-word integer record
-    // (body_a, body_b, n_vel | type << 8 | n_pos << 16, contact) and one read-write quad of accumulated impulses
-    // kept in its own array so that updating it never dirties the read-only lines.
+    // (body_a, body_b, n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25, contact) and one
+    // read-write quad of accumulated impulses kept in its own array so that updating it never dirties the
+    // read-only lines.
     //   q0  normal.x normal.y friction -          q1  rA0.x rA0.y rB0.x rB0.y
     //   q2  nmass0   tmass0   bias0    -          q3  rA1.x rA1.y rB1.x rB1.y
     //   q4  nmass1   tmass1   bias1    -          q5  k11 k12 k22 nm11
@@ -565,10 +608,24 @@ template <class real> struct world_step {
     //   q8  ln.x ln.y lp.x lp.y                   q9  p0.x p0.y p1.x p1.y
     //   q10 radius_a radius_b -  -                q11 lc_a.x lc_a.y lc_b.x lc_b.y
     //   imp ni0 ti0 ni1 ti1
+    // Shared memory holds ONE quad per body: its velocity while velocities are being solved, its sweep position
+    // afterwards.  Static bodies never change, are shared between islands, and are read from global memory.
+    enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D quad* rec(int slot) { return reinterpret_cast<quad*>(cc_real) + (size_t)CC_QUADS * slot; }
     B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
     B2B_D iquad* irec(int slot) { return reinterpret_cast<iquad*>(cc_int) + slot; }
+    B2B_D quad load_vel(int b, bool is_static) const
+    {
+        if (is_static) { const real* v = b_vel + 4 * (size_t)b; return mkq(v[0], v[1], v[2], real(0)); }
+        return s_state[b];
+    }
+    B2B_D quad load_pos(int b, bool is_static) const
+    {
+        if (is_static) { const real* p = b_pos + 4 * (size_t)b; return mkq(p[0], p[1], p[2], real(0)); }
+        return s_state[b];
+    }
+    B2B_D bool is_static_body(int b) const { return (s_flags8[b] & BODY_TYPE_MASK) == BODY_STATIC; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
     {
@@ -576,7 +633,7 @@ template <class real> struct world_step {
     }
     // Records are consumed in slot order, so the lane solving slot s asks for slot s + PREFETCH_AHEAD (a few levels
     // ahead, wrapping to the start of the island for the next sweep) while it computes.
-    enum { PREFETCH_AHEAD = 8 };
+    enum { PREFETCH_AHEAD = 4 };
     B2B_D void prefetch_slot(int s, int c0, int c1, int first_quad)
     {
         int t = s + PREFETCH_AHEAD;
@@ -589,19 +646,35 @@ template <class real> struct world_step {
             B2B_PREFETCH(imp_rec(t));
         }
     }
+    // last slot of the dependency level that starts at slot p (a set bit at or after p in the level mask)
+    B2B_D int level_end(int p) const
+    {
+        int w = p >> 5;
+        uint32_t bits = s_lmask[w] >> (p & 31);
+        if (bits) return p + lowest_bit(bits);
+        do { bits = s_lmask[++w]; } while (!bits);
+        return (w << 5) + lowest_bit(bits);
+    }
+    B2B_D static int lowest_bit(uint32_t x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __ffs((int)x) - 1;
+#else
+        int n = 0;
+        while (!(x & 1u)) { x >>= 1; ++n; }
+        return n;
+#endif
+    }
 
     B2B_D void stage_bodies()
     {
         const int nb = w_count[0];
         B2B_PFOR(b, nb) {
-            const real* p = b_pos + 4 * (size_t)b; const real* v = b_vel + 4 * (size_t)b;
-            s_pos[b] = mkq(p[0], p[1], p[2], real(0));
-            s_vel[b] = mkq(v[0], v[1], v[2], real(0));
-            s_flags[b] = b_flags[b];
+            const real* v = b_vel + 4 * (size_t)b;
+            s_state[b] = mkq(v[0], v[1], v[2], real(0));
+            s_flags8[b] = (uint8_t)(b_flags[b] & (BODY_TYPE_MASK | BODY_ALLOW_SLEEP));
         }
-        const int n_islands = w_island[0], n_lc = w_island[2];
-        B2B_PFOR(k, n_lc + 3 * n_islands + 3) s_ls[k] = g_ls[k];
-        if (B2B_IS_T0) { s_ctl[4] = n_islands; s_ctl[5] = w_island[1]; s_ctl[6] = n_lc; }
+        B2B_PFOR(k, lmask_words(cap)) s_lmask[k] = g_lmask[k];
         B2B_SYNC();
     }
 
@@ -621,12 +694,15 @@ template <class real> struct world_step {
         const real* mass_a = b_mass + 4 * (size_t)ba; const real* mass_b = b_mass + 4 * (size_t)bb;
         const real ma = mass_a[0], mb = mass_b[0], ia = mass_a[1], ib = mass_b[1];
         const V2 lca = mk<real>(mass_a[2], mass_a[3]), lcb = mk<real>(mass_b[2], mass_b[3]);
-        const quad pa_ = s_pos[ba], pb_ = s_pos[bb], va_ = s_vel[ba], vb_ = s_vel[bb];
-        const V2 ca = mk<real>(pa_.x, pa_.y), cb = mk<real>(pb_.x, pb_.y);
+        const bool stat_a = is_static_body(ba), stat_b = is_static_body(bb);
+        // positions are still the step's start positions in global memory; velocities are staged
+        const real* pa_ = b_pos + 4 * (size_t)ba; const real* pb_ = b_pos + 4 * (size_t)bb;
+        const quad va_ = load_vel(ba, stat_a), vb_ = load_vel(bb, stat_b);
+        const V2 ca = mk<real>(pa_[0], pa_[1]), cb = mk<real>(pb_[0], pb_[1]);
         const V2 va = mk<real>(va_.x, va_.y), vb = mk<real>(vb_.x, vb_.y);
         const real wa = va_.z, wb = vb_.z;
-        const XF xa = xf_from_sweep<real>(ca, pa_.z, lca);
-        const XF xb = xf_from_sweep<real>(cb, pb_.z, lcb);
+        const XF xa = xf_from_sweep<real>(ca, pa_[2], lca);
+        const XF xb = xf_from_sweep<real>(cb, pb_[2], lcb);
 
         // world manifold
         V2 normal, wp[2];
@@ -693,11 +769,9 @@ template <class real> struct world_step {
                 n_vel = 1;                                   // redundant point dropped from the velocity rows only
             }
         }
-        // statics are never written back: their flag rides in the sign-free upper bits of `info`
-        const int stat_a = ((s_flags[ba] & BODY_TYPE_MASK) == BODY_STATIC) ? 1 : 0;
-        const int stat_b = ((s_flags[bb] & BODY_TYPE_MASK) == BODY_STATIC) ? 1 : 0;
         iquad iq; iq.body_a = ba; iq.body_b = bb;
-        iq.info = n_vel | (type << 8) | (count << 16) | (stat_a << 24) | (stat_b << 25); iq.contact = ci;
+        iq.info = n_vel | (type << 8) | (count << 16) | (stat_a ? INFO_STATIC_A : 0) | (stat_b ? INFO_STATIC_B : 0);
+        iq.contact = ci;
         *irec(slot) = iq;
         quad* q = rec(slot);
         q[0] = mkq(normal.x, normal.y, friction, real(0));
@@ -715,16 +789,34 @@ template <class real> struct world_step {
         *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
     }
 
-    // ContactSolver.warm_start for one slot (contact.py:498-525)
-    B2B_D void constraint_warm_start(int slot)
+    // A constraint's velocity-phase data in registers.  The level loops load the NEXT level's record while the
+    // current one is being solved, so the L2/HBM latency of the record stream overlaps the arithmetic.
+    struct vrec { iquad iq; quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
+    B2B_D void load_vrec(int slot, vrec& r)
     {
         const quad* q = rec(slot);
-        const iquad iq = *irec(slot);
-        const quad q0 = q[0], q1 = q[1], q3 = q[3], q7 = q[7], qi = *imp_rec(slot);
+        r.iq = *irec(slot);
+        r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3]; r.q4 = q[4]; r.q5 = q[5]; r.q6 = q[6]; r.q7 = q[7];
+        r.qi = *imp_rec(slot);
+    }
+    struct prec { iquad iq; quad q7, q8, q9, q10, q11; };
+    B2B_D void load_prec(int slot, prec& r)
+    {
+        const quad* q = rec(slot);
+        r.iq = *irec(slot);
+        r.q7 = q[7]; r.q8 = q[8]; r.q9 = q[9]; r.q10 = q[10]; r.q11 = q[11];
+    }
+
+    // ContactSolver.warm_start for one slot (contact.py:498-525)
+    B2B_D void constraint_warm_start(const vrec& r)
+    {
+        const iquad iq = r.iq;
+        const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q7, qi = r.qi;
         const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
+        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
-        quad sa = s_vel[ba], sb = s_vel[bb];
+        const quad sa = load_vel(ba, stat_a), sb = load_vel(bb, stat_b);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
         for (int j = 0; j < n_vel; ++j) {
@@ -736,22 +828,22 @@ template <class real> struct world_step {
             wb = wb + ib * cross(rb, p);
             vb = vb + mb * p;
         }
-        if (!(iq.info & (1 << 24))) s_vel[ba] = mkq(va.x, va.y, wa, real(0));
-        if (!(iq.info & (1 << 25))) s_vel[bb] = mkq(vb.x, vb.y, wb, real(0));
+        if (!stat_a) s_state[ba] = mkq(va.x, va.y, wa, real(0));
+        if (!stat_b) s_state[bb] = mkq(vb.x, vb.y, wb, real(0));
     }
 
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
-    B2B_D void constraint_solve_velocity(int slot)
+    B2B_D void constraint_solve_velocity(const vrec& r, int slot)
     {
-        const quad* q = rec(slot);
-        const iquad iq = *irec(slot);
-        const quad q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
-        quad qi = *imp_rec(slot);
+        const iquad iq = r.iq;
+        const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
+        quad qi = r.qi;
         const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
+        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real friction = q0.z;
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
-        const quad sa = s_vel[ba], sb = s_vel[bb];
+        const quad sa = load_vel(ba, stat_a), sb = load_vel(bb, stat_b);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
         const V2 ra0 = mk<real>(q1.x, q1.y), rb0 = mk<real>(q1.z, q1.w), ra1 = mk<real>(q3.x, q3.y), rb1 = mk<real>(q3.z, q3.w);
@@ -824,24 +916,24 @@ template <class real> struct world_step {
             }
         }
         *imp_rec(slot) = qi;
-        if (!(iq.info & (1 << 24))) s_vel[ba] = mkq(va.x, va.y, wa, real(0));
-        if (!(iq.info & (1 << 25))) s_vel[bb] = mkq(vb.x, vb.y, wb, real(0));
+        if (!stat_a) s_state[ba] = mkq(va.x, va.y, wa, real(0));
+        if (!stat_b) s_state[bb] = mkq(vb.x, vb.y, wb, real(0));
     }
 
     // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
     // returns the smallest separation seen.
-    B2B_D real constraint_solve_position(int slot)
+    B2B_D real constraint_solve_position(const prec& r)
     {
-        const quad* q = rec(slot);
-        const iquad iq = *irec(slot);
-        const quad q7 = q[7], q8 = q[8], q9 = q[9], q10 = q[10], q11 = q[11];
+        const iquad iq = r.iq;
+        const quad q7 = r.q7, q8 = r.q8, q9 = r.q9, q10 = r.q10, q11 = r.q11;
         const int ba = iq.body_a, bb = iq.body_b;
+        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
         const int type = (iq.info >> 8) & 0xff, n_pos = (iq.info >> 16) & 0xff;
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
         const V2 lca = mk<real>(q11.x, q11.y), lcb = mk<real>(q11.z, q11.w);
         const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
         const real rad_a = q10.x, rad_b = q10.y;
-        const quad sa = s_pos[ba], sb = s_pos[bb];
+        const quad sa = load_pos(ba, stat_a), sb = load_pos(bb, stat_b);
         V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
         real aa = sa.z, ab = sb.z;
         real min_sep = real(0);
@@ -879,36 +971,37 @@ template <class real> struct world_step {
             ca = ca - ma * P; aa = aa - ia * cross(ra, P);
             cb = cb + mb * P; ab = ab + ib * cross(rb, P);
         }
-        if (!(iq.info & (1 << 24))) s_pos[ba] = mkq(ca.x, ca.y, aa, real(0));
-        if (!(iq.info & (1 << 25))) s_pos[bb] = mkq(cb.x, cb.y, ab, real(0));
+        if (!stat_a) s_state[ba] = mkq(ca.x, ca.y, aa, real(0));
+        if (!stat_b) s_state[bb] = mkq(cb.x, cb.y, ab, real(0));
         return min_sep;
     }
 
     // island.py:71-95 for one non-static body: save the sweep start, integrate gravity/forces, damp
     B2B_D void integrate_velocity(int b, real dt, V2 gravity)
     {
-        const uint32_t fl = s_flags[b];
-        const quad p = s_pos[b];
+        const real* p = b_pos + 4 * (size_t)b;
         real* p0 = b_pos0 + 4 * (size_t)b;
-        p0[0] = p.x; p0[1] = p.y; p0[2] = p.z;
-        if ((fl & BODY_TYPE_MASK) == BODY_DYNAMIC) {
+        p0[0] = p[0]; p0[1] = p[1]; p0[2] = p[2];
+        if ((s_flags8[b] & BODY_TYPE_MASK) == BODY_DYNAMIC) {
             const real* damp = b_damp + 4 * (size_t)b; const real* mass = b_mass + 4 * (size_t)b;
             const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
             const real torque = b_vel[4 * (size_t)b + 3];
-            const quad sv = s_vel[b];
+            const quad sv = s_state[b];
             V2 v = mk<real>(sv.x, sv.y);
             real w = sv.z;
             v = v + dt * (damp[2] * gravity + mass[0] * force);
             w = w + dt * mass[1] * torque;
             v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
             w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
-            s_vel[b] = mkq(v.x, v.y, w, real(0));
+            s_state[b] = mkq(v.x, v.y, w, real(0));
         }
     }
-    // island.py:119-138 for one non-static body: clamp the step, advance the sweep
+    // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity goes to
+    // global memory and the body's shared-memory quad becomes its position.
     B2B_D void integrate_position(int b, real dt)
     {
-        const quad sv = s_vel[b], spv = s_pos[b];
+        const quad sv = s_state[b];
+        const real* p = b_pos + 4 * (size_t)b;
         V2 v = mk<real>(sv.x, sv.y);
         real w = sv.z;
         const V2 translation = dt * v;
@@ -921,16 +1014,16 @@ template <class real> struct world_step {
             const real ratio = K<real>::max_rotation / abs_r(rotation);
             w = w * ratio;
         }
-        s_pos[b] = mkq(spv.x + dt * v.x, spv.y + dt * v.y, spv.z + dt * w, real(0));
-        s_vel[b] = mkq(v.x, v.y, w, real(0));
+        s_state[b] = mkq(p[0] + dt * v.x, p[1] + dt * v.y, p[2] + dt * w, real(0));
+        real* vout = b_vel + 4 * (size_t)b;
+        vout[0] = v.x; vout[1] = v.y; vout[2] = w;
     }
     // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body
     B2B_D void write_back(int b)
     {
-        const quad sp = s_pos[b], sv = s_vel[b];
-        real* p = b_pos + 4 * (size_t)b; real* v = b_vel + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
+        const quad sp = s_state[b];
+        real* p = b_pos + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
         p[0] = sp.x; p[1] = sp.y; p[2] = sp.z;
-        v[0] = sv.x; v[1] = sv.y; v[2] = sv.z;
         const real* mass = b_mass + 4 * (size_t)b;
         const XF tf = xf_from_sweep<real>(mk<real>(sp.x, sp.y), sp.z, mk<real>(mass[2], mass[3]));
         x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
@@ -940,15 +1033,15 @@ template <class real> struct world_step {
     B2B_D void island_sleep(int b0, int b1, real dt, bool position_solved)
     {
         real min_sleep = K<real>::max_float;
-        const bool last_allow = (s_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+        const bool last_allow = (s_flags8[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
         int victim = -1;
         for (int i = b0; i < b1; ++i) {
             const int b = l_body[i];
-            if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+            if (is_static_body(b)) continue;
             victim = b;
-            const quad sv = s_vel[b];
+            const real* sv = b_vel + 4 * (size_t)b;
             real* st = b_pos + 4 * (size_t)b + 3;
-            if (!last_allow || sv.z * sv.z > K<real>::angular_sleep_tol_sqr || sv.x * sv.x + sv.y * sv.y > K<real>::linear_sleep_tol_sqr) {
+            if (!last_allow || sv[2] * sv[2] > K<real>::angular_sleep_tol_sqr || sv[0] * sv[0] + sv[1] * sv[1] > K<real>::linear_sleep_tol_sqr) {
                 *st = real(0);
                 min_sleep = real(0);
             } else {
@@ -968,8 +1061,8 @@ template <class real> struct world_step {
     }
 
     // Island.solve for every island of the world (island.py:65-179).  Islands without contacts (free bodies)
-    // are whole-island-per-lane; islands with contacts are one warp each, their constraints strided over the
-    // lanes level by level (see phase_schedule).
+    // are whole-island-per-lane; islands with contacts are taken one after the other by the whole team, their
+    // constraints strided over the team's lanes level by level (see phase_schedule).
     B2B_D void solve_islands(const step_params& sp, real dt, real dt_ratio)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
@@ -977,7 +1070,7 @@ template <class real> struct world_step {
         const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
-        const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
+        const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
         int max_used = 0;
         // ---- contact-free islands: one lane per island
@@ -986,52 +1079,48 @@ template <class real> struct world_step {
             const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
             const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
             if (c1 != c0) continue;
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_velocity(b, dt, gravity); }
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt); }
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_velocity(b, dt, gravity); }
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_position(b, dt); }
             // an empty constraint list is "solved" by its first position iteration (contact.py:811,864)
             if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) write_back(b); }
+            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) write_back(b); }
             if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
         }
         B2B_PROF(PROF_S_INTEGRATE, t);
-        // ---- islands with contacts: one warp per island
-        for (int isl = B2B_WARP; isl < n_islands; isl += B2B_NWARPS) {
+        // ---- islands with contacts, one after the other
+        for (int isl = 0; isl < n_islands; ++isl) {
             const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
             const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
             const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
             if (c1 == c0) continue;
-            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+            for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
-                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_velocity(b, dt, gravity);
+                if (!is_static_body(b)) integrate_velocity(b, dt, gravity);
             }
-            B2B_WSYNC();
-            const uint16_t* ls = s_ls + c0 + 3 * isl;     // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
-            const int nlev = g_nlev[isl];
-            for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) constraint_init(s, l_contact[g_sched[s]], dt_ratio, warm);
-            B2B_WSYNC();
+            B2B_SYNC();
+            for (int s = c0 + t_id; s < c1; s += t_n) constraint_init(s, l_contact[g_sched[s]], dt_ratio, warm);
+            B2B_SYNC();
             B2B_PROF(PROF_S_INIT, t);
             if (warm) {
-                int begin = c0;
-                for (int l = 1; l <= nlev; ++l) {
-                    const int end = c0 + ls[l + 1];
-                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 0); constraint_warm_start(s); }
+                for (int begin = c0; begin < c1;) {
+                    const int end = level_end(begin) + 1;
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 0); vrec e; load_vrec(s, e); constraint_warm_start(e); }
                     begin = end;
-                    B2B_WSYNC();
+                    B2B_SYNC();
                 }
             }
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
-                int begin = c0;
-                for (int l = 1; l <= nlev; ++l) {
-                    const int end = c0 + ls[l + 1];
-                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 0); constraint_solve_velocity(s); }
+                for (int begin = c0; begin < c1;) {
+                    const int end = level_end(begin) + 1;
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 0); vrec e; load_vrec(s, e); constraint_solve_velocity(e, s); }
                     begin = end;
-                    B2B_WSYNC();
+                    B2B_SYNC();
                 }
             }
             B2B_PROF(PROF_S_VELOCITY, t);
             // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
-            for (int s = c0 + B2B_LANE; s < c1; s += B2B_NLANES) {
+            for (int s = c0 + t_id; s < c1; s += t_n) {
                 const quad qi = *imp_rec(s);
                 const iquad iq = *irec(s);
                 const int ci = iq.contact, n_vel = iq.info & 0xff;
@@ -1039,11 +1128,11 @@ template <class real> struct world_step {
                 if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
                 if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
             }
-            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+            for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
-                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt);
+                if (!is_static_body(b)) integrate_position(b, dt);
             }
-            B2B_WSYNC();
+            B2B_SYNC();
             B2B_PROF(PROF_S_STORE, t);
             // -- position iterations with early exit (island.py:141-153)
             bool position_solved = false;
@@ -1051,17 +1140,16 @@ template <class real> struct world_step {
             for (int it = 0; it < sp.pos_iters; ++it) {
                 real my_min = real(0);
                 ++used;
-                int begin = c0;
-                for (int l = 1; l <= nlev; ++l) {
-                    const int end = c0 + ls[l + 1];
-                    for (int s = begin + B2B_LANE; s < end; s += B2B_NLANES) { prefetch_slot(s, c0, c1, 7); my_min = pymin(my_min, constraint_solve_position(s)); }
+                for (int begin = c0; begin < c1;) {
+                    const int end = level_end(begin) + 1;
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 7); prec e; load_prec(s, e); my_min = pymin(my_min, constraint_solve_position(e)); }
                     begin = end;
-                    B2B_WSYNC();
+                    B2B_SYNC();
                 }
                 real all_min = my_min;
 #if defined(__CUDA_ARCH__)
-                for (int o = 16; o > 0; o >>= 1) {
-                    const real other = __shfl_xor_sync(0xffffffffu, all_min, o);
+                for (int o = t_n >> 1; o > 0; o >>= 1) {
+                    const real other = __shfl_xor_sync(t_mask, all_min, o);
                     all_min = (other < all_min) ? other : all_min;
                 }
 #endif
@@ -1069,15 +1157,17 @@ template <class real> struct world_step {
             }
             if (used > max_used) max_used = used;
             B2B_PROF(PROF_S_POSITION, t);
-            for (int i = b0 + B2B_LANE; i < b1; i += B2B_NLANES) {
+            for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
-                if ((s_flags[b] & BODY_TYPE_MASK) != BODY_STATIC) write_back(b);
+                if (!is_static_body(b)) write_back(b);
             }
-            B2B_WSYNC();
+            B2B_SYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);
-            if (B2B_LANE == 0 && allow_sleep) island_sleep(b0, b1, dt, position_solved);
-            B2B_WSYNC();
+            if (t_id == 0 && allow_sleep) island_sleep(b0, b1, dt, position_solved);
+            B2B_SYNC();
             B2B_PROF(PROF_S_SLEEP, t);
+            // the next island's bodies are disjoint (statics aside), but their quads must hold velocities again:
+            // they were staged as velocities and are only touched by their own island, so nothing to restore.
         }
         // max position iterations used by any island of this world (diagnostic, w_island[3])
 #if defined(__CUDA_ARCH__)

@@ -26,16 +26,20 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     scratch_layout L = scratch_plan(c, (int)sizeof(real));
     plan_layout P = plan_plan(c);
     smem_layout S = smem_plan_layout(c, (int)sizeof(real));
-    std::vector<unsigned char> scratch(L.total + 256), smem(S.total_all + 256);
+    std::vector<unsigned char> aux(L.total_aux + 256), solve(L.total_solve + 256);
+    std::vector<unsigned char> smem_aux(S.total_plan + 256), smem_solve(S.total_solve + 256);
     std::vector<uint16_t> plan(P.stride * (size_t)c.n_worlds + 16);
     step_params sp;
     sp.dt = dt; sp.dt_ratio_first = inv_dt0 * dt; sp.dt_ratio_rest = (dt > 0.0 ? (1.0 / dt) * dt : 0.0);
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = 0;
     for (int w = 0; w < c.n_worlds; ++w) {
         world_step<real> ws;
+        ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan.data(), P);
-        ws.bind_scratch(scratch.data(), L);
-        ws.bind_smem(smem.data(), 0);
+        ws.bind_scratch_aux(aux.data(), L);
+        ws.bind_scratch_solve(solve.data(), L);
+        ws.bind_smem_aux(smem_aux.data());
+        ws.bind_smem_solve(smem_solve.data());
         ws.run(sp);
     }
     return 0;

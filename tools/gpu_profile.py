@@ -25,7 +25,6 @@ def run(n_worlds, real, threads, settle=200, steps=4, ctas=0):
     print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]}, flush=True)
 
 if __name__ == "__main__":
-    run(148, "f32", 32, ctas=1)
-    run(8192, "f32", 32)
-    run(8192, "f32", 64)
-    run(4096, "f64", 32)
+    run(16384, "f32", 8)
+    run(16384, "f32", 16)
+    run(8192, "f64", 8)
