@@ -74,7 +74,10 @@ class BatchedWorld(object):
         for i, w in enumerate(worlds):
             schema.pack_world(w, A, i, table)
         A["s_meta"], A["s_radius"], A["s_data"] = table.arrays("f64")
-        return cls(A, caps, real=real, device=device, **kw)
+        bw = cls(A, caps, real=real, device=device, **kw)
+        if real != "f64":
+            bw.init_proxies()        # proxies are built in the working precision, exactly as `replicate` builds them
+        return bw
 
     @classmethod
     def replicate(cls, world, n, jitter=0.0, config=0, world_offset=0, real="f32", caps=None, device=None, **kw):
