@@ -28,7 +28,8 @@ def test_oracle_replays_reference_trajectory(case):
     for name in gen_golden.INIT_FIELDS:
         ref = g["init_" + name]
         mine = harness.used_view(A, name) if not name.startswith("s_") else A[name][:ref.shape[0]]
-        assert np.array_equal(np.ascontiguousarray(mine).view(np.uint8), np.ascontiguousarray(ref).view(np.uint8)), name
+        assert np.array_equal(np.atleast_1d(np.ascontiguousarray(mine)).view(np.uint8),
+                              np.atleast_1d(np.ascontiguousarray(ref)).view(np.uint8)), name
     orc = oracle.Oracle(A, 0)
     for s in range(steps):
         assert orc.step(dt, vi, pi) == 0
@@ -38,8 +39,8 @@ def test_oracle_replays_reference_trajectory(case):
         for name in gen_golden.CK_FIELDS:
             key = "ck%d_%s" % (s + 1, name)
             if key in g.files:
-                got = np.ascontiguousarray(harness.used_view(A, name))
-                assert np.array_equal(got.view(np.uint8), g[key].view(np.uint8)), key
+                got = np.atleast_1d(np.ascontiguousarray(harness.used_view(A, name)))
+                assert np.array_equal(got.view(np.uint8), np.atleast_1d(g[key]).view(np.uint8)), key
 
 
 def test_checkpoint_restart_matches_straight_run():
