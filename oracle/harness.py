@@ -90,6 +90,9 @@ def diff_state(A, B, w=0, fields=STATE_FIELDS, exact=True, rtol=0.0, atol=0.0):
             if k == "b_flags":      # island flag is transient bookkeeping
                 x = x & ~np.uint32(schema.BODY_ISLAND)
                 y = y & ~np.uint32(schema.BODY_ISLAND)
+            if k == "w_flags":      # device-only bookkeeping bit
+                x = x & ~np.uint32(schema.WORLD_GRAPH_VALID)
+                y = y & ~np.uint32(schema.WORLD_GRAPH_VALID)
             if k == "c_flags":
                 x = x & ~np.uint32(schema.CONTACT_ISLAND)
                 y = y & ~np.uint32(schema.CONTACT_ISLAND)

@@ -59,6 +59,7 @@ def lib():
     L.b2b_status.argtypes = [vp, ctypes.POINTER(u32), vp]
     L.b2b_checksum.argtypes = [vp, vp, vp]
     L.b2b_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), i32]
+    L.b2b_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]
     L.b2b_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)]
     for f in ("b2b_last_error", "b2b_field_names", "b2b_version"):

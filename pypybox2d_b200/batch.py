@@ -33,7 +33,7 @@ def world_caps(worlds, contacts_per_body=4, slack=64):
 
 
 class BatchedWorld(object):
-    def __init__(self, arrays, caps, real="f32", device=None, threads=0, ctas_per_sm=0):
+    def __init__(self, arrays, caps, real="f32", device=None, threads=0, ctas_per_sm=0, lanes_aux=0):
         """`arrays`: host numpy dict laid out as `schema.alloc` (any real dtype; cast to `real`)."""
         torch = _torch()
         if not torch.cuda.is_available():
@@ -55,7 +55,7 @@ class BatchedWorld(object):
         c.n_shapes = self.n_shapes
         c.real_bytes = 8 if real == "f64" else 4
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        c.threads, c.ctas_per_sm = threads, ctas_per_sm
+        c.threads, c.ctas_per_sm, c.reserved = threads, ctas_per_sm, lanes_aux
         self._caps_struct = c
         L = _lib.lib()
         _lib.check(L.b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
@@ -142,7 +142,7 @@ class BatchedWorld(object):
         c.n_shapes = self.n_shapes
         c.real_bytes = 8 if real == "f64" else 4
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        c.threads, c.ctas_per_sm = kw.get("threads", 0), kw.get("ctas_per_sm", 0)
+        c.threads, c.ctas_per_sm, c.reserved = kw.get("threads", 0), kw.get("ctas_per_sm", 0), kw.get("lanes_aux", 0)
         self._caps_struct = c
         _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
         self._bind()
@@ -163,6 +163,8 @@ class BatchedWorld(object):
             assert t.is_contiguous(), name
             setattr(b, name, t.data_ptr())
         self._buffers = b
+        # the context's island schedule is empty: whatever the arrays say, the first step must rebuild it
+        self.t["w_flags"] &= ~schema.WORLD_GRAPH_VALID
         _lib.check(_lib.lib().b2b_bind(self._ctx, ctypes.byref(b)), "b2b_bind")
 
     def __del__(self):
@@ -185,10 +187,11 @@ class BatchedWorld(object):
                      "s_stage", "s_integrate", "s_schedule", "s_init", "s_warm", "s_velocity", "s_store", "s_position",
                      "s_writeback", "s_sleep"]
 
-    def step(self, dt, vel_iters, pos_iters, n_steps=1, profile=False):
+    def step(self, dt, vel_iters, pos_iters, n_steps=1, profile=False, time_kernels=False):
         """World.step for every world, `n_steps` times (asynchronous on the current stream)."""
+        flags = (1 if profile else 0) | (2 if time_kernels else 0)
         _lib.check(_lib.lib().b2b_step(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters),
-                                       int(n_steps), 1 if profile else 0, self._stream()), "b2b_step")
+                                       int(n_steps), flags, self._stream()), "b2b_step")
         if dt > 0.0 and n_steps > 0:
             self.inv_dt0 = 1.0 / dt
 
@@ -221,6 +224,13 @@ class BatchedWorld(object):
         d = {n: int(out[i]) for i, n in enumerate(self.PROFILE_SLOTS)}
         d["world_steps"] = int(out[31])
         return d
+
+    def kernel_ms(self):
+        """{plan, solve, broadphase: total ms} of the steps run with time_kernels=True since the last call."""
+        out = (ctypes.c_float * 3)()
+        n = ctypes.c_int32(0)
+        _lib.check(_lib.lib().b2b_kernel_ms(self._ctx, out, ctypes.byref(n)), "b2b_kernel_ms")
+        return {"plan": float(out[0]), "solve": float(out[1]), "broadphase": float(out[2]), "steps": int(n.value)}
 
     def info(self):
         g, t, s, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
@@ -278,6 +288,7 @@ class BatchedWorld(object):
                 self.t[name][worlds].copy_(src)
             else:
                 self.t[name].copy_(src)
+        self.t["w_flags"] &= ~schema.WORLD_GRAPH_VALID      # host-side mutation: rebuild the island schedule
 
     # -- single-world facade support ----------------------------------------------------------
     def upload_bodies_from_world(self, world, w=0):

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/b2b.h"
 #include "b2b_launch.h"
@@ -27,6 +28,8 @@ struct b2b_ctx {
     const void* fields[B2B_NFIELDS];
     bool bound;
     long long launches;
+    std::vector<cudaEvent_t>* events;   // 4 per timed step (B2B_STEP_TIME)
+    int timed_steps;
 };
 
 static thread_local std::string g_err;
@@ -50,7 +53,8 @@ static bool caps_ok(const b2b_caps* k)
 {
     return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
            (k->real_bytes == 4 || k->real_bytes == 8) && (k->threads == 0 || k->threads == 4 || k->threads == 8 || k->threads == 16 || k->threads == 32) &&
-           k->reserved >= 0 && k->reserved <= 128 && (k->reserved % 32) == 0 && k->nb < 65535 && k->nc < 65535;
+           (k->reserved == 0 || k->reserved == 4 || k->reserved == 8 || k->reserved == 16 || k->reserved == 32) && k->nb < 65535 &&
+           k->nc < 65535;
 }
 
 static caps_t to_caps(const b2b_caps* k)
@@ -96,12 +100,12 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     cudaError_t e = cudaGetDeviceProperties(&prop, caps->device);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaGetDeviceProperties", e); }
     x->n_sm = prop.multiProcessorCount;
-    // caps->threads: lanes of a warp per world in the solve kernel (8, 16 or 32); caps->reserved: threads per CTA
-    // of the plan / broadphase kernels
+    // caps->threads: lanes of a warp per world in the solve kernel (4, 8, 16 or 32); caps->reserved: the same for
+    // the plan / broadphase kernels
     const int lanes = caps->threads > 0 ? caps->threads : 8;
-    const int threads_aux = caps->reserved > 0 ? caps->reserved : 64;
-    int rc = x->f64 ? plan_f64(x->c, lanes, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
-                    : plan_f32(x->c, lanes, threads_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
+    const int lanes_aux = caps->reserved > 0 ? caps->reserved : 32;
+    int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
+                    : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
     if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
     e = cudaMalloc((void**)&x->scratch, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
@@ -128,6 +132,7 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     if (x->d_status) cudaFree(x->d_status);
     if (x->stage_in) cudaFree(x->stage_in);
     if (x->stage_out) cudaFree(x->stage_out);
+    if (x->events) { for (cudaEvent_t e : *x->events) cudaEventDestroy(e); delete x->events; }
     delete x;
 }
 
@@ -178,8 +183,19 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
     const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, flags);
     for (int s = 0; s < n_steps; ++s) {
-        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream);
-        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream);
+        cudaEvent_t* ev = nullptr;
+        if (flags & B2B_STEP_TIME) {
+            if (!x->events) x->events = new std::vector<cudaEvent_t>();
+            while ((int)x->events->size() < 4 * (x->timed_steps + 1)) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e), "cudaEventCreate");
+                x->events->push_back(e);
+            }
+            ev = x->events->data() + 4 * x->timed_steps;
+            ++x->timed_steps;
+        }
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
         x->launches += (dt > 0.0) ? 2 : 1;       // check_launch counted one of the three
@@ -280,5 +296,23 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
             if (reset) CUDA_TRY(cudaMemset(p, 0, sizeof(tmp)), "memset profile");
         }
     }
+    return B2B_OK;
+}
+
+extern "C" int b2b_kernel_ms(b2b_ctx* x, float* out3, int32_t* n_steps)
+{
+    if (!x || !out3) return fail(B2B_ERR_ARG, "b2b_kernel_ms: NULL argument");
+    out3[0] = out3[1] = out3[2] = 0.f;
+    if (n_steps) *n_steps = x->timed_steps;
+    for (int s = 0; s < x->timed_steps; ++s) {
+        cudaEvent_t* ev = x->events->data() + 4 * s;
+        CUDA_TRY(cudaEventSynchronize(ev[3]), "cudaEventSynchronize");
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]), "cudaEventElapsedTime");
+            out3[k] += ms;
+        }
+    }
+    x->timed_steps = 0;
     return B2B_OK;
 }

@@ -22,26 +22,29 @@ typedef B2B_REAL real_t;
 //   broadphase_kernel proxy synchronisation (K4), pair finding (K5), contact creation (K6)      -- CTA per world
 // State lives in the caller's SoA arrays; per-world plan rows carry the island schedule between kernels; the
 // per-CTA scratch slab is reused for every world a CTA owns, so it stays L1/L2 resident.
-__global__ void __launch_bounds__(128) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
-                                                                          scratch_layout L, unsigned char* scratch, step_params sp)
+// All three kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
+// own world, so several worlds share each issued instruction (their work is mostly one or two lanes wide).
+__global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                         scratch_layout L, unsigned char* scratch, step_params sp,
+                                                                         int lanes, size_t team_smem)
 {
     extern __shared__ __align__(32) unsigned char smem[];
-    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total_aux;
-    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
+    world_step<real_t> ws;
+    const int team = ws.bind_team_lanes(lanes);
+    const int teams_per_cta = 32 / lanes;
+    const int slot = blockIdx.x * teams_per_cta + team;
+    unsigned char* my_scratch = scratch + (size_t)slot * L.total_aux;
+    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
         // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
         // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
-        world_step<real_t> ws;
-        ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan, P);
         ws.bind_scratch_aux(my_scratch, L);
-        ws.bind_smem_aux(smem);
+        ws.bind_smem_aux(smem + (size_t)team * team_smem);
         ws.run_plan(sp);
-        __syncthreads();
+        __syncwarp(ws.t_mask);
     }
 }
 
-// One warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its own world, so the
-// (mostly one- or two-lane-wide) dependency levels of several worlds share each issued instruction.
 __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_, B2B_SUFFIX)(
     batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* scratch, step_params sp,
     int first_step, int lanes, size_t team_smem)
@@ -61,19 +64,22 @@ __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_,
     }
 }
 
-__global__ void __launch_bounds__(128) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
-                                                                                scratch_layout L, unsigned char* scratch, step_params sp)
+__global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                               scratch_layout L, unsigned char* scratch, step_params sp,
+                                                                               int lanes, size_t team_smem)
 {
     extern __shared__ __align__(32) unsigned char smem[];
-    unsigned char* my_scratch = scratch + (size_t)blockIdx.x * L.total_aux;
-    for (int w = blockIdx.x; w < c.n_worlds; w += gridDim.x) {
-        world_step<real_t> ws;
-        ws.bind_team_cta();
+    world_step<real_t> ws;
+    const int team = ws.bind_team_lanes(lanes);
+    const int teams_per_cta = 32 / lanes;
+    const int slot = blockIdx.x * teams_per_cta + team;
+    unsigned char* my_scratch = scratch + (size_t)slot * L.total_aux;
+    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
         ws.bind_rows(B, c, w, plan, P);
         ws.bind_scratch_aux(my_scratch, L);
-        ws.bind_smem_aux(smem);
+        ws.bind_smem_aux(smem + (size_t)team * team_smem);
         ws.run_broadphase(sp);
-        __syncthreads();
+        __syncwarp(ws.t_mask);
     }
 }
 
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) B2B_CAT(init_proxies_kernel_, B2B_SUFFIX)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int w = (int)(i / c.nf), f = (int)(i % c.nf);
         const int nf = B.w_count[4 * (size_t)w + 1];
-        if (f == 0) B.w_flags[w] |= WORLD_NEW_FIXTURE;
+        if (f == 0) B.w_flags[w] = (B.w_flags[w] | WORLD_NEW_FIXTURE) & ~WORLD_GRAPH_VALID;
         if (f >= nf) continue;
         const size_t of = (size_t)w * c.nf + f;
         const int b = B.f_body[of];
@@ -208,22 +214,27 @@ static int plan_one(Kern kern, long long n_items, int threads, size_t smem, int 
     return 0;
 }
 
-int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out)
+int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ctas_per_sm, int n_sm, launch_plan* out)
 {
     const smem_layout S = smem_plan_layout(c, (int)sizeof(real_t));
     out->layout = scratch_plan(c, (int)sizeof(real_t));
     out->plan = plan_plan(c);
     out->lanes = lanes;
+    out->lanes_aux = lanes_aux;
     out->team_smem = S.total_solve;
-    const int teams = 32 / lanes;
-    int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), c.n_worlds, threads_aux, S.total_plan, 0, n_sm, &out->k_plan);
+    out->team_smem_plan = S.total_plan;
+    out->team_smem_broad = S.total_broad;
+    const int teams = 32 / lanes, teams_aux = 32 / lanes_aux;
+    int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
+                      S.total_plan * teams_aux, 0, n_sm, &out->k_plan);
     if (rc) return rc;
     rc = plan_one(B2B_CAT(solve_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
                   ctas_per_sm, n_sm, &out->k_solve);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), c.n_worlds, threads_aux, S.total_broad, 0, n_sm, &out->k_broad);
+    rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
+                  S.total_broad * teams_aux, 0, n_sm, &out->k_broad);
     if (rc) return rc;
-    out->aux_slabs = out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid;
+    out->aux_slabs = (out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid) * teams_aux;
     out->solve_slabs = out->k_solve.grid * teams;
     return 0;
 }
@@ -231,14 +242,20 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int threads_aux, int 
 // one World.step = plan + solve + broadphase
 void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
                                        unsigned char* scratch_aux, unsigned char* scratch_solve, const step_params& sp,
-                                       int first_step, cudaStream_t st)
+                                       int first_step, cudaStream_t st, cudaEvent_t* ev)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
-    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, p.k_plan.threads, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp);
+    if (ev) cudaEventRecord(ev[0], st);
+    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp, p.lanes_aux,
+                                                                                 p.team_smem_plan);
+    if (ev) cudaEventRecord(ev[1], st);
     if (sp.dt > 0.0)
         B2B_CAT(solve_kernel_, B2B_SUFFIX)<<<p.k_solve.grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp,
                                                                                         first_step, p.lanes, p.team_smem);
-    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, p.k_broad.threads, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp);
+    if (ev) cudaEventRecord(ev[2], st);
+    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
+                                                                                         p.lanes_aux, p.team_smem_broad);
+    if (ev) cudaEventRecord(ev[3], st);
 }
 
 void B2B_CAT(launch_init_proxies_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, cudaStream_t st)

@@ -17,17 +17,17 @@ struct kernel_plan {
 struct launch_plan {
     kernel_plan k_plan, k_solve, k_broad;
     int aux_slabs, solve_slabs;      // scratch slabs to allocate: per plan/broadphase CTA, per solve team
-    int lanes;                       // lanes of a warp that step one world in the solve kernel
-    size_t team_smem;
+    int lanes, lanes_aux;            // lanes of a warp that step one world: solve kernel / plan + broadphase kernels
+    size_t team_smem, team_smem_plan, team_smem_broad;
     scratch_layout layout;
     plan_layout plan;
 };
 
 #define B2B_DECLARE(S)                                                                                                        \
-    int plan_##S(const caps_t& c, int lanes, int threads_aux, int ctas_per_sm, int n_sm, launch_plan* out);                   \
+    int plan_##S(const caps_t& c, int lanes, int lanes_aux, int ctas_per_sm, int n_sm, launch_plan* out);                     \
     void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,                    \
                          unsigned char* scratch_aux, unsigned char* scratch_solve, const step_params& sp, int first_step,     \
-                         cudaStream_t st);                                                                                    \
+                         cudaStream_t st, cudaEvent_t* ev);                                                                   \
     void launch_init_proxies_##S(const void* const* fields, const caps_t& c, cudaStream_t st);                                \
     void launch_collide_pairs_##S(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,          \
                                   const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st);             \

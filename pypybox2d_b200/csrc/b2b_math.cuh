@@ -32,6 +32,7 @@ enum : uint32_t {
     BODY_WOKEN = 0x100u,   // transient, shared-memory copy only: woken by the island walk this step
     CONTACT_TOUCHING = 0x1u, CONTACT_ENABLED = 0x2u, CONTACT_FILTER = 0x4u, CONTACT_ISLAND = 0x8u,
     WORLD_ALLOW_SLEEP = 0x1u, WORLD_WARM_STARTING = 0x2u, WORLD_NEW_FIXTURE = 0x4u, WORLD_AUTO_CLEAR = 0x8u,
+    WORLD_GRAPH_VALID = 0x10u,   // the island lists / level schedule of the last step still describe this world
     STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u
 };
 enum { BODY_STATIC = 0, BODY_DYNAMIC = 1, BODY_KINEMATIC = 2 };

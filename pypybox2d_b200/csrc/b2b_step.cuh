@@ -34,6 +34,7 @@
 #define B2B_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define B2B_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define B2B_CLOCK() clock64()
 #define B2B_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
@@ -46,10 +47,12 @@ namespace b2b {
 template <class T> inline T host_atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T host_atomic_add(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T host_atomic_or(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T host_atomic_and(T* p, T v) { T o = *p; *p = o & v; return o; }
 }
 #define B2B_ATOMIC_MIN(p, v) b2b::host_atomic_min((p), (v))
 #define B2B_ATOMIC_ADD(p, v) b2b::host_atomic_add((p), (v))
 #define B2B_ATOMIC_OR(p, v) b2b::host_atomic_or((p), (v))
+#define B2B_ATOMIC_AND(p, v) b2b::host_atomic_and((p), (v))
 #endif
 
 // cycle accounting by thread 0 (wall-clock cycles of the CTA, since phases end in CTA barriers)
@@ -356,7 +359,7 @@ template <class real> struct world_step {
         const int NEVER = 0x7fffffff;
         B2B_PFOR(b, nb) wake_at[b] = (b_flags[b] & BODY_AWAKE) ? -1 : NEVER;
         B2B_PFOR(c, nc) scan[c] = 0;           // 0: pending, 1: keep (processed), 2: destroy
-        if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+        if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[10] = 0; }
         B2B_SYNC();
         for (;;) {
             B2B_PFOR(c, nc) {
@@ -373,6 +376,7 @@ template <class real> struct world_step {
                 }
                 scan[c] = 1;
                 if (contact_update(c)) {
+                    s_ctl[10] = 1;             // a touching flag changed: the contact graph is different
                     if (B2B_ATOMIC_MIN(&wake_at[ba], c) == NEVER) s_ctl[0] = 1;
                     if (B2B_ATOMIC_MIN(&wake_at[bb], c) == NEVER) s_ctl[0] = 1;
                 }
@@ -416,6 +420,7 @@ template <class real> struct world_step {
             }
             if (B2B_IS_T0) w_count[2] = kept;
         }
+        if (B2B_IS_T0 && (s_ctl[1] || s_ctl[10])) w_flags[0] &= ~WORLD_GRAPH_VALID;
         B2B_SYNC();
     }
 
@@ -523,13 +528,14 @@ template <class real> struct world_step {
                 ++n_islands;
             }
             if (overflow) w_status[0] |= STATUS_ISLAND_OVERFLOW;
+            s_ctl[11] = 0;
             w_island[0] = n_islands; w_island[1] = lb; w_island[2] = lc; w_island[3] = 0;
             s_ctl[4] = n_islands; s_ctl[5] = lb; s_ctl[6] = lc;
         }
         B2B_SYNC();
         B2B_PFOR(b, nb) {
             uint32_t f = s_flags[b];
-            if (f & BODY_WOKEN) { b_pos[4 * (size_t)b + 3] = real(0); f &= ~BODY_WOKEN; s_flags[b] = f; }
+            if (f & BODY_WOKEN) { b_pos[4 * (size_t)b + 3] = real(0); f &= ~BODY_WOKEN; s_flags[b] = f; s_ctl[11] = 1; }
             b_flags[b] = f;
             s_last[b] = 0;                                 // the DFS stack's storage becomes the scheduler's `last level`
         }
@@ -1057,6 +1063,7 @@ template <class real> struct world_step {
             v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
             b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
             b_flags[victim] &= ~BODY_AWAKE;
+            B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);   // the next island walk must skip this body
         }
     }
 
@@ -1313,6 +1320,7 @@ template <class real> struct world_step {
             if (npairs > cap.npair) st |= STATUS_PAIR_OVERFLOW;
             if (nc1 > cap.nc) { st |= STATUS_CONTACT_OVERFLOW; nc1 = cap.nc; }
             if (st) w_status[0] |= st;
+            if (n_new > 0) w_flags[0] &= ~WORLD_GRAPH_VALID;
             w_count[2] = nc1;
             w_count[3] = npairs;
         }
@@ -1335,13 +1343,21 @@ template <class real> struct world_step {
         phase_collide();                                         // world.py:338
         B2B_PROF(PROF_COLLIDE, t);
         if (sp.dt > 0.0) {                                       // world.py:341-342, 475-580
-            stage_flags();
-            build_adjacency();
-            B2B_PROF(PROF_ADJACENCY, t);
-            phase_islands();
-            B2B_PROF(PROF_ISLANDS, t);
-            phase_schedule();
-            B2B_PROF(PROF_S_SCHEDULE, t);
+            // The island walk is a pure function of the body flags and the contact graph.  While neither changes
+            // (the settled regime) last step's island lists, level schedule and island flags are reused as they are.
+            if (!(w_flags[0] & WORLD_GRAPH_VALID)) {
+                stage_flags();
+                build_adjacency();
+                B2B_PROF(PROF_ADJACENCY, t);
+                phase_islands();
+                B2B_PROF(PROF_ISLANDS, t);
+                phase_schedule();
+                if (B2B_IS_T0 && !s_ctl[11]) w_flags[0] |= WORLD_GRAPH_VALID;   // a body woken by the walk may seed earlier next time
+                B2B_PROF(PROF_S_SCHEDULE, t);
+            } else if (B2B_IS_T0) {
+                w_island[3] = 0;
+            }
+            B2B_SYNC();
         }
     }
     // solve kernel: Island.solve for every island (island.py:65-179)

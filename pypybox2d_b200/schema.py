@@ -32,6 +32,7 @@ WORLD_ALLOW_SLEEP = 0x1       # world.py:77
 WORLD_WARM_STARTING = 0x2     # world.py:74
 WORLD_NEW_FIXTURE = 0x4       # world.py:85
 WORLD_AUTO_CLEAR = 0x8        # world.py:80
+WORLD_GRAPH_VALID = 0x10      # device bookkeeping: last step's island lists / schedule are still valid
 
 STATUS_CONTACT_OVERFLOW = 0x1
 STATUS_PAIR_OVERFLOW = 0x2

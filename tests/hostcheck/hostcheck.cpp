@@ -6,6 +6,7 @@
 // never part of libb2b.so, never imported by the package, never timed.
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "../../include/b2b.h"
@@ -28,7 +29,14 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     smem_layout S = smem_plan_layout(c, (int)sizeof(real));
     std::vector<unsigned char> aux(L.total_aux + 256), solve(L.total_solve + 256);
     std::vector<unsigned char> smem_aux(S.total_plan + 256), smem_solve(S.total_solve + 256);
-    std::vector<uint16_t> plan(P.stride * (size_t)c.n_worlds + 16);
+    // the plan rows persist between calls like the device context's do (the island schedule is reused while the
+    // contact graph is unchanged); keyed by the batch they belong to
+    static std::map<const void*, std::vector<uint16_t>> plans;
+    std::vector<uint16_t>& plan = plans[buf->w_count];
+    if (plan.size() != P.stride * (size_t)c.n_worlds + 16) {
+        plan.assign(P.stride * (size_t)c.n_worlds + 16, 0);
+        for (int w = 0; w < c.n_worlds; ++w) B.w_flags[w] &= ~WORLD_GRAPH_VALID;
+    }
     step_params sp;
     sp.dt = dt; sp.dt_ratio_first = inv_dt0 * dt; sp.dt_ratio_rest = (dt > 0.0 ? (1.0 / dt) * dt : 0.0);
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = 0;
