@@ -639,10 +639,10 @@ template <class real> struct world_step {
     }
     // Records are consumed in slot order, so the lane solving slot s asks for slot s + PREFETCH_AHEAD (a few levels
     // ahead, wrapping to the start of the island for the next sweep) while it computes.
-    enum { PREFETCH_AHEAD = 4 };
+    int prefetch_ahead;      // records ahead of the one being solved (tunable: step flags bits 8..15, default 4)
     B2B_D void prefetch_slot(int s, int c0, int c1, int first_quad)
     {
-        int t = s + PREFETCH_AHEAD;
+        int t = s + prefetch_ahead;
         if (t >= c1) t = c0 + (t - c1);
         if (t < c1) {
             const char* r = reinterpret_cast<const char*>(rec(t)) + first_quad * sizeof(quad);
@@ -1076,6 +1076,7 @@ template <class real> struct world_step {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        prefetch_ahead = ((sp.flags >> 8) & 0xff) ? (int)((sp.flags >> 8) & 0xff) : 4;
         long long t = B2B_CLOCK();
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
