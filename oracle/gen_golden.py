@@ -41,6 +41,8 @@ CASES = {
     "mixed_w0": ("mixed", 0, 1.0 / 60, 8, 3, 400, (100, 400)),
     "mixed_w1": ("mixed", 1, 1.0 / 60, 8, 3, 400, (100, 400)),
     "deep_stacks_w1": ("deep_stacks", 1, 1.0 / 60, 8, 3, 400, (150, 400)),
+    "features_w0": ("features", 0, 1.0 / 60, 8, 3, 400, (100, 400)),
+    "features_w1": ("features", 1, 1.0 / 60, 10, 4, 400, (400,)),
 }
 
 CK_FIELDS = ["w_count", "w_flags", "w_island", "b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island",

@@ -161,5 +161,51 @@ def deep_stacks(b2, world=0, columns=10, rows=20, config=5, **world_kw):
     return w
 
 
-SCENES = {"pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
+# ---- feature coverage scene (not a BASELINE config): every body / fixture option the step path reads ------------
+def features(b2, world=0, config=6, **world_kw):
+    """Edge chain with ghost vertices (EPCollider / edge-circle adjacency), a kinematic platform, restitution,
+    damping, gravity scale, fixed rotation, a two-fixture body, group and category/mask filtering, circles and
+    3..6-gons."""
+    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    chain = [(-20.0, 6.0), (-12.0, 0.0), (-4.0, 0.0), (0.0, 2.5), (4.0, 0.0), (12.0, 0.0), (20.0, 6.0)]
+    edges = []
+    for i in range(len(chain) - 1):
+        v0 = chain[i - 1] if i > 0 else None
+        v3 = chain[i + 2] if i + 2 < len(chain) else None
+        edges.append(b2.Edge(chain[i], chain[i + 1], v0, v3))
+    w.create_static_body(shapes=edges, shape_fixture=b2.Fixture(b2.Circle(1.0), friction=0.6, restitution=0.1))
+    w.create_kinematic_body(position=(-8.0, 3.0), linear_velocity=(0.8, 0.0), angular_velocity=0.1,
+                            fixtures=b2.Fixture(b2.Polygon(box=(2.0, 0.25)), friction=0.5))
+    n = 36
+    jit = jitter(config, world, n + 2)[2:]
+    for k in range(n):
+        i, j = divmod(k, 6)
+        pos = (-7.5 + 3.0 * j + jit[k, 0], 4.0 + 1.6 * i + jit[k, 1])
+        kind = k % 6
+        kw = {}
+        if kind == 0:
+            fx = [b2.Fixture(b2.Circle(0.4), density=1.0, friction=0.3, restitution=0.6)]
+        elif kind == 1:
+            fx = [b2.Fixture(b2.Polygon(box=(0.5, 0.35)), density=2.0, friction=0.4)]
+            kw = dict(linear_damping=0.2, angular_damping=0.4)
+        elif kind == 2:
+            m = 3 + (k // 6) % 4
+            fx = [b2.Fixture(b2.Polygon(vertices=[(0.5 * math.cos(0.3 + 2.0 * math.pi * q / m),
+                                                   0.5 * math.sin(0.3 + 2.0 * math.pi * q / m)) for q in range(m)]),
+                             density=1.5, friction=0.2, restitution=0.2)]
+            kw = dict(angle=0.25 * k, angular_velocity=0.5)
+        elif kind == 3:
+            fx = [b2.Fixture(b2.Polygon(box=(0.45, 0.45)), density=1.0, friction=0.5, group_index=-3)]
+            kw = dict(fixed_rotation=True)
+        elif kind == 4:
+            fx = [b2.Fixture(b2.Polygon(box=(0.6, 0.2, (0.0, 0.0), 0.3)), density=1.0, friction=0.3),
+                  b2.Fixture(b2.Circle(0.25, (0.5, 0.2)), density=3.0, friction=0.3)]
+            kw = dict(gravity_scale=0.5, linear_velocity=(0.5, -1.0))
+        else:
+            fx = [b2.Fixture(b2.Circle(0.3, (0.1, 0.0)), density=1.0, friction=0.9, category_bits=0x0002, mask_bits=0xFFFD)]
+        w.create_dynamic_body(position=pos, fixtures=fx, **kw)
+    return w
+
+
+SCENES = {"features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
           "deep_stacks": deep_stacks}

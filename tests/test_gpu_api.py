@@ -82,3 +82,44 @@ def test_step_host_matches_device_step_and_reports_overflow():
     assert small.status(raise_on_overflow=False) & schema.STATUS_CONTACT_OVERFLOW
     with pytest.raises(Exception):
         small.status()
+
+
+def test_ragged_batch_of_different_scenes():
+    """Worlds with different body / fixture / contact counts in ONE batch, each against its own oracle run."""
+    import pypybox2d_b200 as b2
+    names = [("hello", 0), ("features", 1), ("vertical_stack", 1), ("pyramid", 2), ("hello", 3)]
+    worlds = [scenes.SCENES[n](b2, world=w) for n, w in names]
+    bw = b2.BatchedWorld.from_worlds(worlds, real="f64")
+    oracles = []
+    for n, w in names:
+        mw, A, caps = harness.facade_arrays(n, w)
+        oracles.append((oracle.Oracle(A, 0), A))
+    for s in range(90):
+        bw.step(1 / 60, 8, 3)
+        for o, A in oracles:
+            o.step(1 / 60, 8, 3)
+    G = bw.download()
+    for i, (o, A) in enumerate(oracles):
+        nb, nf, nc = [int(x) for x in A["w_count"][0][:3]]
+        assert [int(x) for x in G["w_count"][i][:3]] == [nb, nf, nc], names[i]
+        assert np.array_equal(G["c_fix"][i][:nc], A["c_fix"][0][:nc]), names[i]
+        assert np.array_equal(G["c_mtype"][i][:nc], A["c_mtype"][0][:nc]), names[i]
+        assert np.allclose(G["b_pos"][i][:nb, :3], A["b_pos"][0][:nb, :3], rtol=0, atol=1e-7), names[i]
+        assert np.allclose(G["b_vel"][i][:nb, :3], A["b_vel"][0][:nb, :3], rtol=0, atol=1e-7), names[i]
+    assert bw.status() == 0
+
+
+def test_zero_dt_and_empty_contact_world():
+    """step(0, ...) only runs the narrowphase (world.py:341-349); a world whose bodies never touch keeps no contacts."""
+    import pypybox2d_b200 as b2
+    w = b2.World((0, -10), True, continuous_physics=False, real="f64")
+    a = w.create_dynamic_body(position=(0, 10), fixtures=b2.Fixture(b2.Circle(0.5), density=1))
+    b = w.create_dynamic_body(position=(5, 10), fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=1))
+    y0 = a.position.y
+    w.step(0.0, 8, 3)
+    assert a.position.y == y0 and a.linear_velocity.y == 0.0
+    for i in range(10):
+        w.step(1 / 60, 8, 3)
+    assert len(w.contact_manager.contacts) == 0
+    assert a.position.y < y0 and a.position.y == pytest.approx(b.position.y, abs=1e-12)
+    assert a.linear_velocity.y == pytest.approx(-10.0 * 10 / 60, abs=1e-12)

@@ -84,7 +84,8 @@ def test_p_exact_fp64_free_running(case):
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 300), ("pyramid_w0", 150), ("mixed_w1", 150),
-                                        ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60)])
+                                        ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60),
+                                        ("features_w0", 200)])
 def test_p_step_fp32_teacher_forced(case, steps):
     import pypybox2d_b200 as b2
     g = load_golden(case)

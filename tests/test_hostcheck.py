@@ -13,7 +13,7 @@ import oracle
 
 INT_FIELDS = ["w_count", "f_moved", "c_fix", "c_flags", "c_mtype", "b_flags"]
 CASES = [("hello", 0, 0.1, 10, 10, 40), ("pyramid", 1, 1 / 60, 8, 3, 80), ("vertical_stack", 1, 1 / 60, 10, 10, 80),
-         ("mixed", 1, 1 / 60, 8, 3, 60), ("deep_stacks", 1, 1 / 60, 8, 3, 60)]
+         ("mixed", 1, 1 / 60, 8, 3, 60), ("deep_stacks", 1, 1 / 60, 8, 3, 60), ("features", 1, 1 / 60, 8, 3, 200)]
 
 
 @pytest.mark.parametrize("scene,world,dt,vi,pi,steps", CASES)
