@@ -136,15 +136,18 @@ def cpu_baseline_port(seconds, settle=300):
 REF_WORKER = r"""
 import sys, os, time, io, contextlib
 sys.path.insert(0, %(ref)r)
+core, settle, steps, warmup = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+pure, ccd = sys.argv[5] == "pure", sys.argv[6] == "ccd"
+if pure:
+    sys.modules["pypybox2d._common"] = None      # the reference's own fallback: common.py:954-979 "Using Pure Python"
 with contextlib.redirect_stdout(io.StringIO()):
     import pypybox2d as b2
-core, settle, steps, warmup = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 try:
     os.sched_setaffinity(0, {core})
 except Exception:
     pass
 from copy import copy
-world = b2.World((0, -10), True, continuous_physics=False)
+world = b2.World((0, -10), True, continuous_physics=ccd)
 world.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
 fixture = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
 x = b2.Vec2(-7, 0.75)
@@ -165,36 +168,53 @@ print("DONE %%.6f %%s" %% (time.perf_counter() - t0, "cext" if b2.Vec2 is not b2
 """
 
 
+def _reference_processes(ref, cores, settle, steps, warmup, pure, ccd):
+    """One pinned process per core, each stepping its own pyramid-20 world through the unmodified reference."""
+    procs = [subprocess.Popen([sys.executable, "-c", REF_WORKER % {"ref": ref}, str(c), str(settle), str(steps), str(warmup),
+                               "pure" if pure else "cext", "ccd" if ccd else "noccd"],
+                              stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True) for c in range(cores)]
+    for p in procs:
+        assert p.stdout.readline().startswith("READY")
+    t0 = time.perf_counter()
+    for p in procs:
+        p.stdin.write("go\n")
+        p.stdin.flush()
+    outs = [p.stdout.readline().split() for p in procs]
+    wall = time.perf_counter() - t0
+    for p in procs:
+        p.wait()
+    per = sorted(float(o[1]) for o in outs)
+    return {"value": N_DYNAMIC * cores * steps / wall, "wall_s": wall, "median_s_per_step": per[len(per) // 2] / steps,
+            "backend": outs[0][2], "cores": cores, "steps": steps}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the UNMODIFIED reference (oracle/_ref, installed with its own C extension by
     __graft_entry__.build) on the host cores, one pinned process per core, each stepping its own settled
-    pyramid world through World.step.  Falls back to the oracle port when oracle/_ref is absent."""
+    pyramid-20 world through World.step.  Headline = the `build_cext` path with continuous_physics=False (the
+    semantics the GPU path implements); the pure-Python path and the script-default CCD-on setting are timed
+    after it on a shorter sample and reported beside it.  Falls back to the oracle port when oracle/_ref is absent."""
     ref = os.path.join(ROOT, "oracle", "_ref")
     steps, warmup = args.steps, max(args.warmup, 3)
+    extras = None
     if os.path.exists(os.path.join(ref, "pypybox2d", "__init__.py")):
         cores = max(1, min(os.cpu_count() or 1, 64))
         settle = min(args.settle, 120)     # one island from ~step 120 (SURVEY A.9 #16); keeps set-up under a minute
-        procs = [subprocess.Popen([sys.executable, "-c", REF_WORKER % {"ref": ref}, str(c), str(settle), str(steps),
-                                   str(warmup)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
-                 for c in range(cores)]
-        for p in procs:
-            assert p.stdout.readline().startswith("READY")
-        t0 = time.perf_counter()
-        for p in procs:
-            p.stdin.write("go\n")
-            p.stdin.flush()
-        outs = [p.stdout.readline().split() for p in procs]
-        wall = time.perf_counter() - t0
-        for p in procs:
-            p.wait()
-        per = sorted(float(o[1]) for o in outs)
-        backend = "C extension (_common, build_cext)" if outs[0][2] == "cext" else "pure Python"
-        value = N_DYNAMIC * cores * steps / wall
+        main = _reference_processes(ref, cores, settle, steps, warmup, pure=False, ccd=False)
+        value, wall = main["value"], main["wall_s"]
+        backend = "C extension (_common, build_cext)" if main["backend"] == "cext" else "pure Python"
         kind, sample = "reference", ("%d processes (one per core, pinned) x %d World.step calls on a settled pyramid-20 "
                                      "world each (%d set-up steps), unmodified pypybox2d from oracle/_ref, %s math "
                                      "types, step(1/60,8,3), continuous_physics=False; median per-core %.3f s/step"
-                                     % (cores, steps, settle + warmup, backend, per[len(per) // 2] / steps))
+                                     % (cores, steps, settle + warmup, backend, main["median_s_per_step"]))
         ms = 1e3 * wall / steps
+        if not args.no_cpu_baseline:
+            few = max(2, min(steps, 3))
+            ccd_on = _reference_processes(ref, cores, settle, few, 1, pure=False, ccd=True)
+            pure_py = _reference_processes(ref, cores, 60, few, 1, pure=True, ccd=False)
+            extras = {"cext_ccd_on": {k: ccd_on[k] for k in ("value", "median_s_per_step", "cores", "steps")},
+                      "pure_python_ccd_off": dict({k: pure_py[k] for k in ("value", "median_s_per_step", "cores", "steps")},
+                                                  note="60 set-up steps (still landing): a lower bound on its cost per step")}
     else:
         cb = cpu_baseline_port(max(5.0, min(args.cpu_seconds, 30.0)), settle=args.settle)
         value, cores, kind, sample = cb["value"], cb["cores"], cb["kind"], cb["sample"]
@@ -204,7 +224,8 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "pyramid-20 (examples/pyramid-bench.py scene), one world per host core, settled regime",
                        "vel_iters": VEL_ITERS, "pos_iters": POS_ITERS, "dt": "1/60", "continuous_physics": False},
-            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                             "other_paths": extras},
             "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -317,6 +338,14 @@ def run_b200_arm(args):
     solve_ms = kms["solve"] / max(kms["steps"], 1)
     achieved = solve_bytes * args.worlds / (solve_ms * 1e-3) / 1e9              # GB/s on this rank's GPU
     step_achieved = step_bytes * args.worlds * K / (ms * 1e-3) / 1e9
+    # FP32 (non-tensor) view: SURVEY §8d's algorithmic FLOPs per world-step against SMs x 128 lanes x 2 x the clock seen
+    npts = 2.0 * nt_mean                                       # settled pyramid: two-point manifolds
+    V_, P_ = VEL_ITERS, max(pos_iters_used, 1.0)
+    flops_per_world_step = 400 * nc_mean + nt_mean * (270 + 165 * V_) + 150 * npts * P_ + 30 * 211 + 100 * 211
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+    fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12           # TFLOP/s
+    fp32_achieved = flops_per_world_step * args.worlds * K / (ms * 1e-3) / 1e12
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -332,6 +361,11 @@ def run_b200_arm(args):
     except Exception:
         pass
 
+    if world_size > 1:
+        import torch.distributed as tdist
+        dist.barrier()
+        if tdist.is_initialized():
+            tdist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -354,10 +388,13 @@ def run_b200_arm(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "solve_kernel_%s" % args.real,
-                     "kernel_ms_per_launch": solve_ms, "kernel_share_of_step": kms["solve"] / max(kms["plan"] + kms["solve"] + kms["broadphase"], 1e-9),
+                     "kernel_ms_per_launch": solve_ms, "kernel_share_of_step": kms["solve"] / max(kms["collide"] + kms["plan"] + kms["solve"] + kms["broadphase"], 1e-9),
                      "algorithmic_bytes_per_world_step": solve_bytes,
                      "step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_world_step": step_bytes,
-                              "kernel_ms": {k: kms[k] / max(kms["steps"], 1) for k in ("plan", "solve", "broadphase")}},
+                              "kernel_ms": {k: kms[k] / max(kms["steps"], 1) for k in ("collide", "plan", "solve", "broadphase")}},
+                     "fp32": {"achieved_tflops": fp32_achieved, "peak_tflops": fp32_peak, "frac": fp32_achieved / fp32_peak,
+                              "algorithmic_flops_per_world_step": flops_per_world_step,
+                              "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (clock sampled during the run)" % (n_sm, sm_mhz)},
                      "note": "latency bound, not HBM bound: the reference's exact Gauss-Seidel order leaves ~1.6 "
                              "independent contacts per dependency level (SURVEY finding 5)"},
     }

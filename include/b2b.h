@@ -37,6 +37,8 @@ typedef enum b2b_error {
 
 #define B2B_STEP_PROFILE 1u   /* b2b_step flags: accumulate per-phase cycle counters (see b2b_profile) */
 #define B2B_STEP_TIME 2u      /* b2b_step flags: bracket every kernel with CUDA events (see b2b_kernel_ms) */
+#define B2B_STEP_NO_FLAT 16u  /* b2b_step flags: run the narrowphase inside the per-world plan kernel (debugging) */
+/* bits 8..15: software-prefetch distance of the solve kernel in records (0 = default) */
 
 typedef struct b2b_caps {
     int32_t n_worlds;        /* worlds in this context (this GPU's shard) */
@@ -119,9 +121,9 @@ int b2b_checksum(b2b_ctx* ctx, void* d_out, void* stream);
 int b2b_profile(b2b_ctx* ctx, int64_t* host_out32, int reset);
 
 /* Device time of the kernels launched by b2b_step calls that had B2B_STEP_TIME set, from CUDA events recorded on
- * the launching stream: out[3] = total milliseconds of {plan, solve, broadphase} kernels, n_steps = steps covered.
- * Synchronises the stream's events; clears the accumulators. */
-int b2b_kernel_ms(b2b_ctx* ctx, float* out3, int32_t* n_steps);
+ * the launching stream: out[4] = total milliseconds of the {collide, plan, solve, broadphase} kernels, n_steps =
+ * steps covered.  Synchronises the stream's events; clears the accumulators. */
+int b2b_kernel_ms(b2b_ctx* ctx, float* out4, int32_t* n_steps);
 
 /* Launch geometry actually used and kernel launches issued so far (for bench.py's gpu_launches). */
 int b2b_info(b2b_ctx* ctx, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches);

@@ -226,11 +226,12 @@ class BatchedWorld(object):
         return d
 
     def kernel_ms(self):
-        """{plan, solve, broadphase: total ms} of the steps run with time_kernels=True since the last call."""
-        out = (ctypes.c_float * 3)()
+        """{collide, plan, solve, broadphase: total ms} of the steps run with time_kernels=True since the last call."""
+        out = (ctypes.c_float * 4)()
         n = ctypes.c_int32(0)
         _lib.check(_lib.lib().b2b_kernel_ms(self._ctx, out, ctypes.byref(n)), "b2b_kernel_ms")
-        return {"plan": float(out[0]), "solve": float(out[1]), "broadphase": float(out[2]), "steps": int(n.value)}
+        return {"collide": float(out[0]), "plan": float(out[1]), "solve": float(out[2]), "broadphase": float(out[3]),
+                "steps": int(n.value)}
 
     def info(self):
         g, t, s, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()

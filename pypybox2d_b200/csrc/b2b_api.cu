@@ -28,7 +28,7 @@ struct b2b_ctx {
     const void* fields[B2B_NFIELDS];
     bool bound;
     long long launches;
-    std::vector<cudaEvent_t>* events;   // 4 per timed step (B2B_STEP_TIME)
+    std::vector<cudaEvent_t>* events;   // 5 per timed step (B2B_STEP_TIME)
     int timed_steps;
 };
 
@@ -181,24 +181,25 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     if (vel_iters < 0 || pos_iters < 0 || n_steps < 0 || !(dt >= 0.0)) return fail(B2B_ERR_ARG, "b2b_step: bad argument");
     if (n_steps == 0) return B2B_OK;
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
-    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, flags);
+    // the flat narrowphase kernel is the default; B2B_STEP_NO_FLAT keeps the narrowphase inside the plan kernel
+    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u));
     for (int s = 0; s < n_steps; ++s) {
         cudaEvent_t* ev = nullptr;
         if (flags & B2B_STEP_TIME) {
             if (!x->events) x->events = new std::vector<cudaEvent_t>();
-            while ((int)x->events->size() < 4 * (x->timed_steps + 1)) {
+            while ((int)x->events->size() < 5 * (x->timed_steps + 1)) {
                 cudaEvent_t e;
                 CUDA_TRY(cudaEventCreate(&e), "cudaEventCreate");
                 x->events->push_back(e);
             }
-            ev = x->events->data() + 4 * x->timed_steps;
+            ev = x->events->data() + 5 * x->timed_steps;
             ++x->timed_steps;
         }
         if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
         else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
-        x->launches += (dt > 0.0) ? 2 : 1;       // check_launch counted one of the three
+        x->launches += ((dt > 0.0) ? 2 : 1) + ((sp.flags & 4u) ? 1 : 0);       // check_launch counted one of them
     }
     return B2B_OK;
 }
@@ -299,18 +300,19 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
     return B2B_OK;
 }
 
-extern "C" int b2b_kernel_ms(b2b_ctx* x, float* out3, int32_t* n_steps)
+extern "C" int b2b_kernel_ms(b2b_ctx* x, float* out4, int32_t* n_steps)
 {
-    if (!x || !out3) return fail(B2B_ERR_ARG, "b2b_kernel_ms: NULL argument");
-    out3[0] = out3[1] = out3[2] = 0.f;
+    if (!x || !out4) return fail(B2B_ERR_ARG, "b2b_kernel_ms: NULL argument");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.f;
     if (n_steps) *n_steps = x->timed_steps;
     for (int s = 0; s < x->timed_steps; ++s) {
-        cudaEvent_t* ev = x->events->data() + 4 * s;
+        cudaEvent_t* ev = x->events->data() + 5 * s;       // 0 start, 4 after collide, 1 after plan, 2 after solve, 3 end
         CUDA_TRY(cudaEventSynchronize(ev[3]), "cudaEventSynchronize");
-        for (int k = 0; k < 3; ++k) {
+        const int from[4] = {0, 4, 1, 2}, to[4] = {4, 1, 2, 3};
+        for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]), "cudaEventElapsedTime");
-            out3[k] += ms;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[from[k]], ev[to[k]]), "cudaEventElapsedTime");
+            out4[k] += ms;
         }
     }
     x->timed_steps = 0;

@@ -49,7 +49,7 @@ template <class real> struct clip_vertex {
 
 // ---------------------------------------------------------------- circles
 template <class real>
-B2B_HD void collide_circles(manifold<real>& m, const shape_view<real>& a, const xform<real>& xa,
+B2B_HD_COLD void collide_circles(manifold<real>& m, const shape_view<real>& a, const xform<real>& xa,
                             const shape_view<real>& b, const xform<real>& xb)
 {
     m.count = 0;
@@ -67,7 +67,7 @@ B2B_HD void collide_circles(manifold<real>& m, const shape_view<real>& a, const 
 
 // ---------------------------------------------------------------- polygon vs circle
 template <class real>
-B2B_HD void collide_polygon_circle(manifold<real>& m, const shape_view<real>& pa, const xform<real>& xa,
+B2B_HD_COLD void collide_polygon_circle(manifold<real>& m, const shape_view<real>& pa, const xform<real>& xa,
                                    const shape_view<real>& cb, const xform<real>& xb)
 {
     m.count = 0;
@@ -251,7 +251,7 @@ B2B_HD void collide_polygons(manifold<real>& m, const shape_view<real>& pa, cons
 
 // ---------------------------------------------------------------- edge vs circle
 template <class real>
-B2B_HD void collide_edge_circle(manifold<real>& m, const shape_view<real>& ea, const xform<real>& xa,
+B2B_HD_COLD void collide_edge_circle(manifold<real>& m, const shape_view<real>& ea, const xform<real>& xa,
                                 const shape_view<real>& cb, const xform<real>& xb)
 {
     m.count = 0;
@@ -314,7 +314,7 @@ template <class real> struct ep_ctx {
 };
 
 template <class real>
-B2B_HD void collide_edge_polygon(manifold<real>& m, const shape_view<real>& ea, const xform<real>& xa,
+B2B_HD_COLD void collide_edge_polygon(manifold<real>& m, const shape_view<real>& ea, const xform<real>& xa,
                                  const shape_view<real>& pb, const xform<real>& xb)
 {
     ep_ctx<real> c;

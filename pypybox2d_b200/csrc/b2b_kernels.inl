@@ -22,7 +22,23 @@ typedef B2B_REAL real_t;
 //   broadphase_kernel proxy synchronisation (K4), pair finding (K5), contact creation (K6)      -- CTA per world
 // State lives in the caller's SoA arrays; per-world plan rows carry the island schedule between kernels; the
 // per-CTA scratch slab is reused for every world a CTA owns, so it stays L1/L2 resident.
-// All three kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
+// Flat narrowphase (K1): one thread per contact of the WHOLE batch -- the colliders are embarrassingly parallel and
+// this shape gives them full lanes and their own register budget.  Worlds that still have to create their first
+// contacts this step (new fixtures) are left to the plan kernel.
+__global__ void __launch_bounds__(128, 5) B2B_CAT(collide_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan)
+{
+    const long long total = (long long)c.n_worlds * c.nc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i / c.nc), ci = (int)(i % c.nc);
+        if (ci >= B.w_count[4 * (size_t)w + 2]) continue;
+        if (B.w_flags[w] & WORLD_NEW_FIXTURE) continue;
+        world_step<real_t> ws;
+        ws.bind_rows(B, c, w, plan, P);
+        ws.collide_one(ci);
+    }
+}
+
+// The other three kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
 // own world, so several worlds share each issued instruction (their work is mostly one or two lanes wide).
 __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                          scratch_layout L, unsigned char* scratch, step_params sp,
@@ -221,6 +237,7 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     out->plan = plan_plan(c);
     out->lanes = lanes;
     out->lanes_aux = lanes_aux;
+    out->n_sm = n_sm;
     out->team_smem = S.total_solve;
     out->team_smem_plan = S.total_plan;
     out->team_smem_broad = S.total_broad;
@@ -246,6 +263,13 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
     if (ev) cudaEventRecord(ev[0], st);
+    if (sp.flags & STEP_FLAT_COLLIDE) {
+        const long long total = (long long)c.n_worlds * c.nc;
+        long long blocks = (total + 127) / 128;
+        if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
+        B2B_CAT(collide_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan);
+    }
+    if (ev) cudaEventRecord(ev[4], st);
     B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp, p.lanes_aux,
                                                                                  p.team_smem_plan);
     if (ev) cudaEventRecord(ev[1], st);

@@ -17,6 +17,7 @@ struct kernel_plan {
 struct launch_plan {
     kernel_plan k_plan, k_solve, k_broad;
     int aux_slabs, solve_slabs;      // scratch slabs to allocate: per plan/broadphase CTA, per solve team
+    int n_sm;
     int lanes, lanes_aux;            // lanes of a warp that step one world: solve kernel / plan + broadphase kernels
     size_t team_smem, team_smem_plan, team_smem_broad;
     scratch_layout layout;

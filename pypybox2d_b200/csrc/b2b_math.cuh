@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)
 #define B2B_HD __host__ __device__ __forceinline__
 #define B2B_D __device__ __forceinline__
+#define B2B_HD_COLD __host__ __device__ __noinline__
 #else
 #define B2B_HD inline
 #define B2B_D inline
+#define B2B_HD_COLD inline
 #endif
 
 namespace b2b {

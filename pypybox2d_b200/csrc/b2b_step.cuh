@@ -85,7 +85,7 @@ template <class real> struct batch_ptrs {
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
 enum { CC_QUADS = 12, CC_REALS = 4 * CC_QUADS };
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
-enum { PROF_SLOTS = 32, STEP_PROFILE = 1 };
+enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4 };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
        PROF_S_STAGE = 8, PROF_S_INTEGRATE, PROF_S_SCHEDULE, PROF_S_INIT, PROF_S_WARM, PROF_S_VELOCITY, PROF_S_STORE,
        PROF_S_POSITION, PROF_S_WRITEBACK, PROF_S_SLEEP, PROF_WORLD_STEPS = 31 };
@@ -95,7 +95,7 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 // kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
 // it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
 struct plan_layout {          // per world, in uint16_t elements
-    size_t off_cbody, off_sched, off_lmask, off_adj, off_adj_start, stride;
+    size_t off_cbody, off_sched, off_lmask, off_adj, off_adj_start, off_cstate, stride;
 };
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 B2B_HD int lmask_words(const caps_t& c) { return (c.nc + 31) / 32 + 2; }
@@ -108,6 +108,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
     P.off_lmask = o; o = align_up(o + 2 * (size_t)lmask_words(c), 8);       // uint32 words, counted in uint16 units
     P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
     P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
+    P.off_cstate = o; o = align_up(o + ((size_t)c.nc + 1) / 2 + 1, 8);      // one byte per contact
     P.stride = o;
     return P;
 }
@@ -161,7 +162,7 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     S.off_cflag = o; o = align_up(o + (size_t)c.nc, 32);
     S.total_plan = o;
     o = 0;
-    S.off_state = o; o = align_up(o + (size_t)real_bytes * 4 * (size_t)c.nb, 32);
+    S.off_state = o; o = align_up(o + (size_t)real_bytes * 3 * (size_t)c.nb, 32);
     S.off_lmask = o; o = align_up(o + sizeof(uint32_t) * (size_t)lmask_words(c), 32);
     S.off_flags8 = o; o = align_up(o + (size_t)c.nb, 32);
     S.total_solve = o;
@@ -192,6 +193,7 @@ template <class real> struct world_step {
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
     uint32_t* g_lmask;       // bit s set: slot s is the last constraint of its dependency level
+    uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan, *cc_int;
     real *cc_real, *cc_imp;
@@ -199,7 +201,7 @@ template <class real> struct world_step {
     int32_t* pair_keep;
     long long* prof;
     // shared memory
-    quad* s_state;           // solve kernel: (v.x, v.y, w, -) during the velocity phase, then (c.x, c.y, a, -)
+    real *s_sx, *s_sy, *s_sz;  // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
     uint32_t* s_lmask;
     uint8_t* s_flags8;       // solve kernel: body type | allow_sleep
     uint32_t* s_flags;       // plan kernel: body flags
@@ -255,6 +257,7 @@ template <class real> struct world_step {
         uint16_t* pw = plan + W * P.stride;
         g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lmask = reinterpret_cast<uint32_t*>(pw + P.off_lmask);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
+        g_cstate = reinterpret_cast<uint8_t*>(pw + P.off_cstate);
     }
     B2B_D void bind_scratch_aux(unsigned char* scratch, const scratch_layout& L)
     {
@@ -285,7 +288,7 @@ template <class real> struct world_step {
     B2B_D void bind_smem_solve(unsigned char* team_smem)
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
-        s_state = (quad*)(team_smem + S.off_state);
+        s_sx = (real*)(team_smem + S.off_state); s_sy = s_sx + cap.nb; s_sz = s_sy + cap.nb;
         s_lmask = (uint32_t*)(team_smem + S.off_lmask);
         s_flags8 = (uint8_t*)(team_smem + S.off_flags8);
     }
@@ -309,43 +312,67 @@ template <class real> struct world_step {
     // ------------------------------------------------------------------------------------ K1
     // Contact.update (contact.py:210-268): evaluate, carry impulses of matching ids, touching flag.
     // Returns true when the touching state changed (both bodies must be woken).
+    // 128-bit (fp32) / 256-bit (fp64) row access: every [.,4] field row is one aligned quad
+    B2B_D static quad ldq(const real* p) { return *reinterpret_cast<const quad*>(p); }
+    B2B_D static void stq(real* p, quad q) { *reinterpret_cast<quad*>(p) = q; }
+
     B2B_D bool contact_update(int ci)
     {
         manifold<real> m, old;
+        const quad qmf = ldq(c_mf + 4 * (size_t)ci), qpts = ldq(c_pts + 4 * (size_t)ci), qimp = ldq(c_imp + 4 * (size_t)ci);
         {
             const int mt = c_mtype[ci];
             m.type = mt & 0xff; m.count = (mt >> 8) & 0xff;
-            const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci;
-            m.local_normal = mk<real>(mf[0], mf[1]); m.local_point = mk<real>(mf[2], mf[3]);
-            m.pt[0] = mk<real>(pts[0], pts[1]); m.pt[1] = mk<real>(pts[2], pts[3]);
+            m.local_normal = mk<real>(qmf.x, qmf.y); m.local_point = mk<real>(qmf.z, qmf.w);
+            m.pt[0] = mk<real>(qpts.x, qpts.y); m.pt[1] = mk<real>(qpts.z, qpts.w);
             m.id[0] = c_id[2 * ci]; m.id[1] = c_id[2 * ci + 1];
         }
         old = m;
-        real* imp = c_imp + 4 * (size_t)ci;
-        const real old_ni0 = imp[0], old_ti0 = imp[1], old_ni1 = imp[2], old_ti1 = imp[3];
         const uint32_t fl = c_flags[ci];
         const bool was_touching = (fl & CONTACT_TOUCHING) != 0;
         const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
         const int ba = f_body[fa], bb = f_body[fb];
-        const XF xa = xf_load<real>(b_xf + 4 * (size_t)ba), xb = xf_load<real>(b_xf + 4 * (size_t)bb);
+        const quad qxa = ldq(b_xf + 4 * (size_t)ba), qxb = ldq(b_xf + 4 * (size_t)bb);
+        const XF xa = xf_make<real>(mk<real>(qxa.x, qxa.y), qxa.z, qxa.w), xb = xf_make<real>(mk<real>(qxb.x, qxb.y), qxb.z, qxb.w);
         const shape_view<real> sa = shape_of_fixture(fa), sb = shape_of_fixture(fb);
         collide_shapes(m, sa, xa, sb, xb);
         const bool touching = m.count > 0;
+        // carry the impulses of matching ids; entries beyond the new point count keep their stale values
+        quad nimp = qimp;
         for (int i = 0; i < m.count; ++i) {
             real ni = real(0), ti = real(0);
-            if (old.count > 0 && old.id[0] == m.id[i]) { ni = old_ni0; ti = old_ti0; }
-            if (old.count > 1 && old.id[1] == m.id[i]) { ni = old_ni1; ti = old_ti1; }   // last duplicate wins
-            imp[2 * i] = ni; imp[2 * i + 1] = ti;
+            if (old.count > 0 && old.id[0] == m.id[i]) { ni = qimp.x; ti = qimp.y; }
+            if (old.count > 1 && old.id[1] == m.id[i]) { ni = qimp.z; ti = qimp.w; }   // last duplicate wins
+            if (i == 0) { nimp.x = ni; nimp.y = ti; } else { nimp.z = ni; nimp.w = ti; }
         }
+        if (m.count > 0) stq(c_imp + 4 * (size_t)ci, nimp);
         c_mtype[ci] = m.type | (m.count << 8);
-        {
-            real* mf = c_mf + 4 * (size_t)ci; real* pts = c_pts + 4 * (size_t)ci;
-            mf[0] = m.local_normal.x; mf[1] = m.local_normal.y; mf[2] = m.local_point.x; mf[3] = m.local_point.y;
-            pts[0] = m.pt[0].x; pts[1] = m.pt[0].y; pts[2] = m.pt[1].x; pts[3] = m.pt[1].y;
-            c_id[2 * ci] = m.id[0]; c_id[2 * ci + 1] = m.id[1];
-        }
+        quad nmf; nmf.x = m.local_normal.x; nmf.y = m.local_normal.y; nmf.z = m.local_point.x; nmf.w = m.local_point.y;
+        quad npts; npts.x = m.pt[0].x; npts.y = m.pt[0].y; npts.z = m.pt[1].x; npts.w = m.pt[1].y;
+        stq(c_mf + 4 * (size_t)ci, nmf);
+        stq(c_pts + 4 * (size_t)ci, npts);
+        c_id[2 * ci] = m.id[0]; c_id[2 * ci + 1] = m.id[1];
         c_flags[ci] = ((fl | CONTACT_ENABLED) & ~CONTACT_TOUCHING) | (touching ? CONTACT_TOUCHING : 0u);
         return touching != was_touching;
+    }
+
+    // Narrowphase for ONE contact of this world, called by the flat kernel (one thread per contact of the whole
+    // batch).  Only contacts whose non-static bodies are all awake are handled here: they are active whatever the
+    // list order, and their touching changes cannot wake anybody.  The rest (a sleeping body is involved) stays
+    // pending for the order-exact walk in phase_collide.
+    B2B_D void collide_one(int c)
+    {
+        const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
+        const int ba = f_body[fa], bb = f_body[fb];
+        const uint32_t fla = b_flags[ba], flb = b_flags[bb];
+        const bool ns_a = (fla & BODY_TYPE_MASK) != BODY_STATIC, ns_b = (flb & BODY_TYPE_MASK) != BODY_STATIC;
+        const bool all_awake = (!ns_a || (fla & BODY_AWAKE)) && (!ns_b || (flb & BODY_AWAKE));
+        uint8_t state = 0;
+        if (all_awake && (ns_a || ns_b)) {
+            if (!aabb_overlap<real>(f_fat + 4 * (size_t)fa, f_fat + 4 * (size_t)fb)) state = 2;
+            else state = contact_update(c) ? 3 : 1;
+        }
+        g_cstate[c] = state;
     }
 
     // ContactManager.collide (contact_manager.py:174-223).  The reference walks the contact list in
@@ -353,15 +380,27 @@ template <class real> struct world_step {
     // step.  wake_at[b] = index of the first contact that wakes body b (-1: awake on entry) makes the
     // parallel evaluation order-exact: contact c sees body b awake iff wake_at[b] < c.  Iterate to the
     // fixed point (one extra round only when a sleeping body is woken).
-    B2B_D void phase_collide()
+    B2B_D void phase_collide(bool after_flat)
     {
         const int nb = w_count[0], nc = w_count[2];
         const int NEVER = 0x7fffffff;
-        B2B_PFOR(b, nb) wake_at[b] = (b_flags[b] & BODY_AWAKE) ? -1 : NEVER;
-        B2B_PFOR(c, nc) scan[c] = 0;           // 0: pending, 1: keep (processed), 2: destroy
-        if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[10] = 0; }
+        if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[10] = 0; s_ctl[12] = 0; }
         B2B_SYNC();
-        for (;;) {
+        // 0: pending, 1: keep (processed), 2: destroy.  After the flat kernel most contacts are already processed.
+        B2B_PFOR(c, nc) {
+            const int st = after_flat ? (int)g_cstate[c] : 0;
+            scan[c] = (st == 3) ? 1 : st;
+            if (st == 3) s_ctl[10] = 1;
+            if (st == 2) s_ctl[1] = 1;
+            if (st == 0) s_ctl[12] = 1;
+        }
+        B2B_SYNC();
+        const bool any_pending = s_ctl[12] != 0;
+        if (any_pending) {
+            B2B_PFOR(b, nb) wake_at[b] = (b_flags[b] & BODY_AWAKE) ? -1 : NEVER;
+        }
+        B2B_SYNC();
+        for (; any_pending;) {
             B2B_PFOR(c, nc) {
                 if (scan[c] != 0) continue;
                 const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
@@ -389,7 +428,7 @@ template <class real> struct world_step {
             B2B_SYNC();
         }
         // Body.awake = True for bodies woken by a touching change (body.py:800-804)
-        B2B_PFOR(b, nb) {
+        if (any_pending) B2B_PFOR(b, nb) {
             if (!(b_flags[b] & BODY_AWAKE) && wake_at[b] != NEVER) {
                 b_flags[b] |= BODY_AWAKE;
                 b_pos[4 * (size_t)b + 3] = real(0);
@@ -621,15 +660,17 @@ template <class real> struct world_step {
     B2B_D quad* rec(int slot) { return reinterpret_cast<quad*>(cc_real) + (size_t)CC_QUADS * slot; }
     B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
     B2B_D iquad* irec(int slot) { return reinterpret_cast<iquad*>(cc_int) + slot; }
+    B2B_D quad state_get(int b) const { return mkq(s_sx[b], s_sy[b], s_sz[b], real(0)); }
+    B2B_D void state_set(int b, real x, real y, real z) { s_sx[b] = x; s_sy[b] = y; s_sz[b] = z; }
     B2B_D quad load_vel(int b, bool is_static) const
     {
         if (is_static) { const real* v = b_vel + 4 * (size_t)b; return mkq(v[0], v[1], v[2], real(0)); }
-        return s_state[b];
+        return state_get(b);
     }
     B2B_D quad load_pos(int b, bool is_static) const
     {
         if (is_static) { const real* p = b_pos + 4 * (size_t)b; return mkq(p[0], p[1], p[2], real(0)); }
-        return s_state[b];
+        return state_get(b);
     }
     B2B_D bool is_static_body(int b) const { return (s_flags8[b] & BODY_TYPE_MASK) == BODY_STATIC; }
 
@@ -677,7 +718,7 @@ template <class real> struct world_step {
         const int nb = w_count[0];
         B2B_PFOR(b, nb) {
             const real* v = b_vel + 4 * (size_t)b;
-            s_state[b] = mkq(v[0], v[1], v[2], real(0));
+            state_set(b, v[0], v[1], v[2]);
             s_flags8[b] = (uint8_t)(b_flags[b] & (BODY_TYPE_MASK | BODY_ALLOW_SLEEP));
         }
         B2B_PFOR(k, lmask_words(cap)) s_lmask[k] = g_lmask[k];
@@ -834,8 +875,8 @@ template <class real> struct world_step {
             wb = wb + ib * cross(rb, p);
             vb = vb + mb * p;
         }
-        if (!stat_a) s_state[ba] = mkq(va.x, va.y, wa, real(0));
-        if (!stat_b) s_state[bb] = mkq(vb.x, vb.y, wb, real(0));
+        if (!stat_a) state_set(ba, va.x, va.y, wa);
+        if (!stat_b) state_set(bb, vb.x, vb.y, wb);
     }
 
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
@@ -922,8 +963,8 @@ template <class real> struct world_step {
             }
         }
         *imp_rec(slot) = qi;
-        if (!stat_a) s_state[ba] = mkq(va.x, va.y, wa, real(0));
-        if (!stat_b) s_state[bb] = mkq(vb.x, vb.y, wb, real(0));
+        if (!stat_a) state_set(ba, va.x, va.y, wa);
+        if (!stat_b) state_set(bb, vb.x, vb.y, wb);
     }
 
     // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
@@ -977,8 +1018,8 @@ template <class real> struct world_step {
             ca = ca - ma * P; aa = aa - ia * cross(ra, P);
             cb = cb + mb * P; ab = ab + ib * cross(rb, P);
         }
-        if (!stat_a) s_state[ba] = mkq(ca.x, ca.y, aa, real(0));
-        if (!stat_b) s_state[bb] = mkq(cb.x, cb.y, ab, real(0));
+        if (!stat_a) state_set(ba, ca.x, ca.y, aa);
+        if (!stat_b) state_set(bb, cb.x, cb.y, ab);
         return min_sep;
     }
 
@@ -992,21 +1033,21 @@ template <class real> struct world_step {
             const real* damp = b_damp + 4 * (size_t)b; const real* mass = b_mass + 4 * (size_t)b;
             const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
             const real torque = b_vel[4 * (size_t)b + 3];
-            const quad sv = s_state[b];
+            const quad sv = state_get(b);
             V2 v = mk<real>(sv.x, sv.y);
             real w = sv.z;
             v = v + dt * (damp[2] * gravity + mass[0] * force);
             w = w + dt * mass[1] * torque;
             v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
             w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
-            s_state[b] = mkq(v.x, v.y, w, real(0));
+            state_set(b, v.x, v.y, w);
         }
     }
     // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity goes to
     // global memory and the body's shared-memory quad becomes its position.
     B2B_D void integrate_position(int b, real dt)
     {
-        const quad sv = s_state[b];
+        const quad sv = state_get(b);
         const real* p = b_pos + 4 * (size_t)b;
         V2 v = mk<real>(sv.x, sv.y);
         real w = sv.z;
@@ -1020,14 +1061,14 @@ template <class real> struct world_step {
             const real ratio = K<real>::max_rotation / abs_r(rotation);
             w = w * ratio;
         }
-        s_state[b] = mkq(p[0] + dt * v.x, p[1] + dt * v.y, p[2] + dt * w, real(0));
+        state_set(b, p[0] + dt * v.x, p[1] + dt * v.y, p[2] + dt * w);
         real* vout = b_vel + 4 * (size_t)b;
         vout[0] = v.x; vout[1] = v.y; vout[2] = w;
     }
     // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body
     B2B_D void write_back(int b)
     {
-        const quad sp = s_state[b];
+        const quad sp = state_get(b);
         real* p = b_pos + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
         p[0] = sp.x; p[1] = sp.y; p[2] = sp.z;
         const real* mass = b_mass + 4 * (size_t)b;
@@ -1064,6 +1105,47 @@ template <class real> struct world_step {
             b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
             b_flags[victim] &= ~BODY_AWAKE;
             B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);   // the next island walk must skip this body
+        }
+    }
+
+    // The same rule evaluated by the whole team: the per-body timer updates are independent, the island only needs
+    // their minimum and the LAST non-static body of the list.
+    B2B_D void island_sleep_team(int b0, int b1, real dt, bool position_solved)
+    {
+        real min_sleep = K<real>::max_float;
+        const bool last_allow = (s_flags8[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+        int last_i = -1;
+        for (int i = b0 + t_id; i < b1; i += t_n) {
+            const int b = l_body[i];
+            if (is_static_body(b)) continue;
+            last_i = i;
+            const real* sv = b_vel + 4 * (size_t)b;
+            real* st = b_pos + 4 * (size_t)b + 3;
+            if (!last_allow || sv[2] * sv[2] > K<real>::angular_sleep_tol_sqr || sv[0] * sv[0] + sv[1] * sv[1] > K<real>::linear_sleep_tol_sqr) {
+                *st = real(0);
+                min_sleep = real(0);
+            } else {
+                const real ts = *st + dt;
+                *st = ts;
+                min_sleep = pymin(min_sleep, ts);
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        for (int o = t_n >> 1; o > 0; o >>= 1) {
+            const real other = __shfl_xor_sync(t_mask, min_sleep, o);
+            const int other_i = __shfl_xor_sync(t_mask, last_i, o);
+            min_sleep = (other < min_sleep) ? other : min_sleep;
+            last_i = (other_i > last_i) ? other_i : last_i;
+        }
+#endif
+        if (t_id == 0 && min_sleep >= K<real>::time_to_sleep && position_solved && last_i >= 0) {
+            const int victim = l_body[last_i];
+            b_pos[4 * (size_t)victim + 3] = real(0);
+            real* v = b_vel + 4 * (size_t)victim;
+            v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
+            b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
+            b_flags[victim] &= ~BODY_AWAKE;
+            B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);
         }
     }
 
@@ -1171,7 +1253,7 @@ template <class real> struct world_step {
             }
             B2B_SYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);
-            if (t_id == 0 && allow_sleep) island_sleep(b0, b1, dt, position_solved);
+            if (allow_sleep) island_sleep_team(b0, b1, dt, position_solved);
             B2B_SYNC();
             B2B_PROF(PROF_S_SLEEP, t);
             // the next island's bodies are disjoint (statics aside), but their quads must hold velocities again:
@@ -1335,13 +1417,15 @@ template <class real> struct world_step {
     {
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
+        // worlds with new fixtures were skipped by the flat narrowphase kernel (their contacts are created only now)
+        const bool after_flat = (sp.flags & STEP_FLAT_COLLIDE) && !(w_flags[0] & WORLD_NEW_FIXTURE);
         if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
             phase_pairs(false);
             if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
             B2B_SYNC();
             B2B_PROF(PROF_PAIRS0, t);
         }
-        phase_collide();                                         // world.py:338
+        phase_collide(after_flat);                               // world.py:338
         B2B_PROF(PROF_COLLIDE, t);
         if (sp.dt > 0.0) {                                       // world.py:341-342, 475-580
             // The island walk is a pure function of the body flags and the contact graph.  While neither changes
@@ -1395,6 +1479,10 @@ template <class real> struct world_step {
     B2B_D void run(const step_params& sp)
     {
         for (int step = 0; step < sp.n_steps; ++step) {
+            if ((sp.flags & STEP_FLAT_COLLIDE) && !(w_flags[0] & WORLD_NEW_FIXTURE)) {
+                const int nc = w_count[2];
+                for (int c = 0; c < nc; ++c) collide_one(c);
+            }
             run_plan(sp);
             run_solve(sp, step == 0);
             run_broadphase(sp);
