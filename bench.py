@@ -248,29 +248,7 @@ def build_batch(b2, args, world_offset, device):
         raise RuntimeError("capacity overflow while settling the seed worlds")
     if distinct == args.worlds:
         return seed, caps
-    A = {}
-    reps = (args.worlds + distinct - 1) // distinct
-    full = b2.BatchedWorld.__new__(b2.BatchedWorld)
-    full.real, full.caps, full.device = args.real, caps, seed.device
-    full.n_worlds, full.n_shapes, full.inv_dt0 = args.worlds, seed.n_shapes, seed.inv_dt0
-    full.t = {}
-    for name, scope, tail, kind in schema.FIELDS:
-        t = seed.t[name]
-        if scope == "S":
-            full.t[name] = t
-        else:
-            full.t[name] = t.repeat((reps,) + (1,) * (t.dim() - 1))[:args.worlds].contiguous()
-    import ctypes
-    from pypybox2d_b200 import _lib
-    c = _lib.Caps()
-    c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = args.worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
-    c.n_shapes, c.real_bytes = full.n_shapes, (8 if args.real == "f64" else 4)
-    c.device = seed.device.index
-    c.threads = args.threads
-    full._caps_struct = c
-    full._ctx = ctypes.c_void_p()
-    _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(full._ctx)), "b2b_create")
-    full._bind()
+    full = seed.tiled(args.worlds, threads=args.threads)
     del seed
     torch.cuda.empty_cache()
     return full, caps

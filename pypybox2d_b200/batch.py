@@ -49,17 +49,45 @@ class BatchedWorld(object):
             want = schema.np_dtype(kind, real)
             host = np.ascontiguousarray(arrays[name]).astype(want, copy=False)
             self.t[name] = self._to_device(host)
+        self._create_context(threads, ctas_per_sm, lanes_aux)
+
+    def _create_context(self, threads=0, ctas_per_sm=0, lanes_aux=0):
+        """b2b_create + b2b_bind for the tensors in self.t."""
+        torch = _torch()
         self._ctx = ctypes.c_void_p()
         c = _lib.Caps()
+        caps = self.caps
         c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = self.n_worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
         c.n_shapes = self.n_shapes
-        c.real_bytes = 8 if real == "f64" else 4
+        c.real_bytes = 8 if self.real == "f64" else 4
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        c.threads, c.ctas_per_sm, c.reserved = threads, ctas_per_sm, lanes_aux
+        c.threads, c.ctas_per_sm, c.reserved = int(threads), int(ctas_per_sm), int(lanes_aux)
         self._caps_struct = c
-        L = _lib.lib()
-        _lib.check(L.b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
+        _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
         self._bind()
+
+    @classmethod
+    def from_tensors(cls, tensors, caps, real="f32", inv_dt0=0.0, **kw):
+        """Wrap existing device tensors (one per schema field, already in the working dtypes) in a new context."""
+        torch = _torch()
+        self = cls.__new__(cls)
+        self.real, self.caps = real, caps
+        self.t = dict(tensors)
+        self.device = self.t["w_flags"].device
+        self.n_worlds, self.n_shapes = int(self.t["w_flags"].shape[0]), int(self.t["s_meta"].shape[0])
+        self.inv_dt0 = float(inv_dt0)
+        self._create_context(kw.get("threads", 0), kw.get("ctas_per_sm", 0), kw.get("lanes_aux", 0))
+        return self
+
+    def tiled(self, n_worlds, **kw):
+        """A new batch of `n_worlds` worlds whose world k is a copy of this batch's world k % len(self): used to
+        spread a set of settled worlds over a large benchmark batch."""
+        reps = (n_worlds + self.n_worlds - 1) // self.n_worlds
+        t = {}
+        for name, scope, tail, kind in schema.FIELDS:
+            x = self.t[name]
+            t[name] = x if scope == "S" else x.repeat((reps,) + (1,) * (x.dim() - 1))[:n_worlds].contiguous()
+        return BatchedWorld.from_tensors(t, self.caps, real=self.real, inv_dt0=self.inv_dt0, **kw)
 
     # -- construction -----------------------------------------------------------------------
     @classmethod
@@ -136,16 +164,7 @@ class BatchedWorld(object):
             self.t["b_pos"] = pos.to(want).contiguous()
             self.t["b_pos0"] = self.t["b_pos"].clone()
             self.t["b_pos0"][..., 3] = 0
-        self._ctx = ctypes.c_void_p()
-        c = _lib.Caps()
-        c.n_worlds, c.nb, c.nf, c.nc, c.npair, c.nl = self.n_worlds, caps.nb, caps.nf, caps.nc, caps.npair, caps.nl
-        c.n_shapes = self.n_shapes
-        c.real_bytes = 8 if real == "f64" else 4
-        c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        c.threads, c.ctas_per_sm, c.reserved = kw.get("threads", 0), kw.get("ctas_per_sm", 0), kw.get("lanes_aux", 0)
-        self._caps_struct = c
-        _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
-        self._bind()
+        self._create_context(kw.get("threads", 0), kw.get("ctas_per_sm", 0), kw.get("lanes_aux", 0))
         if jitter != 0.0:
             self.init_proxies()
         return self

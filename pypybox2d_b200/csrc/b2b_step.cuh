@@ -1,16 +1,17 @@
-// b2b_step.cuh -- one World.step for one world, written as a CTA "block program".
+// b2b_step.cuh -- one World.step for one world, written as a "team program".
 //
-// One CTA owns one world at a time (persistent grid, worlds strided over CTAs).  The step is a
-// sequence of phases separated by CTA barriers; inside a phase, work items (contacts, bodies,
-// proxies, pairs) are strided over the CTA's threads, and islands are strided over its warps with
-// the island's constraints strided over the warp's lanes level by level (see solve_islands).
+// A world is stepped by a TEAM of threads (a group of lanes of one warp; several worlds per warp).  The step is a
+// sequence of phases separated by team barriers; inside a phase, work items (contacts, bodies, proxies, pairs,
+// constraints of one dependency level) are strided over the team's lanes.  The kernels (b2b_kernels.inl) call
+//   collide_one                      from the flat narrowphase kernel, one thread per contact of the whole batch
+//   run_plan / run_solve / run_broadphase   from the three persistent kernels, one team per world
 //
 // Reference call tree being replaced:
 //   World.step                      pypybox2d/world.py:307-354
-//   ContactManager.collide          contact_manager.py:174-223   -> phase_collide        (K1)
+//   ContactManager.collide          contact_manager.py:174-223   -> collide_one, phase_collide   (K1)
 //   Contact.update                  contact.py:210-268           -> contact_update
-//   World._solve (island DFS)       world.py:475-580             -> phase_islands        (K2)
-//   Island.solve / ContactSolver    island.py:65-179, contact.py:375-864 -> solve_islands (K3)
+//   World._solve (island DFS)       world.py:475-580             -> phase_islands, phase_schedule (K2)
+//   Island.solve / ContactSolver    island.py:65-179, contact.py:375-864 -> solve_islands         (K3)
 //   Body._synchronize_fixtures ...  body.py:898-904, fixture.py:287-298, dynamictree.py:152-188 -> phase_sync (K4)
 //   BroadPhase.update_pairs         broadphase.py:83-109         -> phase_pairs          (K5)
 //   ContactManager.find_new_contacts contact_manager.py:102-158  -> phase_pairs          (K6)

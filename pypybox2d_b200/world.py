@@ -187,9 +187,10 @@ class World(object):
 
     def clear_forces(self):
         for b in self.bodies:
+            if b._force.x != 0.0 or b._force.y != 0.0 or b._torque != 0.0:
+                self._host_dirty = True
             b._force = Vec2()
             b._torque = 0.0
-        self._host_dirty = True
 
     def _contact_views(self):
         if self._batch is None:
