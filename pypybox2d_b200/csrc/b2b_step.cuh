@@ -84,7 +84,7 @@ template <class real> struct batch_ptrs {
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
-enum { CC_QUADS = 12, CC_REALS = 4 * CC_QUADS };
+enum { VREC_QUADS = 8, PREC_QUADS = 5 };   // velocity / position record of one constraint, in 4-vectors of reals
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4 };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
@@ -116,7 +116,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
 
 struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `solve` slabs per solve team
     size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
-    size_t off_cc_int, off_cc_real, off_cc_imp, off_sprof, total_solve;
+    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_sprof, total_solve;
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
 {
@@ -132,8 +132,8 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_prof = take(sizeof(long long) * PROF_SLOTS);
     L.total_aux = align_up(o, 256);
     o = 0;
-    L.off_cc_int = take(sizeof(int32_t) * 4 * ((size_t)c.nc + 2));
-    L.off_cc_real = take((size_t)real_bytes * CC_REALS * ((size_t)c.nc + 2));
+    L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
+    L.off_cc_pos = take((size_t)real_bytes * 4 * PREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
     L.off_sprof = take(sizeof(long long) * PROF_SLOTS);
     L.total_solve = align_up(o, 256);
@@ -181,7 +181,6 @@ template <class real> struct world_step {
     typedef vec2<real> V2;
     typedef xform<real> XF;
     struct alignas(4 * sizeof(real)) quad { real x, y, z, w; };
-    struct alignas(16) iquad { int32_t body_a, body_b, info, contact; };
 
     caps_t cap;
     // this world's rows of the batch arrays
@@ -196,8 +195,8 @@ template <class real> struct world_step {
     uint32_t* g_lmask;       // bit s set: slot s is the last constraint of its dependency level
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
-    int32_t *wake_at, *scan, *cc_int;
-    real *cc_real, *cc_imp;
+    int32_t *wake_at, *scan;
+    real *cc_vel, *cc_pos, *cc_imp;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
@@ -270,8 +269,8 @@ template <class real> struct world_step {
     }
     B2B_D void bind_scratch_solve(unsigned char* scratch, const scratch_layout& L)
     {
-        cc_int = (int32_t*)(scratch + L.off_cc_int);
-        cc_real = (real*)(scratch + L.off_cc_real);
+        cc_vel = (real*)(scratch + L.off_cc_vel);
+        cc_pos = (real*)(scratch + L.off_cc_pos);
         cc_imp = (real*)(scratch + L.off_cc_imp);
         prof = (long long*)(scratch + L.off_sprof);
     }
@@ -642,37 +641,42 @@ template <class real> struct world_step {
     }
 
     // ------------------------------------------------------------------------------------ K3 (solve kernel)
-    // One constraint = CC_QUADS read-only 4-vectors of reals (array-of-structures, schedule order, so the lane
-    // that solves it fetches it with a handful of 128-bit loads), one 4-word integer record
-    // (body_a, body_b, n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25, contact) and one
-    // read-write quad of accumulated impulses kept in its own array so that updating it never dirties the
-    // read-only lines.
-    //   q0  normal.x normal.y friction -          q1  rA0.x rA0.y rB0.x rB0.y
-    //   q2  nmass0   tmass0   bias0    -          q3  rA1.x rA1.y rB1.x rB1.y
-    //   q4  nmass1   tmass1   bias1    -          q5  k11 k12 k22 nm11
-    //   q6  nm12     nm22     -        -          q7  inv_mass_a inv_I_a inv_mass_b inv_I_b
-    //   q8  ln.x ln.y lp.x lp.y                   q9  p0.x p0.y p1.x p1.y
-    //   q10 radius_a radius_b -  -                q11 lc_a.x lc_a.y lc_b.x lc_b.y
+    // One constraint = a read-only VELOCITY record of 8 four-vectors (exactly one 128-byte line in fp32: what a
+    // velocity sweep streams per constraint), a read-only POSITION record of 5 four-vectors, and one read-write
+    // four-vector of accumulated impulses in its own array (updating it never dirties the read-only lines).  All
+    // are in schedule order, so the lane that solves a slot fetches it with a handful of 128-bit loads.  The
+    // integer fields ride in spare lanes of the real records as raw bits.
+    //   v0  normal.x normal.y friction [body_a | body_b << 16]     v1  rA0.x rA0.y rB0.x rB0.y
+    //   v2  nmass0   tmass0   bias0    [info]                      v3  rA1.x rA1.y rB1.x rB1.y
+    //   v4  nmass1   tmass1   bias1    -                           v5  k11 k12 k22 nm11
+    //   v6  nm12     nm22     -        -                           v7  inv_mass_a inv_I_a inv_mass_b inv_I_b
+    //   p0  inv_mass_a inv_I_a inv_mass_b inv_I_b                  p1  ln.x ln.y lp.x lp.y
+    //   p2  p0.x p0.y p1.x p1.y                                    p3  radius_a radius_b [bodies] [info]
+    //   p4  lc_a.x lc_a.y lc_b.x lc_b.y
     //   imp ni0 ti0 ni1 ti1
-    // Shared memory holds ONE quad per body: its velocity while velocities are being solved, its sweep position
-    // afterwards.  Static bodies never change, are shared between islands, and are read from global memory.
+    //   info = n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25
+    // Shared memory holds three reals per body: its velocity while velocities are being solved, its sweep position
+    // afterwards.  Static bodies never change and are shared between islands: each island stages their position
+    // for its position phase and puts their velocity back afterwards (islands are solved one after the other).
     enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
-    B2B_D quad* rec(int slot) { return reinterpret_cast<quad*>(cc_real) + (size_t)CC_QUADS * slot; }
+    B2B_D static real real_from_bits(uint32_t u)
+    {
+        union { real r; uint32_t w[sizeof(real) / 4]; } x;
+        x.r = real(0); x.w[0] = u;
+        return x.r;
+    }
+    B2B_D static uint32_t bits_of_real(real r)
+    {
+        union { real r; uint32_t w[sizeof(real) / 4]; } x;
+        x.r = r;
+        return x.w[0];
+    }
+    B2B_D quad* vel_rec(int slot) { return reinterpret_cast<quad*>(cc_vel) + (size_t)VREC_QUADS * slot; }
+    B2B_D quad* pos_rec(int slot) { return reinterpret_cast<quad*>(cc_pos) + (size_t)PREC_QUADS * slot; }
     B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
-    B2B_D iquad* irec(int slot) { return reinterpret_cast<iquad*>(cc_int) + slot; }
     B2B_D quad state_get(int b) const { return mkq(s_sx[b], s_sy[b], s_sz[b], real(0)); }
     B2B_D void state_set(int b, real x, real y, real z) { s_sx[b] = x; s_sy[b] = y; s_sz[b] = z; }
-    B2B_D quad load_vel(int b, bool is_static) const
-    {
-        if (is_static) { const real* v = b_vel + 4 * (size_t)b; return mkq(v[0], v[1], v[2], real(0)); }
-        return state_get(b);
-    }
-    B2B_D quad load_pos(int b, bool is_static) const
-    {
-        if (is_static) { const real* p = b_pos + 4 * (size_t)b; return mkq(p[0], p[1], p[2], real(0)); }
-        return state_get(b);
-    }
     B2B_D bool is_static_body(int b) const { return (s_flags8[b] & BODY_TYPE_MASK) == BODY_STATIC; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
@@ -681,17 +685,28 @@ template <class real> struct world_step {
     }
     // Records are consumed in slot order, so the lane solving slot s asks for slot s + PREFETCH_AHEAD (a few levels
     // ahead, wrapping to the start of the island for the next sweep) while it computes.
-    int prefetch_ahead;      // records ahead of the one being solved (tunable: step flags bits 8..15, default 4)
-    B2B_D void prefetch_slot(int s, int c0, int c1, int first_quad)
+    enum { PREFETCH_AHEAD = 4 };   // measured on B200: 2..12 records ahead are equivalent, none is 16 % slower
+    B2B_D int prefetch_target(int s, int c0, int c1) const
     {
-        int t = s + prefetch_ahead;
-        if (t >= c1) t = c0 + (t - c1);
+        const int t = s + PREFETCH_AHEAD;
+        return (t >= c1) ? t - (c1 - c0) : t;
+    }
+    B2B_D void prefetch_vel(int s, int c0, int c1)
+    {
+        const int t = prefetch_target(s, c0, c1);
         if (t < c1) {
-            const char* r = reinterpret_cast<const char*>(rec(t)) + first_quad * sizeof(quad);
-            B2B_PREFETCH(r);
-            B2B_PREFETCH(r + 128);
-            B2B_PREFETCH(irec(t));
+            B2B_PREFETCH(vel_rec(t));
+            if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(vel_rec(t)) + 128);
             B2B_PREFETCH(imp_rec(t));
+        }
+    }
+    B2B_D void prefetch_pos(int s, int c0, int c1)
+    {
+        const int t = prefetch_target(s, c0, c1);
+        if (t < c1) {
+            const char* r = reinterpret_cast<const char*>(pos_rec(t));
+            B2B_PREFETCH(r);
+            B2B_PREFETCH(r + sizeof(quad) * PREC_QUADS - 1);
         }
     }
     // last slot of the dependency level that starts at slot p (a set bit at or after p in the level mask)
@@ -745,7 +760,7 @@ template <class real> struct world_step {
         const bool stat_a = is_static_body(ba), stat_b = is_static_body(bb);
         // positions are still the step's start positions in global memory; velocities are staged
         const real* pa_ = b_pos + 4 * (size_t)ba; const real* pb_ = b_pos + 4 * (size_t)bb;
-        const quad va_ = load_vel(ba, stat_a), vb_ = load_vel(bb, stat_b);
+        const quad va_ = state_get(ba), vb_ = state_get(bb);
         const V2 ca = mk<real>(pa_[0], pa_[1]), cb = mk<real>(pb_[0], pb_[1]);
         const V2 va = mk<real>(va_.x, va_.y), vb = mk<real>(vb_.x, vb_.y);
         const real wa = va_.z, wb = vb_.z;
@@ -762,25 +777,21 @@ template <class real> struct world_step {
             const V2 c_a = pa + rad_a * normal, c_b = pb - rad_b * normal;
             wp[0] = real(0.5) * (c_a + c_b);
             wp[1] = wp[0];
-        } else if (type == MANIFOLD_FACE_A) {
-            normal = rot_mul(xa, local_normal);
-            const V2 plane = xf_mul(xa, local_point);
-            for (int j = 0; j < 2; ++j) {
-                const V2 clip = xf_mul(xb, lp[j]);
-                const V2 c_a = clip + (rad_a - dot(clip - plane, normal)) * normal;
-                const V2 c_b = clip - rad_b * normal;
-                wp[j] = real(0.5) * (c_a + c_b);
-            }
         } else {
-            normal = rot_mul(xb, local_normal);
-            const V2 plane = xf_mul(xb, local_point);
+            // FACE_A and FACE_B are the same arithmetic with the bodies' roles exchanged (and the normal flipped at
+            // the end for FACE_B); selecting the operands keeps the lanes of a warp on one code path
+            const bool face_a = (type == MANIFOLD_FACE_A);
+            const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
+            const real rad_r = face_a ? rad_a : rad_b, rad_o = face_a ? rad_b : rad_a;
+            normal = rot_mul(xr, local_normal);
+            const V2 plane = xf_mul(xr, local_point);
             for (int j = 0; j < 2; ++j) {
-                const V2 clip = xf_mul(xa, lp[j]);
-                const V2 c_b = clip + (rad_b - dot(clip - plane, normal)) * normal;
-                const V2 c_a = clip - rad_a * normal;
-                wp[j] = real(0.5) * (c_a + c_b);
+                const V2 clip = xf_mul(xo, lp[j]);
+                const V2 c_r = clip + (rad_r - dot(clip - plane, normal)) * normal;
+                const V2 c_o = clip - rad_o * normal;
+                wp[j] = real(0.5) * (c_r + c_o);        // IEEE addition commutes: same bits as 0.5 * (c_a + c_b)
             }
-            normal = -normal;
+            if (!face_a) normal = -normal;
         }
         const V2 tangent = right_perp(normal);
         int n_vel = count;
@@ -817,54 +828,52 @@ template <class real> struct world_step {
                 n_vel = 1;                                   // redundant point dropped from the velocity rows only
             }
         }
-        iquad iq; iq.body_a = ba; iq.body_b = bb;
-        iq.info = n_vel | (type << 8) | (count << 16) | (stat_a ? INFO_STATIC_A : 0) | (stat_b ? INFO_STATIC_B : 0);
-        iq.contact = ci;
-        *irec(slot) = iq;
-        quad* q = rec(slot);
-        q[0] = mkq(normal.x, normal.y, friction, real(0));
+        const uint32_t info = (uint32_t)(n_vel | (type << 8) | (count << 16) | (stat_a ? INFO_STATIC_A : 0) | (stat_b ? INFO_STATIC_B : 0));
+        const real bodies_r = real_from_bits((uint32_t)ba | ((uint32_t)bb << 16)), info_r = real_from_bits(info);
+        quad* q = vel_rec(slot);
+        q[0] = mkq(normal.x, normal.y, friction, bodies_r);
         q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
-        q[2] = mkq(nmass[0], tmass[0], bias[0], real(0));
+        q[2] = mkq(nmass[0], tmass[0], bias[0], info_r);
         q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
         q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
         q[5] = mkq(k11, k12, k22, nm11);
         q[6] = mkq(nm12, nm22, real(0), real(0));
         q[7] = mkq(ma, ia, mb, ib);
-        q[8] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
-        q[9] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
-        q[10] = mkq(rad_a, rad_b, real(0), real(0));
-        q[11] = mkq(lca.x, lca.y, lcb.x, lcb.y);
+        quad* p = pos_rec(slot);
+        p[0] = mkq(ma, ia, mb, ib);
+        p[1] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
+        p[2] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
+        p[3] = mkq(rad_a, rad_b, bodies_r, info_r);
+        p[4] = mkq(lca.x, lca.y, lcb.x, lcb.y);
         *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
     }
 
     // A constraint's velocity-phase data in registers.  The level loops load the NEXT level's record while the
     // current one is being solved, so the L2/HBM latency of the record stream overlaps the arithmetic.
-    struct vrec { iquad iq; quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
+    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
     B2B_D void load_vrec(int slot, vrec& r)
     {
-        const quad* q = rec(slot);
-        r.iq = *irec(slot);
+        const quad* q = vel_rec(slot);
         r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3]; r.q4 = q[4]; r.q5 = q[5]; r.q6 = q[6]; r.q7 = q[7];
         r.qi = *imp_rec(slot);
     }
-    struct prec { iquad iq; quad q7, q8, q9, q10, q11; };
+    struct prec { quad q7, q8, q9, q10, q11; };
     B2B_D void load_prec(int slot, prec& r)
     {
-        const quad* q = rec(slot);
-        r.iq = *irec(slot);
-        r.q7 = q[7]; r.q8 = q[8]; r.q9 = q[9]; r.q10 = q[10]; r.q11 = q[11];
+        const quad* q = pos_rec(slot);
+        r.q7 = q[0]; r.q8 = q[1]; r.q9 = q[2]; r.q10 = q[3]; r.q11 = q[4];
     }
 
     // ContactSolver.warm_start for one slot (contact.py:498-525)
     B2B_D void constraint_warm_start(const vrec& r)
     {
-        const iquad iq = r.iq;
         const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q7, qi = r.qi;
-        const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
-        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
+        const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(r.q2.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(info & 0xff);
+        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
-        const quad sa = load_vel(ba, stat_a), sb = load_vel(bb, stat_b);
+        const quad sa = state_get(ba), sb = state_get(bb);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
         for (int j = 0; j < n_vel; ++j) {
@@ -881,17 +890,17 @@ template <class real> struct world_step {
     }
 
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
-    B2B_D void constraint_solve_velocity(const vrec& r, int slot)
+    B2B_D void constraint_solve_velocity(vrec& r, int slot)
     {
-        const iquad iq = r.iq;
         const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
         quad qi = r.qi;
-        const int ba = iq.body_a, bb = iq.body_b, n_vel = iq.info & 0xff;
-        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
+        const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(q2.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(info & 0xff);
+        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real friction = q0.z;
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
-        const quad sa = load_vel(ba, stat_a), sb = load_vel(bb, stat_b);
+        const quad sa = state_get(ba), sb = state_get(bb);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
         const V2 ra0 = mk<real>(q1.x, q1.y), rb0 = mk<real>(q1.z, q1.w), ra1 = mk<real>(q3.x, q3.y), rb1 = mk<real>(q3.z, q3.w);
@@ -964,6 +973,7 @@ template <class real> struct world_step {
             }
         }
         *imp_rec(slot) = qi;
+        r.qi = qi;
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
     }
@@ -972,16 +982,16 @@ template <class real> struct world_step {
     // returns the smallest separation seen.
     B2B_D real constraint_solve_position(const prec& r)
     {
-        const iquad iq = r.iq;
         const quad q7 = r.q7, q8 = r.q8, q9 = r.q9, q10 = r.q10, q11 = r.q11;
-        const int ba = iq.body_a, bb = iq.body_b;
-        const bool stat_a = (iq.info & INFO_STATIC_A) != 0, stat_b = (iq.info & INFO_STATIC_B) != 0;
-        const int type = (iq.info >> 8) & 0xff, n_pos = (iq.info >> 16) & 0xff;
+        const uint32_t bodies = bits_of_real(q10.z), info = bits_of_real(q10.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
+        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
+        const int type = (int)((info >> 8) & 0xff), n_pos = (int)((info >> 16) & 0xff);
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
         const V2 lca = mk<real>(q11.x, q11.y), lcb = mk<real>(q11.z, q11.w);
         const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
         const real rad_a = q10.x, rad_b = q10.y;
-        const quad sa = load_pos(ba, stat_a), sb = load_pos(bb, stat_b);
+        const quad sa = state_get(ba), sb = state_get(bb);
         V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
         real aa = sa.z, ab = sb.z;
         real min_sep = real(0);
@@ -995,19 +1005,15 @@ template <class real> struct world_step {
                 normal = normalize(pb - pa);
                 point = real(0.5) * (pa + pb);
                 separation = dot(pb - pa, normal) - rad_a - rad_b;
-            } else if (type == MANIFOLD_FACE_A) {
-                normal = rot_mul(xa, local_normal);
-                const V2 plane = xf_mul(xa, local_point);
-                const V2 clip = xf_mul(xb, lpj);
-                separation = dot(clip - plane, normal) - rad_a - rad_b;
-                point = clip;
             } else {
-                normal = rot_mul(xb, local_normal);
-                const V2 plane = xf_mul(xb, local_point);
-                const V2 clip = xf_mul(xa, lpj);
+                const bool face_a = (type == MANIFOLD_FACE_A);
+                const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
+                normal = rot_mul(xr, local_normal);
+                const V2 plane = xf_mul(xr, local_point);
+                const V2 clip = xf_mul(xo, lpj);
                 separation = dot(clip - plane, normal) - rad_a - rad_b;
                 point = clip;
-                normal = -normal;
+                if (!face_a) normal = -normal;
             }
             const V2 ra = point - ca, rb = point - cb;
             min_sep = pymin(min_sep, separation);
@@ -1159,7 +1165,6 @@ template <class real> struct world_step {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
-        prefetch_ahead = ((sp.flags >> 8) & 0xff) ? (int)((sp.flags >> 8) & 0xff) : 4;
         long long t = B2B_CLOCK();
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
@@ -1195,7 +1200,7 @@ template <class real> struct world_step {
             if (warm) {
                 for (int begin = c0; begin < c1;) {
                     const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 0); vrec e; load_vrec(s, e); constraint_warm_start(e); }
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_vel(s, c0, c1); vrec e; load_vrec(s, e); constraint_warm_start(e); }
                     begin = end;
                     B2B_SYNC();
                 }
@@ -1204,7 +1209,7 @@ template <class real> struct world_step {
             for (int it = 0; it < sp.vel_iters; ++it) {
                 for (int begin = c0; begin < c1;) {
                     const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 0); vrec e; load_vrec(s, e); constraint_solve_velocity(e, s); }
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_vel(s, c0, c1); vrec e; load_vrec(s, e); constraint_solve_velocity(e, s); }
                     begin = end;
                     B2B_SYNC();
                 }
@@ -1213,8 +1218,7 @@ template <class real> struct world_step {
             // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
             for (int s = c0 + t_id; s < c1; s += t_n) {
                 const quad qi = *imp_rec(s);
-                const iquad iq = *irec(s);
-                const int ci = iq.contact, n_vel = iq.info & 0xff;
+                const int ci = l_contact[g_sched[s]], n_vel = (int)(bits_of_real(vel_rec(s)[2].w) & 0xff);
                 real* imp = c_imp + 4 * (size_t)ci;
                 if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
                 if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
@@ -1222,6 +1226,7 @@ template <class real> struct world_step {
             for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
                 if (!is_static_body(b)) integrate_position(b, dt);
+                else { const real* p = b_pos + 4 * (size_t)b; state_set(b, p[0], p[1], p[2]); }
             }
             B2B_SYNC();
             B2B_PROF(PROF_S_STORE, t);
@@ -1233,7 +1238,7 @@ template <class real> struct world_step {
                 ++used;
                 for (int begin = c0; begin < c1;) {
                     const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_slot(s, c0, c1, 7); prec e; load_prec(s, e); my_min = pymin(my_min, constraint_solve_position(e)); }
+                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_pos(s, c0, c1); prec e; load_prec(s, e); my_min = pymin(my_min, constraint_solve_position(e)); }
                     begin = end;
                     B2B_SYNC();
                 }
@@ -1251,6 +1256,7 @@ template <class real> struct world_step {
             for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
                 if (!is_static_body(b)) write_back(b);
+                else { const real* v = b_vel + 4 * (size_t)b; state_set(b, v[0], v[1], v[2]); }
             }
             B2B_SYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);

@@ -22,9 +22,10 @@ def run(n_worlds, real, threads, settle=200, steps=4, ctas=0):
     print("%s worlds=%d threads=%d grid=%d smem=%d: %.2f ms/step %.3e body-steps/s; cycles/world-step %.0f status=%d" % (
         real, n_worlds, threads, info["grid"], info["smem_bytes"], ms/steps, 210*n_worlds*steps/(ms*1e-3), tot/ws, bw.status(False)))
     print("   top:", {k: "%.1f%%" % (100*p[k]/tot) for k in ("collide","adjacency","islands","solve","sync","pairs","clear")})
-    print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]}, flush=True)
+    print("   solve:", {k: "%.1f%%" % (100*p[k]/tot) for k in p if k.startswith("s_") and p[k]})
+    print("   solve cycles/world-step:", {k: int(p[k]/ws) for k in p if k.startswith("s_") and p[k]}, flush=True)
 
 if __name__ == "__main__":
-    run(16384, "f32", 8)
-    run(16384, "f32", 16)
-    run(8192, "f64", 8)
+    sizes = [int(a) for a in sys.argv[1:]] or [16384]
+    for n in sizes:
+        run(n, "f32", 8)
