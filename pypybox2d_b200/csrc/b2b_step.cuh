@@ -980,6 +980,44 @@ template <class real> struct world_step {
 
     // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
     // returns the smallest separation seen.
+    // One manifold point of ContactSolver.solve_position_constraints (contact_util.py:323-360 PositionSolverManifold,
+    // contact.py:826-860): evaluate the separation at the bodies' CURRENT sweeps and push them apart.
+    struct pos_state { V2 ca, cb; real aa, ab, min_sep; };
+    B2B_D void position_point(pos_state& p, V2 lpj, int type, V2 local_normal, V2 local_point, V2 lca, V2 lcb,
+                              real rad_a, real rad_b, real ma, real ia, real mb, real ib)
+    {
+        const XF xa = xf_from_sweep<real>(p.ca, p.aa, lca), xb = xf_from_sweep<real>(p.cb, p.ab, lcb);
+        V2 normal, point;
+        real separation;
+        if (type == MANIFOLD_CIRCLES) {
+            const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, lpj);
+            normal = normalize(pb - pa);
+            point = real(0.5) * (pa + pb);
+            separation = dot(pb - pa, normal) - rad_a - rad_b;
+        } else {
+            const bool face_a = (type == MANIFOLD_FACE_A);
+            const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
+            normal = rot_mul(xr, local_normal);
+            const V2 plane = xf_mul(xr, local_point);
+            const V2 clip = xf_mul(xo, lpj);
+            separation = dot(clip - plane, normal) - rad_a - rad_b;
+            point = clip;
+            if (!face_a) normal = -normal;
+        }
+        const V2 ra = point - p.ca, rb = point - p.cb;
+        p.min_sep = pymin(p.min_sep, separation);
+        const real C = clamp_r(K<real>::baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
+        const real rn_a = cross(ra, normal), rn_b = cross(rb, normal);
+        const real Keff = ma + mb + (ia * (rn_a * rn_a)) + (ib * (rn_b * rn_b));
+        const real impulse = (Keff > real(0)) ? -C / Keff : real(0);
+        const V2 P = impulse * normal;
+        p.ca = p.ca - ma * P; p.aa = p.aa - ia * cross(ra, P);
+        p.cb = p.cb + mb * P; p.ab = p.ab + ib * cross(rb, P);
+    }
+
+    // ContactSolver.solve_position_constraints for one slot (contact.py:809-864); returns the smallest separation
+    // seen.  A touching contact has one or two points; the first is solved unconditionally so that the whole
+    // record is requested up front.
     B2B_D real constraint_solve_position(const prec& r)
     {
         const quad q7 = r.q7, q8 = r.q8, q9 = r.q9, q10 = r.q10, q11 = r.q11;
@@ -992,42 +1030,14 @@ template <class real> struct world_step {
         const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
         const real rad_a = q10.x, rad_b = q10.y;
         const quad sa = state_get(ba), sb = state_get(bb);
-        V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
-        real aa = sa.z, ab = sb.z;
-        real min_sep = real(0);
-        for (int j = 0; j < n_pos; ++j) {
-            const XF xa = xf_from_sweep<real>(ca, aa, lca), xb = xf_from_sweep<real>(cb, ab, lcb);
-            const V2 lpj = (j == 0) ? mk<real>(q9.x, q9.y) : mk<real>(q9.z, q9.w);
-            V2 normal, point;
-            real separation;
-            if (type == MANIFOLD_CIRCLES) {
-                const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, mk<real>(q9.x, q9.y));
-                normal = normalize(pb - pa);
-                point = real(0.5) * (pa + pb);
-                separation = dot(pb - pa, normal) - rad_a - rad_b;
-            } else {
-                const bool face_a = (type == MANIFOLD_FACE_A);
-                const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
-                normal = rot_mul(xr, local_normal);
-                const V2 plane = xf_mul(xr, local_point);
-                const V2 clip = xf_mul(xo, lpj);
-                separation = dot(clip - plane, normal) - rad_a - rad_b;
-                point = clip;
-                if (!face_a) normal = -normal;
-            }
-            const V2 ra = point - ca, rb = point - cb;
-            min_sep = pymin(min_sep, separation);
-            const real C = clamp_r(K<real>::baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
-            const real rn_a = cross(ra, normal), rn_b = cross(rb, normal);
-            const real Keff = ma + mb + (ia * (rn_a * rn_a)) + (ib * (rn_b * rn_b));
-            const real impulse = (Keff > real(0)) ? -C / Keff : real(0);
-            const V2 P = impulse * normal;
-            ca = ca - ma * P; aa = aa - ia * cross(ra, P);
-            cb = cb + mb * P; ab = ab + ib * cross(rb, P);
-        }
-        if (!stat_a) state_set(ba, ca.x, ca.y, aa);
-        if (!stat_b) state_set(bb, cb.x, cb.y, ab);
-        return min_sep;
+        pos_state p;
+        p.ca = mk<real>(sa.x, sa.y); p.cb = mk<real>(sb.x, sb.y); p.aa = sa.z; p.ab = sb.z; p.min_sep = real(0);
+        position_point(p, mk<real>(q9.x, q9.y), type, local_normal, local_point, lca, lcb, rad_a, rad_b, ma, ia, mb, ib);
+        if (n_pos > 1)
+            position_point(p, mk<real>(q9.z, q9.w), type, local_normal, local_point, lca, lcb, rad_a, rad_b, ma, ia, mb, ib);
+        if (!stat_a) state_set(ba, p.ca.x, p.ca.y, p.aa);
+        if (!stat_b) state_set(bb, p.cb.x, p.cb.y, p.ab);
+        return p.min_sep;
     }
 
     // island.py:71-95 for one non-static body: save the sweep start, integrate gravity/forces, damp
