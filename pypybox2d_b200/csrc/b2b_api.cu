@@ -3,6 +3,7 @@
 // that computes anything launches a CUDA kernel or fails with B2B_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -20,7 +21,8 @@ struct b2b_ctx {
     int n_sm;
     launch_plan plan;
     unsigned char* scratch;        // plan / broadphase kernels: one slab per CTA
-    unsigned char* scratch_solve;  // solve kernel: one slab per team
+    unsigned char* scratch_solve;  // constraint records: one slab per world of a solve group
+    unsigned char* scratch_sprof;  // solve kernel: cycle counters, one row per team
     uint16_t* plan_rows;
     uint32_t* d_status;
     void* stage_in;       // [n_worlds][nb][3] reals
@@ -79,7 +81,7 @@ extern "C" size_t b2b_scratch_bytes(const b2b_caps* caps)
 {
     if (!caps_ok(caps)) return 0;
     const scratch_layout L = scratch_plan(to_caps(caps), caps->real_bytes);
-    return L.total_aux + L.total_solve;      // per resident CTA / team; the context allocates one of each per slot
+    return L.total_aux + L.total_rec;        // per resident CTA of the plan kernels / per world of a solve group
 }
 
 extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
@@ -102,7 +104,7 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     x->n_sm = prop.multiProcessorCount;
     // caps->threads: lanes of a warp per world in the solve kernel (4, 8, 16 or 32); caps->reserved: the same for
     // the plan / broadphase kernels
-    const int lanes = caps->threads > 0 ? caps->threads : 8;
+    const int lanes = caps->threads > 0 ? caps->threads : 4;
     const int lanes_aux = caps->reserved > 0 ? caps->reserved : 32;
     int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
                     : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
@@ -110,9 +112,29 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     e = cudaMalloc((void**)&x->scratch, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
     if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
     cudaMemset(x->scratch, 0, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
-    e = cudaMalloc((void**)&x->scratch_solve, x->plan.layout.total_solve * (size_t)x->plan.solve_slabs);
-    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(solve scratch)", e); }
-    cudaMemset(x->scratch_solve, 0, x->plan.layout.total_solve * (size_t)x->plan.solve_slabs);
+    // Constraint records live for one group of worlds at a time (prepare kernel -> solve kernel).  The group is
+    // every world when that fits the record budget (B2B_RECORD_GIB, default 24 GiB, at most 40 % of the free
+    // memory), else a whole number of resident-team waves.
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        double budget = 24.0;
+        if (const char* env = getenv("B2B_RECORD_GIB")) { const double v = atof(env); if (v > 0.0) budget = v; }
+        size_t budget_b = (size_t)(budget * 1073741824.0);
+        if (budget_b > free_b / 5 * 2) budget_b = free_b / 5 * 2;
+        const size_t per_world = x->plan.layout.total_rec;
+        long long group = (long long)(budget_b / per_world);
+        const long long wave = x->plan.solve_slabs > 0 ? x->plan.solve_slabs : 1;
+        if (group >= x->c.n_worlds) group = x->c.n_worlds;
+        else if (group > wave) group = group / wave * wave;
+        if (group < 1) group = 1;
+        x->plan.group_worlds = (int)group;
+    }
+    e = cudaMalloc((void**)&x->scratch_solve, x->plan.layout.total_rec * (size_t)x->plan.group_worlds);
+    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(constraint records)", e); }
+    e = cudaMalloc((void**)&x->scratch_sprof, x->plan.layout.total_sprof * (size_t)x->plan.solve_slabs);
+    if (e != cudaSuccess) { cudaFree(x->scratch); cudaFree(x->scratch_solve); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(solve counters)", e); }
+    cudaMemset(x->scratch_sprof, 0, x->plan.layout.total_sprof * (size_t)x->plan.solve_slabs);
     e = cudaMalloc((void**)&x->plan_rows, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(plan rows)", e); }
     cudaMemset(x->plan_rows, 0, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
@@ -128,6 +150,7 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     cudaSetDevice(x->caps.device);
     if (x->scratch) cudaFree(x->scratch);
     if (x->scratch_solve) cudaFree(x->scratch_solve);
+    if (x->scratch_sprof) cudaFree(x->scratch_sprof);
     if (x->plan_rows) cudaFree(x->plan_rows);
     if (x->d_status) cudaFree(x->d_status);
     if (x->stage_in) cudaFree(x->stage_in);
@@ -164,13 +187,14 @@ extern "C" int b2b_init_proxies(b2b_ctx* x, void* stream)
     return check_launch(x, "init_proxies kernel");
 }
 
-static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags)
+static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags, int solve_lanes)
 {
     step_params sp;
     sp.dt = dt;
     sp.dt_ratio_first = inv_dt0 * dt;                              // world.py:328
     sp.dt_ratio_rest = (dt > 0.0) ? (1.0 / dt) * dt : 0.0;         // _inv_dt0 = inv_dt after the first step (world.py:348-349)
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = flags;
+    sp.solve_lanes = solve_lanes;
     return sp;
 }
 
@@ -182,7 +206,8 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     if (n_steps == 0) return B2B_OK;
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
     // the flat narrowphase kernel is the default; B2B_STEP_NO_FLAT keeps the narrowphase inside the plan kernel
-    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u));
+    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u),
+                                       x->plan.lanes);
     for (int s = 0; s < n_steps; ++s) {
         cudaEvent_t* ev = nullptr;
         if (flags & B2B_STEP_TIME) {
@@ -195,11 +220,13 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
             ev = x->events->data() + 5 * x->timed_steps;
             ++x->timed_steps;
         }
-        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
-        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, sp, s == 0, (cudaStream_t)stream, ev);
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, sp, s == 0, (cudaStream_t)stream, ev);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, sp, s == 0, (cudaStream_t)stream, ev);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
-        x->launches += ((dt > 0.0) ? 2 : 1) + ((sp.flags & 4u) ? 1 : 0);       // check_launch counted one of them
+        // check_launch counted one of: plan, broadphase, (collide), and per group of worlds prepare + solve velocity + solve position
+        const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
+        x->launches += 1 + ((dt > 0.0) ? 3 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
     }
     return B2B_OK;
 }
@@ -287,9 +314,9 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
     long long tmp[PROF_SLOTS];
     for (int pass = 0; pass < 2; ++pass) {
         const int n = pass ? x->plan.solve_slabs : x->plan.aux_slabs;
-        const size_t stride = pass ? x->plan.layout.total_solve : x->plan.layout.total_aux;
-        const size_t off = pass ? x->plan.layout.off_sprof : x->plan.layout.off_prof;
-        unsigned char* base = pass ? x->scratch_solve : x->scratch;
+        const size_t stride = pass ? x->plan.layout.total_sprof : x->plan.layout.total_aux;
+        const size_t off = pass ? 0 : x->plan.layout.off_prof;
+        unsigned char* base = pass ? x->scratch_sprof : x->scratch;
         for (int g = 0; g < n; ++g) {
             unsigned char* p = base + (size_t)g * stride + off;
             CUDA_TRY(cudaMemcpy(tmp, p, sizeof(tmp), cudaMemcpyDeviceToHost), "D2H profile");

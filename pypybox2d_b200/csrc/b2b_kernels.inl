@@ -10,9 +10,10 @@ namespace b2b {
 
 typedef B2B_REAL real_t;
 
-// resident solve CTAs (one warp each) per SM the register allocation is sized for
+// resident solve CTAs (one warp each) per SM the register allocation is sized for: two constraint records in
+// flight per lane need ~170 registers, so the default is 4 lanes per world (8 worlds per warp) and 10 CTAs per SM
 #ifndef B2B_SOLVE_MIN_CTAS
-#define B2B_SOLVE_MIN_CTAS 20
+#define B2B_SOLVE_MIN_CTAS 10
 #endif
 
 // The step is three kernels per World.step, each a persistent grid with worlds strided over CTAs:
@@ -61,24 +62,47 @@ __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_pt
     }
 }
 
-__global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(solve_kernel_, B2B_SUFFIX)(
-    batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* scratch, step_params sp,
-    int first_step, int lanes, size_t team_smem)
+// Constraint records (K3 set-up, contact.py:376-496) for a GROUP of worlds [w0, w0 + n_group): one thread per
+// (world, constraint slot), records into the group's slab `rec` (one scratch_layout::total_rec per world).
+__global__ void __launch_bounds__(128) B2B_CAT(prepare_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                            scratch_layout L, unsigned char* rec, step_params sp,
+                                                                            int first_step, int w0, int n_group)
 {
-    extern __shared__ __align__(32) unsigned char smem[];
-    world_step<real_t> ws;
-    const int team = ws.bind_team_lanes(lanes);
-    const int teams_per_cta = 32 / lanes;
-    const int slot = blockIdx.x * teams_per_cta + team;
-    unsigned char* my_scratch = scratch + (size_t)slot * L.total_solve;
-    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
+    const long long total = (long long)n_group * c.nc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / c.nc), slot = (int)(i % c.nc);
+        const int w = w0 + g;
+        if (slot >= B.w_island[4 * (size_t)w + 2]) continue;
+        world_step<real_t> ws;
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch_solve(my_scratch, L);
-        ws.bind_smem_solve(smem + (size_t)team * team_smem);
-        ws.run_solve(sp, first_step != 0);
-        __syncwarp(ws.t_mask);
+        ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
+        ws.prepare_slot(sp, first_step != 0, slot);
     }
 }
+
+// Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): each is one warp per
+// CTA, the warp split into teams of `lanes` lanes, one world per team, worlds of the group strided over the teams.
+#define B2B_SOLVE_KERNEL(NAME, CALL)                                                                                           \
+    __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(NAME, B2B_SUFFIX)(                                       \
+        batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* rec,                   \
+        unsigned char* team_prof, step_params sp, int lanes, size_t team_smem, int w0, int n_group)                            \
+    {                                                                                                                          \
+        extern __shared__ __align__(32) unsigned char smem[];                                                                  \
+        world_step<real_t> ws;                                                                                                 \
+        const int team = ws.bind_team_lanes(lanes);                                                                            \
+        const int teams_per_cta = 32 / lanes;                                                                                  \
+        const int slot = blockIdx.x * teams_per_cta + team;                                                                    \
+        for (int g = slot; g < n_group; g += gridDim.x * teams_per_cta) {                                                      \
+            ws.bind_rows(B, c, w0 + g, plan, P);                                                                               \
+            ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, team_prof + (size_t)slot * L.total_sprof);                 \
+            ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                               \
+            ws.CALL(sp);                                                                                                       \
+            __syncwarp(ws.t_mask);                                                                                             \
+        }                                                                                                                      \
+    }
+B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity)
+B2B_SOLVE_KERNEL(solve_position_kernel_, run_solve_position)
+#undef B2B_SOLVE_KERNEL
 
 __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                                scratch_layout L, unsigned char* scratch, step_params sp,
@@ -245,9 +269,15 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                       S.total_plan * teams_aux, 0, n_sm, &out->k_plan);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(solve_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
+    // the two solve kernels share one launch geometry: the smaller of their occupancies
+    kernel_plan k_pos;
+    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
                   ctas_per_sm, n_sm, &out->k_solve);
     if (rc) return rc;
+    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
+                  ctas_per_sm, n_sm, &k_pos);
+    if (rc) return rc;
+    if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
     rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                   S.total_broad * teams_aux, 0, n_sm, &out->k_broad);
     if (rc) return rc;
@@ -258,8 +288,8 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
 
 // one World.step = plan + solve + broadphase
 void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
-                                       unsigned char* scratch_aux, unsigned char* scratch_solve, const step_params& sp,
-                                       int first_step, cudaStream_t st, cudaEvent_t* ev)
+                                       unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,
+                                       const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
     if (ev) cudaEventRecord(ev[0], st);
@@ -273,9 +303,24 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp, p.lanes_aux,
                                                                                  p.team_smem_plan);
     if (ev) cudaEventRecord(ev[1], st);
-    if (sp.dt > 0.0)
-        B2B_CAT(solve_kernel_, B2B_SUFFIX)<<<p.k_solve.grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp,
-                                                                                        first_step, p.lanes, p.team_smem);
+    if (sp.dt > 0.0) {
+        // groups of worlds: the record slab is sized for one group (launch_plan::group_worlds)
+        for (int w0 = 0; w0 < c.n_worlds; w0 += p.group_worlds) {
+            const int n_group = (c.n_worlds - w0 < p.group_worlds) ? c.n_worlds - w0 : p.group_worlds;
+            const long long total = (long long)n_group * c.nc;
+            long long blocks = (total + 127) / 128;
+            if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
+            B2B_CAT(prepare_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp, first_step,
+                                                                             w0, n_group);
+            const int teams = 32 / p.lanes;
+            int grid = p.k_solve.grid;
+            if ((long long)grid * teams > n_group) grid = (n_group + teams - 1) / teams;
+            B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                           scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+            B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                           scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+        }
+    }
     if (ev) cudaEventRecord(ev[2], st);
     B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
                                                                                          p.lanes_aux, p.team_smem_broad);

@@ -16,7 +16,8 @@ struct kernel_plan {
 };
 struct launch_plan {
     kernel_plan k_plan, k_solve, k_broad;
-    int aux_slabs, solve_slabs;      // scratch slabs to allocate: per plan/broadphase CTA, per solve team
+    int aux_slabs, solve_slabs;      // scratch slabs to allocate: per plan/broadphase CTA; solve teams (cycle counters)
+    int group_worlds;                // worlds whose constraint records are resident at once (one record slab each)
     int n_sm;
     int lanes, lanes_aux;            // lanes of a warp that step one world: solve kernel / plan + broadphase kernels
     size_t team_smem, team_smem_plan, team_smem_broad;
@@ -27,8 +28,8 @@ struct launch_plan {
 #define B2B_DECLARE(S)                                                                                                        \
     int plan_##S(const caps_t& c, int lanes, int lanes_aux, int ctas_per_sm, int n_sm, launch_plan* out);                     \
     void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,                    \
-                         unsigned char* scratch_aux, unsigned char* scratch_solve, const step_params& sp, int first_step,     \
-                         cudaStream_t st, cudaEvent_t* ev);                                                                   \
+                         unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,            \
+                         const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev);                                                                 \
     void launch_init_proxies_##S(const void* const* fields, const caps_t& c, cudaStream_t st);                                \
     void launch_collide_pairs_##S(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,          \
                                   const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st);             \

@@ -19,10 +19,12 @@
 #define B2B_HD __host__ __device__ __forceinline__
 #define B2B_D __device__ __forceinline__
 #define B2B_HD_COLD __host__ __device__ __noinline__
+#define B2B_D_NOINLINE __device__ __noinline__
 #else
 #define B2B_HD inline
 #define B2B_D inline
 #define B2B_HD_COLD inline
+#define B2B_D_NOINLINE inline
 #endif
 
 namespace b2b {

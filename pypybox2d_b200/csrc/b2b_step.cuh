@@ -96,17 +96,23 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 // kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
 // it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
 struct plan_layout {          // per world, in uint16_t elements
-    size_t off_cbody, off_sched, off_lmask, off_adj, off_adj_start, off_cstate, stride;
+    size_t off_cbody, off_sched, off_lv, off_adj, off_adj_start, off_cstate, stride;
 };
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-B2B_HD int lmask_words(const caps_t& c) { return (c.nc + 31) / 32 + 2; }
+// Level-step table of the solve kernel: one 4-bit count per level-step, eight per word.  Island `isl`, whose
+// constraint slots start at c0, owns the words from (c0 >> 3) + 2 * isl on: n slots make at most n level-steps =
+// ceil(n / 8) words plus a closing zero word (the reader runs one word ahead), and the next island starts at
+// least floor(n / 8) + 2 words later, so islands never share a word and can be scheduled concurrently.
+B2B_HD int lv_words(const caps_t& c) { return (c.nc + 7) / 8 + 2 * c.nb + 4; }
+B2B_HD int lv_offset(int c0, int isl) { return (c0 >> 3) + 2 * isl; }
+enum { LV_MAX_LANES = 8 };      // a level-step holds at most min(solve lanes, 8) slots (wider levels are split)
 B2B_HD plan_layout plan_plan(const caps_t& c)
 {
     plan_layout P;
     size_t o = 0;
     P.off_cbody = o; o = align_up(o + 2 * (size_t)c.nc, 8);
     P.off_sched = o; o = align_up(o + (size_t)c.nc + 2, 8);
-    P.off_lmask = o; o = align_up(o + 2 * (size_t)lmask_words(c), 8);       // uint32 words, counted in uint16 units
+    P.off_lv = o; o = align_up(o + 2 * (size_t)lv_words(c), 8);             // uint32 words, counted in uint16 units
     P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
     P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
     P.off_cstate = o; o = align_up(o + ((size_t)c.nc + 1) / 2 + 1, 8);      // one byte per contact
@@ -114,9 +120,10 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
     return P;
 }
 
-struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `solve` slabs per solve team
+struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `rec` slabs per world of a solve group
     size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
-    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_sprof, total_solve;
+    size_t off_cc_vel, off_cc_pos, off_cc_imp, total_rec;
+    size_t total_sprof;       // per solve team: cycle counters
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
 {
@@ -135,16 +142,16 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_pos = take((size_t)real_bytes * 4 * PREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
-    L.off_sprof = take(sizeof(long long) * PROF_SLOTS);
-    L.total_solve = align_up(o, 256);
+    L.total_rec = align_up(o, 256);
+    L.total_sprof = align_up(sizeof(long long) * PROF_SLOTS, 256);
     return L;
 }
 
 // shared memory.  plan kernel (per CTA): [ctl | flags | ls | cbody | adj | adj_start | stack/last | lev | cflag];
-// solve kernel (per team): [state quads | level mask | flags8]; broadphase kernel (per CTA): [ctl].
+// solve kernel (per team): [three reals per body]; broadphase kernel (per CTA): [ctl].
 struct smem_layout {
     size_t off_ctl, off_flags, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag, total_plan;
-    size_t off_state, off_lmask, off_flags8, total_solve;     // relative to the team's base
+    size_t off_state, total_solve;                            // relative to the team's base
     size_t total_broad;
 };
 B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
@@ -164,8 +171,6 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     S.total_plan = o;
     o = 0;
     S.off_state = o; o = align_up(o + (size_t)real_bytes * 3 * (size_t)c.nb, 32);
-    S.off_lmask = o; o = align_up(o + sizeof(uint32_t) * (size_t)lmask_words(c), 32);
-    S.off_flags8 = o; o = align_up(o + (size_t)c.nb, 32);
     S.total_solve = o;
     return S;
 }
@@ -174,6 +179,7 @@ struct step_params {
     double dt, dt_ratio_first, dt_ratio_rest;
     int vel_iters, pos_iters, n_steps;
     uint32_t flags;
+    int solve_lanes;             // lanes per world of the solve kernel: the level-step table is cut to this width
 };
 
 // ================================================================================================
@@ -192,7 +198,7 @@ template <class real> struct world_step {
     const int32_t* s_meta; const real* s_radius; const real* s_data;
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
-    uint32_t* g_lmask;       // bit s set: slot s is the last constraint of its dependency level
+    uint32_t* g_lv;          // level-step table (see lv_words)
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan;
@@ -201,9 +207,7 @@ template <class real> struct world_step {
     int32_t* pair_keep;
     long long* prof;
     // shared memory
-    real *s_sx, *s_sy, *s_sz;  // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
-    uint32_t* s_lmask;
-    uint8_t* s_flags8;       // solve kernel: body type | allow_sleep
+    real* s_state;           // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
     uint32_t* s_flags;       // plan kernel: body flags
     int32_t* s_ctl;          // [16] control words
     uint16_t *s_ls, *s_cbody, *s_adj, *s_adj_start, *s_stack, *s_last, *s_lev;
@@ -255,7 +259,7 @@ template <class real> struct world_step {
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
         uint16_t* pw = plan + W * P.stride;
-        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lmask = reinterpret_cast<uint32_t*>(pw + P.off_lmask);
+        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
         g_cstate = reinterpret_cast<uint8_t*>(pw + P.off_cstate);
     }
@@ -267,12 +271,14 @@ template <class real> struct world_step {
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
     }
-    B2B_D void bind_scratch_solve(unsigned char* scratch, const scratch_layout& L)
+    // `rec`: this world's constraint-record slab (written by the prepare kernel, streamed by the solve kernel);
+    // `team_prof`: the team's cycle counters (may be null outside the solve kernel)
+    B2B_D void bind_scratch_solve(unsigned char* rec, const scratch_layout& L, unsigned char* team_prof)
     {
-        cc_vel = (real*)(scratch + L.off_cc_vel);
-        cc_pos = (real*)(scratch + L.off_cc_pos);
-        cc_imp = (real*)(scratch + L.off_cc_imp);
-        prof = (long long*)(scratch + L.off_sprof);
+        cc_vel = (real*)(rec + L.off_cc_vel);
+        cc_pos = (real*)(rec + L.off_cc_pos);
+        cc_imp = (real*)(rec + L.off_cc_imp);
+        prof = (long long*)team_prof;
     }
     B2B_D void bind_smem_aux(unsigned char* smem)
     {
@@ -288,9 +294,7 @@ template <class real> struct world_step {
     B2B_D void bind_smem_solve(unsigned char* team_smem)
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
-        s_sx = (real*)(team_smem + S.off_state); s_sy = s_sx + cap.nb; s_sz = s_sy + cap.nb;
-        s_lmask = (uint32_t*)(team_smem + S.off_lmask);
-        s_flags8 = (uint8_t*)(team_smem + S.off_flags8);
+        s_state = (real*)(team_smem + S.off_state);
     }
 
     B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
@@ -591,12 +595,11 @@ template <class real> struct world_step {
     // and every body still sees its contacts in list order.  A stable counting sort by level gives `sched`
     // (slot -> position in l_contact) and the per-island level table `ls`; both go to the world's plan rows.
     // Islands are independent, so each one is scheduled by its own thread.
-    B2B_D void phase_schedule()
+    B2B_D void phase_schedule(int solve_lanes)
     {
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
         (void)n_lb;
-        B2B_PFOR(k, lmask_words(cap)) scan[k] = 0;
-        B2B_SYNC();
+        const int chunk = (solve_lanes < (int)LV_MAX_LANES) ? (solve_lanes < 1 ? 1 : solve_lanes) : (int)LV_MAX_LANES;
         B2B_PFOR(isl, n_islands) {
             const int c0 = l_start[2 * isl + 1];
             const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
@@ -628,27 +631,37 @@ template <class real> struct world_step {
                 for (int k = c0; k < c1; ++k) { const int l = s_lev[k]; g_sched[c0 + ls[l]] = (uint16_t)k; ++ls[l]; }
                 for (int l = nlev; l >= 2; --l) ls[l] = ls[l - 1];
                 ls[1] = 0;
-            }
-            // last slot of every level -> one bit in the world's level mask
-            for (int l = 1; l <= nlev; ++l) {
-                const int last_slot = c0 + ls[l + 1] - 1;
-                B2B_ATOMIC_OR(&scan[last_slot >> 5], (int32_t)(1u << (last_slot & 31)));
+                // level-step table: every level in pieces of at most `chunk` slots, one 4-bit count per piece
+                uint32_t* lv = g_lv + lv_offset(c0, isl);
+                uint32_t word = 0;
+                int nib = 0;
+                for (int l = 1; l <= nlev; ++l) {
+                    int left = (int)ls[l + 1] - (int)ls[l];
+                    while (left > 0) {
+                        const int take = left < chunk ? left : chunk;
+                        word |= (uint32_t)take << (4 * nib);
+                        left -= take;
+                        if (++nib == 8) { *lv++ = word; word = 0; nib = 0; }
+                    }
+                }
+                *lv++ = word;                             // the partial word, or a zero word: the reader runs one word ahead
+                if (nib != 0) *lv = 0;
             }
         }
         B2B_SYNC();
-        B2B_PFOR(k, lmask_words(cap)) g_lmask[k] = (uint32_t)scan[k];
-        B2B_SYNC();
     }
 
-    // ------------------------------------------------------------------------------------ K3 (solve kernel)
+    // ------------------------------------------------------------------------------------ K3 (prepare + solve kernels)
     // One constraint = a read-only VELOCITY record of 8 four-vectors (exactly one 128-byte line in fp32: what a
     // velocity sweep streams per constraint), a read-only POSITION record of 5 four-vectors, and one read-write
     // four-vector of accumulated impulses in its own array (updating it never dirties the read-only lines).  All
-    // are in schedule order, so the lane that solves a slot fetches it with a handful of 128-bit loads.  The
-    // integer fields ride in spare lanes of the real records as raw bits.
+    // are in schedule order in the world's record slab, written by the flat prepare kernel (one thread per
+    // constraint of the whole group of worlds) and streamed by the solve kernel, whose lanes fetch the record of
+    // the NEXT level-step into registers while they solve the current one.  Integer fields ride in spare lanes
+    // of the real records as raw bits.
     //   v0  normal.x normal.y friction [body_a | body_b << 16]     v1  rA0.x rA0.y rB0.x rB0.y
     //   v2  nmass0   tmass0   bias0    [info]                      v3  rA1.x rA1.y rB1.x rB1.y
-    //   v4  nmass1   tmass1   bias1    -                           v5  k11 k12 k22 nm11
+    //   v4  nmass1   tmass1   bias1    [contact index]             v5  k11 k12 k22 nm11
     //   v6  nm12     nm22     -        -                           v7  inv_mass_a inv_I_a inv_mass_b inv_I_b
     //   p0  inv_mass_a inv_I_a inv_mass_b inv_I_b                  p1  ln.x ln.y lp.x lp.y
     //   p2  p0.x p0.y p1.x p1.y                                    p3  radius_a radius_b [bodies] [info]
@@ -656,8 +669,8 @@ template <class real> struct world_step {
     //   imp ni0 ti0 ni1 ti1
     //   info = n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25
     // Shared memory holds three reals per body: its velocity while velocities are being solved, its sweep position
-    // afterwards.  Static bodies never change and are shared between islands: each island stages their position
-    // for its position phase and puts their velocity back afterwards (islands are solved one after the other).
+    // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
+    // and later their position for itself (islands are solved one after the other).
     enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D static real real_from_bits(uint32_t u)
@@ -675,17 +688,17 @@ template <class real> struct world_step {
     B2B_D quad* vel_rec(int slot) { return reinterpret_cast<quad*>(cc_vel) + (size_t)VREC_QUADS * slot; }
     B2B_D quad* pos_rec(int slot) { return reinterpret_cast<quad*>(cc_pos) + (size_t)PREC_QUADS * slot; }
     B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
-    B2B_D quad state_get(int b) const { return mkq(s_sx[b], s_sy[b], s_sz[b], real(0)); }
-    B2B_D void state_set(int b, real x, real y, real z) { s_sx[b] = x; s_sy[b] = y; s_sz[b] = z; }
-    B2B_D bool is_static_body(int b) const { return (s_flags8[b] & BODY_TYPE_MASK) == BODY_STATIC; }
+    B2B_D quad state_get(int b) const { const real* s = s_state + 3 * b; return mkq(s[0], s[1], s[2], real(0)); }
+    B2B_D void state_set(int b, real x, real y, real z) { real* s = s_state + 3 * b; s[0] = x; s[1] = y; s[2] = z; }
+    B2B_D bool is_static_body(int b) const { return (b_flags[b] & BODY_TYPE_MASK) == BODY_STATIC; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
     {
         return vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
     }
-    // Records are consumed in slot order, so the lane solving slot s asks for slot s + PREFETCH_AHEAD (a few levels
-    // ahead, wrapping to the start of the island for the next sweep) while it computes.
-    enum { PREFETCH_AHEAD = 4 };   // measured on B200: 2..12 records ahead are equivalent, none is 16 % slower
+    // Records are consumed in slot order; the lane that fetches slot s also asks the L2 for slot s + PREFETCH_AHEAD
+    // (a few level-steps ahead, wrapping to the start of the island for the next sweep).
+    enum { PREFETCH_AHEAD = 6 };
     B2B_D int prefetch_target(int s, int c0, int c1) const
     {
         const int t = s + PREFETCH_AHEAD;
@@ -709,63 +722,124 @@ template <class real> struct world_step {
             B2B_PREFETCH(r + sizeof(quad) * PREC_QUADS - 1);
         }
     }
-    // last slot of the dependency level that starts at slot p (a set bit at or after p in the level mask)
-    B2B_D int level_end(int p) const
+
+    // Reader of an island's level-step table (phase_schedule): one 4-bit slot count per level-step, eight per
+    // word, fetched one word ahead so the load never sits on the level loop's critical path.
+    struct lv_reader {
+        const uint32_t* p;
+        uint32_t cur, next;
+        int left;
+        B2B_D void start(const uint32_t* lv) { cur = lv[0]; next = lv[1]; p = lv + 2; left = 8; }
+        B2B_D int take()
+        {
+            const int c = (int)(cur & 15u);
+            cur >>= 4;
+            if (--left == 0) { cur = next; next = *p++; left = 8; }
+            return c;
+        }
+    };
+
+    // One Gauss-Seidel sweep over an island's constraint slots [c0, c1), level-step by level-step.  The slots of a
+    // level-step touch disjoint non-static bodies, so the team's lanes solve them concurrently and the result is
+    // bit-identical to the reference's sequential sweep.  `load(slot, rec)` fetches a record into registers,
+    // `solve(rec, slot)` applies it to the bodies in shared memory.  On the GPU every lane fetches the record of
+    // its NEXT level-step before it solves the current one, so the L2/HBM latency of the record stream is off the
+    // dependent chain.
+    template <class Rec, class Load, class Solve>
+    B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, Load load, Solve solve)
     {
-        int w = p >> 5;
-        uint32_t bits = s_lmask[w] >> (p & 31);
-        if (bits) return p + lowest_bit(bits);
-        do { bits = s_lmask[++w]; } while (!bits);
-        return (w << 5) + lowest_bit(bits);
-    }
-    B2B_D static int lowest_bit(uint32_t x)
-    {
+        lv_reader rd;
+        rd.start(lv);
 #if defined(__CUDA_ARCH__)
-        return __ffs((int)x) - 1;
+        // two record buffers used alternately (the loop body is written out twice), so nothing is copied
+        int begin = c0, cnt = rd.take();
+        bool act = t_id < cnt;
+        Rec ra, rb;
+        if (act) load(begin + t_id, ra);
+        for (;;) {
+            {
+                const int nbegin = begin + cnt;
+                const int ncnt = rd.take();
+                const bool more = (nbegin < c1) & (ncnt != 0);      // a zero count never occurs in a valid table
+                const bool nact = more & (t_id < ncnt);
+                if (nact) load(nbegin + t_id, rb);
+                if (act) solve(ra, begin + t_id);
+                __syncwarp(t_mask);
+                if (!more) break;
+                act = nact; begin = nbegin; cnt = ncnt;
+            }
+            {
+                const int nbegin = begin + cnt;
+                const int ncnt = rd.take();
+                const bool more = (nbegin < c1) & (ncnt != 0);
+                const bool nact = more & (t_id < ncnt);
+                if (nact) load(nbegin + t_id, ra);
+                if (act) solve(rb, begin + t_id);
+                __syncwarp(t_mask);
+                if (!more) break;
+                act = nact; begin = nbegin; cnt = ncnt;
+            }
+        }
 #else
-        int n = 0;
-        while (!(x & 1u)) { x >>= 1; ++n; }
-        return n;
+        for (int begin = c0; begin < c1;) {
+            const int cnt = rd.take();
+            if (cnt == 0) break;
+            for (int j = 0; j < cnt; ++j) { Rec r; load(begin + j, r); solve(r, begin + j); }
+            begin += cnt;
+        }
 #endif
     }
 
-    B2B_D void stage_bodies()
+    // island.py:84-95: the velocity an island body carries into the contact solver (gravity and forces applied,
+    // then damped); static and kinematic bodies keep theirs.  Evaluated by the prepare kernel (restitution bias)
+    // and by the solve kernel (staging) with the same expression.
+    B2B_D void integrated_velocity(int b, real dt, V2 gravity, V2& v, real& w) const
     {
-        const int nb = w_count[0];
-        B2B_PFOR(b, nb) {
-            const real* v = b_vel + 4 * (size_t)b;
-            state_set(b, v[0], v[1], v[2]);
-            s_flags8[b] = (uint8_t)(b_flags[b] & (BODY_TYPE_MASK | BODY_ALLOW_SLEEP));
+        const quad bv = ldq(b_vel + 4 * (size_t)b);
+        v = mk<real>(bv.x, bv.y);
+        w = bv.z;
+        if ((b_flags[b] & BODY_TYPE_MASK) == BODY_DYNAMIC) {
+            const quad damp = ldq(b_damp + 4 * (size_t)b), mass = ldq(b_mass + 4 * (size_t)b);
+            const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
+            const real torque = bv.w;
+            v = v + dt * (damp.z * gravity + mass.x * force);
+            w = w + dt * mass.y * torque;
+            v = clamp_r(real(1) - dt * damp.x, real(0), real(1)) * v;
+            w = w * clamp_r(real(1) - dt * damp.y, real(0), real(1));
         }
-        B2B_PFOR(k, lmask_words(cap)) s_lmask[k] = g_lmask[k];
-        B2B_SYNC();
     }
 
     // ContactSolver.__init__ + initialize_velocity_constraints for one slot
-    // (contact.py:376-496, contact_util.py:195-245 WorldManifold, :253-277 VelocityConstraintPoint)
-    B2B_D void constraint_init(int slot, int ci, real dt_ratio, bool warm)
+    // (contact.py:376-496, contact_util.py:195-245 WorldManifold, :253-277 VelocityConstraintPoint).
+    // Runs in the flat prepare kernel: reads global state only.
+    B2B_D void constraint_init(int slot, real dt, real dt_ratio)
     {
+        const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
+        const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
+        const int ci = l_contact[g_sched[slot]];
         const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
         const int ba = g_cbody[2 * ci], bb = g_cbody[2 * ci + 1];
         const int mt = c_mtype[ci];
         const int type = mt & 0xff, count = (mt >> 8) & 0xff;
-        const real* mf = c_mf + 4 * (size_t)ci; const real* pts = c_pts + 4 * (size_t)ci; const real* imp = c_imp + 4 * (size_t)ci;
-        const V2 local_normal = mk<real>(mf[0], mf[1]), local_point = mk<real>(mf[2], mf[3]);
-        V2 lp[2]; lp[0] = mk<real>(pts[0], pts[1]); lp[1] = mk<real>(pts[2], pts[3]);
+        const quad mf = ldq(c_mf + 4 * (size_t)ci), pts = ldq(c_pts + 4 * (size_t)ci), imp = ldq(c_imp + 4 * (size_t)ci);
+        const V2 local_normal = mk<real>(mf.x, mf.y), local_point = mk<real>(mf.z, mf.w);
+        V2 lp[2]; lp[0] = mk<real>(pts.x, pts.y); lp[1] = mk<real>(pts.z, pts.w);
+        const real imp_n[2] = {imp.x, imp.z}, imp_t[2] = {imp.y, imp.w};
         const real rad_a = s_radius[f_shape[fa]], rad_b = s_radius[f_shape[fb]];
         const real friction = c_mat[2 * ci], restitution = c_mat[2 * ci + 1];
-        const real* mass_a = b_mass + 4 * (size_t)ba; const real* mass_b = b_mass + 4 * (size_t)bb;
-        const real ma = mass_a[0], mb = mass_b[0], ia = mass_a[1], ib = mass_b[1];
-        const V2 lca = mk<real>(mass_a[2], mass_a[3]), lcb = mk<real>(mass_b[2], mass_b[3]);
+        const quad mass_a = ldq(b_mass + 4 * (size_t)ba), mass_b = ldq(b_mass + 4 * (size_t)bb);
+        const real ma = mass_a.x, mb = mass_b.x, ia = mass_a.y, ib = mass_b.y;
+        const V2 lca = mk<real>(mass_a.z, mass_a.w), lcb = mk<real>(mass_b.z, mass_b.w);
         const bool stat_a = is_static_body(ba), stat_b = is_static_body(bb);
-        // positions are still the step's start positions in global memory; velocities are staged
-        const real* pa_ = b_pos + 4 * (size_t)ba; const real* pb_ = b_pos + 4 * (size_t)bb;
-        const quad va_ = state_get(ba), vb_ = state_get(bb);
-        const V2 ca = mk<real>(pa_[0], pa_[1]), cb = mk<real>(pb_[0], pb_[1]);
-        const V2 va = mk<real>(va_.x, va_.y), vb = mk<real>(vb_.x, vb_.y);
-        const real wa = va_.z, wb = vb_.z;
-        const XF xa = xf_from_sweep<real>(ca, pa_[2], lca);
-        const XF xb = xf_from_sweep<real>(cb, pb_[2], lcb);
+        // positions are the step's start positions; velocities are the integrated ones
+        const quad pa_ = ldq(b_pos + 4 * (size_t)ba), pb_ = ldq(b_pos + 4 * (size_t)bb);
+        const V2 ca = mk<real>(pa_.x, pa_.y), cb = mk<real>(pb_.x, pb_.y);
+        V2 va, vb;
+        real wa, wb;
+        integrated_velocity(ba, dt, gravity, va, wa);
+        integrated_velocity(bb, dt, gravity, vb, wb);
+        const XF xa = xf_from_sweep<real>(ca, pa_.z, lca);
+        const XF xb = xf_from_sweep<real>(cb, pb_.z, lcb);
 
         // world manifold
         V2 normal, wp[2];
@@ -810,8 +884,8 @@ template <class real> struct world_step {
             if (v_rel < -K<real>::velocity_threshold) bias[j] = -restitution * v_rel;
             nmass[j] = (k_normal > real(0)) ? real(1) / k_normal : real(0);
             tmass[j] = (k_tangent > real(0)) ? real(1) / k_tangent : real(0);
-            ni[j] = warm ? dt_ratio * imp[2 * j] : imp[2 * j];
-            ti[j] = warm ? dt_ratio * imp[2 * j + 1] : imp[2 * j + 1];
+            ni[j] = warm ? dt_ratio * imp_n[j] : imp_n[j];
+            ti[j] = warm ? dt_ratio * imp_t[j] : imp_t[j];
         }
         real k11 = real(0), k12 = real(0), k22 = real(0), nm11 = real(0), nm12 = real(0), nm22 = real(0);
         if (count == 2) {
@@ -835,7 +909,7 @@ template <class real> struct world_step {
         q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
         q[2] = mkq(nmass[0], tmass[0], bias[0], info_r);
         q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
-        q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
+        q[4] = mkq(nmass[1], tmass[1], bias[1], real_from_bits((uint32_t)ci));
         q[5] = mkq(k11, k12, k22, nm11);
         q[6] = mkq(nm12, nm22, real(0), real(0));
         q[7] = mkq(ma, ia, mb, ib);
@@ -848,8 +922,7 @@ template <class real> struct world_step {
         *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
     }
 
-    // A constraint's velocity-phase data in registers.  The level loops load the NEXT level's record while the
-    // current one is being solved, so the L2/HBM latency of the record stream overlaps the arithmetic.
+    // A constraint's velocity-phase data in registers.
     struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
     B2B_D void load_vrec(int slot, vrec& r)
     {
@@ -889,8 +962,10 @@ template <class real> struct world_step {
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
     }
 
-    // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799)
-    B2B_D void constraint_solve_velocity(vrec& r, int slot)
+    // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799).  The accumulated impulses go
+    // back to the slot's impulse row, or -- on the last velocity iteration -- straight to the contact's manifold
+    // (store_impulses, contact.py:801-806: only as many points as the velocity rows kept).
+    B2B_D void constraint_solve_velocity(const vrec& r, int slot, bool last)
     {
         const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
         quad qi = r.qi;
@@ -972,14 +1047,17 @@ template <class real> struct world_step {
                 qi.x = x.x; qi.z = x.y;
             }
         }
-        *imp_rec(slot) = qi;
-        r.qi = qi;
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
+        if (!last) {
+            *imp_rec(slot) = qi;
+        } else {
+            real* imp = c_imp + 4 * (size_t)bits_of_real(q4.w);
+            if (n_vel > 1) stq(imp, qi);
+            else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+        }
     }
 
-    // ContactSolver.solve_position_constraints for one slot (contact.py:809-864, contact_util.py:323-360);
-    // returns the smallest separation seen.
     // One manifold point of ContactSolver.solve_position_constraints (contact_util.py:323-360 PositionSolverManifold,
     // contact.py:826-860): evaluate the separation at the bodies' CURRENT sweeps and push them apart.
     struct pos_state { V2 ca, cb; real aa, ab, min_sep; };
@@ -1016,15 +1094,14 @@ template <class real> struct world_step {
     }
 
     // ContactSolver.solve_position_constraints for one slot (contact.py:809-864); returns the smallest separation
-    // seen.  A touching contact has one or two points; the first is solved unconditionally so that the whole
-    // record is requested up front.
+    // seen.  A touching contact has one or two points.
     B2B_D real constraint_solve_position(const prec& r)
     {
         const quad q7 = r.q7, q8 = r.q8, q9 = r.q9, q10 = r.q10, q11 = r.q11;
         const uint32_t bodies = bits_of_real(q10.z), info = bits_of_real(q10.w);
         const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
-        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
         const int type = (int)((info >> 8) & 0xff), n_pos = (int)((info >> 16) & 0xff);
+        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
         const V2 lca = mk<real>(q11.x, q11.y), lcb = mk<real>(q11.z, q11.w);
         const V2 local_normal = mk<real>(q8.x, q8.y), local_point = mk<real>(q8.z, q8.w);
@@ -1046,22 +1123,13 @@ template <class real> struct world_step {
         const real* p = b_pos + 4 * (size_t)b;
         real* p0 = b_pos0 + 4 * (size_t)b;
         p0[0] = p[0]; p0[1] = p[1]; p0[2] = p[2];
-        if ((s_flags8[b] & BODY_TYPE_MASK) == BODY_DYNAMIC) {
-            const real* damp = b_damp + 4 * (size_t)b; const real* mass = b_mass + 4 * (size_t)b;
-            const V2 force = mk<real>(b_force[2 * (size_t)b], b_force[2 * (size_t)b + 1]);
-            const real torque = b_vel[4 * (size_t)b + 3];
-            const quad sv = state_get(b);
-            V2 v = mk<real>(sv.x, sv.y);
-            real w = sv.z;
-            v = v + dt * (damp[2] * gravity + mass[0] * force);
-            w = w + dt * mass[1] * torque;
-            v = clamp_r(real(1) - dt * damp[0], real(0), real(1)) * v;
-            w = w * clamp_r(real(1) - dt * damp[1], real(0), real(1));
-            state_set(b, v.x, v.y, w);
-        }
+        V2 v;
+        real w;
+        integrated_velocity(b, dt, gravity, v, w);
+        state_set(b, v.x, v.y, w);
     }
-    // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity goes to
-    // global memory and the body's shared-memory quad becomes its position.
+    // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity and the
+    // advanced sweep go to global memory (the position kernel stages the sweep again).
     B2B_D void integrate_position(int b, real dt)
     {
         const quad sv = state_get(b);
@@ -1078,18 +1146,26 @@ template <class real> struct world_step {
             const real ratio = K<real>::max_rotation / abs_r(rotation);
             w = w * ratio;
         }
-        state_set(b, p[0] + dt * v.x, p[1] + dt * v.y, p[2] + dt * w);
+        real* pout = b_pos + 4 * (size_t)b;
+        const real nx = p[0] + dt * v.x, ny = p[1] + dt * v.y, na = p[2] + dt * w;
+        pout[0] = nx; pout[1] = ny; pout[2] = na;
         real* vout = b_vel + 4 * (size_t)b;
         vout[0] = v.x; vout[1] = v.y; vout[2] = w;
     }
-    // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body
+    // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body whose solved sweep
+    // is in shared memory
     B2B_D void write_back(int b)
     {
         const quad sp = state_get(b);
-        real* p = b_pos + 4 * (size_t)b; real* x = b_xf + 4 * (size_t)b;
+        real* p = b_pos + 4 * (size_t)b;
         p[0] = sp.x; p[1] = sp.y; p[2] = sp.z;
+        synchronize_transform(b, sp.x, sp.y, sp.z);
+    }
+    B2B_D void synchronize_transform(int b, real cx, real cy, real a)
+    {
+        real* x = b_xf + 4 * (size_t)b;
         const real* mass = b_mass + 4 * (size_t)b;
-        const XF tf = xf_from_sweep<real>(mk<real>(sp.x, sp.y), sp.z, mk<real>(mass[2], mass[3]));
+        const XF tf = xf_from_sweep<real>(mk<real>(cx, cy), a, mk<real>(mass[2], mass[3]));
         x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
     }
     // Sleep bookkeeping exactly as written in the reference (island.py:163-179): the allow-sleep
@@ -1097,7 +1173,7 @@ template <class real> struct world_step {
     B2B_D void island_sleep(int b0, int b1, real dt, bool position_solved)
     {
         real min_sleep = K<real>::max_float;
-        const bool last_allow = (s_flags8[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+        const bool last_allow = (b_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
         int victim = -1;
         for (int i = b0; i < b1; ++i) {
             const int b = l_body[i];
@@ -1130,7 +1206,7 @@ template <class real> struct world_step {
     B2B_D void island_sleep_team(int b0, int b1, real dt, bool position_solved)
     {
         real min_sleep = K<real>::max_float;
-        const bool last_allow = (s_flags8[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
+        const bool last_allow = (b_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
         int last_i = -1;
         for (int i = b0 + t_id; i < b1; i += t_n) {
             const int b = l_body[i];
@@ -1166,10 +1242,27 @@ template <class real> struct world_step {
         }
     }
 
-    // Island.solve for every island of the world (island.py:65-179).  Islands without contacts (free bodies)
-    // are whole-island-per-lane; islands with contacts are taken one after the other by the whole team, their
-    // constraints strided over the team's lanes level by level (see phase_schedule).
-    B2B_D void solve_islands(const step_params& sp, real dt, real dt_ratio)
+    // prepare kernel: the constraint records of every island slot of this world (one call per slot, any order)
+    B2B_D int prepare_count() const { return w_island[2]; }
+    B2B_D void prepare_slot(const step_params& sp, bool first_step, int slot)
+    {
+        constraint_init(slot, (real)sp.dt, (real)(first_step ? sp.dt_ratio_first : sp.dt_ratio_rest));
+    }
+
+    // Island.solve for every island of the world (island.py:65-179), in two kernels.
+    //   velocity kernel: integrate velocities, warm start, velocity iterations, store impulses, integrate
+    //                    positions (island.py:71-138); islands without contacts are finished here, one lane each
+    //   position kernel: position iterations with early exit, write-back, sleep (island.py:141-179)
+    // Islands with contacts are taken one after the other by the whole team, their constraints spread over the
+    // team's lanes level-step by level-step (see phase_schedule, level_sweep).  Between the kernels the bodies'
+    // advanced sweeps live in b_pos and their final velocities in b_vel.
+    B2B_D void island_range(int isl, int n_islands, int n_lb, int n_lc, int& b0, int& b1, int& c0, int& c1) const
+    {
+        b0 = l_start[2 * isl]; c0 = l_start[2 * isl + 1];
+        b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
+        c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+    }
+    B2B_D void solve_velocity_phase(const step_params& sp, real dt)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
@@ -1179,79 +1272,100 @@ template <class real> struct world_step {
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
         int max_used = 0;
-        // ---- contact-free islands: one lane per island
+        // ---- contact-free islands: one lane per island, start to finish
         B2B_PFOR(isl, n_islands) {
-            const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
-            const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
-            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            int b0, b1, c0, c1;
+            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (c1 != c0) continue;
             for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_velocity(b, dt, gravity); }
             for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_position(b, dt); }
             // an empty constraint list is "solved" by its first position iteration (contact.py:811,864)
             if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) write_back(b); }
+            for (int i = b0; i < b1; ++i) {
+                const int b = l_body[i];
+                if (is_static_body(b)) continue;
+                const real* p = b_pos + 4 * (size_t)b;           // the advanced sweep: nothing to correct
+                synchronize_transform(b, p[0], p[1], p[2]);
+            }
             if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
         }
+#if defined(__CUDA_ARCH__)
+        if (max_used > 0) atomicMax(&w_island[3], max_used);
+#else
+        if (max_used > w_island[3]) w_island[3] = max_used;
+#endif
         B2B_PROF(PROF_S_INTEGRATE, t);
         // ---- islands with contacts, one after the other
         for (int isl = 0; isl < n_islands; ++isl) {
-            const int b0 = l_start[2 * isl], c0 = l_start[2 * isl + 1];
-            const int b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
-            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            int b0, b1, c0, c1;
+            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (c1 == c0) continue;
+            const uint32_t* lv = g_lv + lv_offset(c0, isl);
+            // statics are shared between islands: every island stages their (constant) velocity for itself
             for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
                 if (!is_static_body(b)) integrate_velocity(b, dt, gravity);
+                else { const real* v = b_vel + 4 * (size_t)b; state_set(b, v[0], v[1], v[2]); }
             }
-            B2B_SYNC();
-            for (int s = c0 + t_id; s < c1; s += t_n) constraint_init(s, l_contact[g_sched[s]], dt_ratio, warm);
             B2B_SYNC();
             B2B_PROF(PROF_S_INIT, t);
-            if (warm) {
-                for (int begin = c0; begin < c1;) {
-                    const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_vel(s, c0, c1); vrec e; load_vrec(s, e); constraint_warm_start(e); }
-                    begin = end;
-                    B2B_SYNC();
-                }
-            }
+            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
+            if (warm) level_sweep<vrec>(c0, c1, lv, fetch, [&](const vrec& e, int) { constraint_warm_start(e); });
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
-                for (int begin = c0; begin < c1;) {
-                    const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_vel(s, c0, c1); vrec e; load_vrec(s, e); constraint_solve_velocity(e, s); }
-                    begin = end;
-                    B2B_SYNC();
-                }
+                const bool last = (it + 1 == sp.vel_iters);
+                level_sweep<vrec>(c0, c1, lv, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); });
             }
             B2B_PROF(PROF_S_VELOCITY, t);
-            // -- store_impulses (contact.py:801-806): only as many points as the velocity rows kept
-            for (int s = c0 + t_id; s < c1; s += t_n) {
-                const quad qi = *imp_rec(s);
-                const int ci = l_contact[g_sched[s]], n_vel = (int)(bits_of_real(vel_rec(s)[2].w) & 0xff);
-                real* imp = c_imp + 4 * (size_t)ci;
-                if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
-                if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
+            // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
+            // iterations the (warm-started) impulses go back as they are
+            if (sp.vel_iters == 0) {
+                for (int s = c0 + t_id; s < c1; s += t_n) {
+                    const quad qi = *imp_rec(s);
+                    const int ci = l_contact[g_sched[s]], n_vel = (int)(bits_of_real(vel_rec(s)[2].w) & 0xff);
+                    real* imp = c_imp + 4 * (size_t)ci;
+                    if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+                    if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
+                }
             }
             for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
                 if (!is_static_body(b)) integrate_position(b, dt);
-                else { const real* p = b_pos + 4 * (size_t)b; state_set(b, p[0], p[1], p[2]); }
             }
             B2B_SYNC();
             B2B_PROF(PROF_S_STORE, t);
+        }
+        B2B_SYNC();
+    }
+
+    B2B_D void solve_position_phase(const step_params& sp, real dt)
+    {
+        const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
+        const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
+        (void)profiling;
+        int max_used = 0;
+        for (int isl = 0; isl < n_islands; ++isl) {
+            int b0, b1, c0, c1;
+            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
+            if (c1 == c0) continue;
+            const uint32_t* lv = g_lv + lv_offset(c0, isl);
+            for (int i = b0 + t_id; i < b1; i += t_n) {
+                const int b = l_body[i];
+                const real* p = b_pos + 4 * (size_t)b;
+                state_set(b, p[0], p[1], p[2]);
+            }
+            B2B_SYNC();
+            B2B_PROF(PROF_S_STAGE, t);
             // -- position iterations with early exit (island.py:141-153)
             bool position_solved = false;
             int used = 0;
             for (int it = 0; it < sp.pos_iters; ++it) {
                 real my_min = real(0);
                 ++used;
-                for (int begin = c0; begin < c1;) {
-                    const int end = level_end(begin) + 1;
-                    for (int s = begin + t_id; s < end; s += t_n) { prefetch_pos(s, c0, c1); prec e; load_prec(s, e); my_min = pymin(my_min, constraint_solve_position(e)); }
-                    begin = end;
-                    B2B_SYNC();
-                }
+                level_sweep<prec>(c0, c1, lv, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
+                                  [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); });
                 real all_min = my_min;
 #if defined(__CUDA_ARCH__)
                 for (int o = t_n >> 1; o > 0; o >>= 1) {
@@ -1266,15 +1380,12 @@ template <class real> struct world_step {
             for (int i = b0 + t_id; i < b1; i += t_n) {
                 const int b = l_body[i];
                 if (!is_static_body(b)) write_back(b);
-                else { const real* v = b_vel + 4 * (size_t)b; state_set(b, v[0], v[1], v[2]); }
             }
             B2B_SYNC();
             B2B_PROF(PROF_S_WRITEBACK, t);
             if (allow_sleep) island_sleep_team(b0, b1, dt, position_solved);
             B2B_SYNC();
             B2B_PROF(PROF_S_SLEEP, t);
-            // the next island's bodies are disjoint (statics aside), but their quads must hold velocities again:
-            // they were staged as velocities and are only touched by their own island, so nothing to restore.
         }
         // max position iterations used by any island of this world (diagnostic, w_island[3])
 #if defined(__CUDA_ARCH__)
@@ -1453,7 +1564,7 @@ template <class real> struct world_step {
                 B2B_PROF(PROF_ADJACENCY, t);
                 phase_islands();
                 B2B_PROF(PROF_ISLANDS, t);
-                phase_schedule();
+                phase_schedule(sp.solve_lanes);
                 if (B2B_IS_T0 && !s_ctl[11]) w_flags[0] |= WORLD_GRAPH_VALID;   // a body woken by the walk may seed earlier next time
                 B2B_PROF(PROF_S_SCHEDULE, t);
             } else if (B2B_IS_T0) {
@@ -1463,14 +1574,20 @@ template <class real> struct world_step {
         }
     }
     // solve kernel: Island.solve for every island (island.py:65-179)
-    B2B_D void run_solve(const step_params& sp, bool first_step)
+    B2B_D void run_solve_velocity(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
-        stage_bodies();
-        B2B_PROF(PROF_S_STAGE, t);
-        solve_islands(sp, (real)sp.dt, (real)(first_step ? sp.dt_ratio_first : sp.dt_ratio_rest));
+        solve_velocity_phase(sp, (real)sp.dt);
+        B2B_PROF(PROF_SOLVE, t);
+    }
+    B2B_D void run_solve_position(const step_params& sp)
+    {
+        if (!(sp.dt > 0.0)) return;
+        const bool profiling = (sp.flags & STEP_PROFILE) != 0;
+        long long t = B2B_CLOCK();
+        solve_position_phase(sp, (real)sp.dt);
         B2B_PROF(PROF_SOLVE, t);
     }
     // broadphase kernel: proxy synchronisation + find_new_contacts (world.py:582-592) + clear_forces (:351-352)
@@ -1501,7 +1618,12 @@ template <class real> struct world_step {
                 for (int c = 0; c < nc; ++c) collide_one(c);
             }
             run_plan(sp);
-            run_solve(sp, step == 0);
+            if (sp.dt > 0.0) {
+                const int n_slots = prepare_count();
+                for (int s = 0; s < n_slots; ++s) prepare_slot(sp, step == 0, s);
+            }
+            run_solve_velocity(sp);
+            run_solve_position(sp);
             run_broadphase(sp);
         }
     }

@@ -27,7 +27,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     scratch_layout L = scratch_plan(c, (int)sizeof(real));
     plan_layout P = plan_plan(c);
     smem_layout S = smem_plan_layout(c, (int)sizeof(real));
-    std::vector<unsigned char> aux(L.total_aux + 256), solve(L.total_solve + 256);
+    std::vector<unsigned char> aux(L.total_aux + 256), solve(L.total_rec + 256), sprof(L.total_sprof + 256);
     std::vector<unsigned char> smem_aux(S.total_plan + 256), smem_solve(S.total_solve + 256);
     // the plan rows persist between calls like the device context's do (the island schedule is reused while the
     // contact graph is unchanged); keyed by the batch they belong to
@@ -40,12 +40,13 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     step_params sp;
     sp.dt = dt; sp.dt_ratio_first = inv_dt0 * dt; sp.dt_ratio_rest = (dt > 0.0 ? (1.0 / dt) * dt : 0.0);
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = STEP_FLAT_COLLIDE;
+    sp.solve_lanes = 8;
     for (int w = 0; w < c.n_worlds; ++w) {
         world_step<real> ws;
         ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan.data(), P);
         ws.bind_scratch_aux(aux.data(), L);
-        ws.bind_scratch_solve(solve.data(), L);
+        ws.bind_scratch_solve(solve.data(), L, sprof.data());
         ws.bind_smem_aux(smem_aux.data());
         ws.bind_smem_solve(smem_solve.data());
         ws.run(sp);

@@ -28,4 +28,4 @@ def run(n_worlds, real, threads, settle=200, steps=4, ctas=0):
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [16384]
     for n in sizes:
-        run(n, "f32", 8)
+        run(n, "f32", int(os.environ.get("SWEEP_LANES", "4")))

@@ -23,6 +23,7 @@ def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1):
 if __name__ == "__main__":
     import sys
     sizes = [int(a) for a in sys.argv[1:]] or [32768]
+    lanes_list = [int(x) for x in os.environ.get("SWEEP_LANES", "4").split(",")]
     for n in sizes:
-        for lanes in (8,):
+        for lanes in lanes_list:
             run(n, "f32", lanes, 8)
