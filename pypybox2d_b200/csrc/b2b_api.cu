@@ -195,6 +195,7 @@ static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos
     sp.dt_ratio_rest = (dt > 0.0) ? (1.0 / dt) * dt : 0.0;         // _inv_dt0 = inv_dt after the first step (world.py:348-349)
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = flags;
     sp.solve_lanes = solve_lanes;
+    sp.zero = 0;
     return sp;
 }
 

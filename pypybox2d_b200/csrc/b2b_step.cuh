@@ -180,6 +180,7 @@ struct step_params {
     int vel_iters, pos_iters, n_steps;
     uint32_t flags;
     int solve_lanes;             // lanes per world of the solve kernel: the level-step table is cut to this width
+    uint32_t zero;               // always 0: a value the compiler cannot fold (orders the record loads, see level_sweep)
 };
 
 // ================================================================================================
@@ -724,17 +725,20 @@ template <class real> struct world_step {
     }
 
     // Reader of an island's level-step table (phase_schedule): one 4-bit slot count per level-step, eight per
-    // word, fetched one word ahead so the load never sits on the level loop's critical path.
+    // word.  The following word is requested when the current one is half used and only moved in when it runs out,
+    // so its load never sits on the level loop's critical path.
     struct lv_reader {
         const uint32_t* p;
         uint32_t cur, next;
         int left;
-        B2B_D void start(const uint32_t* lv) { cur = lv[0]; next = lv[1]; p = lv + 2; left = 8; }
+        B2B_D void start(const uint32_t* lv) { cur = lv[0]; next = 0u; p = lv + 1; left = 8; }
         B2B_D int take()
         {
             const int c = (int)(cur & 15u);
             cur >>= 4;
-            if (--left == 0) { cur = next; next = *p++; left = 8; }
+            --left;
+            if (left == 0) { cur = next; left = 8; }
+            else if (left == 4) next = *p++;
             return c;
         }
     };
@@ -742,11 +746,14 @@ template <class real> struct world_step {
     // One Gauss-Seidel sweep over an island's constraint slots [c0, c1), level-step by level-step.  The slots of a
     // level-step touch disjoint non-static bodies, so the team's lanes solve them concurrently and the result is
     // bit-identical to the reference's sequential sweep.  `load(slot, rec)` fetches a record into registers,
-    // `solve(rec, slot)` applies it to the bodies in shared memory.  On the GPU every lane fetches the record of
-    // its NEXT level-step before it solves the current one, so the L2/HBM latency of the record stream is off the
-    // dependent chain.
-    template <class Rec, class Load, class Solve>
-    B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, Load load, Solve solve)
+    // `solve(rec, slot)` applies it to the bodies in shared memory, `ready(rec)` returns a word of the record.
+    // On the GPU every lane fetches the record of its NEXT level-step before it solves the current one, so the
+    // L2/HBM latency of the record stream is off the dependent chain.  The fetch address is made to depend on a
+    // word of the CURRENT record (`& zero`, a run-time zero): all record loads share one hardware scoreboard, so
+    // without that order the first use of the current record would also wait for the loads just issued.  The
+    // table reader moves its look-ahead word in at the same point, for the same reason.
+    template <class Rec, class Load, class Solve, class Ready>
+    B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, uint32_t zero, Load load, Solve solve, Ready ready)
     {
         lv_reader rd;
         rd.start(lv);
@@ -758,7 +765,8 @@ template <class real> struct world_step {
         if (act) load(begin + t_id, ra);
         for (;;) {
             {
-                const int nbegin = begin + cnt;
+                // (an idle lane's record is whatever its registers held: `& zero` makes that harmless)
+                const int nbegin = begin + cnt + (int)(ready(ra) & zero);
                 const int ncnt = rd.take();
                 const bool more = (nbegin < c1) & (ncnt != 0);      // a zero count never occurs in a valid table
                 const bool nact = more & (t_id < ncnt);
@@ -769,7 +777,7 @@ template <class real> struct world_step {
                 act = nact; begin = nbegin; cnt = ncnt;
             }
             {
-                const int nbegin = begin + cnt;
+                const int nbegin = begin + cnt + (int)(ready(rb) & zero);
                 const int ncnt = rd.take();
                 const bool more = (nbegin < c1) & (ncnt != 0);
                 const bool nact = more & (t_id < ncnt);
@@ -781,6 +789,7 @@ template <class real> struct world_step {
             }
         }
 #else
+        (void)zero; (void)ready;
         for (int begin = c0; begin < c1;) {
             const int cnt = rd.take();
             if (cnt == 0) break;
@@ -1310,11 +1319,12 @@ template <class real> struct world_step {
             B2B_SYNC();
             B2B_PROF(PROF_S_INIT, t);
             auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
-            if (warm) level_sweep<vrec>(c0, c1, lv, fetch, [&](const vrec& e, int) { constraint_warm_start(e); });
+            auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
+            if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int) { constraint_warm_start(e); }, vready);
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
                 const bool last = (it + 1 == sp.vel_iters);
-                level_sweep<vrec>(c0, c1, lv, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); });
+                level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); }, vready);
             }
             B2B_PROF(PROF_S_VELOCITY, t);
             // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
@@ -1364,8 +1374,9 @@ template <class real> struct world_step {
             for (int it = 0; it < sp.pos_iters; ++it) {
                 real my_min = real(0);
                 ++used;
-                level_sweep<prec>(c0, c1, lv, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
-                                  [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); });
+                level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
+                                  [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); },
+                                  [&](const prec& e) { return bits_of_real(e.q10.z); });
                 real all_min = my_min;
 #if defined(__CUDA_ARCH__)
                 for (int o = t_n >> 1; o > 0; o >>= 1) {

@@ -41,6 +41,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     sp.dt = dt; sp.dt_ratio_first = inv_dt0 * dt; sp.dt_ratio_rest = (dt > 0.0 ? (1.0 / dt) * dt : 0.0);
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = STEP_FLAT_COLLIDE;
     sp.solve_lanes = 8;
+    sp.zero = 0;
     for (int w = 0; w < c.n_worlds; ++w) {
         world_step<real> ws;
         ws.bind_team_cta();
