@@ -24,7 +24,7 @@ struct b2b_ctx {
     unsigned char* scratch_solve;  // constraint records: one slab per world of a solve group
     unsigned char* scratch_sprof;  // solve kernel: cycle counters, one row per team
     uint16_t* plan_rows;
-    uint32_t* d_status;
+    uint32_t* d_status;            // [0] status OR, [1..2] chunk counters of the plan / pair kernels
     void* stage_in;       // [n_worlds][nb][3] reals
     void* stage_out;      // [n_worlds][nb][6] reals
     const void* fields[B2B_NFIELDS];
@@ -54,7 +54,7 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 static bool caps_ok(const b2b_caps* k)
 {
     return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
-           (k->real_bytes == 4 || k->real_bytes == 8) && (k->threads == 0 || k->threads == 4 || k->threads == 8 || k->threads == 16 || k->threads == 32) &&
+           (k->real_bytes == 4 || k->real_bytes == 8) && (k->threads == 0 || k->threads == 2 || k->threads == 4 || k->threads == 8 || k->threads == 16 || k->threads == 32) &&
            (k->reserved == 0 || k->reserved == 4 || k->reserved == 8 || k->reserved == 16 || k->reserved == 32) && k->nb < 65535 &&
            k->nc < 65535;
 }
@@ -138,7 +138,7 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     e = cudaMalloc((void**)&x->plan_rows, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(plan rows)", e); }
     cudaMemset(x->plan_rows, 0, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
-    e = cudaMalloc((void**)&x->d_status, sizeof(uint32_t));
+    e = cudaMalloc((void**)&x->d_status, 4 * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(status)", e); }
     *out = x;
     return B2B_OK;
@@ -221,13 +221,13 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
             ev = x->events->data() + 5 * x->timed_steps;
             ++x->timed_steps;
         }
-        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, sp, s == 0, (cudaStream_t)stream, ev);
-        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, sp, s == 0, (cudaStream_t)stream, ev);
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, ev);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, ev);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
-        // check_launch counted one of: plan, broadphase, (collide), and per group of worlds prepare + solve velocity + solve position
+        // check_launch counted one of: plan, sync, broadphase, (collide), and per group of worlds prepare + solve velocity + solve position
         const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
-        x->launches += 1 + ((dt > 0.0) ? 3 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
+        x->launches += 2 + ((dt > 0.0) ? 3 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
     }
     return B2B_OK;
 }

@@ -39,27 +39,59 @@ __global__ void __launch_bounds__(128, 5) B2B_CAT(collide_kernel_, B2B_SUFFIX)(b
     }
 }
 
-// The other three kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
+// The per-world kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
 // own world, so several worlds share each issued instruction (their work is mostly one or two lanes wide).
+//
+// plan and pair kernels: most worlds of a settled batch have nothing to do (no touching change, nothing to destroy,
+// island graph still valid; no proxy moved).  The warp first looks at 32 worlds at once, one per lane, through the
+// per-world summary word the flat kernels wrote; only the worlds that need work are then handed to the teams.
+// Chunks of 32 worlds are handed out through an atomic counter (zeroed by the host before the launch), so the few
+// expensive worlds of a mostly settled batch spread over the whole grid instead of queueing behind one another.
+template <class Need, class Work>
+__device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, unsigned int* chunk_counter, Need need_of, Work work)
+{
+    const int lane = (int)(threadIdx.x & 31), teams = 32 / lanes, team = lane / lanes;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(chunk_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= c.n_worlds) break;
+        const int w = base + lane;
+        const bool need = (w < c.n_worlds) && need_of(w);
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        for (int ord = team; ord < __popc(m); ord += teams) work(base + (int)__fns(m, 0, ord + 1));
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                          scratch_layout L, unsigned char* scratch, step_params sp,
-                                                                         int lanes, size_t team_smem)
+                                                                         int lanes, size_t team_smem, unsigned int* chunk_counter)
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int team = ws.bind_team_lanes(lanes);
     const int teams_per_cta = 32 / lanes;
-    const int slot = blockIdx.x * teams_per_cta + team;
-    unsigned char* my_scratch = scratch + (size_t)slot * L.total_aux;
-    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
-        // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
-        // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
-        ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch_aux(my_scratch, L);
-        ws.bind_smem_aux(smem + (size_t)team * team_smem);
-        ws.run_plan(sp);
-        __syncwarp(ws.t_mask);
-    }
+    unsigned char* my_scratch = scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux;
+    for_each_needy_world(
+        c, lanes, chunk_counter,
+        [&](int w) {
+            const uint32_t fl = B.w_flags[w];
+            const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
+            const bool settled = (sp.flags & STEP_FLAT_COLLIDE) && !(fl & WORLD_NEW_FIXTURE) && !(sum & SUM_COLLIDE) &&
+                                 (!(sp.dt > 0.0) || (fl & WORLD_GRAPH_VALID));
+            if (settled && sp.dt > 0.0) B.w_island[4 * (size_t)w + 3] = 0;      // what run_plan leaves behind for such a world
+            return !settled;
+        },
+        [&](int w) {
+            // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
+            // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
+            ws.bind_rows(B, c, w, plan, P);
+            ws.bind_scratch_aux(my_scratch, L);
+            ws.bind_smem_aux(smem + (size_t)team * team_smem);
+            ws.run_plan(sp);
+            __syncwarp(ws.t_mask);
+        });
 }
 
 // Constraint records (K3 set-up, contact.py:376-496) for a GROUP of worlds [w0, w0 + n_group): one thread per
@@ -104,23 +136,45 @@ B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity)
 B2B_SOLVE_KERNEL(solve_position_kernel_, run_solve_position)
 #undef B2B_SOLVE_KERNEL
 
+// Proxy synchronisation (K4: body.py:898-904, fixture.py:287-298, dynamictree.py:152-188) and World.clear_forces as a
+// flat grid: one thread per (world, proxy-or-body index).  Worlds with a mover are flagged for the pair kernel.
+__global__ void __launch_bounds__(128) B2B_CAT(sync_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                         step_params sp)
+{
+    const int per_world = c.nf > c.nb ? c.nf : c.nb;
+    const long long total = (long long)c.n_worlds * per_world;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i / per_world), k = (int)(i % per_world);
+        world_step<real_t> ws;
+        ws.bind_rows(B, c, w, plan, P);
+        ws.sync_item(sp, k);
+    }
+}
+
 __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                                scratch_layout L, unsigned char* scratch, step_params sp,
-                                                                               int lanes, size_t team_smem)
+                                                                               int lanes, size_t team_smem, unsigned int* chunk_counter)
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int team = ws.bind_team_lanes(lanes);
     const int teams_per_cta = 32 / lanes;
-    const int slot = blockIdx.x * teams_per_cta + team;
-    unsigned char* my_scratch = scratch + (size_t)slot * L.total_aux;
-    for (int w = slot; w < c.n_worlds; w += gridDim.x * teams_per_cta) {
-        ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch_aux(my_scratch, L);
-        ws.bind_smem_aux(smem + (size_t)team * team_smem);
-        ws.run_broadphase(sp);
-        __syncwarp(ws.t_mask);
-    }
+    unsigned char* my_scratch = scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux;
+    for_each_needy_world(
+        c, lanes, chunk_counter,
+        [&](int w) {
+            // profiling counts world-steps in run_pairs; otherwise only worlds with a mover (or a stale pair count) need it
+            if (sp.flags & STEP_PROFILE) return true;
+            const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
+            return (sp.dt > 0.0) && ((sum & SUM_MOVED) || B.w_count[4 * (size_t)w + 3] != 0);
+        },
+        [&](int w) {
+            ws.bind_rows(B, c, w, plan, P);
+            ws.bind_scratch_aux(my_scratch, L);
+            ws.bind_smem_aux(smem + (size_t)team * team_smem);
+            ws.run_pairs(sp);
+            __syncwarp(ws.t_mask);
+        });
 }
 
 // Fixture._create_proxies + DynamicTree.create_proxy (fixture.py:250-261, dynamictree.py:115-134)
@@ -289,10 +343,11 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
 // one World.step = plan + solve + broadphase
 void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
                                        unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,
-                                       const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev)
+                                       unsigned int* counters, const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
     if (ev) cudaEventRecord(ev[0], st);
+    cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels
     if (sp.flags & STEP_FLAT_COLLIDE) {
         const long long total = (long long)c.n_worlds * c.nc;
         long long blocks = (total + 127) / 128;
@@ -301,7 +356,7 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     }
     if (ev) cudaEventRecord(ev[4], st);
     B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp, p.lanes_aux,
-                                                                                 p.team_smem_plan);
+                                                                                 p.team_smem_plan, counters);
     if (ev) cudaEventRecord(ev[1], st);
     if (sp.dt > 0.0) {
         // groups of worlds: the record slab is sized for one group (launch_plan::group_worlds)
@@ -322,8 +377,14 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
         }
     }
     if (ev) cudaEventRecord(ev[2], st);
+    {
+        const long long total = (long long)c.n_worlds * (c.nf > c.nb ? c.nf : c.nb);
+        long long blocks = (total + 127) / 128;
+        if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
+        B2B_CAT(sync_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan, sp);
+    }
     B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
-                                                                                         p.lanes_aux, p.team_smem_broad);
+                                                                                         p.lanes_aux, p.team_smem_broad, counters + 1);
     if (ev) cudaEventRecord(ev[3], st);
 }
 

@@ -29,7 +29,7 @@ struct launch_plan {
     int plan_##S(const caps_t& c, int lanes, int lanes_aux, int ctas_per_sm, int n_sm, launch_plan* out);                     \
     void launch_step_##S(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,                    \
                          unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,            \
-                         const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev);                                                                 \
+                         unsigned int* counters, const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev);                                                                 \
     void launch_init_proxies_##S(const void* const* fields, const caps_t& c, cudaStream_t st);                                \
     void launch_collide_pairs_##S(const void* const* fields, int n, const void* sa, const void* sb, const void* xfa,          \
                                   const void* xfb, void* mtype, void* mf, void* pts, void* id, cudaStream_t st);             \

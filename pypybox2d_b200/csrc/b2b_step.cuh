@@ -87,6 +87,8 @@ template <class real> struct batch_ptrs {
 enum { VREC_QUADS = 8, PREC_QUADS = 5 };   // velocity / position record of one constraint, in 4-vectors of reals
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4 };
+// per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
+enum { SUM_PENDING = 1u, SUM_DESTROY = 2u, SUM_CHANGED = 4u, SUM_COLLIDE = 7u, SUM_MOVED = 8u };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
        PROF_S_STAGE = 8, PROF_S_INTEGRATE, PROF_S_SCHEDULE, PROF_S_INIT, PROF_S_WARM, PROF_S_VELOCITY, PROF_S_STORE,
        PROF_S_POSITION, PROF_S_WRITEBACK, PROF_S_SLEEP, PROF_WORLD_STEPS = 31 };
@@ -96,7 +98,7 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 // kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
 // it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
 struct plan_layout {          // per world, in uint16_t elements
-    size_t off_cbody, off_sched, off_lv, off_adj, off_adj_start, off_cstate, stride;
+    size_t off_cbody, off_sched, off_lv, off_adj, off_adj_start, off_cstate, off_summary, stride;
 };
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Level-step table of the solve kernel: one 4-bit count per level-step, eight per word.  Island `isl`, whose
@@ -116,6 +118,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
     P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
     P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
     P.off_cstate = o; o = align_up(o + ((size_t)c.nc + 1) / 2 + 1, 8);      // one byte per contact
+    P.off_summary = o; o = align_up(o + 2, 8);                               // one uint32 (SUM_* bits)
     P.stride = o;
     return P;
 }
@@ -200,6 +203,7 @@ template <class real> struct world_step {
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
     uint32_t* g_lv;          // level-step table (see lv_words)
+    uint32_t* g_summary;     // SUM_* bits raised by the flat kernels, consumed (and cleared) by the per-world kernels
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan;
@@ -263,6 +267,7 @@ template <class real> struct world_step {
         g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
         g_cstate = reinterpret_cast<uint8_t*>(pw + P.off_cstate);
+        g_summary = reinterpret_cast<uint32_t*>(pw + P.off_summary);
     }
     B2B_D void bind_scratch_aux(unsigned char* scratch, const scratch_layout& L)
     {
@@ -378,6 +383,10 @@ template <class real> struct world_step {
             else state = contact_update(c) ? 3 : 1;
         }
         g_cstate[c] = state;
+        if (state != 1) {
+            const uint32_t bit = (state == 0) ? SUM_PENDING : (state == 2) ? SUM_DESTROY : SUM_CHANGED;
+            if (!(*g_summary & bit)) B2B_ATOMIC_OR(g_summary, bit);
+        }
     }
 
     // ContactManager.collide (contact_manager.py:174-223).  The reference walks the contact list in
@@ -389,6 +398,13 @@ template <class real> struct world_step {
     {
         const int nb = w_count[0], nc = w_count[2];
         const int NEVER = 0x7fffffff;
+        if (after_flat) {
+            // every contact came back "updated, touching unchanged" (the settled regime): nothing to order, wake or destroy
+            const uint32_t sum = *g_summary & SUM_COLLIDE;
+            B2B_SYNC();
+            if (sum == 0) return;
+            if (B2B_IS_T0) B2B_ATOMIC_AND(g_summary, ~(uint32_t)SUM_COLLIDE);
+        }
         if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[10] = 0; s_ctl[12] = 0; }
         B2B_SYNC();
         // 0: pending, 1: keep (processed), 2: destroy.  After the flat kernel most contacts are already processed.
@@ -1410,35 +1426,46 @@ template <class real> struct world_step {
     // ------------------------------------------------------------------------------------ K4
     // Body._synchronize_fixtures -> Fixture._synchronize -> BroadPhase.move_proxy -> DynamicTree.move_proxy
     // (body.py:898-904, fixture.py:287-298, broadphase.py:61-68, dynamictree.py:152-188)
-    B2B_D void phase_sync()
+    // one proxy; returns true when it went into the move buffer
+    B2B_D bool sync_fixture(int f)
     {
-        const int nf = w_count[1];
-        B2B_PFOR(f, nf) {
-            const int b = f_body[f];
-            const uint32_t fl = b_flags[b];
-            if (!(fl & BODY_ISLAND) || (fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
-            const real* p0 = b_pos0 + 4 * (size_t)b; const real* m = b_mass + 4 * (size_t)b;
-            const XF xf1 = xf_from_sweep<real>(mk<real>(p0[0], p0[1]), p0[2], mk<real>(m[2], m[3]));
-            const XF xf2 = xf_load<real>(b_xf + 4 * (size_t)b);
-            const shape_view<real> s = shape_of_fixture(f);
-            real a1[4], a2[4];
-            shape_aabb(s, xf1, a1);
-            shape_aabb(s, xf2, a2);
-            real* tight = f_tight + 4 * (size_t)f; real* fat = f_fat + 4 * (size_t)f;
-            const real tlx = pymin(a1[0], a2[0]), tly = pymin(a1[1], a2[1]);
-            const real tux = pymax(a1[2], a2[2]), tuy = pymax(a1[3], a2[3]);
-            tight[0] = tlx; tight[1] = tly; tight[2] = tux; tight[3] = tuy;
-            if (fat[0] <= tlx && fat[1] <= tly && tux <= fat[2] && tuy <= fat[3]) continue;   // AABB.contains
-            const real ext = K<real>::aabb_extension;
-            real lx = tlx - ext, ly = tly - ext, ux = tux + ext, uy = tuy + ext;
-            const V2 d = K<real>::aabb_multiplier * (xf2.p - xf1.p);
-            if (d.x < real(0)) lx = lx + d.x; else ux = ux + d.x;
-            if (d.y < real(0)) ly = ly + d.y; else uy = uy + d.y;
-            fat[0] = lx; fat[1] = ly; fat[2] = ux; fat[3] = uy;
-            f_moved[f] = 1;
-        }
-        B2B_SYNC();
+        const int b = f_body[f];
+        const uint32_t fl = b_flags[b];
+        if (!(fl & BODY_ISLAND) || (fl & BODY_TYPE_MASK) == BODY_STATIC) return false;
+        const quad p0 = ldq(b_pos0 + 4 * (size_t)b), m = ldq(b_mass + 4 * (size_t)b);
+        const XF xf1 = xf_from_sweep<real>(mk<real>(p0.x, p0.y), p0.z, mk<real>(m.z, m.w));
+        const XF xf2 = xf_load<real>(b_xf + 4 * (size_t)b);
+        const shape_view<real> s = shape_of_fixture(f);
+        real a1[4], a2[4];
+        shape_aabb(s, xf1, a1);
+        shape_aabb(s, xf2, a2);
+        real* tight = f_tight + 4 * (size_t)f; real* fat = f_fat + 4 * (size_t)f;
+        const real tlx = pymin(a1[0], a2[0]), tly = pymin(a1[1], a2[1]);
+        const real tux = pymax(a1[2], a2[2]), tuy = pymax(a1[3], a2[3]);
+        stq(tight, mkq(tlx, tly, tux, tuy));
+        const quad fq = ldq(fat);
+        if (fq.x <= tlx && fq.y <= tly && tux <= fq.z && tuy <= fq.w) return false;   // AABB.contains
+        const real ext = K<real>::aabb_extension;
+        real lx = tlx - ext, ly = tly - ext, ux = tux + ext, uy = tuy + ext;
+        const V2 d = K<real>::aabb_multiplier * (xf2.p - xf1.p);
+        if (d.x < real(0)) lx = lx + d.x; else ux = ux + d.x;
+        if (d.y < real(0)) ly = ly + d.y; else uy = uy + d.y;
+        stq(fat, mkq(lx, ly, ux, uy));
+        f_moved[f] = 1;
+        return true;
     }
+    // flat sync kernel: one call per (world, index); index < nf synchronises a proxy, index < nb clears a body's
+    // forces (World.clear_forces, world.py:356-369, when auto_clear_forces is set)
+    B2B_D void sync_item(const step_params& sp, int i)
+    {
+        if (sp.dt > 0.0 && i < w_count[1] && sync_fixture(i)) {
+            if (!(*g_summary & SUM_MOVED)) B2B_ATOMIC_OR(g_summary, (uint32_t)SUM_MOVED);
+        }
+        if (i < w_count[0] && (w_flags[0] & WORLD_AUTO_CLEAR)) {
+            b_force[2 * (size_t)i] = real(0); b_force[2 * (size_t)i + 1] = real(0); b_vel[4 * (size_t)i + 3] = real(0);
+        }
+    }
+    B2B_D int sync_items() const { return w_count[1] > w_count[0] ? w_count[1] : w_count[0]; }
 
     // ------------------------------------------------------------------------------------ K5 + K6
     // Pair (a, b) is emitted by mover a for every other proxy b whose fat AABB overlaps, except when b is
@@ -1601,23 +1628,24 @@ template <class real> struct world_step {
         solve_position_phase(sp, (real)sp.dt);
         B2B_PROF(PROF_SOLVE, t);
     }
-    // broadphase kernel: proxy synchronisation + find_new_contacts (world.py:582-592) + clear_forces (:351-352)
-    B2B_D void run_broadphase(const step_params& sp)
+    // broadphase kernel: find_new_contacts (world.py:582-592) for the worlds whose proxies moved (the flat sync
+    // kernel raised SUM_MOVED); a world without movers emits no pairs and creates no contacts
+    B2B_D void run_pairs(const step_params& sp)
     {
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
         if (sp.dt > 0.0) {
-            phase_sync();
-            B2B_PROF(PROF_SYNC, t);
-            phase_pairs(true);
+            const uint32_t moved = *g_summary & SUM_MOVED;
+            B2B_SYNC();
+            if (moved) {
+                if (B2B_IS_T0) B2B_ATOMIC_AND(g_summary, ~(uint32_t)SUM_MOVED);
+                phase_pairs(true);
+            } else if (B2B_IS_T0 && w_count[3] != 0) {
+                w_count[3] = 0;
+            }
             B2B_PROF(PROF_PAIRS, t);
         }
-        if (w_flags[0] & WORLD_AUTO_CLEAR) {
-            const int nb = w_count[0];
-            B2B_PFOR(b, nb) { b_force[2 * (size_t)b] = real(0); b_force[2 * (size_t)b + 1] = real(0); b_vel[4 * (size_t)b + 3] = real(0); }
-        }
         B2B_SYNC();
-        B2B_PROF(PROF_CLEAR, t);
         if (profiling && B2B_IS_T0) prof[PROF_WORLD_STEPS] += 1;
     }
     // the three kernels back to back (host check and single-world debugging)
@@ -1635,7 +1663,9 @@ template <class real> struct world_step {
             }
             run_solve_velocity(sp);
             run_solve_position(sp);
-            run_broadphase(sp);
+            const int n_items = sync_items();
+            for (int i = 0; i < n_items; ++i) sync_item(sp, i);
+            run_pairs(sp);
         }
     }
 };

@@ -29,3 +29,6 @@ if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [16384]
     for n in sizes:
         run(n, "f32", int(os.environ.get("SWEEP_LANES", "4")))
+    if os.environ.get("PROFILE_OCC"):
+        for ctas in (1, 5, 10):
+            run(148 * ctas * 8, "f32", 4, settle=300, ctas=ctas)
