@@ -110,6 +110,18 @@ __global__ void __launch_bounds__(128) B2B_CAT(prepare_kernel_, B2B_SUFFIX)(batc
         ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
         ws.prepare_slot(sp, first_step != 0, slot);
     }
+    // island.py:71-95 for every body of the group (runs after no other thread of this kernel needs b_vel changed:
+    // the integrated velocities go to the staging row, b_vel itself is rewritten by the velocity kernel)
+    const long long total_b = (long long)n_group * c.nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_b; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / c.nb), b = (int)(i % c.nb);
+        const int w = w0 + g;
+        if (b >= B.w_count[4 * (size_t)w]) continue;
+        world_step<real_t> ws;
+        ws.bind_rows(B, c, w, plan, P);
+        ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
+        ws.prepare_body(sp, b);
+    }
 }
 
 // Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): each is one warp per

@@ -125,7 +125,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
 
 struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `rec` slabs per world of a solve group
     size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
-    size_t off_cc_vel, off_cc_pos, off_cc_imp, total_rec;
+    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_state, total_rec;
     size_t total_sprof;       // per solve team: cycle counters
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
@@ -145,6 +145,7 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_pos = take((size_t)real_bytes * 4 * PREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
+    L.off_cc_state = take((size_t)real_bytes * 3 * (size_t)c.nb);      // the velocities the solver starts from, per body
     L.total_rec = align_up(o, 256);
     L.total_sprof = align_up(sizeof(long long) * PROF_SLOTS, 256);
     return L;
@@ -207,7 +208,7 @@ template <class real> struct world_step {
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan;
-    real *cc_vel, *cc_pos, *cc_imp;
+    real *cc_vel, *cc_pos, *cc_imp, *cc_state;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
@@ -284,6 +285,7 @@ template <class real> struct world_step {
         cc_vel = (real*)(rec + L.off_cc_vel);
         cc_pos = (real*)(rec + L.off_cc_pos);
         cc_imp = (real*)(rec + L.off_cc_imp);
+        cc_state = (real*)(rec + L.off_cc_state);
         prof = (long long*)team_prof;
     }
     B2B_D void bind_smem_aux(unsigned char* smem)
@@ -1142,16 +1144,25 @@ template <class real> struct world_step {
         return p.min_sep;
     }
 
-    // island.py:71-95 for one non-static body: save the sweep start, integrate gravity/forces, damp
-    B2B_D void integrate_velocity(int b, real dt, V2 gravity)
+    // island.py:71-95 for one body, in the flat prepare kernel: an island body that is not static saves its sweep
+    // start and integrates gravity / forces / damping; every body's starting velocity goes to the world's staging row
+    // (the velocity kernel copies it to shared memory).
+    B2B_D void prepare_body(const step_params& sp, int b)
     {
-        const real* p = b_pos + 4 * (size_t)b;
-        real* p0 = b_pos0 + 4 * (size_t)b;
-        p0[0] = p[0]; p0[1] = p[1]; p0[2] = p[2];
+        const uint32_t fl = b_flags[b];
         V2 v;
         real w;
-        integrated_velocity(b, dt, gravity, v, w);
-        state_set(b, v.x, v.y, w);
+        if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) {
+            const quad p = ldq(b_pos + 4 * (size_t)b);
+            real* p0 = b_pos0 + 4 * (size_t)b;
+            p0[0] = p.x; p0[1] = p.y; p0[2] = p.z;
+            integrated_velocity(b, (real)sp.dt, mk<real>(w_gravity[0], w_gravity[1]), v, w);
+        } else {
+            const quad bv = ldq(b_vel + 4 * (size_t)b);
+            v = mk<real>(bv.x, bv.y); w = bv.z;
+        }
+        real* o = cc_state + 3 * (size_t)b;
+        o[0] = v.x; o[1] = v.y; o[2] = w;
     }
     // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity and the
     // advanced sweep go to global memory (the position kernel stages the sweep again).
@@ -1269,6 +1280,7 @@ template <class real> struct world_step {
 
     // prepare kernel: the constraint records of every island slot of this world (one call per slot, any order)
     B2B_D int prepare_count() const { return w_island[2]; }
+    B2B_D int prepare_bodies() const { return w_count[0]; }
     B2B_D void prepare_slot(const step_params& sp, bool first_step, int slot)
     {
         constraint_init(slot, (real)sp.dt, (real)(first_step ? sp.dt_ratio_first : sp.dt_ratio_rest));
@@ -1290,50 +1302,24 @@ template <class real> struct world_step {
     B2B_D void solve_velocity_phase(const step_params& sp, real dt)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
-        const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
-        const V2 gravity = mk<real>(w_gravity[0], w_gravity[1]);
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
+        const int nb = w_count[0];
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
-        int max_used = 0;
-        // ---- contact-free islands: one lane per island, start to finish
-        B2B_PFOR(isl, n_islands) {
-            int b0, b1, c0, c1;
-            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
-            if (c1 != c0) continue;
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_velocity(b, dt, gravity); }
-            for (int i = b0; i < b1; ++i) { const int b = l_body[i]; if (!is_static_body(b)) integrate_position(b, dt); }
-            // an empty constraint list is "solved" by its first position iteration (contact.py:811,864)
-            if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
-            for (int i = b0; i < b1; ++i) {
-                const int b = l_body[i];
-                if (is_static_body(b)) continue;
-                const real* p = b_pos + 4 * (size_t)b;           // the advanced sweep: nothing to correct
-                synchronize_transform(b, p[0], p[1], p[2]);
-            }
-            if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
+        // every body's starting velocity (prepare_body), body order: coalesced and independent of the island lists
+        for (int b = t_id; b < nb; b += t_n) {
+            const real* v = cc_state + 3 * (size_t)b;
+            state_set(b, v[0], v[1], v[2]);
         }
-#if defined(__CUDA_ARCH__)
-        if (max_used > 0) atomicMax(&w_island[3], max_used);
-#else
-        if (max_used > w_island[3]) w_island[3] = max_used;
-#endif
-        B2B_PROF(PROF_S_INTEGRATE, t);
-        // ---- islands with contacts, one after the other
+        B2B_SYNC();
+        B2B_PROF(PROF_S_INIT, t);
+        // ---- islands with contacts, one after the other (contact-free islands have nothing to solve)
         for (int isl = 0; isl < n_islands; ++isl) {
             int b0, b1, c0, c1;
             island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            // statics are shared between islands: every island stages their (constant) velocity for itself
-            for (int i = b0 + t_id; i < b1; i += t_n) {
-                const int b = l_body[i];
-                if (!is_static_body(b)) integrate_velocity(b, dt, gravity);
-                else { const real* v = b_vel + 4 * (size_t)b; state_set(b, v[0], v[1], v[2]); }
-            }
-            B2B_SYNC();
-            B2B_PROF(PROF_S_INIT, t);
             auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
             auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
             if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int) { constraint_warm_start(e); }, vready);
@@ -1354,14 +1340,15 @@ template <class real> struct world_step {
                     if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
                 }
             }
-            for (int i = b0 + t_id; i < b1; i += t_n) {
-                const int b = l_body[i];
-                if (!is_static_body(b)) integrate_position(b, dt);
-            }
-            B2B_SYNC();
-            B2B_PROF(PROF_S_STORE, t);
         }
         B2B_SYNC();
+        // island.py:119-138 for every island body that is not static, body order
+        for (int b = t_id; b < nb; b += t_n) {
+            const uint32_t fl = b_flags[b];
+            if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt);
+        }
+        B2B_SYNC();
+        B2B_PROF(PROF_S_STORE, t);
     }
 
     B2B_D void solve_position_phase(const step_params& sp, real dt)
@@ -1369,21 +1356,22 @@ template <class real> struct world_step {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
+        const int nb = w_count[0];
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
         int max_used = 0;
+        // every body's sweep (advanced by the velocity kernel for island bodies), body order
+        for (int b = t_id; b < nb; b += t_n) {
+            const real* p = b_pos + 4 * (size_t)b;
+            state_set(b, p[0], p[1], p[2]);
+        }
+        B2B_SYNC();
+        B2B_PROF(PROF_S_STAGE, t);
         for (int isl = 0; isl < n_islands; ++isl) {
             int b0, b1, c0, c1;
             island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            for (int i = b0 + t_id; i < b1; i += t_n) {
-                const int b = l_body[i];
-                const real* p = b_pos + 4 * (size_t)b;
-                state_set(b, p[0], p[1], p[2]);
-            }
-            B2B_SYNC();
-            B2B_PROF(PROF_S_STAGE, t);
             // -- position iterations with early exit (island.py:141-153)
             bool position_solved = false;
             int used = 0;
@@ -1404,16 +1392,26 @@ template <class real> struct world_step {
             }
             if (used > max_used) max_used = used;
             B2B_PROF(PROF_S_POSITION, t);
-            for (int i = b0 + t_id; i < b1; i += t_n) {
-                const int b = l_body[i];
-                if (!is_static_body(b)) write_back(b);
-            }
-            B2B_SYNC();
-            B2B_PROF(PROF_S_WRITEBACK, t);
             if (allow_sleep) island_sleep_team(b0, b1, dt, position_solved);
             B2B_SYNC();
             B2B_PROF(PROF_S_SLEEP, t);
         }
+        // ---- contact-free islands: an empty constraint list is "solved" by its first position iteration
+        // (contact.py:811,864); one lane per island
+        B2B_PFOR(isl, n_islands) {
+            int b0, b1, c0, c1;
+            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
+            if (c1 != c0) continue;
+            if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
+            if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
+        }
+        B2B_SYNC();
+        // island.py:155-159 + Body._synchronize_transform for every island body that is not static, body order
+        for (int b = t_id; b < nb; b += t_n) {
+            const uint32_t fl = b_flags[b];
+            if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) write_back(b);
+        }
+        B2B_PROF(PROF_S_WRITEBACK, t);
         // max position iterations used by any island of this world (diagnostic, w_island[3])
 #if defined(__CUDA_ARCH__)
         if (max_used > 0) atomicMax(&w_island[3], max_used);
@@ -1660,6 +1658,8 @@ template <class real> struct world_step {
             if (sp.dt > 0.0) {
                 const int n_slots = prepare_count();
                 for (int s = 0; s < n_slots; ++s) prepare_slot(sp, step == 0, s);
+                const int n_bodies = prepare_bodies();
+                for (int b = 0; b < n_bodies; ++b) prepare_body(sp, b);
             }
             run_solve_velocity(sp);
             run_solve_position(sp);
