@@ -328,7 +328,9 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     out->lanes = lanes;
     out->lanes_aux = lanes_aux;
     out->n_sm = n_sm;
-    out->team_smem = S.total_solve;
+    // Teams of one warp look up the same body indices at the same time (settled worlds of one scene share their
+    // schedule): skew every team's state row by 128 / teams bytes so that equal indices fall into different banks.
+    out->team_smem = align_up(S.total_solve, 128) + (size_t)((128 / (32 / lanes)) < 16 ? 16 : (128 / (32 / lanes)));
     out->team_smem_plan = S.total_plan;
     out->team_smem_broad = S.total_broad;
     const int teams = 32 / lanes, teams_aux = 32 / lanes_aux;
@@ -337,10 +339,10 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     if (rc) return rc;
     // the two solve kernels share one launch geometry: the smaller of their occupancies
     kernel_plan k_pos;
-    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
+    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams,
                   ctas_per_sm, n_sm, &out->k_solve);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, S.total_solve * teams,
+    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams,
                   ctas_per_sm, n_sm, &k_pos);
     if (rc) return rc;
     if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;

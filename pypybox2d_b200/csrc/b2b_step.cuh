@@ -213,6 +213,7 @@ template <class real> struct world_step {
     int32_t* pair_keep;
     long long* prof;
     // shared memory
+    real* s_third;           // solve kernel: third component of every body's state (after the (x, y) pairs)
     real* s_state;           // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
     uint32_t* s_flags;       // plan kernel: body flags
     int32_t* s_ctl;          // [16] control words
@@ -303,6 +304,7 @@ template <class real> struct world_step {
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
         s_state = (real*)(team_smem + S.off_state);
+        s_third = s_state + 2 * (size_t)cap.nb;
     }
 
     B2B_D shape_view<real> shape_of_fixture(int f) const { return shape_load<real>(s_meta, s_radius, s_data, f_shape[f]); }
@@ -707,8 +709,19 @@ template <class real> struct world_step {
     B2B_D quad* vel_rec(int slot) { return reinterpret_cast<quad*>(cc_vel) + (size_t)VREC_QUADS * slot; }
     B2B_D quad* pos_rec(int slot) { return reinterpret_cast<quad*>(cc_pos) + (size_t)PREC_QUADS * slot; }
     B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
-    B2B_D quad state_get(int b) const { const real* s = s_state + 3 * b; return mkq(s[0], s[1], s[2], real(0)); }
-    B2B_D void state_set(int b, real x, real y, real z) { real* s = s_state + 3 * b; s[0] = x; s[1] = y; s[2] = z; }
+    // (x, y) pairs first, then the third component: one two-wide and one scalar shared-memory access per body
+    struct alignas(2 * sizeof(real)) pair2 { real x, y; };
+    B2B_D quad state_get(int b) const
+    {
+        const pair2 xy = reinterpret_cast<const pair2*>(s_state)[b];
+        return mkq(xy.x, xy.y, s_third[b], real(0));
+    }
+    B2B_D void state_set(int b, real x, real y, real z)
+    {
+        pair2 xy; xy.x = x; xy.y = y;
+        reinterpret_cast<pair2*>(s_state)[b] = xy;
+        s_third[b] = z;
+    }
     B2B_D bool is_static_body(int b) const { return (b_flags[b] & BODY_TYPE_MASK) == BODY_STATIC; }
 
     B2B_D static V2 rel_velocity(V2 vb, real wb, V2 rb, V2 va, real wa, V2 ra)
