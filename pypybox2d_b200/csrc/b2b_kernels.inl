@@ -3,6 +3,7 @@
 // compiled with -fmad=false so the parity build rounds like the reference's unfused Python floats).
 // B2B_SUFFIX names the exported launchers (launch_step_f32, ...).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "b2b_step.cuh"
 #include "b2b_launch.h"
 
@@ -26,7 +27,10 @@ typedef B2B_REAL real_t;
 // Flat narrowphase (K1): one thread per contact of the WHOLE batch -- the colliders are embarrassingly parallel and
 // this shape gives them full lanes and their own register budget.  Worlds that still have to create their first
 // contacts this step (new fixtures) are left to the plan kernel.
-__global__ void __launch_bounds__(128, 5) B2B_CAT(collide_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan)
+#ifndef B2B_COLLIDE_MIN_CTAS
+#define B2B_COLLIDE_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan)
 {
     const long long total = (long long)c.n_worlds * c.nc;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(128) B2B_CAT(prepare_kernel_, B2B_SUFFIX)(batc
             ws.bind_rows(B, c, w0 + g, plan, P);                                                                               \
             ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, team_prof + (size_t)slot * L.total_sprof);                 \
             ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                               \
+            ws.pf_sink = (uint32_t)__cvta_generic_to_shared(smem + (size_t)teams_per_cta * team_smem + 16 * (threadIdx.x & 31)); \
             ws.CALL(sp);                                                                                                       \
             __syncwarp(ws.t_mask);                                                                                             \
         }                                                                                                                      \
@@ -307,10 +312,13 @@ static int plan_one(Kern kern, long long n_items, int threads, size_t smem, int 
     out->smem = smem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    if (const char* env = getenv("B2B_SMEM_CARVEOUT")) {          // experiment: percent of the unified L1/shared array
+        if (ctas_per_sm > 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env));
+    }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
+    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;     // does not fit an SM (registers or shared memory)
     if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
     out->ctas_per_sm = per_sm;
     long long g = (long long)per_sm * n_sm;
@@ -339,10 +347,10 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     if (rc) return rc;
     // the two solve kernels share one launch geometry: the smaller of their occupancies
     kernel_plan k_pos;
-    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams,
+    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
                   ctas_per_sm, n_sm, &out->k_solve);
     if (rc) return rc;
-    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams,
+    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
                   ctas_per_sm, n_sm, &k_pos);
     if (rc) return rc;
     if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;

@@ -37,7 +37,12 @@
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2B_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define B2B_CLOCK() clock64()
+#if defined(B2B_PF_LDGSTS)
+// experiment: a real 16-byte asynchronous copy into a per-lane sink (with a 128-byte L2 fill) instead of a prefetch hint
+#define B2B_PREFETCH(p) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(pf_sink), "l"(p))
+#else
 #define B2B_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#endif
 #else
 #define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
 #define B2B_SYNC() ((void)0)
@@ -214,6 +219,7 @@ template <class real> struct world_step {
     long long* prof;
     // shared memory
     real* s_third;           // solve kernel: third component of every body's state (after the (x, y) pairs)
+    uint32_t pf_sink;        // (experiment B2B_PF_LDGSTS) shared-space address of this lane's 16-byte sink
     real* s_state;           // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
     uint32_t* s_flags;       // plan kernel: body flags
     int32_t* s_ctl;          // [16] control words
@@ -330,25 +336,49 @@ template <class real> struct world_step {
     B2B_D static quad ldq(const real* p) { return *reinterpret_cast<const quad*>(p); }
     B2B_D static void stq(real* p, quad q) { *reinterpret_cast<quad*>(p) = q; }
 
+    // Everything Contact.update reads, fetched in three rounds of independent loads (contact rows; fixture rows;
+    // body and shape rows) so that the flat kernel's threads wait for three memory round trips, not one per field.
+    struct contact_in {
+        quad qmf, qpts, qimp, qxa, qxb;
+        int mt, fa, fb, ba, bb;
+        uint32_t id0, id1, fl;
+        shape_view<real> sa, sb;
+    };
+    B2B_D void contact_load(int ci, contact_in& in)
+    {
+        in.fa = c_fix[2 * ci]; in.fb = c_fix[2 * ci + 1];
+        in.qmf = ldq(c_mf + 4 * (size_t)ci); in.qpts = ldq(c_pts + 4 * (size_t)ci); in.qimp = ldq(c_imp + 4 * (size_t)ci);
+        in.mt = c_mtype[ci];
+        in.id0 = c_id[2 * ci]; in.id1 = c_id[2 * ci + 1];
+        in.fl = c_flags[ci];
+        in.ba = f_body[in.fa]; in.bb = f_body[in.fb];
+        const int sha = f_shape[in.fa], shb = f_shape[in.fb];
+        in.qxa = ldq(b_xf + 4 * (size_t)in.ba); in.qxb = ldq(b_xf + 4 * (size_t)in.bb);
+        in.sa = shape_load<real>(s_meta, s_radius, s_data, sha);
+        in.sb = shape_load<real>(s_meta, s_radius, s_data, shb);
+    }
     B2B_D bool contact_update(int ci)
     {
+        contact_in in;
+        contact_load(ci, in);
+        return contact_update(ci, in);
+    }
+    B2B_D bool contact_update(int ci, const contact_in& in)
+    {
         manifold<real> m, old;
-        const quad qmf = ldq(c_mf + 4 * (size_t)ci), qpts = ldq(c_pts + 4 * (size_t)ci), qimp = ldq(c_imp + 4 * (size_t)ci);
+        const quad qimp = in.qimp;
         {
-            const int mt = c_mtype[ci];
-            m.type = mt & 0xff; m.count = (mt >> 8) & 0xff;
-            m.local_normal = mk<real>(qmf.x, qmf.y); m.local_point = mk<real>(qmf.z, qmf.w);
-            m.pt[0] = mk<real>(qpts.x, qpts.y); m.pt[1] = mk<real>(qpts.z, qpts.w);
-            m.id[0] = c_id[2 * ci]; m.id[1] = c_id[2 * ci + 1];
+            m.type = in.mt & 0xff; m.count = (in.mt >> 8) & 0xff;
+            m.local_normal = mk<real>(in.qmf.x, in.qmf.y); m.local_point = mk<real>(in.qmf.z, in.qmf.w);
+            m.pt[0] = mk<real>(in.qpts.x, in.qpts.y); m.pt[1] = mk<real>(in.qpts.z, in.qpts.w);
+            m.id[0] = in.id0; m.id[1] = in.id1;
         }
         old = m;
-        const uint32_t fl = c_flags[ci];
+        const uint32_t fl = in.fl;
         const bool was_touching = (fl & CONTACT_TOUCHING) != 0;
-        const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
-        const int ba = f_body[fa], bb = f_body[fb];
-        const quad qxa = ldq(b_xf + 4 * (size_t)ba), qxb = ldq(b_xf + 4 * (size_t)bb);
+        const quad qxa = in.qxa, qxb = in.qxb;
         const XF xa = xf_make<real>(mk<real>(qxa.x, qxa.y), qxa.z, qxa.w), xb = xf_make<real>(mk<real>(qxb.x, qxb.y), qxb.z, qxb.w);
-        const shape_view<real> sa = shape_of_fixture(fa), sb = shape_of_fixture(fb);
+        const shape_view<real> sa = in.sa, sb = in.sb;      // (copies: the out-of-line colliders take their address)
         collide_shapes(m, sa, xa, sb, xb);
         const bool touching = m.count > 0;
         // carry the impulses of matching ids; entries beyond the new point count keep their stale values
@@ -376,15 +406,18 @@ template <class real> struct world_step {
     // pending for the order-exact walk in phase_collide.
     B2B_D void collide_one(int c)
     {
-        const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
-        const int ba = f_body[fa], bb = f_body[fb];
-        const uint32_t fla = b_flags[ba], flb = b_flags[bb];
+        // all rows are fetched before the first decision (every index below w_count[2] is a live contact)
+        contact_in in;
+        contact_load(c, in);
+        const quad fat_a = ldq(f_fat + 4 * (size_t)in.fa), fat_b = ldq(f_fat + 4 * (size_t)in.fb);
+        const uint32_t fla = b_flags[in.ba], flb = b_flags[in.bb];
         const bool ns_a = (fla & BODY_TYPE_MASK) != BODY_STATIC, ns_b = (flb & BODY_TYPE_MASK) != BODY_STATIC;
         const bool all_awake = (!ns_a || (fla & BODY_AWAKE)) && (!ns_b || (flb & BODY_AWAKE));
         uint8_t state = 0;
         if (all_awake && (ns_a || ns_b)) {
-            if (!aabb_overlap<real>(f_fat + 4 * (size_t)fa, f_fat + 4 * (size_t)fb)) state = 2;
-            else state = contact_update(c) ? 3 : 1;
+            const real fa4[4] = {fat_a.x, fat_a.y, fat_a.z, fat_a.w}, fb4[4] = {fat_b.x, fat_b.y, fat_b.z, fat_b.w};
+            if (!aabb_overlap<real>(fa4, fb4)) state = 2;
+            else state = contact_update(c, in) ? 3 : 1;
         }
         g_cstate[c] = state;
         if (state != 1) {
@@ -751,7 +784,7 @@ template <class real> struct world_step {
         if (t < c1) {
             const char* r = reinterpret_cast<const char*>(pos_rec(t));
             B2B_PREFETCH(r);
-            B2B_PREFETCH(r + sizeof(quad) * PREC_QUADS - 1);
+            B2B_PREFETCH(r + sizeof(quad) * (PREC_QUADS - 1));     // the record's last quad: its second line, if it has one
         }
     }
 

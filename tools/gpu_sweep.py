@@ -6,10 +6,10 @@ import torch
 import pypybox2d_b200 as b2
 from pypybox2d_b200 import scenes, schema
 
-def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1):
+def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1, ctas=0):
     w = scenes.pyramid(b2)
     caps = schema.Caps(211, 211, 640, npair=1280)
-    bw = b2.BatchedWorld.replicate(w, n_worlds, jitter=1e-2, config=3, real=real, caps=caps, threads=lanes, lanes_aux=lanes_aux)
+    bw = b2.BatchedWorld.replicate(w, n_worlds, jitter=1e-2, config=3, real=real, caps=caps, threads=lanes, lanes_aux=lanes_aux, ctas_per_sm=ctas)
     bw.step(1/60, 8, 3, settle)
     torch.cuda.synchronize()
     for pf in range(repeats):
@@ -17,8 +17,8 @@ def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1):
         e0.record(); bw.step(1/60, 8, 3, steps, time_kernels=True); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         k = bw.kernel_ms()
-        print("%s worlds=%d lanes=%d aux=%d prefetch=%d: %.2f ms/step %.3e body-steps/s; kernels ms/step collide %.2f plan %.2f solve %.2f broad %.2f status=%d" % (
-            real, n_worlds, lanes, lanes_aux, pf, ms/steps, 210*n_worlds*steps/(ms*1e-3), k["collide"]/steps, k["plan"]/steps, k["solve"]/steps, k["broadphase"]/steps, bw.status(False)), flush=True)
+        print("%s worlds=%d lanes=%d aux=%d ctas=%d: %.2f ms/step %.3e body-steps/s; kernels ms/step collide %.2f plan %.2f solve %.2f broad %.2f status=%d" % (
+            real, n_worlds, lanes, lanes_aux, ctas, ms/steps, 210*n_worlds*steps/(ms*1e-3), k["collide"]/steps, k["plan"]/steps, k["solve"]/steps, k["broadphase"]/steps, bw.status(False)), flush=True)
 
 if __name__ == "__main__":
     import sys

@@ -10,7 +10,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         _lib.SO_PATH = os.path.join(_lib.CSRC, "variants", "libb2b_%s.so" % name)
     import gpu_sweep
     print("variant", name, end=": ", flush=True)
-    gpu_sweep.run(int(sys.argv[2]), "f32", int(os.environ.get("SWEEP_LANES", "4")), 8)
+    gpu_sweep.run(int(sys.argv[2]), "f32", int(os.environ.get("SWEEP_LANES", "4")), 8, ctas=int(os.environ.get("SWEEP_CTAS", "0")))
 else:
     for name in sys.argv[2:]:
         subprocess.run([sys.executable, os.path.abspath(__file__), "--one", sys.argv[1], name], cwd=os.path.join(ROOT, "tools"))
