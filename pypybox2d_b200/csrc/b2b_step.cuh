@@ -726,6 +726,7 @@ template <class real> struct world_step {
     // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
     // and later their position for itself (islands are solved one after the other).
     enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
+    enum { BODY_BATCH = 4 };
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D static real real_from_bits(uint32_t u)
     {
@@ -1212,10 +1213,10 @@ template <class real> struct world_step {
     }
     // island.py:119-138 for one non-static body: clamp the step, advance the sweep.  The final velocity and the
     // advanced sweep go to global memory (the position kernel stages the sweep again).
-    B2B_D void integrate_position(int b, real dt)
+    B2B_D void integrate_position(int b, real dt, quad pos)
     {
         const quad sv = state_get(b);
-        const real* p = b_pos + 4 * (size_t)b;
+        const real p[3] = {pos.x, pos.y, pos.z};
         V2 v = mk<real>(sv.x, sv.y);
         real w = sv.z;
         const V2 translation = dt * v;
@@ -1236,19 +1237,13 @@ template <class real> struct world_step {
     }
     // island.py:155-159 + Body._synchronize_transform (body.py:906-908) for one non-static body whose solved sweep
     // is in shared memory
-    B2B_D void write_back(int b)
+    B2B_D void write_back(int b, quad mass)
     {
         const quad sp = state_get(b);
         real* p = b_pos + 4 * (size_t)b;
         p[0] = sp.x; p[1] = sp.y; p[2] = sp.z;
-        synchronize_transform(b, sp.x, sp.y, sp.z);
-    }
-    B2B_D void synchronize_transform(int b, real cx, real cy, real a)
-    {
-        real* x = b_xf + 4 * (size_t)b;
-        const real* mass = b_mass + 4 * (size_t)b;
-        const XF tf = xf_from_sweep<real>(mk<real>(cx, cy), a, mk<real>(mass[2], mass[3]));
-        x[0] = tf.p.x; x[1] = tf.p.y; x[2] = tf.c1.x; x[3] = tf.c1.y;
+        const XF tf = xf_from_sweep<real>(mk<real>(sp.x, sp.y), sp.z, mk<real>(mass.z, mass.w));
+        stq(b_xf + 4 * (size_t)b, mkq(tf.p.x, tf.p.y, tf.c1.x, tf.c1.y));
     }
     // Sleep bookkeeping exactly as written in the reference (island.py:163-179): the allow-sleep
     // test reads the LAST island body; only the last non-static body is put to sleep.
@@ -1290,19 +1285,37 @@ template <class real> struct world_step {
         real min_sleep = K<real>::max_float;
         const bool last_allow = (b_flags[l_body[b1 - 1]] & BODY_ALLOW_SLEEP) != 0;
         int last_i = -1;
-        for (int i = b0 + t_id; i < b1; i += t_n) {
-            const int b = l_body[i];
-            if (is_static_body(b)) continue;
-            last_i = i;
-            const real* sv = b_vel + 4 * (size_t)b;
-            real* st = b_pos + 4 * (size_t)b + 3;
-            if (!last_allow || sv[2] * sv[2] > K<real>::angular_sleep_tol_sqr || sv[0] * sv[0] + sv[1] * sv[1] > K<real>::linear_sleep_tol_sqr) {
-                *st = real(0);
-                min_sleep = real(0);
-            } else {
-                const real ts = *st + dt;
-                *st = ts;
-                min_sleep = pymin(min_sleep, ts);
+        for (int i0 = b0 + t_id; i0 < b1; i0 += BODY_BATCH * t_n) {
+            int bb[BODY_BATCH];
+            uint32_t fl[BODY_BATCH];
+            quad sv[BODY_BATCH];
+            real ts0[BODY_BATCH];
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int i = i0 + k * t_n;
+                bb[k] = (i < b1) ? (int)l_body[i] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                if (bb[k] < 0) continue;
+                fl[k] = b_flags[bb[k]];
+                sv[k] = ldq(b_vel + 4 * (size_t)bb[k]);
+                ts0[k] = b_pos[4 * (size_t)bb[k] + 3];
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                if (bb[k] < 0 || (fl[k] & BODY_TYPE_MASK) == BODY_STATIC) continue;
+                last_i = i0 + k * t_n;
+                real* st = b_pos + 4 * (size_t)bb[k] + 3;
+                if (!last_allow || sv[k].z * sv[k].z > K<real>::angular_sleep_tol_sqr ||
+                    sv[k].x * sv[k].x + sv[k].y * sv[k].y > K<real>::linear_sleep_tol_sqr) {
+                    *st = real(0);
+                    min_sleep = real(0);
+                } else {
+                    const real ts = ts0[k] + dt;
+                    *st = ts;
+                    min_sleep = pymin(min_sleep, ts);
+                }
             }
         }
 #if defined(__CUDA_ARCH__)
@@ -1354,9 +1367,20 @@ template <class real> struct world_step {
         const int n_islands = w_island[0], n_lb = w_island[1], n_lc = w_island[2];
         (void)profiling;
         // every body's starting velocity (prepare_body), body order: coalesced and independent of the island lists
-        for (int b = t_id; b < nb; b += t_n) {
-            const real* v = cc_state + 3 * (size_t)b;
-            state_set(b, v[0], v[1], v[2]);
+        // (per-body loops of the solve kernels take BODY_BATCH bodies per lane and round and issue every load of a
+        // round before its first store: one memory round trip per round instead of one per body)
+        for (int b0 = t_id; b0 < nb; b0 += BODY_BATCH * t_n) {
+            real v[BODY_BATCH][3];
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb) { const real* src = cc_state + 3 * (size_t)b; v[k][0] = src[0]; v[k][1] = src[1]; v[k][2] = src[2]; }
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb) state_set(b, v[k][0], v[k][1], v[k][2]);
+            }
         }
         B2B_SYNC();
         B2B_PROF(PROF_S_INIT, t);
@@ -1389,9 +1413,20 @@ template <class real> struct world_step {
         }
         B2B_SYNC();
         // island.py:119-138 for every island body that is not static, body order
-        for (int b = t_id; b < nb; b += t_n) {
-            const uint32_t fl = b_flags[b];
-            if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt);
+        for (int b0 = t_id; b0 < nb; b0 += BODY_BATCH * t_n) {
+            uint32_t fl[BODY_BATCH];
+            quad p[BODY_BATCH];
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                fl[k] = 0u;
+                if (b < nb) { fl[k] = b_flags[b]; p[k] = ldq(b_pos + 4 * (size_t)b); }
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb && (fl[k] & BODY_ISLAND) && (fl[k] & BODY_TYPE_MASK) != BODY_STATIC) integrate_position(b, dt, p[k]);
+            }
         }
         B2B_SYNC();
         B2B_PROF(PROF_S_STORE, t);
@@ -1407,9 +1442,18 @@ template <class real> struct world_step {
         (void)profiling;
         int max_used = 0;
         // every body's sweep (advanced by the velocity kernel for island bodies), body order
-        for (int b = t_id; b < nb; b += t_n) {
-            const real* p = b_pos + 4 * (size_t)b;
-            state_set(b, p[0], p[1], p[2]);
+        for (int b0 = t_id; b0 < nb; b0 += BODY_BATCH * t_n) {
+            quad p[BODY_BATCH];
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb) p[k] = ldq(b_pos + 4 * (size_t)b);
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb) state_set(b, p[k].x, p[k].y, p[k].z);
+            }
         }
         B2B_SYNC();
         B2B_PROF(PROF_S_STAGE, t);
@@ -1453,9 +1497,20 @@ template <class real> struct world_step {
         }
         B2B_SYNC();
         // island.py:155-159 + Body._synchronize_transform for every island body that is not static, body order
-        for (int b = t_id; b < nb; b += t_n) {
-            const uint32_t fl = b_flags[b];
-            if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) write_back(b);
+        for (int b0 = t_id; b0 < nb; b0 += BODY_BATCH * t_n) {
+            uint32_t fl[BODY_BATCH];
+            quad mass[BODY_BATCH];
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                fl[k] = 0u;
+                if (b < nb) { fl[k] = b_flags[b]; mass[k] = ldq(b_mass + 4 * (size_t)b); }
+            }
+#pragma unroll
+            for (int k = 0; k < BODY_BATCH; ++k) {
+                const int b = b0 + k * t_n;
+                if (b < nb && (fl[k] & BODY_ISLAND) && (fl[k] & BODY_TYPE_MASK) != BODY_STATIC) write_back(b, mass[k]);
+            }
         }
         B2B_PROF(PROF_S_WRITEBACK, t);
         // max position iterations used by any island of this world (diagnostic, w_island[3])
