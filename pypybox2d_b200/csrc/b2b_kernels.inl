@@ -4,6 +4,7 @@
 // B2B_SUFFIX names the exported launchers (launch_step_f32, ...).
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <map>
 #include "b2b_step.cuh"
 #include "b2b_launch.h"
 
@@ -310,8 +311,15 @@ static int plan_one(Kern kern, long long n_items, int threads, size_t smem, int 
 {
     out->threads = threads;
     out->smem = smem;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    // the attribute belongs to the kernel, not to a context: never lower it below what an earlier context launches with
+    static std::map<const void*, size_t> smem_limit_set;          // keyed by kernel (several share one signature)
+    size_t& limit = smem_limit_set[reinterpret_cast<const void*>(kern)];
+    cudaError_t e = cudaSuccess;
+    if (smem > limit) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        limit = smem;
+    }
     if (const char* env = getenv("B2B_SMEM_CARVEOUT")) {          // experiment: percent of the unified L1/shared array
         if (ctas_per_sm > 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env));
     }

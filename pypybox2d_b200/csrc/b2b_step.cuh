@@ -726,7 +726,7 @@ template <class real> struct world_step {
     // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
     // and later their position for itself (islands are solved one after the other).
     enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
-    enum { BODY_BATCH = 4 };
+    enum { BODY_BATCH = 4 };     // (8 measured slower: register spills reach the level loop)
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D static real real_from_bits(uint32_t u)
     {

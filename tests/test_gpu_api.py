@@ -55,6 +55,21 @@ def test_batch_invariance_and_replicate():
     assert cs.shape == (300, 4) and np.all(cs[:, 2] > 300) and np.isfinite(cs[:, 1]).all()
 
 
+def test_contexts_with_different_shared_memory_sizes_coexist():
+    """The dynamic shared-memory limit is a property of the kernel, not of a context: a later, smaller context must
+    not lower it under an earlier context's launches (regression: `invalid argument` on the first context's step)."""
+    import pypybox2d_b200 as b2
+    w = scenes.pyramid(b2)
+    first = b2.BatchedWorld.replicate(w, 16, jitter=1e-2, config=3, real="f32", threads=4)     # 8 worlds per warp: 20 KB
+    second = b2.BatchedWorld.replicate(w, 16, jitter=1e-2, config=3, real="f32", threads=32)   # 1 world per warp: 3 KB
+    first.step(1 / 60, 8, 3, 5)
+    second.step(1 / 60, 8, 3, 5)
+    A, B = first.download(["b_pos", "b_vel"]), second.download(["b_pos", "b_vel"])
+    for name in A:
+        assert np.array_equal(A[name], B[name]), name
+    assert first.status() == 0 and second.status() == 0
+
+
 def test_step_host_matches_device_step_and_reports_overflow():
     import torch
     import pypybox2d_b200 as b2
