@@ -412,6 +412,10 @@ def run_b200_arm(args):
 
 
 def main():
+    # rank 0's stdout carries exactly one JSON line: keep NCCL's own chatter (version banner, INFO logs) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

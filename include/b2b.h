@@ -50,9 +50,9 @@ typedef struct b2b_caps {
     int32_t n_shapes;        /* rows of the shared shape table */
     int32_t real_bytes;      /* 4: fp32 kernels, 8: fp64 kernels (parity build, no FMA contraction) */
     int32_t device;          /* CUDA device ordinal */
-    int32_t threads;         /* threads per CTA (0: default) */
+    int32_t threads;         /* lanes of a warp that step one world in the solve kernels (0: default 4) */
     int32_t ctas_per_sm;     /* resident CTAs per SM the persistent grid is sized for (0: from occupancy) */
-    int32_t reserved;
+    int32_t reserved;        /* lanes per world in the plan and pair kernels (0: default 8) */
 } b2b_caps;
 
 /* Device pointers, one per schema field, same names and order as pypybox2d_b200/schema.py FIELDS.

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(ba
         [&](int w) {
             ws.bind_rows(B, c, w, plan, P);
             ws.bind_scratch_aux(my_scratch, L);
-            ws.bind_smem_aux(smem + (size_t)team * team_smem);
+            ws.bind_smem_aux(smem + (size_t)team * team_smem, true);
             ws.run_pairs(sp);
             __syncwarp(ws.t_mask);
         });

@@ -159,6 +159,7 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
 // shared memory.  plan kernel (per CTA): [ctl | flags | ls | cbody | adj | adj_start | stack/last | lev | cflag];
 // solve kernel (per team): [three reals per body]; broadphase kernel (per CTA): [ctl].
 struct smem_layout {
+    size_t off_fat, off_moved;                                // (pair finding; part of the broadphase prefix)
     size_t off_ctl, off_flags, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag, total_plan;
     size_t off_state, total_solve;                            // relative to the team's base
     size_t total_broad;
@@ -168,7 +169,11 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     smem_layout S;
     size_t o = 0;
     S.off_ctl = o; o = align_up(o + sizeof(int32_t) * 16, 32);
-    S.total_broad = o;
+    // pair finding stages every proxy's fat box and move flag: right after the control words in the broadphase kernel;
+    // in the plan kernel (first step only, before the contact graph exists) on top of the graph arrays from off_ls on
+    const size_t fat_bytes = align_up((size_t)real_bytes * 4 * (size_t)c.nf, 32), moved_bytes = align_up((size_t)c.nf, 32);
+    S.off_fat = o; S.off_moved = o + fat_bytes;
+    S.total_broad = o + fat_bytes + moved_bytes;
     S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 32);
     S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 32);
     S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 32);
@@ -178,6 +183,7 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 32);
     S.off_cflag = o; o = align_up(o + (size_t)c.nc, 32);
     S.total_plan = o;
+    if (S.total_plan < S.off_ls + fat_bytes + moved_bytes) S.total_plan = S.off_ls + fat_bytes + moved_bytes;
     o = 0;
     S.off_state = o; o = align_up(o + (size_t)real_bytes * 3 * (size_t)c.nb, 32);
     S.total_solve = o;
@@ -208,6 +214,7 @@ template <class real> struct world_step {
     const int32_t* s_meta; const real* s_radius; const real* s_data;
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
+    real* s_fat; uint8_t* s_moved;   // pair finding: fat boxes and move flags staged in shared memory
     uint32_t* g_lv;          // level-step table (see lv_words)
     uint32_t* g_summary;     // SUM_* bits raised by the flat kernels, consumed (and cleared) by the per-world kernels
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
@@ -295,10 +302,12 @@ template <class real> struct world_step {
         cc_state = (real*)(rec + L.off_cc_state);
         prof = (long long*)team_prof;
     }
-    B2B_D void bind_smem_aux(unsigned char* smem)
+    B2B_D void bind_smem_aux(unsigned char* smem, bool broadphase_kernel = false)
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
         s_ctl = (int32_t*)(smem + S.off_ctl);
+        const size_t fat_at = broadphase_kernel ? S.off_fat : S.off_ls;
+        s_fat = (real*)(smem + fat_at); s_moved = (uint8_t*)(smem + fat_at + (S.off_moved - S.off_fat));
         s_flags = (uint32_t*)(smem + S.off_flags);
         s_ls = (uint16_t*)(smem + S.off_ls);
         s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
@@ -321,6 +330,37 @@ template <class real> struct world_step {
     B2B_D void exclusive_scan(int32_t* a, int n, int slot)
     {
         B2B_SYNC();
+#if defined(__CUDA_ARCH__)
+        if (!t_cta) {
+            // lane teams: every lane sums a contiguous chunk (four loads in flight), the chunk totals are scanned with
+            // shuffles, then every lane rewrites its chunk
+            const int chunk = (n + t_n - 1) / t_n, lo = t_id * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+            int sum = 0;
+            for (int i = lo; i < hi; i += 4) {
+                int v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (i + k < hi) ? a[i + k] : 0;
+                sum += (v[0] + v[1]) + (v[2] + v[3]);
+            }
+            int incl = sum;
+            for (int d = 1; d < t_n; d <<= 1) {
+                const int up = __shfl_up_sync(t_mask, incl, d, t_n);
+                if (t_id >= d) incl += up;
+            }
+            int run = incl - sum;
+            const int total = __shfl_sync(t_mask, incl, t_n - 1, t_n);
+            for (int i = lo; i < hi; i += 4) {
+                int v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (i + k < hi) ? a[i + k] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (i + k < hi) { a[i + k] = run; run += v[k]; }
+            }
+            if (t_id == 0) s_ctl[slot] = total;
+            B2B_SYNC();
+            return;
+        }
+#endif
         if (B2B_IS_T0) {
             int run = 0;
             for (int i = 0; i < n; ++i) { int v = a[i]; a[i] = run; run += v; }
@@ -539,14 +579,27 @@ template <class real> struct world_step {
         const int nb = w_count[0], nc = w_count[2];
         B2B_PFOR(b, nb + 1) scan[b] = 0;
         B2B_SYNC();
-        B2B_PFOR(c, nc) {
-            const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
-            s_cbody[2 * c] = (uint16_t)ba; s_cbody[2 * c + 1] = (uint16_t)bb;
-            g_cbody[2 * c] = (uint16_t)ba; g_cbody[2 * c + 1] = (uint16_t)bb;
-            const uint32_t cf = c_flags[c];
-            s_cflag[c] = (uint8_t)(((cf & CONTACT_ENABLED) && (cf & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
-            if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[ba], 1);
-            if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[bb], 1);
+        for (int c0 = t_id; c0 < nc; c0 += 4 * t_n) {
+            int fa[4], fb[4], ba[4], bb[4];
+            uint32_t cf[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k * t_n;
+                fa[k] = fb[k] = 0; cf[k] = 0u;
+                if (c < nc) { fa[k] = c_fix[2 * c]; fb[k] = c_fix[2 * c + 1]; cf[k] = c_flags[c]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ba[k] = f_body[fa[k]]; bb[k] = f_body[fb[k]]; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k * t_n;
+                if (c >= nc) continue;
+                s_cbody[2 * c] = (uint16_t)ba[k]; s_cbody[2 * c + 1] = (uint16_t)bb[k];
+                g_cbody[2 * c] = (uint16_t)ba[k]; g_cbody[2 * c + 1] = (uint16_t)bb[k];
+                s_cflag[c] = (uint8_t)(((cf[k] & CONTACT_ENABLED) && (cf[k] & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
+                if ((s_flags[ba[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[ba[k]], 1);
+                if ((s_flags[bb[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[bb[k]], 1);
+            }
         }
         exclusive_scan(scan, nb + 1, 3);
         B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)scan[b]; g_adj_start[b] = (uint16_t)scan[b]; }
@@ -587,7 +640,8 @@ template <class real> struct world_step {
                 if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
                 if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
                 const int body_start = lb, contact_start = lc;
-                int sp = 0;
+                int sp = 0, n_static = 0;
+                int statics[4];                                        // statics that joined this island
                 s_stack[sp++] = (uint16_t)seed;
                 s_flags[seed] = fl | BODY_ISLAND;
                 while (sp > 0) {
@@ -598,15 +652,18 @@ template <class real> struct world_step {
                     // Body.awake = True (body.py:800-804): a sleeping body that is reached restarts its sleep timer
                     uint32_t bf = s_flags[b];
                     if (!(bf & BODY_AWAKE)) { bf |= BODY_AWAKE | BODY_WOKEN; s_flags[b] = bf; }
-                    if ((bf & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                    const int first = lc;
+                    if ((bf & BODY_TYPE_MASK) == BODY_STATIC) {
+                        if (n_static < 4) statics[n_static] = b;
+                        ++n_static;
+                        continue;
+                    }
+                    // the reference appends all of b's free contacts first and then walks the appended ones
+                    // (world.py:531-546); a contact is in b's list once and the second pass only touches flags the
+                    // first never reads, so one pass gives the same lists without reading l_contact back from memory
                     for (int k = s_adj_start[b]; k < s_adj_start[b + 1]; ++k) {
                         const int c = s_adj[k];
                         if (s_cflag[c] != 1) continue;                 // already in an island, disabled or not touching
                         l_contact[lc++] = c;
-                    }
-                    for (int k = first; k < lc; ++k) {
-                        const int c = l_contact[k];
                         s_cflag[c] = 3;                                // island flag
                         const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
                         const int other = (b == ba) ? bb : ba;
@@ -617,10 +674,15 @@ template <class real> struct world_step {
                 }
                 if (overflow) break;
                 l_start[2 * n_islands] = body_start; l_start[2 * n_islands + 1] = contact_start;
-                // statics may join other islands (world.py:577-580)
-                for (int k = body_start; k < lb; ++k) {
-                    const int b = l_body[k];
-                    if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) s_flags[b] &= ~BODY_ISLAND;
+                // statics may join other islands (world.py:577-580); the few that joined were noted on the way (the
+                // island's body list is in global memory: reading it back would cost a round trip per island)
+                if (n_static <= 4) {
+                    for (int k = 0; k < n_static; ++k) s_flags[statics[k]] &= ~BODY_ISLAND;
+                } else {
+                    for (int k = body_start; k < lb; ++k) {
+                        const int b = l_body[k];
+                        if ((s_flags[b] & BODY_TYPE_MASK) == BODY_STATIC) s_flags[b] &= ~BODY_ISLAND;
+                    }
                 }
                 ++n_islands;
             }
@@ -636,9 +698,16 @@ template <class real> struct world_step {
             b_flags[b] = f;
             s_last[b] = 0;                                 // the DFS stack's storage becomes the scheduler's `last level`
         }
-        B2B_PFOR(c, nc) {
-            const uint32_t cf = c_flags[c];
-            c_flags[c] = (s_cflag[c] == 3) ? (cf | CONTACT_ISLAND) : (cf & ~CONTACT_ISLAND);
+        // (four contacts per lane and round, loads first: one memory round trip per round, not per contact)
+        for (int c0 = t_id; c0 < nc; c0 += 4 * t_n) {
+            uint32_t cf[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int c = c0 + k * t_n; if (c < nc) cf[k] = c_flags[c]; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k * t_n;
+                if (c < nc) c_flags[c] = (s_cflag[c] == 3) ? (cf[k] | CONTACT_ISLAND) : (cf[k] & ~CONTACT_ISLAND);
+            }
         }
         B2B_SYNC();
     }
@@ -1570,11 +1639,11 @@ template <class real> struct world_step {
     // Pair (a, b) is emitted by mover a for every other proxy b whose fat AABB overlaps, except when b is
     // itself an earlier mover (then (b, a) is already in the pair buffer): broadphase.py:83-109 with the
     // emission order pinned to (a, b) ascending (SURVEY §0 finding 1).
-    B2B_D bool pair_candidate(int a, int b) const
+    B2B_D bool pair_candidate(int a, const real* fat_a, int b) const
     {
         if (b == a) return false;
-        if (!aabb_overlap<real>(f_fat + 4 * (size_t)b, f_fat + 4 * (size_t)a)) return false;
-        if (b < a && f_moved[b]) return false;
+        if (!aabb_overlap<real>(s_fat + 4 * (size_t)b, fat_a)) return false;
+        if (b < a && s_moved[b]) return false;
         return true;
     }
 
@@ -1616,21 +1685,32 @@ template <class real> struct world_step {
     B2B_D void phase_pairs(bool have_adjacency)
     {
         const int nf = w_count[1];
+        // the movers x proxies tests read every fat box nf times: stage boxes and move flags in shared memory
+        B2B_PFOR(f, nf) {
+            const quad q = ldq(f_fat + 4 * (size_t)f);
+            real* d = s_fat + 4 * (size_t)f;
+            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            s_moved[f] = (uint8_t)(f_moved[f] != 0);
+        }
+        B2B_SYNC();
         // pass 1: per-mover candidate counts
         B2B_PFOR(a, nf) {
             int n = 0;
-            if (f_moved[a])
-                for (int b = 0; b < nf; ++b) n += pair_candidate(a, b) ? 1 : 0;
+            if (s_moved[a]) {
+                const real fat_a[4] = {s_fat[4 * a], s_fat[4 * a + 1], s_fat[4 * a + 2], s_fat[4 * a + 3]};
+                for (int b = 0; b < nf; ++b) n += pair_candidate(a, fat_a, b) ? 1 : 0;
+            }
             scan[a] = n;
         }
         exclusive_scan(scan, nf, 8);
         const int npairs = s_ctl[8];
         // pass 2: emit in (a, b) order
         B2B_PFOR(a, nf) {
-            if (!f_moved[a]) continue;
+            if (!s_moved[a]) continue;
+            const real fat_a[4] = {s_fat[4 * a], s_fat[4 * a + 1], s_fat[4 * a + 2], s_fat[4 * a + 3]};
             int o = scan[a];
             for (int b = 0; b < nf; ++b) {
-                if (!pair_candidate(a, b)) continue;
+                if (!pair_candidate(a, fat_a, b)) continue;
                 if (o < cap.npair) { p_pairs[2 * o] = a; p_pairs[2 * o + 1] = b; }
                 ++o;
             }

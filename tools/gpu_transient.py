@@ -8,8 +8,8 @@ from pypybox2d_b200 import scenes, schema
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 w = scenes.pyramid(b2)
 caps = schema.Caps(211, 211, 640, npair=1280)
-for prof in (False, True):
-    bw = b2.BatchedWorld.replicate(w, n, jitter=1e-2, config=3, real="f32", caps=caps)
+for prof in ((False,) if os.environ.get("NO_PROF") else (False, True)):
+    bw = b2.BatchedWorld.replicate(w, n, jitter=1e-2, config=3, real="f32", caps=caps, lanes_aux=int(os.environ.get("LANES_AUX", "0")))
     bw.step(1/60, 8, 3, 10)
     torch.cuda.synchronize()
     for lo in (10, 35, 60, 110):
