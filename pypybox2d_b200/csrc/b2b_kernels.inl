@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
 template <class Need, class Work>
 __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, unsigned int* chunk_counter, Need need_of, Work work)
 {
-    const int lane = (int)(threadIdx.x & 31), teams = 32 / lanes, team = lane / lanes;
+    const int lane = (int)(threadIdx.x & 31);
     for (;;) {
         int base = 0;
         if (lane == 0) base = (int)atomicAdd(chunk_counter, 32u);
@@ -64,7 +64,12 @@ __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes,
         const int w = base + lane;
         const bool need = (w < c.n_worlds) && need_of(w);
         const unsigned m = __ballot_sync(0xffffffffu, need);
-        for (int ord = team; ord < __popc(m); ord += teams) work(base + (int)__fns(m, 0, ord + 1));
+        // few needy worlds in this chunk (the settled regime): widen the teams so that each world gets more lanes
+        const int n = __popc(m);
+        int width = lanes;
+        while (width < 32 && 32 / (2 * width) >= n) width *= 2;
+        const int teams_now = 32 / width, team_now = lane / width;
+        for (int ord = team_now; ord < n; ord += teams_now) work(base + (int)__fns(m, 0, ord + 1), width);
         __syncwarp();
     }
 }
@@ -75,9 +80,7 @@ __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_pt
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
-    const int team = ws.bind_team_lanes(lanes);
-    const int teams_per_cta = 32 / lanes;
-    unsigned char* my_scratch = scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux;
+    const int teams_per_cta = 32 / lanes;                 // scratch slabs and shared-memory regions of this CTA
     for_each_needy_world(
         c, lanes, chunk_counter,
         [&](int w) {
@@ -88,11 +91,12 @@ __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_pt
             if (settled && sp.dt > 0.0) B.w_island[4 * (size_t)w + 3] = 0;      // what run_plan leaves behind for such a world
             return !settled;
         },
-        [&](int w) {
+        [&](int w, int width) {
             // every thread derives the world's row pointers from the kernel parameters, so the compiler knows their
             // address space (LDG/STG/LDS instead of generic LD/ST) and rematerialises them from the constant bank
+            const int team = ws.bind_team_lanes(width);   // < teams_per_cta: wider teams use the first slabs / regions
             ws.bind_rows(B, c, w, plan, P);
-            ws.bind_scratch_aux(my_scratch, L);
+            ws.bind_scratch_aux(scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux, L);
             ws.bind_smem_aux(smem + (size_t)team * team_smem);
             ws.run_plan(sp);
             __syncwarp(ws.t_mask);
@@ -175,9 +179,7 @@ __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(ba
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
-    const int team = ws.bind_team_lanes(lanes);
     const int teams_per_cta = 32 / lanes;
-    unsigned char* my_scratch = scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux;
     for_each_needy_world(
         c, lanes, chunk_counter,
         [&](int w) {
@@ -186,9 +188,10 @@ __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(ba
             const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
             return (sp.dt > 0.0) && ((sum & SUM_MOVED) || B.w_count[4 * (size_t)w + 3] != 0);
         },
-        [&](int w) {
+        [&](int w, int width) {
+            const int team = ws.bind_team_lanes(width);
             ws.bind_rows(B, c, w, plan, P);
-            ws.bind_scratch_aux(my_scratch, L);
+            ws.bind_scratch_aux(scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux, L);
             ws.bind_smem_aux(smem + (size_t)team * team_smem, true);
             ws.run_pairs(sp);
             __syncwarp(ws.t_mask);
