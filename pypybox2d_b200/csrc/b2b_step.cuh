@@ -225,6 +225,15 @@ template <class real> struct world_step {
     int32_t* pair_keep;
     long long* prof;
     // shared memory
+#if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
+    // development trace (tools/trace_probe.py): cycles of lane 0 per segment of a level-step, summed over the run
+    unsigned tr[7], tlast;
+#define B2B_TSTAMP(i, dep) do { asm volatile("" :: "r"(dep) : "memory"); const unsigned now_ = (unsigned)clock(); tr[i] += now_ - tlast; tlast = now_; } while (0)
+#define B2B_TSTAMP_F(i, a, b, c, d) do { asm volatile("" :: "f"(a), "f"(b), "f"(c), "f"(d) : "memory"); const unsigned now_ = (unsigned)clock(); tr[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define B2B_TSTAMP(i, dep) ((void)0)
+#define B2B_TSTAMP_F(i, a, b, c, d) ((void)0)
+#endif
     real* s_third;           // solve kernel: third component of every body's state (after the (x, y) pairs)
     uint32_t pf_sink;        // (experiment B2B_PF_LDGSTS) shared-space address of this lane's 16-byte sink
     real* s_state;           // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
@@ -901,23 +910,33 @@ template <class real> struct world_step {
             {
                 // (an idle lane's record is whatever its registers held: `& zero` makes that harmless)
                 const int nbegin = begin + cnt + (int)(ready(ra) & zero);
+                B2B_TSTAMP(0, nbegin);
                 const int ncnt = rd.take();
                 const bool more = (nbegin < c1) & (ncnt != 0);      // a zero count never occurs in a valid table
                 const bool nact = more & (t_id < ncnt);
                 if (nact) load(nbegin + t_id, rb);
+                B2B_TSTAMP(1, ncnt);
                 if (act) solve(ra, begin + t_id);
+                B2B_TSTAMP(4, 0);
                 __syncwarp(t_mask);
+                B2B_TSTAMP(5, 0);
+                B2B_TSTAMP(6, 0);
                 if (!more) break;
                 act = nact; begin = nbegin; cnt = ncnt;
             }
             {
                 const int nbegin = begin + cnt + (int)(ready(rb) & zero);
+                B2B_TSTAMP(0, nbegin);
                 const int ncnt = rd.take();
                 const bool more = (nbegin < c1) & (ncnt != 0);
                 const bool nact = more & (t_id < ncnt);
                 if (nact) load(nbegin + t_id, ra);
+                B2B_TSTAMP(1, ncnt);
                 if (act) solve(rb, begin + t_id);
+                B2B_TSTAMP(4, 0);
                 __syncwarp(t_mask);
+                B2B_TSTAMP(5, 0);
+                B2B_TSTAMP(6, 0);
                 if (!more) break;
                 act = nact; begin = nbegin; cnt = ncnt;
             }
@@ -1121,6 +1140,7 @@ template <class real> struct world_step {
         const quad sa = state_get(ba), sb = state_get(bb);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
+        B2B_TSTAMP_F(2, (float)sa.x, (float)sa.z, (float)sb.x, (float)sb.z);
         const V2 ra0 = mk<real>(q1.x, q1.y), rb0 = mk<real>(q1.z, q1.w), ra1 = mk<real>(q3.x, q3.y), rb1 = mk<real>(q3.z, q3.w);
         // friction rows first, point by point
         {
@@ -1190,6 +1210,7 @@ template <class real> struct world_step {
                 qi.x = x.x; qi.z = x.y;
             }
         }
+        B2B_TSTAMP_F(3, (float)va.x, (float)wa, (float)vb.x, (float)wb);
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
         if (!last) {
@@ -1796,7 +1817,14 @@ template <class real> struct world_step {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
+#if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
+        for (int i = 0; i < 7; ++i) tr[i] = 0u;
+        tlast = (unsigned)clock();
+#endif
         solve_velocity_phase(sp, (real)sp.dt);
+#if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
+        if (t_id == 0) for (int i = 0; i < 7; ++i) prof[20 + i] += (long long)tr[i];
+#endif
         B2B_PROF(PROF_SOLVE, t);
     }
     B2B_D void run_solve_position(const step_params& sp)
