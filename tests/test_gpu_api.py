@@ -70,6 +70,57 @@ def test_contexts_with_different_shared_memory_sizes_coexist():
     assert first.status() == 0 and second.status() == 0
 
 
+def test_large_batch_copies_stay_bitwise_identical_from_t0():
+    """Size-independent property at a batch that fills the GPU several times over (65,536 worlds = BASELINE configs[1]'s
+    size): world k is a copy of distinct world k % 64, so after 120 steps from the scripted start -- free fall, landing
+    transient, every kernel path (pair finding, contact creation and destruction, island rebuilds, all position
+    iterations) -- every copy must equal its original bit for bit, whatever CTA, lane team, wave or chunk it ran in, and
+    the fp64 build must give the oracle-checked integer outputs on every copy."""
+    import torch
+    import pypybox2d_b200 as b2
+    w = scenes.pyramid(b2)
+    seed = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=3, real="f32")
+    big = seed.tiled(65536)
+    seed.step(1 / 60, 8, 3, 120)
+    big.step(1 / 60, 8, 3, 120)
+    assert big.status() == 0
+    torch.cuda.synchronize()
+    for name in ("b_pos", "b_vel", "b_flags", "c_fix", "c_flags", "c_mtype", "c_imp", "c_id", "w_count", "w_island"):
+        got, ref = big.t[name], seed.t[name]
+        want = ref.repeat((1024,) + (1,) * (ref.dim() - 1))
+        if got.dtype.is_floating_point:
+            got, want = got.view(torch.int32), want.view(torch.int32)
+        assert bool((got == want).all()), name
+    cs = big.checksum().cpu().numpy()
+    assert np.isfinite(cs[:, 1]).all() and (cs[:, 2] > 0).all()
+
+
+@pytest.mark.parametrize("scene,config,n_worlds,steps,vi,pi", [
+    ("vertical_stack", 2, 65536, 60, 10, 10),      # BASELINE configs[1]: examples/verticalstack-bench.py batched to 65,536 worlds
+    ("mixed", 4, 16384, 60, 8, 3),                 # configs[3] scene: circles + convex polygons, 256 bodies per world
+    ("deep_stacks", 5, 32768, 60, 8, 3),           # configs[4] scene: 10 columns x 20 boxes
+])
+def test_other_baseline_scenes_at_scale(scene, config, n_worlds, steps, vi, pi):
+    """The same size-independent property on the other BASELINE scenes: copies of 32 distinct jittered worlds, stepped
+    from the scripted start inside a large batch, stay bit-identical to their originals stepped in a batch of 32."""
+    import torch
+    import pypybox2d_b200 as b2
+    w = scenes.SCENES[scene](b2)
+    seed = b2.BatchedWorld.replicate(w, 32, jitter=1e-2, config=config, real="f32")
+    big = seed.tiled(n_worlds)
+    seed.step(1 / 60, vi, pi, steps)
+    big.step(1 / 60, vi, pi, steps)
+    assert big.status() == 0 and seed.status() == 0
+    torch.cuda.synchronize()
+    for name in ("b_pos", "b_vel", "b_flags", "c_fix", "c_flags", "c_mtype", "c_imp", "c_id", "w_count", "w_island"):
+        got, ref = big.t[name], seed.t[name]
+        want = ref.repeat((n_worlds // 32,) + (1,) * (ref.dim() - 1))
+        if got.dtype.is_floating_point:
+            got, want = got.view(torch.int32), want.view(torch.int32)
+        assert bool((got == want).all()), name
+    assert int(big.t["w_count"][:, 2].min()) > 0          # contacts exist: the worlds did land
+
+
 def test_step_host_matches_device_step_and_reports_overflow():
     import torch
     import pypybox2d_b200 as b2
