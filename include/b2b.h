@@ -52,7 +52,7 @@ typedef struct b2b_caps {
     int32_t device;          /* CUDA device ordinal */
     int32_t threads;         /* lanes of a warp that step one world in the solve kernels (0: default 4) */
     int32_t ctas_per_sm;     /* resident CTAs per SM the persistent grid is sized for (0: from occupancy) */
-    int32_t reserved;        /* lanes per world in the plan and pair kernels (0: default 8) */
+    int32_t reserved;        /* lanes per world in the plan and pair kernels (0: default, 8 or 32 by contact capacity) */
 } b2b_caps;
 
 /* Device pointers, one per schema field, same names and order as pypybox2d_b200/schema.py FIELDS.

@@ -105,7 +105,10 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     // caps->threads: lanes of a warp per world in the solve kernel (4, 8, 16 or 32); caps->reserved: the same for
     // the plan / broadphase kernels
     const int lanes = caps->threads > 0 ? caps->threads : 4;
-    const int lanes_aux = caps->reserved > 0 ? caps->reserved : 8;       // measured best in the landing transient (plan 2.3-3.2 ms vs 4.1-5.5 with 32)
+    // default team size of the plan / pair kernels, from measurements on B200 (plan kernel, 16,384 worlds): landing
+    // pyramids (contact capacity 640) 2.3 ms with 8 lanes, 5.4 with 32; vertical stacks (708) 10.0 / 6.3; mixed scene
+    // (1,092) 21.4 / 10.5: worlds with many contacts spend their replans in contact-parallel loops
+    const int lanes_aux = caps->reserved > 0 ? caps->reserved : (caps->nc >= 700 ? 32 : 8);
     int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
                     : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
     if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }

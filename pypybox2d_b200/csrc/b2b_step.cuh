@@ -180,7 +180,10 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     S.off_adj = o; o = align_up(o + sizeof(uint16_t) * (2 * (size_t)c.nc + 2), 32);
     S.off_adj_start = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
     S.off_stack = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nb + 2), 32);
-    S.off_lev = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 2), 32);
+    {   // level of every island slot (phase_schedule); before that the adjacency builder's per-body counters (int32)
+        const size_t lev_bytes = sizeof(uint16_t) * ((size_t)c.nc + 2), cnt_bytes = sizeof(int32_t) * ((size_t)c.nb + 2);
+        S.off_lev = o; o = align_up(o + (lev_bytes > cnt_bytes ? lev_bytes : cnt_bytes), 32);
+    }
     S.off_cflag = o; o = align_up(o + (size_t)c.nc, 32);
     S.total_plan = o;
     if (S.total_plan < S.off_ls + fat_bytes + moved_bytes) S.total_plan = S.off_ls + fat_bytes + moved_bytes;
@@ -586,7 +589,9 @@ template <class real> struct world_step {
     B2B_D void build_adjacency()
     {
         const int nb = w_count[0], nc = w_count[2];
-        B2B_PFOR(b, nb + 1) scan[b] = 0;
+        int32_t* cnt = reinterpret_cast<int32_t*>(s_lev);        // per-body counters / row cursors: shared-memory atomics
+
+        B2B_PFOR(b, nb + 1) cnt[b] = 0;
         B2B_SYNC();
         for (int c0 = t_id; c0 < nc; c0 += 4 * t_n) {
             int fa[4], fb[4], ba[4], bb[4];
@@ -606,17 +611,17 @@ template <class real> struct world_step {
                 s_cbody[2 * c] = (uint16_t)ba[k]; s_cbody[2 * c + 1] = (uint16_t)bb[k];
                 g_cbody[2 * c] = (uint16_t)ba[k]; g_cbody[2 * c + 1] = (uint16_t)bb[k];
                 s_cflag[c] = (uint8_t)(((cf[k] & CONTACT_ENABLED) && (cf[k] & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
-                if ((s_flags[ba[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[ba[k]], 1);
-                if ((s_flags[bb[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&scan[bb[k]], 1);
+                if ((s_flags[ba[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&cnt[ba[k]], 1);
+                if ((s_flags[bb[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&cnt[bb[k]], 1);
             }
         }
-        exclusive_scan(scan, nb + 1, 3);
-        B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)scan[b]; g_adj_start[b] = (uint16_t)scan[b]; }
+        exclusive_scan(cnt, nb + 1, 3);
+        B2B_PFOR(b, nb + 1) { s_adj_start[b] = (uint16_t)cnt[b]; g_adj_start[b] = (uint16_t)cnt[b]; }
         B2B_SYNC();
         B2B_PFOR(c, nc) {
             const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
-            if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&scan[ba], 1)] = (uint16_t)c;
-            if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&scan[bb], 1)] = (uint16_t)c;
+            if ((s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&cnt[ba], 1)] = (uint16_t)c;
+            if ((s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC) s_adj[B2B_ATOMIC_ADD(&cnt[bb], 1)] = (uint16_t)c;
         }
         B2B_SYNC();
         // restore creation order inside each row (rows are short: <= contacts per body)
