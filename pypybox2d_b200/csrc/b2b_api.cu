@@ -24,7 +24,7 @@ struct b2b_ctx {
     unsigned char* scratch_solve;  // constraint records: one slab per world of a solve group
     unsigned char* scratch_sprof;  // solve kernel: cycle counters, one row per team
     uint16_t* plan_rows;
-    uint32_t* d_status;            // [0] status OR, [1..2] chunk counters of the plan / pair kernels
+    uint32_t* d_status;            // [0] status OR, [1..2] chunk counters of the plan / pair kernels, [3] joint-schedule word
     void* stage_in;       // [n_worlds][nb][3] reals
     void* stage_out;      // [n_worlds][nb][6] reals
     const void* fields[B2B_NFIELDS];
@@ -199,6 +199,7 @@ static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = flags;
     sp.solve_lanes = solve_lanes;
     sp.zero = 0;
+    sp.joint_any = nullptr;                                        // bound by launch_step
     return sp;
 }
 

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
         ws.bind_rows(B, c, w, plan, P);
         ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
         ws.prepare_slot(sp, first_step != 0, slot);
+        if (slot == 0 && sp.joint_any != nullptr && ws.g_joint[0] != 0 && *sp.joint_any == 0u) atomicExch(sp.joint_any, 1u);
     }
     // island.py:71-95 for every body of the group (runs after no other thread of this kernel needs b_vel changed:
     // the integrated velocities go to the staging row, b_vel itself is rewritten by the velocity kernel)
@@ -149,12 +150,13 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
 
 // Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): each is one warp per
 // CTA, the warp split into teams of `lanes` lanes, one world per team, worlds of the group strided over the teams.
-#define B2B_SOLVE_KERNEL(NAME, CALL)                                                                                           \
+#define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN)                                                                                          \
     __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(NAME, B2B_SUFFIX)(                                       \
         batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* rec,                   \
         unsigned char* team_prof, step_params sp, int lanes, size_t team_smem, int w0, int n_group)                            \
     {                                                                                                                          \
         extern __shared__ __align__(32) unsigned char smem[];                                                                  \
+        if (NOT_MY_TURN) return;                                                                                               \
         world_step<real_t> ws;                                                                                                 \
         const int team = ws.bind_team_lanes(lanes);                                                                            \
         const int teams_per_cta = 32 / lanes;                                                                                  \
@@ -168,8 +170,10 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
             __syncwarp(ws.t_mask);                                                                                             \
         }                                                                                                                      \
     }
-B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity)
-B2B_SOLVE_KERNEL(solve_position_kernel_, run_solve_position)
+B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity, false)
+// sp.joint_any: raised by this group's prepare kernel (or an earlier group's) when some world has a joint island schedule
+B2B_SOLVE_KERNEL(solve_position_kernel_, template run_solve_position<false>, *sp.joint_any != 0u)
+B2B_SOLVE_KERNEL(solve_position_joint_kernel_, template run_solve_position<true>, *sp.joint_any == 0u)
 #undef B2B_SOLVE_KERNEL
 
 // Proxy synchronisation (K4: body.py:898-904, fixture.py:287-298, dynamictree.py:152-188) and World.clear_forces as a
@@ -379,6 +383,10 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
                   ctas_per_sm, n_sm, &k_pos);
     if (rc) return rc;
     if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+    rc = plan_one(B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
+                  ctas_per_sm, n_sm, &k_pos);
+    if (rc) return rc;
+    if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
     rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                   S.total_broad * teams_aux, 0, n_sm, &out->k_broad);
     if (rc) return rc;
@@ -390,11 +398,13 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
 // one World.step = plan + solve + broadphase
 void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
                                        unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,
-                                       unsigned int* counters, const step_params& sp, int first_step, cudaStream_t st, cudaEvent_t* ev)
+                                       unsigned int* counters, const step_params& sp_in, int first_step, cudaStream_t st, cudaEvent_t* ev)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
     if (ev) cudaEventRecord(ev[0], st);
-    cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels
+    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
+    step_params sp = sp_in;
+    sp.joint_any = counters + 2;
     if (sp.flags & STEP_FLAT_COLLIDE) {
         const long long total = (long long)c.n_worlds * c.nc;
         long long blocks = (total + 127) / 128;
@@ -423,6 +433,8 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
                                                                                            scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
             B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
                                                                                            scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+            B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                                 scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
         }
     }
     if (ev) cudaEventRecord(ev[2], st);

@@ -19,6 +19,8 @@
 // The parallel-loop macros have a sequential expansion when compiled without CUDA so that
 // tests/hostcheck can run this exact source under g++ for debugging; that build is test-only.
 #pragma once
+#include <cstring>
+#include <type_traits>
 #include "b2b_collide.cuh"
 
 // A world is stepped by a TEAM of threads: the whole CTA in the plan and broadphase kernels, a group of
@@ -36,6 +38,8 @@
 #define B2B_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2B_ATOMIC_AND(p, v) atomicAnd((p), (v))
+#define B2B_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define B2B_FENCE() __threadfence()
 #define B2B_CLOCK() clock64()
 #if defined(B2B_PF_LDGSTS)
 // experiment: a real 16-byte asynchronous copy into a per-lane sink (with a 128-byte L2 fill) instead of a prefetch hint
@@ -54,11 +58,14 @@ template <class T> inline T host_atomic_min(T* p, T v) { T o = *p; if (v < o) *p
 template <class T> inline T host_atomic_add(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T host_atomic_or(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T host_atomic_and(T* p, T v) { T o = *p; *p = o & v; return o; }
+template <class T> inline T host_atomic_max(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 }
 #define B2B_ATOMIC_MIN(p, v) b2b::host_atomic_min((p), (v))
 #define B2B_ATOMIC_ADD(p, v) b2b::host_atomic_add((p), (v))
 #define B2B_ATOMIC_OR(p, v) b2b::host_atomic_or((p), (v))
 #define B2B_ATOMIC_AND(p, v) b2b::host_atomic_and((p), (v))
+#define B2B_ATOMIC_MAX(p, v) b2b::host_atomic_max((p), (v))
+#define B2B_FENCE() ((void)0)
 #endif
 
 // cycle accounting by thread 0 (wall-clock cycles of the CTA, since phases end in CTA barriers)
@@ -103,7 +110,7 @@ enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, 
 // kernel and read by the solve / broadphase kernels;  (3) context-owned per-CTA scratch (persistent grids reuse
 // it for every world they own, so it stays L1/L2 resident);  (4) shared memory, one layout per kernel.
 struct plan_layout {          // per world, in uint16_t elements
-    size_t off_cbody, off_sched, off_lv, off_adj, off_adj_start, off_cstate, off_summary, stride;
+    size_t off_cbody, off_sched, off_slot_isl, off_joint, off_lv, off_adj, off_adj_start, off_cstate, off_summary, stride;
 };
 B2B_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Level-step table of the solve kernel: one 4-bit count per level-step, eight per word.  Island `isl`, whose
@@ -119,6 +126,8 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
     size_t o = 0;
     P.off_cbody = o; o = align_up(o + 2 * (size_t)c.nc, 8);
     P.off_sched = o; o = align_up(o + (size_t)c.nc + 2, 8);
+    P.off_slot_isl = o; o = align_up(o + (size_t)c.nc + 2, 8);               // joint schedule: contact island of every slot
+    P.off_joint = o; o = align_up(o + 4, 8);                                 // [0] joint schedule in use, [1] contact islands
     P.off_lv = o; o = align_up(o + 2 * (size_t)lv_words(c), 8);             // uint32 words, counted in uint16 units
     P.off_adj = o; o = align_up(o + 2 * (size_t)c.nc + 2, 8);
     P.off_adj_start = o; o = align_up(o + (size_t)c.nb + 2, 8);
@@ -199,6 +208,8 @@ struct step_params {
     uint32_t flags;
     int solve_lanes;             // lanes per world of the solve kernel: the level-step table is cut to this width
     uint32_t zero;               // always 0: a value the compiler cannot fold (orders the record loads, see level_sweep)
+    unsigned int* joint_any;     // device word, cleared every step: raised by the prepare kernel when some world of the batch
+                                 // has a joint island schedule (the position kernel then runs its group-capable instantiation)
 };
 
 // ================================================================================================
@@ -216,7 +227,7 @@ template <class real> struct world_step {
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     const int32_t* s_meta; const real* s_radius; const real* s_data;
     // this world's rows of the plan arrays (global)
-    uint16_t *g_cbody, *g_sched, *g_adj, *g_adj_start;
+    uint16_t *g_cbody, *g_sched, *g_slot_isl, *g_joint, *g_adj, *g_adj_start;
     real* s_fat; uint8_t* s_moved;   // pair finding: fat boxes and move flags staged in shared memory
     uint32_t* g_lv;          // level-step table (see lv_words)
     uint32_t* g_summary;     // SUM_* bits raised by the flat kernels, consumed (and cleared) by the per-world kernels
@@ -291,7 +302,7 @@ template <class real> struct world_step {
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
         uint16_t* pw = plan + W * P.stride;
-        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);
+        g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_slot_isl = pw + P.off_slot_isl; g_joint = pw + P.off_joint; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
         g_cstate = reinterpret_cast<uint8_t*>(pw + P.off_cstate);
         g_summary = reinterpret_cast<uint32_t*>(pw + P.off_summary);
@@ -737,9 +748,10 @@ template <class real> struct world_step {
         const int n_islands = s_ctl[4], n_lb = s_ctl[5], n_lc = s_ctl[6];
         (void)n_lb;
         const int chunk = (solve_lanes < (int)LV_MAX_LANES) ? (solve_lanes < 1 ? 1 : solve_lanes) : (int)LV_MAX_LANES;
-        B2B_PFOR(isl, n_islands) {
-            const int c0 = l_start[2 * isl + 1];
-            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+        // One island's slots [c0, c1) -- or, for the joint schedule, the slots of ALL islands taken as one list: islands
+        // share no non-static body, so the level of a contact is the same either way and level l of the joint list is
+        // the union of every island's level l.
+        auto schedule_range = [&](int c0, int c1, int isl) {
             const int ncon = c1 - c0;
             uint16_t* ls = s_ls + c0 + 3 * isl;           // level l (1-based) occupies slots [c0 + ls[l], c0 + ls[l+1])
             int nlev = 0;
@@ -784,7 +796,49 @@ template <class real> struct world_step {
                 *lv++ = word;                             // the partial word, or a zero word: the reader runs one word ahead
                 if (nib != 0) *lv = 0;
             }
+        };
+        // Joint schedule (B2B_JOINT_ISLANDS): worlds with several islands that have contacts (stacks side by side) are
+        // solved level-step by level-step across ALL their islands at once instead of island after island; velocity
+        // sweeps are the same operations in the same per-body order, position sweeps skip the slots of islands that are
+        // already solved (island.py:141-153 stops iterating per island).  Up to 32 such islands (one mask word).
+        int n_ci = 0, largest = 0;
+        for (int isl = 0; isl < n_islands; ++isl) {
+            const int c0 = l_start[2 * isl + 1];
+            const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+            n_ci += (c1 > c0) ? 1 : 0;
+            largest = (c1 - c0 > largest) ? c1 - c0 : largest;
         }
+#if defined(B2B_JOINT_ISLANDS) && !B2B_JOINT_ISLANDS
+        const bool joint = false;
+#else
+        // Worth it only when no island dominates: the joint list is at least as long as the largest island's, and one world
+        // with a joint schedule moves the whole batch to the group-capable position kernel (measured 20 % slower per sweep
+        // for the worlds that stay one island per group), so a stray second island next to a big one does not qualify.
+        const bool joint = (n_ci >= 2) && (n_ci <= 32) && (3 * (size_t)cap.nb >= 32) && (4 * largest <= 3 * n_lc);
+#endif
+        if (joint) {
+            if (B2B_IS_T0) schedule_range(0, n_lc, 0);
+            B2B_SYNC();
+            // contact island (ordinal among the islands with contacts) of every list position, then of every slot
+            if (B2B_IS_T0) {
+                int ord = 0;
+                for (int isl = 0; isl < n_islands; ++isl) {
+                    const int c0 = l_start[2 * isl + 1];
+                    const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+                    for (int k = c0; k < c1; ++k) s_lev[k] = (uint16_t)ord;
+                    ord += (c1 > c0) ? 1 : 0;
+                }
+            }
+            B2B_SYNC();
+            B2B_PFOR(slot, n_lc) g_slot_isl[slot] = s_lev[g_sched[slot]];
+        } else {
+            B2B_PFOR(isl, n_islands) {
+                const int c0 = l_start[2 * isl + 1];
+                const int c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
+                schedule_range(c0, c1, isl);
+            }
+        }
+        if (B2B_IS_T0) { g_joint[0] = (uint16_t)(joint ? 1 : 0); g_joint[1] = (uint16_t)n_ci; }
         B2B_SYNC();
     }
 
@@ -808,7 +862,7 @@ template <class real> struct world_step {
     // Shared memory holds three reals per body: its velocity while velocities are being solved, its sweep position
     // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
     // and later their position for itself (islands are solved one after the other).
-    enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25 };
+    enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25, INFO_ISLAND_SHIFT = 26 };   // bits 26-30 (position records): island ordinal of a joint schedule
     enum { BODY_BATCH = 4 };     // (8 measured slower: register spills reach the level loop)
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D static real real_from_bits(uint32_t u)
@@ -1084,7 +1138,7 @@ template <class real> struct world_step {
         p[0] = mkq(ma, ia, mb, ib);
         p[1] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
         p[2] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
-        p[3] = mkq(rad_a, rad_b, bodies_r, info_r);
+        p[3] = mkq(rad_a, rad_b, bodies_r, (g_joint[0] != 0) ? real_from_bits(info | ((uint32_t)g_slot_isl[slot] << INFO_ISLAND_SHIFT)) : info_r);
         p[4] = mkq(lca.x, lca.y, lcb.x, lcb.y);
         *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
     }
@@ -1480,9 +1534,11 @@ template <class real> struct world_step {
         B2B_SYNC();
         B2B_PROF(PROF_S_INIT, t);
         // ---- islands with contacts, one after the other (contact-free islands have nothing to solve)
-        for (int isl = 0; isl < n_islands; ++isl) {
+        const bool joint = g_joint[0] != 0;                // all islands' slots as one schedule (phase_schedule)
+        for (int isl = 0; isl < (joint ? 1 : n_islands); ++isl) {
             int b0, b1, c0, c1;
             island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
+            if (joint) { c0 = 0; c1 = n_lc; }
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
             auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
@@ -1527,7 +1583,9 @@ template <class real> struct world_step {
         B2B_PROF(PROF_S_STORE, t);
     }
 
-    B2B_D void solve_position_phase(const step_params& sp, real dt)
+    // JOINT_CAPABLE = false: no world of the batch has a joint schedule (the common case: one island per world, or none
+    // balanced enough), the island-ordinal and atomic paths compile away.
+    template <bool JOINT_CAPABLE> B2B_D void solve_position_phase(const step_params& sp, real dt)
     {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -1552,34 +1610,114 @@ template <class real> struct world_step {
         }
         B2B_SYNC();
         B2B_PROF(PROF_S_STAGE, t);
-        for (int isl = 0; isl < n_islands; ++isl) {
-            int b0, b1, c0, c1;
-            island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
-            if (c1 == c0) continue;
-            const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            // -- position iterations with early exit (island.py:141-153)
-            bool position_solved = false;
-            int used = 0;
-            for (int it = 0; it < sp.pos_iters; ++it) {
-                real my_min = real(0);
-                ++used;
-                level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
-                                  [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); },
-                                  [&](const prec& e) { return bits_of_real(e.q10.z); });
-                real all_min = my_min;
+        // Islands with contacts are solved in GROUPS: one island per group, or (joint schedule, phase_schedule) one
+        // group holding the slots of all islands level-step by level-step.  An island stops iterating once the smallest
+        // separation of a sweep is above -3 slop (island.py:141-153); in a joint group its slots are skipped from then
+        // on (the slot's island ordinal rides in the record's info word).  A one-island group keeps the sweep's worst
+        // separation in a register; a joint group collects max(-separation) per island with integer atomics
+        // (separations are <= 0 here: the solver starts every sweep from 0, and positive reals order like their bits)
+        // in the world's record slab (the staging row of the starting velocities is free by now).  Both kinds run
+        // the same loop, so the worlds of a warp do not diverge when only some of them have a joint schedule.
+        if constexpr (!JOINT_CAPABLE) {
+            // one island after the other; the sweep's smallest separation stays in a register (this loop's code shape is
+            // the measured one: the group loop below, instantiated for one island per group, ran 20 % slower)
+            for (int isl = 0; isl < n_islands; ++isl) {
+                int b0, b1, c0, c1;
+                island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
+                if (c1 == c0) continue;
+                const uint32_t* lv = g_lv + lv_offset(c0, isl);
+                // -- position iterations with early exit (island.py:141-153)
+                bool position_solved = false;
+                int used = 0;
+                for (int it = 0; it < sp.pos_iters; ++it) {
+                    real my_min = real(0);
+                    ++used;
+                    level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
+                                      [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); },
+                                      [&](const prec& e) { return bits_of_real(e.q10.z); });
+                    real all_min = my_min;
 #if defined(__CUDA_ARCH__)
-                for (int o = t_n >> 1; o > 0; o >>= 1) {
-                    const real other = __shfl_xor_sync(t_mask, all_min, o);
-                    all_min = (other < all_min) ? other : all_min;
-                }
+                    for (int o = t_n >> 1; o > 0; o >>= 1) {
+                        const real other = __shfl_xor_sync(t_mask, all_min, o);
+                        all_min = (other < all_min) ? other : all_min;
+                    }
 #endif
-                if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
+                    if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
+                }
+                if (used > max_used) max_used = used;
+                B2B_PROF(PROF_S_POSITION, t);
+                if (allow_sleep) island_sleep_team(b0, b1, dt, position_solved);
+                B2B_SYNC();
+                B2B_PROF(PROF_S_SLEEP, t);
             }
-            if (used > max_used) max_used = used;
-            B2B_PROF(PROF_S_POSITION, t);
-            if (allow_sleep) island_sleep_team(b0, b1, dt, position_solved);
-            B2B_SYNC();
-            B2B_PROF(PROF_S_SLEEP, t);
+        } else {
+            const bool joint = g_joint[0] != 0;
+            const int n_groups = joint ? 1 : n_islands;
+            const int n_gi = joint ? (int)g_joint[1] : 1;      // islands with contacts in a group
+            const uint32_t all = (n_gi >= 32) ? 0xffffffffu : ((1u << n_gi) - 1u);
+            typedef typename std::conditional<sizeof(real) == 8, unsigned long long, uint32_t>::type sep_bits;   // real's own width: exact
+            sep_bits* worst = reinterpret_cast<sep_bits*>(cc_state);
+            const real solved_above = real(-3) * K<real>::linear_slop;
+            for (int g = 0; g < n_groups; ++g) {
+                int b0, b1, c0, c1;
+                island_range(g, n_islands, n_lb, n_lc, b0, b1, c0, c1);
+                if (joint) { c0 = 0; c1 = n_lc; }
+                if (c1 == c0) continue;
+                const uint32_t* lv = g_lv + lv_offset(c0, g);
+                uint32_t solved_mask = 0u;                     // islands of the group whose position iterations are over
+                int used = 0;
+                for (int it = 0; it < sp.pos_iters && solved_mask != all; ++it) {
+                    ++used;
+                    if (joint) {
+                        for (int i = t_id; i < n_gi; i += t_n) worst[i] = (sep_bits)0;
+                        B2B_FENCE();
+                        B2B_SYNC();
+                    }
+                    const uint32_t skip = solved_mask;
+                    real my_neg = real(0);
+                    level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
+                                      [&](const prec& e, int) {
+                                          const int ci = (int)((bits_of_real(e.q10.w) >> INFO_ISLAND_SHIFT) & 31u);   // 0 unless joint
+                                          if ((skip >> ci) & 1u) return;
+                                          const real neg = -constraint_solve_position(e);
+                                          if (!joint) { my_neg = (neg > my_neg) ? neg : my_neg; }
+                                          else if (neg > real(0)) { sep_bits u; memcpy(&u, &neg, sizeof(u)); B2B_ATOMIC_MAX(&worst[ci], u); }
+                                      },
+                                      [&](const prec& e) { return bits_of_real(e.q10.z); });
+                    uint32_t unsolved = 0u;
+                    if (joint) {
+                        B2B_FENCE();
+                        B2B_SYNC();
+                        for (int i = t_id; i < n_gi; i += t_n) {
+                            const sep_bits u = worst[i];
+                            real neg; memcpy(&neg, &u, sizeof(neg));
+                            if (!(-neg >= solved_above)) unsolved |= 1u << i;
+                        }
+                    } else if (!(-my_neg >= solved_above)) {
+                        unsolved = 1u;
+                    }
+#if defined(__CUDA_ARCH__)
+                    for (int o = t_n >> 1; o > 0; o >>= 1) unsolved |= __shfl_xor_sync(t_mask, unsolved, o);
+#endif
+                    solved_mask |= ~unsolved & all;
+                    if (joint) B2B_SYNC();
+                }
+                if (used > max_used) max_used = used;
+                B2B_PROF(PROF_S_POSITION, t);
+                // the group's islands: sleep bookkeeping (island.py:163-179)
+                if (allow_sleep) {
+                    for (int isl = joint ? 0 : g, ci = 0; isl < (joint ? n_islands : g + 1); ++isl) {
+                        int ib0, ib1, ic0, ic1;
+                        island_range(isl, n_islands, n_lb, n_lc, ib0, ib1, ic0, ic1);
+                        if (ic1 == ic0) continue;
+                        island_sleep_team(ib0, ib1, dt, ((solved_mask >> ci) & 1u) != 0);
+                        ++ci;
+                        B2B_SYNC();
+                    }
+                }
+                B2B_SYNC();
+                B2B_PROF(PROF_S_SLEEP, t);
+            }
         }
         // ---- contact-free islands: an empty constraint list is "solved" by its first position iteration
         // (contact.py:811,864); one lane per island
@@ -1832,12 +1970,14 @@ template <class real> struct world_step {
 #endif
         B2B_PROF(PROF_SOLVE, t);
     }
-    B2B_D void run_solve_position(const step_params& sp)
+    // The position kernel exists twice: JOINT_CAPABLE = false for batches in which no world has a joint schedule, true
+    // otherwise; both are launched and the one whose turn it is not returns at once (b2b_kernels.inl).
+    template <bool JOINT_CAPABLE> B2B_D void run_solve_position(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
-        solve_position_phase(sp, (real)sp.dt);
+        solve_position_phase<JOINT_CAPABLE>(sp, (real)sp.dt);
         B2B_PROF(PROF_SOLVE, t);
     }
     // broadphase kernel: find_new_contacts (world.py:582-592) for the worlds whose proxies moved (the flat sync
@@ -1876,7 +2016,7 @@ template <class real> struct world_step {
                 for (int b = 0; b < n_bodies; ++b) prepare_body(sp, b);
             }
             run_solve_velocity(sp);
-            run_solve_position(sp);
+            run_solve_position<true>(sp);
             const int n_items = sync_items();
             for (int i = 0; i < n_items; ++i) sync_item(sp, i);
             run_pairs(sp);

@@ -42,6 +42,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     sp.vel_iters = vel_iters; sp.pos_iters = pos_iters; sp.n_steps = n_steps; sp.flags = STEP_FLAT_COLLIDE;
     sp.solve_lanes = 8;
     sp.zero = 0;
+    sp.joint_any = nullptr;
     for (int w = 0; w < c.n_worlds; ++w) {
         world_step<real> ws;
         ws.bind_team_cta();
