@@ -229,9 +229,10 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
         else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, ev);
         int rc = check_launch(x, "step kernels");
         if (rc) return rc;
-        // check_launch counted one of: plan, sync, broadphase, (collide), and per group of worlds prepare + solve velocity + solve position
+        // check_launch counted one of: plan, sync, broadphase, (collide), and per group of worlds prepare + solve velocity + the two
+        // solve position kernels (one of them returns at once, see b2b_kernels.inl)
         const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
-        x->launches += 2 + ((dt > 0.0) ? 3 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
+        x->launches += 2 + ((dt > 0.0) ? 4 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
     }
     return B2B_OK;
 }
