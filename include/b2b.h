@@ -38,6 +38,7 @@ typedef enum b2b_error {
 #define B2B_STEP_PROFILE 1u   /* b2b_step flags: accumulate per-phase cycle counters (see b2b_profile) */
 #define B2B_STEP_TIME 2u      /* b2b_step flags: bracket every kernel with CUDA events (see b2b_kernel_ms) */
 #define B2B_STEP_NO_FLAT 16u  /* b2b_step flags: run the narrowphase inside the per-world plan kernel (debugging) */
+#define B2B_STEP_GROUP_KERNEL 32u /* b2b_step flags: run the group-capable position kernel even if no world has a joint island schedule (testing) */
 /* bits 8..15: reserved */
 
 typedef struct b2b_caps {

@@ -206,9 +206,9 @@ class BatchedWorld(object):
                      "s_stage", "s_integrate", "s_schedule", "s_init", "s_warm", "s_velocity", "s_store", "s_position",
                      "s_writeback", "s_sleep"]
 
-    def step(self, dt, vel_iters, pos_iters, n_steps=1, profile=False, time_kernels=False):
+    def step(self, dt, vel_iters, pos_iters, n_steps=1, profile=False, time_kernels=False, group_kernel=False):
         """World.step for every world, `n_steps` times (asynchronous on the current stream)."""
-        flags = (1 if profile else 0) | (2 if time_kernels else 0)
+        flags = (1 if profile else 0) | (2 if time_kernels else 0) | (32 if group_kernel else 0)   # B2B_STEP_* (include/b2b.h)
         _lib.check(_lib.lib().b2b_step(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters),
                                        int(n_steps), flags, self._stream()), "b2b_step")
         if dt > 0.0 and n_steps > 0:

@@ -405,6 +405,7 @@ void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
     step_params sp = sp_in;
     sp.joint_any = counters + 2;
+    if (sp.flags & STEP_GROUP_KERNEL) cudaMemsetAsync(counters + 2, 1, sizeof(unsigned int), st);   // any non-zero word
     if (sp.flags & STEP_FLAT_COLLIDE) {
         const long long total = (long long)c.n_worlds * c.nc;
         long long blocks = (total + 127) / 128;

@@ -98,7 +98,7 @@ template <class real> struct batch_ptrs {
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
 enum { VREC_QUADS = 8, PREC_QUADS = 5 };   // velocity / position record of one constraint, in 4-vectors of reals
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
-enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4 };
+enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32 };
 // per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
 enum { SUM_PENDING = 1u, SUM_DESTROY = 2u, SUM_CHANGED = 4u, SUM_COLLIDE = 7u, SUM_MOVED = 8u };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,

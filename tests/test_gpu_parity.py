@@ -63,8 +63,15 @@ def round32(A):
     return B
 
 
-@pytest.mark.parametrize("case", golden_cases())
-def test_p_exact_fp64_free_running(case):
+def _group_kernel_cases():
+    """Every golden case with the default kernel choice, plus cases without a joint island schedule forced through the
+    group-capable position kernel (in a batch they run there whenever ANOTHER world of the batch has a joint schedule)."""
+    cases = [(c, False) for c in golden_cases()]
+    return cases + [(c, True) for c in ("pyramid_w1", "mixed_w1", "hello_w0", "vertical_stack_w1") if c in golden_cases()]
+
+
+@pytest.mark.parametrize("case,group_kernel", _group_kernel_cases())
+def test_p_exact_fp64_free_running(case, group_kernel):
     import pypybox2d_b200 as b2
     g = load_golden(case)
     dt, vi, pi, steps, world = g["meta"]
@@ -75,7 +82,7 @@ def test_p_exact_fp64_free_running(case):
     for s in range(steps):
         orc.step(dt, vi, pi)
         assert bytes(g["digest"][s]) == gen_golden.state_digest(A)          # the checker itself is on the golden path
-        bw.step(dt, vi, pi)
+        bw.step(dt, vi, pi, group_kernel=group_kernel)
         G = bw.download()
         assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
         dp, dv = state_diff(A, G)
