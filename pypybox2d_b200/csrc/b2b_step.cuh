@@ -39,7 +39,6 @@
 #define B2B_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2B_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define B2B_ATOMIC_MAX(p, v) atomicMax((p), (v))
-#define B2B_FENCE() __threadfence()
 #define B2B_CLOCK() clock64()
 #if defined(B2B_PF_LDGSTS)
 // experiment: a real 16-byte asynchronous copy into a per-lane sink (with a 128-byte L2 fill) instead of a prefetch hint
@@ -65,7 +64,6 @@ template <class T> inline T host_atomic_max(T* p, T v) { T o = *p; if (v > o) *p
 #define B2B_ATOMIC_OR(p, v) b2b::host_atomic_or((p), (v))
 #define B2B_ATOMIC_AND(p, v) b2b::host_atomic_and((p), (v))
 #define B2B_ATOMIC_MAX(p, v) b2b::host_atomic_max((p), (v))
-#define B2B_FENCE() ((void)0)
 #endif
 
 // cycle accounting by thread 0 (wall-clock cycles of the CTA, since phases end in CTA barriers)
@@ -1669,8 +1667,10 @@ template <class real> struct world_step {
                 for (int it = 0; it < sp.pos_iters && solved_mask != all; ++it) {
                     ++used;
                     if (joint) {
-                        for (int i = t_id; i < n_gi; i += t_n) worst[i] = (sep_bits)0;
-                        B2B_FENCE();
+                        // every access to the words is an atomic (performed at L2, so no stale L1 line and no fence: a
+                        // fence here compiled to MEMBAR.SC.GPU + CCTL.IVALL, emptying the SM's L1 twice per sweep); the
+                        // team barrier orders them
+                        for (int i = t_id; i < n_gi; i += t_n) B2B_ATOMIC_AND(&worst[i], (sep_bits)0);
                         B2B_SYNC();
                     }
                     const uint32_t skip = solved_mask;
@@ -1686,10 +1686,9 @@ template <class real> struct world_step {
                                       [&](const prec& e) { return bits_of_real(e.q10.z); });
                     uint32_t unsolved = 0u;
                     if (joint) {
-                        B2B_FENCE();
                         B2B_SYNC();
                         for (int i = t_id; i < n_gi; i += t_n) {
-                            const sep_bits u = worst[i];
+                            const sep_bits u = B2B_ATOMIC_OR(&worst[i], (sep_bits)0);
                             real neg; memcpy(&neg, &u, sizeof(neg));
                             if (!(-neg >= solved_above)) unsolved |= 1u << i;
                         }
