@@ -1678,10 +1678,10 @@ template <class real> struct world_step {
                     level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
                                       [&](const prec& e, int) {
                                           const int ci = (int)((bits_of_real(e.q10.w) >> INFO_ISLAND_SHIFT) & 31u);   // 0 unless joint
-                                          if ((skip >> ci) & 1u) return;
+                                          if (joint && ((skip >> ci) & 1u)) return;
                                           const real neg = -constraint_solve_position(e);
-                                          if (!joint) { my_neg = (neg > my_neg) ? neg : my_neg; }
-                                          else if (neg > real(0)) { sep_bits u; memcpy(&u, &neg, sizeof(u)); B2B_ATOMIC_MAX(&worst[ci], u); }
+                                          my_neg = (neg > my_neg) ? neg : my_neg;            // (used by one-island groups)
+                                          if (joint && neg > real(0)) { sep_bits u; memcpy(&u, &neg, sizeof(u)); B2B_ATOMIC_MAX(&worst[ci], u); }
                                       },
                                       [&](const prec& e) { return bits_of_real(e.q10.z); });
                     uint32_t unsolved = 0u;

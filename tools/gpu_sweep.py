@@ -14,7 +14,7 @@ def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1, ctas=0
     torch.cuda.synchronize()
     for pf in range(repeats):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); bw.step(1/60, 8, 3, steps, time_kernels=True); e1.record(); torch.cuda.synchronize()
+        e0.record(); bw.step(1/60, 8, 3, steps, time_kernels=True, group_kernel=bool(int(os.environ.get('SWEEP_GROUP_KERNEL', '0')))); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         k = bw.kernel_ms()
         print("%s worlds=%d lanes=%d aux=%d ctas=%d: %.2f ms/step %.3e body-steps/s; kernels ms/step collide %.2f plan %.2f solve %.2f broad %.2f status=%d" % (
