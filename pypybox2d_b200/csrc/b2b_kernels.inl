@@ -150,6 +150,21 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
 
 // Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): each is one warp per
 // CTA, the warp split into teams of `lanes` lanes, one world per team, worlds of the group strided over the teams.
+// End of a world: each team on its own (default), or -DB2B_WARP_RECONVERGE=1: the teams of the warp whose world index is
+// inside the group this round (a prefix of the teams) meet again, so the next world starts with the warp's teams issuing
+// together.  Measured (profiles/r1_other_scenes.md): pyramid batch neutral, the group-capable position kernel's penalty for
+// one-island worlds halves (ncu: it executes 13 % more warp instructions for 3 % more thread instructions -- its teams
+// drift apart), vertical stacks 3 % slower (worlds of very different length wait for each other), deep stacks 1 % faster.
+#if defined(B2B_WARP_RECONVERGE) && B2B_WARP_RECONVERGE
+#define B2B_SOLVE_RECONVERGE(g, team, tpc, lanes, n_group, t_mask)                                                            \
+    do {                                                                                                                       \
+        const int rem_ = (n_group) - ((g) - (team));                                                                           \
+        const int act_ = (rem_ < (tpc) ? rem_ : (tpc)) * (lanes);                                                              \
+        __syncwarp(act_ >= 32 ? 0xffffffffu : ((1u << act_) - 1u));                                                            \
+    } while (0)
+#else
+#define B2B_SOLVE_RECONVERGE(g, team, tpc, lanes, n_group, t_mask) __syncwarp(t_mask)
+#endif
 #define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN)                                                                                          \
     __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(NAME, B2B_SUFFIX)(                                       \
         batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* rec,                   \
@@ -167,7 +182,7 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
             ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                               \
             ws.pf_sink = (uint32_t)__cvta_generic_to_shared(smem + (size_t)teams_per_cta * team_smem + 16 * (threadIdx.x & 31)); \
             ws.CALL(sp);                                                                                                       \
-            __syncwarp(ws.t_mask);                                                                                             \
+            B2B_SOLVE_RECONVERGE(g, team, teams_per_cta, lanes, n_group, ws.t_mask);                                           \
         }                                                                                                                      \
     }
 B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity, false)

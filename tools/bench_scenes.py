@@ -5,6 +5,9 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
+if os.environ.get("B2B_VARIANT"):      # development: an experimental build (tools/build_variant.sh)
+    from pypybox2d_b200 import _lib
+    _lib.SO_PATH = os.path.join(_lib.CSRC, "variants", "libb2b_%s.so" % os.environ["B2B_VARIANT"])
 import pypybox2d_b200 as b2
 from pypybox2d_b200 import scenes
 
