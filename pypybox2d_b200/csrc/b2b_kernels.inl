@@ -181,6 +181,11 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
             ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, team_prof + (size_t)slot * L.total_sprof);                 \
             ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                               \
             ws.pf_sink = (uint32_t)__cvta_generic_to_shared(smem + (size_t)teams_per_cta * team_smem + 16 * (threadIdx.x & 31)); \
+            {                                                                                                                  \
+                const int rem_ = n_group - (g - team);                                                                         \
+                const int act_ = (rem_ < teams_per_cta ? rem_ : teams_per_cta) * lanes;                                        \
+                ws.w_mask = act_ >= 32 ? 0xffffffffu : ((1u << act_) - 1u);                                                    \
+            }                                                                                                                  \
             ws.CALL(sp);                                                                                                       \
             B2B_SOLVE_RECONVERGE(g, team, teams_per_cta, lanes, n_group, ws.t_mask);                                           \
         }                                                                                                                      \
