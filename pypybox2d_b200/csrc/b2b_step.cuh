@@ -811,9 +811,10 @@ template <class real> struct world_step {
         const bool joint = false;
 #else
         // Worth it only when no island dominates: the joint list is at least as long as the largest island's, and one world
-        // with a joint schedule moves the whole batch to the group-capable position kernel (measured 20 % slower per sweep
-        // for the worlds that stay one island per group), so a stray second island next to a big one does not qualify.
-        const bool joint = (n_ci >= 2) && (n_ci <= 32) && (3 * (size_t)cap.nb >= 32) && (4 * largest <= 3 * n_lc);
+        // with a joint schedule moves the whole batch to the group-capable position kernel (measured 2 % of the solve time
+        // slower for the worlds that stay one island per group), so a stray second island next to a big one (a box beside a
+        // pyramid: ~1 % of the contacts) does not qualify.
+        const bool joint = (n_ci >= 2) && (n_ci <= 32) && (3 * (size_t)cap.nb >= 32) && (10 * largest <= 9 * n_lc);
 #endif
         if (joint) {
             if (B2B_IS_T0) schedule_range(0, n_lc, 0);
