@@ -14,6 +14,8 @@
 
 using namespace b2b;
 
+static long long g_joint_world_steps = 0;     // world-steps whose plan row carried a joint island schedule (test bookkeeping)
+
 template <class real>
 static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double inv_dt0, int vel_iters, int pos_iters,
                int n_steps)
@@ -52,8 +54,16 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
         ws.bind_smem_aux(smem_aux.data());
         ws.bind_smem_solve(smem_solve.data());
         ws.run(sp);
+        if (dt > 0.0 && ws.g_joint[0] != 0 && ws.w_island[2] > 0) g_joint_world_steps += n_steps;
     }
     return 0;
+}
+
+extern "C" long long hc_joint_world_steps(int reset)
+{
+    const long long v = g_joint_world_steps;
+    if (reset) g_joint_world_steps = 0;
+    return v;
 }
 
 extern "C" int hc_step(const b2b_caps* caps, const b2b_buffers* buf, double dt, double inv_dt0, int vel_iters,

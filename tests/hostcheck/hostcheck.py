@@ -40,6 +40,8 @@ def lib():
         _LIB.hc_step.argtypes = [ctypes.POINTER(Caps), ctypes.POINTER(Buffers), ctypes.c_double, ctypes.c_double,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _LIB.hc_step.restype = ctypes.c_int
+        _LIB.hc_joint_world_steps.argtypes = [ctypes.c_int]
+        _LIB.hc_joint_world_steps.restype = ctypes.c_longlong
     return _LIB
 
 
@@ -60,3 +62,8 @@ def step(arrays, dt, inv_dt0, vel_iters, pos_iters, n_steps=1):
         assert A[n].flags["C_CONTIGUOUS"], n
         setattr(b, n, A[n].ctypes.data)
     return lib().hc_step(ctypes.byref(c), ctypes.byref(b), dt, inv_dt0, vel_iters, pos_iters, n_steps)
+
+
+def joint_world_steps(reset=True):
+    """World-steps so far whose plan row carried a joint island schedule (phase_schedule in b2b_step.cuh)."""
+    return int(lib().hc_joint_world_steps(1 if reset else 0))

@@ -22,6 +22,7 @@ def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps):
     HA = {k: v.copy() for k, v in OA.items()}
     orc = oracle.Oracle(OA, 0)
     inv = 0.0
+    hostcheck.joint_world_steps(reset=True)
     for s in range(steps):
         orc.step(dt, vi, pi)
         hostcheck.step(HA, dt, inv, vi, pi)
@@ -32,3 +33,9 @@ def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps):
         for k in ("b_pos", "b_vel", "b_xf", "f_fat"):
             x, y = harness.used_view(OA, k), harness.used_view(HA, k)
             assert np.allclose(x, y, rtol=1e-9, atol=1e-10), "%s, step %d" % (k, s)
+    # the multi-island scenes must have gone through the joint island schedule, the single-body scene must not
+    joint = hostcheck.joint_world_steps()
+    if scene in ("vertical_stack", "deep_stacks"):
+        assert joint >= steps // 2, joint
+    if scene == "hello":
+        assert joint == 0, joint
