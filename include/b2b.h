@@ -97,9 +97,12 @@ int b2b_step(b2b_ctx* ctx, double dt, double inv_dt0, int vel_iters, int pos_ite
              uint32_t flags, void* stream);
 
 /* Same step driven from HOST buffers (the end-to-end call an environment loop makes):
- * copies h_force_torque [n_worlds][nb][3] (fx, fy, torque; may be NULL) host->device, steps, copies
- * body state [n_worlds][nb][6] (c.x, c.y, a, v.x, v.y, w) device->host into h_state_out (may be NULL),
- * then synchronises the stream.  Host buffers should be pinned for full PCIe bandwidth. */
+ * h_force_torque [n_worlds][nb][3] (fx, fy, torque; may be NULL) goes host->device and is applied as Body.apply_force /
+ * apply_torque before the step would (body.py:477-545: dynamic bodies only; a sleeping body that receives a non-zero
+ * force or torque is woken and its sleep timer restarts); body state [n_worlds][nb][6] (c.x, c.y, a, v.x, v.y, w) of the
+ * last step comes back into h_state_out (may be NULL).  Copies and kernels are pipelined over chunks of worlds on two
+ * internal copy streams and the caller's stream; returns after everything has completed.  Host buffers must be
+ * pinned for the copies to overlap (and for full PCIe bandwidth). */
 int b2b_step_host(b2b_ctx* ctx, const void* h_force_torque, void* h_state_out, double dt, double inv_dt0,
                   int vel_iters, int pos_iters, int n_steps, uint32_t flags, void* stream);
 
@@ -112,8 +115,9 @@ int b2b_collide_pairs(b2b_ctx* ctx, int n, const void* d_shape_a, const void* d_
 int b2b_status(b2b_ctx* ctx, uint32_t* host_out, void* stream);
 
 /* Per-world state checksum and energy for the optional end-of-run gather:
- * d_out real64[n_worlds][4] = {fnv1a64 of packed body state (as double bits), kinetic+potential
- * energy, n_contacts, n_awake}.  masses are passed as inverse mass/inertia already in b_mass. */
+ * d_out real64[n_worlds][4] = {low 52 bits of the FNV-1a hash of the packed body state, as an exactly representable
+ * integer (comparable with ==, never NaN), kinetic+potential energy, n_contacts, n_awake}.  masses are passed as
+ * inverse mass/inertia already in b_mass. */
 int b2b_checksum(b2b_ctx* ctx, void* d_out, void* stream);
 
 /* Per-phase cycle counters of the step kernel, summed over CTAs (only accumulated by steps run with
@@ -122,9 +126,10 @@ int b2b_checksum(b2b_ctx* ctx, void* d_out, void* stream);
 int b2b_profile(b2b_ctx* ctx, int64_t* host_out32, int reset);
 
 /* Device time of the kernels launched by b2b_step calls that had B2B_STEP_TIME set, from CUDA events recorded on
- * the launching stream: out[4] = total milliseconds of the {collide, plan, solve, broadphase} kernels, n_steps =
- * steps covered.  Synchronises the stream's events; clears the accumulators. */
-int b2b_kernel_ms(b2b_ctx* ctx, float* out4, int32_t* n_steps);
+ * the launching stream between the kernels: out[8] = total milliseconds of {collide, plan, prepare, solve_velocity,
+ * solve_position (both instantiations), sync, broadphase (pairs + new contacts), all of them}; n_steps = steps covered.
+ * Synchronises the stream's events; clears the accumulators. */
+int b2b_kernel_ms(b2b_ctx* ctx, float* out8, int32_t* n_steps);
 
 /* Launch geometry actually used and kernel launches issued so far (for bench.py's gpu_launches). */
 int b2b_info(b2b_ctx* ctx, int32_t* grid, int32_t* threads, int32_t* smem_bytes, int64_t* launches);

@@ -27,9 +27,11 @@ def _torch():
 
 
 def world_caps(worlds, contacts_per_body=4, slack=64):
+    """Capacities for a batch of host worlds.  Contacts are between fixtures, so a compound body with many fixtures
+    needs rows per FIXTURE, not per body (`World.step` raises if a step still runs out)."""
     nb = max(len(w.bodies) for w in worlds)
     nf = max(sum(len(b.fixtures) for b in w.bodies) for w in worlds)
-    return schema.Caps(nb, nf, contacts_per_body * nb + slack)
+    return schema.Caps(nb, nf, contacts_per_body * max(nb, nf) + slack)
 
 
 class BatchedWorld(object):
@@ -165,8 +167,8 @@ class BatchedWorld(object):
             self.t["b_pos0"] = self.t["b_pos"].clone()
             self.t["b_pos0"][..., 3] = 0
         self._create_context(kw.get("threads", 0), kw.get("ctas_per_sm", 0), kw.get("lanes_aux", 0))
-        if jitter != 0.0:
-            self.init_proxies()
+        if jitter != 0.0 or real != "f64":
+            self.init_proxies()      # proxies are built in the working precision, exactly as `from_worlds` builds them
         return self
 
     def _to_device(self, host):
@@ -230,7 +232,8 @@ class BatchedWorld(object):
         return int(out.value)
 
     def checksum(self):
-        """[n_worlds, 4] float64 tensor: state hash bits, energy, n_contacts, n_awake (device)."""
+        """[n_worlds, 4] float64 tensor: state hash (the low 52 bits of an FNV-1a over the packed body state, as an exactly
+        representable integer: comparable with ==), energy, n_contacts, n_awake (device)."""
         torch = _torch()
         out = torch.empty((self.n_worlds, 4), dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib().b2b_checksum(self._ctx, ctypes.c_void_p(out.data_ptr()), self._stream()), "b2b_checksum")
@@ -244,13 +247,20 @@ class BatchedWorld(object):
         d["world_steps"] = int(out[31])
         return d
 
+    KERNELS = ["collide", "plan", "prepare", "solve_velocity", "solve_position", "sync", "pairs"]
+
     def kernel_ms(self):
-        """{collide, plan, solve, broadphase: total ms} of the steps run with time_kernels=True since the last call."""
-        out = (ctypes.c_float * 4)()
+        """Total ms per kernel (KERNELS) of the steps run with time_kernels=True since the last call, from CUDA events
+        between the launches; `solve` = prepare + solve_velocity + solve_position, `broadphase` = sync + pairs."""
+        out = (ctypes.c_float * 8)()
         n = ctypes.c_int32(0)
         _lib.check(_lib.lib().b2b_kernel_ms(self._ctx, out, ctypes.byref(n)), "b2b_kernel_ms")
-        return {"collide": float(out[0]), "plan": float(out[1]), "solve": float(out[2]), "broadphase": float(out[3]),
-                "steps": int(n.value)}
+        d = {k: float(out[i]) for i, k in enumerate(self.KERNELS)}
+        d["solve"] = d["prepare"] + d["solve_velocity"] + d["solve_position"]
+        d["broadphase"] = d["sync"] + d["pairs"]
+        d["total"] = float(out[7])
+        d["steps"] = int(n.value)
+        return d
 
     def info(self):
         g, t, s, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()

@@ -30,8 +30,11 @@ struct b2b_ctx {
     const void* fields[B2B_NFIELDS];
     bool bound;
     long long launches;
-    std::vector<cudaEvent_t>* events;   // 5 per timed step (B2B_STEP_TIME)
-    int timed_steps;
+    step_timer* timer;             // B2B_STEP_TIME: event chain of the timed steps
+    // b2b_step_host: copy streams and the events that chain copies and kernels chunk by chunk
+    cudaStream_t s_in, s_out;
+    std::vector<cudaEvent_t>* pipe_ev;
+    int pipe_worlds;               // worlds per chunk of the host-buffer pipeline
 };
 
 static thread_local std::string g_err;
@@ -84,6 +87,8 @@ extern "C" size_t b2b_scratch_bytes(const b2b_caps* caps)
     return L.total_aux + L.total_rec;        // per resident CTA of the plan kernels / per world of a solve group
 }
 
+extern "C" void b2b_destroy(b2b_ctx* x);
+
 extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
 {
     if (!out) return fail(B2B_ERR_ARG, "b2b_create: out is NULL");
@@ -98,9 +103,14 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     x->caps = *caps;
     x->c = to_caps(caps);
     x->f64 = caps->real_bytes == 8;
+    // every failure below leaves through b2b_destroy, which frees whatever was allocated so far
+#define CREATE_TRY(expr, what)                                                 \
+    do {                                                                       \
+        cudaError_t e_ = (expr);                                               \
+        if (e_ != cudaSuccess) { b2b_destroy(x); return fail(B2B_ERR_CUDA, what, e_); } \
+    } while (0)
     cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, caps->device);
-    if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaGetDeviceProperties", e); }
+    CREATE_TRY(cudaGetDeviceProperties(&prop, caps->device), "cudaGetDeviceProperties");
     x->n_sm = prop.multiProcessorCount;
     // caps->threads: lanes of a warp per world in the solve kernel (4, 8, 16 or 32); caps->reserved: the same for
     // the plan / broadphase kernels
@@ -111,16 +121,16 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     const int lanes_aux = caps->reserved > 0 ? caps->reserved : (caps->nc >= 700 ? 32 : 8);
     int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
                     : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
-    if (rc != 0) { delete x; return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
-    e = cudaMalloc((void**)&x->scratch, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
-    if (e != cudaSuccess) { delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(scratch)", e); }
-    cudaMemset(x->scratch, 0, x->plan.layout.total_aux * (size_t)x->plan.aux_slabs);
+    if (rc != 0) { b2b_destroy(x); return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
+    const size_t aux_bytes = x->plan.layout.total_aux * (size_t)x->plan.aux_slabs;
+    CREATE_TRY(cudaMalloc((void**)&x->scratch, aux_bytes), "cudaMalloc(scratch)");
+    CREATE_TRY(cudaMemset(x->scratch, 0, aux_bytes), "cudaMemset(scratch)");
     // Constraint records live for one group of worlds at a time (prepare kernel -> solve kernel).  The group is
     // every world when that fits the record budget (B2B_RECORD_GIB, default 24 GiB, at most 40 % of the free
     // memory), else a whole number of resident-team waves.
     {
         size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
+        CREATE_TRY(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
         double budget = 24.0;
         if (const char* env = getenv("B2B_RECORD_GIB")) { const double v = atof(env); if (v > 0.0) budget = v; }
         size_t budget_b = (size_t)(budget * 1073741824.0);
@@ -132,17 +142,25 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
         else if (group > wave) group = group / wave * wave;
         if (group < 1) group = 1;
         x->plan.group_worlds = (int)group;
+        // host-buffer pipeline (b2b_step_host): about B2B_PIPE_CHUNKS chunks (default 6), each a whole number of waves
+        int chunks = 6;
+        if (const char* env = getenv("B2B_PIPE_CHUNKS")) { const int v = atoi(env); if (v > 0) chunks = v; }
+        long long pipe = ((long long)x->c.n_worlds + chunks - 1) / chunks;
+        if (pipe > wave) pipe = (pipe + wave - 1) / wave * wave;
+        if (pipe > group) pipe = group;
+        if (pipe < 1) pipe = 1;
+        x->pipe_worlds = (int)pipe;
     }
-    e = cudaMalloc((void**)&x->scratch_solve, x->plan.layout.total_rec * (size_t)x->plan.group_worlds);
-    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(constraint records)", e); }
-    e = cudaMalloc((void**)&x->scratch_sprof, x->plan.layout.total_sprof * (size_t)x->plan.solve_slabs);
-    if (e != cudaSuccess) { cudaFree(x->scratch); cudaFree(x->scratch_solve); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(solve counters)", e); }
-    cudaMemset(x->scratch_sprof, 0, x->plan.layout.total_sprof * (size_t)x->plan.solve_slabs);
-    e = cudaMalloc((void**)&x->plan_rows, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
-    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(plan rows)", e); }
-    cudaMemset(x->plan_rows, 0, sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds);
-    e = cudaMalloc((void**)&x->d_status, 4 * sizeof(uint32_t));
-    if (e != cudaSuccess) { cudaFree(x->scratch); delete x; return fail(B2B_ERR_CUDA, "cudaMalloc(status)", e); }
+    CREATE_TRY(cudaMalloc((void**)&x->scratch_solve, x->plan.layout.total_rec * (size_t)x->plan.group_worlds), "cudaMalloc(constraint records)");
+    const size_t sprof_bytes = x->plan.layout.total_sprof * (size_t)x->plan.solve_slabs;
+    CREATE_TRY(cudaMalloc((void**)&x->scratch_sprof, sprof_bytes), "cudaMalloc(solve counters)");
+    CREATE_TRY(cudaMemset(x->scratch_sprof, 0, sprof_bytes), "cudaMemset(solve counters)");
+    const size_t plan_bytes = sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds;
+    CREATE_TRY(cudaMalloc((void**)&x->plan_rows, plan_bytes), "cudaMalloc(plan rows)");
+    CREATE_TRY(cudaMemset(x->plan_rows, 0, plan_bytes), "cudaMemset(plan rows)");
+    CREATE_TRY(cudaMalloc((void**)&x->d_status, 4 * sizeof(uint32_t)), "cudaMalloc(status)");
+    CREATE_TRY(cudaMemset(x->d_status, 0, 4 * sizeof(uint32_t)), "cudaMemset(status)");
+#undef CREATE_TRY
     *out = x;
     return B2B_OK;
 }
@@ -158,7 +176,10 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     if (x->d_status) cudaFree(x->d_status);
     if (x->stage_in) cudaFree(x->stage_in);
     if (x->stage_out) cudaFree(x->stage_out);
-    if (x->events) { for (cudaEvent_t e : *x->events) cudaEventDestroy(e); delete x->events; }
+    if (x->timer) { for (cudaEvent_t e : x->timer->ev) cudaEventDestroy(e); delete x->timer; }
+    if (x->pipe_ev) { for (cudaEvent_t e : *x->pipe_ev) cudaEventDestroy(e); delete x->pipe_ev; }
+    if (x->s_in) cudaStreamDestroy(x->s_in);
+    if (x->s_out) cudaStreamDestroy(x->s_out);
     delete x;
 }
 
@@ -203,6 +224,13 @@ static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos
     return sp;
 }
 
+static int step_launches(const b2b_ctx* x, double dt, uint32_t flags, int groups)
+{
+    // plan, sync, pairs, (collide), and per group of worlds prepare + velocity + the two position kernels (one of them
+    // returns at once, see b2b_kernels.inl)
+    return 3 + ((dt > 0.0) ? 4 * groups : 0) + ((flags & 4u) ? 1 : 0);
+}
+
 extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags,
                         void* stream)
 {
@@ -210,58 +238,119 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     if (vel_iters < 0 || pos_iters < 0 || n_steps < 0 || !(dt >= 0.0)) return fail(B2B_ERR_ARG, "b2b_step: bad argument");
     if (n_steps == 0) return B2B_OK;
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
-    // the flat narrowphase kernel is the default; B2B_STEP_NO_FLAT keeps the narrowphase inside the plan kernel
+    // the flat narrowphase kernel is the default; B2B_STEP_NO_FLAT keeps the narrowphase inside the per-world plan kernel
     const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u),
                                        x->plan.lanes);
+    step_timer* tm = nullptr;
+    if (flags & B2B_STEP_TIME) {
+        if (!x->timer) x->timer = new step_timer();
+        tm = x->timer;
+    }
+    const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
     for (int s = 0; s < n_steps; ++s) {
-        cudaEvent_t* ev = nullptr;
-        if (flags & B2B_STEP_TIME) {
-            if (!x->events) x->events = new std::vector<cudaEvent_t>();
-            while ((int)x->events->size() < 5 * (x->timed_steps + 1)) {
-                cudaEvent_t e;
-                CUDA_TRY(cudaEventCreate(&e), "cudaEventCreate");
-                x->events->push_back(e);
-            }
-            ev = x->events->data() + 5 * x->timed_steps;
-            ++x->timed_steps;
-        }
-        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, ev);
-        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, ev);
-        int rc = check_launch(x, "step kernels");
-        if (rc) return rc;
-        // check_launch counted one of: plan, sync, broadphase, (collide), and per group of worlds prepare + solve velocity + the two
-        // solve position kernels (one of them returns at once, see b2b_kernels.inl)
-        const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
-        x->launches += 2 + ((dt > 0.0) ? 4 * groups : 0) + ((sp.flags & 4u) ? 1 : 0);
+        if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, tm);
+        else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, tm);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "step kernels", e);
+        x->launches += step_launches(x, dt, sp.flags, groups);
     }
     return B2B_OK;
 }
 
+// The end-to-end call.  One World.step with its inputs and outputs in HOST memory, as a pipeline over chunks of worlds
+// (b2b_ctx::pipe_worlds, a whole number of resident waves of the solve kernels) on three streams:
+//   copy-in stream   forces of chunk k host -> device
+//   caller's stream  scatter + narrowphase of chunk k (waits for its forces) ... plan kernel (all worlds) ...
+//                    prepare / velocity / position of chunk k, gather of chunk k ... proxy synchronisation + pairs
+//   copy-out stream  body state of chunk k device -> host (waits for its gather)
+// so the copies run under the kernels of the neighbouring chunks; only the first chunk's forces and the last chunk's state
+// are exposed.  Forces are applied (and wake their bodies) before the chunk's narrowphase, as Body.apply_force before
+// World.step does in the reference.  n_steps > 1: the forces act on the first step only when the world clears forces after
+// a step (auto_clear_forces), on every step otherwise; the state read back is the last step's.
 extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_state_out, double dt, double inv_dt0,
                              int vel_iters, int pos_iters, int n_steps, uint32_t flags, void* stream)
 {
     if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_step_host: no buffers bound");
+    if (vel_iters < 0 || pos_iters < 0 || n_steps < 0 || !(dt >= 0.0)) return fail(B2B_ERR_ARG, "b2b_step_host: bad argument");
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t rb = (size_t)x->caps.real_bytes, n = (size_t)x->c.n_worlds * x->c.nb;
+    const size_t rb = (size_t)x->caps.real_bytes, per_world_in = (size_t)x->c.nb * 3 * rb, per_world_out = (size_t)x->c.nb * 6 * rb;
+    const int W = x->c.n_worlds, chunk = x->pipe_worlds, n_chunks = (W + chunk - 1) / chunk;
+    if (h_force_torque && !x->stage_in) CUDA_TRY(cudaMalloc(&x->stage_in, (size_t)W * per_world_in), "cudaMalloc(stage_in)");
+    if (h_state_out && !x->stage_out) CUDA_TRY(cudaMalloc(&x->stage_out, (size_t)W * per_world_out), "cudaMalloc(stage_out)");
+    if (!x->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&x->s_in, cudaStreamNonBlocking), "cudaStreamCreate(copy-in)");
+    if (!x->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&x->s_out, cudaStreamNonBlocking), "cudaStreamCreate(copy-out)");
+    if (!x->pipe_ev) x->pipe_ev = new std::vector<cudaEvent_t>();
+    while ((int)x->pipe_ev->size() < 2 * n_chunks + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        x->pipe_ev->push_back(e);
+    }
+    cudaEvent_t* ev_in = x->pipe_ev->data();
+    cudaEvent_t* ev_out = ev_in + n_chunks;
+    cudaEvent_t ev_begin = x->pipe_ev->data()[2 * n_chunks];
+    const step_params sp0 = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u),
+                                        x->plan.lanes);
+    // the copy streams start behind whatever the caller queued on its stream before this call
+    CUDA_TRY(cudaEventRecord(ev_begin, st), "cudaEventRecord");
     if (h_force_torque) {
-        if (!x->stage_in) CUDA_TRY(cudaMalloc(&x->stage_in, n * 3 * rb), "cudaMalloc(stage_in)");
-        CUDA_TRY(cudaMemcpyAsync(x->stage_in, h_force_torque, n * 3 * rb, cudaMemcpyHostToDevice, st), "H2D forces");
-        if (x->f64) launch_scatter_forces_f64(x->fields, x->c, x->stage_in, st);
-        else launch_scatter_forces_f32(x->fields, x->c, x->stage_in, st);
-        int rc = check_launch(x, "scatter_forces kernel");
-        if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(x->s_in, ev_begin, 0), "cudaStreamWaitEvent");
+        for (int k = 0; k < n_chunks; ++k) {
+            const int w0 = k * chunk, n = (W - w0 < chunk) ? W - w0 : chunk;
+            CUDA_TRY(cudaMemcpyAsync((char*)x->stage_in + (size_t)w0 * per_world_in, (const char*)h_force_torque + (size_t)w0 * per_world_in,
+                                     (size_t)n * per_world_in, cudaMemcpyHostToDevice, x->s_in), "H2D forces");
+            CUDA_TRY(cudaEventRecord(ev_in[k], x->s_in), "cudaEventRecord");
+        }
     }
-    int rc = b2b_step(x, dt, inv_dt0, vel_iters, pos_iters, n_steps, flags, stream);
-    if (rc) return rc;
-    if (h_state_out) {
-        if (!x->stage_out) CUDA_TRY(cudaMalloc(&x->stage_out, n * 6 * rb), "cudaMalloc(stage_out)");
-        if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, st);
-        else launch_gather_state_f32(x->fields, x->c, x->stage_out, st);
-        rc = check_launch(x, "gather_state kernel");
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_state_out, x->stage_out, n * 6 * rb, cudaMemcpyDeviceToHost, st), "D2H state");
+    if (h_state_out) CUDA_TRY(cudaStreamWaitEvent(x->s_out, ev_begin, 0), "cudaStreamWaitEvent");
+    for (int s = 0; s < n_steps; ++s) {
+        step_params sp = sp0;
+        sp.joint_any = x->d_status + 3;
+        const bool first = (s == 0), last = (s + 1 == n_steps);
+        // forces in + narrowphase, chunk by chunk
+        for (int k = 0; k < n_chunks; ++k) {
+            const int w0 = k * chunk, n = (W - w0 < chunk) ? W - w0 : chunk;
+            if (first && h_force_torque) {
+                CUDA_TRY(cudaStreamWaitEvent(st, ev_in[k], 0), "cudaStreamWaitEvent");
+                if (x->f64) launch_scatter_forces_f64(x->fields, x->c, x->stage_in, w0, n, st);
+                else launch_scatter_forces_f32(x->fields, x->c, x->stage_in, w0, n, st);
+                ++x->launches;
+            }
+            if (sp.flags & 4u) {
+                if (x->f64) launch_collide_f64(x->fields, x->c, x->plan, x->plan_rows, w0, n, st);
+                else launch_collide_f32(x->fields, x->c, x->plan, x->plan_rows, w0, n, st);
+                ++x->launches;
+            }
+        }
+        if (x->f64) launch_plan_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
+        else launch_plan_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
+        ++x->launches;
+        // solve + state out, chunk by chunk (the last step's state is the one read back)
+        for (int k = 0; k < n_chunks; ++k) {
+            const int w0 = k * chunk, n = (W - w0 < chunk) ? W - w0 : chunk;
+            if (dt > 0.0) {
+                if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, first, w0, n, st, nullptr);
+                else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, first, w0, n, st, nullptr);
+                x->launches += 4;
+            }
+            if (last && h_state_out) {
+                if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, w0, n, st);
+                else launch_gather_state_f32(x->fields, x->c, x->stage_out, w0, n, st);
+                ++x->launches;
+                CUDA_TRY(cudaEventRecord(ev_out[k], st), "cudaEventRecord");
+                CUDA_TRY(cudaStreamWaitEvent(x->s_out, ev_out[k], 0), "cudaStreamWaitEvent");
+                CUDA_TRY(cudaMemcpyAsync((char*)h_state_out + (size_t)w0 * per_world_out, (const char*)x->stage_out + (size_t)w0 * per_world_out,
+                                         (size_t)n * per_world_out, cudaMemcpyDeviceToHost, x->s_out), "D2H state");
+            }
+        }
+        if (x->f64) launch_post_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);
+        else launch_post_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);
+        x->launches += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "step kernels", e);
     }
+    if (h_state_out) CUDA_TRY(cudaStreamSynchronize(x->s_out), "cudaStreamSynchronize(copy-out)");
+    if (h_force_torque) CUDA_TRY(cudaStreamSynchronize(x->s_in), "cudaStreamSynchronize(copy-in)");
     CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     return B2B_OK;
 }
@@ -333,21 +422,23 @@ extern "C" int b2b_profile(b2b_ctx* x, int64_t* host_out32, int reset)
     return B2B_OK;
 }
 
-extern "C" int b2b_kernel_ms(b2b_ctx* x, float* out4, int32_t* n_steps)
+extern "C" int b2b_kernel_ms(b2b_ctx* x, float* out8, int32_t* n_steps)
 {
-    if (!x || !out4) return fail(B2B_ERR_ARG, "b2b_kernel_ms: NULL argument");
-    out4[0] = out4[1] = out4[2] = out4[3] = 0.f;
-    if (n_steps) *n_steps = x->timed_steps;
-    for (int s = 0; s < x->timed_steps; ++s) {
-        cudaEvent_t* ev = x->events->data() + 5 * s;       // 0 start, 4 after collide, 1 after plan, 2 after solve, 3 end
-        CUDA_TRY(cudaEventSynchronize(ev[3]), "cudaEventSynchronize");
-        const int from[4] = {0, 4, 1, 2}, to[4] = {4, 1, 2, 3};
-        for (int k = 0; k < 4; ++k) {
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ev[from[k]], ev[to[k]]), "cudaEventElapsedTime");
-            out4[k] += ms;
-        }
+    if (!x || !out8) return fail(B2B_ERR_ARG, "b2b_kernel_ms: NULL argument");
+    for (int k = 0; k < 8; ++k) out8[k] = 0.f;
+    if (n_steps) *n_steps = 0;
+    step_timer* tm = x->timer;
+    if (!tm || tm->used == 0) return B2B_OK;
+    CUDA_TRY(cudaEventSynchronize(tm->ev[tm->used - 1]), "cudaEventSynchronize");
+    for (size_t i = 1; i < tm->used; ++i) {
+        if (tm->kind[i] == T_START) continue;                   // the gap between two steps belongs to nobody
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, tm->ev[i - 1], tm->ev[i]), "cudaEventElapsedTime");
+        out8[tm->kind[i]] += ms;
+        out8[7] += ms;
     }
-    x->timed_steps = 0;
+    if (n_steps) *n_steps = tm->steps;
+    tm->used = 0;
+    tm->steps = 0;
     return B2B_OK;
 }

@@ -31,11 +31,12 @@ typedef B2B_REAL real_t;
 #ifndef B2B_COLLIDE_MIN_CTAS
 #define B2B_COLLIDE_MIN_CTAS 6
 #endif
-__global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan)
+__global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                                                   int w0, int n_range)
 {
-    const long long total = (long long)c.n_worlds * c.nc;
+    const long long total = (long long)n_range * c.nc;                 // worlds [w0, w0 + n_range)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i / c.nc), ci = (int)(i % c.nc);
+        const int w = w0 + (int)(i / c.nc), ci = (int)(i % c.nc);
         if (ci >= B.w_count[4 * (size_t)w + 2]) continue;
         if (B.w_flags[w] & WORLD_NEW_FIXTURE) continue;
         world_step<real_t> ws;
@@ -93,9 +94,12 @@ __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_pt
         [&](int w) {
             const uint32_t fl = B.w_flags[w];
             const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
-            const bool settled = (sp.flags & STEP_FLAT_COLLIDE) && !(fl & WORLD_NEW_FIXTURE) && !(sum & SUM_COLLIDE) &&
+            // pending contacts alone (both bodies inactive) need no walk: without a touching change nobody was woken
+            const bool settled = (sp.flags & STEP_FLAT_COLLIDE) && !(fl & WORLD_NEW_FIXTURE) && !(sum & (SUM_DESTROY | SUM_CHANGED)) &&
                                  (!(sp.dt > 0.0) || (fl & WORLD_GRAPH_VALID));
             if (settled && sp.dt > 0.0) B.w_island[4 * (size_t)w + 3] = 0;      // what run_plan leaves behind for such a world
+            if (settled && (sum & SUM_PENDING))
+                atomicAnd(reinterpret_cast<unsigned int*>(plan + (size_t)w * P.stride + P.off_summary), ~(unsigned int)SUM_PENDING);
             if (settled) return 0;
             const int n_contacts = B.w_count[4 * (size_t)w + 2];
             if (n_contacts < 64) return 1;                            // too few contacts to occupy a warp
@@ -282,20 +286,34 @@ __global__ void __launch_bounds__(256) B2B_CAT(collide_pairs_kernel_, B2B_SUFFIX
 }
 
 // host-driven step: scatter staged (fx, fy, torque) into b_force / b_vel[3]
-__global__ void __launch_bounds__(256) B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, const real_t* stage)
+__global__ void __launch_bounds__(256) B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, const real_t* stage,
+                                                                                   int w0, int n_range)
 {
-    const long long total = (long long)c.n_worlds * c.nb;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        B.b_force[2 * i] = stage[3 * i]; B.b_force[2 * i + 1] = stage[3 * i + 1];
-        B.b_vel[4 * i + 3] = stage[3 * i + 2];
+    const long long first = (long long)w0 * c.nb, total = (long long)(w0 + n_range) * c.nb;      // worlds [w0, w0 + n_range)
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const real_t fx = stage[3 * i], fy = stage[3 * i + 1], tq = stage[3 * i + 2];
+        const uint32_t fl = B.b_flags[i];
+        // Body.apply_force / apply_torque (body.py:477-545): only dynamic bodies take forces, and applying one wakes the
+        // body (Body.awake = True, body.py:800-804: the sleep timer restarts).  A body woken from outside may seed the
+        // next island walk, so the world's island lists are rebuilt.
+        if ((fl & BODY_TYPE_MASK) != BODY_DYNAMIC) continue;
+        if (!(fl & BODY_AWAKE)) {
+            if (fx == real_t(0) && fy == real_t(0) && tq == real_t(0)) continue;       // nothing applied: a sleeper stays asleep
+            B.b_flags[i] = fl | BODY_AWAKE;
+            B.b_pos[4 * i + 3] = real_t(0);
+            atomicAnd(&B.w_flags[i / c.nb], ~(uint32_t)WORLD_GRAPH_VALID);
+        }
+        B.b_force[2 * i] = fx; B.b_force[2 * i + 1] = fy;
+        B.b_vel[4 * i + 3] = tq;
     }
 }
 
 // host-driven step: gather (c.x, c.y, a, v.x, v.y, w) for the device->host copy
-__global__ void __launch_bounds__(256) B2B_CAT(gather_state_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, real_t* stage)
+__global__ void __launch_bounds__(256) B2B_CAT(gather_state_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, real_t* stage,
+                                                                                 int w0, int n_range)
 {
-    const long long total = (long long)c.n_worlds * c.nb;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long first = (long long)w0 * c.nb, total = (long long)(w0 + n_range) * c.nb;      // worlds [w0, w0 + n_range)
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         stage[6 * i] = B.b_pos[4 * i]; stage[6 * i + 1] = B.b_pos[4 * i + 1]; stage[6 * i + 2] = B.b_pos[4 * i + 2];
         stage[6 * i + 3] = B.b_vel[4 * i]; stage[6 * i + 4] = B.b_vel[4 * i + 1]; stage[6 * i + 5] = B.b_vel[4 * i + 2];
     }
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(256) B2B_CAT(checksum_kernel_, B2B_SUFFIX)(bat
                       - mass * (gx * vals[0] + gy * vals[1]);
             awake += (B.b_flags[o] & BODY_AWAKE) ? 1 : 0;
         }
-        out[4 * (size_t)w] = __longlong_as_double((long long)h);
+        out[4 * (size_t)w] = (double)(h & ((1ull << 52) - 1ull));       // an exactly representable integer: never NaN / Inf, == works
         out[4 * (size_t)w + 1] = energy;
         out[4 * (size_t)w + 2] = (double)B.w_count[4 * (size_t)w + 2];
         out[4 * (size_t)w + 3] = (double)awake;
@@ -415,59 +433,87 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     return 0;
 }
 
-// one World.step = plan + solve + broadphase
-void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
-                                       unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,
-                                       unsigned int* counters, const step_params& sp_in, int first_step, cudaStream_t st, cudaEvent_t* ev)
+// One World.step = narrowphase + plan + (per group of worlds: prepare, velocity, position) + sync + pairs.  The parts are
+// separate launchers so that the host-buffer entry point (b2b_step_host) can run them chunk by chunk between its copies.
+static inline int flat_blocks(long long items, int n_sm)
+{
+    long long blocks = (items + 127) / 128;
+    if (blocks > (long long)n_sm * 64) blocks = (long long)n_sm * 64;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+// flat narrowphase (K1) for worlds [w0, w0 + n)
+void B2B_CAT(launch_collide_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan, int w0, int n,
+                                          cudaStream_t st)
+{
+    B2B_CAT(collide_kernel_, B2B_SUFFIX)<<<flat_blocks((long long)n * c.nc, p.n_sm), 128, 0, st>>>(as_ptrs(fields), c, p.plan, plan, w0, n);
+}
+
+// plan kernel (K1 ordering / destruction, K2 islands, level schedule) for every world
+void B2B_CAT(launch_plan_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
+                                       unsigned char* scratch_aux, unsigned int* counters, const step_params& sp, cudaStream_t st)
+{
+    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
+    if (sp.flags & STEP_GROUP_KERNEL) cudaMemsetAsync(counters + 2, 1, sizeof(unsigned int), st);   // any non-zero word
+    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(as_ptrs(fields), c, p.plan, plan, p.layout, scratch_aux, sp,
+                                                                                 p.lanes_aux, p.team_smem_plan, counters);
+}
+
+// K3 for worlds [w0, w0 + n_group): n_group <= launch_plan::group_worlds (one record slab each); timer may be null
+void B2B_CAT(launch_solve_group_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
+                                              unsigned char* scratch_solve, unsigned char* scratch_sprof, const step_params& sp,
+                                              int first_step, int w0, int n_group, cudaStream_t st, step_timer* tm)
 {
     const batch_ptrs<real_t> B = as_ptrs(fields);
-    if (ev) cudaEventRecord(ev[0], st);
-    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
+    B2B_CAT(prepare_kernel_, B2B_SUFFIX)<<<flat_blocks((long long)n_group * c.nc, p.n_sm), 128, 0, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp,
+                                                                                                         first_step, w0, n_group);
+    if (tm) tm->mark(T_PREPARE, st);
+    const int teams = 32 / p.lanes;
+    int grid = p.k_solve.grid;
+    if ((long long)grid * teams > n_group) grid = (n_group + teams - 1) / teams;
+    // (sizing the grid so that the last round of worlds is as full as the others was measured slower: 34.5 vs
+    // 33.5 ms per 131,072 worlds -- the stragglers of a ragged last round run faster on a nearly empty SM)
+    B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                   scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+    if (tm) tm->mark(T_VELOCITY, st);
+    B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                   scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+    B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                         scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+    if (tm) tm->mark(T_POSITION, st);
+}
+
+// K4 (proxy synchronisation, clear forces) + K5/K6 (pairs, new contacts) for every world
+void B2B_CAT(launch_post_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
+                                       unsigned char* scratch_aux, unsigned int* counters, const step_params& sp, cudaStream_t st, step_timer* tm)
+{
+    const batch_ptrs<real_t> B = as_ptrs(fields);
+    B2B_CAT(sync_kernel_, B2B_SUFFIX)<<<flat_blocks((long long)c.n_worlds * (c.nf > c.nb ? c.nf : c.nb), p.n_sm), 128, 0, st>>>(B, c, p.plan, plan, sp);
+    if (tm) tm->mark(T_SYNC, st);
+    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
+                                                                                         p.lanes_aux, p.team_smem_broad, counters + 1);
+    if (tm) tm->mark(T_PAIRS, st);
+}
+
+void B2B_CAT(launch_step_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
+                                       unsigned char* scratch_aux, unsigned char* scratch_solve, unsigned char* scratch_sprof,
+                                       unsigned int* counters, const step_params& sp_in, int first_step, cudaStream_t st, step_timer* tm)
+{
     step_params sp = sp_in;
     sp.joint_any = counters + 2;
-    if (sp.flags & STEP_GROUP_KERNEL) cudaMemsetAsync(counters + 2, 1, sizeof(unsigned int), st);   // any non-zero word
-    if (sp.flags & STEP_FLAT_COLLIDE) {
-        const long long total = (long long)c.n_worlds * c.nc;
-        long long blocks = (total + 127) / 128;
-        if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
-        B2B_CAT(collide_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan);
-    }
-    if (ev) cudaEventRecord(ev[4], st);
-    B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp, p.lanes_aux,
-                                                                                 p.team_smem_plan, counters);
-    if (ev) cudaEventRecord(ev[1], st);
+    if (tm) tm->mark(T_START, st);
+    if (sp.flags & STEP_FLAT_COLLIDE) B2B_CAT(launch_collide_, B2B_SUFFIX)(fields, c, p, plan, 0, c.n_worlds, st);
+    if (tm) tm->mark(T_COLLIDE, st);
+    B2B_CAT(launch_plan_, B2B_SUFFIX)(fields, c, p, plan, scratch_aux, counters, sp, st);
+    if (tm) tm->mark(T_PLAN, st);
     if (sp.dt > 0.0) {
         // groups of worlds: the record slab is sized for one group (launch_plan::group_worlds)
         for (int w0 = 0; w0 < c.n_worlds; w0 += p.group_worlds) {
             const int n_group = (c.n_worlds - w0 < p.group_worlds) ? c.n_worlds - w0 : p.group_worlds;
-            const long long total = (long long)n_group * c.nc;
-            long long blocks = (total + 127) / 128;
-            if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
-            B2B_CAT(prepare_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp, first_step,
-                                                                             w0, n_group);
-            const int teams = 32 / p.lanes;
-            int grid = p.k_solve.grid;
-            if ((long long)grid * teams > n_group) grid = (n_group + teams - 1) / teams;
-            // (sizing the grid so that the last round of worlds is as full as the others was measured slower: 34.5 vs
-            // 33.5 ms per 131,072 worlds -- the stragglers of a ragged last round run faster on a nearly empty SM)
-            B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
-                                                                                           scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
-            B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
-                                                                                           scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
-            B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
-                                                                                                 scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
+            B2B_CAT(launch_solve_group_, B2B_SUFFIX)(fields, c, p, plan, scratch_solve, scratch_sprof, sp, first_step, w0, n_group, st, tm);
         }
     }
-    if (ev) cudaEventRecord(ev[2], st);
-    {
-        const long long total = (long long)c.n_worlds * (c.nf > c.nb ? c.nf : c.nb);
-        long long blocks = (total + 127) / 128;
-        if (blocks > (long long)p.n_sm * 64) blocks = (long long)p.n_sm * 64;
-        B2B_CAT(sync_kernel_, B2B_SUFFIX)<<<(int)blocks, 128, 0, st>>>(B, c, p.plan, plan, sp);
-    }
-    B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
-                                                                                         p.lanes_aux, p.team_smem_broad, counters + 1);
-    if (ev) cudaEventRecord(ev[3], st);
+    B2B_CAT(launch_post_, B2B_SUFFIX)(fields, c, p, plan, scratch_aux, counters, sp, st, tm);
 }
 
 void B2B_CAT(launch_init_proxies_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, cudaStream_t st)
@@ -488,14 +534,18 @@ void B2B_CAT(launch_collide_pairs_, B2B_SUFFIX)(const void* const* fields, int n
                                                                       (real_t*)mf, (real_t*)pts, (uint32_t*)id);
 }
 
-void B2B_CAT(launch_scatter_forces_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const void* stage, cudaStream_t st)
+void B2B_CAT(launch_scatter_forces_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const void* stage, int w0, int n, cudaStream_t st)
 {
-    B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)<<<148 * 8, 256, 0, st>>>(as_ptrs(fields), c, (const real_t*)stage);
+    long long blocks = ((long long)n * c.nb + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    B2B_CAT(scatter_forces_kernel_, B2B_SUFFIX)<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(as_ptrs(fields), c, (const real_t*)stage, w0, n);
 }
 
-void B2B_CAT(launch_gather_state_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, void* stage, cudaStream_t st)
+void B2B_CAT(launch_gather_state_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, void* stage, int w0, int n, cudaStream_t st)
 {
-    B2B_CAT(gather_state_kernel_, B2B_SUFFIX)<<<148 * 8, 256, 0, st>>>(as_ptrs(fields), c, (real_t*)stage);
+    long long blocks = ((long long)n * c.nb + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    B2B_CAT(gather_state_kernel_, B2B_SUFFIX)<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(as_ptrs(fields), c, (real_t*)stage, w0, n);
 }
 
 void B2B_CAT(launch_checksum_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, double* out, cudaStream_t st)

@@ -463,9 +463,11 @@ template <class real> struct world_step {
     }
 
     // Narrowphase for ONE contact of this world, called by the flat kernel (one thread per contact of the whole
-    // batch).  Only contacts whose non-static bodies are all awake are handled here: they are active whatever the
-    // list order, and their touching changes cannot wake anybody.  The rest (a sleeping body is involved) stays
-    // pending for the order-exact walk in phase_collide.
+    // batch).  A contact one of whose bodies is awake and not static on entry is active whatever the list order
+    // (contact_manager.py:193-197; bodies are only ever WOKEN during the walk), so it is evaluated here.  A contact
+    // whose bodies are both inactive on entry stays pending: the reference skips it unless an EARLIER contact's
+    // touching change woke one of its bodies -- which needs a touching change somewhere in the world (SUM_CHANGED);
+    // only then does phase_collide walk the pending ones in list order.
     B2B_D void collide_one(int c)
     {
         // all rows are fetched before the first decision (every index below w_count[2] is a live contact)
@@ -474,9 +476,9 @@ template <class real> struct world_step {
         const quad fat_a = ldq(f_fat + 4 * (size_t)in.fa), fat_b = ldq(f_fat + 4 * (size_t)in.fb);
         const uint32_t fla = b_flags[in.ba], flb = b_flags[in.bb];
         const bool ns_a = (fla & BODY_TYPE_MASK) != BODY_STATIC, ns_b = (flb & BODY_TYPE_MASK) != BODY_STATIC;
-        const bool all_awake = (!ns_a || (fla & BODY_AWAKE)) && (!ns_b || (flb & BODY_AWAKE));
+        const bool active = (ns_a && (fla & BODY_AWAKE)) || (ns_b && (flb & BODY_AWAKE));
         uint8_t state = 0;
-        if (all_awake && (ns_a || ns_b)) {
+        if (active) {
             const real fa4[4] = {fat_a.x, fat_a.y, fat_a.z, fat_a.w}, fb4[4] = {fat_b.x, fat_b.y, fat_b.z, fat_b.w};
             if (!aabb_overlap<real>(fa4, fb4)) state = 2;
             else state = contact_update(c, in) ? 3 : 1;
@@ -498,11 +500,12 @@ template <class real> struct world_step {
         const int nb = w_count[0], nc = w_count[2];
         const int NEVER = 0x7fffffff;
         if (after_flat) {
-            // every contact came back "updated, touching unchanged" (the settled regime): nothing to order, wake or destroy
+            // every contact came back "updated, touching unchanged" or "both bodies inactive" (the settled regime): no
+            // touching change means nobody was woken, so the pending contacts are exactly the ones the reference skips
             const uint32_t sum = *g_summary & SUM_COLLIDE;
             B2B_SYNC();
-            if (sum == 0) return;
-            if (B2B_IS_T0) B2B_ATOMIC_AND(g_summary, ~(uint32_t)SUM_COLLIDE);
+            if (sum != 0 && B2B_IS_T0) B2B_ATOMIC_AND(g_summary, ~(uint32_t)SUM_COLLIDE);
+            if ((sum & (SUM_DESTROY | SUM_CHANGED)) == 0) { B2B_SYNC(); return; }
         }
         if (B2B_IS_T0) { s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[10] = 0; s_ctl[12] = 0; }
         B2B_SYNC();
@@ -518,6 +521,14 @@ template <class real> struct world_step {
         const bool any_pending = s_ctl[12] != 0;
         if (any_pending) {
             B2B_PFOR(b, nb) wake_at[b] = (b_flags[b] & BODY_AWAKE) ? -1 : NEVER;
+            B2B_SYNC();
+            // touching changes the flat kernel found wake their bodies at that point of the list (contact.py:257-259)
+            if (after_flat) B2B_PFOR(c, nc) {
+                if (g_cstate[c] != 3) continue;
+                const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                B2B_ATOMIC_MIN(&wake_at[ba], c);
+                B2B_ATOMIC_MIN(&wake_at[bb], c);
+            }
         }
         B2B_SYNC();
         for (; any_pending;) {
@@ -1345,9 +1356,16 @@ template <class real> struct world_step {
     // (the velocity kernel copies it to shared memory).
     B2B_D void prepare_body(const step_params& sp, int b)
     {
-        const uint32_t fl = b_flags[b];
+        uint32_t fl = b_flags[b];
         V2 v;
         real w;
+        // world.py:520: the island walk wakes every body it visits.  A walk that was skipped because its lists are
+        // still valid (sleep_invalidates) has one effect left: the sleeper it would have reached is awake again.
+        if ((fl & BODY_ISLAND) && !(fl & BODY_AWAKE)) {
+            fl |= BODY_AWAKE;
+            b_flags[b] = fl;
+            b_pos[4 * (size_t)b + 3] = real(0);
+        }
         if ((fl & BODY_ISLAND) && (fl & BODY_TYPE_MASK) != BODY_STATIC) {
             const quad p = ldq(b_pos + 4 * (size_t)b);
             real* p0 = b_pos0 + 4 * (size_t)b;
@@ -1394,6 +1412,18 @@ template <class real> struct world_step {
         const XF tf = xf_from_sweep<real>(mk<real>(sp.x, sp.y), sp.z, mk<real>(mass.z, mass.w));
         stq(b_xf + 4 * (size_t)b, mkq(tf.p.x, tf.p.y, tf.c1.x, tf.c1.y));
     }
+    // A body the sleep rule put to sleep is no seed for the next island walk (world.py:499).  If it was its island's
+    // seed (island index 0) the next walk differs and the lists must be rebuilt.  Otherwise the walk starts from the
+    // same seed, follows the same touching contacts in the same order and reaches the sleeper exactly where it was
+    // (membership and order only depend on awake flags through the seeds, world.py:496-546), wakes it (:520) and
+    // produces the lists the plan rows already hold: they stay valid, and prepare_body does the waking.  This is the
+    // reference's periodic event in a settled pile (the buggy rule of island.py:166-179 puts ONE body to sleep every
+    // TIME_TO_SLEEP / dt + 1 steps and the next walk wakes it again); without this every world replanned on that step.
+    B2B_D void sleep_invalidates(int victim)
+    {
+        if (b_island[victim] == 0) B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);
+    }
+
     // Sleep bookkeeping exactly as written in the reference (island.py:163-179): the allow-sleep
     // test reads the LAST island body; only the last non-static body is put to sleep.
     B2B_D void island_sleep(int b0, int b1, real dt, bool position_solved)
@@ -1423,7 +1453,7 @@ template <class real> struct world_step {
             v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
             b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
             b_flags[victim] &= ~BODY_AWAKE;
-            B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);   // the next island walk must skip this body
+            sleep_invalidates(victim);
         }
     }
 
@@ -1482,7 +1512,7 @@ template <class real> struct world_step {
             v[0] = real(0); v[1] = real(0); v[2] = real(0); v[3] = real(0);
             b_force[2 * (size_t)victim] = real(0); b_force[2 * (size_t)victim + 1] = real(0);
             b_flags[victim] &= ~BODY_AWAKE;
-            B2B_ATOMIC_AND(w_flags, ~(uint32_t)WORLD_GRAPH_VALID);
+            sleep_invalidates(victim);
         }
     }
 

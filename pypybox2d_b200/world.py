@@ -13,6 +13,7 @@ stepping (TOI) and sub-stepping.
 from copy import copy
 
 from .body import Body
+from . import schema
 from .common import Vec2, LockedError
 
 
@@ -178,6 +179,16 @@ class World(object):
             if dt > 0.0:
                 self._inv_dt0 = 1.0 / dt
             self._stepped = True
+            # The device arrays have fixed capacities (the reference's lists have none): a step that ran out of contact,
+            # pair or island-list rows dropped work and its result is NOT the reference's -- fail loudly, never mirror it
+            # back (the read-back below synchronises anyway, so the check costs one small kernel).
+            st = batch.status(raise_on_overflow=False)
+            if st:
+                names = [n for bit, n in ((schema.STATUS_CONTACT_OVERFLOW, "contacts"), (schema.STATUS_PAIR_OVERFLOW, "pairs"),
+                                          (schema.STATUS_ISLAND_OVERFLOW, "island list"), (schema.STATUS_NAN, "NaN")) if st & bit]
+                raise RuntimeError("World.step: device capacity exceeded (%s): contacts %d, pairs %d, island rows %d per world; "
+                                   "the step's result is invalid" % (", ".join(names) or hex(st), batch.caps.nc, batch.caps.npair,
+                                                                      batch.caps.nl))
             batch.download_into_world(self)
             if not self._auto_clear_forces:
                 # forces were cleared on the device only when auto_clear_forces is on

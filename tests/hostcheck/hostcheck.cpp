@@ -15,6 +15,7 @@
 using namespace b2b;
 
 static long long g_joint_world_steps = 0;     // world-steps whose plan row carried a joint island schedule (test bookkeeping)
+static long long g_replans = 0;               // world-steps that entered with invalid island lists (a full replan follows)
 
 template <class real>
 static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double inv_dt0, int vel_iters, int pos_iters,
@@ -53,6 +54,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
         ws.bind_scratch_solve(solve.data(), L, sprof.data());
         ws.bind_smem_aux(smem_aux.data());
         ws.bind_smem_solve(smem_solve.data());
+        if (dt > 0.0 && !(B.w_flags[w] & WORLD_GRAPH_VALID)) g_replans += 1;
         ws.run(sp);
         if (dt > 0.0 && ws.g_joint[0] != 0 && ws.w_island[2] > 0) g_joint_world_steps += n_steps;
     }
@@ -63,6 +65,13 @@ extern "C" long long hc_joint_world_steps(int reset)
 {
     const long long v = g_joint_world_steps;
     if (reset) g_joint_world_steps = 0;
+    return v;
+}
+
+extern "C" long long hc_replans(int reset)
+{
+    const long long v = g_replans;
+    if (reset) g_replans = 0;
     return v;
 }
 

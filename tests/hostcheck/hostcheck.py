@@ -42,6 +42,8 @@ def lib():
         _LIB.hc_step.restype = ctypes.c_int
         _LIB.hc_joint_world_steps.argtypes = [ctypes.c_int]
         _LIB.hc_joint_world_steps.restype = ctypes.c_longlong
+        _LIB.hc_replans.argtypes = [ctypes.c_int]
+        _LIB.hc_replans.restype = ctypes.c_longlong
     return _LIB
 
 
@@ -67,3 +69,8 @@ def step(arrays, dt, inv_dt0, vel_iters, pos_iters, n_steps=1):
 def joint_world_steps(reset=True):
     """World-steps so far whose plan row carried a joint island schedule (phase_schedule in b2b_step.cuh)."""
     return int(lib().hc_joint_world_steps(1 if reset else 0))
+
+
+def replans(reset=True):
+    """World-steps so far that entered the step with invalid island lists (each one rebuilds lists and schedule)."""
+    return int(lib().hc_replans(1 if reset else 0))

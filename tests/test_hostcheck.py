@@ -39,3 +39,31 @@ def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps):
         assert joint >= steps // 2, joint
     if scene == "hello":
         assert joint == 0, joint
+
+
+def test_settled_pile_sleep_event_keeps_the_island_lists():
+    """The reference's buggy sleep rule (island.py:166-179) puts ONE body of a settled pile to sleep every 31 steps and the
+    next island walk wakes it again.  The step keeps its island lists over that event when the sleeper
+    is not its island's seed: same outputs as the oracle at every step, and no replan after the first step."""
+    from conftest import load_golden, arrays_from_golden
+    g = load_golden("pyramid_w1")
+    dt, vi, pi = float(g["meta"][0]), int(g["meta"][1]), int(g["meta"][2])
+    A, caps = arrays_from_golden(g)
+    OA, _ = arrays_from_golden(g, prefix="ck300_", base=A)
+    HA = {k: v.copy() for k, v in OA.items()}
+    orc = oracle.Oracle(OA, 0)
+    orc.inv_dt0 = 1.0 / dt
+    hostcheck.replans(reset=True)
+    awake = []
+    for s in range(75):
+        orc.step(dt, vi, pi)
+        hostcheck.step(HA, dt, 1.0 / dt, vi, pi)
+        assert harness.diff_state(OA, HA, fields=INT_FIELDS) == [], "step %d" % (300 + s)
+        assert harness.oracle_islands(OA) == harness.oracle_islands(HA), "islands, step %d" % (300 + s)
+        for k in ("b_pos", "b_vel", "c_imp", "c_pts"):
+            x, y = harness.used_view(OA, k), harness.used_view(HA, k)
+            assert np.allclose(x, y, rtol=1e-9, atol=1e-10), "%s, step %d" % (k, 300 + s)
+        awake.append(int(((harness.used_view(HA, "b_flags") & 0x4) != 0).sum()))
+    assert min(awake) == 210 and max(awake) == 211, (min(awake), max(awake))       # the event happened (twice)
+    assert awake.count(210) >= 2
+    assert hostcheck.replans() == 1                                                  # only the first step built the lists
