@@ -63,3 +63,24 @@ def arrays_from_golden(g, prefix="init_", base=None):
 def have_gpu():
     import torch
     return torch.cuda.is_available()
+
+
+_PARITY_REPORT = {}
+
+
+@pytest.fixture(scope="session")
+def parity_report():
+    """Collects the measured parity errors of the -m gpu run; written to gpurun_out/parity_report.json (scratch) so that the
+    tolerances pinned in the tests can be checked against what the hardware measured (a copy lives under profiles/)."""
+    import json
+
+    def add(key, value):
+        _PARITY_REPORT[key] = value
+    yield add
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(_PARITY_REPORT, f, indent=1, sort_keys=True, default=str)
+    except Exception:
+        pass

@@ -52,7 +52,27 @@ def test_batch_invariance_and_replicate():
         assert np.array_equal(B[name][103], M[name][0]), name
     assert big.status() == 0
     cs = big.checksum().cpu().numpy()
-    assert cs.shape == (300, 4) and np.all(cs[:, 2] > 300) and np.isfinite(cs[:, 1]).all()
+    assert cs.shape == (300, 4) and np.all(cs[:, 2] > 300) and np.isfinite(cs).all()
+    # the checksum rows of identical worlds are identical (the hash column is an exact integer, never NaN)
+    assert np.array_equal(cs[103], part.checksum().cpu().numpy()[3])
+    assert np.array_equal(cs[103], mw.checksum().cpu().numpy()[0])
+    assert cs[103, 0] == np.floor(cs[103, 0]) and 0 <= cs[103, 0] < 2.0 ** 52 and len(np.unique(cs[:, 0])) == 300
+
+
+def test_replicate_without_jitter_equals_the_facade_path():
+    """T4 for the un-jittered batch: replicate(jitter=0) builds its proxies in the working precision like from_worlds does
+    (host fp64 AABBs rounded to fp32 could differ in the last ulp and move a pair-emission tie)."""
+    import pypybox2d_b200 as b2
+    w = scenes.pyramid(b2)
+    rep = b2.BatchedWorld.replicate(w, 5, jitter=0.0, real="f32")
+    one = b2.BatchedWorld.from_worlds([scenes.pyramid(b2)], real="f32", caps=rep.caps)
+    for name in ("b_xf", "b_pos", "f_fat", "f_tight", "f_moved"):
+        assert np.array_equal(rep.download([name])[name][4], one.download([name])[name][0]), name
+    rep.step(1 / 60, 8, 3, 60)
+    one.step(1 / 60, 8, 3, 60)
+    R, O = rep.download(), one.download()
+    for name in ("b_pos", "b_vel", "c_fix", "c_mtype", "c_imp", "w_count", "p_pairs"):
+        assert np.array_equal(R[name][4], O[name][0]), name
 
 
 def test_contexts_with_different_shared_memory_sizes_coexist():
@@ -121,9 +141,10 @@ def test_other_baseline_scenes_at_scale(scene, config, n_worlds, steps, vi, pi):
     assert int(big.t["w_count"][:, 2].min()) > 0          # contacts exist: the worlds did land
 
 
-def test_step_host_matches_device_step_and_reports_overflow():
+def test_step_host_matches_device_step_and_reports_overflow(monkeypatch):
     import torch
     import pypybox2d_b200 as b2
+    monkeypatch.setenv("B2B_PIPE_CHUNKS", "6")           # 64 worlds in six chunks: the copy / kernel pipeline is really exercised
     w = scenes.vertical_stack(b2)
     a = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
     b = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
@@ -142,12 +163,59 @@ def test_step_host_matches_device_step_and_reports_overflow():
     b.step(1 / 60, 10, 10)
     B = b.download(["b_vel"])
     assert h_out[5, 3, 4] > B["b_vel"][5, 3, 1]
+    # ... and the two paths stay bitwise equal with the force applied on both
+    b.t["b_force"][5, 3, 1] = 500.0
+    h_in[5, 3, 1] = 500.0
+    a2 = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
+    b3 = b2.BatchedWorld.replicate(w, 64, jitter=1e-2, config=2, real="f32")
+    for s in range(5):
+        b3.t["b_force"][5, 3, 1] = 500.0
+        a2.step_host(h_in, h_out, 1 / 60, 10, 10)
+        b3.step(1 / 60, 10, 10)
+    B = b3.download(["b_pos", "b_vel"])
+    assert np.array_equal(h_out.numpy()[..., :3], B["b_pos"][..., :3])
+    assert np.array_equal(h_out.numpy()[..., 3:], B["b_vel"][..., :3])
     # capacity overflow is reported, not silently truncated
     small = b2.BatchedWorld.from_worlds([scenes.pyramid(b2)], real="f32", caps=schema.Caps(211, 211, 300))
     small.step(1 / 60, 8, 3, 60)
     assert small.status(raise_on_overflow=False) & schema.STATUS_CONTACT_OVERFLOW
     with pytest.raises(Exception):
         small.status()
+
+
+def test_world_step_raises_when_a_capacity_overflows(monkeypatch):
+    """The facade never mirrors back a step that dropped contacts (the reference's lists have no capacity)."""
+    import pypybox2d_b200 as b2
+    from pypybox2d_b200 import batch as batch_mod
+    monkeypatch.setattr(batch_mod, "world_caps", lambda worlds, **kw: schema.Caps(211, 211, 300))
+    world = scenes.pyramid(b2)
+    with pytest.raises(RuntimeError, match="capacity"):
+        for i in range(80):
+            world.step(1 / 60, 8, 3)
+
+
+def test_step_host_force_wakes_a_sleeping_body():
+    """Body.apply_force wakes the body (body.py:800-804); forces sent through the end-to-end entry point do the same, so a
+    body that has gone to sleep moves again.  hello scene: the ball comes to rest on the box and falls asleep."""
+    import torch
+    import pypybox2d_b200 as b2
+    bw = b2.BatchedWorld.from_worlds([scenes.SCENES["hello"](b2, world=w) for w in range(4)], real="f64")
+    nb = bw.caps.nb
+    bw.step(0.1, 10, 10, 200)
+    D = bw.download(["b_flags", "b_pos"])
+    assert not (D["b_flags"][:, 1] & schema.BODY_AWAKE).any()            # every ball sleeps
+    y0 = D["b_pos"][:, 1, 1].copy()
+    h_in = torch.zeros((4, nb, 3), dtype=torch.float64).pin_memory()
+    h_out = torch.zeros((4, nb, 6), dtype=torch.float64).pin_memory()
+    bw.step_host(h_in, h_out, 0.1, 10, 10)                                # zero force: a sleeper stays asleep
+    assert not (bw.download(["b_flags"])["b_flags"][:, 1] & schema.BODY_AWAKE).any()
+    h_in[2, 1, 1] = 400.0                                                 # push the ball of world 2 upwards
+    bw.step_host(h_in, h_out, 0.1, 10, 10)
+    D = bw.download(["b_flags", "b_pos"])
+    awake = (D["b_flags"][:, 1] & schema.BODY_AWAKE) != 0
+    assert awake.tolist() == [False, False, True, False]
+    assert D["b_pos"][2, 1, 1] > y0[2] + 1e-3 and np.array_equal(D["b_pos"][[0, 1, 3], 1, 1], y0[[0, 1, 3]])
+    assert h_out[2, 1, 1] == D["b_pos"][2, 1, 1]
 
 
 def test_ragged_batch_of_different_scenes():

@@ -3,19 +3,31 @@
 Tiers (DESIGN.md "Parity"; tolerances are pinned here):
   P-exact  fp64 kernels, free-running from t=0 for the golden trajectory length: every graded integer output
            (contact set + order, flags, manifold type/count/ids, island membership + order, emitted pair lists,
-           awake flags) identical at EVERY step; body state within 1e-5 absolute (scene scale 10 m => 1e-6 rel).
+           awake flags) identical at EVERY step; every float field of the state (bodies: transforms, sweeps,
+           velocities; proxies: fat and tight AABBs; contacts: manifolds and accumulated impulses) within the
+           per-scene bound EXACT_TOL (about ten times what a B200 measures).  The bound differs by seven orders of
+           magnitude between scenes because the ONLY arithmetic that differs from the oracle's is CUDA's sincos
+           (<= 2 ulp from glibc's; sqrt and division are correctly rounded, FMA contraction is off): where bodies
+           keep tiny angles (the box pyramid) sin and cos are exact and the trajectories agree to 1e-13; where
+           they roll and tumble (circles and polygons of the mixed scene) each step injects ~1e-16 and the chaotic
+           pile amplifies it.  test_p_exact_fp64_one_step pins that reading: teacher-forced from the oracle's
+           state, ONE fp64 step agrees to 1e-12 on every step of the mixed scene.
   P-step   fp32 kernels, teacher-forced: the oracle's state at step k (rounded to fp32) is uploaded, both sides
-           take ONE step.  Integer outputs (including the number of position iterations an island used) must
-           agree except on tie steps (a comparison within fp32 rounding of its threshold, e.g. the 0.1 m fat-AABB
-           margin that the lock-step free fall hits exactly at step 8, or the -0.015 m early-exit test of the
-           position solver) -- bounded to <= 10 % of the steps, and on those same inputs the fp64 kernels must
-           still match the oracle exactly.  Body state must agree to |dc| <= 5e-5 m, |dv| <= 1e-3 m/s on every
-           non-tie step and to 1e-3 m, 1e-2 m/s on tie steps (one position iteration more or less).
-  P-steady fp32 kernels free-running 300 steps from the oracle's settled state (golden checkpoint 300):
-           positions within 1e-3 m (1e-4 of the scene scale), same contact / touching-contact / point counts.
+           take ONE step, for EVERY step of the golden trajectory (600 on the pyramid).  Integer outputs (including
+           the number of position iterations an island used) must agree except on tie steps (a comparison within
+           fp32 rounding of its threshold, e.g. the 0.1 m fat-AABB margin that the lock-step free fall hits
+           exactly at step 8, or the -0.015 m early-exit test of the position solver) -- bounded to <= 10 % of
+           the steps, and on those same inputs the fp64 kernels must still match the oracle exactly.  Body state
+           must agree to |dc| <= 5e-5 m, |dv| <= 1e-3 m/s on every non-tie step and to 1e-3 m, 1e-2 m/s on tie
+           steps (one position iteration more or less).  The tie steps are printed.
+  P-steady fp32 kernels free-running 600 steps from the oracle's settled state, 16 jittered worlds per scene in ONE
+           batch against per-world oracle runs from the same fp32-rounded state: contact set + order, touching
+           flags and island membership + order compared at EVERY step, state at the end (see STEADY).
            (The reference's FACE_A/FACE_B hysteresis alternates every step on some resting contacts, and fp32
            picks the other phase of that 2-cycle, so per-step manifold ids are NOT graded here.)
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -26,7 +38,11 @@ pytestmark = pytest.mark.gpu
 import harness
 import oracle
 import gen_golden
-from pypybox2d_b200 import schema
+from pypybox2d_b200 import schema, scenes
+
+# measurement mode: B2B_PARITY_REPORT_ONLY=1 records the errors (gpurun_out/parity_report.json) without enforcing the float
+# tolerances -- used once per change of the kernels to re-pin them; the driver's run enforces them
+STRICT = os.environ.get("B2B_PARITY_REPORT_ONLY") != "1"
 
 INT_FIELDS = ["w_count", "f_moved", "c_fix", "c_flags", "c_mtype", "b_flags"]
 REAL_FIELDS = [f[0] for f in schema.FIELDS if f[3] == "real" and f[1] != "S"]
@@ -70,30 +86,79 @@ def _group_kernel_cases():
     return cases + [(c, True) for c in ("pyramid_w1", "mixed_w1", "hello_w0", "vertical_stack_w1") if c in golden_cases()]
 
 
+# Float fields of the state compared in P-exact, and the per-scene bound on their absolute error (m, m/s, N s):
+# measured maxima on B200 (profiles/r2_parity_report.json) times ~10.
+EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
+EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-9, "deep_stacks": 1e-9, "features": 1e-9, "mixed": 1e-5}
+
+
+def float_diffs(OA, G):
+    out = {}
+    for k in EXACT_FIELDS:
+        x, y = harness.used_view(OA, k), harness.used_view(G, k)
+        if k in ("b_pos", "b_vel"):
+            x, y = x[:, :3], y[:, :3]            # sleep timer / torque ride in the fourth lane
+        out[k] = float(np.abs(x - y.astype(np.float64)).max()) if x.size else 0.0
+    return out
+
+
 @pytest.mark.parametrize("case,group_kernel", _group_kernel_cases())
-def test_p_exact_fp64_free_running(case, group_kernel):
+def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)
     dt, vi, pi, steps, world = g["meta"]
     vi, pi, steps = int(vi), int(pi), int(steps)
+    tol = EXACT_TOL[str(g["scene"])]
     A, caps = arrays_from_golden(g)
     bw = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
     orc = oracle.Oracle(A, 0)
+    worst = {k: 0.0 for k in EXACT_FIELDS}
     for s in range(steps):
         orc.step(dt, vi, pi)
         assert bytes(g["digest"][s]) == gen_golden.state_digest(A)          # the checker itself is on the golden path
         bw.step(dt, vi, pi, group_kernel=group_kernel)
         G = bw.download()
         assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
-        dp, dv = state_diff(A, G)
-        assert dp <= 1e-5 and dv <= 1e-5, "state differs at step %d: %.2e %.2e" % (s, dp, dv)
+        d = float_diffs(A, G)
+        for k, v in d.items():
+            worst[k] = max(worst[k], v)
+            assert v <= tol or not STRICT, "%s differs at step %d: %.2e > %.0e" % (k, s, v, tol)
     assert bw.status() == 0
+    parity_report("p_exact/%s%s" % (case, "/group" if group_kernel else ""), dict(worst, steps=steps, tol=tol))
 
 
-@pytest.mark.parametrize("case,steps", [("pyramid_w1", 300), ("pyramid_w0", 150), ("mixed_w1", 150),
+@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0"])
+def test_p_exact_fp64_one_step(case, parity_report):
+    """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
+    1e-12 in every float field at every k -- the free-running differences of the tumbling scenes are amplification of
+    last-ulp sincos differences by the dynamics, not an arithmetic difference of the step."""
+    import pypybox2d_b200 as b2
+    g = load_golden(case)
+    dt, vi, pi, steps, world = g["meta"]
+    vi, pi, steps = int(vi), int(pi), int(steps)
+    A, caps = arrays_from_golden(g)
+    orc = oracle.Oracle(A, 0)
+    bw = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
+    names = [k for k in schema.FIELD_NAMES if not k.startswith("s_")]
+    inv, worst = 0.0, {k: 0.0 for k in EXACT_FIELDS}
+    for s in range(steps):
+        bw.upload({k: A[k] for k in names})
+        bw.inv_dt0 = inv
+        orc.step(dt, vi, pi)
+        bw.step(dt, vi, pi)
+        G = bw.download()
+        assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
+        for k, v in float_diffs(A, G).items():
+            worst[k] = max(worst[k], v)
+            assert v <= 1e-12 or not STRICT, "%s: one-step difference %.2e at step %d" % (k, v, s)
+        inv = 1.0 / dt
+    parity_report("p_exact_one_step/%s" % case, dict(worst, steps=steps))
+
+
+@pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
                                         ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60),
                                         ("features_w0", 200)])
-def test_p_step_fp32_teacher_forced(case, steps):
+def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)
     dt, vi, pi, _, world = g["meta"]
@@ -103,7 +168,7 @@ def test_p_step_fp32_teacher_forced(case, steps):
     bw32 = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f32")
     bw64 = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
     names = [k for k in schema.FIELD_NAMES if not k.startswith("s_")]
-    inv, ties = 0.0, 0
+    inv, ties, tie_steps, worst_p, worst_v = 0.0, 0, [], 0.0, 0.0
     for s in range(steps):
         T = round32(A)
         o2 = oracle.Oracle(T, 0)
@@ -114,11 +179,15 @@ def test_p_step_fp32_teacher_forced(case, steps):
         bw32.step(dt, vi, pi)
         G = bw32.download()
         dp, dv = state_diff(T, G)
-        tie = bool(int_mismatches(T, G))
+        tie_what = int_mismatches(T, G)
+        tie = bool(tie_what)
         tol_p, tol_v = (1e-3, 1e-2) if tie else (5e-5, 1e-3)
         assert dp <= tol_p and dv <= tol_v, "fp32 one-step state error at step %d (tie=%s): %.2e m, %.2e m/s" % (s, tie, dp, dv)
+        if not tie:
+            worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
         if tie:
             ties += 1
+            tie_steps.append((s, tie_what))
             # same fp32-rounded inputs through the fp64 kernels: must match the oracle exactly
             T2 = round32(A)
             bw64.upload({k: T2[k] for k in names})
@@ -127,30 +196,112 @@ def test_p_step_fp32_teacher_forced(case, steps):
             assert int_mismatches(T, bw64.download()) == [], "fp64 kernels differ from the oracle at step %d" % s
         orc.step(dt, vi, pi)
         inv = 1.0 / dt
+    print("P-step %s: %d tie steps of %d: %s" % (case, ties, steps, tie_steps))
+    parity_report("p_step/%s" % case, {"steps": steps, "ties": ties, "tie_steps": [[k, w] for k, w in tie_steps],
+                                        "max_dp_non_tie": worst_p, "max_dv_non_tie": worst_v})
     assert ties <= 0.10 * steps, "%d of %d teacher-forced steps had integer mismatches" % (ties, steps)
 
 
-@pytest.mark.parametrize("case", ["pyramid_w1", "pyramid_w0"])
-def test_p_steady_fp32_from_settled_state(case):
+# P-steady: scene -> (settle steps, vel_iters, pos_iters, worlds that must keep identical integer outputs for all 600 steps
+# (of 16), bound on the relative position error and on the velocity error (m/s) of those worlds at the end).  Measured on
+# B200: profiles/r2_parity_report.json.  Positions are relative to the scene's extent (largest |coordinate| of a body).
+STEADY = {
+    "pyramid": (300, 8, 3, 16, 1e-4, 1e-3),
+    "deep_stacks": (400, 8, 3, 16, 1e-4, 1e-3),
+    "vertical_stack": (400, 10, 10, 12, 1e-4, 2e-3),
+    # circles and polygons in a box never come to rest and the pile is chaotic: fp32 rounding grows to a different contact
+    # set within a few hundred steps in most worlds (the fp64 kernels on the same inputs do not: test_p_exact).  Graded on
+    # how long the integer outputs stay identical, and on the state up to that point.
+    "mixed": (400, 8, 3, 0, 1e-4, 1e-3),
+}
+STEADY_WORLDS, STEADY_STEPS = 16, 600
+
+
+def _steady_ints(A, w=0):
+    nb, nf, nc, npair = [int(x) for x in A["w_count"][w]]
+    n_isl, nlb, nlc, _ = [int(x) for x in A["w_island"][w]]
+    return (nc, A["c_fix"][w][:nc].tobytes(), (A["c_flags"][w][:nc] & schema.CONTACT_TOUCHING).tobytes(),
+            A["l_body"][w][:nlb].tobytes(), A["l_contact"][w][:nlc].tobytes(), A["l_start"][w][:n_isl].tobytes())
+
+
+@pytest.mark.parametrize("scene", sorted(STEADY))
+def test_p_steady_fp32_free_running_600_steps(scene, parity_report):
     import pypybox2d_b200 as b2
-    g = load_golden(case)
-    dt, vi, pi, _, world = g["meta"]
-    vi, pi = int(vi), int(pi)
-    A, caps = arrays_from_golden(g)
-    A, _ = arrays_from_golden(g, prefix="ck300_", base=A)
+    from concurrent.futures import ThreadPoolExecutor
+    from pypybox2d_b200 import batch as batch_mod
+    settle, vi, pi, need_exact, tol_p, tol_v = STEADY[scene]
+    dt = 1.0 / 60
+    n = STEADY_WORLDS
+    worlds = [scenes.SCENES[scene](b2, world=1 + w) for w in range(n)]
+    caps = batch_mod.world_caps(worlds)
+    table = schema.ShapeTable()
+    for w in worlds:
+        for b in w.bodies:
+            for f in b.fixtures:
+                table.add(f._shape)
+    A = schema.alloc(caps, n, max(len(table), 1), "f64")
+    for i, w in enumerate(worlds):
+        schema.pack_world(w, A, i, table)
+    A["s_meta"], A["s_radius"], A["s_data"] = table.arrays("f64")
+    shared = {k for k, scope, _, _ in schema.FIELDS if scope == "S"}
+
+    def world_slice(src, i):
+        return {k: (v if k in shared else v[i:i + 1].copy()) for k, v in src.items()}
+
+    # settle every world with the oracle (fp64), round the settled state to fp32: the common start
+    def settle_one(i):
+        Ai = world_slice(A, i)
+        o = oracle.Oracle(Ai, 0)
+        o.step(dt, vi, pi, settle)
+        return Ai
+    with ThreadPoolExecutor(8) as ex:
+        settled = list(ex.map(settle_one, range(n)))
+    for i, Ai in enumerate(settled):
+        for k in A:
+            if k not in shared:
+                A[k][i] = Ai[k][0]
     T = round32(A)
-    orc = oracle.Oracle(T, 0)
-    orc.inv_dt0 = 1.0 / dt
+    per_world = [world_slice(T, i) for i in range(n)]
+    oracles = []
+    for Ti in per_world:
+        o = oracle.Oracle(Ti, 0)
+        o.inv_dt0 = 1.0 / dt
+        oracles.append(o)
     bw = b2.BatchedWorld({k: v.copy() for k, v in T.items()}, caps, real="f32")
     bw.inv_dt0 = 1.0 / dt
-    orc.step(dt, vi, pi, 300)
-    bw.step(dt, vi, pi, 300)
-    G = bw.download()
-    dp, dv = state_diff(T, G)
-    assert dp <= 1e-3, "positions drifted %.2e m in 300 steps" % dp
-    assert dv <= 5e-3, "velocities differ by %.2e m/s" % dv
-    assert gen_golden.int_summary(T)[:3] == gen_golden.int_summary(G)[:3]     # contacts, touching, points
+    first_div = [None] * n
+    last_ok_err = [(0.0, 0.0)] * n
+    INT_NAMES = ["w_count", "w_island", "c_fix", "c_flags", "l_body", "l_contact", "l_start", "b_pos", "b_vel"]
+    with ThreadPoolExecutor(8) as ex:
+        for s in range(STEADY_STEPS):
+            list(ex.map(lambda o: o.step(dt, vi, pi), oracles))
+            bw.step(dt, vi, pi)
+            G = bw.download(INT_NAMES)
+            for i in range(n):
+                if first_div[i] is not None:
+                    continue
+                if _steady_ints(per_world[i]) != _steady_ints(G, i):
+                    first_div[i] = s
+                    continue
+                nb = int(per_world[i]["w_count"][0][0])
+                P, Q = per_world[i]["b_pos"][0][:nb, :3], G["b_pos"][i][:nb, :3].astype(np.float64)
+                scale = max(1.0, float(np.abs(P[:, :2]).max()))
+                dp = float(np.abs(P - Q).max()) / scale
+                dv = float(np.abs(per_world[i]["b_vel"][0][:nb, :3] - G["b_vel"][i][:nb, :3].astype(np.float64)).max())
+                last_ok_err[i] = (dp, dv)
     assert bw.status() == 0
+    exact = [i for i in range(n) if first_div[i] is None]
+    report = {"worlds": n, "steps": STEADY_STEPS, "identical_all_steps": len(exact), "first_divergence": first_div,
+              "max_rel_dpos_while_identical": max(e[0] for e in last_ok_err), "max_dvel_while_identical": max(e[1] for e in last_ok_err)}
+    print("P-steady %s: %s" % (scene, report))
+    parity_report("p_steady/%s" % scene, report)
+    assert len(exact) >= need_exact or not STRICT, "only %d of %d worlds kept identical integer outputs for %d steps: %s" % (
+        len(exact), n, STEADY_STEPS, first_div)
+    # state of every world for as long as its integer outputs are the oracle's (all 600 steps for the `exact` worlds)
+    for i in range(n):
+        dp, dv = last_ok_err[i]
+        assert dp <= tol_p or not STRICT, "world %d: relative position error %.2e" % (i, dp)
+        assert dv <= tol_v or not STRICT, "world %d: velocity error %.2e m/s" % (i, dv)
 
 
 def _random_pairs(rng, n, A):
