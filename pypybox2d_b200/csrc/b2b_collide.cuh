@@ -56,7 +56,7 @@ B2B_HD_COLD void collide_circles(manifold<real>& m, const shape_view<real>& a, c
     vec2<real> ca = a.vert(0), cb = b.vert(0);
     vec2<real> d = xf_mul(xb, cb) - xf_mul(xa, ca);
     real rsum = a.radius + b.radius;
-    if (length_sqr(d) > rsum * rsum) return;
+    if (length_sqr(d) > sq_r(rsum)) return;
     m.type = MANIFOLD_CIRCLES;
     m.local_point = ca;
     m.local_normal = mk<real>(real(0), real(0));
@@ -95,12 +95,12 @@ B2B_HD_COLD void collide_polygon_circle(manifold<real>& m, const shape_view<real
     const real u2 = dot(c_local - v2, v1 - v2);
     if (u1 < real(0)) {
         vec2<real> d = c_local - v1;
-        if (dot(d, d) > radius * radius) return;
+        if (dot(d, d) > sq_r(radius)) return;
         m.local_normal = normalize(d);
         m.local_point = v1;
     } else if (u2 < real(0)) {
         vec2<real> d = c_local - v2;
-        if (dot(d, d) > radius * radius) return;
+        if (dot(d, d) > sq_r(radius)) return;
         m.local_normal = normalize(d);
         m.local_point = v2;
     } else {
@@ -264,7 +264,7 @@ B2B_HD_COLD void collide_edge_circle(manifold<real>& m, const shape_view<real>& 
     const real radius = ea.radius + cb.radius;
     if (v <= real(0)) {                                         // vertex region A
         vec2<real> d = Q - A;
-        if (dot(d, d) > radius * radius) return;
+        if (dot(d, d) > sq_r(radius)) return;
         if (ea.has0) {
             vec2<real> A1 = ea.vert(2);
             if (dot(A - A1, A - Q) > real(0)) return;           // belongs to the previous edge
@@ -275,7 +275,7 @@ B2B_HD_COLD void collide_edge_circle(manifold<real>& m, const shape_view<real>& 
     }
     if (u <= real(0)) {                                         // vertex region B
         vec2<real> d = Q - B;
-        if (dot(d, d) > radius * radius) return;
+        if (dot(d, d) > sq_r(radius)) return;
         if (ea.has3) {
             vec2<real> B2 = ea.vert(3);
             if (dot(B2 - B, Q - B) > real(0)) return;           // belongs to the next edge
@@ -287,7 +287,7 @@ B2B_HD_COLD void collide_edge_circle(manifold<real>& m, const shape_view<real>& 
     const real den = dot(e, e);                                 // face region
     const vec2<real> P = (real(1) / den) * (u * A + v * B);
     const vec2<real> d = Q - P;
-    if (dot(d, d) > radius * radius) return;
+    if (dot(d, d) > sq_r(radius)) return;
     vec2<real> n = mk<real>(-e.y, e.x);
     if (dot(n, Q - A) < real(0)) n = mk<real>(-n.x, -n.y);
     m.count = 1; m.type = MANIFOLD_FACE_A; m.local_normal = normalize(n); m.local_point = A;

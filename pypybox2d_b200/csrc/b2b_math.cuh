@@ -14,6 +14,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define B2B_HD __host__ __device__ __forceinline__
@@ -61,10 +62,10 @@ template <class real> struct K {
     static constexpr real max_translation = real(2.0);
     static constexpr real max_translation_sqr = real(4.0);
     static constexpr real max_rotation = real(0.5 * 3.141592653589793);
-    static constexpr real max_rotation_sqr = real((0.5 * 3.141592653589793) * (0.5 * 3.141592653589793));
+    static constexpr real max_rotation_sqr = real(2.4674011002723395);           // (0.5 * pi) ** 2 as CPython evaluates it (settings.py:104)
     static constexpr real baumgarte = real(0.2);
     static constexpr real time_to_sleep = real(0.5);
-    static constexpr real linear_sleep_tol_sqr = real(0.01 * 0.01);
+    static constexpr real linear_sleep_tol_sqr = real(0.0001);   // 0.01 ** 2 (settings.py:119)
     static constexpr real angular_sleep_tol_sqr =
         real((2.0 / 180.0 * 3.141592653589793) * (2.0 / 180.0 * 3.141592653589793));
     static constexpr real max_condition_number = real(1000.0);           // contact.py:488
@@ -87,7 +88,24 @@ template <class real> B2B_HD vec2<real> cross_vs(vec2<real> a, real s) { return 
 template <class real> B2B_HD vec2<real> cross_sv(real s, vec2<real> a) { return mk<real>(-s * a.y, s * a.x); }
 // tangent = normal.cross(1.0)
 template <class real> B2B_HD vec2<real> right_perp(vec2<real> n) { return mk<real>(n.y, -n.x); }
-template <class real> B2B_HD real length_sqr(vec2<real> a) { return a.x * a.x + a.y * a.y; }
+// The reference writes many squares as `x ** 2`, which CPython evaluates with libm's pow: Vec2.length /
+// length_squared / normalized (common.py:186-190, 216-222), the effective-mass terms (contact.py:444-457, 489, 841-842),
+// the step clamps and sleep tests (island.py:124-128, 169-170), the radius tests of the colliders (collision.py:56-336).
+// glibc's pow(x, 2.0) is NOT always the correctly rounded product: it differs from x * x by one ulp in ~0.09 % of
+// evaluations.  sq_r is that square: the host build of the fp64 step (tests/hostcheck) calls pow, like the oracle, and is
+// bit-identical to it on every scene; the device computes the correctly rounded product (CUDA's pow is another
+// algorithm again, 2 ulp) -- together with sincos (<= 2 ulp from glibc's) these are the ONLY operations in which the fp64
+// kernels differ from the reference, one ulp at a time (tests/test_gpu_parity.py test_p_exact_fp64_one_step).
+B2B_HD float sq_r(float x) { return x * x; }
+B2B_HD double sq_r(double x)
+{
+#if defined(__CUDA_ARCH__) || defined(B2B_SQ_PRODUCT)      // (B2B_SQ_PRODUCT: tools/sincos_ulp_probe.py measures what the product costs)
+    return x * x;
+#else
+    return pow(x, 2.0);
+#endif
+}
+template <class real> B2B_HD real length_sqr(vec2<real> a) { return sq_r(a.x) + sq_r(a.y); }
 
 B2B_HD float sqrt_r(float x) { return sqrtf(x); }
 B2B_HD double sqrt_r(double x) { return sqrt(x); }
@@ -107,6 +125,16 @@ B2B_HD void sincos_r(double a, double* s, double* c)
     sincos(a, s, c);
 #else
     *s = sin(a); *c = cos(a);
+#if defined(B2B_SINCOS_ULP_PROBE)
+    // tests/hostcheck experiment (tools/sincos_ulp_probe.py): what a libm that differs from glibc's in the last place does
+    // to a trajectory.  About half of the results are moved by one ulp, chosen by the bits of the angle.
+    {
+        uint64_t u; memcpy(&u, &a, 8);
+        u ^= u >> 29; u *= 0xbf58476d1ce4e5b9ull; u ^= u >> 32;
+        if (u & 1) *s = nextafter(*s, (u & 2) ? 2.0 : -2.0);
+        if (u & 4) *c = nextafter(*c, (u & 8) ? 2.0 : -2.0);
+    }
+#endif
 #endif
 }
 
@@ -117,7 +145,7 @@ template <class real> B2B_HD real clamp_r(real v, real lo, real hi) { return pym
 
 template <class real> B2B_HD vec2<real> normalize(vec2<real> a)
 {
-    real len = sqrt_r(a.x * a.x + a.y * a.y);
+    real len = sqrt_r(sq_r(a.x) + sq_r(a.y));
     if (len < K<real>::epsilon) return a;
     real inv = real(1) / len;
     return mk<real>(a.x * inv, a.y * inv);

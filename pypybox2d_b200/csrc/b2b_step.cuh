@@ -1109,9 +1109,9 @@ template <class real> struct world_step {
             if (j >= count) continue;
             ra[j] = wp[j] - ca; rb[j] = wp[j] - cb;
             const real rn_a = cross(ra[j], normal), rn_b = cross(rb[j], normal);
-            const real k_normal = ma + mb + ia * (rn_a * rn_a) + ib * (rn_b * rn_b);
+            const real k_normal = ma + mb + ia * sq_r(rn_a) + ib * sq_r(rn_b);      // contact.py:444-445: ** 2
             const real rt_a = cross(ra[j], tangent), rt_b = cross(rb[j], tangent);
-            const real k_tangent = ma + mb + ia * (rt_a * rt_a) + ib * (rt_b * rt_b);
+            const real k_tangent = ma + mb + ia * sq_r(rt_a) + ib * sq_r(rt_b);     // contact.py:456-457
             const real v_rel = dot(normal, rel_velocity(vb, wb, rb[j], va, wa, ra[j]));
             if (v_rel < -K<real>::velocity_threshold) bias[j] = -restitution * v_rel;
             nmass[j] = (k_normal > real(0)) ? real(1) / k_normal : real(0);
@@ -1126,7 +1126,7 @@ template <class real> struct world_step {
             k11 = ma + mb + ia * rn1a * rn1a + ib * rn1b * rn1b;
             k22 = ma + mb + ia * rn2a * rn2a + ib * rn2b * rn2b;
             k12 = ma + mb + ia * rn1a * rn2a + ib * rn1b * rn2b;
-            if (k11 * k11 < K<real>::max_condition_number * (k11 * k22 - k12 * k12)) {
+            if (sq_r(k11) < K<real>::max_condition_number * (k11 * k22 - sq_r(k12))) {      // contact.py:489
                 real det = k11 * k22 - k12 * k12;            // Mat22.inverse (common.py:505-519)
                 if (det != real(0)) det = real(1) / det;
                 nm11 = det * k22; nm12 = -det * k12; nm22 = det * k11;
@@ -1320,7 +1320,7 @@ template <class real> struct world_step {
         p.min_sep = pymin(p.min_sep, separation);
         const real C = clamp_r(K<real>::baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
         const real rn_a = cross(ra, normal), rn_b = cross(rb, normal);
-        const real Keff = ma + mb + (ia * (rn_a * rn_a)) + (ib * (rn_b * rn_b));
+        const real Keff = ma + mb + (ia * sq_r(rn_a)) + (ib * sq_r(rn_b));      // contact.py:841-842
         const real impulse = (Keff > real(0)) ? -C / Keff : real(0);
         const V2 P = impulse * normal;
         p.ca = p.ca - ma * P; p.aa = p.aa - ia * cross(ra, P);
@@ -1387,12 +1387,12 @@ template <class real> struct world_step {
         V2 v = mk<real>(sv.x, sv.y);
         real w = sv.z;
         const V2 translation = dt * v;
-        if (dot(translation, translation) > K<real>::max_translation_sqr) {
-            const real ratio = K<real>::max_translation / sqrt_r(translation.x * translation.x + translation.y * translation.y);
+        if (dot(translation, translation) > K<real>::max_translation_sqr) {     // island.py:123-124: dot, then .length (** 2)
+            const real ratio = K<real>::max_translation / sqrt_r(length_sqr(translation));
             v = ratio * v;
         }
         const real rotation = dt * w;
-        if (rotation * rotation > K<real>::max_rotation_sqr) {
+        if (sq_r(rotation) > K<real>::max_rotation_sqr) {                       // island.py:128
             const real ratio = K<real>::max_rotation / abs_r(rotation);
             w = w * ratio;
         }
@@ -1437,7 +1437,7 @@ template <class real> struct world_step {
             victim = b;
             const real* sv = b_vel + 4 * (size_t)b;
             real* st = b_pos + 4 * (size_t)b + 3;
-            if (!last_allow || sv[2] * sv[2] > K<real>::angular_sleep_tol_sqr || sv[0] * sv[0] + sv[1] * sv[1] > K<real>::linear_sleep_tol_sqr) {
+            if (!last_allow || sq_r(sv[2]) > K<real>::angular_sleep_tol_sqr || sq_r(sv[0]) + sq_r(sv[1]) > K<real>::linear_sleep_tol_sqr) {   // island.py:169-170
                 *st = real(0);
                 min_sleep = real(0);
             } else {
@@ -1486,8 +1486,8 @@ template <class real> struct world_step {
                 if (bb[k] < 0 || (fl[k] & BODY_TYPE_MASK) == BODY_STATIC) continue;
                 last_i = i0 + k * t_n;
                 real* st = b_pos + 4 * (size_t)bb[k] + 3;
-                if (!last_allow || sv[k].z * sv[k].z > K<real>::angular_sleep_tol_sqr ||
-                    sv[k].x * sv[k].x + sv[k].y * sv[k].y > K<real>::linear_sleep_tol_sqr) {
+                if (!last_allow || sq_r(sv[k].z) > K<real>::angular_sleep_tol_sqr ||
+                    sq_r(sv[k].x) + sq_r(sv[k].y) > K<real>::linear_sleep_tol_sqr) {
                     *st = real(0);
                     min_sleep = real(0);
                 } else {

@@ -34,7 +34,7 @@ def lib():
         srcs = [os.path.join(_HERE, "hostcheck.cpp")] + [
             os.path.join(_ROOT, "pypybox2d_b200", "csrc", f) for f in ("b2b_step.cuh", "b2b_collide.cuh", "b2b_math.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-builtin-pow", "-o", so,
                                    srcs[0], "-lm"])
         _LIB = ctypes.CDLL(so)
         _LIB.hc_step.argtypes = [ctypes.POINTER(Caps), ctypes.POINTER(Buffers), ctypes.c_double, ctypes.c_double,

@@ -5,13 +5,15 @@ Tiers (DESIGN.md "Parity"; tolerances are pinned here):
            (contact set + order, flags, manifold type/count/ids, island membership + order, emitted pair lists,
            awake flags) identical at EVERY step; every float field of the state (bodies: transforms, sweeps,
            velocities; proxies: fat and tight AABBs; contacts: manifolds and accumulated impulses) within the
-           per-scene bound EXACT_TOL (about ten times what a B200 measures).  The bound differs by seven orders of
-           magnitude between scenes because the ONLY arithmetic that differs from the oracle's is CUDA's sincos
-           (<= 2 ulp from glibc's; sqrt and division are correctly rounded, FMA contraction is off): where bodies
-           keep tiny angles (the box pyramid) sin and cos are exact and the trajectories agree to 1e-13; where
-           they roll and tumble (circles and polygons of the mixed scene) each step injects ~1e-16 and the chaotic
-           pile amplifies it.  test_p_exact_fp64_one_step pins that reading: teacher-forced from the oracle's
-           state, ONE fp64 step agrees to 1e-12 on every step of the mixed scene.
+           per-scene bound EXACT_TOL (about ten times what a B200 measures).  The bounds differ by six orders of
+           magnitude between scenes; profiles/r2_fp64_difference_sources.md pins why: compiled for the host with
+           glibc the device source is BIT-IDENTICAL to the oracle (tests/test_hostcheck.py), and on the GPU exactly
+           two libm operations differ, one ulp at a time -- the squares the reference writes `x ** 2` (libm pow;
+           the device forms the correctly rounded product, which differs from glibc's pow in 0.09 % of evaluations)
+           and sincos (CUDA's is within 2 ulp of glibc's).  A quiet pile keeps that at 1e-13, piles that sway, roll
+           and tumble amplify it to 1e-8..1e-6 over 400 steps (the same sizes the host build shows when one of the
+           two operations is perturbed).  test_p_exact_fp64_one_step gates the step itself: teacher-forced from the
+           oracle's state, ONE fp64 step agrees to 1e-11 in every float field at every step.
   P-step   fp32 kernels, teacher-forced: the oracle's state at step k (rounded to fp32) is uploaded, both sides
            take ONE step, for EVERY step of the golden trajectory (600 on the pyramid).  Integer outputs (including
            the number of position iterations an island used) must agree except on tie steps (a comparison within
@@ -87,9 +89,9 @@ def _group_kernel_cases():
 
 
 # Float fields of the state compared in P-exact, and the per-scene bound on their absolute error (m, m/s, N s):
-# measured maxima on B200 (profiles/r2_parity_report.json) times ~10.
+# measured maxima on B200 (profiles/r2_parity_report.json: 7.6e-13, 0, 4.5e-10, 5.3e-8, 4.2e-9, 5.7e-7) times 10-20.
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
-EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-9, "deep_stacks": 1e-9, "features": 1e-9, "mixed": 1e-5}
+EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5}
 
 
 def float_diffs(OA, G):
@@ -130,8 +132,8 @@ def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
 @pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0"])
 def test_p_exact_fp64_one_step(case, parity_report):
     """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
-    1e-12 in every float field at every k -- the free-running differences of the tumbling scenes are amplification of
-    last-ulp sincos differences by the dynamics, not an arithmetic difference of the step."""
+    1e-11 in every float field at every k (measured: 1.5e-12) -- the free-running differences of the swaying and tumbling
+    scenes are amplification of one-ulp libm differences by the dynamics (profiles/r2_fp64_difference_sources.md)."""
     import pypybox2d_b200 as b2
     g = load_golden(case)
     dt, vi, pi, steps, world = g["meta"]
@@ -150,7 +152,7 @@ def test_p_exact_fp64_one_step(case, parity_report):
         assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
         for k, v in float_diffs(A, G).items():
             worst[k] = max(worst[k], v)
-            assert v <= 1e-12 or not STRICT, "%s: one-step difference %.2e at step %d" % (k, v, s)
+            assert v <= 1e-11 or not STRICT, "%s: one-step difference %.2e at step %d" % (k, v, s)
         inv = 1.0 / dt
     parity_report("p_exact_one_step/%s" % case, dict(worst, steps=steps))
 
