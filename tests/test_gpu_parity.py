@@ -272,7 +272,11 @@ def test_p_steady_fp32_free_running_600_steps(scene, parity_report):
     bw = b2.BatchedWorld({k: v.copy() for k, v in T.items()}, caps, real="f32")
     bw.inv_dt0 = 1.0 / dt
     first_div = [None] * n
+    first_what = [None] * n
+    same_steps = [0] * n                 # steps on which the integer outputs are the oracle's (they can re-agree after a tie)
     last_ok_err = [(0.0, 0.0)] * n
+    final_err = [(0.0, 0.0)] * n
+    PARTS = ["contact count", "contact set / order", "touching flags", "island bodies", "island contacts", "island starts"]
     INT_NAMES = ["w_count", "w_island", "c_fix", "c_flags", "l_body", "l_contact", "l_start", "b_pos", "b_vel"]
     with ThreadPoolExecutor(8) as ex:
         for s in range(STEADY_STEPS):
@@ -280,21 +284,28 @@ def test_p_steady_fp32_free_running_600_steps(scene, parity_report):
             bw.step(dt, vi, pi)
             G = bw.download(INT_NAMES)
             for i in range(n):
-                if first_div[i] is not None:
-                    continue
-                if _steady_ints(per_world[i]) != _steady_ints(G, i):
-                    first_div[i] = s
-                    continue
                 nb = int(per_world[i]["w_count"][0][0])
                 P, Q = per_world[i]["b_pos"][0][:nb, :3], G["b_pos"][i][:nb, :3].astype(np.float64)
                 scale = max(1.0, float(np.abs(P[:, :2]).max()))
                 dp = float(np.abs(P - Q).max()) / scale
                 dv = float(np.abs(per_world[i]["b_vel"][0][:nb, :3] - G["b_vel"][i][:nb, :3].astype(np.float64)).max())
+                final_err[i] = (dp, dv)
+                a, b = _steady_ints(per_world[i]), _steady_ints(G, i)
+                if a == b:
+                    same_steps[i] += 1
+                if first_div[i] is not None:
+                    continue
+                if a != b:
+                    first_div[i] = s
+                    first_what[i] = [PARTS[k] for k in range(len(PARTS)) if a[k] != b[k]][0]
+                    continue
                 last_ok_err[i] = (dp, dv)
     assert bw.status() == 0
     exact = [i for i in range(n) if first_div[i] is None]
     report = {"worlds": n, "steps": STEADY_STEPS, "identical_all_steps": len(exact), "first_divergence": first_div,
-              "max_rel_dpos_while_identical": max(e[0] for e in last_ok_err), "max_dvel_while_identical": max(e[1] for e in last_ok_err)}
+              "first_divergence_in": first_what, "steps_with_identical_integers": same_steps,
+              "max_rel_dpos_while_identical": max(e[0] for e in last_ok_err), "max_dvel_while_identical": max(e[1] for e in last_ok_err),
+              "rel_dpos_after_600_steps": [e[0] for e in final_err], "dvel_after_600_steps": [e[1] for e in final_err]}
     print("P-steady %s: %s" % (scene, report))
     parity_report("p_steady/%s" % scene, report)
     assert len(exact) >= need_exact or not STRICT, "only %d of %d worlds kept identical integer outputs for %d steps: %s" % (
