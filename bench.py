@@ -398,16 +398,25 @@ def run_b200_arm(args):
     torch.cuda.synchronize(device)
     ev[0].record()
     for k in range(K):
-        bw.step(dt, vi, pi, 1, time_kernels=True)
+        bw.step(dt, vi, pi, 1)
         ev[k + 1].record()
     torch.cuda.synchronize(device)
     dist.barrier()
     ms = dist.max_over_ranks(ev[0].elapsed_time(ev[K]), device)
     per_step = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(K))
     clocks = sampler.stop() if sampler else None
-    kms = bw.kernel_ms()
     launches = bw.info()["launches"] - launches0
     value = n_dyn * n_total * K / (ms * 1e-3)
+    # ---- the same K steps once more with a CUDA event between every two launches: per-kernel durations for the roofline.
+    # (A separate pass: with the events in, every kernel runs alone on one stream; the headline pass lets the tails of the
+    # solve kernels of neighbouring chunks of worlds overlap on two streams, b2b_api.cu.)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    bw.step(dt, vi, pi, K, time_kernels=True)
+    k1.record()
+    torch.cuda.synchronize(device)
+    serial_ms = k0.elapsed_time(k1) / K
+    kms = bw.kernel_ms()
 
     # ---- end to end through the host-buffer entry point: pinned H2D forces + step + D2H body state, per step
     Ke = args.e2e_steps or K
@@ -534,7 +543,7 @@ def run_b200_arm(args):
                      "kernel": "b2b::%s_kernel_%s" % (top, args.real),
                      "kernel_ms_per_launch": top_ms, "kernel_share_of_step": top_ms / max(sum(per_kernel_ms.values()), 1e-9),
                      "algorithmic_bytes_per_world_step": kernel_bytes[top],
-                     "kernel_ms": per_kernel_ms,
+                     "kernel_ms": per_kernel_ms, "ms_per_step_one_stream_with_events": serial_ms,
                      "whole_step_frac": step_achieved / peak,
                      "step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_world_step": step_bytes,
                               "formula": "96 Nb + 16 Np + 160 Nc (SURVEY 8d)"},

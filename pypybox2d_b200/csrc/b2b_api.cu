@@ -33,6 +33,10 @@ struct b2b_ctx {
     step_timer* timer;             // B2B_STEP_TIME: event chain of the timed steps
     // b2b_step_host: copy streams and the events that chain copies and kernels chunk by chunk
     cudaStream_t s_in, s_out;
+    // b2b_step: second stream for every other chunk of worlds of the solve kernels (their tails overlap), fork / join events
+    cudaStream_t s_aux;
+    cudaEvent_t ev_fork, ev_join;
+    int step_streams;              // 1: everything on the caller's stream; 2 (default): chunks alternate between two streams
     std::vector<cudaEvent_t>* pipe_ev;
     int pipe_worlds;               // worlds per chunk of the host-buffer pipeline
 };
@@ -158,8 +162,10 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     const size_t plan_bytes = sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds;
     CREATE_TRY(cudaMalloc((void**)&x->plan_rows, plan_bytes), "cudaMalloc(plan rows)");
     CREATE_TRY(cudaMemset(x->plan_rows, 0, plan_bytes), "cudaMemset(plan rows)");
-    CREATE_TRY(cudaMalloc((void**)&x->d_status, 4 * sizeof(uint32_t)), "cudaMalloc(status)");
-    CREATE_TRY(cudaMemset(x->d_status, 0, 4 * sizeof(uint32_t)), "cudaMemset(status)");
+    CREATE_TRY(cudaMalloc((void**)&x->d_status, 8 * sizeof(uint32_t)), "cudaMalloc(status)");
+    CREATE_TRY(cudaMemset(x->d_status, 0, 8 * sizeof(uint32_t)), "cudaMemset(status)");
+    x->step_streams = 2;
+    if (const char* env = getenv("B2B_STEP_STREAMS")) { const int v = atoi(env); if (v == 1 || v == 2) x->step_streams = v; }
 #undef CREATE_TRY
     *out = x;
     return B2B_OK;
@@ -178,6 +184,9 @@ extern "C" void b2b_destroy(b2b_ctx* x)
     if (x->stage_out) cudaFree(x->stage_out);
     if (x->timer) { for (cudaEvent_t e : x->timer->ev) cudaEventDestroy(e); delete x->timer; }
     if (x->pipe_ev) { for (cudaEvent_t e : *x->pipe_ev) cudaEventDestroy(e); delete x->pipe_ev; }
+    if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+    if (x->ev_join) cudaEventDestroy(x->ev_join);
+    if (x->s_aux) cudaStreamDestroy(x->s_aux);
     if (x->s_in) cudaStreamDestroy(x->s_in);
     if (x->s_out) cudaStreamDestroy(x->s_out);
     delete x;
@@ -247,6 +256,49 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
         tm = x->timer;
     }
     const int groups = (x->c.n_worlds + x->plan.group_worlds - 1) / x->plan.group_worlds;
+    // Two-stream schedule: the solve kernels are persistent grids whose last round of worlds leaves most SMs idle for one
+    // world's latency (~2 ms of a 43 ms step at 131,072 pyramids: 11.07 rounds).  With the batch cut into chunks of whole
+    // rounds that alternate between the caller's stream and a second one, the tail of one chunk's kernel runs under the
+    // next chunk's.  Needs every world's record slab resident at once; timing and profiling runs stay on one stream so
+    // that the events between the launches bracket one kernel each.
+    const int chunk = x->pipe_worlds, n_chunks = (x->c.n_worlds + chunk - 1) / chunk;
+    const bool two_streams = x->step_streams == 2 && n_chunks >= 2 && groups == 1 && !(flags & (B2B_STEP_TIME | B2B_STEP_PROFILE)) && dt > 0.0;
+    if (two_streams) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!x->s_aux) CUDA_TRY(cudaStreamCreateWithFlags(&x->s_aux, cudaStreamNonBlocking), "cudaStreamCreate(aux)");
+        if (!x->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+        if (!x->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming), "cudaEventCreate");
+        for (int s = 0; s < n_steps; ++s) {
+            step_params sp2 = sp;
+            sp2.joint_any = x->d_status + 3;
+            if (sp.flags & 4u) {
+                if (x->f64) launch_collide_f64(x->fields, x->c, x->plan, x->plan_rows, 0, x->c.n_worlds, st);
+                else launch_collide_f32(x->fields, x->c, x->plan, x->plan_rows, 0, x->c.n_worlds, st);
+            }
+            if (x->f64) launch_plan_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp2, st);
+            else launch_plan_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp2, st);
+            CUDA_TRY(cudaMemsetAsync(x->d_status + 4, (sp.flags & B2B_STEP_GROUP_KERNEL) ? 1 : 0, sizeof(uint32_t), st), "memset");
+            CUDA_TRY(cudaEventRecord(x->ev_fork, st), "cudaEventRecord");
+            CUDA_TRY(cudaStreamWaitEvent(x->s_aux, x->ev_fork, 0), "cudaStreamWaitEvent");
+            for (int k = 0; k < n_chunks; ++k) {
+                const int w0 = k * chunk, n = (x->c.n_worlds - w0 < chunk) ? x->c.n_worlds - w0 : chunk;
+                cudaStream_t sk = (k & 1) ? x->s_aux : st;
+                step_params spk = sp2;
+                spk.joint_any = x->d_status + ((k & 1) ? 4 : 3);         // one joint-schedule word per stream (position kernels read it)
+                unsigned char* rec = x->scratch_solve + (size_t)w0 * x->plan.layout.total_rec;
+                if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, s == 0, w0, n, sk, nullptr);
+                else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, s == 0, w0, n, sk, nullptr);
+            }
+            CUDA_TRY(cudaEventRecord(x->ev_join, x->s_aux), "cudaEventRecord");
+            CUDA_TRY(cudaStreamWaitEvent(st, x->ev_join, 0), "cudaStreamWaitEvent");
+            if (x->f64) launch_post_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp2, st, nullptr);
+            else launch_post_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp2, st, nullptr);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "step kernels", e);
+            x->launches += step_launches(x, dt, sp.flags, n_chunks);
+        }
+        return B2B_OK;
+    }
     for (int s = 0; s < n_steps; ++s) {
         if (x->f64) launch_step_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, tm);
         else launch_step_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->scratch_solve, x->scratch_sprof, x->d_status + 1, sp, s == 0, (cudaStream_t)stream, tm);
