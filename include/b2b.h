@@ -111,6 +111,12 @@ int b2b_step_host(b2b_ctx* ctx, const void* h_force_torque, void* h_state_out, d
 int b2b_collide_pairs(b2b_ctx* ctx, int n, const void* d_shape_a, const void* d_shape_b, const void* d_xf_a,
                       const void* d_xf_b, void* d_mtype, void* d_mf, void* d_pts, void* d_id, void* stream);
 
+/* Test hook (T1): only the solver stage of World.step -- World._solve's island construction (world.py:475-580) and
+ * Island.solve for every island (island.py:65-179, ContactSolver contact.py:375-864) on the contacts as they are: no
+ * narrowphase before it (run b2b_step with dt = 0 for that, world.py:338-349) and no fixture synchronisation or
+ * find_new_contacts after it.  inv_dt0 as for b2b_step; dt > 0.  Asynchronous on `stream`. */
+int b2b_solve_islands(b2b_ctx* ctx, double dt, double inv_dt0, int vel_iters, int pos_iters, uint32_t flags, void* stream);
+
 /* OR of every world's status word (STATUS_* bits in schema.py); synchronises the stream. */
 int b2b_status(b2b_ctx* ctx, uint32_t* host_out, void* stream);
 

@@ -55,6 +55,7 @@ def lib():
     L.b2b_init_proxies.argtypes = [vp, vp]
     L.b2b_step.argtypes = [vp, dbl, dbl, i32, i32, i32, u32, vp]
     L.b2b_step_host.argtypes = [vp, vp, vp, dbl, dbl, i32, i32, i32, u32, vp]
+    L.b2b_solve_islands.argtypes = [vp, dbl, dbl, i32, i32, u32, vp]
     L.b2b_collide_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.b2b_status.argtypes = [vp, ctypes.POINTER(u32), vp]
     L.b2b_checksum.argtypes = [vp, vp, vp]

@@ -216,6 +216,12 @@ class BatchedWorld(object):
         if dt > 0.0 and n_steps > 0:
             self.inv_dt0 = 1.0 / dt
 
+    def solve_islands(self, dt, vel_iters, pos_iters):
+        """Test hook: island construction + Island.solve only (no narrowphase before, no proxy synchronisation / new contacts
+        after); `step(0, ...)` before it runs the narrowphase alone."""
+        _lib.check(_lib.lib().b2b_solve_islands(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters), 0,
+                                                self._stream()), "b2b_solve_islands")
+
     def step_host(self, h_force_torque, h_state_out, dt, vel_iters, pos_iters, n_steps=1):
         """The end-to-end call: pinned host forces in, pinned host body state out, synchronous."""
         fin = ctypes.c_void_p(h_force_torque.data_ptr()) if h_force_torque is not None else None

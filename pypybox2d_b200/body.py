@@ -65,9 +65,7 @@ class Body(object):
         self._fixed_rotation = bool(fixed_rotation)
         self._bullet = bool(bullet)
         self._type = type
-        self._active = bool(active)
-        if not self._active:
-            raise NotImplementedError("inactive bodies are not supported on the batched step path")
+        self._active = bool(active)      # an inactive body has no proxies: it collides with nothing, is in no island, never moves
         if self._type == Body.DYNAMIC:
             self._mass = 1.0
             self._inv_mass = 1.0
@@ -82,6 +80,18 @@ class Body(object):
                 fixtures = [fixtures]
             for fixture in fixtures:
                 self.attach_fixture(copy(fixture) if copy_fixtures else fixture)
+
+    def __copy__(self):
+        """A detached copy with copies of the fixtures (body.py:118-140); World.create_body(body=...) uses it."""
+        px, py, c, s = self._xf
+        new_body = Body(position=(px, py), angle=self._a, linear_velocity=self._linear_velocity,
+                        angular_velocity=self._angular_velocity, linear_damping=self._linear_damping,
+                        angular_damping=self._angular_damping, allow_sleep=self._allow_sleep, awake=self._awake,
+                        fixed_rotation=self._fixed_rotation, bullet=self._bullet, type=self._type, active=self._active,
+                        gravity_scale=self._gravity_scale, check_args=False, user_data=self.user_data)
+        for fixture in self.fixtures:
+            new_body.attach_fixture(copy(fixture))
+        return new_body
 
     # -- helpers ---------------------------------------------------------------------------
     def _xf_mul(self, v):
@@ -253,7 +263,23 @@ class Body(object):
     static = property(lambda self: self._type == Body.STATIC)
     dynamic = property(lambda self: self._type == Body.DYNAMIC)
     kinematic = property(lambda self: self._type == Body.KINEMATIC)
-    active = property(lambda self: self._active)
+    @property
+    def active(self):
+        return self._active
+
+    @active.setter
+    def active(self, active):
+        # body.py:848-872 creates / destroys the proxies and destroys the contacts.  Before the first step that is a host
+        # flag (the proxies are built from it); afterwards it would be a host mutation of the device contact list
+        self._check_unlocked()
+        if self._active == bool(active):
+            return
+        if self._world is not None and self._world._stepped:
+            raise NotImplementedError("changing Body.active after the first step is not supported yet (SURVEY §8f #4)")
+        self._active = bool(active)
+        if self._world is not None:
+            self._world._batch = None          # proxies are rebuilt from the host state
+            self._world._host_dirty = True
     bullet = property(lambda self: self._bullet)
     fixed_rotation = property(lambda self: self._fixed_rotation)
     linear_damping = property(lambda self: self._linear_damping)

@@ -319,6 +319,29 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     return B2B_OK;
 }
 
+// Test hook (T1): World._solve's islands and Island.solve only.
+extern "C" int b2b_solve_islands(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, int pos_iters, uint32_t flags, void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_solve_islands: no buffers bound");
+    if (vel_iters < 0 || pos_iters < 0 || !(dt > 0.0)) return fail(B2B_ERR_ARG, "b2b_solve_islands: bad argument");
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_PROFILE) | 4u | 64u, x->plan.lanes);
+    sp.joint_any = x->d_status + 3;
+    if (x->f64) launch_plan_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
+    else launch_plan_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
+    int groups = 0;
+    for (int w0 = 0; w0 < x->c.n_worlds; w0 += x->plan.group_worlds, ++groups) {
+        const int n = (x->c.n_worlds - w0 < x->plan.group_worlds) ? x->c.n_worlds - w0 : x->plan.group_worlds;
+        if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, 1, w0, n, st, nullptr);
+        else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, 1, w0, n, st, nullptr);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "solve kernels", e);
+    x->launches += 1 + 4 * groups;
+    return B2B_OK;
+}
+
 // The end-to-end call.  One World.step with its inputs and outputs in HOST memory, as a pipeline over chunks of worlds
 // (b2b_ctx::pipe_worlds, a whole number of resident waves of the solve kernels) on three streams:
 //   copy-in stream   forces of chunk k host -> device

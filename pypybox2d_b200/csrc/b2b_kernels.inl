@@ -251,6 +251,14 @@ __global__ void __launch_bounds__(256) B2B_CAT(init_proxies_kernel_, B2B_SUFFIX)
         if (f >= nf) continue;
         const size_t of = (size_t)w * c.nf + f;
         const int b = B.f_body[of];
+        if (!(B.b_flags[(size_t)w * c.nb + b] & BODY_ACTIVE)) {
+            // no proxies for the fixtures of an inactive body (body.py:288-297): an inverted box overlaps nothing
+            real_t* tight = B.f_tight + 4 * of; real_t* fat = B.f_fat + 4 * of;
+            const real_t big = real_t(1.0e30);
+            tight[0] = tight[1] = fat[0] = fat[1] = big; tight[2] = tight[3] = fat[2] = fat[3] = -big;
+            B.f_moved[of] = 0;
+            continue;
+        }
         const xform<real_t> xf = xf_load<real_t>(B.b_xf + 4 * ((size_t)w * c.nb + b));
         const shape_view<real_t> s = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, B.f_shape[of]);
         real_t a[4];

@@ -96,7 +96,7 @@ template <class real> struct batch_ptrs {
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
 enum { VREC_QUADS = 8, PREC_QUADS = 5 };   // velocity / position record of one constraint, in 4-vectors of reals
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
-enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32 };
+enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32, STEP_SOLVE_ONLY = 64 };
 // per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
 enum { SUM_PENDING = 1u, SUM_DESTROY = 2u, SUM_CHANGED = 4u, SUM_COLLIDE = 7u, SUM_MOVED = 8u };
 enum { PROF_PAIRS0 = 0, PROF_COLLIDE, PROF_ADJACENCY, PROF_ISLANDS, PROF_SOLVE, PROF_SYNC, PROF_PAIRS, PROF_CLEAR,
@@ -1965,7 +1965,7 @@ template <class real> struct world_step {
         long long t = B2B_CLOCK();
         // worlds with new fixtures were skipped by the flat narrowphase kernel (their contacts are created only now)
         const bool after_flat = (sp.flags & STEP_FLAT_COLLIDE) && !(w_flags[0] & WORLD_NEW_FIXTURE);
-        if (w_flags[0] & WORLD_NEW_FIXTURE) {                    // world.py:316-319
+        if ((w_flags[0] & WORLD_NEW_FIXTURE) && !(sp.flags & STEP_SOLVE_ONLY)) {                    // world.py:316-319
             phase_pairs(false);
             if (B2B_IS_T0) w_flags[0] &= ~WORLD_NEW_FIXTURE;
             B2B_SYNC();

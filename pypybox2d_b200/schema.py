@@ -41,6 +41,8 @@ STATUS_ISLAND_OVERFLOW = 0x8
 
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2   # contact_util.py:141-143
 
+NO_PROXY = 1.0e30             # fat / tight AABB (lower = +NO_PROXY, upper = -NO_PROXY) of a fixture without a proxy (inactive body)
+
 SHAPE_DATA = 32               # reals per shape row: polygon = 8 verts + 8 normals (x,y)
 
 # (name, scope, trailing shape, kind).  scope: W = per world, B = per body, F = per fixture/proxy,
@@ -249,6 +251,12 @@ def pack_world(world, arrays, w, table):
         A["f_mat"][w, j] = (f._friction, f._restitution)
         A["f_filter"][w, j] = ((f._category_bits & 0xffff) | ((f._mask_bits & 0xffff) << 16),
                                (f._group_index & 0xffff) | ((1 if f._sensor else 0) << 16))
+        if not body._active:
+            # the fixtures of an inactive body have no proxies (body.py:288-297, 848-872): an inverted box overlaps nothing, the
+            # row never enters the move buffer, so no pair and no contact can ever name it
+            A["f_tight"][w, j] = A["f_fat"][w, j] = (NO_PROXY, NO_PROXY, -NO_PROXY, -NO_PROXY)
+            A["f_moved"][w, j] = 0
+            continue
         lx, ly, ux, uy = f._shape.compute_aabb(body._xf)
         A["f_tight"][w, j] = (lx, ly, ux, uy)
         A["f_fat"][w, j] = (lx - AABB_EXTENSION, ly - AABB_EXTENSION, ux + AABB_EXTENSION, uy + AABB_EXTENSION)

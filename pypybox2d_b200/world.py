@@ -129,8 +129,10 @@ class World(object):
         if self._locked:
             raise LockedError("Cannot create a body while simulating")
         if body is not None:
-            raise NotImplementedError("copying an existing Body into a world is not supported; pass Body kwargs")
-        return self.add_body(Body(**kwargs))
+            body = copy(body)                  # world.py:219-220; kwargs (the type of create_*_body included) are ignored, as there
+        else:
+            body = Body(**kwargs)
+        return self.add_body(body)
 
     def create_dynamic_body(self, body=None, **kwargs):
         return self.create_body(body, type=Body.DYNAMIC, **kwargs)

@@ -18,7 +18,7 @@ def declared_functions():
 def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for must in ("b2b_create", "b2b_destroy", "b2b_bind", "b2b_step", "b2b_step_host", "b2b_init_proxies",
-                 "b2b_collide_pairs", "b2b_status", "b2b_checksum", "b2b_last_error", "b2b_scratch_bytes"):
+                 "b2b_collide_pairs", "b2b_solve_islands", "b2b_status", "b2b_checksum", "b2b_kernel_ms", "b2b_last_error", "b2b_scratch_bytes"):
         assert must in names
 
 

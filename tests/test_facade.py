@@ -81,3 +81,35 @@ def test_default_contact_filter_rule():
     assert f(F(1, 0xffff, 0), F(1, 0xffff, 0))
     assert not f(F(1, 0xfffe, 0), F(1, 0xffff, 0))
     assert f(F(1, 0, 3), F(1, 0, 3)) and not f(F(1, 0xffff, -3), F(1, 0xffff, -3))
+
+
+def test_create_body_copies_an_existing_body_and_inactive_bodies_pack_without_proxies():
+    """World.create_body(body=...) copies the body and its fixtures (world.py:208-224, body.py:118-140); a body created with
+    active=False keeps its fixtures but has no proxies (body.py:288-297): its rows can never be paired."""
+    import numpy as np
+    import pypybox2d_b200 as b2
+    from pypybox2d_b200 import schema
+    w = b2.World((0, -10), True, continuous_physics=False)
+    proto = b2.Body(position=(1.0, 2.0), angle=0.25, linear_velocity=(0.5, -1.0), type=b2.Body.DYNAMIC, linear_damping=0.1,
+                    fixtures=[b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=2.0, friction=0.4),
+                              b2.Fixture(b2.Circle(0.2, (0.3, 0.0)), density=1.0)], user_data="proto")
+    a = w.create_body(proto)
+    b = w.create_dynamic_body(body=proto)
+    assert a is not proto and b is not proto and a is not b and len(w.bodies) == 2
+    for c in (a, b):
+        assert c.type == b2.Body.DYNAMIC and c.user_data == "proto" and len(c.fixtures) == 2
+        assert c.fixtures[0] is not proto.fixtures[0] and c.fixtures[0].body is c
+        assert (c.position.x, c.position.y, c.angle) == (1.0, 2.0, 0.25)
+        assert c.mass == proto.mass and c.inertia == proto.inertia and c.linear_damping == 0.1
+    ghost = w.create_dynamic_body(position=(1.0, 2.0), active=False, fixtures=b2.Fixture(b2.Circle(0.5), density=1.0))
+    assert not ghost.active
+    caps = schema.Caps(4, 8, 32)
+    table = schema.ShapeTable()
+    A = schema.alloc(caps, 1, 8)
+    schema.pack_world(w, A, 0, table)
+    assert not (A["b_flags"][0, 2] & schema.BODY_ACTIVE) and (A["b_flags"][0, 0] & schema.BODY_ACTIVE)
+    assert A["f_moved"][0, :5].tolist() == [1, 1, 1, 1, 0]
+    assert np.all(A["f_fat"][0, 4, :2] > 1e29) and np.all(A["f_fat"][0, 4, 2:] < -1e29)
+    ghost.active = True                        # before the first step the flag is host state
+    schema.pack_world(w, A, 0, schema.ShapeTable())
+    assert A["f_moved"][0, 4] == 1 and abs(A["f_fat"][0, 4, 0] - 0.4) < 1e-12

@@ -257,3 +257,46 @@ def test_zero_dt_and_empty_contact_world():
     assert len(w.contact_manager.contacts) == 0
     assert a.position.y < y0 and a.position.y == pytest.approx(b.position.y, abs=1e-12)
     assert a.linear_velocity.y == pytest.approx(-10.0 * 10 / 60, abs=1e-12)
+
+
+def test_solve_islands_hook_is_the_solver_stage_of_a_step():
+    """T1 hook: step(0) (narrowphase alone, world.py:338-349) followed by b2b_solve_islands gives the bodies and impulses a
+    full step gives -- the hook runs island construction + Island.solve and nothing else."""
+    import pypybox2d_b200 as b2
+    w = scenes.vertical_stack(b2)
+    a = b2.BatchedWorld.replicate(w, 16, jitter=1e-2, config=2, real="f64")
+    b = b2.BatchedWorld.replicate(w, 16, jitter=1e-2, config=2, real="f64")
+    a.step(1 / 60, 10, 10, 40)
+    b.step(1 / 60, 10, 10, 40)
+    a.step(1 / 60, 10, 10)
+    b.step(0.0, 10, 10)
+    before = b.download(["f_fat", "w_count"])
+    b.solve_islands(1 / 60, 10, 10)
+    A, B = a.download(), b.download()
+    for name in ("b_pos", "b_vel", "b_xf", "b_flags", "c_imp", "c_mf", "c_pts", "c_flags", "l_body", "l_contact", "w_island"):
+        assert np.array_equal(A[name], B[name]), name
+    # ... and nothing after it: proxies not synchronised, no new contacts
+    assert np.array_equal(before["f_fat"], B["f_fat"]) and np.array_equal(before["w_count"][:, 2], B["w_count"][:, 2])
+    assert a.status() == 0 and b.status() == 0
+
+
+def test_inactive_body_is_never_simulated():
+    """Body(active=False): no proxies, no contacts, no island -- it stays where it is while an active twin falls onto the
+    ground; the world around it steps exactly like a world without it."""
+    import pypybox2d_b200 as b2
+
+    def build(with_ghost):
+        w = b2.World((0, -10), True, continuous_physics=False, real="f64")
+        w.create_static_body(shapes=b2.Edge((-20, 0), (20, 0)))
+        w.create_dynamic_body(position=(0, 3), fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=1))
+        if with_ghost:
+            w.create_dynamic_body(position=(0.2, 1.0), active=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=1))
+        return w
+    w1, w0 = build(True), build(False)
+    for i in range(90):
+        w1.step(1 / 60, 8, 3)
+        w0.step(1 / 60, 8, 3)
+    ghost = w1.bodies[2]
+    assert (ghost.position.x, ghost.position.y) == (0.2, 1.0) and ghost.linear_velocity.y == 0.0
+    assert w1.bodies[1].position.y == w0.bodies[1].position.y < 0.6           # fell THROUGH the ghost onto the ground
+    assert len(w1.contact_manager.contacts) == len(w0.contact_manager.contacts) == 1
