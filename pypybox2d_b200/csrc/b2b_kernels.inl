@@ -53,16 +53,20 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
 // per-world summary word the flat kernels wrote; only the worlds that need work are then handed to the teams.
 // Chunks of 32 worlds are handed out through an atomic counter (zeroed by the host before the launch), so the few
 // expensive worlds of a mostly settled batch spread over the whole grid instead of queueing behind one another.
+// `chunk` (a power of two <= 32, chosen by the launcher from batch and grid size) is the number of worlds a warp takes at a
+// time: 32 when most worlds are skipped, fewer when the batch is small against the grid -- a batch in which every world needs
+// its walk would otherwise keep only n_worlds / 32 warps busy, each with 32 worlds in a row (measured: deep stacks, 32,768
+// worlds, plan kernel 7.7 ms = one warp's 32 worlds back to back).
 template <class Need, class Work>
-__device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, unsigned int* chunk_counter, Need need_of, Work work)
+__device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, int chunk, unsigned int* chunk_counter, Need need_of, Work work)
 {
     const int lane = (int)(threadIdx.x & 31);
     for (;;) {
         int base = 0;
-        if (lane == 0) base = (int)atomicAdd(chunk_counter, 32u);
+        if (lane == 0) base = (int)atomicAdd(chunk_counter, (unsigned int)chunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= c.n_worlds) break;
-        const int w = base + lane;
+        const int w = (lane < chunk) ? base + lane : c.n_worlds;
         // need_of: 0 = nothing to do, 1 = mostly sequential work (island walk, schedule: narrow teams, several worlds
         // per warp), 2 = contact-parallel work (contacts of sleeping bodies to evaluate, contacts to destroy and
         // compact, or simply many contacts: the whole warp takes one world).  Measured on B200, plan kernel per 16,384 worlds: landing pyramids
@@ -84,13 +88,13 @@ __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes,
 
 __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                          scratch_layout L, unsigned char* scratch, step_params sp,
-                                                                         int lanes, size_t team_smem, unsigned int* chunk_counter)
+                                                                         int lanes, size_t team_smem, unsigned int* chunk_counter, int chunk)
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int teams_per_cta = 32 / lanes;                 // scratch slabs and shared-memory regions of this CTA
     for_each_needy_world(
-        c, lanes, chunk_counter,
+        c, lanes, chunk, chunk_counter,
         [&](int w) {
             const uint32_t fl = B.w_flags[w];
             const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
@@ -217,13 +221,13 @@ __global__ void __launch_bounds__(128) B2B_CAT(sync_kernel_, B2B_SUFFIX)(batch_p
 
 __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                                scratch_layout L, unsigned char* scratch, step_params sp,
-                                                                               int lanes, size_t team_smem, unsigned int* chunk_counter)
+                                                                               int lanes, size_t team_smem, unsigned int* chunk_counter, int chunk)
 {
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int teams_per_cta = 32 / lanes;
     for_each_needy_world(
-        c, lanes, chunk_counter,
+        c, lanes, chunk, chunk_counter,
         [&](int w) {
             // profiling counts world-steps in run_pairs; otherwise only worlds with a mover (or a stale pair count) need it
             if (sp.flags & STEP_PROFILE) return true;
@@ -443,6 +447,15 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
 
 // One World.step = narrowphase + plan + (per group of worlds: prepare, velocity, position) + sync + pairs.  The parts are
 // separate launchers so that the host-buffer entry point (b2b_step_host) can run them chunk by chunk between its copies.
+// worlds a warp of the plan / pair kernels takes at a time (see for_each_needy_world): at least two grabs per warp
+static inline int world_chunk(int n_worlds, int grid)
+{
+    int chunk = 32;
+    while (chunk > 1 && (long long)chunk * grid * 2 > n_worlds) chunk >>= 1;
+    if (const char* env = getenv("B2B_WORLD_CHUNK")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) chunk = v; }
+    return chunk;
+}
+
 static inline int flat_blocks(long long items, int n_sm)
 {
     long long blocks = (items + 127) / 128;
@@ -464,7 +477,7 @@ void B2B_CAT(launch_plan_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
     if (sp.flags & STEP_GROUP_KERNEL) cudaMemsetAsync(counters + 2, 1, sizeof(unsigned int), st);   // any non-zero word
     B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(as_ptrs(fields), c, p.plan, plan, p.layout, scratch_aux, sp,
-                                                                                 p.lanes_aux, p.team_smem_plan, counters);
+                                                                                 p.lanes_aux, p.team_smem_plan, counters, world_chunk(c.n_worlds, p.k_plan.grid));
 }
 
 // K3 for worlds [w0, w0 + n_group): n_group <= launch_plan::group_worlds (one record slab each); timer may be null
@@ -499,7 +512,7 @@ void B2B_CAT(launch_post_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     B2B_CAT(sync_kernel_, B2B_SUFFIX)<<<flat_blocks((long long)c.n_worlds * (c.nf > c.nb ? c.nf : c.nb), p.n_sm), 128, 0, st>>>(B, c, p.plan, plan, sp);
     if (tm) tm->mark(T_SYNC, st);
     B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
-                                                                                         p.lanes_aux, p.team_smem_broad, counters + 1);
+                                                                                         p.lanes_aux, p.team_smem_broad, counters + 1, world_chunk(c.n_worlds, p.k_broad.grid));
     if (tm) tm->mark(T_PAIRS, st);
 }
 

@@ -40,6 +40,8 @@
 #define B2B_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define B2B_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define B2B_CLOCK() clock64()
+#define B2B_POPC(m) __popc(m)
+#define B2B_CTZ(m) (__ffs((int)(m)) - 1)
 #if defined(B2B_PF_LDGSTS)
 // experiment: a real 16-byte asynchronous copy into a per-lane sink (with a 128-byte L2 fill) instead of a prefetch hint
 #define B2B_PREFETCH(p) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(pf_sink), "l"(p))
@@ -51,6 +53,8 @@
 #define B2B_SYNC() ((void)0)
 #define B2B_IS_T0 true
 #define B2B_CLOCK() 0LL
+#define B2B_POPC(m) __builtin_popcount(m)
+#define B2B_CTZ(m) __builtin_ctz(m)
 #define B2B_PREFETCH(p) ((void)0)
 namespace b2b {
 template <class T> inline T host_atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
@@ -170,6 +174,7 @@ struct smem_layout {
     size_t off_ctl, off_flags, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag, total_plan;
     size_t off_state, total_solve;                            // relative to the team's base
     size_t total_broad;
+    size_t off_pairbits;                                      // broadphase kernel: candidate bitmap [nf][ceil(nf / 32)] (0: none, too big)
 };
 B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
 {
@@ -181,6 +186,11 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     const size_t fat_bytes = align_up((size_t)real_bytes * 4 * (size_t)c.nf, 32), moved_bytes = align_up((size_t)c.nf, 32);
     S.off_fat = o; S.off_moved = o + fat_bytes;
     S.total_broad = o + fat_bytes + moved_bytes;
+    {   // one bit per (mover, proxy): the overlap tests of pass 1 are not repeated by pass 2 (when it fits 24 KB)
+        const size_t bits_bytes = sizeof(uint32_t) * (((size_t)c.nf + 31) / 32) * (size_t)c.nf;
+        S.off_pairbits = 0;
+        if (bits_bytes <= 24 * 1024) { S.off_pairbits = S.total_broad; S.total_broad += align_up(bits_bytes, 32); }
+    }
     S.off_flags = o; o = align_up(o + sizeof(uint32_t) * (size_t)c.nb, 32);
     S.off_ls = o; o = align_up(o + sizeof(uint16_t) * ((size_t)c.nc + 3 * (size_t)c.nb + 4), 32);
     S.off_cbody = o; o = align_up(o + sizeof(uint16_t) * 2 * (size_t)c.nc, 32);
@@ -227,6 +237,7 @@ template <class real> struct world_step {
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_slot_isl, *g_joint, *g_adj, *g_adj_start;
     real* s_fat; uint8_t* s_moved;   // pair finding: fat boxes and move flags staged in shared memory
+    uint32_t* s_pairbits = nullptr;  // pair finding: candidate bitmap (broadphase kernel, when it fits)
     uint32_t* g_lv;          // level-step table (see lv_words)
     uint32_t* g_summary;     // SUM_* bits raised by the flat kernels, consumed (and cleared) by the per-world kernels
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
@@ -330,6 +341,7 @@ template <class real> struct world_step {
         s_ctl = (int32_t*)(smem + S.off_ctl);
         const size_t fat_at = broadphase_kernel ? S.off_fat : S.off_ls;
         s_fat = (real*)(smem + fat_at); s_moved = (uint8_t*)(smem + fat_at + (S.off_moved - S.off_fat));
+        s_pairbits = (broadphase_kernel && S.off_pairbits != 0) ? (uint32_t*)(smem + S.off_pairbits) : nullptr;
         s_flags = (uint32_t*)(smem + S.off_flags);
         s_ls = (uint16_t*)(smem + S.off_ls);
         s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
@@ -1894,12 +1906,23 @@ template <class real> struct world_step {
             s_moved[f] = (uint8_t)(f_moved[f] != 0);
         }
         B2B_SYNC();
-        // pass 1: per-mover candidate counts
+        // pass 1: per-mover candidate counts (and, when the bitmap fits, the candidates themselves: one bit per proxy)
+        const int words = (nf + 31) >> 5;
         B2B_PFOR(a, nf) {
             int n = 0;
             if (s_moved[a]) {
                 const real fat_a[4] = {s_fat[4 * a], s_fat[4 * a + 1], s_fat[4 * a + 2], s_fat[4 * a + 3]};
-                for (int b = 0; b < nf; ++b) n += pair_candidate(a, fat_a, b) ? 1 : 0;
+                if (s_pairbits) {
+                    for (int wi = 0; wi < words; ++wi) {
+                        uint32_t m = 0u;
+                        const int b0 = wi << 5, b1 = (b0 + 32 < nf) ? b0 + 32 : nf;
+                        for (int b = b0; b < b1; ++b) m |= pair_candidate(a, fat_a, b) ? (1u << (b - b0)) : 0u;
+                        s_pairbits[(size_t)a * words + wi] = m;
+                        n += B2B_POPC(m);
+                    }
+                } else {
+                    for (int b = 0; b < nf; ++b) n += pair_candidate(a, fat_a, b) ? 1 : 0;
+                }
             }
             scan[a] = n;
         }
@@ -1908,8 +1931,20 @@ template <class real> struct world_step {
         // pass 2: emit in (a, b) order
         B2B_PFOR(a, nf) {
             if (!s_moved[a]) continue;
-            const real fat_a[4] = {s_fat[4 * a], s_fat[4 * a + 1], s_fat[4 * a + 2], s_fat[4 * a + 3]};
             int o = scan[a];
+            if (s_pairbits) {
+                for (int wi = 0; wi < words; ++wi) {
+                    uint32_t m = s_pairbits[(size_t)a * words + wi];
+                    while (m) {
+                        const int b = (wi << 5) + B2B_CTZ(m);
+                        m &= m - 1u;
+                        if (o < cap.npair) { p_pairs[2 * o] = a; p_pairs[2 * o + 1] = b; }
+                        ++o;
+                    }
+                }
+                continue;
+            }
+            const real fat_a[4] = {s_fat[4 * a], s_fat[4 * a + 1], s_fat[4 * a + 2], s_fat[4 * a + 3]};
             for (int b = 0; b < nf; ++b) {
                 if (!pair_candidate(a, fat_a, b)) continue;
                 if (o < cap.npair) { p_pairs[2 * o] = a; p_pairs[2 * o + 1] = b; }

@@ -31,7 +31,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
     plan_layout P = plan_plan(c);
     smem_layout S = smem_plan_layout(c, (int)sizeof(real));
     std::vector<unsigned char> aux(L.total_aux + 256), solve(L.total_rec + 256), sprof(L.total_sprof + 256);
-    std::vector<unsigned char> smem_aux(S.total_plan + 256), smem_solve(S.total_solve + 256);
+    std::vector<unsigned char> smem_aux((S.total_plan > S.total_broad ? S.total_plan : S.total_broad) + 256), smem_solve(S.total_solve + 256);
     // the plan rows persist between calls like the device context's do (the island schedule is reused while the
     // contact graph is unchanged); keyed by the batch they belong to
     static std::map<const void*, std::vector<uint16_t>> plans;
@@ -52,7 +52,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
         ws.bind_rows(B, c, w, plan.data(), P);
         ws.bind_scratch_aux(aux.data(), L);
         ws.bind_scratch_solve(solve.data(), L, sprof.data());
-        ws.bind_smem_aux(smem_aux.data());
+        ws.bind_smem_aux(smem_aux.data(), true);      // the pair kernel's layout (candidate bitmap included): the phases run one after the other here
         ws.bind_smem_solve(smem_solve.data());
         if (dt > 0.0 && !(B.w_flags[w] & WORLD_GRAPH_VALID)) g_replans += 1;
         ws.run(sp);
