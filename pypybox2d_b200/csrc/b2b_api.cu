@@ -123,7 +123,8 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     // default team size of the plan / pair kernels, from measurements on B200 (plan kernel, 16,384 worlds): landing
     // pyramids (contact capacity 640) 2.3 ms with 8 lanes, 5.4 with 32; vertical stacks (708) 10.0 / 6.3; mixed scene
     // (1,092) 21.4 / 10.5: worlds with many contacts spend their replans in contact-parallel loops
-    const int lanes_aux = caps->reserved > 0 ? caps->reserved : (caps->nc >= 700 ? 32 : 8);
+    int lanes_aux = caps->reserved > 0 ? caps->reserved : (caps->nc >= 700 ? 32 : 8);
+    if (const char* env = getenv("B2B_LANES_AUX")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16 || v == 32) lanes_aux = v; }   // experiments
     int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
                     : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
     if (rc != 0) { b2b_destroy(x); return fail(B2B_ERR_CUDA, "kernel launch planning (shared memory / occupancy)", (cudaError_t)rc); }
