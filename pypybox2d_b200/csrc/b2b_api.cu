@@ -120,10 +120,13 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     // caps->threads: lanes of a warp per world in the solve kernel (4, 8, 16 or 32); caps->reserved: the same for
     // the plan / broadphase kernels
     const int lanes = caps->threads > 0 ? caps->threads : 4;
-    // default team size of the plan / pair kernels, from measurements on B200 (plan kernel, 16,384 worlds): landing
-    // pyramids (contact capacity 640) 2.3 ms with 8 lanes, 5.4 with 32; vertical stacks (708) 10.0 / 6.3; mixed scene
-    // (1,092) 21.4 / 10.5: worlds with many contacts spend their replans in contact-parallel loops
-    int lanes_aux = caps->reserved > 0 ? caps->reserved : (caps->nc >= 700 ? 32 : 8);
+    // default team size of the plan / pair kernels: the whole warp per world.  Narrow teams put several worlds' SEQUENTIAL island
+    // walks into one warp, where they diverge and are issued one after the other, and multiply the CTA's shared memory.
+    // Measured on B200 with the per-grab world count sized from the batch (b2b_kernels.inl world_chunk), plan kernel with
+    // 4 / 8 / 16 / 32 lanes per world: deep stacks x 32,768 worlds 24.2 / 12.6 / 7.4 / 5.3 ms, vertical stacks x 65,536
+    // 39.0 / 21.2 / 10.7 / 8.7 ms, mixed x 32,768 51.8 / 22.5 / 11.9 / 6.4 ms; pyramids from t = 0 (65,536 worlds) 24.8 ms per
+    // step with 8 lanes, 24.2 with 32 (profiles/r2_other_scenes.md)
+    int lanes_aux = caps->reserved > 0 ? caps->reserved : 32;
     if (const char* env = getenv("B2B_LANES_AUX")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16 || v == 32) lanes_aux = v; }   // experiments
     int rc = x->f64 ? plan_f64(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan)
                     : plan_f32(x->c, lanes, lanes_aux, caps->ctas_per_sm, x->n_sm, &x->plan);
@@ -411,23 +414,42 @@ extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_sta
         if (x->f64) launch_plan_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
         else launch_plan_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
         ++x->launches;
-        // solve + state out, chunk by chunk (the last step's state is the one read back)
+        // solve + state out, chunk by chunk (the last step's state is the one read back).  When every world's record slab is
+        // resident the chunks alternate between the caller's stream and a second one, as in b2b_step: the tail of one chunk's
+        // persistent solve grid runs under the next chunk's kernels.
+        const bool two = x->step_streams == 2 && n_chunks >= 2 && x->plan.group_worlds >= W && dt > 0.0 && !(flags & B2B_STEP_PROFILE);
+        if (two) {
+            if (!x->s_aux) CUDA_TRY(cudaStreamCreateWithFlags(&x->s_aux, cudaStreamNonBlocking), "cudaStreamCreate(aux)");
+            if (!x->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+            if (!x->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming), "cudaEventCreate");
+            CUDA_TRY(cudaMemsetAsync(x->d_status + 4, (sp.flags & B2B_STEP_GROUP_KERNEL) ? 1 : 0, sizeof(uint32_t), st), "memset");
+            CUDA_TRY(cudaEventRecord(x->ev_fork, st), "cudaEventRecord");
+            CUDA_TRY(cudaStreamWaitEvent(x->s_aux, x->ev_fork, 0), "cudaStreamWaitEvent");
+        }
         for (int k = 0; k < n_chunks; ++k) {
             const int w0 = k * chunk, n = (W - w0 < chunk) ? W - w0 : chunk;
+            cudaStream_t sk = (two && (k & 1)) ? x->s_aux : st;
             if (dt > 0.0) {
-                if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, first, w0, n, st, nullptr);
-                else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch_solve, x->scratch_sprof, sp, first, w0, n, st, nullptr);
+                step_params spk = sp;
+                if (two) spk.joint_any = x->d_status + ((k & 1) ? 4 : 3);       // one joint-schedule word per stream
+                unsigned char* rec = x->scratch_solve + (two ? (size_t)w0 * x->plan.layout.total_rec : (size_t)0);
+                if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, first, w0, n, sk, nullptr);
+                else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, first, w0, n, sk, nullptr);
                 x->launches += 4;
             }
             if (last && h_state_out) {
-                if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, w0, n, st);
-                else launch_gather_state_f32(x->fields, x->c, x->stage_out, w0, n, st);
+                if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, w0, n, sk);
+                else launch_gather_state_f32(x->fields, x->c, x->stage_out, w0, n, sk);
                 ++x->launches;
-                CUDA_TRY(cudaEventRecord(ev_out[k], st), "cudaEventRecord");
+                CUDA_TRY(cudaEventRecord(ev_out[k], sk), "cudaEventRecord");
                 CUDA_TRY(cudaStreamWaitEvent(x->s_out, ev_out[k], 0), "cudaStreamWaitEvent");
                 CUDA_TRY(cudaMemcpyAsync((char*)h_state_out + (size_t)w0 * per_world_out, (const char*)x->stage_out + (size_t)w0 * per_world_out,
                                          (size_t)n * per_world_out, cudaMemcpyDeviceToHost, x->s_out), "D2H state");
             }
+        }
+        if (two) {
+            CUDA_TRY(cudaEventRecord(x->ev_join, x->s_aux), "cudaEventRecord");
+            CUDA_TRY(cudaStreamWaitEvent(st, x->ev_join, 0), "cudaStreamWaitEvent");
         }
         if (x->f64) launch_post_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);
         else launch_post_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);

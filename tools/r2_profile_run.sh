@@ -7,7 +7,7 @@ BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --t0-worlds 0 --no
 # step-kernel launches before the timed steps: settle 300 x 8 + warm-up 3 x 8 (init_proxies does not match the filter)
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:'(collide|plan|prepare|solve_velocity|solve_position|solve_position_joint|sync|broadphase)_kernel_f32' \
-    --launch-skip 2424 --launch-count 64 --csv --log-file $O/launches.csv $BENCH > $O/bench_under_ncu.json 2> $O/ncu.err
+    --launch-skip 2424 --launch-count 16 --csv --log-file $O/launches.csv $BENCH > $O/bench_under_ncu.json 2> $O/ncu.err
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:solve_velocity_kernel --launch-skip 303 --launch-count 1 \
     -o $O/solve_velocity $BENCH > /dev/null 2>> $O/ncu.err
 ncu -i $O/solve_velocity.ncu-rep --page raw --csv > $O/solve_velocity_raw.csv 2>> $O/ncu.err
