@@ -43,13 +43,13 @@ def _scene_table():
         "pyramid": dict(what="pyramid-20 (examples/pyramid-bench.py scene)", config=3, caps=C(211, 211, 640, npair=1280), dt=DT,
                         dt_text="1/60", vi=8, pi=3, n_dyn=210, worlds=131072, distinct=8192),
         "vertical_stack": dict(what="examples/verticalstack-bench.py scene (5 columns x 16 rows of boxes and circles)", config=2,
-                               caps=C(161, 162, 512), dt=DT, dt_text="1/60", vi=10, pi=10, n_dyn=160, worlds=65536, distinct=2048),
+                               caps=C(161, 162, 512, npair=1424), dt=DT, dt_text="1/60", vi=10, pi=10, n_dyn=160, worlds=65536, distinct=2048),
         "hello": dict(what="examples/hello-bench.py scene (one circle on a box)", config=2, caps=None, dt=0.1, dt_text="0.1",
                       vi=10, pi=10, n_dyn=1, worlds=65536, distinct=1024),
         "mixed": dict(what="mixed circles + convex polygons, 256 bodies per world, per-world shape draws (SURVEY 8d config 4)",
                       config=4, caps=C(257, 260, 1104), dt=DT, dt_text="1/60", vi=8, pi=3, n_dyn=256, worlds=131072, distinct=512,
                       per_world_shapes=True),
-        "deep_stacks": dict(what="10 columns x 20 boxes (SURVEY 8d config 5)", config=5, caps=C(201, 201, 512), dt=DT, dt_text="1/60", vi=8,
+        "deep_stacks": dict(what="10 columns x 20 boxes (SURVEY 8d config 5)", config=5, caps=C(201, 201, 640, npair=1736), dt=DT, dt_text="1/60", vi=8,
                             pi=3, n_dyn=200, worlds=32768, distinct=2048),
     }
 
