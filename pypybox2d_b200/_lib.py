@@ -8,7 +8,7 @@ from .schema import FIELD_NAMES
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libb2b.so")
+SO_PATH = os.environ.get("B2B_LIB") or os.path.join(CSRC, "libb2b.so")      # (B2B_LIB: an experimental build, tools/build_variant.sh)
 
 
 class Caps(ctypes.Structure):

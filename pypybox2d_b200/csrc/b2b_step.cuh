@@ -20,6 +20,7 @@
 // tests/hostcheck can run this exact source under g++ for debugging; that build is test-only.
 #pragma once
 #include <cstring>
+#include <cmath>
 #include <type_traits>
 #include "b2b_collide.cuh"
 
@@ -98,7 +99,17 @@ template <class real> struct batch_ptrs {
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
-enum { VREC_QUADS = 8, PREC_QUADS = 5 };   // velocity / position record of one constraint, in 4-vectors of reals
+// velocity / position record of one constraint, in 4-vectors of reals ("quads").  The fp64 (parity) build keeps the reference's
+// operands (anchor vectors, block matrices: 8 quads, impulses in their own row); the fp32 (throughput) build carries the rows
+// in Jacobian form with the accumulated impulses inline and recomputes the 2x2 block per sweep: 6 quads = 96 bytes, one stream
+// instead of two (see the layout table above constraint_init).  -DB2B_EXACT_ROWS keeps the fp64 layout in fp32 too.
+enum { VREC_QUADS_EXACT = 8, VREC_QUADS_FAST = 6, PREC_QUADS = 5 };
+#if defined(B2B_EXACT_ROWS)
+B2B_HD constexpr bool fast_rows(int) { return false; }
+#else
+B2B_HD constexpr bool fast_rows(int real_bytes) { return real_bytes == 4; }
+#endif
+B2B_HD constexpr int vrec_quads(int real_bytes) { return fast_rows(real_bytes) ? VREC_QUADS_FAST : VREC_QUADS_EXACT; }
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32, STEP_SOLVE_ONLY = 64 };
 // per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
@@ -141,7 +152,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
 
 struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `rec` slabs per world of a solve group
     size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
-    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_state, total_rec;
+    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_ci, off_cc_bias, off_cc_state, total_rec;
     size_t total_sprof;       // per solve team: cycle counters
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
@@ -158,9 +169,11 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_prof = take(sizeof(long long) * PROF_SLOTS);
     L.total_aux = align_up(o, 256);
     o = 0;
-    L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
+    L.off_cc_vel = take((size_t)real_bytes * 4 * vrec_quads(real_bytes) * ((size_t)c.nc + 2));
     L.off_cc_pos = take((size_t)real_bytes * 4 * PREC_QUADS * ((size_t)c.nc + 2));
-    L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
+    L.off_cc_imp = take(fast_rows(real_bytes) ? (size_t)0 : (size_t)real_bytes * 4 * ((size_t)c.nc + 2));   // (inline in the Jacobian records)
+    L.off_cc_ci = take(sizeof(int32_t) * ((size_t)c.nc + 2));                    // contact index of every slot (store_impulses)
+    L.off_cc_bias = take(fast_rows(real_bytes) ? (size_t)real_bytes * 2 * ((size_t)c.nc + 2) : (size_t)0);   // restitution bias (Jacobian records: side array)
     L.off_cc_state = take((size_t)real_bytes * 3 * (size_t)c.nb);      // the velocities the solver starts from, per body
     L.total_rec = align_up(o, 256);
     L.total_sprof = align_up(sizeof(long long) * PROF_SLOTS, 256);
@@ -243,7 +256,7 @@ template <class real> struct world_step {
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan;
-    real *cc_vel, *cc_pos, *cc_imp, *cc_state;
+    real *cc_vel, *cc_pos, *cc_imp, *cc_bias, *cc_state; int32_t* cc_ci;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
@@ -332,6 +345,8 @@ template <class real> struct world_step {
         cc_vel = (real*)(rec + L.off_cc_vel);
         cc_pos = (real*)(rec + L.off_cc_pos);
         cc_imp = (real*)(rec + L.off_cc_imp);
+        cc_ci = (int32_t*)(rec + L.off_cc_ci);
+        cc_bias = (real*)(rec + L.off_cc_bias);
         cc_state = (real*)(rec + L.off_cc_state);
         prof = (long long*)team_prof;
     }
@@ -882,6 +897,14 @@ template <class real> struct world_step {
     //   p4  lc_a.x lc_a.y lc_b.x lc_b.y
     //   imp ni0 ti0 ni1 ti1
     //   info = n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25
+    // fp32 build (FAST_ROWS): the velocity rows in Jacobian form, 6 quads = 96 bytes, impulses inline:
+    //   f0  normal.x normal.y [+-]friction [body_a | body_b << 16]   (sign bit of friction: the slot has a restitution bias,
+    //                                                                 kept in the side array cc_bias: rare)
+    //   f1  rA0 x n  rA0 x t  rB0 x n  rB0 x t                       f2  the same for point 1 (zero when the row was dropped)
+    //   f3  nmass0 tmass0 nmass1 tmass1   (nmass1 == 0 <=> one velocity row)
+    //   f4  inv_mass_a inv_I_a inv_mass_b inv_I_b                    f5  ni0 ti0 ni1 ti1
+    //   (a body with zero inverse mass AND inertia is never written back: a static body is shared by the slots of a level)
+    // side arrays per slot: cc_ci (the contact's index, for store_impulses), cc_bias
     // Shared memory holds three reals per body: its velocity while velocities are being solved, its sweep position
     // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
     // and later their position for itself (islands are solved one after the other).
@@ -900,9 +923,12 @@ template <class real> struct world_step {
         x.r = r;
         return x.w[0];
     }
+    static constexpr bool FAST_ROWS = fast_rows((int)sizeof(real));
+    enum { VREC_QUADS = FAST_ROWS ? VREC_QUADS_FAST : VREC_QUADS_EXACT };
     B2B_D quad* vel_rec(int slot) { return reinterpret_cast<quad*>(cc_vel) + (size_t)VREC_QUADS * slot; }
     B2B_D quad* pos_rec(int slot) { return reinterpret_cast<quad*>(cc_pos) + (size_t)PREC_QUADS * slot; }
-    B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
+    // the slot's accumulated impulses: their own row, or the last quad of a Jacobian record
+    B2B_D quad* imp_rec(int slot) { return FAST_ROWS ? vel_rec(slot) + (VREC_QUADS_FAST - 1) : reinterpret_cast<quad*>(cc_imp) + slot; }
     // (x, y) pairs first, then the third component: one two-wide and one scalar shared-memory access per body
     struct alignas(2 * sizeof(real)) pair2 { real x, y; };
     B2B_D quad state_get(int b) const
@@ -936,7 +962,8 @@ template <class real> struct world_step {
         if (t < c1) {
             B2B_PREFETCH(vel_rec(t));
             if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(vel_rec(t)) + 128);
-            B2B_PREFETCH(imp_rec(t));
+            if (FAST_ROWS) { if (t & 3) B2B_PREFETCH(vel_rec(t) + (VREC_QUADS_FAST - 1)); }   // 96-byte records: three of four straddle two lines
+            else B2B_PREFETCH(imp_rec(t));
         }
     }
     B2B_D void prefetch_pos(int s, int c0, int c1)
@@ -1114,15 +1141,18 @@ template <class real> struct world_step {
         const V2 tangent = right_perp(normal);
         int n_vel = count;
         V2 ra[2], rb[2];
+        quad jac[2];                                         // (rA x n, rA x t, rB x n, rB x t) per point
         real nmass[2], tmass[2], bias[2], ni[2], ti[2];
         for (int j = 0; j < 2; ++j) {
             ra[j] = rb[j] = mk<real>(real(0), real(0));
+            jac[j] = mkq(real(0), real(0), real(0), real(0));
             nmass[j] = tmass[j] = bias[j] = ni[j] = ti[j] = real(0);
             if (j >= count) continue;
             ra[j] = wp[j] - ca; rb[j] = wp[j] - cb;
             const real rn_a = cross(ra[j], normal), rn_b = cross(rb[j], normal);
             const real k_normal = ma + mb + ia * sq_r(rn_a) + ib * sq_r(rn_b);      // contact.py:444-445: ** 2
             const real rt_a = cross(ra[j], tangent), rt_b = cross(rb[j], tangent);
+            jac[j] = mkq(rn_a, rt_a, rn_b, rt_b);
             const real k_tangent = ma + mb + ia * sq_r(rt_a) + ib * sq_r(rt_b);     // contact.py:456-457
             const real v_rel = dot(normal, rel_velocity(vb, wb, rb[j], va, wa, ra[j]));
             if (v_rel < -K<real>::velocity_threshold) bias[j] = -restitution * v_rel;
@@ -1148,15 +1178,27 @@ template <class real> struct world_step {
         }
         const uint32_t info = (uint32_t)(n_vel | (type << 8) | (count << 16) | (stat_a ? INFO_STATIC_A : 0) | (stat_b ? INFO_STATIC_B : 0));
         const real bodies_r = real_from_bits((uint32_t)ba | ((uint32_t)bb << 16)), info_r = real_from_bits(info);
+        cc_ci[slot] = ci;
         quad* q = vel_rec(slot);
-        q[0] = mkq(normal.x, normal.y, friction, bodies_r);
-        q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
-        q[2] = mkq(nmass[0], tmass[0], bias[0], info_r);
-        q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
-        q[4] = mkq(nmass[1], tmass[1], bias[1], real_from_bits((uint32_t)ci));
-        q[5] = mkq(k11, k12, k22, nm11);
-        q[6] = mkq(nm12, nm22, real(0), real(0));
-        q[7] = mkq(ma, ia, mb, ib);
+        if constexpr (FAST_ROWS) {
+            const bool has_bias = (bias[0] != real(0)) || (bias[1] != real(0));
+            const bool two = (n_vel == 2);
+            q[0] = mkq(normal.x, normal.y, real_from_bits(bits_of_real(friction) | (has_bias ? 0x80000000u : 0u)), bodies_r);
+            q[1] = jac[0];
+            q[2] = two ? jac[1] : mkq(real(0), real(0), real(0), real(0));
+            q[3] = mkq(nmass[0], tmass[0], two ? nmass[1] : real(0), two ? tmass[1] : real(0));
+            q[4] = mkq(ma, ia, mb, ib);
+            cc_bias[2 * (size_t)slot] = bias[0]; cc_bias[2 * (size_t)slot + 1] = bias[1];
+        } else {
+            q[0] = mkq(normal.x, normal.y, friction, bodies_r);
+            q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
+            q[2] = mkq(nmass[0], tmass[0], bias[0], info_r);
+            q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
+            q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
+            q[5] = mkq(k11, k12, k22, nm11);
+            q[6] = mkq(nm12, nm22, real(0), real(0));
+            q[7] = mkq(ma, ia, mb, ib);
+        }
         quad* p = pos_rec(slot);
         p[0] = mkq(ma, ia, mb, ib);
         p[1] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
@@ -1171,8 +1213,13 @@ template <class real> struct world_step {
     B2B_D void load_vrec(int slot, vrec& r)
     {
         const quad* q = vel_rec(slot);
-        r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3]; r.q4 = q[4]; r.q5 = q[5]; r.q6 = q[6]; r.q7 = q[7];
-        r.qi = *imp_rec(slot);
+        if constexpr (FAST_ROWS) {
+            // f0, jacobian of point 0 / 1, effective masses, inverse masses, impulses (the unused members are never touched)
+            r.q0 = q[0]; r.q1 = q[1]; r.q3 = q[2]; r.q2 = q[3]; r.q7 = q[4]; r.qi = q[5];
+        } else {
+            r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3]; r.q4 = q[4]; r.q5 = q[5]; r.q6 = q[6]; r.q7 = q[7];
+            r.qi = *imp_rec(slot);
+        }
     }
     struct prec { quad q7, q8, q9, q10, q11; };
     B2B_D void load_prec(int slot, prec& r)
@@ -1184,6 +1231,7 @@ template <class real> struct world_step {
     // ContactSolver.warm_start for one slot (contact.py:498-525)
     B2B_D void constraint_warm_start(const vrec& r)
     {
+        if constexpr (FAST_ROWS) { constraint_warm_start_jacobian(r); return; }
         const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q7, qi = r.qi;
         const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(r.q2.w);
         const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(info & 0xff);
@@ -1211,6 +1259,7 @@ template <class real> struct world_step {
     // (store_impulses, contact.py:801-806: only as many points as the velocity rows kept).
     B2B_D void constraint_solve_velocity(const vrec& r, int slot, bool last)
     {
+        if constexpr (FAST_ROWS) { constraint_solve_velocity_jacobian(r, slot, last); return; }
         const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
         quad qi = r.qi;
         const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(q2.w);
@@ -1295,13 +1344,155 @@ template <class real> struct world_step {
         B2B_TSTAMP_F(3, (float)va.x, (float)wa, (float)vb.x, (float)wb);
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
-        if (!last) {
-            *imp_rec(slot) = qi;
-        } else {
-            real* imp = c_imp + 4 * (size_t)bits_of_real(q4.w);
-            if (n_vel > 1) stq(imp, qi);
-            else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+        if (!last) *imp_rec(slot) = qi;
+        else impulses_store(slot, n_vel, qi);
+    }
+
+    // store_impulses (contact.py:801-806): only as many points as the velocity rows kept
+    B2B_D void impulses_store(int slot, int n_vel, quad qi)
+    {
+        real* imp = c_imp + 4 * (size_t)cc_ci[slot];
+        if (n_vel > 1) stq(imp, qi);
+        else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+    }
+
+    // ---- Jacobian-form rows (FAST_ROWS): f1 / f2 = (rA x n, rA x t, rB x n, rB x t) of point 0 / 1.  A row's relative
+    // velocity is (vB - vA).d + wB (rB x d) - wA (rA x d) and its impulse l is applied as v -+= m l d, w -+= I l (r x d):
+    // algebraically the reference's operations with ~40 % fewer floating-point instructions; the results differ from the
+    // operation-by-operation form by fp32 rounding only (the fp32 parity tiers hold tolerances, never bits).  Every
+    // two-product sum is an explicit fused multiply-add so that each compiled copy of this code rounds alike (a world's
+    // trajectory must not depend on the lane-team size or the batch it is in: T4).
+    B2B_D static real fma_r(real a, real b, real c)
+    {
+#if defined(__CUDA_ARCH__)
+        if constexpr (sizeof(real) == 4) return (real)__fmaf_rn((float)a, (float)b, (float)c);
+        else return (real)__fma_rn((double)a, (double)b, (double)c);
+#else
+        if constexpr (sizeof(real) == 4) return (real)fmaf((float)a, (float)b, (float)c);
+        else return (real)fma((double)a, (double)b, (double)c);
+#endif
+    }
+    B2B_D static real mul_r(real a, real b)
+    {
+#if defined(__CUDA_ARCH__)
+        if constexpr (sizeof(real) == 4) return (real)__fmul_rn((float)a, (float)b);
+        else return (real)__dmul_rn((double)a, (double)b);
+#else
+        return a * b;
+#endif
+    }
+    B2B_D static real dot2(real a, real b, real c, real d) { return fma_r(a, b, mul_r(c, d)); }          // a b + c d
+    B2B_D static real diff2(real a, real b, real c, real d) { return fma_r(a, b, -mul_r(c, d)); }        // a b - c d
+    B2B_D void constraint_warm_start_jacobian(const vrec& r)
+    {
+        const quad q0 = r.q0, j0 = r.q1, j1 = r.q3, m = r.q7, qi = r.qi;
+        const uint32_t bodies = bits_of_real(q0.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
+        const bool two = r.q2.z != real(0);
+        const real nx = q0.x, ny = q0.y, tx = ny, ty = -nx;
+        const real ma = m.x, ia = m.y, mb = m.z, ib = m.w;
+        const bool stat_a = (ma == real(0)) && (ia == real(0)), stat_b = (mb == real(0)) && (ib == real(0));
+        const quad sa = state_get(ba), sb = state_get(bb);
+        // the accumulated impulse of the whole contact: P = sum (ni n + ti t), torque arms from the cross products
+        real pn = qi.x, pt = qi.y;
+        real la = dot2(j0.x, qi.x, j0.y, qi.y), lb = dot2(j0.z, qi.x, j0.w, qi.y);
+        if (two) {
+            pn += qi.z; pt += qi.w;
+            la += dot2(j1.x, qi.z, j1.y, qi.w); lb += dot2(j1.z, qi.z, j1.w, qi.w);
         }
+        const real px = dot2(pn, nx, pt, tx), py = dot2(pn, ny, pt, ty);
+        if (!stat_a) state_set(ba, fma_r(-ma, px, sa.x), fma_r(-ma, py, sa.y), fma_r(-ia, la, sa.z));
+        if (!stat_b) state_set(bb, fma_r(mb, px, sb.x), fma_r(mb, py, sb.y), fma_r(ib, lb, sb.z));
+    }
+    // one row's impulse `l` along direction (dx, dy) with torque arms (arm_a, arm_b)
+    struct vel_pair { real vax, vay, wa, vbx, vby, wb; };
+    B2B_D static void apply_row(vel_pair& v, real l, real dx, real dy, real arm_a, real arm_b, real ma, real ia, real mb, real ib)
+    {
+        const real la = mul_r(ma, l), lb = mul_r(mb, l);
+        v.vax = fma_r(-la, dx, v.vax); v.vay = fma_r(-la, dy, v.vay); v.wa = fma_r(-mul_r(ia, l), arm_a, v.wa);
+        v.vbx = fma_r(lb, dx, v.vbx); v.vby = fma_r(lb, dy, v.vby); v.wb = fma_r(mul_r(ib, l), arm_b, v.wb);
+    }
+    // relative velocity of the contact point along (dx, dy): (vB - vA).d + wB * (rB x d) - wA * (rA x d)
+    B2B_D static real row_velocity(const vel_pair& v, real dx, real dy, real arm_a, real arm_b)
+    {
+        return dot2(v.vbx - v.vax, dx, v.vby - v.vay, dy) + diff2(v.wb, arm_b, v.wa, arm_a);
+    }
+    B2B_D void constraint_solve_velocity_jacobian(const vrec& r, int slot, bool last)
+    {
+        const quad q0 = r.q0, j0 = r.q1, j1 = r.q3, em = r.q2, m = r.q7;
+        quad qi = r.qi;
+        const uint32_t bodies = bits_of_real(q0.w), fbits = bits_of_real(q0.z);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
+        const bool two = em.z != real(0);
+        const real nx = q0.x, ny = q0.y, tx = ny, ty = -nx;
+        const real friction = real_from_bits(fbits & 0x7fffffffu);
+        const real ma = m.x, ia = m.y, mb = m.z, ib = m.w;
+        const bool stat_a = (ma == real(0)) && (ia == real(0)), stat_b = (mb == real(0)) && (ib == real(0));
+        real bias0 = real(0), bias1 = real(0);
+        if (fbits & 0x80000000u) { bias0 = cc_bias[2 * (size_t)slot]; bias1 = cc_bias[2 * (size_t)slot + 1]; }   // restitution: rare
+        const quad sa = state_get(ba), sb = state_get(bb);
+        vel_pair v;
+        v.vax = sa.x; v.vay = sa.y; v.wa = sa.z; v.vbx = sb.x; v.vby = sb.y; v.wb = sb.z;
+        // friction rows first, point by point (contact.py:541-573)
+        {
+            const real vt = row_velocity(v, tx, ty, j0.y, j0.w);
+            const real max_friction = mul_r(friction, qi.x);
+            const real new_imp = clamp_r(fma_r(-em.y, vt, qi.y), -max_friction, max_friction);
+            apply_row(v, new_imp - qi.y, tx, ty, j0.y, j0.w, ma, ia, mb, ib);
+            qi.y = new_imp;
+        }
+        if (two) {
+            const real vt = row_velocity(v, tx, ty, j1.y, j1.w);
+            const real max_friction = mul_r(friction, qi.z);
+            const real new_imp = clamp_r(fma_r(-em.w, vt, qi.w), -max_friction, max_friction);
+            apply_row(v, new_imp - qi.w, tx, ty, j1.y, j1.w, ma, ia, mb, ib);
+            qi.w = new_imp;
+        }
+        if (!two) {
+            // contact.py:575-596
+            const real vn = row_velocity(v, nx, ny, j0.x, j0.z);
+            const real new_imp = pymax(fma_r(-em.x, vn - bias0, qi.x), real(0));
+            apply_row(v, new_imp - qi.x, nx, ny, j0.x, j0.z, ma, ia, mb, ib);
+            qi.x = new_imp;
+        } else {
+            // 2x2 LCP by total enumeration; first feasible case wins (contact.py:598-796)
+            const real a0 = qi.x, a1 = qi.z;
+            const real vn1 = row_velocity(v, nx, ny, j0.x, j0.z), vn2 = row_velocity(v, nx, ny, j1.x, j1.z);
+            // K = J M^-1 J^T and its inverse (contact.py:476-495, common.py:505-519), from the Jacobian rows
+            const real mab = ma + mb;
+            const real k11 = fma_r(ib, mul_r(j0.z, j0.z), fma_r(ia, mul_r(j0.x, j0.x), mab));
+            const real k22 = fma_r(ib, mul_r(j1.z, j1.z), fma_r(ia, mul_r(j1.x, j1.x), mab));
+            const real k12 = fma_r(ib, mul_r(j0.z, j1.z), fma_r(ia, mul_r(j0.x, j1.x), mab));
+            real det = diff2(k11, k22, k12, k12);
+            if (det != real(0)) det = real(1) / det;
+            const real nm11 = mul_r(det, k22), nm12 = -mul_r(det, k12), nm22 = mul_r(det, k11);
+            const real b0 = (vn1 - bias0) - dot2(k11, a0, k12, a1), b1 = (vn2 - bias1) - dot2(k12, a0, k22, a1);
+            real x0 = -dot2(nm11, b0, nm12, b1), x1 = -dot2(nm12, b0, nm22, b1);
+            bool solved = (x0 >= real(0) && x1 >= real(0));
+            if (!solved) {
+                x0 = -mul_r(em.x, b0); x1 = real(0);
+                solved = (x0 >= real(0)) && (fma_r(k12, x0, b1) >= real(0));
+                if (!solved) {
+                    x0 = real(0); x1 = -mul_r(em.z, b1);
+                    solved = (x1 >= real(0)) && (fma_r(k12, x1, b0) >= real(0));
+                }
+                if (!solved) {
+                    x0 = real(0); x1 = real(0);
+                    solved = (b0 >= real(0)) && (b1 >= real(0));
+                }
+            }
+            if (solved) {
+                const real d0 = x0 - a0, d1 = x1 - a1, d = d0 + d1;
+                const real la = mul_r(ma, d), lb = mul_r(mb, d);
+                v.vax = fma_r(-la, nx, v.vax); v.vay = fma_r(-la, ny, v.vay); v.wa = fma_r(-ia, dot2(j0.x, d0, j1.x, d1), v.wa);
+                v.vbx = fma_r(lb, nx, v.vbx); v.vby = fma_r(lb, ny, v.vby); v.wb = fma_r(ib, dot2(j0.z, d0, j1.z, d1), v.wb);
+                qi.x = x0; qi.z = x1;
+            }
+        }
+        if (!stat_a) state_set(ba, v.vax, v.vay, v.wa);
+        if (!stat_b) state_set(bb, v.vbx, v.vby, v.wb);
+        if (!last) *imp_rec(slot) = qi;
+        else impulses_store(slot, two ? 2 : 1, qi);
     }
 
     // One manifold point of ContactSolver.solve_position_constraints (contact_util.py:323-360 PositionSolverManifold,
@@ -1597,10 +1788,8 @@ template <class real> struct world_step {
             if (sp.vel_iters == 0) {
                 for (int s = c0 + t_id; s < c1; s += t_n) {
                     const quad qi = *imp_rec(s);
-                    const int ci = l_contact[g_sched[s]], n_vel = (int)(bits_of_real(vel_rec(s)[2].w) & 0xff);
-                    real* imp = c_imp + 4 * (size_t)ci;
-                    if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
-                    if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
+                    const int n_vel = FAST_ROWS ? ((vel_rec(s)[3].z != real(0)) ? 2 : 1) : (int)(bits_of_real(vel_rec(s)[2].w) & 0xff);
+                    impulses_store(s, n_vel, qi);
                 }
             }
         }

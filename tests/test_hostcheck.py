@@ -71,3 +71,36 @@ def test_settled_pile_sleep_event_keeps_the_island_lists():
     assert min(awake) == 210 and max(awake) == 211, (min(awake), max(awake))       # the event happened (twice)
     assert awake.count(210) >= 2
     assert hostcheck.replans() == 1                                                  # only the first step built the lists
+
+
+@pytest.mark.parametrize("scene,world,dt,vi,pi,steps", [("pyramid", 1, 1 / 60, 8, 3, 150), ("mixed", 1, 1 / 60, 8, 3, 100),
+                                                         ("features", 1, 1 / 60, 8, 3, 150), ("vertical_stack", 1, 1 / 60, 10, 10, 100)])
+def test_host_compiled_fp32_step_tracks_the_oracle_one_step_at_a_time(scene, world, dt, vi, pi, steps):
+    """The fp32 instantiation (Jacobian-form velocity rows, 96-byte records) against the oracle, teacher-forced: from the
+    oracle's fp32-rounded state ONE step agrees to fp32 accuracy and gives the same integer outputs except on tie steps.
+    CPU pre-check of the arithmetic the -m gpu P-step tier grades on the device."""
+    from pypybox2d_b200 import schema
+    REAL = [f[0] for f in schema.FIELDS if f[3] == "real"]
+    mw, OA, caps = harness.facade_arrays(scene, world)
+    orc = oracle.Oracle(OA, 0)
+    inv, ties, worst_p, worst_v = 0.0, 0, 0.0, 0.0
+    for s in range(steps):
+        T = {k: (v.astype(np.float32).astype(np.float64) if k in REAL else v.copy()) for k, v in OA.items()}
+        H = {k: (v.astype(np.float32) if k in REAL else v.copy()) for k, v in T.items()}
+        o2 = oracle.Oracle(T, 0)
+        o2.inv_dt0 = inv
+        o2.step(dt, vi, pi)
+        hostcheck.step(H, dt, inv, vi, pi)
+        dp = float(np.abs(harness.used_view(T, "b_pos")[:, :3] - harness.used_view(H, "b_pos")[:, :3]).max())
+        dv = float(np.abs(harness.used_view(T, "b_vel")[:, :3] - harness.used_view(H, "b_vel")[:, :3]).max())
+        tie = bool(harness.diff_state(T, H, fields=["w_count", "c_fix", "c_flags", "c_mtype", "b_flags"])) or \
+            harness.oracle_islands(T) != harness.oracle_islands(H) or int(T["w_island"][0][3]) != int(H["w_island"][0][3])
+        if tie:
+            ties += 1
+            assert dp <= 1e-3 and dv <= 1e-2, "step %d (tie): %.2e m, %.2e m/s" % (s, dp, dv)
+        else:
+            worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
+            assert dp <= 5e-5 and dv <= 1e-3, "step %d: %.2e m, %.2e m/s" % (s, dp, dv)
+        orc.step(dt, vi, pi)
+        inv = 1.0 / dt
+    assert ties <= 0.10 * steps, ties
