@@ -1209,9 +1209,13 @@ template <class real> struct world_step {
     }
 
     // A constraint's velocity-phase data in registers.
-    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
-    B2B_D void load_vrec(int slot, vrec& r)
+    // (`ci`: the slot's contact index, fetched WITH the record in the last sweep only -- store_impulses needs it at the end of the
+    // solve, and a global load issued inside the solve would be waited for, on the level loop's scoreboard, together with the
+    // next record's loads)
+    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; int ci; };
+    B2B_D void load_vrec(int slot, vrec& r, bool last)
     {
+        if (last) r.ci = cc_ci[slot];
         const quad* q = vel_rec(slot);
         if constexpr (FAST_ROWS) {
             // f0, jacobian of point 0 / 1, effective masses, inverse masses, impulses (the unused members are never touched)
@@ -1257,9 +1261,9 @@ template <class real> struct world_step {
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799).  The accumulated impulses go
     // back to the slot's impulse row, or -- on the last velocity iteration -- straight to the contact's manifold
     // (store_impulses, contact.py:801-806: only as many points as the velocity rows kept).
-    B2B_D void constraint_solve_velocity(const vrec& r, int slot)
+    B2B_D void constraint_solve_velocity(const vrec& r, int slot, bool last)
     {
-        if constexpr (FAST_ROWS) { constraint_solve_velocity_jacobian(r, slot); return; }
+        if constexpr (FAST_ROWS) { constraint_solve_velocity_jacobian(r, slot, last); return; }
         const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
         quad qi = r.qi;
         const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(q2.w);
@@ -1344,7 +1348,16 @@ template <class real> struct world_step {
         B2B_TSTAMP_F(3, (float)va.x, (float)wa, (float)vb.x, (float)wb);
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
-        *imp_rec(slot) = qi;
+        if (!last) *imp_rec(slot) = qi;
+        else impulses_store(r.ci, n_vel, qi);
+    }
+
+    // store_impulses (contact.py:801-806): only as many points as the velocity rows kept
+    B2B_D void impulses_store(int ci, int n_vel, quad qi)
+    {
+        real* imp = c_imp + 4 * (size_t)ci;
+        if (n_vel > 1) stq(imp, qi);
+        else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
     }
 
     // ---- Jacobian-form rows (FAST_ROWS): f1 / f2 = (rA x n, rA x t, rB x n, rB x t) of point 0 / 1.  A row's relative
@@ -1408,7 +1421,7 @@ template <class real> struct world_step {
     {
         return dot2(v.vbx - v.vax, dx, v.vby - v.vay, dy) + diff2(v.wb, arm_b, v.wa, arm_a);
     }
-    B2B_D void constraint_solve_velocity_jacobian(const vrec& r, int slot)
+    B2B_D void constraint_solve_velocity_jacobian(const vrec& r, int slot, bool last)
     {
         const quad q0 = r.q0, j0 = r.q1, j1 = r.q3, em = r.q2, m = r.q7;
         quad qi = r.qi;
@@ -1482,7 +1495,8 @@ template <class real> struct world_step {
         }
         if (!stat_a) state_set(ba, v.vax, v.vay, v.wa);
         if (!stat_b) state_set(bb, v.vbx, v.vby, v.wb);
-        *imp_rec(slot) = qi;
+        if (!last) *imp_rec(slot) = qi;
+        else impulses_store(r.ci, two ? 2 : 1, qi);
     }
 
     // One manifold point of ContactSolver.solve_position_constraints (contact_util.py:323-360 PositionSolverManifold,
@@ -1764,35 +1778,23 @@ template <class real> struct world_step {
             if (joint) { c0 = 0; c1 = n_lc; }
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
+            bool last = false;                               // the sweep in progress is the last velocity iteration
+            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e, last); };
             auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
             if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int) { constraint_warm_start(e); }, vready);
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
-                level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s); }, vready);
+                last = (it + 1 == sp.vel_iters);
+                level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); }, vready);
             }
             B2B_PROF(PROF_S_VELOCITY, t);
-            // -- store_impulses (contact.py:801-806): a pass of its own over the island's slots once the sweeps are done (every
-            // sweep leaves a slot's accumulated impulses in its record); four slots per lane and round, loads first.  It used
-            // to ride in the last sweep: any global access inside the level loop is waited for, on the loop's scoreboard,
-            // together with the NEXT record's loads, which serialises the record stream (measured: +9 ms per 131,072 worlds).
-            B2B_SYNC();
-            for (int s0 = c0 + t_id; s0 < c1; s0 += 4 * t_n) {
-                quad qi[4], em[4];
-                int ci[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int sl = s0 + k * t_n;
-                    if (sl < c1) { qi[k] = *imp_rec(sl); em[k] = vel_rec(sl)[FAST_ROWS ? 3 : 2]; ci[k] = cc_ci[sl]; }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int sl = s0 + k * t_n;
-                    if (sl >= c1) continue;
-                    const int n_vel = FAST_ROWS ? ((em[k].z != real(0)) ? 2 : 1) : (int)(bits_of_real(em[k].w) & 0xff);
-                    real* imp = c_imp + 4 * (size_t)ci[k];
-                    if (n_vel > 1) stq(imp, qi[k]);
-                    else if (n_vel > 0) { imp[0] = qi[k].x; imp[1] = qi[k].y; }
+            // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
+            // iterations the (warm-started) impulses go back as they are
+            if (sp.vel_iters == 0) {
+                B2B_SYNC();
+                for (int sl = c0 + t_id; sl < c1; sl += t_n) {
+                    const quad qi = *imp_rec(sl), em = vel_rec(sl)[FAST_ROWS ? 3 : 2];
+                    impulses_store(cc_ci[sl], FAST_ROWS ? ((em.z != real(0)) ? 2 : 1) : (int)(bits_of_real(em.w) & 0xff), qi);
                 }
             }
         }
