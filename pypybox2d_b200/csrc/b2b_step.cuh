@@ -20,7 +20,6 @@
 // tests/hostcheck can run this exact source under g++ for debugging; that build is test-only.
 #pragma once
 #include <cstring>
-#include <cmath>
 #include <type_traits>
 #include "b2b_collide.cuh"
 
@@ -99,17 +98,7 @@ template <class real> struct batch_ptrs {
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
-// velocity / position record of one constraint, in 4-vectors of reals ("quads").  The fp64 (parity) build keeps the reference's
-// operands (anchor vectors, block matrices: 8 quads, impulses in their own row); the fp32 (throughput) build carries the rows
-// in Jacobian form with the accumulated impulses inline and recomputes the 2x2 block per sweep: 6 quads = 96 bytes, one stream
-// instead of two (see the layout table above constraint_init).  -DB2B_EXACT_ROWS keeps the fp64 layout in fp32 too.
-enum { VREC_QUADS_EXACT = 8, VREC_QUADS_FAST = 6, PREC_QUADS = 5 };
-#if defined(B2B_EXACT_ROWS)
-B2B_HD constexpr bool fast_rows(int) { return false; }
-#else
-B2B_HD constexpr bool fast_rows(int real_bytes) { return real_bytes == 4; }
-#endif
-B2B_HD constexpr int vrec_quads(int real_bytes) { return fast_rows(real_bytes) ? VREC_QUADS_FAST : VREC_QUADS_EXACT; }
+enum { VREC_QUADS = 8, PREC_QUADS = 6 };   // velocity / position record of one constraint, in 4-vectors of reals ("quads")
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
 enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32, STEP_SOLVE_ONLY = 64 };
 // per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
@@ -152,7 +141,7 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
 
 struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `rec` slabs per world of a solve group
     size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
-    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_ci, off_cc_bias, off_cc_state, total_rec;
+    size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_state, total_rec;
     size_t total_sprof;       // per solve team: cycle counters
 };
 inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
@@ -169,11 +158,9 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_prof = take(sizeof(long long) * PROF_SLOTS);
     L.total_aux = align_up(o, 256);
     o = 0;
-    L.off_cc_vel = take((size_t)real_bytes * 4 * vrec_quads(real_bytes) * ((size_t)c.nc + 2));
+    L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
     L.off_cc_pos = take((size_t)real_bytes * 4 * PREC_QUADS * ((size_t)c.nc + 2));
-    L.off_cc_imp = take(fast_rows(real_bytes) ? (size_t)0 : (size_t)real_bytes * 4 * ((size_t)c.nc + 2));   // (inline in the Jacobian records)
-    L.off_cc_ci = take(sizeof(int32_t) * ((size_t)c.nc + 2));                    // contact index of every slot (store_impulses)
-    L.off_cc_bias = take(fast_rows(real_bytes) ? (size_t)real_bytes * 2 * ((size_t)c.nc + 2) : (size_t)0);   // restitution bias (Jacobian records: side array)
+    L.off_cc_imp = take((size_t)real_bytes * 4 * ((size_t)c.nc + 2));
     L.off_cc_state = take((size_t)real_bytes * 3 * (size_t)c.nb);      // the velocities the solver starts from, per body
     L.total_rec = align_up(o, 256);
     L.total_sprof = align_up(sizeof(long long) * PROF_SLOTS, 256);
@@ -256,7 +243,7 @@ template <class real> struct world_step {
     uint8_t* g_cstate;       // per contact, written by the flat narrowphase kernel: 0 pending, 1 updated, 2 destroy, 3 updated + touching changed
     // scratch (global): per CTA (plan / broadphase kernels) or per team (solve kernel)
     int32_t *wake_at, *scan;
-    real *cc_vel, *cc_pos, *cc_imp, *cc_bias, *cc_state; int32_t* cc_ci;
+    real *cc_vel, *cc_pos, *cc_imp, *cc_state;
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
@@ -345,8 +332,6 @@ template <class real> struct world_step {
         cc_vel = (real*)(rec + L.off_cc_vel);
         cc_pos = (real*)(rec + L.off_cc_pos);
         cc_imp = (real*)(rec + L.off_cc_imp);
-        cc_ci = (int32_t*)(rec + L.off_cc_ci);
-        cc_bias = (real*)(rec + L.off_cc_bias);
         cc_state = (real*)(rec + L.off_cc_state);
         prof = (long long*)team_prof;
     }
@@ -881,34 +866,33 @@ template <class real> struct world_step {
     }
 
     // ------------------------------------------------------------------------------------ K3 (prepare + solve kernels)
-    // One constraint = a read-only VELOCITY record of 8 four-vectors (exactly one 128-byte line in fp32: what a
-    // velocity sweep streams per constraint), a read-only POSITION record of 5 four-vectors, and one read-write
-    // four-vector of accumulated impulses in its own array (updating it never dirties the read-only lines).  All
-    // are in schedule order in the world's record slab, written by the flat prepare kernel (one thread per
-    // constraint of the whole group of worlds) and streamed by the solve kernel, whose lanes fetch the record of
-    // the NEXT level-step into registers while they solve the current one.  Integer fields ride in spare lanes
-    // of the real records as raw bits.
+    // One constraint = a read-only VELOCITY record of 8 four-vectors ("quads": exactly one 128-byte line in fp32 -- what a
+    // velocity sweep streams per constraint), a read-only POSITION record of 6 quads, and one read-write quad of accumulated
+    // impulses in its own array (updating it never dirties the read-only lines).  All are in schedule order in the world's
+    // record slab, written by the flat prepare kernel (one thread per constraint of the whole group of worlds) and streamed
+    // by the solve kernels, whose lanes fetch the record of the NEXT level-step into registers while they solve the current
+    // one.  Records are read and written two quads ("oct", 32 bytes in fp32) at a time: every lane of a level-step reads its
+    // own line, so a load instruction costs the L1 one wavefront per active lane whatever its width, and the 256-bit form
+    // (LDG.E.256) needs four per velocity record where 128-bit loads needed eight.  Integer fields ride in spare lanes of
+    // the real records as raw bits.  NOTHING else is read from global memory while a slot is solved: every load of the level
+    // loop shares one hardware scoreboard with the record stream, so a load inside the solve -- even a predicated-off one --
+    // makes its first use wait for the next record as well (measured: +20 % on the velocity kernel).
     //   v0  normal.x normal.y friction [body_a | body_b << 16]     v1  rA0.x rA0.y rB0.x rB0.y
-    //   v2  nmass0   tmass0   bias0    [info]                      v3  rA1.x rA1.y rB1.x rB1.y
-    //   v4  nmass1   tmass1   bias1    [contact index]             v5  k11 k12 k22 nm11
-    //   v6  nm12     nm22     -        -                           v7  inv_mass_a inv_I_a inv_mass_b inv_I_b
+    //   v2  nmass0   tmass0   nmass1   tmass1                      v3  rA1.x rA1.y rB1.x rB1.y
+    //   v4  k11      k12      k22      [vinfo]                     v5  nm11 nm12 nm22 -
+    //   v6  inv_mass_a inv_I_a inv_mass_b inv_I_b                  v7  bias0 bias1 - -
     //   p0  inv_mass_a inv_I_a inv_mass_b inv_I_b                  p1  ln.x ln.y lp.x lp.y
     //   p2  p0.x p0.y p1.x p1.y                                    p3  radius_a radius_b [bodies] [info]
-    //   p4  lc_a.x lc_a.y lc_b.x lc_b.y
+    //   p4  lc_a.x lc_a.y lc_b.x lc_b.y                            p5  -
     //   imp ni0 ti0 ni1 ti1
-    //   info = n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25
-    // fp32 build (FAST_ROWS): the velocity rows in Jacobian form, 6 quads = 96 bytes, impulses inline:
-    //   f0  normal.x normal.y [+-]friction [body_a | body_b << 16]   (sign bit of friction: the slot has a restitution bias,
-    //                                                                 kept in the side array cc_bias: rare)
-    //   f1  rA0 x n  rA0 x t  rB0 x n  rB0 x t                       f2  the same for point 1 (zero when the row was dropped)
-    //   f3  nmass0 tmass0 nmass1 tmass1   (nmass1 == 0 <=> one velocity row)
-    //   f4  inv_mass_a inv_I_a inv_mass_b inv_I_b                    f5  ni0 ti0 ni1 ti1
-    //   (a body with zero inverse mass AND inertia is never written back: a static body is shared by the slots of a level)
-    // side arrays per slot: cc_ci (the contact's index, for store_impulses), cc_bias
+    //   vinfo = n_vel | static_a << 2 | static_b << 3 | contact index << 8
+    //   info  = n_vel | type << 8 | n_pos << 16 | static_a << 24 | static_b << 25
     // Shared memory holds three reals per body: its velocity while velocities are being solved, its sweep position
     // afterwards.  Static bodies never change and are shared between islands: each island stages their velocity
     // and later their position for itself (islands are solved one after the other).
     enum { INFO_STATIC_A = 1 << 24, INFO_STATIC_B = 1 << 25, INFO_ISLAND_SHIFT = 26 };   // bits 26-30 (position records): island ordinal of a joint schedule
+    enum { VINFO_NVEL_MASK = 3, VINFO_STATIC_A = 1 << 2, VINFO_STATIC_B = 1 << 3, VINFO_CI_SHIFT = 8 };
+    struct alignas(8 * sizeof(real)) oct { quad lo, hi; };
     enum { BODY_BATCH = 4 };     // (8 measured slower: register spills reach the level loop)
     B2B_D static quad mkq(real x, real y, real z, real w) { quad q; q.x = x; q.y = y; q.z = z; q.w = w; return q; }
     B2B_D static real real_from_bits(uint32_t u)
@@ -923,12 +907,9 @@ template <class real> struct world_step {
         x.r = r;
         return x.w[0];
     }
-    static constexpr bool FAST_ROWS = fast_rows((int)sizeof(real));
-    enum { VREC_QUADS = FAST_ROWS ? VREC_QUADS_FAST : VREC_QUADS_EXACT };
-    B2B_D quad* vel_rec(int slot) { return reinterpret_cast<quad*>(cc_vel) + (size_t)VREC_QUADS * slot; }
-    B2B_D quad* pos_rec(int slot) { return reinterpret_cast<quad*>(cc_pos) + (size_t)PREC_QUADS * slot; }
-    // the slot's accumulated impulses: their own row, or the last quad of a Jacobian record
-    B2B_D quad* imp_rec(int slot) { return FAST_ROWS ? vel_rec(slot) + (VREC_QUADS_FAST - 1) : reinterpret_cast<quad*>(cc_imp) + slot; }
+    B2B_D oct* vel_rec(int slot) { return reinterpret_cast<oct*>(cc_vel) + (size_t)(VREC_QUADS / 2) * slot; }
+    B2B_D oct* pos_rec(int slot) { return reinterpret_cast<oct*>(cc_pos) + (size_t)(PREC_QUADS / 2) * slot; }
+    B2B_D quad* imp_rec(int slot) { return reinterpret_cast<quad*>(cc_imp) + slot; }
     // (x, y) pairs first, then the third component: one two-wide and one scalar shared-memory access per body
     struct alignas(2 * sizeof(real)) pair2 { real x, y; };
     B2B_D quad state_get(int b) const
@@ -962,8 +943,7 @@ template <class real> struct world_step {
         if (t < c1) {
             B2B_PREFETCH(vel_rec(t));
             if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(vel_rec(t)) + 128);
-            if (FAST_ROWS) { if (t & 3) B2B_PREFETCH(vel_rec(t) + (VREC_QUADS_FAST - 1)); }   // 96-byte records: three of four straddle two lines
-            else B2B_PREFETCH(imp_rec(t));
+            B2B_PREFETCH(imp_rec(t));
         }
     }
     B2B_D void prefetch_pos(int s, int c0, int c1)
@@ -972,7 +952,7 @@ template <class real> struct world_step {
         if (t < c1) {
             const char* r = reinterpret_cast<const char*>(pos_rec(t));
             B2B_PREFETCH(r);
-            B2B_PREFETCH(r + sizeof(quad) * (PREC_QUADS - 1));     // the record's last quad: its second line, if it has one
+            B2B_PREFETCH(r + sizeof(oct) * (PREC_QUADS / 2 - 1));  // the record's last oct: its second line, if it has one
         }
     }
 
@@ -1004,6 +984,11 @@ template <class real> struct world_step {
     // word of the CURRENT record (`& zero`, a run-time zero): all record loads share one hardware scoreboard, so
     // without that order the first use of the current record would also wait for the loads just issued.  The
     // table reader moves its look-ahead word in at the same point, for the same reason.
+#if defined(B2B_VAR_NOSYNC)
+#define B2B_LEVEL_SYNC() ((void)0)
+#else
+#define B2B_LEVEL_SYNC() __syncwarp(t_mask)
+#endif
     template <class Rec, class Load, class Solve, class Ready>
     B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, uint32_t zero, Load load, Solve solve, Ready ready)
     {
@@ -1027,7 +1012,7 @@ template <class real> struct world_step {
                 B2B_TSTAMP(1, ncnt);
                 if (act) solve(ra, begin + t_id);
                 B2B_TSTAMP(4, 0);
-                __syncwarp(t_mask);
+                B2B_LEVEL_SYNC();
                 B2B_TSTAMP(5, 0);
                 B2B_TSTAMP(6, 0);
                 if (!more) break;
@@ -1043,7 +1028,7 @@ template <class real> struct world_step {
                 B2B_TSTAMP(1, ncnt);
                 if (act) solve(rb, begin + t_id);
                 B2B_TSTAMP(4, 0);
-                __syncwarp(t_mask);
+                B2B_LEVEL_SYNC();
                 B2B_TSTAMP(5, 0);
                 B2B_TSTAMP(6, 0);
                 if (!more) break;
@@ -1141,18 +1126,15 @@ template <class real> struct world_step {
         const V2 tangent = right_perp(normal);
         int n_vel = count;
         V2 ra[2], rb[2];
-        quad jac[2];                                         // (rA x n, rA x t, rB x n, rB x t) per point
         real nmass[2], tmass[2], bias[2], ni[2], ti[2];
         for (int j = 0; j < 2; ++j) {
             ra[j] = rb[j] = mk<real>(real(0), real(0));
-            jac[j] = mkq(real(0), real(0), real(0), real(0));
             nmass[j] = tmass[j] = bias[j] = ni[j] = ti[j] = real(0);
             if (j >= count) continue;
             ra[j] = wp[j] - ca; rb[j] = wp[j] - cb;
             const real rn_a = cross(ra[j], normal), rn_b = cross(rb[j], normal);
             const real k_normal = ma + mb + ia * sq_r(rn_a) + ib * sq_r(rn_b);      // contact.py:444-445: ** 2
             const real rt_a = cross(ra[j], tangent), rt_b = cross(rb[j], tangent);
-            jac[j] = mkq(rn_a, rt_a, rn_b, rt_b);
             const real k_tangent = ma + mb + ia * sq_r(rt_a) + ib * sq_r(rt_b);     // contact.py:456-457
             const real v_rel = dot(normal, rel_velocity(vb, wb, rb[j], va, wa, ra[j]));
             if (v_rel < -K<real>::velocity_threshold) bias[j] = -restitution * v_rel;
@@ -1178,68 +1160,50 @@ template <class real> struct world_step {
         }
         const uint32_t info = (uint32_t)(n_vel | (type << 8) | (count << 16) | (stat_a ? INFO_STATIC_A : 0) | (stat_b ? INFO_STATIC_B : 0));
         const real bodies_r = real_from_bits((uint32_t)ba | ((uint32_t)bb << 16)), info_r = real_from_bits(info);
-        cc_ci[slot] = ci;
-        quad* q = vel_rec(slot);
-        if constexpr (FAST_ROWS) {
-            const bool has_bias = (bias[0] != real(0)) || (bias[1] != real(0));
-            const bool two = (n_vel == 2);
-            q[0] = mkq(normal.x, normal.y, real_from_bits(bits_of_real(friction) | (has_bias ? 0x80000000u : 0u)), bodies_r);
-            q[1] = jac[0];
-            q[2] = two ? jac[1] : mkq(real(0), real(0), real(0), real(0));
-            q[3] = mkq(nmass[0], tmass[0], two ? nmass[1] : real(0), two ? tmass[1] : real(0));
-            q[4] = mkq(ma, ia, mb, ib);
-            cc_bias[2 * (size_t)slot] = bias[0]; cc_bias[2 * (size_t)slot + 1] = bias[1];
-        } else {
-            q[0] = mkq(normal.x, normal.y, friction, bodies_r);
-            q[1] = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);
-            q[2] = mkq(nmass[0], tmass[0], bias[0], info_r);
-            q[3] = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);
-            q[4] = mkq(nmass[1], tmass[1], bias[1], real(0));
-            q[5] = mkq(k11, k12, k22, nm11);
-            q[6] = mkq(nm12, nm22, real(0), real(0));
-            q[7] = mkq(ma, ia, mb, ib);
-        }
-        quad* p = pos_rec(slot);
-        p[0] = mkq(ma, ia, mb, ib);
-        p[1] = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
-        p[2] = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
-        p[3] = mkq(rad_a, rad_b, bodies_r, (g_joint[0] != 0) ? real_from_bits(info | ((uint32_t)g_slot_isl[slot] << INFO_ISLAND_SHIFT)) : info_r);
-        p[4] = mkq(lca.x, lca.y, lcb.x, lcb.y);
+        const uint32_t vinfo = (uint32_t)n_vel | (stat_a ? VINFO_STATIC_A : 0u) | (stat_b ? VINFO_STATIC_B : 0u) | ((uint32_t)ci << VINFO_CI_SHIFT);
+        oct* q = vel_rec(slot);
+        oct o;
+        o.lo = mkq(normal.x, normal.y, friction, bodies_r);      o.hi = mkq(ra[0].x, ra[0].y, rb[0].x, rb[0].y);          q[0] = o;
+        o.lo = mkq(nmass[0], tmass[0], nmass[1], tmass[1]);      o.hi = mkq(ra[1].x, ra[1].y, rb[1].x, rb[1].y);          q[1] = o;
+        o.lo = mkq(k11, k12, k22, real_from_bits(vinfo));        o.hi = mkq(nm11, nm12, nm22, real(0));                   q[2] = o;
+        o.lo = mkq(ma, ia, mb, ib);                              o.hi = mkq(bias[0], bias[1], real(0), real(0));          q[3] = o;
         *imp_rec(slot) = mkq(ni[0], ti[0], ni[1], ti[1]);
+        oct* p = pos_rec(slot);
+        o.lo = mkq(ma, ia, mb, ib);
+        o.hi = mkq(local_normal.x, local_normal.y, local_point.x, local_point.y);
+        p[0] = o;
+        o.lo = mkq(lp[0].x, lp[0].y, lp[1].x, lp[1].y);
+        o.hi = mkq(rad_a, rad_b, bodies_r, (g_joint[0] != 0) ? real_from_bits(info | ((uint32_t)g_slot_isl[slot] << INFO_ISLAND_SHIFT)) : info_r);
+        p[1] = o;
+        o.lo = mkq(lca.x, lca.y, lcb.x, lcb.y);                  o.hi = mkq(real(0), real(0), real(0), real(0));
+        p[2] = o;
     }
 
     // A constraint's velocity-phase data in registers.
-    // (`ci`: the slot's contact index, fetched WITH the record in the last sweep only -- store_impulses needs it at the end of the
-    // solve, and a global load issued inside the solve would be waited for, on the level loop's scoreboard, together with the
-    // next record's loads)
-    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; int ci; };
-    B2B_D void load_vrec(int slot, vrec& r, bool last)
+    // (members: the quads v0..v7 / p0..p4 of the layout above)
+    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
+    B2B_D void load_vrec(int slot, vrec& r)
     {
-        if (last) r.ci = cc_ci[slot];
-        const quad* q = vel_rec(slot);
-        if constexpr (FAST_ROWS) {
-            // f0, jacobian of point 0 / 1, effective masses, inverse masses, impulses (the unused members are never touched)
-            r.q0 = q[0]; r.q1 = q[1]; r.q3 = q[2]; r.q2 = q[3]; r.q7 = q[4]; r.qi = q[5];
-        } else {
-            r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3]; r.q4 = q[4]; r.q5 = q[5]; r.q6 = q[6]; r.q7 = q[7];
-            r.qi = *imp_rec(slot);
-        }
+        const oct* q = vel_rec(slot);
+        const oct o0 = q[0], o1 = q[1], o2 = q[2], o3 = q[3];
+        r.q0 = o0.lo; r.q1 = o0.hi; r.q2 = o1.lo; r.q3 = o1.hi; r.q4 = o2.lo; r.q5 = o2.hi; r.q6 = o3.lo; r.q7 = o3.hi;
+        r.qi = *imp_rec(slot);
     }
     struct prec { quad q7, q8, q9, q10, q11; };
     B2B_D void load_prec(int slot, prec& r)
     {
-        const quad* q = pos_rec(slot);
-        r.q7 = q[0]; r.q8 = q[1]; r.q9 = q[2]; r.q10 = q[3]; r.q11 = q[4];
+        const oct* q = pos_rec(slot);
+        const oct o0 = q[0], o1 = q[1], o2 = q[2];
+        r.q7 = o0.lo; r.q8 = o0.hi; r.q9 = o1.lo; r.q10 = o1.hi; r.q11 = o2.lo;
     }
 
     // ContactSolver.warm_start for one slot (contact.py:498-525)
     B2B_D void constraint_warm_start(const vrec& r)
     {
-        if constexpr (FAST_ROWS) { constraint_warm_start_jacobian(r); return; }
-        const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q7, qi = r.qi;
-        const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(r.q2.w);
-        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(info & 0xff);
-        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
+        const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q6, qi = r.qi;
+        const uint32_t bodies = bits_of_real(q0.w), vinfo = bits_of_real(r.q4.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(vinfo & VINFO_NVEL_MASK);
+        const bool stat_a = (vinfo & VINFO_STATIC_A) != 0, stat_b = (vinfo & VINFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
         const quad sa = state_get(ba), sb = state_get(bb);
@@ -1263,15 +1227,16 @@ template <class real> struct world_step {
     // (store_impulses, contact.py:801-806: only as many points as the velocity rows kept).
     B2B_D void constraint_solve_velocity(const vrec& r, int slot, bool last)
     {
-        if constexpr (FAST_ROWS) { constraint_solve_velocity_jacobian(r, slot, last); return; }
-        const quad q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6, q7 = r.q7;
+        const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q6;
         quad qi = r.qi;
-        const uint32_t bodies = bits_of_real(q0.w), info = bits_of_real(q2.w);
-        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(info & 0xff);
-        const bool stat_a = (info & INFO_STATIC_A) != 0, stat_b = (info & INFO_STATIC_B) != 0;
+        const uint32_t bodies = bits_of_real(q0.w), vinfo = bits_of_real(r.q4.w);
+        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16), n_vel = (int)(vinfo & VINFO_NVEL_MASK);
+        const bool stat_a = (vinfo & VINFO_STATIC_A) != 0, stat_b = (vinfo & VINFO_STATIC_B) != 0;
         const V2 normal = mk<real>(q0.x, q0.y), tangent = right_perp(normal);
         const real friction = q0.z;
         const real ma = q7.x, ia = q7.y, mb = q7.z, ib = q7.w;
+        const real nmass0 = r.q2.x, tmass0 = r.q2.y, nmass1 = r.q2.z, tmass1 = r.q2.w;
+        const real bias0 = r.q7.x, bias1 = r.q7.y;
         const quad sa = state_get(ba), sb = state_get(bb);
         V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
         real wa = sa.z, wb = sb.z;
@@ -1281,7 +1246,7 @@ template <class real> struct world_step {
         {
             const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vt = dot(dv, tangent);
-            real lambda = q2.y * (-vt);
+            real lambda = tmass0 * (-vt);
             const real max_friction = friction * qi.x;
             const real new_imp = clamp_r(qi.y + lambda, -max_friction, max_friction);
             lambda = new_imp - qi.y;
@@ -1293,7 +1258,7 @@ template <class real> struct world_step {
         if (n_vel == 2) {
             const V2 dv = rel_velocity(vb, wb, rb1, va, wa, ra1);
             const real vt = dot(dv, tangent);
-            real lambda = q4.y * (-vt);
+            real lambda = tmass1 * (-vt);
             const real max_friction = friction * qi.z;
             const real new_imp = clamp_r(qi.w + lambda, -max_friction, max_friction);
             lambda = new_imp - qi.w;
@@ -1305,7 +1270,7 @@ template <class real> struct world_step {
         if (n_vel == 1) {
             const V2 dv = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const real vn = dot(dv, normal);
-            real lambda = -q2.x * (vn - q2.z);
+            real lambda = -nmass0 * (vn - bias0);
             const real new_imp = pymax(qi.x + lambda, real(0));
             lambda = new_imp - qi.x;
             const V2 P = lambda * normal;
@@ -1318,18 +1283,18 @@ template <class real> struct world_step {
             const V2 dv1 = rel_velocity(vb, wb, rb0, va, wa, ra0);
             const V2 dv2 = rel_velocity(vb, wb, rb1, va, wa, ra1);
             const real vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-            const real k11 = q5.x, k12 = q5.y, k22 = q5.z;
-            V2 b = mk<real>(vn1 - q2.z, vn2 - q4.z);
+            const real k11 = r.q4.x, k12 = r.q4.y, k22 = r.q4.z;
+            V2 b = mk<real>(vn1 - bias0, vn2 - bias1);
             b = b - mk<real>(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
-            const real nm11 = q5.w, nm12 = q6.x, nm22 = q6.y;
+            const real nm11 = r.q5.x, nm12 = r.q5.y, nm22 = r.q5.z;
             V2 x = -mk<real>(nm11 * b.x + nm12 * b.y, nm12 * b.x + nm22 * b.y);
             bool solved = (x.x >= real(0) && x.y >= real(0));
             if (!solved) {
-                x = mk<real>(-q2.x * b.x, real(0));
+                x = mk<real>(-nmass0 * b.x, real(0));
                 solved = (x.x >= real(0)) && (k12 * x.x + b.y >= real(0));
             }
             if (!solved) {
-                x = mk<real>(real(0), -q4.x * b.y);
+                x = mk<real>(real(0), -nmass1 * b.y);
                 solved = (x.y >= real(0)) && (k12 * x.y + b.x >= real(0));
             }
             if (!solved) {
@@ -1348,155 +1313,13 @@ template <class real> struct world_step {
         B2B_TSTAMP_F(3, (float)va.x, (float)wa, (float)vb.x, (float)wb);
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
-        if (!last) *imp_rec(slot) = qi;
-        else impulses_store(r.ci, n_vel, qi);
-    }
-
-    // store_impulses (contact.py:801-806): only as many points as the velocity rows kept
-    B2B_D void impulses_store(int ci, int n_vel, quad qi)
-    {
-        real* imp = c_imp + 4 * (size_t)ci;
-        if (n_vel > 1) stq(imp, qi);
-        else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
-    }
-
-    // ---- Jacobian-form rows (FAST_ROWS): f1 / f2 = (rA x n, rA x t, rB x n, rB x t) of point 0 / 1.  A row's relative
-    // velocity is (vB - vA).d + wB (rB x d) - wA (rA x d) and its impulse l is applied as v -+= m l d, w -+= I l (r x d):
-    // algebraically the reference's operations with ~40 % fewer floating-point instructions; the results differ from the
-    // operation-by-operation form by fp32 rounding only (the fp32 parity tiers hold tolerances, never bits).  Every
-    // two-product sum is an explicit fused multiply-add so that each compiled copy of this code rounds alike (a world's
-    // trajectory must not depend on the lane-team size or the batch it is in: T4).
-    B2B_D static real fma_r(real a, real b, real c)
-    {
-#if defined(__CUDA_ARCH__)
-        if constexpr (sizeof(real) == 4) return (real)__fmaf_rn((float)a, (float)b, (float)c);
-        else return (real)__fma_rn((double)a, (double)b, (double)c);
-#else
-        if constexpr (sizeof(real) == 4) return (real)fmaf((float)a, (float)b, (float)c);
-        else return (real)fma((double)a, (double)b, (double)c);
-#endif
-    }
-    B2B_D static real mul_r(real a, real b)
-    {
-#if defined(__CUDA_ARCH__)
-        if constexpr (sizeof(real) == 4) return (real)__fmul_rn((float)a, (float)b);
-        else return (real)__dmul_rn((double)a, (double)b);
-#else
-        return a * b;
-#endif
-    }
-    B2B_D static real dot2(real a, real b, real c, real d) { return fma_r(a, b, mul_r(c, d)); }          // a b + c d
-    B2B_D static real diff2(real a, real b, real c, real d) { return fma_r(a, b, -mul_r(c, d)); }        // a b - c d
-    B2B_D void constraint_warm_start_jacobian(const vrec& r)
-    {
-        const quad q0 = r.q0, j0 = r.q1, j1 = r.q3, m = r.q7, qi = r.qi;
-        const uint32_t bodies = bits_of_real(q0.w);
-        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
-        const bool two = r.q2.z != real(0);
-        const real nx = q0.x, ny = q0.y, tx = ny, ty = -nx;
-        const real ma = m.x, ia = m.y, mb = m.z, ib = m.w;
-        const bool stat_a = (ma == real(0)) && (ia == real(0)), stat_b = (mb == real(0)) && (ib == real(0));
-        const quad sa = state_get(ba), sb = state_get(bb);
-        // the accumulated impulse of the whole contact: P = sum (ni n + ti t), torque arms from the cross products
-        real pn = qi.x, pt = qi.y;
-        real la = dot2(j0.x, qi.x, j0.y, qi.y), lb = dot2(j0.z, qi.x, j0.w, qi.y);
-        if (two) {
-            pn += qi.z; pt += qi.w;
-            la += dot2(j1.x, qi.z, j1.y, qi.w); lb += dot2(j1.z, qi.z, j1.w, qi.w);
-        }
-        const real px = dot2(pn, nx, pt, tx), py = dot2(pn, ny, pt, ty);
-        if (!stat_a) state_set(ba, fma_r(-ma, px, sa.x), fma_r(-ma, py, sa.y), fma_r(-ia, la, sa.z));
-        if (!stat_b) state_set(bb, fma_r(mb, px, sb.x), fma_r(mb, py, sb.y), fma_r(ib, lb, sb.z));
-    }
-    // one row's impulse `l` along direction (dx, dy) with torque arms (arm_a, arm_b)
-    struct vel_pair { real vax, vay, wa, vbx, vby, wb; };
-    B2B_D static void apply_row(vel_pair& v, real l, real dx, real dy, real arm_a, real arm_b, real ma, real ia, real mb, real ib)
-    {
-        const real la = mul_r(ma, l), lb = mul_r(mb, l);
-        v.vax = fma_r(-la, dx, v.vax); v.vay = fma_r(-la, dy, v.vay); v.wa = fma_r(-mul_r(ia, l), arm_a, v.wa);
-        v.vbx = fma_r(lb, dx, v.vbx); v.vby = fma_r(lb, dy, v.vby); v.wb = fma_r(mul_r(ib, l), arm_b, v.wb);
-    }
-    // relative velocity of the contact point along (dx, dy): (vB - vA).d + wB * (rB x d) - wA * (rA x d)
-    B2B_D static real row_velocity(const vel_pair& v, real dx, real dy, real arm_a, real arm_b)
-    {
-        return dot2(v.vbx - v.vax, dx, v.vby - v.vay, dy) + diff2(v.wb, arm_b, v.wa, arm_a);
-    }
-    B2B_D void constraint_solve_velocity_jacobian(const vrec& r, int slot, bool last)
-    {
-        const quad q0 = r.q0, j0 = r.q1, j1 = r.q3, em = r.q2, m = r.q7;
-        quad qi = r.qi;
-        const uint32_t bodies = bits_of_real(q0.w), fbits = bits_of_real(q0.z);
-        const int ba = (int)(bodies & 0xffffu), bb = (int)(bodies >> 16);
-        const bool two = em.z != real(0);
-        const real nx = q0.x, ny = q0.y, tx = ny, ty = -nx;
-        const real friction = real_from_bits(fbits & 0x7fffffffu);
-        const real ma = m.x, ia = m.y, mb = m.z, ib = m.w;
-        const bool stat_a = (ma == real(0)) && (ia == real(0)), stat_b = (mb == real(0)) && (ib == real(0));
-        real bias0 = real(0), bias1 = real(0);
-        if (fbits & 0x80000000u) { bias0 = cc_bias[2 * (size_t)slot]; bias1 = cc_bias[2 * (size_t)slot + 1]; }   // restitution: rare
-        const quad sa = state_get(ba), sb = state_get(bb);
-        vel_pair v;
-        v.vax = sa.x; v.vay = sa.y; v.wa = sa.z; v.vbx = sb.x; v.vby = sb.y; v.wb = sb.z;
-        // friction rows first, point by point (contact.py:541-573)
-        {
-            const real vt = row_velocity(v, tx, ty, j0.y, j0.w);
-            const real max_friction = mul_r(friction, qi.x);
-            const real new_imp = clamp_r(fma_r(-em.y, vt, qi.y), -max_friction, max_friction);
-            apply_row(v, new_imp - qi.y, tx, ty, j0.y, j0.w, ma, ia, mb, ib);
-            qi.y = new_imp;
-        }
-        if (two) {
-            const real vt = row_velocity(v, tx, ty, j1.y, j1.w);
-            const real max_friction = mul_r(friction, qi.z);
-            const real new_imp = clamp_r(fma_r(-em.w, vt, qi.w), -max_friction, max_friction);
-            apply_row(v, new_imp - qi.w, tx, ty, j1.y, j1.w, ma, ia, mb, ib);
-            qi.w = new_imp;
-        }
-        if (!two) {
-            // contact.py:575-596
-            const real vn = row_velocity(v, nx, ny, j0.x, j0.z);
-            const real new_imp = pymax(fma_r(-em.x, vn - bias0, qi.x), real(0));
-            apply_row(v, new_imp - qi.x, nx, ny, j0.x, j0.z, ma, ia, mb, ib);
-            qi.x = new_imp;
+        if (!last) {
+            *imp_rec(slot) = qi;
         } else {
-            // 2x2 LCP by total enumeration; first feasible case wins (contact.py:598-796)
-            const real a0 = qi.x, a1 = qi.z;
-            const real vn1 = row_velocity(v, nx, ny, j0.x, j0.z), vn2 = row_velocity(v, nx, ny, j1.x, j1.z);
-            // K = J M^-1 J^T and its inverse (contact.py:476-495, common.py:505-519), from the Jacobian rows
-            const real mab = ma + mb;
-            const real k11 = fma_r(ib, mul_r(j0.z, j0.z), fma_r(ia, mul_r(j0.x, j0.x), mab));
-            const real k22 = fma_r(ib, mul_r(j1.z, j1.z), fma_r(ia, mul_r(j1.x, j1.x), mab));
-            const real k12 = fma_r(ib, mul_r(j0.z, j1.z), fma_r(ia, mul_r(j0.x, j1.x), mab));
-            real det = diff2(k11, k22, k12, k12);
-            if (det != real(0)) det = real(1) / det;
-            const real nm11 = mul_r(det, k22), nm12 = -mul_r(det, k12), nm22 = mul_r(det, k11);
-            const real b0 = (vn1 - bias0) - dot2(k11, a0, k12, a1), b1 = (vn2 - bias1) - dot2(k12, a0, k22, a1);
-            real x0 = -dot2(nm11, b0, nm12, b1), x1 = -dot2(nm12, b0, nm22, b1);
-            bool solved = (x0 >= real(0) && x1 >= real(0));
-            if (!solved) {
-                x0 = -mul_r(em.x, b0); x1 = real(0);
-                solved = (x0 >= real(0)) && (fma_r(k12, x0, b1) >= real(0));
-                if (!solved) {
-                    x0 = real(0); x1 = -mul_r(em.z, b1);
-                    solved = (x1 >= real(0)) && (fma_r(k12, x1, b0) >= real(0));
-                }
-                if (!solved) {
-                    x0 = real(0); x1 = real(0);
-                    solved = (b0 >= real(0)) && (b1 >= real(0));
-                }
-            }
-            if (solved) {
-                const real d0 = x0 - a0, d1 = x1 - a1, d = d0 + d1;
-                const real la = mul_r(ma, d), lb = mul_r(mb, d);
-                v.vax = fma_r(-la, nx, v.vax); v.vay = fma_r(-la, ny, v.vay); v.wa = fma_r(-ia, dot2(j0.x, d0, j1.x, d1), v.wa);
-                v.vbx = fma_r(lb, nx, v.vbx); v.vby = fma_r(lb, ny, v.vby); v.wb = fma_r(ib, dot2(j0.z, d0, j1.z, d1), v.wb);
-                qi.x = x0; qi.z = x1;
-            }
+            real* imp = c_imp + 4 * (size_t)(vinfo >> VINFO_CI_SHIFT);
+            if (n_vel > 1) stq(imp, qi);
+            else if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
         }
-        if (!stat_a) state_set(ba, v.vax, v.vay, v.wa);
-        if (!stat_b) state_set(bb, v.vbx, v.vby, v.wb);
-        if (!last) *imp_rec(slot) = qi;
-        else impulses_store(r.ci, two ? 2 : 1, qi);
     }
 
     // One manifold point of ContactSolver.solve_position_constraints (contact_util.py:323-360 PositionSolverManifold,
@@ -1778,23 +1601,24 @@ template <class real> struct world_step {
             if (joint) { c0 = 0; c1 = n_lc; }
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            bool last = false;                               // the sweep in progress is the last velocity iteration
-            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e, last); };
+            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
             auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
             if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int) { constraint_warm_start(e); }, vready);
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
-                last = (it + 1 == sp.vel_iters);
+                const bool last = (it + 1 == sp.vel_iters);
                 level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); }, vready);
             }
             B2B_PROF(PROF_S_VELOCITY, t);
             // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
             // iterations the (warm-started) impulses go back as they are
             if (sp.vel_iters == 0) {
-                B2B_SYNC();
-                for (int sl = c0 + t_id; sl < c1; sl += t_n) {
-                    const quad qi = *imp_rec(sl), em = vel_rec(sl)[FAST_ROWS ? 3 : 2];
-                    impulses_store(cc_ci[sl], FAST_ROWS ? ((em.z != real(0)) ? 2 : 1) : (int)(bits_of_real(em.w) & 0xff), qi);
+                for (int s = c0 + t_id; s < c1; s += t_n) {
+                    const quad qi = *imp_rec(s);
+                    const int ci = l_contact[g_sched[s]], n_vel = (int)(bits_of_real(vel_rec(s)[2].lo.w) & VINFO_NVEL_MASK);
+                    real* imp = c_imp + 4 * (size_t)ci;
+                    if (n_vel > 0) { imp[0] = qi.x; imp[1] = qi.y; }
+                    if (n_vel > 1) { imp[2] = qi.z; imp[3] = qi.w; }
                 }
             }
         }

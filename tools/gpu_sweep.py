@@ -17,8 +17,9 @@ def run(n_worlds, real, lanes, lanes_aux, settle=300, steps=5, repeats=1, ctas=0
         e0.record(); bw.step(1/60, 8, 3, steps, time_kernels=True, group_kernel=bool(int(os.environ.get('SWEEP_GROUP_KERNEL', '0')))); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         k = bw.kernel_ms()
-        print("%s worlds=%d lanes=%d aux=%d ctas=%d: %.2f ms/step %.3e body-steps/s; kernels ms/step collide %.2f plan %.2f solve %.2f broad %.2f status=%d" % (
-            real, n_worlds, lanes, lanes_aux, ctas, ms/steps, 210*n_worlds*steps/(ms*1e-3), k["collide"]/steps, k["plan"]/steps, k["solve"]/steps, k["broadphase"]/steps, bw.status(False)), flush=True)
+        print("%s worlds=%d lanes=%d aux=%d ctas=%d: %.2f ms/step %.3e body-steps/s; kernels ms/step collide %.2f plan %.2f prepare %.2f velocity %.2f position %.2f broad %.2f status=%d" % (
+            real, n_worlds, lanes, lanes_aux, ctas, ms/steps, 210*n_worlds*steps/(ms*1e-3), k["collide"]/steps, k["plan"]/steps, k["prepare"]/steps,
+            k["solve_velocity"]/steps, k["solve_position"]/steps, k["broadphase"]/steps, bw.status(False)), flush=True)
 
 if __name__ == "__main__":
     import sys
