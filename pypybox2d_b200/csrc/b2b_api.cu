@@ -24,7 +24,7 @@ struct b2b_ctx {
     unsigned char* scratch_solve;  // constraint records: one slab per world of a solve group
     unsigned char* scratch_sprof;  // solve kernel: cycle counters, one row per team
     uint16_t* plan_rows;
-    uint32_t* d_status;            // [0] status OR, [1..2] chunk counters of the plan / pair kernels, [3] joint-schedule word
+    uint32_t* d_status;            // [0] status OR, [1..2] chunk counters of the plan / pair kernels, [3..4] joint-schedule words, [8..15] world counters of the solve kernels (two sets)
     void* stage_in;       // [n_worlds][nb][3] reals
     void* stage_out;      // [n_worlds][nb][6] reals
     const void* fields[B2B_NFIELDS];
@@ -36,7 +36,7 @@ struct b2b_ctx {
     // b2b_step: second stream for every other chunk of worlds of the solve kernels (their tails overlap), fork / join events
     cudaStream_t s_aux;
     cudaEvent_t ev_fork, ev_join;
-    int step_streams;              // 1: everything on the caller's stream; 2 (default): chunks alternate between two streams
+    int step_streams;              // 1 (default): everything on the caller's stream; 2: the solve chunks alternate between two streams
     std::vector<cudaEvent_t>* pipe_ev;
     int pipe_worlds;               // worlds per chunk of the host-buffer pipeline
     int stream_worlds;             // worlds per chunk of b2b_step's two-stream schedule
@@ -176,9 +176,11 @@ extern "C" int b2b_create(const b2b_caps* caps, b2b_ctx** out)
     const size_t plan_bytes = sizeof(uint16_t) * x->plan.plan.stride * (size_t)x->c.n_worlds;
     CREATE_TRY(cudaMalloc((void**)&x->plan_rows, plan_bytes), "cudaMalloc(plan rows)");
     CREATE_TRY(cudaMemset(x->plan_rows, 0, plan_bytes), "cudaMemset(plan rows)");
-    CREATE_TRY(cudaMalloc((void**)&x->d_status, 8 * sizeof(uint32_t)), "cudaMalloc(status)");
-    CREATE_TRY(cudaMemset(x->d_status, 0, 8 * sizeof(uint32_t)), "cudaMemset(status)");
-    x->step_streams = 2;
+    CREATE_TRY(cudaMalloc((void**)&x->d_status, 16 * sizeof(uint32_t)), "cudaMalloc(status)");
+    CREATE_TRY(cudaMemset(x->d_status, 0, 16 * sizeof(uint32_t)), "cudaMemset(status)");
+    // (round 2, one solve CTA per SM with worlds handed out through a counter: a launch has no ragged last round any more and two
+    // solve grids cannot share an SM's shared memory, so chunks on two streams only add tails: 39.9 ms vs 38.2 ms on one stream)
+    x->step_streams = 1;
     if (const char* env = getenv("B2B_STEP_STREAMS")) { const int v = atoi(env); if (v == 1 || v == 2) x->step_streams = v; }
 #undef CREATE_TRY
     *out = x;
@@ -244,7 +246,15 @@ static step_params make_params(double dt, double inv_dt0, int vel_iters, int pos
     sp.solve_lanes = solve_lanes;
     sp.zero = 0;
     sp.joint_any = nullptr;                                        // bound by launch_step
+    sp.solve_ctr = nullptr;                                        // bound by the callers (solve_counters)
     return sp;
+}
+
+// world counters of the solve kernels for the launches on stream `parity` (B2B_STATIC_WORLDS=1: none, worlds strided over the warps)
+static unsigned int* solve_counters(const b2b_ctx* x, int parity)
+{
+    static const bool off = [] { const char* e = getenv("B2B_STATIC_WORLDS"); return e && atoi(e) != 0; }();
+    return off ? nullptr : x->d_status + 8 + 4 * (parity & 1);
 }
 
 static int step_launches(const b2b_ctx* x, double dt, uint32_t flags, int groups)
@@ -262,8 +272,9 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
     if (n_steps == 0) return B2B_OK;
     CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
     // the flat narrowphase kernel is the default; B2B_STEP_NO_FLAT keeps the narrowphase inside the per-world plan kernel
-    const step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u),
-                                       x->plan.lanes);
+    step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_NO_FLAT) ? (flags & ~4u) : (flags | 4u),
+                                 x->plan.lanes);
+    sp.solve_ctr = solve_counters(x, 0);
     step_timer* tm = nullptr;
     if (flags & B2B_STEP_TIME) {
         if (!x->timer) x->timer = new step_timer();
@@ -299,6 +310,7 @@ extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, in
                 cudaStream_t sk = (k & 1) ? x->s_aux : st;
                 step_params spk = sp2;
                 spk.joint_any = x->d_status + ((k & 1) ? 4 : 3);         // one joint-schedule word per stream (position kernels read it)
+                spk.solve_ctr = solve_counters(x, k & 1);
                 unsigned char* rec = x->scratch_solve + (size_t)w0 * x->plan.layout.total_rec;
                 if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, s == 0, w0, n, sk, nullptr);
                 else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, s == 0, w0, n, sk, nullptr);
@@ -332,6 +344,7 @@ extern "C" int b2b_solve_islands(b2b_ctx* x, double dt, double inv_dt0, int vel_
     cudaStream_t st = (cudaStream_t)stream;
     step_params sp = make_params(dt, inv_dt0, vel_iters, pos_iters, 1, (flags & B2B_STEP_PROFILE) | 4u | 64u, x->plan.lanes);
     sp.joint_any = x->d_status + 3;
+    sp.solve_ctr = solve_counters(x, 0);
     if (x->f64) launch_plan_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
     else launch_plan_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st);
     int groups = 0;
@@ -432,6 +445,7 @@ extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_sta
             if (dt > 0.0) {
                 step_params spk = sp;
                 if (two) spk.joint_any = x->d_status + ((k & 1) ? 4 : 3);       // one joint-schedule word per stream
+                spk.solve_ctr = solve_counters(x, two ? (k & 1) : 0);
                 unsigned char* rec = x->scratch_solve + (two ? (size_t)w0 * x->plan.layout.total_rec : (size_t)0);
                 if (x->f64) launch_solve_group_f64(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, first, w0, n, sk, nullptr);
                 else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, first, w0, n, sk, nullptr);

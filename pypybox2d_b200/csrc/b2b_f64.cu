@@ -1,5 +1,4 @@
 // fp64 instantiation of the step kernels (parity build; compile this unit with -fmad=false).
 #define B2B_REAL double
 #define B2B_SUFFIX f64
-#define B2B_SOLVE_MIN_CTAS 12
 #include "b2b_kernels.inl"

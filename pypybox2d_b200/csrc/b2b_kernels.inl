@@ -12,10 +12,12 @@ namespace b2b {
 
 typedef B2B_REAL real_t;
 
-// resident solve CTAs (one warp each) per SM the register allocation is sized for: two constraint records in
-// flight per lane need ~170 registers, so the default is 4 lanes per world (8 worlds per warp) and 10 CTAs per SM
-#ifndef B2B_SOLVE_MIN_CTAS
-#define B2B_SOLVE_MIN_CTAS 10
+// The solve kernels run ONE CTA per SM, a team of lanes per world: two constraint records in flight per lane need ~170
+// registers, which lets 12 warps share an SM's register file (three per scheduler); how many of them a CTA gets is decided
+// by the shared memory the bodies' state of its worlds needs (plan_: 11 warps = 88 pyramid worlds).  One CTA per SM pays the
+// per-CTA shared-memory reservation once: one-warp CTAs stopped at 10 warps per SM.
+#ifndef B2B_SOLVE_MAX_WARPS
+#define B2B_SOLVE_MAX_WARPS 12
 #endif
 
 // The step is three kernels per World.step, each a persistent grid with worlds strided over CTAs:
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
         if (slot >= B.w_island[4 * (size_t)w + 2]) continue;
         world_step<real_t> ws;
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
+        ws.bind_scratch_solve(rec, (size_t)g * L.total_rec, L, nullptr);
         ws.prepare_slot(sp, first_step != 0, slot);
         if (slot == 0 && sp.joint_any != nullptr && ws.g_joint[0] != 0 && *sp.joint_any == 0u) atomicExch(sp.joint_any, 1u);
     }
@@ -151,57 +153,56 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
         if (b >= B.w_count[4 * (size_t)w]) continue;
         world_step<real_t> ws;
         ws.bind_rows(B, c, w, plan, P);
-        ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, nullptr);
+        ws.bind_scratch_solve(rec, (size_t)g * L.total_rec, L, nullptr);
         ws.prepare_body(sp, b);
     }
 }
 
-// Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): each is one warp per
-// CTA, the warp split into teams of `lanes` lanes, one world per team, worlds of the group strided over the teams.
-// End of a world: each team on its own (default), or -DB2B_WARP_RECONVERGE=1: the teams of the warp whose world index is
-// inside the group this round (a prefix of the teams) meet again, so the next world starts with the warp's teams issuing
-// together.  Measured (profiles/r1_other_scenes.md): pyramid batch neutral, the group-capable position kernel's penalty for
-// one-island worlds halves (ncu: it executes 13 % more warp instructions for 3 % more thread instructions -- its teams
-// drift apart), vertical stacks 3 % slower (worlds of very different length wait for each other), deep stacks 1 % faster.
-#if defined(B2B_WARP_RECONVERGE) && B2B_WARP_RECONVERGE
-#define B2B_SOLVE_RECONVERGE(g, team, tpc, lanes, n_group, t_mask)                                                            \
-    do {                                                                                                                       \
-        const int rem_ = (n_group) - ((g) - (team));                                                                           \
-        const int act_ = (rem_ < (tpc) ? rem_ : (tpc)) * (lanes);                                                              \
-        __syncwarp(act_ >= 32 ? 0xffffffffu : ((1u << act_) - 1u));                                                            \
-    } while (0)
-#else
-#define B2B_SOLVE_RECONVERGE(g, team, tpc, lanes, n_group, t_mask) __syncwarp(t_mask)
-#endif
-#define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN)                                                                                          \
-    __global__ void __launch_bounds__(32, B2B_SOLVE_MIN_CTAS) B2B_CAT(NAME, B2B_SUFFIX)(                                       \
+// Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): one CTA per SM, every warp
+// split into teams of `lanes` lanes, one world per team.  The teams of a warp start their worlds together and meet again
+// after them: they share every issued instruction, so they must stay in step.
+#define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN, KIND)                                                                                        \
+    __global__ void __launch_bounds__(32 * B2B_SOLVE_MAX_WARPS, 1) B2B_CAT(NAME, B2B_SUFFIX)(                                  \
         batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* rec,                   \
         unsigned char* team_prof, step_params sp, int lanes, size_t team_smem, int w0, int n_group)                            \
     {                                                                                                                          \
         extern __shared__ __align__(32) unsigned char smem[];                                                                  \
         if (NOT_MY_TURN) return;                                                                                               \
         world_step<real_t> ws;                                                                                                 \
-        const int team = ws.bind_team_lanes(lanes);                                                                            \
-        const int teams_per_cta = 32 / lanes;                                                                                  \
+        const int team = ws.bind_team_lanes(lanes);                /* index among the CTA's teams */                           \
+        const int teams_per_warp = 32 / lanes, teams_per_cta = (int)(blockDim.x >> 5) * teams_per_warp;                        \
+        const int team_in_warp = team % teams_per_warp;                                                                        \
         const int slot = blockIdx.x * teams_per_cta + team;                                                                    \
-        for (int g = slot; g < n_group; g += gridDim.x * teams_per_cta) {                                                      \
-            ws.bind_rows(B, c, w0 + g, plan, P);                                                                               \
-            ws.bind_scratch_solve(rec + (size_t)g * L.total_rec, L, team_prof + (size_t)slot * L.total_sprof);                 \
-            ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                               \
-            ws.pf_sink = (uint32_t)__cvta_generic_to_shared(smem + (size_t)teams_per_cta * team_smem + 16 * (threadIdx.x & 31)); \
-            {                                                                                                                  \
-                const int rem_ = n_group - (g - team);                                                                         \
-                const int act_ = (rem_ < teams_per_cta ? rem_ : teams_per_cta) * lanes;                                        \
-                ws.w_mask = act_ >= 32 ? 0xffffffffu : ((1u << act_) - 1u);                                                    \
+        /* Worlds are handed out a warp's worth at a time (its teams stay in step: they share every issued instruction)     */ \
+        /* through a counter (sp.solve_ctr[KIND], zeroed by the launcher): a warp on a less crowded scheduler takes more of */ \
+        /* them, and the last worlds of a launch go to whoever is free first.  Without a counter: strided over the warps.   */ \
+        unsigned int* const ctr = sp.solve_ctr ? sp.solve_ctr + KIND : nullptr;                                                \
+        for (int g0 = slot - team_in_warp;; g0 += gridDim.x * teams_per_cta) {                                                 \
+            if (ctr) {                                                                                                         \
+                int v = 0;                                                                                                     \
+                if ((threadIdx.x & 31) == 0) v = (int)atomicAdd(ctr, (unsigned int)teams_per_warp);                            \
+                g0 = __shfl_sync(0xffffffffu, v, 0);                                                                           \
             }                                                                                                                  \
-            ws.CALL(sp);                                                                                                       \
-            B2B_SOLVE_RECONVERGE(g, team, teams_per_cta, lanes, n_group, ws.t_mask);                                           \
+            if (g0 >= n_group) break;                                                                                          \
+            const int g = g0 + team_in_warp;                                                                                   \
+            if (g < n_group) {                                                                                                 \
+                ws.bind_rows(B, c, w0 + g, plan, P);                                                                           \
+                ws.bind_scratch_solve(rec, (size_t)g * L.total_rec, L, team_prof + (size_t)slot * L.total_sprof);             \
+                ws.bind_smem_solve(smem + (size_t)team * team_smem);                                                           \
+                {                                                  /* lanes of this warp whose team has a world this round */  \
+                    const int rem_ = n_group - g0;                                                                             \
+                    const int act_ = (rem_ < teams_per_warp ? rem_ : teams_per_warp) * lanes;                                  \
+                    ws.w_mask = act_ >= 32 ? 0xffffffffu : ((1u << act_) - 1u);                                                \
+                }                                                                                                              \
+                ws.CALL(sp);                                                                                                   \
+            }                                                                                                                  \
+            __syncwarp();                                                                                                      \
         }                                                                                                                      \
     }
-B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity, false)
+B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity, false, 0)
 // sp.joint_any: raised by this group's prepare kernel (or an earlier group's) when some world has a joint island schedule
-B2B_SOLVE_KERNEL(solve_position_kernel_, template run_solve_position<false>, *sp.joint_any != 0u)
-B2B_SOLVE_KERNEL(solve_position_joint_kernel_, template run_solve_position<true>, *sp.joint_any == 0u)
+B2B_SOLVE_KERNEL(solve_position_kernel_, template run_solve_position<false>, *sp.joint_any != 0u, 1)
+B2B_SOLVE_KERNEL(solve_position_joint_kernel_, template run_solve_position<true>, *sp.joint_any == 0u, 2)
 #undef B2B_SOLVE_KERNEL
 
 // Proxy synchronisation (K4: body.py:898-904, fixture.py:287-298, dynamictree.py:152-188) and World.clear_forces as a
@@ -424,24 +425,36 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     int rc = plan_one(B2B_CAT(plan_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                       S.total_plan * teams_aux, 0, n_sm, &out->k_plan);
     if (rc) return rc;
-    // the two solve kernels share one launch geometry: the smaller of their occupancies
-    kernel_plan k_pos;
-    rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
-                  ctas_per_sm, n_sm, &out->k_solve);
-    if (rc) return rc;
-    rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
-                  ctas_per_sm, n_sm, &k_pos);
-    if (rc) return rc;
-    if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
-    rc = plan_one(B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams - 1) / teams, 32, out->team_smem * teams + 512,
-                  ctas_per_sm, n_sm, &k_pos);
-    if (rc) return rc;
-    if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+    // the solve kernels share one launch geometry: one CTA per SM with as many warps as the bodies' state of their worlds
+    // leaves room for (`ctas_per_sm` > 0, a development knob, caps the warps per SM)
+    {
+        int dev = 0, smem_max = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t per_warp = out->team_smem * teams;
+        int warps = (int)((size_t)smem_max / per_warp);
+        if (warps > B2B_SOLVE_MAX_WARPS) warps = B2B_SOLVE_MAX_WARPS;
+        if (ctas_per_sm > 0 && warps > ctas_per_sm) warps = ctas_per_sm;
+        if (warps < 1) return (int)cudaErrorInvalidConfiguration;       // one warp's worlds do not fit an SM's shared memory
+        const long long per_cta = (long long)warps * teams;
+        kernel_plan k_pos;
+        rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                      1, n_sm, &out->k_solve);
+        if (rc) return rc;
+        rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                      1, n_sm, &k_pos);
+        if (rc) return rc;
+        if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+        rc = plan_one(B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                      1, n_sm, &k_pos);
+        if (rc) return rc;
+        if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+    }
     rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                   S.total_broad * teams_aux, 0, n_sm, &out->k_broad);
     if (rc) return rc;
     out->aux_slabs = (out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid) * teams_aux;
-    out->solve_slabs = out->k_solve.grid * teams;
+    out->solve_slabs = out->k_solve.grid * (out->k_solve.threads / 32) * teams;
     return 0;
 }
 
@@ -489,17 +502,19 @@ void B2B_CAT(launch_solve_group_, B2B_SUFFIX)(const void* const* fields, const c
     B2B_CAT(prepare_kernel_, B2B_SUFFIX)<<<flat_blocks((long long)n_group * c.nc, p.n_sm), 128, 0, st>>>(B, c, p.plan, plan, p.layout, scratch_solve, sp,
                                                                                                          first_step, w0, n_group);
     if (tm) tm->mark(T_PREPARE, st);
-    const int teams = 32 / p.lanes;
+    if (sp.solve_ctr) cudaMemsetAsync(sp.solve_ctr, 0, 3 * sizeof(unsigned int), st);
+    const int per_cta = (p.k_solve.threads / 32) * (32 / p.lanes);       // worlds a CTA holds at a time
     int grid = p.k_solve.grid;
-    if ((long long)grid * teams > n_group) grid = (n_group + teams - 1) / teams;
+    if ((long long)grid * per_cta > n_group) grid = (n_group + per_cta - 1) / per_cta;
     // (sizing the grid so that the last round of worlds is as full as the others was measured slower: 34.5 vs
     // 33.5 ms per 131,072 worlds -- the stragglers of a ragged last round run faster on a nearly empty SM)
-    B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+    const int threads = p.k_solve.threads;
+    B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
                                                                                    scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
     if (tm) tm->mark(T_VELOCITY, st);
-    B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+    B2B_CAT(solve_position_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
                                                                                    scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
-    B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX)<<<grid, 32, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+    B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
                                                                                          scratch_sprof, sp, p.lanes, p.team_smem, w0, n_group);
     if (tm) tm->mark(T_POSITION, st);
 }

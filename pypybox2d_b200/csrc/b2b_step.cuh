@@ -42,12 +42,7 @@
 #define B2B_CLOCK() clock64()
 #define B2B_POPC(m) __popc(m)
 #define B2B_CTZ(m) (__ffs((int)(m)) - 1)
-#if defined(B2B_PF_LDGSTS)
-// experiment: a real 16-byte asynchronous copy into a per-lane sink (with a 128-byte L2 fill) instead of a prefetch hint
-#define B2B_PREFETCH(p) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(pf_sink), "l"(p))
-#else
 #define B2B_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
-#endif
 #else
 #define B2B_PFOR(i, n) for (int i = 0; i < (n); ++i)
 #define B2B_SYNC() ((void)0)
@@ -216,6 +211,8 @@ struct step_params {
     uint32_t flags;
     int solve_lanes;             // lanes per world of the solve kernel: the level-step table is cut to this width
     uint32_t zero;               // always 0: a value the compiler cannot fold (orders the record loads, see level_sweep)
+    unsigned int* solve_ctr;     // three device words per launch_solve_group call (zeroed by it): the next world of the group for the
+                                 // velocity / position / joint position kernel's teams (null: worlds strided over the teams)
     unsigned int* joint_any;     // device word, cleared every step: raised by the prepare kernel when some world of the batch
                                  // has a joint island schedule (the position kernel then runs its group-capable instantiation)
 };
@@ -258,7 +255,6 @@ template <class real> struct world_step {
 #define B2B_TSTAMP_F(i, a, b, c, d) ((void)0)
 #endif
     real* s_third;           // solve kernel: third component of every body's state (after the (x, y) pairs)
-    uint32_t pf_sink;        // (experiment B2B_PF_LDGSTS) shared-space address of this lane's 16-byte sink
     real* s_state;           // solve kernel: per body (v.x, v.y, w) during the velocity phase, then (c.x, c.y, a)
     uint32_t* s_flags;       // plan kernel: body flags
     int32_t* s_ctl;          // [16] control words
@@ -325,14 +321,21 @@ template <class real> struct world_step {
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
     }
-    // `rec`: this world's constraint-record slab (written by the prepare kernel, streamed by the solve kernel);
-    // `team_prof`: the team's cycle counters (may be null outside the solve kernel)
-    B2B_D void bind_scratch_solve(unsigned char* rec, const scratch_layout& L, unsigned char* team_prof)
+    // `slabs` + `off`: this world's constraint-record slab (written by the prepare kernel, streamed by the solve kernels);
+    // `team_prof`: the team's cycle counters (may be null outside the solve kernels)
+    B2B_D void bind_scratch_solve(unsigned char* slabs, size_t off, const scratch_layout& L, unsigned char* team_prof)
     {
-        cc_vel = (real*)(rec + L.off_cc_vel);
-        cc_pos = (real*)(rec + L.off_cc_pos);
-        cc_imp = (real*)(rec + L.off_cc_imp);
-        cc_state = (real*)(rec + L.off_cc_state);
+        size_t o_vel = off + L.off_cc_vel, o_pos = off + L.off_cc_pos, o_imp = off + L.off_cc_imp;
+#if defined(__CUDA_ARCH__)
+        // keep the offsets of the record streams in registers: the compiler would otherwise re-derive them from the kernel's
+        // parameters (64-bit multiplies and constant-bank loads) in every level-step when registers are tight.  (Offsets,
+        // not pointers: a pointer that went through an asm loses its address space and is loaded from with generic LDs.)
+        asm volatile("" : "+l"(o_vel), "+l"(o_pos), "+l"(o_imp));
+#endif
+        cc_vel = (real*)(slabs + o_vel);
+        cc_pos = (real*)(slabs + o_pos);
+        cc_imp = (real*)(slabs + o_imp);
+        cc_state = (real*)(slabs + off + L.off_cc_state);
         prof = (long long*)team_prof;
     }
     B2B_D void bind_smem_aux(unsigned char* smem, bool broadphase_kernel = false)
@@ -931,7 +934,10 @@ template <class real> struct world_step {
     }
     // Records are consumed in slot order; the lane that fetches slot s also asks the L2 for slot s + PREFETCH_AHEAD
     // (a few level-steps ahead, wrapping to the start of the island for the next sweep).
-    enum { PREFETCH_AHEAD = 6 };
+#ifndef B2B_PREFETCH_AHEAD
+#define B2B_PREFETCH_AHEAD 6
+#endif
+    enum { PREFETCH_AHEAD = B2B_PREFETCH_AHEAD };
     B2B_D int prefetch_target(int s, int c0, int c1) const
     {
         const int t = s + PREFETCH_AHEAD;
@@ -939,11 +945,14 @@ template <class real> struct world_step {
     }
     B2B_D void prefetch_vel(int s, int c0, int c1)
     {
+#ifndef B2B_PF_MODE
+#define B2B_PF_MODE 2
+#endif
         const int t = prefetch_target(s, c0, c1);
-        if (t < c1) {
+        if (B2B_PF_MODE > 0 && t < c1) {
             B2B_PREFETCH(vel_rec(t));
             if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(vel_rec(t)) + 128);
-            B2B_PREFETCH(imp_rec(t));
+            if (B2B_PF_MODE > 1) B2B_PREFETCH(imp_rec(t));
         }
     }
     B2B_D void prefetch_pos(int s, int c0, int c1)

@@ -51,7 +51,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
         ws.bind_team_cta();
         ws.bind_rows(B, c, w, plan.data(), P);
         ws.bind_scratch_aux(aux.data(), L);
-        ws.bind_scratch_solve(solve.data(), L, sprof.data());
+        ws.bind_scratch_solve(solve.data(), 0, L, sprof.data());
         ws.bind_smem_aux(smem_aux.data(), true);      // the pair kernel's layout (candidate bitmap included): the phases run one after the other here
         ws.bind_smem_solve(smem_solve.data());
         if (dt > 0.0 && !(B.w_flags[w] & WORLD_GRAPH_VALID)) g_replans += 1;
