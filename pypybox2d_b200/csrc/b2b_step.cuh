@@ -932,38 +932,57 @@ template <class real> struct world_step {
     {
         return vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
     }
-    // Records are consumed in slot order; the lane that fetches slot s also asks the L2 for slot s + PREFETCH_AHEAD
-    // (a few level-steps ahead, wrapping to the start of the island for the next sweep).
+    // A lane's position in the record streams of the world: the velocity record + impulse row, or the position record, of
+    // one slot.  Records are consumed in slot order, so the position only ever moves forward by a few slots (pointer
+    // arithmetic, no index -> address conversion on the level loop's dependent chain); `prefetch` asks the L2 for the slot
+    // PREFETCH_AHEAD further on (an immediate offset of the same pointers; a request past the island's last slot is
+    // harmless, it stays inside the world's slab), `prefetch_first` for the first slots of the island: the next sweep.
 #ifndef B2B_PREFETCH_AHEAD
 #define B2B_PREFETCH_AHEAD 6
 #endif
-    enum { PREFETCH_AHEAD = B2B_PREFETCH_AHEAD };
-    B2B_D int prefetch_target(int s, int c0, int c1) const
-    {
-        const int t = s + PREFETCH_AHEAD;
-        return (t >= c1) ? t - (c1 - c0) : t;
-    }
-    B2B_D void prefetch_vel(int s, int c0, int c1)
-    {
-#ifndef B2B_PF_MODE
-#define B2B_PF_MODE 2
-#endif
-        const int t = prefetch_target(s, c0, c1);
-        if (B2B_PF_MODE > 0 && t < c1) {
-            B2B_PREFETCH(vel_rec(t));
-            if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(vel_rec(t)) + 128);
-            if (B2B_PF_MODE > 1) B2B_PREFETCH(imp_rec(t));
+    enum { PREFETCH_AHEAD = B2B_PREFETCH_AHEAD, VREC_OCTS = VREC_QUADS / 2, PREC_OCTS = PREC_QUADS / 2 };
+    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };      // the quads v0..v7 + imp of the layout above, in registers
+    struct prec { quad q7, q8, q9, q10, q11; };                    // p0..p4
+    struct vel_stream {
+        const oct* rec; quad* imp;
+        B2B_D vel_stream ahead(int n) const { vel_stream t; t.rec = rec + (int)VREC_OCTS * n; t.imp = imp + n; return t; }
+        B2B_D void prefetch() const
+        {
+            B2B_PREFETCH(rec + (int)VREC_OCTS * (int)PREFETCH_AHEAD);
+            if (sizeof(real) > 4) B2B_PREFETCH(reinterpret_cast<const char*>(rec + (int)VREC_OCTS * (int)PREFETCH_AHEAD) + 128);
+            B2B_PREFETCH(imp + (int)PREFETCH_AHEAD);
         }
-    }
-    B2B_D void prefetch_pos(int s, int c0, int c1)
-    {
-        const int t = prefetch_target(s, c0, c1);
-        if (t < c1) {
-            const char* r = reinterpret_cast<const char*>(pos_rec(t));
-            B2B_PREFETCH(r);
-            B2B_PREFETCH(r + sizeof(oct) * (PREC_QUADS / 2 - 1));  // the record's last oct: its second line, if it has one
+        B2B_D void prefetch_first(int t_n) const
+        {
+            for (int k = 0; k < (int)PREFETCH_AHEAD; k += t_n) { B2B_PREFETCH(rec + (int)VREC_OCTS * k); B2B_PREFETCH(imp + k); }
         }
-    }
+        B2B_D void load(vrec& r) const
+        {
+            const oct o0 = rec[0], o1 = rec[1], o2 = rec[2], o3 = rec[3];
+            r.q0 = o0.lo; r.q1 = o0.hi; r.q2 = o1.lo; r.q3 = o1.hi; r.q4 = o2.lo; r.q5 = o2.hi; r.q6 = o3.lo; r.q7 = o3.hi;
+            r.qi = *imp;
+        }
+    };
+    struct pos_stream {
+        const oct* rec;
+        B2B_D pos_stream ahead(int n) const { pos_stream t; t.rec = rec + (int)PREC_OCTS * n; return t; }
+        B2B_D void prefetch() const
+        {
+            B2B_PREFETCH(rec + (int)PREC_OCTS * (int)PREFETCH_AHEAD);
+            B2B_PREFETCH(rec + (int)PREC_OCTS * (int)PREFETCH_AHEAD + ((int)PREC_OCTS - 1));   // the record's last oct: its second line, if it has one
+        }
+        B2B_D void prefetch_first(int t_n) const
+        {
+            for (int k = 0; k < (int)PREFETCH_AHEAD; k += t_n) { B2B_PREFETCH(rec + (int)PREC_OCTS * k); B2B_PREFETCH(rec + (int)PREC_OCTS * k + ((int)PREC_OCTS - 1)); }
+        }
+        B2B_D void load(prec& r) const
+        {
+            const oct o0 = rec[0], o1 = rec[1], o2 = rec[2];
+            r.q7 = o0.lo; r.q8 = o0.hi; r.q9 = o1.lo; r.q10 = o1.hi; r.q11 = o2.lo;
+        }
+    };
+    B2B_D vel_stream vel_stream_at(int slot) { vel_stream t; t.rec = vel_rec(slot); t.imp = imp_rec(slot); return t; }
+    B2B_D pos_stream pos_stream_at(int slot) { pos_stream t; t.rec = pos_rec(slot); return t; }
 
     // Reader of an island's level-step table (phase_schedule): one 4-bit slot count per level-step, eight per
     // word.  The following word is requested when the current one is half used and only moved in when it runs out,
@@ -978,6 +997,8 @@ template <class real> struct world_step {
             const int c = (int)(cur & 15u);
             cur >>= 4;
             --left;
+            // (branches, not selects: a select would read `next` in every level-step, i.e. wait for its load -- and with it for
+            // the record loads just issued, which share its scoreboard -- right after it was requested)
             if (left == 0) { cur = next; left = 8; }
             else if (left == 4) next = *p++;
             return c;
@@ -986,72 +1007,63 @@ template <class real> struct world_step {
 
     // One Gauss-Seidel sweep over an island's constraint slots [c0, c1), level-step by level-step.  The slots of a
     // level-step touch disjoint non-static bodies, so the team's lanes solve them concurrently and the result is
-    // bit-identical to the reference's sequential sweep.  `load(slot, rec)` fetches a record into registers,
-    // `solve(rec, slot)` applies it to the bodies in shared memory, `ready(rec)` returns a word of the record.
+    // bit-identical to the reference's sequential sweep.  `at` is the lane's stream position at slot c0 + t_id,
+    // `solve(rec, at)` applies a record to the bodies in shared memory, `ready(rec)` returns a word of the record.
     // On the GPU every lane fetches the record of its NEXT level-step before it solves the current one, so the
-    // L2/HBM latency of the record stream is off the dependent chain.  The fetch address is made to depend on a
-    // word of the CURRENT record (`& zero`, a run-time zero): all record loads share one hardware scoreboard, so
-    // without that order the first use of the current record would also wait for the loads just issued.  The
-    // table reader moves its look-ahead word in at the same point, for the same reason.
+    // L2/HBM latency of the record stream is off the dependent chain.  The advance of the stream positions is made to
+    // depend on a word of the CURRENT record (`& zero`, a run-time zero -- it has to be a real instruction: the hardware
+    // scheduler's view is the machine code): all loads of the loop share one hardware scoreboard, so without that order
+    // the first use of the current record would also wait for the loads just issued.  The table reader moves its
+    // look-ahead word in at the same point, for the same reason.
 #if defined(B2B_VAR_NOSYNC)
 #define B2B_LEVEL_SYNC() ((void)0)
 #else
 #define B2B_LEVEL_SYNC() __syncwarp(t_mask)
 #endif
-    template <class Rec, class Load, class Solve, class Ready>
-    B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, uint32_t zero, Load load, Solve solve, Ready ready)
+    template <class Rec, class Stream, class Solve, class Ready>
+    B2B_D void level_sweep(int c0, int c1, const uint32_t* lv, uint32_t zero, Stream at, Solve solve, Ready ready)
     {
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+r"(zero));                              // (kept in a register: not re-read from the parameters every level-step)
         lv_reader rd;
         rd.start(lv);
-#if defined(__CUDA_ARCH__)
         // two record buffers used alternately (the loop body is written out twice), so nothing is copied
         int begin = c0, cnt = rd.take();
         bool act = t_id < cnt;
+        Stream sa = at, sb = at;
         Rec ra, rb;
-        if (act) load(begin + t_id, ra);
+        if (act) sa.load(ra);
+#define B2B_LEVEL_STEP(CUR, SCUR, NXT, SNXT)                                                                          \
+            {                                                                                                         \
+                /* (an idle lane's record is whatever its registers held: only its arrival matters) */                \
+                const int adv = cnt + (int)(ready(CUR) & zero);                                                       \
+                const int nbegin = begin + adv;                                                                       \
+                B2B_TSTAMP(0, nbegin);                                                                                \
+                const int ncnt = rd.take();                                                                           \
+                const bool more = (nbegin < c1) & (ncnt != 0);      /* a zero count never occurs in a valid table */  \
+                const bool nact = more & (t_id < ncnt);                                                               \
+                SNXT = SCUR.ahead(adv);                                                                               \
+                if (nact) { SNXT.prefetch(); SNXT.load(NXT); }                                                        \
+                B2B_TSTAMP(1, ncnt);                                                                                  \
+                if (act) solve(CUR, SCUR);                                                                            \
+                B2B_TSTAMP(4, 0);                                                                                     \
+                B2B_LEVEL_SYNC();                                                                                     \
+                B2B_TSTAMP(5, 0);                                                                                     \
+                B2B_TSTAMP(6, 0);                                                                                     \
+                if (!more) break;                                                                                     \
+                act = nact; begin = nbegin; cnt = ncnt;                                                               \
+            }
         for (;;) {
-            {
-                // (an idle lane's record is whatever its registers held: `& zero` makes that harmless)
-                const int nbegin = begin + cnt + (int)(ready(ra) & zero);
-                B2B_TSTAMP(0, nbegin);
-                const int ncnt = rd.take();
-                const bool more = (nbegin < c1) & (ncnt != 0);      // a zero count never occurs in a valid table
-                const bool nact = more & (t_id < ncnt);
-                if (nact) load(nbegin + t_id, rb);
-                B2B_TSTAMP(1, ncnt);
-                if (act) solve(ra, begin + t_id);
-                B2B_TSTAMP(4, 0);
-                B2B_LEVEL_SYNC();
-                B2B_TSTAMP(5, 0);
-                B2B_TSTAMP(6, 0);
-                if (!more) break;
-                act = nact; begin = nbegin; cnt = ncnt;
-            }
-            {
-                const int nbegin = begin + cnt + (int)(ready(rb) & zero);
-                B2B_TSTAMP(0, nbegin);
-                const int ncnt = rd.take();
-                const bool more = (nbegin < c1) & (ncnt != 0);
-                const bool nact = more & (t_id < ncnt);
-                if (nact) load(nbegin + t_id, ra);
-                B2B_TSTAMP(1, ncnt);
-                if (act) solve(rb, begin + t_id);
-                B2B_TSTAMP(4, 0);
-                B2B_LEVEL_SYNC();
-                B2B_TSTAMP(5, 0);
-                B2B_TSTAMP(6, 0);
-                if (!more) break;
-                act = nact; begin = nbegin; cnt = ncnt;
-            }
+            B2B_LEVEL_STEP(ra, sa, rb, sb)
+            B2B_LEVEL_STEP(rb, sb, ra, sa)
         }
+#undef B2B_LEVEL_STEP
+        at.prefetch_first(t_n);                                     // the sweep that follows, if any
 #else
-        (void)zero; (void)ready;
-        for (int begin = c0; begin < c1;) {
-            const int cnt = rd.take();
-            if (cnt == 0) break;
-            for (int j = 0; j < cnt; ++j) { Rec r; load(begin + j, r); solve(r, begin + j); }
-            begin += cnt;
-        }
+        // (sequential build: slot order is the level-step order; the table is the GPU schedule's business)
+        (void)ready; (void)lv; (void)zero;
+        Stream s = at;
+        for (int slot = c0; slot < c1; ++slot) { Rec r; s.load(r); solve(r, s); s = s.ahead(1); }
 #endif
     }
 
@@ -1188,24 +1200,6 @@ template <class real> struct world_step {
         p[2] = o;
     }
 
-    // A constraint's velocity-phase data in registers.
-    // (members: the quads v0..v7 / p0..p4 of the layout above)
-    struct vrec { quad q0, q1, q2, q3, q4, q5, q6, q7, qi; };
-    B2B_D void load_vrec(int slot, vrec& r)
-    {
-        const oct* q = vel_rec(slot);
-        const oct o0 = q[0], o1 = q[1], o2 = q[2], o3 = q[3];
-        r.q0 = o0.lo; r.q1 = o0.hi; r.q2 = o1.lo; r.q3 = o1.hi; r.q4 = o2.lo; r.q5 = o2.hi; r.q6 = o3.lo; r.q7 = o3.hi;
-        r.qi = *imp_rec(slot);
-    }
-    struct prec { quad q7, q8, q9, q10, q11; };
-    B2B_D void load_prec(int slot, prec& r)
-    {
-        const oct* q = pos_rec(slot);
-        const oct o0 = q[0], o1 = q[1], o2 = q[2];
-        r.q7 = o0.lo; r.q8 = o0.hi; r.q9 = o1.lo; r.q10 = o1.hi; r.q11 = o2.lo;
-    }
-
     // ContactSolver.warm_start for one slot (contact.py:498-525)
     B2B_D void constraint_warm_start(const vrec& r)
     {
@@ -1234,7 +1228,7 @@ template <class real> struct world_step {
     // ContactSolver.solve_velocity_constraints for one slot (contact.py:527-799).  The accumulated impulses go
     // back to the slot's impulse row, or -- on the last velocity iteration -- straight to the contact's manifold
     // (store_impulses, contact.py:801-806: only as many points as the velocity rows kept).
-    B2B_D void constraint_solve_velocity(const vrec& r, int slot, bool last)
+    B2B_D void constraint_solve_velocity(const vrec& r, quad* imp_row, bool last)
     {
         const quad q0 = r.q0, q1 = r.q1, q3 = r.q3, q7 = r.q6;
         quad qi = r.qi;
@@ -1323,7 +1317,7 @@ template <class real> struct world_step {
         if (!stat_a) state_set(ba, va.x, va.y, wa);
         if (!stat_b) state_set(bb, vb.x, vb.y, wb);
         if (!last) {
-            *imp_rec(slot) = qi;
+            *imp_row = qi;
         } else {
             real* imp = c_imp + 4 * (size_t)(vinfo >> VINFO_CI_SHIFT);
             if (n_vel > 1) stq(imp, qi);
@@ -1610,13 +1604,13 @@ template <class real> struct world_step {
             if (joint) { c0 = 0; c1 = n_lc; }
             if (c1 == c0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
-            auto fetch = [&](int s, vrec& e) { prefetch_vel(s, c0, c1); load_vrec(s, e); };
+            const vel_stream vat = vel_stream_at(c0 + t_id);
             auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
-            if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int) { constraint_warm_start(e); }, vready);
+            if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream&) { constraint_warm_start(e); }, vready);
             B2B_PROF(PROF_S_WARM, t);
             for (int it = 0; it < sp.vel_iters; ++it) {
                 const bool last = (it + 1 == sp.vel_iters);
-                level_sweep<vrec>(c0, c1, lv, sp.zero, fetch, [&](const vrec& e, int s) { constraint_solve_velocity(e, s, last); }, vready);
+                level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);
             }
             B2B_PROF(PROF_S_VELOCITY, t);
             // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
@@ -1701,8 +1695,8 @@ template <class real> struct world_step {
                 for (int it = 0; it < sp.pos_iters; ++it) {
                     real my_min = real(0);
                     ++used;
-                    level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
-                                      [&](const prec& e, int) { my_min = pymin(my_min, constraint_solve_position(e)); },
+                    level_sweep<prec>(c0, c1, lv, sp.zero, pos_stream_at(c0 + t_id),
+                                      [&](const prec& e, const pos_stream&) { my_min = pymin(my_min, constraint_solve_position(e)); },
                                       [&](const prec& e) { return bits_of_real(e.q10.z); });
                     real all_min = my_min;
 #if defined(__CUDA_ARCH__)
@@ -1746,8 +1740,8 @@ template <class real> struct world_step {
                     }
                     const uint32_t skip = solved_mask;
                     real my_neg = real(0);
-                    level_sweep<prec>(c0, c1, lv, sp.zero, [&](int s, prec& e) { prefetch_pos(s, c0, c1); load_prec(s, e); },
-                                      [&](const prec& e, int) {
+                    level_sweep<prec>(c0, c1, lv, sp.zero, pos_stream_at(c0 + t_id),
+                                      [&](const prec& e, const pos_stream&) {
                                           const int ci = (int)((bits_of_real(e.q10.w) >> INFO_ISLAND_SHIFT) & 31u);   // 0 unless joint
                                           if (joint && ((skip >> ci) & 1u)) return;
                                           const real neg = -constraint_solve_position(e);
