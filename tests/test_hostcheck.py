@@ -76,7 +76,7 @@ def test_settled_pile_sleep_event_keeps_the_island_lists():
 @pytest.mark.parametrize("scene,world,dt,vi,pi,steps", [("pyramid", 1, 1 / 60, 8, 3, 150), ("mixed", 1, 1 / 60, 8, 3, 100),
                                                          ("features", 1, 1 / 60, 8, 3, 150), ("vertical_stack", 1, 1 / 60, 10, 10, 100)])
 def test_host_compiled_fp32_step_tracks_the_oracle_one_step_at_a_time(scene, world, dt, vi, pi, steps):
-    """The fp32 instantiation (Jacobian-form velocity rows, 96-byte records) against the oracle, teacher-forced: from the
+    """The fp32 instantiation against the oracle, teacher-forced: from the
     oracle's fp32-rounded state ONE step agrees to fp32 accuracy and gives the same integer outputs except on tie steps.
     CPU pre-check of the arithmetic the -m gpu P-step tier grades on the device."""
     from pypybox2d_b200 import schema
