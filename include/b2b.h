@@ -39,6 +39,8 @@ typedef enum b2b_error {
 #define B2B_STEP_TIME 2u      /* b2b_step flags: bracket every kernel with CUDA events (see b2b_kernel_ms) */
 #define B2B_STEP_NO_FLAT 16u  /* b2b_step flags: run the narrowphase inside the per-world plan kernel (debugging) */
 #define B2B_STEP_GROUP_KERNEL 32u /* b2b_step flags: run the group-capable position kernel even if no world has a joint island schedule (testing) */
+#define B2B_STEP_CONTINUOUS 128u /* b2b_step_host flags: some world of the batch has continuous collision on (w_flags WORLD_CONTINUOUS), so body
+                                   * state is final only after the last kernel of the step: read it back after World.solve_toi */
 /* bits 8..15: reserved */
 
 typedef struct b2b_caps {
@@ -86,10 +88,13 @@ int b2b_bind(b2b_ctx* ctx, const b2b_buffers* buffers);
 int b2b_init_proxies(b2b_ctx* ctx, void* stream);
 
 /* World.step(dt, vel_iters, pos_iters), n_steps times, for every world of the batch
- * (world.py:307-354 with continuous_physics=False): find_new_contacts if new fixtures,
+ * (world.py:307-354): find_new_contacts if new fixtures,
  * ContactManager.collide (contact_manager.py:174-223), World._solve (world.py:475-592: island DFS,
  * Island.solve island.py:65-179, ContactSolver contact.py:375-864, fixture synchronisation,
- * find_new_contacts contact_manager.py:102-158), clear forces.
+ * find_new_contacts contact_manager.py:102-158), and for the worlds whose w_flags carry WORLD_CONTINUOUS
+ * (World(continuous_physics=True), the reference's default) World.solve_toi (world.py:594-821: time_of_impact toi.py:223-391
+ * on shape_distance distance.py:419-561, Island.solve_toi island.py:181-243, solve_toi_position_constraints
+ * contact.py:866-933), clear forces.
  * inv_dt0 is World._inv_dt0 before the first of the n_steps (0 for a fresh world); the first step
  * uses dt_ratio = inv_dt0 * dt, later ones (1/dt) * dt, both evaluated in double as world.py:323-328.
  * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */

@@ -898,35 +898,9 @@ static inline v2 rel_vel(v2 vb, double wb, v2 rb, v2 va, double wa, v2 ra)
     return vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
 }
 
-static void island_solve(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts,
-                         double dt, double dt_ratio, int vel_iters, int pos_iters, int* pos_iters_used)
+/* ContactSolver.__init__: contact.py:376-412 (warm: step.warm_starting, contact_util.py:260-265) */
+static void solver_ctor(const orc_world* w, cc_t* C, const int* contacts, int ncontacts, int warm, double dt_ratio)
 {
-    pos_t* P = (pos_t*)malloc(sizeof(pos_t) * (size_t)(nbodies + 1));
-    vel_t* Vv = (vel_t*)malloc(sizeof(vel_t) * (size_t)(nbodies + 1));
-    cc_t* C = (cc_t*)malloc(sizeof(cc_t) * (size_t)(ncontacts + 1));
-    v2 gravity = V(w->w_gravity[0], w->w_gravity[1]);
-    int warm = (w->w_flags[0] & W_WARM_START) != 0;
-
-    /* island.py:71-95 */
-    for (int i = 0; i < nbodies; ++i) {
-        int b = bodies[i];
-        double* pos = w->b_pos + 4 * (size_t)b; double* vel = w->b_vel + 4 * (size_t)b;
-        v2 c = V(pos[0], pos[1]); double a = pos[2];
-        v2 v = V(vel[0], vel[1]); double wv = vel[2];
-        w->b_pos0[4 * b + 0] = c.x; w->b_pos0[4 * b + 1] = c.y; w->b_pos0[4 * b + 2] = a;
-        if (body_type(w, b) == T_DYNAMIC) {
-            const double* mass = w->b_mass + 4 * (size_t)b; const double* damp = w->b_damp + 4 * (size_t)b;
-            v2 force = V(w->b_force[2 * b], w->b_force[2 * b + 1]);
-            v2 acc = vadd(vscale(damp[2], gravity), vscale(mass[0], force));
-            v = vadd(v, vscale(dt, acc));
-            wv = wv + dt * mass[1] * vel[3];
-            v = vscale(pyclamp(1.0 - dt * damp[0], 0.0, 1.0), v);
-            wv = wv * pyclamp(1.0 - dt * damp[1], 0.0, 1.0);
-        }
-        P[i].c = c; P[i].a = a; Vv[i].v = v; Vv[i].w = wv;
-    }
-
-    /* ContactSolver.__init__: contact.py:376-412 */
     for (int k = 0; k < ncontacts; ++k) {
         int ci = contacts[k];
         cc_t* cc = &C[k];
@@ -952,8 +926,11 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
             else { cc->p[j].normal_impulse = imp[2 * j]; cc->p[j].tangent_impulse = imp[2 * j + 1]; }
         }
     }
+}
 
-    /* initialize_velocity_constraints: contact.py:414-496 */
+/* initialize_velocity_constraints: contact.py:414-496 */
+static void solver_init_velocity(cc_t* C, int ncontacts, const pos_t* P, const vel_t* Vv)
+{
     for (int k = 0; k < ncontacts; ++k) {
         cc_t* cc = &C[k];
         double ma = cc->ima, mb = cc->imb, ia = cc->iia, ib = cc->iib;
@@ -997,6 +974,124 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
             }
         }
     }
+}
+
+/* solve_velocity_constraints: contact.py:527-799 (one sweep) */
+static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
+{
+    for (int k = 0; k < ncontacts; ++k) {
+        cc_t* cc = &C[k];
+        double ima = cc->ima, imb = cc->imb, iia = cc->iia, iib = cc->iib;
+        v2 normal = cc->normal, tangent = vcross_s(normal, 1.0);
+        v2 va = Vv[cc->ia].v, vb = Vv[cc->ib].v; double wa = Vv[cc->ia].w, wb = Vv[cc->ib].w;
+        double friction = cc->friction;
+        for (int j = 0; j < cc->npoints; ++j) {
+            vcp_t* p = &cc->p[j];
+            v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
+            double vt = vdot(dv, tangent);
+            double lambda = p->tangent_mass * (-vt);
+            double max_friction = friction * p->normal_impulse;
+            double new_impulse = pyclamp(p->tangent_impulse + lambda, -max_friction, max_friction);
+            lambda = new_impulse - p->tangent_impulse;
+            v2 Pv = vscale(lambda, tangent);
+            va = vsub(va, vscale(ima, Pv));
+            wa = wa - iia * vcross(p->ra, Pv);
+            vb = vadd(vb, vscale(imb, Pv));
+            wb = wb + iib * vcross(p->rb, Pv);
+            p->tangent_impulse = new_impulse;
+        }
+        if (cc->npoints == 1) {
+            vcp_t* p = &cc->p[0];
+            v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
+            double vn = vdot(dv, normal);
+            double lambda = -p->normal_mass * (vn - p->velocity_bias);
+            double t = p->normal_impulse + lambda;
+            double new_impulse = PYMAX(t, 0.0);
+            lambda = new_impulse - p->normal_impulse;
+            v2 Pv = vscale(lambda, normal);
+            va = vsub(va, vscale(ima, Pv));
+            wa = wa - iia * vcross(p->ra, Pv);
+            vb = vadd(vb, vscale(imb, Pv));
+            wb = wb + iib * vcross(p->rb, Pv);
+            p->normal_impulse = new_impulse;
+        } else if (cc->npoints == 2) {
+            vcp_t *cp1 = &cc->p[0], *cp2 = &cc->p[1];
+            v2 a = V(cp1->normal_impulse, cp2->normal_impulse);
+            v2 dv1 = rel_vel(vb, wb, cp1->rb, va, wa, cp1->ra);
+            v2 dv2 = rel_vel(vb, wb, cp2->rb, va, wa, cp2->ra);
+            double vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+            v2 b = V(vn1 - cp1->velocity_bias, vn2 - cp2->velocity_bias);
+            /* b -= K * a  with K = Mat22((k11,k12),(k12,k22)) */
+            v2 Ka = V(cc->k11 * a.x + cc->k12 * a.y, cc->k12 * a.x + cc->k22 * a.y);
+            b = vsub(b, Ka);
+            v2 x; int solved = 0;
+            /* case 1 */
+            {
+                v2 nb = V(cc->nm_c1x * b.x + cc->nm_c2x * b.y, cc->nm_c1y * b.x + cc->nm_c2y * b.y);
+                x = vneg(nb);
+                if (x.x >= 0.0 && x.y >= 0.0) solved = 1;
+            }
+            if (!solved) {                                   /* case 2 */
+                x = V(-cp1->normal_mass * b.x, 0.0);
+                double vn2c = cc->k12 * x.x + b.y;          /* K.col1.y */
+                if (x.x >= 0.0 && vn2c >= 0.0) solved = 1;
+            }
+            if (!solved) {                                   /* case 3 */
+                x = V(0.0, -cp2->normal_mass * b.y);
+                double vn1c = cc->k12 * x.y + b.x;          /* K.col2.x */
+                if (x.y >= 0.0 && vn1c >= 0.0) solved = 1;
+            }
+            if (!solved) {                                   /* case 4 */
+                x = V(0.0, 0.0);
+                if (b.x >= 0.0 && b.y >= 0.0) solved = 1;
+            }
+            if (solved) {
+                v2 d = vsub(x, a);
+                v2 p1 = vscale(d.x, normal), p2 = vscale(d.y, normal);
+                v2 p12 = vadd(p1, p2);
+                va = vsub(va, vscale(ima, p12));
+                wa = wa - iia * (vcross(cp1->ra, p1) + vcross(cp2->ra, p2));
+                vb = vadd(vb, vscale(imb, p12));
+                wb = wb + iib * (vcross(cp1->rb, p1) + vcross(cp2->rb, p2));
+                cp1->normal_impulse = x.x;
+                cp2->normal_impulse = x.y;
+            }
+        }
+        Vv[cc->ia].v = va; Vv[cc->ia].w = wa;
+        Vv[cc->ib].v = vb; Vv[cc->ib].w = wb;
+    }
+}
+
+static void island_solve(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts,
+                         double dt, double dt_ratio, int vel_iters, int pos_iters, int* pos_iters_used)
+{
+    pos_t* P = (pos_t*)malloc(sizeof(pos_t) * (size_t)(nbodies + 1));
+    vel_t* Vv = (vel_t*)malloc(sizeof(vel_t) * (size_t)(nbodies + 1));
+    cc_t* C = (cc_t*)malloc(sizeof(cc_t) * (size_t)(ncontacts + 1));
+    v2 gravity = V(w->w_gravity[0], w->w_gravity[1]);
+    int warm = (w->w_flags[0] & W_WARM_START) != 0;
+
+    /* island.py:71-95 */
+    for (int i = 0; i < nbodies; ++i) {
+        int b = bodies[i];
+        double* pos = w->b_pos + 4 * (size_t)b; double* vel = w->b_vel + 4 * (size_t)b;
+        v2 c = V(pos[0], pos[1]); double a = pos[2];
+        v2 v = V(vel[0], vel[1]); double wv = vel[2];
+        w->b_pos0[4 * b + 0] = c.x; w->b_pos0[4 * b + 1] = c.y; w->b_pos0[4 * b + 2] = a;
+        if (body_type(w, b) == T_DYNAMIC) {
+            const double* mass = w->b_mass + 4 * (size_t)b; const double* damp = w->b_damp + 4 * (size_t)b;
+            v2 force = V(w->b_force[2 * b], w->b_force[2 * b + 1]);
+            v2 acc = vadd(vscale(damp[2], gravity), vscale(mass[0], force));
+            v = vadd(v, vscale(dt, acc));
+            wv = wv + dt * mass[1] * vel[3];
+            v = vscale(pyclamp(1.0 - dt * damp[0], 0.0, 1.0), v);
+            wv = wv * pyclamp(1.0 - dt * damp[1], 0.0, 1.0);
+        }
+        P[i].c = c; P[i].a = a; Vv[i].v = v; Vv[i].w = wv;
+    }
+
+    solver_ctor(w, C, contacts, ncontacts, warm, dt_ratio);
+    solver_init_velocity(C, ncontacts, P, Vv);
 
     /* warm_start: contact.py:498-525 */
     if (warm) {
@@ -1017,90 +1112,7 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
         }
     }
 
-    /* solve_velocity_constraints: contact.py:527-799 */
-    for (int it = 0; it < vel_iters; ++it) {
-        for (int k = 0; k < ncontacts; ++k) {
-            cc_t* cc = &C[k];
-            double ima = cc->ima, imb = cc->imb, iia = cc->iia, iib = cc->iib;
-            v2 normal = cc->normal, tangent = vcross_s(normal, 1.0);
-            v2 va = Vv[cc->ia].v, vb = Vv[cc->ib].v; double wa = Vv[cc->ia].w, wb = Vv[cc->ib].w;
-            double friction = cc->friction;
-            for (int j = 0; j < cc->npoints; ++j) {
-                vcp_t* p = &cc->p[j];
-                v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
-                double vt = vdot(dv, tangent);
-                double lambda = p->tangent_mass * (-vt);
-                double max_friction = friction * p->normal_impulse;
-                double new_impulse = pyclamp(p->tangent_impulse + lambda, -max_friction, max_friction);
-                lambda = new_impulse - p->tangent_impulse;
-                v2 Pv = vscale(lambda, tangent);
-                va = vsub(va, vscale(ima, Pv));
-                wa = wa - iia * vcross(p->ra, Pv);
-                vb = vadd(vb, vscale(imb, Pv));
-                wb = wb + iib * vcross(p->rb, Pv);
-                p->tangent_impulse = new_impulse;
-            }
-            if (cc->npoints == 1) {
-                vcp_t* p = &cc->p[0];
-                v2 dv = rel_vel(vb, wb, p->rb, va, wa, p->ra);
-                double vn = vdot(dv, normal);
-                double lambda = -p->normal_mass * (vn - p->velocity_bias);
-                double t = p->normal_impulse + lambda;
-                double new_impulse = PYMAX(t, 0.0);
-                lambda = new_impulse - p->normal_impulse;
-                v2 Pv = vscale(lambda, normal);
-                va = vsub(va, vscale(ima, Pv));
-                wa = wa - iia * vcross(p->ra, Pv);
-                vb = vadd(vb, vscale(imb, Pv));
-                wb = wb + iib * vcross(p->rb, Pv);
-                p->normal_impulse = new_impulse;
-            } else if (cc->npoints == 2) {
-                vcp_t *cp1 = &cc->p[0], *cp2 = &cc->p[1];
-                v2 a = V(cp1->normal_impulse, cp2->normal_impulse);
-                v2 dv1 = rel_vel(vb, wb, cp1->rb, va, wa, cp1->ra);
-                v2 dv2 = rel_vel(vb, wb, cp2->rb, va, wa, cp2->ra);
-                double vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
-                v2 b = V(vn1 - cp1->velocity_bias, vn2 - cp2->velocity_bias);
-                /* b -= K * a  with K = Mat22((k11,k12),(k12,k22)) */
-                v2 Ka = V(cc->k11 * a.x + cc->k12 * a.y, cc->k12 * a.x + cc->k22 * a.y);
-                b = vsub(b, Ka);
-                v2 x; int solved = 0;
-                /* case 1 */
-                {
-                    v2 nb = V(cc->nm_c1x * b.x + cc->nm_c2x * b.y, cc->nm_c1y * b.x + cc->nm_c2y * b.y);
-                    x = vneg(nb);
-                    if (x.x >= 0.0 && x.y >= 0.0) solved = 1;
-                }
-                if (!solved) {                                   /* case 2 */
-                    x = V(-cp1->normal_mass * b.x, 0.0);
-                    double vn2c = cc->k12 * x.x + b.y;          /* K.col1.y */
-                    if (x.x >= 0.0 && vn2c >= 0.0) solved = 1;
-                }
-                if (!solved) {                                   /* case 3 */
-                    x = V(0.0, -cp2->normal_mass * b.y);
-                    double vn1c = cc->k12 * x.y + b.x;          /* K.col2.x */
-                    if (x.y >= 0.0 && vn1c >= 0.0) solved = 1;
-                }
-                if (!solved) {                                   /* case 4 */
-                    x = V(0.0, 0.0);
-                    if (b.x >= 0.0 && b.y >= 0.0) solved = 1;
-                }
-                if (solved) {
-                    v2 d = vsub(x, a);
-                    v2 p1 = vscale(d.x, normal), p2 = vscale(d.y, normal);
-                    v2 p12 = vadd(p1, p2);
-                    va = vsub(va, vscale(ima, p12));
-                    wa = wa - iia * (vcross(cp1->ra, p1) + vcross(cp2->ra, p2));
-                    vb = vadd(vb, vscale(imb, p12));
-                    wb = wb + iib * (vcross(cp1->rb, p1) + vcross(cp2->rb, p2));
-                    cp1->normal_impulse = x.x;
-                    cp2->normal_impulse = x.y;
-                }
-            }
-            Vv[cc->ia].v = va; Vv[cc->ia].w = wa;
-            Vv[cc->ib].v = vb; Vv[cc->ib].w = wb;
-        }
-    }
+    for (int it = 0; it < vel_iters; ++it) solver_velocity_sweep(C, ncontacts, Vv);
 
     /* store_impulses: contact.py:801-806 (zip over vc.points, which may be shorter) */
     for (int k = 0; k < ncontacts; ++k) {
@@ -1283,6 +1295,577 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
     cm_find_new_contacts(w);
 }
 
+
+/* =====================================================================================================
+ * Continuous collision (World(continuous_physics=True), the reference's default): world.py:594-821,
+ * island.py:181-243, contact.py:866-933, toi.py:46-391, distance.py:39-561, common.py:871-923,
+ * body.py:930-937.  No sensors, no sub_stepping.
+ * ===================================================================================================== */
+#define W_CONTINUOUS       0x20u
+#define BODY_BULLET        0x40u
+#define MAX_SUB_STEPS      8         /* settings.py:73 */
+#define MAX_TOI_CONTACTS   32        /* settings.py:79 */
+#define TOI_MAX_ITERS      20        /* settings.py:82 */
+#define TOI_BAUMGARTE      0.75      /* settings.py:110 */
+#define DISTANCE_MAX_ITERS 20        /* settings.py:129 */
+
+/* Sweep: common.py:871-923.  alpha0 lives in the spare column of b_pos0. */
+typedef struct { v2 lc, c0, c; double a0, a, alpha0; } sweep_t;
+static sweep_t sweep_load(const orc_world* w, int b)
+{
+    sweep_t s;
+    s.lc = V(w->b_mass[4 * b + 2], w->b_mass[4 * b + 3]);
+    s.c0 = V(w->b_pos0[4 * b], w->b_pos0[4 * b + 1]); s.a0 = w->b_pos0[4 * b + 2]; s.alpha0 = w->b_pos0[4 * b + 3];
+    s.c = V(w->b_pos[4 * b], w->b_pos[4 * b + 1]); s.a = w->b_pos[4 * b + 2];
+    return s;
+}
+static void sweep_store(orc_world* w, int b, const sweep_t* s)
+{
+    w->b_pos0[4 * b] = s->c0.x; w->b_pos0[4 * b + 1] = s->c0.y; w->b_pos0[4 * b + 2] = s->a0; w->b_pos0[4 * b + 3] = s->alpha0;
+    w->b_pos[4 * b] = s->c.x; w->b_pos[4 * b + 1] = s->c.y; w->b_pos[4 * b + 2] = s->a;
+}
+/* Sweep.get_transform: common.py:893-904 */
+static xform sweep_xf(const sweep_t* s, double beta)
+{
+    v2 p = vadd(vscale(1.0 - beta, s->c0), vscale(beta, s->c));
+    double angle = (1.0 - beta) * s->a0 + beta * s->a;
+    return xf_from_sweep(p, angle, s->lc);
+}
+/* Sweep.advance: common.py:906-915 */
+static void sweep_advance(sweep_t* s, double alpha)
+{
+    double beta = (alpha - s->alpha0) / (1.0 - s->alpha0);
+    s->c0 = vadd(vscale(1.0 - beta, s->c0), vscale(beta, s->c));
+    s->a0 = (1.0 - beta) * s->a0 + beta * s->a;
+    s->alpha0 = alpha;
+}
+/* Sweep.normalize: common.py:917-923 */
+static void sweep_normalize(sweep_t* s)
+{
+    double d = 2.0 * PI_ * floor(s->a0 / (2.0 * PI_));
+    s->a0 -= d;
+    s->a -= d;
+}
+/* Body._synchronize_transform: body.py:906-908 */
+static void body_sync_transform(orc_world* w, int b)
+{
+    v2 lc = V(w->b_mass[4 * b + 2], w->b_mass[4 * b + 3]);
+    xform t = xf_from_sweep(V(w->b_pos[4 * b], w->b_pos[4 * b + 1]), w->b_pos[4 * b + 2], lc);
+    w->b_xf[4 * b + 0] = t.p.x; w->b_xf[4 * b + 1] = t.p.y; w->b_xf[4 * b + 2] = t.c1.x; w->b_xf[4 * b + 3] = t.c1.y;
+}
+/* Body._advance: body.py:930-937 (the rotation is rebuilt from the angle, the position from the centre: the same
+ * arithmetic as _synchronize_transform) */
+static void body_advance(orc_world* w, int b, double alpha)
+{
+    sweep_t s = sweep_load(w, b);
+    sweep_advance(&s, alpha);
+    s.c = s.c0; s.a = s.a0;
+    sweep_store(w, b, &s);
+    body_sync_transform(w, b);
+}
+
+/* DistanceProxy: distance.py:354-409 */
+typedef struct { int count; double radius; const double* v; } dproxy;
+static dproxy dproxy_get(const orc_world* w, int shape_row)
+{
+    shape_t s = shape_get(w, shape_row);
+    dproxy p; p.v = s.d; p.radius = s.radius;
+    p.count = (s.type == S_CIRCLE) ? 1 : (s.type == S_POLYGON) ? s.count : 2;
+    return p;
+}
+static inline v2 dvert(const dproxy* p, int i) { return V(p->v[2 * i], p->v[2 * i + 1]); }
+/* get_support: distance.py:393-396 -- dots.index(max(dots)): the first index holding the maximum */
+static int dproxy_support(const dproxy* p, v2 d)
+{
+    int best = 0; double bv = vdot(dvert(p, 0), d);
+    for (int i = 1; i < p->count; ++i) { double v = vdot(dvert(p, i), d); if (v > bv) { bv = v; best = i; } }
+    return best;
+}
+
+typedef struct { double metric; int count; int ia[3], ib[3]; } simplex_cache;
+typedef struct { v2 wa, wb, w; double a; int ia, ib; } svert;
+static inline double vdist(v2 a, v2 b) { v2 c = vsub(a, b); return sqrt(sq(c.x) + sq(c.y)); }   /* common.py:947-949 */
+
+/* Simplex: distance.py:76-352.  The reference holds its three vertices as attributes that solve2 / solve3 REBIND to copies
+ * (self._v1 = copy(self._v2)), while shape_distance keeps writing new support points through the list it took BEFORE the
+ * loop (vertices = simplex.vertices, distance.py:458): after a rebind the list entry and the attribute are different
+ * objects.  Restated with explicit object identities: `pool` are the objects, cur[k] the attribute _v(k+1), lst[k] the
+ * entry of the list taken before the loop. */
+typedef struct { svert pool[3 + 2 * DISTANCE_MAX_ITERS + 4]; int npool; int cur[3], lst[3]; int count; } simplex_t;
+static int simplex_copy(simplex_t* s, int src) { s->pool[s->npool] = s->pool[src]; return s->npool++; }
+static double simplex_metric(const simplex_t* s)                                   /* distance.py:189-203 */
+{
+    const svert *v1 = &s->pool[s->cur[0]], *v2_ = &s->pool[s->cur[1]], *v3 = &s->pool[s->cur[2]];
+    if (s->count == 1) return 0.0;
+    if (s->count == 2) return vdist(v1->w, v2_->w);
+    return vcross(vsub(v2_->w, v1->w), vsub(v3->w, v1->w));
+}
+static void simplex_solve2(simplex_t* s)                                           /* distance.py:205-253 */
+{
+    svert *v1 = &s->pool[s->cur[0]], *v2_ = &s->pool[s->cur[1]];
+    v2 w1 = v1->w, w2 = v2_->w, e12 = vsub(w2, w1);
+    double d12_2 = -vdot(w1, e12);
+    if (d12_2 <= 0.0) { v1->a = 1.0; s->count = 1; return; }
+    double d12_1 = vdot(w2, e12);
+    if (d12_1 <= 0.0) { v2_->a = 1.0; s->count = 1; s->cur[0] = simplex_copy(s, s->cur[1]); return; }
+    double inv_d12 = 1.0 / (d12_1 + d12_2);
+    v1->a = d12_1 * inv_d12; v2_->a = d12_2 * inv_d12; s->count = 2;
+}
+static void simplex_solve3(simplex_t* s)                                           /* distance.py:255-352 */
+{
+    svert *v1 = &s->pool[s->cur[0]], *v2_ = &s->pool[s->cur[1]], *v3 = &s->pool[s->cur[2]];
+    v2 w1 = v1->w, w2 = v2_->w, w3 = v3->w;
+    v2 e12 = vsub(w2, w1);
+    double w1e12 = vdot(w1, e12), w2e12 = vdot(w2, e12), d12_1 = w2e12, d12_2 = -w1e12;
+    v2 e13 = vsub(w3, w1);
+    double w1e13 = vdot(w1, e13), w3e13 = vdot(w3, e13), d13_1 = w3e13, d13_2 = -w1e13;
+    v2 e23 = vsub(w3, w2);
+    double w2e23 = vdot(w2, e23), w3e23 = vdot(w3, e23), d23_1 = w3e23, d23_2 = -w2e23;
+    double n123 = vcross(e12, e13);
+    double d123_1 = n123 * vcross(w2, w3), d123_2 = n123 * vcross(w3, w1), d123_3 = n123 * vcross(w1, w2);
+    if (d12_2 <= 0.0 && d13_2 <= 0.0) { v1->a = 1.0; s->count = 1; return; }
+    if (d12_1 > 0.0 && d12_2 > 0.0 && d123_3 <= 0.0) {
+        double inv = 1.0 / (d12_1 + d12_2);
+        v1->a = d12_1 * inv; v2_->a = d12_2 * inv; s->count = 2; return;
+    }
+    if (d13_1 > 0.0 && d13_2 > 0.0 && d123_2 <= 0.0) {
+        double inv = 1.0 / (d13_1 + d13_2);
+        v1->a = d13_1 * inv; v3->a = d13_2 * inv; s->count = 2; s->cur[1] = simplex_copy(s, s->cur[2]); return;
+    }
+    if (d12_1 <= 0.0 && d23_2 <= 0.0) { v2_->a = 1.0; s->count = 1; s->cur[0] = simplex_copy(s, s->cur[1]); return; }
+    if (d13_1 <= 0.0 && d23_1 <= 0.0) { v3->a = 1.0; s->count = 1; s->cur[0] = simplex_copy(s, s->cur[2]); return; }
+    if (d23_1 > 0.0 && d23_2 > 0.0 && d123_1 <= 0.0) {
+        double inv = 1.0 / (d23_1 + d23_2);
+        v2_->a = d23_1 * inv; v3->a = d23_2 * inv; s->count = 2; s->cur[0] = simplex_copy(s, s->cur[2]); return;
+    }
+    double inv = 1.0 / (d123_1 + d123_2 + d123_3);
+    v1->a = d123_1 * inv; v2_->a = d123_2 * inv; v3->a = d123_3 * inv; s->count = 3;
+}
+
+/* shape_distance: distance.py:419-561.  Returns the distance; the cache is read and written. */
+static double shape_distance(const dproxy* pa, const dproxy* pb, const xform* xa, const xform* xb, int use_radii,
+                             simplex_cache* cache)
+{
+    simplex_t S; memset(&S, 0, sizeof(S));
+    S.npool = 3;
+    for (int k = 0; k < 3; ++k) { S.cur[k] = k; S.lst[k] = k; }
+    /* read_cache: distance.py:97-135 */
+    S.count = cache->count;
+    for (int i = 0; i < S.count; ++i) {
+        svert* v = &S.pool[S.cur[i]];
+        v->ia = cache->ia[i]; v->ib = cache->ib[i];
+        v->wa = xf_mul(xa, dvert(pa, v->ia));
+        v->wb = xf_mul(xb, dvert(pb, v->ib));
+        v->w = vsub(v->wb, v->wa);
+        v->a = 0.0;
+    }
+    if (S.count > 1) {
+        double metric1 = cache->metric, metric2 = simplex_metric(&S);
+        if (metric2 < (0.5 * metric1) || (2.0 * metric1) < metric2 || metric2 < EPS) S.count = 0;
+    }
+    if (S.count == 0) {
+        svert* v = &S.pool[S.cur[0]];
+        v->ia = 0; v->ib = 0;
+        v->wa = xf_mul(xa, dvert(pa, 0));
+        v->wb = xf_mul(xb, dvert(pb, 0));
+        v->w = vsub(v->wb, v->wa);
+        S.count = 1;
+    }
+    int iter = 0;
+    while (iter < DISTANCE_MAX_ITERS) {
+        int save_a[3], save_b[3], nsave = S.count;
+        for (int i = 0; i < nsave; ++i) { save_a[i] = S.pool[S.cur[i]].ia; save_b[i] = S.pool[S.cur[i]].ib; }
+        if (S.count == 2) simplex_solve2(&S);
+        else if (S.count == 3) { simplex_solve3(&S); break; }
+        /* search_direction: distance.py:152-169 */
+        v2 d;
+        if (S.count == 1) d = vneg(S.pool[S.cur[0]].w);
+        else {
+            v2 e12 = vsub(S.pool[S.cur[1]].w, S.pool[S.cur[0]].w);
+            double sgn = vcross(e12, vneg(S.pool[S.cur[0]].w));
+            d = (sgn > 0.0) ? scross(1.0, e12) : vcross_s(e12, 1.0);
+        }
+        if (vlen2(d) < EPS_SQR) break;
+        svert* vertex = &S.pool[S.lst[S.count]];
+        vertex->ia = dproxy_support(pa, rot_mul_t(xa, vneg(d)));
+        vertex->wa = xf_mul(xa, dvert(pa, vertex->ia));
+        vertex->ib = dproxy_support(pb, rot_mul_t(xb, d));
+        vertex->wb = xf_mul(xb, dvert(pb, vertex->ib));
+        vertex->w = vsub(vertex->wb, vertex->wa);
+        ++iter;
+        int dup = 0;
+        for (int i = 0; i < nsave; ++i) if (save_a[i] == vertex->ia && save_b[i] == vertex->ib) dup = 1;
+        if (dup) break;
+        S.count += 1;
+    }
+    /* witness_points: distance.py:171-187 */
+    const svert *v1 = &S.pool[S.cur[0]], *v2_ = &S.pool[S.cur[1]], *v3 = &S.pool[S.cur[2]];
+    v2 point_a, point_b;
+    if (S.count == 1) { point_a = v1->wa; point_b = v1->wb; }
+    else if (S.count == 2) {
+        point_a = vadd(vscale(v1->a, v1->wa), vscale(v2_->a, v2_->wa));
+        point_b = vadd(vscale(v1->a, v1->wb), vscale(v2_->a, v2_->wb));
+    } else {
+        point_a = vadd(vadd(vscale(v1->a, v1->wa), vscale(v2_->a, v2_->wa)), vscale(v3->a, v3->wa));
+        point_b = point_a;
+    }
+    double dist = vdist(point_a, point_b);
+    /* write_cache: distance.py:137-142 */
+    cache->metric = simplex_metric(&S);
+    cache->count = S.count;
+    for (int i = 0; i < S.count; ++i) { cache->ia[i] = S.pool[S.cur[i]].ia; cache->ib[i] = S.pool[S.cur[i]].ib; }
+    if (use_radii) {
+        double ra = pa->radius, rb = pb->radius;
+        if (dist > (ra + rb) && dist > EPS) dist -= ra + rb;
+        else dist = 0.0;
+    }
+    return dist;
+}
+
+/* SeparationFunction: toi.py:46-221 */
+enum { SEP_POINTS, SEP_FACE_A, SEP_FACE_B };
+typedef struct { const dproxy *pa, *pb; const sweep_t *sa, *sb; int type; v2 axis, local_point; } sepfn;
+static void sep_initialize(sepfn* f, const simplex_cache* cache, double t1)
+{
+    xform xa = sweep_xf(f->sa, t1), xb = sweep_xf(f->sb, t1);
+    int ia0 = cache->ia[0], ib0 = cache->ib[0];
+    if (cache->count == 1) {
+        /* toi.py:64-75: `s = self.axis.normalized` builds a new vector; the axis itself stays UN-normalised */
+        f->type = SEP_POINTS;
+        v2 point_a = xf_mul(&xa, dvert(f->pa, ia0)), point_b = xf_mul(&xb, dvert(f->pb, ib0));
+        f->axis = vsub(point_b, point_a);
+        return;
+    }
+    int ia1 = cache->ia[1], ib1 = cache->ib[1];
+    if (ia0 == ia1) {
+        f->type = SEP_FACE_B;
+        v2 b1 = dvert(f->pb, ib0), b2 = dvert(f->pb, ib1);
+        f->axis = vnorm(vcross_s(vsub(b2, b1), 1.0));
+        v2 normal = rot_mul(&xb, f->axis);
+        f->local_point = vscale(0.5, vadd(b1, b2));
+        v2 point_b = xf_mul(&xb, f->local_point);
+        v2 point_a = xf_mul(&xa, dvert(f->pa, ia0));
+        double s = vdot(vsub(point_a, point_b), normal);
+        if (s < 0.0) f->axis = vneg(f->axis);
+    } else {
+        f->type = SEP_FACE_A;
+        v2 a1 = dvert(f->pa, ia0), a2 = dvert(f->pa, ia1);
+        f->axis = vnorm(vcross_s(vsub(a2, a1), 1.0));
+        v2 normal = rot_mul(&xa, f->axis);
+        f->local_point = vscale(0.5, vadd(a1, a2));
+        v2 point_a = xf_mul(&xa, f->local_point);
+        v2 point_b = xf_mul(&xb, dvert(f->pb, ib0));
+        double s = vdot(vsub(point_b, point_a), normal);
+        if (s < 0.0) f->axis = vneg(f->axis);
+    }
+}
+static double sep_find_min(const sepfn* f, double t, int* index_a, int* index_b)     /* toi.py:126-183 */
+{
+    xform xa = sweep_xf(f->sa, t), xb = sweep_xf(f->sb, t);
+    if (f->type == SEP_POINTS) {
+        v2 axis_a = rot_mul_t(&xa, f->axis), axis_b = rot_mul_t(&xb, vneg(f->axis));
+        *index_a = dproxy_support(f->pa, axis_a);
+        *index_b = dproxy_support(f->pb, axis_b);
+        v2 point_a = xf_mul(&xa, dvert(f->pa, *index_a)), point_b = xf_mul(&xb, dvert(f->pb, *index_b));
+        return vdot(vsub(point_b, point_a), f->axis);
+    } else if (f->type == SEP_FACE_A) {
+        v2 normal = rot_mul(&xa, f->axis);
+        v2 point_a = xf_mul(&xa, f->local_point);
+        v2 axis_b = rot_mul_t(&xb, vneg(normal));
+        *index_a = -1;
+        *index_b = dproxy_support(f->pb, axis_b);
+        v2 point_b = xf_mul(&xb, dvert(f->pb, *index_b));
+        return vdot(vsub(point_b, point_a), normal);
+    } else {
+        v2 normal = rot_mul(&xb, f->axis);
+        v2 point_b = xf_mul(&xb, f->local_point);
+        v2 axis_a = rot_mul_t(&xa, vneg(normal));
+        *index_b = -1;
+        *index_a = dproxy_support(f->pa, axis_a);
+        v2 point_a = xf_mul(&xa, dvert(f->pa, *index_a));
+        return vdot(vsub(point_a, point_b), normal);
+    }
+}
+static double sep_evaluate(const sepfn* f, int index_a, int index_b, double t)       /* toi.py:185-221 */
+{
+    xform xa = sweep_xf(f->sa, t), xb = sweep_xf(f->sb, t);
+    if (f->type == SEP_POINTS) {
+        v2 point_a = xf_mul(&xa, dvert(f->pa, index_a)), point_b = xf_mul(&xb, dvert(f->pb, index_b));
+        return vdot(vsub(point_b, point_a), f->axis);
+    } else if (f->type == SEP_FACE_A) {
+        v2 normal = rot_mul(&xa, f->axis);
+        v2 point_a = xf_mul(&xa, f->local_point);
+        v2 point_b = xf_mul(&xb, dvert(f->pb, index_b));
+        return vdot(vsub(point_b, point_a), normal);
+    } else {
+        v2 normal = rot_mul(&xb, f->axis);
+        v2 point_b = xf_mul(&xb, f->local_point);
+        v2 point_a = xf_mul(&xa, dvert(f->pa, index_a));
+        return vdot(vsub(point_a, point_b), normal);
+    }
+}
+
+/* time_of_impact: toi.py:223-391 */
+enum { TOI_UNKNOWN, TOI_FAILED, TOI_OVERLAPPED, TOI_TOUCHING, TOI_SEPARATED };
+static int time_of_impact(const dproxy* pa, const dproxy* pb, sweep_t sweep_a, sweep_t sweep_b, double t_max, double* out_t)
+{
+    int state = TOI_UNKNOWN;
+    double output_t = t_max;
+    sweep_normalize(&sweep_a);
+    sweep_normalize(&sweep_b);
+    double total_radius = pa->radius + pb->radius;
+    double target = PYMAX(LINEAR_SLOP, total_radius - 3.0 * LINEAR_SLOP);
+    double tolerance = 0.25 * LINEAR_SLOP;
+    double t1 = 0.0;
+    int iter = 0;
+    simplex_cache cache; memset(&cache, 0, sizeof(cache));
+    for (;;) {
+        xform xa = sweep_xf(&sweep_a, t1), xb = sweep_xf(&sweep_b, t1);
+        double out_distance = shape_distance(pa, pb, &xa, &xb, 0, &cache);
+        if (out_distance <= 0.0) { state = TOI_OVERLAPPED; output_t = 0.0; break; }
+        if (out_distance < target + tolerance) { state = TOI_TOUCHING; output_t = t1; break; }
+        sepfn fcn; memset(&fcn, 0, sizeof(fcn));
+        fcn.pa = pa; fcn.pb = pb; fcn.sa = &sweep_a; fcn.sb = &sweep_b;
+        sep_initialize(&fcn, &cache, t1);
+        int done = 0;
+        double t2 = t_max;
+        for (;;) {
+            int index_a, index_b;
+            double s2 = sep_find_min(&fcn, t2, &index_a, &index_b);
+            if (s2 > (target + tolerance)) { state = TOI_SEPARATED; output_t = t_max; done = 1; break; }
+            if (s2 > (target - tolerance)) { t1 = t2; break; }
+            double s1 = sep_evaluate(&fcn, index_a, index_b, t1);
+            if (s1 < (target - tolerance)) { state = TOI_FAILED; output_t = t1; done = 1; break; }
+            if (s1 <= (target + tolerance)) { state = TOI_TOUCHING; output_t = t1; done = 1; break; }
+            int root_iter_count = 0;
+            double a1 = t1, a2 = t2;
+            for (;;) {
+                double t;
+                if (root_iter_count & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
+                else t = 0.5 * (a1 + a2);
+                double s = sep_evaluate(&fcn, index_a, index_b, t);
+                if (fabs(s - target) < tolerance) { t2 = t; break; }
+                if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
+                ++root_iter_count;
+                if (root_iter_count == 50) break;
+            }
+        }
+        ++iter;
+        if (done) break;
+        if (iter == TOI_MAX_ITERS) { state = TOI_FAILED; output_t = t1; break; }
+    }
+    *out_t = output_t;
+    return state;
+}
+
+/* solve_toi_position_constraints: contact.py:866-933 */
+static int solver_toi_position_sweep(const cc_t* C, int ncontacts, pos_t* P, int toi_a, int toi_b)
+{
+    double min_separation = 0.0;
+    for (int k = 0; k < ncontacts; ++k) {
+        const cc_t* cc = &C[k];
+        v2 ca = P[cc->ia].c, cb = P[cc->ib].c; double aa = P[cc->ia].a, ab = P[cc->ib].a;
+        double ima = 0.0, iia = 0.0, imb = 0.0, iib = 0.0;
+        if (cc->ia == toi_a || cc->ia == toi_b) { ima = cc->ima; iia = cc->iia; }
+        if (cc->ib == toi_a || cc->ib == toi_b) { imb = cc->imb; iib = cc->iib; }
+        for (int j = 0; j < cc->n_local_points; ++j) {
+            xform xa = xf_from_sweep(ca, aa, cc->lca), xb = xf_from_sweep(cb, ab, cc->lcb);
+            v2 normal, point; double separation;
+            solver_manifold(cc, &xa, &xb, j, &normal, &point, &separation);
+            v2 ra = vsub(point, ca), rb = vsub(point, cb);
+            min_separation = PYMIN(min_separation, separation);
+            double Cc = pyclamp(TOI_BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LIN_CORR, 0.0);
+            double rn_a = sq(vcross(ra, normal)), rn_b = sq(vcross(rb, normal));
+            double K = ima + imb + (iia * rn_a) + (iib * rn_b);
+            double impulse = (K > 0.0) ? -Cc / K : 0.0;
+            v2 Pv = vscale(impulse, normal);
+            ca = vsub(ca, vscale(ima, Pv));
+            aa = aa - iia * vcross(ra, Pv);
+            cb = vadd(cb, vscale(imb, Pv));
+            ab = ab + iib * vcross(rb, Pv);
+        }
+        P[cc->ia].c = ca; P[cc->ia].a = aa;
+        P[cc->ib].c = cb; P[cc->ib].a = ab;
+    }
+    return min_separation >= -1.5 * LINEAR_SLOP;
+}
+
+/* Island.solve_toi: island.py:181-243 */
+static void island_solve_toi(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts,
+                             double dt, int vel_iters, int toi_a, int toi_b)
+{
+    pos_t P[2 * MAX_TOI_CONTACTS + 1]; vel_t Vv[2 * MAX_TOI_CONTACTS + 1]; cc_t C[MAX_TOI_CONTACTS + 1];
+    for (int i = 0; i < nbodies; ++i) {
+        int b = bodies[i];
+        P[i].c = V(w->b_pos[4 * b], w->b_pos[4 * b + 1]); P[i].a = w->b_pos[4 * b + 2];
+        Vv[i].v = V(w->b_vel[4 * b], w->b_vel[4 * b + 1]); Vv[i].w = w->b_vel[4 * b + 2];
+    }
+    solver_ctor(w, C, contacts, ncontacts, 0, 1.0);
+    for (int it = 0; it < 20; ++it)
+        if (solver_toi_position_sweep(C, ncontacts, P, toi_a, toi_b)) break;
+    /* leap of faith to the new safe state */
+    {
+        int ba = bodies[toi_a], bb = bodies[toi_b];
+        w->b_pos0[4 * ba] = P[toi_a].c.x; w->b_pos0[4 * ba + 1] = P[toi_a].c.y; w->b_pos0[4 * ba + 2] = P[toi_a].a;
+        w->b_pos0[4 * bb] = P[toi_b].c.x; w->b_pos0[4 * bb + 1] = P[toi_b].c.y; w->b_pos0[4 * bb + 2] = P[toi_b].a;
+    }
+    solver_init_velocity(C, ncontacts, P, Vv);
+    for (int it = 0; it < vel_iters; ++it) solver_velocity_sweep(C, ncontacts, Vv);
+    /* (impulses are not stored) integrate: island.py:213-241 */
+    for (int i = 0; i < nbodies; ++i) {
+        int b = bodies[i];
+        v2 c = P[i].c; double a = P[i].a; v2 v = Vv[i].v; double wv = Vv[i].w;
+        v2 translation = vscale(dt, v);
+        if (vlen2(translation) > MAX_TRANS_SQR) {
+            double ratio = MAX_TRANS / sqrt(sq(translation.x) + sq(translation.y));
+            v = vscale(ratio, v);                       /* v *= ratio */
+        }
+        double rotation = dt * wv;
+        if (sq(rotation) > MAX_ROT_SQR) {
+            double ratio = MAX_ROT / fabs(rotation);
+            wv = wv * ratio;
+        }
+        c = vadd(c, vscale(dt, v));
+        a = a + dt * wv;
+        w->b_pos[4 * b] = c.x; w->b_pos[4 * b + 1] = c.y; w->b_pos[4 * b + 2] = a;
+        w->b_vel[4 * b] = v.x; w->b_vel[4 * b + 1] = v.y; w->b_vel[4 * b + 2] = wv;
+        body_sync_transform(w, b);
+    }
+}
+
+/* World.solve_toi: world.py:594-821 */
+static void world_solve_toi(orc_world* w, double dt, int vel_iters)
+{
+    int nb = w->w_count[0];
+    int cap = w->nc_cap;
+    double* toi = (double*)malloc(sizeof(double) * (size_t)(cap + 1));
+    uint8_t* toi_flag = (uint8_t*)calloc((size_t)cap + 1, 1);
+    int* toi_count = (int*)calloc((size_t)cap + 1, sizeof(int));
+    /* world.py:599-609 (step_complete is always true here: no sub_stepping) */
+    for (int b = 0; b < nb; ++b) { w->b_flags[b] &= ~BODY_ISLAND; w->b_pos0[4 * b + 3] = 0.0; }
+    for (int c = 0; c < w->w_count[2]; ++c) { w->c_flags[c] &= ~C_ISLAND; toi[c] = 1.0; }
+
+    for (;;) {
+        int min_contact = -1;
+        double min_alpha = 1.0;
+        int nc = w->w_count[2];
+        for (int c = 0; c < nc; ++c) {
+            if (!(w->c_flags[c] & C_ENABLED) || toi_count[c] > MAX_SUB_STEPS) continue;
+            double alpha = 1.0;
+            if (toi_flag[c]) alpha = toi[c];
+            else {
+                int fa = w->c_fix[2 * c], fb = w->c_fix[2 * c + 1];
+                int ba = w->f_body[fa], bb = w->f_body[fb];
+                int type_a = body_type(w, ba), type_b = body_type(w, bb);
+                int active_a = body_awake(w, ba) && type_a != T_STATIC;
+                int active_b = body_awake(w, bb) && type_b != T_STATIC;
+                if (!active_a && !active_b) continue;
+                int collide_a = (w->b_flags[ba] & BODY_BULLET) || type_a != T_DYNAMIC;
+                int collide_b = (w->b_flags[bb] & BODY_BULLET) || type_b != T_DYNAMIC;
+                if (!collide_a && !collide_b) continue;
+                sweep_t sa = sweep_load(w, ba), sb = sweep_load(w, bb);
+                double alpha0 = sa.alpha0;
+                if (sa.alpha0 < sb.alpha0) { alpha0 = sb.alpha0; sweep_advance(&sa, alpha0); sweep_store(w, ba, &sa); }
+                else if (sb.alpha0 < sa.alpha0) { sweep_advance(&sb, alpha0); sweep_store(w, bb, &sb); }
+                dproxy pa = dproxy_get(w, w->f_shape[fa]), pb = dproxy_get(w, w->f_shape[fb]);
+                double beta;
+                int state = time_of_impact(&pa, &pb, sa, sb, 1.0, &beta);
+                if (state == TOI_TOUCHING) { double t = alpha0 + (1.0 - alpha0) * beta; alpha = PYMIN(t, 1.0); }
+                else alpha = 1.0;
+                toi[c] = alpha;
+                toi_flag[c] = 1;
+            }
+            if (alpha < min_alpha) { min_contact = c; min_alpha = alpha; }
+        }
+        if (min_contact < 0 || (1.0 - (10.0 * EPS)) < min_alpha) break;
+
+        int mc = min_contact;
+        int fa = w->c_fix[2 * mc], fb = w->c_fix[2 * mc + 1];
+        int body_a = w->f_body[fa], body_b = w->f_body[fb];
+        sweep_t backup_a = sweep_load(w, body_a), backup_b = sweep_load(w, body_b);
+        body_advance(w, body_a, min_alpha);
+        body_advance(w, body_b, min_alpha);
+        contact_update(w, mc);
+        toi_flag[mc] = 0;
+        toi_count[mc] += 1;
+        if (!(w->c_flags[mc] & C_ENABLED) || !(w->c_flags[mc] & C_TOUCHING)) {
+            w->c_flags[mc] &= ~C_ENABLED;
+            sweep_store(w, body_a, &backup_a);
+            sweep_store(w, body_b, &backup_b);
+            body_sync_transform(w, body_a);
+            body_sync_transform(w, body_b);
+            continue;
+        }
+        body_wake(w, body_a);
+        body_wake(w, body_b);
+
+        int ibodies[2 * MAX_TOI_CONTACTS + 2], icontacts[MAX_TOI_CONTACTS + 2];
+        int nib = 0, nic = 0;
+        w->b_island[body_a] = nib; ibodies[nib++] = body_a;
+        w->b_island[body_b] = nib; ibodies[nib++] = body_b;
+        icontacts[nic++] = mc;
+        w->b_flags[body_a] |= BODY_ISLAND;
+        w->b_flags[body_b] |= BODY_ISLAND;
+        w->c_flags[mc] |= C_ISLAND;
+        int seeds[2] = {body_a, body_b};
+        for (int si = 0; si < 2; ++si) {
+            int body = seeds[si];
+            if (body_type(w, body) != T_DYNAMIC) continue;
+            for (int c = 0; c < nc; ++c) {                      /* body._contacts: the world's list filtered by body */
+                int cfa = w->c_fix[2 * c], cfb = w->c_fix[2 * c + 1];
+                int cba = w->f_body[cfa], cbb = w->f_body[cfb];
+                if (cba != body && cbb != body) continue;
+                if (nib == 2 * MAX_TOI_CONTACTS) break;
+                if (nic == MAX_TOI_CONTACTS) break;
+                if (w->c_flags[c] & C_ISLAND) continue;
+                int other = (cba == body) ? cbb : cba;
+                if (body_type(w, other) == T_DYNAMIC && !(w->b_flags[body] & BODY_BULLET) && !(w->b_flags[other] & BODY_BULLET))
+                    continue;
+                sweep_t backup = sweep_load(w, other);
+                if (!(w->b_flags[other] & BODY_ISLAND)) body_advance(w, other, min_alpha);
+                contact_update(w, c);
+                if (!(w->c_flags[c] & C_ENABLED) || !(w->c_flags[c] & C_TOUCHING)) {
+                    sweep_store(w, other, &backup);
+                    body_sync_transform(w, other);
+                    continue;
+                }
+                w->c_flags[c] |= C_ISLAND;
+                icontacts[nic++] = c;
+                if (w->b_flags[other] & BODY_ISLAND) continue;
+                w->b_flags[other] |= BODY_ISLAND;
+                if (body_type(w, other) != T_STATIC) body_wake(w, other);
+                w->b_island[other] = nib; ibodies[nib++] = other;
+            }
+        }
+        double sub_dt = (1.0 - min_alpha) * dt;
+        island_solve_toi(w, ibodies, nib, icontacts, nic, sub_dt, vel_iters, w->b_island[body_a], w->b_island[body_b]);
+
+        for (int i = 0; i < nib; ++i) {
+            int body = ibodies[i];
+            w->b_flags[body] &= ~BODY_ISLAND;
+            if (body_type(w, body) != T_DYNAMIC) continue;
+            /* Body._synchronize_fixtures: body.py:898-904 */
+            v2 c0 = V(w->b_pos0[4 * body], w->b_pos0[4 * body + 1]); double a0 = w->b_pos0[4 * body + 2];
+            v2 lcen = V(w->b_mass[4 * body + 2], w->b_mass[4 * body + 3]);
+            xform xf1 = xf_from_sweep(c0, a0, lcen);
+            xform xf2 = xf_row(w->b_xf + 4 * (size_t)body);
+            for (int f = 0; f < w->w_count[1]; ++f) if (w->f_body[f] == body) fixture_synchronize(w, f, &xf1, &xf2);
+            for (int c = 0; c < nc; ++c) {
+                int cba = w->f_body[w->c_fix[2 * c]], cbb = w->f_body[w->c_fix[2 * c + 1]];
+                if (cba != body && cbb != body) continue;
+                toi_flag[c] = 0;
+                w->c_flags[c] &= ~C_ISLAND;
+            }
+        }
+        {
+            int before = w->w_count[2];
+            cm_find_new_contacts(w);
+            for (int c = before; c < w->w_count[2]; ++c) { toi[c] = 1.0; toi_flag[c] = 0; toi_count[c] = 0; }
+        }
+    }
+    free(toi); free(toi_flag); free(toi_count);
+}
+
 /* ---- World.step: world.py:307-354 ---- */
 int orc_step(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters)
 {
@@ -1293,6 +1876,7 @@ int orc_step(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_ite
     double dt_ratio = inv_dt0 * dt;
     cm_collide(w);
     if (dt > 0.0) world_solve(w, dt, dt_ratio, vel_iters, pos_iters);
+    if ((w->w_flags[0] & W_CONTINUOUS) && dt > 0.0) world_solve_toi(w, dt, vel_iters);
     if (w->w_flags[0] & W_AUTO_CLEAR) {
         int nb = w->w_count[0];
         for (int b = 0; b < nb; ++b) { w->b_force[2 * b] = 0.0; w->b_force[2 * b + 1] = 0.0; w->b_vel[4 * b + 3] = 0.0; }

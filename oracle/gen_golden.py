@@ -16,6 +16,7 @@ bit-for-bit at any step: that is what pins the oracle.  It then writes a small f
 Usage: python oracle/gen_golden.py [case ...]
 """
 import hashlib
+import json
 import os
 import sys
 import time
@@ -30,7 +31,9 @@ from pypybox2d_b200 import schema  # noqa: E402
 
 OUT = os.path.join(harness._ROOT, "tests", "golden")
 
-# name: (scene, world, dt, vel_iters, pos_iters, steps, checkpoints)
+CCD = {"continuous_physics": True}
+
+# name: (scene, world, dt, vel_iters, pos_iters, steps, checkpoints[, scene keywords])
 CASES = {
     "pyramid_w0": ("pyramid", 0, 1.0 / 60, 8, 3, 600, (1, 60, 300, 600)),
     "pyramid_w1": ("pyramid", 1, 1.0 / 60, 8, 3, 600, (1, 30, 300, 600)),
@@ -43,6 +46,15 @@ CASES = {
     "deep_stacks_w1": ("deep_stacks", 1, 1.0 / 60, 8, 3, 400, (150, 400)),
     "features_w0": ("features", 0, 1.0 / 60, 8, 3, 400, (100, 400)),
     "features_w1": ("features", 1, 1.0 / 60, 10, 4, 400, (400,)),
+    # continuous collision ON (World.solve_toi, world.py:594-821): the reference's default world
+    "hello_ccd_w0": ("hello", 0, 0.1, 10, 10, 200, (20, 200), CCD),
+    "bullets_w0": ("bullets", 0, 1.0 / 60, 8, 3, 300, (10, 300)),
+    "bullets_w1": ("bullets", 1, 1.0 / 60, 8, 3, 300, (10, 300)),
+    "bullets_w2": ("bullets", 2, 1.0 / 30, 10, 4, 200, (200,)),
+    "pyramid_ccd_w1": ("pyramid", 1, 1.0 / 60, 8, 3, 300, (60, 300), CCD),
+    "vertical_stack_ccd_w1": ("vertical_stack", 1, 1.0 / 60, 10, 10, 200, (200,), CCD),
+    "features_ccd_w1": ("features", 1, 1.0 / 60, 8, 3, 300, (300,), CCD),
+    "mixed_ccd_w1": ("mixed", 1, 1.0 / 60, 8, 3, 200, (200,), CCD),
 }
 
 CK_FIELDS = ["w_count", "w_flags", "w_island", "b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island",
@@ -93,15 +105,18 @@ def used(A, name, w=0):
 
 
 def generate(case):
-    scene, world, dt, vi, pi, steps, cks = CASES[case]
-    rw, RA, caps, table = harness.reference_arrays(scene, world)
-    mw, OA, _ = harness.facade_arrays(scene, world, caps=caps)
+    scene, world, dt, vi, pi, steps, cks = CASES[case][:7]
+    kw = CASES[case][7] if len(CASES[case]) > 7 else {}
+    rw, RA, caps, table = harness.reference_arrays(scene, world, **kw)
+    mw, OA, _ = harness.facade_arrays(scene, world, caps=caps, **kw)
     bad = harness.diff_state(RA, OA, fields=[f for f in INIT_FIELDS if not f.startswith("s_")])
     if bad:
         raise SystemExit("%s: facade initial state differs from the reference: %s" % (case, bad))
     out = {"meta": np.array([dt, vi, pi, steps, world], dtype=np.float64),
            "caps": np.array([caps.nb, caps.nf, caps.nc, caps.npair, caps.nl], dtype=np.int32),
            "scene": np.array(scene)}
+    if kw:
+        out["scene_kw"] = np.array(json.dumps(kw, sort_keys=True))      # scene keywords (read back by tests/conftest.py)
     for f in INIT_FIELDS:
         out["init_" + f] = used(RA, f)
     n_sh = len(table)

@@ -108,6 +108,8 @@ def extract(world, arrays, w, table, schema):
         flags |= schema.WORLD_NEW_FIXTURE
     if world._auto_clear_forces:
         flags |= schema.WORLD_AUTO_CLEAR
+    if world._continuous_physics:
+        flags |= schema.WORLD_CONTINUOUS
     A["w_flags"][w] = flags
     A["w_gravity"][w] = (world._gravity.x, world._gravity.y)
     for i, b in enumerate(bodies):
@@ -116,7 +118,7 @@ def extract(world, arrays, w, table, schema):
         s = b._sweep
         A["b_pos"][w, i] = (s.c.x, s.c.y, s.a, b._sleep_time)
         A["b_vel"][w, i] = (b._linear_velocity.x, b._linear_velocity.y, b._angular_velocity, b._torque)
-        A["b_pos0"][w, i] = (s.c0.x, s.c0.y, s.a0, 0.0)
+        A["b_pos0"][w, i] = (s.c0.x, s.c0.y, s.a0, s.alpha0)
         A["b_force"][w, i] = (b._force.x, b._force.y)
         A["b_mass"][w, i] = (b._inv_mass, b._invI, s.local_center.x, s.local_center.y)
         A["b_damp"][w, i] = (b._linear_damping, b._angular_damping, b._gravity_scale, 0.0)

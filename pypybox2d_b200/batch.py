@@ -222,12 +222,29 @@ class BatchedWorld(object):
         _lib.check(_lib.lib().b2b_solve_islands(self._ctx, float(dt), float(self.inv_dt0), int(vel_iters), int(pos_iters), 0,
                                                 self._stream()), "b2b_solve_islands")
 
+    @property
+    def continuous(self):
+        """True when some world of the batch has continuous collision on (World(continuous_physics=True), world.py:78):
+        World.solve_toi then runs in the last kernel of every step."""
+        if getattr(self, "_continuous", None) is None:
+            self._continuous = bool((self.t["w_flags"] & schema.WORLD_CONTINUOUS).any().item())
+        return self._continuous
+
+    def set_continuous(self, on):
+        """World.continuous_physics = on, for every world of the batch."""
+        if on:
+            self.t["w_flags"] |= schema.WORLD_CONTINUOUS
+        else:
+            self.t["w_flags"] &= ~schema.WORLD_CONTINUOUS
+        self._continuous = bool(on)
+
     def step_host(self, h_force_torque, h_state_out, dt, vel_iters, pos_iters, n_steps=1):
         """The end-to-end call: pinned host forces in, pinned host body state out, synchronous."""
         fin = ctypes.c_void_p(h_force_torque.data_ptr()) if h_force_torque is not None else None
         fout = ctypes.c_void_p(h_state_out.data_ptr()) if h_state_out is not None else None
+        flags = 128 if self.continuous else 0          # B2B_STEP_CONTINUOUS: the state is read back after World.solve_toi
         _lib.check(_lib.lib().b2b_step_host(self._ctx, fin, fout, float(dt), float(self.inv_dt0), int(vel_iters),
-                                            int(pos_iters), int(n_steps), 0, self._stream()), "b2b_step_host")
+                                            int(pos_iters), int(n_steps), flags, self._stream()), "b2b_step_host")
         if dt > 0.0 and n_steps > 0:
             self.inv_dt0 = 1.0 / dt
 
@@ -325,6 +342,7 @@ class BatchedWorld(object):
             else:
                 self.t[name].copy_(src)
         self.t["w_flags"] &= ~schema.WORLD_GRAPH_VALID      # host-side mutation: rebuild the island schedule
+        self._continuous = None                             # (w_flags may have been replaced)
 
     # -- single-world facade support ----------------------------------------------------------
     def upload_bodies_from_world(self, world, w=0):

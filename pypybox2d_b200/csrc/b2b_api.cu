@@ -265,8 +265,8 @@ static unsigned int* solve_counters(const b2b_ctx* x, int parity)
 static int step_launches(const b2b_ctx* x, double dt, uint32_t flags, int groups)
 {
     // plan, sync, pairs, (collide), and per group of worlds prepare + velocity + the two position kernels (one of them
-    // returns at once, see b2b_kernels.inl)
-    return 3 + ((dt > 0.0) ? 4 * groups : 0) + ((flags & 4u) ? 1 : 0);
+    // returns at once, see b2b_kernels.inl); the TOI kernel (worlds without continuous collision return at once)
+    return 3 + ((dt > 0.0) ? 4 * groups + 1 : 0) + ((flags & 4u) ? 1 : 0);
 }
 
 extern "C" int b2b_step(b2b_ctx* x, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps, uint32_t flags,
@@ -456,7 +456,7 @@ extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_sta
                 else launch_solve_group_f32(x->fields, x->c, x->plan, x->plan_rows, rec, x->scratch_sprof, spk, first, w0, n, sk, nullptr);
                 x->launches += 4;
             }
-            if (last && h_state_out) {
+            if (last && h_state_out && !(flags & B2B_STEP_CONTINUOUS)) {
                 if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, w0, n, sk);
                 else launch_gather_state_f32(x->fields, x->c, x->stage_out, w0, n, sk);
                 ++x->launches;
@@ -472,7 +472,20 @@ extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_sta
         }
         if (x->f64) launch_post_f64(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);
         else launch_post_f32(x->fields, x->c, x->plan, x->plan_rows, x->scratch, x->d_status + 1, sp, st, nullptr);
-        x->launches += 2;
+        x->launches += (dt > 0.0) ? 3 : 2;
+        // continuous collision moves bodies after the discrete solve (World.solve_toi runs in the last kernel): read back now
+        if (last && h_state_out && (flags & B2B_STEP_CONTINUOUS)) {
+            for (int k = 0; k < n_chunks; ++k) {
+                const int w0 = k * chunk, n = (W - w0 < chunk) ? W - w0 : chunk;
+                if (x->f64) launch_gather_state_f64(x->fields, x->c, x->stage_out, w0, n, st);
+                else launch_gather_state_f32(x->fields, x->c, x->stage_out, w0, n, st);
+                ++x->launches;
+                CUDA_TRY(cudaEventRecord(ev_out[k], st), "cudaEventRecord");
+                CUDA_TRY(cudaStreamWaitEvent(x->s_out, ev_out[k], 0), "cudaStreamWaitEvent");
+                CUDA_TRY(cudaMemcpyAsync((char*)h_state_out + (size_t)w0 * per_world_out, (const char*)x->stage_out + (size_t)w0 * per_world_out,
+                                         (size_t)n * per_world_out, cudaMemcpyDeviceToHost, x->s_out), "D2H state");
+            }
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "step kernels", e);
     }

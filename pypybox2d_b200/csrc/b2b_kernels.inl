@@ -245,6 +245,30 @@ __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(ba
         });
 }
 
+// Continuous collision: World.solve_toi (world.py:594-821) for the worlds whose flags carry WORLD_CONTINUOUS, after the
+// discrete step's find_new_contacts.  Same launch shape, shared-memory layout and scratch slabs as the pair kernel (the
+// loop calls phase_pairs after every solved event).  The candidates' times of impact are contact-parallel, so the whole warp
+// takes one world; a batch without such worlds costs one flag word per world.
+__global__ void __launch_bounds__(32) B2B_CAT(toi_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+                                                                        scratch_layout L, unsigned char* scratch, step_params sp,
+                                                                        int lanes, size_t team_smem, unsigned int* chunk_counter, int chunk)
+{
+    extern __shared__ __align__(32) unsigned char smem[];
+    world_step<real_t> ws;
+    const int teams_per_cta = 32 / lanes;
+    for_each_needy_world(
+        c, lanes, chunk, chunk_counter,
+        [&](int w) { return ((sp.dt > 0.0) && (B.w_flags[w] & WORLD_CONTINUOUS)) ? 2 : 0; },
+        [&](int w, int width) {
+            const int team = ws.bind_team_lanes(width);
+            ws.bind_rows(B, c, w, plan, P);
+            ws.bind_scratch_aux(scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux, L);
+            ws.bind_smem_aux(smem + (size_t)team * team_smem, true);
+            ws.run_toi(sp);
+            __syncwarp(ws.t_mask);
+        });
+}
+
 // Fixture._create_proxies + DynamicTree.create_proxy (fixture.py:250-261, dynamictree.py:115-134)
 __global__ void __launch_bounds__(256) B2B_CAT(init_proxies_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c)
 {
@@ -453,7 +477,15 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
                   S.total_broad * teams_aux, 0, n_sm, &out->k_broad);
     if (rc) return rc;
+    {   // the TOI kernel runs on the pair kernel's geometry: its grid may only be smaller (more registers)
+        kernel_plan k_toi;
+        rc = plan_one(B2B_CAT(toi_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
+                      S.total_broad * teams_aux, 0, n_sm, &k_toi);
+        if (rc) return rc;
+        out->k_toi = k_toi;
+    }
     out->aux_slabs = (out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid) * teams_aux;
+    if (out->aux_slabs < out->k_toi.grid * teams_aux) out->aux_slabs = out->k_toi.grid * teams_aux;
     out->solve_slabs = out->k_solve.grid * (out->k_solve.threads / 32) * teams;
     return 0;
 }
@@ -487,7 +519,7 @@ void B2B_CAT(launch_collide_, B2B_SUFFIX)(const void* const* fields, const caps_
 void B2B_CAT(launch_plan_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, const launch_plan& p, uint16_t* plan,
                                        unsigned char* scratch_aux, unsigned int* counters, const step_params& sp, cudaStream_t st)
 {
-    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule word
+    cudaMemsetAsync(counters, 0, 5 * sizeof(unsigned int), st);     // chunk counters of the plan and pair kernels, joint-schedule words, chunk counter of the TOI kernel
     if (sp.flags & STEP_GROUP_KERNEL) cudaMemsetAsync(counters + 2, 1, sizeof(unsigned int), st);   // any non-zero word
     B2B_CAT(plan_kernel_, B2B_SUFFIX)<<<p.k_plan.grid, 32, p.k_plan.smem, st>>>(as_ptrs(fields), c, p.plan, plan, p.layout, scratch_aux, sp,
                                                                                  p.lanes_aux, p.team_smem_plan, counters, world_chunk(c.n_worlds, p.k_plan.grid));
@@ -528,6 +560,9 @@ void B2B_CAT(launch_post_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
     if (tm) tm->mark(T_SYNC, st);
     B2B_CAT(broadphase_kernel_, B2B_SUFFIX)<<<p.k_broad.grid, 32, p.k_broad.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
                                                                                          p.lanes_aux, p.team_smem_broad, counters + 1, world_chunk(c.n_worlds, p.k_broad.grid));
+    if (sp.dt > 0.0)
+        B2B_CAT(toi_kernel_, B2B_SUFFIX)<<<p.k_toi.grid, 32, p.k_toi.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
+                                                                              p.lanes_aux, p.team_smem_broad, counters + 4, world_chunk(c.n_worlds, p.k_toi.grid));
     if (tm) tm->mark(T_PAIRS, st);
 }
 

@@ -16,7 +16,7 @@ struct kernel_plan {
     size_t smem;
 };
 struct launch_plan {
-    kernel_plan k_plan, k_solve, k_broad;
+    kernel_plan k_plan, k_solve, k_broad, k_toi;
     int aux_slabs, solve_slabs;      // scratch slabs to allocate: per plan/broadphase CTA; solve teams (cycle counters)
     int group_worlds;                // worlds whose constraint records are resident at once (one record slab each)
     int n_sm;

@@ -38,7 +38,9 @@ enum : uint32_t {
     CONTACT_TOUCHING = 0x1u, CONTACT_ENABLED = 0x2u, CONTACT_FILTER = 0x4u, CONTACT_ISLAND = 0x8u,
     WORLD_ALLOW_SLEEP = 0x1u, WORLD_WARM_STARTING = 0x2u, WORLD_NEW_FIXTURE = 0x4u, WORLD_AUTO_CLEAR = 0x8u,
     WORLD_GRAPH_VALID = 0x10u,   // the island lists / level schedule of the last step still describe this world
-    STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u
+    WORLD_CONTINUOUS = 0x20u,    // continuous_physics (world.py:78): World.solve_toi runs after the discrete solve
+    STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u,
+    STATUS_TOI_STUCK = 0x10u     // a time-of-impact push-back loop was cut off (b2b_toi.cuh TOI_MAX_PUSH_BACK)
 };
 enum { BODY_STATIC = 0, BODY_DYNAMIC = 1, BODY_KINEMATIC = 2 };
 enum { MANIFOLD_CIRCLES = 0, MANIFOLD_FACE_A = 1, MANIFOLD_FACE_B = 2 };

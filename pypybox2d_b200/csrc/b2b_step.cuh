@@ -22,6 +22,7 @@
 #include <cstring>
 #include <type_traits>
 #include "b2b_collide.cuh"
+#include "b2b_toi.cuh"
 
 // A world is stepped by a TEAM of threads: the whole CTA in the plan and broadphase kernels, a group of
 // `t_n` lanes of one warp in the solve kernel (several worlds per warp).  Work items are strided over the team
@@ -134,8 +135,31 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
     return P;
 }
 
+// continuous collision (phase_toi): per-contact time of impact + state word, a batch of sweep snapshots, the team's
+// reduction words, and the sub-island World.solve_toi solves (at most 2 * MAX_TOI_CONTACTS bodies, MAX_TOI_CONTACTS contacts)
+enum { TOI_BATCH = 32, TOI_SNAP_REALS = 13, TOI_CC_REALS = 56 };
+struct toi_layout { size_t off_alpha, off_state, off_snap, off_snap_ci, off_red_a, off_red_i, off_ib, off_ic, off_P, off_V, off_cc, total; };
+B2B_HD toi_layout toi_plan(const caps_t& c, int real_bytes)
+{
+    toi_layout T;
+    size_t o = 0;
+    T.off_alpha = o; o = align_up(o + (size_t)real_bytes * ((size_t)c.nc + 2), 32);
+    T.off_state = o; o = align_up(o + sizeof(int32_t) * ((size_t)c.nc + 2), 32);
+    T.off_snap = o; o = align_up(o + (size_t)real_bytes * TOI_SNAP_REALS * TOI_BATCH, 32);
+    T.off_snap_ci = o; o = align_up(o + sizeof(int32_t) * TOI_BATCH, 32);
+    T.off_red_a = o; o = align_up(o + (size_t)real_bytes * 32, 32);
+    T.off_red_i = o; o = align_up(o + sizeof(int32_t) * 32, 32);
+    T.off_ib = o; o = align_up(o + sizeof(int32_t) * (2 * MAX_TOI_CONTACTS + 2), 32);
+    T.off_ic = o; o = align_up(o + sizeof(int32_t) * (MAX_TOI_CONTACTS + 2), 32);
+    T.off_P = o; o = align_up(o + (size_t)real_bytes * 3 * (2 * MAX_TOI_CONTACTS + 2), 32);
+    T.off_V = o; o = align_up(o + (size_t)real_bytes * 3 * (2 * MAX_TOI_CONTACTS + 2), 32);
+    T.off_cc = o; o = align_up(o + (size_t)real_bytes * TOI_CC_REALS * (MAX_TOI_CONTACTS + 1), 32);
+    T.total = o;
+    return T;
+}
+
 struct scratch_layout {       // bytes; `aux` slabs are per CTA of the plan/broadphase kernels, `rec` slabs per world of a solve group
-    size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, total_aux;
+    size_t off_wake, off_scan, off_tmp_contact, off_pair_keep, off_prof, off_toi, total_aux;
     size_t off_cc_vel, off_cc_pos, off_cc_imp, off_cc_state, total_rec;
     size_t total_sprof;       // per solve team: cycle counters
 };
@@ -151,6 +175,7 @@ inline scratch_layout scratch_plan(const caps_t& c, int real_bytes)
     L.off_tmp_contact = take((sizeof(int32_t) * 6 + (size_t)real_bytes * 14) * ((size_t)c.nc + 2));
     L.off_pair_keep = take(sizeof(int32_t) * ((size_t)c.npair + 2));
     L.off_prof = take(sizeof(long long) * PROF_SLOTS);
+    L.off_toi = take(toi_plan(c, real_bytes).total);
     L.total_aux = align_up(o, 256);
     o = 0;
     L.off_cc_vel = take((size_t)real_bytes * 4 * VREC_QUADS * ((size_t)c.nc + 2));
@@ -244,6 +269,11 @@ template <class real> struct world_step {
     int32_t* tmp_ci; real* tmp_cr;
     int32_t* pair_keep;
     long long* prof;
+    // continuous collision (phase_toi): see toi_layout
+    struct toi_cc;
+    real *toi_alpha, *toi_snap, *toi_red_a, *toi_P, *toi_V;
+    int32_t *toi_state, *toi_snap_ci, *toi_red_i, *toi_ib, *toi_ic;
+    toi_cc* toi_C;
     // shared memory
 #if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
     // development trace (tools/trace_probe.py): cycles of lane 0 per segment of a level-step, summed over the run
@@ -320,6 +350,14 @@ template <class real> struct world_step {
         tmp_ci = (int32_t*)(scratch + L.off_tmp_contact + sizeof(real) * 14 * ((size_t)cap.nc + 2));
         pair_keep = (int32_t*)(scratch + L.off_pair_keep);
         prof = (long long*)(scratch + L.off_prof);
+        const toi_layout T = toi_plan(cap, (int)sizeof(real));
+        unsigned char* tb = scratch + L.off_toi;
+        toi_alpha = (real*)(tb + T.off_alpha); toi_state = (int32_t*)(tb + T.off_state);
+        toi_snap = (real*)(tb + T.off_snap); toi_snap_ci = (int32_t*)(tb + T.off_snap_ci);
+        toi_red_a = (real*)(tb + T.off_red_a); toi_red_i = (int32_t*)(tb + T.off_red_i);
+        toi_ib = (int32_t*)(tb + T.off_ib); toi_ic = (int32_t*)(tb + T.off_ic);
+        toi_P = (real*)(tb + T.off_P); toi_V = (real*)(tb + T.off_V);
+        toi_C = (toi_cc*)(tb + T.off_cc);
     }
     // `slabs` + `off`: this world's constraint-record slab (written by the prepare kernel, streamed by the solve kernels);
     // `team_prof`: the team's cycle counters (may be null outside the solve kernels)
@@ -1086,6 +1124,36 @@ template <class real> struct world_step {
         }
     }
 
+    // WorldManifold (contact_util.py:195-245): the contact normal and the world points of both manifold points
+    B2B_D static void world_manifold(int type, V2 local_normal, V2 local_point, const V2* lp, const XF& xa, const XF& xb,
+                                     real rad_a, real rad_b, V2& normal, V2* wp)
+    {
+        if (type == MANIFOLD_CIRCLES) {
+            normal = mk<real>(real(1), real(0));
+            const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, lp[0]);
+            const V2 d = pa - pb;
+            if (dot(d, d) > K<real>::epsilon_sqr) normal = normalize(pb - pa);
+            const V2 c_a = pa + rad_a * normal, c_b = pb - rad_b * normal;
+            wp[0] = real(0.5) * (c_a + c_b);
+            wp[1] = wp[0];
+        } else {
+            // FACE_A and FACE_B are the same arithmetic with the bodies' roles exchanged (and the normal flipped at
+            // the end for FACE_B); selecting the operands keeps the lanes of a warp on one code path
+            const bool face_a = (type == MANIFOLD_FACE_A);
+            const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
+            const real rad_r = face_a ? rad_a : rad_b, rad_o = face_a ? rad_b : rad_a;
+            normal = rot_mul(xr, local_normal);
+            const V2 plane = xf_mul(xr, local_point);
+            for (int j = 0; j < 2; ++j) {
+                const V2 clip = xf_mul(xo, lp[j]);
+                const V2 c_r = clip + (rad_r - dot(clip - plane, normal)) * normal;
+                const V2 c_o = clip - rad_o * normal;
+                wp[j] = real(0.5) * (c_r + c_o);        // IEEE addition commutes: same bits as 0.5 * (c_a + c_b)
+            }
+            if (!face_a) normal = -normal;
+        }
+    }
+
     // ContactSolver.__init__ + initialize_velocity_constraints for one slot
     // (contact.py:376-496, contact_util.py:195-245 WorldManifold, :253-277 VelocityConstraintPoint).
     // Runs in the flat prepare kernel: reads global state only.
@@ -1120,30 +1188,7 @@ template <class real> struct world_step {
 
         // world manifold
         V2 normal, wp[2];
-        if (type == MANIFOLD_CIRCLES) {
-            normal = mk<real>(real(1), real(0));
-            const V2 pa = xf_mul(xa, local_point), pb = xf_mul(xb, lp[0]);
-            const V2 d = pa - pb;
-            if (dot(d, d) > K<real>::epsilon_sqr) normal = normalize(pb - pa);
-            const V2 c_a = pa + rad_a * normal, c_b = pb - rad_b * normal;
-            wp[0] = real(0.5) * (c_a + c_b);
-            wp[1] = wp[0];
-        } else {
-            // FACE_A and FACE_B are the same arithmetic with the bodies' roles exchanged (and the normal flipped at
-            // the end for FACE_B); selecting the operands keeps the lanes of a warp on one code path
-            const bool face_a = (type == MANIFOLD_FACE_A);
-            const XF xr = face_a ? xa : xb, xo = face_a ? xb : xa;
-            const real rad_r = face_a ? rad_a : rad_b, rad_o = face_a ? rad_b : rad_a;
-            normal = rot_mul(xr, local_normal);
-            const V2 plane = xf_mul(xr, local_point);
-            for (int j = 0; j < 2; ++j) {
-                const V2 clip = xf_mul(xo, lp[j]);
-                const V2 c_r = clip + (rad_r - dot(clip - plane, normal)) * normal;
-                const V2 c_o = clip - rad_o * normal;
-                wp[j] = real(0.5) * (c_r + c_o);        // IEEE addition commutes: same bits as 0.5 * (c_a + c_b)
-            }
-            if (!face_a) normal = -normal;
-        }
+        world_manifold(type, local_normal, local_point, lp, xa, xb, rad_a, rad_b, normal, wp);
         const V2 tangent = right_perp(normal);
         int n_vel = count;
         V2 ra[2], rb[2];
@@ -1329,7 +1374,7 @@ template <class real> struct world_step {
     // contact.py:826-860): evaluate the separation at the bodies' CURRENT sweeps and push them apart.
     struct pos_state { V2 ca, cb; real aa, ab, min_sep; };
     B2B_D void position_point(pos_state& p, V2 lpj, int type, V2 local_normal, V2 local_point, V2 lca, V2 lcb,
-                              real rad_a, real rad_b, real ma, real ia, real mb, real ib)
+                              real rad_a, real rad_b, real ma, real ia, real mb, real ib, real baumgarte = K<real>::baumgarte)
     {
         const XF xa = xf_from_sweep<real>(p.ca, p.aa, lca), xb = xf_from_sweep<real>(p.cb, p.ab, lcb);
         V2 normal, point;
@@ -1351,7 +1396,7 @@ template <class real> struct world_step {
         }
         const V2 ra = point - p.ca, rb = point - p.cb;
         p.min_sep = pymin(p.min_sep, separation);
-        const real C = clamp_r(K<real>::baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
+        const real C = clamp_r(baumgarte * (separation + K<real>::linear_slop), -K<real>::max_linear_correction, real(0));
         const real rn_a = cross(ra, normal), rn_b = cross(rb, normal);
         const real Keff = ma + mb + (ia * sq_r(rn_a)) + (ib * sq_r(rn_b));      // contact.py:841-842
         const real impulse = (Keff > real(0)) ? -C / Keff : real(0);
@@ -1834,6 +1879,10 @@ template <class real> struct world_step {
         const int b = f_body[f];
         const uint32_t fl = b_flags[b];
         if (!(fl & BODY_ISLAND) || (fl & BODY_TYPE_MASK) == BODY_STATIC) return false;
+        return sync_fixture_of(f, b);
+    }
+    B2B_D bool sync_fixture_of(int f, int b)
+    {
         const quad p0 = ldq(b_pos0 + 4 * (size_t)b), m = ldq(b_mass + 4 * (size_t)b);
         const XF xf1 = xf_from_sweep<real>(mk<real>(p0.x, p0.y), p0.z, mk<real>(m.z, m.w));
         const XF xf2 = xf_load<real>(b_xf + 4 * (size_t)b);
@@ -2012,7 +2061,484 @@ template <class real> struct world_step {
         B2B_SYNC();
     }
 
-    // ------------------------------------------------------------------------------------ World.step
+
+    // ------------------------------------------------------------------------------------ continuous collision (TOI)
+    // World.solve_toi (world.py:594-821): find the contact with the earliest time of impact among the contacts of bullets
+    // and of non-dynamic bodies, advance its two bodies to that time, solve a small island around them for the rest of the
+    // step, synchronise their proxies, find new contacts, repeat until no impact is left inside the step.
+    //
+    // Work decomposition: the times of impact of the candidate contacts are independent GJK / root-finding problems, one
+    // lane each (`toi_evaluate`).  Everything that happens per EVENT is sequential in the reference (advance, narrowphase of
+    // the island's contacts, the island's position / velocity sweeps) and a few contacts wide: thread 0 does it.  Proxy
+    // synchronisation and pair finding are team-parallel again.  The reference equalises the two sweeps of a contact by
+    // advancing the one that lags (a side effect on the BODY, in contact order); once a body has been advanced this step
+    // the candidates are therefore snapshotted in list order by thread 0, in batches, and evaluated from the snapshots.
+    // The reference's island flags / indices of bodies and contacts are bookkeeping of this loop only; here they live in
+    // the scratch words (toi_state, wake_at) so that BODY_ISLAND / CONTACT_ISLAND / b_island keep describing the discrete
+    // step's islands (the incremental plan relies on them).
+    enum { TS_COUNT_MASK = 15, TS_FLAG = 16, TS_NEED = 32, TS_SEED_A = 64, TS_SEED_B = 128, TS_ISLAND = 256 };
+    struct toi_cc {
+        real ima, imb, iia, iib, friction, restitution, rad_a, rad_b;
+        V2 lca, lcb, local_normal, local_point, lp[2], normal;
+        V2 ra[2], rb[2];
+        real ni[2], ti[2], nmass[2], tmass[2], bias[2];
+        real k11, k12, k22, nm11, nm12, nm22;
+        int ia, ib, type, n_local, npoints;
+    };
+    static_assert(sizeof(toi_cc) <= sizeof(real) * TOI_CC_REALS, "toi_layout::off_cc is sized by TOI_CC_REALS");
+
+    B2B_D sweep_t<real> sweep_load(int b) const
+    {
+        const quad p0 = ldq(b_pos0 + 4 * (size_t)b), p = ldq(b_pos + 4 * (size_t)b), m = ldq(b_mass + 4 * (size_t)b);
+        sweep_t<real> s;
+        s.lc = mk<real>(m.z, m.w); s.c0 = mk<real>(p0.x, p0.y); s.a0 = p0.z; s.alpha0 = p0.w;
+        s.c = mk<real>(p.x, p.y); s.a = p.z;
+        return s;
+    }
+    B2B_D void sweep_store(int b, const sweep_t<real>& s)
+    {
+        stq(b_pos0 + 4 * (size_t)b, mkq(s.c0.x, s.c0.y, s.a0, s.alpha0));
+        real* p = b_pos + 4 * (size_t)b;
+        p[0] = s.c.x; p[1] = s.c.y; p[2] = s.a;
+    }
+    B2B_D void body_sync_transform(int b)                                     // body.py:906-908
+    {
+        const quad p = ldq(b_pos + 4 * (size_t)b), m = ldq(b_mass + 4 * (size_t)b);
+        const XF tf = xf_from_sweep<real>(mk<real>(p.x, p.y), p.z, mk<real>(m.z, m.w));
+        stq(b_xf + 4 * (size_t)b, mkq(tf.p.x, tf.p.y, tf.c1.x, tf.c1.y));
+    }
+    B2B_D void body_advance(int b, real alpha)                                // body.py:930-937
+    {
+        sweep_t<real> s = sweep_load(b);
+        sweep_advance(s, alpha);
+        s.c = s.c0; s.a = s.a0;
+        sweep_store(b, s);
+        body_sync_transform(b);
+    }
+    B2B_D void body_wake(int b)                                               // body.py:800-804, 812
+    {
+        const uint32_t fl = b_flags[b];
+        if (!(fl & BODY_AWAKE)) { b_pos[4 * (size_t)b + 3] = real(0); b_flags[b] = fl | BODY_AWAKE; }
+    }
+    // Contact.update with its waking of both bodies on a touching change (contact.py:257-259)
+    B2B_D void toi_contact_update(int c)
+    {
+        if (contact_update(c)) { body_wake(f_body[c_fix[2 * c]]); body_wake(f_body[c_fix[2 * c + 1]]); }
+    }
+
+    // world.py:621-653: is contact c a candidate whose time of impact has to be computed now?
+    B2B_D bool toi_candidate(int c, int st) const
+    {
+        if (!(c_flags[c] & CONTACT_ENABLED) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || (st & TS_FLAG)) return false;
+        const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
+        const uint32_t fla = b_flags[f_body[fa]], flb = b_flags[f_body[fb]];
+        const int type_a = (int)(fla & BODY_TYPE_MASK), type_b = (int)(flb & BODY_TYPE_MASK);
+        const bool active_a = (fla & BODY_AWAKE) && type_a != BODY_STATIC, active_b = (flb & BODY_AWAKE) && type_b != BODY_STATIC;
+        if (!active_a && !active_b) return false;
+        const bool collide_a = (fla & BODY_BULLET) || type_a != BODY_DYNAMIC, collide_b = (flb & BODY_BULLET) || type_b != BODY_DYNAMIC;
+        return collide_a || collide_b;
+    }
+    // world.py:670-683: the contact's time of impact on the two (equalised) sweeps
+    B2B_D void toi_evaluate(int c, const sweep_t<real>& sa, const sweep_t<real>& sb, real alpha0)
+    {
+        const shape_view<real> pa = shape_of_fixture(c_fix[2 * c]), pb = shape_of_fixture(c_fix[2 * c + 1]);
+        real beta = real(1);
+        bool stuck = false;
+        const int state = time_of_impact<real>(pa, pb, sa, sb, real(1), beta, stuck);
+        real alpha = real(1);
+        if (state == TOI_TOUCHING) alpha = pymin(alpha0 + (real(1) - alpha0) * beta, real(1));
+        toi_alpha[c] = alpha;
+        toi_state[c] = (toi_state[c] | TS_FLAG) & ~TS_NEED;
+        if (stuck) B2B_ATOMIC_OR(w_status, (uint32_t)STATUS_TOI_STUCK);
+    }
+
+    // ContactSolver.__init__ for the sub-island's contact k (contact.py:376-412; no warm-start scaling: step.warm_starting is False)
+    B2B_D void toi_constraint_ctor(toi_cc& cc, int ci)
+    {
+        const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
+        const int ba = f_body[fa], bb = f_body[fb];
+        const quad mass_a = ldq(b_mass + 4 * (size_t)ba), mass_b = ldq(b_mass + 4 * (size_t)bb);
+        cc.ia = wake_at[ba]; cc.ib = wake_at[bb];
+        cc.ima = mass_a.x; cc.imb = mass_b.x; cc.iia = mass_a.y; cc.iib = mass_b.y;
+        cc.lca = mk<real>(mass_a.z, mass_a.w); cc.lcb = mk<real>(mass_b.z, mass_b.w);
+        cc.friction = c_mat[2 * ci]; cc.restitution = c_mat[2 * ci + 1];
+        cc.rad_a = s_radius[f_shape[fa]]; cc.rad_b = s_radius[f_shape[fb]];
+        const int mt = c_mtype[ci];
+        const quad mf = ldq(c_mf + 4 * (size_t)ci), pts = ldq(c_pts + 4 * (size_t)ci), imp = ldq(c_imp + 4 * (size_t)ci);
+        cc.type = mt & 0xff; cc.n_local = (mt >> 8) & 0xff; cc.npoints = cc.n_local;
+        cc.local_normal = mk<real>(mf.x, mf.y); cc.local_point = mk<real>(mf.z, mf.w);
+        cc.lp[0] = mk<real>(pts.x, pts.y); cc.lp[1] = mk<real>(pts.z, pts.w);
+        cc.ni[0] = imp.x; cc.ti[0] = imp.y; cc.ni[1] = imp.z; cc.ti[1] = imp.w;
+        cc.normal = mk<real>(real(0), real(0));
+        for (int j = 0; j < 2; ++j) {
+            cc.ra[j] = cc.rb[j] = mk<real>(real(0), real(0));
+            cc.nmass[j] = cc.tmass[j] = cc.bias[j] = real(0);
+        }
+        cc.k11 = cc.k12 = cc.k22 = cc.nm11 = cc.nm12 = cc.nm22 = real(0);
+    }
+    // solve_toi_position_constraints (contact.py:866-933): only the two TOI bodies have mass; true when separated enough
+    B2B_D bool toi_position_sweep(int ncontacts, int toi_a, int toi_b)
+    {
+        real min_separation = real(0);
+        for (int k = 0; k < ncontacts; ++k) {
+            const toi_cc& cc = toi_C[k];
+            pos_state p;
+            p.ca = mk<real>(toi_P[3 * cc.ia], toi_P[3 * cc.ia + 1]); p.aa = toi_P[3 * cc.ia + 2];
+            p.cb = mk<real>(toi_P[3 * cc.ib], toi_P[3 * cc.ib + 1]); p.ab = toi_P[3 * cc.ib + 2];
+            p.min_sep = min_separation;
+            real ima = real(0), iia = real(0), imb = real(0), iib = real(0);
+            if (cc.ia == toi_a || cc.ia == toi_b) { ima = cc.ima; iia = cc.iia; }
+            if (cc.ib == toi_a || cc.ib == toi_b) { imb = cc.imb; iib = cc.iib; }
+            for (int j = 0; j < cc.n_local; ++j)
+                position_point(p, cc.lp[j], cc.type, cc.local_normal, cc.local_point, cc.lca, cc.lcb, cc.rad_a, cc.rad_b,
+                               ima, iia, imb, iib, real(0.75));                       // settings.py:110 TOI_BAUMGARTE
+            min_separation = p.min_sep;
+            toi_P[3 * cc.ia] = p.ca.x; toi_P[3 * cc.ia + 1] = p.ca.y; toi_P[3 * cc.ia + 2] = p.aa;
+            toi_P[3 * cc.ib] = p.cb.x; toi_P[3 * cc.ib + 1] = p.cb.y; toi_P[3 * cc.ib + 2] = p.ab;
+        }
+        return min_separation >= real(-1.5) * K<real>::linear_slop;
+    }
+    // initialize_velocity_constraints (contact.py:414-496) on the sub-island's positions and velocities
+    B2B_D void toi_init_velocity(toi_cc& cc)
+    {
+        const real ma = cc.ima, mb = cc.imb, ia = cc.iia, ib = cc.iib;
+        const V2 ca = mk<real>(toi_P[3 * cc.ia], toi_P[3 * cc.ia + 1]), cb = mk<real>(toi_P[3 * cc.ib], toi_P[3 * cc.ib + 1]);
+        const real aa = toi_P[3 * cc.ia + 2], ab = toi_P[3 * cc.ib + 2];
+        const V2 va = mk<real>(toi_V[3 * cc.ia], toi_V[3 * cc.ia + 1]), vb = mk<real>(toi_V[3 * cc.ib], toi_V[3 * cc.ib + 1]);
+        const real wa = toi_V[3 * cc.ia + 2], wb = toi_V[3 * cc.ib + 2];
+        const XF xa = xf_from_sweep<real>(ca, aa, cc.lca), xb = xf_from_sweep<real>(cb, ab, cc.lcb);
+        V2 normal, wp[2];
+        world_manifold(cc.type, cc.local_normal, cc.local_point, cc.lp, xa, xb, cc.rad_a, cc.rad_b, normal, wp);
+        cc.normal = normal;
+        const V2 tangent = right_perp(normal);
+        for (int j = 0; j < cc.n_local; ++j) {
+            cc.ra[j] = wp[j] - ca; cc.rb[j] = wp[j] - cb;
+            const real rn_a = cross(cc.ra[j], normal), rn_b = cross(cc.rb[j], normal);
+            const real k_normal = ma + mb + ia * sq_r(rn_a) + ib * sq_r(rn_b);
+            const real rt_a = cross(cc.ra[j], tangent), rt_b = cross(cc.rb[j], tangent);
+            const real k_tangent = ma + mb + ia * sq_r(rt_a) + ib * sq_r(rt_b);
+            cc.nmass[j] = (k_normal > real(0)) ? real(1) / k_normal : real(0);
+            cc.tmass[j] = (k_tangent > real(0)) ? real(1) / k_tangent : real(0);
+            cc.bias[j] = real(0);
+            const real v_rel = dot(normal, rel_velocity(vb, wb, cc.rb[j], va, wa, cc.ra[j]));
+            if (v_rel < -K<real>::velocity_threshold) cc.bias[j] = -cc.restitution * v_rel;
+        }
+        if (cc.npoints == 2) {
+            const real rn1a = cross(cc.ra[0], normal), rn1b = cross(cc.rb[0], normal);
+            const real rn2a = cross(cc.ra[1], normal), rn2b = cross(cc.rb[1], normal);
+            const real k11 = ma + mb + ia * rn1a * rn1a + ib * rn1b * rn1b;
+            const real k22 = ma + mb + ia * rn2a * rn2a + ib * rn2b * rn2b;
+            const real k12 = ma + mb + ia * rn1a * rn2a + ib * rn1b * rn2b;
+            if (sq_r(k11) < K<real>::max_condition_number * (k11 * k22 - sq_r(k12))) {
+                cc.k11 = k11; cc.k12 = k12; cc.k22 = k22;
+                real det = k11 * k22 - k12 * k12;
+                if (det != real(0)) det = real(1) / det;
+                cc.nm11 = det * k22; cc.nm12 = -det * k12; cc.nm22 = det * k11;
+            } else {
+                cc.npoints = 1;
+            }
+        }
+    }
+    // solve_velocity_constraints (contact.py:527-799) for one contact of the sub-island
+    B2B_D void toi_solve_velocity(toi_cc& cc)
+    {
+        const real ma = cc.ima, mb = cc.imb, ia = cc.iia, ib = cc.iib;
+        const V2 normal = cc.normal, tangent = right_perp(normal);
+        V2 va = mk<real>(toi_V[3 * cc.ia], toi_V[3 * cc.ia + 1]), vb = mk<real>(toi_V[3 * cc.ib], toi_V[3 * cc.ib + 1]);
+        real wa = toi_V[3 * cc.ia + 2], wb = toi_V[3 * cc.ib + 2];
+        for (int j = 0; j < cc.npoints; ++j) {
+            const V2 dv = rel_velocity(vb, wb, cc.rb[j], va, wa, cc.ra[j]);
+            const real vt = dot(dv, tangent);
+            real lambda = cc.tmass[j] * (-vt);
+            const real max_friction = cc.friction * cc.ni[j];
+            const real new_imp = clamp_r(cc.ti[j] + lambda, -max_friction, max_friction);
+            lambda = new_imp - cc.ti[j];
+            const V2 P = lambda * tangent;
+            va = va - ma * P; wa = wa - ia * cross(cc.ra[j], P);
+            vb = vb + mb * P; wb = wb + ib * cross(cc.rb[j], P);
+            cc.ti[j] = new_imp;
+        }
+        if (cc.npoints == 1) {
+            const V2 dv = rel_velocity(vb, wb, cc.rb[0], va, wa, cc.ra[0]);
+            const real vn = dot(dv, normal);
+            real lambda = -cc.nmass[0] * (vn - cc.bias[0]);
+            const real new_imp = pymax(cc.ni[0] + lambda, real(0));
+            lambda = new_imp - cc.ni[0];
+            const V2 P = lambda * normal;
+            va = va - ma * P; wa = wa - ia * cross(cc.ra[0], P);
+            vb = vb + mb * P; wb = wb + ib * cross(cc.rb[0], P);
+            cc.ni[0] = new_imp;
+        } else if (cc.npoints == 2) {
+            const V2 a = mk<real>(cc.ni[0], cc.ni[1]);
+            const V2 dv1 = rel_velocity(vb, wb, cc.rb[0], va, wa, cc.ra[0]);
+            const V2 dv2 = rel_velocity(vb, wb, cc.rb[1], va, wa, cc.ra[1]);
+            const real vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+            V2 b = mk<real>(vn1 - cc.bias[0], vn2 - cc.bias[1]);
+            b = b - mk<real>(cc.k11 * a.x + cc.k12 * a.y, cc.k12 * a.x + cc.k22 * a.y);
+            V2 x = -mk<real>(cc.nm11 * b.x + cc.nm12 * b.y, cc.nm12 * b.x + cc.nm22 * b.y);
+            bool solved = (x.x >= real(0) && x.y >= real(0));
+            if (!solved) {
+                x = mk<real>(-cc.nmass[0] * b.x, real(0));
+                solved = (x.x >= real(0)) && (cc.k12 * x.x + b.y >= real(0));
+            }
+            if (!solved) {
+                x = mk<real>(real(0), -cc.nmass[1] * b.y);
+                solved = (x.y >= real(0)) && (cc.k12 * x.y + b.x >= real(0));
+            }
+            if (!solved) {
+                x = mk<real>(real(0), real(0));
+                solved = (b.x >= real(0)) && (b.y >= real(0));
+            }
+            if (solved) {
+                const V2 d = x - a;
+                const V2 p1 = d.x * normal, p2 = d.y * normal;
+                const V2 p12 = p1 + p2;
+                va = va - ma * p12; wa = wa - ia * (cross(cc.ra[0], p1) + cross(cc.ra[1], p2));
+                vb = vb + mb * p12; wb = wb + ib * (cross(cc.rb[0], p1) + cross(cc.rb[1], p2));
+                cc.ni[0] = x.x; cc.ni[1] = x.y;
+            }
+        }
+        toi_V[3 * cc.ia] = va.x; toi_V[3 * cc.ia + 1] = va.y; toi_V[3 * cc.ia + 2] = wa;
+        toi_V[3 * cc.ib] = vb.x; toi_V[3 * cc.ib + 1] = vb.y; toi_V[3 * cc.ib + 2] = wb;
+    }
+    // Island.solve_toi (island.py:181-243) for the sub-island in toi_ib / toi_ic; thread 0 only
+    B2B_D void toi_island_solve(int nbodies, int ncontacts, real dt, int vel_iters, int toi_a, int toi_b)
+    {
+        for (int i = 0; i < nbodies; ++i) {
+            const int b = toi_ib[i];
+            const quad p = ldq(b_pos + 4 * (size_t)b), v = ldq(b_vel + 4 * (size_t)b);
+            toi_P[3 * i] = p.x; toi_P[3 * i + 1] = p.y; toi_P[3 * i + 2] = p.z;
+            toi_V[3 * i] = v.x; toi_V[3 * i + 1] = v.y; toi_V[3 * i + 2] = v.z;
+        }
+        for (int k = 0; k < ncontacts; ++k) toi_constraint_ctor(toi_C[k], toi_ic[k]);
+        for (int it = 0; it < 20; ++it)                                       // world.py:785 pos_iters = 20
+            if (toi_position_sweep(ncontacts, toi_a, toi_b)) break;
+        {   // the leap of faith to the new safe state: island.py:196-202
+            const int ba = toi_ib[toi_a], bb = toi_ib[toi_b];
+            real* pa = b_pos0 + 4 * (size_t)ba; real* pb = b_pos0 + 4 * (size_t)bb;
+            pa[0] = toi_P[3 * toi_a]; pa[1] = toi_P[3 * toi_a + 1]; pa[2] = toi_P[3 * toi_a + 2];
+            pb[0] = toi_P[3 * toi_b]; pb[1] = toi_P[3 * toi_b + 1]; pb[2] = toi_P[3 * toi_b + 2];
+        }
+        for (int k = 0; k < ncontacts; ++k) toi_init_velocity(toi_C[k]);
+        for (int it = 0; it < vel_iters; ++it)
+            for (int k = 0; k < ncontacts; ++k) toi_solve_velocity(toi_C[k]);
+        // (the impulses are not stored) integrate: island.py:213-241
+        for (int i = 0; i < nbodies; ++i) {
+            const int b = toi_ib[i];
+            V2 c = mk<real>(toi_P[3 * i], toi_P[3 * i + 1]), v = mk<real>(toi_V[3 * i], toi_V[3 * i + 1]);
+            real a = toi_P[3 * i + 2], w = toi_V[3 * i + 2];
+            const V2 translation = dt * v;
+            if (length_sqr(translation) > K<real>::max_translation_sqr) {       // island.py:219: .length_squared (** 2)
+                const real ratio = K<real>::max_translation / sqrt_r(length_sqr(translation));
+                v = ratio * v;
+            }
+            const real rotation = dt * w;
+            if (sq_r(rotation) > K<real>::max_rotation_sqr) {
+                const real ratio = K<real>::max_rotation / abs_r(rotation);
+                w = w * ratio;
+            }
+            c = c + dt * v;
+            a = a + dt * w;
+            real* p = b_pos + 4 * (size_t)b; real* vo = b_vel + 4 * (size_t)b;
+            p[0] = c.x; p[1] = c.y; p[2] = a;
+            vo[0] = v.x; vo[1] = v.y; vo[2] = w;
+            body_sync_transform(b);
+        }
+    }
+
+    // One TOI event up to the solved sub-island (world.py:696-790), thread 0 only.  Returns the number of sub-island
+    // bodies (0: the contact was not solid, the sweeps were restored).
+    B2B_D int toi_event(const step_params& sp, int mc, real min_alpha)
+    {
+        const int nc = w_count[2];
+        const int body_a = f_body[c_fix[2 * mc]], body_b = f_body[c_fix[2 * mc + 1]];
+        const sweep_t<real> backup_a = sweep_load(body_a), backup_b = sweep_load(body_b);
+        body_advance(body_a, min_alpha);
+        body_advance(body_b, min_alpha);
+        toi_contact_update(mc);
+        toi_state[mc] = ((toi_state[mc] & ~TS_FLAG) & ~TS_COUNT_MASK) | (((toi_state[mc] & TS_COUNT_MASK) + 1) & TS_COUNT_MASK);
+        if (!(c_flags[mc] & CONTACT_ENABLED) || !(c_flags[mc] & CONTACT_TOUCHING)) {
+            c_flags[mc] &= ~CONTACT_ENABLED;
+            sweep_store(body_a, backup_a);
+            sweep_store(body_b, backup_b);
+            body_sync_transform(body_a);
+            body_sync_transform(body_b);
+            return 0;
+        }
+        body_wake(body_a);
+        body_wake(body_b);
+        int nib = 0, nic = 0;
+        wake_at[body_a] = nib; toi_ib[nib++] = body_a;
+        wake_at[body_b] = nib; toi_ib[nib++] = body_b;
+        toi_ic[nic++] = mc;
+        toi_state[mc] |= TS_ISLAND;
+        for (int si = 0; si < 2; ++si) {
+            const int body = si ? body_b : body_a;
+            const int seed_bit = si ? TS_SEED_B : TS_SEED_A;
+            if (body_type(body) != BODY_DYNAMIC) continue;
+            const bool body_bullet = (b_flags[body] & BODY_BULLET) != 0;
+            for (int c = 0; c < nc; ++c) {                                    // body._contacts: the world's list, filtered
+                const int st = toi_state[c];
+                if (!(st & seed_bit)) continue;
+                if (nib == 2 * (int)MAX_TOI_CONTACTS) break;
+                if (nic == (int)MAX_TOI_CONTACTS) break;
+                if (st & TS_ISLAND) continue;
+                const int cba = f_body[c_fix[2 * c]], cbb = f_body[c_fix[2 * c + 1]];
+                const int other = (cba == body) ? cbb : cba;
+                if (body_type(other) == BODY_DYNAMIC && !body_bullet && !(b_flags[other] & BODY_BULLET)) continue;
+                const sweep_t<real> backup = sweep_load(other);
+                if (wake_at[other] < 0) body_advance(other, min_alpha);
+                toi_contact_update(c);
+                if (!(c_flags[c] & CONTACT_ENABLED) || !(c_flags[c] & CONTACT_TOUCHING)) {
+                    sweep_store(other, backup);
+                    body_sync_transform(other);
+                    continue;
+                }
+                toi_state[c] = st | TS_ISLAND;
+                toi_ic[nic++] = c;
+                if (wake_at[other] >= 0) continue;
+                if (body_type(other) != BODY_STATIC) body_wake(other);
+                wake_at[other] = nib; toi_ib[nib++] = other;
+            }
+        }
+        const real sub_dt = (real(1) - min_alpha) * (real)sp.dt;
+        toi_island_solve(nib, nic, sub_dt, sp.vel_iters, wake_at[body_a], wake_at[body_b]);
+        return nib;
+    }
+
+    B2B_D void phase_toi(const step_params& sp)
+    {
+        const int nb = w_count[0];
+        // world.py:599-609 (the step is always complete here: no sub_stepping)
+        B2B_PFOR(b, nb) { b_pos0[4 * (size_t)b + 3] = real(0); wake_at[b] = -1; }
+        { const int nc = w_count[2]; B2B_PFOR(c, nc) { toi_alpha[c] = real(1); toi_state[c] = 0; } }
+        B2B_SYNC();
+        bool advanced = false;          // some body's sweep starts later than the step does (after the first solved event)
+        for (;;) {
+            const int nc = w_count[2];
+            B2B_PFOR(c, nc) {
+                const int st = toi_state[c];
+                toi_state[c] = toi_candidate(c, st) ? (st | TS_NEED) : (st & ~TS_NEED);
+            }
+            B2B_SYNC();
+            if (!advanced) {
+                // every sweep starts at alpha0 = 0: nothing to equalise, the candidates are independent
+                B2B_PFOR(c, nc) {
+                    if (!(toi_state[c] & TS_NEED)) continue;
+                    const sweep_t<real> sa = sweep_load(f_body[c_fix[2 * c]]), sb = sweep_load(f_body[c_fix[2 * c + 1]]);
+                    toi_evaluate(c, sa, sb, real(0));
+                }
+                B2B_SYNC();
+            } else {
+                int c_next = 0;
+                for (;;) {
+                    if (B2B_IS_T0) {
+                        int n = 0, c = c_next;
+                        for (; c < nc && n < (int)TOI_BATCH; ++c) {
+                            if (!(toi_state[c] & TS_NEED)) continue;
+                            const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
+                            sweep_t<real> sa = sweep_load(ba), sb = sweep_load(bb);
+                            real alpha0 = sa.alpha0;                          // world.py:657-666
+                            if (sa.alpha0 < sb.alpha0) { alpha0 = sb.alpha0; sweep_advance(sa, alpha0); sweep_store(ba, sa); }
+                            else if (sb.alpha0 < sa.alpha0) { sweep_advance(sb, alpha0); sweep_store(bb, sb); }
+                            real* q = toi_snap + (size_t)TOI_SNAP_REALS * n;
+                            q[0] = sa.c0.x; q[1] = sa.c0.y; q[2] = sa.a0; q[3] = sa.c.x; q[4] = sa.c.y; q[5] = sa.a;
+                            q[6] = sb.c0.x; q[7] = sb.c0.y; q[8] = sb.a0; q[9] = sb.c.x; q[10] = sb.c.y; q[11] = sb.a;
+                            q[12] = alpha0;
+                            toi_snap_ci[n++] = c;
+                        }
+                        s_ctl[13] = n; s_ctl[14] = c;
+                    }
+                    B2B_SYNC();
+                    const int n = s_ctl[13];
+                    c_next = s_ctl[14];
+                    B2B_PFOR(k, n) {
+                        const int c = toi_snap_ci[k];
+                        const real* q = toi_snap + (size_t)TOI_SNAP_REALS * k;
+                        const quad ma = ldq(b_mass + 4 * (size_t)f_body[c_fix[2 * c]]), mb = ldq(b_mass + 4 * (size_t)f_body[c_fix[2 * c + 1]]);
+                        sweep_t<real> sa, sb;
+                        sa.lc = mk<real>(ma.z, ma.w); sa.c0 = mk<real>(q[0], q[1]); sa.a0 = q[2]; sa.c = mk<real>(q[3], q[4]); sa.a = q[5];
+                        sb.lc = mk<real>(mb.z, mb.w); sb.c0 = mk<real>(q[6], q[7]); sb.a0 = q[8]; sb.c = mk<real>(q[9], q[10]); sb.a = q[11];
+                        sa.alpha0 = sb.alpha0 = q[12];
+                        toi_evaluate(c, sa, sb, q[12]);
+                    }
+                    B2B_SYNC();
+                    if (c_next >= nc) break;
+                }
+            }
+            // the first contact of the list with the smallest time of impact (world.py:688-691: strict <)
+            {
+                real best = real(1);
+                int best_c = -1;
+                B2B_PFOR(c, nc) {
+                    const int st = toi_state[c];
+                    if (!(st & TS_FLAG) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || !(c_flags[c] & CONTACT_ENABLED)) continue;
+                    const real a = toi_alpha[c];
+                    if (a < best) { best = a; best_c = c; }
+                }
+                toi_red_a[t_id & 31] = best; toi_red_i[t_id & 31] = best_c;
+                B2B_SYNC();
+                if (B2B_IS_T0) {
+                    const int lanes = t_n < 32 ? t_n : 32;
+                    for (int l = 1; l < lanes; ++l) {
+                        const real a = toi_red_a[l];
+                        const int ci = toi_red_i[l];
+                        if (ci >= 0 && (a < best || (a == best && ci < best_c))) { best = a; best_c = ci; }
+                    }
+                    toi_red_a[0] = best;
+                    s_ctl[13] = best_c;
+                }
+                B2B_SYNC();
+            }
+            const int min_contact = s_ctl[13];
+            const real min_alpha = toi_red_a[0];
+            B2B_SYNC();
+            if (min_contact < 0 || (real(1) - (real(10) * K<real>::epsilon)) < min_alpha) break;
+
+            // the event.  Which contacts touch the two bodies (body._contacts of the sub-island's seeds): in parallel
+            const int body_a = f_body[c_fix[2 * min_contact]], body_b = f_body[c_fix[2 * min_contact + 1]];
+            B2B_PFOR(c, nc) {
+                const int cba = f_body[c_fix[2 * c]], cbb = f_body[c_fix[2 * c + 1]];
+                int st = toi_state[c] & ~(TS_SEED_A | TS_SEED_B | TS_ISLAND);
+                if (cba == body_a || cbb == body_a) st |= TS_SEED_A;
+                if (cba == body_b || cbb == body_b) st |= TS_SEED_B;
+                toi_state[c] = st;
+            }
+            B2B_SYNC();
+            if (B2B_IS_T0) {
+                s_ctl[14] = toi_event(sp, min_contact, min_alpha);
+                w_flags[0] &= ~WORLD_GRAPH_VALID;       // manifolds, touching flags, awake flags and positions changed under the plan
+            }
+            B2B_SYNC();
+            const int nib = s_ctl[14];
+            B2B_SYNC();
+            if (nib == 0) continue;
+            advanced = true;
+            // world.py:794-806: proxies of the sub-island's dynamic bodies, and the cached times of impact of their contacts
+            const int nf = w_count[1];
+            B2B_PFOR(f, nf) {
+                const int b = f_body[f];
+                if (wake_at[b] >= 0 && body_type(b) == BODY_DYNAMIC) sync_fixture_of(f, b);
+            }
+            B2B_PFOR(c, nc) {
+                const int cba = f_body[c_fix[2 * c]], cbb = f_body[c_fix[2 * c + 1]];
+                const bool hit = (wake_at[cba] >= 0 && body_type(cba) == BODY_DYNAMIC) || (wake_at[cbb] >= 0 && body_type(cbb) == BODY_DYNAMIC);
+                if (hit) toi_state[c] &= ~(TS_FLAG | TS_ISLAND);
+            }
+            B2B_SYNC();
+            B2B_PFOR(i, nib) wake_at[toi_ib[i]] = -1;
+            B2B_SYNC();
+            // world.py:810: find_new_contacts (a contact created here is not enabled before the next step's narrowphase)
+            phase_pairs(false);
+            { const int nc1 = w_count[2]; B2B_PFOR(c, nc1) if (c >= nc) { toi_alpha[c] = real(1); toi_state[c] = 0; } }
+            B2B_SYNC();
+        }
+    }
+    B2B_D void run_toi(const step_params& sp)
+    {
+        if (sp.dt > 0.0 && (w_flags[0] & WORLD_CONTINUOUS)) phase_toi(sp);
+    }
+
     // ------------------------------------------------------------------------------------ World.step
     // plan kernel: (find_new_contacts if new fixtures) + collide + island construction + level schedule
     B2B_D void run_plan(const step_params& sp)
@@ -2113,6 +2639,7 @@ template <class real> struct world_step {
             const int n_items = sync_items();
             for (int i = 0; i < n_items; ++i) sync_item(sp, i);
             run_pairs(sp);
+            run_toi(sp);
         }
     }
 };

@@ -73,9 +73,16 @@ def jitter(config, world, n_bodies, amp=JITTER_AMP):
     return amp * (2.0 * u - 1.0)
 
 
+def _kw(world_kw):
+    """World keywords of a scene: continuous collision is OFF unless the caller asks for it (the parity setting)."""
+    kw = dict(world_kw)
+    kw.setdefault("continuous_physics", False)
+    return kw
+
+
 # ---- config 1 / 3: examples/pyramid-bench.py:32-53 -------------------------------------------
 def pyramid(b2, world=0, rows=20, config=1, **world_kw):
-    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w = b2.World((0, -10), True, **_kw(world_kw))
     w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
     fixture = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
     n_dyn = rows * (rows + 1) // 2
@@ -94,7 +101,7 @@ def pyramid(b2, world=0, rows=20, config=1, **world_kw):
 
 # ---- config 2(i): examples/hello-bench.py:21-36 ---------------------------------------------
 def hello(b2, world=0, config=2, **world_kw):
-    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w = b2.World((0, -10), True, **_kw(world_kw))
     ground = w.create_static_body(position=(0, -10))
     ground.create_polygon_fixture(box=(50, 10))
     jit = jitter(config, world, 2)[1:]
@@ -105,7 +112,7 @@ def hello(b2, world=0, config=2, **world_kw):
 
 # ---- config 2(ii): examples/verticalstack-bench.py:33-75 ------------------------------------
 def vertical_stack(b2, world=0, columns=5, rows=16, config=2, **world_kw):
-    w = b2.World(continuous_physics=False, **world_kw)
+    w = b2.World(**_kw(world_kw))
     w.create_static_body(shapes=[b2.Edge((-40, 0), (40, 0)), b2.Edge((20, 0), (20, 20))])
     box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
     circle = b2.Fixture(shape=b2.Circle(0.5), density=1, friction=0.3)
@@ -122,7 +129,7 @@ def vertical_stack(b2, world=0, columns=5, rows=16, config=2, **world_kw):
 
 # ---- config 4: mixed circles + convex polygons in a box of edges (testbed/confined.py:35-41) --
 def mixed(b2, world=0, side=16, config=4, **world_kw):
-    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w = b2.World((0, -10), True, **_kw(world_kw))
     w.create_static_body(shapes=[b2.Edge((-10, 0), (10, 0)), b2.Edge((-10, 0), (-10, 20)),
                                  b2.Edge((10, 0), (10, 20)), b2.Edge((-10, 20), (10, 20))])
     n = side * side
@@ -149,7 +156,7 @@ def mixed(b2, world=0, side=16, config=4, **world_kw):
 
 # ---- config 5: deep vertical stacks, 10 columns x 20 boxes -----------------------------------
 def deep_stacks(b2, world=0, columns=10, rows=20, config=5, **world_kw):
-    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w = b2.World((0, -10), True, **_kw(world_kw))
     w.create_static_body(shapes=b2.Edge((-40, 0), (40, 0)))
     box = b2.Fixture(shape=b2.Polygon(box=(0.5, 0.5)), density=1, friction=0.3)
     jit = jitter(config, world, columns * rows + 1)[1:]
@@ -166,7 +173,7 @@ def features(b2, world=0, config=6, **world_kw):
     """Edge chain with ghost vertices (EPCollider / edge-circle adjacency), a kinematic platform, restitution,
     damping, gravity scale, fixed rotation, a two-fixture body, group and category/mask filtering, circles and
     3..6-gons."""
-    w = b2.World((0, -10), True, continuous_physics=False, **world_kw)
+    w = b2.World((0, -10), True, **_kw(world_kw))
     chain = [(-20.0, 6.0), (-12.0, 0.0), (-4.0, 0.0), (0.0, 2.5), (4.0, 0.0), (12.0, 0.0), (20.0, 6.0)]
     edges = []
     for i in range(len(chain) - 1):
@@ -207,5 +214,56 @@ def features(b2, world=0, config=6, **world_kw):
     return w
 
 
+# ---- continuous-collision coverage scene (not a BASELINE config): bullets, thin walls, fast bodies --------------
+def bullets(b2, world=0, config=7, **world_kw):
+    """What World.solve_toi (world.py:594-821) reads: bullet bodies against static walls, against a kinematic
+    platform and against ordinary dynamic bodies; fast non-bullet bodies against static geometry (the only TOI
+    events of a scene without bullets); a thin spinning rod; circles, boxes, polygons and edges as TOI proxies.
+    Continuous collision is ON by default here."""
+    kw = dict(world_kw)
+    kw.setdefault("continuous_physics", True)
+    w = b2.World((0, -10), True, **kw)
+    w.create_static_body(shapes=[b2.Edge((-20.0, 0.0), (20.0, 0.0)), b2.Edge((-12.0, 0.0), (-12.0, 12.0))])
+    w.create_static_body(position=(8.0, 3.0), shapes=b2.Polygon(box=(0.05, 3.0)))
+    w.create_kinematic_body(position=(-4.0, 6.0), linear_velocity=(1.5, 0.0), angular_velocity=0.3,
+                            fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), friction=0.4))
+    n = 24
+    jit = jitter(config, world, n + 3)[3:]
+    k = 0
+
+    def at(x, y):
+        return (x + jit[k, 0], y + jit[k, 1])
+
+    box = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=1.0, friction=0.3)
+    for i in range(6):                                            # a stack the bullets hit
+        w.create_dynamic_body(position=at(2.0, 0.51 + 1.02 * i), fixtures=box)
+        k += 1
+    for i in range(4):                                            # bullets at the thin wall, the stack, the edge wall
+        w.create_dynamic_body(position=at(-2.0 - 1.5 * i, 1.0 + 1.1 * i), bullet=True, linear_velocity=(70.0 + 25.0 * i, 2.0 * i),
+                              fixtures=b2.Fixture(b2.Circle(0.12 + 0.03 * i), density=4.0, friction=0.2, restitution=0.3))
+        k += 1
+    for i in range(3):
+        w.create_dynamic_body(position=at(-3.0 + 0.8 * i, 8.0 + 0.9 * i), bullet=True, linear_velocity=(-90.0, -20.0 - 10.0 * i),
+                              angular_velocity=5.0, fixtures=b2.Fixture(b2.Polygon(box=(0.2, 0.1)), density=2.0, friction=0.5))
+        k += 1
+    for i in range(5):                                            # fast ordinary bodies: TOI against static geometry only
+        m = 3 + i
+        shape = b2.Polygon(vertices=[(0.4 * math.cos(0.2 + 2.0 * math.pi * q / m), 0.4 * math.sin(0.2 + 2.0 * math.pi * q / m))
+                                     for q in range(m)])
+        w.create_dynamic_body(position=at(-10.0 + 1.7 * i, 9.0 + 0.7 * i), linear_velocity=(3.0 - i, -45.0 - 8.0 * i), angle=0.3 * i,
+                              fixtures=b2.Fixture(shape, density=1.0, friction=0.3, restitution=0.1 * i))
+        k += 1
+    for i in range(3):                                            # thin rods, spinning
+        w.create_dynamic_body(position=at(11.0 + 2.2 * i, 5.0 + 2.0 * i), angular_velocity=25.0 - 20.0 * i, linear_velocity=(-6.0, -30.0),
+                              fixtures=b2.Fixture(b2.Polygon(box=(1.2, 0.04)), density=1.0, friction=0.3))
+        k += 1
+    for i in range(3):                                            # bullets dropped on the kinematic platform
+        w.create_dynamic_body(position=at(-5.0 + 1.2 * i, 9.0 + 1.5 * i), bullet=True, linear_velocity=(0.0, -60.0),
+                              fixtures=b2.Fixture(b2.Circle(0.2), density=1.0, friction=0.3, restitution=0.5))
+        k += 1
+    assert k == n
+    return w
+
+
 SCENES = {"features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
-          "deep_stacks": deep_stacks}
+          "deep_stacks": deep_stacks, "bullets": bullets}

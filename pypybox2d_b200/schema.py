@@ -33,11 +33,13 @@ WORLD_WARM_STARTING = 0x2     # world.py:74
 WORLD_NEW_FIXTURE = 0x4       # world.py:85
 WORLD_AUTO_CLEAR = 0x8        # world.py:80
 WORLD_GRAPH_VALID = 0x10      # device bookkeeping: last step's island lists / schedule are still valid
+WORLD_CONTINUOUS = 0x20       # world.py:78 continuous_physics: World.solve_toi runs after the discrete solve
 
 STATUS_CONTACT_OVERFLOW = 0x1
 STATUS_PAIR_OVERFLOW = 0x2
 STATUS_NAN = 0x4
 STATUS_ISLAND_OVERFLOW = 0x8
+STATUS_TOI_STUCK = 0x10        # a time-of-impact push-back loop was cut off (csrc/b2b_toi.cuh TOI_MAX_PUSH_BACK)
 
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2   # contact_util.py:141-143
 
@@ -58,7 +60,7 @@ FIELDS = [
     ("b_xf",      "B", (4,), "real"),  # origin x, y, cos, sin            (Body._xf)
     ("b_pos",     "B", (4,), "real"),  # sweep.c x, y, sweep.a, sleep_time
     ("b_vel",     "B", (4,), "real"),  # v x, y, w, torque
-    ("b_pos0",    "B", (4,), "real"),  # sweep.c0 x, y, sweep.a0, (unused)
+    ("b_pos0",    "B", (4,), "real"),  # sweep.c0 x, y, sweep.a0, sweep.alpha0
     ("b_force",   "B", (2,), "real"),
     ("b_mass",    "B", (4,), "real"),  # inv_mass, inv_I, local_center x, y
     ("b_damp",    "B", (4,), "real"),  # linear_damping, angular_damping, gravity_scale, (unused)
@@ -228,6 +230,8 @@ def pack_world(world, arrays, w, table):
         flags |= WORLD_WARM_STARTING
     if world._auto_clear_forces:
         flags |= WORLD_AUTO_CLEAR
+    if getattr(world, "_continuous_physics", False):
+        flags |= WORLD_CONTINUOUS
     A["w_flags"][w] = flags
     A["w_status"][w] = 0
     A["w_gravity"][w] = (world._gravity.x, world._gravity.y)

@@ -7,8 +7,8 @@ objects.  A single `World` is a batch of one; large batches use `BatchedWorld` d
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
 Unsupported on this path (raise `NotImplementedError`): joints, controllers,
-contact listeners, custom contact filters, sensors, Loop shapes, `continuous_physics=True`
-stepping (TOI) and sub-stepping.
+contact listeners, custom contact filters, sensors, Loop shapes and sub-stepping.  Continuous collision
+(`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
 """
 from copy import copy
 
@@ -63,7 +63,7 @@ class World(object):
         if contact_filter is not None:
             raise NotImplementedError("custom contact filters cannot run inside the device step")
         if sub_stepping:
-            raise NotImplementedError("sub_stepping belongs to the TOI path (SURVEY §8f #1)")
+            raise NotImplementedError("sub_stepping (single-stepping through TOI events, a testbed debugging aid) is not supported")
         self._gravity = Vec2(*gravity)
         self.bodies = []
         self.joints = []
@@ -109,6 +109,8 @@ class World(object):
     @continuous_physics.setter
     def continuous_physics(self, v):
         self._continuous_physics = bool(v)
+        if self._batch is not None:
+            self._batch.set_continuous(self._continuous_physics)
 
     @property
     def contact_filter(self):
@@ -167,10 +169,6 @@ class World(object):
         return self._batch
 
     def step(self, dt, vel_iters, pos_iters):
-        if self._continuous_physics and dt > 0.0:
-            raise NotImplementedError(
-                "continuous_physics=True (TOI) is not implemented on the device path; "
-                "construct World(..., continuous_physics=False) (SURVEY §0 finding 2, §8f #1)")
         if self._locked:
             raise LockedError("step is not re-entrant")
         batch = self._ensure_batch()

@@ -24,6 +24,12 @@ def load_golden(case):
     return np.load(os.path.join(GOLDEN, case + ".npz"))
 
 
+def golden_scene_kw(g):
+    """Scene keywords a fixture was generated with (oracle/gen_golden.py; absent = none)."""
+    import json
+    return json.loads(str(g["scene_kw"])) if "scene_kw" in g.files else {}
+
+
 def arrays_from_golden(g, prefix="init_", base=None):
     """Schema arrays (fp64, batch of one) filled from a golden fixture's used rows."""
     from pypybox2d_b200 import schema

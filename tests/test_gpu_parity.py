@@ -91,7 +91,8 @@ def _group_kernel_cases():
 # Float fields of the state compared in P-exact, and the per-scene bound on their absolute error (m, m/s, N s):
 # measured maxima on B200 (profiles/r2_parity_report.json: 7.6e-13, 0, 4.5e-10, 5.3e-8, 4.2e-9, 5.7e-7) times 10-20.
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
-EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5}
+EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5,
+             "bullets": 1e-5}
 
 
 def float_diffs(OA, G):

@@ -17,9 +17,15 @@ CASES = [("hello", 0, 0.1, 10, 10, 40), ("pyramid", 1, 1 / 60, 8, 3, 120), ("ver
          ("mixed", 1, 1 / 60, 8, 3, 150), ("deep_stacks", 1, 1 / 60, 8, 3, 150), ("features", 1, 1 / 60, 8, 3, 200)]
 
 
-@pytest.mark.parametrize("scene,world,dt,vi,pi,steps", CASES)
-def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps):
-    mw, OA, caps = harness.facade_arrays(scene, world)
+CCD = {"continuous_physics": True}
+# continuous collision on (World.solve_toi, world.py:594-821): the bullets scene has it on by construction
+CCD_CASES = [("bullets", 0, 1 / 60, 8, 3, 300, {}), ("bullets", 2, 1 / 30, 10, 4, 200, {}), ("hello", 0, 0.1, 10, 10, 60, CCD),
+             ("features", 1, 1 / 60, 8, 3, 150, CCD), ("pyramid", 1, 1 / 60, 8, 3, 90, CCD), ("vertical_stack", 1, 1 / 60, 10, 10, 80, CCD)]
+
+
+@pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES)
+def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps, kw):
+    mw, OA, caps = harness.facade_arrays(scene, world, **kw)
     HA = {k: v.copy() for k, v in OA.items()}
     orc = oracle.Oracle(OA, 0)
     inv = 0.0

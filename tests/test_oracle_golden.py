@@ -8,7 +8,7 @@ the reference's initial state too.
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden, arrays_from_golden
+from conftest import golden_cases, load_golden, arrays_from_golden, golden_scene_kw
 
 import harness
 import oracle
@@ -23,7 +23,7 @@ def test_oracle_replays_reference_trajectory(case):
     vi, pi, steps, world = int(vi), int(pi), int(steps), int(world)
     scene = str(g["scene"])
     caps = schema.Caps(*[int(x) for x in g["caps"]])
-    mw, A, _ = harness.facade_arrays(scene, world, caps=caps, n_shapes=int(g["init_s_meta"].shape[0]))
+    mw, A, _ = harness.facade_arrays(scene, world, caps=caps, n_shapes=int(g["init_s_meta"].shape[0]), **golden_scene_kw(g))
     # facade-built initial state == reference-built initial state (bitwise)
     for name in gen_golden.INIT_FIELDS:
         ref = g["init_" + name]
