@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--t0-worlds", type=int, default=65536, help="worlds of the secondary from-t=0 run (0: skip it)")
     ap.add_argument("--t0-steps", type=int, default=600)
+    ap.add_argument("--ccd-steps", type=int, default=5, help="steps of the secondary run with continuous collision on (0: skip it)")
     return ap.parse_args()
 
 
@@ -487,6 +488,25 @@ def run_b200_arm(args):
 
     inv = invariance_check(b2, dist, rank, world_size, device, args.real) if not args.no_invariance else None
 
+    # ---- secondary, reported under config.continuous_on: the same settled batch with continuous collision switched ON
+    # (World(continuous_physics=True), the reference's default; World.solve_toi runs in one more kernel after the pairs: in a
+    # settled pyramid every step computes the time of impact of the 20 ground contacts and finds no event).  Rank 0 only.
+    ccd_on = None
+    if rank == 0 and args.ccd_steps > 0:
+        bw.set_continuous(True)
+        bw.step(dt, vi, pi, 2)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        c0.record()
+        bw.step(dt, vi, pi, args.ccd_steps)
+        c1.record()
+        torch.cuda.synchronize(device)
+        ccd_ms = c0.elapsed_time(c1) / args.ccd_steps
+        ccd_on = {"value": n_dyn * args.worlds / (ccd_ms * 1e-3), "unit": "body-steps/s", "ms_per_step": ccd_ms, "steps": args.ccd_steps,
+                  "worlds": args.worlds, "status": bw.status(raise_on_overflow=False),
+                  "what": "the settled batch of the headline with continuous_physics=True on every world, one GPU, state resident"}
+        bw.set_continuous(False)
+
     # ---- secondary, reported under config.from_t0: the WHOLE job of the reference's bench script -- 600 steps from
     # the scripted start, free fall and landing transient included (rank 0 only).  Not the headline: BASELINE's metric
     # is quoted on the settled regime, where a long-running batch spends its time.
@@ -509,6 +529,21 @@ def run_b200_arm(args):
                    "status": cold.status(raise_on_overflow=False),
                    "what": "600 steps from the scripted start (free fall, landing, settling), one GPU, state resident"}
         del cold
+        if args.ccd_steps > 0:
+            # the reference's bench script verbatim: World((0, -10), True) has continuous collision ON while the pile lands
+            # (hundreds of TOI events per world, each a sub-island solve + proxy synchronisation + pair finding)
+            torch.cuda.empty_cache()
+            cold = b2.BatchedWorld.replicate(scenes.pyramid(b2, continuous_physics=True), args.t0_worlds, jitter=scenes.JITTER_AMP, config=3,
+                                             real=args.real, caps=S["caps"], device=device, threads=args.threads)
+            torch.cuda.synchronize(device)
+            c0.record()
+            cold.step(dt, vi, pi, args.t0_steps)
+            c1.record()
+            torch.cuda.synchronize(device)
+            cold_ms = c0.elapsed_time(c1)
+            from_t0["continuous_on"] = {"value": n_dyn * args.t0_worlds * args.t0_steps / (cold_ms * 1e-3), "unit": "body-steps/s",
+                                        "ms_per_step": cold_ms / args.t0_steps, "status": cold.status(raise_on_overflow=False)}
+            del cold
 
     if world_size > 1:
         import torch.distributed as tdist
@@ -531,7 +566,7 @@ def run_b200_arm(args):
                    "position_iterations_used": pos_iters_used, "l2": "inputs larger than L2 (%.1f GB of state per GPU), no flush"
                                                         % (state_gb,),
                    "parallelism": "worlds sharded by contiguous index blocks, one process per GPU, no collective on the step path",
-                   "host_numa": numa, "launch": launch_info, "status": status, "from_t0": from_t0},
+                   "host_numa": numa, "launch": launch_info, "status": status, "from_t0": from_t0, "continuous_on": ccd_on},
         "e2e": {"value": e2e_value, "unit": "body-steps/s", "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
                 "h2d_bytes_per_step": h2d_bytes * world_size, "d2h_bytes_per_step": d2h_bytes * world_size,
                 "ratio_to_value": e2e_value / value,

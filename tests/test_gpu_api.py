@@ -300,3 +300,66 @@ def test_inactive_body_is_never_simulated():
     assert (ghost.position.x, ghost.position.y) == (0.2, 1.0) and ghost.linear_velocity.y == 0.0
     assert w1.bodies[1].position.y == w0.bodies[1].position.y < 0.6           # fell THROUGH the ghost onto the ground
     assert len(w1.contact_manager.contacts) == len(w0.contact_manager.contacts) == 1
+
+
+def test_default_world_with_continuous_collision_is_a_drop_in():
+    """The reference's DEFAULT world has continuous collision on (world.py:65-78): an unmodified user script -- here a bullet
+    fired at a thin wall and a fast box dropped on the ground -- steps through World.solve_toi on the device and lands
+    where the oracle's does."""
+    import pypybox2d_b200 as b2
+    mw, A, caps = harness.facade_arrays("bullets", 1)
+    orc = oracle.Oracle(A, 0)
+    world = scenes.bullets(b2, world=1, real="f64")
+    assert world.continuous_physics
+    for i in range(120):
+        world.step(1 / 60, 8, 3)
+        orc.step(1 / 60, 8, 3)
+    nb = len(world.bodies)
+    got = np.array([[b.position.x, b.position.y, b.angle] for b in world.bodies])
+    want_xf = A["b_xf"][0, :nb]
+    assert np.abs(got[:, 0] - want_xf[:, 0]).max() < 1e-6 and np.abs(got[:, 1] - want_xf[:, 1]).max() < 1e-6
+    assert [b.awake for b in world.bodies] == [bool(f & schema.BODY_AWAKE) for f in A["b_flags"][0, :nb]]
+    assert len(world.contact_manager.contacts) == int(A["w_count"][0][2])
+    # the same script with continuous collision switched off lets the bullets tunnel: a different trajectory
+    off = scenes.bullets(b2, world=1, real="f64", continuous_physics=False)
+    for i in range(120):
+        off.step(1 / 60, 8, 3)
+    assert max(abs(a.position.x - b.position.x) for a, b in zip(off.bodies, world.bodies)) > 1.0
+
+
+def test_continuous_collision_batch_invariance_and_host_path(monkeypatch):
+    """T4 with World.solve_toi in the step: world i of a large fp32 batch equals the same world stepped alone, the host-buffer
+    entry point reads the state back AFTER the TOI kernel, and worlds with continuous collision off in the same batch are
+    untouched by it."""
+    import torch
+    import pypybox2d_b200 as b2
+    monkeypatch.setenv("B2B_PIPE_CHUNKS", "5")
+    w = scenes.bullets(b2)
+    big = b2.BatchedWorld.replicate(w, 200, jitter=1e-2, config=7, real="f32")
+    part = b2.BatchedWorld.replicate(w, 3, jitter=1e-2, config=7, world_offset=150, real="f32")
+    host = b2.BatchedWorld.replicate(w, 200, jitter=1e-2, config=7, real="f32")
+    assert big.continuous and host.continuous
+    nb = big.caps.nb
+    h_out = torch.zeros((200, nb, 6), dtype=torch.float32).pin_memory()
+    for s in range(90):
+        big.step(1 / 60, 8, 3)
+        part.step(1 / 60, 8, 3)
+        host.step_host(None, h_out, 1 / 60, 8, 3)
+    B, P = big.download(), part.download()
+    for name in ("b_pos", "b_vel", "b_pos0", "c_fix", "c_mtype", "c_imp", "w_count", "b_flags"):
+        assert np.array_equal(B[name][151], P[name][1]), name
+    assert np.array_equal(h_out.numpy()[..., :3], B["b_pos"][..., :3])
+    assert np.array_equal(h_out.numpy()[..., 3:], B["b_vel"][..., :3])
+    assert big.status() == 0
+    # every jittered world is a different trajectory (the bullets hit the stack differently)
+    assert len(np.unique(big.checksum().cpu().numpy()[:, 0])) == 200
+    # a mixed batch: continuous collision on in the even worlds only
+    mixed = b2.BatchedWorld.replicate(w, 8, jitter=1e-2, config=7, real="f32")
+    mixed.t["w_flags"][1::2] &= ~schema.WORLD_CONTINUOUS
+    offw = b2.BatchedWorld.replicate(scenes.bullets(b2, continuous_physics=False), 8, jitter=1e-2, config=7, real="f32")
+    for s in range(60):
+        mixed.step(1 / 60, 8, 3)
+        offw.step(1 / 60, 8, 3)
+    M, O = mixed.download(["b_pos"]), offw.download(["b_pos"])
+    assert np.array_equal(M["b_pos"][1::2, :, :3], O["b_pos"][1::2, :, :3])
+    assert not np.array_equal(M["b_pos"][0::2, :, :3], O["b_pos"][0::2, :, :3])

@@ -93,6 +93,14 @@ def _group_kernel_cases():
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
 EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5,
              "bullets": 1e-5}
+# Continuous collision on (World.solve_toi; measured by tools/ccd_parity_probe.py on B200, profiles/r2_ccd_parity.json): the
+# TOI sub-steps amplify the same one-ulp libm differences further.  Free-running, seven of the eight cases keep the oracle's
+# integer outputs for their whole length (worst float difference: pyramid landing 5.2e-13, features 1.4e-9, bullets 4.5e-9 /
+# 5.1e-7, mixed 4.2e-8, the swaying vertical stacks 9.3e-4); bullets_w2 (dt = 1/30, bullets at 70-150 m/s into a stack)
+# leaves them at step 35, a step on which the SAME kernels teacher-forced from the oracle's state are exact -- as they are
+# on every step of every case (test_p_exact_fp64_one_step: integers identical, floats <= 1.3e-12).
+EXACT_TOL_CASE = {"vertical_stack_ccd_w1": 1e-2}
+FREE_RUN_STEPS = {"bullets_w2": 35}
 
 
 def float_diffs(OA, G):
@@ -111,7 +119,8 @@ def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
     g = load_golden(case)
     dt, vi, pi, steps, world = g["meta"]
     vi, pi, steps = int(vi), int(pi), int(steps)
-    tol = EXACT_TOL[str(g["scene"])]
+    tol = EXACT_TOL_CASE.get(case, EXACT_TOL[str(g["scene"])])
+    steps = min(steps, FREE_RUN_STEPS.get(case, steps))
     A, caps = arrays_from_golden(g)
     bw = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
     orc = oracle.Oracle(A, 0)
@@ -130,7 +139,11 @@ def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
     parity_report("p_exact/%s%s" % (case, "/group" if group_kernel else ""), dict(worst, steps=steps, tol=tol))
 
 
-@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0"])
+CCD_CASES = ["bullets_w0", "bullets_w1", "bullets_w2", "hello_ccd_w0", "pyramid_ccd_w1", "vertical_stack_ccd_w1", "features_ccd_w1",
+             "mixed_ccd_w1"]
+
+
+@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0"] + CCD_CASES)
 def test_p_exact_fp64_one_step(case, parity_report):
     """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
     1e-11 in every float field at every k (measured: 1.5e-12) -- the free-running differences of the swaying and tumbling
@@ -158,9 +171,20 @@ def test_p_exact_fp64_one_step(case, parity_report):
     parity_report("p_exact_one_step/%s" % case, dict(worst, steps=steps))
 
 
+# fp32 one-step bounds (m, m/s) on steps whose integer outputs are the oracle's.  With continuous collision on there is a
+# knife edge in the reference's own algorithm: a TOI sub-island starts 3 slops deep (target separation, toi.py:258), the
+# first TOI position sweep removes 0.75 of the excess (TOI_BAUMGARTE) and leaves the contact at EXACTLY -1.5 slops, which
+# is the sweep loop's exit test (contact.py:933 `min_separation >= -1.5 * LINEAR_SLOP`): rounding decides whether a second
+# sweep runs, and one sweep more or less is 0.0075 / 16 = 4.7e-4 m of position (measured: 4.69e-4 on every scene with
+# TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
+P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES}
+
+
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
                                         ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60),
-                                        ("features_w0", 200)])
+                                        ("features_w0", 200), ("bullets_w0", 300), ("bullets_w2", 200), ("hello_ccd_w0", 100),
+                                        ("pyramid_ccd_w1", 300), ("features_ccd_w1", 300), ("mixed_ccd_w1", 120),
+                                        ("vertical_stack_ccd_w1", 200)])
 def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)
@@ -185,6 +209,8 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
         tie_what = int_mismatches(T, G)
         tie = bool(tie_what)
         tol_p, tol_v = (1e-3, 1e-2) if tie else (5e-5, 1e-3)
+        if case in P_STEP_BOUNDS:
+            tol_p, tol_v = P_STEP_BOUNDS[case]
         assert dp <= tol_p and dv <= tol_v, "fp32 one-step state error at step %d (tie=%s): %.2e m, %.2e m/s" % (s, tie, dp, dv)
         if not tie:
             worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
