@@ -91,8 +91,8 @@ def diff_state(A, B, w=0, fields=STATE_FIELDS, exact=True, rtol=0.0, atol=0.0):
                 x = x & ~np.uint32(schema.BODY_ISLAND)
                 y = y & ~np.uint32(schema.BODY_ISLAND)
             if k == "w_flags":      # device-only bookkeeping bit
-                x = x & ~np.uint32(schema.WORLD_GRAPH_VALID)
-                y = y & ~np.uint32(schema.WORLD_GRAPH_VALID)
+                x = x & ~np.uint32(schema.WORLD_GRAPH_VALID | schema.WORLD_TOI_DIRTY)
+                y = y & ~np.uint32(schema.WORLD_GRAPH_VALID | schema.WORLD_TOI_DIRTY)
             if k == "c_flags":
                 x = x & ~np.uint32(schema.CONTACT_ISLAND)
                 y = y & ~np.uint32(schema.CONTACT_ISLAND)

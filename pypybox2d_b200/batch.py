@@ -342,6 +342,7 @@ class BatchedWorld(object):
             else:
                 self.t[name].copy_(src)
         self.t["w_flags"] &= ~schema.WORLD_GRAPH_VALID      # host-side mutation: rebuild the island schedule
+        self.t["w_flags"] |= schema.WORLD_TOI_DIRTY         # ... and let the next World.solve_toi reset whatever alpha0 came in
         self._continuous = None                             # (w_flags may have been replaced)
 
     # -- single-world facade support ----------------------------------------------------------

@@ -39,6 +39,7 @@ enum : uint32_t {
     WORLD_ALLOW_SLEEP = 0x1u, WORLD_WARM_STARTING = 0x2u, WORLD_NEW_FIXTURE = 0x4u, WORLD_AUTO_CLEAR = 0x8u,
     WORLD_GRAPH_VALID = 0x10u,   // the island lists / level schedule of the last step still describe this world
     WORLD_CONTINUOUS = 0x20u,    // continuous_physics (world.py:78): World.solve_toi runs after the discrete solve
+    WORLD_TOI_DIRTY = 0x40u,     // device bookkeeping: some body's sweep.alpha0 is non-zero (a TOI event was solved last step)
     STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u,
     STATUS_TOI_STUCK = 0x10u     // a time-of-impact push-back loop was cut off (b2b_toi.cuh TOI_MAX_PUSH_BACK)
 };

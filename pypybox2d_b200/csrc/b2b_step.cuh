@@ -1947,9 +1947,13 @@ template <class real> struct world_step {
                 exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
             }
         } else {
-            for (int c = 0; c < nc && !exists; ++c) {
-                const int ca = c_fix[2 * c], cb = c_fix[2 * c + 1];
-                exists = (ca == fa && cb == fb) || (ca == fb && cb == fa);
+            // (four rows per round, loaded before they are looked at: the loop is a chain of dependent loads otherwise)
+            for (int c = 0; c < nc && !exists; c += 4) {
+                int ca[4], cb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const int ck = (c + k < nc) ? c + k : c; ca[k] = c_fix[2 * ck]; cb[k] = c_fix[2 * ck + 1]; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) exists = exists || (ca[k] == fa && cb[k] == fb) || (ca[k] == fb && cb[k] == fa);
             }
         }
         if (exists) return false;
@@ -2076,7 +2080,7 @@ template <class real> struct world_step {
     // The reference's island flags / indices of bodies and contacts are bookkeeping of this loop only; here they live in
     // the scratch words (toi_state, wake_at) so that BODY_ISLAND / CONTACT_ISLAND / b_island keep describing the discrete
     // step's islands (the incremental plan relies on them).
-    enum { TS_COUNT_MASK = 15, TS_FLAG = 16, TS_NEED = 32, TS_SEED_A = 64, TS_SEED_B = 128, TS_ISLAND = 256 };
+    enum { TS_COUNT_MASK = 15, TS_FLAG = 16, TS_NEED = 32, TS_SEED_A = 64, TS_SEED_B = 128, TS_ISLAND = 256, TS_NEVER = 512 };
     struct toi_cc {
         real ima, imb, iia, iib, friction, restitution, rad_a, rad_b;
         V2 lca, lcb, local_normal, local_point, lp[2], normal;
@@ -2126,20 +2130,23 @@ template <class real> struct world_step {
         if (contact_update(c)) { body_wake(f_body[c_fix[2 * c]]); body_wake(f_body[c_fix[2 * c + 1]]); }
     }
 
-    // world.py:621-653: is contact c a candidate whose time of impact has to be computed now?
-    B2B_D bool toi_candidate(int c, int st) const
+    // world.py:621-653: is contact c a candidate whose time of impact has to be computed now?  0: no, 1: yes, 2: never in
+    // this step (two ordinary dynamic bodies, world.py:651-653: body types and bullet flags do not change inside a step)
+    B2B_D static int toi_classify(uint32_t cfl, int st, uint32_t fla, uint32_t flb)
     {
-        if (!(c_flags[c] & CONTACT_ENABLED) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || (st & TS_FLAG)) return false;
-        const int fa = c_fix[2 * c], fb = c_fix[2 * c + 1];
-        const uint32_t fla = b_flags[f_body[fa]], flb = b_flags[f_body[fb]];
         const int type_a = (int)(fla & BODY_TYPE_MASK), type_b = (int)(flb & BODY_TYPE_MASK);
-        const bool active_a = (fla & BODY_AWAKE) && type_a != BODY_STATIC, active_b = (flb & BODY_AWAKE) && type_b != BODY_STATIC;
-        if (!active_a && !active_b) return false;
         const bool collide_a = (fla & BODY_BULLET) || type_a != BODY_DYNAMIC, collide_b = (flb & BODY_BULLET) || type_b != BODY_DYNAMIC;
-        return collide_a || collide_b;
+        if (!collide_a && !collide_b) return 2;
+        if (!(cfl & CONTACT_ENABLED) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || (st & TS_FLAG)) return 0;
+        const bool active_a = (fla & BODY_AWAKE) && type_a != BODY_STATIC, active_b = (flb & BODY_AWAKE) && type_b != BODY_STATIC;
+        return (active_a || active_b) ? 1 : 0;
+    }
+    B2B_D int toi_candidate(int c, int st) const
+    {
+        return toi_classify(c_flags[c], st, b_flags[f_body[c_fix[2 * c]]], b_flags[f_body[c_fix[2 * c + 1]]]);
     }
     // world.py:670-683: the contact's time of impact on the two (equalised) sweeps
-    B2B_D void toi_evaluate(int c, const sweep_t<real>& sa, const sweep_t<real>& sb, real alpha0)
+    B2B_D real toi_alpha_of(int c, const sweep_t<real>& sa, const sweep_t<real>& sb, real alpha0)
     {
         const shape_view<real> pa = shape_of_fixture(c_fix[2 * c]), pb = shape_of_fixture(c_fix[2 * c + 1]);
         real beta = real(1);
@@ -2147,9 +2154,34 @@ template <class real> struct world_step {
         const int state = time_of_impact<real>(pa, pb, sa, sb, real(1), beta, stuck);
         real alpha = real(1);
         if (state == TOI_TOUCHING) alpha = pymin(alpha0 + (real(1) - alpha0) * beta, real(1));
-        toi_alpha[c] = alpha;
-        toi_state[c] = (toi_state[c] | TS_FLAG) & ~TS_NEED;
         if (stuck) B2B_ATOMIC_OR(w_status, (uint32_t)STATUS_TOI_STUCK);
+        return alpha;
+    }
+    B2B_D void toi_evaluate(int c, const sweep_t<real>& sa, const sweep_t<real>& sb, real alpha0)
+    {
+        toi_alpha[c] = toi_alpha_of(c, sa, sb, alpha0);
+        toi_state[c] = (toi_state[c] | TS_FLAG) & ~TS_NEED;
+    }
+    // The team's (smallest value, lowest index among equals) of every lane's (a, ci); ci < 0: the lane has none.  Returns the
+    // index (or -1) and leaves the value in toi_red_a[0].
+    B2B_D int toi_reduce_min(real a, int ci)
+    {
+        toi_red_a[t_id & 31] = a; toi_red_i[t_id & 31] = ci;
+        B2B_SYNC();
+        if (B2B_IS_T0) {
+            const int lanes = t_n < 32 ? t_n : 32;
+            for (int l = 1; l < lanes; ++l) {
+                const real al = toi_red_a[l];
+                const int cl = toi_red_i[l];
+                if (cl >= 0 && (ci < 0 || al < a || (al == a && cl < ci))) { a = al; ci = cl; }
+            }
+            toi_red_a[0] = a;
+            s_ctl[13] = ci;
+        }
+        B2B_SYNC();
+        const int r = s_ctl[13];
+        B2B_SYNC();
+        return r;
     }
 
     // ContactSolver.__init__ for the sub-island's contact k (contact.py:376-412; no warm-start scaling: step.warm_starting is False)
@@ -2409,8 +2441,52 @@ template <class real> struct world_step {
     B2B_D void phase_toi(const step_params& sp)
     {
         const int nb = w_count[0];
-        // world.py:599-609 (the step is always complete here: no sub_stepping)
-        B2B_PFOR(b, nb) { b_pos0[4 * (size_t)b + 3] = real(0); wake_at[b] = -1; }
+        // world.py:599-609 (the step is always complete here: no sub_stepping).  Sweeps only start later than the step
+        // (alpha0 != 0) after a solved event: WORLD_TOI_DIRTY remembers that, so a world without events pays no reset.
+        if (w_flags[0] & WORLD_TOI_DIRTY) {
+            B2B_PFOR(b, nb) b_pos0[4 * (size_t)b + 3] = real(0);
+            B2B_SYNC();
+            if (B2B_IS_T0) w_flags[0] &= ~WORLD_TOI_DIRTY;
+        }
+        // First look, the common case (nothing is about to hit anything): every sweep starts at alpha0 = 0, the candidates are
+        // independent, no cached value exists yet.  One pass, four contacts per lane at a time with their row loads batched (a
+        // world's rows are cold in this kernel: the dependent loads of one contact after the other were most of its time);
+        // nothing is written unless an event is found.
+        {
+            const int nc = w_count[2];
+            real best = real(1);
+            int best_c = -1;
+            for (int base = 0; base < nc; base += 4 * t_n) {
+                int cls[4];
+                uint32_t cfl[4];
+                int ba[4], bb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = base + k * t_n + t_id;
+                    cfl[k] = 0u; ba[k] = bb[k] = 0;
+                    if (c < nc) { cfl[k] = c_flags[c]; ba[k] = c_fix[2 * c]; bb[k] = c_fix[2 * c + 1]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const int c = base + k * t_n + t_id; if (c < nc) { ba[k] = f_body[ba[k]]; bb[k] = f_body[bb[k]]; } }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = base + k * t_n + t_id;
+                    cls[k] = (c < nc) ? toi_classify(cfl[k], 0, b_flags[ba[k]], b_flags[bb[k]]) : 0;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    if (cls[k] != 1) continue;
+                    const int c = base + k * t_n + t_id;
+                    sweep_t<real> sa = sweep_load(ba[k]), sb = sweep_load(bb[k]);
+                    sa.alpha0 = sb.alpha0 = real(0);
+                    const real a = toi_alpha_of(c, sa, sb, real(0));
+                    if (a < best) { best = a; best_c = c; }
+                }
+            }
+            const int first = toi_reduce_min(best, best_c);
+            if (first < 0 || (real(1) - (real(10) * K<real>::epsilon)) < toi_red_a[0]) return;      // world.py:693-696
+        }
+        // There is an event: the loop proper, with the per-contact words in scratch
+        B2B_PFOR(b, nb) wake_at[b] = -1;
         { const int nc = w_count[2]; B2B_PFOR(c, nc) { toi_alpha[c] = real(1); toi_state[c] = 0; } }
         B2B_SYNC();
         bool advanced = false;          // some body's sweep starts later than the step does (after the first solved event)
@@ -2418,7 +2494,9 @@ template <class real> struct world_step {
             const int nc = w_count[2];
             B2B_PFOR(c, nc) {
                 const int st = toi_state[c];
-                toi_state[c] = toi_candidate(c, st) ? (st | TS_NEED) : (st & ~TS_NEED);
+                if (st & TS_NEVER) continue;
+                const int cls = toi_candidate(c, st);
+                toi_state[c] = (cls == 2) ? (st | TS_NEVER) : (cls == 1) ? (st | TS_NEED) : (st & ~TS_NEED);
             }
             B2B_SYNC();
             if (!advanced) {
@@ -2467,47 +2545,39 @@ template <class real> struct world_step {
                 }
             }
             // the first contact of the list with the smallest time of impact (world.py:688-691: strict <)
-            {
-                real best = real(1);
-                int best_c = -1;
-                B2B_PFOR(c, nc) {
-                    const int st = toi_state[c];
-                    if (!(st & TS_FLAG) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || !(c_flags[c] & CONTACT_ENABLED)) continue;
-                    const real a = toi_alpha[c];
-                    if (a < best) { best = a; best_c = c; }
-                }
-                toi_red_a[t_id & 31] = best; toi_red_i[t_id & 31] = best_c;
-                B2B_SYNC();
-                if (B2B_IS_T0) {
-                    const int lanes = t_n < 32 ? t_n : 32;
-                    for (int l = 1; l < lanes; ++l) {
-                        const real a = toi_red_a[l];
-                        const int ci = toi_red_i[l];
-                        if (ci >= 0 && (a < best || (a == best && ci < best_c))) { best = a; best_c = ci; }
-                    }
-                    toi_red_a[0] = best;
-                    s_ctl[13] = best_c;
-                }
-                B2B_SYNC();
+            real best = real(1);
+            int best_c = -1;
+            B2B_PFOR(c, nc) {
+                const int st = toi_state[c];
+                if (!(st & TS_FLAG) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS) continue;
+                if (!(c_flags[c] & CONTACT_ENABLED)) continue;
+                const real a = toi_alpha[c];
+                if (a < best) { best = a; best_c = c; }
             }
-            const int min_contact = s_ctl[13];
+            const int min_contact = toi_reduce_min(best, best_c);
             const real min_alpha = toi_red_a[0];
             B2B_SYNC();
             if (min_contact < 0 || (real(1) - (real(10) * K<real>::epsilon)) < min_alpha) break;
 
-            // the event.  Which contacts touch the two bodies (body._contacts of the sub-island's seeds): in parallel
+            // the event.  Which contacts touch the two bodies (body._contacts of the sub-island's seeds): in parallel.  Contacts
+            // of two ordinary dynamic bodies (TS_NEVER) are never taken into a sub-island (world.py:751-753) and never hold a
+            // cached time of impact, so they are skipped here and below.
             const int body_a = f_body[c_fix[2 * min_contact]], body_b = f_body[c_fix[2 * min_contact + 1]];
             B2B_PFOR(c, nc) {
+                int st = toi_state[c];
+                if (st & TS_NEVER) continue;
                 const int cba = f_body[c_fix[2 * c]], cbb = f_body[c_fix[2 * c + 1]];
-                int st = toi_state[c] & ~(TS_SEED_A | TS_SEED_B | TS_ISLAND);
+                st &= ~(TS_SEED_A | TS_SEED_B | TS_ISLAND);
                 if (cba == body_a || cbb == body_a) st |= TS_SEED_A;
                 if (cba == body_b || cbb == body_b) st |= TS_SEED_B;
                 toi_state[c] = st;
             }
             B2B_SYNC();
             if (B2B_IS_T0) {
-                s_ctl[14] = toi_event(sp, min_contact, min_alpha);
-                w_flags[0] &= ~WORLD_GRAPH_VALID;       // manifolds, touching flags, awake flags and positions changed under the plan
+                const int nib = toi_event(sp, min_contact, min_alpha);
+                s_ctl[14] = nib;
+                // manifolds, touching flags, awake flags and positions changed under the plan; sweeps now start inside the step
+                w_flags[0] = (w_flags[0] & ~WORLD_GRAPH_VALID) | (nib ? (uint32_t)WORLD_TOI_DIRTY : 0u);
             }
             B2B_SYNC();
             const int nib = s_ctl[14];
@@ -2521,9 +2591,11 @@ template <class real> struct world_step {
                 if (wake_at[b] >= 0 && body_type(b) == BODY_DYNAMIC) sync_fixture_of(f, b);
             }
             B2B_PFOR(c, nc) {
+                const int st = toi_state[c];
+                if (st & TS_NEVER) continue;
                 const int cba = f_body[c_fix[2 * c]], cbb = f_body[c_fix[2 * c + 1]];
                 const bool hit = (wake_at[cba] >= 0 && body_type(cba) == BODY_DYNAMIC) || (wake_at[cbb] >= 0 && body_type(cbb) == BODY_DYNAMIC);
-                if (hit) toi_state[c] &= ~(TS_FLAG | TS_ISLAND);
+                if (hit) toi_state[c] = st & ~(TS_FLAG | TS_ISLAND);
             }
             B2B_SYNC();
             B2B_PFOR(i, nib) wake_at[toi_ib[i]] = -1;

@@ -34,6 +34,7 @@ WORLD_NEW_FIXTURE = 0x4       # world.py:85
 WORLD_AUTO_CLEAR = 0x8        # world.py:80
 WORLD_GRAPH_VALID = 0x10      # device bookkeeping: last step's island lists / schedule are still valid
 WORLD_CONTINUOUS = 0x20       # world.py:78 continuous_physics: World.solve_toi runs after the discrete solve
+WORLD_TOI_DIRTY = 0x40        # device bookkeeping: some sweep.alpha0 (b_pos0[3]) is non-zero and is reset by the next World.solve_toi
 
 STATUS_CONTACT_OVERFLOW = 0x1
 STATUS_PAIR_OVERFLOW = 0x2
