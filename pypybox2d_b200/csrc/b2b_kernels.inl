@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
 // time: 32 when most worlds are skipped, fewer when the batch is small against the grid -- a batch in which every world needs
 // its walk would otherwise keep only n_worlds / 32 warps busy, each with 32 worlds in a row (measured: deep stacks, 32,768
 // worlds, plan kernel 7.7 ms = one warp's 32 worlds back to back).
-template <class Need, class Work>
+template <bool HEAVY_ONLY = false, class Need, class Work>
 __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, int chunk, unsigned int* chunk_counter, Need need_of, Work work)
 {
     const int lane = (int)(threadIdx.x & 31);
@@ -77,6 +77,7 @@ __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes,
         const unsigned heavy = __ballot_sync(0xffffffffu, cls == 2);
         for (int ord = 0; ord < __popc(heavy); ++ord) work(base + (int)__fns(heavy, 0, ord + 1), 32);
         __syncwarp();
+        if (HEAVY_ONLY) continue;            // (a kernel whose worlds are all of class 2 carries one copy of its work, not two)
         const unsigned m = __ballot_sync(0xffffffffu, cls == 1);
         // few needy worlds in this chunk (the settled regime): widen the teams so that each world gets more lanes
         const int n = __popc(m);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(32) B2B_CAT(toi_kernel_, B2B_SUFFIX)(batch_ptr
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int teams_per_cta = 32 / lanes;
-    for_each_needy_world(
+    for_each_needy_world<true>(
         c, lanes, chunk, chunk_counter,
         [&](int w) { return ((sp.dt > 0.0) && (B.w_flags[w] & WORLD_CONTINUOUS)) ? 2 : 0; },
         [&](int w, int width) {

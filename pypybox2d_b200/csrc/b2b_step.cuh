@@ -138,13 +138,14 @@ B2B_HD plan_layout plan_plan(const caps_t& c)
 // continuous collision (phase_toi): per-contact time of impact + state word, a batch of sweep snapshots, the team's
 // reduction words, and the sub-island World.solve_toi solves (at most 2 * MAX_TOI_CONTACTS bodies, MAX_TOI_CONTACTS contacts)
 enum { TOI_BATCH = 32, TOI_SNAP_REALS = 13, TOI_CC_REALS = 56 };
-struct toi_layout { size_t off_alpha, off_state, off_snap, off_snap_ci, off_red_a, off_red_i, off_ib, off_ic, off_P, off_V, off_cc, total; };
+struct toi_layout { size_t off_alpha, off_state, off_list, off_snap, off_snap_ci, off_red_a, off_red_i, off_ib, off_ic, off_P, off_V, off_cc, total; };
 B2B_HD toi_layout toi_plan(const caps_t& c, int real_bytes)
 {
     toi_layout T;
     size_t o = 0;
     T.off_alpha = o; o = align_up(o + (size_t)real_bytes * ((size_t)c.nc + 2), 32);
     T.off_state = o; o = align_up(o + sizeof(int32_t) * ((size_t)c.nc + 2), 32);
+    T.off_list = o; o = align_up(o + sizeof(int32_t) * 3 * ((size_t)c.nc + 2), 32);     // compacted index lists: candidates, contacts of seed a / b
     T.off_snap = o; o = align_up(o + (size_t)real_bytes * TOI_SNAP_REALS * TOI_BATCH, 32);
     T.off_snap_ci = o; o = align_up(o + sizeof(int32_t) * TOI_BATCH, 32);
     T.off_red_a = o; o = align_up(o + (size_t)real_bytes * 32, 32);
@@ -272,7 +273,7 @@ template <class real> struct world_step {
     // continuous collision (phase_toi): see toi_layout
     struct toi_cc;
     real *toi_alpha, *toi_snap, *toi_red_a, *toi_P, *toi_V;
-    int32_t *toi_state, *toi_snap_ci, *toi_red_i, *toi_ib, *toi_ic;
+    int32_t *toi_state, *toi_list, *toi_snap_ci, *toi_red_i, *toi_ib, *toi_ic;
     toi_cc* toi_C;
     // shared memory
 #if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
@@ -353,6 +354,7 @@ template <class real> struct world_step {
         const toi_layout T = toi_plan(cap, (int)sizeof(real));
         unsigned char* tb = scratch + L.off_toi;
         toi_alpha = (real*)(tb + T.off_alpha); toi_state = (int32_t*)(tb + T.off_state);
+        toi_list = (int32_t*)(tb + T.off_list);
         toi_snap = (real*)(tb + T.off_snap); toi_snap_ci = (int32_t*)(tb + T.off_snap_ci);
         toi_red_a = (real*)(tb + T.off_red_a); toi_red_i = (int32_t*)(tb + T.off_red_i);
         toi_ib = (int32_t*)(tb + T.off_ib); toi_ic = (int32_t*)(tb + T.off_ic);
@@ -2125,7 +2127,7 @@ template <class real> struct world_step {
         if (!(fl & BODY_AWAKE)) { b_pos[4 * (size_t)b + 3] = real(0); b_flags[b] = fl | BODY_AWAKE; }
     }
     // Contact.update with its waking of both bodies on a touching change (contact.py:257-259)
-    B2B_D void toi_contact_update(int c)
+    B2B_D_NOINLINE void toi_contact_update(int c)
     {
         if (contact_update(c)) { body_wake(f_body[c_fix[2 * c]]); body_wake(f_body[c_fix[2 * c + 1]]); }
     }
@@ -2161,6 +2163,35 @@ template <class real> struct world_step {
     {
         toi_alpha[c] = toi_alpha_of(c, sa, sb, alpha0);
         toi_state[c] = (toi_state[c] | TS_FLAG) & ~TS_NEED;
+    }
+    // out[0..n_out) = the indices c < n with (toi_state[c] & bit), ascending; returns n_out (the same value on every lane).
+    // Lane teams of a warp compact with ballots, 32 (or t_n) consecutive indices at a time; the sequential build just loops.
+    B2B_D int toi_compact(int n, int bit, int32_t* out)
+    {
+        int count = 0;
+#if defined(__CUDA_ARCH__)
+        if (!t_cta) {
+            const int shift = __ffs((int)t_mask) - 1;
+            for (int base = 0; base < n; base += t_n) {
+                const int c = base + t_id;
+                const bool f = (c < n) && (toi_state[c] & bit);
+                const unsigned m = (__ballot_sync(t_mask, f) & t_mask) >> shift;
+                if (f) out[count + __popc(m & ((1u << t_id) - 1u))] = c;
+                count += __popc(m);
+            }
+            B2B_SYNC();
+            return count;
+        }
+#endif
+        B2B_SYNC();
+        if (B2B_IS_T0) {
+            for (int c = 0; c < n; ++c) if (toi_state[c] & bit) out[count++] = c;
+            s_ctl[13] = count;
+        }
+        B2B_SYNC();
+        count = s_ctl[13];
+        B2B_SYNC();
+        return count;
     }
     // The team's (smallest value, lowest index among equals) of every lane's (a, ci); ci < 0: the lane has none.  Returns the
     // index (or -1) and leaves the value in toi_red_a[0].
@@ -2334,7 +2365,7 @@ template <class real> struct world_step {
         toi_V[3 * cc.ib] = vb.x; toi_V[3 * cc.ib + 1] = vb.y; toi_V[3 * cc.ib + 2] = wb;
     }
     // Island.solve_toi (island.py:181-243) for the sub-island in toi_ib / toi_ic; thread 0 only
-    B2B_D void toi_island_solve(int nbodies, int ncontacts, real dt, int vel_iters, int toi_a, int toi_b)
+    B2B_D_NOINLINE void toi_island_solve(int nbodies, int ncontacts, real dt, int vel_iters, int toi_a, int toi_b)
     {
         for (int i = 0; i < nbodies; ++i) {
             const int b = toi_ib[i];
@@ -2380,9 +2411,8 @@ template <class real> struct world_step {
 
     // One TOI event up to the solved sub-island (world.py:696-790), thread 0 only.  Returns the number of sub-island
     // bodies (0: the contact was not solid, the sweeps were restored).
-    B2B_D int toi_event(const step_params& sp, int mc, real min_alpha)
+    B2B_D int toi_event(const step_params& sp, int mc, real min_alpha, const int32_t* list_a, int n_a, const int32_t* list_b, int n_b)
     {
-        const int nc = w_count[2];
         const int body_a = f_body[c_fix[2 * mc]], body_b = f_body[c_fix[2 * mc + 1]];
         const sweep_t<real> backup_a = sweep_load(body_a), backup_b = sweep_load(body_b);
         body_advance(body_a, min_alpha);
@@ -2406,12 +2436,13 @@ template <class real> struct world_step {
         toi_state[mc] |= TS_ISLAND;
         for (int si = 0; si < 2; ++si) {
             const int body = si ? body_b : body_a;
-            const int seed_bit = si ? TS_SEED_B : TS_SEED_A;
+            const int32_t* list = si ? list_b : list_a;                       // body._contacts: the world's list, filtered
+            const int n_list = si ? n_b : n_a;
             if (body_type(body) != BODY_DYNAMIC) continue;
             const bool body_bullet = (b_flags[body] & BODY_BULLET) != 0;
-            for (int c = 0; c < nc; ++c) {                                    // body._contacts: the world's list, filtered
+            for (int k = 0; k < n_list; ++k) {
+                const int c = list[k];
                 const int st = toi_state[c];
-                if (!(st & seed_bit)) continue;
                 if (nib == 2 * (int)MAX_TOI_CONTACTS) break;
                 if (nic == (int)MAX_TOI_CONTACTS) break;
                 if (st & TS_ISLAND) continue;
@@ -2499,39 +2530,35 @@ template <class real> struct world_step {
                 toi_state[c] = (cls == 2) ? (st | TS_NEVER) : (cls == 1) ? (st | TS_NEED) : (st & ~TS_NEED);
             }
             B2B_SYNC();
+            const int n_need = toi_compact(nc, TS_NEED, toi_list);
             if (!advanced) {
                 // every sweep starts at alpha0 = 0: nothing to equalise, the candidates are independent
-                B2B_PFOR(c, nc) {
-                    if (!(toi_state[c] & TS_NEED)) continue;
+                B2B_PFOR(k, n_need) {
+                    const int c = toi_list[k];
                     const sweep_t<real> sa = sweep_load(f_body[c_fix[2 * c]]), sb = sweep_load(f_body[c_fix[2 * c + 1]]);
                     toi_evaluate(c, sa, sb, real(0));
                 }
                 B2B_SYNC();
             } else {
-                int c_next = 0;
-                for (;;) {
+                for (int k0 = 0; k0 < n_need; k0 += (int)TOI_BATCH) {
+                    const int n = (n_need - k0 < (int)TOI_BATCH) ? n_need - k0 : (int)TOI_BATCH;
                     if (B2B_IS_T0) {
-                        int n = 0, c = c_next;
-                        for (; c < nc && n < (int)TOI_BATCH; ++c) {
-                            if (!(toi_state[c] & TS_NEED)) continue;
+                        for (int k = 0; k < n; ++k) {
+                            const int c = toi_list[k0 + k];
                             const int ba = f_body[c_fix[2 * c]], bb = f_body[c_fix[2 * c + 1]];
                             sweep_t<real> sa = sweep_load(ba), sb = sweep_load(bb);
                             real alpha0 = sa.alpha0;                          // world.py:657-666
                             if (sa.alpha0 < sb.alpha0) { alpha0 = sb.alpha0; sweep_advance(sa, alpha0); sweep_store(ba, sa); }
                             else if (sb.alpha0 < sa.alpha0) { sweep_advance(sb, alpha0); sweep_store(bb, sb); }
-                            real* q = toi_snap + (size_t)TOI_SNAP_REALS * n;
+                            real* q = toi_snap + (size_t)TOI_SNAP_REALS * k;
                             q[0] = sa.c0.x; q[1] = sa.c0.y; q[2] = sa.a0; q[3] = sa.c.x; q[4] = sa.c.y; q[5] = sa.a;
                             q[6] = sb.c0.x; q[7] = sb.c0.y; q[8] = sb.a0; q[9] = sb.c.x; q[10] = sb.c.y; q[11] = sb.a;
                             q[12] = alpha0;
-                            toi_snap_ci[n++] = c;
                         }
-                        s_ctl[13] = n; s_ctl[14] = c;
                     }
                     B2B_SYNC();
-                    const int n = s_ctl[13];
-                    c_next = s_ctl[14];
                     B2B_PFOR(k, n) {
-                        const int c = toi_snap_ci[k];
+                        const int c = toi_list[k0 + k];
                         const real* q = toi_snap + (size_t)TOI_SNAP_REALS * k;
                         const quad ma = ldq(b_mass + 4 * (size_t)f_body[c_fix[2 * c]]), mb = ldq(b_mass + 4 * (size_t)f_body[c_fix[2 * c + 1]]);
                         sweep_t<real> sa, sb;
@@ -2541,7 +2568,6 @@ template <class real> struct world_step {
                         toi_evaluate(c, sa, sb, q[12]);
                     }
                     B2B_SYNC();
-                    if (c_next >= nc) break;
                 }
             }
             // the first contact of the list with the smallest time of impact (world.py:688-691: strict <)
@@ -2573,8 +2599,11 @@ template <class real> struct world_step {
                 toi_state[c] = st;
             }
             B2B_SYNC();
+            int32_t* list_a = toi_list + ((size_t)cap.nc + 2);
+            int32_t* list_b = toi_list + 2 * ((size_t)cap.nc + 2);
+            const int n_a = toi_compact(nc, TS_SEED_A, list_a), n_b = toi_compact(nc, TS_SEED_B, list_b);
             if (B2B_IS_T0) {
-                const int nib = toi_event(sp, min_contact, min_alpha);
+                const int nib = toi_event(sp, min_contact, min_alpha, list_a, n_a, list_b, n_b);
                 s_ctl[14] = nib;
                 // manifolds, touching flags, awake flags and positions changed under the plan; sweeps now start inside the step
                 w_flags[0] = (w_flags[0] & ~WORLD_GRAPH_VALID) | (nib ? (uint32_t)WORLD_TOI_DIRTY : 0u);
@@ -2586,9 +2615,11 @@ template <class real> struct world_step {
             advanced = true;
             // world.py:794-806: proxies of the sub-island's dynamic bodies, and the cached times of impact of their contacts
             const int nf = w_count[1];
+            if (B2B_IS_T0) s_ctl[14] = 0;
+            B2B_SYNC();
             B2B_PFOR(f, nf) {
                 const int b = f_body[f];
-                if (wake_at[b] >= 0 && body_type(b) == BODY_DYNAMIC) sync_fixture_of(f, b);
+                if (wake_at[b] >= 0 && body_type(b) == BODY_DYNAMIC && sync_fixture_of(f, b)) s_ctl[14] = 1;   // (benign same-value race)
             }
             B2B_PFOR(c, nc) {
                 const int st = toi_state[c];
@@ -2600,9 +2631,16 @@ template <class real> struct world_step {
             B2B_SYNC();
             B2B_PFOR(i, nib) wake_at[toi_ib[i]] = -1;
             B2B_SYNC();
-            // world.py:810: find_new_contacts (a contact created here is not enabled before the next step's narrowphase)
-            phase_pairs(false);
-            { const int nc1 = w_count[2]; B2B_PFOR(c, nc1) if (c >= nc) { toi_alpha[c] = real(1); toi_state[c] = 0; } }
+            // world.py:810: find_new_contacts (a contact created here is not enabled before the next step's narrowphase).  With
+            // an empty move buffer (the usual case: the fat boxes still hold the displaced bodies) it emits no pair.
+            const bool any_moved = s_ctl[14] != 0;
+            B2B_SYNC();
+            if (any_moved) {
+                phase_pairs(false);
+                { const int nc1 = w_count[2]; B2B_PFOR(c, nc1) if (c >= nc) { toi_alpha[c] = real(1); toi_state[c] = 0; } }
+            } else if (B2B_IS_T0) {
+                w_count[3] = 0;
+            }
             B2B_SYNC();
         }
     }

@@ -32,7 +32,8 @@ template <class real> struct sweep_t {
     vec2<real> lc, c0, c;
     real a0, a, alpha0;
 };
-template <class real> B2B_HD xform<real> sweep_xf(const sweep_t<real>& s, real beta)                   // common.py:893-904
+// (out of line everywhere: every copy carries a sincos with its large-argument path, and the TOI kernel is bound by instruction fetch)
+template <class real> B2B_HD_COLD xform<real> sweep_xf(const sweep_t<real>& s, real beta)                   // common.py:893-904
 {
     const vec2<real> p = (real(1) - beta) * s.c0 + beta * s.c;
     const real angle = (real(1) - beta) * s.a0 + beta * s.a;
@@ -232,7 +233,7 @@ template <class real> struct sep_function {
     int type;
     vec2<real> axis, local_point;
 
-    B2B_HD void initialize(const simplex_cache<real>& cache, real t1)
+    B2B_HD_COLD void initialize(const simplex_cache<real>& cache, real t1)
     {
         const xform<real> xa = sweep_xf(sa, t1), xb = sweep_xf(sb, t1);
         const int ia0 = cache.ia[0], ib0 = cache.ib[0];
@@ -266,7 +267,7 @@ template <class real> struct sep_function {
             if (s < real(0)) axis = -axis;
         }
     }
-    B2B_HD real find_min_separation(real t, int& index_a, int& index_b) const                          // toi.py:126-183
+    B2B_HD_COLD real find_min_separation(real t, int& index_a, int& index_b) const                          // toi.py:126-183
     {
         const xform<real> xa = sweep_xf(sa, t), xb = sweep_xf(sb, t);
         if (type == SEP_POINTS) {
@@ -293,7 +294,7 @@ template <class real> struct sep_function {
             return dot(point_a - point_b, normal);
         }
     }
-    B2B_HD real evaluate(int index_a, int index_b, real t) const                                        // toi.py:185-221
+    B2B_HD_COLD real evaluate(int index_a, int index_b, real t) const                                        // toi.py:185-221
     {
         const xform<real> xa = sweep_xf(sa, t), xb = sweep_xf(sb, t);
         if (type == SEP_POINTS) {
