@@ -122,6 +122,30 @@ int b2b_collide_pairs(b2b_ctx* ctx, int n, const void* d_shape_a, const void* d_
  * find_new_contacts after it.  inv_dt0 as for b2b_step; dt > 0.  Asynchronous on `stream`. */
 int b2b_solve_islands(b2b_ctx* ctx, double dt, double inv_dt0, int vel_iters, int pos_iters, uint32_t flags, void* stream);
 
+/* Queries, the callers either side of the step.  All arrays are device arrays of the caller; one warp per
+ * query scans the world's proxies (the reference's tree only prunes: DynamicTree.query / ray_cast, dynamictree.py:190-262, report
+ * a proxy iff its fat box passes the tests restated here), so results come in ascending fixture order where the reference
+ * reports them in tree order -- the same SET.  Asynchronous on `stream`.
+ *
+ * World.query_aabb (world.py:371-385): for query q, world d_world[q] (int32) and box d_box[q] = (lx, ly, ux, uy) (real):
+ * d_count[q] = number of fixtures whose fat AABB overlaps the box, the first max_hits of them in d_fix[q][max_hits] (int32). */
+int b2b_query_aabb(b2b_ctx* ctx, int n_queries, const void* d_world, const void* d_box, int max_hits, void* d_count, void* d_fix,
+                   void* stream);
+
+/* World.ray_cast (world.py:387-440) of the segment d_seg[q] = (x1, y1, x2, y2) in world d_world[q], shape by shape as
+ * Shape.ray_cast (shapes.py:147-176 circle, 266-314 polygon, 655-700 edge: the port returns an edge's normal in the edge's
+ * local frame).  mode 0: every fixture hit (a callback that never clips), d_count[q] of them, the first max_hits in
+ * d_fix[q][.] with d_hit[q][.][5] = {fraction, normal.x, normal.y, point.x, point.y} (real); mode 1: the closest hit only
+ * (a callback that clips to each reported fraction; ties: the lowest fixture index) in slot 0, d_count[q] = 0 or 1.
+ * A zero-length segment (the reference raises ValueError, dynamictree.py:222-223) gets d_count[q] = -1. */
+int b2b_ray_cast(b2b_ctx* ctx, int n_rays, const void* d_world, const void* d_seg, int mode, int max_hits, void* d_count,
+                 void* d_fix, void* d_hit, void* stream);
+
+/* Fixture.test_point (fixture.py:228-233, shapes.py:141-145, 256-263) for n triples (d_world[i], d_fixture[i], d_point[i][2]):
+ * d_inside[i] (uint8) = 1 when the point is inside the fixture's shape (an edge contains no point). */
+int b2b_test_points(b2b_ctx* ctx, int n, const void* d_world, const void* d_fixture, const void* d_point, void* d_inside,
+                    void* stream);
+
 /* OR of every world's status word (STATUS_* bits in schema.py); synchronises the stream. */
 int b2b_status(b2b_ctx* ctx, uint32_t* host_out, void* stream);
 

@@ -1866,6 +1866,151 @@ static void world_solve_toi(orc_world* w, double dt, int vel_iters)
     free(toi); free(toi_flag); free(toi_count);
 }
 
+
+/* =====================================================================================================
+ * Queries: World.query_aabb / World.ray_cast world.py:371-440, DynamicTree.query / ray_cast
+ * dynamictree.py:190-262, Shape.test_point / ray_cast shapes.py:141-176, 256-314, 655-700.  The tree only
+ * prunes: a leaf is reported iff its fat box passes the tests below, so the answers are restated as a scan
+ * over the proxies in fixture order (the reference reports them in tree order; the SET is the same).
+ * ===================================================================================================== */
+/* fixtures whose fat AABB overlaps `box` (lx, ly, ux, uy), ascending; returns the total count */
+int orc_query_aabb(const orc_world* w, const double* box, int32_t* out, int max_out)
+{
+    int n = 0, nf = w->w_count[1];
+    for (int f = 0; f < nf; ++f) {
+        if (!aabb_overlap(w->f_fat + 4 * (size_t)f, box)) continue;            /* node.aabb.test_overlap(aabb) */
+        if (n < max_out) out[n] = f;
+        ++n;
+    }
+    return n;
+}
+
+/* Shape.ray_cast: 1 on a hit */
+static int shape_ray_cast(const shape_t* s, const xform* xf, v2 p1, v2 p2, double max_fraction, v2* normal_out, double* fraction_out)
+{
+    if (s->type == S_CIRCLE) {                                                  /* shapes.py:147-176 */
+        v2 position = vadd(xf->p, rot_mul(xf, V(s->d[0], s->d[1])));
+        v2 sv = vsub(p1, position);
+        double b = vdot(sv, sv) - sq(s->radius);
+        v2 r = vsub(p2, p1);
+        double c = vdot(sv, r), rr = vdot(r, r);
+        double sigma = c * c - rr * b;
+        if (sigma < 0.0 || rr < EPS) return 0;
+        double a = -(c + sqrt(sigma));
+        if (0.0 <= a && a <= max_fraction * rr) {
+            a /= rr;
+            *fraction_out = a;
+            *normal_out = vnorm(vadd(sv, vscale(a, r)));
+            return 1;
+        }
+        return 0;
+    }
+    if (s->type == S_POLYGON) {                                                 /* shapes.py:266-314 */
+        v2 q1 = rot_mul_t(xf, vsub(p1, xf->p)), q2 = rot_mul_t(xf, vsub(p2, xf->p));
+        v2 d = vsub(q2, q1);
+        double lower = 0.0, upper = max_fraction;
+        int tagged = -1;
+        for (int i = 0; i < s->count; ++i) {
+            v2 normal = pnorm(s, i), vertex = pvert(s, i);
+            double numerator = vdot(normal, vsub(vertex, q1));
+            double denominator = vdot(normal, d);
+            if (denominator == 0.0) {
+                if (numerator < 0.0) return 0;
+            } else {
+                if (denominator < 0.0 && numerator < lower * denominator) { lower = numerator / denominator; tagged = i; }
+                else if (denominator > 0.0 && numerator < upper * denominator) upper = numerator / denominator;
+            }
+            if (upper < lower) return 0;
+        }
+        if (tagged >= 0) {
+            *normal_out = rot_mul(xf, pnorm(s, tagged));
+            *fraction_out = lower;
+            return 1;
+        }
+        return 0;
+    }
+    {                                                                           /* edge: shapes.py:655-700 */
+        v2 q1 = rot_mul_t(xf, vsub(p1, xf->p)), q2 = rot_mul_t(xf, vsub(p2, xf->p));
+        v2 d = vsub(q2, q1);
+        v2 v1 = V(s->d[0], s->d[1]), v2_ = V(s->d[2], s->d[3]);
+        v2 e = vsub(v2_, v1);
+        v2 normal = vnorm(V(e.y, -e.x));
+        double numerator = vdot(normal, vsub(v1, q1));
+        double denominator = vdot(normal, d);
+        if (denominator == 0.0) return 0;
+        double t = numerator / denominator;
+        if (t < 0.0 || 1.0 < t) return 0;
+        v2 q = vadd(q1, vscale(t, d));
+        v2 r = vsub(v2_, v1);
+        double rr = vdot(r, r);
+        if (rr == 0.0) return 0;
+        double sp = vdot(vsub(q, v1), r) / rr;
+        if (sp < 0.0 || 1.0 < sp) return 0;
+        *fraction_out = t;
+        if (numerator > 0.0) normal = vneg(normal);
+        *normal_out = normal;                           /* (the port returns the normal in the edge's LOCAL frame) */
+        return 1;
+    }
+}
+
+/* DynamicTree.ray_cast's tests on a leaf box (dynamictree.py:226-246), un-clipped segment: max_fraction = 1 */
+static int ray_leaf_test(const double* box, v2 p1, v2 p2)
+{
+    v2 r = vnorm(vsub(p2, p1));
+    v2 v = scross(1.0, r);
+    v2 abs_v = V(fabs(v.x), fabs(v.y));
+    v2 t = vadd(p1, vscale(1.0, vsub(p2, p1)));
+    double seg[4] = {PYMIN(p1.x, t.x), PYMIN(p1.y, t.y), PYMAX(p1.x, t.x), PYMAX(p1.y, t.y)};
+    if (!aabb_overlap(box, seg)) return 0;
+    v2 c = vscale(0.5, vadd(V(box[0], box[1]), V(box[2], box[3])));
+    v2 h = vscale(0.5, vsub(V(box[2], box[3]), V(box[0], box[1])));
+    double separation = fabs(vdot(v, vsub(p1, c))) - vdot(abs_v, h);
+    return !(separation > 0.0);
+}
+
+/* World.ray_cast with a callback that never clips (returns 1): every fixture the ray hits, ascending fixture index.
+ * out_hit[k] = {fraction, normal.x, normal.y, point.x, point.y}; returns the total count */
+int orc_ray_cast(const orc_world* w, const double* p1p2, int32_t* out_fix, double* out_hit, int max_out)
+{
+    v2 p1 = V(p1p2[0], p1p2[1]), p2 = V(p1p2[2], p1p2[3]);
+    int n = 0, nf = w->w_count[1];
+    for (int f = 0; f < nf; ++f) {
+        if (!ray_leaf_test(w->f_fat + 4 * (size_t)f, p1, p2)) continue;
+        shape_t s = shape_get(w, w->f_shape[f]);
+        xform xf = xf_row(w->b_xf + 4 * (size_t)w->f_body[f]);
+        v2 normal; double fraction;
+        if (!shape_ray_cast(&s, &xf, p1, p2, 1.0, &normal, &fraction)) continue;
+        if (n < max_out) {
+            v2 point = vadd(vscale(1.0 - fraction, p1), vscale(fraction, p2));   /* world.py:427 */
+            out_fix[n] = f;
+            out_hit[5 * n] = fraction; out_hit[5 * n + 1] = normal.x; out_hit[5 * n + 2] = normal.y;
+            out_hit[5 * n + 3] = point.x; out_hit[5 * n + 4] = point.y;
+        }
+        ++n;
+    }
+    return n;
+}
+
+/* Fixture.test_point (fixture.py:228-233; circles and polygons: shapes.py:141-145, 256-263; an edge contains no point) */
+int orc_test_point(const orc_world* w, int f, const double* p)
+{
+    shape_t s = shape_get(w, w->f_shape[f]);
+    xform xf = xf_row(w->b_xf + 4 * (size_t)w->f_body[f]);
+    v2 pt = V(p[0], p[1]);
+    if (s.type == S_CIRCLE) {
+        v2 center = vadd(xf.p, rot_mul(&xf, V(s.d[0], s.d[1])));
+        v2 d = vsub(pt, center);
+        return vdot(d, d) <= sq(s.radius);
+    }
+    if (s.type == S_POLYGON) {
+        v2 pl = rot_mul_t(&xf, vsub(pt, xf.p));
+        for (int i = 0; i < s.count; ++i)
+            if (vdot(pnorm(&s, i), vsub(pl, pvert(&s, i))) > 0.0) return 0;
+        return 1;
+    }
+    return 0;
+}
+
 /* ---- World.step: world.py:307-354 ---- */
 int orc_step(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters)
 {

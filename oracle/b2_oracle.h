@@ -73,6 +73,13 @@ typedef struct orc_world {
  * before the call.  Returns 0, or <0 on capacity overflow (also flagged in w_status). */
 int orc_step(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters);
 
+/* Queries (world.py:371-440): fixtures whose fat AABB overlaps `box`; every fixture hit by the segment p1p2 = (x1, y1, x2, y2)
+ * with out_hit[k] = {fraction, normal.x, normal.y, point.x, point.y}; Fixture.test_point.  Lists are ascending in the
+ * fixture index; the returned count is the total (it may exceed max_out). */
+int orc_query_aabb(const orc_world* w, const double* box, int32_t* out, int max_out);
+int orc_ray_cast(const orc_world* w, const double* p1p2, int32_t* out_fix, double* out_hit, int max_out);
+int orc_test_point(const orc_world* w, int f, const double* p);
+
 /* n_steps calls of orc_step with the reference's inv_dt0 bookkeeping (world.py:348-349). */
 int orc_run(orc_world* w, double dt, double inv_dt0, int vel_iters, int pos_iters, int n_steps);
 

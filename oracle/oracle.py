@@ -46,6 +46,12 @@ def lib():
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]
         L.orc_collide_pair.restype = ctypes.c_int
+        L.orc_query_aabb.argtypes = [ctypes.POINTER(OrcWorld), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.orc_query_aabb.restype = ctypes.c_int
+        L.orc_ray_cast.argtypes = [ctypes.POINTER(OrcWorld), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.orc_ray_cast.restype = ctypes.c_int
+        L.orc_test_point.argtypes = [ctypes.POINTER(OrcWorld), ctypes.c_int, ctypes.c_void_p]
+        L.orc_test_point.restype = ctypes.c_int
         L.orc_field_names.restype = ctypes.c_char_p
         _LIB = L
     return _LIB
@@ -96,3 +102,23 @@ class Oracle(object):
         lib().orc_collide_pair(ctypes.byref(self._s), sa, sb, xfa.ctypes.data, xfb.ctypes.data, mtype.ctypes.data,
                                mf.ctypes.data, pts.ctypes.data, ids.ctypes.data)
         return int(mtype[0]), mf, pts, ids
+
+    def query_aabb(self, box, max_out=1024):
+        """Fixture indices (ascending) whose fat AABB overlaps box = (lx, ly, ux, uy): World.query_aabb as a set."""
+        box = np.ascontiguousarray(box, np.float64)
+        out = np.zeros(max_out, np.int32)
+        n = lib().orc_query_aabb(ctypes.byref(self._s), box.ctypes.data, out.ctypes.data, max_out)
+        return out[:min(n, max_out)].copy()
+
+    def ray_cast(self, p1, p2, max_out=1024):
+        """(fixture indices, [fraction, nx, ny, px, py] rows) of every fixture the segment hits, ascending fixture index."""
+        seg = np.ascontiguousarray([p1[0], p1[1], p2[0], p2[1]], np.float64)
+        fix = np.zeros(max_out, np.int32)
+        hit = np.zeros((max_out, 5))
+        n = lib().orc_ray_cast(ctypes.byref(self._s), seg.ctypes.data, fix.ctypes.data, hit.ctypes.data, max_out)
+        n = min(n, max_out)
+        return fix[:n].copy(), hit[:n].copy()
+
+    def test_point(self, f, p):
+        pt = np.ascontiguousarray(p, np.float64)
+        return bool(lib().orc_test_point(ctypes.byref(self._s), int(f), pt.ctypes.data))

@@ -57,6 +57,9 @@ def lib():
     L.b2b_step_host.argtypes = [vp, vp, vp, dbl, dbl, i32, i32, i32, u32, vp]
     L.b2b_solve_islands.argtypes = [vp, dbl, dbl, i32, i32, u32, vp]
     L.b2b_collide_pairs.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.b2b_query_aabb.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp]
+    L.b2b_ray_cast.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.b2b_test_points.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.b2b_status.argtypes = [vp, ctypes.POINTER(u32), vp]
     L.b2b_checksum.argtypes = [vp, vp, vp]
     L.b2b_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), i32]

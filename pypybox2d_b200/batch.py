@@ -310,6 +310,58 @@ class BatchedWorld(object):
         torch.cuda.synchronize(self.device)
         return mtype.cpu().numpy(), mf.cpu().numpy(), pts.cpu().numpy(), ids.cpu().numpy().view(np.uint32)
 
+    # -- queries (World.query_aabb / ray_cast, Fixture.test_point; include/b2b.h) -----------------------------
+    def _query_inputs(self, worlds, reals, width):
+        torch = _torch()
+        rd = torch.float64 if self.real == "f64" else torch.float32
+        w = torch.as_tensor(np.ascontiguousarray(worlds, dtype=np.int32), device=self.device)
+        x = torch.as_tensor(np.ascontiguousarray(reals, dtype=np.float64).reshape(-1, width), device=self.device).to(rd).contiguous()
+        if w.numel() != x.shape[0]:
+            raise ValueError("one world index per query")
+        return w, x, rd
+
+    def query_aabb(self, worlds, boxes, max_hits=64):
+        """World.query_aabb for a batch of queries: worlds[q] (int), boxes[q] = (lx, ly, ux, uy).  Returns (counts[q], fixtures[q,
+        max_hits]) as numpy arrays: the number of fixtures whose fat AABB overlaps the box and the first `max_hits` of them in
+        ascending fixture order (-1 padding)."""
+        torch = _torch()
+        w, box, rd = self._query_inputs(worlds, boxes, 4)
+        n = int(w.numel())
+        count = torch.zeros(n, dtype=torch.int32, device=self.device)
+        fix = torch.full((n, max_hits), -1, dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().b2b_query_aabb(self._ctx, n, p(w), p(box), int(max_hits), p(count), p(fix), self._stream()), "b2b_query_aabb")
+        torch.cuda.synchronize(self.device)
+        return count.cpu().numpy(), fix.cpu().numpy()
+
+    def ray_cast(self, worlds, segments, closest=False, max_hits=64):
+        """World.ray_cast for a batch of rays: segments[q] = (x1, y1, x2, y2).  Returns (counts[q], fixtures[q, max_hits],
+        hits[q, max_hits, 5] = fraction, normal.x, normal.y, point.x, point.y): every fixture hit in ascending fixture order, or
+        with closest=True only the closest one in slot 0.  counts[q] = -1 for a zero-length segment."""
+        torch = _torch()
+        w, seg, rd = self._query_inputs(worlds, segments, 4)
+        n = int(w.numel())
+        count = torch.zeros(n, dtype=torch.int32, device=self.device)
+        fix = torch.full((n, max_hits), -1, dtype=torch.int32, device=self.device)
+        hit = torch.zeros((n, max_hits, 5), dtype=rd, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().b2b_ray_cast(self._ctx, n, p(w), p(seg), 1 if closest else 0, int(max_hits), p(count), p(fix), p(hit),
+                                           self._stream()), "b2b_ray_cast")
+        torch.cuda.synchronize(self.device)
+        return count.cpu().numpy(), fix.cpu().numpy(), hit.cpu().numpy().astype(np.float64)
+
+    def test_points(self, worlds, fixtures, points):
+        """Fixture.test_point for a batch of (world, fixture, point) triples -> bool array."""
+        torch = _torch()
+        w, pt, rd = self._query_inputs(worlds, points, 2)
+        f = torch.as_tensor(np.ascontiguousarray(fixtures, dtype=np.int32), device=self.device)
+        n = int(w.numel())
+        out = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().b2b_test_points(self._ctx, n, p(w), p(f), p(pt), p(out), self._stream()), "b2b_test_points")
+        torch.cuda.synchronize(self.device)
+        return out.cpu().numpy().astype(bool)
+
     # -- transfers --------------------------------------------------------------------------
     def download(self, names=None, worlds=None):
         """Host numpy copies (uint32 fields restored) of the named fields, optionally for a slice of worlds."""

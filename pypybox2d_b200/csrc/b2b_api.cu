@@ -495,6 +495,52 @@ extern "C" int b2b_step_host(b2b_ctx* x, const void* h_force_torque, void* h_sta
     return B2B_OK;
 }
 
+extern "C" int b2b_query_aabb(b2b_ctx* x, int n, const void* d_world, const void* d_box, int max_hits, void* d_count, void* d_fix,
+                              void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_query_aabb: no buffers bound");
+    if (n < 0 || max_hits < 0 || (n > 0 && (!d_world || !d_box || !d_count || (max_hits > 0 && !d_fix)))) return fail(B2B_ERR_ARG, "b2b_query_aabb: bad argument");
+    if (n == 0) return B2B_OK;
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_query_aabb_f64(x->fields, x->c, n, d_world, d_box, max_hits, d_count, d_fix, (cudaStream_t)stream);
+    else launch_query_aabb_f32(x->fields, x->c, n, d_world, d_box, max_hits, d_count, d_fix, (cudaStream_t)stream);
+    ++x->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "query_aabb kernel", e);
+    return B2B_OK;
+}
+
+extern "C" int b2b_ray_cast(b2b_ctx* x, int n, const void* d_world, const void* d_seg, int mode, int max_hits, void* d_count,
+                            void* d_fix, void* d_hit, void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_ray_cast: no buffers bound");
+    if (n < 0 || max_hits < 1 || (mode != 0 && mode != 1) || (n > 0 && (!d_world || !d_seg || !d_count || !d_fix || !d_hit)))
+        return fail(B2B_ERR_ARG, "b2b_ray_cast: bad argument");
+    if (n == 0) return B2B_OK;
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_ray_cast_f64(x->fields, x->c, n, d_world, d_seg, mode, max_hits, d_count, d_fix, d_hit, (cudaStream_t)stream);
+    else launch_ray_cast_f32(x->fields, x->c, n, d_world, d_seg, mode, max_hits, d_count, d_fix, d_hit, (cudaStream_t)stream);
+    ++x->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "ray_cast kernel", e);
+    return B2B_OK;
+}
+
+extern "C" int b2b_test_points(b2b_ctx* x, int n, const void* d_world, const void* d_fixture, const void* d_point, void* d_inside,
+                               void* stream)
+{
+    if (!x || !x->bound) return fail(B2B_ERR_UNBOUND, "b2b_test_points: no buffers bound");
+    if (n < 0 || (n > 0 && (!d_world || !d_fixture || !d_point || !d_inside))) return fail(B2B_ERR_ARG, "b2b_test_points: bad argument");
+    if (n == 0) return B2B_OK;
+    CUDA_TRY(cudaSetDevice(x->caps.device), "cudaSetDevice");
+    if (x->f64) launch_test_points_f64(x->fields, x->c, n, d_world, d_fixture, d_point, d_inside, (cudaStream_t)stream);
+    else launch_test_points_f32(x->fields, x->c, n, d_world, d_fixture, d_point, d_inside, (cudaStream_t)stream);
+    ++x->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2B_ERR_CUDA, "test_points kernel", e);
+    return B2B_OK;
+}
+
 extern "C" int b2b_collide_pairs(b2b_ctx* x, int n, const void* d_shape_a, const void* d_shape_b, const void* d_xf_a,
                                  const void* d_xf_b, void* d_mtype, void* d_mf, void* d_pts, void* d_id, void* stream)
 {

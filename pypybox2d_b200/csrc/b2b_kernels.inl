@@ -7,6 +7,7 @@
 #include <map>
 #include "b2b_step.cuh"
 #include "b2b_launch.h"
+#include "b2b_query.cuh"
 
 namespace b2b {
 
@@ -394,6 +395,130 @@ __global__ void B2B_CAT(status_kernel_, B2B_SUFFIX)(const uint32_t* w_status, in
     if (acc) atomicOr(out, acc);
 }
 
+
+// ---- queries (b2b_query.cuh): one warp per query, the world's proxies strided over its lanes -----------------
+// World.query_aabb (world.py:371-385): out_count[q] = fixtures of world q_world[q] whose fat AABB overlaps q_box[q]; the first
+// max_hits of them, ascending, in out_fix[q][.]
+__global__ void __launch_bounds__(128) B2B_CAT(query_aabb_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, int n_q, const int32_t* q_world,
+                                                                                const real_t* q_box, int max_hits, int32_t* out_count,
+                                                                                int32_t* out_fix)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < n_q; q += warps) {
+        const int w = q_world[q];
+        int total = 0;
+        if (w >= 0 && w < c.n_worlds) {
+            const real_t box[4] = {q_box[4 * (size_t)q], q_box[4 * (size_t)q + 1], q_box[4 * (size_t)q + 2], q_box[4 * (size_t)q + 3]};
+            const int nf = B.w_count[4 * (size_t)w + 1];
+            const real_t* fat = B.f_fat + 4 * (size_t)w * c.nf;
+            for (int base = 0; base < nf; base += 32) {
+                const int f = base + lane;
+                bool hit = false;
+                if (f < nf) {
+                    const real_t fb[4] = {fat[4 * (size_t)f], fat[4 * (size_t)f + 1], fat[4 * (size_t)f + 2], fat[4 * (size_t)f + 3]};
+                    hit = aabb_overlap<real_t>(fb, box);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                const int at = total + __popc(m & ((1u << lane) - 1u));
+                if (hit && at < max_hits) out_fix[(size_t)q * max_hits + at] = f;
+                total += __popc(m);
+            }
+        }
+        if (lane == 0) out_count[q] = total;
+    }
+}
+
+// World.ray_cast (world.py:387-440).  mode 0: every fixture the segment hits (a callback that returns 1), ascending fixture
+// index, out_hit[q][k] = {fraction, normal.x, normal.y, point.x, point.y}; mode 1: the closest hit only (a callback that returns
+// the fraction; ties: the lowest fixture index), in slot 0.  out_count[q] = number of hits found (mode 1: 0 or 1).
+__global__ void __launch_bounds__(128) B2B_CAT(ray_cast_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, int n_q, const int32_t* q_world,
+                                                                              const real_t* q_seg, int mode, int max_hits, int32_t* out_count,
+                                                                              int32_t* out_fix, real_t* out_hit)
+{
+    typedef vec2<real_t> V2;
+    const int lane = (int)(threadIdx.x & 31);
+    const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < n_q; q += warps) {
+        const int w = q_world[q];
+        int total = 0;
+        real_t best_fr = real_t(2);
+        int best_f = 0x7fffffff;
+        V2 best_n = mk<real_t>(real_t(0), real_t(0));
+        const V2 p1 = mk<real_t>(q_seg[4 * (size_t)q], q_seg[4 * (size_t)q + 1]), p2 = mk<real_t>(q_seg[4 * (size_t)q + 2], q_seg[4 * (size_t)q + 3]);
+        const V2 dseg = p2 - p1;
+        const bool valid = (w >= 0 && w < c.n_worlds) && (length_sqr(dseg) > real_t(0));      // dynamictree.py:222-223 raises ValueError
+        if (valid) {
+            const int nf = B.w_count[4 * (size_t)w + 1];
+            const size_t of = (size_t)w * c.nf, ob = (size_t)w * c.nb;
+            for (int base = 0; base < nf; base += 32) {
+                const int f = base + lane;
+                bool hit = false;
+                V2 normal = mk<real_t>(real_t(0), real_t(0));
+                real_t fraction = real_t(0);
+                if (f < nf) {
+                    const real_t* fp = B.f_fat + 4 * (of + f);
+                    const real_t fb[4] = {fp[0], fp[1], fp[2], fp[3]};
+                    if (ray_leaf_test<real_t>(fb, p1, p2)) {
+                        const shape_view<real_t> s = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, B.f_shape[of + f]);
+                        const xform<real_t> xf = xf_load<real_t>(B.b_xf + 4 * (ob + B.f_body[of + f]));
+                        hit = shape_ray_cast<real_t>(s, xf, p1, p2, normal, fraction);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (mode == 0) {
+                    const int at = total + __popc(m & ((1u << lane) - 1u));
+                    if (hit && at < max_hits) {
+                        const size_t o = (size_t)q * max_hits + at;
+                        const V2 point = (real_t(1) - fraction) * p1 + fraction * p2;            // world.py:427
+                        out_fix[o] = f;
+                        out_hit[5 * o] = fraction; out_hit[5 * o + 1] = normal.x; out_hit[5 * o + 2] = normal.y;
+                        out_hit[5 * o + 3] = point.x; out_hit[5 * o + 4] = point.y;
+                    }
+                } else if (hit && (fraction < best_fr || (fraction == best_fr && f < best_f))) {
+                    best_fr = fraction; best_f = f; best_n = normal;
+                }
+                total += __popc(m);
+            }
+            if (mode != 0) {
+                // warp argmin over (fraction, fixture)
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const real_t ofr = __shfl_xor_sync(0xffffffffu, best_fr, d);
+                    const int ofx = __shfl_xor_sync(0xffffffffu, best_f, d);
+                    const real_t onx = __shfl_xor_sync(0xffffffffu, best_n.x, d), ony = __shfl_xor_sync(0xffffffffu, best_n.y, d);
+                    if (ofr < best_fr || (ofr == best_fr && ofx < best_f)) { best_fr = ofr; best_f = ofx; best_n = mk<real_t>(onx, ony); }
+                }
+                if (lane == 0 && total > 0 && max_hits > 0) {
+                    const size_t o = (size_t)q * max_hits;
+                    const V2 point = (real_t(1) - best_fr) * p1 + best_fr * p2;
+                    out_fix[o] = best_f;
+                    out_hit[5 * o] = best_fr; out_hit[5 * o + 1] = best_n.x; out_hit[5 * o + 2] = best_n.y;
+                    out_hit[5 * o + 3] = point.x; out_hit[5 * o + 4] = point.y;
+                }
+                total = total > 0 ? 1 : 0;
+            }
+        }
+        if (lane == 0) out_count[q] = valid ? total : -1;
+    }
+}
+
+// Fixture.test_point (fixture.py:228-233) for n (world, fixture, point) triples
+__global__ void __launch_bounds__(256) B2B_CAT(test_points_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, int n, const int32_t* q_world,
+                                                                                 const int32_t* q_fix, const real_t* q_pt, uint8_t* out)
+{
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += (int)(gridDim.x * blockDim.x)) {
+        const int w = q_world[i], f = q_fix[i];
+        bool in = false;
+        if (w >= 0 && w < c.n_worlds && f >= 0 && f < B.w_count[4 * (size_t)w + 1]) {
+            const size_t of = (size_t)w * c.nf, ob = (size_t)w * c.nb;
+            const shape_view<real_t> s = shape_load<real_t>(B.s_meta, B.s_radius, B.s_data, B.f_shape[of + f]);
+            const xform<real_t> xf = xf_load<real_t>(B.b_xf + 4 * (ob + B.f_body[of + f]));
+            in = shape_test_point<real_t>(s, xf, mk<real_t>(q_pt[2 * (size_t)i], q_pt[2 * (size_t)i + 1]));
+        }
+        out[i] = in ? 1 : 0;
+    }
+}
+
 // ---- launchers (plain C++ so b2b_api.cpp stays free of templates) ----
 static inline batch_ptrs<real_t> as_ptrs(const void* const* fields)
 {
@@ -632,6 +757,30 @@ void B2B_CAT(launch_status_, B2B_SUFFIX)(const void* const* fields, const caps_t
     int grid = (c.n_worlds + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
     B2B_CAT(status_kernel_, B2B_SUFFIX)<<<grid, 256, 0, st>>>(B.w_status, c.n_worlds, out);
+}
+
+void B2B_CAT(launch_query_aabb_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, int n_q, const void* q_world, const void* q_box,
+                                             int max_hits, void* out_count, void* out_fix, cudaStream_t st)
+{
+    const int grid = (n_q + 3) / 4 < 148 * 16 ? (n_q + 3) / 4 : 148 * 16;
+    B2B_CAT(query_aabb_kernel_, B2B_SUFFIX)<<<grid < 1 ? 1 : grid, 128, 0, st>>>(as_ptrs(fields), c, n_q, (const int32_t*)q_world, (const real_t*)q_box,
+                                                                                 max_hits, (int32_t*)out_count, (int32_t*)out_fix);
+}
+
+void B2B_CAT(launch_ray_cast_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, int n_q, const void* q_world, const void* q_seg, int mode,
+                                           int max_hits, void* out_count, void* out_fix, void* out_hit, cudaStream_t st)
+{
+    const int grid = (n_q + 3) / 4 < 148 * 16 ? (n_q + 3) / 4 : 148 * 16;
+    B2B_CAT(ray_cast_kernel_, B2B_SUFFIX)<<<grid < 1 ? 1 : grid, 128, 0, st>>>(as_ptrs(fields), c, n_q, (const int32_t*)q_world, (const real_t*)q_seg,
+                                                                               mode, max_hits, (int32_t*)out_count, (int32_t*)out_fix, (real_t*)out_hit);
+}
+
+void B2B_CAT(launch_test_points_, B2B_SUFFIX)(const void* const* fields, const caps_t& c, int n, const void* q_world, const void* q_fix,
+                                              const void* q_pt, void* out, cudaStream_t st)
+{
+    const int grid = (n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8;
+    B2B_CAT(test_points_kernel_, B2B_SUFFIX)<<<grid < 1 ? 1 : grid, 256, 0, st>>>(as_ptrs(fields), c, n, (const int32_t*)q_world, (const int32_t*)q_fix,
+                                                                                  (const real_t*)q_pt, (uint8_t*)out);
 }
 
 }  // namespace b2b

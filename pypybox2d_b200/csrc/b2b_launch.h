@@ -65,7 +65,13 @@ struct step_timer {
     void launch_scatter_forces_##S(const void* const* fields, const caps_t& c, const void* stage, int w0, int n, cudaStream_t st); \
     void launch_gather_state_##S(const void* const* fields, const caps_t& c, void* stage, int w0, int n, cudaStream_t st);    \
     void launch_checksum_##S(const void* const* fields, const caps_t& c, double* out, cudaStream_t st);                       \
-    void launch_status_##S(const void* const* fields, const caps_t& c, uint32_t* out, cudaStream_t st);
+    void launch_status_##S(const void* const* fields, const caps_t& c, uint32_t* out, cudaStream_t st);                         \
+    void launch_query_aabb_##S(const void* const* fields, const caps_t& c, int n_q, const void* q_world, const void* q_box,   \
+                               int max_hits, void* out_count, void* out_fix, cudaStream_t st);                                \
+    void launch_ray_cast_##S(const void* const* fields, const caps_t& c, int n_q, const void* q_world, const void* q_seg, int mode, \
+                             int max_hits, void* out_count, void* out_fix, void* out_hit, cudaStream_t st);                   \
+    void launch_test_points_##S(const void* const* fields, const caps_t& c, int n, const void* q_world, const void* q_fix,    \
+                                const void* q_pt, void* out, cudaStream_t st);
 
 B2B_DECLARE(f32)
 B2B_DECLARE(f64)

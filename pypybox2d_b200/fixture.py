@@ -53,6 +53,28 @@ class Fixture(object):
     mask_bits = property(lambda self: self._mask_bits)
     group_index = property(lambda self: self._group_index)
 
+    def test_point(self, p):
+        """Is the world point inside this fixture's shape?  (fixture.py:228-233; evaluated on the device)"""
+        world = self.world
+        if world is None:
+            raise ValueError("fixture is not attached to a world")
+        batch = world._ensure_batch()
+        return bool(batch.test_points([0], [world._fixture_list().index(self)], [(p[0], p[1])])[0])
+
+    def ray_cast(self, p1, p2, max_fraction=1.0, child_index=0):
+        """(hit, normal, fraction) of the segment against this fixture's shape (fixture.py:235-240; evaluated on the device)."""
+        from .common import Vec2
+        world = self.world
+        if world is None:
+            raise ValueError("fixture is not attached to a world")
+        batch = world._ensure_batch()
+        me = world._fixture_list().index(self)
+        count, fix, hit = batch.ray_cast([0], [(p1[0], p1[1], p2[0], p2[1])], max_hits=max(len(world._fixture_list()), 1))
+        for k in range(max(int(count[0]), 0)):
+            if int(fix[0][k]) == me and float(hit[0][k][0]) <= max_fraction:
+                return True, Vec2(float(hit[0][k][1]), float(hit[0][k][2])), float(hit[0][k][0])
+        return False, None, 0.0
+
     @property
     def mass_data(self):
         return self._shape.compute_mass(self._density)

@@ -203,6 +203,65 @@ class World(object):
             b._force = Vec2()
             b._torque = 0.0
 
+    # -- queries (world.py:371-440) ----------------------------------------------------------------
+    def _fixture_list(self):
+        return [f for b in self.bodies for f in b.fixtures]
+
+    def query_aabb(self, aabb, callback=None):
+        """Every fixture whose broadphase (fat) AABB overlaps `aabb` -- an object with lower_bound / upper_bound, or
+        ((lx, ly), (ux, uy)).  A generator, or calls `callback(fixture)` until it returns a false value, as the reference
+        (world.py:371-385).  Fixtures come in creation order (the reference: tree order; the set is the same)."""
+        lo, hi = (aabb.lower_bound, aabb.upper_bound) if hasattr(aabb, "lower_bound") else aabb
+        hits = self._query_aabb((lo[0], lo[1], hi[0], hi[1]))
+        if callback is not None:
+            for f in hits:
+                if not callback(f):
+                    break
+            return None
+        return iter(hits)
+
+    def _query_aabb(self, box):
+        batch = self._ensure_batch()
+        fixtures = self._fixture_list()
+        count, fix = batch.query_aabb([0], [box], max_hits=max(len(fixtures), 1))
+        return [fixtures[j] for j in fix[0][:int(count[0])]]
+
+    def ray_cast(self, point1, point2, callback=None):
+        """Every fixture in the path of the ray, with the reference's protocol (world.py:387-440): yields (or passes to the
+        callback) [fixture, point, normal, fraction]; a returned / assigned last entry of -1 ignores the fixture, 0 ends the
+        cast, a fraction clips the ray there, 1 continues.  The shape ray casts run on the device; fixtures are visited in
+        creation order (the reference: tree order, which Box2D leaves unspecified)."""
+        p1, p2 = Vec2(*point1), Vec2(*point2)
+        batch = self._ensure_batch()
+        fixtures = self._fixture_list()
+        count, fix, hit = batch.ray_cast([0], [(p1.x, p1.y, p2.x, p2.y)], max_hits=max(len(fixtures), 1))
+        if int(count[0]) < 0:
+            raise ValueError("||p2 - p1||^2 > 0.0")
+        hits = [(fixtures[int(fix[0][k])], hit[0][k]) for k in range(int(count[0]))]
+
+        def walk():
+            max_fraction = 1.0
+            for fixture, h in hits:
+                fraction = float(h[0])
+                if fraction > max_fraction:          # outside the clipped segment: the tree would have pruned it
+                    continue
+                ret = [fixture, Vec2(float(h[3]), float(h[4])), Vec2(float(h[1]), float(h[2])), fraction]
+                if callback is not None:
+                    value = callback(*ret)
+                else:
+                    yield ret
+                    value = ret[-1]
+                if value == 0.0:
+                    return
+                if value > 0.0:
+                    max_fraction = value
+
+        if callback is not None:
+            for _ in walk():
+                pass
+            return None
+        return walk()
+
     def _contact_views(self):
         if self._batch is None:
             return []
