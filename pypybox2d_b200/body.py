@@ -119,14 +119,23 @@ class Body(object):
     def attach_fixture(self, fixture):
         if fixture in self.fixtures:
             raise ValueError("Fixture is already attached to this body")
-        if self._world is not None and self._world._stepped:
-            raise NotImplementedError("adding fixtures after the first step is not supported yet (SURVEY §8f #4)")
         fixture._attach_to_body(self)
         self.fixtures.append(fixture)
         if fixture._density > 0.0:
             self.reset_mass_data()
         if self._world is not None:
             self._world._fixture_attached(self, fixture)
+
+    def destroy_fixture(self, fixture):
+        """body.py:258-286: the fixture leaves the body with its proxy and its contacts; the mass is recomputed."""
+        self._check_unlocked()
+        if fixture._body is not self or fixture not in self.fixtures:
+            raise ValueError("This fixture does not belong to this body")
+        self.fixtures.remove(fixture)
+        fixture._body = None
+        self.reset_mass_data()
+        if self._world is not None:
+            self._world._fixture_detached(self, fixture)
 
     def create_circle_fixture(self, radius=0.2, position=(0, 0), **kwargs):
         return self.create_fixture(_shapes.Circle(radius, position), **kwargs)

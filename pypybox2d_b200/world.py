@@ -80,6 +80,8 @@ class World(object):
         self._locked = False
         self._stepped = False
         self._host_dirty = True
+        self._structure_dirty = False
+        self._packed_fixtures = []
         self._batch = None
         self._real = real
         self._device = device
@@ -120,11 +122,11 @@ class World(object):
     def add_body(self, body):
         if self._locked:
             raise LockedError("Cannot create a body while simulating")
-        if self._stepped:
-            raise NotImplementedError("adding bodies after the first step is not supported yet (SURVEY §8f #4)")
         self.bodies.append(body)
         body._world = self
         self._host_dirty = True
+        if self._stepped:
+            self._structure_dirty = True       # the device arrays are re-packed before the next step (_rebuild_batch)
         return body
 
     def create_body(self, body=None, **kwargs):
@@ -146,7 +148,16 @@ class World(object):
         return self.create_body(body, type=Body.KINEMATIC, **kwargs)
 
     def destroy_body(self, body):
-        raise NotImplementedError("destroy_body is not supported on the batched step path (SURVEY §8f #4)")
+        """world.py:235-251: the body leaves the world with its fixtures' proxies and its contacts (Body._detached_from_world,
+        body.py:310-346); it stays a valid object and can be added to a world again."""
+        if self._locked:
+            raise LockedError("Cannot remove a body while simulating")
+        if body not in self.bodies:
+            raise ValueError("Body not in this world")
+        self.bodies.remove(body)
+        body._world = None
+        self._host_dirty = True
+        self._structure_dirty = True
 
     def add_joint(self, joint, duplicate=False):
         raise NotImplementedError("joints are not supported on the batched step path (SURVEY §8f #3)")
@@ -156,6 +167,12 @@ class World(object):
 
     def _fixture_attached(self, body, fixture):
         self._host_dirty = True
+        if self._stepped:
+            self._structure_dirty = True
+
+    def _fixture_detached(self, body, fixture):
+        self._host_dirty = True
+        self._structure_dirty = True
 
     # -- stepping (world.py:307-369) ----------------------------------------------------------
     def _ensure_batch(self):
@@ -163,10 +180,68 @@ class World(object):
         if self._batch is None:
             self._batch = BatchedWorld.from_worlds([self], real=self._real, device=self._device)
             self._host_dirty = False
+            self._structure_dirty = False
+            self._packed_fixtures = self._fixture_list()
+        elif self._structure_dirty:
+            self._rebuild_batch()
         elif self._host_dirty:
             self._batch.upload_bodies_from_world(self)
             self._host_dirty = False
         return self._batch
+
+    def _rebuild_batch(self):
+        """Host mutation between steps (create_body / destroy_body / create_fixture / destroy_fixture after the
+        first step, world.py:183-251, body.py:164-286): the world is packed again from the Python objects (which mirror the
+        device state after every step) and what only the device knows is carried over by object identity -- the broadphase
+        proxies of the surviving fixtures (fat / tight boxes, move buffer) and every contact whose two fixtures survive, in
+        list order with its manifold, impulses and flags; a destroyed body's or fixture's contacts and proxies go with it
+        (ContactManager.destroy, contact_manager.py:160-172), a new fixture gets a fresh proxy in the move buffer and raises
+        the world's new-fixture flag (fixture.py:250-261, world.py:85)."""
+        import numpy as np
+        from .batch import BatchedWorld, world_caps
+        old = self._batch
+        D = old.download()
+        old_index = {id(f): j for j, f in enumerate(self._packed_fixtures)}
+        fixtures = self._fixture_list()
+        caps = world_caps([self])
+        caps = schema.Caps(max(caps.nb, 1), max(caps.nf, 1), max(caps.nc, old.caps.nc))
+        table = schema.ShapeTable()
+        for f in fixtures:
+            table.add(f._shape)
+        A = schema.alloc(caps, 1, max(len(table), 1), "f64")
+        schema.pack_world(self, A, 0, table)
+        A["s_meta"], A["s_radius"], A["s_data"] = table.arrays("f64")
+        remap = np.full(len(self._packed_fixtures) + 1, -1, np.int64)
+        any_new = False
+        for j2, f in enumerate(fixtures):
+            j = old_index.get(id(f), -1)
+            if j < 0:
+                any_new = True
+                continue
+            remap[j] = j2
+            if f._body._active:
+                for name in ("f_fat", "f_tight", "f_moved"):
+                    A[name][0, j2] = D[name][0, j]
+        k2 = 0
+        for k in range(int(D["w_count"][0, 2])):
+            a2, b2 = int(remap[int(D["c_fix"][0, k, 0])]), int(remap[int(D["c_fix"][0, k, 1])])
+            if a2 < 0 or b2 < 0:
+                continue
+            A["c_fix"][0, k2] = (a2, b2)
+            for name in ("c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"):
+                A[name][0, k2] = D[name][0, k]
+            k2 += 1
+        A["w_count"][0, 2] = k2
+        flags = int(A["w_flags"][0])
+        if not any_new and not (int(D["w_flags"][0]) & schema.WORLD_NEW_FIXTURE):
+            flags &= ~schema.WORLD_NEW_FIXTURE
+        A["w_flags"][0] = flags
+        batch = BatchedWorld(A, caps, real=self._real, device=self._device)
+        batch.inv_dt0 = old.inv_dt0
+        self._batch = batch
+        self._packed_fixtures = fixtures
+        self._host_dirty = False
+        self._structure_dirty = False
 
     def step(self, dt, vel_iters, pos_iters):
         if self._locked:
