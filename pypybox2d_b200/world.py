@@ -52,7 +52,53 @@ class _ContactManagerView(object):
     def contacts(self):
         return self._world._contact_views()
 
-    begin_contact = end_contact = pre_solve = post_solve = None
+    # Contact listeners (contact_manager.py:46-100).  begin_contact / end_contact are delivered after the step that caused
+    # them, in the reference's order (the narrowphase walks the contact list: contact.py:263-266, contact_manager.py:167-168),
+    # from the difference between the device contact lists before and after the step; pre_solve / post_solve would have to
+    # run inside the solver kernels and are not supported.
+    def __init_listeners(self):
+        self._begin_contact = None
+        self._end_contact = None
+
+    @property
+    def begin_contact(self):
+        return getattr(self, "_begin_contact", None)
+
+    @begin_contact.setter
+    def begin_contact(self, fcn):
+        self._begin_contact = fcn
+        self._world._listeners_changed()
+
+    @property
+    def end_contact(self):
+        return getattr(self, "_end_contact", None)
+
+    @end_contact.setter
+    def end_contact(self, fcn):
+        self._end_contact = fcn
+        self._world._listeners_changed()
+
+    @property
+    def pre_solve(self):
+        return None
+
+    @pre_solve.setter
+    def pre_solve(self, fcn):
+        if fcn is not None:
+            raise NotImplementedError("pre_solve callbacks cannot run inside the device step (SURVEY §8b)")
+
+    @property
+    def post_solve(self):
+        return None
+
+    @post_solve.setter
+    def post_solve(self, fcn):
+        if fcn is not None:
+            raise NotImplementedError("post_solve callbacks cannot run inside the device step (SURVEY §8b)")
+
+    @property
+    def contact_listener(self):
+        return [self.begin_contact, self.end_contact, None, None]
 
 
 class World(object):
@@ -82,6 +128,7 @@ class World(object):
         self._host_dirty = True
         self._structure_dirty = False
         self._packed_fixtures = []
+        self._prev_contacts = None
         self._batch = None
         self._real = real
         self._device = device
@@ -265,6 +312,7 @@ class World(object):
                                    "the step's result is invalid" % (", ".join(names) or hex(st), batch.caps.nc, batch.caps.npair,
                                                                       batch.caps.nl))
             batch.download_into_world(self)
+            self._deliver_contact_events()
             if not self._auto_clear_forces:
                 # forces were cleared on the device only when auto_clear_forces is on
                 pass
@@ -336,6 +384,43 @@ class World(object):
                 pass
             return None
         return walk()
+
+    def _listeners_changed(self):
+        # a listener attached to a world that is already stepping hears about changes from now on
+        if self._batch is not None and self._stepped and self._prev_contacts is None:
+            self._prev_contacts = self._contact_views()
+
+    def _deliver_contact_events(self):
+        """begin_contact / end_contact for the step that just ran.  Within one step the reference touches every contact that
+        existed before it at most once in ContactManager.collide, in list order: destroyed (end_contact if it was touching,
+        contact_manager.py:167-168) or updated (begin / end on a touching change, contact.py:263-266); contacts created by the
+        step are not touching yet.  So the events are the ordered difference of the two contact lists.  (With continuous
+        collision on, a TOI sub-step can change a flag again inside the step: only the net change is reported.)"""
+        cm = self.contact_manager
+        if cm.begin_contact is None and cm.end_contact is None:
+            self._prev_contacts = None
+            return
+        cur = self._contact_views()
+        prev = self._prev_contacts
+        self._prev_contacts = cur
+        if prev is None:
+            prev = []
+        now = {(id(c.fixture_a), id(c.fixture_b)): c for c in cur}
+        for old in prev:
+            c = now.get((id(old.fixture_a), id(old.fixture_b)))
+            if c is None:
+                if old.touching and cm.end_contact is not None:
+                    cm.end_contact(old)
+            elif c.touching and not old.touching:
+                if cm.begin_contact is not None:
+                    cm.begin_contact(c)
+            elif old.touching and not c.touching:
+                if cm.end_contact is not None:
+                    cm.end_contact(c)
+        seen = set((id(c.fixture_a), id(c.fixture_b)) for c in prev)
+        for c in cur:                                   # (a contact cannot be created touching; kept for robustness)
+            if (id(c.fixture_a), id(c.fixture_b)) not in seen and c.touching and cm.begin_contact is not None:
+                cm.begin_contact(c)
 
     def _contact_views(self):
         if self._batch is None:
