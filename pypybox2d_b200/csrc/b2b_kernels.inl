@@ -38,6 +38,46 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
                                                                                                    int w0, int n_range)
 {
     const long long total = (long long)n_range * c.nc;                 // worlds [w0, w0 + n_range)
+#if defined(B2B_COLLIDE_SORT) && B2B_COLLIDE_SORT
+    // EXPERIMENT, off by default (measured slower on B200: 7.05 -> 7.62 ms per 131,072 pyramid worlds -- the flag load in front
+    // of the row loads and the two barriers cost more than the divergence they remove, and the permuted rows load uncoalesced).
+    // The 128 contacts of a CTA's round are handed to its threads sorted by what they cost: contacts that were touching last
+    // step first (SAT of both polygons, incident edge, clipping: ~1,500 instructions), then the others (they usually leave
+    // after the first polygon's separating axis: ~400), unused rows last.  A warp runs the long path if ONE of its contacts
+    // takes it; unsorted, every warp of a settled pile has such a contact (two thirds of the rows touch).
+    __shared__ int s_perm[128];
+    __shared__ int s_warp[8];
+    const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (long long base = (long long)blockIdx.x * 128; base < total; base += (long long)gridDim.x * 128) {
+        const long long i = base + tid;
+        int key = 2;
+        if (i < total) {
+            const int w = w0 + (int)(i / c.nc), ci = (int)(i % c.nc);
+            if (ci < B.w_count[4 * (size_t)w + 2] && !(B.w_flags[w] & WORLD_NEW_FIXTURE))
+                key = (B.c_flags[(size_t)w * c.nc + ci] & CONTACT_TOUCHING) ? 0 : 1;
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, key == 0), m1 = __ballot_sync(0xffffffffu, key == 1);
+        if (lane == 0) { s_warp[wid] = __popc(m0); s_warp[4 + wid] = __popc(m1); }
+        __syncthreads();
+        int off0 = 0, off1 = 0, n0 = 0, n1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < wid) { off0 += s_warp[k]; off1 += s_warp[4 + k]; }
+            n0 += s_warp[k]; n1 += s_warp[4 + k];
+        }
+        const unsigned below = (1u << lane) - 1u;
+        if (key == 0) s_perm[off0 + __popc(m0 & below)] = tid;
+        else if (key == 1) s_perm[n0 + off1 + __popc(m1 & below)] = tid;
+        __syncthreads();
+        if (tid < n0 + n1) {
+            const long long j = base + s_perm[tid];
+            world_step<real_t> ws;
+            ws.bind_rows(B, c, w0 + (int)(j / c.nc), plan, P);
+            ws.collide_one((int)(j % c.nc));
+        }
+        __syncthreads();
+    }
+#else
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int w = w0 + (int)(i / c.nc), ci = (int)(i % c.nc);
         if (ci >= B.w_count[4 * (size_t)w + 2]) continue;
@@ -46,6 +86,7 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
         ws.bind_rows(B, c, w, plan, P);
         ws.collide_one(ci);
     }
+#endif
 }
 
 // The per-world kernels are one warp per CTA; the warp is split into teams of `lanes` lanes and every team steps its
