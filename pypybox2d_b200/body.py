@@ -331,6 +331,53 @@ class Body(object):
         self._torque += (p - self._c).cross(f)
         self._dirty()
 
+    def apply_force_to_center(self, force):
+        """body.py:493-503: a force through the centre of mass (no torque); wakes the body."""
+        if self._type != Body.DYNAMIC:
+            return
+        if not self._awake:
+            self.awake = True
+        self._force = self._force + Vec2(*force)
+        self._dirty()
+
+    # -- frames (body.py:662-708): host arithmetic on the transform mirrored from the device after every step -----------
+    def get_world_point(self, local_point):
+        x, y, c, s = self._xf
+        p = Vec2(*local_point)
+        return Vec2(x + c * p.x - s * p.y, y + s * p.x + c * p.y)
+
+    def get_world_vector(self, local_vector):
+        x, y, c, s = self._xf
+        v = Vec2(*local_vector)
+        return Vec2(c * v.x - s * v.y, s * v.x + c * v.y)
+
+    def get_local_point(self, world_point):
+        x, y, c, s = self._xf
+        p = Vec2(*world_point)
+        dx, dy = p.x - x, p.y - y
+        return Vec2(c * dx + s * dy, -s * dx + c * dy)
+
+    def get_local_vector(self, world_vector):
+        x, y, c, s = self._xf
+        v = Vec2(*world_vector)
+        return Vec2(c * v.x + s * v.y, -s * v.x + c * v.y)
+
+    def get_linear_velocity_from_world_point(self, world_point):
+        p = Vec2(*world_point)
+        rx, ry = p.x - self._c.x, p.y - self._c.y
+        w = self._angular_velocity
+        return Vec2(self._linear_velocity.x - w * ry, self._linear_velocity.y + w * rx)
+
+    def get_linear_velocity_from_local_point(self, local_point):
+        return self.get_linear_velocity_from_world_point(self.get_world_point(local_point))
+
+    @property
+    def contact_list(self):
+        """Contacts attached to this body (body.py:889-896), read back from the device contact list."""
+        if self._world is None:
+            return []
+        return [c for c in self._world.contact_manager.contacts if c.body_a is self or c.body_b is self]
+
     def apply_torque(self, torque):
         if self._type != Body.DYNAMIC:
             return

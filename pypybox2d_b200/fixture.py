@@ -53,6 +53,17 @@ class Fixture(object):
     mask_bits = property(lambda self: self._mask_bits)
     group_index = property(lambda self: self._group_index)
 
+    def get_aabb(self, child_index=0):
+        """The fixture's broadphase AABB as ((lx, ly), (ux, uy)) -- the swept box of the last synchronisation, possibly stale
+        (fixture.py:242-248) -- read back from the device proxy rows."""
+        world = self.world
+        if world is None or world._batch is None:
+            lx, ly, ux, uy = self._shape.compute_aabb(self._body._xf)
+            return (lx, ly), (ux, uy)
+        j = world._fixture_list().index(self)
+        t = world._ensure_batch().download(["f_tight"], worlds=slice(0, 1))["f_tight"][0, j]
+        return (float(t[0]), float(t[1])), (float(t[2]), float(t[3]))
+
     def test_point(self, p):
         """Is the world point inside this fixture's shape?  (fixture.py:228-233; evaluated on the device)"""
         world = self.world

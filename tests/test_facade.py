@@ -113,3 +113,22 @@ def test_create_body_copies_an_existing_body_and_inactive_bodies_pack_without_pr
     ghost.active = True                        # before the first step the flag is host state
     schema.pack_world(w, A, 0, schema.ShapeTable())
     assert A["f_moved"][0, 4] == 1 and abs(A["f_fat"][0, 4, 0] - 0.4) < 1e-12
+
+
+def test_body_frame_helpers_match_the_reference_values():
+    """Body.get_world_point / get_world_vector / get_local_point / get_local_vector / velocity-of-point (body.py:662-708):
+    the expected numbers are the live reference's for the same body (printed by the build container, 12 digits)."""
+    w = b2.World((0, -10), True, continuous_physics=False)
+    b = w.create_dynamic_body(position=(1.5, 2.0), angle=0.7, linear_velocity=(0.3, -0.2), angular_velocity=1.1,
+                              fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=2.0))
+    want = [(1.47176558129, 2.499202181085), (-0.02823441871, 0.499202181085), (0.382421093642, -0.322108843619),
+            (2.818119749044, 0.241249000094), (-0.8, 0.35), (0.060870773201, -0.257595250591)]
+    got = [b.get_world_point((0.3, 0.4)), b.get_world_vector((0.3, 0.4)), b.get_local_point((2, 2)), b.get_local_vector((2, 2)),
+           b.get_linear_velocity_from_world_point((2, 3)), b.get_linear_velocity_from_local_point((0.1, 0.2))]
+    for g, e in zip(got, want):
+        assert abs(g.x - e[0]) < 1e-11 and abs(g.y - e[1]) < 1e-11
+    b.apply_force_to_center((1.0, 2.0))
+    assert b._force == b2.Vec2(1.0, 2.0) and b._torque == 0.0
+    assert b.contact_list == []
+    (lx, ly), (ux, uy) = b.fixtures[0].get_aabb()
+    assert lx < 1.5 < ux and ly < 2.0 < uy
