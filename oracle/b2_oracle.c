@@ -51,6 +51,7 @@
 #define C_ENABLED  0x2u
 #define C_FILTER   0x4u
 #define C_ISLAND   0x8u
+#define C_SENSOR   0x10u      /* one of the contact's fixtures is a sensor (fixture.py:163-168); set when the contact is created */
 #define W_ALLOW_SLEEP 0x1u
 #define W_WARM_START  0x2u
 #define W_NEW_FIXTURE 0x4u
@@ -609,9 +610,22 @@ static void body_sleep(orc_world* w, int b)
     w->b_flags[b] &= ~BODY_AWAKE;
 }
 
-/* ---- Contact.update: contact.py:210-268 (no sensors, no listeners) ---- */
+static int sensor_test_overlap(const orc_world* w, int fa, int fb, const xform* xa, const xform* xb);
+
+/* ---- Contact.update: contact.py:210-268 (no listeners) ---- */
 static void contact_update(orc_world* w, int ci)
 {
+    if (w->c_flags[ci] & C_SENSOR) {
+        /* contact.py:232-239: a sensor contact has no manifold points; touching = the shapes overlap (GJK with radii);
+         * nobody is woken by a change (contact.py:257-259 sits in the other branch) */
+        int fa = w->c_fix[2 * ci], fb = w->c_fix[2 * ci + 1];
+        xform xa = xf_row(w->b_xf + 4 * (size_t)w->f_body[fa]), xb = xf_row(w->b_xf + 4 * (size_t)w->f_body[fb]);
+        int touching = sensor_test_overlap(w, fa, fb, &xa, &xb);
+        w->c_flags[ci] |= C_ENABLED;
+        w->c_mtype[ci] = w->c_mtype[ci] & 0xff;                                  /* point_count = 0 */
+        if (touching) w->c_flags[ci] |= C_TOUCHING; else w->c_flags[ci] &= ~C_TOUCHING;
+        return;
+    }
     manifold_t m; manifold_load(w, ci, &m);
     manifold_t old = m;
     double* imp = w->c_imp + 4 * (size_t)ci;
@@ -736,7 +750,7 @@ static void cm_find_new_contacts(orc_world* w)
             if (nc >= w->nc_cap) { w->w_status[0] |= ST_CONTACT_OVERFLOW; continue; }
             int ci = nc;
             w->c_fix[2 * ci] = fixture_a; w->c_fix[2 * ci + 1] = fixture_b;
-            w->c_flags[ci] = 0;
+            w->c_flags[ci] = (((w->f_filter[2 * fixture_a + 1] | w->f_filter[2 * fixture_b + 1]) >> 16) & 1u) ? C_SENSOR : 0;
             /* mix_friction / mix_restitution: contact_util.py:36-48 */
             w->c_mat[2 * ci] = sqrt(w->f_mat[2 * fixture_a] * w->f_mat[2 * fixture_b]);
             {
@@ -1256,7 +1270,7 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
             for (int k = adj_start[b]; k < adj_start[b + 1]; ++k) {
                 int c = adj[k];
                 uint32_t cf = w->c_flags[c];
-                if ((cf & C_ISLAND) || !(cf & C_ENABLED) || !(cf & C_TOUCHING)) continue;
+                if ((cf & C_ISLAND) || !(cf & C_ENABLED) || !(cf & C_TOUCHING) || (cf & C_SENSOR)) continue;   /* world.py:528-533 */
                 w->l_contact[lc++] = c;
             }
             for (int k = first; k < lc; ++k) {
@@ -1522,6 +1536,14 @@ static double shape_distance(const dproxy* pa, const dproxy* pb, const xform* xa
     return dist;
 }
 
+/* test_overlap: distance.py:411-417 */
+static int sensor_test_overlap(const orc_world* w, int fa, int fb, const xform* xa, const xform* xb)
+{
+    dproxy pa = dproxy_get(w, w->f_shape[fa]), pb = dproxy_get(w, w->f_shape[fb]);
+    simplex_cache cache; memset(&cache, 0, sizeof(cache));
+    return shape_distance(&pa, &pb, xa, xb, 1, &cache) < (10.0 * EPS);
+}
+
 /* SeparationFunction: toi.py:46-221 */
 enum { SEP_POINTS, SEP_FACE_A, SEP_FACE_B };
 typedef struct { const dproxy *pa, *pb; const sweep_t *sa, *sb; int type; v2 axis, local_point; } sepfn;
@@ -1755,6 +1777,7 @@ static void world_solve_toi(orc_world* w, double dt, int vel_iters)
             if (toi_flag[c]) alpha = toi[c];
             else {
                 int fa = w->c_fix[2 * c], fb = w->c_fix[2 * c + 1];
+                if (w->c_flags[c] & C_SENSOR) continue;                           /* world.py:631-633 */
                 int ba = w->f_body[fa], bb = w->f_body[fb];
                 int type_a = body_type(w, ba), type_b = body_type(w, bb);
                 int active_a = body_awake(w, ba) && type_a != T_STATIC;
@@ -1821,6 +1844,7 @@ static void world_solve_toi(orc_world* w, double dt, int vel_iters)
                 int other = (cba == body) ? cbb : cba;
                 if (body_type(w, other) == T_DYNAMIC && !(w->b_flags[body] & BODY_BULLET) && !(w->b_flags[other] & BODY_BULLET))
                     continue;
+                if (w->c_flags[c] & C_SENSOR) continue;                           /* world.py:757-759 */
                 sweep_t backup = sweep_load(w, other);
                 if (!(w->b_flags[other] & BODY_ISLAND)) body_advance(w, other, min_alpha);
                 contact_update(w, c);

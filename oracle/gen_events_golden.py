@@ -13,7 +13,8 @@ import refpin  # noqa: E402
 
 # scene, world, scene keywords, dt, vel_iters, pos_iters, steps
 CASES = [("features", 1, {}, 1.0 / 60, 8, 3, 220), ("pyramid", 1, {"rows": 8}, 1.0 / 60, 8, 3, 160),
-         ("vertical_stack", 1, {}, 1.0 / 60, 10, 10, 200), ("bullets", 1, {}, 1.0 / 60, 8, 3, 200)]
+         ("vertical_stack", 1, {}, 1.0 / 60, 10, 10, 200), ("bullets", 1, {}, 1.0 / 60, 8, 3, 200),
+         ("sensors", 1, {}, 1.0 / 60, 8, 3, 300)]
 
 
 def run(b2, scene, world, kw, dt, vi, pi, steps, prepare=lambda w: None):

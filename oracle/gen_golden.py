@@ -55,6 +55,10 @@ CASES = {
     "vertical_stack_ccd_w1": ("vertical_stack", 1, 1.0 / 60, 10, 10, 200, (200,), CCD),
     "features_ccd_w1": ("features", 1, 1.0 / 60, 8, 3, 300, (300,), CCD),
     "mixed_ccd_w1": ("mixed", 1, 1.0 / 60, 8, 3, 200, (200,), CCD),
+    # sensor fixtures (contact.py:232-239, distance.test_overlap): trigger zones, proximity rings, with and without CCD
+    "sensors_w0": ("sensors", 0, 1.0 / 60, 8, 3, 300, (100, 300)),
+    "sensors_w1": ("sensors", 1, 1.0 / 60, 8, 3, 300, (300,)),
+    "sensors_ccd_w2": ("sensors", 2, 1.0 / 60, 8, 3, 300, (300,), CCD),
 }
 
 CK_FIELDS = ["w_count", "w_flags", "w_island", "b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island",

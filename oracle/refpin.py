@@ -161,6 +161,8 @@ def extract(world, arrays, w, table, schema):
             cf |= schema.CONTACT_FILTER
         if c._island_flag:
             cf |= schema.CONTACT_ISLAND
+        if c._fixture_a.sensor or c._fixture_b.sensor:
+            cf |= schema.CONTACT_SENSOR
         A["c_flags"][w, k] = cf
         A["c_mat"][w, k] = (c._friction, c._restitution)
         m = c._manifold

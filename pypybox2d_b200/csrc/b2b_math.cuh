@@ -36,6 +36,7 @@ enum : uint32_t {
     BODY_FIXED_ROT = 0x20u, BODY_BULLET = 0x40u, BODY_ISLAND = 0x80u,
     BODY_WOKEN = 0x100u,   // transient, shared-memory copy only: woken by the island walk this step
     CONTACT_TOUCHING = 0x1u, CONTACT_ENABLED = 0x2u, CONTACT_FILTER = 0x4u, CONTACT_ISLAND = 0x8u,
+    CONTACT_SENSOR = 0x10u,      // one of the two fixtures is a sensor (set when the contact is created): no manifold, touching = GJK overlap
     WORLD_ALLOW_SLEEP = 0x1u, WORLD_WARM_STARTING = 0x2u, WORLD_NEW_FIXTURE = 0x4u, WORLD_AUTO_CLEAR = 0x8u,
     WORLD_GRAPH_VALID = 0x10u,   // the island lists / level schedule of the last step still describe this world
     WORLD_CONTINUOUS = 0x20u,    // continuous_physics (world.py:78): World.solve_toi runs after the discrete solve

@@ -480,8 +480,21 @@ template <class real> struct world_step {
         contact_load(ci, in);
         return contact_update(ci, in);
     }
+    // A sensor contact (contact.py:232-239): no manifold points; touching = the shapes overlap (GJK with radii,
+    // distance.test_overlap); a change wakes nobody and is not a change of the contact graph.
+    B2B_D_NOINLINE void contact_update_sensor(int ci, uint32_t fl, int mt)
+    {
+        // (scalars in, rows fetched again here: handing the caller's row struct to an out-of-line function would put it --
+        // and with it the hot narrowphase path -- into local memory)
+        const int fa = c_fix[2 * ci], fb = c_fix[2 * ci + 1];
+        const XF xa = xf_load<real>(b_xf + 4 * (size_t)f_body[fa]), xb = xf_load<real>(b_xf + 4 * (size_t)f_body[fb]);
+        const bool touching = shapes_overlap<real>(shape_of_fixture(fa), shape_of_fixture(fb), xa, xb);
+        c_mtype[ci] = mt & 0xff;
+        c_flags[ci] = ((fl | CONTACT_ENABLED) & ~CONTACT_TOUCHING) | (touching ? CONTACT_TOUCHING : 0u);
+    }
     B2B_D bool contact_update(int ci, const contact_in& in)
     {
+        if (in.fl & CONTACT_SENSOR) { contact_update_sensor(ci, in.fl, in.mt); return false; }
         manifold<real> m, old;
         const quad qimp = in.qimp;
         {
@@ -686,7 +699,7 @@ template <class real> struct world_step {
                 if (c >= nc) continue;
                 s_cbody[2 * c] = (uint16_t)ba[k]; s_cbody[2 * c + 1] = (uint16_t)bb[k];
                 g_cbody[2 * c] = (uint16_t)ba[k]; g_cbody[2 * c + 1] = (uint16_t)bb[k];
-                s_cflag[c] = (uint8_t)(((cf[k] & CONTACT_ENABLED) && (cf[k] & CONTACT_TOUCHING)) ? 1 : 0);   // solid + touching
+                s_cflag[c] = (uint8_t)(((cf[k] & CONTACT_ENABLED) && (cf[k] & CONTACT_TOUCHING) && !(cf[k] & CONTACT_SENSOR)) ? 1 : 0);   // solid + touching (world.py:528-533)
                 if ((s_flags[ba[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&cnt[ba[k]], 1);
                 if ((s_flags[bb[k]] & BODY_TYPE_MASK) != BODY_STATIC) B2B_ATOMIC_ADD(&cnt[bb[k]], 1);
             }
@@ -2045,7 +2058,7 @@ template <class real> struct world_step {
             const bool swap = (t1 == SHAPE_CIRCLE && (t2 == SHAPE_POLYGON || t2 == SHAPE_EDGE)) || (t1 == SHAPE_POLYGON && t2 == SHAPE_EDGE);
             if (swap) { const int t = fa; fa = fb; fb = t; }
             c_fix[2 * ci] = fa; c_fix[2 * ci + 1] = fb;
-            c_flags[ci] = 0u;
+            c_flags[ci] = (((f_filter[2 * fa + 1] | f_filter[2 * fb + 1]) >> 16) & 1u) ? (uint32_t)CONTACT_SENSOR : 0u;
             c_mat[2 * ci] = sqrt_r(f_mat[2 * fa] * f_mat[2 * fb]);                 // mix_friction
             c_mat[2 * ci + 1] = pymax(f_mat[2 * fa + 1], f_mat[2 * fb + 1]);       // mix_restitution
             c_mtype[ci] = 0;
@@ -2138,7 +2151,7 @@ template <class real> struct world_step {
     {
         const int type_a = (int)(fla & BODY_TYPE_MASK), type_b = (int)(flb & BODY_TYPE_MASK);
         const bool collide_a = (fla & BODY_BULLET) || type_a != BODY_DYNAMIC, collide_b = (flb & BODY_BULLET) || type_b != BODY_DYNAMIC;
-        if (!collide_a && !collide_b) return 2;
+        if ((!collide_a && !collide_b) || (cfl & CONTACT_SENSOR)) return 2;            // (sensors: world.py:631-633, 757-759)
         if (!(cfl & CONTACT_ENABLED) || (st & TS_COUNT_MASK) > (int)MAX_SUB_STEPS || (st & TS_FLAG)) return 0;
         const bool active_a = (fla & BODY_AWAKE) && type_a != BODY_STATIC, active_b = (flb & BODY_AWAKE) && type_b != BODY_STATIC;
         return (active_a || active_b) ? 1 : 0;

@@ -142,10 +142,11 @@ template <class real> struct simplex_t {
     }
 };
 
-// shape_distance without radii (the only form World.solve_toi uses): distance.py:419-561.  The cache is read and written.
+// shape_distance: distance.py:419-561.  The cache is read and written.  use_radii: World.solve_toi passes False; test_overlap
+// (sensor contacts) passes True -- the distance then is the gap between the rounded shapes, 0 when they overlap.
 template <class real>
 B2B_HD_COLD real shape_distance(const shape_view<real>& pa, const shape_view<real>& pb, const xform<real>& xa,
-                                const xform<real>& xb, simplex_cache<real>& cache)
+                                const xform<real>& xb, simplex_cache<real>& cache, bool use_radii = false)
 {
     simplex_t<real> S;
     for (int k = 0; k < 3; ++k) {
@@ -222,7 +223,22 @@ B2B_HD_COLD real shape_distance(const shape_view<real>& pa, const shape_view<rea
     cache.metric = S.metric();
     cache.count = S.count;
     for (int i = 0; i < 3; ++i) if (i < S.count) { cache.ia[i] = S.v[i].ia; cache.ib[i] = S.v[i].ib; }
+    if (use_radii) {                                                                                    // distance.py:541-559
+        const real ra = pa.radius, rb = pb.radius;
+        if (dist > (ra + rb) && dist > K<real>::epsilon) return dist - (ra + rb);
+        return real(0);
+    }
     return dist;
+}
+
+// test_overlap: distance.py:411-417
+template <class real>
+B2B_HD bool shapes_overlap(const shape_view<real>& pa, const shape_view<real>& pb, const xform<real>& xa, const xform<real>& xb)
+{
+    simplex_cache<real> cache;
+    cache.metric = real(0); cache.count = 0;
+    for (int k = 0; k < 3; ++k) { cache.ia[k] = 0; cache.ib[k] = 0; }
+    return shape_distance(pa, pb, xa, xb, cache, true) < (real(10) * K<real>::epsilon);
 }
 
 // SeparationFunction: toi.py:46-221

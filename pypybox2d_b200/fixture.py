@@ -13,12 +13,10 @@ class Fixture(object):
     def __init__(self, shape=None, friction=0.2, restitution=0.0, density=0.0,
                  category_bits=0x0001, mask_bits=0xFFFF, group_index=0,
                  sensor=False, user_data=None, body=None):
-        if sensor:
-            raise NotImplementedError("sensor fixtures are not supported on the batched step path (SURVEY §8b)")
         self._friction = friction
         self._restitution = restitution
         self._density = density
-        self._sensor = sensor
+        self._sensor = bool(sensor)      # a sensor collects contact information but never generates a collision response (fixture.py:163-168)
         self._category_bits = category_bits
         self._mask_bits = mask_bits
         self._group_index = group_index

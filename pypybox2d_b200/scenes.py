@@ -265,5 +265,42 @@ def bullets(b2, world=0, config=7, **world_kw):
     return w
 
 
+# ---- sensor coverage scene (not a BASELINE config): trigger zones and proximity sensors -------------------------------------
+def sensors(b2, world=0, config=8, **world_kw):
+    """Sensor fixtures (fixture.py:163-168, contact.py:232-239): a static trigger zone, a sensor ring around a dynamic body (a
+    second fixture, with density), a sensor on a kinematic sweeper, and ordinary bodies that fall through / pile up around them.
+    Sensor contacts have no manifold, wake nobody, join no island and are never TOI candidates; their touching flag is GJK overlap."""
+    w = b2.World((0, -10), True, **_kw(world_kw))
+    w.create_static_body(shapes=[b2.Edge((-20.0, 0.0), (20.0, 0.0)), b2.Edge((-14.0, 0.0), (-14.0, 10.0)), b2.Edge((14.0, 0.0), (14.0, 10.0))])
+    zone = w.create_static_body(position=(0.0, 3.0))
+    zone.create_fixture(b2.Polygon(box=(4.0, 1.0)), sensor=True)
+    zone.create_fixture(b2.Circle(1.5, (-8.0, 1.0)), sensor=True)
+    sweeper = w.create_kinematic_body(position=(-10.0, 1.2), linear_velocity=(2.0, 0.0))
+    sweeper.create_fixture(b2.Polygon(box=(0.4, 0.4)), friction=0.5)
+    sweeper.create_fixture(b2.Circle(1.6), sensor=True)
+    n = 30
+    jit = jitter(config, world, n + 3)[3:]
+    for k in range(n):
+        i, j = divmod(k, 6)
+        pos = (-7.0 + 2.8 * j + jit[k, 0], 5.0 + 1.5 * i + jit[k, 1])
+        if k % 5 == 0:
+            body = w.create_dynamic_body(position=pos, angular_velocity=0.7)
+            body.create_fixture(b2.Polygon(box=(0.4, 0.3)), density=1.0, friction=0.4)
+            body.create_fixture(b2.Circle(1.1), density=0.05, sensor=True)         # proximity ring: it has mass, no response
+        elif k % 5 == 1:
+            w.create_dynamic_body(position=pos, fixtures=b2.Fixture(b2.Circle(0.35), density=1.0, friction=0.3, restitution=0.4))
+        elif k % 5 == 2:
+            m = 3 + (k // 5) % 4
+            shape = b2.Polygon(vertices=[(0.45 * math.cos(0.1 + 2.0 * math.pi * q / m), 0.45 * math.sin(0.1 + 2.0 * math.pi * q / m))
+                                         for q in range(m)])
+            w.create_dynamic_body(position=pos, angle=0.2 * k, fixtures=b2.Fixture(shape, density=1.5, friction=0.3))
+        elif k % 5 == 3:
+            w.create_dynamic_body(position=pos, bullet=(k % 2 == 1), linear_velocity=(0.0, -25.0),
+                                  fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=2.0, friction=0.3))
+        else:
+            w.create_dynamic_body(position=pos, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.6))
+    return w
+
+
 SCENES = {"features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
-          "deep_stacks": deep_stacks, "bullets": bullets}
+          "deep_stacks": deep_stacks, "bullets": bullets, "sensors": sensors}

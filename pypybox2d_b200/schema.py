@@ -27,6 +27,7 @@ CONTACT_TOUCHING = 0x1        # contact.py:73
 CONTACT_ENABLED = 0x2         # contact.py:75
 CONTACT_FILTER = 0x4          # contact.py:77
 CONTACT_ISLAND = 0x8          # contact.py:71
+CONTACT_SENSOR = 0x10        # one of the two fixtures is a sensor (fixture.py:163-168): no manifold, touching = GJK overlap
 
 WORLD_ALLOW_SLEEP = 0x1       # world.py:77
 WORLD_WARM_STARTING = 0x2     # world.py:74

@@ -92,7 +92,7 @@ def _group_kernel_cases():
 # measured maxima on B200 (profiles/r2_parity_report.json: 7.6e-13, 0, 4.5e-10, 5.3e-8, 4.2e-9, 5.7e-7) times 10-20.
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
 EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5,
-             "bullets": 1e-5}
+             "bullets": 1e-5, "sensors": 1e-6}
 # Continuous collision on (World.solve_toi; measured by tools/ccd_parity_probe.py on B200, profiles/r2_ccd_parity.json): the
 # TOI sub-steps amplify the same one-ulp libm differences further.  Free-running, seven of the eight cases keep the oracle's
 # integer outputs for their whole length (worst float difference: pyramid landing 5.2e-13, features 1.4e-9, bullets 4.5e-9 /
@@ -140,10 +140,10 @@ def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
 
 
 CCD_CASES = ["bullets_w0", "bullets_w1", "bullets_w2", "hello_ccd_w0", "pyramid_ccd_w1", "vertical_stack_ccd_w1", "features_ccd_w1",
-             "mixed_ccd_w1"]
+             "mixed_ccd_w1", "sensors_ccd_w2"]
 
 
-@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0"] + CCD_CASES)
+@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0", "sensors_w0"] + CCD_CASES)
 def test_p_exact_fp64_one_step(case, parity_report):
     """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
     1e-11 in every float field at every k (measured: 1.5e-12) -- the free-running differences of the swaying and tumbling
@@ -184,7 +184,7 @@ P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES}
                                         ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60),
                                         ("features_w0", 200), ("bullets_w0", 300), ("bullets_w2", 200), ("hello_ccd_w0", 100),
                                         ("pyramid_ccd_w1", 300), ("features_ccd_w1", 300), ("mixed_ccd_w1", 120),
-                                        ("vertical_stack_ccd_w1", 200)])
+                                        ("vertical_stack_ccd_w1", 200), ("sensors_w1", 300), ("sensors_ccd_w2", 300)])
 def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)

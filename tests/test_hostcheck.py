@@ -20,7 +20,8 @@ CASES = [("hello", 0, 0.1, 10, 10, 40), ("pyramid", 1, 1 / 60, 8, 3, 120), ("ver
 CCD = {"continuous_physics": True}
 # continuous collision on (World.solve_toi, world.py:594-821): the bullets scene has it on by construction
 CCD_CASES = [("bullets", 0, 1 / 60, 8, 3, 300, {}), ("bullets", 2, 1 / 30, 10, 4, 200, {}), ("hello", 0, 0.1, 10, 10, 60, CCD),
-             ("features", 1, 1 / 60, 8, 3, 150, CCD), ("pyramid", 1, 1 / 60, 8, 3, 90, CCD), ("vertical_stack", 1, 1 / 60, 10, 10, 80, CCD)]
+             ("features", 1, 1 / 60, 8, 3, 150, CCD), ("pyramid", 1, 1 / 60, 8, 3, 90, CCD), ("vertical_stack", 1, 1 / 60, 10, 10, 80, CCD),
+             ("sensors", 0, 1 / 60, 8, 3, 250, {}), ("sensors", 2, 1 / 60, 8, 3, 250, CCD)]
 
 
 @pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES)
