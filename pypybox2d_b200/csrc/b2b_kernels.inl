@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_pt
             const uint32_t fl = B.w_flags[w];
             const uint32_t sum = *reinterpret_cast<const uint32_t*>(plan + (size_t)w * P.stride + P.off_summary);
             // pending contacts alone (both bodies inactive) need no walk: without a touching change nobody was woken
-            const bool settled = (sp.flags & STEP_FLAT_COLLIDE) && !(fl & WORLD_NEW_FIXTURE) && !(sum & (SUM_DESTROY | SUM_CHANGED)) &&
+            const bool settled = (sp.flags & STEP_FLAT_COLLIDE) && !(fl & WORLD_NEW_FIXTURE) && !(sum & (SUM_DESTROY | SUM_CHANGED | SUM_SENSOR)) &&
                                  (!(sp.dt > 0.0) || (fl & WORLD_GRAPH_VALID));
             if (settled && sp.dt > 0.0) B.w_island[4 * (size_t)w + 3] = 0;      // what run_plan leaves behind for such a world
             if (settled && (sum & SUM_PENDING))
