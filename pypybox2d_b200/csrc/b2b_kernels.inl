@@ -131,7 +131,15 @@ __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes,
     }
 }
 
-__global__ void __launch_bounds__(32) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
+// B2B_PLAN_MIN_CTAS: resident one-warp CTAs per SM the register allocation is capped for.  The kernel is a sequential walk per
+// world -- latency bound -- so it runs on the number of resident worlds: uncapped it took 168 registers = 12 worlds per SM.
+// Measured on B200 (plan kernel, ms per step; 1 = uncapped / 16 / 20 / 24): vertical stacks x 65,536 worlds 10.34 / 7.56 / 6.80 /
+// 6.75 (31.6 -> 28.1 ms per step); deep stacks x 32,768 6.51 / 6.27 / 6.27 / 6.33 and mixed x 32,768 7.21 / 7.22 / 7.34 / 7.38:
+// those two are capped by the shared memory of their contact capacities (14 and 12 worlds per SM) before registers matter.
+#ifndef B2B_PLAN_MIN_CTAS
+#define B2B_PLAN_MIN_CTAS 20
+#endif
+__global__ void __launch_bounds__(32, B2B_PLAN_MIN_CTAS) B2B_CAT(plan_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                          scratch_layout L, unsigned char* scratch, step_params sp,
                                                                          int lanes, size_t team_smem, unsigned int* chunk_counter, int chunk)
 {

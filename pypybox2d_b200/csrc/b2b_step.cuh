@@ -776,16 +776,33 @@ template <class real> struct world_step {
                     // the reference appends all of b's free contacts first and then walks the appended ones
                     // (world.py:531-546); a contact is in b's list once and the second pass only touches flags the
                     // first never reads, so one pass gives the same lists without reading l_contact back from memory
-                    for (int k = s_adj_start[b]; k < s_adj_start[b + 1]; ++k) {
-                        const int c = s_adj[k];
-                        if (s_cflag[c] != 1) continue;                 // already in an island, disabled or not touching
-                        l_contact[lc++] = c;
-                        s_cflag[c] = 3;                                // island flag
-                        const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
-                        const int other = (b == ba) ? bb : ba;
-                        if (s_flags[other] & BODY_ISLAND) continue;
-                        s_stack[sp++] = (uint16_t)other;
-                        s_flags[other] |= BODY_ISLAND;
+                    // (four entries of the row at a time, their contact words fetched before any of them is looked at: a row
+                    // names a contact once, so nothing this round writes can change what was fetched, and the walk -- a chain
+                    // of dependent shared-memory loads, ~110 cycles per entry -- waits once per round instead of per entry)
+                    const int row_end = s_adj_start[b + 1];
+                    for (int k0 = s_adj_start[b]; k0 < row_end; k0 += 4) {
+                        int cs[4];
+                        uint8_t fs[4];
+                        uint32_t pair[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cs[j] = s_adj[(k0 + j < row_end) ? k0 + j : k0];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            fs[j] = s_cflag[cs[j]];
+                            pair[j] = (uint32_t)s_cbody[2 * cs[j]] | ((uint32_t)s_cbody[2 * cs[j] + 1] << 16);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (k0 + j >= row_end || fs[j] != 1) continue;   // already in an island, disabled, a sensor or not touching
+                            const int c = cs[j];
+                            l_contact[lc++] = c;
+                            s_cflag[c] = 3;                            // island flag
+                            const int ba = (int)(pair[j] & 0xffffu), bb = (int)(pair[j] >> 16);
+                            const int other = (b == ba) ? bb : ba;
+                            if (s_flags[other] & BODY_ISLAND) continue;
+                            s_stack[sp++] = (uint16_t)other;
+                            s_flags[other] |= BODY_ISLAND;
+                        }
                     }
                 }
                 if (overflow) break;
@@ -848,20 +865,34 @@ template <class real> struct world_step {
             int nlev = 0;
             if (ncon > 0) {
                 for (int k = 0; k < ncon + 3; ++k) ls[k] = 0;
-                for (int k = c0; k < c1; ++k) {
-                    const int c = l_contact[k];
-                    const int ba = s_cbody[2 * c], bb = s_cbody[2 * c + 1];
-                    const bool dyn_a = (s_flags[ba] & BODY_TYPE_MASK) != BODY_STATIC;
-                    const bool dyn_b = (s_flags[bb] & BODY_TYPE_MASK) != BODY_STATIC;
-                    int l = 0;
-                    if (dyn_a) l = s_last[ba];
-                    if (dyn_b && s_last[bb] > l) l = s_last[bb];
-                    ++l;
-                    if (dyn_a) s_last[ba] = (uint16_t)l;
-                    if (dyn_b) s_last[bb] = (uint16_t)l;
-                    s_lev[k] = (uint16_t)l;
-                    ++ls[l + 1];                          // count of level l parked one slot up
-                    if (l > nlev) nlev = l;
+                // (four slots per round: the island's contact list is in global memory, so its entries -- and with them the
+                // body pairs and body types, which this loop never writes -- are fetched before the round's sequential part)
+                for (int k0 = c0; k0 < c1; k0 += 4) {
+                    int cs[4], ba[4], bb[4];
+                    bool dyn_a[4], dyn_b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] = l_contact[(k0 + j < c1) ? k0 + j : k0];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { ba[j] = s_cbody[2 * cs[j]]; bb[j] = s_cbody[2 * cs[j] + 1]; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dyn_a[j] = (s_flags[ba[j]] & BODY_TYPE_MASK) != BODY_STATIC;
+                        dyn_b[j] = (s_flags[bb[j]] & BODY_TYPE_MASK) != BODY_STATIC;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k0 + j;
+                        if (k >= c1) continue;
+                        int l = 0;
+                        if (dyn_a[j]) l = s_last[ba[j]];
+                        if (dyn_b[j] && s_last[bb[j]] > l) l = s_last[bb[j]];
+                        ++l;
+                        if (dyn_a[j]) s_last[ba[j]] = (uint16_t)l;
+                        if (dyn_b[j]) s_last[bb[j]] = (uint16_t)l;
+                        s_lev[k] = (uint16_t)l;
+                        ++ls[l + 1];                      // count of level l parked one slot up
+                        if (l > nlev) nlev = l;
+                    }
                 }
                 // ls[l + 1] = count(l)  ->  ls[l] = start(l) for l = 1..nlev+1  (ls[nlev + 1] = ncon)
                 int run = 0;
