@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128, B2B_COLLIDE_MIN_CTAS) B2B_CAT(collide_ker
 // time: 32 when most worlds are skipped, fewer when the batch is small against the grid -- a batch in which every world needs
 // its walk would otherwise keep only n_worlds / 32 warps busy, each with 32 worlds in a row (measured: deep stacks, 32,768
 // worlds, plan kernel 7.7 ms = one warp's 32 worlds back to back).
-template <bool HEAVY_ONLY = false, class Need, class Work>
+template <int ONLY = 0, class Need, class Work>      // ONLY 2 / 1: the kernel's worlds are all of that class (one copy of its work, not two)
 __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes, int chunk, unsigned int* chunk_counter, Need need_of, Work work)
 {
     const int lane = (int)(threadIdx.x & 31);
@@ -117,9 +117,10 @@ __device__ __forceinline__ void for_each_needy_world(const caps_t& c, int lanes,
         // 2.3 ms with 8 lanes / 5.4 with 32; vertical stacks 10.0 / 6.3; mixed scene 21.4 / 10.5.
         const int cls = (w < c.n_worlds) ? (int)need_of(w) : 0;
         const unsigned heavy = __ballot_sync(0xffffffffu, cls == 2);
-        for (int ord = 0; ord < __popc(heavy); ++ord) work(base + (int)__fns(heavy, 0, ord + 1), 32);
+        if (ONLY != 1)
+            for (int ord = 0; ord < __popc(heavy); ++ord) work(base + (int)__fns(heavy, 0, ord + 1), 32);
         __syncwarp();
-        if (HEAVY_ONLY) continue;            // (a kernel whose worlds are all of class 2 carries one copy of its work, not two)
+        if (ONLY == 2) continue;
         const unsigned m = __ballot_sync(0xffffffffu, cls == 1);
         // few needy worlds in this chunk (the settled regime): widen the teams so that each world gets more lanes
         const int n = __popc(m);
@@ -297,9 +298,16 @@ __global__ void __launch_bounds__(32) B2B_CAT(broadphase_kernel_, B2B_SUFFIX)(ba
 }
 
 // Continuous collision: World.solve_toi (world.py:594-821) for the worlds whose flags carry WORLD_CONTINUOUS, after the
-// discrete step's find_new_contacts.  Same launch shape, shared-memory layout and scratch slabs as the pair kernel (the
-// loop calls phase_pairs after every solved event).  The candidates' times of impact are contact-parallel, so the whole warp
-// takes one world; a batch without such worlds costs one flag word per world.
+// discrete step's find_new_contacts.  Same launch shape and scratch slabs as the pair kernel (the loop calls phase_pairs
+// after every solved event), its shared-memory layout without the candidate bitmap.  TOI_LANES lanes per world: what happens
+// per event is sequential (one lane) and the kernel is bound by instruction fetch and latency, so it runs on the number of worlds
+// in flight and on how many of them share an instruction; the contact-parallel first look is a few rounds either way.  A batch
+// without such worlds costs one flag word per world.  Measured on B200 (ms per step with continuous collision on: 131,072 settled
+// pyramids / 65,536 landing pyramids; the same steps without it: 36.6 / 20.9): 4 lanes 40.7 / 34.1, 8 lanes 39.2 / 31.8, 16 lanes
+// 39.6 / 31.9, 32 lanes (with the bitmap) 40.7 / 33.5.
+#ifndef B2B_TOI_LANES
+#define B2B_TOI_LANES 8
+#endif
 __global__ void __launch_bounds__(32) B2B_CAT(toi_kernel_, B2B_SUFFIX)(batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan,
                                                                         scratch_layout L, unsigned char* scratch, step_params sp,
                                                                         int lanes, size_t team_smem, unsigned int* chunk_counter, int chunk)
@@ -307,14 +315,14 @@ __global__ void __launch_bounds__(32) B2B_CAT(toi_kernel_, B2B_SUFFIX)(batch_ptr
     extern __shared__ __align__(32) unsigned char smem[];
     world_step<real_t> ws;
     const int teams_per_cta = 32 / lanes;
-    for_each_needy_world<true>(
+    for_each_needy_world<1>(
         c, lanes, chunk, chunk_counter,
-        [&](int w) { return ((sp.dt > 0.0) && (B.w_flags[w] & WORLD_CONTINUOUS)) ? 2 : 0; },
+        [&](int w) { return ((sp.dt > 0.0) && (B.w_flags[w] & WORLD_CONTINUOUS)) ? 1 : 0; },
         [&](int w, int width) {
             const int team = ws.bind_team_lanes(width);
             ws.bind_rows(B, c, w, plan, P);
             ws.bind_scratch_aux(scratch + (size_t)(blockIdx.x * teams_per_cta + team) * L.total_aux, L);
-            ws.bind_smem_aux(smem + (size_t)team * team_smem, true);
+            ws.bind_smem_aux(smem + (size_t)team * team_smem, true, false);
             ws.run_toi(sp);
             __syncwarp(ws.t_mask);
         });
@@ -654,13 +662,15 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
     if (rc) return rc;
     {   // the TOI kernel runs on the pair kernel's geometry: its grid may only be smaller (more registers)
         kernel_plan k_toi;
-        rc = plan_one(B2B_CAT(toi_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
-                      S.total_broad * teams_aux, 0, n_sm, &k_toi);
+        const int teams_toi = 32 / B2B_TOI_LANES;
+        out->team_smem_toi = S.total_broad_nobits;
+        rc = plan_one(B2B_CAT(toi_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_toi - 1) / teams_toi, 32,
+                      S.total_broad_nobits * teams_toi, 0, n_sm, &k_toi);
         if (rc) return rc;
         out->k_toi = k_toi;
     }
     out->aux_slabs = (out->k_plan.grid > out->k_broad.grid ? out->k_plan.grid : out->k_broad.grid) * teams_aux;
-    if (out->aux_slabs < out->k_toi.grid * teams_aux) out->aux_slabs = out->k_toi.grid * teams_aux;
+    if (out->aux_slabs < out->k_toi.grid * (32 / B2B_TOI_LANES)) out->aux_slabs = out->k_toi.grid * (32 / B2B_TOI_LANES);
     out->solve_slabs = out->k_solve.grid * (out->k_solve.threads / 32) * teams;
     return 0;
 }
@@ -737,7 +747,7 @@ void B2B_CAT(launch_post_, B2B_SUFFIX)(const void* const* fields, const caps_t& 
                                                                                          p.lanes_aux, p.team_smem_broad, counters + 1, world_chunk(c.n_worlds, p.k_broad.grid));
     if (sp.dt > 0.0)
         B2B_CAT(toi_kernel_, B2B_SUFFIX)<<<p.k_toi.grid, 32, p.k_toi.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_aux, sp,
-                                                                              p.lanes_aux, p.team_smem_broad, counters + 4, world_chunk(c.n_worlds, p.k_toi.grid));
+                                                                              B2B_TOI_LANES, p.team_smem_toi, counters + 4, world_chunk(c.n_worlds, p.k_toi.grid));
     if (tm) tm->mark(T_PAIRS, st);
 }
 

@@ -21,7 +21,7 @@ struct launch_plan {
     int group_worlds;                // worlds whose constraint records are resident at once (one record slab each)
     int n_sm;
     int lanes, lanes_aux;            // lanes of a warp that step one world: solve kernel / plan + broadphase kernels
-    size_t team_smem, team_smem_plan, team_smem_broad;
+    size_t team_smem, team_smem_plan, team_smem_broad, team_smem_toi;
     scratch_layout layout;
     plan_layout plan;
 };

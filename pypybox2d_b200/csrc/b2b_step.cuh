@@ -197,6 +197,7 @@ struct smem_layout {
     size_t off_ctl, off_flags, off_ls, off_cbody, off_adj, off_adj_start, off_stack, off_lev, off_cflag, total_plan;
     size_t off_state, total_solve;                            // relative to the team's base
     size_t total_broad;
+    size_t total_broad_nobits;                                // the pair-finding layout without the candidate bitmap (TOI kernel)
     size_t off_pairbits;                                      // broadphase kernel: candidate bitmap [nf][ceil(nf / 32)] (0: none, too big)
 };
 B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
@@ -209,6 +210,7 @@ B2B_HD smem_layout smem_plan_layout(const caps_t& c, int real_bytes)
     const size_t fat_bytes = align_up((size_t)real_bytes * 4 * (size_t)c.nf, 32), moved_bytes = align_up((size_t)c.nf, 32);
     S.off_fat = o; S.off_moved = o + fat_bytes;
     S.total_broad = o + fat_bytes + moved_bytes;
+    S.total_broad_nobits = S.total_broad;
     {   // one bit per (mover, proxy): the overlap tests of pass 1 are not repeated by pass 2 (when it fits 24 KB)
         const size_t bits_bytes = sizeof(uint32_t) * (((size_t)c.nf + 31) / 32) * (size_t)c.nf;
         S.off_pairbits = 0;
@@ -380,13 +382,13 @@ template <class real> struct world_step {
         cc_state = (real*)(slabs + off + L.off_cc_state);
         prof = (long long*)team_prof;
     }
-    B2B_D void bind_smem_aux(unsigned char* smem, bool broadphase_kernel = false)
+    B2B_D void bind_smem_aux(unsigned char* smem, bool broadphase_kernel = false, bool with_pairbits = true)
     {
         const smem_layout S = smem_plan_layout(cap, (int)sizeof(real));
         s_ctl = (int32_t*)(smem + S.off_ctl);
         const size_t fat_at = broadphase_kernel ? S.off_fat : S.off_ls;
         s_fat = (real*)(smem + fat_at); s_moved = (uint8_t*)(smem + fat_at + (S.off_moved - S.off_fat));
-        s_pairbits = (broadphase_kernel && S.off_pairbits != 0) ? (uint32_t*)(smem + S.off_pairbits) : nullptr;
+        s_pairbits = (broadphase_kernel && with_pairbits && S.off_pairbits != 0) ? (uint32_t*)(smem + S.off_pairbits) : nullptr;
         s_flags = (uint32_t*)(smem + S.off_flags);
         s_ls = (uint16_t*)(smem + S.off_ls);
         s_cbody = (uint16_t*)(smem + S.off_cbody); s_adj = (uint16_t*)(smem + S.off_adj);
