@@ -724,8 +724,16 @@ static void cm_find_new_contacts(orc_world* w)
                 if ((ca == fixture_a && cb == fixture_b) || (ca == fixture_b && cb == fixture_a)) { exists = 1; break; }
             }
             if (exists) continue;
-            /* Body._should_collide: body.py:910-928 (no joints) */
+            /* Body._should_collide: body.py:910-928 */
             if (body_type(w, body_b) != T_DYNAMIC && body_type(w, body_a) != T_DYNAMIC) continue;
+            {
+                int blocked = 0;
+                for (int k = w->b_jadj[2 * body_b], ke = k + w->b_jadj[2 * body_b + 1]; k < ke; ++k) {
+                    const int32_t* def = w->j_def + 4 * (size_t)w->j_adj[k];
+                    if (((def[1] == body_b && def[2] == body_a) || (def[2] == body_b && def[1] == body_a)) && !(def[3] & 0x1)) { blocked = 1; break; }
+                }
+                if (blocked) continue;
+            }
             /* World.default_contact_filter: world.py:958-970 */
             {
                 uint32_t fa0 = w->f_filter[2 * fixture_a], fa1 = w->f_filter[2 * fixture_a + 1];
@@ -1076,7 +1084,339 @@ static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
     }
 }
 
-static void island_solve(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts,
+
+/* =====================================================================================================
+ * Joints in the island solver: joints/revolute.py, joints/distance.py, joints/weld.py on the
+ * pure-Python Vec3 / Mat33 of common.py:227-358, 533-614.  One joint = row k of j_def (type, body_a, body_b,
+ * flags | _limit_state << 8), j_par (parameters, layout in pypybox2d_b200/joints.py), j_imp (_impulse x, y, z,
+ * _motor_impulse) and j_tmp (the attributes _init_velocity_constraints leaves for the sweeps).
+ * ===================================================================================================== */
+#define J_REVOLUTE 1
+#define J_DISTANCE 2
+#define J_WELD     3
+#define JF_COLLIDE 0x1
+#define JF_LIMIT   0x2
+#define JF_MOTOR   0x4
+#define JF_ISLAND  0x8
+#define JF_LS_SHIFT 8
+#define LS_INACTIVE 0
+#define LS_LOWER 1
+#define LS_UPPER 2
+#define LS_EQUAL 3
+#define MAX_ANG_CORR (8.0 / 180.0 * PI_)            /* settings.py:92 */
+#define ST_JOINT_OVERFLOW 0x20u
+
+typedef struct { double x, y, z; } v3;
+static inline v3 V3(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static inline double v3dot(v3 a, v3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }               /* common.py:342-344 */
+static inline v3 v3cross(v3 s, v3 v) { return V3(s.y * v.z - s.z * v.y, s.z * v.x - s.x * v.z, s.x * v.y - s.y * v.x); } /* :353-358 */
+static inline v3 v3neg(v3 a) { return V3(-a.x, -a.y, -a.z); }
+static inline v3 v3add(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+typedef struct { v3 c1, c2, c3; } m33;
+static v3 m33_solve3(const m33* m, v3 b)                                                                /* common.py:587-599 */
+{
+    double det = v3dot(m->c1, v3cross(m->c2, m->c3));
+    if (det != 0.0) det = 1.0 / det;
+    return V3(det * v3dot(b, v3cross(m->c2, m->c3)), det * v3dot(m->c1, v3cross(b, m->c3)), det * v3dot(m->c1, v3cross(m->c2, b)));
+}
+static v2 m33_solve2(const m33* m, v2 vec)                                                              /* common.py:601-614 */
+{
+    double a11 = m->c1.x, a12 = m->c2.x, a21 = m->c1.y, a22 = m->c2.y;
+    double det = a11 * a22 - a12 * a21;
+    if (det != 0.0) det = 1.0 / det;
+    return V(det * (a22 * vec.x - a12 * vec.y), det * (a11 * vec.y - a21 * vec.x));
+}
+static inline xform rot_make(double a) { return xf_make(V(0, 0), cos(a), sin(a)); }                     /* Mat22(angle=a) */
+static inline m33 m33_load(const double* t) { m33 m; m.c1 = V3(t[0], t[1], t[2]); m.c2 = V3(t[3], t[4], t[5]); m.c3 = V3(t[6], t[7], t[8]); return m; }
+static inline void m33_store(double* t, const m33* m)
+{
+    t[0] = m->c1.x; t[1] = m->c1.y; t[2] = m->c1.z; t[3] = m->c2.x; t[4] = m->c2.y; t[5] = m->c2.z; t[6] = m->c3.x; t[7] = m->c3.y; t[8] = m->c3.z;
+}
+
+
+/* _init_velocity_constraints: revolute.py:208-300, distance.py:155-250, weld.py:106-169 */
+static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm, pos_t* P, vel_t* Vv)
+{
+    int32_t* def = w->j_def + 4 * (size_t)k;
+    const double* par = w->j_par + 12 * (size_t)k;
+    double* imp = w->j_imp + 4 * (size_t)k;
+    double* tmp = w->j_tmp + 20 * (size_t)k;
+    int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
+    v2 lca = V(w->b_mass[4 * ba + 2], w->b_mass[4 * ba + 3]), lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);
+    double ma = w->b_mass[4 * ba], mb = w->b_mass[4 * bb], ia = w->b_mass[4 * ba + 1], ib = w->b_mass[4 * bb + 1];
+    v2 ca = P[ia_].c, cb = P[ib_].c; double aa = P[ia_].a, ab = P[ib_].a;
+    v2 va = Vv[ia_].v, vb = Vv[ib_].v; double wa = Vv[ia_].w, wb = Vv[ib_].w;
+    xform qa = rot_make(aa), qb = rot_make(ab);
+    v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+    tmp[0] = ra.x; tmp[1] = ra.y; tmp[2] = rb.x; tmp[3] = rb.y;
+    if (type == J_REVOLUTE) {
+        m33 m;
+        m.c3 = V3(-ra.y * ia - rb.y * ib, ra.x * ia + rb.x * ib, ia + ib);
+        m.c2 = V3(-ra.y * ra.x * ia - rb.y * rb.x * ib, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, m.c3.y);
+        m.c1 = V3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, m.c2.x, m.c3.x);
+        m33_store(tmp + 4, &m);
+        double motor_mass = ia + ib;
+        int fixed_rotation = (motor_mass == 0.0);
+        if (motor_mass > 0.0) motor_mass = 1.0 / motor_mass;
+        tmp[13] = motor_mass;
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        if (!(flags & JF_MOTOR) || fixed_rotation) imp[3] = 0.0;
+        if ((flags & JF_LIMIT) && !fixed_rotation) {
+            double joint_angle = ab - aa - par[4];
+            if (fabs(par[6] - par[5]) < 2.0 * ANGULAR_SLOP) ls = LS_EQUAL;
+            else if (joint_angle <= par[5]) {
+                if (ls != LS_LOWER) imp[2] = imp[2] - imp[2];
+                ls = LS_LOWER;
+            } else if (joint_angle >= par[6]) {
+                if (ls != LS_UPPER) imp[2] = imp[2] - imp[2];
+                ls = LS_UPPER;
+            } else {
+                ls = LS_INACTIVE;
+                imp[2] = imp[2] - imp[2];
+            }
+        } else ls = LS_INACTIVE;
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (warm) {
+            imp[0] = dt_ratio * imp[0]; imp[1] = dt_ratio * imp[1]; imp[2] = dt_ratio * imp[2];
+            imp[3] *= dt_ratio;
+            v2 Pv = V(imp[0], imp[1]);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * (vcross(ra, Pv) + imp[3] + imp[2]);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * (vcross(rb, Pv) + imp[3] + imp[2]);
+        } else { imp[0] = imp[1] = imp[2] = 0.0; imp[3] = 0.0; }
+    } else if (type == J_DISTANCE) {
+        v2 u = vsub(vsub(vadd(cb, rb), ca), ra);
+        double length = sqrt(sq(u.x) + sq(u.y));
+        v2 un = (length > LINEAR_SLOP) ? vscale(1.0 / length, u) : V(0.0, 0.0);     /* self._u; the local `u` stays as it was */
+        tmp[4] = un.x; tmp[5] = un.y;
+        double cr_au = sq(vcross(ra, u)), cr_bu = sq(vcross(rb, u));
+        double inv_mass = ma + ia * cr_au + mb + ib * cr_bu;
+        double mass = (inv_mass != 0.0) ? 1.0 / inv_mass : 0.0;
+        double gamma = tmp[7], bias = tmp[8];                                       /* attributes persist when frequency == 0 */
+        if (!(par[5] > 0.0)) { gamma = 0.0; bias = 0.0; }                           /* (never assigned: stay at the constructor's 0) */
+        if (par[5] > 0.0) {
+            double Cc = length - par[4];
+            double omega = 2.0 * PI_ * par[5];
+            double d = 2.0 * mass * par[6] * omega;
+            double kk = mass * sq(omega);
+            gamma = dt * (d + dt * kk);
+            gamma = (gamma != 0.0) ? 1.0 / gamma : 0.0;
+            bias = Cc * dt * kk * gamma;
+            double m2 = inv_mass + gamma;
+            mass = (m2 != 0.0) ? 1.0 / m2 : 0.0;
+        }
+        tmp[6] = mass; tmp[7] = gamma; tmp[8] = bias;
+        if (warm) {
+            imp[0] *= dt_ratio;
+            v2 Pv = vscale(imp[0], un);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * vcross(ra, Pv);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * vcross(rb, Pv);
+        } else imp[0] = 0.0;
+    } else if (type == J_WELD) {
+        m33 m;
+        double c2x = -ra.y * ra.x * ia - rb.y * rb.x * ib;
+        double c3x = -ra.y * ia - rb.y * ib;
+        m.c1 = V3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, c2x, c3x);
+        m.c2 = V3(c2x, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, c3x);          /* weld.py:148-150: c3x, as written */
+        m.c3 = V3(c3x, ra.x * ia + rb.x * ib, ia + ib);
+        m33_store(tmp + 4, &m);
+        if (warm) {
+            imp[0] = dt_ratio * imp[0]; imp[1] = dt_ratio * imp[1]; imp[2] = dt_ratio * imp[2];
+            v2 Pv = V(imp[0], imp[1]);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * (vcross(ra, Pv) + imp[2]);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * (vcross(rb, Pv) + imp[2]);
+        } else imp[0] = imp[1] = imp[2] = 0.0;
+    }
+    Vv[ia_].v = va; Vv[ia_].w = wa;
+    Vv[ib_].v = vb; Vv[ib_].w = wb;
+}
+
+/* _solve_velocity_constraints: revolute.py:302-378, distance.py:252-275, weld.py:171-199 */
+static void joint_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
+{
+    const int32_t* def = w->j_def + 4 * (size_t)k;
+    const double* par = w->j_par + 12 * (size_t)k;
+    double* imp = w->j_imp + 4 * (size_t)k;
+    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
+    double ma = w->b_mass[4 * ba], mb = w->b_mass[4 * bb], ia = w->b_mass[4 * ba + 1], ib = w->b_mass[4 * bb + 1];
+    v2 va = Vv[ia_].v, vb = Vv[ib_].v; double wa = Vv[ia_].w, wb = Vv[ib_].w;
+    v2 ra = V(tmp[0], tmp[1]), rb = V(tmp[2], tmp[3]);
+    if (type == J_REVOLUTE) {
+        m33 m = m33_load(tmp + 4);
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        int fixed_rotation = ((ia + ib) == 0.0);
+        if ((flags & JF_MOTOR) && ls != LS_EQUAL && !fixed_rotation) {
+            double Cdot = wb - wa - par[8];
+            double impulse = tmp[13] * (-Cdot);
+            double old_impulse = imp[3];
+            double max_impulse = dt * par[7];
+            imp[3] = pyclamp(imp[3] + impulse, -max_impulse, max_impulse);
+            impulse = imp[3] - old_impulse;
+            wa -= ia * impulse;
+            wb += ib * impulse;
+        }
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE && !fixed_rotation) {
+            v2 Cdot1 = vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
+            double Cdot2 = wb - wa;
+            v3 Cdot = V3(Cdot1.x, Cdot1.y, Cdot2);
+            v3 impulse = v3neg(m33_solve3(&m, Cdot));
+            if (ls == LS_EQUAL) {
+                imp[0] += impulse.x; imp[1] += impulse.y; imp[2] += impulse.z;
+            } else if (ls == LS_LOWER || ls == LS_UPPER) {
+                double new_impulse = imp[2] + impulse.z;
+                if ((ls == LS_LOWER) ? (new_impulse < 0.0) : (new_impulse > 0.0)) {
+                    v2 rhs = vadd(vneg(Cdot1), vscale(imp[2], V(m.c3.x, m.c3.y)));
+                    v2 reduced = m33_solve2(&m, rhs);
+                    impulse = V3(reduced.x, reduced.y, -imp[2]);
+                    imp[0] += reduced.x; imp[1] += reduced.y; imp[2] += -imp[2];
+                } else {
+                    imp[0] += impulse.x; imp[1] += impulse.y; imp[2] += impulse.z;
+                }
+            }
+            v2 Pv = V(impulse.x, impulse.y);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * (vcross(ra, Pv) + impulse.z);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * (vcross(rb, Pv) + impulse.z);
+        } else {
+            v2 Cdot = vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
+            v2 impulse = m33_solve2(&m, vneg(Cdot));
+            imp[0] += impulse.x; imp[1] += impulse.y; imp[2] += 0.0;
+            va = vsub(va, vscale(ma, impulse));
+            wa -= ia * vcross(ra, impulse);
+            vb = vadd(vb, vscale(mb, impulse));
+            wb += ib * vcross(rb, impulse);
+        }
+    } else if (type == J_DISTANCE) {
+        v2 u = V(tmp[4], tmp[5]);
+        v2 vpa = vadd(va, scross(wa, ra)), vpb = vadd(vb, scross(wb, rb));
+        double Cdot = vdot(u, vsub(vpb, vpa));
+        double impulse = -tmp[6] * (Cdot + tmp[8] + tmp[7] * imp[0]);
+        imp[0] += impulse;
+        v2 Pv = vscale(impulse, u);
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * vcross(ra, Pv);
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * vcross(rb, Pv);
+    } else if (type == J_WELD) {
+        m33 m = m33_load(tmp + 4);
+        v2 Cdot1 = vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
+        double Cdot2 = wb - wa;
+        v3 impulse = m33_solve3(&m, v3neg(V3(Cdot1.x, Cdot1.y, Cdot2)));
+        imp[0] += impulse.x; imp[1] += impulse.y; imp[2] += impulse.z;
+        v2 Pv = V(impulse.x, impulse.y);
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * (vcross(ra, Pv) + impulse.z);
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * (vcross(rb, Pv) + impulse.z);
+    }
+    Vv[ia_].v = va; Vv[ia_].w = wa;
+    Vv[ib_].v = vb; Vv[ib_].w = wb;
+}
+
+/* _solve_position_constraints: revolute.py:380-453, distance.py:277-311, weld.py:201-257; returns "within tolerance" */
+static int joint_solve_position(orc_world* w, int k, pos_t* P)
+{
+    const int32_t* def = w->j_def + 4 * (size_t)k;
+    const double* par = w->j_par + 12 * (size_t)k;
+    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
+    v2 lca = V(w->b_mass[4 * ba + 2], w->b_mass[4 * ba + 3]), lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);
+    double ma = w->b_mass[4 * ba], mb = w->b_mass[4 * bb], ia = w->b_mass[4 * ba + 1], ib = w->b_mass[4 * bb + 1];
+    v2 ca = P[ia_].c, cb = P[ib_].c; double aa = P[ia_].a, ab = P[ib_].a;
+    int ok = 1;
+    if (type == J_REVOLUTE) {
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        int fixed_rotation = ((ia + ib) == 0.0);
+        double angular_error = 0.0, position_error = 0.0;
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE && !fixed_rotation) {
+            double angle = ab - aa - par[4];
+            double limit_impulse = 0.0;
+            if (ls == LS_EQUAL) {
+                double Cc = pyclamp(angle - par[5], -MAX_ANG_CORR, MAX_ANG_CORR);
+                limit_impulse = -tmp[13] * Cc;
+                angular_error = fabs(Cc);
+            } else if (ls == LS_LOWER) {
+                double Cc = angle - par[5];
+                angular_error = -Cc;
+                Cc = pyclamp(Cc + ANGULAR_SLOP, -MAX_ANG_CORR, 0.0);
+                limit_impulse = -tmp[13] * Cc;
+            } else if (ls == LS_UPPER) {
+                double Cc = angle - par[6];
+                angular_error = Cc;
+                Cc = pyclamp(Cc - ANGULAR_SLOP, 0.0, MAX_ANG_CORR);
+                limit_impulse = -tmp[13] * Cc;
+            }
+            aa -= ia * limit_impulse;
+            ab += ib * limit_impulse;
+        }
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 Cc = vsub(vsub(vadd(cb, rb), ca), ra);
+        position_error = sqrt(sq(Cc.x) + sq(Cc.y));
+        double k1x = ma + mb + ia * ra.y * ra.y + ib * rb.y * rb.y;
+        double k1y = -ia * ra.x * ra.y - ib * rb.x * rb.y;
+        double k2x = k1y;
+        double k2y = ma + mb + ia * ra.x * ra.x + ib * rb.x * rb.x;
+        double det = k1x * k2y - k2x * k1y;                                          /* Mat22.solve: common.py:521-531 */
+        if (det != 0.0) det = 1.0 / det;
+        v2 impulse = vneg(V(det * (k2y * Cc.x - k2x * Cc.y), det * (k1x * Cc.y - k1y * Cc.x)));
+        ca = vsub(ca, vscale(ma, impulse));
+        aa -= ia * vcross(ra, impulse);
+        cb = vadd(cb, vscale(mb, impulse));
+        ab += ib * vcross(rb, impulse);
+        ok = (position_error <= LINEAR_SLOP) && (angular_error <= ANGULAR_SLOP);
+    } else if (type == J_DISTANCE) {
+        if (par[5] > 0.0) return 1;
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 u = vsub(vsub(vadd(cb, rb), ca), ra);
+        double length = sqrt(sq(u.x) + sq(u.y));
+        u = vnorm(u);
+        double Cc = length - par[4];
+        double impulse = -tmp[6] * pyclamp(Cc, -MAX_LIN_CORR, MAX_LIN_CORR);
+        v2 Pv = vscale(impulse, u);
+        ca = vsub(ca, vscale(ma, Pv));
+        aa -= ia * vcross(ra, Pv);
+        cb = vadd(cb, vscale(mb, Pv));
+        ab += ib * vcross(rb, Pv);
+        ok = fabs(Cc) < LINEAR_SLOP;
+    } else if (type == J_WELD) {
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 C1 = vsub(vsub(vadd(cb, rb), ca), ra);
+        double C2 = ab - aa - par[4];
+        double position_error = sqrt(sq(C1.x) + sq(C1.y)), angular_error = fabs(C2);
+        m33 m;
+        double c2x = -ra.y * ra.x * ia - rb.y * rb.x * ib;
+        double c3x = -ra.y * ia - rb.y * ib;
+        double c3y = ra.x * ia + rb.x * ib;
+        m.c1 = V3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, c2x, c3x);
+        m.c2 = V3(c2x, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, c3y);
+        m.c3 = V3(-ra.y * ia - rb.y * ib, ra.x * ia + rb.x * ib, ia + ib);
+        v3 impulse = v3neg(m33_solve3(&m, V3(C1.x, C1.y, C2)));
+        v2 Pv = V(impulse.x, impulse.y);
+        ca = vsub(ca, vscale(ma, Pv));
+        aa -= ia * (vcross(ra, Pv) + impulse.z);
+        cb = vadd(cb, vscale(mb, Pv));
+        ab += ib * (vcross(rb, Pv) + impulse.z);
+        ok = (position_error <= LINEAR_SLOP) && (angular_error <= ANGULAR_SLOP);
+    }
+    P[ia_].c = ca; P[ia_].a = aa;
+    P[ib_].c = cb; P[ib_].a = ab;
+    return ok;
+}
+
+static void island_solve(orc_world* w, const int* bodies, int nbodies, const int* contacts, int ncontacts, const int* joints, int njoints,
                          double dt, double dt_ratio, int vel_iters, int pos_iters, int* pos_iters_used)
 {
     pos_t* P = (pos_t*)malloc(sizeof(pos_t) * (size_t)(nbodies + 1));
@@ -1126,7 +1466,12 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
         }
     }
 
-    for (int it = 0; it < vel_iters; ++it) solver_velocity_sweep(C, ncontacts, Vv);
+    /* island.py:107-113 */
+    for (int k = 0; k < njoints; ++k) joint_init(w, joints[k], dt, dt_ratio, warm, P, Vv);
+    for (int it = 0; it < vel_iters; ++it) {
+        for (int k = 0; k < njoints; ++k) joint_solve_velocity(w, joints[k], dt, Vv);
+        solver_velocity_sweep(C, ncontacts, Vv);
+    }
 
     /* store_impulses: contact.py:801-806 (zip over vc.points, which may be shorter) */
     for (int k = 0; k < ncontacts; ++k) {
@@ -1182,7 +1527,10 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
             P[cc->ia].c = ca; P[cc->ia].a = aa;
             P[cc->ib].c = cb; P[cc->ib].a = ab;
         }
-        if (min_separation >= -3.0 * LINEAR_SLOP) { position_solved = 1; break; }
+        /* island.py:145-153 */
+        int joints_okay = 1;
+        for (int k = 0; k < njoints; ++k) { int okay = joint_solve_position(w, joints[k], P); joints_okay = joints_okay && okay; }
+        if (min_separation >= -3.0 * LINEAR_SLOP && joints_okay) { position_solved = 1; break; }
     }
     *pos_iters_used = used;
 
@@ -1229,6 +1577,9 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
     int nb = w->w_count[0], nf = w->w_count[1], nc = w->w_count[2];
     for (int b = 0; b < nb; ++b) { w->b_flags[b] &= ~BODY_ISLAND; w->b_island[b] = -1; }
     for (int c = 0; c < nc; ++c) w->c_flags[c] &= ~C_ISLAND;
+    int nj = w->w_joint[0], lj = 0;
+    if (nj > w->nj_cap) { w->w_status[0] |= ST_JOINT_OVERFLOW; nj = w->nj_cap; }
+    for (int j = 0; j < nj; ++j) w->j_def[4 * j + 3] &= ~JF_ISLAND;                /* world.py:491-492 */
 
     /* Body._contacts == world contact list filtered by body, same order (contact_manager.py:157-158,170-172) */
     int* adj_start = (int*)calloc((size_t)nb + 2, sizeof(int));
@@ -1253,7 +1604,7 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
         if (fl & BODY_ISLAND) continue;
         if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
         if ((fl & BODY_TYPE_MASK) == T_STATIC) continue;
-        int body_start = lb, contact_start = lc;
+        int body_start = lb, contact_start = lc, joint_start = lj;
         int sp = 0;
         stack[sp++] = seed;
         w->b_flags[seed] |= BODY_ISLAND;
@@ -1282,18 +1633,33 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
                 stack[sp++] = other;
                 w->b_flags[other] |= BODY_ISLAND;
             }
+            /* world.py:548-572: Body.joints in append order */
+            for (int k = w->b_jadj[2 * b], ke = k + w->b_jadj[2 * b + 1]; k < ke; ++k) {
+                int j = w->j_adj[k];
+                int32_t* def = w->j_def + 4 * (size_t)j;
+                if (def[3] & JF_ISLAND) continue;
+                int other = (def[1] == b) ? def[2] : def[1];
+                if (!(w->b_flags[other] & BODY_ACTIVE)) continue;
+                w->l_joint[lj++] = j;
+                def[3] |= JF_ISLAND;
+                if (w->b_flags[other] & BODY_ISLAND) continue;
+                stack[sp++] = other;
+                w->b_flags[other] |= BODY_ISLAND;
+            }
         }
         if (overflow) { w->w_status[0] |= ST_ISLAND_OVERFLOW; break; }
         w->l_start[2 * n_islands] = body_start; w->l_start[2 * n_islands + 1] = contact_start;
+        w->l_jstart[n_islands] = joint_start;
         int used = 0;
         island_solve(w, w->l_body + body_start, lb - body_start, w->l_contact + contact_start, lc - contact_start,
-                     dt, dt_ratio, vel_iters, pos_iters, &used);
+                     w->l_joint + joint_start, lj - joint_start, dt, dt_ratio, vel_iters, pos_iters, &used);
         if (used > pos_max) pos_max = used;
         for (int k = body_start; k < lb; ++k)
             if (body_type(w, w->l_body[k]) == T_STATIC) w->b_flags[w->l_body[k]] &= ~BODY_ISLAND;
         ++n_islands;
     }
     w->w_island[0] = n_islands; w->w_island[1] = lb; w->w_island[2] = lc; w->w_island[3] = pos_max;
+    w->w_joint[1] = lj;
 
     /* world.py:582-589 + body.py:898-904 */
     for (int f = 0; f < nf; ++f) {
@@ -2083,5 +2449,6 @@ const char* orc_field_names(void)
            "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
            "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
            "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
-           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data";
+           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data,"
+           "w_joint,j_def,j_par,j_imp,j_tmp,j_adj,b_jadj,l_joint,l_jstart";
 }

@@ -24,7 +24,7 @@ extern "C" {
 
 typedef struct orc_world {
     /* capacities */
-    int32_t nb_cap, nf_cap, nc_cap, npair_cap, nl_cap, n_shapes;
+    int32_t nb_cap, nf_cap, nc_cap, npair_cap, nl_cap, n_shapes, nj_cap;
     /* per world */
     int32_t*  w_count;    /* [4] n_bodies, n_fixtures, n_contacts, n_pairs */
     uint32_t* w_flags;    /* [1] */
@@ -67,6 +67,16 @@ typedef struct orc_world {
     int32_t*  s_meta;
     double*   s_radius;
     double*   s_data;     /* [n_shapes][32] */
+    /* joints (layout: pypybox2d_b200/joints.py) */
+    int32_t*  w_joint;    /* [4] n_joints, n_island_joints */
+    int32_t*  j_def;      /* [nj][4] type, body_a, body_b, flags | limit_state << 8 */
+    double*   j_par;      /* [nj][12] */
+    double*   j_imp;      /* [nj][4] */
+    double*   j_tmp;      /* [nj][20] */
+    int32_t*  j_adj;      /* [2 nj] Body.joints rows */
+    int32_t*  b_jadj;     /* [nb][2] start, count in j_adj */
+    int32_t*  l_joint;    /* [nj] island joint lists */
+    int32_t*  l_jstart;   /* [nb] per island: start in l_joint */
 } orc_world;
 
 /* One World.step (world.py:307-354) with continuous_physics=False.  inv_dt0 is World._inv_dt0

@@ -59,17 +59,29 @@ CASES = {
     "sensors_w0": ("sensors", 0, 1.0 / 60, 8, 3, 300, (100, 300)),
     "sensors_w1": ("sensors", 1, 1.0 / 60, 8, 3, 300, (300,)),
     "sensors_ccd_w2": ("sensors", 2, 1.0 / 60, 8, 3, 300, (300,), CCD),
+    # joints in the island solver: revolute (limits, motor), distance (rigid, soft), weld
+    "joints_w0": ("joints", 0, 1.0 / 60, 8, 3, 400, (100, 400)),
+    "joints_w1": ("joints", 1, 1.0 / 60, 10, 4, 300, (300,)),
+    "joints_ccd_w2": ("joints", 2, 1.0 / 60, 8, 3, 300, (300,), CCD),
+    "bridge_w1": ("bridge", 1, 1.0 / 60, 8, 3, 300, (150, 300)),
 }
 
 CK_FIELDS = ["w_count", "w_flags", "w_island", "b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island",
              "f_fat", "f_tight", "f_moved", "c_fix", "c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"]
 INIT_FIELDS = [f[0] for f in schema.FIELDS if f[0][0] in "wbfc" or f[0].startswith("s_")]
+JOINT_INIT_FIELDS = ["w_joint", "j_def", "j_par", "j_imp", "j_adj", "b_jadj"]      # only stored by fixtures of scenes with joints
+INIT_FIELDS = [f for f in INIT_FIELDS if f not in JOINT_INIT_FIELDS]
+JOINT_CK_FIELDS = ["j_def", "j_imp"]
 
 
 def state_digest(A, w=0):
     nb = int(A["w_count"][w][0])
     buf = np.concatenate([A["b_pos"][w][:nb, :3], A["b_vel"][w][:nb, :3]], axis=1).astype("<f8")
-    return hashlib.sha256(np.ascontiguousarray(buf).tobytes()).digest()
+    h = hashlib.sha256(np.ascontiguousarray(buf).tobytes())
+    nj = int(A["w_joint"][w][0])
+    if nj:
+        h.update(np.ascontiguousarray(A["j_imp"][w][:nj].astype("<f8")).tobytes())
+    return h.digest()
 
 
 def int_summary(A, w=0):
@@ -101,6 +113,11 @@ def int_hash(A, w=0):
     h.update(np.ascontiguousarray(A["l_contact"][w][:nlc]).tobytes())
     h.update(np.ascontiguousarray(A["l_start"][w][:n_isl]).tobytes())
     h.update(np.ascontiguousarray(A["p_pairs"][w][:min(npair, A["p_pairs"].shape[1])]).tobytes())
+    nj = int(A["w_joint"][w][0])
+    if nj:                                                  # scenes with joints: limit states, island joint lists
+        h.update(np.ascontiguousarray(A["j_def"][w][:nj] & np.int32(~schema.JOINT_ISLAND)).tobytes())
+        h.update(np.ascontiguousarray(A["l_joint"][w][:int(A["w_joint"][w][1])]).tobytes())
+        h.update(np.ascontiguousarray(A["l_jstart"][w][:n_isl]).tobytes())
     return h.digest()
 
 
@@ -113,15 +130,18 @@ def generate(case):
     kw = CASES[case][7] if len(CASES[case]) > 7 else {}
     rw, RA, caps, table = harness.reference_arrays(scene, world, **kw)
     mw, OA, _ = harness.facade_arrays(scene, world, caps=caps, **kw)
-    bad = harness.diff_state(RA, OA, fields=[f for f in INIT_FIELDS if not f.startswith("s_")])
+    has_joints = len(rw.joints) > 0
+    init_fields = INIT_FIELDS + (JOINT_INIT_FIELDS if has_joints else [])
+    state_fields = harness.STATE_FIELDS + (harness.JOINT_STATE_FIELDS if has_joints else [])
+    bad = harness.diff_state(RA, OA, fields=[f for f in init_fields if not f.startswith("s_")])
     if bad:
         raise SystemExit("%s: facade initial state differs from the reference: %s" % (case, bad))
     out = {"meta": np.array([dt, vi, pi, steps, world], dtype=np.float64),
-           "caps": np.array([caps.nb, caps.nf, caps.nc, caps.npair, caps.nl], dtype=np.int32),
+           "caps": np.array([caps.nb, caps.nf, caps.nc, caps.npair, caps.nl] + ([caps.nj] if has_joints else []), dtype=np.int32),
            "scene": np.array(scene)}
     if kw:
         out["scene_kw"] = np.array(json.dumps(kw, sort_keys=True))      # scene keywords (read back by tests/conftest.py)
-    for f in INIT_FIELDS:
+    for f in init_fields:
         out["init_" + f] = used(RA, f)
     n_sh = len(table)
     for f in ("s_meta", "s_radius", "s_data"):
@@ -137,9 +157,11 @@ def generate(case):
         rw.step(dt, vi, pi)
         orc.step(dt, vi, pi)
         refpin.extract(rw, RA, 0, table, schema)
-        bad = harness.diff_state(RA, OA)
+        bad = harness.diff_state(RA, OA, fields=state_fields)
         if rec.islands != harness.oracle_islands(OA):
             bad.append("islands")
+        if has_joints and rec.island_joints != harness.oracle_island_joints(OA):
+            bad.append("island joints")
         if rec.pairs[-1] != harness.oracle_pairs(OA):
             bad.append("pairs")
         if bad:
@@ -148,7 +170,7 @@ def generate(case):
         ihash[s] = np.frombuffer(int_hash(OA), np.uint8)
         ints[s] = int_summary(OA)
         if (s + 1) in cks:
-            for f in CK_FIELDS:
+            for f in CK_FIELDS + (JOINT_CK_FIELDS if has_joints else []):
                 out["ck%d_%s" % (s + 1, f)] = used(OA, f)
     out["digest"] = digests
     out["ihash"] = ihash

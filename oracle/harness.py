@@ -17,8 +17,8 @@ STATE_FIELDS = ["w_count", "w_flags", "b_xf", "b_pos", "b_vel", "b_pos0", "b_for
                 "c_id"]
 
 
-def default_caps(nb, nf):
-    return schema.Caps(nb, nf, 4 * nb + 64)
+def default_caps(nb, nf, nj=0):
+    return schema.Caps(nb, nf, 4 * nb + 64, nj=nj)
 
 
 def set_shapes(A, table):
@@ -37,7 +37,7 @@ def facade_arrays(name, world=0, caps=None, n_shapes=512, **kw):
     mw = scenes.SCENES[name](mine, world=world, **kw)
     nb = len(mw.bodies)
     nf = sum(len(b.fixtures) for b in mw.bodies)
-    caps = caps or default_caps(nb, nf)
+    caps = caps or default_caps(nb, nf, len(mw.joints))
     table = schema.ShapeTable()
     A = schema.alloc(caps, 1, n_shapes)
     schema.pack_world(mw, A, 0, table)
@@ -53,7 +53,7 @@ def reference_arrays(name, world=0, caps=None, n_shapes=512, **kw):
     refpin.index_fixtures(rw)
     nb = len(rw.bodies)
     nf = sum(len(b.fixtures) for b in rw.bodies)
-    caps = caps or default_caps(nb, nf)
+    caps = caps or default_caps(nb, nf, len(rw.joints))
     table = schema.ShapeTable()
     A = schema.alloc(caps, 1, n_shapes)
     refpin.extract(rw, A, 0, table, schema)
@@ -72,6 +72,8 @@ def used_view(A, name, w=0):
         return a[:nf]
     if scope == "C":
         return a[:nc]
+    if scope == "J":
+        return a[:int(A["w_joint"][w][0])]
     return a
 
 
@@ -82,6 +84,8 @@ def diff_state(A, B, w=0, fields=STATE_FIELDS, exact=True, rtol=0.0, atol=0.0):
         x, y = used_view(A, k, w), used_view(B, k, w)
         if k == "w_count":
             x, y = x[:3], y[:3]
+        if k == "w_joint":
+            x, y = x[:1], y[:1]
         if x.shape != y.shape:
             bad.append(k)
             continue
@@ -96,12 +100,31 @@ def diff_state(A, B, w=0, fields=STATE_FIELDS, exact=True, rtol=0.0, atol=0.0):
             if k == "c_flags":
                 x = x & ~np.uint32(schema.CONTACT_ISLAND)
                 y = y & ~np.uint32(schema.CONTACT_ISLAND)
+            if k == "j_def":        # island flag is transient bookkeeping
+                x = x & ~np.int32(schema.JOINT_ISLAND)
+                y = y & ~np.int32(schema.JOINT_ISLAND)
             if not np.array_equal(x, y):
                 bad.append(k)
         else:
             if not np.allclose(x, y, rtol=rtol, atol=atol):
                 bad.append(k)
     return bad
+
+
+JOINT_STATE_FIELDS = ["w_joint", "j_def", "j_par", "j_imp", "j_adj", "b_jadj"]
+
+
+def oracle_island_joints(A, w=0):
+    """[joint list] per island of the last step."""
+    n_isl = int(A["w_island"][w][0])
+    nlj = int(A["w_joint"][w][1])
+    st = A["l_jstart"][w]
+    out = []
+    for i in range(n_isl):
+        j0 = int(st[i])
+        j1 = int(st[i + 1]) if i + 1 < n_isl else nlj
+        out.append([int(v) for v in A["l_joint"][w][j0:j1]])
+    return out
 
 
 def oracle_pairs(A, w=0):

@@ -16,11 +16,12 @@ FIELD_ORDER = ("w_count,w_flags,w_status,w_gravity,w_island,"
                "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
                "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
                "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
-               "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data").split(",")
+               "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data,"
+               "w_joint,j_def,j_par,j_imp,j_tmp,j_adj,b_jadj,l_joint,l_jstart").split(",")
 
 
 class OrcWorld(ctypes.Structure):
-    _fields_ = ([(n, ctypes.c_int32) for n in ("nb_cap", "nf_cap", "nc_cap", "npair_cap", "nl_cap", "n_shapes")] +
+    _fields_ = ([(n, ctypes.c_int32) for n in ("nb_cap", "nf_cap", "nc_cap", "npair_cap", "nl_cap", "n_shapes", "nj_cap")] +
                 [(n, ctypes.c_void_p) for n in FIELD_ORDER])
 
 
@@ -78,6 +79,7 @@ class Oracle(object):
         s.npair_cap = A["p_pairs"].shape[1]
         s.nl_cap = A["l_body"].shape[1]
         s.n_shapes = A["s_meta"].shape[0]
+        s.nj_cap = A["j_def"].shape[1]
         for name in FIELD_ORDER:
             a = A[name]
             ptr = a.ctypes.data

@@ -172,7 +172,55 @@ def extract(world, arrays, w, table, schema):
         A["c_pts"][w, k] = (p0.local_point.x, p0.local_point.y, p1.local_point.x, p1.local_point.y)
         A["c_imp"][w, k] = (p0.normal_impulse, p0.tangent_impulse, p1.normal_impulse, p1.tangent_impulse)
         A["c_id"][w, k] = (pack_id(p0.id), pack_id(p1.id))
+    extract_joints(world, A, w, bidx, schema)
     return len(bodies), len(fixtures), len(contacts)
+
+
+def extract_joints(world, A, w, bidx, schema):
+    """World.joints / Body.joints of the live reference into the joint rows (layout: pypybox2d_b200/joints.py)."""
+    b2 = load()
+    from pypybox2d import joints as _j
+    joints = world.joints
+    if len(joints) > A["j_def"].shape[1] and joints:
+        raise ValueError("joint capacity")
+    A["w_joint"][w][0] = len(joints)
+    jidx = {id(j): k for k, j in enumerate(joints)}
+    for k, j in enumerate(joints):
+        flags = 0
+        if j._collide_connected:
+            flags |= schema.JOINT_COLLIDE_CONNECTED
+        if getattr(j, "_limit_enabled", False):
+            flags |= schema.JOINT_LIMIT_ENABLED
+        if getattr(j, "_motor_enabled", False):
+            flags |= schema.JOINT_MOTOR_ENABLED
+        flags |= int(getattr(j, "_limit_state", 0)) << schema.JOINT_LIMIT_SHIFT
+        la, lb = j._local_anchor_a, j._local_anchor_b
+        par = [la.x, la.y, lb.x, lb.y]
+        if isinstance(j, _j.RevoluteJoint):
+            t = schema.JOINT_REVOLUTE
+            par += [j._reference_angle, j._lower_angle, j._upper_angle, j._max_motor_torque, j._motor_speed]
+            imp = (j._impulse.x, j._impulse.y, j._impulse.z, j._motor_impulse)
+        elif isinstance(j, _j.DistanceJoint):
+            t = schema.JOINT_DISTANCE
+            par += [j._length, j._frequency, j._damping_ratio]
+            imp = (j._impulse, 0.0, 0.0, 0.0)
+        elif isinstance(j, _j.WeldJoint):
+            t = schema.JOINT_WELD
+            par += [j._reference_angle]
+            imp = (j._impulse.x, j._impulse.y, j._impulse.z, 0.0)
+        else:
+            raise NotImplementedError(type(j))
+        A["j_def"][w, k] = (t, bidx[id(j._body_a)], bidx[id(j._body_b)], flags)
+        A["j_par"][w, k] = 0.0
+        A["j_par"][w, k, :len(par)] = par
+        A["j_imp"][w, k] = imp
+    pos = 0
+    flat = A["j_adj"][w].reshape(-1)
+    for i, b in enumerate(world.bodies):
+        row = [jidx[id(j)] for j in b.joints]
+        A["b_jadj"][w, i] = (pos, len(row))
+        flat[pos:pos + len(row)] = row
+        pos += len(row)
 
 
 class _ShapeAdapter(object):
@@ -212,6 +260,7 @@ class Recorder(object):
         b2 = load()
         self.world = world
         self.islands = []      # per step: list of (body index list, contact index list)
+        self.island_joints = []  # per step: list of joint index lists
         self.pairs = []        # per update_pairs call: list of (a, b)
         world.contact_manager.broadphase._pair_log = self.pairs
         from pypybox2d import island as _island
@@ -225,6 +274,8 @@ class Recorder(object):
                     bi = {id(b): i for i, b in enumerate(r.world.bodies)}
                     ci = {id(c): i for i, c in enumerate(r.world.contact_manager.contacts)}
                     r.islands.append(([bi[id(b)] for b in self_i.bodies], [ci[id(c)] for c in self_i.contacts]))
+                    ji = {id(j): i for i, j in enumerate(r.world.joints)}
+                    r.island_joints.append([ji[id(j)] for j in self_i.joints])
                 return _island.Island._b2b_orig_solve(self_i, step, gravity, allow_sleep)
 
             _island.Island.solve = solve
@@ -232,6 +283,7 @@ class Recorder(object):
 
     def begin_step(self):
         del self.islands[:]
+        del self.island_joints[:]
         del self.pairs[:]
 
 

@@ -31,7 +31,8 @@ def world_caps(worlds, contacts_per_body=4, slack=64):
     needs rows per FIXTURE, not per body (`World.step` raises if a step still runs out)."""
     nb = max(len(w.bodies) for w in worlds)
     nf = max(sum(len(b.fixtures) for b in w.bodies) for w in worlds)
-    return schema.Caps(nb, nf, contacts_per_body * max(nb, nf) + slack)
+    nj = max(len(getattr(w, "joints", ())) for w in worlds)
+    return schema.Caps(nb, nf, contacts_per_body * max(nb, nf) + slack, nj=nj)
 
 
 class BatchedWorld(object):
@@ -64,6 +65,7 @@ class BatchedWorld(object):
         c.real_bytes = 8 if self.real == "f64" else 4
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         c.threads, c.ctas_per_sm, c.reserved = int(threads), int(ctas_per_sm), int(lanes_aux)
+        c.nj = int(getattr(caps, "nj", 0))
         self._caps_struct = c
         _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
         self._bind()
@@ -403,6 +405,11 @@ class BatchedWorld(object):
         table = schema.ShapeTable()
         schema.pack_world(world, A, 0, table)
         names = ["b_xf", "b_pos", "b_vel", "b_force", "b_flags", "w_gravity"]
+        if getattr(world, "_joints_dirty", False):
+            # a joint's parameters or flags were set between steps (joints.py setters); the joint list itself only changes
+            # through World.add_joint / destroy_joint, which re-pack the world
+            names += ["j_def", "j_par", "j_imp"]
+            world._joints_dirty = False
         self.upload({k: A[k] for k in names}, worlds=slice(w, w + 1))
 
     def download_into_world(self, world, w=0):
@@ -419,6 +426,12 @@ class BatchedWorld(object):
             b._awake = bool(int(D["b_flags"][0, i]) & schema.BODY_AWAKE)
             isl = int(D["b_island"][0, i])
             b._island_index = isl if isl >= 0 else b._island_index
+        if getattr(world, "joints", None):
+            J = self.download(["j_def", "j_imp", "j_tmp"], worlds=slice(w, w + 1))
+            for k, j in enumerate(world.joints):
+                j._read_back(J["j_def"][0, k, 3], J["j_imp"][0, k])
+                if j._type == schema.JOINT_DISTANCE:
+                    j._u = (float(J["j_tmp"][0, k, 4]), float(J["j_tmp"][0, k, 5]))
 
     def contact_views(self, world, w=0):
         from .world import ContactView

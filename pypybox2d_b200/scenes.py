@@ -304,5 +304,108 @@ def sensors(b2, world=0, config=8, **world_kw):
     return w
 
 
-SCENES = {"features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
+# ---- joint coverage scene (not a BASELINE config): revolute, distance and weld joints in the island solver -----
+def joints(b2, world=0, config=9, **world_kw):
+    """What the joint hooks of Island.solve (island.py:107-113, 145-148) and of the island walk (world.py:548-572) read: a plank
+    bridge of revolute joints between two ground anchors (testbed/bridge.py) with bodies dropped on it, a hanging chain, a
+    motorised arm with angle limits, a door with equal limits, a flail on a rigid distance joint, a soft (frequency > 0)
+    distance spring, a welded cantilever, a joint with collide_connected=True, and a joint between two dynamic bodies that
+    start asleep."""
+    w = b2.World((0, -10), True, **_kw(world_kw))
+    ground = w.create_static_body(shapes=b2.Edge((-40.0, 0.0), (40.0, 0.0)))
+    n_free = 12
+    jit = jitter(config, world, 64)
+    k = [1]
+
+    def at(x, y):
+        j = jit[k[0] % 64]
+        k[0] += 1
+        return (x + j[0], y + j[1])
+
+    plank = b2.Fixture(b2.Polygon(box=(0.5, 0.125)), density=20.0, friction=0.2)
+    # bridge: 10 planks from (-15, 5) to (-5, 5)
+    prev = ground
+    for i in range(10):
+        body = w.create_dynamic_body(position=(-14.5 + 1.0 * i, 5.0), fixtures=plank)
+        w.create_revolute_joint(prev, body, anchor=(-15.0 + 1.0 * i, 5.0))
+        prev = body
+    w.create_revolute_joint(prev, ground, anchor=(-5.0, 5.0))
+    # hanging chain of 8 links from (0, 12)
+    link = b2.Fixture(b2.Polygon(box=(0.6, 0.125)), density=20.0, friction=0.2)
+    prev = ground
+    for i in range(8):
+        body = w.create_dynamic_body(position=(0.5 + 1.0 * i, 12.0), fixtures=link)
+        w.create_revolute_joint(prev, body, anchor=(1.0 * i, 12.0), collide_connected=False)
+        prev = body
+    # motorised arm with limits; door with equal limits (a revolute that cannot turn)
+    arm = w.create_dynamic_body(position=(8.0, 4.0), fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), density=2.0, friction=0.3))
+    w.create_revolute_joint(ground, arm, anchor=(6.5, 4.0), lower_angle=-0.4, upper_angle=0.9, limit_enabled=True,
+                            motor_enabled=True, motor_speed=1.5, max_motor_torque=400.0)
+    arm2 = w.create_dynamic_body(position=(8.0, 7.0), fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), density=2.0, friction=0.3))
+    w.create_revolute_joint(ground, arm2, anchor=(6.5, 7.0), lower_angle=-0.5, upper_angle=0.3, limit_enabled=True,
+                            motor_enabled=True, motor_speed=-2.0, max_motor_torque=10.0)
+    door = w.create_dynamic_body(position=(12.0, 3.0), fixtures=b2.Fixture(b2.Polygon(box=(0.1, 1.0)), density=1.0, friction=0.3))
+    w.create_revolute_joint(ground, door, anchor=(12.0, 2.0), lower_angle=0.0, upper_angle=0.0, limit_enabled=True)
+    # free-spinning motor without limit on a wheel that touches the ground (collide_connected=True keeps the contact)
+    wheel = w.create_dynamic_body(position=at(16.0, 0.6), fixtures=b2.Fixture(b2.Circle(0.6), density=1.0, friction=0.9))
+    axle = w.create_dynamic_body(position=(16.0, 0.6), fixtures=b2.Fixture(b2.Polygon(box=(0.2, 0.2)), density=1.0,
+                                                                         category_bits=0x0004, mask_bits=0x0000))
+    w.create_revolute_joint(axle, wheel, anchor=(16.0, 0.6), motor_enabled=True, motor_speed=-3.0, max_motor_torque=50.0,
+                            collide_connected=True)
+    # flail: rigid distance joint; spring: soft distance joint
+    ball = w.create_dynamic_body(position=at(-20.0, 6.0), fixtures=b2.Fixture(b2.Circle(0.4), density=2.0, friction=0.3))
+    w.create_distance_joint(ground, ball, anchor_a=(-20.0, 10.0), anchor_b=ball.position)
+    swing = w.create_dynamic_body(position=at(-24.0, 7.0), linear_velocity=(3.0, 0.0),
+                                  fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.4)), density=1.0, friction=0.3))
+    w.create_distance_joint(ground, swing, anchor_a=(-22.0, 11.0), anchor_b=(-24.0, 7.4), frequency=2.0, damping_ratio=0.3)
+    pair_a = w.create_dynamic_body(position=at(-28.0, 3.0), fixtures=b2.Fixture(b2.Circle(0.3), density=1.0, friction=0.3))
+    pair_b = w.create_dynamic_body(position=at(-27.0, 4.5), fixtures=b2.Fixture(b2.Circle(0.3), density=3.0, friction=0.3))
+    w.create_distance_joint(pair_a, pair_b, anchor_a=pair_a.position, anchor_b=pair_b.position, length=2.2, collide_connected=True)
+    # welded cantilever of 5 beams from the ground anchor (20, 6)
+    beam = b2.Fixture(b2.Polygon(box=(0.5, 0.125)), density=20.0, friction=0.3)
+    prev = ground
+    for i in range(5):
+        body = w.create_dynamic_body(position=(20.5 + 1.0 * i, 6.0), fixtures=beam)
+        w.create_weld_joint(prev, body, anchor=(20.0 + 1.0 * i, 6.0))
+        prev = body
+    # two sleeping bodies joined by a revolute joint, woken when something lands on them
+    sa = w.create_dynamic_body(position=(28.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))
+    sb = w.create_dynamic_body(position=(29.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))
+    w.create_revolute_joint(sa, sb, anchor=(28.5, 0.26))
+    # loose bodies dropped on the bridge, the cantilever, the arm and the sleepers
+    for i in range(n_free):
+        x = (-13.0 + 1.6 * i) if i < 6 else (21.0 + 1.4 * (i - 6))
+        if i % 3 == 0:
+            shape = b2.Circle(0.35)
+        elif i % 3 == 1:
+            shape = b2.Polygon(box=(0.35, 0.35))
+        else:
+            shape = b2.Polygon(vertices=[(0.4 * math.cos(0.4 + 2.0 * math.pi * q / 5), 0.4 * math.sin(0.4 + 2.0 * math.pi * q / 5))
+                                         for q in range(5)])
+        w.create_dynamic_body(position=at(x, 9.0 + 0.8 * (i % 4)), fixtures=b2.Fixture(shape, density=1.0, friction=0.4))
+    w.create_dynamic_body(position=at(8.5, 8.0), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=1.0, friction=0.5))
+    w.create_dynamic_body(position=at(28.6, 5.0), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=2.0, friction=0.5))
+    return w
+
+
+# ---- joint throughput scene: a plank bridge of revolute joints under a row of boxes (testbed/bridge.py) --------------------------
+def bridge(b2, world=0, planks=30, config=10, **world_kw):
+    w = b2.World((0, -10), True, **_kw(world_kw))
+    ground = w.create_static_body(shapes=b2.Edge((-40.0, 0.0), (40.0, 0.0)))
+    plank = b2.Fixture(b2.Polygon(box=(0.5, 0.125)), density=20.0, friction=0.2)
+    jit = jitter(config, world, planks + 1 + 8)
+    prev = ground
+    for i in range(planks):
+        body = w.create_dynamic_body(position=(-14.5 + 1.0 * i, 5.0), fixtures=plank)
+        w.create_revolute_joint(prev, body, anchor=(-15.0 + 1.0 * i, 5.0))
+        prev = body
+    w.create_revolute_joint(prev, ground, anchor=(-15.0 + 1.0 * planks, 5.0))
+    for i in range(8):
+        shape = b2.Circle(0.5) if i % 2 else b2.Polygon(box=(0.5, 0.5))
+        j = jit[planks + 1 + i]
+        w.create_dynamic_body(position=(-8.0 + 2.0 * i + j[0], 6.0 + 1.2 * (i % 3) + j[1]), fixtures=b2.Fixture(shape, density=1.0, friction=0.4))
+    return w
+
+
+SCENES = {"joints": joints, "bridge": bridge, "features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
           "deep_stacks": deep_stacks, "bullets": bullets, "sensors": sensors}

@@ -42,6 +42,17 @@ STATUS_PAIR_OVERFLOW = 0x2
 STATUS_NAN = 0x4
 STATUS_ISLAND_OVERFLOW = 0x8
 STATUS_TOI_STUCK = 0x10        # a time-of-impact push-back loop was cut off (csrc/b2b_toi.cuh TOI_MAX_PUSH_BACK)
+STATUS_JOINT_OVERFLOW = 0x20   # more joints than the batch's joint capacity
+
+# joints (pypybox2d/joints/*.py): j_def = (type, body_a, body_b, flags)
+JOINT_REVOLUTE, JOINT_DISTANCE, JOINT_WELD, JOINT_PRISMATIC = 1, 2, 3, 4
+JOINT_COLLIDE_CONNECTED = 0x1  # joint.py:52
+JOINT_LIMIT_ENABLED = 0x2      # revolute.py:85 / prismatic
+JOINT_MOTOR_ENABLED = 0x4      # revolute.py:86 / prismatic
+JOINT_ISLAND = 0x8             # Joint._island_flag (transient bookkeeping of the island walk)
+JOINT_LIMIT_SHIFT = 8          # bits 8..9: _limit_state (joint.py:36: INACTIVE, AT_LOWER, AT_UPPER, EQUAL), carried over steps
+JOINT_PAR = 12                 # reals per joint parameter row (see joints.py `_par`)
+JOINT_TMP = 20                 # reals per joint of solver temporaries (ra, rb, effective masses ...), written by the step
 
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2   # contact_util.py:141-143
 
@@ -94,6 +105,16 @@ FIELDS = [
     ("s_meta",    "S", (),   "i32"),   # type | vertex_count << 8 | has_v0 << 16 | has_v3 << 17
     ("s_radius",  "S", (),   "real"),
     ("s_data",    "S", (SHAPE_DATA,), "real"),
+    # -- joints, creation order == World.joints; appended so that the rows above keep their positions --
+    ("w_joint",   "W", (4,), "i32"),   # n_joints, n_island_joints (last step), unused, unused
+    ("j_def",     "J", (4,), "i32"),   # type, body_a, body_b, flags (JOINT_* bits | _limit_state << 8)
+    ("j_par",     "J", (JOINT_PAR,), "real"),  # constructor parameters (joints.py `_par`)
+    ("j_imp",     "J", (4,), "real"),  # accumulated impulses: _impulse x, y, z, _motor_impulse (distance: _impulse in [0])
+    ("j_tmp",     "J", (JOINT_TMP,), "real"),  # solver temporaries of the current step
+    ("j_adj",     "J", (2,), "i32"),   # Body.joints of every body as rows of joint indices, flattened (2 entries per joint)
+    ("b_jadj",    "B", (2,), "i32"),   # this body's row in j_adj: start, count (body.py:75, world.py:270-273 append order)
+    ("l_joint",   "J", (),   "i32"),   # island joint lists, concatenated in island order
+    ("l_jstart",  "B", (),   "i32"),   # per island: start in l_joint
 ]
 
 FIELD_NAMES = [f[0] for f in FIELDS]
@@ -102,7 +123,8 @@ FIELD_NAMES = [f[0] for f in FIELDS]
 class Caps(object):
     """Per-world capacities.  `nl` (island-list slots) and `npair` default from the others."""
 
-    def __init__(self, nb, nf, nc, npair=None, nl=None):
+    def __init__(self, nb, nf, nc, npair=None, nl=None, nj=0):
+        self.nj = int(nj)           # joints per world (0: the batch has none; the J arrays keep one unused row)
         self.nb = int(nb)
         self.nf = int(nf)
         self.nc = int(nc)
@@ -112,10 +134,10 @@ class Caps(object):
     def dim(self, scope, n_worlds, n_shapes):
         return {"W": (n_worlds,), "B": (n_worlds, self.nb), "F": (n_worlds, self.nf),
                 "C": (n_worlds, self.nc), "P": (n_worlds, self.npair), "L": (n_worlds, self.nl),
-                "S": (n_shapes,)}[scope]
+                "J": (n_worlds, max(self.nj, 1)), "S": (n_shapes,)}[scope]
 
     def __repr__(self):
-        return "Caps(nb=%d, nf=%d, nc=%d, npair=%d, nl=%d)" % (self.nb, self.nf, self.nc, self.npair, self.nl)
+        return "Caps(nb=%d, nf=%d, nc=%d, npair=%d, nl=%d, nj=%d)" % (self.nb, self.nf, self.nc, self.npair, self.nl, self.nj)
 
 
 def np_dtype(kind, real):
@@ -267,4 +289,6 @@ def pack_world(world, arrays, w, table):
         A["f_tight"][w, j] = (lx, ly, ux, uy)
         A["f_fat"][w, j] = (lx - AABB_EXTENSION, ly - AABB_EXTENSION, ux + AABB_EXTENSION, uy + AABB_EXTENSION)
         A["f_moved"][w, j] = 1
+    from .joints import pack_joints
+    pack_joints(world, A, w, index)
     return nb, nf

@@ -6,14 +6,16 @@ step through the C-ABI (`include/b2b.h`) and mirrors the body state back into th
 objects.  A single `World` is a batch of one; large batches use `BatchedWorld` directly
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
-Unsupported on this path (raise `NotImplementedError`): joints, controllers,
-contact listeners, custom contact filters, sensors, Loop shapes and sub-stepping.  Continuous collision
+Revolute, distance and weld joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
+(raise `NotImplementedError`): the other joint types, controllers, `pre_solve` / `post_solve` listeners,
+custom contact filters, Loop shapes and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
 """
 from copy import copy
 
 from .body import Body
 from . import schema
+from . import joints as _joints
 from .common import Vec2, LockedError
 
 
@@ -201,13 +203,65 @@ class World(object):
             raise LockedError("Cannot remove a body while simulating")
         if body not in self.bodies:
             raise ValueError("Body not in this world")
+        for joint in list(body.joints):          # Body._detached_from_world, body.py:313-320
+            if self.joint_destruction_listener:
+                self.joint_destruction_listener(joint)
+            self.destroy_joint(joint)
         self.bodies.remove(body)
         body._world = None
         self._host_dirty = True
         self._structure_dirty = True
 
+    # -- joints (world.py:252-305, 823-915) ------------------------------------------------------------------------------
     def add_joint(self, joint, duplicate=False):
-        raise NotImplementedError("joints are not supported on the batched step path (SURVEY §8f #3)")
+        """world.py:252-283: the joint joins World.joints and its bodies' lists (body_a's first); creating a joint does not
+        wake the bodies.  On a world that is already stepping the device arrays are re-packed before the next step; contacts
+        between two bodies that a joint with collide_connected=False now connects are destroyed by that step's narrowphase
+        (the reference flags them for filtering, contact_manager.py:199-207) -- here they are dropped by the re-pack."""
+        if self._locked:
+            raise LockedError('Cannot create a joint while simulating')
+        if duplicate:
+            joint = copy(joint)
+        self.joints.append(joint)
+        joint._world = self
+        if joint._body_a is not None:
+            joint._body_a.joints.append(joint)
+        if joint._body_b is not None:
+            joint._body_b.joints.append(joint)
+        self._host_dirty = True
+        if self._stepped:
+            self._structure_dirty = True
+        return joint
+
+    def destroy_joint(self, joint):
+        """world.py:285-305"""
+        if self._locked:
+            raise LockedError('Cannot destroy a joint while simulating')
+        if joint not in self.joints:
+            raise ValueError('Joint not in world')
+        self.joints.remove(joint)
+        joint._world = None
+        for body in joint.bodies:
+            if body is not None:
+                body.awake = True
+                body.joints.remove(joint)
+        self._host_dirty = True
+        self._structure_dirty = True
+
+    def create_revolute_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.RevoluteJoint(*args, **kwargs))
+
+    def create_distance_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.DistanceJoint(*args, **kwargs))
+
+    def create_weld_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.WeldJoint(*args, **kwargs))
+
+    def _create_unsupported_joint(self, *args, **kwargs):
+        raise NotImplementedError("only revolute, distance and weld joints run on the batched step path (SURVEY §8f #3)")
+
+    create_prismatic_joint = create_wheel_joint = create_pulley_joint = create_gear_joint = _create_unsupported_joint
+    create_rope_joint = create_friction_joint = create_mouse_joint = _create_unsupported_joint
 
     def add_controller(self, controller):
         raise NotImplementedError("controllers are not supported on the batched step path")
@@ -251,7 +305,7 @@ class World(object):
         old_index = {id(f): j for j, f in enumerate(self._packed_fixtures)}
         fixtures = self._fixture_list()
         caps = world_caps([self])
-        caps = schema.Caps(max(caps.nb, 1), max(caps.nf, 1), max(caps.nc, old.caps.nc))
+        caps = schema.Caps(max(caps.nb, 1), max(caps.nf, 1), max(caps.nc, old.caps.nc), nj=caps.nj)
         table = schema.ShapeTable()
         for f in fixtures:
             table.add(f._shape)
@@ -274,6 +328,9 @@ class World(object):
             a2, b2 = int(remap[int(D["c_fix"][0, k, 0])]), int(remap[int(D["c_fix"][0, k, 1])])
             if a2 < 0 or b2 < 0:
                 continue
+            ba, bb = fixtures[a2]._body, fixtures[b2]._body
+            if any(not j._collide_connected and j.other_body(ba) is bb for j in ba.joints):
+                continue                       # Body._should_collide (body.py:920-926), see add_joint
             A["c_fix"][0, k2] = (a2, b2)
             for name in ("c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"):
                 A[name][0, k2] = D[name][0, k]
