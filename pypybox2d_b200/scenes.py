@@ -341,8 +341,8 @@ def joints(b2, world=0, config=9, **world_kw):
     arm = w.create_dynamic_body(position=(8.0, 4.0), fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), density=2.0, friction=0.3))
     w.create_revolute_joint(ground, arm, anchor=(6.5, 4.0), lower_angle=-0.4, upper_angle=0.9, limit_enabled=True,
                             motor_enabled=True, motor_speed=1.5, max_motor_torque=400.0)
-    arm2 = w.create_dynamic_body(position=(8.0, 7.0), fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), density=2.0, friction=0.3))
-    w.create_revolute_joint(ground, arm2, anchor=(6.5, 7.0), lower_angle=-0.5, upper_angle=0.3, limit_enabled=True,
+    arm2 = w.create_dynamic_body(position=(-32.0, 5.0), fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.1)), density=2.0, friction=0.3))
+    w.create_revolute_joint(ground, arm2, anchor=(-33.5, 5.0), lower_angle=-0.5, upper_angle=0.3, limit_enabled=True,
                             motor_enabled=True, motor_speed=-2.0, max_motor_torque=10.0)
     door = w.create_dynamic_body(position=(12.0, 3.0), fixtures=b2.Fixture(b2.Polygon(box=(0.1, 1.0)), density=1.0, friction=0.3))
     w.create_revolute_joint(ground, door, anchor=(12.0, 2.0), lower_angle=0.0, upper_angle=0.0, limit_enabled=True)
