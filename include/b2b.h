@@ -56,6 +56,9 @@ typedef struct b2b_caps {
     int32_t threads;         /* lanes of a warp that step one world in the solve kernels (0: default 4) */
     int32_t ctas_per_sm;     /* resident CTAs per SM the persistent grid is sized for (0: from occupancy) */
     int32_t reserved;        /* lanes per world in the plan and pair kernels (0: default, 8 or 32 by contact capacity) */
+    int32_t nj;              /* joints per world (World.joints); 0: the batch has no joints -- the step then runs the kernels without
+                              * the joint hooks, and the j_* arrays keep one unused row per world */
+    int32_t reserved2;       /* 0 */
 } b2b_caps;
 
 /* Device pointers, one per schema field, same names and order as pypybox2d_b200/schema.py FIELDS.
@@ -68,6 +71,9 @@ typedef struct b2b_buffers {
     void *c_fix, *c_flags, *c_mat, *c_mtype, *c_mf, *c_pts, *c_imp, *c_id;
     void *p_pairs, *l_body, *l_contact, *l_start;
     void *s_meta, *s_radius, *s_data;
+    /* joints of the island solver: replaces the attribute storage of RevoluteJoint / DistanceJoint / WeldJoint
+     * (pypybox2d/joints/revolute.py:58-93, distance.py:57-93, weld.py:56-81), World.joints and Body.joints (world.py:268-273) */
+    void *w_joint, *j_def, *j_par, *j_imp, *j_tmp, *j_adj, *b_jadj, *l_joint, *l_jstart;
 } b2b_buffers;
 
 typedef struct b2b_ctx b2b_ctx;

@@ -66,13 +66,14 @@ static bool caps_ok(const b2b_caps* k)
     return k && k->n_worlds > 0 && k->nb > 0 && k->nf > 0 && k->nc > 0 && k->npair > 0 && k->nl >= k->nb && k->n_shapes > 0 &&
            (k->real_bytes == 4 || k->real_bytes == 8) && (k->threads == 0 || k->threads == 2 || k->threads == 4 || k->threads == 8 || k->threads == 16 || k->threads == 32) &&
            (k->reserved == 0 || k->reserved == 4 || k->reserved == 8 || k->reserved == 16 || k->reserved == 32) && k->nb < 65535 &&
-           k->nc < 65535;
+           k->nc < 65535 && k->nj >= 0 && k->nj < 65535;
 }
 
 static caps_t to_caps(const b2b_caps* k)
 {
     caps_t c;
     c.n_worlds = k->n_worlds; c.nb = k->nb; c.nf = k->nf; c.nc = k->nc; c.npair = k->npair; c.nl = k->nl; c.n_shapes = k->n_shapes;
+    c.nj = k->nj;
     return c;
 }
 
@@ -84,7 +85,8 @@ extern "C" const char* b2b_field_names(void)
            "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
            "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
            "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
-           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data";
+           "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data,"
+           "w_joint,j_def,j_par,j_imp,j_tmp,j_adj,b_jadj,l_joint,l_jstart";
 }
 
 extern "C" size_t b2b_scratch_bytes(const b2b_caps* caps)

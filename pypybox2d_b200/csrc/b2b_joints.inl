@@ -1,0 +1,358 @@
+// b2b_joints.inl -- joints of the island solver, included INSIDE world_step<real> (b2b_step.cuh).
+//
+// RevoluteJoint (pypybox2d/joints/revolute.py:208-453), DistanceJoint (joints/distance.py:155-311) and WeldJoint
+// (joints/weld.py:106-257) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
+// fp64 host build of this file is bit-identical to the oracle, which is pinned bit-identical to the live reference.
+//
+// Island.solve visits an island's joints one after the other, before the contacts in every velocity iteration and after them in
+// every position iteration (island.py:107-113, 145-148); a joint reads and writes the velocities / positions of its two bodies,
+// which live in the team's shared memory (state_get / state_set).  Joint lists are short next to contact lists (a bridge has one
+// joint per plank, a pile has hundreds of contacts), and consecutive joints of a chain share a body, so the sweep over an island's
+// joints is a dependent chain like the contact sweep: one lane (the team's first) walks it while the others wait at the barrier.
+// Only batches created with a joint capacity (b2b_caps::nj > 0) run the kernels instantiated with these hooks.
+//
+// Rows (layout: pypybox2d_b200/joints.py): j_def = (type, body_a, body_b, flags | _limit_state << 8), j_par[12], j_imp = (_impulse
+// x, y, z, _motor_impulse), j_tmp[20] = what _init_velocity_constraints leaves for the sweeps (ra, rb, then per type: the 3x3 mass
+// matrix by columns and the motor mass; or u, mass, gamma, bias).
+
+enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3 };
+enum { JF_COLLIDE = 0x1, JF_LIMIT = 0x2, JF_MOTOR = 0x4, JF_ISLAND = 0x8, JF_LS_SHIFT = 8 };
+enum { LS_INACTIVE = 0, LS_LOWER = 1, LS_UPPER = 2, LS_EQUAL = 3 };               // joints/joint.py:36
+enum { JOINT_PAR = 12, JOINT_TMP = 20 };
+
+struct V3 { real x, y, z; };
+B2B_D static V3 mk3(real x, real y, real z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+B2B_D static real dot3(V3 a, V3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }                                  // common.py:342-344
+B2B_D static V3 cross3(V3 s, V3 v) { return mk3(s.y * v.z - s.z * v.y, s.z * v.x - s.x * v.z, s.x * v.y - s.y * v.x); } // common.py:353-358
+B2B_D static V3 neg3(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+struct M33 { V3 c1, c2, c3; };
+B2B_D static V3 solve33(const M33& m, V3 b)                                                                             // common.py:587-599
+{
+    real det = dot3(m.c1, cross3(m.c2, m.c3));
+    if (det != real(0)) det = real(1) / det;
+    return mk3(det * dot3(b, cross3(m.c2, m.c3)), det * dot3(m.c1, cross3(b, m.c3)), det * dot3(m.c1, cross3(m.c2, b)));
+}
+B2B_D static V2 solve22(const M33& m, V2 vec)                                                                           // common.py:601-614
+{
+    const real a11 = m.c1.x, a12 = m.c2.x, a21 = m.c1.y, a22 = m.c2.y;
+    real det = a11 * a22 - a12 * a21;
+    if (det != real(0)) det = real(1) / det;
+    return mk<real>(det * (a22 * vec.x - a12 * vec.y), det * (a11 * vec.y - a21 * vec.x));
+}
+B2B_D static XF rot_of(real a)                                                                                          // Mat22(angle=a)
+{
+    real s, c;
+    sincos_r(a, &s, &c);
+    return xf_make<real>(mk<real>(real(0), real(0)), c, s);
+}
+B2B_D static M33 m33_load(const real* t) { M33 m; m.c1 = mk3(t[0], t[1], t[2]); m.c2 = mk3(t[3], t[4], t[5]); m.c3 = mk3(t[6], t[7], t[8]); return m; }
+B2B_D static void m33_store(real* t, const M33& m)
+{
+    t[0] = m.c1.x; t[1] = m.c1.y; t[2] = m.c1.z; t[3] = m.c2.x; t[4] = m.c2.y; t[5] = m.c2.z; t[6] = m.c3.x; t[7] = m.c3.y; t[8] = m.c3.z;
+}
+
+// _init_velocity_constraints (revolute.py:208-300, distance.py:155-250, weld.py:106-169).  Velocities: the team's shared state;
+// positions: b_pos (the sweeps before this step's integration -- the velocity kernel runs before integrate_position).
+B2B_D void joint_init(int k, real dt, real dt_ratio, bool warm)
+{
+    int32_t* def = j_def + 4 * (size_t)k;
+    const real* par = j_par + JOINT_PAR * (size_t)k;
+    real* imp = j_imp + 4 * (size_t)k;
+    real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    const quad mqa = ldq(b_mass + 4 * (size_t)ba), mqb = ldq(b_mass + 4 * (size_t)bb);
+    const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
+    const V2 lca = mk<real>(mqa.z, mqa.w), lcb = mk<real>(mqb.z, mqb.w);
+    const quad pa = ldq(b_pos + 4 * (size_t)ba), pb = ldq(b_pos + 4 * (size_t)bb);
+    const V2 ca = mk<real>(pa.x, pa.y), cb = mk<real>(pb.x, pb.y);
+    const real aa = pa.z, ab = pb.z;
+    const quad sa = state_get(ba), sb = state_get(bb);
+    V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
+    real wa = sa.z, wb = sb.z;
+    const XF qa = rot_of(aa), qb = rot_of(ab);
+    const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+    tmp[0] = ra.x; tmp[1] = ra.y; tmp[2] = rb.x; tmp[3] = rb.y;
+    if (type == JOINT_REVOLUTE) {
+        M33 m;
+        m.c3 = mk3(-ra.y * ia - rb.y * ib, ra.x * ia + rb.x * ib, ia + ib);
+        m.c2 = mk3(-ra.y * ra.x * ia - rb.y * rb.x * ib, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, m.c3.y);
+        m.c1 = mk3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, m.c2.x, m.c3.x);
+        m33_store(tmp + 4, m);
+        real motor_mass = ia + ib;
+        const bool fixed_rotation = (motor_mass == real(0));
+        if (motor_mass > real(0)) motor_mass = real(1) / motor_mass;
+        tmp[13] = motor_mass;
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2], im = imp[3];
+        if (!(flags & JF_MOTOR) || fixed_rotation) im = real(0);
+        if ((flags & JF_LIMIT) && !fixed_rotation) {
+            const real joint_angle = ab - aa - par[4];
+            if (abs_r(par[6] - par[5]) < real(2) * K<real>::angular_slop) ls = LS_EQUAL;
+            else if (joint_angle <= par[5]) {
+                if (ls != LS_LOWER) i2 = i2 - i2;
+                ls = LS_LOWER;
+            } else if (joint_angle >= par[6]) {
+                if (ls != LS_UPPER) i2 = i2 - i2;
+                ls = LS_UPPER;
+            } else {
+                ls = LS_INACTIVE;
+                i2 = i2 - i2;
+            }
+        } else ls = LS_INACTIVE;
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (warm) {
+            i0 = dt_ratio * i0; i1 = dt_ratio * i1; i2 = dt_ratio * i2;
+            im = im * dt_ratio;
+            const V2 P = mk<real>(i0, i1);
+            va = va - ma * P;
+            wa = wa - ia * (cross(ra, P) + im + i2);
+            vb = vb + mb * P;
+            wb = wb + ib * (cross(rb, P) + im + i2);
+        } else { i0 = i1 = i2 = real(0); im = real(0); }
+        imp[0] = i0; imp[1] = i1; imp[2] = i2; imp[3] = im;
+    } else if (type == JOINT_DISTANCE) {
+        const V2 u = cb + rb - ca - ra;
+        const real length = sqrt_r(sq_r(u.x) + sq_r(u.y));
+        const V2 un = (length > K<real>::linear_slop) ? (real(1) / length) * u : mk<real>(real(0), real(0));   // self._u; the local `u` is not normalised
+        tmp[4] = un.x; tmp[5] = un.y;
+        const real cr_au = sq_r(cross(ra, u)), cr_bu = sq_r(cross(rb, u));
+        const real inv_mass = ma + ia * cr_au + mb + ib * cr_bu;
+        real mass = (inv_mass != real(0)) ? real(1) / inv_mass : real(0);
+        real gamma = real(0), bias = real(0);
+        if (par[5] > real(0)) {
+            const real C = length - par[4];
+            const real omega = real(2) * K<real>::pi * par[5];
+            const real d = real(2) * mass * par[6] * omega;
+            const real kk = mass * sq_r(omega);
+            gamma = dt * (d + dt * kk);
+            gamma = (gamma != real(0)) ? real(1) / gamma : real(0);
+            bias = C * dt * kk * gamma;
+            const real m2 = inv_mass + gamma;
+            mass = (m2 != real(0)) ? real(1) / m2 : real(0);
+        }
+        tmp[6] = mass; tmp[7] = gamma; tmp[8] = bias;
+        real i0 = imp[0];
+        if (warm) {
+            i0 = i0 * dt_ratio;
+            const V2 P = i0 * un;
+            va = va - ma * P;
+            wa = wa - ia * cross(ra, P);
+            vb = vb + mb * P;
+            wb = wb + ib * cross(rb, P);
+        } else i0 = real(0);
+        imp[0] = i0;
+    } else if (type == JOINT_WELD) {
+        M33 m;
+        const real c2x = -ra.y * ra.x * ia - rb.y * rb.x * ib;
+        const real c3x = -ra.y * ia - rb.y * ib;
+        m.c1 = mk3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, c2x, c3x);
+        m.c2 = mk3(c2x, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, c3x);          // weld.py:148-150: c3x, as written
+        m.c3 = mk3(c3x, ra.x * ia + rb.x * ib, ia + ib);
+        m33_store(tmp + 4, m);
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2];
+        if (warm) {
+            i0 = dt_ratio * i0; i1 = dt_ratio * i1; i2 = dt_ratio * i2;
+            const V2 P = mk<real>(i0, i1);
+            va = va - ma * P;
+            wa = wa - ia * (cross(ra, P) + i2);
+            vb = vb + mb * P;
+            wb = wb + ib * (cross(rb, P) + i2);
+        } else i0 = i1 = i2 = real(0);
+        imp[0] = i0; imp[1] = i1; imp[2] = i2;
+    }
+    state_set(ba, va.x, va.y, wa);
+    state_set(bb, vb.x, vb.y, wb);
+}
+
+// _solve_velocity_constraints (revolute.py:302-378, distance.py:252-275, weld.py:171-199)
+B2B_D void joint_solve_velocity(int k, real dt)
+{
+    const int32_t* def = j_def + 4 * (size_t)k;
+    const real* par = j_par + JOINT_PAR * (size_t)k;
+    real* imp = j_imp + 4 * (size_t)k;
+    const real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    const real ma = b_mass[4 * (size_t)ba], ia = b_mass[4 * (size_t)ba + 1], mb = b_mass[4 * (size_t)bb], ib = b_mass[4 * (size_t)bb + 1];
+    const quad sa = state_get(ba), sb = state_get(bb);
+    V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
+    real wa = sa.z, wb = sb.z;
+    const V2 ra = mk<real>(tmp[0], tmp[1]), rb = mk<real>(tmp[2], tmp[3]);
+    if (type == JOINT_REVOLUTE) {
+        const M33 m = m33_load(tmp + 4);
+        const int ls = (flags >> JF_LS_SHIFT) & 3;
+        const bool fixed_rotation = ((ia + ib) == real(0));
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2];
+        if ((flags & JF_MOTOR) && ls != LS_EQUAL && !fixed_rotation) {
+            const real Cdot = wb - wa - par[8];
+            real impulse = tmp[13] * (-Cdot);
+            const real old_impulse = imp[3];
+            const real max_impulse = dt * par[7];
+            const real im = clamp_r(old_impulse + impulse, -max_impulse, max_impulse);
+            imp[3] = im;
+            impulse = im - old_impulse;
+            wa = wa - ia * impulse;
+            wb = wb + ib * impulse;
+        }
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE && !fixed_rotation) {
+            const V2 Cdot1 = vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+            const real Cdot2 = wb - wa;
+            V3 impulse = neg3(solve33(m, mk3(Cdot1.x, Cdot1.y, Cdot2)));
+            if (ls == LS_EQUAL) {
+                i0 = i0 + impulse.x; i1 = i1 + impulse.y; i2 = i2 + impulse.z;
+            } else {
+                const real new_impulse = i2 + impulse.z;
+                if ((ls == LS_LOWER) ? (new_impulse < real(0)) : (new_impulse > real(0))) {
+                    const V2 rhs = (-Cdot1) + i2 * mk<real>(m.c3.x, m.c3.y);
+                    const V2 reduced = solve22(m, rhs);
+                    impulse = mk3(reduced.x, reduced.y, -i2);
+                    i0 = i0 + reduced.x; i1 = i1 + reduced.y; i2 = i2 + (-i2);
+                } else {
+                    i0 = i0 + impulse.x; i1 = i1 + impulse.y; i2 = i2 + impulse.z;
+                }
+            }
+            const V2 P = mk<real>(impulse.x, impulse.y);
+            va = va - ma * P;
+            wa = wa - ia * (cross(ra, P) + impulse.z);
+            vb = vb + mb * P;
+            wb = wb + ib * (cross(rb, P) + impulse.z);
+        } else {
+            const V2 Cdot = vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+            const V2 impulse = solve22(m, -Cdot);
+            i0 = i0 + impulse.x; i1 = i1 + impulse.y; i2 = i2 + real(0);
+            va = va - ma * impulse;
+            wa = wa - ia * cross(ra, impulse);
+            vb = vb + mb * impulse;
+            wb = wb + ib * cross(rb, impulse);
+        }
+        imp[0] = i0; imp[1] = i1; imp[2] = i2;
+    } else if (type == JOINT_DISTANCE) {
+        const V2 u = mk<real>(tmp[4], tmp[5]);
+        const V2 vpa = va + cross_sv(wa, ra), vpb = vb + cross_sv(wb, rb);
+        const real Cdot = dot(u, vpb - vpa);
+        const real i0 = imp[0];
+        const real impulse = -tmp[6] * (Cdot + tmp[8] + tmp[7] * i0);
+        imp[0] = i0 + impulse;
+        const V2 P = impulse * u;
+        va = va - ma * P;
+        wa = wa - ia * cross(ra, P);
+        vb = vb + mb * P;
+        wb = wb + ib * cross(rb, P);
+    } else if (type == JOINT_WELD) {
+        const M33 m = m33_load(tmp + 4);
+        const V2 Cdot1 = vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+        const real Cdot2 = wb - wa;
+        const V3 impulse = solve33(m, neg3(mk3(Cdot1.x, Cdot1.y, Cdot2)));
+        imp[0] = imp[0] + impulse.x; imp[1] = imp[1] + impulse.y; imp[2] = imp[2] + impulse.z;
+        const V2 P = mk<real>(impulse.x, impulse.y);
+        va = va - ma * P;
+        wa = wa - ia * (cross(ra, P) + impulse.z);
+        vb = vb + mb * P;
+        wb = wb + ib * (cross(rb, P) + impulse.z);
+    }
+    state_set(ba, va.x, va.y, wa);
+    state_set(bb, vb.x, vb.y, wb);
+}
+
+// _solve_position_constraints (revolute.py:380-453, distance.py:277-311, weld.py:201-257) on the sweeps in the team's shared
+// state; true when the joint's errors are within tolerance
+B2B_D bool joint_solve_position(int k)
+{
+    const int32_t* def = j_def + 4 * (size_t)k;
+    const real* par = j_par + JOINT_PAR * (size_t)k;
+    const real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
+    const quad mqa = ldq(b_mass + 4 * (size_t)ba), mqb = ldq(b_mass + 4 * (size_t)bb);
+    const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
+    const V2 lca = mk<real>(mqa.z, mqa.w), lcb = mk<real>(mqb.z, mqb.w);
+    const quad sa = state_get(ba), sb = state_get(bb);
+    V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
+    real aa = sa.z, ab = sb.z;
+    bool ok = true;
+    if (type == JOINT_REVOLUTE) {
+        const int ls = (flags >> JF_LS_SHIFT) & 3;
+        const bool fixed_rotation = ((ia + ib) == real(0));
+        real angular_error = real(0), position_error = real(0);
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE && !fixed_rotation) {
+            const real angle = ab - aa - par[4];
+            real limit_impulse = real(0);
+            if (ls == LS_EQUAL) {
+                const real C = clamp_r(angle - par[5], -K<real>::max_angular_correction, K<real>::max_angular_correction);
+                limit_impulse = -tmp[13] * C;
+                angular_error = abs_r(C);
+            } else if (ls == LS_LOWER) {
+                real C = angle - par[5];
+                angular_error = -C;
+                C = clamp_r(C + K<real>::angular_slop, -K<real>::max_angular_correction, real(0));
+                limit_impulse = -tmp[13] * C;
+            } else if (ls == LS_UPPER) {
+                real C = angle - par[6];
+                angular_error = C;
+                C = clamp_r(C - K<real>::angular_slop, real(0), K<real>::max_angular_correction);
+                limit_impulse = -tmp[13] * C;
+            }
+            aa = aa - ia * limit_impulse;
+            ab = ab + ib * limit_impulse;
+        }
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 C = cb + rb - ca - ra;
+        position_error = sqrt_r(sq_r(C.x) + sq_r(C.y));
+        const real k1x = ma + mb + ia * ra.y * ra.y + ib * rb.y * rb.y;
+        const real k1y = -ia * ra.x * ra.y - ib * rb.x * rb.y;
+        const real k2x = k1y;
+        const real k2y = ma + mb + ia * ra.x * ra.x + ib * rb.x * rb.x;
+        real det = k1x * k2y - k2x * k1y;                                            // Mat22.solve, common.py:521-531
+        if (det != real(0)) det = real(1) / det;
+        const V2 impulse = -mk<real>(det * (k2y * C.x - k2x * C.y), det * (k1x * C.y - k1y * C.x));
+        ca = ca - ma * impulse;
+        aa = aa - ia * cross(ra, impulse);
+        cb = cb + mb * impulse;
+        ab = ab + ib * cross(rb, impulse);
+        ok = (position_error <= K<real>::linear_slop) && (angular_error <= K<real>::angular_slop);
+    } else if (type == JOINT_DISTANCE) {
+        if (par[5] > real(0)) return true;                                           // no position correction for soft constraints
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        V2 u = cb + rb - ca - ra;
+        const real length = sqrt_r(sq_r(u.x) + sq_r(u.y));
+        u = normalize(u);
+        const real C = length - par[4];
+        const real impulse = -tmp[6] * clamp_r(C, -K<real>::max_linear_correction, K<real>::max_linear_correction);
+        const V2 P = impulse * u;
+        ca = ca - ma * P;
+        aa = aa - ia * cross(ra, P);
+        cb = cb + mb * P;
+        ab = ab + ib * cross(rb, P);
+        ok = abs_r(C) < K<real>::linear_slop;
+    } else if (type == JOINT_WELD) {
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 C1 = cb + rb - ca - ra;
+        const real C2 = ab - aa - par[4];
+        const real position_error = sqrt_r(sq_r(C1.x) + sq_r(C1.y)), angular_error = abs_r(C2);
+        M33 m;
+        const real c2x = -ra.y * ra.x * ia - rb.y * rb.x * ib;
+        const real c3x = -ra.y * ia - rb.y * ib;
+        const real c3y = ra.x * ia + rb.x * ib;
+        m.c1 = mk3(ma + mb + ra.y * ra.y * ia + rb.y * rb.y * ib, c2x, c3x);
+        m.c2 = mk3(c2x, ma + mb + ra.x * ra.x * ia + rb.x * rb.x * ib, c3y);
+        m.c3 = mk3(-ra.y * ia - rb.y * ib, ra.x * ia + rb.x * ib, ia + ib);
+        const V3 impulse = neg3(solve33(m, mk3(C1.x, C1.y, C2)));
+        const V2 P = mk<real>(impulse.x, impulse.y);
+        ca = ca - ma * P;
+        aa = aa - ia * (cross(ra, P) + impulse.z);
+        cb = cb + mb * P;
+        ab = ab + ib * (cross(rb, P) + impulse.z);
+        ok = (position_error <= K<real>::linear_slop) && (angular_error <= K<real>::angular_slop);
+    }
+    state_set(ba, ca.x, ca.y, aa);
+    state_set(bb, cb.x, cb.y, ab);
+    return ok;
+}
+
+// one island's joint range in l_joint
+B2B_D void island_joint_range(int isl, int n_islands, int& j0, int& j1) const
+{
+    j0 = l_jstart[isl];
+    j1 = (isl + 1 < n_islands) ? l_jstart[isl + 1] : w_joint[1];
+}

@@ -5,7 +5,7 @@
 #include <vector>
 #include "b2b_step.cuh"
 
-#define B2B_NFIELDS 36
+#define B2B_NFIELDS 45
 #define B2B_CAT_(a, b) a##b
 #define B2B_CAT(a, b) B2B_CAT_(a, b)
 

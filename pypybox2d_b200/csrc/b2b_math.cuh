@@ -42,7 +42,8 @@ enum : uint32_t {
     WORLD_CONTINUOUS = 0x20u,    // continuous_physics (world.py:78): World.solve_toi runs after the discrete solve
     WORLD_TOI_DIRTY = 0x40u,     // device bookkeeping: some body's sweep.alpha0 is non-zero (a TOI event was solved last step)
     STATUS_CONTACT_OVERFLOW = 0x1u, STATUS_PAIR_OVERFLOW = 0x2u, STATUS_NAN = 0x4u, STATUS_ISLAND_OVERFLOW = 0x8u,
-    STATUS_TOI_STUCK = 0x10u     // a time-of-impact push-back loop was cut off (b2b_toi.cuh TOI_MAX_PUSH_BACK)
+    STATUS_TOI_STUCK = 0x10u,    // a time-of-impact push-back loop was cut off (b2b_toi.cuh TOI_MAX_PUSH_BACK)
+    STATUS_JOINT_OVERFLOW = 0x20u // more joints than the batch's joint capacity
 };
 enum { BODY_STATIC = 0, BODY_DYNAMIC = 1, BODY_KINEMATIC = 2 };
 enum { MANIFOLD_CIRCLES = 0, MANIFOLD_FACE_A = 1, MANIFOLD_FACE_B = 2 };
@@ -63,6 +64,7 @@ template <class real> struct K {
     static constexpr real polygon_radius = real(2.0 * 0.005);
     static constexpr real velocity_threshold = real(1.0);
     static constexpr real max_linear_correction = real(0.2);
+    static constexpr real max_angular_correction = real(8.0 / 180.0 * 3.141592653589793);   // settings.py:92
     static constexpr real max_translation = real(2.0);
     static constexpr real max_translation_sqr = real(4.0);
     static constexpr real max_rotation = real(0.5 * 3.141592653589793);

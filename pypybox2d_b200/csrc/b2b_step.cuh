@@ -81,6 +81,7 @@ namespace b2b {
 
 struct caps_t {
     int n_worlds, nb, nf, nc, npair, nl, n_shapes;
+    int nj = 0;              // joints per world (0: the batch has none and runs the kernels without the joint hooks); the J arrays have max(nj, 1) rows
 };
 
 // Pointers to the batch arrays (world-major).  Field order == schema.FIELDS == b2b_buffers.
@@ -91,12 +92,14 @@ template <class real> struct batch_ptrs {
     int32_t* c_fix; uint32_t* c_flags; real* c_mat; int32_t* c_mtype; real *c_mf, *c_pts, *c_imp; uint32_t* c_id;
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     int32_t* s_meta; real* s_radius; real* s_data;
+    int32_t *w_joint, *j_def; real *j_par, *j_imp, *j_tmp; int32_t *j_adj, *b_jadj, *l_joint, *l_jstart;   // joints (b2b_joints.inl)
 };
 
 // number of real-valued SoA rows per constraint slot (see cc_* accessors below)
 enum { VREC_QUADS = 8, PREC_QUADS = 6 };   // velocity / position record of one constraint, in 4-vectors of reals ("quads")
 // per-CTA cycle counters (step_params.flags & STEP_PROFILE): see PROF_* below
-enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32, STEP_SOLVE_ONLY = 64 };
+enum { PROF_SLOTS = 32, STEP_PROFILE = 1, STEP_FLAT_COLLIDE = 4, STEP_GROUP_KERNEL = 32, STEP_SOLVE_ONLY = 64,
+       STEP_FIRST = 256 };      // (set by the launcher) the first of a call's n_steps: joints scale their impulses by dt_ratio_first
 // per-world summary word: what the flat kernels found, so that the per-world kernels can skip a settled world in O(1)
 enum { SUM_PENDING = 1u, SUM_DESTROY = 2u, SUM_CHANGED = 4u, SUM_MOVED = 8u,
        SUM_SENSOR = 16u,          // an ACTIVE sensor contact was left to the plan kernel: its pending contacts have to be walked
@@ -261,6 +264,7 @@ template <class real> struct world_step {
     int32_t* c_fix; uint32_t* c_flags; real* c_mat; int32_t* c_mtype; real *c_mf, *c_pts, *c_imp; uint32_t* c_id;
     int32_t *p_pairs, *l_body, *l_contact, *l_start;
     const int32_t* s_meta; const real* s_radius; const real* s_data;
+    int32_t *w_joint, *j_def; const real* j_par; real *j_imp, *j_tmp; const int32_t *j_adj, *b_jadj; int32_t *l_joint, *l_jstart;
     // this world's rows of the plan arrays (global)
     uint16_t *g_cbody, *g_sched, *g_slot_isl, *g_joint, *g_adj, *g_adj_start;
     real* s_fat; uint8_t* s_moved;   // pair finding: fat boxes and move flags staged in shared memory
@@ -342,6 +346,9 @@ template <class real> struct world_step {
         p_pairs = B.p_pairs + 2 * W * c.npair; l_body = B.l_body + W * c.nl; l_contact = B.l_contact + oc;
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
+        const size_t oj = W * (size_t)(c.nj > 0 ? c.nj : 1);
+        w_joint = B.w_joint + 4 * W; j_def = B.j_def + 4 * oj; j_par = B.j_par + 12 * oj; j_imp = B.j_imp + 4 * oj; j_tmp = B.j_tmp + 20 * oj;
+        j_adj = B.j_adj + 2 * oj; b_jadj = B.b_jadj + 2 * ob; l_joint = B.l_joint + oj; l_jstart = B.l_jstart + ob;
         uint16_t* pw = plan + W * P.stride;
         g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_slot_isl = pw + P.off_slot_isl; g_joint = pw + P.off_joint; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);
         g_adj = pw + P.off_adj; g_adj_start = pw + P.off_adj_start;
@@ -648,6 +655,17 @@ template <class real> struct world_step {
                 b_pos[4 * (size_t)b + 3] = real(0);
             }
         }
+        // ... also when no contact was pending: a sleeping body whose ONLY contact is with an awake body (it hangs on a joint, or
+        // floats without gravity: a body asleep on something has a pending contact with it) is woken by that contact's touching change
+        if (!any_pending && after_flat && s_ctl[10]) B2B_PFOR(c, nc) {
+            if (g_cstate[c] != 3) continue;
+            const int bs[2] = {f_body[c_fix[2 * c]], f_body[c_fix[2 * c + 1]]};
+            for (int k = 0; k < 2; ++k) {
+                if (b_flags[bs[k]] & BODY_AWAKE) continue;
+                B2B_ATOMIC_OR(&b_flags[bs[k]], (uint32_t)BODY_AWAKE);
+                b_pos[4 * (size_t)bs[k] + 3] = real(0);
+            }
+        }
         // ContactManager.destroy (contact_manager.py:160-172): order-preserving removal, nobody is woken (A.9 #12)
         if (s_ctl[1]) {
             B2B_PFOR(c, nc) scan[c] = (scan[c] == 2) ? 0 : 1;
@@ -749,15 +767,23 @@ template <class real> struct world_step {
     B2B_D void phase_islands()
     {
         const int nb = w_count[0], nc = w_count[2];
+        // Joint._island_flag of every joint cleared (world.py:491-492); only batches with a joint capacity have joints
+        int nj = 0;
+        if (cap.nj > 0) {
+            nj = w_joint[0];
+            if (nj > cap.nj) { nj = cap.nj; if (B2B_IS_T0) w_status[0] |= STATUS_JOINT_OVERFLOW; }
+            B2B_PFOR(j, nj) j_def[4 * j + 3] &= ~(int32_t)JF_ISLAND;
+            B2B_SYNC();
+        }
         if (B2B_IS_T0) {
-            int n_islands = 0, lb = 0, lc = 0;
+            int n_islands = 0, lb = 0, lc = 0, lj = 0;
             bool overflow = false;
             for (int seed = 0; seed < nb && !overflow; ++seed) {
                 const uint32_t fl = s_flags[seed];
                 if (fl & BODY_ISLAND) continue;
                 if (!(fl & BODY_AWAKE) || !(fl & BODY_ACTIVE)) continue;
                 if ((fl & BODY_TYPE_MASK) == BODY_STATIC) continue;
-                const int body_start = lb, contact_start = lc;
+                const int body_start = lb, contact_start = lc, joint_start = lj;
                 int sp = 0, n_static = 0;
                 int statics[4];                                        // statics that joined this island
                 s_stack[sp++] = (uint16_t)seed;
@@ -806,9 +832,26 @@ template <class real> struct world_step {
                             s_flags[other] |= BODY_ISLAND;
                         }
                     }
+                    // Body.joints in append order (world.py:548-572): a joint joins the island of the first of its bodies the
+                    // walk expands, unless its other body is inactive; the other body is taken along
+                    if (nj > 0) {
+                        for (int k = b_jadj[2 * b], ke = k + b_jadj[2 * b + 1]; k < ke; ++k) {
+                            const int j = j_adj[k];
+                            int32_t* def = j_def + 4 * (size_t)j;
+                            if (def[3] & JF_ISLAND) continue;
+                            const int other = (def[1] == b) ? def[2] : def[1];
+                            if (!(s_flags[other] & BODY_ACTIVE)) continue;
+                            l_joint[lj++] = j;
+                            def[3] |= JF_ISLAND;
+                            if (s_flags[other] & BODY_ISLAND) continue;
+                            s_stack[sp++] = (uint16_t)other;
+                            s_flags[other] |= BODY_ISLAND;
+                        }
+                    }
                 }
                 if (overflow) break;
                 l_start[2 * n_islands] = body_start; l_start[2 * n_islands + 1] = contact_start;
+                if (cap.nj > 0) l_jstart[n_islands] = joint_start;
                 // statics may join other islands (world.py:577-580); the few that joined were noted on the way (the
                 // island's body list is in global memory: reading it back would cost a round trip per island)
                 if (n_static <= 4) {
@@ -824,6 +867,7 @@ template <class real> struct world_step {
             if (overflow) w_status[0] |= STATUS_ISLAND_OVERFLOW;
             s_ctl[11] = 0;
             w_island[0] = n_islands; w_island[1] = lb; w_island[2] = lc; w_island[3] = 0;
+            if (cap.nj > 0) w_joint[1] = lj;
             s_ctl[4] = n_islands; s_ctl[5] = lb; s_ctl[6] = lc;
         }
         B2B_SYNC();
@@ -939,7 +983,8 @@ template <class real> struct world_step {
         // with a joint schedule moves the whole batch to the group-capable position kernel (measured 2 % of the solve time
         // slower for the worlds that stay one island per group), so a stray second island next to a big one (a box beside a
         // pyramid: ~1 % of the contacts) does not qualify.
-        const bool joint = (n_ci >= 2) && (n_ci <= 32) && (3 * (size_t)cap.nb >= 32) && (10 * largest <= 9 * n_lc);
+        // (batches with a joint capacity solve island after island: an island's joints are visited between its contact sweeps)
+        const bool joint = (n_ci >= 2) && (n_ci <= 32) && (3 * (size_t)cap.nb >= 32) && (10 * largest <= 9 * n_lc) && cap.nj == 0;
 #endif
         if (joint) {
             if (B2B_IS_T0) schedule_range(0, n_lc, 0);
@@ -966,6 +1011,8 @@ template <class real> struct world_step {
         if (B2B_IS_T0) { g_joint[0] = (uint16_t)(joint ? 1 : 0); g_joint[1] = (uint16_t)n_ci; }
         B2B_SYNC();
     }
+
+#include "b2b_joints.inl"
 
     // ------------------------------------------------------------------------------------ K3 (prepare + solve kernels)
     // One constraint = a read-only VELOCITY record of 8 four-vectors ("quads": exactly one 128-byte line in fp32 -- what a
@@ -1676,7 +1723,9 @@ template <class real> struct world_step {
         b1 = (isl + 1 < n_islands) ? l_start[2 * isl + 2] : n_lb;
         c1 = (isl + 1 < n_islands) ? l_start[2 * isl + 3] : n_lc;
     }
-    B2B_D void solve_velocity_phase(const step_params& sp, real dt)
+    // PJ: the batch has a joint capacity (b2b_caps::nj > 0): an island's joints are initialised after the contacts' warm start and
+    // visited before the contacts in every velocity iteration (island.py:107-113), by the team's first lane (b2b_joints.inl)
+    template <bool PJ> B2B_D void solve_velocity_phase(const step_params& sp, real dt)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -1708,15 +1757,34 @@ template <class real> struct world_step {
             int b0, b1, c0, c1;
             island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (joint) { c0 = 0; c1 = n_lc; }
-            if (c1 == c0) continue;
+            int j0 = 0, j1 = 0;
+            if constexpr (PJ) island_joint_range(isl, n_islands, j0, j1);
+            if (c1 == c0 && j1 == j0) continue;
             const uint32_t* lv = g_lv + lv_offset(c0, isl);
             const vel_stream vat = vel_stream_at(c0 + t_id);
             auto vready = [&](const vrec& e) { return bits_of_real(e.q0.w); };
-            if (warm) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream&) { constraint_warm_start(e); }, vready);
+            if (warm && c1 > c0) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream&) { constraint_warm_start(e); }, vready);
             B2B_PROF(PROF_S_WARM, t);
+            if constexpr (PJ) {
+                if (j1 > j0) {
+                    B2B_SYNC();
+                    if (t_id == 0) {
+                        const real dt_ratio = (real)(((sp.flags & STEP_FIRST) != 0) ? sp.dt_ratio_first : sp.dt_ratio_rest);
+                        for (int k = j0; k < j1; ++k) joint_init(l_joint[k], dt, dt_ratio, warm);
+                    }
+                    B2B_SYNC();
+                }
+            }
             for (int it = 0; it < sp.vel_iters; ++it) {
                 const bool last = (it + 1 == sp.vel_iters);
-                level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);
+                if constexpr (PJ) {
+                    if (j1 > j0) {
+                        B2B_SYNC();
+                        if (t_id == 0) for (int k = j0; k < j1; ++k) joint_solve_velocity(l_joint[k], dt);
+                        B2B_SYNC();
+                    }
+                }
+                if (c1 > c0) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);
             }
             B2B_PROF(PROF_S_VELOCITY, t);
             // -- store_impulses (contact.py:801-806) is part of the last velocity iteration; without velocity
@@ -1754,7 +1822,9 @@ template <class real> struct world_step {
 
     // JOINT_CAPABLE = false: no world of the batch has a joint schedule (the common case: one island per world, or none
     // balanced enough), the island-ordinal and atomic paths compile away.
-    template <bool JOINT_CAPABLE> B2B_D void solve_position_phase(const step_params& sp, real dt)
+    // PJ (with JOINT_CAPABLE = false): the batch has a joint capacity; an island's joints are visited after its contacts in every
+    // position iteration and the island is solved when both are within tolerance (island.py:141-153).
+    template <bool JOINT_CAPABLE, bool PJ = false> B2B_D void solve_position_phase(const step_params& sp, real dt)
     {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -1793,7 +1863,9 @@ template <class real> struct world_step {
             for (int isl = 0; isl < n_islands; ++isl) {
                 int b0, b1, c0, c1;
                 island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
-                if (c1 == c0) continue;
+                int j0 = 0, j1 = 0;
+                if constexpr (PJ) island_joint_range(isl, n_islands, j0, j1);
+                if (c1 == c0 && j1 == j0) continue;
                 const uint32_t* lv = g_lv + lv_offset(c0, isl);
                 // -- position iterations with early exit (island.py:141-153)
                 bool position_solved = false;
@@ -1801,9 +1873,10 @@ template <class real> struct world_step {
                 for (int it = 0; it < sp.pos_iters; ++it) {
                     real my_min = real(0);
                     ++used;
-                    level_sweep<prec>(c0, c1, lv, sp.zero, pos_stream_at(c0 + t_id),
-                                      [&](const prec& e, const pos_stream&) { my_min = pymin(my_min, constraint_solve_position(e)); },
-                                      [&](const prec& e) { return bits_of_real(e.q10.z); });
+                    if (c1 > c0)
+                        level_sweep<prec>(c0, c1, lv, sp.zero, pos_stream_at(c0 + t_id),
+                                          [&](const prec& e, const pos_stream&) { my_min = pymin(my_min, constraint_solve_position(e)); },
+                                          [&](const prec& e) { return bits_of_real(e.q10.z); });
                     real all_min = my_min;
 #if defined(__CUDA_ARCH__)
                     for (int o = t_n >> 1; o > 0; o >>= 1) {
@@ -1811,7 +1884,18 @@ template <class real> struct world_step {
                         all_min = (other < all_min) ? other : all_min;
                     }
 #endif
-                    if (all_min >= real(-3) * K<real>::linear_slop) { position_solved = true; break; }
+                    int joints_okay = 1;
+                    if constexpr (PJ) {
+                        if (j1 > j0) {
+                            B2B_SYNC();
+                            if (t_id == 0) for (int k = j0; k < j1; ++k) { const bool okay = joint_solve_position(l_joint[k]); joints_okay = (joints_okay && okay) ? 1 : 0; }
+#if defined(__CUDA_ARCH__)
+                            for (int o = t_n >> 1; o > 0; o >>= 1) joints_okay &= __shfl_xor_sync(t_mask, joints_okay, o);
+#endif
+                            B2B_SYNC();
+                        }
+                    }
+                    if (all_min >= real(-3) * K<real>::linear_slop && joints_okay) { position_solved = true; break; }
                 }
                 if (used > max_used) max_used = used;
                 B2B_PROF(PROF_S_POSITION, t);
@@ -1901,6 +1985,7 @@ template <class real> struct world_step {
             int b0, b1, c0, c1;
             island_range(isl, n_islands, n_lb, n_lc, b0, b1, c0, c1);
             if (c1 != c0) continue;
+            if constexpr (PJ) { int j0, j1; island_joint_range(isl, n_islands, j0, j1); if (j1 != j0) continue; }   // solved above
             if (sp.pos_iters > 0 && max_used < 1) max_used = 1;
             if (allow_sleep) island_sleep(b0, b1, dt, sp.pos_iters > 0);
         }
@@ -2018,6 +2103,13 @@ template <class real> struct world_step {
             }
         }
         if (exists) return false;
+        // Body._should_collide (body.py:920-926): a joint between the two bodies that does not let them collide
+        if (cap.nj > 0) {
+            for (int k = b_jadj[2 * bb], ke = k + b_jadj[2 * bb + 1]; k < ke; ++k) {
+                const int32_t* def = j_def + 4 * (size_t)j_adj[k];
+                if (((def[1] == bb && def[2] == ba) || (def[2] == bb && def[1] == ba)) && !(def[3] & JF_COLLIDE)) return false;
+            }
+        }
         // World.default_contact_filter (world.py:958-970)
         const uint32_t fa0 = f_filter[2 * fa], fa1 = f_filter[2 * fa + 1], fb0 = f_filter[2 * fb], fb1 = f_filter[2 * fb + 1];
         const int ga = (int)(int16_t)(fa1 & 0xffff), gb = (int)(int16_t)(fb1 & 0xffff);
@@ -2743,7 +2835,7 @@ template <class real> struct world_step {
         }
     }
     // solve kernel: Island.solve for every island (island.py:65-179)
-    B2B_D void run_solve_velocity(const step_params& sp)
+    template <bool PJ = false> B2B_D void run_solve_velocity(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -2752,7 +2844,7 @@ template <class real> struct world_step {
         for (int i = 0; i < 7; ++i) tr[i] = 0u;
         tlast = (unsigned)clock();
 #endif
-        solve_velocity_phase(sp, (real)sp.dt);
+        solve_velocity_phase<PJ>(sp, (real)sp.dt);
 #if defined(B2B_TRACE) && defined(__CUDA_ARCH__)
         if (t_id == 0) for (int i = 0; i < 7; ++i) prof[20 + i] += (long long)tr[i];
 #endif
@@ -2760,14 +2852,17 @@ template <class real> struct world_step {
     }
     // The position kernel exists twice: JOINT_CAPABLE = false for batches in which no world has a joint schedule, true
     // otherwise; both are launched and the one whose turn it is not returns at once (b2b_kernels.inl).
-    template <bool JOINT_CAPABLE> B2B_D void run_solve_position(const step_params& sp)
+    template <bool JOINT_CAPABLE, bool PJ = false> B2B_D void run_solve_position(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
         long long t = B2B_CLOCK();
-        solve_position_phase<JOINT_CAPABLE>(sp, (real)sp.dt);
+        solve_position_phase<JOINT_CAPABLE, PJ>(sp, (real)sp.dt);
         B2B_PROF(PROF_SOLVE, t);
     }
+    // the solve kernels of batches with a joint capacity
+    B2B_D void run_solve_velocity_joints(const step_params& sp) { run_solve_velocity<true>(sp); }
+    B2B_D void run_solve_position_joints(const step_params& sp) { run_solve_position<false, true>(sp); }
     // broadphase kernel: find_new_contacts (world.py:582-592) for the worlds whose proxies moved (the flat sync
     // kernel raised SUM_MOVED); a world without movers emits no pairs and creates no contacts
     B2B_D void run_pairs(const step_params& sp)
@@ -2803,8 +2898,15 @@ template <class real> struct world_step {
                 const int n_bodies = prepare_bodies();
                 for (int b = 0; b < n_bodies; ++b) prepare_body(sp, b);
             }
-            run_solve_velocity(sp);
-            run_solve_position<true>(sp);
+            if (cap.nj > 0) {
+                step_params spj = sp;
+                if (step == 0) spj.flags |= STEP_FIRST;
+                run_solve_velocity<true>(spj);
+                run_solve_position<false, true>(spj);
+            } else {
+                run_solve_velocity(sp);
+                run_solve_position<true>(sp);
+            }
             const int n_items = sync_items();
             for (int i = 0; i < n_items; ++i) sync_item(sp, i);
             run_pairs(sp);

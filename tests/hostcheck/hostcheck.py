@@ -12,12 +12,13 @@ FIELD_ORDER = ("w_count,w_flags,w_status,w_gravity,w_island,"
                "b_xf,b_pos,b_vel,b_pos0,b_force,b_mass,b_damp,b_flags,b_island,"
                "f_body,f_shape,f_mat,f_filter,f_fat,f_tight,f_moved,"
                "c_fix,c_flags,c_mat,c_mtype,c_mf,c_pts,c_imp,c_id,"
-               "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data").split(",")
+               "p_pairs,l_body,l_contact,l_start,s_meta,s_radius,s_data,"
+               "w_joint,j_def,j_par,j_imp,j_tmp,j_adj,b_jadj,l_joint,l_jstart").split(",")
 
 
 class Caps(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("n_worlds", "nb", "nf", "nc", "npair", "nl", "n_shapes", "real_bytes",
-                                              "device", "threads", "ctas_per_sm", "reserved")]
+                                              "device", "threads", "ctas_per_sm", "reserved", "nj", "reserved2")]
 
 
 class Buffers(ctypes.Structure):
@@ -32,7 +33,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, "libhostcheck.so")
         srcs = [os.path.join(_HERE, "hostcheck.cpp")] + [
-            os.path.join(_ROOT, "pypybox2d_b200", "csrc", f) for f in ("b2b_step.cuh", "b2b_collide.cuh", "b2b_math.cuh")]
+            os.path.join(_ROOT, "pypybox2d_b200", "csrc", f) for f in ("b2b_step.cuh", "b2b_collide.cuh", "b2b_math.cuh", "b2b_joints.inl", "b2b_toi.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-builtin-pow", "-o", so,
                                    srcs[0], "-lm"])
@@ -59,6 +60,7 @@ def step(arrays, dt, inv_dt0, vel_iters, pos_iters, n_steps=1):
     c.nl = A["l_body"].shape[1]
     c.n_shapes = A["s_meta"].shape[0]
     c.real_bytes = A["b_xf"].dtype.itemsize
+    c.nj = A["j_def"].shape[1] if int(A["w_joint"][:, 0].max()) > 0 else 0
     b = Buffers()
     for n in FIELD_ORDER:
         assert A[n].flags["C_CONTIGUOUS"], n

@@ -58,8 +58,43 @@ def test_unsupported_features_fail_loudly():
     assert w.continuous_physics
     with pytest.raises(NotImplementedError):
         b2.World(sub_stepping=True)
-    with pytest.raises(NotImplementedError):
-        w.add_joint(None)
+    # revolute, distance and weld joints run on the device since round 2; the other joint types still raise
+    a, b = w.create_dynamic_body(position=(0, 1)), w.create_dynamic_body(position=(1, 1))
+    for make in (w.create_prismatic_joint, w.create_wheel_joint, w.create_pulley_joint, w.create_gear_joint, w.create_rope_joint,
+                 w.create_friction_joint, w.create_mouse_joint):
+        with pytest.raises(NotImplementedError):
+            make(a, b)
+
+
+def test_joint_constructors_mirror_the_reference():
+    """joints/revolute.py:58-93, distance.py:57-93, weld.py:56-81: anchors, reference angle and rest length from the bodies'
+    transforms; World.add_joint appends to body_a's list first (world.py:268-273); destroy_body takes its joints along."""
+    w = b2.World(continuous_physics=False)
+    ground = w.create_static_body()
+    a = w.create_dynamic_body(position=(1.0, 2.0), angle=0.5)
+    b = w.create_dynamic_body(position=(3.0, 2.0))
+    rj = w.create_revolute_joint(a, b, anchor=(2.0, 2.0), lower_angle=-0.1, upper_angle=0.2, limit_enabled=True)
+    assert rj.body_a is a and rj.body_b is b and not rj.collide_connected and rj.limit_enabled and not rj.motor_enabled
+    assert rj._reference_angle == b.angle - a.angle and rj.joint_angle == 0.0
+    wa = a.get_world_point(rj.local_anchor_a)
+    assert abs(wa.x - 2.0) < 1e-12 and abs(wa.y - 2.0) < 1e-12
+    dj = w.create_distance_joint(ground, b, anchor_a=(3.0, 6.0), anchor_b=(3.0, 2.0))
+    assert dj.length == 4.0
+    with pytest.raises(ValueError):
+        w.create_distance_joint(ground, b, anchor_a=(3.0, 2.0), anchor_b=(3.0, 2.0))
+    wj = w.create_weld_joint(a, ground, anchor=(0.0, 0.0))
+    assert w.joints == [rj, dj, wj]
+    assert a.joints == [rj, wj] and b.joints == [rj, dj] and ground.joints == [dj, wj]
+    with pytest.raises(ValueError):
+        b2.RevoluteJoint(None, b)
+    rj.motor_speed = 2.0
+    assert rj.motor_speed == 2.0
+    w.destroy_body(a)
+    assert w.joints == [dj] and b.joints == [dj] and ground.joints == [dj]
+    w.destroy_joint(dj)
+    assert w.joints == [] and b.joints == []
+    with pytest.raises(ValueError):
+        w.destroy_joint(dj)
 
 
 def test_vec2_operator_conventions():

@@ -363,3 +363,77 @@ def test_continuous_collision_batch_invariance_and_host_path(monkeypatch):
     M, O = mixed.download(["b_pos"]), offw.download(["b_pos"])
     assert np.array_equal(M["b_pos"][1::2, :, :3], O["b_pos"][1::2, :, :3])
     assert not np.array_equal(M["b_pos"][0::2, :, :3], O["b_pos"][0::2, :, :3])
+
+
+def test_world_with_joints_is_a_drop_in():
+    """a scene script that creates revolute / distance / weld joints steps on the device through the facade; body
+    state, joint limit states and accumulated joint impulses follow the oracle's (fp64: to the one-ulp libm differences), and a
+    joint created or destroyed on a stepping world re-packs it."""
+    import pypybox2d_b200 as b2
+    world = scenes.joints(b2, world=0, real="f64")
+    mw, A, caps = harness.facade_arrays("joints", 0)
+    orc = oracle.Oracle(A, 0)
+    nb, nj = len(world.bodies), len(world.joints)
+    for i in range(120):
+        world.step(1 / 60, 8, 3)
+        orc.step(1 / 60, 8, 3)
+    pos = np.array([[b._c.x, b._c.y, b._a] for b in world.bodies])
+    assert np.abs(pos - A["b_pos"][0, :nb, :3]).max() < 1e-6
+    assert [j._limit_state for j in world.joints] == [(int(f) >> schema.JOINT_LIMIT_SHIFT) & 3 for f in A["j_def"][0, :nj, 3]]
+    assert max(j._limit_state for j in world.joints) > 0                         # an arm sits on a limit
+    imp = np.array([list(j._imp()) for j in world.joints])
+    assert np.abs(imp - A["j_imp"][0, :nj]).max() < 1e-5 * max(1.0, np.abs(imp).max())
+    arm = world.joints[19]
+    assert arm.get_motor_torque(60.0) != 0.0 and abs(arm.joint_angle) > 0.1
+    # host mutation: cut the chain, hang a new body on a new joint
+    chain_joint = world.joints[14]
+    world.destroy_joint(chain_joint)
+    extra = world.create_dynamic_body(position=(4.0, 14.0), fixtures=b2.Fixture(b2.Circle(0.3), density=1.0))
+    world.create_distance_joint(world.bodies[0], extra, anchor_a=(4.0, 16.0), anchor_b=(4.0, 14.0))
+    y_before = world.bodies[18].position.y
+    for i in range(60):
+        world.step(1 / 60, 8, 3)
+    assert world.bodies[18].position.y < y_before - 1.0                          # the cut end of the chain falls
+    assert abs(extra.position.y - 14.0) < 0.05 and len(world.joints) == nj       # the new body hangs on its joint
+
+
+def test_joint_batches_fp32_invariance_and_sleeping_bridge():
+    """Batches with a joint capacity run the solve kernels with the joint hooks (fp32): world i's trajectory does not depend on
+    batch size, shard offset or lane-team width (T4), worlds without joints in the same batch step as before, and the bridge
+    keeps its joints together."""
+    import pypybox2d_b200 as b2
+    w = scenes.bridge(b2)
+    big = b2.BatchedWorld.replicate(w, 200, jitter=1e-2, config=10, real="f32")
+    part = b2.BatchedWorld.replicate(w, 5, jitter=1e-2, config=10, world_offset=60, real="f32", threads=32)
+    assert big.caps.nj == 31
+    for bw in (big, part):
+        bw.step(1 / 60, 8, 3, 150)
+    B, P = big.download(), part.download()
+    for name in ("b_pos", "b_vel", "c_fix", "c_mtype", "c_imp", "w_count", "j_imp", "j_def", "l_joint"):
+        assert np.array_equal(B[name][62], P[name][2]), name
+    assert big.status() == 0
+    # every joint holds: the anchors of consecutive planks coincide to the solver's tolerance
+    xf = B["b_xf"].astype(np.float64)
+    d = B["j_def"]
+    par = B["j_par"].astype(np.float64)
+    wi = np.arange(200)[:, None]
+    ba, bb = d[:, :, 1], d[:, :, 2]
+    def anchor(body, lx, ly):
+        t = xf[wi, body]
+        return t[..., 0] + t[..., 2] * lx - t[..., 3] * ly, t[..., 1] + t[..., 3] * lx + t[..., 2] * ly
+    ax, ay = anchor(ba, par[..., 0], par[..., 1])
+    bx, by = anchor(bb, par[..., 2], par[..., 3])
+    assert np.hypot(ax - bx, ay - by).max() < 0.05
+    # a ragged batch: a world with joints next to worlds without (they share the joint-capable kernels)
+    mixed = b2.BatchedWorld.from_worlds([scenes.bridge(b2, world=1), scenes.hello(b2), scenes.pyramid(b2, rows=6)], real="f64")
+    refs = [harness.facade_arrays(n, wd, **kw) for n, wd, kw in (("bridge", 1, {}), ("hello", 0, {}), ("pyramid", 0, {"rows": 6}))]
+    orcs = [oracle.Oracle(r[1], 0) for r in refs]
+    for s in range(100):
+        mixed.step(1 / 60, 8, 3)
+        for o in orcs:
+            o.step(1 / 60, 8, 3)
+    M = mixed.download()
+    for i, r in enumerate(refs):
+        n = int(r[1]["w_count"][0][0])
+        assert np.abs(M["b_pos"][i, :n, :3] - r[1]["b_pos"][0, :n, :3]).max() < 1e-7, i
+        assert int(M["w_count"][i][2]) == int(r[1]["w_count"][0][2])

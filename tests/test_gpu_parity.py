@@ -58,6 +58,10 @@ def int_mismatches(OA, G):
         bad.append("pairs")
     if int(OA["w_island"][0][3]) != int(G["w_island"][0][3]):
         bad.append("position iterations used")
+    if int(OA["w_joint"][0][0]) > 0:             # scenes with joints: limit states, island joint lists
+        bad += harness.diff_state(OA, G, fields=["j_def"])
+        if harness.oracle_island_joints(OA) != harness.oracle_island_joints(G):
+            bad.append("island joints")
     nc = int(OA["w_count"][0][2])
     if nc == int(G["w_count"][0][2]):
         cnt = (OA["c_mtype"][0][:nc] >> 8) & 0xff
@@ -92,7 +96,7 @@ def _group_kernel_cases():
 # measured maxima on B200 (profiles/r2_parity_report.json: 7.6e-13, 0, 4.5e-10, 5.3e-8, 4.2e-9, 5.7e-7) times 10-20.
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
 EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5,
-             "bullets": 1e-5, "sensors": 1e-5}
+             "bullets": 1e-5, "sensors": 1e-5, "joints": 1e-5, "bridge": 1e-6}
 # Continuous collision on (World.solve_toi; measured by tools/ccd_parity_probe.py on B200, profiles/r2_ccd_parity.json): the
 # TOI sub-steps amplify the same one-ulp libm differences further.  Free-running, seven of the eight cases keep the oracle's
 # integer outputs for their whole length (worst float difference: pyramid landing 5.2e-13, features 1.4e-9, bullets 4.5e-9 /
@@ -114,6 +118,9 @@ def float_diffs(OA, G):
         if k in ("b_pos", "b_vel"):
             x, y = x[:, :3], y[:, :3]            # sleep timer / torque ride in the fourth lane
         out[k] = float(np.abs(x - y.astype(np.float64)).max()) if x.size else 0.0
+    if int(OA["w_joint"][0][0]) > 0:             # accumulated joint impulses (N s)
+        x, y = harness.used_view(OA, "j_imp"), harness.used_view(G, "j_imp")
+        out["j_imp"] = float(np.abs(x - y.astype(np.float64)).max())
     return out
 
 
@@ -128,7 +135,7 @@ def test_p_exact_fp64_free_running(case, group_kernel, parity_report):
     A, caps = arrays_from_golden(g)
     bw = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
     orc = oracle.Oracle(A, 0)
-    worst = {k: 0.0 for k in EXACT_FIELDS}
+    worst = {k: 0.0 for k in EXACT_FIELDS + ["j_imp"]}
     for s in range(steps):
         orc.step(dt, vi, pi)
         assert bytes(g["digest"][s]) == gen_golden.state_digest(A)          # the checker itself is on the golden path
@@ -147,7 +154,10 @@ CCD_CASES = ["bullets_w0", "bullets_w1", "bullets_w2", "hello_ccd_w0", "pyramid_
              "mixed_ccd_w1", "sensors_ccd_w2"]
 
 
-@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0", "sensors_w0"] + CCD_CASES)
+JOINT_CASES = ["joints_w0", "joints_w1", "joints_ccd_w2", "bridge_w1"]
+
+
+@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0", "sensors_w0"] + CCD_CASES + JOINT_CASES)
 def test_p_exact_fp64_one_step(case, parity_report):
     """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
     1e-11 in every float field at every k (measured: 1.5e-12) -- the free-running differences of the swaying and tumbling
@@ -160,7 +170,7 @@ def test_p_exact_fp64_one_step(case, parity_report):
     orc = oracle.Oracle(A, 0)
     bw = b2.BatchedWorld({k: v.copy() for k, v in A.items()}, caps, real="f64")
     names = [k for k in schema.FIELD_NAMES if not k.startswith("s_")]
-    inv, worst, sweep_ties = 0.0, {k: 0.0 for k in EXACT_FIELDS}, []
+    inv, worst, sweep_ties = 0.0, {k: 0.0 for k in EXACT_FIELDS + ["j_imp"]}, []
     for s in range(steps):
         bw.upload({k: A[k] for k in names})
         bw.inv_dt0 = inv
@@ -169,10 +179,10 @@ def test_p_exact_fp64_one_step(case, parity_report):
         G = bw.download()
         assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
         d = float_diffs(A, G)
-        if case in CCD_CASES and max(d.values()) > 1e-11:
+        if (case in CCD_CASES or case == "joints_ccd_w2") and max(d.values()) > 1e-11:
             # the TOI position loop's knife-edge exit test (P_STEP_BOUNDS below): one sweep more or less, 0.0075 * 0.25^k m
             sweep_ties.append((s, max(d.values())))
-            assert max(v for k, v in d.items() if k not in ("b_vel", "c_imp")) <= 2.5e-3 and d["b_vel"] <= 0.05, \
+            assert max(v for k, v in d.items() if k not in ("b_vel", "c_imp", "j_imp")) <= 2.5e-3 and d["b_vel"] <= 0.05, \
                 "one-step difference %s at step %d" % (d, s)
         else:
             for k, v in d.items():

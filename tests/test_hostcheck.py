@@ -24,7 +24,12 @@ CCD_CASES = [("bullets", 0, 1 / 60, 8, 3, 300, {}), ("bullets", 2, 1 / 30, 10, 4
              ("sensors", 0, 1 / 60, 8, 3, 250, {}), ("sensors", 2, 1 / 60, 8, 3, 250, CCD)]
 
 
-@pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES)
+# joints in the island solver: revolute (limits, motor), distance (rigid, soft), weld; with and without CCD
+JOINT_CASES = [("joints", 0, 1 / 60, 8, 3, 400, {}), ("joints", 1, 1 / 60, 10, 4, 200, {}), ("bridge", 1, 1 / 60, 8, 3, 200, {}),
+               ("joints", 2, 1 / 60, 8, 3, 200, CCD)]
+
+
+@pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES + JOINT_CASES)
 def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps, kw):
     mw, OA, caps = harness.facade_arrays(scene, world, **kw)
     HA = {k: v.copy() for k, v in OA.items()}
@@ -38,6 +43,10 @@ def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps, 
         assert harness.diff_state(OA, HA, fields=INT_FIELDS) == [], "step %d" % s
         assert harness.oracle_islands(OA) == harness.oracle_islands(HA), "islands, step %d" % s
         assert harness.oracle_pairs(OA) == harness.oracle_pairs(HA), "pairs, step %d" % s
+        if scene in ("joints", "bridge"):
+            assert harness.diff_state(OA, HA, fields=["j_def"]) == [], "joint limit states, step %d" % s
+            assert harness.oracle_island_joints(OA) == harness.oracle_island_joints(HA), "island joints, step %d" % s
+            assert np.array_equal(harness.used_view(OA, "j_imp"), harness.used_view(HA, "j_imp")), "joint impulses, step %d" % s
         # BITWISE: compiled for the host the device source performs the oracle's floating-point operations one for one
         # (squares the reference writes `x ** 2` go through libm's pow on both sides, b2b_math.cuh sq_r; glibc sin / cos on
         # both sides), so every float of the state is identical after every step

@@ -25,7 +25,7 @@ def test_oracle_replays_reference_trajectory(case):
     caps = schema.Caps(*[int(x) for x in g["caps"]])
     mw, A, _ = harness.facade_arrays(scene, world, caps=caps, n_shapes=int(g["init_s_meta"].shape[0]), **golden_scene_kw(g))
     # facade-built initial state == reference-built initial state (bitwise)
-    for name in gen_golden.INIT_FIELDS:
+    for name in gen_golden.INIT_FIELDS + [f for f in gen_golden.JOINT_INIT_FIELDS if "init_" + f in g.files]:
         ref = g["init_" + name]
         mine = harness.used_view(A, name) if not name.startswith("s_") else A[name][:ref.shape[0]]
         assert np.array_equal(np.atleast_1d(np.ascontiguousarray(mine)).view(np.uint8),
@@ -36,7 +36,7 @@ def test_oracle_replays_reference_trajectory(case):
         assert bytes(g["digest"][s]) == gen_golden.state_digest(A), "state digest differs at step %d" % s
         assert bytes(g["ihash"][s]) == gen_golden.int_hash(A), "integer outputs differ at step %d" % s
         assert g["ints"][s].tolist() == gen_golden.int_summary(A), "integer summary differs at step %d" % s
-        for name in gen_golden.CK_FIELDS:
+        for name in gen_golden.CK_FIELDS + gen_golden.JOINT_CK_FIELDS:
             key = "ck%d_%s" % (s + 1, name)
             if key in g.files:
                 got = np.atleast_1d(np.ascontiguousarray(harness.used_view(A, name)))
