@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path, on the host cores
     python bench.py --scene {vertical_stack,mixed,deep_stacks,hello}   # the other BASELINE.json configurations
+    python bench.py --scene bridge                                     # joints in the island solver
 
 Workload (config.workload): the pyramid-20 scene of examples/pyramid-bench.py (210 dynamic boxes on an edge
 ground), step(1/60, 8, 3), CCD off, `--worlds` independent worlds PER GPU (131,072 by default, i.e. 1,048,576
@@ -51,6 +52,9 @@ def _scene_table():
                       per_world_shapes=True),
         "deep_stacks": dict(what="10 columns x 20 boxes (SURVEY 8d config 5)", config=5, caps=C(201, 201, 1024, npair=2560), dt=DT, dt_text="1/60", vi=8,
                             pi=3, n_dyn=200, worlds=32768, distinct=2048),
+        # not a BASELINE config: the joint hooks of the island solver, 30 planks on 31 revolute joints under 8 loose bodies
+        "bridge": dict(what="plank bridge of 31 revolute joints under 8 loose bodies (testbed/bridge.py style; SURVEY 8f #3)", config=10,
+                       caps=C(39, 39, 220, nj=31), dt=DT, dt_text="1/60", vi=8, pi=3, n_dyn=38, worlds=131072, distinct=2048),
     }
 
 
@@ -63,7 +67,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scene", default="pyramid", choices=["pyramid", "vertical_stack", "mixed", "deep_stacks", "hello"],
+    ap.add_argument("--scene", default="pyramid", choices=["pyramid", "vertical_stack", "mixed", "deep_stacks", "hello", "bridge"],
                     help="BASELINE.json configuration (default: the headline pyramid batch)")
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (0: the configuration's own size, 131,072 for the pyramid)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct jittered worlds settled, then tiled (0: per scene)")

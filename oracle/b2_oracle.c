@@ -1094,6 +1094,7 @@ static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
 #define J_REVOLUTE 1
 #define J_DISTANCE 2
 #define J_WELD     3
+#define J_PRISMATIC 4
 #define JF_COLLIDE 0x1
 #define JF_LIMIT   0x2
 #define JF_MOTOR   0x4
@@ -1233,8 +1234,56 @@ static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm
             wb += ib * (vcross(rb, Pv) + imp[2]);
         } else imp[0] = imp[1] = imp[2] = 0.0;
     }
+    else if (type == J_PRISMATIC) {                                                  /* prismatic.py:232-335 */
+        v2 d = vsub(vsub(vadd(cb, rb), ca), ra);
+        v2 lx = V(par[9], par[10]), ly = scross(1.0, lx);
+        v2 axis = rot_mul(&qa, lx);
+        double a1 = vcross(vadd(d, ra), axis), a2 = vcross(rb, axis);
+        double motor_mass = ma + mb + ia * sq(a1) + ib * sq(a2);
+        if (motor_mass > 0.0) motor_mass = 1.0 / motor_mass;
+        v2 perp = rot_mul(&qa, ly);
+        double s1 = vcross(vadd(d, ra), perp), s2 = vcross(rb, perp);
+        double k11 = ma + mb + ia * sq(s1) + ib * sq(s2);
+        double k12 = ia * s1 + ib * s2;
+        double k13 = ia * s1 * a1 + ib * s2 * a2;
+        double k22 = ia + ib;
+        if (k22 == 0.0) k22 = 1.0;
+        double k23 = ia * a1 + ib * a2;
+        double k33 = ma + mb + ia * sq(a1) + ib * sq(a2);
+        tmp[4] = axis.x; tmp[5] = axis.y; tmp[6] = perp.x; tmp[7] = perp.y; tmp[8] = s1; tmp[9] = s2; tmp[10] = a1; tmp[11] = a2;
+        tmp[12] = motor_mass; tmp[13] = k11; tmp[14] = k12; tmp[15] = k13; tmp[16] = k22; tmp[17] = k23; tmp[18] = k33;
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        if (flags & JF_LIMIT) {
+            double joint_translation = vdot(axis, d);
+            if (fabs(par[6] - par[5]) < (2.0 * LINEAR_SLOP)) ls = LS_EQUAL;
+            else if (joint_translation <= par[5]) {
+                if (ls != LS_LOWER) { ls = LS_LOWER; imp[2] = imp[2] - imp[2]; }
+            } else if (joint_translation >= par[6]) {
+                if (ls != LS_UPPER) { ls = LS_UPPER; imp[2] = imp[2] - imp[2]; }
+            } else { ls = LS_INACTIVE; imp[2] = imp[2] - imp[2]; }
+        } else { ls = LS_INACTIVE; imp[2] = imp[2] - imp[2]; }
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (!(flags & JF_MOTOR)) imp[3] = 0.0;
+        if (warm) {
+            imp[0] = dt_ratio * imp[0]; imp[1] = dt_ratio * imp[1]; imp[2] = dt_ratio * imp[2];
+            imp[3] *= dt_ratio;
+            double ix = imp[0], iy = imp[1], iz = imp[2], mi = imp[3];
+            v2 Pv = vadd(vscale(ix, perp), vscale(mi + iz, axis));
+            double L1 = ix * s1 + iy + (mi + iz) * a1;
+            double L2 = ix * s2 + iy + (mi + iz) * a2;
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * L1;
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * L2;
+        } else { imp[0] = imp[1] = imp[2] = 0.0; imp[3] = 0.0; }
+    }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
+}
+
+static inline m33 m33_sym(const double* k)     /* Mat33((k11, k12, k13), (k12, k22, k23), (k13, k23, k33)) */
+{
+    m33 m; m.c1 = V3(k[0], k[1], k[2]); m.c2 = V3(k[1], k[3], k[4]); m.c3 = V3(k[2], k[4], k[5]); return m;
 }
 
 /* _solve_velocity_constraints: revolute.py:302-378, distance.py:252-275, weld.py:171-199 */
@@ -1317,6 +1366,55 @@ static void joint_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
         wa -= ia * (vcross(ra, Pv) + impulse.z);
         vb = vadd(vb, vscale(mb, Pv));
         wb += ib * (vcross(rb, Pv) + impulse.z);
+    }
+    else if (type == J_PRISMATIC) {                                                  /* prismatic.py:337-419 */
+        v2 axis = V(tmp[4], tmp[5]), perp = V(tmp[6], tmp[7]);
+        double s1 = tmp[8], s2 = tmp[9], a1 = tmp[10], a2 = tmp[11];
+        m33 m = m33_sym(tmp + 13);
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        if ((flags & JF_MOTOR) && ls != LS_EQUAL) {
+            double Cdot = vdot(axis, vsub(vb, va)) + a2 * wb - a1 * wa;
+            double impulse = tmp[12] * (par[8] - Cdot);
+            double old_impulse = imp[3];
+            double max_impulse = dt * par[7];
+            imp[3] = pyclamp(imp[3] + impulse, -max_impulse, max_impulse);
+            impulse = imp[3] - old_impulse;
+            v2 Pv = vscale(impulse, axis);
+            double L1 = impulse * a1, L2 = impulse * a2;
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * L1;
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * L2;
+        }
+        v2 Cdot1 = V(vdot(perp, vsub(vb, va)) + s2 * wb - s1 * wa, wb - wa);
+        v2 Pv; double L1, L2;
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE) {
+            double Cdot2 = vdot(axis, vsub(vb, va)) + a2 * wb - a1 * wa;
+            v3 old_impulse = V3(imp[0], imp[1], imp[2]);
+            v3 df = m33_solve3(&m, v3neg(V3(Cdot1.x, Cdot1.y, Cdot2)));
+            v3 cur = v3add(old_impulse, df);
+            double iz;
+            if (ls == LS_LOWER) iz = PYMAX(cur.z, 0.0);
+            else if (ls == LS_UPPER) iz = PYMIN(cur.z, 0.0);
+            else iz = cur.z;
+            v2 b = vsub(vneg(Cdot1), vscale(cur.z - old_impulse.z, V(m.c3.x, m.c3.y)));
+            v2 f2r = vadd(m33_solve2(&m, b), V(old_impulse.x, old_impulse.y));
+            imp[0] = f2r.x; imp[1] = f2r.y; imp[2] = iz;
+            df = V3(f2r.x - old_impulse.x, f2r.y - old_impulse.y, iz - old_impulse.z);
+            Pv = vadd(vscale(df.x, perp), vscale(df.z, axis));
+            L1 = df.x * s1 + df.y + df.z * a1;
+            L2 = df.x * s2 + df.y + df.z * a2;
+        } else {
+            v2 df = m33_solve2(&m, vneg(Cdot1));
+            imp[0] += df.x; imp[1] += df.y; imp[2] += 0.0;
+            Pv = vscale(df.x, perp);
+            L1 = df.x * s1 + df.y;
+            L2 = df.x * s2 + df.y;
+        }
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * L1;
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * L2;
     }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
@@ -1410,6 +1508,65 @@ static int joint_solve_position(orc_world* w, int k, pos_t* P)
         cb = vadd(cb, vscale(mb, Pv));
         ab += ib * (vcross(rb, Pv) + impulse.z);
         ok = (position_error <= LINEAR_SLOP) && (angular_error <= ANGULAR_SLOP);
+    }
+    else if (type == J_PRISMATIC) {                                                  /* prismatic.py:421-513 */
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 d = vsub(vsub(vadd(cb, rb), ca), ra);
+        v2 lx = V(par[9], par[10]), ly = scross(1.0, lx);
+        v2 axis = rot_mul(&qa, lx);
+        double a1 = vcross(vadd(d, ra), axis), a2 = vcross(rb, axis);
+        v2 perp = rot_mul(&qa, ly);
+        double s1 = vcross(vadd(d, ra), perp), s2 = vcross(rb, perp);
+        v2 C1 = V(vdot(perp, d), ab - aa - par[4]);
+        double linear_error = fabs(C1.x), angular_error = fabs(C1.y);
+        int active = 0;
+        double C2 = 0.0;
+        if (flags & JF_LIMIT) {
+            double translation = vdot(axis, d);
+            if (fabs(par[6] - par[5]) < 2.0 * LINEAR_SLOP) {
+                C2 = pyclamp(translation, -MAX_LIN_CORR, MAX_LIN_CORR);
+                linear_error = PYMAX(linear_error, translation);
+                active = 1;
+            } else if (translation <= par[5]) {
+                C2 = pyclamp(translation - par[5] + LINEAR_SLOP, -MAX_LIN_CORR, 0.0);
+                linear_error = PYMAX(linear_error, par[5] - translation);
+                active = 1;
+            } else if (translation >= par[6]) {
+                C2 = pyclamp(translation - par[6] - LINEAR_SLOP, 0.0, MAX_LIN_CORR);
+                linear_error = PYMAX(linear_error, translation - par[6]);
+                active = 1;
+            }
+        }
+        v3 impulse;
+        if (active) {
+            double k[6];
+            k[0] = ma + mb + ia * sq(s1) + ib * sq(s2);
+            k[1] = ia * s1 + ib * s2;
+            k[2] = ia * s1 * a1 + ib * s2 * a2;
+            k[3] = ia + ib;
+            if (k[3] == 0.0) k[3] = 1.0;
+            k[4] = ia * a1 + ib * a2;
+            k[5] = ma + mb + ia * sq(a1) + ib * sq(a2);
+            m33 m = m33_sym(k);
+            impulse = m33_solve3(&m, v3neg(V3(C1.x, C1.y, C2)));
+        } else {
+            double k11 = ma + mb + ia * s1 * s1 + ib * s2 * s2;
+            double k12 = ia * s1 + ib * s2;
+            double k22 = ia + ib;
+            if (k22 == 0.0) k22 = 1.0;
+            m33 m; m.c1 = V3(k11, k12, 0.0); m.c2 = V3(k12, k22, 0.0); m.c3 = V3(0.0, 0.0, 0.0);
+            v2 impulse1 = m33_solve2(&m, vneg(C1));
+            impulse = V3(impulse1.x, impulse1.y, 0.0);
+        }
+        v2 Pv = vadd(vscale(impulse.x, perp), vscale(impulse.z, axis));
+        double L1 = impulse.x * s1 + impulse.y + impulse.z * a1;
+        double L2 = impulse.x * s2 + impulse.y + impulse.z * a2;
+        ca = vsub(ca, vscale(ma, Pv));
+        cb = vadd(cb, vscale(mb, Pv));
+        aa -= ia * L1;
+        ab += ib * L2;
+        ok = (linear_error <= LINEAR_SLOP) && (angular_error <= ANGULAR_SLOP);
     }
     P[ia_].c = ca; P[ia_].a = aa;
     P[ib_].c = cb; P[ib_].a = ab;

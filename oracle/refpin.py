@@ -208,6 +208,11 @@ def extract_joints(world, A, w, bidx, schema):
             t = schema.JOINT_WELD
             par += [j._reference_angle]
             imp = (j._impulse.x, j._impulse.y, j._impulse.z, 0.0)
+        elif isinstance(j, _j.PrismaticJoint):
+            t = schema.JOINT_PRISMATIC
+            par += [j._reference_angle, j._lower_limit, j._upper_limit, j._max_motor_force, j._motor_speed,
+                    j._local_x_axis.x, j._local_x_axis.y]
+            imp = (j._impulse.x, j._impulse.y, j._impulse.z, j._motor_impulse)
         else:
             raise NotImplementedError(type(j))
         A["j_def"][w, k] = (t, bidx[id(j._body_a)], bidx[id(j._body_b)], flags)

@@ -432,6 +432,9 @@ class BatchedWorld(object):
                 j._read_back(J["j_def"][0, k, 3], J["j_imp"][0, k])
                 if j._type == schema.JOINT_DISTANCE:
                     j._u = (float(J["j_tmp"][0, k, 4]), float(J["j_tmp"][0, k, 5]))
+                elif j._type == schema.JOINT_PRISMATIC:
+                    t = J["j_tmp"][0, k]
+                    j._axis_perp = ((float(t[4]), float(t[5])), (float(t[6]), float(t[7])))
 
     def contact_views(self, world, w=0):
         from .world import ContactView

@@ -1,7 +1,7 @@
 // b2b_joints.inl -- joints of the island solver, included INSIDE world_step<real> (b2b_step.cuh).
 //
-// RevoluteJoint (pypybox2d/joints/revolute.py:208-453), DistanceJoint (joints/distance.py:155-311) and WeldJoint
-// (joints/weld.py:106-257) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
+// RevoluteJoint (pypybox2d/joints/revolute.py:208-453), DistanceJoint (joints/distance.py:155-311), WeldJoint
+// (joints/weld.py:106-257) and PrismaticJoint (joints/prismatic.py:232-513) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
 // fp64 host build of this file is bit-identical to the oracle, which is pinned bit-identical to the live reference.
 //
 // Island.solve visits an island's joints one after the other, before the contacts in every velocity iteration and after them in
@@ -13,9 +13,10 @@
 //
 // Rows (layout: pypybox2d_b200/joints.py): j_def = (type, body_a, body_b, flags | _limit_state << 8), j_par[12], j_imp = (_impulse
 // x, y, z, _motor_impulse), j_tmp[20] = what _init_velocity_constraints leaves for the sweeps (ra, rb, then per type: the 3x3 mass
-// matrix by columns and the motor mass; or u, mass, gamma, bias).
+// matrix by columns and the motor mass; or u, mass, gamma, bias; prismatic: axis, perp, s1, s2, a1, a2, motor mass and the six
+// distinct entries of its symmetric K).
 
-enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3 };
+enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4 };
 enum { JF_COLLIDE = 0x1, JF_LIMIT = 0x2, JF_MOTOR = 0x4, JF_ISLAND = 0x8, JF_LS_SHIFT = 8 };
 enum { LS_INACTIVE = 0, LS_LOWER = 1, LS_UPPER = 2, LS_EQUAL = 3 };               // joints/joint.py:36
 enum { JOINT_PAR = 12, JOINT_TMP = 20 };
@@ -46,6 +47,10 @@ B2B_D static XF rot_of(real a)                                                  
     return xf_make<real>(mk<real>(real(0), real(0)), c, s);
 }
 B2B_D static M33 m33_load(const real* t) { M33 m; m.c1 = mk3(t[0], t[1], t[2]); m.c2 = mk3(t[3], t[4], t[5]); m.c3 = mk3(t[6], t[7], t[8]); return m; }
+B2B_D static M33 m33_sym(const real* k)      // Mat33((k11, k12, k13), (k12, k22, k23), (k13, k23, k33))
+{
+    M33 m; m.c1 = mk3(k[0], k[1], k[2]); m.c2 = mk3(k[1], k[3], k[4]); m.c3 = mk3(k[2], k[4], k[5]); return m;
+}
 B2B_D static void m33_store(real* t, const M33& m)
 {
     t[0] = m.c1.x; t[1] = m.c1.y; t[2] = m.c1.z; t[3] = m.c2.x; t[4] = m.c2.y; t[5] = m.c2.z; t[6] = m.c3.x; t[7] = m.c3.y; t[8] = m.c3.z;
@@ -160,6 +165,50 @@ B2B_D void joint_init(int k, real dt, real dt_ratio, bool warm)
         } else i0 = i1 = i2 = real(0);
         imp[0] = i0; imp[1] = i1; imp[2] = i2;
     }
+    else if (type == JOINT_PRISMATIC) {                                              // prismatic.py:232-335
+        const V2 d = cb + rb - ca - ra;
+        const V2 lx = mk<real>(par[9], par[10]), ly = cross_sv(real(1), lx);
+        const V2 axis = rot_mul(qa, lx);
+        const real a1 = cross(d + ra, axis), a2 = cross(rb, axis);
+        real motor_mass = ma + mb + ia * sq_r(a1) + ib * sq_r(a2);
+        if (motor_mass > real(0)) motor_mass = real(1) / motor_mass;
+        const V2 perp = rot_mul(qa, ly);
+        const real s1 = cross(d + ra, perp), s2 = cross(rb, perp);
+        const real k11 = ma + mb + ia * sq_r(s1) + ib * sq_r(s2);
+        const real k12 = ia * s1 + ib * s2;
+        const real k13 = ia * s1 * a1 + ib * s2 * a2;
+        real k22 = ia + ib;
+        if (k22 == real(0)) k22 = real(1);
+        const real k23 = ia * a1 + ib * a2;
+        const real k33 = ma + mb + ia * sq_r(a1) + ib * sq_r(a2);
+        tmp[4] = axis.x; tmp[5] = axis.y; tmp[6] = perp.x; tmp[7] = perp.y; tmp[8] = s1; tmp[9] = s2; tmp[10] = a1; tmp[11] = a2;
+        tmp[12] = motor_mass; tmp[13] = k11; tmp[14] = k12; tmp[15] = k13; tmp[16] = k22; tmp[17] = k23; tmp[18] = k33;
+        int ls = (flags >> JF_LS_SHIFT) & 3;
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2], im = imp[3];
+        if (flags & JF_LIMIT) {
+            const real joint_translation = dot(axis, d);
+            if (abs_r(par[6] - par[5]) < (real(2) * K<real>::linear_slop)) ls = LS_EQUAL;
+            else if (joint_translation <= par[5]) {
+                if (ls != LS_LOWER) { ls = LS_LOWER; i2 = i2 - i2; }
+            } else if (joint_translation >= par[6]) {
+                if (ls != LS_UPPER) { ls = LS_UPPER; i2 = i2 - i2; }
+            } else { ls = LS_INACTIVE; i2 = i2 - i2; }
+        } else { ls = LS_INACTIVE; i2 = i2 - i2; }
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (!(flags & JF_MOTOR)) im = real(0);
+        if (warm) {
+            i0 = dt_ratio * i0; i1 = dt_ratio * i1; i2 = dt_ratio * i2;
+            im = im * dt_ratio;
+            const V2 P = i0 * perp + (im + i2) * axis;
+            const real L1 = i0 * s1 + i1 + (im + i2) * a1;
+            const real L2 = i0 * s2 + i1 + (im + i2) * a2;
+            va = va - ma * P;
+            wa = wa - ia * L1;
+            vb = vb + mb * P;
+            wb = wb + ib * L2;
+        } else { i0 = i1 = i2 = real(0); im = real(0); }
+        imp[0] = i0; imp[1] = i1; imp[2] = i2; imp[3] = im;
+    }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
 }
@@ -248,6 +297,57 @@ B2B_D void joint_solve_velocity(int k, real dt)
         wa = wa - ia * (cross(ra, P) + impulse.z);
         vb = vb + mb * P;
         wb = wb + ib * (cross(rb, P) + impulse.z);
+    }
+    else if (type == JOINT_PRISMATIC) {                                              // prismatic.py:337-419
+        const V2 axis = mk<real>(tmp[4], tmp[5]), perp = mk<real>(tmp[6], tmp[7]);
+        const real s1 = tmp[8], s2 = tmp[9], a1 = tmp[10], a2 = tmp[11];
+        const M33 m = m33_sym(tmp + 13);
+        const int ls = (flags >> JF_LS_SHIFT) & 3;
+        if ((flags & JF_MOTOR) && ls != LS_EQUAL) {
+            const real Cdot = dot(axis, vb - va) + a2 * wb - a1 * wa;
+            real impulse = tmp[12] * (par[8] - Cdot);
+            const real old_impulse = imp[3];
+            const real max_impulse = dt * par[7];
+            const real im = clamp_r(old_impulse + impulse, -max_impulse, max_impulse);
+            imp[3] = im;
+            impulse = im - old_impulse;
+            const V2 P = impulse * axis;
+            const real L1 = impulse * a1, L2 = impulse * a2;
+            va = va - ma * P;
+            wa = wa - ia * L1;
+            vb = vb + mb * P;
+            wb = wb + ib * L2;
+        }
+        const V2 Cdot1 = mk<real>(dot(perp, vb - va) + s2 * wb - s1 * wa, wb - wa);
+        V2 P;
+        real L1, L2;
+        if ((flags & JF_LIMIT) && ls != LS_INACTIVE) {
+            const real Cdot2 = dot(axis, vb - va) + a2 * wb - a1 * wa;
+            const V3 old_impulse = mk3(imp[0], imp[1], imp[2]);
+            V3 df = solve33(m, neg3(mk3(Cdot1.x, Cdot1.y, Cdot2)));
+            const real cz = old_impulse.z + df.z;
+            real iz;
+            if (ls == LS_LOWER) iz = pymax(cz, real(0));
+            else if (ls == LS_UPPER) iz = pymin(cz, real(0));
+            else iz = cz;
+            const V2 b = (-Cdot1) - (cz - old_impulse.z) * mk<real>(m.c3.x, m.c3.y);
+            const V2 f2r = solve22(m, b) + mk<real>(old_impulse.x, old_impulse.y);
+            imp[0] = f2r.x; imp[1] = f2r.y; imp[2] = iz;
+            df = mk3(f2r.x - old_impulse.x, f2r.y - old_impulse.y, iz - old_impulse.z);
+            P = df.x * perp + df.z * axis;
+            L1 = df.x * s1 + df.y + df.z * a1;
+            L2 = df.x * s2 + df.y + df.z * a2;
+        } else {
+            const V2 df = solve22(m, -Cdot1);
+            imp[0] = imp[0] + df.x; imp[1] = imp[1] + df.y; imp[2] = imp[2] + real(0);
+            P = df.x * perp;
+            L1 = df.x * s1 + df.y;
+            L2 = df.x * s2 + df.y;
+        }
+        va = va - ma * P;
+        wa = wa - ia * L1;
+        vb = vb + mb * P;
+        wb = wb + ib * L2;
     }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
@@ -344,6 +444,65 @@ B2B_D bool joint_solve_position(int k)
         cb = cb + mb * P;
         ab = ab + ib * (cross(rb, P) + impulse.z);
         ok = (position_error <= K<real>::linear_slop) && (angular_error <= K<real>::angular_slop);
+    }
+    else if (type == JOINT_PRISMATIC) {                                              // prismatic.py:421-513
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 d = cb + rb - ca - ra;
+        const V2 lx = mk<real>(par[9], par[10]), ly = cross_sv(real(1), lx);
+        const V2 axis = rot_mul(qa, lx);
+        const real a1 = cross(d + ra, axis), a2 = cross(rb, axis);
+        const V2 perp = rot_mul(qa, ly);
+        const real s1 = cross(d + ra, perp), s2 = cross(rb, perp);
+        const V2 C1 = mk<real>(dot(perp, d), ab - aa - par[4]);
+        real linear_error = abs_r(C1.x);
+        const real angular_error = abs_r(C1.y);
+        bool active = false;
+        real C2 = real(0);
+        if (flags & JF_LIMIT) {
+            const real translation = dot(axis, d);
+            if (abs_r(par[6] - par[5]) < real(2) * K<real>::linear_slop) {
+                C2 = clamp_r(translation, -K<real>::max_linear_correction, K<real>::max_linear_correction);
+                linear_error = pymax(linear_error, translation);
+                active = true;
+            } else if (translation <= par[5]) {
+                C2 = clamp_r(translation - par[5] + K<real>::linear_slop, -K<real>::max_linear_correction, real(0));
+                linear_error = pymax(linear_error, par[5] - translation);
+                active = true;
+            } else if (translation >= par[6]) {
+                C2 = clamp_r(translation - par[6] - K<real>::linear_slop, real(0), K<real>::max_linear_correction);
+                linear_error = pymax(linear_error, translation - par[6]);
+                active = true;
+            }
+        }
+        V3 impulse;
+        if (active) {
+            real k[6];
+            k[0] = ma + mb + ia * sq_r(s1) + ib * sq_r(s2);
+            k[1] = ia * s1 + ib * s2;
+            k[2] = ia * s1 * a1 + ib * s2 * a2;
+            k[3] = ia + ib;
+            if (k[3] == real(0)) k[3] = real(1);
+            k[4] = ia * a1 + ib * a2;
+            k[5] = ma + mb + ia * sq_r(a1) + ib * sq_r(a2);
+            impulse = solve33(m33_sym(k), neg3(mk3(C1.x, C1.y, C2)));
+        } else {
+            const real k11 = ma + mb + ia * s1 * s1 + ib * s2 * s2;
+            const real k12 = ia * s1 + ib * s2;
+            real k22 = ia + ib;
+            if (k22 == real(0)) k22 = real(1);
+            M33 m; m.c1 = mk3(k11, k12, real(0)); m.c2 = mk3(k12, k22, real(0)); m.c3 = mk3(real(0), real(0), real(0));
+            const V2 impulse1 = solve22(m, -C1);
+            impulse = mk3(impulse1.x, impulse1.y, real(0));
+        }
+        const V2 P = impulse.x * perp + impulse.z * axis;
+        const real L1 = impulse.x * s1 + impulse.y + impulse.z * a1;
+        const real L2 = impulse.x * s2 + impulse.y + impulse.z * a2;
+        ca = ca - ma * P;
+        cb = cb + mb * P;
+        aa = aa - ia * L1;
+        ab = ab + ib * L2;
+        ok = (linear_error <= K<real>::linear_slop) && (angular_error <= K<real>::angular_slop);
     }
     state_set(ba, ca.x, ca.y, aa);
     state_set(bb, cb.x, cb.y, ab);

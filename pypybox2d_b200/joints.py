@@ -1,6 +1,7 @@
 """Joints of the island solver: the drop-in surface of `pypybox2d/joints/`.
 
-`RevoluteJoint` (`joints/revolute.py`), `DistanceJoint` (`joints/distance.py`) and `WeldJoint` (`joints/weld.py`) with the
+`RevoluteJoint` (`joints/revolute.py`), `DistanceJoint` (`joints/distance.py`), `WeldJoint` (`joints/weld.py`) and
+`PrismaticJoint` (`joints/prismatic.py`) with the
 reference's constructor keywords, read-backs and setters.  A joint object only holds its definition: one row of the device
 arrays `j_def` (type, bodies, flags), `j_par` (parameters, layout below) and `j_imp` (accumulated impulses, mirrored back
 after every step).  The constraint itself -- `_init_velocity_constraints`, `_solve_velocity_constraints`,
@@ -11,7 +12,8 @@ after every step).  The constraint itself -- `_init_velocity_constraints`, `_sol
   revolute    [4] reference_angle, [5] lower_angle, [6] upper_angle, [7] max_motor_torque, [8] motor_speed
   distance    [4] length, [5] frequency, [6] damping_ratio
   weld        [4] reference_angle
-The other joint types of the reference (prismatic, wheel, pulley, gear, rope, friction, mouse) raise NotImplementedError.
+  prismatic   [4] reference_angle, [5] lower_limit, [6] upper_limit, [7] max_motor_force, [8] motor_speed, [9:11] local_x_axis
+The other joint types of the reference (wheel, pulley, gear, rope, friction, mouse) raise NotImplementedError.
 """
 import math
 
@@ -309,14 +311,123 @@ class WeldJoint(Joint):
                 self._reference_angle]
 
 
+class PrismaticJoint(Joint):
+    """joints/prismatic.py:33-513"""
+    _type = schema.JOINT_PRISMATIC
+
+    def __init__(self, body_a, body_b, anchor=(0, 0), axis=(0, 1), lower_limit=0.0, upper_limit=0.0, max_motor_force=0.0,
+                 max_motor_torque=0.0, motor_speed=0.0, reference_angle=None, limit_enabled=False, motor_enabled=False,
+                 collide_connected=False, local_anchor_a=None, local_anchor_b=None, local_x_axis=None):
+        if body_a is None or body_b is None:
+            raise ValueError('body_a and body_b must be set')
+        Joint.__init__(self, body_a, body_b, collide_connected)
+        self._local_anchor_a = Vec2(*local_anchor_a) if local_anchor_a is not None else body_a.get_local_point(anchor)
+        self._local_anchor_b = Vec2(*local_anchor_b) if local_anchor_b is not None else body_b.get_local_point(anchor)
+        self._reference_angle = float(reference_angle) if reference_angle is not None else body_b.angle - body_a.angle
+        self._local_x_axis = Vec2(*local_x_axis) if local_x_axis is not None else body_a.get_local_vector(axis)
+        self._lower_limit = float(lower_limit)
+        self._upper_limit = float(upper_limit)
+        self._max_motor_force = float(max_motor_force)
+        self._limit_enabled = bool(limit_enabled)
+        self._motor_enabled = bool(motor_enabled)
+        self._motor_speed = float(motor_speed)
+
+    def _par(self):
+        return [self._local_anchor_a.x, self._local_anchor_a.y, self._local_anchor_b.x, self._local_anchor_b.y,
+                self._reference_angle, self._lower_limit, self._upper_limit, self._max_motor_force, self._motor_speed,
+                self._local_x_axis.x, self._local_x_axis.y]
+
+    @property
+    def axis(self):
+        return self._body_a.get_world_vector(self._local_x_axis)
+
+    @property
+    def joint_translation(self):
+        d = self.anchor_b - self.anchor_a
+        return d.dot(self.axis)
+
+    @property
+    def limit_enabled(self):
+        return self._limit_enabled
+
+    @limit_enabled.setter
+    def limit_enabled(self, limit_enabled):
+        if limit_enabled != self._limit_enabled:
+            self._limit_enabled = bool(limit_enabled)
+            self._impulse3[2] = 0.0
+            self._changed()
+
+    @property
+    def lower_limit(self):
+        return self._lower_limit
+
+    @lower_limit.setter
+    def lower_limit(self, lower_limit):
+        if self._lower_limit != lower_limit:
+            self._impulse3[2] = 0.0
+            self._lower_limit = float(lower_limit)
+            self._changed()
+
+    @property
+    def upper_limit(self):
+        return self._upper_limit
+
+    @upper_limit.setter
+    def upper_limit(self, upper_limit):
+        if self._upper_limit != upper_limit:
+            self._impulse3[2] = 0.0
+            self._upper_limit = float(upper_limit)
+            self._changed()
+
+    @property
+    def motor_enabled(self):
+        return self._motor_enabled
+
+    @motor_enabled.setter
+    def motor_enabled(self, motor_enabled):
+        if motor_enabled != self._motor_enabled:
+            self._motor_enabled = bool(motor_enabled)
+            self._changed()
+
+    @property
+    def motor_speed(self):
+        return self._motor_speed
+
+    @motor_speed.setter
+    def motor_speed(self, speed):
+        self._motor_speed = float(speed)
+        self._changed()
+
+    @property
+    def max_motor_force(self):
+        return self._max_motor_force
+
+    @max_motor_force.setter
+    def max_motor_force(self, force):
+        self._max_motor_force = float(force)
+        self._changed()
+
+    def get_motor_force(self, inv_dt):
+        return inv_dt * self._motor_impulse
+
+    def get_reaction_torque(self, inv_dt):
+        return inv_dt * self._impulse3[1]
+
+    def get_reaction_force(self, inv_dt):
+        # prismatic.py:108-110: inv_dt * (impulse.x * perp + (motor_impulse + impulse.z) * axis); perp and axis are solver
+        # temporaries of the last step (device `j_tmp`)
+        ax, px = getattr(self, "_axis_perp", ((0.0, 0.0), (0.0, 0.0)))
+        k = self._motor_impulse + self._impulse3[2]
+        return Vec2(inv_dt * (self._impulse3[0] * px[0] + k * ax[0]), inv_dt * (self._impulse3[0] * px[1] + k * ax[1]))
+
+
 def _unsupported(name):
     def ctor(*args, **kwargs):
-        raise NotImplementedError("%s is not supported on the batched step path (built: RevoluteJoint, DistanceJoint, WeldJoint)" % name)
+        raise NotImplementedError("%s is not supported on the batched step path (built: RevoluteJoint, DistanceJoint, WeldJoint, PrismaticJoint)" % name)
     ctor.__name__ = name
     return ctor
 
 
-PrismaticJoint = _unsupported("PrismaticJoint")
 WheelJoint = _unsupported("WheelJoint")
 PulleyJoint = _unsupported("PulleyJoint")
 GearJoint = _unsupported("GearJoint")

@@ -309,8 +309,8 @@ def joints(b2, world=0, config=9, **world_kw):
     """What the joint hooks of Island.solve (island.py:107-113, 145-148) and of the island walk (world.py:548-572) read: a plank
     bridge of revolute joints between two ground anchors (testbed/bridge.py) with bodies dropped on it, a hanging chain, a
     motorised arm with angle limits, a door with equal limits, a flail on a rigid distance joint, a soft (frequency > 0)
-    distance spring, a welded cantilever, a joint with collide_connected=True, and a joint between two dynamic bodies that
-    start asleep."""
+    distance spring, a welded cantilever, a joint with collide_connected=True, prismatic joints (motorised lift with limits, slider
+    between two dynamic bodies, equal limits, lower stop) and a joint between two dynamic bodies that start asleep."""
     w = b2.World((0, -10), True, **_kw(world_kw))
     ground = w.create_static_body(shapes=b2.Edge((-40.0, 0.0), (40.0, 0.0)))
     n_free = 12
@@ -368,6 +368,21 @@ def joints(b2, world=0, config=9, **world_kw):
         body = w.create_dynamic_body(position=(20.5 + 1.0 * i, 6.0), fixtures=beam)
         w.create_weld_joint(prev, body, anchor=(20.0 + 1.0 * i, 6.0))
         prev = body
+    # prismatic joints: a motorised lift with limits that a box rides on, a free slider on a tilted axis between two dynamic
+    # bodies, a piston with equal limits (rigid) and a lower-limit stop
+    lift = w.create_dynamic_body(position=(-36.0, 2.0), fixtures=b2.Fixture(b2.Polygon(box=(1.0, 0.2)), density=2.0, friction=0.6))
+    w.create_prismatic_joint(ground, lift, anchor=(-36.0, 2.0), axis=(0.0, 1.0), lower_limit=-1.0, upper_limit=3.0,
+                             limit_enabled=True, motor_enabled=True, motor_speed=1.5, max_motor_force=2000.0)
+    w.create_dynamic_body(position=at(-36.0, 2.6), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=1.0, friction=0.6))
+    rail = w.create_dynamic_body(position=at(33.0, 3.0), angle=0.3, fixtures=b2.Fixture(b2.Polygon(box=(1.5, 0.15)), density=1.0, friction=0.3))
+    cart = w.create_dynamic_body(position=at(33.0, 3.6), angle=0.3, fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.3)), density=2.0, friction=0.3))
+    w.create_prismatic_joint(rail, cart, anchor=(33.0, 3.3), axis=(math.cos(0.3), math.sin(0.3)), lower_limit=-1.0, upper_limit=1.0,
+                             limit_enabled=True)
+    piston = w.create_dynamic_body(position=(37.0, 4.0), fixtures=b2.Fixture(b2.Circle(0.4), density=1.0, friction=0.3))
+    w.create_prismatic_joint(ground, piston, anchor=(37.0, 4.0), axis=(1.0, 0.0), lower_limit=0.0, upper_limit=0.0, limit_enabled=True)
+    drop = w.create_dynamic_body(position=(39.0, 6.0), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=1.0, friction=0.3))
+    w.create_prismatic_joint(ground, drop, anchor=(39.0, 6.0), axis=(0.0, 1.0), lower_limit=-2.0, upper_limit=0.5, limit_enabled=True,
+                             motor_enabled=True, motor_speed=0.0, max_motor_force=1.0)
     # two sleeping bodies joined by a revolute joint, woken when something lands on them
     sa = w.create_dynamic_body(position=(28.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))
     sb = w.create_dynamic_body(position=(29.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))

@@ -390,10 +390,14 @@ def test_world_with_joints_is_a_drop_in():
     world.destroy_joint(chain_joint)
     extra = world.create_dynamic_body(position=(4.0, 14.0), fixtures=b2.Fixture(b2.Circle(0.3), density=1.0))
     world.create_distance_joint(world.bodies[0], extra, anchor_a=(4.0, 16.0), anchor_b=(4.0, 14.0))
-    y_before = world.bodies[18].position.y
+    def gap(j):
+        pa, pb = j.anchor_a, j.anchor_b
+        return float(np.hypot(pa.x - pb.x, pa.y - pb.y))
+    assert gap(chain_joint) < 0.05 and all(gap(j) < 0.05 for j in world.joints[11:18])
     for i in range(60):
         world.step(1 / 60, 8, 3)
-    assert world.bodies[18].position.y < y_before - 1.0                          # the cut end of the chain falls
+    assert gap(chain_joint) > 0.5                                                # the cut end of the chain falls away
+    assert all(gap(j) < 0.05 for j in world.joints[11:18])                       # ... the joints that remain hold
     assert abs(extra.position.y - 14.0) < 0.05 and len(world.joints) == nj       # the new body hangs on its joint
 
 
