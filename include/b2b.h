@@ -100,7 +100,10 @@ int b2b_init_proxies(b2b_ctx* ctx, void* stream);
  * find_new_contacts contact_manager.py:102-158), and for the worlds whose w_flags carry WORLD_CONTINUOUS
  * (World(continuous_physics=True), the reference's default) World.solve_toi (world.py:594-821: time_of_impact toi.py:223-391
  * on shape_distance distance.py:419-561, Island.solve_toi island.py:181-243, solve_toi_position_constraints
- * contact.py:866-933), clear forces.
+ * contact.py:866-933), clear forces.  Batches created with a joint capacity (b2b_caps.nj > 0) also walk Body.joints in the island
+ * DFS (world.py:548-572) and run Joint._init_velocity_constraints / _solve_velocity_constraints / _solve_position_constraints of
+ * their revolute, distance, weld and prismatic joints inside Island.solve (island.py:107-113, 145-148; joints/revolute.py:208-453,
+ * distance.py:155-311, weld.py:106-257, prismatic.py:232-513), and Body._should_collide's joint test (body.py:920-926).
  * inv_dt0 is World._inv_dt0 before the first of the n_steps (0 for a fresh world); the first step
  * uses dt_ratio = inv_dt0 * dt, later ones (1/dt) * dt, both evaluated in double as world.py:323-328.
  * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */

@@ -56,19 +56,89 @@ B2B_D static void m33_store(real* t, const M33& m)
     t[0] = m.c1.x; t[1] = m.c1.y; t[2] = m.c1.z; t[3] = m.c2.x; t[4] = m.c2.y; t[5] = m.c2.z; t[6] = m.c3.x; t[7] = m.c3.y; t[8] = m.c3.z;
 }
 
+// One joint's rows in registers.  The lanes of a team fetch the rows of t_n consecutive island joints at once (one memory round
+// trip for t_n joints) and then take turns applying them to the shared body state in list order (joint_sweep below): the
+// dependent part of a joint visit is then shared-memory reads, arithmetic and shared-memory writes only.
+struct alignas(16) int4v { int32_t x, y, z, w; };
+struct jrow {
+    int k;
+    int32_t def[4];
+    real par[JOINT_PAR], imp[4], tmp[JOINT_TMP];
+    quad mqa, mqb, pa, pb;
+};
+enum { JFETCH_INIT = 0, JFETCH_VELOCITY = 1, JFETCH_POSITION = 2 };
+B2B_D void joint_fetch(int k, jrow& r, int what) const
+{
+    r.k = k;
+    const int4v d = *reinterpret_cast<const int4v*>(j_def + 4 * (size_t)k);
+    r.def[0] = d.x; r.def[1] = d.y; r.def[2] = d.z; r.def[3] = d.w;
+    const quad* par = reinterpret_cast<const quad*>(j_par + JOINT_PAR * (size_t)k);
+    const quad p0 = par[0], p1 = par[1], p2 = par[2];
+    r.par[0] = p0.x; r.par[1] = p0.y; r.par[2] = p0.z; r.par[3] = p0.w; r.par[4] = p1.x; r.par[5] = p1.y; r.par[6] = p1.z; r.par[7] = p1.w;
+    r.par[8] = p2.x; r.par[9] = p2.y; r.par[10] = p2.z; r.par[11] = p2.w;
+    if (what != JFETCH_POSITION) {
+        const quad q = ldq(j_imp + 4 * (size_t)k);
+        r.imp[0] = q.x; r.imp[1] = q.y; r.imp[2] = q.z; r.imp[3] = q.w;
+    }
+    if (what != JFETCH_INIT) {
+        const quad* t = reinterpret_cast<const quad*>(j_tmp + JOINT_TMP * (size_t)k);
+#pragma unroll
+        for (int i = 0; i < JOINT_TMP / 4; ++i) { const quad q = t[i]; r.tmp[4 * i] = q.x; r.tmp[4 * i + 1] = q.y; r.tmp[4 * i + 2] = q.z; r.tmp[4 * i + 3] = q.w; }
+    }
+    r.mqa = ldq(b_mass + 4 * (size_t)r.def[1]); r.mqb = ldq(b_mass + 4 * (size_t)r.def[2]);
+    if (what == JFETCH_INIT) { r.pa = ldq(b_pos + 4 * (size_t)r.def[1]); r.pb = ldq(b_pos + 4 * (size_t)r.def[2]); }
+}
+B2B_D void joint_store(const jrow& r, int what)
+{
+    if (what == JFETCH_POSITION) return;
+    stq(j_imp + 4 * (size_t)r.k, mkq(r.imp[0], r.imp[1], r.imp[2], r.imp[3]));
+    if (what == JFETCH_INIT) {
+        j_def[4 * (size_t)r.k + 3] = r.def[3];
+        quad* t = reinterpret_cast<quad*>(j_tmp + JOINT_TMP * (size_t)r.k);
+#pragma unroll
+        for (int i = 0; i < JOINT_TMP / 4; ++i) t[i] = mkq(r.tmp[4 * i], r.tmp[4 * i + 1], r.tmp[4 * i + 2], r.tmp[4 * i + 3]);
+    }
+}
+// One pass over the island's joints [j0, j1) of l_joint, in list order (island.py:107-113, 145-148); `apply` is called by the lane
+// whose turn it is with the joint's rows; returns on every lane the AND of the values apply returned (the position pass's
+// "joints_okay").  B2B_SYNC orders the lanes' accesses to the shared body state.
+template <class Apply> B2B_D int joint_sweep(int j0, int j1, int what, Apply apply)
+{
+    int all_ok = 1;
+    for (int k0 = j0; k0 < j1; k0 += t_n) {
+        jrow r;
+        const int mine = k0 + t_id;
+        if (mine < j1) joint_fetch(l_joint[mine], r, what);
+        const int n = (j1 - k0 < t_n) ? j1 - k0 : t_n;
+        for (int i = 0; i < n; ++i) {
+            if (t_id == i) {
+                if (!apply(r)) all_ok = 0;
+                joint_store(r, what);
+            }
+            B2B_SYNC();
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    for (int o = t_n >> 1; o > 0; o >>= 1) all_ok &= __shfl_xor_sync(t_mask, all_ok, o);
+#endif
+    return all_ok;
+}
+
 // _init_velocity_constraints (revolute.py:208-300, distance.py:155-250, weld.py:106-169).  Velocities: the team's shared state;
 // positions: b_pos (the sweeps before this step's integration -- the velocity kernel runs before integrate_position).
-B2B_D void joint_init(int k, real dt, real dt_ratio, bool warm)
+B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
 {
-    int32_t* def = j_def + 4 * (size_t)k;
-    const real* par = j_par + JOINT_PAR * (size_t)k;
-    real* imp = j_imp + 4 * (size_t)k;
-    real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    int32_t* def = r.def;
+    const real* par = r.par;
+    real* imp = r.imp;
+    real* tmp = r.tmp;
+#pragma unroll
+    for (int i = 0; i < JOINT_TMP; ++i) tmp[i] = real(0);
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
-    const quad mqa = ldq(b_mass + 4 * (size_t)ba), mqb = ldq(b_mass + 4 * (size_t)bb);
+    const quad mqa = r.mqa, mqb = r.mqb;
     const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
     const V2 lca = mk<real>(mqa.z, mqa.w), lcb = mk<real>(mqb.z, mqb.w);
-    const quad pa = ldq(b_pos + 4 * (size_t)ba), pb = ldq(b_pos + 4 * (size_t)bb);
+    const quad pa = r.pa, pb = r.pb;
     const V2 ca = mk<real>(pa.x, pa.y), cb = mk<real>(pb.x, pb.y);
     const real aa = pa.z, ab = pb.z;
     const quad sa = state_get(ba), sb = state_get(bb);
@@ -214,14 +284,14 @@ B2B_D void joint_init(int k, real dt, real dt_ratio, bool warm)
 }
 
 // _solve_velocity_constraints (revolute.py:302-378, distance.py:252-275, weld.py:171-199)
-B2B_D void joint_solve_velocity(int k, real dt)
+B2B_D void joint_solve_velocity(jrow& r, real dt)
 {
-    const int32_t* def = j_def + 4 * (size_t)k;
-    const real* par = j_par + JOINT_PAR * (size_t)k;
-    real* imp = j_imp + 4 * (size_t)k;
-    const real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    const int32_t* def = r.def;
+    const real* par = r.par;
+    real* imp = r.imp;
+    const real* tmp = r.tmp;
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
-    const real ma = b_mass[4 * (size_t)ba], ia = b_mass[4 * (size_t)ba + 1], mb = b_mass[4 * (size_t)bb], ib = b_mass[4 * (size_t)bb + 1];
+    const real ma = r.mqa.x, ia = r.mqa.y, mb = r.mqb.x, ib = r.mqb.y;
     const quad sa = state_get(ba), sb = state_get(bb);
     V2 va = mk<real>(sa.x, sa.y), vb = mk<real>(sb.x, sb.y);
     real wa = sa.z, wb = sb.z;
@@ -355,13 +425,13 @@ B2B_D void joint_solve_velocity(int k, real dt)
 
 // _solve_position_constraints (revolute.py:380-453, distance.py:277-311, weld.py:201-257) on the sweeps in the team's shared
 // state; true when the joint's errors are within tolerance
-B2B_D bool joint_solve_position(int k)
+B2B_D bool joint_solve_position(const jrow& r)
 {
-    const int32_t* def = j_def + 4 * (size_t)k;
-    const real* par = j_par + JOINT_PAR * (size_t)k;
-    const real* tmp = j_tmp + JOINT_TMP * (size_t)k;
+    const int32_t* def = r.def;
+    const real* par = r.par;
+    const real* tmp = r.tmp;
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
-    const quad mqa = ldq(b_mass + 4 * (size_t)ba), mqb = ldq(b_mass + 4 * (size_t)bb);
+    const quad mqa = r.mqa, mqb = r.mqb;
     const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
     const V2 lca = mk<real>(mqa.z, mqa.w), lcb = mk<real>(mqb.z, mqb.w);
     const quad sa = state_get(ba), sb = state_get(bb);

@@ -1768,11 +1768,8 @@ template <class real> struct world_step {
             if constexpr (PJ) {
                 if (j1 > j0) {
                     B2B_SYNC();
-                    if (t_id == 0) {
-                        const real dt_ratio = (real)(((sp.flags & STEP_FIRST) != 0) ? sp.dt_ratio_first : sp.dt_ratio_rest);
-                        for (int k = j0; k < j1; ++k) joint_init(l_joint[k], dt, dt_ratio, warm);
-                    }
-                    B2B_SYNC();
+                    const real dt_ratio = (real)(((sp.flags & STEP_FIRST) != 0) ? sp.dt_ratio_first : sp.dt_ratio_rest);
+                    joint_sweep(j0, j1, JFETCH_INIT, [&](jrow& r) { joint_init(r, dt, dt_ratio, warm); return true; });
                 }
             }
             for (int it = 0; it < sp.vel_iters; ++it) {
@@ -1780,8 +1777,7 @@ template <class real> struct world_step {
                 if constexpr (PJ) {
                     if (j1 > j0) {
                         B2B_SYNC();
-                        if (t_id == 0) for (int k = j0; k < j1; ++k) joint_solve_velocity(l_joint[k], dt);
-                        B2B_SYNC();
+                        joint_sweep(j0, j1, JFETCH_VELOCITY, [&](jrow& r) { joint_solve_velocity(r, dt); return true; });
                     }
                 }
                 if (c1 > c0) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);
@@ -1888,11 +1884,7 @@ template <class real> struct world_step {
                     if constexpr (PJ) {
                         if (j1 > j0) {
                             B2B_SYNC();
-                            if (t_id == 0) for (int k = j0; k < j1; ++k) { const bool okay = joint_solve_position(l_joint[k]); joints_okay = (joints_okay && okay) ? 1 : 0; }
-#if defined(__CUDA_ARCH__)
-                            for (int o = t_n >> 1; o > 0; o >>= 1) joints_okay &= __shfl_xor_sync(t_mask, joints_okay, o);
-#endif
-                            B2B_SYNC();
+                            joints_okay = joint_sweep(j0, j1, JFETCH_POSITION, [&](jrow& r) { return joint_solve_position(r); });
                         }
                     }
                     if (all_min >= real(-3) * K<real>::linear_slop && joints_okay) { position_solved = true; break; }

@@ -96,7 +96,10 @@ def _group_kernel_cases():
 # measured maxima on B200 (profiles/r2_parity_report.json: 7.6e-13, 0, 4.5e-10, 5.3e-8, 4.2e-9, 5.7e-7) times 10-20.
 EXACT_FIELDS = ["b_pos", "b_vel", "b_xf", "f_fat", "f_tight", "c_mf", "c_pts", "c_imp"]
 EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_stacks": 1e-6, "features": 1e-7, "mixed": 1e-5,
-             "bullets": 1e-5, "sensors": 1e-5, "joints": 1e-5, "bridge": 1e-6}
+             "bullets": 1e-5, "sensors": 1e-5,
+             # joints in the island solver (measured on B200, profiles/r2_joints/parity_report_joints.json: joints_w0 6.8e-6 over 400
+             # steps of tumbling bodies on a bridge, the other three cases <= 3.1e-11; one step teacher-forced: <= 2.8e-14)
+             "joints": 1e-4, "bridge": 1e-11}
 # Continuous collision on (World.solve_toi; measured by tools/ccd_parity_probe.py on B200, profiles/r2_ccd_parity.json): the
 # TOI sub-steps amplify the same one-ulp libm differences further.  Free-running, seven of the eight cases keep the oracle's
 # integer outputs for their whole length (worst float difference: pyramid landing 5.2e-13, features 1.4e-9, bullets 4.5e-9 /
@@ -199,14 +202,15 @@ def test_p_exact_fp64_one_step(case, parity_report):
 # is the sweep loop's exit test (contact.py:933 `min_separation >= -1.5 * LINEAR_SLOP`): rounding decides whether a second
 # sweep runs, and one sweep more or less is 0.0075 / 16 = 4.7e-4 m of position (measured: 4.69e-4 on every scene with
 # TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
-P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES}
+P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2"]}
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
                                         ("vertical_stack_w1", 150), ("deep_stacks_w1", 150), ("hello_w0", 60),
                                         ("features_w0", 200), ("bullets_w0", 300), ("bullets_w2", 200), ("hello_ccd_w0", 100),
                                         ("pyramid_ccd_w1", 300), ("features_ccd_w1", 300), ("mixed_ccd_w1", 120),
-                                        ("vertical_stack_ccd_w1", 200), ("sensors_w1", 300), ("sensors_ccd_w2", 300)])
+                                        ("vertical_stack_ccd_w1", 200), ("sensors_w1", 300), ("sensors_ccd_w2", 300),
+                                        ("joints_w0", 400), ("joints_w1", 300), ("bridge_w1", 300), ("joints_ccd_w2", 300)])
 def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)
@@ -252,7 +256,10 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     print("P-step %s: %d tie steps of %d: %s" % (case, ties, steps, tie_steps))
     parity_report("p_step/%s" % case, {"steps": steps, "ties": ties, "tie_steps": [[k, w] for k, w in tie_steps],
                                         "max_dp_non_tie": worst_p, "max_dv_non_tie": worst_v})
-    assert ties <= 0.10 * steps, "%d of %d teacher-forced steps had integer mismatches" % (ties, steps)
+    # (the joints scene has nine small islands, each with its own periodic sleep event -- the reference's rule puts one body to
+    # sleep when 30 additions of 1/60 reach 0.5 s, which fp32 hits within rounding: measured 34 tie steps of 300, every one an
+    # awake flag or a fat-AABB pair tie, and the fp64 kernels reproduce the oracle on each of them)
+    assert ties <= (0.15 if case.startswith("joints") else 0.10) * steps, "%d of %d teacher-forced steps had integer mismatches" % (ties, steps)
 
 
 # P-steady: 16 jittered worlds per scene, 600 free-running fp32 steps from the oracle's state after `settle` steps.
