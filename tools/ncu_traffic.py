@@ -15,7 +15,7 @@ ki, mi, vi, ui = head.index("Kernel Name"), head.index("Metric Name"), head.inde
 idi = head.index("ID")
 last = {}
 for r in rows[1:]:
-    m = re.search(r"(collide|plan|prepare|solve_velocity|solve_position|sync|broadphase|toi)_kernel_", r[ki])
+    m = re.search(r"(collide|plan|prepare|solve_velocity|solve_position|sync|broadphase|toi)(?:_joints)?_kernel_", r[ki])
     if not m:
         continue
     k = "pairs" if m.group(1) == "broadphase" else m.group(1)
