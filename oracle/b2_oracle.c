@@ -1095,6 +1095,9 @@ static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
 #define J_DISTANCE 2
 #define J_WELD     3
 #define J_PRISMATIC 4
+#define J_ROPE     5
+#define J_FRICTION 6
+#define J_WHEEL    7
 #define JF_COLLIDE 0x1
 #define JF_LIMIT   0x2
 #define JF_MOTOR   0x4
@@ -1277,6 +1280,92 @@ static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm
             wb += ib * L2;
         } else { imp[0] = imp[1] = imp[2] = 0.0; imp[3] = 0.0; }
     }
+    else if (type == J_ROPE) {                                                       /* rope.py:106-176 */
+        v2 u0 = vsub(vsub(vadd(cb, rb), ca), ra);                                    /* self._u: never normalised (`u /= ...` rebinds the local) */
+        double length = sqrt(sq(u0.x) + sq(u0.y));
+        tmp[4] = u0.x; tmp[5] = u0.y; tmp[7] = length;
+        double Cc = length - par[4];
+        int ls = (Cc > 0.0) ? LS_UPPER : LS_INACTIVE;
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (!(length > LINEAR_SLOP)) { tmp[6] = 0.0; imp[0] = 0.0; return; }        /* rope.py:147-151: returns before the velocities are stored */
+        v2 u = V(u0.x / length, u0.y / length);
+        double cra = vcross(ra, u), crb = vcross(rb, u);
+        double inv_mass = ma + ia * cra * cra + mb + ib * crb * crb;
+        tmp[6] = (inv_mass != 0.0) ? 1.0 / inv_mass : 0.0;
+        if (warm) {
+            imp[0] *= dt_ratio;
+            v2 Pv = vscale(imp[0], u0);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * vcross(ra, Pv);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * vcross(rb, Pv);
+        } else imp[0] = 0.0;
+    }
+    else if (type == J_FRICTION) {                                                   /* friction.py:105-176 */
+        double k1x = ma + mb + ia * ra.y * ra.y + ib * rb.y * rb.y;
+        double k1y = -ia * ra.x * ra.y - ib * rb.x * rb.y;
+        double k2x = k1y;
+        double k2y = ma + mb + ia * ra.x * ra.x + ib * rb.x * rb.x;
+        double det = k1x * k2y - k2x * k1y;                                          /* Mat22.inverse: common.py:506-519 */
+        if (det != 0.0) det = 1.0 / det;
+        tmp[4] = det * k2y; tmp[5] = -det * k1y; tmp[6] = -det * k2x; tmp[7] = det * k1x;
+        double angular_mass = ia + ib;
+        if (angular_mass > 0.0) angular_mass = 1.0 / angular_mass;
+        tmp[8] = angular_mass;
+        if (warm) {
+            imp[0] = dt_ratio * imp[0]; imp[1] = dt_ratio * imp[1];
+            imp[2] *= dt_ratio;
+            v2 Pv = V(imp[0], imp[1]);
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * (vcross(ra, Pv) + imp[2]);
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * (vcross(rb, Pv) + imp[2]);
+        } else { imp[0] = imp[1] = 0.0; imp[2] = 0.0; }
+    }
+    else if (type == J_WHEEL) {                                                      /* wheel.py:202-318 */
+        v2 d = vsub(vsub(vadd(cb, rb), ca), ra);
+        v2 lx = V(par[4], par[5]), ly = scross(1.0, lx);
+        v2 ay = rot_mul(&qa, ly);
+        double s_ay = vcross(vadd(d, ra), ay), s_by = vcross(rb, ay);
+        double mass = ma + mb + ia * sq(s_ay) + ib * sq(s_by);
+        if (mass > 0.0) mass = 1.0 / mass;
+        double spring_mass = 0.0, bias = 0.0, gamma = 0.0;
+        v2 ax = V(tmp[9], tmp[10]); double s_ax = tmp[11], s_bx = tmp[12];          /* attributes keep their last values when frequency <= 0 */
+        if (par[6] > 0.0) {
+            ax = rot_mul(&qa, lx);
+            s_ax = vcross(vadd(d, ra), ax); s_bx = vcross(rb, ax);
+            double inv_mass = ma + mb + ia * sq(s_ax) + ib * sq(s_bx);
+            if (inv_mass > 0.0) {
+                spring_mass = 1.0 / inv_mass;
+                double Cc = vdot(d, ax);
+                double omega = 2.0 * PI_ * par[6];
+                double dd = 2.0 * spring_mass * par[7] * omega;
+                double kk = spring_mass * sq(omega);
+                gamma = dt * (dd + dt * kk);
+                if (gamma > 0.0) gamma = 1.0 / gamma;
+                bias = Cc * dt * kk * gamma;
+                spring_mass = inv_mass + gamma;
+                if (spring_mass > 0.0) spring_mass = 1.0 / spring_mass;
+            }
+        } else imp[1] = 0.0;
+        double motor_mass;
+        if (flags & JF_MOTOR) {
+            motor_mass = ia + ib;
+            if (motor_mass > 0.0) motor_mass = 1.0 / motor_mass;
+        } else { motor_mass = 0.0; imp[2] = 0.0; }
+        tmp[4] = ay.x; tmp[5] = ay.y; tmp[6] = s_ay; tmp[7] = s_by; tmp[8] = mass; tmp[9] = ax.x; tmp[10] = ax.y; tmp[11] = s_ax; tmp[12] = s_bx;
+        tmp[13] = spring_mass; tmp[14] = bias; tmp[15] = gamma; tmp[16] = motor_mass;
+        if (warm) {
+            imp[0] *= dt_ratio; imp[1] *= dt_ratio; imp[2] *= dt_ratio;
+            v2 Pv = vadd(vscale(imp[0], ay), vscale(imp[1], ax));
+            double La = imp[0] * s_ay + imp[1] * s_ax + imp[2];
+            double Lb = imp[0] * s_by + imp[1] * s_bx + imp[2];
+            va = vsub(va, vscale(ma, Pv));
+            wa -= ia * La;
+            vb = vadd(vb, vscale(mb, Pv));
+            wb += ib * Lb;
+        } else { imp[0] = 0.0; imp[1] = 0.0; imp[2] = 0.0; }
+    }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
 }
@@ -1287,7 +1376,7 @@ static inline m33 m33_sym(const double* k)     /* Mat33((k11, k12, k13), (k12, k
 }
 
 /* _solve_velocity_constraints: revolute.py:302-378, distance.py:252-275, weld.py:171-199 */
-static void joint_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
+static void joint_solve_velocity(orc_world* w, int k, double dt, double inv_dt, vel_t* Vv)
 {
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
@@ -1415,6 +1504,69 @@ static void joint_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
         wa -= ia * L1;
         vb = vadd(vb, vscale(mb, Pv));
         wb += ib * L2;
+    }
+    else if (type == J_ROPE) {                                                       /* rope.py:178-207 */
+        v2 u0 = V(tmp[4], tmp[5]);
+        v2 vpa = vadd(va, scross(wa, ra)), vpb = vadd(vb, scross(wb, rb));
+        double Cc = tmp[7] - par[4];
+        double Cdot = vdot(u0, vsub(vpb, vpa));
+        if (Cc < 0.0) Cdot += inv_dt * Cc;
+        double impulse = -tmp[6] * Cdot;
+        double old_impulse = imp[0];
+        imp[0] = PYMIN(0.0, imp[0] + impulse);
+        impulse = imp[0] - old_impulse;
+        v2 Pv = vscale(impulse, u0);
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * vcross(ra, Pv);
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * vcross(rb, Pv);
+    }
+    else if (type == J_FRICTION) {                                                   /* friction.py:178-230: the result goes to `positions`, */
+        double Cdot = wb - wa;                                                       /* i.e. nowhere; only the accumulated impulses change */
+        double impulse = -tmp[8] * Cdot;
+        double old_impulse = imp[2];
+        double max_impulse = dt * par[5];
+        imp[2] = pyclamp(imp[2] + impulse, -max_impulse, max_impulse);
+        impulse = imp[2] - old_impulse;
+        wa -= ia * impulse;
+        wb += ib * impulse;
+        v2 Cd = vsub(vsub(vadd(vb, scross(wb, rb)), va), scross(wa, ra));
+        v2 li = vneg(V(tmp[4] * Cd.x + tmp[6] * Cd.y, tmp[5] * Cd.x + tmp[7] * Cd.y));
+        v2 lin = vadd(V(imp[0], imp[1]), li);
+        max_impulse = dt * par[4];
+        if (vlen2(lin) > sq(max_impulse)) { v2 n = vnorm(lin); lin = V(max_impulse * n.x, max_impulse * n.y); }
+        imp[0] = lin.x; imp[1] = lin.y;
+        return;
+    }
+    else if (type == J_WHEEL) {                                                      /* wheel.py:320-373 */
+        v2 ay = V(tmp[4], tmp[5]), ax = V(tmp[9], tmp[10]);
+        double s_ay = tmp[6], s_by = tmp[7], s_ax = tmp[11], s_bx = tmp[12];
+        double Cdot = vdot(ax, vsub(vb, va)) + s_bx * wb - s_ax * wa;
+        double impulse = -tmp[13] * (Cdot + tmp[14] + tmp[15] * imp[1]);
+        imp[1] += impulse;
+        v2 Pv = vscale(impulse, ax);
+        double La = impulse * s_ax, Lb = impulse * s_bx;
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * La;
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * Lb;
+        Cdot = wb - wa - par[9];
+        impulse = -tmp[16] * Cdot;
+        double old_impulse = imp[2];
+        double max_impulse = dt * par[8];
+        imp[2] = pyclamp(imp[2] + impulse, -max_impulse, max_impulse);
+        impulse = imp[2] - old_impulse;
+        wa -= ia * impulse;
+        wb += ib * impulse;
+        Cdot = vdot(ay, vsub(vb, va)) + s_by * wb - s_ay * wa;
+        impulse = -tmp[8] * Cdot;
+        imp[0] += impulse;
+        Pv = vscale(impulse, ay);
+        La = impulse * s_ay; Lb = impulse * s_by;
+        va = vsub(va, vscale(ma, Pv));
+        wa -= ia * La;
+        vb = vadd(vb, vscale(mb, Pv));
+        wb += ib * Lb;
     }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
@@ -1568,6 +1720,40 @@ static int joint_solve_position(orc_world* w, int k, pos_t* P)
         ab += ib * L2;
         ok = (linear_error <= LINEAR_SLOP) && (angular_error <= ANGULAR_SLOP);
     }
+    else if (type == J_ROPE) {                                                       /* rope.py:209-248 */
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 u = vsub(vsub(vadd(cb, rb), ca), ra);
+        double length = sqrt(sq(u.x) + sq(u.y));
+        u = vnorm(u);
+        double Cc = pyclamp(length - par[4], 0.0, MAX_LIN_CORR);
+        double impulse = -tmp[6] * Cc;
+        v2 Pv = vscale(impulse, u);
+        ca = vsub(ca, vscale(ma, Pv));
+        aa -= ia * vcross(ra, Pv);
+        cb = vadd(cb, vscale(mb, Pv));
+        ab += ib * vcross(rb, Pv);
+        ok = (length - par[4]) < LINEAR_SLOP;
+    }
+    else if (type == J_FRICTION) return 1;                                           /* friction.py:232-233 */
+    else if (type == J_WHEEL) {                                                      /* wheel.py:375-416 */
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 d = vsub(vadd(vsub(cb, ca), rb), ra);
+        double kk = ma + mb + ia * sq(tmp[6]) + ib * sq(tmp[7]);
+        v2 ly = scross(1.0, V(par[4], par[5]));
+        v2 ay = rot_mul(&qa, ly);
+        double s_ay = vcross(vadd(d, ra), ay), s_by = vcross(rb, ay);
+        double Cc = vdot(d, ay);
+        double impulse = (kk != 0.0) ? -Cc / kk : 0.0;
+        v2 Pv = vscale(impulse, ay);
+        double La = impulse * s_ay, Lb = impulse * s_by;
+        ca = vsub(ca, vscale(ma, Pv));
+        aa -= ia * La;
+        cb = vadd(cb, vscale(mb, Pv));
+        ab += ib * Lb;
+        ok = fabs(Cc) <= LINEAR_SLOP;
+    }
     P[ia_].c = ca; P[ia_].a = aa;
     P[ib_].c = cb; P[ib_].a = ab;
     return ok;
@@ -1626,7 +1812,7 @@ static void island_solve(orc_world* w, const int* bodies, int nbodies, const int
     /* island.py:107-113 */
     for (int k = 0; k < njoints; ++k) joint_init(w, joints[k], dt, dt_ratio, warm, P, Vv);
     for (int it = 0; it < vel_iters; ++it) {
-        for (int k = 0; k < njoints; ++k) joint_solve_velocity(w, joints[k], dt, Vv);
+        for (int k = 0; k < njoints; ++k) joint_solve_velocity(w, joints[k], dt, 1.0 / dt, Vv);
         solver_velocity_sweep(C, ncontacts, Vv);
     }
 

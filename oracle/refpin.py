@@ -213,6 +213,19 @@ def extract_joints(world, A, w, bidx, schema):
             par += [j._reference_angle, j._lower_limit, j._upper_limit, j._max_motor_force, j._motor_speed,
                     j._local_x_axis.x, j._local_x_axis.y]
             imp = (j._impulse.x, j._impulse.y, j._impulse.z, j._motor_impulse)
+        elif isinstance(j, _j.RopeJoint):
+            t = schema.JOINT_ROPE
+            par += [j._max_length]
+            imp = (j._impulse, 0.0, 0.0, 0.0)
+            flags |= int(j._state) << schema.JOINT_LIMIT_SHIFT
+        elif isinstance(j, _j.FrictionJoint):
+            t = schema.JOINT_FRICTION
+            par += [j._max_force, j._max_torque]
+            imp = (j._linear_impulse.x, j._linear_impulse.y, j._angular_impulse, 0.0)
+        elif isinstance(j, _j.WheelJoint):
+            t = schema.JOINT_WHEEL
+            par += [j._local_x_axis.x, j._local_x_axis.y, j._frequency, j._damping_ratio, j._max_motor_torque, j._motor_speed]
+            imp = (j._impulse, j._spring_impulse, j._motor_impulse, 0.0)
         else:
             raise NotImplementedError(type(j))
         A["j_def"][w, k] = (t, bidx[id(j._body_a)], bidx[id(j._body_b)], flags)

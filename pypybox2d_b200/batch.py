@@ -430,7 +430,7 @@ class BatchedWorld(object):
             J = self.download(["j_def", "j_imp", "j_tmp"], worlds=slice(w, w + 1))
             for k, j in enumerate(world.joints):
                 j._read_back(J["j_def"][0, k, 3], J["j_imp"][0, k])
-                if j._type == schema.JOINT_DISTANCE:
+                if j._type in (schema.JOINT_DISTANCE, schema.JOINT_ROPE):
                     j._u = (float(J["j_tmp"][0, k, 4]), float(J["j_tmp"][0, k, 5]))
                 elif j._type == schema.JOINT_PRISMATIC:
                     t = J["j_tmp"][0, k]

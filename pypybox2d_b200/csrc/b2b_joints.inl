@@ -1,7 +1,8 @@
 // b2b_joints.inl -- joints of the island solver, included INSIDE world_step<real> (b2b_step.cuh).
 //
 // RevoluteJoint (pypybox2d/joints/revolute.py:208-453), DistanceJoint (joints/distance.py:155-311), WeldJoint
-// (joints/weld.py:106-257) and PrismaticJoint (joints/prismatic.py:232-513) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
+// (joints/weld.py:106-257), PrismaticJoint (joints/prismatic.py:232-513), RopeJoint (joints/rope.py:106-248), FrictionJoint
+// (joints/friction.py:105-233) and WheelJoint (joints/wheel.py:202-416) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
 // fp64 host build of this file is bit-identical to the oracle, which is pinned bit-identical to the live reference.
 //
 // Island.solve visits an island's joints one after the other, before the contacts in every velocity iteration and after them in
@@ -16,7 +17,7 @@
 // matrix by columns and the motor mass; or u, mass, gamma, bias; prismatic: axis, perp, s1, s2, a1, a2, motor mass and the six
 // distinct entries of its symmetric K).
 
-enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4 };
+enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4, JOINT_ROPE = 5, JOINT_FRICTION = 6, JOINT_WHEEL = 7 };
 enum { JF_COLLIDE = 0x1, JF_LIMIT = 0x2, JF_MOTOR = 0x4, JF_ISLAND = 0x8, JF_LS_SHIFT = 8 };
 enum { LS_INACTIVE = 0, LS_LOWER = 1, LS_UPPER = 2, LS_EQUAL = 3 };               // joints/joint.py:36
 enum { JOINT_PAR = 12, JOINT_TMP = 20 };
@@ -279,12 +280,105 @@ B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
         } else { i0 = i1 = i2 = real(0); im = real(0); }
         imp[0] = i0; imp[1] = i1; imp[2] = i2; imp[3] = im;
     }
+    else if (type == JOINT_ROPE) {                                                   // rope.py:106-176
+        const V2 u0 = cb + rb - ca - ra;                                             // self._u: never normalised (`u /= ...` rebinds the local)
+        const real length = sqrt_r(sq_r(u0.x) + sq_r(u0.y));
+        tmp[4] = u0.x; tmp[5] = u0.y; tmp[7] = length;
+        const real C = length - par[4];
+        const int ls = (C > real(0)) ? LS_UPPER : LS_INACTIVE;
+        def[3] = (flags & ~(3 << JF_LS_SHIFT)) | (ls << JF_LS_SHIFT);
+        if (!(length > K<real>::linear_slop)) { tmp[6] = real(0); imp[0] = real(0); return; }   // rope.py:147-151: returns before the velocities are stored
+        const V2 u = mk<real>(u0.x / length, u0.y / length);
+        const real cra = cross(ra, u), crb = cross(rb, u);
+        const real inv_mass = ma + ia * cra * cra + mb + ib * crb * crb;
+        tmp[6] = (inv_mass != real(0)) ? real(1) / inv_mass : real(0);
+        real i0 = imp[0];
+        if (warm) {
+            i0 = i0 * dt_ratio;
+            const V2 P = i0 * u0;
+            va = va - ma * P;
+            wa = wa - ia * cross(ra, P);
+            vb = vb + mb * P;
+            wb = wb + ib * cross(rb, P);
+        } else i0 = real(0);
+        imp[0] = i0;
+    }
+    else if (type == JOINT_FRICTION) {                                               // friction.py:105-176
+        const real k1x = ma + mb + ia * ra.y * ra.y + ib * rb.y * rb.y;
+        const real k1y = -ia * ra.x * ra.y - ib * rb.x * rb.y;
+        const real k2x = k1y;
+        const real k2y = ma + mb + ia * ra.x * ra.x + ib * rb.x * rb.x;
+        real det = k1x * k2y - k2x * k1y;                                            // Mat22.inverse, common.py:506-519
+        if (det != real(0)) det = real(1) / det;
+        tmp[4] = det * k2y; tmp[5] = -det * k1y; tmp[6] = -det * k2x; tmp[7] = det * k1x;
+        real angular_mass = ia + ib;
+        if (angular_mass > real(0)) angular_mass = real(1) / angular_mass;
+        tmp[8] = angular_mass;
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2];
+        if (warm) {
+            i0 = dt_ratio * i0; i1 = dt_ratio * i1;
+            i2 = i2 * dt_ratio;
+            const V2 P = mk<real>(i0, i1);
+            va = va - ma * P;
+            wa = wa - ia * (cross(ra, P) + i2);
+            vb = vb + mb * P;
+            wb = wb + ib * (cross(rb, P) + i2);
+        } else { i0 = i1 = real(0); i2 = real(0); }
+        imp[0] = i0; imp[1] = i1; imp[2] = i2;
+    }
+    else if (type == JOINT_WHEEL) {                                                  // wheel.py:202-318
+        const V2 d = cb + rb - ca - ra;
+        const V2 lx = mk<real>(par[4], par[5]), ly = cross_sv(real(1), lx);
+        const V2 ay = rot_mul(qa, ly);
+        const real s_ay = cross(d + ra, ay), s_by = cross(rb, ay);
+        real mass = ma + mb + ia * sq_r(s_ay) + ib * sq_r(s_by);
+        if (mass > real(0)) mass = real(1) / mass;
+        real spring_mass = real(0), bias = real(0), gamma = real(0);
+        V2 ax = mk<real>(real(0), real(0));                                          // (the attributes of a wheel without a spring stay at the constructor's zeros)
+        real s_ax = real(0), s_bx = real(0);
+        real i0 = imp[0], i1 = imp[1], i2 = imp[2];
+        if (par[6] > real(0)) {
+            ax = rot_mul(qa, lx);
+            s_ax = cross(d + ra, ax); s_bx = cross(rb, ax);
+            const real inv_mass = ma + mb + ia * sq_r(s_ax) + ib * sq_r(s_bx);
+            if (inv_mass > real(0)) {
+                spring_mass = real(1) / inv_mass;
+                const real C = dot(d, ax);
+                const real omega = real(2) * K<real>::pi * par[6];
+                const real dd = real(2) * spring_mass * par[7] * omega;
+                const real kk = spring_mass * sq_r(omega);
+                gamma = dt * (dd + dt * kk);
+                if (gamma > real(0)) gamma = real(1) / gamma;
+                bias = C * dt * kk * gamma;
+                spring_mass = inv_mass + gamma;
+                if (spring_mass > real(0)) spring_mass = real(1) / spring_mass;
+            }
+        } else i1 = real(0);
+        real motor_mass;
+        if (flags & JF_MOTOR) {
+            motor_mass = ia + ib;
+            if (motor_mass > real(0)) motor_mass = real(1) / motor_mass;
+        } else { motor_mass = real(0); i2 = real(0); }
+        tmp[4] = ay.x; tmp[5] = ay.y; tmp[6] = s_ay; tmp[7] = s_by; tmp[8] = mass; tmp[9] = ax.x; tmp[10] = ax.y; tmp[11] = s_ax; tmp[12] = s_bx;
+        tmp[13] = spring_mass; tmp[14] = bias; tmp[15] = gamma; tmp[16] = motor_mass;
+        if (warm) {
+            i0 = i0 * dt_ratio; i1 = i1 * dt_ratio; i2 = i2 * dt_ratio;
+            const V2 P = i0 * ay + i1 * ax;
+            const real La = i0 * s_ay + i1 * s_ax + i2;
+            const real Lb = i0 * s_by + i1 * s_bx + i2;
+            va = va - ma * P;
+            wa = wa - ia * La;
+            vb = vb + mb * P;
+            wb = wb + ib * Lb;
+        } else { i0 = real(0); i1 = real(0); i2 = real(0); }
+        imp[0] = i0; imp[1] = i1; imp[2] = i2;
+    }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
 }
 
 // _solve_velocity_constraints (revolute.py:302-378, distance.py:252-275, weld.py:171-199)
-B2B_D void joint_solve_velocity(jrow& r, real dt)
+B2B_D void joint_solve_velocity(jrow& r, real dt, real inv_dt)
 {
     const int32_t* def = r.def;
     const real* par = r.par;
@@ -418,6 +512,72 @@ B2B_D void joint_solve_velocity(jrow& r, real dt)
         wa = wa - ia * L1;
         vb = vb + mb * P;
         wb = wb + ib * L2;
+    }
+    else if (type == JOINT_ROPE) {                                                   // rope.py:178-207
+        const V2 u0 = mk<real>(tmp[4], tmp[5]);
+        const V2 vpa = va + cross_sv(wa, ra), vpb = vb + cross_sv(wb, rb);
+        const real C = tmp[7] - par[4];
+        real Cdot = dot(u0, vpb - vpa);
+        if (C < real(0)) Cdot = Cdot + inv_dt * C;
+        real impulse = -tmp[6] * Cdot;
+        const real old_impulse = imp[0];
+        const real ni = pymin(real(0), old_impulse + impulse);
+        imp[0] = ni;
+        impulse = ni - old_impulse;
+        const V2 P = impulse * u0;
+        va = va - ma * P;
+        wa = wa - ia * cross(ra, P);
+        vb = vb + mb * P;
+        wb = wb + ib * cross(rb, P);
+    }
+    else if (type == JOINT_FRICTION) {                                               // friction.py:178-230: the port stores the result into
+        const real Cdot = wb - wa;                                                   // `positions`, i.e. nowhere: only the accumulated impulses change
+        real impulse = -tmp[8] * Cdot;
+        const real old_impulse = imp[2];
+        real max_impulse = dt * par[5];
+        const real na = clamp_r(old_impulse + impulse, -max_impulse, max_impulse);
+        imp[2] = na;
+        impulse = na - old_impulse;
+        wa = wa - ia * impulse;
+        wb = wb + ib * impulse;
+        const V2 Cd = vb + cross_sv(wb, rb) - va - cross_sv(wa, ra);
+        const V2 li = -mk<real>(tmp[4] * Cd.x + tmp[6] * Cd.y, tmp[5] * Cd.x + tmp[7] * Cd.y);
+        V2 lin = mk<real>(imp[0], imp[1]) + li;
+        max_impulse = dt * par[4];
+        if (sq_r(lin.x) + sq_r(lin.y) > sq_r(max_impulse)) { const V2 n = normalize(lin); lin = mk<real>(max_impulse * n.x, max_impulse * n.y); }
+        imp[0] = lin.x; imp[1] = lin.y;
+        return;
+    }
+    else if (type == JOINT_WHEEL) {                                                  // wheel.py:320-373
+        const V2 ay = mk<real>(tmp[4], tmp[5]), ax = mk<real>(tmp[9], tmp[10]);
+        const real s_ay = tmp[6], s_by = tmp[7], s_ax = tmp[11], s_bx = tmp[12];
+        real Cdot = dot(ax, vb - va) + s_bx * wb - s_ax * wa;
+        real impulse = -tmp[13] * (Cdot + tmp[14] + tmp[15] * imp[1]);
+        imp[1] = imp[1] + impulse;
+        V2 P = impulse * ax;
+        real La = impulse * s_ax, Lb = impulse * s_bx;
+        va = va - ma * P;
+        wa = wa - ia * La;
+        vb = vb + mb * P;
+        wb = wb + ib * Lb;
+        Cdot = wb - wa - par[9];
+        impulse = -tmp[16] * Cdot;
+        const real old_impulse = imp[2];
+        const real max_impulse = dt * par[8];
+        const real nm = clamp_r(old_impulse + impulse, -max_impulse, max_impulse);
+        imp[2] = nm;
+        impulse = nm - old_impulse;
+        wa = wa - ia * impulse;
+        wb = wb + ib * impulse;
+        Cdot = dot(ay, vb - va) + s_by * wb - s_ay * wa;
+        impulse = -tmp[8] * Cdot;
+        imp[0] = imp[0] + impulse;
+        P = impulse * ay;
+        La = impulse * s_ay; Lb = impulse * s_by;
+        va = va - ma * P;
+        wa = wa - ia * La;
+        vb = vb + mb * P;
+        wb = wb + ib * Lb;
     }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
@@ -573,6 +733,40 @@ B2B_D bool joint_solve_position(const jrow& r)
         aa = aa - ia * L1;
         ab = ab + ib * L2;
         ok = (linear_error <= K<real>::linear_slop) && (angular_error <= K<real>::angular_slop);
+    }
+    else if (type == JOINT_ROPE) {                                                   // rope.py:209-248
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        V2 u = cb + rb - ca - ra;
+        const real length = sqrt_r(sq_r(u.x) + sq_r(u.y));
+        u = normalize(u);
+        const real C = clamp_r(length - par[4], real(0), K<real>::max_linear_correction);
+        const real impulse = -tmp[6] * C;
+        const V2 P = impulse * u;
+        ca = ca - ma * P;
+        aa = aa - ia * cross(ra, P);
+        cb = cb + mb * P;
+        ab = ab + ib * cross(rb, P);
+        ok = (length - par[4]) < K<real>::linear_slop;
+    }
+    else if (type == JOINT_FRICTION) return true;                                    // friction.py:232-233
+    else if (type == JOINT_WHEEL) {                                                  // wheel.py:375-416
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 d = (cb - ca) + rb - ra;
+        const real kk = ma + mb + ia * sq_r(tmp[6]) + ib * sq_r(tmp[7]);
+        const V2 ly = cross_sv(real(1), mk<real>(par[4], par[5]));
+        const V2 ay = rot_mul(qa, ly);
+        const real s_ay = cross(d + ra, ay), s_by = cross(rb, ay);
+        const real C = dot(d, ay);
+        const real impulse = (kk != real(0)) ? -C / kk : real(0);
+        const V2 P = impulse * ay;
+        const real La = impulse * s_ay, Lb = impulse * s_by;
+        ca = ca - ma * P;
+        aa = aa - ia * La;
+        cb = cb + mb * P;
+        ab = ab + ib * Lb;
+        ok = abs_r(C) <= K<real>::linear_slop;
     }
     state_set(ba, ca.x, ca.y, aa);
     state_set(bb, cb.x, cb.y, ab);

@@ -1777,7 +1777,8 @@ template <class real> struct world_step {
                 if constexpr (PJ) {
                     if (j1 > j0) {
                         B2B_SYNC();
-                        joint_sweep(j0, j1, JFETCH_VELOCITY, [&](jrow& r) { joint_solve_velocity(r, dt); return true; });
+                        const real inv_dt = (real)(1.0 / sp.dt);                    // TimeStep.inv_dt (world.py:322)
+                        joint_sweep(j0, j1, JFETCH_VELOCITY, [&](jrow& r) { joint_solve_velocity(r, dt, inv_dt); return true; });
                     }
                 }
                 if (c1 > c0) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);

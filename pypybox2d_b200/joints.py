@@ -1,7 +1,8 @@
 """Joints of the island solver: the drop-in surface of `pypybox2d/joints/`.
 
 `RevoluteJoint` (`joints/revolute.py`), `DistanceJoint` (`joints/distance.py`), `WeldJoint` (`joints/weld.py`) and
-`PrismaticJoint` (`joints/prismatic.py`) with the
+`PrismaticJoint` (`joints/prismatic.py`), `RopeJoint` (`joints/rope.py`), `FrictionJoint` (`joints/friction.py`) and `WheelJoint`
+(`joints/wheel.py`) with the
 reference's constructor keywords, read-backs and setters.  A joint object only holds its definition: one row of the device
 arrays `j_def` (type, bodies, flags), `j_par` (parameters, layout below) and `j_imp` (accumulated impulses, mirrored back
 after every step).  The constraint itself -- `_init_velocity_constraints`, `_solve_velocity_constraints`,
@@ -13,7 +14,10 @@ after every step).  The constraint itself -- `_init_velocity_constraints`, `_sol
   distance    [4] length, [5] frequency, [6] damping_ratio
   weld        [4] reference_angle
   prismatic   [4] reference_angle, [5] lower_limit, [6] upper_limit, [7] max_motor_force, [8] motor_speed, [9:11] local_x_axis
-The other joint types of the reference (wheel, pulley, gear, rope, friction, mouse) raise NotImplementedError.
+  rope        [4] max_length
+  friction    [4] max_force, [5] max_torque
+  wheel       [4:6] local_x_axis, [6] frequency, [7] damping_ratio, [8] max_motor_torque, [9] motor_speed
+The other joint types of the reference (pulley, gear, mouse) raise NotImplementedError.
 """
 import math
 
@@ -421,18 +425,180 @@ class PrismaticJoint(Joint):
         return Vec2(inv_dt * (self._impulse3[0] * px[0] + k * ax[0]), inv_dt * (self._impulse3[0] * px[1] + k * ax[1]))
 
 
+class RopeJoint(Joint):
+    """joints/rope.py:33-248: a maximum distance between two anchor points."""
+    _type = schema.JOINT_ROPE
+
+    def __init__(self, body_a, body_b, local_anchor_a=(0, 0), local_anchor_b=(0, 0), max_length=0.0, collide_connected=False):
+        if body_a is None or body_b is None:
+            raise ValueError('body_a and body_b must be set')
+        Joint.__init__(self, body_a, body_b, collide_connected)
+        self._local_anchor_a = Vec2(*local_anchor_a)
+        self._local_anchor_b = Vec2(*local_anchor_b)
+        self._max_length = float(max_length)
+
+    def __copy__(self):
+        return RopeJoint(self._body_a, self._body_b, self._local_anchor_a, self._local_anchor_b, self._max_length,
+                         self._collide_connected)
+
+    def _par(self):
+        return [self._local_anchor_a.x, self._local_anchor_a.y, self._local_anchor_b.x, self._local_anchor_b.y, self._max_length]
+
+    max_length = property(lambda self: self._max_length)
+    limit_state = property(lambda self: self._limit_state)
+
+    def get_reaction_force(self, inv_dt):
+        u = getattr(self, "_u", (0.0, 0.0))
+        return Vec2((inv_dt * self._impulse3[0]) * u[0], (inv_dt * self._impulse3[0]) * u[1])
+
+    def get_reaction_torque(self, inv_dt):
+        return 0.0
+
+
+class FrictionJoint(Joint):
+    """joints/friction.py:33-233 (as the port behaves: its velocity solve stores its result into `positions`, so only the warm
+    start of the accumulated impulses acts on the bodies)."""
+    _type = schema.JOINT_FRICTION
+
+    def __init__(self, body_a, body_b, local_anchor_a=(0, 0), local_anchor_b=(0, 0), max_force=0.0, max_torque=0.0,
+                 collide_connected=False):
+        if body_a is None or body_b is None:
+            raise ValueError('body_a and body_b must be set')
+        Joint.__init__(self, body_a, body_b, collide_connected)
+        self._local_anchor_a = Vec2(*local_anchor_a)
+        self._local_anchor_b = Vec2(*local_anchor_b)
+        self._max_force = float(max_force)
+        self._max_torque = float(max_torque)
+
+    def __copy__(self):
+        return FrictionJoint(self._body_a, self._body_b, self._local_anchor_a, self._local_anchor_b, self._max_force,
+                             self._max_torque, self._collide_connected)
+
+    def _par(self):
+        return [self._local_anchor_a.x, self._local_anchor_a.y, self._local_anchor_b.x, self._local_anchor_b.y,
+                self._max_force, self._max_torque]
+
+    @property
+    def max_force(self):
+        return self._max_force
+
+    @max_force.setter
+    def max_force(self, force):
+        self._max_force = float(force)
+        self._changed(wake=False)
+
+    @property
+    def max_torque(self):
+        return self._max_torque
+
+    @max_torque.setter
+    def max_torque(self, torque):
+        self._max_torque = float(torque)
+        self._changed(wake=False)
+
+
+class WheelJoint(Joint):
+    """joints/wheel.py:33-417: a point of body_b on a line fixed in body_a, with a spring along it and a rotational motor."""
+    _type = schema.JOINT_WHEEL
+
+    def __init__(self, body_a, body_b, anchor=None, axis=None, frequency=2.0, damping_ratio=0.7, motor_enabled=False,
+                 motor_speed=0.0, max_motor_torque=0.0, local_anchor_a=None, local_anchor_b=None, local_x_axis=None,
+                 collide_connected=False):
+        if body_a is None or body_b is None:
+            raise ValueError('body_a and body_b must be set')
+        Joint.__init__(self, body_a, body_b, collide_connected)
+        self._local_anchor_a = Vec2(*local_anchor_a) if local_anchor_a is not None else body_a.get_local_point(anchor)
+        self._local_anchor_b = Vec2(*local_anchor_b) if local_anchor_b is not None else body_b.get_local_point(anchor)
+        self._local_x_axis = Vec2(*local_x_axis) if local_x_axis is not None else body_a.get_local_vector(axis)
+        self._frequency = float(frequency)
+        self._damping_ratio = float(damping_ratio)
+        self._max_motor_torque = float(max_motor_torque)
+        self._motor_speed = float(motor_speed)
+        self._motor_enabled = bool(motor_enabled)
+
+    def __copy__(self):
+        return WheelJoint(self._body_a, self._body_b, None, None, self._frequency, self._damping_ratio, self._motor_enabled,
+                          self._motor_speed, self._max_motor_torque, self._local_anchor_a, self._local_anchor_b,
+                          self._local_x_axis, self._collide_connected)
+
+    def _par(self):
+        return [self._local_anchor_a.x, self._local_anchor_a.y, self._local_anchor_b.x, self._local_anchor_b.y,
+                self._local_x_axis.x, self._local_x_axis.y, self._frequency, self._damping_ratio, self._max_motor_torque,
+                self._motor_speed]
+
+    # accumulated impulses: _impulse (point to line), _spring_impulse, _motor_impulse ride in j_imp[0:3]
+    def _imp(self):
+        return (self._impulse3[0], self._impulse3[1], self._impulse3[2], 0.0)
+
+    def _read_back(self, flags, imp):
+        Joint._read_back(self, flags, imp)
+        self._motor_impulse = float(imp[2])
+
+    @property
+    def joint_speed(self):
+        return self._body_b._angular_velocity - self._body_a._angular_velocity
+
+    @property
+    def motor_enabled(self):
+        return self._motor_enabled
+
+    @motor_enabled.setter
+    def motor_enabled(self, motor_enabled):
+        self._motor_enabled = bool(motor_enabled)
+        self._changed()
+
+    @property
+    def motor_speed(self):
+        return self._motor_speed
+
+    @motor_speed.setter
+    def motor_speed(self, speed):
+        self._motor_speed = float(speed)
+        self._changed()
+
+    @property
+    def max_motor_torque(self):
+        return self._max_motor_torque
+
+    @max_motor_torque.setter
+    def max_motor_torque(self, torque):
+        self._max_motor_torque = float(torque)
+        self._changed()
+
+    @property
+    def spring_frequency(self):
+        return self._frequency
+
+    @spring_frequency.setter
+    def spring_frequency(self, frequency):
+        self._frequency = float(frequency)
+        self._changed(wake=False)
+
+    @property
+    def spring_damping_ratio(self):
+        return self._damping_ratio
+
+    @spring_damping_ratio.setter
+    def spring_damping_ratio(self, damping_ratio):
+        self._damping_ratio = float(damping_ratio)
+        self._changed(wake=False)
+
+    def get_motor_torque(self, inv_dt):
+        return inv_dt * self._impulse3[2]
+
+    def get_reaction_torque(self, inv_dt):
+        return inv_dt * self._impulse3[2]
+
+
 def _unsupported(name):
     def ctor(*args, **kwargs):
-        raise NotImplementedError("%s is not supported on the batched step path (built: RevoluteJoint, DistanceJoint, WeldJoint, PrismaticJoint)" % name)
+        raise NotImplementedError("%s is not supported on the batched step path (built: revolute, distance, weld, prismatic, rope, friction, wheel)" % name)
     ctor.__name__ = name
     return ctor
 
 
-WheelJoint = _unsupported("WheelJoint")
 PulleyJoint = _unsupported("PulleyJoint")
 GearJoint = _unsupported("GearJoint")
-RopeJoint = _unsupported("RopeJoint")
-FrictionJoint = _unsupported("FrictionJoint")
 MouseJoint = _unsupported("MouseJoint")
 
 

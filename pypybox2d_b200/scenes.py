@@ -310,15 +310,15 @@ def joints(b2, world=0, config=9, **world_kw):
     bridge of revolute joints between two ground anchors (testbed/bridge.py) with bodies dropped on it, a hanging chain, a
     motorised arm with angle limits, a door with equal limits, a flail on a rigid distance joint, a soft (frequency > 0)
     distance spring, a welded cantilever, a joint with collide_connected=True, prismatic joints (motorised lift with limits, slider
-    between two dynamic bodies, equal limits, lower stop) and a joint between two dynamic bodies that start asleep."""
+    between two dynamic bodies, equal limits, lower stop), rope joints (taut and slack), a friction joint, a car on wheel joints and a joint between two dynamic bodies that start asleep."""
     w = b2.World((0, -10), True, **_kw(world_kw))
     ground = w.create_static_body(shapes=b2.Edge((-40.0, 0.0), (40.0, 0.0)))
     n_free = 12
-    jit = jitter(config, world, 64)
+    jit = jitter(config, world, 96)
     k = [1]
 
     def at(x, y):
-        j = jit[k[0] % 64]
+        j = jit[k[0] % 96]
         k[0] += 1
         return (x + j[0], y + j[1])
 
@@ -383,6 +383,24 @@ def joints(b2, world=0, config=9, **world_kw):
     drop = w.create_dynamic_body(position=(39.0, 6.0), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=1.0, friction=0.3))
     w.create_prismatic_joint(ground, drop, anchor=(39.0, 6.0), axis=(0.0, 1.0), lower_limit=-2.0, upper_limit=0.5, limit_enabled=True,
                              motor_enabled=True, motor_speed=0.0, max_motor_force=1.0)
+    # rope joints (a tethered ball that is thrown, a slack tether), a friction joint (top-down damping of a sliding puck) and a
+    # car on two wheel joints (spring suspension, one motorised wheel) that drives along the ground
+    tball = w.create_dynamic_body(position=at(-30.0, 9.0), linear_velocity=(6.0, 4.0), fixtures=b2.Fixture(b2.Circle(0.3), density=1.0, friction=0.3))
+    w.create_rope_joint(ground, tball, local_anchor_a=(-30.0, 12.0), local_anchor_b=(0.0, 0.0), max_length=3.5)
+    slack = w.create_dynamic_body(position=at(-26.0, 11.0), fixtures=b2.Fixture(b2.Polygon(box=(0.2, 0.2)), density=1.0, friction=0.3))
+    w.create_rope_joint(ground, slack, local_anchor_a=(-26.0, 12.0), local_anchor_b=(0.1, 0.1), max_length=6.0, collide_connected=True)
+    puck = w.create_dynamic_body(position=at(-18.0, 0.3), linear_velocity=(4.0, 0.0), angular_velocity=3.0,
+                                 fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.25)), density=1.0, friction=0.1))
+    w.create_friction_joint(ground, puck, local_anchor_a=(-18.0, 0.3), local_anchor_b=(0.0, 0.0), max_force=6.0, max_torque=2.0,
+                            collide_connected=True)
+    chassis = w.create_dynamic_body(position=(-2.0, 1.0), fixtures=b2.Fixture(b2.Polygon(box=(1.2, 0.25)), density=1.0, friction=0.3))
+    for side, motor in ((-1.0, True), (1.0, False)):
+        tyre = w.create_dynamic_body(position=at(-2.0 + 0.9 * side, 0.45), fixtures=b2.Fixture(b2.Circle(0.4), density=1.0, friction=0.9))
+        w.create_wheel_joint(chassis, tyre, anchor=tyre.position, axis=(0.0, 1.0), frequency=4.0, damping_ratio=0.7,
+                             motor_enabled=motor, motor_speed=-6.0, max_motor_torque=20.0)
+    idler = w.create_dynamic_body(position=at(3.5, 0.5), fixtures=b2.Fixture(b2.Circle(0.4), density=1.0, friction=0.5))
+    post = w.create_dynamic_body(position=(3.5, 1.5), fixtures=b2.Fixture(b2.Polygon(box=(0.2, 0.5)), density=1.0, friction=0.3))
+    w.create_wheel_joint(post, idler, anchor=idler.position, axis=(0.0, 1.0), frequency=0.0, damping_ratio=0.0)   # no spring: a rigid line
     # two sleeping bodies joined by a revolute joint, woken when something lands on them
     sa = w.create_dynamic_body(position=(28.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))
     sb = w.create_dynamic_body(position=(29.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))

@@ -6,7 +6,7 @@ step through the C-ABI (`include/b2b.h`) and mirrors the body state back into th
 objects.  A single `World` is a batch of one; large batches use `BatchedWorld` directly
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
-Revolute, distance, weld and prismatic joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
+Revolute, distance, weld, prismatic, rope, friction and wheel joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
 (raise `NotImplementedError`): the other joint types, controllers, `pre_solve` / `post_solve` listeners,
 custom contact filters, Loop shapes and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
@@ -260,11 +260,20 @@ class World(object):
     def create_prismatic_joint(self, *args, **kwargs):
         return self.add_joint(_joints.PrismaticJoint(*args, **kwargs))
 
-    def _create_unsupported_joint(self, *args, **kwargs):
-        raise NotImplementedError("only revolute, distance, weld and prismatic joints run on the batched step path (SURVEY §8f #3)")
+    def create_rope_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.RopeJoint(*args, **kwargs))
 
-    create_wheel_joint = create_pulley_joint = create_gear_joint = _create_unsupported_joint
-    create_rope_joint = create_friction_joint = create_mouse_joint = _create_unsupported_joint
+    def create_friction_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.FrictionJoint(*args, **kwargs))
+
+    def create_wheel_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.WheelJoint(*args, **kwargs))
+
+    def _create_unsupported_joint(self, *args, **kwargs):
+        raise NotImplementedError("pulley, gear and mouse joints do not run on the batched step path (SURVEY §8f #3: revolute, distance, "
+                                  "weld, prismatic, rope, friction and wheel joints do)")
+
+    create_pulley_joint = create_gear_joint = create_mouse_joint = _create_unsupported_joint
 
     def add_controller(self, controller):
         raise NotImplementedError("controllers are not supported on the batched step path")

@@ -58,10 +58,9 @@ def test_unsupported_features_fail_loudly():
     assert w.continuous_physics
     with pytest.raises(NotImplementedError):
         b2.World(sub_stepping=True)
-    # revolute, distance, weld and prismatic joints run on the device since round 2; the other joint types still raise
+    # revolute, distance, weld, prismatic, rope, friction and wheel joints run on the device since round 2; the other joint types still raise
     a, b = w.create_dynamic_body(position=(0, 1)), w.create_dynamic_body(position=(1, 1))
-    for make in (w.create_wheel_joint, w.create_pulley_joint, w.create_gear_joint, w.create_rope_joint,
-                 w.create_friction_joint, w.create_mouse_joint):
+    for make in (w.create_pulley_joint, w.create_gear_joint, w.create_mouse_joint):
         with pytest.raises(NotImplementedError):
             make(a, b)
 
@@ -86,6 +85,13 @@ def test_joint_constructors_mirror_the_reference():
     pj = w.create_prismatic_joint(ground, b, anchor=(3.0, 2.0), axis=(0.0, 1.0), lower_limit=-1.0, upper_limit=2.0, limit_enabled=True)
     assert (pj._local_x_axis.x, pj._local_x_axis.y) == (0.0, 1.0) and pj.joint_translation == 0.0 and pj.limit_enabled
     w.destroy_joint(pj)
+    rope = w.create_rope_joint(ground, b, local_anchor_a=(3.0, 6.0), max_length=5.0)
+    fj = w.create_friction_joint(ground, b, max_force=2.0, max_torque=1.0)
+    wheel = w.create_wheel_joint(a, b, anchor=(3.0, 2.0), axis=(0.0, 1.0), motor_enabled=True, motor_speed=1.0, max_motor_torque=5.0)
+    assert rope.max_length == 5.0 and fj.max_force == 2.0 and wheel.spring_frequency == 2.0 and wheel.motor_enabled
+    assert len(rope._par()) <= 12 and len(wheel._par()) <= 12
+    for j in (rope, fj, wheel):
+        w.destroy_joint(j)
     assert w.joints == [rj, dj, wj]
     assert a.joints == [rj, wj] and b.joints == [rj, dj] and ground.joints == [dj, wj]
     with pytest.raises(ValueError):
