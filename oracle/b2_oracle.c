@@ -1098,6 +1098,8 @@ static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
 #define J_ROPE     5
 #define J_FRICTION 6
 #define J_WHEEL    7
+#define J_PULLEY   8
+#define J_MOUSE    9
 #define JF_COLLIDE 0x1
 #define JF_LIMIT   0x2
 #define JF_MOTOR   0x4
@@ -1138,9 +1140,73 @@ static inline void m33_store(double* t, const m33* m)
 }
 
 
+/* MouseJoint (mouse.py:138-229): one body (j_def body_a = -1); par: [2:4] local_anchor_b, [4:6] target, [6] max_force, [7] frequency,
+ * [8] damping_ratio, [9] Body.mass; tmp: [2:4] rb, [4:8] the inverse of K by columns, [8:10] c, [10] gamma */
+static void mouse_init(orc_world* w, int k, double dt, double dt_ratio, int warm, pos_t* P, vel_t* Vv)
+{
+    const int32_t* def = w->j_def + 4 * (size_t)k;
+    const double* par = w->j_par + 12 * (size_t)k;
+    double* imp = w->j_imp + 4 * (size_t)k;
+    double* tmp = w->j_tmp + 20 * (size_t)k;
+    int bb = def[2], ib_ = w->b_island[bb];
+    v2 cb = P[ib_].c; double ab = P[ib_].a;
+    v2 vb = Vv[ib_].v; double wb = Vv[ib_].w;
+    double mb = w->b_mass[4 * bb], ib = w->b_mass[4 * bb + 1];
+    v2 lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);
+    xform qb = rot_make(ab);
+    double mass = par[9];
+    double omega = 2.0 * PI_ * par[7];
+    double d = 2.0 * mass * par[8] * omega;
+    double kk = mass * sq(omega);
+    double gamma = dt * (d + dt * kk);
+    if (gamma != 0.0) gamma = 1.0 / gamma;
+    double beta = dt * kk * gamma;
+    v2 rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+    double k1x = mb + ib * sq(rb.y) + gamma, k1y = -ib * rb.x * rb.y;
+    double k2x = k1y, k2y = mb + ib * sq(rb.x) + gamma;
+    double det = k1x * k2y - k2x * k1y;
+    if (det != 0.0) det = 1.0 / det;
+    tmp[2] = rb.x; tmp[3] = rb.y;
+    tmp[4] = det * k2y; tmp[5] = -det * k1y; tmp[6] = -det * k2x; tmp[7] = det * k1x;
+    v2 c = vscale(beta, vsub(vadd(cb, rb), V(par[4], par[5])));
+    tmp[8] = c.x; tmp[9] = c.y; tmp[10] = gamma;
+    wb *= 0.98;
+    if (warm) {
+        imp[0] = dt_ratio * imp[0]; imp[1] = dt_ratio * imp[1];
+        v2 I = V(imp[0], imp[1]);
+        vb = vadd(vb, vscale(mb, I));
+        wb += ib * vcross(rb, I);
+    } else { imp[0] = 0.0; imp[1] = 0.0; }
+    Vv[ib_].v = vb; Vv[ib_].w = wb;
+}
+static void mouse_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
+{
+    const int32_t* def = w->j_def + 4 * (size_t)k;
+    const double* par = w->j_par + 12 * (size_t)k;
+    double* imp = w->j_imp + 4 * (size_t)k;
+    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    int bb = def[2], ib_ = w->b_island[bb];
+    v2 vb = Vv[ib_].v; double wb = Vv[ib_].w;
+    double mb = w->b_mass[4 * bb], ib = w->b_mass[4 * bb + 1];
+    v2 rb = V(tmp[2], tmp[3]);
+    v2 Cdot = vadd(vb, scross(wb, rb));
+    v2 rhs = vneg(vadd(vadd(Cdot, V(tmp[8], tmp[9])), vscale(tmp[10], V(imp[0], imp[1]))));
+    v2 impulse = V(tmp[4] * rhs.x + tmp[6] * rhs.y, tmp[5] * rhs.x + tmp[7] * rhs.y);
+    v2 old_impulse = V(imp[0], imp[1]);
+    v2 cur = vadd(old_impulse, impulse);
+    double max_impulse = dt * par[6];
+    if (vlen2(cur) > sq(max_impulse)) { double f = max_impulse / sqrt(sq(cur.x) + sq(cur.y)); cur = V(f * cur.x, f * cur.y); }
+    imp[0] = cur.x; imp[1] = cur.y;
+    impulse = vsub(cur, old_impulse);
+    vb = vadd(vb, vscale(mb, impulse));
+    wb += ib * vcross(rb, impulse);
+    Vv[ib_].v = vb; Vv[ib_].w = wb;
+}
+
 /* _init_velocity_constraints: revolute.py:208-300, distance.py:155-250, weld.py:106-169 */
 static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm, pos_t* P, vel_t* Vv)
 {
+    if (w->j_def[4 * (size_t)k] == J_MOUSE) { mouse_init(w, k, dt, dt_ratio, warm, P, Vv); return; }
     int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
@@ -1366,6 +1432,26 @@ static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm
             wb += ib * Lb;
         } else { imp[0] = 0.0; imp[1] = 0.0; imp[2] = 0.0; }
     }
+    else if (type == J_PULLEY) {                                                     /* pulley.py:156-228 */
+        v2 ua = vsub(vadd(ca, ra), V(par[4], par[5])), ub = vsub(vadd(cb, rb), V(par[6], par[7]));
+        double length_a = sqrt(sq(ua.x) + sq(ua.y)), length_b = sqrt(sq(ub.x) + sq(ub.y));
+        ua = (length_a > 10.0 * LINEAR_SLOP) ? V(ua.x / length_a, ua.y / length_a) : V(0.0, 0.0);
+        ub = (length_b > 10.0 * LINEAR_SLOP) ? V(ub.x / length_b, ub.y / length_b) : V(0.0, 0.0);
+        tmp[4] = ua.x; tmp[5] = ua.y; tmp[6] = ub.x; tmp[7] = ub.y;
+        double rua = vcross(ra, ua), rub = vcross(rb, ub);
+        double ema = ma + ia * sq(rua), emb = mb + ib * sq(rub);                     /* the locals `ma`, `mb` are rebound: the warm start below uses them */
+        double mass = ema + par[8] * par[8] * emb;
+        if (mass > 0.0) mass = 1.0 / mass;
+        tmp[8] = mass;
+        if (warm) {
+            imp[0] *= dt_ratio;
+            v2 Pa = vscale(-imp[0], ua), Pb = vscale(-par[8] * imp[0], ub);
+            va = vadd(va, vscale(ema, Pa));
+            wa += ia * vcross(ra, Pa);
+            vb = vadd(vb, vscale(emb, Pb));
+            wb += ib * vcross(rb, Pb);
+        } else imp[0] = 0.0;
+    }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
 }
@@ -1378,6 +1464,7 @@ static inline m33 m33_sym(const double* k)     /* Mat33((k11, k12, k13), (k12, k
 /* _solve_velocity_constraints: revolute.py:302-378, distance.py:252-275, weld.py:171-199 */
 static void joint_solve_velocity(orc_world* w, int k, double dt, double inv_dt, vel_t* Vv)
 {
+    if (w->j_def[4 * (size_t)k] == J_MOUSE) { mouse_solve_velocity(w, k, dt, Vv); return; }
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
@@ -1568,6 +1655,18 @@ static void joint_solve_velocity(orc_world* w, int k, double dt, double inv_dt, 
         vb = vadd(vb, vscale(mb, Pv));
         wb += ib * Lb;
     }
+    else if (type == J_PULLEY) {                                                     /* pulley.py:230-256 */
+        v2 ua = V(tmp[4], tmp[5]), ub = V(tmp[6], tmp[7]);
+        v2 vpa = vadd(va, scross(wa, ra)), vpb = vadd(vb, scross(wb, rb));
+        double Cdot = -vdot(ua, vpa) - par[8] * vdot(ub, vpb);
+        double impulse = -tmp[8] * Cdot;
+        imp[0] += impulse;
+        v2 Pa = vscale(-impulse, ua), Pb = vscale(-par[8] * impulse, ub);
+        va = vadd(va, vscale(ma, Pa));
+        wa += ia * vcross(ra, Pa);
+        vb = vadd(vb, vscale(mb, Pb));
+        wb += ib * vcross(rb, Pb);
+    }
     Vv[ia_].v = va; Vv[ia_].w = wa;
     Vv[ib_].v = vb; Vv[ib_].w = wb;
 }
@@ -1575,6 +1674,7 @@ static void joint_solve_velocity(orc_world* w, int k, double dt, double inv_dt, 
 /* _solve_position_constraints: revolute.py:380-453, distance.py:277-311, weld.py:201-257; returns "within tolerance" */
 static int joint_solve_position(orc_world* w, int k, pos_t* P)
 {
+    if (w->j_def[4 * (size_t)k] == J_MOUSE) return 1;                                  /* mouse.py:227-229 */
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     const double* tmp = w->j_tmp + 20 * (size_t)k;
@@ -1753,6 +1853,27 @@ static int joint_solve_position(orc_world* w, int k, pos_t* P)
         cb = vadd(cb, vscale(mb, Pv));
         ab += ib * Lb;
         ok = fabs(Cc) <= LINEAR_SLOP;
+    }
+    else if (type == J_PULLEY) {                                                     /* pulley.py:258-318 */
+        xform qa = rot_make(aa), qb = rot_make(ab);
+        v2 ra = rot_mul(&qa, vsub(V(par[0], par[1]), lca)), rb = rot_mul(&qb, vsub(V(par[2], par[3]), lcb));
+        v2 ua = vsub(vadd(ca, ra), V(par[4], par[5])), ub = vsub(vadd(cb, rb), V(par[6], par[7]));
+        double length_a = sqrt(sq(ua.x) + sq(ua.y)), length_b = sqrt(sq(ub.x) + sq(ub.y));
+        ua = (length_a > 10.0 * LINEAR_SLOP) ? V(ua.x / length_a, ua.y / length_a) : V(0.0, 0.0);
+        ub = (length_b > 10.0 * LINEAR_SLOP) ? V(ub.x / length_b, ub.y / length_b) : V(0.0, 0.0);
+        double rua = vcross(ra, ua), rub = vcross(rb, ub);
+        double ema = ma + ia * sq(rua), emb = mb + ib * sq(rub);
+        double mass = ema + sq(par[8]) * emb;
+        if (mass > 0.0) mass = 1.0 / mass;
+        double Cc = par[9] - length_a - par[8] * length_b;
+        double linear_error = fabs(Cc);
+        double impulse = -mass * Cc;
+        v2 Pa = vscale(-impulse, ua), Pb = vscale(-par[8] * impulse, ub);
+        ca = vadd(ca, vscale(ema, Pa));
+        aa += ia * vcross(ra, Pa);
+        cb = vadd(cb, vscale(emb, Pb));
+        ab += ib * vcross(rb, Pb);
+        ok = linear_error < LINEAR_SLOP;
     }
     P[ia_].c = ca; P[ia_].a = aa;
     P[ib_].c = cb; P[ib_].a = ab;
@@ -1982,6 +2103,7 @@ static void world_solve(orc_world* w, double dt, double dt_ratio, int vel_iters,
                 int32_t* def = w->j_def + 4 * (size_t)j;
                 if (def[3] & JF_ISLAND) continue;
                 int other = (def[1] == b) ? def[2] : def[1];
+                if (other < 0) { w->l_joint[lj++] = j; def[3] |= JF_ISLAND; continue; }   /* a joint on one body (MouseJoint): world.py:556-560 */
                 if (!(w->b_flags[other] & BODY_ACTIVE)) continue;
                 w->l_joint[lj++] = j;
                 def[3] |= JF_ISLAND;

@@ -194,7 +194,8 @@ def extract_joints(world, A, w, bidx, schema):
         if getattr(j, "_motor_enabled", False):
             flags |= schema.JOINT_MOTOR_ENABLED
         flags |= int(getattr(j, "_limit_state", 0)) << schema.JOINT_LIMIT_SHIFT
-        la, lb = j._local_anchor_a, j._local_anchor_b
+        lb = j._local_anchor_b
+        la = getattr(j, "_local_anchor_a", None) or b2.Vec2()
         par = [la.x, la.y, lb.x, lb.y]
         if isinstance(j, _j.RevoluteJoint):
             t = schema.JOINT_REVOLUTE
@@ -226,9 +227,17 @@ def extract_joints(world, A, w, bidx, schema):
             t = schema.JOINT_WHEEL
             par += [j._local_x_axis.x, j._local_x_axis.y, j._frequency, j._damping_ratio, j._max_motor_torque, j._motor_speed]
             imp = (j._impulse, j._spring_impulse, j._motor_impulse, 0.0)
+        elif isinstance(j, _j.PulleyJoint):
+            t = schema.JOINT_PULLEY
+            par += [j._ground_anchor_a.x, j._ground_anchor_a.y, j._ground_anchor_b.x, j._ground_anchor_b.y, j._ratio, j._constant]
+            imp = (j._impulse, 0.0, 0.0, 0.0)
+        elif isinstance(j, _j.MouseJoint):
+            t = schema.JOINT_MOUSE
+            par += [j._target.x, j._target.y, j._max_force, j._frequency, j._damping_ratio, j._body_b.mass]
+            imp = (j._impulse.x, j._impulse.y, 0.0, 0.0)
         else:
             raise NotImplementedError(type(j))
-        A["j_def"][w, k] = (t, bidx[id(j._body_a)], bidx[id(j._body_b)], flags)
+        A["j_def"][w, k] = (t, bidx[id(j._body_a)] if j._body_a is not None else -1, bidx[id(j._body_b)], flags)
         A["j_par"][w, k] = 0.0
         A["j_par"][w, k, :len(par)] = par
         A["j_imp"][w, k] = imp

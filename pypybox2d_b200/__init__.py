@@ -13,10 +13,10 @@ from .fixture import Fixture
 from .body import Body
 from .world import World, TimeStep
 from . import joints
-from .joints import RevoluteJoint, DistanceJoint, WeldJoint, PrismaticJoint, RopeJoint, FrictionJoint, WheelJoint
+from .joints import RevoluteJoint, DistanceJoint, WeldJoint, PrismaticJoint, RopeJoint, FrictionJoint, WheelJoint, PulleyJoint, MouseJoint
 from .batch import BatchedWorld
 
 __all__ = ["World", "Body", "Fixture", "Circle", "Polygon", "Edge", "Loop", "Vec2", "BatchedWorld",
            "PhysicsError", "LockedError", "EmptyFixtureError", "TimeStep", "MassData",
            "scalar_cross", "clamp", "is_valid_float", "PI", "EPSILON", "MAX_FLOAT",
-           "settings", "shapes", "scenes", "schema", "joints", "RevoluteJoint", "DistanceJoint", "WeldJoint", "PrismaticJoint", "RopeJoint", "FrictionJoint", "WheelJoint"]
+           "settings", "shapes", "scenes", "schema", "joints", "RevoluteJoint", "DistanceJoint", "WeldJoint", "PrismaticJoint", "RopeJoint", "FrictionJoint", "WheelJoint", "PulleyJoint", "MouseJoint"]

@@ -2,7 +2,7 @@
 //
 // RevoluteJoint (pypybox2d/joints/revolute.py:208-453), DistanceJoint (joints/distance.py:155-311), WeldJoint
 // (joints/weld.py:106-257), PrismaticJoint (joints/prismatic.py:232-513), RopeJoint (joints/rope.py:106-248), FrictionJoint
-// (joints/friction.py:105-233) and WheelJoint (joints/wheel.py:202-416) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
+// (joints/friction.py:105-233), WheelJoint (joints/wheel.py:202-416), PulleyJoint (joints/pulley.py:156-318) and MouseJoint (joints/mouse.py:138-229) on the reference's pure-Python Vec3 / Mat33 (common.py:227-358, 533-614), operand by operand: the
 // fp64 host build of this file is bit-identical to the oracle, which is pinned bit-identical to the live reference.
 //
 // Island.solve visits an island's joints one after the other, before the contacts in every velocity iteration and after them in
@@ -17,7 +17,7 @@
 // matrix by columns and the motor mass; or u, mass, gamma, bias; prismatic: axis, perp, s1, s2, a1, a2, motor mass and the six
 // distinct entries of its symmetric K).
 
-enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4, JOINT_ROPE = 5, JOINT_FRICTION = 6, JOINT_WHEEL = 7 };
+enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4, JOINT_ROPE = 5, JOINT_FRICTION = 6, JOINT_WHEEL = 7, JOINT_PULLEY = 8, JOINT_MOUSE = 9 };
 enum { JF_COLLIDE = 0x1, JF_LIMIT = 0x2, JF_MOTOR = 0x4, JF_ISLAND = 0x8, JF_LS_SHIFT = 8 };
 enum { LS_INACTIVE = 0, LS_LOWER = 1, LS_UPPER = 2, LS_EQUAL = 3 };               // joints/joint.py:36
 enum { JOINT_PAR = 12, JOINT_TMP = 20 };
@@ -86,8 +86,9 @@ B2B_D void joint_fetch(int k, jrow& r, int what) const
 #pragma unroll
         for (int i = 0; i < JOINT_TMP / 4; ++i) { const quad q = t[i]; r.tmp[4 * i] = q.x; r.tmp[4 * i + 1] = q.y; r.tmp[4 * i + 2] = q.z; r.tmp[4 * i + 3] = q.w; }
     }
-    r.mqa = ldq(b_mass + 4 * (size_t)r.def[1]); r.mqb = ldq(b_mass + 4 * (size_t)r.def[2]);
-    if (what == JFETCH_INIT) { r.pa = ldq(b_pos + 4 * (size_t)r.def[1]); r.pb = ldq(b_pos + 4 * (size_t)r.def[2]); }
+    const int ba = (r.def[1] >= 0) ? r.def[1] : r.def[2];          // a joint on one body (MouseJoint) has body_a = -1
+    r.mqa = ldq(b_mass + 4 * (size_t)ba); r.mqb = ldq(b_mass + 4 * (size_t)r.def[2]);
+    if (what == JFETCH_INIT) { r.pa = ldq(b_pos + 4 * (size_t)ba); r.pb = ldq(b_pos + 4 * (size_t)r.def[2]); }
 }
 B2B_D void joint_store(const jrow& r, int what)
 {
@@ -125,6 +126,74 @@ template <class Apply> B2B_D int joint_sweep(int j0, int j1, int what, Apply app
     return all_ok;
 }
 
+// MouseJoint (mouse.py:138-229): one body (j_def body_a = -1); par: [2:4] local_anchor_b, [4:6] target, [6] max_force, [7] frequency,
+// [8] damping_ratio, [9] Body.mass; tmp: [2:4] rb, [4:8] the inverse of K by columns, [8:10] c, [10] gamma
+B2B_D void mouse_init(jrow& r, real dt, real dt_ratio, bool warm)
+{
+    const real* par = r.par;
+    real* imp = r.imp;
+    real* tmp = r.tmp;
+    const int bb = r.def[2];
+    const real mb = r.mqb.x, ib = r.mqb.y;
+    const V2 lcb = mk<real>(r.mqb.z, r.mqb.w);
+    const V2 cb = mk<real>(r.pb.x, r.pb.y);
+    const real ab = r.pb.z;
+    const quad sb = state_get(bb);
+    V2 vb = mk<real>(sb.x, sb.y);
+    real wb = sb.z;
+    const XF qb = rot_of(ab);
+    const real mass = par[9];
+    const real omega = real(2) * K<real>::pi * par[7];
+    const real d = real(2) * mass * par[8] * omega;
+    const real kk = mass * sq_r(omega);
+    real gamma = dt * (d + dt * kk);
+    if (gamma != real(0)) gamma = real(1) / gamma;
+    const real beta = dt * kk * gamma;
+    const V2 rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+    const real k1x = mb + ib * sq_r(rb.y) + gamma, k1y = -ib * rb.x * rb.y;
+    const real k2x = k1y, k2y = mb + ib * sq_r(rb.x) + gamma;
+    real det = k1x * k2y - k2x * k1y;
+    if (det != real(0)) det = real(1) / det;
+    tmp[2] = rb.x; tmp[3] = rb.y;
+    tmp[4] = det * k2y; tmp[5] = -det * k1y; tmp[6] = -det * k2x; tmp[7] = det * k1x;
+    const V2 c = beta * (cb + rb - mk<real>(par[4], par[5]));
+    tmp[8] = c.x; tmp[9] = c.y; tmp[10] = gamma;
+    wb = wb * real(0.98);
+    real i0 = imp[0], i1 = imp[1];
+    if (warm) {
+        i0 = dt_ratio * i0; i1 = dt_ratio * i1;
+        const V2 I = mk<real>(i0, i1);
+        vb = vb + mb * I;
+        wb = wb + ib * cross(rb, I);
+    } else { i0 = real(0); i1 = real(0); }
+    imp[0] = i0; imp[1] = i1;
+    state_set(bb, vb.x, vb.y, wb);
+}
+B2B_D void mouse_solve_velocity(jrow& r, real dt)
+{
+    const real* par = r.par;
+    real* imp = r.imp;
+    const real* tmp = r.tmp;
+    const int bb = r.def[2];
+    const real mb = r.mqb.x, ib = r.mqb.y;
+    const quad sb = state_get(bb);
+    V2 vb = mk<real>(sb.x, sb.y);
+    real wb = sb.z;
+    const V2 rb = mk<real>(tmp[2], tmp[3]);
+    const V2 Cdot = vb + cross_sv(wb, rb);
+    const V2 rhs = -(Cdot + mk<real>(tmp[8], tmp[9]) + tmp[10] * mk<real>(imp[0], imp[1]));
+    V2 impulse = mk<real>(tmp[4] * rhs.x + tmp[6] * rhs.y, tmp[5] * rhs.x + tmp[7] * rhs.y);
+    const V2 old_impulse = mk<real>(imp[0], imp[1]);
+    V2 cur = old_impulse + impulse;
+    const real max_impulse = dt * par[6];
+    if (sq_r(cur.x) + sq_r(cur.y) > sq_r(max_impulse)) { const real f = max_impulse / sqrt_r(sq_r(cur.x) + sq_r(cur.y)); cur = mk<real>(f * cur.x, f * cur.y); }
+    imp[0] = cur.x; imp[1] = cur.y;
+    impulse = cur - old_impulse;
+    vb = vb + mb * impulse;
+    wb = wb + ib * cross(rb, impulse);
+    state_set(bb, vb.x, vb.y, wb);
+}
+
 // _init_velocity_constraints (revolute.py:208-300, distance.py:155-250, weld.py:106-169).  Velocities: the team's shared state;
 // positions: b_pos (the sweeps before this step's integration -- the velocity kernel runs before integrate_position).
 B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
@@ -135,6 +204,7 @@ B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
     real* tmp = r.tmp;
 #pragma unroll
     for (int i = 0; i < JOINT_TMP; ++i) tmp[i] = real(0);
+    if (def[0] == JOINT_MOUSE) { mouse_init(r, dt, dt_ratio, warm); return; }
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     const quad mqa = r.mqa, mqb = r.mqb;
     const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
@@ -373,6 +443,28 @@ B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
         } else { i0 = real(0); i1 = real(0); i2 = real(0); }
         imp[0] = i0; imp[1] = i1; imp[2] = i2;
     }
+    else if (type == JOINT_PULLEY) {                                                 // pulley.py:156-228
+        V2 ua = ca + ra - mk<real>(par[4], par[5]), ub = cb + rb - mk<real>(par[6], par[7]);
+        const real length_a = sqrt_r(sq_r(ua.x) + sq_r(ua.y)), length_b = sqrt_r(sq_r(ub.x) + sq_r(ub.y));
+        ua = (length_a > real(10) * K<real>::linear_slop) ? mk<real>(ua.x / length_a, ua.y / length_a) : mk<real>(real(0), real(0));
+        ub = (length_b > real(10) * K<real>::linear_slop) ? mk<real>(ub.x / length_b, ub.y / length_b) : mk<real>(real(0), real(0));
+        tmp[4] = ua.x; tmp[5] = ua.y; tmp[6] = ub.x; tmp[7] = ub.y;
+        const real rua = cross(ra, ua), rub = cross(rb, ub);
+        const real ema = ma + ia * sq_r(rua), emb = mb + ib * sq_r(rub);             // the port rebinds `ma`, `mb`: its warm start uses these
+        real mass = ema + par[8] * par[8] * emb;
+        if (mass > real(0)) mass = real(1) / mass;
+        tmp[8] = mass;
+        real i0 = imp[0];
+        if (warm) {
+            i0 = i0 * dt_ratio;
+            const V2 Pa = (-i0) * ua, Pb = (-par[8] * i0) * ub;
+            va = va + ema * Pa;
+            wa = wa + ia * cross(ra, Pa);
+            vb = vb + emb * Pb;
+            wb = wb + ib * cross(rb, Pb);
+        } else i0 = real(0);
+        imp[0] = i0;
+    }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
 }
@@ -384,6 +476,7 @@ B2B_D void joint_solve_velocity(jrow& r, real dt, real inv_dt)
     const real* par = r.par;
     real* imp = r.imp;
     const real* tmp = r.tmp;
+    if (def[0] == JOINT_MOUSE) { mouse_solve_velocity(r, dt); return; }
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     const real ma = r.mqa.x, ia = r.mqa.y, mb = r.mqb.x, ib = r.mqb.y;
     const quad sa = state_get(ba), sb = state_get(bb);
@@ -579,6 +672,18 @@ B2B_D void joint_solve_velocity(jrow& r, real dt, real inv_dt)
         vb = vb + mb * P;
         wb = wb + ib * Lb;
     }
+    else if (type == JOINT_PULLEY) {                                                 // pulley.py:230-256
+        const V2 ua = mk<real>(tmp[4], tmp[5]), ub = mk<real>(tmp[6], tmp[7]);
+        const V2 vpa = va + cross_sv(wa, ra), vpb = vb + cross_sv(wb, rb);
+        const real Cdot = -dot(ua, vpa) - par[8] * dot(ub, vpb);
+        const real impulse = -tmp[8] * Cdot;
+        imp[0] = imp[0] + impulse;
+        const V2 Pa = (-impulse) * ua, Pb = (-par[8] * impulse) * ub;
+        va = va + ma * Pa;
+        wa = wa + ia * cross(ra, Pa);
+        vb = vb + mb * Pb;
+        wb = wb + ib * cross(rb, Pb);
+    }
     state_set(ba, va.x, va.y, wa);
     state_set(bb, vb.x, vb.y, wb);
 }
@@ -590,6 +695,7 @@ B2B_D bool joint_solve_position(const jrow& r)
     const int32_t* def = r.def;
     const real* par = r.par;
     const real* tmp = r.tmp;
+    if (def[0] == JOINT_MOUSE) return true;                                          // mouse.py:227-229
     const int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     const quad mqa = r.mqa, mqb = r.mqb;
     const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
@@ -767,6 +873,27 @@ B2B_D bool joint_solve_position(const jrow& r)
         cb = cb + mb * P;
         ab = ab + ib * Lb;
         ok = abs_r(C) <= K<real>::linear_slop;
+    }
+    else if (type == JOINT_PULLEY) {                                                 // pulley.py:258-318
+        const XF qa = rot_of(aa), qb = rot_of(ab);
+        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        V2 ua = ca + ra - mk<real>(par[4], par[5]), ub = cb + rb - mk<real>(par[6], par[7]);
+        const real length_a = sqrt_r(sq_r(ua.x) + sq_r(ua.y)), length_b = sqrt_r(sq_r(ub.x) + sq_r(ub.y));
+        ua = (length_a > real(10) * K<real>::linear_slop) ? mk<real>(ua.x / length_a, ua.y / length_a) : mk<real>(real(0), real(0));
+        ub = (length_b > real(10) * K<real>::linear_slop) ? mk<real>(ub.x / length_b, ub.y / length_b) : mk<real>(real(0), real(0));
+        const real rua = cross(ra, ua), rub = cross(rb, ub);
+        const real ema = ma + ia * sq_r(rua), emb = mb + ib * sq_r(rub);
+        real mass = ema + sq_r(par[8]) * emb;
+        if (mass > real(0)) mass = real(1) / mass;
+        const real C = par[9] - length_a - par[8] * length_b;
+        const real linear_error = abs_r(C);
+        const real impulse = -mass * C;
+        const V2 Pa = (-impulse) * ua, Pb = (-par[8] * impulse) * ub;
+        ca = ca + ema * Pa;
+        aa = aa + ia * cross(ra, Pa);
+        cb = cb + emb * Pb;
+        ab = ab + ib * cross(rb, Pb);
+        ok = linear_error < K<real>::linear_slop;
     }
     state_set(ba, ca.x, ca.y, aa);
     state_set(bb, cb.x, cb.y, ab);

@@ -840,6 +840,7 @@ template <class real> struct world_step {
                             int32_t* def = j_def + 4 * (size_t)j;
                             if (def[3] & JF_ISLAND) continue;
                             const int other = (def[1] == b) ? def[2] : def[1];
+                            if (other < 0) { l_joint[lj++] = j; def[3] |= JF_ISLAND; continue; }   // a joint on one body (MouseJoint): world.py:556-560
                             if (!(s_flags[other] & BODY_ACTIVE)) continue;
                             l_joint[lj++] = j;
                             def[3] |= JF_ISLAND;

@@ -1,8 +1,8 @@
 """Joints of the island solver: the drop-in surface of `pypybox2d/joints/`.
 
 `RevoluteJoint` (`joints/revolute.py`), `DistanceJoint` (`joints/distance.py`), `WeldJoint` (`joints/weld.py`) and
-`PrismaticJoint` (`joints/prismatic.py`), `RopeJoint` (`joints/rope.py`), `FrictionJoint` (`joints/friction.py`) and `WheelJoint`
-(`joints/wheel.py`) with the
+`PrismaticJoint` (`joints/prismatic.py`), `RopeJoint` (`joints/rope.py`), `FrictionJoint` (`joints/friction.py`), `WheelJoint`
+(`joints/wheel.py`), `PulleyJoint` (`joints/pulley.py`) and `MouseJoint` (`joints/mouse.py`) with the
 reference's constructor keywords, read-backs and setters.  A joint object only holds its definition: one row of the device
 arrays `j_def` (type, bodies, flags), `j_par` (parameters, layout below) and `j_imp` (accumulated impulses, mirrored back
 after every step).  The constraint itself -- `_init_velocity_constraints`, `_solve_velocity_constraints`,
@@ -17,7 +17,9 @@ after every step).  The constraint itself -- `_init_velocity_constraints`, `_sol
   rope        [4] max_length
   friction    [4] max_force, [5] max_torque
   wheel       [4:6] local_x_axis, [6] frequency, [7] damping_ratio, [8] max_motor_torque, [9] motor_speed
-The other joint types of the reference (pulley, gear, mouse) raise NotImplementedError.
+  pulley      [4:6] ground_anchor_a, [6:8] ground_anchor_b, [8] ratio, [9] constant = length_a + ratio * length_b
+  mouse       (one body: j_def body_a = -1) [4:6] target, [6] max_force, [7] frequency, [8] damping_ratio, [9] Body.mass
+GearJoint (a constraint between two other joints) raises NotImplementedError.
 """
 import math
 
@@ -113,7 +115,8 @@ class Joint(object):
     def _changed(self, wake=True):
         if wake:
             for body in self.bodies:
-                body.awake = True
+                if body is not None:
+                    body.awake = True
         if self._world is not None:
             self._world._joints_dirty = True
             self._world._host_dirty = True
@@ -590,16 +593,149 @@ class WheelJoint(Joint):
         return inv_dt * self._impulse3[2]
 
 
+class PulleyJoint(Joint):
+    """joints/pulley.py:33-320: length_a + ratio * length_b stays constant; the ground anchors are world points."""
+    _type = schema.JOINT_PULLEY
+
+    def __init__(self, body_a, body_b, ground_anchor_a=(0, 0), ground_anchor_b=(0, 0), anchor_a=(0, 0), anchor_b=(0, 0), ratio=1.0,
+                 length_a=None, length_b=None, collide_connected=False, local_anchor_a=None, local_anchor_b=None):
+        from .settings import EPSILON
+        if body_a is None or body_b is None:
+            raise ValueError('body_a and body_b must be set')
+        Joint.__init__(self, body_a, body_b, collide_connected)
+        if ratio == 0.0 or ratio < EPSILON:
+            raise ValueError('Ratio must be positive, non-zero and not too small')
+        self._local_anchor_a = body_a.get_local_point(anchor_a) if local_anchor_a is None else Vec2(*local_anchor_a)
+        self._local_anchor_b = body_b.get_local_point(anchor_b) if local_anchor_b is None else Vec2(*local_anchor_b)
+        self._ground_anchor_a = Vec2(*ground_anchor_a)
+        self._ground_anchor_b = Vec2(*ground_anchor_b)
+        if length_a is None:
+            dx, dy = anchor_a[0] - self._ground_anchor_a.x, anchor_a[1] - self._ground_anchor_a.y
+            length_a = math.sqrt(dx ** 2 + dy ** 2)
+        if length_b is None:
+            dx, dy = anchor_b[0] - self._ground_anchor_b.x, anchor_b[1] - self._ground_anchor_b.y
+            length_b = math.sqrt(dx ** 2 + dy ** 2)
+        self._length_a = length_a
+        self._length_b = length_b
+        self._constant = length_a + ratio * length_b
+        self._ratio = ratio
+
+    def __copy__(self):
+        return PulleyJoint(self._body_a, self._body_b, self._ground_anchor_a, self._ground_anchor_b, None, None, self._ratio,
+                           self._length_a, self._length_b, self._collide_connected, self._local_anchor_a, self._local_anchor_b)
+
+    def _par(self):
+        return [self._local_anchor_a.x, self._local_anchor_a.y, self._local_anchor_b.x, self._local_anchor_b.y,
+                self._ground_anchor_a.x, self._ground_anchor_a.y, self._ground_anchor_b.x, self._ground_anchor_b.y,
+                self._ratio, self._constant]
+
+    ground_anchor_a = property(lambda self: Vec2(*self._ground_anchor_a))
+    ground_anchor_b = property(lambda self: Vec2(*self._ground_anchor_b))
+    ratio = property(lambda self: self._ratio)
+
+    @property
+    def length_a(self):
+        p = self.anchor_a
+        return math.hypot(p.x - self._ground_anchor_a.x, p.y - self._ground_anchor_a.y)
+
+    @property
+    def length_b(self):
+        p = self.anchor_b
+        return math.hypot(p.x - self._ground_anchor_b.x, p.y - self._ground_anchor_b.y)
+
+    def get_reaction_force(self, inv_dt):
+        u = getattr(self, "_ub", (0.0, 0.0))
+        return Vec2(inv_dt * (self._impulse3[0] * u[0]), inv_dt * (self._impulse3[0] * u[1]))
+
+    def get_reaction_torque(self, inv_dt):
+        return 0.0
+
+
+class MouseJoint(Joint):
+    """joints/mouse.py:33-229: a soft constraint that pulls a point of ONE body to a world target (body_a is None)."""
+    _type = schema.JOINT_MOUSE
+
+    def __init__(self, body, target=(0, 0), max_force=0.0, frequency=5.0, damping_ratio=0.7):
+        from .common import is_valid_float
+        if body is None:
+            raise ValueError('body must be set')
+        target = Vec2(*target)
+        if not (is_valid_float(target.x) and is_valid_float(target.y)):
+            raise ValueError('Invalid target')
+        if not is_valid_float(max_force) or max_force < 0.0:
+            raise ValueError('Invalid maximum force')
+        if not is_valid_float(frequency) or frequency < 0.0:
+            raise ValueError('Invalid frequency')
+        if not is_valid_float(damping_ratio) or damping_ratio < 0.0:
+            raise ValueError('Invalid damping ratio')
+        Joint.__init__(self, None, body, False)
+        self._target = target
+        self._local_anchor_a = Vec2()
+        self._local_anchor_b = body.get_local_point(target)
+        self._max_force = float(max_force)
+        self._frequency = float(frequency)
+        self._damping_ratio = float(damping_ratio)
+
+    def __copy__(self):
+        return MouseJoint(self._body_b, self._target, self._max_force, self._frequency, self._damping_ratio)
+
+    def _par(self):
+        return [0.0, 0.0, self._local_anchor_b.x, self._local_anchor_b.y, self._target.x, self._target.y, self._max_force,
+                self._frequency, self._damping_ratio, self._body_b.mass]
+
+    active = property(lambda self: self._body_b.active)
+    anchor_a = property(lambda self: Vec2(*self._target))
+
+    @property
+    def target(self):
+        return Vec2(*self._target)
+
+    @target.setter
+    def target(self, target):
+        if not self._body_b.awake:
+            self._body_b.awake = True
+        self._target = Vec2(*target)
+        self._changed(wake=False)
+
+    @property
+    def max_force(self):
+        return self._max_force
+
+    @max_force.setter
+    def max_force(self, max_force):
+        self._max_force = float(max_force)
+        self._changed(wake=False)
+
+    @property
+    def frequency(self):
+        return self._frequency
+
+    @frequency.setter
+    def frequency(self, frequency):
+        self._frequency = float(frequency)
+        self._changed(wake=False)
+
+    @property
+    def damping_ratio(self):
+        return self._damping_ratio
+
+    @damping_ratio.setter
+    def damping_ratio(self, damping_ratio):
+        self._damping_ratio = float(damping_ratio)
+        self._changed(wake=False)
+
+    def get_reaction_torque(self, inv_dt):
+        return 0.0
+
+
 def _unsupported(name):
     def ctor(*args, **kwargs):
-        raise NotImplementedError("%s is not supported on the batched step path (built: revolute, distance, weld, prismatic, rope, friction, wheel)" % name)
+        raise NotImplementedError("%s is not supported on the batched step path (built: revolute, distance, weld, prismatic, rope, friction, wheel, pulley, mouse)" % name)
     ctor.__name__ = name
     return ctor
 
 
-PulleyJoint = _unsupported("PulleyJoint")
 GearJoint = _unsupported("GearJoint")
-MouseJoint = _unsupported("MouseJoint")
 
 
 def pack_joints(world, arrays, w, body_index):
@@ -613,7 +749,7 @@ def pack_joints(world, arrays, w, body_index):
     A["w_joint"][w] = (nj, 0, 0, 0)
     jidx = {id(j): k for k, j in enumerate(joints)}
     for k, j in enumerate(joints):
-        A["j_def"][w, k] = (j._type, body_index[id(j._body_a)], body_index[id(j._body_b)], j._flags())
+        A["j_def"][w, k] = (j._type, body_index[id(j._body_a)] if j._body_a is not None else -1, body_index[id(j._body_b)], j._flags())
         par = j._par()
         A["j_par"][w, k, :len(par)] = par
         A["j_imp"][w, k] = j._imp()

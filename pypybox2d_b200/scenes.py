@@ -310,7 +310,7 @@ def joints(b2, world=0, config=9, **world_kw):
     bridge of revolute joints between two ground anchors (testbed/bridge.py) with bodies dropped on it, a hanging chain, a
     motorised arm with angle limits, a door with equal limits, a flail on a rigid distance joint, a soft (frequency > 0)
     distance spring, a welded cantilever, a joint with collide_connected=True, prismatic joints (motorised lift with limits, slider
-    between two dynamic bodies, equal limits, lower stop), rope joints (taut and slack), a friction joint, a car on wheel joints and a joint between two dynamic bodies that start asleep."""
+    between two dynamic bodies, equal limits, lower stop), rope joints (taut and slack), a friction joint, a car on wheel joints, a pulley, a mouse joint and a joint between two dynamic bodies that start asleep."""
     w = b2.World((0, -10), True, **_kw(world_kw))
     ground = w.create_static_body(shapes=b2.Edge((-40.0, 0.0), (40.0, 0.0)))
     n_free = 12
@@ -401,6 +401,14 @@ def joints(b2, world=0, config=9, **world_kw):
     idler = w.create_dynamic_body(position=at(3.5, 0.5), fixtures=b2.Fixture(b2.Circle(0.4), density=1.0, friction=0.5))
     post = w.create_dynamic_body(position=(3.5, 1.5), fixtures=b2.Fixture(b2.Polygon(box=(0.2, 0.5)), density=1.0, friction=0.3))
     w.create_wheel_joint(post, idler, anchor=idler.position, axis=(0.0, 1.0), frequency=0.0, damping_ratio=0.0)   # no spring: a rigid line
+    # pulley: two unequal boxes over two ground anchors, ratio 1.5
+    pa_ = w.create_dynamic_body(position=at(-10.0, 14.0), fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.4)), density=2.0, friction=0.3))
+    pb_ = w.create_dynamic_body(position=at(-7.0, 14.0), fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.4)), density=1.0, friction=0.3))
+    w.create_pulley_joint(pa_, pb_, ground_anchor_a=(-10.0, 18.0), ground_anchor_b=(-7.0, 18.0), anchor_a=(-10.0, 14.4),
+                          anchor_b=(-7.0, 14.4), ratio=1.5)
+    # mouse joint: a box dragged to a target above the bridge by a soft one-body constraint
+    drag = w.create_dynamic_body(position=at(-12.0, 7.0), fixtures=b2.Fixture(b2.Polygon(box=(0.3, 0.3)), density=1.0, friction=0.4))
+    w.create_mouse_joint(drag, target=(-9.0, 9.5), max_force=200.0, frequency=3.0, damping_ratio=0.5)
     # two sleeping bodies joined by a revolute joint, woken when something lands on them
     sa = w.create_dynamic_body(position=(28.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))
     sb = w.create_dynamic_body(position=(29.0, 0.26), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.5, 0.25)), density=1.0, friction=0.4))

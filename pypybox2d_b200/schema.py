@@ -45,7 +45,7 @@ STATUS_TOI_STUCK = 0x10        # a time-of-impact push-back loop was cut off (cs
 STATUS_JOINT_OVERFLOW = 0x20   # more joints than the batch's joint capacity
 
 # joints (pypybox2d/joints/*.py): j_def = (type, body_a, body_b, flags)
-JOINT_REVOLUTE, JOINT_DISTANCE, JOINT_WELD, JOINT_PRISMATIC, JOINT_ROPE, JOINT_FRICTION, JOINT_WHEEL = 1, 2, 3, 4, 5, 6, 7
+JOINT_REVOLUTE, JOINT_DISTANCE, JOINT_WELD, JOINT_PRISMATIC, JOINT_ROPE, JOINT_FRICTION, JOINT_WHEEL, JOINT_PULLEY, JOINT_MOUSE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 JOINT_COLLIDE_CONNECTED = 0x1  # joint.py:52
 JOINT_LIMIT_ENABLED = 0x2      # revolute.py:85 / prismatic
 JOINT_MOTOR_ENABLED = 0x4      # revolute.py:86 / prismatic

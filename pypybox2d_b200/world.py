@@ -6,7 +6,7 @@ step through the C-ABI (`include/b2b.h`) and mirrors the body state back into th
 objects.  A single `World` is a batch of one; large batches use `BatchedWorld` directly
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
-Revolute, distance, weld, prismatic, rope, friction and wheel joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
+Revolute, distance, weld, prismatic, rope, friction, wheel, pulley and mouse joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
 (raise `NotImplementedError`): the other joint types, controllers, `pre_solve` / `post_solve` listeners,
 custom contact filters, Loop shapes and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
@@ -269,11 +269,15 @@ class World(object):
     def create_wheel_joint(self, *args, **kwargs):
         return self.add_joint(_joints.WheelJoint(*args, **kwargs))
 
-    def _create_unsupported_joint(self, *args, **kwargs):
-        raise NotImplementedError("pulley, gear and mouse joints do not run on the batched step path (SURVEY §8f #3: revolute, distance, "
-                                  "weld, prismatic, rope, friction and wheel joints do)")
+    def create_pulley_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.PulleyJoint(*args, **kwargs))
 
-    create_pulley_joint = create_gear_joint = create_mouse_joint = _create_unsupported_joint
+    def create_mouse_joint(self, *args, **kwargs):
+        return self.add_joint(_joints.MouseJoint(*args, **kwargs))
+
+    def create_gear_joint(self, *args, **kwargs):
+        raise NotImplementedError("gear joints do not run on the batched step path (SURVEY §8f #3: revolute, distance, weld, prismatic, "
+                                  "rope, friction, wheel, pulley and mouse joints do)")
 
     def add_controller(self, controller):
         raise NotImplementedError("controllers are not supported on the batched step path")
@@ -341,7 +345,7 @@ class World(object):
             if a2 < 0 or b2 < 0:
                 continue
             ba, bb = fixtures[a2]._body, fixtures[b2]._body
-            if any(not j._collide_connected and j.other_body(ba) is bb for j in ba.joints):
+            if any(not j._collide_connected and j._body_a is not None and j.other_body(ba) is bb for j in ba.joints):
                 continue                       # Body._should_collide (body.py:920-926), see add_joint
             A["c_fix"][0, k2] = (a2, b2)
             for name in ("c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"):

@@ -59,7 +59,15 @@ def int_mismatches(OA, G):
     if int(OA["w_island"][0][3]) != int(G["w_island"][0][3]):
         bad.append("position iterations used")
     if int(OA["w_joint"][0][0]) > 0:             # scenes with joints: limit states, island joint lists
-        bad += harness.diff_state(OA, G, fields=["j_def"])
+        # (a taut rope's limit state is `length - max_length > 0` right after the position solver removed exactly that difference:
+        # its sign is rounding noise in the reference itself, and nothing in the solver reads it -- rope.py:139-143, 97-99)
+        nj = int(OA["w_joint"][0][0])
+        jo, jg = OA["j_def"][0][:nj].copy(), G["j_def"][0][:nj].copy()
+        for d in (jo, jg):
+            d[:, 3] &= ~np.int32(schema.JOINT_ISLAND)
+            d[d[:, 0] == schema.JOINT_ROPE, 3] &= ~np.int32(3 << schema.JOINT_LIMIT_SHIFT)
+        if not np.array_equal(jo, jg):
+            bad.append("j_def")
         if harness.oracle_island_joints(OA) != harness.oracle_island_joints(G):
             bad.append("island joints")
     nc = int(OA["w_count"][0][2])
@@ -203,6 +211,8 @@ def test_p_exact_fp64_one_step(case, parity_report):
 # sweep runs, and one sweep more or less is 0.0075 / 16 = 4.7e-4 m of position (measured: 4.69e-4 on every scene with
 # TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
 P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2"]}
+# joints: motors, springs and 3x3 solves inside one step (measured on B200: 2.1e-5 m, 1.3e-3 m/s on the non-tie steps)
+P_STEP_BOUNDS.update({"joints_w0": (1e-4, 5e-3), "joints_w1": (1e-4, 5e-3)})
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
@@ -238,7 +248,7 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
         if case in P_STEP_BOUNDS:
             # (on a tie step a bullet's contact exists in one arithmetic and not in the other: the step's outcome is a
             # different event, not an error bound; the fp64 kernels are checked on the same inputs below)
-            tol_p, tol_v = (float("inf"), float("inf")) if tie else P_STEP_BOUNDS[case]
+            tol_p, tol_v = ((float("inf"), float("inf")) if case not in ("joints_w0", "joints_w1") else (1e-3, 1e-2)) if tie else P_STEP_BOUNDS[case]
         assert dp <= tol_p and dv <= tol_v, "fp32 one-step state error at step %d (tie=%s): %.2e m, %.2e m/s" % (s, tie, dp, dv)
         if not tie:
             worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
