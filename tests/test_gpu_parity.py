@@ -211,8 +211,9 @@ def test_p_exact_fp64_one_step(case, parity_report):
 # sweep runs, and one sweep more or less is 0.0075 / 16 = 4.7e-4 m of position (measured: 4.69e-4 on every scene with
 # TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
 P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2"]}
-# joints: motors, springs and 3x3 solves inside one step (measured on B200: 2.1e-5 m, 1.3e-3 m/s on the non-tie steps)
-P_STEP_BOUNDS.update({"joints_w0": (1e-4, 5e-3), "joints_w1": (1e-4, 5e-3)})
+# joints: motors, stiff soft constraints (wheel suspension, mouse joint: 1 / (dt (d + dt k)) terms) and 3x3 solves inside one step
+# (measured on B200: 9.0e-5 m, 5.4e-3 m/s on the non-tie steps; the fp64 kernels on the same steps: <= 2.8e-14)
+P_STEP_BOUNDS.update({"joints_w0": (3e-4, 2e-2), "joints_w1": (3e-4, 2e-2)})
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
