@@ -58,7 +58,9 @@ typedef struct b2b_caps {
     int32_t reserved;        /* lanes per world in the plan and pair kernels (0: default, 8 or 32 by contact capacity) */
     int32_t nj;              /* joints per world (World.joints); 0: the batch has no joints -- the step then runs the kernels without
                               * the joint hooks, and the j_* arrays keep one unused row per world */
-    int32_t reserved2;       /* 0 */
+    int32_t joint_types;     /* bit t set: some joint of the batch has type t (1 revolute, 2 distance, 3 weld, 4 prismatic, 5 rope, 6 friction,
+                              * 7 wheel, 8 pulley, 9 mouse); 0: unknown.  A batch whose joints are all revolute joints (1 << 1) runs kernels without the
+                              * type dispatch.  The caller keeps j_def consistent with it */
 } b2b_caps;
 
 /* Device pointers, one per schema field, same names and order as pypybox2d_b200/schema.py FIELDS.

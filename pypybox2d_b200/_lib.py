@@ -13,7 +13,7 @@ SO_PATH = os.environ.get("B2B_LIB") or os.path.join(CSRC, "libb2b.so")      # (B
 
 class Caps(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("n_worlds", "nb", "nf", "nc", "npair", "nl", "n_shapes", "real_bytes",
-                                              "device", "threads", "ctas_per_sm", "reserved", "nj", "reserved2")]
+                                              "device", "threads", "ctas_per_sm", "reserved", "nj", "joint_types")]
 
 
 class Buffers(ctypes.Structure):

@@ -66,9 +66,22 @@ class BatchedWorld(object):
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         c.threads, c.ctas_per_sm, c.reserved = int(threads), int(ctas_per_sm), int(lanes_aux)
         c.nj = int(getattr(caps, "nj", 0))
+        c.joint_types = int(self._joint_types()) if c.nj > 0 else 0
         self._caps_struct = c
         _lib.check(_lib.lib().b2b_create(ctypes.byref(c), ctypes.byref(self._ctx)), "b2b_create")
         self._bind()
+
+    def _joint_types(self):
+        """Bit t set: some joint of the batch has type t (b2b_caps.joint_types: a batch of revolute joints only runs kernels
+        without the type dispatch)."""
+        d, n = self.t["j_def"][..., 0], self.t["w_joint"][:, 0:1]
+        torch = _torch()
+        used = torch.arange(d.shape[1], device=d.device).unsqueeze(0) < n
+        types = torch.unique(d[used]).tolist()
+        mask = 0
+        for t in types:
+            mask |= 1 << int(t)
+        return mask
 
     @classmethod
     def from_tensors(cls, tensors, caps, real="f32", inv_dt0=0.0, **kw):
@@ -395,6 +408,8 @@ class BatchedWorld(object):
                 self.t[name][worlds].copy_(src)
             else:
                 self.t[name].copy_(src)
+        if "j_def" in arrays and self.caps.nj > 0 and (self._joint_types() & ~int(self._caps_struct.joint_types)):
+            raise _lib.B2BError("upload: a joint type that this batch was not created with (b2b_caps.joint_types); create a new batch")
         self.t["w_flags"] &= ~schema.WORLD_GRAPH_VALID      # host-side mutation: rebuild the island schedule
         self.t["w_flags"] |= schema.WORLD_TOI_DIRTY         # ... and let the next World.solve_toi reset whatever alpha0 came in
         self._continuous = None                             # (w_flags may have been replaced)

@@ -74,6 +74,7 @@ static caps_t to_caps(const b2b_caps* k)
     caps_t c;
     c.n_worlds = k->n_worlds; c.nb = k->nb; c.nf = k->nf; c.nc = k->nc; c.npair = k->npair; c.nl = k->nl; c.n_shapes = k->n_shapes;
     c.nj = k->nj;
+    c.joint_types = k->joint_types;
     return c;
 }
 

@@ -196,9 +196,11 @@ B2B_D void mouse_solve_velocity(jrow& r, real dt)
 
 // _init_velocity_constraints (revolute.py:208-300, distance.py:155-250, weld.py:106-169).  Velocities: the team's shared state;
 // positions: b_pos (the sweeps before this step's integration -- the velocity kernel runs before integrate_position).
-// (HOT: the revolute joint -- bridges, chains, ragdolls, wheels on axles -- compiled in line; every other type goes through ONE
-// out-of-line copy of the same function, so that the kernels' hot loops do not carry nine joint types' worth of instructions:
-// bridge x 131,072 worlds, velocity kernel 3.73 ms with all nine types in line)
+// (HOT: only the revolute joint's code -- the instantiation for batches whose joints are all revolute joints (bridges, chains,
+// ragdolls: b2b_caps::joint_types), where the type dispatch compiles away.  Measured on bridge x 131,072 worlds, velocity kernel:
+// 3.16 ms when four joint types existed, 3.71 ms with all nine in line; a hot / cold split INSIDE one kernel -- the other eight
+// types behind one out-of-line call -- is slower than either (4.33 ms taking the caller's rows, 4.62 ms taking a copy:
+// the rows then live in local memory).  B2B_JOINT_COLD keeps those experiments.)
 template <bool HOT> B2B_D void joint_init_impl(jrow& r, real dt, real dt_ratio, bool warm)
 {
     int32_t* def = r.def;
@@ -909,6 +911,14 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
 B2B_D_NOINLINE void joint_init_cold(jrow& r, real dt, real dt_ratio, bool warm) { joint_init_impl<false>(r, dt, dt_ratio, warm); }
 B2B_D_NOINLINE void joint_solve_velocity_cold(jrow& r, real dt, real inv_dt) { joint_solve_velocity_impl<false>(r, dt, inv_dt); }
 B2B_D_NOINLINE bool joint_solve_position_cold(const jrow& r) { return joint_solve_position_impl<false>(r); }
+#ifndef B2B_JOINT_COLD
+#define B2B_JOINT_COLD 0         // experiments: 0 all nine types in line, 1 the out-of-line copy takes the caller's rows, 2 it takes a copy of them
+#endif
+#if B2B_JOINT_COLD == 0
+B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm) { joint_init_impl<false>(r, dt, dt_ratio, warm); }
+B2B_D void joint_solve_velocity(jrow& r, real dt, real inv_dt) { joint_solve_velocity_impl<false>(r, dt, inv_dt); }
+B2B_D bool joint_solve_position(const jrow& r) { return joint_solve_position_impl<false>(r); }
+#elif B2B_JOINT_COLD == 1
 B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
 {
     if (r.def[0] == JOINT_REVOLUTE) joint_init_impl<true>(r, dt, dt_ratio, warm); else joint_init_cold(r, dt, dt_ratio, warm);
@@ -921,6 +931,23 @@ B2B_D bool joint_solve_position(const jrow& r)
 {
     return (r.def[0] == JOINT_REVOLUTE) ? joint_solve_position_impl<true>(r) : joint_solve_position_cold(r);
 }
+#else
+B2B_D void joint_init(jrow& r, real dt, real dt_ratio, bool warm)
+{
+    // (the out-of-line copy gets its own jrow: handing out `r` itself would pin the caller's rows to local memory on the hot path too)
+    if (r.def[0] == JOINT_REVOLUTE) joint_init_impl<true>(r, dt, dt_ratio, warm); else { jrow c = r; joint_init_cold(c, dt, dt_ratio, warm); r = c; }
+}
+B2B_D void joint_solve_velocity(jrow& r, real dt, real inv_dt)
+{
+    if (r.def[0] == JOINT_REVOLUTE) joint_solve_velocity_impl<true>(r, dt, inv_dt); else { jrow c = r; joint_solve_velocity_cold(c, dt, inv_dt); r = c; }
+}
+B2B_D bool joint_solve_position(const jrow& r)
+{
+    if (r.def[0] == JOINT_REVOLUTE) return joint_solve_position_impl<true>(r);
+    jrow c = r;
+    return joint_solve_position_cold(c);
+}
+#endif
 
 // one island's joint range in l_joint
 B2B_D void island_joint_range(int isl, int n_islands, int& j0, int& j1) const

@@ -258,6 +258,9 @@ B2B_SOLVE_KERNEL(solve_position_joint_kernel_, template run_solve_position<true>
 // batches with a joint capacity (caps_t::nj > 0): the same two kernels with the joint hooks of b2b_joints.inl compiled in
 B2B_SOLVE_KERNEL(solve_velocity_joints_kernel_, run_solve_velocity_joints, false, 0)
 B2B_SOLVE_KERNEL(solve_position_joints_kernel_, run_solve_position_joints, false, 1)
+// ... and for batches whose joints are all revolute joints (caps_t::joint_types): no type dispatch
+B2B_SOLVE_KERNEL(solve_velocity_revolute_kernel_, run_solve_velocity_revolute, false, 0)
+B2B_SOLVE_KERNEL(solve_position_revolute_kernel_, run_solve_position_revolute, false, 1)
 #undef B2B_SOLVE_KERNEL
 
 // Proxy synchronisation (K4: body.py:898-904, fixture.py:287-298, dynamictree.py:152-188) and World.clear_forces as a
@@ -668,6 +671,14 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
                           1, n_sm, &k_pos);
             if (rc) return rc;
             if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+            rc = plan_one(B2B_CAT(solve_velocity_revolute_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                          1, n_sm, &k_pos);
+            if (rc) return rc;
+            if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+            rc = plan_one(B2B_CAT(solve_position_revolute_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                          1, n_sm, &k_pos);
+            if (rc) return rc;
+            if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
         }
     }
     rc = plan_one(B2B_CAT(broadphase_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + teams_aux - 1) / teams_aux, 32,
@@ -743,11 +754,20 @@ void B2B_CAT(launch_solve_group_, B2B_SUFFIX)(const void* const* fields, const c
         // joints: island after island with the joint passes between the contact sweeps (no joint island schedule in such a batch)
         step_params spj = sp;
         if (first_step) spj.flags |= STEP_FIRST;
-        B2B_CAT(solve_velocity_joints_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
-                                                                                              scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
+        const bool revolute_only = c.joint_types == (1 << 1);          // every joint of the batch is a revolute joint
+        if (revolute_only)
+            B2B_CAT(solve_velocity_revolute_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                                    scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
+        else
+            B2B_CAT(solve_velocity_joints_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                                  scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
         if (tm) tm->mark(T_VELOCITY, st);
-        B2B_CAT(solve_position_joints_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
-                                                                                              scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
+        if (revolute_only)
+            B2B_CAT(solve_position_revolute_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                                    scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
+        else
+            B2B_CAT(solve_position_joints_kernel_, B2B_SUFFIX)<<<grid, threads, p.k_solve.smem, st>>>(B, c, p.plan, plan, p.layout, scratch_solve,
+                                                                                                  scratch_sprof, spj, p.lanes, p.team_smem, w0, n_group);
         if (tm) tm->mark(T_POSITION, st);
         return;
     }

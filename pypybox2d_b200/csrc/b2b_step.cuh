@@ -82,6 +82,7 @@ namespace b2b {
 struct caps_t {
     int n_worlds, nb, nf, nc, npair, nl, n_shapes;
     int nj = 0;              // joints per world (0: the batch has none and runs the kernels without the joint hooks); the J arrays have max(nj, 1) rows
+    int joint_types = 0;     // bit t set: some joint of the batch has type t (b2b_joints.inl); 0: unknown (any type)
 };
 
 // Pointers to the batch arrays (world-major).  Field order == schema.FIELDS == b2b_buffers.
@@ -1726,7 +1727,8 @@ template <class real> struct world_step {
     }
     // PJ: the batch has a joint capacity (b2b_caps::nj > 0): an island's joints are initialised after the contacts' warm start and
     // visited before the contacts in every velocity iteration (island.py:107-113), by the team's first lane (b2b_joints.inl)
-    template <bool PJ> B2B_D void solve_velocity_phase(const step_params& sp, real dt)
+    // (PJ = 2: every joint of the batch is a revolute joint -- b2b_caps::joint_types -- and the type dispatch compiles away)
+    template <int PJ> B2B_D void solve_velocity_phase(const step_params& sp, real dt)
     {
         const bool warm = (w_flags[0] & WORLD_WARM_STARTING) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -1770,7 +1772,9 @@ template <class real> struct world_step {
                 if (j1 > j0) {
                     B2B_SYNC();
                     const real dt_ratio = (real)(((sp.flags & STEP_FIRST) != 0) ? sp.dt_ratio_first : sp.dt_ratio_rest);
-                    joint_sweep(j0, j1, JFETCH_INIT, [&](jrow& r) { joint_init(r, dt, dt_ratio, warm); return true; });
+                    joint_sweep(j0, j1, JFETCH_INIT, [&](jrow& r) {
+                        if constexpr (PJ == 2) joint_init_impl<true>(r, dt, dt_ratio, warm); else joint_init(r, dt, dt_ratio, warm);
+                        return true; });
                 }
             }
             for (int it = 0; it < sp.vel_iters; ++it) {
@@ -1779,7 +1783,9 @@ template <class real> struct world_step {
                     if (j1 > j0) {
                         B2B_SYNC();
                         const real inv_dt = (real)(1.0 / sp.dt);                    // TimeStep.inv_dt (world.py:322)
-                        joint_sweep(j0, j1, JFETCH_VELOCITY, [&](jrow& r) { joint_solve_velocity(r, dt, inv_dt); return true; });
+                        joint_sweep(j0, j1, JFETCH_VELOCITY, [&](jrow& r) {
+                            if constexpr (PJ == 2) joint_solve_velocity_impl<true>(r, dt, inv_dt); else joint_solve_velocity(r, dt, inv_dt);
+                            return true; });
                     }
                 }
                 if (c1 > c0) level_sweep<vrec>(c0, c1, lv, sp.zero, vat, [&](const vrec& e, const vel_stream& at) { constraint_solve_velocity(e, at.imp, last); }, vready);
@@ -1822,7 +1828,7 @@ template <class real> struct world_step {
     // balanced enough), the island-ordinal and atomic paths compile away.
     // PJ (with JOINT_CAPABLE = false): the batch has a joint capacity; an island's joints are visited after its contacts in every
     // position iteration and the island is solved when both are within tolerance (island.py:141-153).
-    template <bool JOINT_CAPABLE, bool PJ = false> B2B_D void solve_position_phase(const step_params& sp, real dt)
+    template <bool JOINT_CAPABLE, int PJ = 0> B2B_D void solve_position_phase(const step_params& sp, real dt)
     {
         const bool allow_sleep = (w_flags[0] & WORLD_ALLOW_SLEEP) != 0;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -1886,7 +1892,8 @@ template <class real> struct world_step {
                     if constexpr (PJ) {
                         if (j1 > j0) {
                             B2B_SYNC();
-                            joints_okay = joint_sweep(j0, j1, JFETCH_POSITION, [&](jrow& r) { return joint_solve_position(r); });
+                            joints_okay = joint_sweep(j0, j1, JFETCH_POSITION, [&](jrow& r) {
+                                if constexpr (PJ == 2) return joint_solve_position_impl<true>(r); else return joint_solve_position(r); });
                         }
                     }
                     if (all_min >= real(-3) * K<real>::linear_slop && joints_okay) { position_solved = true; break; }
@@ -2829,7 +2836,7 @@ template <class real> struct world_step {
         }
     }
     // solve kernel: Island.solve for every island (island.py:65-179)
-    template <bool PJ = false> B2B_D void run_solve_velocity(const step_params& sp)
+    template <int PJ = 0> B2B_D void run_solve_velocity(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -2846,7 +2853,7 @@ template <class real> struct world_step {
     }
     // The position kernel exists twice: JOINT_CAPABLE = false for batches in which no world has a joint schedule, true
     // otherwise; both are launched and the one whose turn it is not returns at once (b2b_kernels.inl).
-    template <bool JOINT_CAPABLE, bool PJ = false> B2B_D void run_solve_position(const step_params& sp)
+    template <bool JOINT_CAPABLE, int PJ = 0> B2B_D void run_solve_position(const step_params& sp)
     {
         if (!(sp.dt > 0.0)) return;
         const bool profiling = (sp.flags & STEP_PROFILE) != 0;
@@ -2855,8 +2862,10 @@ template <class real> struct world_step {
         B2B_PROF(PROF_SOLVE, t);
     }
     // the solve kernels of batches with a joint capacity
-    B2B_D void run_solve_velocity_joints(const step_params& sp) { run_solve_velocity<true>(sp); }
-    B2B_D void run_solve_position_joints(const step_params& sp) { run_solve_position<false, true>(sp); }
+    B2B_D void run_solve_velocity_joints(const step_params& sp) { run_solve_velocity<1>(sp); }
+    B2B_D void run_solve_position_joints(const step_params& sp) { run_solve_position<false, 1>(sp); }
+    B2B_D void run_solve_velocity_revolute(const step_params& sp) { run_solve_velocity<2>(sp); }
+    B2B_D void run_solve_position_revolute(const step_params& sp) { run_solve_position<false, 2>(sp); }
     // broadphase kernel: find_new_contacts (world.py:582-592) for the worlds whose proxies moved (the flat sync
     // kernel raised SUM_MOVED); a world without movers emits no pairs and creates no contacts
     B2B_D void run_pairs(const step_params& sp)
@@ -2895,8 +2904,8 @@ template <class real> struct world_step {
             if (cap.nj > 0) {
                 step_params spj = sp;
                 if (step == 0) spj.flags |= STEP_FIRST;
-                run_solve_velocity<true>(spj);
-                run_solve_position<false, true>(spj);
+                if (cap.joint_types == (1 << JOINT_REVOLUTE)) { run_solve_velocity<2>(spj); run_solve_position<false, 2>(spj); }
+                else { run_solve_velocity<1>(spj); run_solve_position<false, 1>(spj); }
             } else {
                 run_solve_velocity(sp);
                 run_solve_position<true>(sp);

@@ -23,7 +23,7 @@ static int run(const b2b_caps* caps, const b2b_buffers* buf, double dt, double i
 {
     caps_t c;
     c.n_worlds = caps->n_worlds; c.nb = caps->nb; c.nf = caps->nf; c.nc = caps->nc; c.npair = caps->npair;
-    c.nl = caps->nl; c.n_shapes = caps->n_shapes; c.nj = caps->nj;
+    c.nl = caps->nl; c.n_shapes = caps->n_shapes; c.nj = caps->nj; c.joint_types = caps->joint_types;
     batch_ptrs<real> B;
     static_assert(sizeof(B) == sizeof(*buf), "b2b_buffers and batch_ptrs must have the same members");
     std::memcpy(&B, buf, sizeof(B));

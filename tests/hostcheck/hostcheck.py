@@ -18,7 +18,7 @@ FIELD_ORDER = ("w_count,w_flags,w_status,w_gravity,w_island,"
 
 class Caps(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("n_worlds", "nb", "nf", "nc", "npair", "nl", "n_shapes", "real_bytes",
-                                              "device", "threads", "ctas_per_sm", "reserved", "nj", "reserved2")]
+                                              "device", "threads", "ctas_per_sm", "reserved", "nj", "joint_types")]
 
 
 class Buffers(ctypes.Structure):
@@ -61,6 +61,10 @@ def step(arrays, dt, inv_dt0, vel_iters, pos_iters, n_steps=1):
     c.n_shapes = A["s_meta"].shape[0]
     c.real_bytes = A["b_xf"].dtype.itemsize
     c.nj = A["j_def"].shape[1] if int(A["w_joint"][:, 0].max()) > 0 else 0
+    c.joint_types = 0
+    for w in range(A["w_joint"].shape[0]):
+        for t in A["j_def"][w, :int(A["w_joint"][w, 0]), 0]:
+            c.joint_types |= 1 << int(t)
     b = Buffers()
     for n in FIELD_ORDER:
         assert A[n].flags["C_CONTIGUOUS"], n
