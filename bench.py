@@ -583,7 +583,7 @@ def run_b200_arm(args):
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "traffic_gbs": (None if not traffic else traffic / (top_ms * 1e-3) / 1e9),
                      "traffic_frac": (None if not traffic else traffic / (top_ms * 1e-3) / 1e9 / peak),
-                     "kernel": "b2b::%s_kernel_%s" % (top + ("_joints" if caps.nj > 0 and top.startswith("solve_") else ""), args.real),
+                     "kernel": "b2b::%s_kernel_%s" % (top + (("_revolute" if bw._caps_struct.joint_types == 2 else "_joints") if caps.nj > 0 and top.startswith("solve_") else ""), args.real),
                      "kernel_ms_per_launch": top_ms, "kernel_share_of_step": top_ms / max(sum(per_kernel_ms.values()), 1e-9),
                      "algorithmic_bytes_per_world_step": kernel_bytes[top],
                      "kernel_ms": per_kernel_ms, "ms_per_step_one_stream_with_events": serial_ms,
