@@ -104,8 +104,10 @@ int b2b_init_proxies(b2b_ctx* ctx, void* stream);
  * on shape_distance distance.py:419-561, Island.solve_toi island.py:181-243, solve_toi_position_constraints
  * contact.py:866-933), clear forces.  Batches created with a joint capacity (b2b_caps.nj > 0) also walk Body.joints in the island
  * DFS (world.py:548-572) and run Joint._init_velocity_constraints / _solve_velocity_constraints / _solve_position_constraints of
- * their revolute, distance, weld and prismatic joints inside Island.solve (island.py:107-113, 145-148; joints/revolute.py:208-453,
- * distance.py:155-311, weld.py:106-257, prismatic.py:232-513), and Body._should_collide's joint test (body.py:920-926).
+ * their revolute, distance, weld, prismatic, rope, friction, wheel, pulley and mouse joints inside Island.solve (island.py:107-113,
+ * 145-148; joints/revolute.py:208-453, distance.py:155-311, weld.py:106-257, prismatic.py:232-513, rope.py:106-248,
+ * friction.py:105-233, wheel.py:202-416, pulley.py:156-318, mouse.py:138-229), and Body._should_collide's joint test
+ * (body.py:920-926).
  * inv_dt0 is World._inv_dt0 before the first of the n_steps (0 for a fresh world); the first step
  * uses dt_ratio = inv_dt0 * dt, later ones (1/dt) * dt, both evaluated in double as world.py:323-328.
  * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */

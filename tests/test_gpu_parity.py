@@ -212,8 +212,11 @@ def test_p_exact_fp64_one_step(case, parity_report):
 # TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
 P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2"]}
 # joints: motors, stiff soft constraints (wheel suspension, mouse joint: 1 / (dt (d + dt k)) terms) and 3x3 solves inside one step
-# (measured on B200: 9.0e-5 m, 5.4e-3 m/s on the non-tie steps; the fp64 kernels on the same steps: <= 2.8e-14)
-P_STEP_BOUNDS.update({"joints_w0": (3e-4, 2e-2), "joints_w1": (3e-4, 2e-2)})
+# and branches inside the limit handling that have no integer output (revolute.py:343-360 `new_impulse < 0`, prismatic.py:384-389
+# max / min of the limit impulse, the motor clamps): a branch taken the other way within fp32 rounding is a different impulse.
+# Measured on B200 (profiles/r2_joints/parity_report_joints.json): 2.0e-4 m, 1.2e-2 m/s on the non-tie steps; the fp64 kernels
+# on the same steps: <= 2.8e-14
+P_STEP_BOUNDS.update({"joints_w0": (1e-3, 5e-2), "joints_w1": (1e-3, 5e-2)})
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
@@ -249,7 +252,7 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
         if case in P_STEP_BOUNDS:
             # (on a tie step a bullet's contact exists in one arithmetic and not in the other: the step's outcome is a
             # different event, not an error bound; the fp64 kernels are checked on the same inputs below)
-            tol_p, tol_v = ((float("inf"), float("inf")) if case not in ("joints_w0", "joints_w1") else (1e-3, 1e-2)) if tie else P_STEP_BOUNDS[case]
+            tol_p, tol_v = ((float("inf"), float("inf")) if case not in ("joints_w0", "joints_w1") else (5e-3, 0.1)) if tie else P_STEP_BOUNDS[case]
         assert dp <= tol_p and dv <= tol_v, "fp32 one-step state error at step %d (tie=%s): %.2e m, %.2e m/s" % (s, tie, dp, dv)
         if not tie:
             worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
