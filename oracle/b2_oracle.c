@@ -1091,6 +1091,7 @@ static void solver_velocity_sweep(cc_t* C, int ncontacts, vel_t* Vv)
  * flags | _limit_state << 8), j_par (parameters, layout in pypybox2d_b200/joints.py), j_imp (_impulse x, y, z,
  * _motor_impulse) and j_tmp (the attributes _init_velocity_constraints leaves for the sweeps).
  * ===================================================================================================== */
+#define J_TMP 28                                    /* reals per j_tmp row (pypybox2d_b200/schema.py JOINT_TMP) */
 #define J_REVOLUTE 1
 #define J_DISTANCE 2
 #define J_WELD     3
@@ -1147,7 +1148,7 @@ static void mouse_init(orc_world* w, int k, double dt, double dt_ratio, int warm
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
-    double* tmp = w->j_tmp + 20 * (size_t)k;
+    double* tmp = w->j_tmp + J_TMP * (size_t)k;
     int bb = def[2], ib_ = w->b_island[bb];
     v2 cb = P[ib_].c; double ab = P[ib_].a;
     v2 vb = Vv[ib_].v; double wb = Vv[ib_].w;
@@ -1184,7 +1185,7 @@ static void mouse_solve_velocity(orc_world* w, int k, double dt, vel_t* Vv)
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
-    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    const double* tmp = w->j_tmp + J_TMP * (size_t)k;
     int bb = def[2], ib_ = w->b_island[bb];
     v2 vb = Vv[ib_].v; double wb = Vv[ib_].w;
     double mb = w->b_mass[4 * bb], ib = w->b_mass[4 * bb + 1];
@@ -1210,7 +1211,7 @@ static void joint_init(orc_world* w, int k, double dt, double dt_ratio, int warm
     int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
-    double* tmp = w->j_tmp + 20 * (size_t)k;
+    double* tmp = w->j_tmp + J_TMP * (size_t)k;
     int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
     v2 lca = V(w->b_mass[4 * ba + 2], w->b_mass[4 * ba + 3]), lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);
@@ -1468,7 +1469,7 @@ static void joint_solve_velocity(orc_world* w, int k, double dt, double inv_dt, 
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
     double* imp = w->j_imp + 4 * (size_t)k;
-    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    const double* tmp = w->j_tmp + J_TMP * (size_t)k;
     int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
     double ma = w->b_mass[4 * ba], mb = w->b_mass[4 * bb], ia = w->b_mass[4 * ba + 1], ib = w->b_mass[4 * bb + 1];
@@ -1677,7 +1678,7 @@ static int joint_solve_position(orc_world* w, int k, pos_t* P)
     if (w->j_def[4 * (size_t)k] == J_MOUSE) return 1;                                  /* mouse.py:227-229 */
     const int32_t* def = w->j_def + 4 * (size_t)k;
     const double* par = w->j_par + 12 * (size_t)k;
-    const double* tmp = w->j_tmp + 20 * (size_t)k;
+    const double* tmp = w->j_tmp + J_TMP * (size_t)k;
     int type = def[0], ba = def[1], bb = def[2], flags = def[3];
     int ia_ = w->b_island[ba], ib_ = w->b_island[bb];
     v2 lca = V(w->b_mass[4 * ba + 2], w->b_mass[4 * ba + 3]), lcb = V(w->b_mass[4 * bb + 2], w->b_mass[4 * bb + 3]);

@@ -72,7 +72,7 @@ typedef struct orc_world {
     int32_t*  j_def;      /* [nj][4] type, body_a, body_b, flags | limit_state << 8 */
     double*   j_par;      /* [nj][12] */
     double*   j_imp;      /* [nj][4] */
-    double*   j_tmp;      /* [nj][20] */
+    double*   j_tmp;      /* [nj][28] */
     int32_t*  j_adj;      /* [2 nj] Body.joints rows */
     int32_t*  b_jadj;     /* [nb][2] start, count in j_adj */
     int32_t*  l_joint;    /* [nj] island joint lists */

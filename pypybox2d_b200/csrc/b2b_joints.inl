@@ -15,12 +15,14 @@
 // Rows (layout: pypybox2d_b200/joints.py): j_def = (type, body_a, body_b, flags | _limit_state << 8), j_par[12], j_imp = (_impulse
 // x, y, z, _motor_impulse), j_tmp[20] = what _init_velocity_constraints leaves for the sweeps (ra, rb, then per type: the 3x3 mass
 // matrix by columns and the motor mass; or u, mass, gamma, bias; prismatic: axis, perp, s1, s2, a1, a2, motor mass and the six
-// distinct entries of its symmetric K).
+// distinct entries of its symmetric K); tmp[20:24] = the two bodies' inverse mass and inertia, tmp[24:28] = the local anchors minus
+// the local centres of mass, both copied by the set-up pass so that the velocity and position passes need no row of the bodies
+// (their addresses would only be known after the joint's definition has arrived: a third dependent round trip per fetch).
 
 enum { JOINT_REVOLUTE = 1, JOINT_DISTANCE = 2, JOINT_WELD = 3, JOINT_PRISMATIC = 4, JOINT_ROPE = 5, JOINT_FRICTION = 6, JOINT_WHEEL = 7, JOINT_PULLEY = 8, JOINT_MOUSE = 9 };
 enum { JF_COLLIDE = 0x1, JF_LIMIT = 0x2, JF_MOTOR = 0x4, JF_ISLAND = 0x8, JF_LS_SHIFT = 8 };
 enum { LS_INACTIVE = 0, LS_LOWER = 1, LS_UPPER = 2, LS_EQUAL = 3 };               // joints/joint.py:36
-enum { JOINT_PAR = 12, JOINT_TMP = 20 };
+enum { JOINT_PAR = 12, JOINT_TMP = 28 };        // (schema.py JOINT_PAR / JOINT_TMP)
 
 struct V3 { real x, y, z; };
 B2B_D static V3 mk3(real x, real y, real z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -86,9 +88,13 @@ B2B_D void joint_fetch(int k, jrow& r, int what) const
 #pragma unroll
         for (int i = 0; i < JOINT_TMP / 4; ++i) { const quad q = t[i]; r.tmp[4 * i] = q.x; r.tmp[4 * i + 1] = q.y; r.tmp[4 * i + 2] = q.z; r.tmp[4 * i + 3] = q.w; }
     }
-    const int ba = (r.def[1] >= 0) ? r.def[1] : r.def[2];          // a joint on one body (MouseJoint) has body_a = -1
-    r.mqa = ldq(b_mass + 4 * (size_t)ba); r.mqb = ldq(b_mass + 4 * (size_t)r.def[2]);
-    if (what == JFETCH_INIT) { r.pa = ldq(b_pos + 4 * (size_t)ba); r.pb = ldq(b_pos + 4 * (size_t)r.def[2]); }
+    if (what == JFETCH_INIT) {
+        const int ba = (r.def[1] >= 0) ? r.def[1] : r.def[2];      // a joint on one body (MouseJoint) has body_a = -1
+        r.mqa = ldq(b_mass + 4 * (size_t)ba); r.mqb = ldq(b_mass + 4 * (size_t)r.def[2]);
+        r.pa = ldq(b_pos + 4 * (size_t)ba); r.pb = ldq(b_pos + 4 * (size_t)r.def[2]);
+    } else {
+        r.mqa = mkq(r.tmp[20], r.tmp[21], real(0), real(0)); r.mqb = mkq(r.tmp[22], r.tmp[23], real(0), real(0));
+    }
 }
 B2B_D void joint_store(const jrow& r, int what)
 {
@@ -111,6 +117,16 @@ template <class Apply> B2B_D int joint_sweep(int j0, int j1, int what, Apply app
         jrow r;
         const int mine = k0 + t_id;
         if (mine < j1) joint_fetch(l_joint[mine], r, what);
+#if defined(__CUDA_ARCH__)
+        // the rows of this lane's NEXT joint are asked for now (L2 prefetch): they arrive while the team applies this round's joints
+        if (mine + t_n < j1) {
+            const int nk = l_joint[mine + t_n];
+            B2B_PREFETCH(j_def + 4 * (size_t)nk);
+            B2B_PREFETCH(j_par + JOINT_PAR * (size_t)nk); B2B_PREFETCH(j_par + JOINT_PAR * (size_t)nk + JOINT_PAR - 1);
+            if (what != JFETCH_POSITION) B2B_PREFETCH(j_imp + 4 * (size_t)nk);
+            if (what != JFETCH_INIT) { B2B_PREFETCH(j_tmp + JOINT_TMP * (size_t)nk); B2B_PREFETCH(j_tmp + JOINT_TMP * (size_t)nk + JOINT_TMP - 1); }
+        }
+#endif
         const int n = (j1 - k0 < t_n) ? j1 - k0 : t_n;
         for (int i = 0; i < n; ++i) {
             if (t_id == i) {
@@ -209,6 +225,11 @@ template <bool HOT> B2B_D void joint_init_impl(jrow& r, real dt, real dt_ratio, 
     real* tmp = r.tmp;
 #pragma unroll
     for (int i = 0; i < JOINT_TMP; ++i) tmp[i] = real(0);
+    tmp[20] = r.mqa.x; tmp[21] = r.mqa.y; tmp[22] = r.mqb.x; tmp[23] = r.mqb.y;
+    {
+        const V2 la = mk<real>(par[0], par[1]) - mk<real>(r.mqa.z, r.mqa.w), lb = mk<real>(par[2], par[3]) - mk<real>(r.mqb.z, r.mqb.w);
+        tmp[24] = la.x; tmp[25] = la.y; tmp[26] = lb.x; tmp[27] = lb.y;
+    }
     if (!HOT && def[0] == JOINT_MOUSE) { mouse_init(r, dt, dt_ratio, warm); return; }
     const int type = HOT ? (int)JOINT_REVOLUTE : def[0];
     const int ba = def[1], bb = def[2], flags = def[3];
@@ -707,7 +728,6 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     const int ba = def[1], bb = def[2], flags = def[3];
     const quad mqa = r.mqa, mqb = r.mqb;
     const real ma = mqa.x, ia = mqa.y, mb = mqb.x, ib = mqb.y;
-    const V2 lca = mk<real>(mqa.z, mqa.w), lcb = mk<real>(mqb.z, mqb.w);
     const quad sa = state_get(ba), sb = state_get(bb);
     V2 ca = mk<real>(sa.x, sa.y), cb = mk<real>(sb.x, sb.y);
     real aa = sa.z, ab = sb.z;
@@ -738,7 +758,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
             ab = ab + ib * limit_impulse;
         }
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         const V2 C = cb + rb - ca - ra;
         position_error = sqrt_r(sq_r(C.x) + sq_r(C.y));
         const real k1x = ma + mb + ia * ra.y * ra.y + ib * rb.y * rb.y;
@@ -756,7 +776,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     } else if (type == JOINT_DISTANCE) {
         if (par[5] > real(0)) return true;                                           // no position correction for soft constraints
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         V2 u = cb + rb - ca - ra;
         const real length = sqrt_r(sq_r(u.x) + sq_r(u.y));
         u = normalize(u);
@@ -770,7 +790,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
         ok = abs_r(C) < K<real>::linear_slop;
     } else if (type == JOINT_WELD) {
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         const V2 C1 = cb + rb - ca - ra;
         const real C2 = ab - aa - par[4];
         const real position_error = sqrt_r(sq_r(C1.x) + sq_r(C1.y)), angular_error = abs_r(C2);
@@ -791,7 +811,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     }
     else if (type == JOINT_PRISMATIC) {                                              // prismatic.py:421-513
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         const V2 d = cb + rb - ca - ra;
         const V2 lx = mk<real>(par[9], par[10]), ly = cross_sv(real(1), lx);
         const V2 axis = rot_mul(qa, lx);
@@ -850,7 +870,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     }
     else if (type == JOINT_ROPE) {                                                   // rope.py:209-248
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         V2 u = cb + rb - ca - ra;
         const real length = sqrt_r(sq_r(u.x) + sq_r(u.y));
         u = normalize(u);
@@ -866,7 +886,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     else if (type == JOINT_FRICTION) return true;                                    // friction.py:232-233
     else if (type == JOINT_WHEEL) {                                                  // wheel.py:375-416
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         const V2 d = (cb - ca) + rb - ra;
         const real kk = ma + mb + ia * sq_r(tmp[6]) + ib * sq_r(tmp[7]);
         const V2 ly = cross_sv(real(1), mk<real>(par[4], par[5]));
@@ -884,7 +904,7 @@ template <bool HOT> B2B_D bool joint_solve_position_impl(const jrow& r)
     }
     else if (type == JOINT_PULLEY) {                                                 // pulley.py:258-318
         const XF qa = rot_of(aa), qb = rot_of(ab);
-        const V2 ra = rot_mul(qa, mk<real>(par[0], par[1]) - lca), rb = rot_mul(qb, mk<real>(par[2], par[3]) - lcb);
+        const V2 ra = rot_mul(qa, mk<real>(tmp[24], tmp[25])), rb = rot_mul(qb, mk<real>(tmp[26], tmp[27]));
         V2 ua = ca + ra - mk<real>(par[4], par[5]), ub = cb + rb - mk<real>(par[6], par[7]);
         const real length_a = sqrt_r(sq_r(ua.x) + sq_r(ua.y)), length_b = sqrt_r(sq_r(ub.x) + sq_r(ub.y));
         ua = (length_a > real(10) * K<real>::linear_slop) ? mk<real>(ua.x / length_a, ua.y / length_a) : mk<real>(real(0), real(0));

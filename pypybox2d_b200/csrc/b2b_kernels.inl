@@ -17,6 +17,11 @@ typedef B2B_REAL real_t;
 // registers, which lets 12 warps share an SM's register file (three per scheduler); how many of them a CTA gets is decided
 // by the shared memory the bodies' state of its worlds needs (plan_: 11 warps = 88 pyramid worlds).  One CTA per SM pays the
 // per-CTA shared-memory reservation once: one-warp CTAs stopped at 10 warps per SM.
+#ifndef B2B_JOINT_MAX_WARPS
+#define B2B_JOINT_MAX_WARPS 12      // warps per CTA of the joint-capable solve kernels (their register budget: 65,536 / 32 / warps).  Measured on
+                                    // bridge x 131,072 worlds, velocity + position kernel: 12 warps 2.77 + 1.09 ms, 16 warps 3.28 + 0.93, 24 warps 3.79 + 1.06
+                                    // (the level sweep's register prefetch spills below 168 registers)
+#endif
 #ifndef B2B_SOLVE_MAX_WARPS
 #define B2B_SOLVE_MAX_WARPS 12
 #endif
@@ -213,8 +218,9 @@ __global__ void __launch_bounds__(128, B2B_PREPARE_MIN_CTAS) B2B_CAT(prepare_ker
 // Island.solve in two kernels (see world_step::solve_velocity_phase / solve_position_phase): one CTA per SM, every warp
 // split into teams of `lanes` lanes, one world per team.  The teams of a warp start their worlds together and meet again
 // after them: they share every issued instruction, so they must stay in step.
-#define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN, KIND)                                                                                        \
-    __global__ void __launch_bounds__(32 * B2B_SOLVE_MAX_WARPS, 1) B2B_CAT(NAME, B2B_SUFFIX)(                                  \
+#define B2B_SOLVE_KERNEL(NAME, CALL, NOT_MY_TURN, KIND) B2B_SOLVE_KERNEL_W(NAME, CALL, NOT_MY_TURN, KIND, B2B_SOLVE_MAX_WARPS)
+#define B2B_SOLVE_KERNEL_W(NAME, CALL, NOT_MY_TURN, KIND, MAXW)                                                                                \
+    __global__ void __launch_bounds__(32 * MAXW, 1) B2B_CAT(NAME, B2B_SUFFIX)(                                                \
         batch_ptrs<real_t> B, caps_t c, plan_layout P, uint16_t* plan, scratch_layout L, unsigned char* rec,                   \
         unsigned char* team_prof, step_params sp, int lanes, size_t team_smem, int w0, int n_group)                            \
     {                                                                                                                          \
@@ -256,12 +262,13 @@ B2B_SOLVE_KERNEL(solve_velocity_kernel_, run_solve_velocity, false, 0)
 B2B_SOLVE_KERNEL(solve_position_kernel_, template run_solve_position<false>, *sp.joint_any != 0u, 1)
 B2B_SOLVE_KERNEL(solve_position_joint_kernel_, template run_solve_position<true>, *sp.joint_any == 0u, 2)
 // batches with a joint capacity (caps_t::nj > 0): the same two kernels with the joint hooks of b2b_joints.inl compiled in
-B2B_SOLVE_KERNEL(solve_velocity_joints_kernel_, run_solve_velocity_joints, false, 0)
-B2B_SOLVE_KERNEL(solve_position_joints_kernel_, run_solve_position_joints, false, 1)
+B2B_SOLVE_KERNEL_W(solve_velocity_joints_kernel_, run_solve_velocity_joints, false, 0, B2B_JOINT_MAX_WARPS)
+B2B_SOLVE_KERNEL_W(solve_position_joints_kernel_, run_solve_position_joints, false, 1, B2B_JOINT_MAX_WARPS)
 // ... and for batches whose joints are all revolute joints (caps_t::joint_types): no type dispatch
-B2B_SOLVE_KERNEL(solve_velocity_revolute_kernel_, run_solve_velocity_revolute, false, 0)
-B2B_SOLVE_KERNEL(solve_position_revolute_kernel_, run_solve_position_revolute, false, 1)
+B2B_SOLVE_KERNEL_W(solve_velocity_revolute_kernel_, run_solve_velocity_revolute, false, 0, B2B_JOINT_MAX_WARPS)
+B2B_SOLVE_KERNEL_W(solve_position_revolute_kernel_, run_solve_position_revolute, false, 1, B2B_JOINT_MAX_WARPS)
 #undef B2B_SOLVE_KERNEL
+#undef B2B_SOLVE_KERNEL_W
 
 // Proxy synchronisation (K4: body.py:898-904, fixture.py:287-298, dynamictree.py:152-188) and World.clear_forces as a
 // flat grid: one thread per (world, proxy-or-body index).  Worlds with a mover are flagged for the pair kernel.
@@ -646,27 +653,28 @@ int B2B_CAT(plan_, B2B_SUFFIX)(const caps_t& c, int lanes, int lanes_aux, int ct
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         const size_t per_warp = out->team_smem * teams;
         int warps = (int)((size_t)smem_max / per_warp);
-        if (warps > B2B_SOLVE_MAX_WARPS) warps = B2B_SOLVE_MAX_WARPS;
+        const int max_warps = (c.nj > 0) ? B2B_JOINT_MAX_WARPS : B2B_SOLVE_MAX_WARPS;     // batches with joints launch the joint-capable kernels only
+        if (warps > max_warps) warps = max_warps;
         if (ctas_per_sm > 0 && warps > ctas_per_sm) warps = ctas_per_sm;
         if (warps < 1) return (int)cudaErrorInvalidConfiguration;       // one warp's worlds do not fit an SM's shared memory
         const long long per_cta = (long long)warps * teams;
         kernel_plan k_pos;
-        rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
-                      1, n_sm, &out->k_solve);
-        if (rc) return rc;
-        rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
-                      1, n_sm, &k_pos);
-        if (rc) return rc;
-        if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
-        rc = plan_one(B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
-                      1, n_sm, &k_pos);
-        if (rc) return rc;
-        if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
-        if (c.nj > 0) {
-            rc = plan_one(B2B_CAT(solve_velocity_joints_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+        if (c.nj == 0) {
+            rc = plan_one(B2B_CAT(solve_velocity_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                          1, n_sm, &out->k_solve);
+            if (rc) return rc;
+            rc = plan_one(B2B_CAT(solve_position_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
                           1, n_sm, &k_pos);
             if (rc) return rc;
             if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+            rc = plan_one(B2B_CAT(solve_position_joint_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                          1, n_sm, &k_pos);
+            if (rc) return rc;
+            if (k_pos.grid < out->k_solve.grid) out->k_solve = k_pos;
+        } else {
+            rc = plan_one(B2B_CAT(solve_velocity_joints_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
+                          1, n_sm, &out->k_solve);
+            if (rc) return rc;
             rc = plan_one(B2B_CAT(solve_position_joints_kernel_, B2B_SUFFIX), ((long long)c.n_worlds + per_cta - 1) / per_cta, 32 * warps, per_warp * warps,
                           1, n_sm, &k_pos);
             if (rc) return rc;

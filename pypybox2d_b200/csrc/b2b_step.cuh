@@ -348,7 +348,7 @@ template <class real> struct world_step {
         l_start = B.l_start + 2 * ob;
         s_meta = B.s_meta; s_radius = B.s_radius; s_data = B.s_data;
         const size_t oj = W * (size_t)(c.nj > 0 ? c.nj : 1);
-        w_joint = B.w_joint + 4 * W; j_def = B.j_def + 4 * oj; j_par = B.j_par + 12 * oj; j_imp = B.j_imp + 4 * oj; j_tmp = B.j_tmp + 20 * oj;
+        w_joint = B.w_joint + 4 * W; j_def = B.j_def + 4 * oj; j_par = B.j_par + 12 * oj; j_imp = B.j_imp + 4 * oj; j_tmp = B.j_tmp + JOINT_TMP * oj;
         j_adj = B.j_adj + 2 * oj; b_jadj = B.b_jadj + 2 * ob; l_joint = B.l_joint + oj; l_jstart = B.l_jstart + ob;
         uint16_t* pw = plan + W * P.stride;
         g_cbody = pw + P.off_cbody; g_sched = pw + P.off_sched; g_slot_isl = pw + P.off_slot_isl; g_joint = pw + P.off_joint; g_lv = reinterpret_cast<uint32_t*>(pw + P.off_lv);

@@ -52,7 +52,8 @@ JOINT_MOTOR_ENABLED = 0x4      # revolute.py:86 / prismatic
 JOINT_ISLAND = 0x8             # Joint._island_flag (transient bookkeeping of the island walk)
 JOINT_LIMIT_SHIFT = 8          # bits 8..9: _limit_state (joint.py:36: INACTIVE, AT_LOWER, AT_UPPER, EQUAL), carried over steps
 JOINT_PAR = 12                 # reals per joint parameter row (see joints.py `_par`)
-JOINT_TMP = 20                 # reals per joint of solver temporaries (ra, rb, effective masses ...), written by the step
+JOINT_TMP = 28                 # reals per joint of solver temporaries (ra, rb, effective masses ...; [20:24] the bodies' inverse masses,
+                               # [24:28] the local anchors relative to the centres of mass), written by the step's joint set-up
 
 MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2   # contact_util.py:141-143
 
