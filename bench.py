@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path, on the host cores
     python bench.py --scene {vertical_stack,mixed,deep_stacks,hello}   # the other BASELINE.json configurations
-    python bench.py --scene bridge                                     # joints in the island solver
+    python bench.py --scene {bridge,joints}                            # joints in the island solver
 
 Workload (config.workload): the pyramid-20 scene of examples/pyramid-bench.py (210 dynamic boxes on an edge
 ground), step(1/60, 8, 3), CCD off, `--worlds` independent worlds PER GPU (131,072 by default, i.e. 1,048,576
@@ -55,6 +55,9 @@ def _scene_table():
         # not a BASELINE config: the joint hooks of the island solver, 30 planks on 31 revolute joints under 8 loose bodies
         "bridge": dict(what="plank bridge of 31 revolute joints under 8 loose bodies (testbed/bridge.py style; SURVEY 8f #3)", config=10,
                        caps=C(39, 39, 220, nj=31), dt=DT, dt_text="1/60", vi=8, pi=3, n_dyn=38, worlds=131072, distinct=2048),
+        # the joint coverage scene: 44 joints of all nine built types (the generic joint-capable kernels, with the type dispatch)
+        "joints": dict(what="joint coverage scene: 65 dynamic bodies, 44 joints of nine types (bridge, chain, motorised arms, lift, car, pulley ...)",
+                       config=9, caps=C(66, 66, 328, nj=44), dt=DT, dt_text="1/60", vi=8, pi=3, n_dyn=65, worlds=65536, distinct=1024),
     }
 
 
@@ -67,7 +70,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scene", default="pyramid", choices=["pyramid", "vertical_stack", "mixed", "deep_stacks", "hello", "bridge"],
+    ap.add_argument("--scene", default="pyramid", choices=["pyramid", "vertical_stack", "mixed", "deep_stacks", "hello", "bridge", "joints"],
                     help="BASELINE.json configuration (default: the headline pyramid batch)")
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (0: the configuration's own size, 131,072 for the pyramid)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct jittered worlds settled, then tiled (0: per scene)")
