@@ -824,7 +824,8 @@ template <class real> struct world_step {
                         for (int j = 0; j < 4; ++j) {
                             if (k0 + j >= row_end || fs[j] != 1) continue;   // already in an island, disabled, a sensor or not touching
                             const int c = cs[j];
-                            l_contact[lc++] = c;
+                            s_lev[lc] = (uint16_t)c;                   // (a shared-memory copy of the list for phase_schedule: its sequential
+                            l_contact[lc++] = c;                       //  loop then waits on no global load; the per-body counters are done with)
                             s_cflag[c] = 3;                            // island flag
                             const int ba = (int)(pair[j] & 0xffffu), bb = (int)(pair[j] >> 16);
                             const int other = (b == ba) ? bb : ba;
@@ -919,7 +920,7 @@ template <class real> struct world_step {
                     int cs[4], ba[4], bb[4];
                     bool dyn_a[4], dyn_b[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cs[j] = l_contact[(k0 + j < c1) ? k0 + j : k0];
+                    for (int j = 0; j < 4; ++j) cs[j] = s_lev[(k0 + j < c1) ? k0 + j : k0];   // the list as phase_islands left it; overwritten by the levels below
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { ba[j] = s_cbody[2 * cs[j]]; bb[j] = s_cbody[2 * cs[j] + 1]; }
 #pragma unroll
