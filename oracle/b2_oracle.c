@@ -129,11 +129,12 @@ static inline v2 rot_mul_t(const xform* t, v2 v)                                
 static inline v2 xf_mul_t(const xform* t, v2 v) { return rot_mul_t(t, vsub(v, t->p)); } /* common.py:669-670 */
 
 /* ---- shape table access ---- */
-typedef struct { int type, count, has0, has3; double radius; const double* d; } shape_t;
+typedef struct { int type, count, has0, has3, loop_child; double radius; const double* d; } shape_t;
 static inline shape_t shape_get(const orc_world* w, int row)
 {
     shape_t s; int m = w->s_meta[row];
     s.type = m & 0xff; s.count = (m >> 8) & 0xff; s.has0 = (m >> 16) & 1; s.has3 = (m >> 17) & 1;
+    s.loop_child = (m >> 18) & 1;           /* a child edge of a Loop shape (contact.py:363-373): Loop.compute_aabb has no radius margin */
     s.radius = w->s_radius[row]; s.d = w->s_data + 32 * (size_t)row;
     return s;
 }
@@ -795,6 +796,7 @@ static void shape_aabb(const shape_t* s, const xform* t, double out[4])
     } else {
         v2 a = xf_mul(t, V(s->d[0], s->d[1])), b = xf_mul(t, V(s->d[2], s->d[3]));
         v2 lower = V(PYMIN(a.x, b.x), PYMIN(a.y, b.y)), upper = V(PYMAX(a.x, b.x), PYMAX(a.y, b.y));
+        if (s->loop_child) { out[0] = lower.x; out[1] = lower.y; out[2] = upper.x; out[3] = upper.y; return; }   /* shapes.py:822-837 */
         out[0] = lower.x - s->radius; out[1] = lower.y - s->radius; out[2] = upper.x + s->radius; out[3] = upper.y + s->radius;
     }
 }

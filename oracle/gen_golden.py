@@ -64,6 +64,9 @@ CASES = {
     "joints_w1": ("joints", 1, 1.0 / 60, 10, 4, 300, (300,)),
     "joints_ccd_w2": ("joints", 2, 1.0 / 60, 8, 3, 300, (300,), CCD),
     "bridge_w1": ("bridge", 1, 1.0 / 60, 8, 3, 300, (150, 300)),
+    # Loop shapes: one proxy and one contact slot per child edge
+    "loops_w0": ("loops", 0, 1.0 / 60, 8, 3, 300, (100, 300)),
+    "loops_ccd_w1": ("loops", 1, 1.0 / 60, 8, 3, 300, (300,), CCD),
 }
 
 CK_FIELDS = ["w_count", "w_flags", "w_island", "b_xf", "b_pos", "b_vel", "b_pos0", "b_force", "b_flags", "b_island",

@@ -36,7 +36,7 @@ def facade_arrays(name, world=0, caps=None, n_shapes=512, **kw):
     import pypybox2d_b200 as mine
     mw = scenes.SCENES[name](mine, world=world, **kw)
     nb = len(mw.bodies)
-    nf = sum(len(b.fixtures) for b in mw.bodies)
+    nf = sum(f._shape.child_count for b in mw.bodies for f in b.fixtures)      # proxies: one per shape child (Loop)
     caps = caps or default_caps(nb, nf, len(mw.joints))
     table = schema.ShapeTable()
     A = schema.alloc(caps, 1, n_shapes)
@@ -52,7 +52,7 @@ def reference_arrays(name, world=0, caps=None, n_shapes=512, **kw):
     rw = scenes.SCENES[name](b2, world=world, **kw)
     refpin.index_fixtures(rw)
     nb = len(rw.bodies)
-    nf = sum(len(b.fixtures) for b in rw.bodies)
+    nf = sum(f._shape.child_count for b in rw.bodies for f in b.fixtures)
     caps = caps or default_caps(nb, nf, len(rw.joints))
     table = schema.ShapeTable()
     A = schema.alloc(caps, 1, n_shapes)

@@ -69,7 +69,8 @@ _INDEX = {}
 
 
 def _pid(node):
-    return _INDEX[id(node.user_data.fixture)]
+    p = node.user_data
+    return _INDEX[(id(p.fixture), p.child_index)]
 
 
 def index_fixtures(world):
@@ -77,8 +78,9 @@ def index_fixtures(world):
     k = 0
     for body in world.bodies:
         for f in body.fixtures:
-            _INDEX[id(f)] = k
-            k += 1
+            for c in range(f._shape.child_count):
+                _INDEX[(id(f), c)] = k
+                k += 1
     return k
 
 
@@ -87,6 +89,7 @@ def pack_id(t):
 
 
 def extract(world, arrays, w, table, schema):
+    b2 = load()
     """Copy the reference world's live state into row `w` of fp64 schema arrays.
 
     Sources are the attributes listed in SURVEY Appendix C.  `table` is a schema.ShapeTable fed with
@@ -95,8 +98,11 @@ def extract(world, arrays, w, table, schema):
     A = arrays
     bodies = world.bodies
     bidx = {id(b): i for i, b in enumerate(bodies)}
-    fixtures = [f for b in bodies for f in b.fixtures]
-    fidx = {id(f): j for j, f in enumerate(fixtures)}
+    # one row per broadphase proxy: (fixture, child index) in world.bodies x body.fixtures x children order (Loop shapes have
+    # one proxy per child edge, fixture.py:250-261)
+    proxies = [(f, c) for b in bodies for f in b.fixtures for c in range(f._shape.child_count)]
+    fixtures = [f for f, c in proxies]
+    fidx = {(id(f), c): j for j, (f, c) in enumerate(proxies)}
     contacts = world.contact_manager.contacts
     A["w_count"][w] = (len(bodies), len(fixtures), len(contacts), A["w_count"][w][3])
     flags = 0
@@ -137,13 +143,14 @@ def extract(world, arrays, w, table, schema):
             f |= schema.BODY_ISLAND
         A["b_flags"][w, i] = f
     moved = set(id(n) for n in world.contact_manager.broadphase._move_buffer)
-    for j, fx in enumerate(fixtures):
+    for j, (fx, child) in enumerate(proxies):
         A["f_body"][w, j] = bidx[id(fx._body)]
-        A["f_shape"][w, j] = table.add(_ShapeAdapter(fx._shape))
+        A["f_shape"][w, j] = table.add(_ShapeAdapter(fx._shape.child_edge(child), loop_child=True) if isinstance(fx._shape, b2.Loop)
+                                       else _ShapeAdapter(fx._shape))
         A["f_mat"][w, j] = (fx._friction, fx._restitution)
         A["f_filter"][w, j] = ((fx._category_bits & 0xffff) | ((fx._mask_bits & 0xffff) << 16),
                                (fx._group_index & 0xffff) | ((1 if fx._sensor else 0) << 16))
-        proxy = fx._proxies[0]
+        proxy = fx._proxies[child]
         node = proxy.proxy_ref
         A["f_fat"][w, j] = (node.aabb.lower_bound.x, node.aabb.lower_bound.y,
                             node.aabb.upper_bound.x, node.aabb.upper_bound.y)
@@ -151,7 +158,7 @@ def extract(world, arrays, w, table, schema):
                               proxy.aabb.upper_bound.x, proxy.aabb.upper_bound.y)
         A["f_moved"][w, j] = 1 if id(node) in moved else 0
     for k, c in enumerate(contacts):
-        A["c_fix"][w, k] = (fidx[id(c._fixture_a)], fidx[id(c._fixture_b)])
+        A["c_fix"][w, k] = (fidx[(id(c._fixture_a), c._index_a)], fidx[(id(c._fixture_b), c._index_b)])
         cf = 0
         if c._touching_flag:
             cf |= schema.CONTACT_TOUCHING
@@ -253,8 +260,9 @@ def extract_joints(world, A, w, bidx, schema):
 class _ShapeAdapter(object):
     """Presents a reference shape with the attribute names schema.ShapeTable.add reads."""
 
-    def __init__(self, s):
+    def __init__(self, s, loop_child=False):
         b2 = load()
+        self._loop_child = loop_child
         self.radius = s.radius
         if isinstance(s, b2.Circle):
             self._type = 0
@@ -277,7 +285,7 @@ class _ShapeAdapter(object):
             return (1, float(self.radius)) + tuple(c for v in self._vertices for c in (v.x, v.y))
         v0, v3 = self._vertex0, self._vertex3
         return (3, float(self.radius), self._vertex1.x, self._vertex1.y, self._vertex2.x, self._vertex2.y,
-                None if v0 is None else (v0.x, v0.y), None if v3 is None else (v3.x, v3.y))
+                None if v0 is None else (v0.x, v0.y), None if v3 is None else (v3.x, v3.y), bool(self._loop_child))
 
 
 class Recorder(object):

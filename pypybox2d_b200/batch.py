@@ -30,7 +30,7 @@ def world_caps(worlds, contacts_per_body=4, slack=64):
     """Capacities for a batch of host worlds.  Contacts are between fixtures, so a compound body with many fixtures
     needs rows per FIXTURE, not per body (`World.step` raises if a step still runs out)."""
     nb = max(len(w.bodies) for w in worlds)
-    nf = max(sum(len(b.fixtures) for b in w.bodies) for w in worlds)
+    nf = max(sum(f._shape.child_count for b in w.bodies for f in b.fixtures) for w in worlds)    # proxies: one per shape child
     nj = max(len(getattr(w, "joints", ())) for w in worlds)
     return schema.Caps(nb, nf, contacts_per_body * max(nb, nf) + slack, nj=nj)
 
@@ -112,9 +112,7 @@ class BatchedWorld(object):
         caps = caps or world_caps(worlds)
         table = schema.ShapeTable()
         for w in worlds:
-            for b in w.bodies:
-                for f in b.fixtures:
-                    table.add(f._shape)
+            schema.add_shapes(table, w)
         A = schema.alloc(caps, len(worlds), max(len(table), 1), "f64")
         for i, w in enumerate(worlds):
             schema.pack_world(w, A, i, table)
@@ -136,9 +134,7 @@ class BatchedWorld(object):
         caps = caps or world_caps([world])
         table = schema.ShapeTable()
         A1 = schema.alloc(caps, 1, 1, "f64")
-        for b in world.bodies:
-            for f in b.fixtures:
-                table.add(f._shape)
+        schema.add_shapes(table, world)
         A1 = schema.alloc(caps, 1, max(len(table), 1), "f64")
         schema.pack_world(world, A1, 0, table)
         A1["s_meta"], A1["s_radius"], A1["s_data"] = table.arrays("f64")
@@ -456,7 +452,7 @@ class BatchedWorld(object):
         from .common import Vec2
         D = self.download(["w_count", "c_fix", "c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp"],
                           worlds=slice(w, w + 1))
-        fixtures = [f for b in world.bodies for f in b.fixtures]
+        fixtures = [f for f, c in schema.world_proxies(world)]      # device fixture rows are proxies: (fixture, child)
         out = []
         for k in range(int(D["w_count"][0, 2])):
             c = ContactView()

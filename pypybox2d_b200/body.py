@@ -147,7 +147,7 @@ class Body(object):
         return self.create_fixture(_shapes.Edge(v1, v2, v0, v3), **kwargs)
 
     def create_loop_fixture(self, vertices, *args, **kwargs):
-        raise NotImplementedError("Loop shapes are not supported on the batched step path")
+        return self.create_fixture(_shapes.Loop(vertices, *args), **kwargs)
 
     def create_fixtures(self, shape_list, fixture=None, friction=0.2, restitution=0.0,
                         density=0.0, category_bits=0x0001, mask_bits=0xFFFF,

@@ -19,6 +19,7 @@ namespace b2b {
 template <class real> struct shape_view {
     int type, count, has0, has3;
     real radius;
+    real aabb_radius;        // the margin of Shape.compute_aabb: the radius, or 0 for a child edge of a Loop (shapes.py:822-837)
     const real* d;
     B2B_HD vec2<real> vert(int i) const { return mk<real>(d[2 * i], d[2 * i + 1]); }
     B2B_HD vec2<real> norm(int i) const { return mk<real>(d[16 + 2 * i], d[16 + 2 * i + 1]); }
@@ -31,6 +32,7 @@ B2B_HD shape_view<real> shape_load(const int32_t* s_meta, const real* s_radius, 
     int m = s_meta[row];
     s.type = m & 0xff; s.count = (m >> 8) & 0xff; s.has0 = (m >> 16) & 1; s.has3 = (m >> 17) & 1;
     s.radius = s_radius[row];
+    s.aabb_radius = ((m >> 18) & 1) ? real(0) : s.radius;
     s.d = s_data + (size_t)SHAPE_DATA * row;
     return s;
 }
@@ -472,7 +474,7 @@ B2B_HD void collide_shapes(manifold<real>& m, const shape_view<real>& a, const x
     else m.count = 0;
 }
 
-// Shape.compute_aabb (shapes.py:178-189 circle, 316-334 polygon, 702-718 edge) -> (lx, ly, ux, uy)
+// Shape.compute_aabb (shapes.py:178-189 circle, 316-334 polygon, 702-718 edge, 822-837 a Loop's child edge) -> (lx, ly, ux, uy)
 template <class real> B2B_HD void shape_aabb(const shape_view<real>& s, const xform<real>& t, real out[4])
 {
     vec2<real> lo, hi;
@@ -487,6 +489,7 @@ template <class real> B2B_HD void shape_aabb(const shape_view<real>& s, const xf
             hi = mk<real>(pymax(hi.x, v.x), pymax(hi.y, v.y));
         }
     }
+    if (s.type == SHAPE_EDGE && s.aabb_radius == real(0)) { out[0] = lo.x; out[1] = lo.y; out[2] = hi.x; out[3] = hi.y; return; }   // Loop.compute_aabb
     out[0] = lo.x - s.radius; out[1] = lo.y - s.radius; out[2] = hi.x + s.radius; out[3] = hi.y + s.radius;
 }
 

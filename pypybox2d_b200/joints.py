@@ -31,9 +31,9 @@ INACTIVE_LIMIT, AT_LOWER_LIMIT, AT_UPPER_LIMIT, EQUAL_LIMITS = range(4)   # join
 
 
 def _world_point(body, lp):
-    # Transform.__mul__ (common.py): position + rotation * point, in that association
+    # Transform.__mul__ (common.py:677-685): position.x + col1.x * v.x + col2.x * v.y, left to right
     x, y, c, s = body._xf
-    return Vec2(x + (c * lp.x + (-s) * lp.y), y + (s * lp.x + c * lp.y))
+    return Vec2(x + c * lp.x + (-s) * lp.y, y + s * lp.x + c * lp.y)
 
 
 class Joint(object):

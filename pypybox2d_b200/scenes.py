@@ -448,5 +448,38 @@ def bridge(b2, world=0, planks=30, config=10, **world_kw):
     return w
 
 
-SCENES = {"joints": joints, "bridge": bridge, "features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
+# ---- Loop shape coverage scene (not a BASELINE config): closed chains of edges with ghost vertices ---------------------
+def loops(b2, world=0, config=11, **world_kw):
+    """Loop shapes (shapes.py:780-880): a static terrain loop the bodies live INSIDE (a bowl with a bump: inside collision, convex
+    and concave corners), a loop on a kinematic body that turns (a tumbler: the proxies of its eight child edges move every
+    step), a small loop fixture on a dynamic body next to a polygon fixture with density (loops have no mass), circles and polygons
+    dropped into all of it."""
+    w = b2.World((0, -10), True, **_kw(world_kw))
+    terrain = [(-16.0, 0.0), (-6.0, 0.0), (-3.0, 1.5), (0.0, 0.0), (16.0, 0.0), (18.0, 8.0), (16.0, 16.0), (-16.0, 16.0), (-18.0, 8.0)]
+    w.create_static_body(shapes=b2.Loop(terrain), shape_fixture=b2.Fixture(b2.Circle(1.0), friction=0.5))
+    tumbler = w.create_kinematic_body(position=(8.0, 6.0), angular_velocity=0.6)
+    tumbler.create_loop_fixture([(3.0 * math.cos(2.0 * math.pi * q / 8), 3.0 * math.sin(2.0 * math.pi * q / 8)) for q in range(8)], friction=0.6)
+    cart = w.create_dynamic_body(position=(-10.0, 3.0))
+    cart.create_polygon_fixture(box=(1.0, 0.2), density=2.0, friction=0.4)
+    cart.create_loop_fixture([(-1.0, 0.2), (1.0, 0.2), (1.0, 1.0), (-1.0, 1.0)], friction=0.4)       # an open-topped tray would be edges; this is a frame
+    n = 28
+    jit = jitter(config, world, n + 3)[3:]
+    for k in range(n):
+        i, j = divmod(k, 7)
+        inside = k % 4 == 0
+        pos = ((8.0 + 0.9 * (j - 3), 6.0 + 0.8 * (i - 1.5)) if inside else (-13.0 + 3.2 * j, 5.0 + 1.7 * i))
+        pos = (pos[0] + jit[k, 0], pos[1] + jit[k, 1])
+        if k % 3 == 0:
+            shape = b2.Circle(0.3)
+        elif k % 3 == 1:
+            shape = b2.Polygon(box=(0.3, 0.25))
+        else:
+            m = 3 + (k // 3) % 4
+            shape = b2.Polygon(vertices=[(0.35 * math.cos(0.2 + 2.0 * math.pi * q / m), 0.35 * math.sin(0.2 + 2.0 * math.pi * q / m)) for q in range(m)])
+        w.create_dynamic_body(position=pos, angle=0.1 * k, fixtures=b2.Fixture(shape, density=1.0, friction=0.4, restitution=0.1 * (k % 3)))
+    w.create_dynamic_body(position=(-4.0, 12.0), bullet=True, linear_velocity=(15.0, -60.0), fixtures=b2.Fixture(b2.Circle(0.15), density=4.0, friction=0.2))
+    return w
+
+
+SCENES = {"loops": loops, "joints": joints, "bridge": bridge, "features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
           "deep_stacks": deep_stacks, "bullets": bullets, "sensors": sensors}

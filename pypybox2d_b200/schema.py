@@ -103,7 +103,7 @@ FIELDS = [
     ("l_contact", "C", (),   "i32"),   # island contact lists, concatenated in island order
     ("l_start",   "B", (2,), "i32"),   # per island: start in l_body, start in l_contact (ends: next row / w_island)
     # -- shared shape table --
-    ("s_meta",    "S", (),   "i32"),   # type | vertex_count << 8 | has_v0 << 16 | has_v3 << 17
+    ("s_meta",    "S", (),   "i32"),   # type | vertex_count << 8 | has_v0 << 16 | has_v3 << 17 | loop_child << 18
     ("s_radius",  "S", (),   "real"),
     ("s_data",    "S", (SHAPE_DATA,), "real"),
     # -- joints, creation order == World.joints; appended so that the rows above keep their positions --
@@ -193,6 +193,8 @@ class ShapeTable(object):
             if shape._vertex3 is not None:
                 meta |= 1 << 17
                 data[6], data[7] = shape._vertex3.x, shape._vertex3.y
+            if getattr(shape, "_loop_child", False):
+                meta |= 1 << 18              # a Loop's child edge: AABB without the radius margin (shapes.py:822-837)
         else:
             raise NotImplementedError("unsupported shape type")
         row = len(self.meta)
@@ -216,6 +218,24 @@ class ShapeTable(object):
             radius[:len(self.meta)] = self.radius
             data[:len(self.meta)] = np.asarray(self.data, dtype=np.float64)
         return meta, radius, data
+
+
+def world_proxies(world):
+    """[(fixture, child index)] in world.bodies x body.fixtures x children order: one row of the F arrays each (a fixture has
+    one broadphase proxy per child of its shape: fixture.py:250-261; only Loop shapes have more than one child)."""
+    return [(f, c) for b in world.bodies for f in b.fixtures for c in range(f._shape.child_count)]
+
+
+def proxy_shape(fixture, child):
+    """The shape a proxy collides as: the fixture's shape, or the child edge of its Loop (contact.py:363-373)."""
+    s = fixture._shape
+    return s.child_edge(child) if s._type == _shapes.LOOP else s
+
+
+def add_shapes(table, world):
+    """Every proxy shape of `world` into the shape table (de-duplicated)."""
+    for f, c in world_proxies(world):
+        table.add(proxy_shape(f, c))
 
 
 def body_flags(body):
@@ -242,8 +262,8 @@ def pack_world(world, arrays, w, table):
     """
     from .settings import AABB_EXTENSION
     nb = len(world.bodies)
-    fixtures = [f for b in world.bodies for f in b.fixtures]
-    nf = len(fixtures)
+    proxies = world_proxies(world)
+    nf = len(proxies)
     A = arrays
     if nb > A["b_flags"].shape[1] or nf > A["f_body"].shape[1]:
         raise ValueError("world exceeds batch capacity")
@@ -272,11 +292,13 @@ def pack_world(world, arrays, w, table):
         A["b_damp"][w, i] = (b._linear_damping, b._angular_damping, b._gravity_scale, 0.0)
         A["b_flags"][w, i] = body_flags(b)
         A["b_island"][w, i] = -1
-    for j, f in enumerate(fixtures):
-        f._index = j
+    for j, (f, child) in enumerate(proxies):
+        if child == 0:
+            f._index = j
         body = f._body
+        shape = proxy_shape(f, child)
         A["f_body"][w, j] = index[id(body)]
-        A["f_shape"][w, j] = table.add(f._shape)
+        A["f_shape"][w, j] = table.add(shape)
         A["f_mat"][w, j] = (f._friction, f._restitution)
         A["f_filter"][w, j] = ((f._category_bits & 0xffff) | ((f._mask_bits & 0xffff) << 16),
                                (f._group_index & 0xffff) | ((1 if f._sensor else 0) << 16))
@@ -286,7 +308,7 @@ def pack_world(world, arrays, w, table):
             A["f_tight"][w, j] = A["f_fat"][w, j] = (NO_PROXY, NO_PROXY, -NO_PROXY, -NO_PROXY)
             A["f_moved"][w, j] = 0
             continue
-        lx, ly, ux, uy = f._shape.compute_aabb(body._xf)
+        lx, ly, ux, uy = shape.compute_aabb(body._xf)
         A["f_tight"][w, j] = (lx, ly, ux, uy)
         A["f_fat"][w, j] = (lx - AABB_EXTENSION, ly - AABB_EXTENSION, ux + AABB_EXTENSION, uy + AABB_EXTENSION)
         A["f_moved"][w, j] = 1

@@ -226,11 +226,13 @@ class Edge(Shape):
     vertex0 = property(lambda self: None if self._vertex0 is None else Vec2(*self._vertex0))
     vertex3 = property(lambda self: None if self._vertex3 is None else Vec2(*self._vertex3))
 
+    _loop_child = False          # a child edge of a Loop: its AABB has no radius margin (shapes.py:822-837)
+
     def compute_aabb(self, xf):
         # shapes.py:702-718
         x1, y1 = _xf_mul(xf, self._vertex1)
         x2, y2 = _xf_mul(xf, self._vertex2)
-        r = self.radius
+        r = 0.0 if self._loop_child else self.radius
         return (min(x1, x2) - r, min(y1, y2) - r, max(x1, x2) + r, max(y1, y2) + r)
 
     def compute_mass(self, density):
@@ -241,11 +243,59 @@ class Edge(Shape):
         v0 = self._vertex0
         v3 = self._vertex3
         return (EDGE, float(self.radius), self._vertex1.x, self._vertex1.y, self._vertex2.x, self._vertex2.y,
-                None if v0 is None else (v0.x, v0.y), None if v3 is None else (v3.x, v3.y))
+                None if v0 is None else (v0.x, v0.y), None if v3 is None else (v3.x, v3.y), bool(self._loop_child))
 
 
 class Loop(Shape):
+    """A closed sequence of line segments (shapes.py:780-880): one broadphase proxy and one contact slot per child edge, each
+    child colliding as an Edge with its two neighbours as ghost vertices (Loop.child_edge); zero mass; a child's AABB is the
+    segment's box WITHOUT the radius margin (shapes.py:822-837, unlike Edge.compute_aabb)."""
     _type = LOOP
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("Loop shapes are not supported on the batched step path (SURVEY §8f #4)")
+    def __init__(self, vertices, *args):
+        if len(vertices) == 2 and isinstance(vertices[0], (int, float)):
+            vertices = [vertices]
+            vertices.extend(args)
+        if len(vertices) < 2:
+            raise ValueError('Must be >= 2 vertices')
+        self.radius = POLYGON_RADIUS
+        self._vertices = [Vec2(*v) for v in vertices]
+
+    def __copy__(self):
+        return Loop(self._vertices)
+
+    def __repr__(self):
+        return 'Loop(vertices=%s)' % self._vertices
+
+    @property
+    def child_count(self):
+        return len(self._vertices)
+
+    @property
+    def vertices(self):
+        return [Vec2(*v) for v in self._vertices]
+
+    def get_vertex(self, index):
+        return Vec2(*self._vertices[index])
+
+    def child_edge(self, index):
+        count = len(self._vertices)
+        assert 0 <= index < count
+        e = Edge(self._vertices[index], self._vertices[(index + 1) % count], self._vertices[(index - 1) % count],
+                 self._vertices[(index + 2) % count])
+        e._loop_child = True
+        return e
+
+    def test_point(self, xf, p):
+        return False
+
+    def compute_aabb(self, xf, child_index=0):
+        x1, y1 = _xf_mul(xf, self._vertices[child_index])
+        x2, y2 = _xf_mul(xf, self._vertices[(child_index + 1) % len(self._vertices)])
+        return (min(x1, x2), min(y1, y2), max(x1, x2), max(y1, y2))
+
+    def compute_mass(self, density):
+        return MassData()
+
+    def _key(self):
+        return (LOOP, float(self.radius)) + tuple(c for v in self._vertices for c in (v.x, v.y))

@@ -130,6 +130,7 @@ class World(object):
         self._host_dirty = True
         self._structure_dirty = False
         self._packed_fixtures = []
+        self._packed_keys = []
         self._prev_contacts = None
         self._batch = None
         self._real = real
@@ -299,6 +300,7 @@ class World(object):
             self._host_dirty = False
             self._structure_dirty = False
             self._packed_fixtures = self._fixture_list()
+            self._packed_keys = self._proxy_keys()
         elif self._structure_dirty:
             self._rebuild_batch()
         elif self._host_dirty:
@@ -318,20 +320,20 @@ class World(object):
         from .batch import BatchedWorld, world_caps
         old = self._batch
         D = old.download()
-        old_index = {id(f): j for j, f in enumerate(self._packed_fixtures)}
+        old_index = {k: j for j, k in enumerate(self._packed_keys)}
         fixtures = self._fixture_list()
+        keys = self._proxy_keys()
         caps = world_caps([self])
         caps = schema.Caps(max(caps.nb, 1), max(caps.nf, 1), max(caps.nc, old.caps.nc), nj=caps.nj)
         table = schema.ShapeTable()
-        for f in fixtures:
-            table.add(f._shape)
+        schema.add_shapes(table, self)
         A = schema.alloc(caps, 1, max(len(table), 1), "f64")
         schema.pack_world(self, A, 0, table)
         A["s_meta"], A["s_radius"], A["s_data"] = table.arrays("f64")
         remap = np.full(len(self._packed_fixtures) + 1, -1, np.int64)
         any_new = False
         for j2, f in enumerate(fixtures):
-            j = old_index.get(id(f), -1)
+            j = old_index.get(keys[j2], -1)
             if j < 0:
                 any_new = True
                 continue
@@ -360,6 +362,7 @@ class World(object):
         batch.inv_dt0 = old.inv_dt0
         self._batch = batch
         self._packed_fixtures = fixtures
+        self._packed_keys = keys
         self._host_dirty = False
         self._structure_dirty = False
 
@@ -401,7 +404,11 @@ class World(object):
 
     # -- queries (world.py:371-440) ----------------------------------------------------------------
     def _fixture_list(self):
-        return [f for b in self.bodies for f in b.fixtures]
+        """The fixture of every device proxy row (a Loop fixture appears once per child edge, as in the reference's broadphase)."""
+        return [f for f, c in schema.world_proxies(self)]
+
+    def _proxy_keys(self):
+        return [(id(f), c) for f, c in schema.world_proxies(self)]
 
     def query_aabb(self, aabb, callback=None):
         """Every fixture whose broadphase (fat) AABB overlaps `aabb` -- an object with lower_bound / upper_bound, or

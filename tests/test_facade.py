@@ -180,3 +180,28 @@ def test_body_frame_helpers_match_the_reference_values():
     assert b.contact_list == []
     (lx, ly), (ux, uy) = b.fixtures[0].get_aabb()
     assert lx < 1.5 < ux and ly < 2.0 < uy
+
+
+def test_loop_shape_packs_one_proxy_per_child_edge():
+    """shapes.py:780-880: a Loop fixture has one broadphase proxy per child edge (fixture.py:250-261), each colliding as an Edge with
+    its neighbours as ghost vertices; zero mass; a child's AABB has no radius margin."""
+    import numpy as np
+    from pypybox2d_b200 import schema
+    w = b2.World(continuous_physics=False)
+    ground = w.create_static_body(shapes=b2.Loop([(-5, 0), (5, 0), (5, 5), (-5, 5)]))
+    body = w.create_dynamic_body(position=(0, 2), fixtures=b2.Fixture(b2.Circle(0.5), density=1.0))
+    frame = body.create_loop_fixture([(-1, -1), (1, -1), (0, 1)])
+    assert ground.fixtures[0].shape.child_count == 4 and frame.shape.child_count == 3 and body.mass == pytest.approx(math.pi * 0.25)
+    e = ground.fixtures[0].shape.child_edge(3)
+    assert (e.vertex1, e.vertex2, e.vertex0, e.vertex3) == (b2.Vec2(-5, 5), b2.Vec2(-5, 0), b2.Vec2(5, 5), b2.Vec2(5, 0))
+    with pytest.raises(ValueError):
+        b2.Loop([(0, 0)])
+    assert [f is ground.fixtures[0] for f in w._fixture_list()] == [True] * 4 + [False] * 4
+    caps = schema.Caps(2, 8, 32)
+    table = schema.ShapeTable()
+    A = schema.alloc(caps, 1, 16)
+    schema.pack_world(w, A, 0, table)
+    assert A["w_count"][0].tolist()[:2] == [2, 8] and A["f_body"][0].tolist() == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert len(table) == 8 and sum((m >> 18) & 1 for m in table.meta) == 7            # seven child edges, one circle
+    assert A["f_tight"][0, 0].tolist() == [-5.0, 0.0, 5.0, 0.0]                          # no radius margin (shapes.py:822-837)
+    assert np.allclose(A["f_fat"][0, 0], [-5.1, -0.1, 5.1, 0.1])

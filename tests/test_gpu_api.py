@@ -441,3 +441,26 @@ def test_joint_batches_fp32_invariance_and_sleeping_bridge():
         n = int(r[1]["w_count"][0][0])
         assert np.abs(M["b_pos"][i, :n, :3] - r[1]["b_pos"][0, :n, :3]).max() < 1e-7, i
         assert int(M["w_count"][i][2]) == int(r[1]["w_count"][0][2])
+
+
+def test_world_with_loop_shapes_is_a_drop_in():
+    """Loop shapes through the facade -- bodies inside a terrain loop and a turning loop on a kinematic body follow the
+    oracle; contacts and queries name the Loop fixture once per child edge, as the reference's broadphase does."""
+    import pypybox2d_b200 as b2
+    world = scenes.loops(b2, world=0, real="f64")
+    mw, A, caps = harness.facade_arrays("loops", 0)
+    orc = oracle.Oracle(A, 0)
+    nb = len(world.bodies)
+    for i in range(120):
+        world.step(1 / 60, 8, 3)
+        orc.step(1 / 60, 8, 3)
+    pos = np.array([[b._c.x, b._c.y, b._a] for b in world.bodies])
+    assert np.abs(pos - A["b_pos"][0, :nb, :3]).max() < 1e-6
+    contacts = world.contact_manager.contacts
+    assert len(contacts) == int(A["w_count"][0][2]) and sum(c.touching for c in contacts) > 10
+    terrain = world.bodies[0].fixtures[0]
+    assert any(c.fixture_a is terrain for c in contacts)                             # the loop is fixture A (contact.py:310-311)
+    hits = list(world.query_aabb(((-20.0, -1.0), (20.0, 0.5))))
+    assert hits.count(terrain) >= 4                                                  # one hit per child edge whose fat box overlaps
+    rc = [h for h in world.ray_cast((0.0, 10.0), (0.0, -5.0))]
+    assert any(h[0] is terrain and abs(h[1].y) < 1e-9 for h in rc)                   # the ray reaches the floor edge of the loop

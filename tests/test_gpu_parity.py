@@ -107,7 +107,8 @@ EXACT_TOL = {"pyramid": 1e-11, "hello": 1e-11, "vertical_stack": 1e-8, "deep_sta
              "bullets": 1e-5, "sensors": 1e-5,
              # joints in the island solver (measured on B200, profiles/r2_joints/parity_report_joints.json: joints_w0 6.8e-6 over 400
              # steps of tumbling bodies on a bridge, the other three cases <= 3.1e-11; one step teacher-forced: <= 2.8e-14)
-             "joints": 1e-4, "bridge": 1e-11}
+             "joints": 1e-4, "bridge": 1e-11,
+             "loops": 1e-5}       # Loop shapes: bodies tumbling inside a turning loop
 # Continuous collision on (World.solve_toi; measured by tools/ccd_parity_probe.py on B200, profiles/r2_ccd_parity.json): the
 # TOI sub-steps amplify the same one-ulp libm differences further.  Free-running, seven of the eight cases keep the oracle's
 # integer outputs for their whole length (worst float difference: pyramid landing 5.2e-13, features 1.4e-9, bullets 4.5e-9 /
@@ -166,9 +167,10 @@ CCD_CASES = ["bullets_w0", "bullets_w1", "bullets_w2", "hello_ccd_w0", "pyramid_
 
 
 JOINT_CASES = ["joints_w0", "joints_w1", "joints_ccd_w2", "bridge_w1"]
+LOOP_CASES = ["loops_w0", "loops_ccd_w1"]
 
 
-@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0", "sensors_w0"] + CCD_CASES + JOINT_CASES)
+@pytest.mark.parametrize("case", ["mixed_w1", "pyramid_w1", "features_w0", "sensors_w0"] + CCD_CASES + JOINT_CASES + LOOP_CASES)
 def test_p_exact_fp64_one_step(case, parity_report):
     """Teacher-forced fp64: from the oracle's state at step k, ONE step of the fp64 kernels agrees with the oracle's to
     1e-11 in every float field at every k (measured: 1.5e-12) -- the free-running differences of the swaying and tumbling
@@ -190,7 +192,7 @@ def test_p_exact_fp64_one_step(case, parity_report):
         G = bw.download()
         assert int_mismatches(A, G) == [], "integer outputs differ at step %d" % s
         d = float_diffs(A, G)
-        if (case in CCD_CASES or case == "joints_ccd_w2") and max(d.values()) > 1e-11:
+        if (case in CCD_CASES or case in ("joints_ccd_w2", "loops_ccd_w1")) and max(d.values()) > 1e-11:
             # the TOI position loop's knife-edge exit test (P_STEP_BOUNDS below): one sweep more or less, 0.0075 * 0.25^k m
             sweep_ties.append((s, max(d.values())))
             assert max(v for k, v in d.items() if k not in ("b_vel", "c_imp", "j_imp")) <= 2.5e-3 and d["b_vel"] <= 0.05, \
@@ -210,7 +212,7 @@ def test_p_exact_fp64_one_step(case, parity_report):
 # is the sweep loop's exit test (contact.py:933 `min_separation >= -1.5 * LINEAR_SLOP`): rounding decides whether a second
 # sweep runs, and one sweep more or less is 0.0075 / 16 = 4.7e-4 m of position (measured: 4.69e-4 on every scene with
 # TOI events against round bodies) and the restitution / friction response of the different lever arms in velocity.
-P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2"]}
+P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2", "loops_ccd_w1"]}
 # joints: motors, stiff soft constraints (wheel suspension, mouse joint: 1 / (dt (d + dt k)) terms) and 3x3 solves inside one step
 # and branches inside the limit handling that have no integer output (revolute.py:343-360 `new_impulse < 0`, prismatic.py:384-389
 # max / min of the limit impulse, the motor clamps): a branch taken the other way within fp32 rounding is a different impulse.
@@ -224,7 +226,8 @@ P_STEP_BOUNDS.update({"joints_w0": (1e-3, 5e-2), "joints_w1": (1e-3, 5e-2)})
                                         ("features_w0", 200), ("bullets_w0", 300), ("bullets_w2", 200), ("hello_ccd_w0", 100),
                                         ("pyramid_ccd_w1", 300), ("features_ccd_w1", 300), ("mixed_ccd_w1", 120),
                                         ("vertical_stack_ccd_w1", 200), ("sensors_w1", 300), ("sensors_ccd_w2", 300),
-                                        ("joints_w0", 400), ("joints_w1", 300), ("bridge_w1", 300), ("joints_ccd_w2", 300)])
+                                        ("joints_w0", 400), ("joints_w1", 300), ("bridge_w1", 300), ("joints_ccd_w2", 300),
+                                        ("loops_w0", 300), ("loops_ccd_w1", 300)])
 def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     import pypybox2d_b200 as b2
     g = load_golden(case)

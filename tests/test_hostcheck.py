@@ -25,11 +25,13 @@ CCD_CASES = [("bullets", 0, 1 / 60, 8, 3, 300, {}), ("bullets", 2, 1 / 30, 10, 4
 
 
 # joints in the island solver: revolute (limits, motor), distance (rigid, soft), weld; with and without CCD
+# Loop shapes: one proxy and one contact slot per child edge, AABBs without the radius margin
+LOOP_CASES = [("loops", 0, 1 / 60, 8, 3, 300, {}), ("loops", 1, 1 / 60, 8, 3, 200, CCD)]
 JOINT_CASES = [("joints", 0, 1 / 60, 8, 3, 400, {}), ("joints", 1, 1 / 60, 10, 4, 200, {}), ("bridge", 1, 1 / 60, 8, 3, 200, {}),
                ("joints", 2, 1 / 60, 8, 3, 200, CCD)]
 
 
-@pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES + JOINT_CASES)
+@pytest.mark.parametrize("scene,world,dt,vi,pi,steps,kw", [c + ({},) for c in CASES] + CCD_CASES + JOINT_CASES + LOOP_CASES)
 def test_host_compiled_step_matches_oracle_f64(scene, world, dt, vi, pi, steps, kw):
     mw, OA, caps = harness.facade_arrays(scene, world, **kw)
     HA = {k: v.copy() for k, v in OA.items()}
