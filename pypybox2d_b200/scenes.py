@@ -459,7 +459,9 @@ def loops(b2, world=0, config=11, **world_kw):
     w.create_static_body(shapes=b2.Loop(terrain), shape_fixture=b2.Fixture(b2.Circle(1.0), friction=0.5))
     tumbler = w.create_kinematic_body(position=(8.0, 6.0), angular_velocity=0.6)
     tumbler.create_loop_fixture([(3.0 * math.cos(2.0 * math.pi * q / 8), 3.0 * math.sin(2.0 * math.pi * q / 8)) for q in range(8)], friction=0.6)
-    cart = w.create_dynamic_body(position=(-10.0, 3.0))
+    # (an initial velocity: a body that falls from rest has moved EXACTLY the 0.1 m fat-box margin after eight steps at 60 Hz --
+    # g dt^2 n (n + 1) / 2 -- and rounding decides the containment test of DynamicTree.move_proxy)
+    cart = w.create_dynamic_body(position=(-10.0, 3.0), linear_velocity=(0.4, -0.3))
     cart.create_polygon_fixture(box=(1.0, 0.2), density=2.0, friction=0.4)
     cart.create_loop_fixture([(-1.0, 0.2), (1.0, 0.2), (1.0, 1.0), (-1.0, 1.0)], friction=0.4)       # an open-topped tray would be edges; this is a frame
     n = 28

@@ -219,6 +219,9 @@ P_STEP_BOUNDS = {c: (2e-3, 0.25) for c in CCD_CASES + ["joints_ccd_w2", "loops_c
 # Measured on B200 (profiles/r2_joints/parity_report_joints.json): 2.0e-4 m, 1.2e-2 m/s on the non-tie steps; the fp64 kernels
 # on the same steps: <= 2.8e-14
 P_STEP_BOUNDS.update({"joints_w0": (1e-3, 5e-2), "joints_w1": (1e-3, 5e-2)})
+# Loop shapes: the default bounds on the non-tie steps; on a tie step (a manifold point more or less on an edge of the turning
+# loop) the velocities of the bodies in that contact differ by the impulse of one point (measured 1.1e-2 m/s)
+P_STEP_BOUNDS.update({"loops_w0": (5e-5, 1e-3)})
 
 
 @pytest.mark.parametrize("case,steps", [("pyramid_w1", 600), ("pyramid_w0", 150), ("mixed_w1", 150),
@@ -255,7 +258,7 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
         if case in P_STEP_BOUNDS:
             # (on a tie step a bullet's contact exists in one arithmetic and not in the other: the step's outcome is a
             # different event, not an error bound; the fp64 kernels are checked on the same inputs below)
-            tol_p, tol_v = ((float("inf"), float("inf")) if case not in ("joints_w0", "joints_w1") else (5e-3, 0.1)) if tie else P_STEP_BOUNDS[case]
+            tol_p, tol_v = ((float("inf"), float("inf")) if case not in ("joints_w0", "joints_w1", "loops_w0") else (5e-3, 0.1)) if tie else P_STEP_BOUNDS[case]
         assert dp <= tol_p and dv <= tol_v, "fp32 one-step state error at step %d (tie=%s): %.2e m, %.2e m/s" % (s, tie, dp, dv)
         if not tie:
             worst_p, worst_v = max(worst_p, dp), max(worst_v, dv)
@@ -276,7 +279,7 @@ def test_p_step_fp32_teacher_forced(case, steps, parity_report):
     # (the joints scene has nine small islands, each with its own periodic sleep event -- the reference's rule puts one body to
     # sleep when 30 additions of 1/60 reach 0.5 s, which fp32 hits within rounding: measured 34 tie steps of 300, every one an
     # awake flag or a fat-AABB pair tie, and the fp64 kernels reproduce the oracle on each of them)
-    assert ties <= (0.15 if case.startswith("joints") else 0.10) * steps, "%d of %d teacher-forced steps had integer mismatches" % (ties, steps)
+    assert ties <= (0.15 if case.startswith(("joints", "loops")) else 0.10) * steps, "%d of %d teacher-forced steps had integer mismatches" % (ties, steps)
 
 
 # P-steady: 16 jittered worlds per scene, 600 free-running fp32 steps from the oracle's state after `settle` steps.
