@@ -478,7 +478,8 @@ def loops(b2, world=0, config=11, **world_kw):
         else:
             m = 3 + (k // 3) % 4
             shape = b2.Polygon(vertices=[(0.35 * math.cos(0.2 + 2.0 * math.pi * q / m), 0.35 * math.sin(0.2 + 2.0 * math.pi * q / m)) for q in range(m)])
-        w.create_dynamic_body(position=pos, angle=0.1 * k, fixtures=b2.Fixture(shape, density=1.0, friction=0.4, restitution=0.1 * (k % 3)))
+        w.create_dynamic_body(position=pos, angle=0.1 * k, linear_velocity=(0.0, -0.2 - 0.01 * k),      # (not from rest: see the cart)
+                              fixtures=b2.Fixture(shape, density=1.0, friction=0.4, restitution=0.1 * (k % 3)))
     w.create_dynamic_body(position=(-4.0, 12.0), bullet=True, linear_velocity=(15.0, -60.0), fixtures=b2.Fixture(b2.Circle(0.15), density=4.0, friction=0.2))
     return w
 
