@@ -8,7 +8,7 @@ objects.  A single `World` is a batch of one; large batches use `BatchedWorld` d
 
 Revolute, distance, weld, prismatic, rope, friction, wheel, pulley and mouse joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
 (raise `NotImplementedError`): the other joint types, controllers, `pre_solve` / `post_solve` listeners,
-custom contact filters, Loop shapes and sub-stepping.  Continuous collision
+custom contact filters and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
 """
 from copy import copy
