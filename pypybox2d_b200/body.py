@@ -52,6 +52,7 @@ class Body(object):
         self._sleep_time = 0.0
         self.fixtures = []
         self.joints = []
+        self._controllers = []
         self.user_data = user_data
         self._world = world
         self._linear_velocity = linear_velocity

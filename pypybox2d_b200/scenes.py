@@ -484,5 +484,35 @@ def loops(b2, world=0, config=11, **world_kw):
     return w
 
 
-SCENES = {"loops": loops, "joints": joints, "bridge": bridge, "features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
+# ---- controller coverage scene (not a BASELINE config): buoyancy and pairwise gravity as per-step host forces -------
+def controllers(b2, world=0, config=12, **world_kw):
+    """controllers.py: a pool (half plane y < 4) with buoyancy, linear and angular drag into which boxes, circles, a triangle and a
+    two-fixture body are dropped, one of them asleep; three bodies without world gravity that attract each other through a
+    GravityController (1 / r^2) next to it."""
+    w = b2.World((0, -10), True, **_kw(world_kw))
+    w.create_static_body(shapes=[b2.Edge((-20.0, 0.0), (20.0, 0.0)), b2.Edge((-12.0, 0.0), (-12.0, 10.0)), b2.Edge((12.0, 0.0), (12.0, 10.0))])
+    jit = jitter(config, world, 16)
+    pool = []
+    for k in range(9):
+        pos = (-9.0 + 2.2 * k + jit[k, 0], 5.0 + 0.9 * (k % 3) + jit[k, 1])
+        if k % 4 == 0:
+            fx = [b2.Fixture(b2.Circle(0.4), density=0.6, friction=0.3)]
+        elif k % 4 == 1:
+            fx = [b2.Fixture(b2.Polygon(box=(0.5, 0.3)), density=0.8, friction=0.3)]
+        elif k % 4 == 2:
+            fx = [b2.Fixture(b2.Polygon(vertices=[(-0.5, -0.3), (0.5, -0.3), (0.0, 0.6)]), density=1.5, friction=0.3)]
+        else:
+            fx = [b2.Fixture(b2.Polygon(box=(0.6, 0.15)), density=0.5, friction=0.3), b2.Fixture(b2.Circle(0.25, (0.5, 0.2)), density=2.0, friction=0.3)]
+        pool.append(w.create_dynamic_body(position=pos, angle=0.3 * k, linear_velocity=(0.0, -0.5 - 0.1 * k), fixtures=fx))
+    pool.append(w.create_dynamic_body(position=(10.5, 0.31), awake=False, fixtures=b2.Fixture(b2.Polygon(box=(0.4, 0.3)), density=0.7, friction=0.3)))
+    w.create_buoyancy_controller(bodies=pool, normal=(0, 1), offset=4.0, density=2.0, velocity=(0.5, 0.0), linear_drag=2.0, angular_drag=1.0)
+    stars = []
+    for k, (x, y, vx, vy, r) in enumerate(((-30.0, 12.0, 0.0, 1.0, 0.6), (-26.0, 12.0, 0.0, -1.5, 0.4), (-28.0, 15.0, 1.2, 0.0, 0.3))):
+        stars.append(w.create_dynamic_body(position=(x + jit[10 + k, 0], y + jit[10 + k, 1]), linear_velocity=(vx, vy), gravity_scale=0.0,
+                                           fixtures=b2.Fixture(b2.Circle(r), density=2.0, friction=0.3, restitution=0.5)))
+    w.create_gravity_controller(bodies=stars, G=8.0, inv_sqr=True)
+    return w
+
+
+SCENES = {"controllers": controllers, "loops": loops, "joints": joints, "bridge": bridge, "features": features, "pyramid": pyramid, "hello": hello, "vertical_stack": vertical_stack, "mixed": mixed,
           "deep_stacks": deep_stacks, "bullets": bullets, "sensors": sensors}

@@ -7,7 +7,7 @@ objects.  A single `World` is a batch of one; large batches use `BatchedWorld` d
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
 Revolute, distance, weld, prismatic, rope, friction, wheel, pulley and mouse joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
-(raise `NotImplementedError`): the other joint types, controllers, `pre_solve` / `post_solve` listeners,
+(raise `NotImplementedError`): the gear joint, `pre_solve` / `post_solve` listeners,
 custom contact filters and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
 """
@@ -280,8 +280,22 @@ class World(object):
         raise NotImplementedError("gear joints do not run on the batched step path (SURVEY §8f #3: revolute, distance, weld, prismatic, "
                                   "rope, friction, wheel, pulley and mouse joints do)")
 
+    # -- controllers (world.py:923-956; controllers.py) -----------------------------------------------------------------------
     def add_controller(self, controller):
-        raise NotImplementedError("controllers are not supported on the batched step path")
+        self.controllers.append(controller)
+        return controller
+
+    def destroy_controller(self, controller):
+        controller.clear()
+        self.controllers.remove(controller)
+
+    def create_gravity_controller(self, *args, **kwargs):
+        from . import controllers
+        return self.add_controller(controllers.GravityController(self, *args, **kwargs))
+
+    def create_buoyancy_controller(self, *args, **kwargs):
+        from . import controllers
+        return self.add_controller(controllers.BuoyancyController(self, *args, **kwargs))
 
     def _fixture_attached(self, body, fixture):
         self._host_dirty = True
@@ -370,6 +384,18 @@ class World(object):
         if self._locked:
             raise LockedError("step is not re-entrant")
         batch = self._ensure_batch()
+        if self.controllers and dt > 0.0:
+            # controllers act between the narrowphase and the island solver (world.py:338-342, 477-479): run the narrowphase
+            # alone (a step with dt = 0: contacts updated, bodies woken by touching changes), mirror the awake flags back,
+            # let the controllers apply their forces on the host as the reference does, upload them; the step below repeats the
+            # narrowphase on unchanged transforms, which changes nothing
+            batch.inv_dt0 = self._inv_dt0
+            batch.step(0.0, vel_iters, pos_iters, 1)
+            batch.download_into_world(self)
+            step = TimeStep(dt, 1.0 / dt, self._inv_dt0 * dt, vel_iters, pos_iters, self._warm_starting)
+            for controller in self.controllers:
+                controller.step(step)
+            batch = self._ensure_batch()
         self._locked = True
         try:
             batch.inv_dt0 = self._inv_dt0
