@@ -17,6 +17,8 @@ from .body import Body
 from . import schema
 from . import joints as _joints
 from .common import Vec2, LockedError
+from .proxytree import ProxyTree
+from .settings import AABB_EXTENSION
 
 
 class TimeStep(object):
@@ -46,9 +48,36 @@ class ContactView(object):
         return self.fixture_b.body
 
 
+class _BroadPhaseView(object):
+    """`world.contact_manager.broadphase` as far as a caller can observe it (broadphase.py:78-81, 137-150): the proxy count and
+    the tree observables, from the host replay of the reference's tree topology (`proxytree.ProxyTree`)."""
+    def __init__(self, world):
+        self._world = world
+
+    @property
+    def proxy_count(self):
+        """The reference's counter, not the number of leaves: `destroy_body` walks the body's fixtures twice
+        (body.py:330-340) and `BroadPhase.destroy_proxy` decrements before it looks at the proxy (broadphase.py:53-59), so
+        every proxy of a destroyed body is subtracted twice."""
+        return self._world._proxy_count
+
+    @property
+    def tree_height(self):
+        return self._world._tree.tree_height
+
+    @property
+    def tree_balance(self):
+        return self._world._tree.tree_balance
+
+    @property
+    def tree_quality(self):
+        return self._world._tree.tree_quality
+
+
 class _ContactManagerView(object):
     def __init__(self, world):
         self._world = world
+        self.broadphase = _BroadPhaseView(world)
 
     @property
     def contacts(self):
@@ -135,6 +164,11 @@ class World(object):
         self._batch = None
         self._real = real
         self._device = device
+        # the reference's broadphase tree topology (row a19), replayed for tree_height / tree_balance / tree_quality
+        self._tree = ProxyTree()
+        self._tree_leaf = {}            # (id(fixture), child) -> leaf slot
+        self._proxy_count = 0
+        self._tree_fat = None           # the device's fat boxes as of the last replay, rows in `_packed_keys` order
 
     # -- properties (world.py:93-181) ------------------------------------------------------
     @property
@@ -174,6 +208,8 @@ class World(object):
             raise LockedError("Cannot create a body while simulating")
         self.bodies.append(body)
         body._world = self
+        for fixture in body.fixtures:          # Body._attached_to_world, body.py:292-297
+            self._tree_create(body, fixture)
         self._host_dirty = True
         if self._stepped:
             self._structure_dirty = True       # the device arrays are re-packed before the next step (_rebuild_batch)
@@ -208,6 +244,9 @@ class World(object):
             if self.joint_destruction_listener:
                 self.joint_destruction_listener(joint)
             self.destroy_joint(joint)
+        for fixture in body.fixtures:            # body.py:330-335
+            n = self._tree_destroy(fixture)
+            self._proxy_count -= n               # ... and 337-340: the second walk only moves the counter
         self.bodies.remove(body)
         body._world = None
         self._host_dirty = True
@@ -298,15 +337,54 @@ class World(object):
         return self.add_controller(controllers.BuoyancyController(self, *args, **kwargs))
 
     def _fixture_attached(self, body, fixture):
+        self._tree_create(body, fixture)         # body.py:203-205
         self._host_dirty = True
         if self._stepped:
             self._structure_dirty = True
 
     def _fixture_detached(self, body, fixture):
+        self._tree_destroy(fixture)              # body.py:281-283
         self._host_dirty = True
         self._structure_dirty = True
 
-    # -- stepping (world.py:307-369) ----------------------------------------------------------
+    # -- the broadphase tree's topology (row a19; proxytree.py) ---------------------------------------------------------------
+    def _tree_create(self, body, fixture):
+        """fixture.py:250-261: one leaf per child of the fixture's shape, fat box = the child's box at the body's transform
+        grown by AABB_EXTENSION (dynamictree.py:121-126); an inactive body's fixtures have no proxies."""
+        if not body._active:
+            return
+        shape = fixture._shape
+        for child in range(shape.child_count):
+            lx, ly, ux, uy = shape.compute_aabb(body._xf, child) if shape.child_count > 1 else shape.compute_aabb(body._xf)
+            self._tree_leaf[(id(fixture), child)] = self._tree.create_leaf(
+                (lx - AABB_EXTENSION, ly - AABB_EXTENSION, ux + AABB_EXTENSION, uy + AABB_EXTENSION))
+            self._proxy_count += 1
+        self._tree_fat = None
+
+    def _tree_destroy(self, fixture):
+        n = 0
+        for child in range(fixture._shape.child_count):
+            slot = self._tree_leaf.pop((id(fixture), child), None)
+            if slot is not None:
+                self._tree.destroy_leaf(slot)
+                self._proxy_count -= 1
+                n += 1
+        self._tree_fat = None
+        return n
+
+    def _tree_replay(self, batch):
+        """After a step: every proxy whose fat box the device replaced was taken out of the reference's tree and put back with
+        that box (dynamictree.py:152-188), in synchronisation order = proxy row order (world.py:582-588)."""
+        import numpy as np
+        fat = batch.download(["f_fat"])["f_fat"][0]
+        before = self._tree_fat
+        if before is not None and before.shape == fat.shape:
+            for j in np.nonzero((fat != before).any(axis=1))[0]:
+                slot = self._tree_leaf.get(self._packed_keys[j])
+                if slot is not None:
+                    self._tree.reinsert_leaf(slot, fat[j])
+        self._tree_fat = fat
+
     def _ensure_batch(self):
         from .batch import BatchedWorld
         if self._batch is None:
@@ -398,6 +476,8 @@ class World(object):
             batch = self._ensure_batch()
         self._locked = True
         try:
+            if self._tree_fat is None:             # the device's boxes before the step (its fp32 boxes are not the host's fp64 ones)
+                self._tree_fat = batch.download(["f_fat"])["f_fat"][0]
             batch.inv_dt0 = self._inv_dt0
             batch.step(dt, vel_iters, pos_iters, 1)
             if dt > 0.0:
@@ -414,6 +494,7 @@ class World(object):
                                    "the step's result is invalid" % (", ".join(names) or hex(st), batch.caps.nc, batch.caps.npair,
                                                                       batch.caps.nl))
             batch.download_into_world(self)
+            self._tree_replay(batch)
             self._deliver_contact_events()
             if not self._auto_clear_forces:
                 # forces were cleared on the device only when auto_clear_forces is on
