@@ -215,13 +215,50 @@ class Body(object):
     def position(self):
         return Vec2(self._xf[0], self._xf[1])
 
+    @position.setter
+    def position(self, pos):
+        # body.py:420-423: the origin moves, the rotation stays
+        self._check_unlocked()
+        pos = Vec2(*pos)
+        self._xf = (pos.x, pos.y, self._xf[2], self._xf[3])
+        self._transform_updated()
+
     @property
     def angle(self):
         return math.atan2(self._xf[3], self._xf[2])
 
+    @angle.setter
+    def angle(self, angle):
+        # body.py:430-433
+        self._check_unlocked()
+        angle = float(angle)
+        self._xf = (self._xf[0], self._xf[1], math.cos(angle), math.sin(angle))
+        self._transform_updated()
+
     @property
     def transform(self):
         return self._xf
+
+    @transform.setter
+    def transform(self, position_angle):
+        """body.py:384-395: `(position, angle)`, or a transform as this facade hands them out (`(px, py, cos, sin)`)."""
+        self._check_unlocked()
+        if len(position_angle) == 4:
+            self._xf = tuple(float(v) for v in position_angle)
+        else:
+            pos, angle = Vec2(*position_angle[0]), float(position_angle[1])
+            self._xf = (pos.x, pos.y, math.cos(angle), math.sin(angle))
+        self._transform_updated()
+
+    def _transform_updated(self):
+        """body.py:404-413: the sweep restarts at the new transform (the angle read back from the rotation, as there), every
+        fixture's proxy is moved with no displacement and the world looks for new contacts (`World._body_moved_by_host`)."""
+        self._c0 = Vec2(*self._xf_mul(self._local_center))
+        self._c = copy(self._c0)
+        self._a0 = self._a = math.atan2(self._xf[3], self._xf[2])
+        self._dirty()
+        if self._world is not None:
+            self._world._body_moved_by_host(self)
 
     @property
     def world_center(self):
@@ -290,12 +327,30 @@ class Body(object):
         if self._world is not None:
             self._world._batch = None          # proxies are rebuilt from the host state
             self._world._host_dirty = True
-    bullet = property(lambda self: self._bullet)
-    fixed_rotation = property(lambda self: self._fixed_rotation)
-    linear_damping = property(lambda self: self._linear_damping)
-    angular_damping = property(lambda self: self._angular_damping)
-    gravity_scale = property(lambda self: self._gravity_scale)
-    allow_sleep = property(lambda self: self._allow_sleep)
+
+    # plain per-body parameters the step reads (body.py:710-790, 880-890): set on the host, uploaded before the next step
+    def _parameter(name, convert, after=None):
+        def fget(self):
+            return getattr(self, name)
+
+        def fset(self, value):
+            setattr(self, name, convert(value))
+            if after is not None:
+                after(self)
+            self._dirty()
+        return property(fget, fset)
+
+    def _woken_unless_allowed_to_sleep(self):
+        if not self._allow_sleep:
+            self.awake = True
+
+    bullet = _parameter("_bullet", bool)
+    fixed_rotation = _parameter("_fixed_rotation", bool, lambda self: self.reset_mass_data())
+    linear_damping = _parameter("_linear_damping", float)
+    angular_damping = _parameter("_angular_damping", float)
+    gravity_scale = _parameter("_gravity_scale", float)
+    allow_sleep = _parameter("_allow_sleep", bool, _woken_unless_allowed_to_sleep)
+    del _parameter, _woken_unless_allowed_to_sleep
 
     @property
     def awake(self):
@@ -319,6 +374,10 @@ class Body(object):
     @property
     def sleeping(self):
         return not self._awake
+
+    @sleeping.setter
+    def sleeping(self, sleeping):
+        self.awake = not sleeping
 
     # -- forces (host-side inputs consumed by the next step; body.py:477-545) ---------------
     def apply_force(self, force, point):
