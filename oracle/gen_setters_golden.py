@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
+ -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
+once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
+(823-825) and `fixed_rotation` (884-887) on a world that is already stepping.
+
+The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
+awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
+tests/test_setters.py plays the same script through pypybox2d_b200.World.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import harness  # noqa: E402
+import refpin  # noqa: E402
+import gen_mutation_golden as gm  # noqa: E402
+import gen_tree_golden as gt  # noqa: E402
+
+DT, VI, PI = 1.0 / 60, 8, 3
+
+
+def script(b2, world, record):
+    """The scenario, written against the API module `b2` (the reference or this package)."""
+    def run(n):
+        for _ in range(n):
+            world.step(DT, VI, PI)
+            record(world)
+    B = world.bodies
+    run(40)
+    B[5].linear_damping = 0.5
+    B[6].gravity_scale = -0.5                      # floats up into the box above it
+    B[7].angular_damping = 0.3
+    run(30)
+    B[20].position = (8.0, 6.0)                    # out of the pile: the proxy leaves its fat box, its contacts end
+    run(30)
+    B[20].transform = ((0.2, 9.0), 0.3)            # back above the pile, rotated
+    run(40)
+    p = B[3].position
+    B[3].position = (p.x + 0.01, p.y)              # inside the fat box: no re-insertion
+    run(20)
+    B[10].fixed_rotation = True
+    B[11].allow_sleep = False
+    B[12].bullet = True
+    run(40)
+    p = B[0].position
+    B[0].position = (p.x, p.y - 0.05)              # the static ground drops by half a slop-and-a-bit under the pile
+    run(30)
+    B[15].angle = 0.5
+    run(30)
+    B[8].sleeping = True                           # velocities and forces zeroed (body.py:800-812)
+    B[30].transform = ((-6.0, 0.6), 0.0)
+    B[31].transform = ((-6.0, 1.7), 0.0)           # two bodies moved between the same two steps, onto each other
+    run(40)
+
+
+def main():
+    from pypybox2d_b200 import scenes
+    b2 = refpin.load()
+    world = scenes.pyramid(b2, world=1, rows=8)
+    refpin.index_fixtures(world)
+    states, awakes, contacts, obs, pre = [], [], [], [], []
+
+    def record(w):
+        st, aw, con = gm.snapshot_reference(w)
+        states.append(st); awakes.append(aw); contacts.append(con)
+        bp = w.contact_manager.broadphase
+        fidx = {id(f): j for j, f in enumerate([f for b in w.bodies for f in b.fixtures])}
+        obs.append((bp.tree_height, bp.tree_quality))
+        pre.append(np.array(gt.preorder(bp._tree._root, lambda n: fidx[id(n.user_data.fixture)]), np.int32))
+    script(b2, world, record)
+    out = {"states": np.array(states), "awake": np.array(awakes), "n_contacts": np.array([len(c) for c in contacts], np.int32),
+           "contacts": np.concatenate(contacts), "tree_obs": np.array(obs), "tree_pre": np.array(pre)}
+    path = os.path.join(harness._ROOT, "tests", "golden_queries", "setters.npz")
+    np.savez_compressed(path, **out)
+    print("%d steps, contacts %d..%d, awake at the end %d of %d -> %s (%d KB)" % (
+        len(states), out["n_contacts"].min(), out["n_contacts"].max(), int(awakes[-1].sum()), len(awakes[-1]),
+        os.path.relpath(path, harness._ROOT), os.path.getsize(path) // 1024))
+
+
+if __name__ == "__main__":
+    if not refpin.available():
+        raise SystemExit("reference tree not available; golden fixtures can only be generated in the build container")
+    main()

@@ -219,6 +219,7 @@ class Body(object):
     def position(self, pos):
         # body.py:420-423: the origin moves, the rotation stays
         self._check_unlocked()
+        self._before_transform_update()
         pos = Vec2(*pos)
         self._xf = (pos.x, pos.y, self._xf[2], self._xf[3])
         self._transform_updated()
@@ -231,6 +232,7 @@ class Body(object):
     def angle(self, angle):
         # body.py:430-433
         self._check_unlocked()
+        self._before_transform_update()
         angle = float(angle)
         self._xf = (self._xf[0], self._xf[1], math.cos(angle), math.sin(angle))
         self._transform_updated()
@@ -243,12 +245,17 @@ class Body(object):
     def transform(self, position_angle):
         """body.py:384-395: `(position, angle)`, or a transform as this facade hands them out (`(px, py, cos, sin)`)."""
         self._check_unlocked()
+        self._before_transform_update()
         if len(position_angle) == 4:
             self._xf = tuple(float(v) for v in position_angle)
         else:
             pos, angle = Vec2(*position_angle[0]), float(position_angle[1])
             self._xf = (pos.x, pos.y, math.cos(angle), math.sin(angle))
         self._transform_updated()
+
+    def _before_transform_update(self):
+        if self._world is not None:
+            self._world._before_host_move(self)
 
     def _transform_updated(self):
         """body.py:404-413: the sweep restarts at the new transform (the angle read back from the rotation, as there), every

@@ -169,6 +169,8 @@ class World(object):
         self._tree_leaf = {}            # (id(fixture), child) -> leaf slot
         self._proxy_count = 0
         self._tree_fat = None           # the device's fat boxes as of the last replay, rows in `_packed_keys` order
+        self._moved_proxies = {}        # proxies of bodies whose transform the host set: key -> (tight box, re-inserted?)
+        self._moved_body = None
 
     # -- properties (world.py:93-181) ------------------------------------------------------
     @property
@@ -385,7 +387,70 @@ class World(object):
                     self._tree.reinsert_leaf(slot, fat[j])
         self._tree_fat = fat
 
+    def _before_host_move(self, body):
+        """The reference looks for new contacts at the end of EVERY transform setter (body.py:413), so the contacts of a body
+        moved earlier exist, in that call's pair order, before the next body moves.  When proxies of ANOTHER body are still
+        waiting for their pass, run it now: a narrowphase-only device step (dt = 0) with the new-fixture flag finds their
+        contacts first; its narrowphase runs on the transforms as they are and is repeated unchanged by the next real step."""
+        if self._moved_body is None or self._moved_body is body or not self._moved_proxies:
+            return
+        batch = self._ensure_batch()
+        batch.inv_dt0 = self._inv_dt0
+        batch.step(0.0, 1, 1, 1)
+        batch.download_into_world(self)
+        self._tree_fat = None
+
+    def _body_moved_by_host(self, body):
+        """`Body._transform_updated` (body.py:404-413): every proxy of the body is moved with no displacement
+        (`Fixture._synchronize(xf, xf)`, fixture.py:287-298 -> `DynamicTree.move_proxy`, dynamictree.py:152-188: nothing happens
+        while the old fat box still contains the new tight box, otherwise the leaf is re-inserted with the tight box grown by
+        AABB_EXTENSION and the proxy enters the move buffer), then `find_new_contacts` runs.  The boxes are decided here, on the
+        tree replay's leaf boxes (the device's fat boxes as of the last step), and uploaded before the next step with the world's
+        new-fixture flag, which makes that step find the new contacts before its narrowphase -- the same contacts as the
+        reference's immediate call; a second body moved before the next step first gets the first one's pass run
+        (`_before_host_move`), so that every setter has its own pass, as there."""
+        if not body._active:
+            return
+        tree = self._tree
+        for fixture in body.fixtures:
+            shape = fixture._shape
+            for child in range(shape.child_count):
+                key = (id(fixture), child)
+                slot = self._tree_leaf.get(key)
+                if slot is None:
+                    continue
+                tight = shape.compute_aabb(body._xf, child) if shape.child_count > 1 else shape.compute_aabb(body._xf)
+                moved = tree.move_leaf(slot, tight, (0.0, 0.0), AABB_EXTENSION, 0.0)
+                self._moved_proxies[key] = (tight, moved or self._moved_proxies.get(key, (None, False))[1])
+        self._moved_body = body
+        self._host_dirty = True
+
+    def _upload_moved_proxies(self):
+        import numpy as np
+        batch = self._batch
+        D = batch.download(["f_fat", "f_tight", "f_moved", "w_flags"])
+        row = {k: j for j, k in enumerate(self._packed_keys)}
+        for key, (tight, moved) in self._moved_proxies.items():
+            j, slot = row.get(key), self._tree_leaf.get(key)
+            if j is None or slot is None:
+                continue
+            D["f_tight"][0, j] = tight
+            D["f_fat"][0, j] = self._tree._box(slot)
+            if moved:
+                D["f_moved"][0, j] = 1
+        D["w_flags"] = D["w_flags"] | np.uint32(schema.WORLD_NEW_FIXTURE)
+        batch.upload(D)
+        self._moved_proxies = {}
+        self._moved_body = None
+        self._tree_fat = None
+
     def _ensure_batch(self):
+        batch = self._ensure_batch_packed()
+        if self._moved_proxies:
+            self._upload_moved_proxies()
+        return batch
+
+    def _ensure_batch_packed(self):
         from .batch import BatchedWorld
         if self._batch is None:
             self._batch = BatchedWorld.from_worlds([self], real=self._real, device=self._device)
