@@ -2,7 +2,7 @@
 """Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
  -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
 once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
-(823-825) and `fixed_rotation` (884-887) on a world that is already stepping.
+(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144) on a world that is already stepping.
 
 The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
 awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
@@ -54,6 +54,15 @@ def script(b2, world, record):
     B[30].transform = ((-6.0, 0.6), 0.0)
     B[31].transform = ((-6.0, 1.7), 0.0)           # two bodies moved between the same two steps, onto each other
     run(40)
+    md = B[25].mass_data                           # body.py:577-604: three times as heavy, the centre of mass off the box's centre
+    B[25].mass_data = type(md)(mass=3.0 * md.mass, center=(0.1, -0.05), I=3.0 * md.I + 0.2)
+    B[25].linear_velocity = (0.0, 3.0)
+    run(40)
+    f = B[22].fixtures[0]                          # fixture.py:130-144: the contacts created from now on mix the new values
+    f.friction = 0.9
+    f.restitution = 0.6
+    B[22].transform = ((1.0, 10.0), 0.1)           # dropped onto the pile: it bounces
+    run(70)
 
 
 def main():

@@ -415,7 +415,7 @@ class BatchedWorld(object):
         A = schema.alloc(self.caps, 1, 1, "f64")
         table = schema.ShapeTable()
         schema.pack_world(world, A, 0, table)
-        names = ["b_xf", "b_pos", "b_pos0", "b_vel", "b_force", "b_flags", "b_mass", "b_damp", "w_gravity"]
+        names = ["b_xf", "b_pos", "b_pos0", "b_vel", "b_force", "b_flags", "b_mass", "b_damp", "f_mat", "w_gravity"]
         if getattr(world, "_joints_dirty", False):
             # a joint's parameters or flags were set between steps (joints.py setters); the joint list itself only changes
             # through World.add_joint / destroy_joint, which re-pack the world

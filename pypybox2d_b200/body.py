@@ -311,6 +311,39 @@ class Body(object):
         return self._I + self._mass * self._local_center.length_squared
 
     @property
+    def mass_data(self):
+        # body.py:563-575
+        lc = self._local_center
+        return _shapes.MassData(mass=self._mass, center=(lc.x, lc.y), I=self._I + self._mass * (lc.x * lc.x + lc.y * lc.y))
+
+    @mass_data.setter
+    def mass_data(self, md):
+        """body.py:577-604: override the fixtures' mass properties (dynamic bodies only); the centre of mass moves and the
+        linear velocity follows it."""
+        self._check_unlocked()
+        if self._type != Body.DYNAMIC:
+            return
+        self._I = 0.0
+        self._invI = 0.0
+        self._mass = md.mass
+        if self._mass <= 0.0:
+            self._mass = 1.0
+        self._inv_mass = 1.0 / self._mass
+        center = Vec2(*md.center)
+        if md.I > 0.0 and not self._fixed_rotation:
+            self._I = md.I - self._mass * (center.x * center.x + center.y * center.y)
+            assert self._I > 0.0
+            self._invI = 1.0 / self._I
+        old = self._c
+        self._local_center = center
+        self._c0 = Vec2(*self._xf_mul(self._local_center))
+        self._c = copy(self._c0)
+        dx, dy = self._c.x - old.x, self._c.y - old.y
+        w = float(self._angular_velocity)
+        self._linear_velocity = Vec2(self._linear_velocity.x + (-w * dy), self._linear_velocity.y + (w * dx))
+        self._dirty()
+
+    @property
     def type(self):
         return self._type
 

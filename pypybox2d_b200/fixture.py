@@ -6,7 +6,7 @@ becomes one row of the per-world proxy arrays when the world is packed (`schema.
 """
 from copy import copy
 
-from .common import EmptyFixtureError
+from .common import EmptyFixtureError, is_valid_float
 
 
 class Fixture(object):
@@ -43,10 +43,58 @@ class Fixture(object):
 
     shape = property(lambda self: self._shape)
     body = property(lambda self: self._body)
-    friction = property(lambda self: self._friction)
-    restitution = property(lambda self: self._restitution)
-    density = property(lambda self: self._density)
-    sensor = property(lambda self: self._sensor)
+
+    def _dirty(self):
+        if self._body is not None:
+            self._body._dirty()
+
+    @property
+    def friction(self):
+        return self._friction
+
+    @friction.setter
+    def friction(self, friction):
+        # fixture.py:130-132; existing contacts keep the mixed value they were created with (contact.py:165-166)
+        self._friction = friction
+        self._dirty()
+
+    @property
+    def restitution(self):
+        return self._restitution
+
+    @restitution.setter
+    def restitution(self, restitution):
+        self._restitution = restitution      # fixture.py:142-144
+        self._dirty()
+
+    @property
+    def density(self):
+        return self._density
+
+    @density.setter
+    def density(self, density):
+        # fixture.py:155-160: takes effect at the body's next reset_mass_data
+        if not is_valid_float(density) or density < 0:
+            raise ValueError("Invalid density")
+        self._density = density
+
+    @property
+    def sensor(self):
+        return self._sensor
+
+    @sensor.setter
+    def sensor(self, sensor):
+        # fixture.py:169-174: the body is woken.  The reference's narrowphase reads the flag at every update (contact.py:229-239);
+        # the device keeps it per contact from the contact's creation, so the flag can only change while no contact exists yet
+        if bool(sensor) != self._sensor:
+            world = self.world
+            if world is not None and world._stepped:
+                raise NotImplementedError("changing Fixture.sensor after the first step is not supported (the device keeps the "
+                                          "sensor flag per contact)")
+            if self._body is not None:
+                self._body.awake = True
+            self._sensor = bool(sensor)
+            self._dirty()
     category_bits = property(lambda self: self._category_bits)
     mask_bits = property(lambda self: self._mask_bits)
     group_index = property(lambda self: self._group_index)

@@ -44,6 +44,22 @@ def test_setters_on_the_host_without_a_device():
     a.linear_velocity = (1.0, 0.0)
     a.sleeping = True
     assert not a.awake and a.linear_velocity.x == 0.0
+    md = a.mass_data                                        # body.py:563-604
+    assert md.mass == 1.0 and md.center.x == 0.0 and abs(md.I - 1.0 / 6.0) < 1e-15
+    a.mass_data = b2.MassData(mass=2.0, center=(0.25, 0.0), I=1.0)
+    assert a.mass == 2.0 and a.local_center.x == 0.25 and a._invI == 1.0 / (1.0 - 2.0 * 0.0625)
+    assert abs(a.world_center.x - (3.0 + 0.25 * math.cos(1.0))) < 1e-15
+    g.mass_data = b2.MassData(mass=5.0)                     # no effect on a static body
+    assert g.mass == 0.0
+    f = a.fixtures[0]
+    f.friction, f.restitution, f.density = 0.7, 0.4, 3.0    # fixture.py:130-160
+    assert (f.friction, f.restitution, f.density) == (0.7, 0.4, 3.0) and a.mass == 2.0
+    a.reset_mass_data()
+    assert a.mass == 3.0
+    with pytest.raises(ValueError):
+        f.density = -1.0
+    f.sensor = True                                         # before the first step: a host flag; the body is woken (fixture.py:169-174)
+    assert f.sensor and a.awake
 
 
 @pytest.mark.gpu
