@@ -2,7 +2,7 @@
 """Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
  -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
 once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
-(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144) on a world that is already stepping.
+(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225) on a world that is already stepping.
 
 The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
 awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
@@ -63,6 +63,19 @@ def script(b2, world, record):
     f.restitution = 0.6
     B[22].transform = ((1.0, 10.0), 0.1)           # dropped onto the pile: it bounces
     run(70)
+    f14 = B[14].fixtures[0]                        # fixture.py:176-225, 269-285: collides with nothing any more, falls out of the pile
+    f14.mask_bits = 0x0000
+    run(25)
+    B[16].fixtures[0].group_index = -3             # two boxes of one negative group stop colliding with each other
+    B[17].fixtures[0].group_index = -3
+    run(30)
+    f14.mask_bits = 0xFFFF                         # collides again, and is dropped back onto the pile
+    B[14].transform = ((0.0, 12.0), 0.0)
+    B[14].linear_velocity = (0.0, 0.0)
+    run(60)
+    B[18].fixtures[0].category_bits = 0x0002       # B[19] no longer accepts B[18]'s category
+    B[19].fixtures[0].mask_bits = 0xFFFD
+    run(40)
 
 
 def main():

@@ -95,9 +95,29 @@ class Fixture(object):
                 self._body.awake = True
             self._sensor = bool(sensor)
             self._dirty()
-    category_bits = property(lambda self: self._category_bits)
-    mask_bits = property(lambda self: self._mask_bits)
-    group_index = property(lambda self: self._group_index)
+
+    # collision filter (fixture.py:176-225): the fixture's contacts are flagged for re-filtering and its proxies touched
+    def _filter_field(name):
+        def fget(self):
+            return getattr(self, name)
+
+        def fset(self, value):
+            setattr(self, name, int(value))
+            self._refilter()
+        return property(fget, fset)
+
+    category_bits = _filter_field("_category_bits")
+    mask_bits = _filter_field("_mask_bits")
+    group_index = _filter_field("_group_index")
+    del _filter_field
+
+    def _refilter(self):
+        # fixture.py:269-285
+        if self._body is None:
+            return
+        world = self.world
+        if world is not None:
+            world._fixture_refiltered(self)
 
     def get_aabb(self, child_index=0):
         """The fixture's broadphase AABB as ((lx, ly), (ux, uy)) -- the swept box of the last synchronisation, possibly stale

@@ -171,6 +171,8 @@ class World(object):
         self._tree_fat = None           # the device's fat boxes as of the last replay, rows in `_packed_keys` order
         self._moved_proxies = {}        # proxies of bodies whose transform the host set: key -> (tight box, re-inserted?)
         self._moved_body = None
+        self._flagged_contacts = set()  # contacts flagged for re-filtering (contact.py:77): (proxy key a, proxy key b)
+        self._touched_proxies = set()   # proxies put back into the move buffer by Fixture._refilter (fixture.py:283-285)
 
     # -- properties (world.py:93-181) ------------------------------------------------------
     @property
@@ -387,6 +389,24 @@ class World(object):
                     self._tree.reinsert_leaf(slot, fat[j])
         self._tree_fat = fat
 
+    def _fixture_refiltered(self, fixture):
+        """`Fixture._refilter` (fixture.py:269-285) after a filter change: the fixture's contacts are flagged -- the next
+        narrowphase pass that looks at them (one of the two bodies awake and not static, contact_manager.py:192-208) drops those
+        that may no longer collide -- and its proxies go back into the move buffer, so that the pair pass at the end of the next
+        step can create the contacts the new filter allows.  Host mutation of the device contact list: applied when the world is
+        packed again before the next step (`_rebuild_batch`)."""
+        self._host_dirty = True
+        if not self._stepped or self._batch is None:
+            return                              # no contacts yet, and every proxy is still in the move buffer
+        D = self._batch.download(["c_fix", "w_count"])
+        for k in range(int(D["w_count"][0, 2])):
+            a, b = int(D["c_fix"][0, k, 0]), int(D["c_fix"][0, k, 1])
+            if self._packed_fixtures[a] is fixture or self._packed_fixtures[b] is fixture:
+                self._flagged_contacts.add((self._packed_keys[a], self._packed_keys[b]))
+        for child in range(fixture._shape.child_count):
+            self._touched_proxies.add((id(fixture), child))
+        self._structure_dirty = True
+
     def _before_host_move(self, body):
         """The reference looks for new contacts at the end of EVERY transform setter (body.py:413), so the contacts of a body
         moved earlier exist, in that call's pair order, before the next body moves.  When proxies of ANOTHER body are still
@@ -499,6 +519,7 @@ class World(object):
                 for name in ("f_fat", "f_tight", "f_moved"):
                     A[name][0, j2] = D[name][0, j]
         k2 = 0
+        still_flagged = set()
         for k in range(int(D["w_count"][0, 2])):
             a2, b2 = int(remap[int(D["c_fix"][0, k, 0])]), int(remap[int(D["c_fix"][0, k, 1])])
             if a2 < 0 or b2 < 0:
@@ -506,11 +527,24 @@ class World(object):
             ba, bb = fixtures[a2]._body, fixtures[b2]._body
             if any(not j._collide_connected and j._body_a is not None and j.other_body(ba) is bb for j in ba.joints):
                 continue                       # Body._should_collide (body.py:920-926), see add_joint
+            ck = (keys[a2], keys[b2])
+            if ck in self._flagged_contacts:   # contact_manager.py:192-208
+                if (ba._awake and ba._type != Body.STATIC) or (bb._awake and bb._type != Body.STATIC):
+                    if (ba._type != Body.DYNAMIC and bb._type != Body.DYNAMIC) or \
+                            not self.default_contact_filter(fixtures[a2], fixtures[b2]):
+                        continue
+                else:
+                    still_flagged.add(ck)      # both bodies rest: the pass skips the contact, the flag stays
             A["c_fix"][0, k2] = (a2, b2)
             for name in ("c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"):
                 A[name][0, k2] = D[name][0, k]
             k2 += 1
         A["w_count"][0, 2] = k2
+        self._flagged_contacts = still_flagged
+        for j2, key in enumerate(keys):
+            if key in self._touched_proxies and fixtures[j2]._body._active:
+                A["f_moved"][0, j2] = 1        # BroadPhase.touch_proxy (broadphase.py:70-72)
+        self._touched_proxies = set()
         flags = int(A["w_flags"][0])
         if not any_new and not (int(D["w_flags"][0]) & schema.WORLD_NEW_FIXTURE):
             flags &= ~schema.WORLD_NEW_FIXTURE
@@ -521,7 +555,8 @@ class World(object):
         self._packed_fixtures = fixtures
         self._packed_keys = keys
         self._host_dirty = False
-        self._structure_dirty = False
+        self._structure_dirty = bool(still_flagged)      # flagged contacts of resting pairs are looked at again before the next step
+        self._tree_fat = None
 
     def step(self, dt, vel_iters, pos_iters):
         if self._locked:

@@ -1,5 +1,6 @@
 """Body properties set between steps: `Body.position / angle / transform` (body.py:384-433), the damping, gravity
-scale, bullet, allow_sleep, sleeping and fixed_rotation setters (body.py:710-890) on a world that is already stepping.
+scale, bullet, allow_sleep, sleeping, fixed_rotation and mass_data setters (body.py:577-604, 710-890), `Fixture.friction /
+restitution` and the collision filter (`mask_bits / category_bits / group_index`, fixture.py:130-225) on a world that is already stepping.
 tests/golden_queries/setters.npz is the LIVE reference's trajectory of the scenario in oracle/gen_setters_golden.py (`script`);
 the same script runs here through pypybox2d_b200.World on the fp64 kernels."""
 import math
@@ -58,6 +59,8 @@ def test_setters_on_the_host_without_a_device():
     assert a.mass == 3.0
     with pytest.raises(ValueError):
         f.density = -1.0
+    f.mask_bits, f.category_bits, f.group_index = 0xFFFD, 0x0004, -2     # fixture.py:176-225 (before the first step: host fields)
+    assert (f.mask_bits, f.category_bits, f.group_index) == (0xFFFD, 0x0004, -2) and not w._flagged_contacts
     f.sensor = True                                         # before the first step: a host flag; the body is woken (fixture.py:169-174)
     assert f.sensor and a.awake
 
