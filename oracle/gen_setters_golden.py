@@ -2,7 +2,7 @@
 """Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
  -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
 once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
-(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225) on a world that is already stepping.
+(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225), `Fixture.sensor` (169-174) on a world that is already stepping.
 
 The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
 awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
@@ -75,6 +75,10 @@ def script(b2, world, record):
     run(60)
     B[18].fixtures[0].category_bits = 0x0002       # B[19] no longer accepts B[18]'s category
     B[19].fixtures[0].mask_bits = 0xFFFD
+    run(40)
+    B[23].fixtures[0].sensor = True                # fixture.py:169-174: no collision response any more: it sinks through the pile
+    run(12)
+    B[23].fixtures[0].sensor = False               # solid again, inside other boxes
     run(40)
 
 

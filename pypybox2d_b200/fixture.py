@@ -85,16 +85,16 @@ class Fixture(object):
     @sensor.setter
     def sensor(self, sensor):
         # fixture.py:169-174: the body is woken.  The reference's narrowphase reads the flag at every update (contact.py:229-239);
-        # the device keeps it per contact from the contact's creation, so the flag can only change while no contact exists yet
+        # the device keeps it per contact from the contact's creation, so the world is packed again before the next step and the
+        # flag of every carried contact is set from its two fixtures (World._rebuild_batch)
         if bool(sensor) != self._sensor:
-            world = self.world
-            if world is not None and world._stepped:
-                raise NotImplementedError("changing Fixture.sensor after the first step is not supported (the device keeps the "
-                                          "sensor flag per contact)")
             if self._body is not None:
                 self._body.awake = True
             self._sensor = bool(sensor)
             self._dirty()
+            world = self.world
+            if world is not None and world._stepped:
+                world._structure_dirty = True
 
     # collision filter (fixture.py:176-225): the fixture's contacts are flagged for re-filtering and its proxies touched
     def _filter_field(name):

@@ -538,6 +538,10 @@ class World(object):
             A["c_fix"][0, k2] = (a2, b2)
             for name in ("c_flags", "c_mat", "c_mtype", "c_mf", "c_pts", "c_imp", "c_id"):
                 A[name][0, k2] = D[name][0, k]
+            if fixtures[a2]._sensor or fixtures[b2]._sensor:       # Fixture.sensor may have been set since (contact.py:229-231)
+                A["c_flags"][0, k2] |= schema.CONTACT_SENSOR
+            else:
+                A["c_flags"][0, k2] &= ~np.uint32(schema.CONTACT_SENSOR)
             k2 += 1
         A["w_count"][0, 2] = k2
         self._flagged_contacts = still_flagged

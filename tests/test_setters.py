@@ -61,7 +61,7 @@ def test_setters_on_the_host_without_a_device():
         f.density = -1.0
     f.mask_bits, f.category_bits, f.group_index = 0xFFFD, 0x0004, -2     # fixture.py:176-225 (before the first step: host fields)
     assert (f.mask_bits, f.category_bits, f.group_index) == (0xFFFD, 0x0004, -2) and not w._flagged_contacts
-    f.sensor = True                                         # before the first step: a host flag; the body is woken (fixture.py:169-174)
+    f.sensor = True                                         # the body is woken (fixture.py:169-174)
     assert f.sensor and a.awake
 
 
