@@ -2,7 +2,7 @@
 """Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
  -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
 once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
-(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225), `Fixture.sensor` (169-174) on a world that is already stepping.
+(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225), `Fixture.sensor` (169-174), `Body.type` (body.py:742-767) on a world that is already stepping.
 
 The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
 awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
@@ -80,6 +80,16 @@ def script(b2, world, record):
     run(12)
     B[23].fixtures[0].sensor = False               # solid again, inside other boxes
     run(40)
+    B[22].transform = ((0.5, 14.0), 0.0)           # lifted above the pile and frozen there: body.py:742-767
+    B[22].type = b2.Body.STATIC
+    B[20].transform = ((0.6, 16.0), 0.2)           # dropped onto the frozen box
+    B[20].linear_velocity = (0.0, 0.0)
+    run(60)
+    B[22].type = b2.Body.KINEMATIC                 # the platform moves away sideways under the box
+    B[22].linear_velocity = (1.5, 0.0)
+    run(40)
+    B[22].type = b2.Body.DYNAMIC                   # and is released
+    run(50)
 
 
 def main():

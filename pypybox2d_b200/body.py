@@ -347,6 +347,28 @@ class Body(object):
     def type(self):
         return self._type
 
+    @type.setter
+    def type(self, _type):
+        """body.py:742-767: mass data recomputed for the new type, a body that turns static stops, the body is woken, its forces
+        are dropped and the contacts of its fixtures are flagged for re-filtering (two bodies of which none is dynamic may not
+        collide, body.py:910-918)."""
+        self._check_unlocked()
+        if self._type == _type:
+            return
+        if _type not in (Body.STATIC, Body.DYNAMIC, Body.KINEMATIC):
+            raise ValueError("Invalid body type")
+        self._type = _type
+        self.reset_mass_data()
+        if _type == Body.STATIC:
+            self._linear_velocity = Vec2()
+            self._angular_velocity = 0.0
+        self.awake = True
+        self._force = Vec2()
+        self._torque = 0.0
+        for fixture in self.fixtures:
+            fixture._refilter()
+        self._dirty()
+
     static = property(lambda self: self._type == Body.STATIC)
     dynamic = property(lambda self: self._type == Body.DYNAMIC)
     kinematic = property(lambda self: self._type == Body.KINEMATIC)

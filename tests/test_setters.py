@@ -59,6 +59,13 @@ def test_setters_on_the_host_without_a_device():
     assert a.mass == 3.0
     with pytest.raises(ValueError):
         f.density = -1.0
+    a.linear_velocity = (1.0, 2.0)
+    a.type = b2.Body.STATIC                                 # body.py:742-767
+    assert a.static and a.mass == 0.0 and a.linear_velocity.x == 0.0 and a.awake
+    a.type = b2.Body.DYNAMIC
+    assert a.dynamic and a.mass == 3.0
+    with pytest.raises(ValueError):
+        a.type = 7
     f.mask_bits, f.category_bits, f.group_index = 0xFFFD, 0x0004, -2     # fixture.py:176-225 (before the first step: host fields)
     assert (f.mask_bits, f.category_bits, f.group_index) == (0xFFFD, 0x0004, -2) and not w._flagged_contacts
     f.sensor = True                                         # the body is woken (fixture.py:169-174)
