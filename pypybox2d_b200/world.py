@@ -7,7 +7,7 @@ objects.  A single `World` is a batch of one; large batches use `BatchedWorld` d
 (`BatchedWorld.replicate(world, n, ...)`), which never touches per-body Python on the step path.
 
 Revolute, distance, weld, prismatic, rope, friction, wheel, pulley and mouse joints (`joints.py`) are solved inside the island solver kernels.  Unsupported on this path
-(raise `NotImplementedError`): the gear joint, `pre_solve` / `post_solve` listeners,
+(raise `NotImplementedError`): the gear joint, the `pre_solve` listener,
 custom contact filters and sub-stepping.  Continuous collision
 (`continuous_physics=True`, the reference's default: `World.solve_toi`, world.py:594-821) runs on the device.
 """
@@ -78,6 +78,7 @@ class _ContactManagerView(object):
     def __init__(self, world):
         self._world = world
         self.broadphase = _BroadPhaseView(world)
+        self._post_solve = None
 
     @property
     def contacts(self):
@@ -85,8 +86,9 @@ class _ContactManagerView(object):
 
     # Contact listeners (contact_manager.py:46-100).  begin_contact / end_contact are delivered after the step that caused
     # them, in the reference's order (the narrowphase walks the contact list: contact.py:263-266, contact_manager.py:167-168),
-    # from the difference between the device contact lists before and after the step; pre_solve / post_solve would have to
-    # run inside the solver kernels and are not supported.
+    # from the difference between the device contact lists before and after the step; post_solve is delivered after the step from the island
+    # lists and the stored impulses (World._deliver_post_solve); pre_solve would have to run between the narrowphase and the
+    # solver kernels of every step and is not supported.
     def __init_listeners(self):
         self._begin_contact = None
         self._end_contact = None
@@ -120,16 +122,19 @@ class _ContactManagerView(object):
 
     @property
     def post_solve(self):
-        return None
+        return self._post_solve
 
     @post_solve.setter
     def post_solve(self, fcn):
-        if fcn is not None:
-            raise NotImplementedError("post_solve callbacks cannot run inside the device step (SURVEY §8b)")
+        """`post_solve(contact, impulses)` (contact_manager.py:82-96): what `Island.report` (island.py:245-252) hands out after an
+        island's solve -- the island's contacts in island order with the accumulated (normal, tangent) impulse of every manifold
+        point.  Nothing in it feeds back into the step, so it is delivered after the device step from the island lists and the
+        stored impulses (`World._deliver_post_solve`)."""
+        self._post_solve = fcn
 
     @property
     def contact_listener(self):
-        return [self.begin_contact, self.end_contact, None, None]
+        return [self.begin_contact, self.end_contact, None, self.post_solve]
 
 
 class World(object):
@@ -600,6 +605,8 @@ class World(object):
             batch.download_into_world(self)
             self._tree_replay(batch)
             self._deliver_contact_events()
+            if dt > 0.0:
+                self._deliver_post_solve(batch)
             if not self._auto_clear_forces:
                 # forces were cleared on the device only when auto_clear_forces is on
                 pass
@@ -712,6 +719,24 @@ class World(object):
         for c in cur:                                   # (a contact cannot be created touching; kept for robustness)
             if (id(c.fixture_a), id(c.fixture_b)) not in seen and c.touching and cm.begin_contact is not None:
                 cm.begin_contact(c)
+
+    def _deliver_post_solve(self, batch):
+        """island.py:245-252 for every island the step solved, in island order (world.py:574): the step's end only appends
+        contacts, so the island lists' contact rows still name the same contacts; the impulses are the ones the solver stored
+        (contact.py:801-810).  Not reproduced: the reports of the TOI sub-islands of a world with continuous collision
+        (island.py:243), and the shortened impulse list of a two-point contact whose block matrix was ill-conditioned
+        (contact.py:507-510: both stored impulses are handed out here)."""
+        fcn = self.contact_manager._post_solve
+        if fcn is None:
+            return
+        D = batch.download(["w_island", "l_contact"])
+        n = int(D["w_island"][0, 2])
+        if n == 0:
+            return
+        views = self._contact_views()
+        for k in range(n):
+            c = views[int(D["l_contact"][0, k])]
+            fcn(c, [(ni, ti) for _, ni, ti in c.points])
 
     def _contact_views(self):
         if self._batch is None:
