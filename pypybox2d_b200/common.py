@@ -133,6 +133,62 @@ class Vec2(object):
         return not (math.isnan(self.x) or math.isnan(self.y))
 
 
+class AABB(object):
+    """An axis-aligned box as callers of `World.query_aabb` build it (common.py:707-870: `AABB(lower_bound, upper_bound)`): a value
+    object over four floats with the reference's read-outs."""
+    __slots__ = ("lx", "ly", "ux", "uy")
+
+    def __init__(self, lower_bound=(0, 0), upper_bound=(0, 0)):
+        (self.lx, self.ly), (self.ux, self.uy) = (float(v) for v in lower_bound), (float(v) for v in upper_bound)
+
+    def __repr__(self):
+        return "AABB(lower_bound=%s, upper_bound=%s)" % (self.lower_bound, self.upper_bound)
+
+    def __copy__(self):
+        return AABB((self.lx, self.ly), (self.ux, self.uy))
+
+    @property
+    def lower_bound(self):
+        return Vec2(self.lx, self.ly)
+
+    @lower_bound.setter
+    def lower_bound(self, v):
+        self.lx, self.ly = (float(x) for x in v)
+
+    @property
+    def upper_bound(self):
+        return Vec2(self.ux, self.uy)
+
+    @upper_bound.setter
+    def upper_bound(self, v):
+        self.ux, self.uy = (float(x) for x in v)
+
+    @property
+    def valid(self):
+        return self.ux - self.lx >= 0.0 and self.uy - self.ly >= 0.0 and all(is_valid_float(v) for v in (self.lx, self.ly, self.ux, self.uy))
+
+    @property
+    def center(self):
+        return Vec2(0.5 * (self.lx + self.ux), 0.5 * (self.ly + self.uy))
+
+    @property
+    def extents(self):
+        return Vec2(0.5 * (self.ux - self.lx), 0.5 * (self.uy - self.ly))
+
+    @property
+    def perimeter(self):
+        return 2.0 * ((self.ux - self.lx) + (self.uy - self.ly))
+
+    def __add__(self, other):
+        return AABB((min(self.lx, other.lx), min(self.ly, other.ly)), (max(self.ux, other.ux), max(self.uy, other.uy)))
+
+    def contains(self, other):
+        return self.lx <= other.lx and self.ly <= other.ly and other.ux <= self.ux and other.uy <= self.uy
+
+    def test_overlap(self, other):
+        return not (other.lx - self.ux > 0.0 or other.ly - self.uy > 0.0 or self.lx - other.ux > 0.0 or self.ly - other.uy > 0.0)
+
+
 def scalar_cross(s, v):
     """scalar x vector (common.py:195-202)."""
     return Vec2(-float(s) * v[1], float(s) * v[0])

@@ -205,3 +205,17 @@ def test_loop_shape_packs_one_proxy_per_child_edge():
     assert len(table) == 8 and sum((m >> 18) & 1 for m in table.meta) == 7            # seven child edges, one circle
     assert A["f_tight"][0, 0].tolist() == [-5.0, 0.0, 5.0, 0.0]                          # no radius margin (shapes.py:822-837)
     assert np.allclose(A["f_fat"][0, 0], [-5.1, -0.1, 5.1, 0.1])
+
+
+def test_aabb_value_class_and_controller_exports():
+    """`AABB` as callers of `World.query_aabb` build it (common.py:707-870), and the controller classes on the package."""
+    import pypybox2d_b200 as b2
+    a, b = b2.AABB((0, 0), (2, 1)), b2.AABB(lower_bound=(1, 0.5), upper_bound=(3, 3))
+    assert a.perimeter == 6.0 and a.center.x == 1.0 and a.extents.y == 0.5 and a.valid
+    assert (a + b).lower_bound.x == 0.0 and (a + b).upper_bound.y == 3.0
+    assert a.test_overlap(b) and not a.contains(b) and (a + b).contains(a)
+    assert not a.test_overlap(b2.AABB((2.5, 0), (3, 1)))
+    a.lower_bound = (-1, -1)
+    assert a.lower_bound.x == -1.0 and a.perimeter == 10.0
+    assert not b2.AABB((1, 1), (0, 0)).valid
+    assert issubclass(b2.GravityController, b2.Controller) and issubclass(b2.BuoyancyController, b2.Controller)
