@@ -6,7 +6,7 @@ hand-written sm_100a CUDA kernels (`csrc/`) reached through the C-ABI in `includ
 there is no CPU implementation of the step in this package.
 """
 from . import settings, shapes, scenes, schema
-from .common import Vec2, AABB, PhysicsError, LockedError, EmptyFixtureError, scalar_cross, clamp, is_valid_float
+from .common import Vec2, AABB, Transform, PhysicsError, LockedError, EmptyFixtureError, scalar_cross, clamp, is_valid_float
 from .settings import PI, EPSILON, MAX_FLOAT
 from .shapes import Circle, Polygon, Edge, Loop, MassData
 from .fixture import Fixture
@@ -18,7 +18,7 @@ from . import controllers
 from .controllers import Controller, GravityController, BuoyancyController
 from .batch import BatchedWorld
 
-__all__ = ["World", "Body", "Fixture", "Circle", "Polygon", "Edge", "Loop", "Vec2", "AABB", "BatchedWorld", "controllers", "Controller", "GravityController", "BuoyancyController",
+__all__ = ["World", "Body", "Fixture", "Circle", "Polygon", "Edge", "Loop", "Vec2", "AABB", "Transform", "BatchedWorld", "controllers", "Controller", "GravityController", "BuoyancyController",
            "PhysicsError", "LockedError", "EmptyFixtureError", "TimeStep", "MassData",
            "scalar_cross", "clamp", "is_valid_float", "PI", "EPSILON", "MAX_FLOAT",
            "settings", "shapes", "scenes", "schema", "joints", "RevoluteJoint", "DistanceJoint", "WeldJoint", "PrismaticJoint", "RopeJoint", "FrictionJoint", "WheelJoint", "PulleyJoint", "MouseJoint"]

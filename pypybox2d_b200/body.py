@@ -10,7 +10,7 @@ import math
 from copy import copy
 
 from . import shapes as _shapes
-from .common import Vec2, LockedError, is_valid_float
+from .common import Vec2, Transform, LockedError, is_valid_float
 from .fixture import Fixture
 
 
@@ -239,7 +239,7 @@ class Body(object):
 
     @property
     def transform(self):
-        return self._xf
+        return Transform(self._xf[:2], cos_sin=self._xf[2:])
 
     @transform.setter
     def transform(self, position_angle):

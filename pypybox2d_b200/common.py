@@ -133,6 +133,35 @@ class Vec2(object):
         return not (math.isnan(self.x) or math.isnan(self.y))
 
 
+class Transform(tuple):
+    """A rigid transform as `Body.transform` hands it out (common.py:618-706: `.position`, `.angle`, `xf * v`, `xf.mul_t(v)`),
+    stored the way this package keeps transforms everywhere: the tuple (px, py, cos, sin)."""
+    __slots__ = ()
+
+    def __new__(cls, position=(0, 0), angle=0.0, cos_sin=None):
+        c, s = cos_sin if cos_sin is not None else (math.cos(angle), math.sin(angle))
+        return tuple.__new__(cls, (float(position[0]), float(position[1]), float(c), float(s)))
+
+    def __repr__(self):
+        return "Transform(position=%s, angle=%g)" % (self.position, self.angle)
+
+    @property
+    def position(self):
+        return Vec2(self[0], self[1])
+
+    @property
+    def angle(self):
+        return math.atan2(self[3], self[2])
+
+    def __mul__(self, v):
+        x, y = v
+        return Vec2(self[0] + self[2] * x + (-self[3]) * y, self[1] + self[3] * x + self[2] * y)
+
+    def mul_t(self, v):
+        x, y = v[0] - self[0], v[1] - self[1]
+        return Vec2(self[2] * x + self[3] * y, (-self[3]) * x + self[2] * y)
+
+
 class AABB(object):
     """An axis-aligned box as callers of `World.query_aabb` build it (common.py:707-870: `AABB(lower_bound, upper_bound)`): a value
     object over four floats with the reference's read-outs."""

@@ -219,3 +219,22 @@ def test_aabb_value_class_and_controller_exports():
     assert a.lower_bound.x == -1.0 and a.perimeter == 10.0
     assert not b2.AABB((1, 1), (0, 0)).valid
     assert issubclass(b2.GravityController, b2.Controller) and issubclass(b2.BuoyancyController, b2.Controller)
+
+
+def test_transform_value_class():
+    """`Body.transform` as a value with the reference's read-outs (common.py:618-706)."""
+    import math
+    import pypybox2d_b200 as b2
+    w = b2.World(continuous_physics=False)
+    a = w.create_dynamic_body(position=(1, 2), angle=0.5, fixtures=b2.Fixture(b2.Circle(0.5), density=1))
+    xf = a.transform
+    assert xf.position.x == 1.0 and xf.position.y == 2.0 and abs(xf.angle - 0.5) < 1e-15
+    p = xf * (1.0, 0.0)
+    assert abs(p.x - (1.0 + math.cos(0.5))) < 1e-15 and abs(p.y - (2.0 + math.sin(0.5))) < 1e-15
+    q = xf.mul_t(p)
+    assert abs(q.x - 1.0) < 1e-15 and abs(q.y) < 1e-15
+    b = w.create_dynamic_body(fixtures=b2.Fixture(b2.Circle(0.5), density=1))
+    b.transform = xf                                        # a transform, or (position, angle): body.py:384-395
+    assert b.transform == xf and b.position.y == 2.0
+    b.transform = b2.Transform(position=(4, 5), angle=0.25)
+    assert b.position.x == 4.0 and abs(b.angle - 0.25) < 1e-15
