@@ -254,6 +254,8 @@ class World(object):
                 self.joint_destruction_listener(joint)
             self.destroy_joint(joint)
         for fixture in body.fixtures:            # body.py:330-335
+            if self.fixture_destruction_listener:
+                self.fixture_destruction_listener(fixture)
             n = self._tree_destroy(fixture)
             self._proxy_count -= n               # ... and 337-340: the second walk only moves the counter
         self.bodies.remove(body)

@@ -31,8 +31,10 @@ def test_facade_mutation_guards_without_a_device():
     assert a.mass < m2 and f.body is None and len(a.fixtures) == 1
     with pytest.raises(ValueError):
         a.destroy_fixture(f)
+    gone = []
+    w.fixture_destruction_listener = gone.append            # body.py:330-333: told about every fixture of a destroyed body
     w.destroy_body(a)
-    assert a not in w.bodies and a._world is None
+    assert a not in w.bodies and a._world is None and gone == list(a.fixtures)
     with pytest.raises(ValueError):
         w.destroy_body(a)
     w.add_body(a)                                           # a destroyed body can be attached again (world.py:238-241)
