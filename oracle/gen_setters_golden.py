@@ -2,7 +2,7 @@
 """Generate tests/golden_queries/setters.npz from the LIVE reference (build container only): body properties set between steps
  -- `Body.position / angle / transform` (body.py:384-433: the proxies are moved and new contacts are looked for at
 once), `linear_damping / angular_damping / gravity_scale / bullet` (body.py:710-775), `allow_sleep` (785-790), `sleeping`
-(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225), `Fixture.sensor` (169-174), `Body.type` (body.py:742-767) on a world that is already stepping.
+(823-825), `fixed_rotation` (884-887), `mass_data` (577-604) and `Fixture.friction / restitution` (fixture.py:130-144), `Fixture.mask_bits / category_bits / group_index` (fixture.py:176-225), `Fixture.sensor` (169-174), `Body.type` (body.py:742-767), `Body.active` (848-872) on a world that is already stepping.
 
 The script is the scenario: an 8-row pyramid (pair order pinned, continuous collision off).  After every step the body state, the
 awake flags, the contact list and the broadphase tree (height, quality, preorder by fixture index) are stored;
@@ -22,7 +22,7 @@ import gen_tree_golden as gt  # noqa: E402
 DT, VI, PI = 1.0 / 60, 8, 3
 
 
-def script(b2, world, record):
+def script(b2, world, record, reindex=lambda w: None):
     """The scenario, written against the API module `b2` (the reference or this package)."""
     def run(n):
         for _ in range(n):
@@ -90,6 +90,19 @@ def script(b2, world, record):
     run(40)
     B[22].type = b2.Body.DYNAMIC                   # and is released
     run(50)
+    box = b2.Fixture(b2.Polygon(box=(0.5, 0.5)), density=5.0)
+    ghost = world.create_dynamic_body(position=(0.3, 15.0), active=False, fixtures=box)    # body.py:848-872
+    reindex(world)
+    run(15)                                        # an inactive body has no proxies and is not simulated: it hangs there
+    ghost.active = True                            # proxies created; the pair pass at the end of the next step sees them
+    run(12)                                        # in free fall, no contact yet
+    ghost.active = False                           # proxies and (no) contacts gone: it hangs again, keeping its velocity
+    run(10)
+    late = world.create_dynamic_body(position=(-0.4, 13.0), angle=0.3, active=False, fixtures=box)
+    reindex(world)
+    run(5)
+    late.active = True
+    run(70)                                        # lands on the pile
 
 
 def main():
@@ -106,9 +119,10 @@ def main():
         fidx = {id(f): j for j, f in enumerate([f for b in w.bodies for f in b.fixtures])}
         obs.append((bp.tree_height, bp.tree_quality))
         pre.append(np.array(gt.preorder(bp._tree._root, lambda n: fidx[id(n.user_data.fixture)]), np.int32))
-    script(b2, world, record)
-    out = {"states": np.array(states), "awake": np.array(awakes), "n_contacts": np.array([len(c) for c in contacts], np.int32),
-           "contacts": np.concatenate(contacts), "tree_obs": np.array(obs), "tree_pre": np.array(pre)}
+    script(b2, world, record, reindex=refpin.index_fixtures)
+    out = {"n_bodies": np.array([len(x) for x in states], np.int32), "states": np.concatenate(states), "awake": np.concatenate(awakes),
+           "n_contacts": np.array([len(c) for c in contacts], np.int32), "contacts": np.concatenate(contacts),
+           "tree_obs": np.array(obs), "tree_len": np.array([len(x) for x in pre], np.int32), "tree_pre": np.concatenate(pre)}
     path = os.path.join(harness._ROOT, "tests", "golden_queries", "setters.npz")
     np.savez_compressed(path, **out)
     print("%d steps, contacts %d..%d, awake at the end %d of %d -> %s (%d KB)" % (

@@ -384,11 +384,19 @@ class Body(object):
         if self._active == bool(active):
             return
         if self._world is not None and self._world._stepped:
-            raise NotImplementedError("changing Body.active after the first step is not supported yet (SURVEY §8f #4)")
+            # host mutation of the device proxy rows and contact list: applied when the world is packed again before the next
+            # step.  Activation gives every fixture a fresh proxy in the move buffer (the pair pass at the END of the next step
+            # finds its contacts: no new-fixture flag, body.py:858-862); deactivation takes the proxies and ALL of the body's
+            # contacts away (the reference, iterating over the list it removes from, leaves every other one behind as a zombie
+            # without proxies, body.py:868-870 with contact_manager.py:170-172: identical for a body with at most one contact).
+            self._active = bool(active)
+            self._world._body_activation_changed(self)
+            return
         self._active = bool(active)
         if self._world is not None:
             self._world._batch = None          # proxies are rebuilt from the host state
             self._world._host_dirty = True
+            self._world._body_activation_changed(self)
 
     # plain per-body parameters the step reads (body.py:710-790, 880-890): set on the host, uploaded before the next step
     def _parameter(name, convert, after=None):

@@ -176,6 +176,7 @@ class World(object):
         self._tree_fat = None           # the device's fat boxes as of the last replay, rows in `_packed_keys` order
         self._moved_proxies = {}        # proxies of bodies whose transform the host set: key -> (tight box, re-inserted?)
         self._moved_body = None
+        self._activated = set()         # proxies of bodies activated since the world was packed: fresh boxes, in the move buffer
         self._flagged_contacts = set()  # contacts flagged for re-filtering (contact.py:77): (proxy key a, proxy key b)
         self._touched_proxies = set()   # proxies put back into the move buffer by Fixture._refilter (fixture.py:283-285)
 
@@ -396,6 +397,19 @@ class World(object):
                     self._tree.reinsert_leaf(slot, fat[j])
         self._tree_fat = fat
 
+    def _body_activation_changed(self, body):
+        """`Body.active` setter (body.py:848-872): proxies created (fixture.py:250-261) or destroyed (263-267) in the tree replay;
+        on a stepping world the device rows follow when the world is packed again (`_rebuild_batch`)."""
+        for fixture in body.fixtures:
+            if body._active:
+                self._tree_create(body, fixture)
+                self._activated.update((id(fixture), child) for child in range(fixture._shape.child_count))
+            else:
+                self._tree_destroy(fixture)
+        self._host_dirty = True
+        if self._stepped:
+            self._structure_dirty = True
+
     def _fixture_refiltered(self, fixture):
         """`Fixture._refilter` (fixture.py:269-285) after a filter change: the fixture's contacts are flagged -- the next
         narrowphase pass that looks at them (one of the two bodies awake and not static, contact_manager.py:192-208) drops those
@@ -522,9 +536,10 @@ class World(object):
                 any_new = True
                 continue
             remap[j] = j2
-            if f._body._active:
+            if f._body._active and keys[j2] not in self._activated:
                 for name in ("f_fat", "f_tight", "f_moved"):
                     A[name][0, j2] = D[name][0, j]
+        self._activated = set()
         k2 = 0
         still_flagged = set()
         for k in range(int(D["w_count"][0, 2])):
@@ -532,6 +547,8 @@ class World(object):
             if a2 < 0 or b2 < 0:
                 continue
             ba, bb = fixtures[a2]._body, fixtures[b2]._body
+            if not (ba._active and bb._active):
+                continue                       # Body.active = False took the body's contacts with it (body.py:868-872)
             if any(not j._collide_connected and j._body_a is not None and j.other_body(ba) is bb for j in ba.joints):
                 continue                       # Body._should_collide (body.py:920-926), see add_joint
             ck = (keys[a2], keys[b2])

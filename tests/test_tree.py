@@ -85,6 +85,10 @@ def test_facade_tracks_proxies_without_a_device():
     assert bp.proxy_count == 0                          # the reference's counter loses two per proxy of a destroyed body (body.py:330-340)
     off = w.create_dynamic_body(position=(3, 3), active=False, fixtures=b2.Fixture(b2.Circle(0.5), density=1))
     assert bp.proxy_count == 0 and len(w._tree_leaf) == 1 and off in w.bodies      # an inactive body's fixtures have no proxies (body.py:292-297)
+    off.active = True                                   # body.py:858-862: proxies created
+    assert bp.proxy_count == 1 and len(w._tree_leaf) == 2 and bp.tree_height == 1
+    off.active = False                                  # body.py:863-866
+    assert bp.proxy_count == 0 and len(w._tree_leaf) == 1 and bp.tree_height == 0
 
 
 @pytest.mark.gpu
